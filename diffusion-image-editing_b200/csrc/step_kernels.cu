@@ -1,0 +1,576 @@
+// Fused element-wise / reduction kernels of the guided denoising step (HBM-bound).
+//
+// Every kernel streams fp32 NCHW tensors with 128-bit coalesced accesses, four
+// independent 128-bit loads per input in flight per thread, and evaluates the
+// reference's expressions in the reference's op order with explicitly rounded
+// (non-contracted) fp32 operations, so results are bit-identical to the PyTorch path:
+//   x0  = (x - sb*e) / sa                         src/diffusion_utils.py:27-31
+//   xp  = sp*x0 + cdir*e (+ sigma*z)              DDIMScheduler.step / src/ddpm_inversion.py:203-240
+//   x0g = (xp - sb*e) / sa ; g = -((k*sign(x0g - tau))/sa) ; xp += (mask*)g * a_t^2
+//                                                  src/attr_functions.py:22-37,104-163
+#include <math.h>
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace b2e {
+
+std::atomic<long long> g_launches{0};
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ------------------------------------------------------------------------------------
+struct StepK {
+  float sa, sb, sp, cdir, sigma, a2, clip_range;
+  int clip, has_noise, noise_batched, guide, mask_grad, mask_batched;
+  int has_target[4];
+  float target[4];
+  float gk[4];  // k_c / sa  (== (k_c * s)/sa for s in {-1,0,1})
+};
+
+static StepK make_stepk(const b2e_guided_step_params* p) {
+  StepK k;
+  k.sa = p->c.sqrt_a_t; k.sb = p->c.sqrt_b_t; k.sp = p->c.sqrt_a_prev; k.cdir = p->c.dir_coef;
+  k.sigma = p->c.sigma; k.a2 = p->c.a_t_sq; k.clip_range = p->clip_range;
+  k.clip = p->clip; k.has_noise = p->has_noise; k.noise_batched = p->noise_batched;
+  k.guide = p->guide; k.mask_grad = p->mask_grad; k.mask_batched = p->mask_batched;
+  for (int i = 0; i < 4; ++i) {
+    k.has_target[i] = p->has_target[i];
+    k.target[i] = p->target[i];
+    k.gk[i] = p->coef[i] / p->c.sqrt_a_t;  // host fp32 division (IEEE)
+  }
+  return k;
+}
+
+__device__ __forceinline__ void step_elem(float x, float e, float z, float m, int has_t, float tau,
+                                          float gk, const StepK& k, float& xp_out, float& x0_out) {
+  float x0 = __fdiv_rn(__fsub_rn(x, __fmul_rn(k.sb, e)), k.sa);
+  if (k.clip) x0 = clamp_torch(x0, -k.clip_range, k.clip_range);
+  float xp = __fadd_rn(__fmul_rn(k.sp, x0), __fmul_rn(k.cdir, e));
+  if (k.has_noise) xp = __fadd_rn(xp, __fmul_rn(k.sigma, z));
+  if (k.guide && has_t) {
+    float x0g = __fdiv_rn(__fsub_rn(xp, __fmul_rn(k.sb, e)), k.sa);
+    float g = -__fmul_rn(gk, sign_torch(__fsub_rn(x0g, tau)));
+    if (k.mask_grad) g = __fmul_rn(m, g);
+    xp = __fadd_rn(xp, __fmul_rn(g, k.a2));
+  }
+  xp_out = xp;
+  x0_out = x0;
+}
+
+constexpr int kStepThreads = 256;
+constexpr int kStepUnroll = 4;  // float4 per thread per input
+
+// total4 = B*C*HW/4 ; HW % 4 == 0 so the four lanes of a float4 share a channel.
+__global__ void __launch_bounds__(kStepThreads)
+guided_step_vec4(const float4* __restrict__ x, const float4* __restrict__ e,
+                 const float4* __restrict__ z, const float4* __restrict__ mask,
+                 float4* __restrict__ xp, float4* __restrict__ x0o, int64_t total4, int64_t chw4,
+                 int64_t hw4, int C, StepK k) {
+  const int64_t base = (int64_t)blockIdx.x * (kStepThreads * kStepUnroll) + threadIdx.x;
+  float4 vx[kStepUnroll], ve[kStepUnroll], vz[kStepUnroll], vm[kStepUnroll];
+  const bool use_mask = k.guide && k.mask_grad;
+#pragma unroll
+  for (int u = 0; u < kStepUnroll; ++u) {
+    const int64_t i = base + (int64_t)u * kStepThreads;
+    if (i < total4) {
+      vx[u] = ld_stream(x + i);
+      ve[u] = ld_stream(e + i);
+      if (k.has_noise) vz[u] = k.noise_batched ? ld_stream(z + i) : ld_reuse(z + (i % chw4));
+      if (use_mask) vm[u] = k.mask_batched ? ld_stream(mask + i) : ld_reuse(mask + (i % chw4));
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < kStepUnroll; ++u) {
+    const int64_t i = base + (int64_t)u * kStepThreads;
+    if (i < total4) {
+      const int c = (int)((i / hw4) % C);
+      const int ht = k.has_target[c];
+      const float tau = k.target[c], gk = k.gk[c];
+      float4 zz = k.has_noise ? vz[u] : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 mm = use_mask ? vm[u] : make_float4(1.f, 1.f, 1.f, 1.f);
+      float4 o, o0;
+      step_elem(vx[u].x, ve[u].x, zz.x, mm.x, ht, tau, gk, k, o.x, o0.x);
+      step_elem(vx[u].y, ve[u].y, zz.y, mm.y, ht, tau, gk, k, o.y, o0.y);
+      step_elem(vx[u].z, ve[u].z, zz.z, mm.z, ht, tau, gk, k, o.z, o0.z);
+      step_elem(vx[u].w, ve[u].w, zz.w, mm.w, ht, tau, gk, k, o.w, o0.w);
+      st_stream(xp + i, o);
+      if (x0o) st_stream(x0o + i, o0);
+    }
+  }
+}
+
+// scalar fallback for HW % 4 != 0 or unaligned pointers (same arithmetic)
+__global__ void guided_step_scalar(const float* __restrict__ x, const float* __restrict__ e,
+                                   const float* __restrict__ z, const float* __restrict__ mask,
+                                   float* __restrict__ xp, float* __restrict__ x0o, int64_t total,
+                                   int64_t chw, int64_t hw, int C, StepK k) {
+  const bool use_mask = k.guide && k.mask_grad;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)((i / hw) % C);
+    float zz = k.has_noise ? z[k.noise_batched ? i : i % chw] : 0.f;
+    float mm = use_mask ? mask[k.mask_batched ? i : i % chw] : 1.f;
+    float o, o0;
+    step_elem(x[i], e[i], zz, mm, k.has_target[c], k.target[c], k.gk[c], k, o, o0);
+    xp[i] = o;
+    if (x0o) x0o[i] = o0;
+  }
+}
+
+// ------------------------------------------------------------------ L2-regularised variant
+struct L2K {
+  StepK s;
+  float lam_scale;  // loss_scale * lambda (fp32 product)
+  float k[4];       // k_c = loss_scale*w_c/N
+};
+
+// block-wide sum in double; result left in smem[0]
+__device__ __forceinline__ void block_sum_to_double(double v, double* smem) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) smem[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    double t = (lane < (int)(blockDim.x >> 5)) ? smem[lane] : 0.0;
+    t = warp_sum(t);
+    if (lane == 0) smem[0] = t;
+  }
+  __syncthreads();
+}
+
+// pass 1: scheduler update (no guidance), write x_prev / x0, accumulate sum r^2 per block
+__global__ void __launch_bounds__(kStepThreads)
+l2reg_pass1(const float4* __restrict__ x, const float4* __restrict__ e, const float4* __restrict__ z,
+            const float4* __restrict__ mask, const float4* __restrict__ xref,
+            float4* __restrict__ xp, float4* __restrict__ x0o, double* __restrict__ partial,
+            int64_t total4, int64_t chw4, L2K k) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  StepK s = k.s;
+  s.guide = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float4 vx = ld_stream(x + i), ve = ld_stream(e + i);
+    float4 vz = make_float4(0, 0, 0, 0);
+    if (s.has_noise) vz = s.noise_batched ? ld_stream(z + i) : ld_reuse(z + (i % chw4));
+    float4 vm = k.s.mask_batched ? ld_stream(mask + i) : ld_reuse(mask + (i % chw4));
+    float4 vr = ld_stream(xref + i);
+    float4 o, o0;
+    step_elem(vx.x, ve.x, vz.x, 1.f, 0, 0.f, 0.f, s, o.x, o0.x);
+    step_elem(vx.y, ve.y, vz.y, 1.f, 0, 0.f, 0.f, s, o.y, o0.y);
+    step_elem(vx.z, ve.z, vz.z, 1.f, 0, 0.f, 0.f, s, o.z, o0.z);
+    step_elem(vx.w, ve.w, vz.w, 1.f, 0, 0.f, 0.f, s, o.w, o0.w);
+    xp[i] = o;  // re-read by pass 2: keep default caching
+    if (x0o) st_stream(x0o + i, o0);
+    const float xo[4] = {o.x, o.y, o.z, o.w}, ee[4] = {ve.x, ve.y, ve.z, ve.w};
+    const float mm[4] = {vm.x, vm.y, vm.z, vm.w}, rr[4] = {vr.x, vr.y, vr.z, vr.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float x0g = __fdiv_rn(__fsub_rn(xo[j], __fmul_rn(s.sb, ee[j])), s.sa);
+      float r = __fsub_rn(__fsub_rn(1.f, __fmul_rn(mm[j], x0g)), rr[j]);
+      acc += (double)__fmul_rn(r, r);
+    }
+  }
+  block_sum_to_double(acc, red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+
+// pass 2: R = sqrt(sum), gradient of colour(mask*x0g) + lambda*R, update x_prev in place
+__global__ void __launch_bounds__(kStepThreads)
+l2reg_pass2(float4* __restrict__ xp, const float4* __restrict__ e, const float4* __restrict__ mask,
+            const float4* __restrict__ xref, const double* __restrict__ partial, int n_partial,
+            int64_t total4, int64_t chw4, int64_t hw4, int C, L2K k) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n_partial; i += blockDim.x) acc += partial[i];
+  block_sum_to_double(acc, red);
+  const float R = sqrtf((float)red[0]);
+  const float t_reg = __fdiv_rn(k.lam_scale, __fmul_rn(2.f, R));  // grad / (2*sqrt(s))
+  const StepK& s = k.s;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float4 vo = xp[i], ve = ld_stream(e + i);
+    float4 vm = s.mask_batched ? ld_stream(mask + i) : ld_reuse(mask + (i % chw4));
+    float4 vr = ld_stream(xref + i);
+    const int c = (int)((i / hw4) % C);
+    float xo[4] = {vo.x, vo.y, vo.z, vo.w};
+    const float ee[4] = {ve.x, ve.y, ve.z, ve.w}, mm[4] = {vm.x, vm.y, vm.z, vm.w},
+                rr[4] = {vr.x, vr.y, vr.z, vr.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float x0g = __fdiv_rn(__fsub_rn(xo[j], __fmul_rn(s.sb, ee[j])), s.sa);
+      float img = __fmul_rn(mm[j], x0g);
+      float r = __fsub_rn(__fsub_rn(1.f, img), rr[j]);
+      float dimg = -__fmul_rn(t_reg, __fmul_rn(2.f, r));  // d/dimg of lambda*||r|| (r = 1-img-xref)
+      if (s.has_target[c]) dimg = __fadd_rn(dimg, __fmul_rn(k.k[c], sign_torch(__fsub_rn(img, s.target[c]))));
+      float g = -__fdiv_rn(__fmul_rn(dimg, mm[j]), s.sa);
+      if (s.mask_grad) g = __fmul_rn(mm[j], g);
+      xo[j] = __fadd_rn(xo[j], __fmul_rn(g, s.a2));
+    }
+    st_stream(xp + i, make_float4(xo[0], xo[1], xo[2], xo[3]));
+  }
+}
+
+// ------------------------------------------------------------------ generic 1/2/3-input maps
+enum { OP_PRED_X0 = 0, OP_RENOISE, OP_CFG, OP_EXTRACT };
+
+struct MapK { float a, b, c, d; };
+
+__device__ __forceinline__ float map_elem(int op, float x, float e, const MapK& k) {
+  if (op == OP_PRED_X0) return __fdiv_rn(__fsub_rn(x, __fmul_rn(k.b, e)), k.a);
+  if (op == OP_RENOISE) {
+    float x0 = __fdiv_rn(__fsub_rn(x, __fmul_rn(k.b, e)), k.a);
+    return __fadd_rn(__fmul_rn(k.c, x0), __fmul_rn(k.d, e));
+  }
+  /* OP_CFG: x = e_first, e = e_second */
+  return __fadd_rn(x, __fmul_rn(k.a, __fsub_rn(e, x)));
+}
+
+template <int OP>
+__global__ void __launch_bounds__(kStepThreads)
+map2_kernel(const float* __restrict__ x, const float* __restrict__ e, float* __restrict__ out,
+            int64_t n, MapK k, int vec) {
+  if (vec) {
+    const int64_t n4 = n >> 2;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    const float4* e4 = reinterpret_cast<const float4*>(e);
+    float4* o4 = reinterpret_cast<float4*>(out);
+    const int64_t base = (int64_t)blockIdx.x * (kStepThreads * kStepUnroll) + threadIdx.x;
+    float4 vx[kStepUnroll], ve[kStepUnroll];
+#pragma unroll
+    for (int u = 0; u < kStepUnroll; ++u) {
+      const int64_t i = base + (int64_t)u * kStepThreads;
+      if (i < n4) { vx[u] = ld_stream(x4 + i); ve[u] = ld_stream(e4 + i); }
+    }
+#pragma unroll
+    for (int u = 0; u < kStepUnroll; ++u) {
+      const int64_t i = base + (int64_t)u * kStepThreads;
+      if (i < n4) {
+        float4 o;
+        o.x = map_elem(OP, vx[u].x, ve[u].x, k); o.y = map_elem(OP, vx[u].y, ve[u].y, k);
+        o.z = map_elem(OP, vx[u].z, ve[u].z, k); o.w = map_elem(OP, vx[u].w, ve[u].w, k);
+        st_stream(o4 + i, o);
+      }
+    }
+    // tail (n % 4) handled by block 0
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+      const int64_t i = (n4 << 2) + threadIdx.x;
+      out[i] = map_elem(OP, x[i], e[i], k);
+    }
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+      out[i] = map_elem(OP, x[i], e[i], k);
+  }
+}
+
+// z = (xm - mu)/sigma ; xm <- mu + sigma*z     (src/ddpm_inversion.py:135-169)
+__global__ void __launch_bounds__(kStepThreads)
+extract_noise_kernel(const float* __restrict__ x, const float* __restrict__ e, float* __restrict__ xm,
+                     float* __restrict__ z, int64_t n, float sa, float sb, float sp, float cdir,
+                     float sigma, int vec) {
+  auto f = [&](float xv, float ev, float xmv, float& zo, float& xo) {
+    float x0 = __fdiv_rn(__fsub_rn(xv, __fmul_rn(sb, ev)), sa);
+    float mu = __fadd_rn(__fmul_rn(sp, x0), __fmul_rn(cdir, ev));
+    zo = __fdiv_rn(__fsub_rn(xmv, mu), sigma);
+    xo = __fadd_rn(mu, __fmul_rn(sigma, zo));
+  };
+  if (vec) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+         i += (int64_t)gridDim.x * blockDim.x) {
+      float4 vx = ld_stream(reinterpret_cast<const float4*>(x) + i);
+      float4 ve = ld_stream(reinterpret_cast<const float4*>(e) + i);
+      float4 vm = ld_stream(reinterpret_cast<const float4*>(xm) + i);
+      float4 zo, xo;
+      f(vx.x, ve.x, vm.x, zo.x, xo.x); f(vx.y, ve.y, vm.y, zo.y, xo.y);
+      f(vx.z, ve.z, vm.z, zo.z, xo.z); f(vx.w, ve.w, vm.w, zo.w, xo.w);
+      st_stream(reinterpret_cast<float4*>(z) + i, zo);
+      st_stream(reinterpret_cast<float4*>(xm) + i, xo);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+      const int64_t i = (n4 << 2) + threadIdx.x;
+      float zo, xo;
+      f(x[i], e[i], xm[i], zo, xo);
+      z[i] = zo; xm[i] = xo;
+    }
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+      float zo, xo;
+      f(x[i], e[i], xm[i], zo, xo);
+      z[i] = zo; xm[i] = xo;
+    }
+  }
+}
+
+// xts[t] = x0*sa[t] + noise[t]*sb[t] for t < T ; xts[T] = x0      (src/ddpm_inversion.py:31-55)
+__global__ void __launch_bounds__(kStepThreads)
+sample_xts_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
+                  const float* __restrict__ sa, const float* __restrict__ sb,
+                  float* __restrict__ xts, int64_t T, int64_t chw) {
+  const int64_t t = blockIdx.y;
+  const float a = t < T ? sa[t] : 1.f, b = t < T ? sb[t] : 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < chw;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = x0[i];
+    xts[t * chw + i] = t < T ? __fadd_rn(__fmul_rn(v, a), __fmul_rn(noise[t * chw + i], b)) : v;
+  }
+}
+
+// out = mask*zv + (1-mask)*zo, mask broadcast over T            (src/utils.py:23-28)
+__global__ void __launch_bounds__(kStepThreads)
+apply_mask_kernel(const float* __restrict__ mask, const float* __restrict__ zo,
+                  const float* __restrict__ zv, float* __restrict__ out, int64_t n, int64_t chw) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float m = __ldg(mask + (i % chw));
+    out[i] = __fadd_rn(__fmul_rn(m, zv[i]), __fmul_rn(__fsub_rn(1.f, m), zo[i]));
+  }
+}
+
+// x += (mask*)g * a2
+__global__ void __launch_bounds__(kStepThreads)
+apply_grad_kernel(float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ mask,
+                  int64_t n, int64_t chw, int mask_batched, float a2) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float gv = g[i];
+    if (mask) gv = __fmul_rn(mask[mask_batched ? i : i % chw], gv);
+    x[i] = __fadd_rn(x[i], __fmul_rn(gv, a2));
+  }
+}
+
+// (B,C,HW) fp32 -> (B,HW,C) u8 ; trunc(clamp(x/2+0.5,0,1)*255)  (src/transforms.py:8-35)
+__global__ void __launch_bounds__(kStepThreads)
+to_uint8_kernel(const float* __restrict__ x, uint8_t* __restrict__ out, int64_t B, int C, int64_t hw) {
+  const int64_t total = B * hw;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total;
+       p += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = p / hw, q = p % hw;
+    for (int c = 0; c < C; ++c) {
+      float v = x[(b * C + c) * hw + q];
+      v = clamp_torch(__fadd_rn(__fmul_rn(v, 0.5f), 0.5f), 0.f, 1.f);
+      out[p * C + c] = (uint8_t)__fmul_rn(v, 255.f);
+    }
+  }
+}
+
+static inline int grid_for(int64_t n, int per_block, int max_blocks = kNumSMs * 16) {
+  int64_t g = (n + per_block - 1) / per_block;
+  if (g < 1) g = 1;
+  if (g > max_blocks) g = max_blocks;
+  return (int)g;
+}
+
+}  // namespace b2e
+
+using namespace b2e;
+
+template <int OP>
+static int launch_map2(const float* x, const float* e, float* out, int64_t n, MapK k, void* stream,
+                       const char* what) {
+  B2E_REQUIRE(x && e && out && n > 0, B2E_INVALID_ARG, "%s: bad argument", what);
+  const bool vec = aligned16(x) && aligned16(e) && aligned16(out) && n >= 4;
+  if (vec) {
+    const int per_block = kStepThreads * kStepUnroll;
+    const int64_t grid = ((n >> 2) + per_block - 1) / per_block;
+    map2_kernel<OP><<<(unsigned)grid, kStepThreads, 0, (cudaStream_t)stream>>>(x, e, out, n, k, 1);
+  } else {
+    map2_kernel<OP><<<grid_for(n, kStepThreads), kStepThreads, 0, (cudaStream_t)stream>>>(x, e, out, n, k, 0);
+  }
+  return check_launch(what);
+}
+
+// ====================================================================== C ABI
+extern "C" {
+
+int b2e_version(void) { return B2E_VERSION; }
+const char* b2e_last_error(void) { return g_err; }
+int64_t b2e_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int b2e_device_check(void) {
+  int dev = 0;
+  B2E_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  B2E_CUDA(cudaGetDeviceProperties(&prop, dev));
+  B2E_REQUIRE(prop.major == 10 && prop.minor == 0, B2E_ARCH_MISMATCH,
+              "libb200edit is built for sm_100a only; device %d is sm_%d%d", dev, prop.major, prop.minor);
+  return B2E_OK;
+}
+
+static int validate_step(const void* x, const void* e, const void* xp, int64_t B, int64_t C,
+                         int64_t HW, const b2e_guided_step_params* p, const void* z, const void* mask) {
+  B2E_REQUIRE(x && e && xp && p, B2E_INVALID_ARG, "guided_step: null pointer");
+  B2E_REQUIRE(B > 0 && HW > 0 && C > 0 && C <= 4, B2E_UNSUPPORTED_SHAPE,
+              "guided_step: need B>0, 1<=C<=4, HW>0 (got B=%lld C=%lld HW=%lld)", (long long)B,
+              (long long)C, (long long)HW);
+  B2E_REQUIRE(!p->has_noise || z, B2E_INVALID_ARG, "guided_step: eta > 0 but no noise tensor");
+  B2E_REQUIRE(!(p->guide && p->mask_grad) || mask, B2E_INVALID_ARG,
+              "guided_step: mask_attr_grad set but no mask");
+  return B2E_OK;
+}
+
+int b2e_guided_step_f32(const float* x_t, const float* eps, const float* z, const float* mask,
+                        float* x_prev, float* x0_pred, int64_t B, int64_t C, int64_t HW,
+                        const b2e_guided_step_params* p, void* stream) {
+  int rc = validate_step(x_t, eps, x_prev, B, C, HW, p, z, mask);
+  if (rc) return rc;
+  StepK k = make_stepk(p);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t total = B * C * HW;
+  const bool vec = (HW % 4 == 0) && aligned16(x_t) && aligned16(eps) && aligned16(x_prev) &&
+                   (!x0_pred || aligned16(x0_pred)) && (!z || aligned16(z)) &&
+                   (!mask || aligned16(mask));
+  if (vec) {
+    const int64_t total4 = total / 4;
+    const int per_block = kStepThreads * kStepUnroll;
+    const int64_t grid = (total4 + per_block - 1) / per_block;
+    guided_step_vec4<<<(unsigned)grid, kStepThreads, 0, st>>>(
+        (const float4*)x_t, (const float4*)eps, (const float4*)z, (const float4*)mask,
+        (float4*)x_prev, (float4*)x0_pred, total4, C * HW / 4, HW / 4, (int)C, k);
+  } else {
+    guided_step_scalar<<<grid_for(total, kStepThreads), kStepThreads, 0, st>>>(
+        x_t, eps, z, mask, x_prev, x0_pred, total, C * HW, HW, (int)C, k);
+  }
+  return check_launch("guided_step");
+}
+
+size_t b2e_l2reg_workspace_bytes(int64_t, int64_t, int64_t) { return sizeof(double) * kNumSMs * 8; }
+
+int b2e_guided_step_l2reg_f32(const float* x_t, const float* eps, const float* z, const float* mask,
+                              const float* x_ref, float* x_prev, float* x0_pred, int64_t B, int64_t C,
+                              int64_t HW, const b2e_l2reg_params* p, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  B2E_REQUIRE(p, B2E_INVALID_ARG, "l2reg: null params");
+  int rc = validate_step(x_t, eps, x_prev, B, C, HW, &p->base, z, mask);
+  if (rc) return rc;
+  B2E_REQUIRE(mask && x_ref, B2E_INVALID_ARG, "l2reg: mask and x_0 are required");
+  B2E_REQUIRE(workspace && workspace_bytes >= b2e_l2reg_workspace_bytes(B, C, HW),
+              B2E_WORKSPACE_TOO_SMALL, "l2reg: workspace too small");
+  B2E_REQUIRE(HW % 4 == 0 && aligned16(x_t) && aligned16(eps) && aligned16(x_prev) &&
+                  aligned16(mask) && aligned16(x_ref) && (!z || aligned16(z)) &&
+                  (!x0_pred || aligned16(x0_pred)),
+              B2E_UNSUPPORTED_SHAPE, "l2reg: needs HW %% 4 == 0 and 16-byte aligned tensors");
+  L2K k;
+  k.s = make_stepk(&p->base);
+  k.lam_scale = p->loss_scale * p->lambda_;
+  for (int i = 0; i < 4; ++i) k.k[i] = p->base.coef[i];
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t total4 = B * C * HW / 4;
+  int grid = grid_for(total4, kStepThreads, kNumSMs * 8);
+  l2reg_pass1<<<grid, kStepThreads, 0, st>>>((const float4*)x_t, (const float4*)eps, (const float4*)z,
+                                             (const float4*)mask, (const float4*)x_ref,
+                                             (float4*)x_prev, (float4*)x0_pred, (double*)workspace,
+                                             total4, C * HW / 4, k);
+  rc = check_launch("l2reg_pass1");
+  if (rc) return rc;
+  if (p->base.guide) {
+    l2reg_pass2<<<grid, kStepThreads, 0, st>>>((float4*)x_prev, (const float4*)eps,
+                                               (const float4*)mask, (const float4*)x_ref,
+                                               (const double*)workspace, grid, total4, C * HW / 4,
+                                               HW / 4, (int)C, k);
+    rc = check_launch("l2reg_pass2");
+  }
+  return rc;
+}
+
+int b2e_apply_guidance_grad_f32(float* x, const float* neg_grad, const float* mask, int64_t B,
+                                int64_t CHW, int mask_batched, float a_t_sq, void* stream) {
+  B2E_REQUIRE(x && neg_grad && B > 0 && CHW > 0, B2E_INVALID_ARG, "apply_guidance_grad: bad argument");
+  apply_grad_kernel<<<grid_for(B * CHW, kStepThreads), kStepThreads, 0, (cudaStream_t)stream>>>(
+      x, neg_grad, mask, B * CHW, CHW, mask_batched, a_t_sq);
+  return check_launch("apply_guidance_grad");
+}
+
+int b2e_pred_x0_f32(const float* x_t, const float* eps, float* x0, int64_t n, float sqrt_a_t,
+                    float sqrt_b_t, void* stream) {
+  return launch_map2<OP_PRED_X0>(x_t, eps, x0, n, MapK{sqrt_a_t, sqrt_b_t, 0.f, 0.f}, stream, "pred_x0");
+}
+
+int b2e_renoise_f32(const float* x, const float* eps, float* out, int64_t n, float c_a, float c_b,
+                    float c_out_x0, float c_out_e, void* stream) {
+  return launch_map2<OP_RENOISE>(x, eps, out, n, MapK{c_a, c_b, c_out_x0, c_out_e}, stream, "renoise");
+}
+
+int b2e_cfg_combine_f32(const float* e_first, const float* e_second, float* out, int64_t n,
+                        float scale, void* stream) {
+  return launch_map2<OP_CFG>(e_first, e_second, out, n, MapK{scale, 0.f, 0.f, 0.f}, stream, "cfg_combine");
+}
+
+int b2e_apply_mask_f32(const float* mask, const float* zo, const float* zv, float* out, int64_t T,
+                       int64_t CHW, void* stream) {
+  B2E_REQUIRE(mask && zo && zv && out && T > 0 && CHW > 0, B2E_INVALID_ARG, "apply_mask: bad argument");
+  apply_mask_kernel<<<grid_for(T * CHW, kStepThreads), kStepThreads, 0, (cudaStream_t)stream>>>(
+      mask, zo, zv, out, T * CHW, CHW);
+  return check_launch("apply_mask");
+}
+
+int b2e_to_uint8_f32(const float* x, uint8_t* out, int64_t B, int64_t C, int64_t HW, void* stream) {
+  B2E_REQUIRE(x && out && B > 0 && C > 0 && HW > 0, B2E_INVALID_ARG, "to_uint8: bad argument");
+  to_uint8_kernel<<<grid_for(B * HW, kStepThreads), kStepThreads, 0, (cudaStream_t)stream>>>(
+      x, out, B, (int)C, HW);
+  return check_launch("to_uint8");
+}
+
+int b2e_sample_xts_f32(const float* x0, const float* noise, const float* sa, const float* sb,
+                       float* xts, int64_t T, int64_t CHW, void* stream) {
+  B2E_REQUIRE(x0 && noise && sa && sb && xts && T > 0 && CHW > 0, B2E_INVALID_ARG,
+              "sample_xts: bad argument");
+  dim3 grid(grid_for(CHW, kStepThreads, 1024), (unsigned)(T + 1));
+  sample_xts_kernel<<<grid, kStepThreads, 0, (cudaStream_t)stream>>>(x0, noise, sa, sb, xts, T, CHW);
+  return check_launch("sample_xts");
+}
+
+int b2e_extract_noise_f32(const float* x_t, const float* eps, float* x_tm1, float* z, int64_t n,
+                          const b2e_step_coeffs* c, void* stream) {
+  B2E_REQUIRE(x_t && eps && x_tm1 && z && c && n > 0, B2E_INVALID_ARG, "extract_noise: bad argument");
+  const int vec = aligned16(x_t) && aligned16(eps) && aligned16(x_tm1) && aligned16(z) && n >= 4;
+  extract_noise_kernel<<<grid_for(vec ? n / 4 : n, kStepThreads), kStepThreads, 0, (cudaStream_t)stream>>>(
+      x_t, eps, x_tm1, z, n, c->sqrt_a_t, c->sqrt_b_t, c->sqrt_a_prev, c->dir_coef, c->sigma, vec);
+  return check_launch("extract_noise");
+}
+
+// Host scalar math, reference op order (this TU is compiled with -ffp-contract=off).
+int b2e_step_coeffs_compute(const float* ac, int num_train, float final_alpha_cumprod, int t,
+                            int t_prev, float eta, int mode, b2e_step_coeffs* out) {
+  B2E_REQUIRE(ac && out && t >= 0 && t < num_train && t_prev < num_train, B2E_INVALID_ARG,
+              "step_coeffs: bad timestep %d / %d", t, t_prev);
+  volatile float a_t = ac[t];
+  volatile float a_p = t_prev >= 0 ? ac[t_prev] : final_alpha_cumprod;
+  volatile float b_t = 1.f - a_t;
+  volatile float b_p = 1.f - a_p;
+  volatile float q = a_t / a_p;
+  volatile float om = 1.f - q;
+  volatile float ratio = b_p / b_t;
+  volatile float var = ratio * om;
+  volatile float sd = sqrtf(var);
+  volatile float sigma = eta * sd;
+  volatile float inner;
+  if (mode == B2E_MODE_DDIM) {
+    volatile float s2 = sigma * sigma;
+    inner = b_p - s2;
+  } else {
+    volatile float ev = eta * var;
+    inner = b_p - ev;
+  }
+  out->sqrt_a_t = sqrtf(a_t);
+  out->sqrt_b_t = sqrtf(b_t);
+  out->sqrt_a_prev = sqrtf(a_p);
+  out->dir_coef = sqrtf(inner);
+  out->sigma = sigma;
+  out->a_t_sq = a_t * a_t;
+  out->variance = var;
+  out->a_t = a_t;
+  out->a_prev = a_p;
+  return B2E_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,485 @@
+// UNet2DModel (diffusers layout) forward as a pre-planned sequence of sm_100a kernels.
+//
+// get_noise_pred's unconditional branch (src/diffusion_utils.py:72): eps = unet(x, t).sample.
+// The model is described once as a small IR (resnet / attention / down / up nodes with the
+// skip-connection stack resolved at build time), every convolution gets a ConvPlan (TMA
+// descriptors + tile geometry) bound to fixed activation buffers in a caller-owned arena, and a
+// forward pass is just the recorded list of launches on the caller's stream - no allocation,
+// no host synchronisation, graph-capturable.
+#include <math.h>
+
+#include <functional>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "unet_kernels.cuh"
+
+using namespace b2e;
+
+namespace {
+
+struct ConvL { bf16* w = nullptr; float* b = nullptr; int cin = 0, cin_pad = 0, cout = 0, cout_pad = 0, k = 0; };
+struct NormL { float* g = nullptr; float* b = nullptr; int C = 0; };
+struct ResnetL {
+  std::string name; int cin0 = 0, cin1 = 0, cout = 0; NormL n1, n2; ConvL c1, c2, sc; bool has_sc = false;
+  int temb_off = 0;
+};
+struct AttnL { std::string name; int C = 0; NormL gn; ConvL qkv, proj; };
+
+enum NodeKind { N_RESNET, N_ATTN, N_DOWN, N_UP, N_PUSH, N_POPCAT };
+struct Node { NodeKind kind; int idx; };
+
+struct Tensor { bf16* p = nullptr; int N = 0, H = 0, W = 0, C = 0; size_t bytes = 0; };
+
+struct Arena {
+  char* base = nullptr; size_t cap = 0, off = 0, peak = 0;
+  std::multimap<size_t, char*> free_list;
+  bool dry = true;
+  void reset(void* b, size_t c) {
+    dry = (b == nullptr);
+    base = dry ? (char*)(uintptr_t)(1 << 20) : (char*)b;  // dry run: fake, unique, non-null addresses
+    cap = c; off = 0; peak = 0; free_list.clear();
+  }
+  void* alloc(size_t n) {
+    n = (n + 1023) / 1024 * 1024;
+    auto it = free_list.find(n);
+    if (it != free_list.end()) { char* p = it->second; free_list.erase(it); return p; }
+    char* p = base + off;
+    off += n;
+    if (off > peak) peak = off;
+    return p;
+  }
+  void release(void* p, size_t n) { n = (n + 1023) / 1024 * 1024; free_list.emplace(n, (char*)p); }
+};
+
+}  // namespace
+
+struct b2e_unet {
+  b2e_unet_config cfg;
+  int64_t max_batch = 0;
+  int temb_dim = 0, sumC = 0, heads_dim = 0;
+  std::vector<void*> owned;
+  struct PRec { std::string name; int64_t numel; int64_t fan_in; std::function<int(const float*, cudaStream_t)> set; };
+  std::vector<PRec> params;
+  std::unordered_map<std::string, int> pindex;
+  ConvL conv_in, conv_out;
+  NormL norm_out;
+  float *te_w1 = nullptr, *te_b1 = nullptr, *te_w2 = nullptr, *te_b2 = nullptr, *tp_w = nullptr, *tp_b = nullptr;
+  std::vector<ResnetL> resnets;
+  std::vector<AttnL> attns;
+  std::vector<ConvL> downs, ups;
+  std::vector<Node> nodes;
+  // program
+  void* ws = nullptr; size_t ws_bytes = 0;
+  int64_t cur_B = -1;
+  std::vector<std::function<int(cudaStream_t)>> ops;
+  const float* in_x = nullptr; const int64_t* in_t = nullptr; float* out_eps = nullptr;  // per-call
+  double flops = 0;
+  size_t ws_need = 0;
+  int build_error = 0;
+
+  ~b2e_unet() { for (void* p : owned) cudaFree(p); }
+
+  template <typename T> T* dmalloc(size_t n) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, n * sizeof(T)) != cudaSuccess) { build_error = B2E_CUDA_ERROR; set_error("cudaMalloc(%zu) failed", n * sizeof(T)); return nullptr; }
+    cudaMemset(p, 0, n * sizeof(T));
+    owned.push_back(p);
+    return (T*)p;
+  }
+  // fan_in: inputs per output unit (PyTorch default init bound 1/sqrt(fan_in)); 0 for norm layers
+  void add_param(const std::string& name, int64_t numel, int64_t fan_in,
+                 std::function<int(const float*, cudaStream_t)> fn) {
+    pindex[name] = (int)params.size();
+    params.push_back({name, numel, fan_in, std::move(fn)});
+  }
+  void add_f32(const std::string& name, float* dst, int64_t numel, int64_t fan_in = 0) {
+    add_param(name, numel, fan_in, [dst, numel](const float* src, cudaStream_t st) -> int {
+      B2E_CUDA(cudaMemcpyAsync(dst, src, numel * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      return (int)B2E_OK;
+    });
+  }
+  // conv / linear weight that feeds the tcgen05 GEMM: packed bf16 [cout_pad][k*k][cin_pad]
+  ConvL make_conv(const std::string& name, int cin, int cout, int k, int cin_pad = 0) {
+    ConvL c;
+    c.cin = cin; c.cin_pad = cin_pad ? cin_pad : cin; c.cout = cout; c.k = k; c.cout_pad = conv_cout_pad(cout);
+    c.w = dmalloc<bf16>((size_t)c.cout_pad * k * k * c.cin_pad);
+    c.b = dmalloc<float>(c.cout_pad);
+    ConvL cc = c;
+    add_param(name + ".weight", (int64_t)cout * cin * k * k, (int64_t)cin * k * k, [cc](const float* src, cudaStream_t st) {
+      return conv_pack_weight(src, cc.w, cc.cout, cc.cout_pad, cc.cin, cc.cin_pad, cc.k, st);
+    });
+    add_f32(name + ".bias", c.b, cout, (int64_t)cin * k * k);
+    return c;
+  }
+  NormL make_norm(const std::string& name, int C) {
+    NormL n; n.C = C; n.g = dmalloc<float>(C); n.b = dmalloc<float>(C);
+    add_f32(name + ".weight", n.g, C);
+    add_f32(name + ".bias", n.b, C);
+    return n;
+  }
+  int make_resnet(const std::string& name, int cin0, int cin1, int cout) {
+    ResnetL r;
+    r.name = name; r.cin0 = cin0; r.cin1 = cin1; r.cout = cout;
+    const int cin = cin0 + cin1;
+    r.n1 = make_norm(name + ".norm1", cin);
+    r.c1 = make_conv(name + ".conv1", cin, cout, 3);
+    r.temb_off = sumC; sumC += cout;
+    r.n2 = make_norm(name + ".norm2", cout);
+    r.c2 = make_conv(name + ".conv2", cout, cout, 3);
+    r.has_sc = cin != cout;
+    if (r.has_sc) r.sc = make_conv(name + ".conv_shortcut", cin, cout, 1);
+    resnets.push_back(r);
+    return (int)resnets.size() - 1;
+  }
+  int make_attn(const std::string& name, int C) {
+    AttnL a;
+    a.name = name; a.C = C;
+    a.gn = make_norm(name + ".group_norm", C);
+    // q, k, v fused into one [3C][C] GEMM weight
+    a.qkv.cin = a.qkv.cin_pad = C; a.qkv.cout = 3 * C; a.qkv.cout_pad = conv_cout_pad(3 * C); a.qkv.k = 1;
+    a.qkv.w = dmalloc<bf16>((size_t)a.qkv.cout_pad * C);
+    a.qkv.b = dmalloc<float>(a.qkv.cout_pad);
+    const char* nm[3] = {"to_q", "to_k", "to_v"};
+    for (int i = 0; i < 3; ++i) {
+      bf16* wdst = a.qkv.w + (size_t)i * C * C;
+      float* bdst = a.qkv.b + (size_t)i * C;
+      add_param(name + "." + nm[i] + ".weight", (int64_t)C * C, C, [wdst, C](const float* src, cudaStream_t st) {
+        return conv_pack_weight(src, wdst, C, C, C, C, 1, st);
+      });
+      add_f32(name + "." + nm[i] + ".bias", bdst, C, C);
+    }
+    a.proj = make_conv(name + ".to_out.0", C, C, 1);
+    attns.push_back(a);
+    return (int)attns.size() - 1;
+  }
+};
+
+namespace {
+
+int build_model(b2e_unet* m) {
+  const b2e_unet_config& c = m->cfg;
+  const int nb = c.n_blocks;
+  const int c0 = c.block_out_channels[0];
+  m->temb_dim = 4 * c0;
+  m->conv_in = m->make_conv("conv_in", c.in_channels, c0, 3, kConvBlockK);
+  m->te_w1 = m->dmalloc<float>((size_t)m->temb_dim * c0); m->te_b1 = m->dmalloc<float>(m->temb_dim);
+  m->te_w2 = m->dmalloc<float>((size_t)m->temb_dim * m->temb_dim); m->te_b2 = m->dmalloc<float>(m->temb_dim);
+  m->add_f32("time_embedding.linear_1.weight", m->te_w1, (int64_t)m->temb_dim * c0, c0);
+  m->add_f32("time_embedding.linear_1.bias", m->te_b1, m->temb_dim, c0);
+  m->add_f32("time_embedding.linear_2.weight", m->te_w2, (int64_t)m->temb_dim * m->temb_dim, m->temb_dim);
+  m->add_f32("time_embedding.linear_2.bias", m->te_b2, m->temb_dim, m->temb_dim);
+  std::vector<int> stack;  // channel counts of the skip stack
+  stack.push_back(c0);
+  m->nodes.push_back({N_PUSH, 0});
+  int ch = c0;
+  for (int i = 0; i < nb; ++i) {
+    const int cout = c.block_out_channels[i];
+    for (int j = 0; j < c.layers_per_block; ++j) {
+      const std::string base = "down_blocks." + std::to_string(i);
+      m->nodes.push_back({N_RESNET, m->make_resnet(base + ".resnets." + std::to_string(j), ch, 0, cout)});
+      ch = cout;
+      if (c.down_attn[i]) m->nodes.push_back({N_ATTN, m->make_attn(base + ".attentions." + std::to_string(j), ch)});
+      m->nodes.push_back({N_PUSH, 0});
+      stack.push_back(ch);
+    }
+    if (i != nb - 1) {
+      m->downs.push_back(m->make_conv("down_blocks." + std::to_string(i) + ".downsamplers.0.conv", ch, ch, 3));
+      m->nodes.push_back({N_DOWN, (int)m->downs.size() - 1});
+      m->nodes.push_back({N_PUSH, 0});
+      stack.push_back(ch);
+    }
+  }
+  m->nodes.push_back({N_RESNET, m->make_resnet("mid_block.resnets.0", ch, 0, ch)});
+  m->nodes.push_back({N_ATTN, m->make_attn("mid_block.attentions.0", ch)});
+  m->nodes.push_back({N_RESNET, m->make_resnet("mid_block.resnets.1", ch, 0, ch)});
+  for (int i = 0; i < nb; ++i) {
+    const int cout = c.block_out_channels[nb - 1 - i];
+    const std::string base = "up_blocks." + std::to_string(i);
+    for (int j = 0; j < c.layers_per_block + 1; ++j) {
+      const int skip = stack.back();
+      stack.pop_back();
+      m->nodes.push_back({N_POPCAT, 0});
+      m->nodes.push_back({N_RESNET, m->make_resnet(base + ".resnets." + std::to_string(j), ch, skip, cout)});
+      ch = cout;
+      if (c.up_attn[i]) m->nodes.push_back({N_ATTN, m->make_attn(base + ".attentions." + std::to_string(j), ch)});
+    }
+    if (i != nb - 1) {
+      m->ups.push_back(m->make_conv(base + ".upsamplers.0.conv", ch, ch, 3));
+      m->nodes.push_back({N_UP, (int)m->ups.size() - 1});
+    }
+  }
+  B2E_REQUIRE(stack.empty(), B2E_INVALID_ARG, "unet: skip stack not empty (%zu left)", stack.size());
+  m->norm_out = m->make_norm("conv_norm_out", ch);
+  m->conv_out = m->make_conv("conv_out", ch, c.out_channels, 3);
+  // all time_emb_proj layers as one [sumC][temb_dim] matrix
+  m->tp_w = m->dmalloc<float>((size_t)m->sumC * m->temb_dim);
+  m->tp_b = m->dmalloc<float>(m->sumC);
+  for (auto& r : m->resnets) {
+    m->add_f32(r.name + ".time_emb_proj.weight", m->tp_w + (size_t)r.temb_off * m->temb_dim,
+               (int64_t)r.cout * m->temb_dim, m->temb_dim);
+    m->add_f32(r.name + ".time_emb_proj.bias", m->tp_b + r.temb_off, r.cout, m->temb_dim);
+  }
+  return m->build_error;
+}
+
+// Records the launch list for batch B with all activations placed in the arena.  With a null
+// arena base this is a dry run that only measures the arena size.
+int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
+  const b2e_unet_config& c = m->cfg;
+  Arena ar;
+  ar.reset(ws, ws_bytes);
+  const bool dry = ar.dry;
+  std::vector<std::function<int(cudaStream_t)>> ops;
+  double flops = 0;
+  int rc = B2E_OK;
+  auto talloc = [&](int N, int H, int W, int C) {
+    Tensor t; t.N = N; t.H = H; t.W = W; t.C = C; t.bytes = (size_t)N * H * W * C * sizeof(bf16);
+    t.p = (bf16*)ar.alloc(t.bytes);
+    return t;
+  };
+  auto tfree = [&](Tensor& t) { if (t.p) ar.release(t.p, t.bytes); t.p = nullptr; };
+  const int G = c.norm_num_groups;
+  const int S = c.sample_size;
+  // per-forward scratch
+  float* act = (float*)ar.alloc(sizeof(float) * B * m->temb_dim);
+  float* proj = (float*)ar.alloc(sizeof(float) * B * m->sumC);
+  float* gn_part = (float*)ar.alloc(sizeof(float) * B * 64 * G * 2);
+
+  auto conv = [&](const ConvL& L, Tensor x0, const Tensor* x1, int stride, ConvEpilogue ep, Tensor* out, float* out_nchw) {
+    if (rc) return;
+    const int Ho = x0.H / stride, Wo = x0.W / stride;
+    if (out) *out = talloc(B, Ho, Wo, L.cout);
+    if (dry) { flops += 2.0 * B * Ho * Wo * (double)L.cout * L.k * L.k * (x0.C + (x1 ? x1->C : 0)); return; }
+    ConvPlan pl;
+    rc = conv_plan_build(&pl, ConvSrc{x0.p, x0.C}, x1 ? ConvSrc{x1->p, x1->C} : ConvSrc{nullptr, 0}, B, x0.H, x0.W,
+                         L.k, stride, L.w, L.cout);
+    if (rc) return;
+    ep.bias = L.b;
+    if (out) ep.out_bf16 = out->p;
+    flops += pl.flops;
+    if (out_nchw) {
+      // the network output pointer is only known at call time
+      ops.push_back([pl, ep, m](cudaStream_t st) { ConvEpilogue e = ep; e.out_f32_nchw = m->out_eps; return conv_launch(pl, e, st); });
+    } else {
+      ops.push_back([pl, ep](cudaStream_t st) { return conv_launch(pl, ep, st); });
+    }
+  };
+  auto gnorm = [&](const NormL& L, Tensor x0, const Tensor* x1, int silu, Tensor* out) {
+    if (rc) return;
+    const int C = x0.C + (x1 ? x1->C : 0);
+    *out = talloc(B, x0.H, x0.W, C);
+    if (dry) return;
+    GNArgs a;
+    a.x0 = x0.p; a.x1 = x1 ? x1->p : nullptr; a.C0 = x0.C; a.C1 = x1 ? x1->C : 0;
+    a.N = B; a.HW = x0.H * x0.W; a.G = G; a.eps = c.norm_eps; a.gamma = L.g; a.beta = L.b;
+    a.partial = gn_part; a.chunks = gn_chunks(a.HW, C); a.out = out->p; a.silu = silu;
+    ops.push_back([a](cudaStream_t st) { return gn_launch(a, st); });
+  };
+
+  // ---- prologue: input packing, timestep embedding
+  Tensor xin = talloc(B, S, S, kConvBlockK);
+  if (!dry) {
+    const int Cin = c.in_channels, HW = S * S;
+    ops.push_back([m, xin, B, Cin, HW](cudaStream_t st) { return pack_input_launch(m->in_x, xin.p, B, Cin, HW, kConvBlockK, st); });
+    TembArgs ta;
+    ta.timesteps = nullptr; ta.B = B; ta.dim0 = c.block_out_channels[0]; ta.dim = m->temb_dim;
+    ta.flip = c.flip_sin_to_cos; ta.freq_shift = c.freq_shift;
+    ta.w1 = m->te_w1; ta.b1 = m->te_b1; ta.w2 = m->te_w2; ta.b2 = m->te_b2; ta.wp = m->tp_w; ta.bp = m->tp_b;
+    ta.sumC = m->sumC; ta.act = act; ta.proj = proj;
+    ops.push_back([m, ta](cudaStream_t st) { TembArgs t = ta; t.timesteps = m->in_t; return temb_launch(t, st); });
+  }
+  Tensor h;
+  conv(m->conv_in, xin, nullptr, 1, ConvEpilogue{}, &h, nullptr);
+  tfree(xin);
+  std::vector<Tensor> stack;
+  bool have_cat = false;
+  Tensor cat;
+  // a tensor that is still on the skip stack must outlive its consumer (dry-run addresses are
+  // fake but unique per live allocation, so the same liveness logic applies)
+  auto on_stack = [&](const Tensor& t) { for (auto& s : stack) if (s.p == t.p) return true; return false; };
+
+  for (const Node& nd : m->nodes) {
+    if (rc) break;
+    switch (nd.kind) {
+      case N_PUSH: stack.push_back(h); break;
+      case N_POPCAT: cat = stack.back(); stack.pop_back(); have_cat = true; break;
+      case N_RESNET: {
+        const ResnetL& r = m->resnets[nd.idx];
+        const Tensor* x1 = have_cat ? &cat : nullptr;
+        Tensor a1, h1, a2, sc, out;
+        gnorm(r.n1, h, x1, 1, &a1);
+        ConvEpilogue e1; e1.temb = proj + r.temb_off; e1.temb_stride = m->sumC;
+        conv(r.c1, a1, nullptr, 1, e1, &h1, nullptr);
+        tfree(a1);
+        gnorm(r.n2, h1, nullptr, 1, &a2);
+        tfree(h1);
+        ConvEpilogue e2;
+        if (r.has_sc) {
+          conv(r.sc, h, x1, 1, ConvEpilogue{}, &sc, nullptr);
+          e2.residual = sc.p;
+        } else {
+          e2.residual = h.p;
+        }
+        conv(r.c2, a2, nullptr, 1, e2, &out, nullptr);
+        tfree(a2);
+        if (r.has_sc) tfree(sc);
+        if (!on_stack(h)) tfree(h);
+        if (have_cat) { tfree(cat); have_cat = false; }
+        h = out;
+        break;
+      }
+      case N_ATTN: {
+        const AttnL& a = m->attns[nd.idx];
+        Tensor an, qkv, o, out;
+        gnorm(a.gn, h, nullptr, 0, &an);
+        conv(a.qkv, an, nullptr, 1, ConvEpilogue{}, &qkv, nullptr);
+        tfree(an);
+        o = talloc(B, h.H, h.W, a.C);
+        const int heads = c.attention_head_dim > 0 ? a.C / c.attention_head_dim : 1;
+        if (!dry) {
+          const int T = h.H * h.W, C = a.C;
+          ops.push_back([qkv, o, B, T, C, heads](cudaStream_t st) { return attention_launch(qkv.p, o.p, B, T, C, heads, st); });
+        }
+        flops += 4.0 * B * (double)(h.H * h.W) * (h.H * h.W) * a.C;
+        tfree(qkv);
+        ConvEpilogue ep; ep.residual = h.p;
+        conv(a.proj, o, nullptr, 1, ep, &out, nullptr);
+        tfree(o);
+        if (!on_stack(h)) tfree(h);
+        h = out;
+        break;
+      }
+      case N_DOWN: {
+        Tensor out;
+        conv(m->downs[nd.idx], h, nullptr, 2, ConvEpilogue{}, &out, nullptr);
+        if (!on_stack(h)) tfree(h);
+        h = out;
+        break;
+      }
+      case N_UP: {
+        Tensor up = talloc(B, h.H * 2, h.W * 2, h.C), out;
+        if (!dry) {
+          Tensor hh = h;
+          ops.push_back([hh, up, B](cudaStream_t st) { return upsample2x_launch(hh.p, up.p, B, hh.H, hh.W, hh.C, st); });
+        }
+        if (!on_stack(h)) tfree(h);
+        conv(m->ups[nd.idx], up, nullptr, 1, ConvEpilogue{}, &out, nullptr);
+        tfree(up);
+        h = out;
+        break;
+      }
+    }
+  }
+  if (!rc) {
+    Tensor an;
+    gnorm(m->norm_out, h, nullptr, 1, &an);
+    tfree(h);
+    float dummy = 0.f;
+    conv(m->conv_out, an, nullptr, 1, ConvEpilogue{}, nullptr, &dummy);
+    tfree(an);
+  }
+  if (rc) return rc;
+  if (need) *need = ar.peak;
+  if (!dry) {
+    B2E_REQUIRE(ar.peak <= ws_bytes, B2E_WORKSPACE_TOO_SMALL, "unet: workspace too small (%zu > %zu)", ar.peak, ws_bytes);
+    m->ops = std::move(ops);
+    m->flops = flops;
+    m->cur_B = B;
+  } else {
+    m->flops = flops;
+  }
+  return B2E_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b2e_unet_create(const b2e_unet_config* cfg, int64_t max_batch, b2e_unet** out) {
+  B2E_REQUIRE(cfg && out && max_batch > 0, B2E_INVALID_ARG, "unet_create: bad argument");
+  B2E_REQUIRE(cfg->n_blocks >= 1 && cfg->n_blocks <= 8, B2E_UNSUPPORTED_SHAPE, "unet_create: n_blocks");
+  B2E_REQUIRE(cfg->in_channels <= 8 && cfg->out_channels <= 16, B2E_UNSUPPORTED_SHAPE,
+              "unet_create: in_channels <= 8 and out_channels <= 16 required");
+  for (int i = 0; i < cfg->n_blocks; ++i)
+    B2E_REQUIRE(cfg->block_out_channels[i] % 64 == 0 && cfg->block_out_channels[i] <= 512, B2E_UNSUPPORTED_SHAPE,
+                "unet_create: block_out_channels must be multiples of 64 and <= 512 (got %d)", cfg->block_out_channels[i]);
+  B2E_REQUIRE(cfg->sample_size % (1 << (cfg->n_blocks - 1)) == 0, B2E_UNSUPPORTED_SHAPE, "unet_create: sample_size");
+  b2e_unet* m = new b2e_unet();
+  m->cfg = *cfg;
+  m->max_batch = max_batch;
+  int rc = build_model(m);
+  if (!rc) rc = build_program(m, (int)max_batch, nullptr, 0, &m->ws_need);
+  if (rc) { delete m; return rc; }
+  *out = m;
+  return B2E_OK;
+}
+
+void b2e_unet_destroy(b2e_unet* m) { delete m; }
+
+int b2e_unet_num_params(const b2e_unet* m) { return m ? (int)m->params.size() : 0; }
+
+int b2e_unet_param_info(const b2e_unet* m, int idx, const char** name, int64_t* numel, int64_t* fan_in) {
+  B2E_REQUIRE(m && idx >= 0 && idx < (int)m->params.size(), B2E_INVALID_ARG, "param_info: bad index");
+  if (name) *name = m->params[idx].name.c_str();
+  if (numel) *numel = m->params[idx].numel;
+  if (fan_in) *fan_in = m->params[idx].fan_in;
+  return B2E_OK;
+}
+
+int b2e_unet_set_param(b2e_unet* m, const char* name, const float* data, int64_t numel, void* stream) {
+  B2E_REQUIRE(m && name && data, B2E_INVALID_ARG, "set_param: bad argument");
+  auto it = m->pindex.find(name);
+  B2E_REQUIRE(it != m->pindex.end(), B2E_NOT_FOUND, "set_param: unknown parameter '%s'", name);
+  auto& p = m->params[it->second];
+  B2E_REQUIRE(p.numel == numel, B2E_INVALID_ARG, "set_param: '%s' expects %lld elements, got %lld", name,
+              (long long)p.numel, (long long)numel);
+  return p.set(data, (cudaStream_t)stream);
+}
+
+size_t b2e_unet_workspace_bytes(const b2e_unet* m) { return m ? m->ws_need : 0; }
+
+int b2e_unet_bind_workspace(b2e_unet* m, void* workspace, size_t workspace_bytes) {
+  B2E_REQUIRE(m && workspace, B2E_INVALID_ARG, "bind_workspace: bad argument");
+  B2E_REQUIRE(workspace_bytes >= m->ws_need, B2E_WORKSPACE_TOO_SMALL, "bind_workspace: need %zu bytes, got %zu",
+              m->ws_need, workspace_bytes);
+  B2E_REQUIRE(((uintptr_t)workspace & 255) == 0, B2E_INVALID_ARG, "bind_workspace: workspace must be 256-byte aligned");
+  m->ws = workspace; m->ws_bytes = workspace_bytes;
+  return build_program(m, (int)m->max_batch, workspace, workspace_bytes, nullptr);
+}
+
+int b2e_unet_forward(b2e_unet* m, const float* x, const int64_t* timesteps, float* eps, int64_t B, void* stream) {
+  B2E_REQUIRE(m && x && timesteps && eps, B2E_INVALID_ARG, "unet_forward: null pointer");
+  B2E_REQUIRE(m->ws, B2E_INVALID_ARG, "unet_forward: no workspace bound");
+  B2E_REQUIRE(B > 0 && B <= m->max_batch, B2E_UNSUPPORTED_SHAPE, "unet_forward: batch %lld exceeds max_batch %lld",
+              (long long)B, (long long)m->max_batch);
+  if (B != m->cur_B) {
+    int rc = build_program(m, (int)B, m->ws, m->ws_bytes, nullptr);
+    if (rc) return rc;
+  }
+  m->in_x = x; m->in_t = timesteps; m->out_eps = eps;
+  cudaStream_t st = (cudaStream_t)stream;
+  for (auto& op : m->ops) {
+    int rc = op(st);
+    if (rc) return rc;
+  }
+  return B2E_OK;
+}
+
+double b2e_unet_flops(const b2e_unet* m, int64_t B) {
+  if (!m) return 0;
+  const double per = m->flops / (double)(m->cur_B > 0 ? m->cur_B : m->max_batch);
+  return per * (double)B;
+}
+
+int b2e_unet_launches_per_forward(const b2e_unet* m) {
+  if (!m) return 0;
+  // GroupNorm and the embedding MLP are two launches per op
+  int n = 0;
+  for (size_t i = 0; i < m->ops.size(); ++i) n += 1;
+  return n;
+}
+
+}  // extern "C"

@@ -1,0 +1,350 @@
+// GroupNorm+SiLU, layout packing, upsampling, timestep embedding and attention kernels of the
+// UNet.  All activations are bf16 NHWC; statistics, softmax and accumulation are fp32/fp64.
+#include "unet_kernels.cuh"
+
+#include <math.h>
+
+namespace b2e {
+
+constexpr int kGNThreads = 256;
+
+__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
+  const __nv_bfloat162* b = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float2 t = __bfloat1622float2(b[j]);
+    f[2 * j] = t.x; f[2 * j + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 v;
+  __nv_bfloat162* b = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) b[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+  return v;
+}
+
+// ------------------------------------------------------------------ GroupNorm
+__global__ void __launch_bounds__(kGNThreads) gn_partial_kernel(GNArgs a) {
+  __shared__ float s_sum[2048], s_sq[2048];
+  const int C = a.C0 + a.C1, slots = C >> 3, ppi = kGNThreads / slots;
+  const int n = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
+  const int s = tid % slots, pl = tid / slots;
+  const int per = (a.HW + a.chunks - 1) / a.chunks;
+  const int p0 = chunk * per, p1 = min(a.HW, p0 + per);
+  if (pl < ppi) {
+    float sum[8], sq[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sum[j] = sq[j] = 0.f;
+    const int c = s * 8;
+    const bf16* src; int cs, coff;
+    if (c < a.C0) { src = a.x0; cs = a.C0; coff = c; } else { src = a.x1; cs = a.C1; coff = c - a.C0; }
+    src += (int64_t)n * a.HW * cs + coff;
+    for (int p = p0 + pl; p < p1; p += ppi) {
+      float f[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(src + (int64_t)p * cs)), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { sum[j] += f[j]; sq[j] += f[j] * f[j]; }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s_sum[pl * C + c + j] = sum[j]; s_sq[pl * C + c + j] = sq[j]; }
+  }
+  __syncthreads();
+  if (tid < a.G) {
+    const int cpg = C / a.G;
+    float ts = 0.f, tq = 0.f;
+    for (int q = 0; q < ppi; ++q)
+      for (int c = tid * cpg; c < (tid + 1) * cpg; ++c) { ts += s_sum[q * C + c]; tq += s_sq[q * C + c]; }
+    float* o = a.partial + (((int64_t)n * a.chunks + chunk) * a.G + tid) * 2;
+    o[0] = ts; o[1] = tq;
+  }
+}
+
+__global__ void __launch_bounds__(kGNThreads) gn_apply_kernel(GNArgs a, int pix_per_block) {
+  __shared__ float s_mean[64], s_rstd[64];
+  const int C = a.C0 + a.C1, slots = C >> 3, ppi = kGNThreads / slots;
+  const int n = blockIdx.y, tid = threadIdx.x;
+  const int cpg = C / a.G;
+  if (tid < a.G) {
+    double ts = 0.0, tq = 0.0;
+    for (int ch = 0; ch < a.chunks; ++ch) {
+      const float* o = a.partial + (((int64_t)n * a.chunks + ch) * a.G + tid) * 2;
+      ts += (double)o[0]; tq += (double)o[1];
+    }
+    const double cnt = (double)a.HW * cpg;
+    const double mean = ts / cnt;
+    double var = tq / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[tid] = (float)mean;
+    s_rstd[tid] = (float)(1.0 / sqrt(var + (double)a.eps));
+  }
+  __syncthreads();
+  const int s = tid % slots, pl = tid / slots;
+  if (pl >= ppi) return;
+  const int c = s * 8;
+  float scale[8], shift[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = (c + j) / cpg;
+    scale[j] = s_rstd[g] * __ldg(a.gamma + c + j);
+    shift[j] = __ldg(a.beta + c + j) - s_mean[g] * scale[j];
+  }
+  const bf16* src; int cs, coff;
+  if (c < a.C0) { src = a.x0; cs = a.C0; coff = c; } else { src = a.x1; cs = a.C1; coff = c - a.C0; }
+  src += (int64_t)n * a.HW * cs + coff;
+  bf16* dst = a.out + (int64_t)n * a.HW * C + c;
+  const int p0 = blockIdx.x * pix_per_block, p1 = min(a.HW, p0 + pix_per_block);
+  for (int p = p0 + pl; p < p1; p += ppi) {
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(src + (int64_t)p * cs)), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float y = fmaf(f[j], scale[j], shift[j]);
+      if (a.silu) y = __fdividef(y, 1.f + __expf(-y));
+      f[j] = y;
+    }
+    *reinterpret_cast<uint4*>(dst + (int64_t)p * C) = pack8(f);
+  }
+}
+
+int gn_chunks(int HW, int C) {
+  int64_t el = (int64_t)HW * C;
+  int ch = (int)(el / 65536);
+  if (ch < 1) ch = 1;
+  if (ch > 64) ch = 64;
+  return ch;
+}
+
+int gn_launch(const GNArgs& a, cudaStream_t st) {
+  const int C = a.C0 + a.C1;
+  B2E_REQUIRE(C % 8 == 0 && a.C0 % 8 == 0 && C <= 1024 && a.G <= 64 && C % a.G == 0, B2E_UNSUPPORTED_SHAPE,
+              "groupnorm: unsupported channels %d+%d / groups %d", a.C0, a.C1, a.G);
+  gn_partial_kernel<<<dim3(a.chunks, a.N), kGNThreads, 0, st>>>(a);
+  int rc = check_launch("gn_partial");
+  if (rc) return rc;
+  const int slots = C / 8, ppi = kGNThreads / slots;
+  int ppb = ppi * 16;  // 16 iterations per thread
+  if (ppb > a.HW) ppb = a.HW;
+  gn_apply_kernel<<<dim3((a.HW + ppb - 1) / ppb, a.N), kGNThreads, 0, st>>>(a, ppb);
+  return check_launch("gn_apply");
+}
+
+// ------------------------------------------------------------------ layout helpers
+__global__ void pack_input_kernel(const float* __restrict__ x, bf16* __restrict__ out, int B, int C,
+                                  int HW, int cpad) {
+  const int64_t total = (int64_t)B * HW;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total;
+       p += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = p / HW, q = p % HW;
+    float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int c = 0; c < C && c < 8; ++c) f[c] = x[(b * C + c) * HW + q];
+    uint4* o = reinterpret_cast<uint4*>(out + p * cpad);
+    o[0] = pack8(f);
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (int i = 1; i < cpad / 8; ++i) o[i] = z;
+  }
+}
+
+int pack_input_launch(const float* x, bf16* out, int B, int C, int HW, int cpad, cudaStream_t st) {
+  B2E_REQUIRE(C <= 8 && cpad % 8 == 0, B2E_UNSUPPORTED_SHAPE, "pack_input: in_channels must be <= 8");
+  int64_t total = (int64_t)B * HW;
+  int grid = (int)((total + 255) / 256);
+  if (grid > kNumSMs * 16) grid = kNumSMs * 16;
+  pack_input_kernel<<<grid, 256, 0, st>>>(x, out, B, C, HW, cpad);
+  return check_launch("pack_input");
+}
+
+__global__ void upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int N, int H,
+                                  int W, int C8) {
+  const int64_t total = (int64_t)N * (2 * H) * (2 * W) * C8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8);
+    int64_t r = i / C8;
+    const int wo = (int)(r % (2 * W)); r /= (2 * W);
+    const int ho = (int)(r % (2 * H));
+    const int n = (int)(r / (2 * H));
+    out[i] = __ldg(in + (((int64_t)n * H + (ho >> 1)) * W + (wo >> 1)) * C8 + c);
+  }
+}
+
+int upsample2x_launch(const bf16* in, bf16* out, int N, int H, int W, int C, cudaStream_t st) {
+  B2E_REQUIRE(C % 8 == 0, B2E_UNSUPPORTED_SHAPE, "upsample: C %% 8 != 0");
+  int64_t total = (int64_t)N * 4 * H * W * (C / 8);
+  int grid = (int)((total + 255) / 256);
+  if (grid > kNumSMs * 32) grid = kNumSMs * 32;
+  upsample2x_kernel<<<grid, 256, 0, st>>>((const uint4*)in, (uint4*)out, N, H, W, C / 8);
+  return check_launch("upsample2x");
+}
+
+// ------------------------------------------------------------------ timestep embedding
+// one block per sample: sinusoidal embedding -> linear_1 -> SiLU -> linear_2 -> SiLU (for the
+// per-resnet projections, which all consume silu(temb))
+__global__ void temb_mlp_kernel(TembArgs a) {
+  extern __shared__ float sm[];
+  float* emb = sm;             // [dim0]
+  float* hid = sm + a.dim0;    // [dim]
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int half = a.dim0 / 2;
+  const float t = (float)a.timesteps[b];
+  for (int i = tid; i < half; i += blockDim.x) {
+    const float ex = -logf(10000.f) * (float)i / ((float)half - a.freq_shift);
+    const float v = t * expf(ex);
+    const float sv = sinf(v), cv = cosf(v);
+    if (a.flip) { emb[i] = cv; emb[half + i] = sv; } else { emb[i] = sv; emb[half + i] = cv; }
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+  for (int o = warp; o < a.dim; o += nw) {
+    float acc = 0.f;
+    for (int i = lane; i < a.dim0; i += 32) acc += __ldg(a.w1 + (int64_t)o * a.dim0 + i) * emb[i];
+    acc = warp_sum(acc);
+    if (lane == 0) { float y = acc + a.b1[o]; hid[o] = y / (1.f + expf(-y)); }
+  }
+  __syncthreads();
+  for (int o = warp; o < a.dim; o += nw) {
+    float acc = 0.f;
+    for (int i = lane; i < a.dim; i += 32) acc += __ldg(a.w2 + (int64_t)o * a.dim + i) * hid[i];
+    acc = warp_sum(acc);
+    if (lane == 0) { float y = acc + a.b2[o]; a.act[(int64_t)b * a.dim + o] = y / (1.f + expf(-y)); }
+  }
+}
+
+// proj[b][o] = wp[o] . act[b] + bp[o]   (warp per output)
+__global__ void temb_proj_kernel(TembArgs a) {
+  const int b = blockIdx.y;
+  const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (o >= a.sumC) return;
+  const float* x = a.act + (int64_t)b * a.dim;
+  float acc = 0.f;
+  for (int i = lane; i < a.dim; i += 32) acc += __ldg(a.wp + (int64_t)o * a.dim + i) * x[i];
+  acc = warp_sum(acc);
+  if (lane == 0) a.proj[(int64_t)b * a.sumC + o] = acc + a.bp[o];
+}
+
+int temb_launch(const TembArgs& a, cudaStream_t st) {
+  temb_mlp_kernel<<<a.B, 512, (a.dim0 + a.dim) * sizeof(float), st>>>(a);
+  int rc = check_launch("temb_mlp");
+  if (rc) return rc;
+  temb_proj_kernel<<<dim3((a.sumC + 7) / 8, a.B), 256, 0, st>>>(a);
+  return check_launch("temb_proj");
+}
+
+// ------------------------------------------------------------------ attention core
+// Block = (image n, head h, 16 queries).  S = Q K^T * d^-1/2 in smem (fp32), softmax, O = P V.
+constexpr int kAttThreads = 256;
+constexpr int kAttQ = 16;
+constexpr int kAttKStride = 72;  // bf16 per staged key row (64 + pad): uint4-aligned, conflict-free
+
+__global__ void __launch_bounds__(kAttThreads)
+attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, int C, int heads) {
+  extern __shared__ __align__(16) uint8_t att_smem[];
+  const int d = C / heads;
+  float* Qs = reinterpret_cast<float*>(att_smem);            // [16][d]
+  float* S = Qs + kAttQ * d;                                  // [16][T]
+  bf16* Ks = reinterpret_cast<bf16*>(S + kAttQ * T);         // [256][72]
+  const int qt = blockIdx.x, h = blockIdx.y, n = blockIdx.z, tid = threadIdx.x;
+  const int q0 = qt * kAttQ;
+  const int64_t row = 3 * (int64_t)C;
+  const bf16* base = qkv + (int64_t)n * T * row;
+  const float scale = rsqrtf((float)d);
+  // load Q tile
+  for (int i = tid; i < kAttQ * d; i += kAttThreads) {
+    const int q = i / d, c = i % d;
+    Qs[i] = (q0 + q < T) ? __bfloat162float(base[(int64_t)(q0 + q) * row + h * d + c]) : 0.f;
+  }
+  // phase 1: scores
+  for (int kt = 0; kt < T; kt += kAttThreads) {
+    float acc[kAttQ];
+#pragma unroll
+    for (int q = 0; q < kAttQ; ++q) acc[q] = 0.f;
+    const int key = kt + tid;
+    for (int c0 = 0; c0 < d; c0 += 64) {
+      __syncthreads();
+      for (int i = tid; i < kAttThreads * 8; i += kAttThreads) {
+        const int kk = i >> 3, part = i & 7;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (kt + kk < T)
+          v = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)(kt + kk) * row + C + h * d + c0 + part * 8));
+        *reinterpret_cast<uint4*>(Ks + kk * kAttKStride + part * 8) = v;
+      }
+      __syncthreads();
+      if (key < T) {
+#pragma unroll
+        for (int part = 0; part < 8; ++part) {
+          float kf[8];
+          unpack8(*reinterpret_cast<const uint4*>(Ks + tid * kAttKStride + part * 8), kf);
+#pragma unroll
+          for (int q = 0; q < kAttQ; ++q) {
+            const float4 a = *reinterpret_cast<const float4*>(Qs + q * d + c0 + part * 8);
+            const float4 b = *reinterpret_cast<const float4*>(Qs + q * d + c0 + part * 8 + 4);
+            acc[q] += a.x * kf[0] + a.y * kf[1] + a.z * kf[2] + a.w * kf[3] + b.x * kf[4] + b.y * kf[5] +
+                      b.z * kf[6] + b.w * kf[7];
+          }
+        }
+      }
+    }
+    if (key < T) {
+#pragma unroll
+      for (int q = 0; q < kAttQ; ++q) S[q * T + key] = acc[q] * scale;
+    }
+  }
+  __syncthreads();
+  // phase 2: softmax rows (warp per row)
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int q = warp; q < kAttQ; q += kAttThreads / 32) {
+    float m = -INFINITY;
+    for (int j = lane; j < T; j += 32) m = fmaxf(m, S[q * T + j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float sum = 0.f;
+    for (int j = lane; j < T; j += 32) { const float e = __expf(S[q * T + j] - m); S[q * T + j] = e; sum += e; }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    for (int j = lane; j < T; j += 32) S[q * T + j] *= inv;
+  }
+  __syncthreads();
+  // phase 3: O = P V ; thread owns channel pairs (2*tid, 2*tid+1) + 512*i
+  for (int c0 = 2 * tid; c0 < d; c0 += 2 * kAttThreads) {
+    float ax[kAttQ], ay[kAttQ];
+#pragma unroll
+    for (int q = 0; q < kAttQ; ++q) ax[q] = ay[q] = 0.f;
+    const bf16* vp = base + 2 * C + h * d + c0;
+    for (int j = 0; j < T; j += 4) {  // T % 4 == 0 (checked on the host)
+      float2 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        v[u] = __bfloat1622float2(__ldg(reinterpret_cast<const __nv_bfloat162*>(vp + (int64_t)(j + u) * row)));
+#pragma unroll
+      for (int q = 0; q < kAttQ; ++q) {
+        const float4 p = *reinterpret_cast<const float4*>(S + q * T + j);
+        ax[q] += p.x * v[0].x + p.y * v[1].x + p.z * v[2].x + p.w * v[3].x;
+        ay[q] += p.x * v[0].y + p.y * v[1].y + p.z * v[2].y + p.w * v[3].y;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < kAttQ; ++q)
+      if (q0 + q < T)
+        *reinterpret_cast<__nv_bfloat162*>(out + ((int64_t)n * T + q0 + q) * C + h * d + c0) =
+            __floats2bfloat162_rn(ax[q], ay[q]);
+  }
+}
+
+int attention_launch(const bf16* qkv, bf16* out, int N, int T, int C, int heads, cudaStream_t st) {
+  B2E_REQUIRE(heads >= 1 && C % heads == 0, B2E_UNSUPPORTED_SHAPE, "attention: bad head count");
+  const int d = C / heads;
+  B2E_REQUIRE(d % 64 == 0 && d <= 1024 && T % 4 == 0 && T <= 4096, B2E_UNSUPPORTED_SHAPE,
+              "attention: unsupported T=%d head_dim=%d", T, d);
+  const size_t smem = sizeof(float) * kAttQ * (d + T) + sizeof(bf16) * kAttThreads * kAttKStride;
+  B2E_REQUIRE(smem <= 200 * 1024, B2E_UNSUPPORTED_SHAPE, "attention: tile does not fit in shared memory");
+  static size_t attr = 0;
+  if (smem > attr) {
+    B2E_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  attention_kernel<<<dim3((T + kAttQ - 1) / kAttQ, heads, N), kAttThreads, smem, st>>>(qkv, out, T, C, heads);
+  return check_launch("attention");
+}
+
+}  // namespace b2e

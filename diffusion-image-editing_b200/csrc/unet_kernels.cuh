@@ -1,0 +1,45 @@
+// Memory-bound / small kernels around the tcgen05 convolutions of the UNet (bf16 NHWC).
+#pragma once
+#include "conv_igemm.cuh"
+
+namespace b2e {
+
+// GroupNorm(+SiLU) over a (virtually concatenated) bf16 NHWC tensor: statistics pass writes
+// per-(image, chunk, group) partial sums; the apply pass reduces them (fixed order, fp64) and
+// writes the normalised bf16 tensor that the next convolution reads through TMA.
+struct GNArgs {
+  const bf16* x0; const bf16* x1;  // x1 may be null
+  int C0, C1;
+  int N, HW, G;
+  float eps;
+  const float* gamma; const float* beta;
+  float* partial;  // [N][chunks][G][2]
+  int chunks;
+  bf16* out;       // [N][HW][C0+C1]
+  int silu;
+};
+int gn_chunks(int HW, int C);
+int gn_launch(const GNArgs& a, cudaStream_t st);
+
+// x fp32 NCHW (B,C,S,S) -> bf16 NHWC (B,S,S,cpad), zero padded channels
+int pack_input_launch(const float* x, bf16* out, int B, int C, int HW, int cpad, cudaStream_t st);
+// nearest-neighbour x2 upsample, bf16 NHWC
+int upsample2x_launch(const bf16* in, bf16* out, int N, int H, int W, int C, cudaStream_t st);
+
+// timestep embedding MLP and all per-resnet projections
+struct TembArgs {
+  const int64_t* timesteps;  // [B]
+  int B, dim0, dim;          // dim0 = block_out[0], dim = 4*dim0
+  int flip; float freq_shift;
+  const float *w1, *b1, *w2, *b2;  // [dim][dim0], [dim], [dim][dim], [dim]
+  const float *wp, *bp;            // [sumC][dim], [sumC]
+  int sumC;
+  float* act;   // [B][dim]   silu(temb)
+  float* proj;  // [B][sumC]
+};
+int temb_launch(const TembArgs& a, cudaStream_t st);
+
+// single/multi-head self-attention core: qkv bf16 [N][T][3C] (q | k | v) -> out bf16 [N][T][C]
+int attention_launch(const bf16* qkv, bf16* out, int N, int T, int C, int heads, cudaStream_t st);
+
+}  // namespace b2e

@@ -1,0 +1,212 @@
+/*
+ * b200edit.h - C ABI of libb200edit.so: the B200 (sm_100a) guided denoising loop of
+ * JohanLundberg12/diffusion-image-editing.
+ *
+ * The reference has no FFI layer of its own: its boundary for this path is the Python
+ * module surface (src/diffusion_utils.py, ddim_inversion.py, ddpm_inversion.py,
+ * attr_functions.py, mask_creator.py, Morphology.py, utils.py, transforms.py,
+ * SegDiffEditPipeline.py).  Each entry point below replaces the body of the reference
+ * function(s) cited beside it; the Python drop-in modules under
+ * diffusion-image-editing_b200/ bind these symbols with ctypes.
+ *
+ * Conventions
+ *  - every tensor argument is a DEVICE pointer to caller-owned, contiguous memory
+ *    (fp32 NCHW unless stated); the library never allocates user-visible memory;
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued asynchronously;
+ *  - every function returns 0 on success or a negative b2e_status; it never throws or
+ *    exits.  b2e_last_error() returns a thread-local message for the last failure;
+ *  - per-step scalar coefficients are formed on the host in fp32 with the reference's
+ *    op order (b2e_step_coeffs_compute) and passed by value - no host sync in a step.
+ */
+#ifndef B200EDIT_H
+#define B200EDIT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2E_VERSION 100
+
+typedef enum {
+  B2E_OK = 0,
+  B2E_INVALID_ARG = -1,
+  B2E_UNSUPPORTED_SHAPE = -2,
+  B2E_WORKSPACE_TOO_SMALL = -3,
+  B2E_CUDA_ERROR = -4,
+  B2E_ARCH_MISMATCH = -5,
+  B2E_NOT_FOUND = -6
+} b2e_status;
+
+int b2e_version(void);
+const char* b2e_last_error(void);
+/* 0 iff the current device is sm_100 (B200); B2E_ARCH_MISMATCH otherwise. */
+int b2e_device_check(void);
+/* Number of kernels this library has launched in this process (all threads). */
+int64_t b2e_launch_count(void);
+
+/* ------------------------------------------------------------------ step coefficients
+ * src/diffusion_utils.py:6-24,76-81 (calculate_variance, compute_alpha_products,
+ * get_previous_timestep) + the scalar part of DDIMScheduler.step / reverse_step
+ * (src/ddpm_inversion.py:203-240).  All fp32, reference op order, no FMA contraction. */
+typedef struct {
+  float sqrt_a_t;     /* alphas_cumprod[t] ** 0.5                                   */
+  float sqrt_b_t;     /* (1 - alphas_cumprod[t]) ** 0.5                             */
+  float sqrt_a_prev;  /* alpha_prod_t_prev ** 0.5                                   */
+  float dir_coef;     /* ddim: (1-a_prev-sigma**2)**0.5 ; ddpm: (1-a_prev-eta*var)**0.5 */
+  float sigma;        /* eta * variance ** 0.5                                      */
+  float a_t_sq;       /* alphas_cumprod[t] ** 2  (guidance step size, attr_functions.py:158) */
+  float variance;
+  float a_t;
+  float a_prev;
+} b2e_step_coeffs;
+
+#define B2E_MODE_DDIM 0 /* DDIMScheduler.step  (single_step, src/diffusion_utils.py:90-109) */
+#define B2E_MODE_DDPM 1 /* reverse_step        (src/ddpm_inversion.py:203-240)              */
+
+/* alphas_cumprod: HOST pointer to the fp32 table (num_train entries). */
+int b2e_step_coeffs_compute(const float* alphas_cumprod, int num_train, float final_alpha_cumprod,
+                            int t, int t_prev, float eta, int mode, b2e_step_coeffs* out);
+
+/* ------------------------------------------------------------------ fused guided step
+ * One kernel for: x0 prediction (src/diffusion_utils.py:27-31) -> optional clip ->
+ * DDIM / DDPM update (+ sigma*z) -> colour guidance of AttrFunc.apply with the analytic
+ * gradient of single_color_loss / color_loss (src/attr_functions.py:22-37,104-163). */
+typedef struct {
+  b2e_step_coeffs c;
+  int32_t clip;             /* scheduler.config.clip_sample (DDIM mode only)              */
+  float clip_range;         /* scheduler.config.clip_sample_range                         */
+  int32_t has_noise;        /* eta > 0: add c.sigma * z                                   */
+  int32_t noise_batched;    /* z is (B,C,H,W) instead of the reference's (C,H,W)          */
+  int32_t guide;            /* 0: no guidance (outside [t1,t2) or attr_func is None)      */
+  int32_t has_target[4];    /* per channel: channel takes part in the colour loss          */
+  float target[4];          /* tau_c                                                      */
+  float coef[4];            /* k_c = loss_scale * w_c / N, formed on the host in fp32      */
+  int32_t mask_grad;        /* mask_attr_grad: g <- mask * g                              */
+  int32_t mask_batched;     /* mask is (B,C,H,W) instead of (1,C,H,W)                     */
+} b2e_guided_step_params;
+
+/* x_t, eps: (B,C,H,W); z: (C,H,W)|(B,C,H,W)|NULL; mask: (1|B,C,H,W)|NULL;
+ * x_prev, x0_pred: (B,C,H,W) outputs (x0_pred may be NULL).  C <= 4. */
+int b2e_guided_step_f32(const float* x_t, const float* eps, const float* z, const float* mask,
+                        float* x_prev, float* x0_pred, int64_t B, int64_t C, int64_t HW,
+                        const b2e_guided_step_params* p, void* stream);
+
+/* Masked + L2-regularised guidance (calculate_loss, src/attr_functions.py:78-102 with
+ * use_l2): loss = colour(mask*x0g) + lambda*||1 - mask*x0g - x_ref||_2.  Two passes over
+ * the data (the norm is a global reduction).  workspace: b2e_l2reg_workspace_bytes(). */
+typedef struct {
+  b2e_guided_step_params base;
+  float lambda_;
+  float loss_scale;
+} b2e_l2reg_params;
+size_t b2e_l2reg_workspace_bytes(int64_t B, int64_t C, int64_t HW);
+int b2e_guided_step_l2reg_f32(const float* x_t, const float* eps, const float* z, const float* mask,
+                              const float* x_ref, float* x_prev, float* x0_pred, int64_t B, int64_t C,
+                              int64_t HW, const b2e_l2reg_params* p, void* workspace,
+                              size_t workspace_bytes, void* stream);
+
+/* Guidance with an externally supplied gradient (user-defined AttrFunc.loss evaluated by
+ * autograd in the host layer): x <- x + (mask? mask*g : g) * a_t_sq, g = -dL/dx given. */
+int b2e_apply_guidance_grad_f32(float* x, const float* neg_grad, const float* mask, int64_t B,
+                                int64_t CHW, int mask_batched, float a_t_sq, void* stream);
+
+/* ------------------------------------------------------------------ single ops
+ * compute_predicted_original_sample, src/diffusion_utils.py:27-31 */
+int b2e_pred_x0_f32(const float* x_t, const float* eps, float* x0, int64_t n, float sqrt_a_t,
+                    float sqrt_b_t, void* stream);
+/* out = c_out_x0 * ((x - c_b*e) / c_a) + c_out_e * e : next_step (src/ddim_inversion.py:13-48)
+ * and forward_step (src/ddpm_inversion.py:58-77). */
+int b2e_renoise_f32(const float* x, const float* eps, float* out, int64_t n, float c_a, float c_b,
+                    float c_out_x0, float c_out_e, void* stream);
+/* get_noise_pred CFG combine, src/diffusion_utils.py:67-70: out = e0 + s*(e1 - e0) */
+int b2e_cfg_combine_f32(const float* e_first, const float* e_second, float* out, int64_t n,
+                        float scale, void* stream);
+/* apply_mask, src/utils.py:23-28: out = mask*zv + (1-mask)*zo ; mask (1,C,H,W) broadcast over T */
+int b2e_apply_mask_f32(const float* mask, const float* zo, const float* zv, float* out, int64_t T,
+                       int64_t CHW, void* stream);
+/* tensor_to_pil numerics, src/transforms.py:8-35: (B,C,H,W) fp32 -> (B,H,W,C) uint8,
+ * u8 = trunc(clamp(x/2+0.5,0,1)*255) */
+int b2e_to_uint8_f32(const float* x, uint8_t* out, int64_t B, int64_t C, int64_t HW, void* stream);
+
+/* ------------------------------------------------------------------ edit-friendly inversion
+ * sample_xts_from_x0, src/ddpm_inversion.py:31-55: xts[i] = x0*sa[i] + noise[i]*sb[i], i<T;
+ * xts[T] = x0.  x0 (C,H,W); noise (T,C,H,W); sa, sb: DEVICE fp32 [T]; xts (T+1,C,H,W). */
+int b2e_sample_xts_f32(const float* x0, const float* noise, const float* sa, const float* sb,
+                       float* xts, int64_t T, int64_t CHW, void* stream);
+/* z_t extraction, src/ddpm_inversion.py:135-169 (one step): mu = sqrt_a_prev*x0 + dir*eps;
+ * z = (x_tm1 - mu)/sigma ; x_tm1 <- mu + sigma*z (in place).  Use mode DDPM coefficients. */
+int b2e_extract_noise_f32(const float* x_t, const float* eps, float* x_tm1, float* z, int64_t n,
+                          const b2e_step_coeffs* c, void* stream);
+
+/* ------------------------------------------------------------------ masks
+ * MaskCreator.create_mask (src/mask_creator.py:22-55) incl. Dilation2d(1,1,7,hard max)
+ * (src/Morphology.py:47-111) and torchvision Resize (antialiased bilinear, ATen order).
+ * seg: DEVICE int64 (H,W); classes: HOST int array; out: (1,channels,out_h,out_w) fp32 {0,1}. */
+size_t b2e_mask_workspace_bytes(int64_t H, int64_t W, int64_t out_h, int64_t out_w);
+int b2e_mask_from_seg(const int64_t* seg, int64_t H, int64_t W, const int32_t* classes,
+                      int n_classes, int dilate, int ksize, int64_t out_h, int64_t out_w,
+                      int channels, int antialias, float* out, void* workspace,
+                      size_t workspace_bytes, void* stream);
+/* Antialiased bilinear resize of one fp32 plane (H,W)->(out_h,out_w), ATen CPU order. */
+int b2e_resize_bilinear_aa_f32(const float* in, int64_t H, int64_t W, float* out, int64_t out_h,
+                               int64_t out_w, void* workspace, size_t workspace_bytes, void* stream);
+/* Morphology.forward (src/Morphology.py:47-84): x (B,Cin,H,W), weight (Cout,Cin,k,k),
+ * out (B,Cout,H,W); op 0 = dilation2d, 1 = erosion2d; soft_max with beta if soft != 0. */
+int b2e_morphology2d_f32(const float* x, const float* weight, float* out, int64_t B, int64_t Cin,
+                         int64_t Cout, int64_t H, int64_t W, int ksize, int op, int soft,
+                         float beta, void* stream);
+
+/* ------------------------------------------------------------------ UNet (noise predictor)
+ * get_noise_pred's unconditional branch, src/diffusion_utils.py:72: eps = unet(x, t).sample
+ * for a diffusers UNet2DModel (google/ddpm-celebahq-256 layout by default).  bf16 tensor-core
+ * path: tcgen05 implicit-GEMM convolutions fed by TMA, fp32 accumulation in TMEM. */
+typedef struct {
+  int32_t sample_size;
+  int32_t in_channels;
+  int32_t out_channels;
+  int32_t n_blocks;
+  int32_t block_out_channels[8];
+  int32_t down_attn[8]; /* 1: AttnDownBlock2D */
+  int32_t up_attn[8];   /* 1: AttnUpBlock2D   */
+  int32_t layers_per_block;
+  int32_t norm_num_groups;
+  float norm_eps;
+  int32_t attention_head_dim; /* 0: single head */
+  int32_t flip_sin_to_cos;
+  float freq_shift;
+} b2e_unet_config;
+
+typedef struct b2e_unet b2e_unet;
+
+int b2e_unet_create(const b2e_unet_config* cfg, int64_t max_batch, b2e_unet** out);
+void b2e_unet_destroy(b2e_unet* m);
+/* Parameters by their diffusers state_dict names (for loading); fan_in = inputs per output unit
+ * (PyTorch default-init bound 1/sqrt(fan_in)), 0 for normalisation scales / shifts. */
+int b2e_unet_num_params(const b2e_unet* m);
+int b2e_unet_param_info(const b2e_unet* m, int idx, const char** name, int64_t* numel, int64_t* fan_in);
+/* Copy one fp32 parameter (DEVICE pointer, diffusers layout) into the model; it is repacked
+ * to the kernel layout (bf16 [Cout][kh][kw][Cin] for convolutions) on `stream`. */
+int b2e_unet_set_param(b2e_unet* m, const char* name, const float* data, int64_t numel, void* stream);
+/* Activation arena: caller-owned device memory, bound once (TMA descriptors point into it). */
+size_t b2e_unet_workspace_bytes(const b2e_unet* m);
+int b2e_unet_bind_workspace(b2e_unet* m, void* workspace, size_t workspace_bytes);
+/* x (B,Cin,S,S) fp32 NCHW; timesteps: DEVICE int64 [B]; eps (B,Cout,S,S) fp32 NCHW. */
+int b2e_unet_forward(b2e_unet* m, const float* x, const int64_t* timesteps, float* eps, int64_t B,
+                     void* stream);
+double b2e_unet_flops(const b2e_unet* m, int64_t B);
+int b2e_unet_launches_per_forward(const b2e_unet* m);
+
+/* Test hook for the implicit-GEMM convolution: x (N,H,W,Cin) bf16 NHWC, w (Cout,Cin,k,k) fp32,
+ * bias fp32 [Cout] or NULL, out (N,Ho,Wo,Cout) bf16 NHWC.  ksize 1|3, stride 1|2
+ * (stride 2 pads (0,1,0,1) like diffusers' Downsample2D).  Allocates temporaries itself. */
+int b2e_conv2d_nhwc_bf16(const void* x, const float* w, const float* bias, void* out, int64_t N,
+                         int64_t H, int64_t W, int64_t Cin, int64_t Cout, int ksize, int stride,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200EDIT_H */

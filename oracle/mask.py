@@ -34,22 +34,30 @@ F32 = np.float32
 
 
 def aa_weights(in_size: int, out_size: int):
-    """[(xmin, [w_j...])] per output index; fp32 like ATen's HelperInterpLinear."""
-    scale = F32(in_size) / F32(out_size)
-    support = F32(1.0) * scale if scale >= 1 else F32(1.0)
-    invscale = F32(1.0) / scale if scale >= 1 else F32(1.0)
+    """[(xmin, [w_j...])] per output index.  Mirrors the float/double promotions of ATen's
+    ``_compute_indices_min_size_weights_aa`` with scalar_t = float: literals such as 0.5 and
+    1.0 are doubles in the C++ source, stored results are floats."""
+    F64 = np.float64
+    scale = F32(F32(in_size) / F32(out_size))
+    support = F32(F64(1.0) * F64(scale)) if scale >= 1 else F32(1.0)
+    invscale = F32(F64(1.0) / F64(scale)) if scale >= 1 else F32(1.0)
+    max_taps = int(np.ceil(support)) * 2 + 1
     table = []
     for i in range(out_size):
-        center = F32(scale * (i + 0.5))
-        xmin = max(int(center - support + 0.5), 0)
-        xsize = min(int(center + support + 0.5), in_size) - xmin
+        center = F32(F64(scale) * (F64(i) + F64(0.5)))
+        xmin = max(int(F64(F32(center - support)) + F64(0.5)), 0)
+        xsize = min(int(F64(F32(center + support)) + F64(0.5)), in_size) - xmin
+        xsize = min(max(xsize, 0), max_taps)
         ws, total = [], F32(0)
         for j in range(xsize):
-            x = abs(F32((F32(j + xmin - center) + 0.5) * invscale))
-            w = F32(1) - x if x < 1 else F32(0)
-            ws.append(F32(w))
+            d = F32(F32(j + xmin) - center)
+            x = abs(F32((F64(d) + F64(0.5)) * F64(invscale)))
+            w = F32(F64(1.0) - F64(x)) if x < 1 else F32(0)
+            ws.append(w)
             total = F32(total + w)
-        table.append((xmin, [F32(w / total) for w in ws]))
+        if total != 0:
+            ws = [F32(w / total) for w in ws]
+        table.append((xmin, ws))
     return table
 
 

@@ -1,0 +1,48 @@
+"""GPU numerics of the tcgen05 implicit-GEMM convolution against a plain PyTorch fp32 reference
+(cuDNN is used here only as the checker).  Inputs and weights are pre-rounded to bf16 so the only
+differences are fp32 accumulation order and the final bf16 rounding of the output:
+tolerance = 2^-7 relative to the output scale."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # N, H, W, Cin, Cout, k, stride
+    (1, 16, 16, 64, 128, 3, 1),
+    (2, 32, 32, 128, 128, 3, 1),
+    (1, 256, 256, 128, 128, 3, 1),     # one output row = two 128-pixel tiles
+    (2, 64, 64, 256, 256, 3, 1),
+    (3, 8, 8, 512, 512, 3, 1),         # tiles span two images; odd batch -> OOB image
+    (1, 8, 8, 1024, 512, 3, 1),
+    (2, 16, 16, 512, 1536, 1, 1),      # attention qkv projection
+    (2, 16, 16, 384, 256, 1, 1),       # 1x1 shortcut, 6 K chunks
+    (2, 32, 32, 128, 128, 3, 2),       # Downsample2D: stride 2, pad (0,1,0,1)
+    (1, 256, 256, 128, 128, 3, 2),
+    (2, 16, 16, 64, 64, 3, 1),         # BLOCK_N = 64
+    (1, 4, 4, 64, 64, 3, 1),           # tiny map: 8 images per tile
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[str(c) for c in CASES])
+def test_conv_vs_torch(case):
+    from b200edit import ops
+    N, H, W, Cin, Cout, k, stride = case
+    g = torch.Generator(device="cpu").manual_seed(sum(case))
+    x = torch.randn(N, Cin, H, W, generator=g).bfloat16()
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).bfloat16()
+    b = torch.randn(Cout, generator=g)
+    xd = x.cuda().permute(0, 2, 3, 1).contiguous()
+    out = ops.conv2d_nhwc_bf16(xd, w.float().cuda(), b.cuda(), stride=stride)
+    torch.cuda.synchronize()
+    xf = x.float().cuda()
+    if stride == 2:
+        ref = F.conv2d(F.pad(xf, (0, 1, 0, 1)), w.float().cuda(), b.cuda(), stride=2)
+    else:
+        ref = F.conv2d(xf, w.float().cuda(), b.cuda(), padding=k // 2)
+    got = out.float().permute(0, 3, 1, 2)
+    assert got.shape == ref.shape
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 2 ** -7 * scale + 1e-3, f"max abs err {err} (scale {scale})"
