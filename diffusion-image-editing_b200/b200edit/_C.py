@@ -21,7 +21,7 @@ class GuidedStepParams(C.Structure):
     _fields_ = [("c", StepCoeffs), ("clip", C.c_int32), ("clip_range", C.c_float),
                 ("has_noise", C.c_int32), ("noise_batched", C.c_int32), ("guide", C.c_int32),
                 ("has_target", C.c_int32 * 4), ("target", C.c_float * 4), ("coef", C.c_float * 4),
-                ("mask_grad", C.c_int32), ("mask_batched", C.c_int32)]
+                ("mask_grad", C.c_int32), ("mask_batched", C.c_int32), ("no_step", C.c_int32)]
 
 
 class L2RegParams(C.Structure):
@@ -56,6 +56,10 @@ PROTOTYPES = {
     "b2e_cfg_combine_f32": (_I, [_P, _P, _P, _I64, _F, _P]),
     "b2e_apply_mask_f32": (_I, [_P, _P, _P, _P, _I64, _I64, _P]),
     "b2e_to_uint8_f32": (_I, [_P, _P, _I64, _I64, _I64, _P]),
+    "b2e_axpby_f32": (_I, [_P, _P, _P, _I64, _F, _F, _P]),
+    "b2e_loss_workspace_bytes": (_SZ, []),
+    "b2e_l2_distance_f32": (_I, [_P, _P, _I64, _P, _P, _SZ, _P]),
+    "b2e_channel_l1_f32": (_I, [_P, _I64, _I64, _I64, _P, _P, _P, _SZ, _P]),
     "b2e_sample_xts_f32": (_I, [_P, _P, _P, _P, _P, _I64, _I64, _P]),
     "b2e_extract_noise_f32": (_I, [_P, _P, _P, _P, _I64, C.POINTER(StepCoeffs), _P]),
     "b2e_mask_workspace_bytes": (_SZ, [_I64, _I64, _I64, _I64]),
@@ -73,6 +77,8 @@ PROTOTYPES = {
     "b2e_unet_forward": (_I, [_P, _P, _P, _P, _I64, _P]),
     "b2e_unet_flops": (C.c_double, [_P, _I64]),
     "b2e_unet_launches_per_forward": (_I, [_P]),
+    "b2e_unet_profile": (_I, [_P, _P, _P, _P, _I64, _P, _I, C.POINTER(_I), C.POINTER(C.c_float),
+                              C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_I)]),
     "b2e_conv2d_nhwc_bf16": (_I, [_P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I, _I, _P]),
 }
 

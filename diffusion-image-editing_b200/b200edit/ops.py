@@ -105,7 +105,8 @@ def _fill_params(p: GuidedStepParams, c: StepCoeffs, B, Cc, HW, clip, clip_range
 def guided_step(x_t: torch.Tensor, eps: torch.Tensor, c: StepCoeffs, *, clip=False, clip_range=1.0,
                 noise: Optional[torch.Tensor] = None, targets: Optional[Sequence] = None,
                 weights: Optional[Sequence] = None, loss_scale: float = 1.0,
-                mask: Optional[torch.Tensor] = None, mask_grad=False, n_mean=None, want_x0=True):
+                mask: Optional[torch.Tensor] = None, mask_grad=False, n_mean=None, want_x0=True,
+                no_step=False):
     """Fused x0-prediction + scheduler update (+ sigma*z) + colour guidance.
     Returns (x_prev, x0_pred)."""
     x_t, eps = _f32(x_t, "x_t"), _f32(eps, "eps")
@@ -126,6 +127,7 @@ def guided_step(x_t: torch.Tensor, eps: torch.Tensor, c: StepCoeffs, *, clip=Fal
     p = GuidedStepParams()
     _fill_params(p, c, B, Cc, H * W, clip, clip_range, noise, mask, targets, weights, loss_scale,
                  mask_grad, n_mean)
+    p.no_step = int(bool(no_step))
     x_prev = torch.empty_like(x_t)
     x0 = torch.empty_like(x_t) if want_x0 else None
     check(lib.b2e_guided_step_f32(_p(x_t), _p(eps), _p(noise), _p(mask), _p(x_prev), _p(x0), B, Cc,
@@ -135,7 +137,7 @@ def guided_step(x_t: torch.Tensor, eps: torch.Tensor, c: StepCoeffs, *, clip=Fal
 
 def guided_step_l2reg(x_t, eps, c: StepCoeffs, *, x_ref, mask, lambda_, targets, weights=None,
                       loss_scale=1.0, clip=False, clip_range=1.0, noise=None, mask_grad=False,
-                      guide=True, n_mean=None):
+                      guide=True, n_mean=None, no_step=False):
     """Masked + L2-regularised colour guidance (two-pass).  Returns (x_prev, x0_pred)."""
     x_t, eps, x_ref, mask = _f32(x_t, "x_t"), _f32(eps, "eps"), _f32(x_ref, "x_0"), _f32(mask, "mask")
     B, Cc, H, W = x_t.shape
@@ -148,6 +150,7 @@ def guided_step_l2reg(x_t, eps, c: StepCoeffs, *, x_ref, mask, lambda_, targets,
     _fill_params(p.base, c, B, Cc, H * W, clip, clip_range, noise, mask, targets, weights, loss_scale,
                  mask_grad, n_mean)
     p.base.guide = int(bool(guide))
+    p.base.no_step = int(bool(no_step))
     p.base.mask_batched = int(mask.shape[0] == B and B > 1)
     p.lambda_ = float(lambda_)
     p.loss_scale = float(loss_scale)
@@ -187,6 +190,43 @@ def renoise(x, eps, c_a: float, c_b: float, c_out_x0: float, c_out_e: float):
     check(lib.b2e_renoise_f32(_p(x), _p(eps), _p(out), x.numel(), c_a, c_b, c_out_x0, c_out_e, _stream()),
           "renoise")
     return out
+
+
+def axpby(x, y, a: float, b: float):
+    """out = a*x + b*y (two rounded products, one rounded sum)."""
+    x, y = _f32(x, "x"), _f32(y, "y")
+    if x.shape != y.shape:
+        y = y.expand_as(x).contiguous()
+    out = torch.empty_like(x)
+    check(lib.b2e_axpby_f32(_p(x), _p(y), _p(out), x.numel(), float(a), float(b), _stream()), "axpby")
+    return out
+
+
+def _loss_ws(device):
+    n = lib.b2e_loss_workspace_bytes()
+    return torch.empty(n, dtype=torch.uint8, device=device), n
+
+
+def l2_distance(x, y):
+    """sqrt(sum((x-y)^2)) as a 0-d CUDA tensor (src/attr_functions.py:11-13)."""
+    x, y = _f32(x, "x"), _f32(y, "y")
+    if x.shape != y.shape:
+        y = y.expand_as(x).contiguous()
+    ws, n = _loss_ws(x.device)
+    out = torch.empty(1, dtype=torch.float32, device=x.device)
+    check(lib.b2e_l2_distance_f32(_p(x), _p(y), x.numel(), _p(out), _p(ws), n, _stream()), "l2_distance")
+    return out[0]
+
+
+def channel_l1(img, targets):
+    """Per-channel mean |img[:,c] - targets[c]| over (B,H,W) -> fp32 CUDA tensor [C]."""
+    img = _f32(img, "images")
+    B, Cc, H, W = img.shape
+    tg = (C.c_float * 4)(*([float(t if t is not None else 0.0) for t in targets] + [0.0] * (4 - len(targets))))
+    ws, n = _loss_ws(img.device)
+    out = torch.empty(4, dtype=torch.float32, device=img.device)
+    check(lib.b2e_channel_l1_f32(_p(img), B, Cc, H * W, tg, _p(out), _p(ws), n, _stream()), "channel_l1")
+    return out[:Cc]
 
 
 def cfg_combine(e_first, e_second, scale: float):

@@ -127,6 +127,23 @@ class UNet2DModel:
     def launches_per_forward(self) -> int:
         return int(lib.b2e_unet_launches_per_forward(self._h))
 
+    def profile(self, sample, timestep):
+        """Per-op CUDA-event timings of one forward: list of dicts(kind, ms, flops, bytes)."""
+        x = sample.to(torch.float32).contiguous()
+        B = x.shape[0]
+        t = self._timesteps(timestep, B)
+        eps = torch.empty((B, self.config.out_channels, self.config.sample_size, self.config.sample_size),
+                          dtype=torch.float32, device=x.device)
+        cap = 1024
+        n = C.c_int()
+        ms, fl, by, kd = (C.c_float * cap)(), (C.c_double * cap)(), (C.c_double * cap)(), (C.c_int * cap)()
+        check(lib.b2e_unet_profile(self._h, C.c_void_p(x.data_ptr()), C.c_void_p(t.data_ptr()),
+                                   C.c_void_p(eps.data_ptr()), B,
+                                   C.c_void_p(torch.cuda.current_stream().cuda_stream), cap, C.byref(n), ms, fl, by, kd),
+              "unet_profile")
+        names = {0: "conv_igemm", 1: "groupnorm", 2: "attention", 3: "other"}
+        return [dict(kind=names[kd[i]], ms=ms[i], flops=fl[i], bytes=by[i]) for i in range(n.value)]
+
     # ------------------------------------------------------------------ forward
     def _timesteps(self, timestep, B):
         if torch.is_tensor(timestep) and timestep.is_cuda:

@@ -28,7 +28,7 @@ void set_error(const char* fmt, ...) {
 // ------------------------------------------------------------------------------------
 struct StepK {
   float sa, sb, sp, cdir, sigma, a2, clip_range;
-  int clip, has_noise, noise_batched, guide, mask_grad, mask_batched;
+  int clip, has_noise, noise_batched, guide, mask_grad, mask_batched, no_step;
   int has_target[4];
   float target[4];
   float gk[4];  // k_c / sa  (== (k_c * s)/sa for s in {-1,0,1})
@@ -40,6 +40,7 @@ static StepK make_stepk(const b2e_guided_step_params* p) {
   k.sigma = p->c.sigma; k.a2 = p->c.a_t_sq; k.clip_range = p->clip_range;
   k.clip = p->clip; k.has_noise = p->has_noise; k.noise_batched = p->noise_batched;
   k.guide = p->guide; k.mask_grad = p->mask_grad; k.mask_batched = p->mask_batched;
+  k.no_step = p->no_step;
   for (int i = 0; i < 4; ++i) {
     k.has_target[i] = p->has_target[i];
     k.target[i] = p->target[i];
@@ -51,9 +52,12 @@ static StepK make_stepk(const b2e_guided_step_params* p) {
 __device__ __forceinline__ void step_elem(float x, float e, float z, float m, int has_t, float tau,
                                           float gk, const StepK& k, float& xp_out, float& x0_out) {
   float x0 = __fdiv_rn(__fsub_rn(x, __fmul_rn(k.sb, e)), k.sa);
-  if (k.clip) x0 = clamp_torch(x0, -k.clip_range, k.clip_range);
-  float xp = __fadd_rn(__fmul_rn(k.sp, x0), __fmul_rn(k.cdir, e));
-  if (k.has_noise) xp = __fadd_rn(xp, __fmul_rn(k.sigma, z));
+  float xp = x;  // no_step: x already is the post-step sample (AttrFunc.apply called on its own)
+  if (!k.no_step) {
+    if (k.clip) x0 = clamp_torch(x0, -k.clip_range, k.clip_range);
+    xp = __fadd_rn(__fmul_rn(k.sp, x0), __fmul_rn(k.cdir, e));
+    if (k.has_noise) xp = __fadd_rn(xp, __fmul_rn(k.sigma, z));
+  }
   if (k.guide && has_t) {
     float x0g = __fdiv_rn(__fsub_rn(xp, __fmul_rn(k.sb, e)), k.sa);
     float g = -__fmul_rn(gk, sign_torch(__fsub_rn(x0g, tau)));
@@ -363,6 +367,58 @@ to_uint8_kernel(const float* __restrict__ x, uint8_t* __restrict__ out, int64_t 
   }
 }
 
+
+// out = a*x + b*y
+__global__ void __launch_bounds__(kStepThreads)
+axpby_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ out,
+             int64_t n, float a, float b) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = __fadd_rn(__fmul_rn(a, x[i]), __fmul_rn(b, y[i]));
+}
+
+// Loss values (reductions; the guidance update itself never needs them).
+// mode 0: sum (x-y)^2 -> partial[block][0]
+// mode 1: per channel sum |x - target_c| -> partial[block][c]   (x is (B,C,HW))
+__global__ void __launch_bounds__(kStepThreads)
+loss_partial_kernel(const float* __restrict__ x, const float* __restrict__ y, double* __restrict__ partial,
+                    int64_t n, int64_t hw, int C, int mode, float t0, float t1, float t2, float t3) {
+  __shared__ double red[32];
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  const float tg[4] = {t0, t1, t2, t3};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    if (mode == 0) {
+      const float d = __fsub_rn(x[i], y[i]);
+      acc[0] += (double)__fmul_rn(d, d);
+    } else {
+      const int c = (int)((i / hw) % C);
+      const double v = (double)fabsf(__fsub_rn(x[i], tg[c]));
+      if (c == 0) acc[0] += v; else if (c == 1) acc[1] += v; else if (c == 2) acc[2] += v; else acc[3] += v;
+    }
+  }
+  for (int j = 0; j < 4; ++j) {
+    block_sum_to_double(acc[j], red);
+    if (threadIdx.x == 0) partial[(int64_t)blockIdx.x * 4 + j] = red[0];
+    __syncthreads();
+  }
+}
+// mode 0: out[0] = sqrt(sum) ; mode 1: out[c] = sum_c / count
+__global__ void loss_final_kernel(const double* __restrict__ partial, int n_partial, float* __restrict__ out,
+                                  int mode, double count) {
+  __shared__ double red[32];
+  for (int j = 0; j < 4; ++j) {
+    double a = 0.0;
+    for (int i = threadIdx.x; i < n_partial; i += blockDim.x) a += partial[(int64_t)i * 4 + j];
+    block_sum_to_double(a, red);
+    if (threadIdx.x == 0) {
+      if (mode == 0) { if (j == 0) out[0] = sqrtf((float)red[0]); }
+      else out[j] = (float)(red[0] / count);
+    }
+    __syncthreads();
+  }
+}
+
 static inline int grid_for(int64_t n, int per_block, int max_blocks = kNumSMs * 16) {
   int64_t g = (n + per_block - 1) / per_block;
   if (g < 1) g = 1;
@@ -536,6 +592,41 @@ int b2e_extract_noise_f32(const float* x_t, const float* eps, float* x_tm1, floa
   extract_noise_kernel<<<grid_for(vec ? n / 4 : n, kStepThreads), kStepThreads, 0, (cudaStream_t)stream>>>(
       x_t, eps, x_tm1, z, n, c->sqrt_a_t, c->sqrt_b_t, c->sqrt_a_prev, c->dir_coef, c->sigma, vec);
   return check_launch("extract_noise");
+}
+
+int b2e_axpby_f32(const float* x, const float* y, float* out, int64_t n, float a, float b, void* stream) {
+  B2E_REQUIRE(x && y && out && n > 0, B2E_INVALID_ARG, "axpby: bad argument");
+  axpby_kernel<<<grid_for(n, kStepThreads), kStepThreads, 0, (cudaStream_t)stream>>>(x, y, out, n, a, b);
+  return check_launch("axpby");
+}
+
+size_t b2e_loss_workspace_bytes(void) { return sizeof(double) * 4 * kNumSMs * 4; }
+
+static int run_loss(const float* x, const float* y, int64_t n, int64_t hw, int C, int mode, const float* tg,
+                    double count, float* out, void* ws, size_t ws_bytes, void* stream, const char* what) {
+  B2E_REQUIRE(x && out && ws && n > 0, B2E_INVALID_ARG, "%s: bad argument", what);
+  B2E_REQUIRE(ws_bytes >= b2e_loss_workspace_bytes(), B2E_WORKSPACE_TOO_SMALL, "%s: workspace too small", what);
+  const int grid = grid_for(n, kStepThreads, kNumSMs * 4);
+  loss_partial_kernel<<<grid, kStepThreads, 0, (cudaStream_t)stream>>>(x, y, (double*)ws, n, hw, C, mode, tg[0],
+                                                                         tg[1], tg[2], tg[3]);
+  int rc = check_launch(what);
+  if (rc) return rc;
+  loss_final_kernel<<<1, kStepThreads, 0, (cudaStream_t)stream>>>((const double*)ws, grid, out, mode, count);
+  return check_launch(what);
+}
+
+int b2e_l2_distance_f32(const float* x, const float* y, int64_t n, float* out, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  B2E_REQUIRE(y, B2E_INVALID_ARG, "l2_distance: bad argument");
+  const float tg[4] = {0, 0, 0, 0};
+  return run_loss(x, y, n, 1, 1, 0, tg, 1.0, out, workspace, workspace_bytes, stream, "l2_distance");
+}
+
+int b2e_channel_l1_f32(const float* img, int64_t B, int64_t C, int64_t HW, const float* targets4, float* out4,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+  B2E_REQUIRE(targets4 && C > 0 && C <= 4 && B > 0 && HW > 0, B2E_INVALID_ARG, "channel_l1: bad argument");
+  return run_loss(img, nullptr, B * C * HW, HW, (int)C, 1, targets4, (double)(B * HW), out4, workspace,
+                  workspace_bytes, stream, "channel_l1");
 }
 
 // Host scalar math, reference op order (this TU is compiled with -ffp-contract=off).

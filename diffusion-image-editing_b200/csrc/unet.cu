@@ -74,7 +74,8 @@ struct b2e_unet {
   // program
   void* ws = nullptr; size_t ws_bytes = 0;
   int64_t cur_B = -1;
-  std::vector<std::function<int(cudaStream_t)>> ops;
+  struct Op { std::function<int(cudaStream_t)> fn; int kind; double flops; double bytes; };  // kind: 0 conv, 1 groupnorm, 2 attention, 3 other
+  std::vector<Op> ops;
   const float* in_x = nullptr; const int64_t* in_t = nullptr; float* out_eps = nullptr;  // per-call
   double flops = 0;
   size_t ws_need = 0;
@@ -232,7 +233,7 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
   Arena ar;
   ar.reset(ws, ws_bytes);
   const bool dry = ar.dry;
-  std::vector<std::function<int(cudaStream_t)>> ops;
+  std::vector<b2e_unet::Op> ops;
   double flops = 0;
   int rc = B2E_OK;
   auto talloc = [&](int N, int H, int W, int C) {
@@ -262,9 +263,10 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
     flops += pl.flops;
     if (out_nchw) {
       // the network output pointer is only known at call time
-      ops.push_back([pl, ep, m](cudaStream_t st) { ConvEpilogue e = ep; e.out_f32_nchw = m->out_eps; return conv_launch(pl, e, st); });
+      ops.push_back({[pl, ep, m](cudaStream_t st) { ConvEpilogue e = ep; e.out_f32_nchw = m->out_eps; return conv_launch(pl, e, st); },
+                     0, pl.flops, 0.0});
     } else {
-      ops.push_back([pl, ep](cudaStream_t st) { return conv_launch(pl, ep, st); });
+      ops.push_back({[pl, ep](cudaStream_t st) { return conv_launch(pl, ep, st); }, 0, pl.flops, 0.0});
     }
   };
   auto gnorm = [&](const NormL& L, Tensor x0, const Tensor* x1, int silu, Tensor* out) {
@@ -276,20 +278,22 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
     a.x0 = x0.p; a.x1 = x1 ? x1->p : nullptr; a.C0 = x0.C; a.C1 = x1 ? x1->C : 0;
     a.N = B; a.HW = x0.H * x0.W; a.G = G; a.eps = c.norm_eps; a.gamma = L.g; a.beta = L.b;
     a.partial = gn_part; a.chunks = gn_chunks(a.HW, C); a.out = out->p; a.silu = silu;
-    ops.push_back([a](cudaStream_t st) { return gn_launch(a, st); });
+    // algorithmic traffic: statistics pass reads x, apply pass reads x and writes y (bf16)
+    ops.push_back({[a](cudaStream_t st) { return gn_launch(a, st); }, 1, 0.0, 6.0 * B * a.HW * C});
   };
 
   // ---- prologue: input packing, timestep embedding
   Tensor xin = talloc(B, S, S, kConvBlockK);
   if (!dry) {
     const int Cin = c.in_channels, HW = S * S;
-    ops.push_back([m, xin, B, Cin, HW](cudaStream_t st) { return pack_input_launch(m->in_x, xin.p, B, Cin, HW, kConvBlockK, st); });
+    ops.push_back({[m, xin, B, Cin, HW](cudaStream_t st) { return pack_input_launch(m->in_x, xin.p, B, Cin, HW, kConvBlockK, st); },
+                   3, 0.0, (double)B * HW * (4.0 * Cin + 2.0 * kConvBlockK)});
     TembArgs ta;
     ta.timesteps = nullptr; ta.B = B; ta.dim0 = c.block_out_channels[0]; ta.dim = m->temb_dim;
     ta.flip = c.flip_sin_to_cos; ta.freq_shift = c.freq_shift;
     ta.w1 = m->te_w1; ta.b1 = m->te_b1; ta.w2 = m->te_w2; ta.b2 = m->te_b2; ta.wp = m->tp_w; ta.bp = m->tp_b;
     ta.sumC = m->sumC; ta.act = act; ta.proj = proj;
-    ops.push_back([m, ta](cudaStream_t st) { TembArgs t = ta; t.timesteps = m->in_t; return temb_launch(t, st); });
+    ops.push_back({[m, ta](cudaStream_t st) { TembArgs t = ta; t.timesteps = m->in_t; return temb_launch(t, st); }, 3, 0.0, 0.0});
   }
   Tensor h;
   conv(m->conv_in, xin, nullptr, 1, ConvEpilogue{}, &h, nullptr);
@@ -341,7 +345,8 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
         const int heads = c.attention_head_dim > 0 ? a.C / c.attention_head_dim : 1;
         if (!dry) {
           const int T = h.H * h.W, C = a.C;
-          ops.push_back([qkv, o, B, T, C, heads](cudaStream_t st) { return attention_launch(qkv.p, o.p, B, T, C, heads, st); });
+          ops.push_back({[qkv, o, B, T, C, heads](cudaStream_t st) { return attention_launch(qkv.p, o.p, B, T, C, heads, st); },
+                         2, 4.0 * B * (double)T * T * C, 0.0});
         }
         flops += 4.0 * B * (double)(h.H * h.W) * (h.H * h.W) * a.C;
         tfree(qkv);
@@ -363,7 +368,8 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
         Tensor up = talloc(B, h.H * 2, h.W * 2, h.C), out;
         if (!dry) {
           Tensor hh = h;
-          ops.push_back([hh, up, B](cudaStream_t st) { return upsample2x_launch(hh.p, up.p, B, hh.H, hh.W, hh.C, st); });
+          ops.push_back({[hh, up, B](cudaStream_t st) { return upsample2x_launch(hh.p, up.p, B, hh.H, hh.W, hh.C, st); },
+                         3, 0.0, 10.0 * B * hh.H * hh.W * hh.C});
         }
         if (!on_stack(h)) tfree(h);
         conv(m->ups[nd.idx], up, nullptr, 1, ConvEpilogue{}, &out, nullptr);
@@ -462,10 +468,37 @@ int b2e_unet_forward(b2e_unet* m, const float* x, const int64_t* timesteps, floa
   m->in_x = x; m->in_t = timesteps; m->out_eps = eps;
   cudaStream_t st = (cudaStream_t)stream;
   for (auto& op : m->ops) {
-    int rc = op(st);
+    int rc = op.fn(st);
     if (rc) return rc;
   }
   return B2E_OK;
+}
+
+int b2e_unet_profile(b2e_unet* m, const float* x, const int64_t* timesteps, float* eps, int64_t B, void* stream,
+                     int max_ops, int* n_ops, float* ms, double* flops, double* bytes, int* kind) {
+  B2E_REQUIRE(m && x && timesteps && eps && n_ops && ms && flops && bytes && kind, B2E_INVALID_ARG,
+              "unet_profile: null pointer");
+  // one plain pass first (plan rebuild / lazy function attributes), then the instrumented pass
+  int rc = b2e_unet_forward(m, x, timesteps, eps, B, stream);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = (int)m->ops.size();
+  B2E_REQUIRE(n <= max_ops, B2E_INVALID_ARG, "unet_profile: %d ops, room for %d", n, max_ops);
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) B2E_CUDA(cudaEventCreate(&e));
+  B2E_CUDA(cudaEventRecord(ev[0], st));
+  for (int i = 0; i < n && !rc; ++i) {
+    rc = m->ops[i].fn(st);
+    cudaEventRecord(ev[i + 1], st);
+  }
+  cudaStreamSynchronize(st);
+  for (int i = 0; i < n; ++i) {
+    cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
+    flops[i] = m->ops[i].flops; bytes[i] = m->ops[i].bytes; kind[i] = m->ops[i].kind;
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  *n_ops = n;
+  return rc;
 }
 
 double b2e_unet_flops(const b2e_unet* m, int64_t B) {
@@ -478,7 +511,7 @@ int b2e_unet_launches_per_forward(const b2e_unet* m) {
   if (!m) return 0;
   // GroupNorm and the embedding MLP are two launches per op
   int n = 0;
-  for (size_t i = 0; i < m->ops.size(); ++i) n += 1;
+  for (auto& op : m->ops) n += (op.kind == 1 || (op.kind == 3 && op.bytes == 0.0)) ? 2 : 1;
   return n;
 }
 

@@ -1,0 +1,64 @@
+"""Model wrappers that define the image <-> latent maps (drop-in for src/diffusion_classes.py)."""
+import torch
+
+from base_diffusion import Diffusion
+from diffusion_utils import prep_text
+
+
+class DDPM(Diffusion):
+    """Pixel-space diffusion: encode/decode are the identity, which is what lets the guidance
+    gradient be evaluated analytically inside the fused step kernel."""
+
+    decode_is_identity = True
+
+    def encode(self, sample: torch.Tensor, **kwargs) -> torch.Tensor:
+        return sample
+
+    def decode(self, latent: torch.Tensor, **kwargs) -> torch.Tensor:
+        return latent
+
+
+class LDM(Diffusion):
+    """Latent diffusion with a VQ-VAE (``model.vqvae`` must provide encode().latents / decode().sample)."""
+
+    def __init__(self, model):
+        super().__init__(model)
+        self.vqvae = model.vqvae
+
+    def encode(self, sample: torch.Tensor) -> torch.Tensor:
+        with torch.no_grad():
+            return self.vqvae.encode(sample.to(dtype=torch.float32)).latents
+
+    def decode(self, latent: torch.Tensor, no_grad=True) -> torch.Tensor:
+        latent = latent.to(dtype=torch.float32)
+        if no_grad:
+            with torch.no_grad():
+                return self.vqvae.decode(latent).sample
+        return self.vqvae.decode(latent).sample
+
+
+class SD(Diffusion):
+    """Stable Diffusion: KL-VAE latents scaled by 0.18215, CLIP text conditioning."""
+
+    SCALE = 0.18215
+
+    def __init__(self, model):
+        super().__init__(model)
+        self.vae = model.vae
+        self.tokenizer = model.tokenizer
+        self.text_encoder = model.text_encoder
+
+    def encode(self, sample: torch.Tensor) -> torch.Tensor:
+        with torch.no_grad():
+            latent = self.vae.encode(sample).latent_dist.mode().detach()
+        return self.SCALE * latent
+
+    def decode(self, latent: torch.Tensor, no_grad=True) -> torch.Tensor:
+        latent = 1 / self.SCALE * latent
+        if no_grad:
+            with torch.no_grad():
+                return self.vae.decode(latent).sample
+        return self.vae.decode(latent).sample
+
+    def additional_prep(self, model, prompt):
+        return prep_text(model, prompt)

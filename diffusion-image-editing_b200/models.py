@@ -1,0 +1,64 @@
+"""Model factory (drop-in for src/models.py).
+
+The reference downloads hub checkpoints; offline the factory builds the same architectures with
+random-init weights (seeded) on the native sm_100a engine, and accepts a diffusers-layout
+``state_dict`` so real checkpoints can be dropped in later."""
+from types import SimpleNamespace
+from typing import Optional
+
+import torch
+
+from b200edit.scheduler import DDIMScheduler
+from b200edit.unet import DDPM256_CONFIG, UNet2DModel
+from diffusion_classes import DDPM, LDM, SD  # noqa: F401
+from utils import get_device
+
+
+class NativePipeline(SimpleNamespace):
+    """Duck-type of the diffusers pipeline object the path uses: .unet, .scheduler, .device."""
+
+    def to(self, device):
+        return self
+
+
+def create_diffusion_model(name: str, sample_clipping: bool = True, *, max_batch: int = 8, seed: int = 0,
+                           state_dict: Optional[dict] = None, unet_config: Optional[dict] = None):
+    device = get_device()
+    if name == "ddpm":
+        unet = UNet2DModel(**(unet_config or DDPM256_CONFIG), max_batch=max_batch, device=device)
+        if state_dict is not None:
+            unet.load_state_dict(state_dict)
+        else:
+            unet.init_random(seed)
+        scheduler = DDIMScheduler.from_preset("ddpm")
+        scheduler.config.clip_sample = sample_clipping   # True for synthetic data, False for real images
+        return DDPM(NativePipeline(unet=unet, scheduler=scheduler, device=device))
+    if name in ("ldm", "sd"):
+        raise NotImplementedError(
+            f"create_diffusion_model({name!r}): the {name.upper()} UNet / autoencoder are not on the native "
+            "engine yet (SURVEY.md section 8f); wrap your own modules with diffusion_classes.LDM / SD")
+    raise ValueError(f"Unknown model name: {name}")
+
+
+class SegmentationModel:
+    """Face parser front-end.  The BiSeNet weights (79999_iter.pth) are a missing blob of the
+    reference and the network is outside the hot path; pass any callable ``net`` that maps a
+    (1,3,512,512) image to ([1,19,H,W] logits, ...)."""
+
+    def __init__(self, net=None, n_classes: int = 19, image_size: tuple = (512, 512)) -> None:
+        if net is None:
+            raise NotImplementedError("SegmentationModel needs a parsing network (BiSeNet weights are "
+                                      "not available offline)")
+        self.device = get_device()
+        self.net = net
+        self.image_size = image_size
+        self.mean = torch.tensor((0.485, 0.456, 0.406)).view(1, 3, 1, 1)
+        self.std = torch.tensor((0.229, 0.224, 0.225)).view(1, 3, 1, 1)
+
+    def process(self, image: torch.Tensor) -> torch.Tensor:
+        x = torch.nn.functional.interpolate(image, size=self.image_size, mode="bilinear", antialias=True)
+        return ((x - self.mean.to(x.device)) / self.std.to(x.device)).to(self.device)
+
+    def __call__(self, image: torch.Tensor) -> torch.Tensor:
+        out = self.net(self.process(image))[0]
+        return out.squeeze(0).argmax(0)

@@ -86,6 +86,8 @@ typedef struct {
   float coef[4];            /* k_c = loss_scale * w_c / N, formed on the host in fp32      */
   int32_t mask_grad;        /* mask_attr_grad: g <- mask * g                              */
   int32_t mask_batched;     /* mask is (B,C,H,W) instead of (1,C,H,W)                     */
+  int32_t no_step;          /* x_t already is the post-step sample: guidance only
+                               (AttrFunc.apply called on its own, attr_functions.py:120) */
 } b2e_guided_step_params;
 
 /* x_t, eps: (B,C,H,W); z: (C,H,W)|(B,C,H,W)|NULL; mask: (1|B,C,H,W)|NULL;
@@ -130,6 +132,17 @@ int b2e_apply_mask_f32(const float* mask, const float* zo, const float* zv, floa
 /* tensor_to_pil numerics, src/transforms.py:8-35: (B,C,H,W) fp32 -> (B,H,W,C) uint8,
  * u8 = trunc(clamp(x/2+0.5,0,1)*255) */
 int b2e_to_uint8_f32(const float* x, uint8_t* out, int64_t B, int64_t C, int64_t HW, void* stream);
+
+/* mu_tilde (src/ddpm_inversion.py:16-28) and other two-term blends: out = a*x + b*y */
+int b2e_axpby_f32(const float* x, const float* y, float* out, int64_t n, float a, float b, void* stream);
+/* Loss VALUES (the guidance update never needs them; kept for the reference's call surface).
+ * l2_norm, src/attr_functions.py:11-13: out[0] = sqrt(sum (x-y)^2).
+ * single_color_loss, src/attr_functions.py:22-25: out4[c] = mean_{b,h,w} |img[:,c] - targets4[c]|. */
+size_t b2e_loss_workspace_bytes(void);
+int b2e_l2_distance_f32(const float* x, const float* y, int64_t n, float* out, void* workspace,
+                        size_t workspace_bytes, void* stream);
+int b2e_channel_l1_f32(const float* img, int64_t B, int64_t C, int64_t HW, const float* targets4,
+                       float* out4, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------ edit-friendly inversion
  * sample_xts_from_x0, src/ddpm_inversion.py:31-55: xts[i] = x0*sa[i] + noise[i]*sb[i], i<T;
@@ -197,6 +210,12 @@ int b2e_unet_bind_workspace(b2e_unet* m, void* workspace, size_t workspace_bytes
 int b2e_unet_forward(b2e_unet* m, const float* x, const int64_t* timesteps, float* eps, int64_t B,
                      void* stream);
 double b2e_unet_flops(const b2e_unet* m, int64_t B);
+/* One instrumented forward: CUDA events on `stream` around every op of the plan.  Per op: elapsed ms,
+ * algorithmic FLOPs (convolutions / attention) or bytes (memory-bound ops) and kind
+ * (0 tcgen05 convolution, 1 GroupNorm(+SiLU), 2 attention core, 3 other).  Synchronises the stream. */
+int b2e_unet_profile(b2e_unet* m, const float* x, const int64_t* timesteps, float* eps, int64_t B,
+                     void* stream, int max_ops, int* n_ops, float* ms, double* flops, double* bytes,
+                     int* kind);
 int b2e_unet_launches_per_forward(const b2e_unet* m);
 
 /* Test hook for the implicit-GEMM convolution: x (N,H,W,Cin) bf16 NHWC, w (Cout,Cin,k,k) fp32,

@@ -1,0 +1,249 @@
+"""GPU parity of the drop-in modules (the reference's call surface) against the goldens produced
+by the unmodified reference and against the oracle loops.  The noise predictor is teacher-forced
+(recorded eps replayed) so every comparison is exact: uint8 images and fp32 tensors bit-identical
+to the oracle; golden comparisons allow the few-ulp host-scalar slack explained in
+test_gpu_step_kernels.py."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import loops, step_math as sm
+from oracle.ddim_scheduler import DDIMScheduler as OracleScheduler
+
+pytestmark = pytest.mark.gpu
+T_ = torch.from_numpy
+
+
+class ReplayUnet:
+    """Returns recorded noise predictions in call order (test infrastructure)."""
+
+    def __init__(self, eps, C=3, S=16):
+        self.eps = T_(np.asarray(eps)).cuda()
+        self.i = 0
+        self.config = SimpleNamespace(in_channels=C, sample_size=S)
+        self.in_channels, self.sample_size = C, S
+        self.device = torch.device("cuda")
+
+    def __call__(self, sample, timestep, **_):
+        self.i += 1
+        e = self.eps[self.i - 1]
+        return {"sample": e[None] if e.dim() == 3 else e}
+
+
+def make_model(eps, preset="ddpm", T=20, clip=None):
+    from b200edit.scheduler import DDIMScheduler
+    s = DDIMScheduler.from_preset(preset)
+    if clip is not None:
+        s.config.clip_sample = clip
+    s.set_timesteps(T)
+    return SimpleNamespace(unet=ReplayUnet(eps), scheduler=s, device=torch.device("cuda"))
+
+
+def osched(preset, T, clip=None):
+    s = OracleScheduler.from_preset(preset)
+    if clip is not None:
+        s.config.clip_sample = clip
+    s.set_timesteps(T)
+    return s
+
+
+def imgs_close(a, b):
+    # uint8 images; a one-level difference can only come from an ulp of host-scalar slack vs the golden
+    return np.abs(np.asarray(a).astype(int) - np.asarray(b).astype(int)).max() <= 1
+
+
+def test_edit_image_vs_reference_golden(golden):
+    from attr_functions import SingleColorAttrFunc
+    from diffusion_classes import DDPM
+    from SegDiffEditPipeline import EditorOutput, SegDiffEditPipeline
+    g = golden("pipeline")
+    T = int(g["T"])
+    xt, zs, mask = T_(g["xt"]).cuda(), T_(g["zs"]).cuda(), T_(g["mask"]).cuda()
+    cases = {
+        "color_eta0": (dict(eta=0), SingleColorAttrFunc(target=0.8, color_idx=0, loss_scale=100.0, t1=0, t2=T)),
+        "color_eta1_window": (dict(eta=1.0, zs=zs),
+                              SingleColorAttrFunc(target=0.8, color_idx=0, loss_scale=100.0, t1=3, t2=15)),
+        "color_maskgrad": (dict(eta=0, mask=mask),
+                           SingleColorAttrFunc(target=-0.5, color_idx=1, loss_scale=60.0, use_mask=True,
+                                               mask_attr_grad=True)),
+    }
+    exact = 0
+    for tag, (kw, f) in cases.items():
+        model = make_model(g[f"{tag}/eps"], T=T, clip=True)
+        pipe = SegDiffEditPipeline(DDPM(model), None)
+        out = pipe.edit_image(xt=xt, attr_func=f, prog_bar=False, **kw)
+        assert isinstance(out, EditorOutput) and out[0] is out.imgs
+        assert len(out.pred_original_samples) == T and len(out.model_outputs) == T
+        assert imgs_close(out.imgs, g[f"{tag}/img"]), tag
+        assert imgs_close(np.stack([np.asarray(p) for p in out.pred_original_samples]), g[f"{tag}/x0_imgs"]), tag
+        exact += np.array_equal(np.asarray(out.imgs), g[f"{tag}/img"])
+        # exact against the oracle loop evaluated in this process
+        s = osched("ddpm", T, clip=True)
+        guidance = loops.color_guidance([f.target if i == f.color_idx else None for i in range(3)], [1, 1, 1],
+                                        f.loss_scale, f.t1, f.t2, mask=T_(g["mask"]) if "mask" in kw else None,
+                                        mask_grad="mask" in kw)
+        rep = iter(T_(g[f"{tag}/eps"]))
+        xf, _, x0_h = loops.guided_edit_loop(s, lambda x, t: next(rep)[None], T_(g["xt"]), eta=kw.get("eta", 0),
+                                             zs=T_(g["zs"]) if "zs" in kw else None, guidance=guidance)
+        assert np.array_equal(np.asarray(out.imgs), sm.to_uint8_image(xf)[0].permute(1, 2, 0).numpy()), tag
+    print(f"edit_image bit-exact vs golden images: {exact}/{len(cases)}")
+    # validation errors, same messages as the reference
+    model = make_model(g["color_eta0/eps"], T=T)
+    pipe = SegDiffEditPipeline(DDPM(model), None)
+    f = cases["color_eta0"][1]
+    errs = list(g["check_inputs_errors"])
+    for kw, msg in ((dict(eta=1.0, zs=None, attr_func=f), errs[0]), (dict(eta=0, zs=zs, attr_func=f), errs[1]),
+                    (dict(eta=0, attr_func=None, mask=None), errs[2])):
+        with pytest.raises(ValueError) as ex:
+            pipe.edit_image(xt=xt, **kw)
+        assert str(ex.value) == str(msg)
+
+
+def test_generate_image_vs_reference_golden(golden):
+    from diffusion_classes import DDPM
+    g = golden("pipeline")
+    T = int(g["T"])
+    xt, zs = T_(g["xt"]).cuda(), T_(g["zs"]).cuda()
+    for eta, tag in ((0, "gen_eta0"), (0.8, "gen_eta08")):
+        w = DDPM(make_model(g[f"{tag}/eps"], T=T, clip=True))
+        img, eps_list, x0_imgs, xt_imgs = w.generate_image(xt, eta=eta, zs=zs if eta > 0 else None,
+                                                           num_inference_steps=T, return_xts=True)
+        assert imgs_close(img, g[f"{tag}/img"])
+        assert imgs_close(np.stack([np.asarray(p) for p in x0_imgs]), g[f"{tag}/x0_imgs"])
+        assert imgs_close(np.stack([np.asarray(p) for p in xt_imgs]), g[f"{tag}/xts_imgs"])
+        assert len(eps_list) == T
+
+
+@pytest.mark.parametrize("preset", ["ddpm", "sd"])
+def test_inversion_and_sampling_vs_reference_golden(golden, preset):
+    import ddim_inversion as di
+    import ddpm_inversion as dp
+    g = golden("inversion")
+    T = int(g["T"])
+    x0 = T_(g[f"{preset}/x0"]).cuda()
+    noises = T_(g[f"{preset}/fwd_noises"]).cuda()
+
+    def close(a, ref):
+        return np.allclose(a.cpu().numpy(), ref, rtol=2e-5, atol=2e-5, equal_nan=True)
+
+    for eta in (1.0, 0.6):
+        p = f"{preset}/eta{eta}/"
+        model = make_model(g[p + "inv_eps"], preset, T, clip=False)
+        xT, zs, xts = dp.invert(model, x0, num_inference_steps=T, eta=eta, prog_bar=False, noise=noises)
+        assert xts.shape == (T + 1, 3, 16, 16) and zs.shape == (T, 3, 16, 16)
+        assert close(xT, g[p + "xT"]) and close(zs, g[p + "zs"]) and close(xts, g[p + "xts"])
+        assert float(zs[-1].abs().max()) == 0.0
+        # exact vs the oracle loop
+        rep = iter(T_(g[p + "inv_eps"]))
+        oxT, ozs, oxts = loops.invert_ddpm(osched(preset, T, False), lambda x, t: next(rep)[None],
+                                           T_(g[f"{preset}/x0"]), T_(g[f"{preset}/fwd_noises"]), eta)
+        assert np.array_equal(zs.cpu().numpy(), ozs.numpy(), equal_nan=True)
+        assert np.array_equal(xts.cpu().numpy(), oxts.numpy(), equal_nan=True)
+        for tskip in (0, 7):
+            model = make_model(g[p + f"sample_T{tskip}_eps"], preset, T, clip=False)
+            xr = dp.sample(model, zs, xts, Tskip=tskip, eta=eta, prog_bar=False)
+            assert xr.shape == (1, 3, 16, 16) and close(xr, g[p + f"sample_T{tskip}"])
+    model = make_model(g[f"{preset}/eta0/eps"], preset, T, clip=False)
+    xt0, zs0, xts0 = dp.inversion_forward_process(model, x0, etas=0, num_inference_steps=T)
+    assert zs0 is None and xts0 is None and close(xt0, g[f"{preset}/eta0/xT"])
+    model = make_model(g[f"{preset}/ddim_inv/eps"], preset, T, clip=False)
+    assert close(di.ddim_inversion(model, x0), g[f"{preset}/ddim_inv/xT"])
+
+
+def test_inversion_round_trip_property():
+    """Edit-friendly inversion is self-consistent: regenerating from xts[0] with the extracted zs
+    reproduces every intermediate xts[k], at full DDPM-256 size, free-running
+    toy predictor on the device."""
+    import ddpm_inversion as dp
+    from b200edit.scheduler import DDIMScheduler
+    from oracle.unet2d import ToyEpsModel
+    s = DDIMScheduler.from_preset("ddpm", clip_sample=False)
+    s.set_timesteps(50)
+    unet = ToyEpsModel(3, 256).cuda()
+    unet.device = torch.device("cuda")
+    model = SimpleNamespace(unet=unet, scheduler=s, device=torch.device("cuda"))
+    x0 = (torch.randn(1, 3, 256, 256, generator=torch.Generator().manual_seed(7)) * 0.5).clamp(-1, 1).cuda()
+    xT, zs, xts = dp.invert(model, x0, num_inference_steps=50, eta=1, prog_bar=False)
+    assert torch.isfinite(zs).all() and torch.isfinite(xts[:50]).all()
+    xt = xts[0][None]
+    for idx, t in enumerate([int(t) for t in s.timesteps][:-1]):
+        eps = unet(xt, t)["sample"].detach()
+        xt = dp.reverse_step(model, eps, t, xt, eta=1, variance_noise=zs[idx])
+        assert (xt[0] - xts[idx + 1]).abs().max().item() < 2e-4 * max(1.0, xts[idx + 1].abs().max().item())
+
+
+def test_autograd_fallback_matches_fused_kernel(golden):
+    """A user-defined strategy (python loss, autograd) gives the same nudge as the fused analytic kernel."""
+    from attr_functions import AttrFunc, MultiColorAttrFunc, SingleColorAttrFunc
+    from diffusion_classes import DDPM
+    g = golden("guidance")
+    e, xpost, mask, x_ref = (T_(g[k]).cuda() for k in ("e", "xpost", "mask", "x_ref"))
+    w = DDPM(make_model(g["e"], T=50))
+
+    class MyColour(AttrFunc):
+        def loss(self, img, **kw):
+            return torch.abs(img[:, 0] - 0.8).mean()
+
+    for t in (980, 500, 20):
+        tt = torch.tensor(t)
+        a, _ = SingleColorAttrFunc(target=0.8, color_idx=0, loss_scale=100.0).apply(xpost, None, e, tt, 3, w)
+        b, _ = MyColour(loss_scale=100.0).apply(xpost, None, e, tt, 3, w)
+        assert torch.allclose(a, b, rtol=1e-6, atol=1e-7)
+        assert np.allclose(a.cpu().numpy(), g[f"single/t{t}_s100.0"], rtol=3e-6, atol=1e-6)
+        m, _ = MultiColorAttrFunc(0.9, -0.3, 0.45, loss_scale=37.5).apply(xpost, None, e, tt, 3, w)
+        assert np.allclose(m.cpu().numpy(), g[f"multi/t{t}_s37.5"], rtol=3e-6, atol=1e-6)
+        f = SingleColorAttrFunc(target=0.8, color_idx=1, loss_scale=37.5, use_l2=True)
+        kw = dict(mask_pred_original_sample=True, use_l2=True, lambda_=0.1, mask=mask, x_0=x_ref)
+        r, _ = f.apply(xpost, None, e, tt, 3, w, **kw)
+        ref = g[f"single_l2reg/t{t}_s37.5"]
+        upd = ref - g["xpost"]
+        assert np.allclose(r.cpu().numpy() - g["xpost"], upd, rtol=1e-4, atol=1e-5 * np.abs(upd).max())
+    out, _ = SingleColorAttrFunc(target=0.8, color_idx=0, loss_scale=100.0, t1=5, t2=10).apply(
+        xpost, None, e, torch.tensor(500), 3, w)
+    assert out is xpost
+
+
+def test_batched_per_sample_equals_independent_runs():
+    """B images in one call with per_sample=True == B independent batch-1 runs (the sharding contract)."""
+    from attr_functions import SingleColorAttrFunc
+    from diffusion_classes import DDPM
+    from SegDiffEditPipeline import SegDiffEditPipeline
+    T, B = 10, 4
+    gen = torch.Generator().manual_seed(3)
+    eps = torch.randn(T, B, 3, 16, 16, generator=gen)
+    xt = torch.randn(B, 3, 16, 16, generator=gen)
+    f = SingleColorAttrFunc(target=0.3, color_idx=2, loss_scale=80.0, per_sample=True)
+    pipe = SegDiffEditPipeline(DDPM(make_model(eps.numpy(), T=T, clip=True)), None)
+    full = pipe.edit_image(xt=xt.cuda(), attr_func=f, prog_bar=False, output_type="tensor")
+    for b in range(B):
+        pipe1 = SegDiffEditPipeline(DDPM(make_model(eps[:, b].numpy(), T=T, clip=True)), None)
+        one = pipe1.edit_image(xt=xt[b:b + 1].cuda(), attr_func=f, prog_bar=False, output_type="tensor")
+        assert torch.equal(full.imgs[b], one.imgs[0])
+    pil = SegDiffEditPipeline(DDPM(make_model(eps.numpy(), T=T, clip=True)), None).edit_image(
+        xt=xt.cuda(), attr_func=f, prog_bar=False)
+    assert len(pil.imgs) == B and len(pil.pred_original_samples) == T and len(pil.pred_original_samples[0]) == B
+
+
+def test_end_to_end_with_native_unet():
+    """Full path on the device: native UNet + fused guided step; the recorded eps replayed through
+    the oracle loop must reproduce the images exactly."""
+    from attr_functions import SingleColorAttrFunc
+    from models import create_diffusion_model
+    from SegDiffEditPipeline import SegDiffEditPipeline
+    cfg = dict(sample_size=32, in_channels=3, out_channels=3, block_out_channels=(64, 128), layers_per_block=1,
+               down_block_types=("DownBlock2D", "AttnDownBlock2D"), up_block_types=("AttnUpBlock2D", "UpBlock2D"))
+    w = create_diffusion_model("ddpm", sample_clipping=True, max_batch=2, seed=1, unet_config=cfg)
+    w.scheduler.set_timesteps(10)
+    pipe = SegDiffEditPipeline(w, None)
+    xt = torch.randn(2, 3, 32, 32, generator=torch.Generator().manual_seed(11))
+    f = SingleColorAttrFunc(target=0.8, color_idx=0, loss_scale=100.0, t1=0, t2=10)
+    out = pipe.edit_image(xt=xt.cuda(), attr_func=f, prog_bar=False, output_type="tensor")
+    assert torch.isfinite(out.imgs).all()
+    rep = iter([e.cpu() for e in out.model_outputs])
+    s = osched("ddpm", 10, clip=True)
+    xf, _, x0_h = loops.guided_edit_loop(s, lambda x, t: next(rep), xt, eta=0.0, zs=None,
+                                         guidance=loops.color_guidance([0.8, None, None], [1, 1, 1], 100.0, 0, 10))
+    assert np.array_equal(out.imgs.cpu().numpy(), xf.numpy())
+    assert np.array_equal(out.pred_original_samples[-1].cpu().numpy(), x0_h[-1].numpy())
