@@ -323,13 +323,14 @@ def morphology2d(x, weight, op: str, soft_max=False, beta=20.0):
     return out
 
 
-def conv2d_nhwc_bf16(x, w, bias, stride=1):
-    """Test hook for the tcgen05 implicit-GEMM convolution."""
+def conv2d_nhwc_bf16(x, w, bias, stride=1, residual=None):
+    """Test hook for the tcgen05 implicit-GEMM convolution (optionally + residual, bf16 NHWC)."""
     _C.require_device()
     N, H, W, Cin = x.shape
     Cout, _, k, _ = w.shape
     out = torch.empty((N, H // stride, W // stride, Cout), dtype=torch.bfloat16, device=x.device)
     check(lib.b2e_conv2d_nhwc_bf16(_p(x.contiguous()), _p(w.contiguous().float()),
-                                   _p(bias.contiguous().float()) if bias is not None else None, _p(out), N, H, W,
+                                   _p(bias.contiguous().float()) if bias is not None else None,
+                                   _p(residual.contiguous()) if residual is not None else None, _p(out), N, H, W,
                                    Cin, Cout, k, stride, _stream()), "conv2d_nhwc_bf16")
     return out

@@ -9,13 +9,16 @@
 //    into a 128B-swizzled K-major smem tile; the conv zero padding is TMA out-of-bounds fill.
 //    Stride-2 convolutions view the input as (2C, W/2, 2, H/2, N) so a tap is again a box.
 //    The K loop can draw chunks from two tensors (skip concatenation without a copy).
-//  * B (weights, bf16 [Cout][tap][Cin]) is a plain 2-D TMA tile.
+//    After the taps, an optional 1x1 "residual segment" (K chunks read at the output pixel from up to
+//    two more tensors, weights appended to B along K) fuses the ResNet shortcut convolution or, with
+//    identity weights, the residual add - the epilogue never reads the residual.
+//  * B (weights, bf16 [Cout][tap][Cin | residual]) is a plain 2-D TMA tile.
 //  * one elected thread issues tcgen05.mma (UMMA 128 x BN x 16, bf16 in, fp32 accumulate in
 //    TMEM); tcgen05.commit releases smem stages / signals the epilogue through mbarriers.
 //  * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 =
-//    epilogue (tcgen05.ld TMEM -> registers, + bias + time-embedding + residual, bf16 NHWC or
-//    fp32 NCHW store).  3-stage smem ring, two CTAs per SM so one CTA's epilogue overlaps the
-//    other's main loop.
+//    epilogue (tcgen05.ld TMEM -> registers, + bias + time-embedding, bf16 tile staged in 128B-swizzled
+//    smem and written with one TMA store per 64-channel slab; fp32 NCHW direct store for conv_out).  Persistent CTAs (one per SM), 6-8 stage smem ring that never drains
+//    between tiles, double-buffered TMEM accumulator so the epilogue overlaps the next main loop.
 #include "conv_igemm.cuh"
 
 #include <cudaTypedefs.h>
@@ -25,27 +28,31 @@ namespace b2e {
 constexpr int kConvThreads = 192;
 constexpr int kABytes = kConvBlockM * kConvBlockK * 2;  // 16 KB
 
-template <int BN>
+// One persistent CTA per SM; STAGES x (A 16 KB + B) fills the ~190 KB of shared memory it can use, so
+// enough TMA loads are in flight to cover the load round trip (small grids are latency-bound).
+template <int BN, int STAGES>
 struct ConvCfg {
   static constexpr int kBBytes = BN * kConvBlockK * 2;
   static constexpr int kBBytesPad = (kBBytes + 1023) / 1024 * 1024;
   static constexpr int kStageBytes = kABytes + kBBytesPad;
-  static constexpr int kStages = BN == 128 ? 3 : 4;
-  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kStages = STAGES;
+  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;   // double-buffered accumulator
+  static constexpr int kSlabs = BN / 64;                        // 64-channel output slabs (0: fp32 NCHW path)
+  static constexpr int kStagingBytes = kSlabs * kConvBlockM * 128;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 struct ConvKParams {
   int N, Ho, Wo, Cout;
   int Wt, Ht, Nt, w_blks, h_blks;
-  int taps, c0_chunks, c1_chunks;
+  int taps, c0_chunks, c1_chunks, r0_chunks, r1_chunks;
   int tap_dc[9], tap_dw[9], tap_da[9], tap_dh[9];
-  int n_tiles;
+  int n_tiles, num_tiles;
   const float* bias;
+  const float* bias2;
   const float* temb;
   int temb_stride;
-  const bf16* residual;
-  bf16* out_bf16;
+  int out_bf16;         // 1: stage + TMA-store the bf16 NHWC tile through map_out
   float* out_f32_nchw;
 };
 
@@ -59,6 +66,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
@@ -90,6 +100,18 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, const void* src, int c0, int c1, int c2,
+                                             int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -152,34 +174,51 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 }
 
 // ------------------------------------------------------------------ the kernel
-template <int BN>
-__global__ void __launch_bounds__(kConvThreads, BN == 128 ? 2 : 2)
+// Persistent: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The accumulator is
+// double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the main loop of tile
+// i+1, and the TMA producer runs ahead across tile boundaries (the smem ring never drains).
+struct TileCoord { int n_tile, w0, h0, n0; };
+
+__device__ __forceinline__ TileCoord tile_coord(const ConvKParams& p, int tile) {
+  TileCoord t;
+  t.n_tile = tile % p.n_tiles;
+  int m = tile / p.n_tiles;
+  t.w0 = (m % p.w_blks) * p.Wt; m /= p.w_blks;
+  t.h0 = (m % p.h_blks) * p.Ht;
+  t.n0 = (m / p.h_blks) * p.Nt;
+  return t;
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
-                  const __grid_constant__ CUtensorMap map_b, const ConvKParams p) {
-  using Cfg = ConvCfg<BN>;
+                  const __grid_constant__ CUtensorMap map_r0, const __grid_constant__ CUtensorMap map_r1,
+                  const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out,
+                  const __grid_constant__ ConvKParams p) {
+  using Cfg = ConvCfg<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* staging = smem + Cfg::kStages * Cfg::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
-  uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tile = blockIdx.x % p.n_tiles;
-  int m_tile = blockIdx.x / p.n_tiles;
-  const int w_blk = m_tile % p.w_blks; m_tile /= p.w_blks;
-  const int h_blk = m_tile % p.h_blks;
-  const int n_blk = m_tile / p.h_blks;
-  const int w0 = w_blk * p.Wt, h0 = h_blk * p.Ht, n0 = n_blk * p.Nt;
   const int chunks = p.c0_chunks + p.c1_chunks;
-  const int num_kb = p.taps * chunks;
+  const int r_chunks = p.r0_chunks + p.r1_chunks;
+  const int num_kb = p.taps * chunks + r_chunks;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_a0);
     if (p.c1_chunks) prefetch_tmap(&map_a1);
+    if (p.r0_chunks) prefetch_tmap(&map_r0);
+    if (p.r1_chunks) prefetch_tmap(&map_r1);
     prefetch_tmap(&map_b);
+    if (p.out_bf16) prefetch_tmap(&map_out);
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-    mbar_init(tmem_full_bar, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar + s, 1); mbar_init(tmem_empty_bar + s, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -189,108 +228,164 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===== TMA producer
+    // ===== TMA producer (one thread)
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tap = 0; tap < p.taps; ++tap) {
-        const int cw = w0 + p.tap_dw[tap], ch = h0 + p.tap_dh[tap], ca = p.tap_da[tap], cc = p.tap_dc[tap];
-        for (int ck = 0; ck < chunks; ++ck) {
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const TileCoord tc = tile_coord(p, tile);
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int cw = tc.w0 + p.tap_dw[tap], ch = tc.h0 + p.tap_dh[tap], ca = p.tap_da[tap], cc = p.tap_dc[tap];
+          for (int ck = 0; ck < chunks; ++ck) {
+            mbar_wait(empty_bar + stage, phase ^ 1);
+            uint8_t* sa = smem + stage * Cfg::kStageBytes;
+            uint8_t* sb = sa + kABytes;
+            mbar_expect_tx(full_bar + stage, kABytes + Cfg::kBBytes);
+            if (ck < p.c0_chunks)
+              tma_load_5d(sa, &map_a0, full_bar + stage, cc + ck * kConvBlockK, cw, ca, ch, tc.n0);
+            else
+              tma_load_5d(sa, &map_a1, full_bar + stage, cc + (ck - p.c0_chunks) * kConvBlockK, cw, ca, ch, tc.n0);
+            tma_load_2d(sb, &map_b, full_bar + stage, (tap * chunks + ck) * kConvBlockK, tc.n_tile * BN);
+            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+        // residual segment: 1x1 at the output pixel
+        for (int ck = 0; ck < r_chunks; ++ck) {
           mbar_wait(empty_bar + stage, phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + kABytes;
           mbar_expect_tx(full_bar + stage, kABytes + Cfg::kBBytes);
-          if (ck < p.c0_chunks)
-            tma_load_5d(sa, &map_a0, full_bar + stage, cc + ck * kConvBlockK, cw, ca, ch, n0);
+          if (ck < p.r0_chunks)
+            tma_load_5d(sa, &map_r0, full_bar + stage, ck * kConvBlockK, tc.w0, 0, tc.h0, tc.n0);
           else
-            tma_load_5d(sa, &map_a1, full_bar + stage, cc + (ck - p.c0_chunks) * kConvBlockK, cw, ca, ch, n0);
-          tma_load_2d(sb, &map_b, full_bar + stage, (tap * chunks + ck) * kConvBlockK, n_tile * BN);
+            tma_load_5d(sa, &map_r1, full_bar + stage, (ck - p.r0_chunks) * kConvBlockK, tc.w0, 0, tc.h0, tc.n0);
+          tma_load_2d(sb, &map_b, full_bar + stage, (p.taps * chunks + ck) * kConvBlockK, tc.n_tile * BN);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (single thread)
+    // ===== MMA issuer (one thread)
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(kConvBlockM, BN);
       int stage = 0; uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(full_bar + stage, phase);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        mbar_wait(tmem_empty_bar + acc, ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-        const uint64_t adesc = make_smem_desc(sa);
-        const uint64_t bdesc = make_smem_desc(sa + kABytes);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar + stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint64_t adesc = make_smem_desc(sa);
+          const uint64_t bdesc = make_smem_desc(sa + kABytes);
 #pragma unroll
-        for (int k = 0; k < kConvBlockK / 16; ++k) {
-          // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in the (addr >> 4) field
-          umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          for (int k = 0; k < kConvBlockK / 16; ++k) {
+            // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in the (addr >> 4) field
+            umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          }
+          umma_commit(empty_bar + stage);  // frees this smem stage once the MMAs above retire
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(empty_bar + stage);  // frees this smem stage once the MMAs above retire
-        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        umma_commit(tmem_full_bar + acc);  // accumulator complete
       }
-      umma_commit(tmem_full_bar);  // accumulator complete
     }
   } else {
     // ===== epilogue: 4 warps, warp w owns TMEM lanes 32*(w%4) .. +31
     const int q = warp & 3;
     const int r = q * 32 + lane;  // row of the tile = output pixel
     const int w_l = r % p.Wt, h_l = (r / p.Wt) % p.Ht, n_l = r / (p.Wt * p.Ht);
-    const int n = n0 + n_l, h = h0 + h_l, w = w0 + w_l;
-    const bool valid = n < p.N;
-    const int64_t pix = ((int64_t)n * p.Ho + h) * p.Wo + w;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const bool store_leader = (warp == 2 && lane == 0);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const TileCoord tc = tile_coord(p, tile);
+      const int acc = it & 1;
+      const int n = tc.n0 + n_l, h = tc.h0 + h_l, w = tc.w0 + w_l;
+      const bool valid = n < p.N;
+      mbar_wait(tmem_full_bar + acc, (it >> 1) & 1);
+      tc_fence_after();
+      if (Cfg::kSlabs > 0 && p.out_bf16) {
+        // the previous tile's TMA store must have finished reading the staging buffer
+        if (store_leader) tma_store_wait_read();
+        epi_bar_sync();
+      }
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-    for (int c = 0; c < BN / 16; ++c) {
-      float v[16];
-      tmem_ld16(taddr + c * 16, v);
-      const int col0 = n_tile * BN + c * 16;
-      if (!valid || col0 >= p.Cout) continue;
-      if (p.bias) {
+      for (int c = 0; c < BN / 16; ++c) {
+        float v[16];
+        tmem_ld16(taddr + c * 16, v);
+        if (c == BN / 16 - 1) {
+          // all of this warp's accumulator columns are in registers: hand the buffer back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty_bar + acc);
+        }
+        const int col0 = tc.n_tile * BN + c * 16;
+        if (Cfg::kSlabs > 0 && p.out_bf16) {
+          // Cout % 64 == 0 on this path (host-checked): whole chunks are in range
+          if (p.bias) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (col0 + j < p.Cout) v[j] += __ldg(p.bias + col0 + j);
-      }
-      if (p.temb) {
-        const float* t = p.temb + (int64_t)n * p.temb_stride + col0;
+            for (int j = 0; j < 4; ++j) {
+              const float4 b = __ldg(bp + j);
+              v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+            }
+          }
+          if (p.bias2) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias2 + col0);
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (col0 + j < p.Cout) v[j] += __ldg(t + j);
-      }
-      if (p.out_bf16) {
-        // Cout % 16 == 0 on this path (checked on the host)
-        if (p.residual) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.Cout + col0);
-          uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
-          const __nv_bfloat162* rb0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
-          const __nv_bfloat162* rb1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
+            for (int j = 0; j < 4; ++j) {
+              const float4 b = __ldg(bp + j);
+              v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+            }
+          }
+          if (p.temb && valid) {
+            const float4* tp = reinterpret_cast<const float4*>(p.temb + (int64_t)n * p.temb_stride + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 b = __ldg(tp + j);
+              v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+            }
+          }
+          uint4 o0, o1;
+          __nv_bfloat162* ob0 = reinterpret_cast<__nv_bfloat162*>(&o0);
+          __nv_bfloat162* ob1 = reinterpret_cast<__nv_bfloat162*>(&o1);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            float2 a = __bfloat1622float2(rb0[j]), b = __bfloat1622float2(rb1[j]);
-            v[2 * j] += a.x; v[2 * j + 1] += a.y;
-            v[8 + 2 * j] += b.x; v[8 + 2 * j + 1] += b.y;
+            ob0[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+            ob1[j] = __floats2bfloat162_rn(v[8 + 2 * j], v[8 + 2 * j + 1]);
           }
-        }
-        uint4 o0, o1;
-        __nv_bfloat162* ob0 = reinterpret_cast<__nv_bfloat162*>(&o0);
-        __nv_bfloat162* ob1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+          // 128B-swizzled staging tile: row r, 16-byte chunk j stored at chunk (j ^ (r & 7))
+          uint8_t* row = staging + (c >> 2) * (kConvBlockM * 128) + r * 128;
+          const int j0 = (c & 3) * 2;
+          *reinterpret_cast<uint4*>(row + (((j0) ^ (r & 7)) << 4)) = o0;
+          *reinterpret_cast<uint4*>(row + (((j0 + 1) ^ (r & 7)) << 4)) = o1;
+        } else if (p.out_f32_nchw && valid) {
+          const int64_t hw = (int64_t)p.Ho * p.Wo;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          ob0[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-          ob1[j] = __floats2bfloat162_rn(v[8 + 2 * j], v[8 + 2 * j + 1]);
+          for (int j = 0; j < 16; ++j)
+            if (col0 + j < p.Cout) {
+              float o = v[j];
+              if (p.bias) o += __ldg(p.bias + col0 + j);
+              if (p.bias2) o += __ldg(p.bias2 + col0 + j);
+              if (p.temb) o += __ldg(p.temb + (int64_t)n * p.temb_stride + col0 + j);
+              p.out_f32_nchw[((int64_t)n * p.Cout + col0 + j) * hw + (int64_t)h * p.Wo + w] = o;
+            }
         }
-        uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + pix * p.Cout + col0);
-        op[0] = o0;
-        op[1] = o1;
       }
-      if (p.out_f32_nchw) {
-        const int64_t hw = (int64_t)p.Ho * p.Wo;
+      if (Cfg::kSlabs > 0 && p.out_bf16) {
+        fence_async_smem();   // generic-proxy smem writes -> visible to the TMA (async proxy)
+        epi_bar_sync();
+        if (store_leader) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (col0 + j < p.Cout)
-            p.out_f32_nchw[((int64_t)n * p.Cout + col0 + j) * hw + (int64_t)h * p.Wo + w] = v[j];
+          for (int sl = 0; sl < Cfg::kSlabs; ++sl)
+            tma_store_5d(&map_out, staging + sl * (kConvBlockM * 128), tc.n_tile * BN + sl * 64, tc.w0, 0, tc.h0, tc.n0);
+          tma_store_commit();
+        }
       }
     }
+    if (store_leader) tma_store_wait_all();
     tc_fence_before();
   }
   __syncthreads();
@@ -301,28 +396,38 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
 }
 
 // ------------------------------------------------------------------ weight packing
-__global__ void pack_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout,
-                                   int Cin, int cin_total, int cin_off, int kk) {
-  // out[(co*kk + t)*cin_total + cin_off + ci] = w[(co*Cin + ci)*kk + t]
+__global__ void pack_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int Cin,
+                                   int kk, int tap_width, int row_len, int col_off) {
+  // out[co*row_len + col_off + t*tap_width + ci] = w[(co*Cin + ci)*kk + t]
   const int64_t total = (int64_t)Cout * kk * Cin;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int ci = (int)(i % Cin);
     const int t = (int)((i / Cin) % kk);
     const int co = (int)(i / ((int64_t)Cin * kk));
-    out[((int64_t)co * kk + t) * cin_total + cin_off + ci] = __float2bfloat16_rn(w[((int64_t)co * Cin + ci) * kk + t]);
+    out[(int64_t)co * row_len + col_off + (int64_t)t * tap_width + ci] =
+        __float2bfloat16_rn(w[((int64_t)co * Cin + ci) * kk + t]);
   }
 }
 
-int conv_pack_weight(const float* w, bf16* out, int Cout, int cout_pad, int Cin, int cin_total,
-                     int ksize, cudaStream_t st) {
-  (void)cout_pad;
+__global__ void fill_identity_kernel(bf16* __restrict__ out, int C, int row_len, int col_off) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) out[(int64_t)c * row_len + col_off + c] = __float2bfloat16_rn(1.f);
+}
+
+int conv_pack_weight(const float* w, bf16* out, int Cout, int Cin, int ksize, int tap_width, int row_len,
+                     int col_off, cudaStream_t st) {
   const int kk = ksize * ksize;
   const int64_t total = (int64_t)Cout * kk * Cin;
   int grid = (int)((total + 255) / 256);
   if (grid > kNumSMs * 16) grid = kNumSMs * 16;
-  pack_weight_kernel<<<grid, 256, 0, st>>>(w, out, Cout, Cin, cin_total, 0, kk);
+  pack_weight_kernel<<<grid, 256, 0, st>>>(w, out, Cout, Cin, kk, tap_width, row_len, col_off);
   return check_launch("pack_weight");
+}
+
+int conv_fill_identity(bf16* out, int C, int row_len, int col_off, cudaStream_t st) {
+  fill_identity_kernel<<<(C + 255) / 256, 256, 0, st>>>(out, C, row_len, col_off);
+  return check_launch("fill_identity");
 }
 
 // ------------------------------------------------------------------ host: TMA descriptors
@@ -368,6 +473,7 @@ int conv_cout_pad(int Cout) {
   return (Cout + 63) / 64 * 64;
 }
 
+// (C, W, 1, H, N) view of an NHWC tensor (stride 1) or (2C, W/2, 2, H/2, N) (stride 2), box = one tile brick
 static int encode_act_map(CUtensorMap* m, const bf16* ptr, int N, int H, int W, int C, int stride,
                           int Wt, int Ht, int Nt) {
   const uint64_t e = 2;
@@ -385,82 +491,95 @@ static int encode_act_map(CUtensorMap* m, const bf16* ptr, int N, int H, int W, 
   return encode_map(m, ptr, 5, dims, str, box);
 }
 
-int conv_plan_build(ConvPlan* pl, ConvSrc s0, ConvSrc s1, int N, int H, int W, int ksize, int stride,
-                    const bf16* w_packed, int Cout) {
-  B2E_REQUIRE(s0.ptr && s0.C > 0 && s0.C % kConvBlockK == 0 && (s1.C % kConvBlockK == 0), B2E_UNSUPPORTED_SHAPE,
-              "conv: input channels must be multiples of %d (got %d + %d)", kConvBlockK, s0.C, s1.C);
-  B2E_REQUIRE((ksize == 1 || ksize == 3) && (stride == 1 || (stride == 2 && ksize == 3 && !s1.ptr)),
-              B2E_UNSUPPORTED_SHAPE, "conv: unsupported ksize/stride %d/%d", ksize, stride);
-  B2E_REQUIRE(stride == 1 || (H % 2 == 0 && W % 2 == 0), B2E_UNSUPPORTED_SHAPE, "conv: stride 2 needs even H, W");
-  B2E_REQUIRE(aligned16(s0.ptr) && (!s1.ptr || aligned16(s1.ptr)) && aligned16(w_packed), B2E_INVALID_ARG,
-              "conv: unaligned tensor");
+int conv_plan_build(ConvPlan* pl, const ConvDesc& d) {
+  const int K = kConvBlockK;
+  B2E_REQUIRE(d.s0.ptr && d.s0.C > 0 && d.s0.C % K == 0 && d.s1.C % K == 0 && d.r0.C % K == 0 && d.r1.C % K == 0,
+              B2E_UNSUPPORTED_SHAPE, "conv: channel counts must be multiples of %d (got %d+%d, residual %d+%d)", K,
+              d.s0.C, d.s1.C, d.r0.C, d.r1.C);
+  B2E_REQUIRE((d.ksize == 1 || d.ksize == 3) &&
+                  (d.stride == 1 || (d.stride == 2 && d.ksize == 3 && !d.s1.ptr && !d.r0.ptr)),
+              B2E_UNSUPPORTED_SHAPE, "conv: unsupported ksize/stride %d/%d", d.ksize, d.stride);
+  B2E_REQUIRE(d.stride == 1 || (d.H % 2 == 0 && d.W % 2 == 0), B2E_UNSUPPORTED_SHAPE, "conv: stride 2 needs even H, W");
+  B2E_REQUIRE(aligned16(d.s0.ptr) && (!d.s1.ptr || aligned16(d.s1.ptr)) && (!d.r0.ptr || aligned16(d.r0.ptr)) &&
+                  (!d.r1.ptr || aligned16(d.r1.ptr)) && aligned16(d.w_packed) && (!d.out_bf16 || aligned16(d.out_bf16)),
+              B2E_INVALID_ARG, "conv: unaligned tensor");
+  B2E_REQUIRE(!d.r1.ptr || d.r0.ptr, B2E_INVALID_ARG, "conv: r1 without r0");
+  B2E_REQUIRE(!d.out_bf16 || d.Cout % 64 == 0, B2E_UNSUPPORTED_SHAPE,
+              "conv: bf16 NHWC output needs Cout %% 64 == 0 (got %d)", d.Cout);
   ConvPlan& p = *pl;
-  p.N = N; p.Ho = H / stride; p.Wo = W / stride; p.Cout = Cout; p.cout_pad = conv_cout_pad(Cout);
-  p.block_n = p.cout_pad <= 16 ? 16 : (p.cout_pad % 128 == 0 ? 128 : 64);
+  p.N = d.N; p.Ho = d.H / d.stride; p.Wo = d.W / d.stride; p.Cout = d.Cout; p.cout_pad = conv_cout_pad(d.Cout);
   p.Wt = pow2_divisor(p.Wo, kConvBlockM);
   p.Ht = pow2_divisor(p.Ho, kConvBlockM / p.Wt);
   p.Nt = kConvBlockM / (p.Wt * p.Ht);
-  p.w_blks = p.Wo / p.Wt; p.h_blks = p.Ho / p.Ht; p.n_blks = (N + p.Nt - 1) / p.Nt;
-  p.taps = ksize * ksize;
-  p.c0_chunks = s0.C / kConvBlockK;
-  p.c1_chunks = s1.ptr ? s1.C / kConvBlockK : 0;
+  p.w_blks = p.Wo / p.Wt; p.h_blks = p.Ho / p.Ht; p.n_blks = (d.N + p.Nt - 1) / p.Nt;
+  p.block_n = p.cout_pad <= 16 ? 16 : (p.cout_pad % 128 == 0 ? 128 : 64);
+  // few output tiles (low-resolution levels): halve the N tile to double the number of CTAs
+  if (p.block_n == 128 && p.w_blks * p.h_blks * p.n_blks * (p.cout_pad / 128) < kNumSMs) p.block_n = 64;
+  p.taps = d.ksize * d.ksize;
+  p.c0_chunks = d.s0.C / K;
+  p.c1_chunks = d.s1.ptr ? d.s1.C / K : 0;
+  p.r0_chunks = d.r0.ptr ? d.r0.C / K : 0;
+  p.r1_chunks = d.r1.ptr ? d.r1.C / K : 0;
   for (int t = 0; t < p.taps; ++t) {
-    const int kh = t / ksize, kw = t % ksize;
-    if (stride == 1) {
-      p.tap_dc[t] = 0; p.tap_dw[t] = kw - ksize / 2; p.tap_da[t] = 0; p.tap_dh[t] = kh - ksize / 2;
+    const int kh = t / d.ksize, kw = t % d.ksize;
+    if (d.stride == 1) {
+      p.tap_dc[t] = 0; p.tap_dw[t] = kw - d.ksize / 2; p.tap_da[t] = 0; p.tap_dh[t] = kh - d.ksize / 2;
     } else {
-      p.tap_dc[t] = (kw & 1) * s0.C; p.tap_dw[t] = kw >> 1; p.tap_da[t] = kh & 1; p.tap_dh[t] = kh >> 1;
+      p.tap_dc[t] = (kw & 1) * d.s0.C; p.tap_dw[t] = kw >> 1; p.tap_da[t] = kh & 1; p.tap_dh[t] = kh >> 1;
     }
   }
-  int rc = encode_act_map(&p.map_a0, s0.ptr, N, H, W, s0.C, stride, p.Wt, p.Ht, p.Nt);
+  int rc = encode_act_map(&p.map_a0, d.s0.ptr, d.N, d.H, d.W, d.s0.C, d.stride, p.Wt, p.Ht, p.Nt);
   if (rc) return rc;
-  if (s1.ptr) {
-    rc = encode_act_map(&p.map_a1, s1.ptr, N, H, W, s1.C, stride, p.Wt, p.Ht, p.Nt);
-    if (rc) return rc;
-  } else {
-    p.map_a1 = p.map_a0;
-  }
-  const uint64_t ktot = (uint64_t)p.taps * (s0.C + (s1.ptr ? s1.C : 0));
+  p.map_a1 = p.map_a0; p.map_r0 = p.map_a0; p.map_r1 = p.map_a0; p.map_out = p.map_a0;
+  if (d.s1.ptr && (rc = encode_act_map(&p.map_a1, d.s1.ptr, d.N, d.H, d.W, d.s1.C, d.stride, p.Wt, p.Ht, p.Nt))) return rc;
+  if (d.r0.ptr && (rc = encode_act_map(&p.map_r0, d.r0.ptr, d.N, p.Ho, p.Wo, d.r0.C, 1, p.Wt, p.Ht, p.Nt))) return rc;
+  if (d.r1.ptr && (rc = encode_act_map(&p.map_r1, d.r1.ptr, d.N, p.Ho, p.Wo, d.r1.C, 1, p.Wt, p.Ht, p.Nt))) return rc;
+  p.has_out_bf16 = d.out_bf16 != nullptr;
+  if (d.out_bf16 && (rc = encode_act_map(&p.map_out, d.out_bf16, d.N, p.Ho, p.Wo, d.Cout, 1, p.Wt, p.Ht, p.Nt))) return rc;
+  const uint64_t ktot = (uint64_t)p.taps * (d.s0.C + (d.s1.ptr ? d.s1.C : 0)) + (d.r0.ptr ? d.r0.C : 0) +
+                        (d.r1.ptr ? d.r1.C : 0);
   uint64_t bd[2] = {ktot, (uint64_t)p.cout_pad};
   uint64_t bs[1] = {ktot * 2};
-  uint32_t bb[2] = {(uint32_t)kConvBlockK, (uint32_t)p.block_n};
-  rc = encode_map(&p.map_b, w_packed, 2, bd, bs, bb);
+  uint32_t bb[2] = {(uint32_t)K, (uint32_t)p.block_n};
+  rc = encode_map(&p.map_b, d.w_packed, 2, bd, bs, bb);
   if (rc) return rc;
-  p.flops = 2.0 * N * p.Ho * p.Wo * (double)Cout * (double)ktot;
+  p.flops = 2.0 * d.N * p.Ho * p.Wo * (double)d.Cout * (double)ktot;
   return B2E_OK;
 }
 
-template <int BN>
+template <int BN, int STAGES>
 static int launch_t(const ConvPlan& pl, const ConvKParams& kp, int grid, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    B2E_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  ConvCfg<BN>::kSmemBytes));
+    B2E_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  ConvCfg<BN, STAGES>::kSmemBytes));
     attr_set = true;
   }
-  conv_igemm_kernel<BN><<<grid, kConvThreads, ConvCfg<BN>::kSmemBytes, st>>>(pl.map_a0, pl.map_a1, pl.map_b, kp);
+  conv_igemm_kernel<BN, STAGES><<<grid < kNumSMs ? grid : kNumSMs, kConvThreads, ConvCfg<BN, STAGES>::kSmemBytes, st>>>(
+      pl.map_a0, pl.map_a1, pl.map_r0, pl.map_r1, pl.map_b, pl.map_out, kp);
   return check_launch("conv_igemm");
 }
 
 int conv_launch(const ConvPlan& pl, const ConvEpilogue& ep, cudaStream_t st) {
-  B2E_REQUIRE(ep.out_bf16 || ep.out_f32_nchw, B2E_INVALID_ARG, "conv: no output");
-  B2E_REQUIRE(!ep.out_bf16 || pl.Cout % 16 == 0, B2E_UNSUPPORTED_SHAPE,
-              "conv: bf16 NHWC output needs Cout %% 16 == 0 (got %d)", pl.Cout);
+  B2E_REQUIRE(pl.has_out_bf16 || ep.out_f32_nchw, B2E_INVALID_ARG, "conv: no output");
+  B2E_REQUIRE(!(pl.has_out_bf16 && pl.block_n == 16), B2E_UNSUPPORTED_SHAPE, "conv: bf16 output with Cout <= 16");
   ConvKParams kp;
   kp.N = pl.N; kp.Ho = pl.Ho; kp.Wo = pl.Wo; kp.Cout = pl.Cout;
   kp.Wt = pl.Wt; kp.Ht = pl.Ht; kp.Nt = pl.Nt; kp.w_blks = pl.w_blks; kp.h_blks = pl.h_blks;
   kp.taps = pl.taps; kp.c0_chunks = pl.c0_chunks; kp.c1_chunks = pl.c1_chunks;
+  kp.r0_chunks = pl.r0_chunks; kp.r1_chunks = pl.r1_chunks;
   for (int t = 0; t < 9; ++t) {
     kp.tap_dc[t] = pl.tap_dc[t]; kp.tap_dw[t] = pl.tap_dw[t]; kp.tap_da[t] = pl.tap_da[t]; kp.tap_dh[t] = pl.tap_dh[t];
   }
   kp.n_tiles = pl.cout_pad / pl.block_n;
-  kp.bias = ep.bias; kp.temb = ep.temb; kp.temb_stride = ep.temb_stride; kp.residual = ep.residual;
-  kp.out_bf16 = ep.out_bf16; kp.out_f32_nchw = ep.out_f32_nchw;
+  kp.bias = ep.bias; kp.bias2 = ep.bias2; kp.temb = ep.temb; kp.temb_stride = ep.temb_stride;
+  kp.out_bf16 = pl.has_out_bf16; kp.out_f32_nchw = pl.has_out_bf16 ? nullptr : ep.out_f32_nchw;
   const int grid = pl.w_blks * pl.h_blks * pl.n_blks * kp.n_tiles;
+  kp.num_tiles = grid;
   switch (pl.block_n) {
-    case 16: return launch_t<16>(pl, kp, grid, st);
-    case 64: return launch_t<64>(pl, kp, grid, st);
-    default: return launch_t<128>(pl, kp, grid, st);
+    case 16: return launch_t<16, 8>(pl, kp, grid, st);
+    case 64: return launch_t<64, 8>(pl, kp, grid, st);
+    default: return launch_t<128, 6>(pl, kp, grid, st);
   }
 }
 
@@ -468,27 +587,38 @@ int conv_launch(const ConvPlan& pl, const ConvEpilogue& ep, cudaStream_t st) {
 
 using namespace b2e;
 
-extern "C" int b2e_conv2d_nhwc_bf16(const void* x, const float* w, const float* bias, void* out, int64_t N,
-                                    int64_t H, int64_t W, int64_t Cin, int64_t Cout, int ksize, int stride,
+// Test hook: y = conv(x) (+ residual) as bf16 NHWC; residual (N,Ho,Wo,Cout) bf16 or NULL exercises the
+// identity residual segment.
+extern "C" int b2e_conv2d_nhwc_bf16(const void* x, const float* w, const float* bias, const void* residual, void* out,
+                                    int64_t N, int64_t H, int64_t W, int64_t Cin, int64_t Cout, int ksize, int stride,
                                     void* stream) {
   B2E_REQUIRE(x && w && out, B2E_INVALID_ARG, "conv2d: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const int cout_pad = conv_cout_pad((int)Cout);
-  const size_t wbytes = (size_t)cout_pad * ksize * ksize * Cin * sizeof(bf16);
+  const int kk = ksize * ksize;
+  const int row_len = (int)(kk * Cin + (residual ? Cout : 0));
+  const size_t wbytes = (size_t)cout_pad * row_len * sizeof(bf16);
   bf16* wp = nullptr;
   B2E_CUDA(cudaMalloc(&wp, wbytes));
   int rc = B2E_OK;
   do {
     if (cudaMemsetAsync(wp, 0, wbytes, st) != cudaSuccess) { set_error("conv2d: memset failed"); rc = B2E_CUDA_ERROR; break; }
-    rc = conv_pack_weight(w, wp, (int)Cout, cout_pad, (int)Cin, (int)Cin, ksize, st);
+    rc = conv_pack_weight(w, wp, (int)Cout, (int)Cin, ksize, (int)Cin, row_len, 0, st);
     if (rc) break;
+    if (residual) {
+      rc = conv_fill_identity(wp, (int)Cout, row_len, (int)(kk * Cin), st);
+      if (rc) break;
+    }
+    ConvDesc d;
+    d.s0 = ConvSrc{(const bf16*)x, (int)Cin};
+    if (residual) d.r0 = ConvSrc{(const bf16*)residual, (int)Cout};
+    d.N = (int)N; d.H = (int)H; d.W = (int)W; d.ksize = ksize; d.stride = stride;
+    d.w_packed = wp; d.Cout = (int)Cout; d.out_bf16 = (bf16*)out;
     ConvPlan plan;
-    rc = conv_plan_build(&plan, ConvSrc{(const bf16*)x, (int)Cin}, ConvSrc{nullptr, 0}, (int)N, (int)H, (int)W,
-                         ksize, stride, wp, (int)Cout);
+    rc = conv_plan_build(&plan, d);
     if (rc) break;
     ConvEpilogue ep;
     ep.bias = bias;
-    ep.out_bf16 = (bf16*)out;
     rc = conv_launch(plan, ep, st);
   } while (0);
   cudaStreamSynchronize(st);

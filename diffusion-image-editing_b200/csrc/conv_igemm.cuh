@@ -12,43 +12,53 @@ typedef __nv_bfloat16 bf16;
 constexpr int kConvBlockM = 128;  // output pixels per CTA tile (UMMA_M)
 constexpr int kConvBlockK = 64;   // bf16 channels per pipeline stage (one 128B swizzle row)
 
+struct ConvSrc {
+  const bf16* ptr = nullptr;  // NHWC
+  int C = 0;
+};
+
+// y = conv_{k x k, stride}(x0 ++ x1)  [+ W_r (r0 ++ r1)]  + bias (+ bias2) (+ temb[n, :])
+// The optional second term is a 1x1 "residual segment" appended to the GEMM K dimension: with
+// W_r = conv_shortcut weights it fuses the ResNet shortcut convolution, with W_r = I it is the plain
+// residual add - either way the epilogue never touches the residual tensor.
+struct ConvDesc {
+  ConvSrc s0, s1;            // input (virtually concatenated along channels), (N,H,W,C)
+  ConvSrc r0, r1;            // residual sources at OUTPUT resolution, (N,Ho,Wo,C); stride must be 1
+  int N = 0, H = 0, W = 0;
+  int ksize = 3, stride = 1; // stride 1: padding ksize/2; stride 2: ksize 3, padding (0,1,0,1)
+  const bf16* w_packed = nullptr;  // bf16 [cout_pad][row_len], row_len = k*k*(C0+C1) + Cr0 + Cr1
+  int Cout = 0;
+  bf16* out_bf16 = nullptr;  // NHWC (N,Ho,Wo,Cout) through TMA store; null -> fp32 NCHW output only
+};
+
 struct ConvEpilogue {
-  const float* bias = nullptr;     // [Cout]
-  const float* temb = nullptr;     // [N][temb_stride], already offset to this layer's columns
+  const float* bias = nullptr;    // [Cout]
+  const float* bias2 = nullptr;   // [Cout] (shortcut bias)
+  const float* temb = nullptr;    // [N][temb_stride], already offset to this layer's columns
   int temb_stride = 0;
-  const bf16* residual = nullptr;  // NHWC, same shape as the output
-  bf16* out_bf16 = nullptr;        // NHWC [N,Ho,Wo,Cout]
-  float* out_f32_nchw = nullptr;   // NCHW [N,Cout,Ho,Wo] (network output)
-  float* gn_partial = nullptr;     // reserved: fused GroupNorm statistics
+  float* out_f32_nchw = nullptr;  // NCHW [N,Cout,Ho,Wo] (network output)
 };
 
 // Everything the kernel needs that is fixed per layer; built once at model-build time.
 struct ConvPlan {
-  CUtensorMap map_a0, map_a1, map_b;
+  CUtensorMap map_a0, map_a1, map_r0, map_r1, map_b, map_out;
   int N, Ho, Wo, Cout, cout_pad;
   int Wt, Ht, Nt, w_blks, h_blks, n_blks;
-  int taps, c0_chunks, c1_chunks;
+  int taps, c0_chunks, c1_chunks, r0_chunks, r1_chunks;
   int tap_dc[9], tap_dw[9], tap_da[9], tap_dh[9];
   int block_n;  // 16, 64 or 128
+  int has_out_bf16;
   double flops;
 };
 
-struct ConvSrc {
-  const bf16* ptr;  // NHWC [N,H,W,C]
-  int C;
-};
-
-// Builds the TMA descriptors and tile geometry for y = conv(x0 ++ x1) with a ksize x ksize
-// kernel.  stride 1: padding ksize/2.  stride 2: ksize 3, padding (0,1,0,1) (Downsample2D).
-// w_packed: bf16 [cout_pad][ksize*ksize][C0+C1].
-int conv_plan_build(ConvPlan* plan, ConvSrc s0, ConvSrc s1, int N, int H, int W, int ksize, int stride,
-                    const bf16* w_packed, int Cout);
+int conv_plan_build(ConvPlan* plan, const ConvDesc& d);
 int conv_cout_pad(int Cout);
 int conv_launch(const ConvPlan& plan, const ConvEpilogue& ep, cudaStream_t st);
 
-// fp32 [Cout][Cin][k][k] -> bf16 [cout_pad][k][k][cin_pad] (zero padded), Cin placed at
-// channel offset cin_off of a cin_total-wide K row.
-int conv_pack_weight(const float* w, bf16* out, int Cout, int cout_pad, int Cin, int cin_total,
-                     int ksize, cudaStream_t st);
+// fp32 [Cout][Cin][k][k] -> bf16 out[co*row_len + col_off + t*tap_width + ci]   (t = kh*k + kw)
+int conv_pack_weight(const float* w, bf16* out, int Cout, int Cin, int ksize, int tap_width, int row_len,
+                     int col_off, cudaStream_t st);
+// out[c*row_len + col_off + c] = 1 for c < C (identity residual segment)
+int conv_fill_identity(bf16* out, int C, int row_len, int col_off, cudaStream_t st);
 
 }  // namespace b2e

@@ -71,32 +71,47 @@ __device__ __forceinline__ void step_elem(float x, float e, float z, float m, in
 constexpr int kStepThreads = 256;
 constexpr int kStepUnroll = 4;  // float4 per thread per input
 
+// per-channel parameters without dynamic indexing (keeps StepK in constant bank / registers)
+__device__ __forceinline__ void chan_params(const StepK& k, int c, int& ht, float& tau, float& gk) {
+  ht = c == 0 ? k.has_target[0] : c == 1 ? k.has_target[1] : c == 2 ? k.has_target[2] : k.has_target[3];
+  tau = c == 0 ? k.target[0] : c == 1 ? k.target[1] : c == 2 ? k.target[2] : k.target[3];
+  gk = c == 0 ? k.gk[0] : c == 1 ? k.gk[1] : c == 2 ? k.gk[2] : k.gk[3];
+}
+
 // total4 = B*C*HW/4 ; HW % 4 == 0 so the four lanes of a float4 share a channel.
-__global__ void __launch_bounds__(kStepThreads)
+// Index math is 32-bit (the host guarantees total4 < 2^31): one division per thread, then the
+// (plane, offset) pair is advanced incrementally across the unrolled accesses.
+__global__ void __launch_bounds__(kStepThreads, 3)
 guided_step_vec4(const float4* __restrict__ x, const float4* __restrict__ e,
                  const float4* __restrict__ z, const float4* __restrict__ mask,
-                 float4* __restrict__ xp, float4* __restrict__ x0o, int64_t total4, int64_t chw4,
-                 int64_t hw4, int C, StepK k) {
-  const int64_t base = (int64_t)blockIdx.x * (kStepThreads * kStepUnroll) + threadIdx.x;
+                 float4* __restrict__ xp, float4* __restrict__ x0o, uint32_t total4, uint32_t hw4,
+                 uint32_t C, const __grid_constant__ StepK k) {
+  const uint32_t base = blockIdx.x * (uint32_t)(kStepThreads * kStepUnroll) + threadIdx.x;
   float4 vx[kStepUnroll], ve[kStepUnroll], vz[kStepUnroll], vm[kStepUnroll];
+  uint32_t ch[kStepUnroll];
   const bool use_mask = k.guide && k.mask_grad;
+  uint32_t plane = base / hw4, off = base - plane * hw4;
 #pragma unroll
   for (int u = 0; u < kStepUnroll; ++u) {
-    const int64_t i = base + (int64_t)u * kStepThreads;
+    const uint32_t i = base + (uint32_t)u * kStepThreads;
+    const uint32_t c = plane % C;
+    ch[u] = c;
     if (i < total4) {
       vx[u] = ld_stream(x + i);
       ve[u] = ld_stream(e + i);
-      if (k.has_noise) vz[u] = k.noise_batched ? ld_stream(z + i) : ld_reuse(z + (i % chw4));
-      if (use_mask) vm[u] = k.mask_batched ? ld_stream(mask + i) : ld_reuse(mask + (i % chw4));
+      const uint32_t bi = c * hw4 + off;  // index inside one (C,H,W) image
+      if (k.has_noise) vz[u] = k.noise_batched ? ld_stream(z + i) : ld_reuse(z + bi);
+      if (use_mask) vm[u] = k.mask_batched ? ld_stream(mask + i) : ld_reuse(mask + bi);
     }
+    off += kStepThreads;
+    while (off >= hw4) { off -= hw4; ++plane; }
   }
 #pragma unroll
   for (int u = 0; u < kStepUnroll; ++u) {
-    const int64_t i = base + (int64_t)u * kStepThreads;
+    const uint32_t i = base + (uint32_t)u * kStepThreads;
     if (i < total4) {
-      const int c = (int)((i / hw4) % C);
-      const int ht = k.has_target[c];
-      const float tau = k.target[c], gk = k.gk[c];
+      int ht; float tau, gk;
+      chan_params(k, (int)ch[u], ht, tau, gk);
       float4 zz = k.has_noise ? vz[u] : make_float4(0.f, 0.f, 0.f, 0.f);
       float4 mm = use_mask ? vm[u] : make_float4(1.f, 1.f, 1.f, 1.f);
       float4 o, o0;
@@ -122,7 +137,9 @@ __global__ void guided_step_scalar(const float* __restrict__ x, const float* __r
     float zz = k.has_noise ? z[k.noise_batched ? i : i % chw] : 0.f;
     float mm = use_mask ? mask[k.mask_batched ? i : i % chw] : 1.f;
     float o, o0;
-    step_elem(x[i], e[i], zz, mm, k.has_target[c], k.target[c], k.gk[c], k, o, o0);
+    int ht; float tau, gk;
+    chan_params(k, c, ht, tau, gk);
+    step_elem(x[i], e[i], zz, mm, ht, tau, gk, k, o, o0);
     xp[i] = o;
     if (x0o) x0o[i] = o0;
   }
@@ -482,16 +499,16 @@ int b2e_guided_step_f32(const float* x_t, const float* eps, const float* z, cons
   StepK k = make_stepk(p);
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t total = B * C * HW;
-  const bool vec = (HW % 4 == 0) && aligned16(x_t) && aligned16(eps) && aligned16(x_prev) &&
-                   (!x0_pred || aligned16(x0_pred)) && (!z || aligned16(z)) &&
-                   (!mask || aligned16(mask));
+  const bool vec = (HW % 4 == 0) && total / 4 < (int64_t)0x7fffffff - kStepThreads * kStepUnroll &&
+                   aligned16(x_t) && aligned16(eps) && aligned16(x_prev) && (!x0_pred || aligned16(x0_pred)) &&
+                   (!z || aligned16(z)) && (!mask || aligned16(mask));
   if (vec) {
     const int64_t total4 = total / 4;
     const int per_block = kStepThreads * kStepUnroll;
     const int64_t grid = (total4 + per_block - 1) / per_block;
     guided_step_vec4<<<(unsigned)grid, kStepThreads, 0, st>>>(
         (const float4*)x_t, (const float4*)eps, (const float4*)z, (const float4*)mask,
-        (float4*)x_prev, (float4*)x0_pred, total4, C * HW / 4, HW / 4, (int)C, k);
+        (float4*)x_prev, (float4*)x0_pred, (uint32_t)total4, (uint32_t)(HW / 4), (uint32_t)C, k);
   } else {
     guided_step_scalar<<<grid_for(total, kStepThreads), kStepThreads, 0, st>>>(
         x_t, eps, z, mask, x_prev, x0_pred, total, C * HW, HW, (int)C, k);

@@ -20,7 +20,8 @@ using namespace b2e;
 
 namespace {
 
-struct ConvL { bf16* w = nullptr; float* b = nullptr; int cin = 0, cin_pad = 0, cout = 0, cout_pad = 0, k = 0; };
+// res_c > 0: a 1x1 residual segment of res_c channels is appended to every weight row (shortcut / identity)
+struct ConvL { bf16* w = nullptr; float* b = nullptr; float* b2 = nullptr; int cin = 0, cin_pad = 0, cout = 0, cout_pad = 0, k = 0, res_c = 0, row_len = 0; };
 struct NormL { float* g = nullptr; float* b = nullptr; int C = 0; };
 struct ResnetL {
   std::string name; int cin0 = 0, cin1 = 0, cout = 0; NormL n1, n2; ConvL c1, c2, sc; bool has_sc = false;
@@ -103,14 +104,15 @@ struct b2e_unet {
     });
   }
   // conv / linear weight that feeds the tcgen05 GEMM: packed bf16 [cout_pad][k*k][cin_pad]
-  ConvL make_conv(const std::string& name, int cin, int cout, int k, int cin_pad = 0) {
+  ConvL make_conv(const std::string& name, int cin, int cout, int k, int cin_pad = 0, int res_c = 0) {
     ConvL c;
     c.cin = cin; c.cin_pad = cin_pad ? cin_pad : cin; c.cout = cout; c.k = k; c.cout_pad = conv_cout_pad(cout);
-    c.w = dmalloc<bf16>((size_t)c.cout_pad * k * k * c.cin_pad);
+    c.res_c = res_c; c.row_len = k * k * c.cin_pad + res_c;
+    c.w = dmalloc<bf16>((size_t)c.cout_pad * c.row_len);
     c.b = dmalloc<float>(c.cout_pad);
     ConvL cc = c;
     add_param(name + ".weight", (int64_t)cout * cin * k * k, (int64_t)cin * k * k, [cc](const float* src, cudaStream_t st) {
-      return conv_pack_weight(src, cc.w, cc.cout, cc.cout_pad, cc.cin, cc.cin_pad, cc.k, st);
+      return conv_pack_weight(src, cc.w, cc.cout, cc.cin, cc.k, cc.cin_pad, cc.row_len, 0, st);
     });
     add_f32(name + ".bias", c.b, cout, (int64_t)cin * k * k);
     return c;
@@ -129,9 +131,20 @@ struct b2e_unet {
     r.c1 = make_conv(name + ".conv1", cin, cout, 3);
     r.temb_off = sumC; sumC += cout;
     r.n2 = make_norm(name + ".norm2", cout);
-    r.c2 = make_conv(name + ".conv2", cout, cout, 3);
+    // conv2 carries the block input as a fused 1x1 residual segment: conv_shortcut weights when the
+    // channel count changes, the identity otherwise
+    r.c2 = make_conv(name + ".conv2", cout, cout, 3, 0, cin);
     r.has_sc = cin != cout;
-    if (r.has_sc) r.sc = make_conv(name + ".conv_shortcut", cin, cout, 1);
+    if (r.has_sc) {
+      r.c2.b2 = dmalloc<float>(r.c2.cout_pad);
+      ConvL cc = r.c2;
+      add_param(name + ".conv_shortcut.weight", (int64_t)cout * cin, cin, [cc, cin](const float* src, cudaStream_t st) {
+        return conv_pack_weight(src, cc.w, cc.cout, cin, 1, cin, cc.row_len, 9 * cc.cin_pad, st);
+      });
+      add_f32(name + ".conv_shortcut.bias", r.c2.b2, cout, cin);
+    } else if (r.c2.w) {
+      if (conv_fill_identity(r.c2.w, cout, r.c2.row_len, 9 * r.c2.cin_pad, 0)) build_error = B2E_CUDA_ERROR;
+    }
     resnets.push_back(r);
     return (int)resnets.size() - 1;
   }
@@ -148,11 +161,13 @@ struct b2e_unet {
       bf16* wdst = a.qkv.w + (size_t)i * C * C;
       float* bdst = a.qkv.b + (size_t)i * C;
       add_param(name + "." + nm[i] + ".weight", (int64_t)C * C, C, [wdst, C](const float* src, cudaStream_t st) {
-        return conv_pack_weight(src, wdst, C, C, C, C, 1, st);
+        return conv_pack_weight(src, wdst, C, C, 1, C, C, 0, st);
       });
       add_f32(name + "." + nm[i] + ".bias", bdst, C, C);
     }
-    a.proj = make_conv(name + ".to_out.0", C, C, 1);
+    a.qkv.row_len = C;
+    a.proj = make_conv(name + ".to_out.0", C, C, 1, 0, C);   // + identity residual segment
+    if (a.proj.w && conv_fill_identity(a.proj.w, C, a.proj.row_len, C, 0)) build_error = B2E_CUDA_ERROR;
     attns.push_back(a);
     return (int)attns.size() - 1;
   }
@@ -249,17 +264,25 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
   float* proj = (float*)ar.alloc(sizeof(float) * B * m->sumC);
   float* gn_part = (float*)ar.alloc(sizeof(float) * B * 64 * G * 2);
 
-  auto conv = [&](const ConvL& L, Tensor x0, const Tensor* x1, int stride, ConvEpilogue ep, Tensor* out, float* out_nchw) {
+  auto conv = [&](const ConvL& L, Tensor x0, const Tensor* x1, int stride, ConvEpilogue ep, Tensor* out, float* out_nchw,
+                  const Tensor* r0 = nullptr, const Tensor* r1 = nullptr) {
     if (rc) return;
     const int Ho = x0.H / stride, Wo = x0.W / stride;
     if (out) *out = talloc(B, Ho, Wo, L.cout);
-    if (dry) { flops += 2.0 * B * Ho * Wo * (double)L.cout * L.k * L.k * (x0.C + (x1 ? x1->C : 0)); return; }
+    if (dry) { flops += 2.0 * B * Ho * Wo * (double)L.cout * (L.k * L.k * (x0.C + (x1 ? x1->C : 0)) + L.res_c); return; }
+    ConvDesc d;
+    d.s0 = ConvSrc{x0.p, x0.C};
+    if (x1) d.s1 = ConvSrc{x1->p, x1->C};
+    if (r0) d.r0 = ConvSrc{r0->p, r0->C};
+    if (r1) d.r1 = ConvSrc{r1->p, r1->C};
+    d.N = B; d.H = x0.H; d.W = x0.W; d.ksize = L.k; d.stride = stride; d.w_packed = L.w; d.Cout = L.cout;
+    d.out_bf16 = out ? out->p : nullptr;
+    if (L.res_c != (r0 ? r0->C : 0) + (r1 ? r1->C : 0)) { rc = B2E_INVALID_ARG; set_error("unet: residual segment mismatch"); return; }
     ConvPlan pl;
-    rc = conv_plan_build(&pl, ConvSrc{x0.p, x0.C}, x1 ? ConvSrc{x1->p, x1->C} : ConvSrc{nullptr, 0}, B, x0.H, x0.W,
-                         L.k, stride, L.w, L.cout);
+    rc = conv_plan_build(&pl, d);
     if (rc) return;
     ep.bias = L.b;
-    if (out) ep.out_bf16 = out->p;
+    ep.bias2 = L.b2;
     flops += pl.flops;
     if (out_nchw) {
       // the network output pointer is only known at call time
@@ -313,23 +336,16 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
       case N_RESNET: {
         const ResnetL& r = m->resnets[nd.idx];
         const Tensor* x1 = have_cat ? &cat : nullptr;
-        Tensor a1, h1, a2, sc, out;
+        Tensor a1, h1, a2, out;
         gnorm(r.n1, h, x1, 1, &a1);
         ConvEpilogue e1; e1.temb = proj + r.temb_off; e1.temb_stride = m->sumC;
         conv(r.c1, a1, nullptr, 1, e1, &h1, nullptr);
         tfree(a1);
         gnorm(r.n2, h1, nullptr, 1, &a2);
         tfree(h1);
-        ConvEpilogue e2;
-        if (r.has_sc) {
-          conv(r.sc, h, x1, 1, ConvEpilogue{}, &sc, nullptr);
-          e2.residual = sc.p;
-        } else {
-          e2.residual = h.p;
-        }
-        conv(r.c2, a2, nullptr, 1, e2, &out, nullptr);
+        // out = conv2(a2) + shortcut(x) : the block input rides along as a 1x1 K segment of conv2
+        conv(r.c2, a2, nullptr, 1, ConvEpilogue{}, &out, nullptr, &h, x1);
         tfree(a2);
-        if (r.has_sc) tfree(sc);
         if (!on_stack(h)) tfree(h);
         if (have_cat) { tfree(cat); have_cat = false; }
         h = out;
@@ -350,8 +366,7 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
         }
         flops += 4.0 * B * (double)(h.H * h.W) * (h.H * h.W) * a.C;
         tfree(qkv);
-        ConvEpilogue ep; ep.residual = h.p;
-        conv(a.proj, o, nullptr, 1, ep, &out, nullptr);
+        conv(a.proj, o, nullptr, 1, ConvEpilogue{}, &out, nullptr, &h);
         tfree(o);
         if (!on_stack(h)) tfree(h);
         h = out;
@@ -417,6 +432,7 @@ int b2e_unet_create(const b2e_unet_config* cfg, int64_t max_batch, b2e_unet** ou
   m->cfg = *cfg;
   m->max_batch = max_batch;
   int rc = build_model(m);
+  if (!rc && cudaDeviceSynchronize() != cudaSuccess) { set_error("unet_create: device error"); rc = B2E_CUDA_ERROR; }
   if (!rc) rc = build_program(m, (int)max_batch, nullptr, 0, &m->ws_need);
   if (rc) { delete m; return rc; }
   *out = m;

@@ -25,6 +25,11 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 }
 
 // ------------------------------------------------------------------ GroupNorm
+// Thread layout: a "slot" is 8 consecutive channels (one 16-byte access); 256 / slots pixels are
+// processed per sweep and four sweeps are unrolled so every thread keeps four independent 16-byte
+// loads in flight.
+constexpr int kGNUnroll = 4;
+
 __global__ void __launch_bounds__(kGNThreads) gn_partial_kernel(GNArgs a) {
   __shared__ float s_sum[2048], s_sq[2048];
   const int C = a.C0 + a.C1, slots = C >> 3, ppi = kGNThreads / slots;
@@ -40,11 +45,20 @@ __global__ void __launch_bounds__(kGNThreads) gn_partial_kernel(GNArgs a) {
     const bf16* src; int cs, coff;
     if (c < a.C0) { src = a.x0; cs = a.C0; coff = c; } else { src = a.x1; cs = a.C1; coff = c - a.C0; }
     src += (int64_t)n * a.HW * cs + coff;
-    for (int p = p0 + pl; p < p1; p += ppi) {
-      float f[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(src + (int64_t)p * cs)), f);
+    for (int p = p0 + pl; p < p1; p += ppi * kGNUnroll) {
+      uint4 v[kGNUnroll];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { sum[j] += f[j]; sq[j] += f[j] * f[j]; }
+      for (int u = 0; u < kGNUnroll; ++u) {
+        const int q = p + u * ppi;
+        v[u] = q < p1 ? __ldg(reinterpret_cast<const uint4*>(src + (int64_t)q * cs)) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < kGNUnroll; ++u) {
+        float f[8];
+        unpack8(v[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { sum[j] += f[j]; sq[j] += f[j] * f[j]; }
+      }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s_sum[pl * C + c + j] = sum[j]; s_sq[pl * C + c + j] = sq[j]; }
@@ -94,22 +108,35 @@ __global__ void __launch_bounds__(kGNThreads) gn_apply_kernel(GNArgs a, int pix_
   src += (int64_t)n * a.HW * cs + coff;
   bf16* dst = a.out + (int64_t)n * a.HW * C + c;
   const int p0 = blockIdx.x * pix_per_block, p1 = min(a.HW, p0 + pix_per_block);
-  for (int p = p0 + pl; p < p1; p += ppi) {
-    float f[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(src + (int64_t)p * cs)), f);
+  for (int p = p0 + pl; p < p1; p += ppi * kGNUnroll) {
+    uint4 v[kGNUnroll];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float y = fmaf(f[j], scale[j], shift[j]);
-      if (a.silu) y = __fdividef(y, 1.f + __expf(-y));
-      f[j] = y;
+    for (int u = 0; u < kGNUnroll; ++u) {
+      const int q = p + u * ppi;
+      if (q < p1) v[u] = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)q * cs));
     }
-    *reinterpret_cast<uint4*>(dst + (int64_t)p * C) = pack8(f);
+#pragma unroll
+    for (int u = 0; u < kGNUnroll; ++u) {
+      const int q = p + u * ppi;
+      if (q < p1) {
+        float f[8];
+        unpack8(v[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float y = fmaf(f[j], scale[j], shift[j]);
+          if (a.silu) y = __fdividef(y, 1.f + __expf(-y));
+          f[j] = y;
+        }
+        *reinterpret_cast<uint4*>(dst + (int64_t)q * C) = pack8(f);
+      }
+    }
   }
 }
 
 int gn_chunks(int HW, int C) {
+  // ~16K elements (two unrolled sweeps) per block, at most 64 partial rows per image
   int64_t el = (int64_t)HW * C;
-  int ch = (int)(el / 65536);
+  int ch = (int)((el + 16383) / 16384);
   if (ch < 1) ch = 1;
   if (ch > 64) ch = 64;
   return ch;
@@ -123,7 +150,7 @@ int gn_launch(const GNArgs& a, cudaStream_t st) {
   int rc = check_launch("gn_partial");
   if (rc) return rc;
   const int slots = C / 8, ppi = kGNThreads / slots;
-  int ppb = ppi * 16;  // 16 iterations per thread
+  int ppb = ppi * kGNUnroll * 2;  // two unrolled sweeps per thread
   if (ppb > a.HW) ppb = a.HW;
   gn_apply_kernel<<<dim3((a.HW + ppb - 1) / ppb, a.N), kGNThreads, 0, st>>>(a, ppb);
   return check_launch("gn_apply");

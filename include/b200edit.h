@@ -219,11 +219,12 @@ int b2e_unet_profile(b2e_unet* m, const float* x, const int64_t* timesteps, floa
 int b2e_unet_launches_per_forward(const b2e_unet* m);
 
 /* Test hook for the implicit-GEMM convolution: x (N,H,W,Cin) bf16 NHWC, w (Cout,Cin,k,k) fp32,
- * bias fp32 [Cout] or NULL, out (N,Ho,Wo,Cout) bf16 NHWC.  ksize 1|3, stride 1|2
- * (stride 2 pads (0,1,0,1) like diffusers' Downsample2D).  Allocates temporaries itself. */
-int b2e_conv2d_nhwc_bf16(const void* x, const float* w, const float* bias, void* out, int64_t N,
-                         int64_t H, int64_t W, int64_t Cin, int64_t Cout, int ksize, int stride,
-                         void* stream);
+ * bias fp32 [Cout] or NULL, residual (N,Ho,Wo,Cout) bf16 NHWC or NULL (added through the fused
+ * residual K-segment), out (N,Ho,Wo,Cout) bf16 NHWC.  ksize 1|3, stride 1|2 (stride 2 pads
+ * (0,1,0,1) like diffusers' Downsample2D).  Allocates temporaries itself and synchronises. */
+int b2e_conv2d_nhwc_bf16(const void* x, const float* w, const float* bias, const void* residual,
+                         void* out, int64_t N, int64_t H, int64_t W, int64_t Cin, int64_t Cout,
+                         int ksize, int stride, void* stream);
 
 #ifdef __cplusplus
 }

@@ -46,3 +46,12 @@ def test_conv_vs_torch(case):
     err = (got - ref).abs().max().item()
     scale = ref.abs().max().item()
     assert err <= 2 ** -7 * scale + 1e-3, f"max abs err {err} (scale {scale})"
+    # fused residual segment (identity weights appended to K): out = conv(x) + r
+    r = torch.randn(ref.shape, generator=g).bfloat16()
+    out_r = ops.conv2d_nhwc_bf16(xd, w.float().cuda(), b.cuda(), stride=stride,
+                                 residual=r.cuda().permute(0, 2, 3, 1).contiguous()) if stride == 1 else None
+    if out_r is not None:
+        ref_r = ref + r.float().cuda()
+        err = (out_r.float().permute(0, 3, 1, 2) - ref_r).abs().max().item()
+        scale = ref_r.abs().max().item()
+        assert err <= 2 ** -7 * scale + 1e-3, f"residual: max abs err {err} (scale {scale})"

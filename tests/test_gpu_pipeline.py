@@ -153,25 +153,41 @@ def test_inversion_and_sampling_vs_reference_golden(golden, preset):
 
 
 def test_inversion_round_trip_property():
-    """Edit-friendly inversion is self-consistent: regenerating from xts[0] with the extracted zs
-    reproduces every intermediate xts[k], at full DDPM-256 size, free-running
-    toy predictor on the device."""
+    """Edit-friendly inversion is self-consistent at full DDPM-256 size: regenerating from xts[0] with
+    the extracted zs and the SAME noise predictions reproduces every intermediate xts[k]
+    (SURVEY section 8c).  The predictions are teacher-forced (recorded during the inversion) so the
+    check isolates the kernels: a free-running random predictor is chaotic and amplifies fp32 rounding.
+    Tolerance 5e-4 relative to max|x|: per step the deviation grows by at most sqrt(a_prev/a_t)
+    (product over the trajectory <= 1/sqrt(alphas_cumprod[T]) ~ 157) from ~1e-7 roundings."""
     import ddpm_inversion as dp
     from b200edit.scheduler import DDIMScheduler
     from oracle.unet2d import ToyEpsModel
     s = DDIMScheduler.from_preset("ddpm", clip_sample=False)
     s.set_timesteps(50)
-    unet = ToyEpsModel(3, 256).cuda()
-    unet.device = torch.device("cuda")
-    model = SimpleNamespace(unet=unet, scheduler=s, device=torch.device("cuda"))
+    toy = ToyEpsModel(3, 256).cuda()
+    rec = []
+
+    class Recorder:
+        config, in_channels, sample_size, device = toy.config, 3, 256, torch.device("cuda")
+
+        def __call__(self, sample, timestep, **_):
+            out = toy(sample, timestep)
+            rec.append(out["sample"].detach().clone())
+            return out
+
+    model = SimpleNamespace(unet=Recorder(), scheduler=s, device=torch.device("cuda"))
     x0 = (torch.randn(1, 3, 256, 256, generator=torch.Generator().manual_seed(7)) * 0.5).clamp(-1, 1).cuda()
     xT, zs, xts = dp.invert(model, x0, num_inference_steps=50, eta=1, prog_bar=False)
-    assert torch.isfinite(zs).all() and torch.isfinite(xts[:50]).all()
+    assert len(rec) == 50 and torch.isfinite(zs).all() and torch.isfinite(xts[:50]).all()
+    assert torch.equal(xT, xts[0][None]) and float(zs[-1].abs().max()) == 0.0
+    eps_by_idx = rec[::-1]          # the inversion visits idx = T-1 .. 0
     xt = xts[0][None]
+    worst = 0.0
     for idx, t in enumerate([int(t) for t in s.timesteps][:-1]):
-        eps = unet(xt, t)["sample"].detach()
-        xt = dp.reverse_step(model, eps, t, xt, eta=1, variance_noise=zs[idx])
-        assert (xt[0] - xts[idx + 1]).abs().max().item() < 2e-4 * max(1.0, xts[idx + 1].abs().max().item())
+        xt = dp.reverse_step(model, eps_by_idx[idx], t, xt, eta=1, variance_noise=zs[idx])
+        worst = max(worst, (xt[0] - xts[idx + 1]).abs().max().item() / max(1.0, xts[idx + 1].abs().max().item()))
+    print(f"round-trip worst relative deviation over 49 steps: {worst:.3e}")
+    assert worst < 5e-4
 
 
 def test_autograd_fallback_matches_fused_kernel(golden):
