@@ -39,7 +39,8 @@ struct ConvCfg {
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;   // double-buffered accumulator
   static constexpr int kSlabs = BN / 64;                        // 64-channel output slabs (0: fp32 NCHW path)
   static constexpr int kStagingBytes = kSlabs * kConvBlockM * 128;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kRedBytes = kSlabs > 0 ? 8192 : 0;       // GroupNorm-statistics scratch [row groups][BN][2]
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kRedBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 struct ConvKParams {
@@ -54,6 +55,7 @@ struct ConvKParams {
   int temb_stride;
   int out_bf16;         // 1: stage + TMA-store the bf16 NHWC tile through map_out
   float* out_f32_nchw;
+  float* tile_stats;    // fused GroupNorm statistics or null
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -177,12 +179,13 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 // Persistent: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The accumulator is
 // double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the main loop of tile
 // i+1, and the TMA producer runs ahead across tile boundaries (the smem ring never drains).
-struct TileCoord { int n_tile, w0, h0, n0; };
+struct TileCoord { int n_tile, m_tile, w0, h0, n0; };
 
 __device__ __forceinline__ TileCoord tile_coord(const ConvKParams& p, int tile) {
   TileCoord t;
   t.n_tile = tile % p.n_tiles;
   int m = tile / p.n_tiles;
+  t.m_tile = m;
   t.w0 = (m % p.w_blks) * p.Wt; m /= p.w_blks;
   t.h0 = (m % p.h_blks) * p.Ht;
   t.n0 = (m / p.h_blks) * p.Nt;
@@ -199,7 +202,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* staging = smem + Cfg::kStages * Cfg::kStageBytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes);
+  float* red = reinterpret_cast<float*>(staging + Cfg::kStagingBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes + Cfg::kRedBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;         // [2]
@@ -383,6 +387,45 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             tma_store_5d(&map_out, staging + sl * (kConvBlockM * 128), tc.n_tile * BN + sl * 64, tc.w0, 0, tc.h0, tc.n0);
           tma_store_commit();
         }
+        if (p.tile_stats) {
+          // GroupNorm statistics of the bf16 tile just staged: per-channel sum / sum of squares over the
+          // rows of each image in the tile (thread = 8 channels x a group of rows; deterministic order)
+          constexpr int NC = BN / 8, NG = kConvBlockM / NC, RP = kConvBlockM / NG;
+          const int t = threadIdx.x - 64;
+          const int j = t % NC, g = t / NC;
+          float sum[8], sq[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) sum[e] = sq[e] = 0.f;
+#pragma unroll 4
+          for (int rr = 0; rr < RP; ++rr) {
+            const int row = g * RP + rr;
+            const uint4 v = *reinterpret_cast<const uint4*>(staging + (j >> 3) * (kConvBlockM * 128) + row * 128 +
+                                                            (((j & 7) ^ (row & 7)) << 4));
+            const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __bfloat1622float2(b2[e]);
+              sum[2 * e] += f.x; sq[2 * e] += f.x * f.x;
+              sum[2 * e + 1] += f.y; sq[2 * e + 1] += f.y * f.y;
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            *reinterpret_cast<float2*>(red + ((g * BN) + j * 8 + e) * 2) = make_float2(sum[e], sq[e]);
+          epi_bar_sync();
+          if (t < BN) {
+            const int groups_per_img = (p.Wt * p.Ht) / RP;
+            for (int nl = 0; nl < p.Nt; ++nl) {
+              float s1 = 0.f, s2 = 0.f;
+              for (int gg = nl * groups_per_img; gg < (nl + 1) * groups_per_img; ++gg) {
+                const float2 f = *reinterpret_cast<const float2*>(red + (gg * BN + t) * 2);
+                s1 += f.x; s2 += f.y;
+              }
+              const int64_t slot = (int64_t)tc.m_tile * p.Nt + nl;
+              *reinterpret_cast<float2*>(p.tile_stats + (slot * p.Cout + tc.n_tile * BN + t) * 2) = make_float2(s1, s2);
+            }
+          }
+        }
       }
     }
     if (store_leader) tma_store_wait_all();
@@ -473,6 +516,21 @@ int conv_cout_pad(int Cout) {
   return (Cout + 63) / 64 * 64;
 }
 
+ConvGeom conv_geometry(int N, int Ho, int Wo, int Cout) {
+  ConvGeom g;
+  const int cout_pad = conv_cout_pad(Cout);
+  g.Wt = pow2_divisor(Wo, kConvBlockM);
+  g.Ht = pow2_divisor(Ho, kConvBlockM / g.Wt);
+  g.Nt = kConvBlockM / (g.Wt * g.Ht);
+  g.w_blks = Wo / g.Wt; g.h_blks = Ho / g.Ht; g.n_blks = (N + g.Nt - 1) / g.Nt;
+  g.block_n = cout_pad <= 16 ? 16 : (cout_pad % 128 == 0 ? 128 : 64);
+  // few output tiles (low-resolution levels): halve the N tile to double the number of CTAs
+  if (g.block_n == 128 && g.w_blks * g.h_blks * g.n_blks * (cout_pad / 128) < kNumSMs) g.block_n = 64;
+  // statistics are reduced over groups of block_n/8 rows, which must not straddle images
+  g.stats_ok = g.block_n >= 64 && Cout % 64 == 0 && (g.Wt * g.Ht) % (g.block_n / 8) == 0;
+  return g;
+}
+
 // (C, W, 1, H, N) view of an NHWC tensor (stride 1) or (2C, W/2, 2, H/2, N) (stride 2), box = one tile brick
 static int encode_act_map(CUtensorMap* m, const bf16* ptr, int N, int H, int W, int C, int stride,
                           int Wt, int Ht, int Nt) {
@@ -508,13 +566,12 @@ int conv_plan_build(ConvPlan* pl, const ConvDesc& d) {
               "conv: bf16 NHWC output needs Cout %% 64 == 0 (got %d)", d.Cout);
   ConvPlan& p = *pl;
   p.N = d.N; p.Ho = d.H / d.stride; p.Wo = d.W / d.stride; p.Cout = d.Cout; p.cout_pad = conv_cout_pad(d.Cout);
-  p.Wt = pow2_divisor(p.Wo, kConvBlockM);
-  p.Ht = pow2_divisor(p.Ho, kConvBlockM / p.Wt);
-  p.Nt = kConvBlockM / (p.Wt * p.Ht);
-  p.w_blks = p.Wo / p.Wt; p.h_blks = p.Ho / p.Ht; p.n_blks = (d.N + p.Nt - 1) / p.Nt;
-  p.block_n = p.cout_pad <= 16 ? 16 : (p.cout_pad % 128 == 0 ? 128 : 64);
-  // few output tiles (low-resolution levels): halve the N tile to double the number of CTAs
-  if (p.block_n == 128 && p.w_blks * p.h_blks * p.n_blks * (p.cout_pad / 128) < kNumSMs) p.block_n = 64;
+  const ConvGeom g = conv_geometry(d.N, p.Ho, p.Wo, d.Cout);
+  p.Wt = g.Wt; p.Ht = g.Ht; p.Nt = g.Nt; p.w_blks = g.w_blks; p.h_blks = g.h_blks; p.n_blks = g.n_blks;
+  p.block_n = g.block_n;
+  B2E_REQUIRE(!d.tile_stats || (g.stats_ok && d.out_bf16), B2E_UNSUPPORTED_SHAPE,
+              "conv: fused GroupNorm statistics are not available for this output shape");
+  p.tile_stats = d.tile_stats;
   p.taps = d.ksize * d.ksize;
   p.c0_chunks = d.s0.C / K;
   p.c1_chunks = d.s1.ptr ? d.s1.C / K : 0;
@@ -574,12 +631,13 @@ int conv_launch(const ConvPlan& pl, const ConvEpilogue& ep, cudaStream_t st) {
   kp.n_tiles = pl.cout_pad / pl.block_n;
   kp.bias = ep.bias; kp.bias2 = ep.bias2; kp.temb = ep.temb; kp.temb_stride = ep.temb_stride;
   kp.out_bf16 = pl.has_out_bf16; kp.out_f32_nchw = pl.has_out_bf16 ? nullptr : ep.out_f32_nchw;
+  kp.tile_stats = pl.tile_stats;
   const int grid = pl.w_blks * pl.h_blks * pl.n_blks * kp.n_tiles;
   kp.num_tiles = grid;
   switch (pl.block_n) {
     case 16: return launch_t<16, 8>(pl, kp, grid, st);
     case 64: return launch_t<64, 8>(pl, kp, grid, st);
-    default: return launch_t<128, 6>(pl, kp, grid, st);
+    default: return launch_t<128, 5>(pl, kp, grid, st);
   }
 }
 

@@ -29,6 +29,9 @@ struct ConvDesc {
   const bf16* w_packed = nullptr;  // bf16 [cout_pad][row_len], row_len = k*k*(C0+C1) + Cr0 + Cr1
   int Cout = 0;
   bf16* out_bf16 = nullptr;  // NHWC (N,Ho,Wo,Cout) through TMA store; null -> fp32 NCHW output only
+  // optional fused GroupNorm statistics of the (bf16-rounded) output: per (tile slot, channel) sum and
+  // sum of squares, [conv_stats_slots()][Cout][2] floats; reduced per image by gn_finalize
+  float* tile_stats = nullptr;
 };
 
 struct ConvEpilogue {
@@ -48,11 +51,16 @@ struct ConvPlan {
   int tap_dc[9], tap_dw[9], tap_da[9], tap_dh[9];
   int block_n;  // 16, 64 or 128
   int has_out_bf16;
+  float* tile_stats;
   double flops;
 };
 
 int conv_plan_build(ConvPlan* plan, const ConvDesc& d);
 int conv_cout_pad(int Cout);
+// Tile geometry of an (N,Ho,Wo,Cout) output and whether the epilogue can emit GroupNorm statistics for it.
+struct ConvGeom { int Wt, Ht, Nt, w_blks, h_blks, n_blks, block_n, stats_ok; };
+ConvGeom conv_geometry(int N, int Ho, int Wo, int Cout);
+inline int64_t conv_stats_slots(const ConvGeom& g) { return (int64_t)g.w_blks * g.h_blks * g.n_blks * g.Nt; }
 int conv_launch(const ConvPlan& plan, const ConvEpilogue& ep, cudaStream_t st);
 
 // fp32 [Cout][Cin][k][k] -> bf16 out[co*row_len + col_off + t*tap_width + ci]   (t = kh*k + kw)

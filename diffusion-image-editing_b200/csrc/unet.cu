@@ -32,7 +32,10 @@ struct AttnL { std::string name; int C = 0; NormL gn; ConvL qkv, proj; };
 enum NodeKind { N_RESNET, N_ATTN, N_DOWN, N_UP, N_PUSH, N_POPCAT };
 struct Node { NodeKind kind; int idx; };
 
-struct Tensor { bf16* p = nullptr; int N = 0, H = 0, W = 0, C = 0; size_t bytes = 0; };
+struct Tensor {
+  bf16* p = nullptr; int N = 0, H = 0, W = 0, C = 0; size_t bytes = 0;
+  float* cstats = nullptr;  // per-(image, channel) sum / sum of squares from the producing conv's epilogue
+};
 
 struct Arena {
   char* base = nullptr; size_t cap = 0, off = 0, peak = 0;
@@ -256,7 +259,11 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
     t.p = (bf16*)ar.alloc(t.bytes);
     return t;
   };
-  auto tfree = [&](Tensor& t) { if (t.p) ar.release(t.p, t.bytes); t.p = nullptr; };
+  auto tfree = [&](Tensor& t) {
+    if (t.p) ar.release(t.p, t.bytes);
+    if (t.cstats) ar.release(t.cstats, sizeof(float) * 2 * t.N * t.C);
+    t.p = nullptr; t.cstats = nullptr;
+  };
   const int G = c.norm_num_groups;
   const int S = c.sample_size;
   // per-forward scratch
@@ -265,11 +272,23 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
   float* gn_part = (float*)ar.alloc(sizeof(float) * B * 64 * G * 2);
 
   auto conv = [&](const ConvL& L, Tensor x0, const Tensor* x1, int stride, ConvEpilogue ep, Tensor* out, float* out_nchw,
-                  const Tensor* r0 = nullptr, const Tensor* r1 = nullptr) {
+                  const Tensor* r0 = nullptr, const Tensor* r1 = nullptr, bool want_stats = true) {
     if (rc) return;
     const int Ho = x0.H / stride, Wo = x0.W / stride;
     if (out) *out = talloc(B, Ho, Wo, L.cout);
-    if (dry) { flops += 2.0 * B * Ho * Wo * (double)L.cout * (L.k * L.k * (x0.C + (x1 ? x1->C : 0)) + L.res_c); return; }
+    // GroupNorm statistics of the output, emitted by the epilogue (the consumer skips its statistics pass)
+    const ConvGeom geo = conv_geometry(B, Ho, Wo, L.cout);
+    float* tstats = nullptr;
+    const size_t tstats_bytes = sizeof(float) * 2 * (size_t)conv_stats_slots(geo) * L.cout;
+    if (out && want_stats && geo.stats_ok) {
+      tstats = (float*)ar.alloc(tstats_bytes);
+      out->cstats = (float*)ar.alloc(sizeof(float) * 2 * B * L.cout);
+    }
+    if (dry) {
+      flops += 2.0 * B * Ho * Wo * (double)L.cout * (L.k * L.k * (x0.C + (x1 ? x1->C : 0)) + L.res_c);
+      if (tstats) ar.release(tstats, tstats_bytes);
+      return;
+    }
     ConvDesc d;
     d.s0 = ConvSrc{x0.p, x0.C};
     if (x1) d.s1 = ConvSrc{x1->p, x1->C};
@@ -277,6 +296,7 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
     if (r1) d.r1 = ConvSrc{r1->p, r1->C};
     d.N = B; d.H = x0.H; d.W = x0.W; d.ksize = L.k; d.stride = stride; d.w_packed = L.w; d.Cout = L.cout;
     d.out_bf16 = out ? out->p : nullptr;
+    d.tile_stats = tstats;
     if (L.res_c != (r0 ? r0->C : 0) + (r1 ? r1->C : 0)) { rc = B2E_INVALID_ARG; set_error("unet: residual segment mismatch"); return; }
     ConvPlan pl;
     rc = conv_plan_build(&pl, d);
@@ -291,6 +311,14 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
     } else {
       ops.push_back({[pl, ep](cudaStream_t st) { return conv_launch(pl, ep, st); }, 0, pl.flops, 0.0});
     }
+    if (tstats) {
+      float* cst = out->cstats;
+      const int C = L.cout;
+      ops.push_back({[tstats, cst, B, C, geo](cudaStream_t st) {
+                       return gn_finalize_launch(tstats, cst, B, C, geo.Nt, geo.w_blks, geo.h_blks, st);
+                     }, 3, 0.0, (double)tstats_bytes});
+      ar.release(tstats, tstats_bytes);   // dead after the finalize kernel (stream order)
+    }
   };
   auto gnorm = [&](const NormL& L, Tensor x0, const Tensor* x1, int silu, Tensor* out) {
     if (rc) return;
@@ -301,8 +329,11 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
     a.x0 = x0.p; a.x1 = x1 ? x1->p : nullptr; a.C0 = x0.C; a.C1 = x1 ? x1->C : 0;
     a.N = B; a.HW = x0.H * x0.W; a.G = G; a.eps = c.norm_eps; a.gamma = L.g; a.beta = L.b;
     a.partial = gn_part; a.chunks = gn_chunks(a.HW, C); a.out = out->p; a.silu = silu;
+    const bool fused = x0.cstats && (!x1 || x1->cstats);
+    a.cs0 = fused ? x0.cstats : nullptr;
+    a.cs1 = fused && x1 ? x1->cstats : nullptr;
     // algorithmic traffic: statistics pass reads x, apply pass reads x and writes y (bf16)
-    ops.push_back({[a](cudaStream_t st) { return gn_launch(a, st); }, 1, 0.0, 6.0 * B * a.HW * C});
+    ops.push_back({[a](cudaStream_t st) { return gn_launch(a, st); }, 1, 0.0, (fused ? 4.0 : 6.0) * B * a.HW * C});
   };
 
   // ---- prologue: input packing, timestep embedding
@@ -355,7 +386,7 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
         const AttnL& a = m->attns[nd.idx];
         Tensor an, qkv, o, out;
         gnorm(a.gn, h, nullptr, 0, &an);
-        conv(a.qkv, an, nullptr, 1, ConvEpilogue{}, &qkv, nullptr);
+        conv(a.qkv, an, nullptr, 1, ConvEpilogue{}, &qkv, nullptr, nullptr, nullptr, false);
         tfree(an);
         o = talloc(B, h.H, h.W, a.C);
         const int heads = c.attention_head_dim > 0 ? a.C / c.attention_head_dim : 1;

@@ -81,9 +81,17 @@ __global__ void __launch_bounds__(kGNThreads) gn_apply_kernel(GNArgs a, int pix_
   const int cpg = C / a.G;
   if (tid < a.G) {
     double ts = 0.0, tq = 0.0;
-    for (int ch = 0; ch < a.chunks; ++ch) {
-      const float* o = a.partial + (((int64_t)n * a.chunks + ch) * a.G + tid) * 2;
-      ts += (double)o[0]; tq += (double)o[1];
+    if (a.cs0) {
+      // per-channel sums from the producing convolutions' epilogues (concat-aware)
+      for (int c = tid * cpg; c < (tid + 1) * cpg; ++c) {
+        const float* o = c < a.C0 ? a.cs0 + ((int64_t)n * a.C0 + c) * 2 : a.cs1 + ((int64_t)n * a.C1 + (c - a.C0)) * 2;
+        ts += (double)o[0]; tq += (double)o[1];
+      }
+    } else {
+      for (int ch = 0; ch < a.chunks; ++ch) {
+        const float* o = a.partial + (((int64_t)n * a.chunks + ch) * a.G + tid) * 2;
+        ts += (double)o[0]; tq += (double)o[1];
+      }
     }
     const double cnt = (double)a.HW * cpg;
     const double mean = ts / cnt;
@@ -124,7 +132,13 @@ __global__ void __launch_bounds__(kGNThreads) gn_apply_kernel(GNArgs a, int pix_
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float y = fmaf(f[j], scale[j], shift[j]);
-          if (a.silu) y = __fdividef(y, 1.f + __expf(-y));
+          if (a.silu) {
+            // y*sigmoid(y) = 0.5y + 0.5y*tanh(0.5y): one MUFU op per element
+            const float hy = 0.5f * y;
+            float th;
+            asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(hy));
+            y = fmaf(hy, th, hy);
+          }
           f[j] = y;
         }
         *reinterpret_cast<uint4*>(dst + (int64_t)q * C) = pack8(f);
@@ -146,14 +160,53 @@ int gn_launch(const GNArgs& a, cudaStream_t st) {
   const int C = a.C0 + a.C1;
   B2E_REQUIRE(C % 8 == 0 && a.C0 % 8 == 0 && C <= 1024 && a.G <= 64 && C % a.G == 0, B2E_UNSUPPORTED_SHAPE,
               "groupnorm: unsupported channels %d+%d / groups %d", a.C0, a.C1, a.G);
-  gn_partial_kernel<<<dim3(a.chunks, a.N), kGNThreads, 0, st>>>(a);
-  int rc = check_launch("gn_partial");
-  if (rc) return rc;
+  int rc = B2E_OK;
+  if (!a.cs0) {
+    gn_partial_kernel<<<dim3(a.chunks, a.N), kGNThreads, 0, st>>>(a);
+    rc = check_launch("gn_partial");
+    if (rc) return rc;
+  }
   const int slots = C / 8, ppi = kGNThreads / slots;
   int ppb = ppi * kGNUnroll * 2;  // two unrolled sweeps per thread
   if (ppb > a.HW) ppb = a.HW;
   gn_apply_kernel<<<dim3((a.HW + ppb - 1) / ppb, a.N), kGNThreads, 0, st>>>(a, ppb);
   return check_launch("gn_apply");
+}
+
+// block = 16 channels x 16 slot lanes: every thread sums a strided subset of the image's tile slots
+// (independent loads in flight), then the 16 slot lanes are combined in a fixed order through smem.
+__global__ void __launch_bounds__(256)
+gn_finalize_kernel(const float* __restrict__ tile_stats, float* __restrict__ chan_stats, int C, int Nt, int w_blks,
+                   int h_blks) {
+  __shared__ double s_s[16][16], s_q[16][16];
+  const int cl = threadIdx.x & 15, sl = threadIdx.x >> 4;
+  const int c = blockIdx.x * 16 + cl, n = blockIdx.y;
+  const int n_blk = n / Nt, nl = n % Nt;
+  const int per_img = h_blks * w_blks;
+  double s = 0.0, q = 0.0;
+  if (c < C) {
+    const int64_t base = (int64_t)n_blk * per_img;
+#pragma unroll 8
+    for (int i = sl; i < per_img; i += 16) {
+      const int64_t slot = (base + i) * Nt + nl;
+      const float2 v = __ldg(reinterpret_cast<const float2*>(tile_stats + (slot * C + c) * 2));
+      s += (double)v.x; q += (double)v.y;
+    }
+  }
+  s_s[sl][cl] = s; s_q[sl][cl] = q;
+  __syncthreads();
+  if (sl == 0 && c < C) {
+    double ts = 0.0, tq = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { ts += s_s[i][cl]; tq += s_q[i][cl]; }
+    *reinterpret_cast<float2*>(chan_stats + ((int64_t)n * C + c) * 2) = make_float2((float)ts, (float)tq);
+  }
+}
+
+int gn_finalize_launch(const float* tile_stats, float* chan_stats, int N, int C, int Nt, int w_blks, int h_blks,
+                       cudaStream_t st) {
+  gn_finalize_kernel<<<dim3((C + 15) / 16, N), 256, 0, st>>>(tile_stats, chan_stats, C, Nt, w_blks, h_blks);
+  return check_launch("gn_finalize");
 }
 
 // ------------------------------------------------------------------ layout helpers

@@ -13,13 +13,17 @@ struct GNArgs {
   int N, HW, G;
   float eps;
   const float* gamma; const float* beta;
-  float* partial;  // [N][chunks][G][2]
+  float* partial;  // [N][chunks][G][2]   (statistics pass; unused when cs0 is given)
+  const float* cs0; const float* cs1;  // per-channel (sum, sumsq) of x0 / x1, [N][C][2], from the conv epilogue
   int chunks;
   bf16* out;       // [N][HW][C0+C1]
   int silu;
 };
 int gn_chunks(int HW, int C);
 int gn_launch(const GNArgs& a, cudaStream_t st);
+// tile statistics written by the conv epilogue -> per-(image, channel) sums
+int gn_finalize_launch(const float* tile_stats, float* chan_stats, int N, int C, int Nt, int w_blks, int h_blks,
+                       cudaStream_t st);
 
 // x fp32 NCHW (B,C,S,S) -> bf16 NHWC (B,S,S,cpad), zero padded channels
 int pack_input_launch(const float* x, bf16* out, int B, int C, int HW, int cpad, cudaStream_t st);
