@@ -30,9 +30,13 @@ constexpr int kABytes = kConvBlockM * kConvBlockK * 2;  // 16 KB
 
 // One persistent CTA per SM; STAGES x (A 16 KB + B) fills the ~190 KB of shared memory it can use, so
 // enough TMA loads are in flight to cover the load round trip (small grids are latency-bound).
-template <int BN, int STAGES>
+// PAIR: two CTAs of a cluster (an SM pair) run ONE tcgen05.mma.cta_group::2 of shape 256 x BN x 16: each CTA
+// stages its own 128 output pixels of A and only HALF of the B tile, so a stage is 24 KB instead of 32 KB
+// for the same tensor work - the main loop needs 25 % fewer bytes in flight / from L2 per FLOP.
+template <int BN, int STAGES, bool PAIR = false>
 struct ConvCfg {
-  static constexpr int kBBytes = BN * kConvBlockK * 2;
+  static constexpr int kBRows = PAIR ? BN / 2 : BN;             // B rows staged by this CTA
+  static constexpr int kBBytes = kBRows * kConvBlockK * 2;
   static constexpr int kBBytesPad = (kBBytes + 1023) / 1024 * 1024;
   static constexpr int kStageBytes = kABytes + kBBytesPad;
   static constexpr int kStages = STAGES;
@@ -48,7 +52,7 @@ struct ConvKParams {
   int Wt, Ht, Nt, w_blks, h_blks;
   int taps, c0_chunks, c1_chunks, r0_chunks, r1_chunks;
   int tap_dc[9], tap_dw[9], tap_da[9], tap_dh[9];
-  int n_tiles, num_tiles;
+  int n_tiles, num_tiles;   // PAIR kernels: num_tiles counts tile PAIRS (two adjacent M tiles, same N tile)
   const float* bias;
   const float* bias2;
   const float* temb;
@@ -114,6 +118,68 @@ __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.b
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// ---- cta_group::2 (SM pair) variants: TMA completion, MMA commits and accumulator hand-back all target
+// barriers of the LEADER CTA (rank 0); clearing bit 24 of a shared::cluster address selects rank 0's copy.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_5d_2sm(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                                int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+      "r"(c4), "l"(kEvictNormal)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "l"(kEvictNormal)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  const uint32_t z = 0;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(z)
+      : "memory");
+}
+// arrive on the same barrier offset in BOTH CTAs of the pair once the MMAs issued so far retire
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -181,10 +247,12 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 // i+1, and the TMA producer runs ahead across tile boundaries (the smem ring never drains).
 struct TileCoord { int n_tile, m_tile, w0, h0, n0; };
 
-__device__ __forceinline__ TileCoord tile_coord(const ConvKParams& p, int tile) {
+// pair kernels: `tile` indexes a pair of adjacent M tiles; this CTA takes M tile 2*(tile / n_tiles) + rank
+__device__ __forceinline__ TileCoord tile_coord(const ConvKParams& p, int tile, int pair = 0, int rank = 0) {
   TileCoord t;
   t.n_tile = tile % p.n_tiles;
   int m = tile / p.n_tiles;
+  if (pair) m = 2 * m + rank;
   t.m_tile = m;
   t.w0 = (m % p.w_blks) * p.Wt; m /= p.w_blks;
   t.h0 = (m % p.h_blks) * p.Ht;
@@ -192,13 +260,13 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvKParams& p, int tile) 
   return t;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool PAIR>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                   const __grid_constant__ CUtensorMap map_r0, const __grid_constant__ CUtensorMap map_r1,
                   const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out,
                   const __grid_constant__ ConvKParams p) {
-  using Cfg = ConvCfg<BN, STAGES>;
+  using Cfg = ConvCfg<BN, STAGES, PAIR>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* staging = smem + Cfg::kStages * Cfg::kStageBytes;
@@ -210,6 +278,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;      // 0 = leader CTA of the SM pair
+  const int tile_begin = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int chunks = p.c0_chunks + p.c1_chunks;
   const int r_chunks = p.r0_chunks + p.r1_chunks;
   const int num_kb = p.taps * chunks + r_chunks;
@@ -222,12 +293,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     prefetch_tmap(&map_b);
     if (p.out_bf16) prefetch_tmap(&map_out);
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar + s, 1); mbar_init(tmem_empty_bar + s, 4); }
+    // pair: the leader's tmem_empty barrier collects the 4 epilogue warps of BOTH CTAs
+    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar + s, 1); mbar_init(tmem_empty_bar + s, PAIR ? 8 : 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_2sm<Cfg::kTmemCols>(tmem_slot); else tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // peer barriers are initialised before any remote arrive / TMA completion
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -235,45 +310,51 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     // ===== TMA producer (one thread)
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const TileCoord tc = tile_coord(p, tile);
+      // one k-block: this CTA's A brick + its share of the B tile (pair: both CTAs complete on the leader's barrier)
+      auto load_kb = [&](const CUtensorMap* ma, int c0, int c1, int c2, int c3, int c4, int kcol, int brow) {
+        mbar_wait(empty_bar + stage, phase ^ 1);
+        uint8_t* sa = smem + stage * Cfg::kStageBytes;
+        uint8_t* sb = sa + kABytes;
+        if (PAIR) {
+          if (rank == 0) mbar_expect_tx(full_bar + stage, 2 * (kABytes + Cfg::kBBytes));
+          tma_load_5d_2sm(sa, ma, full_bar + stage, c0, c1, c2, c3, c4);
+          tma_load_2d_2sm(sb, &map_b, full_bar + stage, kcol, brow + rank * Cfg::kBRows);
+        } else {
+          mbar_expect_tx(full_bar + stage, kABytes + Cfg::kBBytes);
+          tma_load_5d(sa, ma, full_bar + stage, c0, c1, c2, c3, c4);
+          tma_load_2d(sb, &map_b, full_bar + stage, kcol, brow);
+        }
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      };
+      for (int tile = tile_begin; tile < p.num_tiles; tile += tile_step) {
+        const TileCoord tc = tile_coord(p, tile, PAIR, rank);
         for (int tap = 0; tap < p.taps; ++tap) {
           const int cw = tc.w0 + p.tap_dw[tap], ch = tc.h0 + p.tap_dh[tap], ca = p.tap_da[tap], cc = p.tap_dc[tap];
           for (int ck = 0; ck < chunks; ++ck) {
-            mbar_wait(empty_bar + stage, phase ^ 1);
-            uint8_t* sa = smem + stage * Cfg::kStageBytes;
-            uint8_t* sb = sa + kABytes;
-            mbar_expect_tx(full_bar + stage, kABytes + Cfg::kBBytes);
             if (ck < p.c0_chunks)
-              tma_load_5d(sa, &map_a0, full_bar + stage, cc + ck * kConvBlockK, cw, ca, ch, tc.n0);
+              load_kb(&map_a0, cc + ck * kConvBlockK, cw, ca, ch, tc.n0, (tap * chunks + ck) * kConvBlockK, tc.n_tile * BN);
             else
-              tma_load_5d(sa, &map_a1, full_bar + stage, cc + (ck - p.c0_chunks) * kConvBlockK, cw, ca, ch, tc.n0);
-            tma_load_2d(sb, &map_b, full_bar + stage, (tap * chunks + ck) * kConvBlockK, tc.n_tile * BN);
-            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+              load_kb(&map_a1, cc + (ck - p.c0_chunks) * kConvBlockK, cw, ca, ch, tc.n0,
+                      (tap * chunks + ck) * kConvBlockK, tc.n_tile * BN);
           }
         }
         // residual segment: 1x1 at the output pixel
         for (int ck = 0; ck < r_chunks; ++ck) {
-          mbar_wait(empty_bar + stage, phase ^ 1);
-          uint8_t* sa = smem + stage * Cfg::kStageBytes;
-          uint8_t* sb = sa + kABytes;
-          mbar_expect_tx(full_bar + stage, kABytes + Cfg::kBBytes);
           if (ck < p.r0_chunks)
-            tma_load_5d(sa, &map_r0, full_bar + stage, ck * kConvBlockK, tc.w0, 0, tc.h0, tc.n0);
+            load_kb(&map_r0, ck * kConvBlockK, tc.w0, 0, tc.h0, tc.n0, (p.taps * chunks + ck) * kConvBlockK, tc.n_tile * BN);
           else
-            tma_load_5d(sa, &map_r1, full_bar + stage, (ck - p.r0_chunks) * kConvBlockK, tc.w0, 0, tc.h0, tc.n0);
-          tma_load_2d(sb, &map_b, full_bar + stage, (p.taps * chunks + ck) * kConvBlockK, tc.n_tile * BN);
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+            load_kb(&map_r1, (ck - p.r0_chunks) * kConvBlockK, tc.w0, 0, tc.h0, tc.n0,
+                    (p.taps * chunks + ck) * kConvBlockK, tc.n_tile * BN);
         }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (one thread)
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(kConvBlockM, BN);
+    if (lane == 0 && rank == 0) {   // pair: only the leader issues (for both SMs)
+      constexpr uint32_t idesc = make_idesc(PAIR ? 2 * kConvBlockM : kConvBlockM, BN);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = tile_begin; tile < p.num_tiles; tile += tile_step, ++it) {
         const int acc = it & 1;
         mbar_wait(tmem_empty_bar + acc, ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
@@ -287,12 +368,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
 #pragma unroll
           for (int k = 0; k < kConvBlockK / 16; ++k) {
             // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in the (addr >> 4) field
-            umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            if (PAIR) umma_bf16_2sm(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            else umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
           }
-          umma_commit(empty_bar + stage);  // frees this smem stage once the MMAs above retire
+          // frees this smem stage (in both CTAs of a pair) once the MMAs above retire
+          if (PAIR) umma_commit_2sm(empty_bar + stage); else umma_commit(empty_bar + stage);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(tmem_full_bar + acc);  // accumulator complete
+        // accumulator complete (pair: rows 0-127 in the leader's TMEM, 128-255 in the peer's)
+        if (PAIR) umma_commit_2sm(tmem_full_bar + acc); else umma_commit(tmem_full_bar + acc);
       }
     }
   } else {
@@ -302,8 +386,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     const int w_l = r % p.Wt, h_l = (r / p.Wt) % p.Ht, n_l = r / (p.Wt * p.Ht);
     const bool store_leader = (warp == 2 && lane == 0);
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      const TileCoord tc = tile_coord(p, tile);
+    for (int tile = tile_begin; tile < p.num_tiles; tile += tile_step, ++it) {
+      const TileCoord tc = tile_coord(p, tile, PAIR, rank);
       const int acc = it & 1;
       const int n = tc.n0 + n_l, h = tc.h0 + h_l, w = tc.w0 + w_l;
       const bool valid = n < p.N;
@@ -323,7 +407,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           // all of this warp's accumulator columns are in registers: hand the buffer back
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tmem_empty_bar + acc);
+          if (lane == 0) { if (PAIR) mbar_arrive_leader(tmem_empty_bar + acc); else mbar_arrive(tmem_empty_bar + acc); }
         }
         const int col0 = tc.n_tile * BN + c * 16;
         if (Cfg::kSlabs > 0 && p.out_bf16) {
@@ -432,9 +516,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     tc_fence_before();
   }
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // no CTA leaves while its peer may still signal its barriers / read its smem
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if (PAIR) tmem_dealloc_2sm<Cfg::kTmemCols>(tmem_base); else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 
@@ -597,23 +682,38 @@ int conv_plan_build(ConvPlan* pl, const ConvDesc& d) {
                         (d.r1.ptr ? d.r1.C : 0);
   uint64_t bd[2] = {ktot, (uint64_t)p.cout_pad};
   uint64_t bs[1] = {ktot * 2};
-  uint32_t bb[2] = {(uint32_t)K, (uint32_t)p.block_n};
+  // SM-pair mode: 128-wide N tiles and an even number of M tiles (each CTA stages half of the B rows)
+  p.pair = (p.block_n == 128 && ((p.w_blks * p.h_blks * p.n_blks) % 2 == 0)) ? 1 : 0;
+  uint32_t bb[2] = {(uint32_t)K, (uint32_t)(p.pair ? p.block_n / 2 : p.block_n)};
   rc = encode_map(&p.map_b, d.w_packed, 2, bd, bs, bb);
   if (rc) return rc;
   p.flops = 2.0 * d.N * p.Ho * p.Wo * (double)d.Cout * (double)ktot;
   return B2E_OK;
 }
 
-template <int BN, int STAGES>
-static int launch_t(const ConvPlan& pl, const ConvKParams& kp, int grid, cudaStream_t st) {
+template <int BN, int STAGES, bool PAIR>
+static int launch_t(const ConvPlan& pl, const ConvKParams& kp, int tiles, cudaStream_t st) {
+  using Cfg = ConvCfg<BN, STAGES, PAIR>;
+  static_assert(Cfg::kSmemBytes <= 227 * 1024, "shared memory budget");
   static bool attr_set = false;
   if (!attr_set) {
-    B2E_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  ConvCfg<BN, STAGES>::kSmemBytes));
+    B2E_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Cfg::kSmemBytes));
     attr_set = true;
   }
-  conv_igemm_kernel<BN, STAGES><<<grid < kNumSMs ? grid : kNumSMs, kConvThreads, ConvCfg<BN, STAGES>::kSmemBytes, st>>>(
-      pl.map_a0, pl.map_a1, pl.map_r0, pl.map_r1, pl.map_b, pl.map_out, kp);
+  cudaLaunchConfig_t cfg = {};
+  const int units = PAIR ? kNumSMs / 2 : kNumSMs;   // tiles (or tile pairs) in flight
+  cfg.gridDim = dim3((unsigned)((tiles < units ? tiles : units) * (PAIR ? 2 : 1)));
+  cfg.blockDim = dim3(kConvThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BN, STAGES, PAIR>, pl.map_a0, pl.map_a1, pl.map_r0,
+                                     pl.map_r1, pl.map_b, pl.map_out, kp);
+  if (e != cudaSuccess) { set_error("conv_igemm launch: %s", cudaGetErrorString(e)); return B2E_CUDA_ERROR; }
   return check_launch("conv_igemm");
 }
 
@@ -633,11 +733,12 @@ int conv_launch(const ConvPlan& pl, const ConvEpilogue& ep, cudaStream_t st) {
   kp.out_bf16 = pl.has_out_bf16; kp.out_f32_nchw = pl.has_out_bf16 ? nullptr : ep.out_f32_nchw;
   kp.tile_stats = pl.tile_stats;
   const int grid = pl.w_blks * pl.h_blks * pl.n_blks * kp.n_tiles;
-  kp.num_tiles = grid;
+  kp.num_tiles = pl.pair ? grid / 2 : grid;
   switch (pl.block_n) {
-    case 16: return launch_t<16, 8>(pl, kp, grid, st);
-    case 64: return launch_t<64, 8>(pl, kp, grid, st);
-    default: return launch_t<128, 5>(pl, kp, grid, st);
+    case 16: return launch_t<16, 8, false>(pl, kp, kp.num_tiles, st);
+    case 64: return launch_t<64, 8, false>(pl, kp, kp.num_tiles, st);
+    default: return pl.pair ? launch_t<128, 7, true>(pl, kp, kp.num_tiles, st)
+                            : launch_t<128, 5, false>(pl, kp, kp.num_tiles, st);
   }
 }
 

@@ -50,6 +50,7 @@ struct ConvPlan {
   int taps, c0_chunks, c1_chunks, r0_chunks, r1_chunks;
   int tap_dc[9], tap_dw[9], tap_da[9], tap_dh[9];
   int block_n;  // 16, 64 or 128
+  int pair;     // 1: SM-pair kernel (tcgen05.mma.cta_group::2, 256 x 128 tile per cluster)
   int has_out_bf16;
   float* tile_stats;
   double flops;
