@@ -52,6 +52,7 @@ struct ConvKParams {
   int Wt, Ht, Nt, w_blks, h_blks;
   int taps, c0_chunks, c1_chunks, r0_chunks, r1_chunks;
   int tap_dc[9], tap_dw[9], tap_da[9], tap_dh[9];
+  int b_batch_rows;         // rows of B per image (attention GEMMs), 0 for shared weights
   int n_tiles, num_tiles;   // PAIR kernels: num_tiles counts tile PAIRS (two adjacent M tiles, same N tile)
   const float* bias;
   const float* bias2;
@@ -328,23 +329,24 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       };
       for (int tile = tile_begin; tile < p.num_tiles; tile += tile_step) {
         const TileCoord tc = tile_coord(p, tile, PAIR, rank);
+        const int brow0 = tc.n_tile * BN + tc.n0 * p.b_batch_rows;   // per-image B rows for batched GEMMs (Nt == 1)
         for (int tap = 0; tap < p.taps; ++tap) {
           const int cw = tc.w0 + p.tap_dw[tap], ch = tc.h0 + p.tap_dh[tap], ca = p.tap_da[tap], cc = p.tap_dc[tap];
           for (int ck = 0; ck < chunks; ++ck) {
             if (ck < p.c0_chunks)
-              load_kb(&map_a0, cc + ck * kConvBlockK, cw, ca, ch, tc.n0, (tap * chunks + ck) * kConvBlockK, tc.n_tile * BN);
+              load_kb(&map_a0, cc + ck * kConvBlockK, cw, ca, ch, tc.n0, (tap * chunks + ck) * kConvBlockK, brow0);
             else
               load_kb(&map_a1, cc + (ck - p.c0_chunks) * kConvBlockK, cw, ca, ch, tc.n0,
-                      (tap * chunks + ck) * kConvBlockK, tc.n_tile * BN);
+                      (tap * chunks + ck) * kConvBlockK, brow0);
           }
         }
         // residual segment: 1x1 at the output pixel
         for (int ck = 0; ck < r_chunks; ++ck) {
           if (ck < p.r0_chunks)
-            load_kb(&map_r0, ck * kConvBlockK, tc.w0, 0, tc.h0, tc.n0, (p.taps * chunks + ck) * kConvBlockK, tc.n_tile * BN);
+            load_kb(&map_r0, ck * kConvBlockK, tc.w0, 0, tc.h0, tc.n0, (p.taps * chunks + ck) * kConvBlockK, brow0);
           else
             load_kb(&map_r1, (ck - p.r0_chunks) * kConvBlockK, tc.w0, 0, tc.h0, tc.n0,
-                    (p.taps * chunks + ck) * kConvBlockK, tc.n_tile * BN);
+                    (p.taps * chunks + ck) * kConvBlockK, brow0);
         }
       }
     }
@@ -618,14 +620,15 @@ ConvGeom conv_geometry(int N, int Ho, int Wo, int Cout) {
 
 // (C, W, 1, H, N) view of an NHWC tensor (stride 1) or (2C, W/2, 2, H/2, N) (stride 2), box = one tile brick
 static int encode_act_map(CUtensorMap* m, const bf16* ptr, int N, int H, int W, int C, int stride,
-                          int Wt, int Ht, int Nt) {
+                          int Wt, int Ht, int Nt, int pitch = 0) {
   const uint64_t e = 2;
   uint64_t dims[5], str[4];
   uint32_t box[5] = {(uint32_t)kConvBlockK, (uint32_t)Wt, 1, (uint32_t)Ht, (uint32_t)Nt};
   if (stride == 1) {
+    const uint64_t P = pitch ? pitch : C;   // pixel pitch in elements (channel window of a wider tensor)
     dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = N;
-    str[0] = (uint64_t)C * e; str[1] = (uint64_t)W * C * e; str[2] = (uint64_t)W * C * e;
-    str[3] = (uint64_t)H * W * C * e;
+    str[0] = P * e; str[1] = (uint64_t)W * P * e; str[2] = (uint64_t)W * P * e;
+    str[3] = (uint64_t)H * W * P * e;
   } else {
     dims[0] = 2 * (uint64_t)C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = N;
     str[0] = 2 * (uint64_t)C * e; str[1] = (uint64_t)W * C * e; str[2] = 2 * (uint64_t)W * C * e;
@@ -670,7 +673,9 @@ int conv_plan_build(ConvPlan* pl, const ConvDesc& d) {
       p.tap_dc[t] = (kw & 1) * d.s0.C; p.tap_dw[t] = kw >> 1; p.tap_da[t] = kh & 1; p.tap_dh[t] = kh >> 1;
     }
   }
-  int rc = encode_act_map(&p.map_a0, d.s0.ptr, d.N, d.H, d.W, d.s0.C, d.stride, p.Wt, p.Ht, p.Nt);
+  B2E_REQUIRE(d.stride == 1 || !d.s0.pitch, B2E_UNSUPPORTED_SHAPE, "conv: pitched input with stride 2");
+  B2E_REQUIRE(!d.b_batch_rows || p.Nt == 1, B2E_UNSUPPORTED_SHAPE, "conv: batched B needs tiles within one image");
+  int rc = encode_act_map(&p.map_a0, d.s0.ptr, d.N, d.H, d.W, d.s0.C, d.stride, p.Wt, p.Ht, p.Nt, d.s0.pitch);
   if (rc) return rc;
   p.map_a1 = p.map_a0; p.map_r0 = p.map_a0; p.map_r1 = p.map_a0; p.map_out = p.map_a0;
   if (d.s1.ptr && (rc = encode_act_map(&p.map_a1, d.s1.ptr, d.N, d.H, d.W, d.s1.C, d.stride, p.Wt, p.Ht, p.Nt))) return rc;
@@ -680,8 +685,9 @@ int conv_plan_build(ConvPlan* pl, const ConvDesc& d) {
   if (d.out_bf16 && (rc = encode_act_map(&p.map_out, d.out_bf16, d.N, p.Ho, p.Wo, d.Cout, 1, p.Wt, p.Ht, p.Nt))) return rc;
   const uint64_t ktot = (uint64_t)p.taps * (d.s0.C + (d.s1.ptr ? d.s1.C : 0)) + (d.r0.ptr ? d.r0.C : 0) +
                         (d.r1.ptr ? d.r1.C : 0);
-  uint64_t bd[2] = {ktot, (uint64_t)p.cout_pad};
-  uint64_t bs[1] = {ktot * 2};
+  uint64_t bd[2] = {ktot, d.b_batch_rows ? (uint64_t)d.N * d.b_batch_rows : (uint64_t)p.cout_pad};
+  uint64_t bs[1] = {(d.b_pitch ? (uint64_t)d.b_pitch : ktot) * 2};
+  p.b_batch_rows = d.b_batch_rows;
   // SM-pair mode: 128-wide N tiles and an even number of M tiles (each CTA stages half of the B rows)
   p.pair = (p.block_n == 128 && ((p.w_blks * p.h_blks * p.n_blks) % 2 == 0)) ? 1 : 0;
   uint32_t bb[2] = {(uint32_t)K, (uint32_t)(p.pair ? p.block_n / 2 : p.block_n)};
@@ -729,6 +735,7 @@ int conv_launch(const ConvPlan& pl, const ConvEpilogue& ep, cudaStream_t st) {
     kp.tap_dc[t] = pl.tap_dc[t]; kp.tap_dw[t] = pl.tap_dw[t]; kp.tap_da[t] = pl.tap_da[t]; kp.tap_dh[t] = pl.tap_dh[t];
   }
   kp.n_tiles = pl.cout_pad / pl.block_n;
+  kp.b_batch_rows = pl.b_batch_rows;
   kp.bias = ep.bias; kp.bias2 = ep.bias2; kp.temb = ep.temb; kp.temb_stride = ep.temb_stride;
   kp.out_bf16 = pl.has_out_bf16; kp.out_f32_nchw = pl.has_out_bf16 ? nullptr : ep.out_f32_nchw;
   kp.tile_stats = pl.tile_stats;

@@ -14,7 +14,8 @@ constexpr int kConvBlockK = 64;   // bf16 channels per pipeline stage (one 128B 
 
 struct ConvSrc {
   const bf16* ptr = nullptr;  // NHWC
-  int C = 0;
+  int C = 0;                  // channels used
+  int pitch = 0;              // elements between consecutive pixels (0: = C); > C selects a channel window
 };
 
 // y = conv_{k x k, stride}(x0 ++ x1)  [+ W_r (r0 ++ r1)]  + bias (+ bias2) (+ temb[n, :])
@@ -27,6 +28,9 @@ struct ConvDesc {
   int N = 0, H = 0, W = 0;
   int ksize = 3, stride = 1; // stride 1: padding ksize/2; stride 2: ksize 3, padding (0,1,0,1)
   const bf16* w_packed = nullptr;  // bf16 [cout_pad][row_len], row_len = k*k*(C0+C1) + Cr0 + Cr1
+  // batched B operand (attention: Q K^T and P V): image n uses rows [n*b_batch_rows, +Cout) of a
+  // [N*b_batch_rows][row_len] matrix whose rows are b_pitch elements apart (0: shared weights / dense rows)
+  int b_batch_rows = 0, b_pitch = 0;
   int Cout = 0;
   bf16* out_bf16 = nullptr;  // NHWC (N,Ho,Wo,Cout) through TMA store; null -> fp32 NCHW output only
   // optional fused GroupNorm statistics of the (bf16-rounded) output: per (tile slot, channel) sum and
@@ -50,6 +54,7 @@ struct ConvPlan {
   int taps, c0_chunks, c1_chunks, r0_chunks, r1_chunks;
   int tap_dc[9], tap_dw[9], tap_da[9], tap_dh[9];
   int block_n;  // 16, 64 or 128
+  int b_batch_rows;
   int pair;     // 1: SM-pair kernel (tcgen05.mma.cta_group::2, 256 x 128 tile per cluster)
   int has_out_bf16;
   float* tile_stats;

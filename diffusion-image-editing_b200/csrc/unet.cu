@@ -35,6 +35,8 @@ struct Node { NodeKind kind; int idx; };
 struct Tensor {
   bf16* p = nullptr; int N = 0, H = 0, W = 0, C = 0; size_t bytes = 0;
   float* cstats = nullptr;  // per-(image, channel) sum / sum of squares from the producing conv's epilogue
+  float* tstats = nullptr;  // small tensors: raw per-(tile slot, channel) statistics instead (no finalize kernel)
+  size_t tstats_bytes = 0; int ts_nt = 0, ts_per_img = 0;
 };
 
 struct Arena {
@@ -262,7 +264,8 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
   auto tfree = [&](Tensor& t) {
     if (t.p) ar.release(t.p, t.bytes);
     if (t.cstats) ar.release(t.cstats, sizeof(float) * 2 * t.N * t.C);
-    t.p = nullptr; t.cstats = nullptr;
+    if (t.tstats) ar.release(t.tstats, t.tstats_bytes);
+    t.p = nullptr; t.cstats = nullptr; t.tstats = nullptr;
   };
   const int G = c.norm_num_groups;
   const int S = c.sample_size;
@@ -280,13 +283,19 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
     const ConvGeom geo = conv_geometry(B, Ho, Wo, L.cout);
     float* tstats = nullptr;
     const size_t tstats_bytes = sizeof(float) * 2 * (size_t)conv_stats_slots(geo) * L.cout;
+    // few tile slots per image (low-resolution levels): the consumer reduces them itself
+    const bool raw_stats = geo.w_blks * geo.h_blks <= 16;
     if (out && want_stats && geo.stats_ok) {
       tstats = (float*)ar.alloc(tstats_bytes);
-      out->cstats = (float*)ar.alloc(sizeof(float) * 2 * B * L.cout);
+      if (raw_stats) {
+        out->tstats = tstats; out->tstats_bytes = tstats_bytes; out->ts_nt = geo.Nt; out->ts_per_img = geo.w_blks * geo.h_blks;
+      } else {
+        out->cstats = (float*)ar.alloc(sizeof(float) * 2 * B * L.cout);
+      }
     }
     if (dry) {
       flops += 2.0 * B * Ho * Wo * (double)L.cout * (L.k * L.k * (x0.C + (x1 ? x1->C : 0)) + L.res_c);
-      if (tstats) ar.release(tstats, tstats_bytes);
+      if (tstats && !raw_stats) ar.release(tstats, tstats_bytes);
       return;
     }
     ConvDesc d;
@@ -311,7 +320,7 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
     } else {
       ops.push_back({[pl, ep](cudaStream_t st) { return conv_launch(pl, ep, st); }, 0, pl.flops, 0.0});
     }
-    if (tstats) {
+    if (tstats && !raw_stats) {
       float* cst = out->cstats;
       const int C = L.cout;
       ops.push_back({[tstats, cst, B, C, geo](cudaStream_t st) {
@@ -329,9 +338,14 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
     a.x0 = x0.p; a.x1 = x1 ? x1->p : nullptr; a.C0 = x0.C; a.C1 = x1 ? x1->C : 0;
     a.N = B; a.HW = x0.H * x0.W; a.G = G; a.eps = c.norm_eps; a.gamma = L.g; a.beta = L.b;
     a.partial = gn_part; a.chunks = gn_chunks(a.HW, C); a.out = out->p; a.silu = silu;
-    const bool fused = x0.cstats && (!x1 || x1->cstats);
+    bool fused = x0.cstats && (!x1 || x1->cstats);
     a.cs0 = fused ? x0.cstats : nullptr;
     a.cs1 = fused && x1 ? x1->cstats : nullptr;
+    const bool raw = x0.tstats && (!x1 || (x1->tstats && x1->ts_nt == x0.ts_nt && x1->ts_per_img == x0.ts_per_img));
+    a.ts0 = raw ? x0.tstats : nullptr;
+    a.ts1 = raw && x1 ? x1->tstats : nullptr;
+    a.ts_nt = x0.ts_nt; a.ts_per_img = x0.ts_per_img;
+    if (raw) fused = true;
     // algorithmic traffic: statistics pass reads x, apply pass reads x and writes y (bf16)
     ops.push_back({[a](cudaStream_t st) { return gn_launch(a, st); }, 1, 0.0, (fused ? 4.0 : 6.0) * B * a.HW * C});
   };
@@ -390,12 +404,51 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
         tfree(an);
         o = talloc(B, h.H, h.W, a.C);
         const int heads = c.attention_head_dim > 0 ? a.C / c.attention_head_dim : 1;
-        if (!dry) {
-          const int T = h.H * h.W, C = a.C;
-          ops.push_back({[qkv, o, B, T, C, heads](cudaStream_t st) { return attention_launch(qkv.p, o.p, B, T, C, heads, st); },
-                         2, 4.0 * B * (double)T * T * C, 0.0});
+        const int T = h.H * h.W, C = a.C;
+        const ConvGeom gq = conv_geometry(B, h.H, h.W, T);
+        if (heads == 1 && T % 128 == 0 && T <= 1024 && gq.Nt == 1 && C % 64 == 0) {
+          // tensor-core attention: S = Q K^T and O = P V are batched GEMMs on the tcgen05 kernel (the per-image
+          // B operand is read straight from the qkv tensor / a transposed copy of V); softmax in fp32 between
+          Tensor sc = talloc(B, h.H, h.W, T);
+          Tensor vt = talloc(B, 1, C, T);   // V^T: [N][C][T]
+          if (!dry) {
+            ConvDesc d1;
+            d1.s0.ptr = qkv.p; d1.s0.C = C; d1.s0.pitch = 3 * C;        // Q = channel window [0,C) of qkv
+            d1.N = B; d1.H = h.H; d1.W = h.W; d1.ksize = 1; d1.stride = 1;
+            d1.w_packed = qkv.p + C; d1.b_batch_rows = T; d1.b_pitch = 3 * C;   // K rows of image n
+            d1.Cout = T; d1.out_bf16 = sc.p;
+            ConvPlan p1;
+            rc = conv_plan_build(&p1, d1);
+            ConvDesc d2;
+            d2.s0.ptr = sc.p; d2.s0.C = T;                               // P
+            d2.N = B; d2.H = h.H; d2.W = h.W; d2.ksize = 1; d2.stride = 1;
+            d2.w_packed = vt.p; d2.b_batch_rows = C; d2.b_pitch = T;     // V^T rows of image n
+            d2.Cout = C; d2.out_bf16 = o.p;
+            ConvPlan p2;
+            if (!rc) rc = conv_plan_build(&p2, d2);
+            if (!rc) {
+              const float scale = 1.0f / sqrtf((float)C);
+              const int64_t rows = (int64_t)B * T;
+              ops.push_back({[p1](cudaStream_t st) { return conv_launch(p1, ConvEpilogue{}, st); }, 0, p1.flops, 0.0});
+              ops.push_back({[sc, rows, T, scale](cudaStream_t st) { return softmax_rows_launch(sc.p, rows, T, scale, st); },
+                             3, 0.0, 4.0 * rows * T});
+              ops.push_back({[qkv, vt, B, T, C](cudaStream_t st) { return transpose_v_launch(qkv.p, vt.p, B, T, C, st); },
+                             3, 0.0, 4.0 * B * T * C});
+              ops.push_back({[p2](cudaStream_t st) { return conv_launch(p2, ConvEpilogue{}, st); }, 0, p2.flops, 0.0});
+              flops += p1.flops + p2.flops;
+            }
+          } else {
+            flops += 4.0 * B * (double)T * T * C;
+          }
+          tfree(sc);
+          tfree(vt);
+        } else {
+          if (!dry) {
+            ops.push_back({[qkv, o, B, T, C, heads](cudaStream_t st) { return attention_launch(qkv.p, o.p, B, T, C, heads, st); },
+                           2, 4.0 * B * (double)T * T * C, 0.0});
+          }
+          flops += 4.0 * B * (double)(h.H * h.W) * (h.H * h.W) * a.C;
         }
-        flops += 4.0 * B * (double)(h.H * h.W) * (h.H * h.W) * a.C;
         tfree(qkv);
         conv(a.proj, o, nullptr, 1, ConvEpilogue{}, &out, nullptr, &h);
         tfree(o);

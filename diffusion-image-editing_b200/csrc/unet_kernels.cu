@@ -81,7 +81,20 @@ __global__ void __launch_bounds__(kGNThreads) gn_apply_kernel(GNArgs a, int pix_
   const int cpg = C / a.G;
   if (tid < a.G) {
     double ts = 0.0, tq = 0.0;
-    if (a.cs0) {
+    if (a.ts0) {
+      // raw tile statistics of a small tensor: slots of image n are (n/Nt * per_img + i) * Nt + n % Nt
+      const int64_t base = (int64_t)(n / a.ts_nt) * a.ts_per_img;
+      const int nl = n % a.ts_nt;
+      for (int c = tid * cpg; c < (tid + 1) * cpg; ++c) {
+        const bool first = c < a.C0;
+        const float* t = first ? a.ts0 : a.ts1;
+        const int Cs = first ? a.C0 : a.C1, cc = first ? c : c - a.C0;
+        for (int i = 0; i < a.ts_per_img; ++i) {
+          const float2 v = __ldg(reinterpret_cast<const float2*>(t + (((base + i) * a.ts_nt + nl) * Cs + cc) * 2));
+          ts += (double)v.x; tq += (double)v.y;
+        }
+      }
+    } else if (a.cs0) {
       // per-channel sums from the producing convolutions' epilogues (concat-aware)
       for (int c = tid * cpg; c < (tid + 1) * cpg; ++c) {
         const float* o = c < a.C0 ? a.cs0 + ((int64_t)n * a.C0 + c) * 2 : a.cs1 + ((int64_t)n * a.C1 + (c - a.C0)) * 2;
@@ -161,7 +174,7 @@ int gn_launch(const GNArgs& a, cudaStream_t st) {
   B2E_REQUIRE(C % 8 == 0 && a.C0 % 8 == 0 && C <= 1024 && a.G <= 64 && C % a.G == 0, B2E_UNSUPPORTED_SHAPE,
               "groupnorm: unsupported channels %d+%d / groups %d", a.C0, a.C1, a.G);
   int rc = B2E_OK;
-  if (!a.cs0) {
+  if (!a.cs0 && !a.ts0) {
     gn_partial_kernel<<<dim3(a.chunks, a.N), kGNThreads, 0, st>>>(a);
     rc = check_launch("gn_partial");
     if (rc) return rc;
@@ -309,6 +322,51 @@ int temb_launch(const TembArgs& a, cudaStream_t st) {
   if (rc) return rc;
   temb_proj_kernel<<<dim3((a.sumC + 7) / 8, a.B), 256, 0, st>>>(a);
   return check_launch("temb_proj");
+}
+
+// ------------------------------------------------------------------ tensor-core attention helpers
+// one warp per row: logits (bf16) * scale -> softmax in fp32 -> probabilities (bf16), in place
+__global__ void __launch_bounds__(256) softmax_rows_kernel(bf16* __restrict__ s, int64_t rows, int T, float scale) {
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  bf16* r = s + row * T;
+  float v[32];   // T <= 1024 -> at most 32 values per lane
+  const int per = T / 32;
+  float m = -INFINITY;
+  for (int i = 0; i < per; ++i) { v[i] = __bfloat162float(r[lane + 32 * i]) * scale; m = fmaxf(m, v[i]); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float sum = 0.f;
+  for (int i = 0; i < per; ++i) { v[i] = __expf(v[i] - m); sum += v[i]; }
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+  for (int i = 0; i < per; ++i) r[lane + 32 * i] = __float2bfloat16_rn(v[i] * inv);
+}
+
+int softmax_rows_launch(bf16* s, int64_t rows, int T, float scale, cudaStream_t st) {
+  B2E_REQUIRE(T % 32 == 0 && T <= 1024, B2E_UNSUPPORTED_SHAPE, "softmax: unsupported row length %d", T);
+  softmax_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(s, rows, T, scale);
+  return check_launch("softmax_rows");
+}
+
+// 32x32 smem-tiled transpose of the V columns of qkv
+__global__ void transpose_v_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ vt, int T, int C) {
+  __shared__ bf16 tile[32][33];
+  const int n = blockIdx.z, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const bf16* src = qkv + ((int64_t)n * T) * 3 * C + 2 * C;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y)
+    tile[i][threadIdx.x] = src[(int64_t)(t0 + i) * 3 * C + c0 + threadIdx.x];
+  __syncthreads();
+  bf16* dst = vt + (int64_t)n * C * T;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y)
+    dst[(int64_t)(c0 + i) * T + t0 + threadIdx.x] = tile[threadIdx.x][i];
+}
+
+int transpose_v_launch(const bf16* qkv, bf16* vt, int N, int T, int C, cudaStream_t st) {
+  B2E_REQUIRE(T % 32 == 0 && C % 32 == 0, B2E_UNSUPPORTED_SHAPE, "transpose_v: T and C must be multiples of 32");
+  transpose_v_kernel<<<dim3(T / 32, C / 32, N), dim3(32, 8), 0, st>>>(qkv, vt, T, C);
+  return check_launch("transpose_v");
 }
 
 // ------------------------------------------------------------------ attention core

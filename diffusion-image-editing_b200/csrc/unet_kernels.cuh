@@ -15,6 +15,9 @@ struct GNArgs {
   const float* gamma; const float* beta;
   float* partial;  // [N][chunks][G][2]   (statistics pass; unused when cs0 is given)
   const float* cs0; const float* cs1;  // per-channel (sum, sumsq) of x0 / x1, [N][C][2], from the conv epilogue
+  // small tensors: raw per-(tile slot, channel) statistics, reduced by gn_apply itself (no finalize launch)
+  const float* ts0; const float* ts1;
+  int ts_nt, ts_per_img;               // images per tile, tile slots per image (same geometry for both sources)
   int chunks;
   bf16* out;       // [N][HW][C0+C1]
   int silu;
@@ -42,6 +45,11 @@ struct TembArgs {
   float* proj;  // [B][sumC]
 };
 int temb_launch(const TembArgs& a, cudaStream_t st);
+
+// tensor-core attention pieces (single head, T >= 128): softmax over rows of S (bf16 [rows][T], in place,
+// logits scaled by `scale`) and V^T extraction qkv[N][T][3C] (v = columns [2C,3C)) -> vt[N][C][T]
+int softmax_rows_launch(bf16* s, int64_t rows, int T, float scale, cudaStream_t st);
+int transpose_v_launch(const bf16* qkv, bf16* vt, int N, int T, int C, cudaStream_t st);
 
 // single/multi-head self-attention core: qkv bf16 [N][T][3C] (q | k | v) -> out bf16 [N][T][C]
 int attention_launch(const bf16* qkv, bf16* out, int N, int T, int C, int heads, cudaStream_t st);

@@ -51,7 +51,7 @@ def pil_to_tensor(pil_imgs: Union[Image.Image, List[Image.Image]]) -> torch.Tens
         a = np.asarray(img)
         if a.ndim == 2:
             a = a[:, :, None]
-        t = torch.from_numpy(np.ascontiguousarray(a)).permute(2, 0, 1).to(torch.float32).div(255)
+        t = torch.from_numpy(np.array(a, copy=True)).permute(2, 0, 1).to(torch.float32).div(255)
         return (t * 2 - 1).unsqueeze(0)
     if isinstance(pil_imgs, Image.Image):
         return one(pil_imgs)
