@@ -77,6 +77,7 @@ PROTOTYPES = {
     "b2e_unet_forward": (_I, [_P, _P, _P, _P, _I64, _P]),
     "b2e_unet_flops": (C.c_double, [_P, _I64]),
     "b2e_unet_launches_per_forward": (_I, [_P]),
+    "b2e_unet_op_desc": (C.c_char_p, [_P, _I]),
     "b2e_unet_profile": (_I, [_P, _P, _P, _P, _I64, _P, _I, C.POINTER(_I), C.POINTER(C.c_float),
                               C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_I)]),
     "b2e_conv2d_nhwc_bf16": (_I, [_P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I, _I, _P]),

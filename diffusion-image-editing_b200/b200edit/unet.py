@@ -142,7 +142,8 @@ class UNet2DModel:
                                    C.c_void_p(torch.cuda.current_stream().cuda_stream), cap, C.byref(n), ms, fl, by, kd),
               "unet_profile")
         names = {0: "conv_igemm", 1: "groupnorm", 2: "attention", 3: "other"}
-        return [dict(kind=names[kd[i]], ms=ms[i], flops=fl[i], bytes=by[i]) for i in range(n.value)]
+        return [dict(kind=names[kd[i]], ms=ms[i], flops=fl[i], bytes=by[i],
+                     desc=lib.b2e_unet_op_desc(self._h, i).decode()) for i in range(n.value)]
 
     # ------------------------------------------------------------------ forward
     def _timesteps(self, timestep, B):

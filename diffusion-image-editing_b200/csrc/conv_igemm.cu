@@ -22,6 +22,7 @@
 #include "conv_igemm.cuh"
 
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 namespace b2e {
 
@@ -53,6 +54,9 @@ struct ConvKParams {
   int taps, c0_chunks, c1_chunks, r0_chunks, r1_chunks;
   int tap_dc[9], tap_dw[9], tap_da[9], tap_dh[9];
   int b_batch_rows;         // rows of B per image (attention GEMMs), 0 for shared weights
+  int splits;               // split-K factor (>1: partial accumulators meet in split_ws, last CTA finishes the tile)
+  float* split_ws;          // [num_tiles][splits][128][BN] fp32
+  int* split_counters;      // [num_tiles], zero between launches
   int n_tiles, num_tiles;   // PAIR kernels: num_tiles counts tile PAIRS (two adjacent M tiles, same N tile)
   const float* bias;
   const float* bias2;
@@ -277,6 +281,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;         // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  volatile uint32_t* split_flag = tmem_slot + 1;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = PAIR ? (int)cluster_ctarank() : 0;      // 0 = leader CTA of the SM pair
@@ -285,6 +290,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   const int chunks = p.c0_chunks + p.c1_chunks;
   const int r_chunks = p.r0_chunks + p.r1_chunks;
   const int num_kb = p.taps * chunks + r_chunks;
+  const int main_kb = p.taps * chunks;
+  // work item = (tile, K split); consecutive CTAs take the splits of one tile
+  const int splits = PAIR ? 1 : p.splits;
+  const int num_work = p.num_tiles * splits;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_a0);
@@ -327,26 +336,33 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         }
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       };
-      for (int tile = tile_begin; tile < p.num_tiles; tile += tile_step) {
+      for (int wi = tile_begin; wi < num_work; wi += tile_step) {
+        const int tile = wi / splits, split = wi - tile * splits;
         const TileCoord tc = tile_coord(p, tile, PAIR, rank);
         const int brow0 = tc.n_tile * BN + tc.n0 * p.b_batch_rows;   // per-image B rows for batched GEMMs (Nt == 1)
-        for (int tap = 0; tap < p.taps; ++tap) {
-          const int cw = tc.w0 + p.tap_dw[tap], ch = tc.h0 + p.tap_dh[tap], ca = p.tap_da[tap], cc = p.tap_dc[tap];
-          for (int ck = 0; ck < chunks; ++ck) {
+        const int kb0 = (int)((int64_t)split * num_kb / splits), kb1 = (int)((int64_t)(split + 1) * num_kb / splits);
+        // walk (tap, chunk) incrementally: the producer is one thread and sits on the critical path
+        int tap = kb0 < main_kb ? kb0 / chunks : p.taps, ck = kb0 < main_kb ? kb0 - tap * chunks : kb0 - main_kb;
+        int cw = 0, ch = 0, ca = 0, cc = 0;
+        if (tap < p.taps) { cw = tc.w0 + p.tap_dw[tap]; ch = tc.h0 + p.tap_dh[tap]; ca = p.tap_da[tap]; cc = p.tap_dc[tap]; }
+        for (int kb = kb0; kb < kb1; ++kb) {
+          if (tap < p.taps) {
             if (ck < p.c0_chunks)
-              load_kb(&map_a0, cc + ck * kConvBlockK, cw, ca, ch, tc.n0, (tap * chunks + ck) * kConvBlockK, brow0);
+              load_kb(&map_a0, cc + ck * kConvBlockK, cw, ca, ch, tc.n0, kb * kConvBlockK, brow0);
             else
-              load_kb(&map_a1, cc + (ck - p.c0_chunks) * kConvBlockK, cw, ca, ch, tc.n0,
-                      (tap * chunks + ck) * kConvBlockK, brow0);
+              load_kb(&map_a1, cc + (ck - p.c0_chunks) * kConvBlockK, cw, ca, ch, tc.n0, kb * kConvBlockK, brow0);
+            if (++ck == chunks) {
+              ck = 0;
+              if (++tap < p.taps) { cw = tc.w0 + p.tap_dw[tap]; ch = tc.h0 + p.tap_dh[tap]; ca = p.tap_da[tap]; cc = p.tap_dc[tap]; }
+            }
+          } else {
+            // residual segment: 1x1 at the output pixel
+            if (ck < p.r0_chunks)
+              load_kb(&map_r0, ck * kConvBlockK, tc.w0, 0, tc.h0, tc.n0, kb * kConvBlockK, brow0);
+            else
+              load_kb(&map_r1, (ck - p.r0_chunks) * kConvBlockK, tc.w0, 0, tc.h0, tc.n0, kb * kConvBlockK, brow0);
+            ++ck;
           }
-        }
-        // residual segment: 1x1 at the output pixel
-        for (int ck = 0; ck < r_chunks; ++ck) {
-          if (ck < p.r0_chunks)
-            load_kb(&map_r0, ck * kConvBlockK, tc.w0, 0, tc.h0, tc.n0, (p.taps * chunks + ck) * kConvBlockK, brow0);
-          else
-            load_kb(&map_r1, (ck - p.r0_chunks) * kConvBlockK, tc.w0, 0, tc.h0, tc.n0,
-                    (p.taps * chunks + ck) * kConvBlockK, brow0);
         }
       }
     }
@@ -356,12 +372,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       constexpr uint32_t idesc = make_idesc(PAIR ? 2 * kConvBlockM : kConvBlockM, BN);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
-      for (int tile = tile_begin; tile < p.num_tiles; tile += tile_step, ++it) {
+      for (int wi = tile_begin; wi < num_work; wi += tile_step, ++it) {
+        const int split = wi % splits;
+        const int kb0 = (int)((int64_t)split * num_kb / splits), kb1 = (int)((int64_t)(split + 1) * num_kb / splits);
         const int acc = it & 1;
         mbar_wait(tmem_empty_bar + acc, ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar + stage, phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
@@ -370,8 +388,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
 #pragma unroll
           for (int k = 0; k < kConvBlockK / 16; ++k) {
             // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in the (addr >> 4) field
-            if (PAIR) umma_bf16_2sm(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-            else umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            const uint32_t accum = (kb > kb0 || k > 0) ? 1u : 0u;
+            if (PAIR) umma_bf16_2sm(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accum);
+            else umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accum);
           }
           // frees this smem stage (in both CTAs of a pair) once the MMAs above retire
           if (PAIR) umma_commit_2sm(empty_bar + stage); else umma_commit(empty_bar + stage);
@@ -388,28 +407,72 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     const int w_l = r % p.Wt, h_l = (r / p.Wt) % p.Ht, n_l = r / (p.Wt * p.Ht);
     const bool store_leader = (warp == 2 && lane == 0);
     int it = 0;
-    for (int tile = tile_begin; tile < p.num_tiles; tile += tile_step, ++it) {
+    for (int wi = tile_begin; wi < num_work; wi += tile_step, ++it) {
+      const int tile = wi / splits, split = wi - tile * splits;
       const TileCoord tc = tile_coord(p, tile, PAIR, rank);
       const int acc = it & 1;
       const int n = tc.n0 + n_l, h = tc.h0 + h_l, w = tc.w0 + w_l;
       const bool valid = n < p.N;
       mbar_wait(tmem_full_bar + acc, (it >> 1) & 1);
       tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      auto release_tmem = [&]() {
+        // all of this warp's accumulator columns are in registers: hand the buffer back
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { if (PAIR) mbar_arrive_leader(tmem_empty_bar + acc); else mbar_arrive(tmem_empty_bar + acc); }
+      };
+      const float* part_row = nullptr;
+      if (splits > 1) {
+        // split-K: park the raw fp32 partial tile; the CTA that arrives last sums all partials (fixed order) and
+        // runs the normal epilogue - no extra kernel, deterministic result
+        // layout [tile][split][16-col chunk][row][16]: a warp's 32 rows write / read 2 KB contiguous
+        float* mine = p.split_ws + ((int64_t)tile * splits + split) * (kConvBlockM * BN) + r * 16;
+#pragma unroll 1
+        for (int c = 0; c < BN / 16; ++c) {
+          float v[16];
+          tmem_ld16(taddr + c * 16, v);
+          if (c == BN / 16 - 1) release_tmem();
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            __stcg(reinterpret_cast<float4*>(mine + c * (kConvBlockM * 16)) + j,
+                   make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+        }
+        __threadfence();
+        epi_bar_sync();
+        if (store_leader) {
+          const int old = atomicAdd(p.split_counters + tile, 1);
+          const bool last = old == splits - 1;
+          if (last) p.split_counters[tile] = 0;   // every split has arrived: re-arm for the next launch
+          *split_flag = last ? 1u : 0u;
+        }
+        epi_bar_sync();
+        if (!*split_flag) continue;
+        __threadfence();
+        part_row = p.split_ws + (int64_t)tile * splits * (kConvBlockM * BN) + r * 16;
+      }
       if (Cfg::kSlabs > 0 && p.out_bf16) {
         // the previous tile's TMA store must have finished reading the staging buffer
         if (store_leader) tma_store_wait_read();
         epi_bar_sync();
       }
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
       for (int c = 0; c < BN / 16; ++c) {
         float v[16];
-        tmem_ld16(taddr + c * 16, v);
-        if (c == BN / 16 - 1) {
-          // all of this warp's accumulator columns are in registers: hand the buffer back
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) { if (PAIR) mbar_arrive_leader(tmem_empty_bar + acc); else mbar_arrive(tmem_empty_bar + acc); }
+        if (part_row) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = 0.f;
+          for (int sp = 0; sp < splits; ++sp) {
+            const float4* pp = reinterpret_cast<const float4*>(part_row + (int64_t)sp * (kConvBlockM * BN) + c * (kConvBlockM * 16));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 b = __ldcg(pp + j);
+              v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+            }
+          }
+        } else {
+          tmem_ld16(taddr + c * 16, v);
+          if (c == BN / 16 - 1) release_tmem();
         }
         const int col0 = tc.n_tile * BN + c * 16;
         if (Cfg::kSlabs > 0 && p.out_bf16) {
@@ -612,7 +675,7 @@ ConvGeom conv_geometry(int N, int Ho, int Wo, int Cout) {
   g.w_blks = Wo / g.Wt; g.h_blks = Ho / g.Ht; g.n_blks = (N + g.Nt - 1) / g.Nt;
   g.block_n = cout_pad <= 16 ? 16 : (cout_pad % 128 == 0 ? 128 : 64);
   // few output tiles (low-resolution levels): halve the N tile to double the number of CTAs
-  if (g.block_n == 128 && g.w_blks * g.h_blks * g.n_blks * (cout_pad / 128) < kNumSMs) g.block_n = 64;
+  if (g.block_n == 128 && g.w_blks * g.h_blks * g.n_blks * (cout_pad / 128) < kNumSMs / 2) g.block_n = 64;
   // statistics are reduced over groups of block_n/8 rows, which must not straddle images
   g.stats_ok = g.block_n >= 64 && Cout % 64 == 0 && (g.Wt * g.Ht) % (g.block_n / 8) == 0;
   return g;
@@ -688,8 +751,22 @@ int conv_plan_build(ConvPlan* pl, const ConvDesc& d) {
   uint64_t bd[2] = {ktot, d.b_batch_rows ? (uint64_t)d.N * d.b_batch_rows : (uint64_t)p.cout_pad};
   uint64_t bs[1] = {(d.b_pitch ? (uint64_t)d.b_pitch : ktot) * 2};
   p.b_batch_rows = d.b_batch_rows;
-  // SM-pair mode: 128-wide N tiles and an even number of M tiles (each CTA stages half of the B rows)
-  p.pair = (p.block_n == 128 && ((p.w_blks * p.h_blks * p.n_blks) % 2 == 0)) ? 1 : 0;
+  // SM-pair mode: 128-wide N tiles, an even number of M tiles and enough tiles to keep every SM pair busy
+  const int m_tiles = p.w_blks * p.h_blks * p.n_blks, tiles = m_tiles * (p.cout_pad / p.block_n);
+  p.pair = (p.block_n == 128 && m_tiles % 2 == 0 && tiles >= kNumSMs) ? 1 : 0;
+  // split-K when the tiles alone cannot fill the chip: up to 8 splits of at least 8 k-blocks each
+  const int num_kb = (int)(ktot / K);
+  p.splits = 1;
+  // (measured on B200 at batch 8: the extra fp32 round trip through L2 costs more than the added parallelism
+  //  buys for this network, so split-K is opt-in: B2E_SPLITK=1)
+  static const bool splitk_on = getenv("B2E_SPLITK") && atoi(getenv("B2E_SPLITK")) > 0;
+  if (splitk_on && !p.pair && d.split_ws && d.out_bf16 && tiles * 2 <= kNumSMs) {
+    int sp = kNumSMs / tiles;
+    if (sp > num_kb / 8) sp = num_kb / 8;
+    if (sp > 8) sp = 8;
+    if (sp >= 2 && (size_t)tiles * sp * kConvBlockM * p.block_n * sizeof(float) <= d.split_ws_bytes) p.splits = sp;
+  }
+  p.split_ws = d.split_ws; p.split_counters = d.split_counters;
   uint32_t bb[2] = {(uint32_t)K, (uint32_t)(p.pair ? p.block_n / 2 : p.block_n)};
   rc = encode_map(&p.map_b, d.w_packed, 2, bd, bs, bb);
   if (rc) return rc;
@@ -708,8 +785,9 @@ static int launch_t(const ConvPlan& pl, const ConvKParams& kp, int tiles, cudaSt
     attr_set = true;
   }
   cudaLaunchConfig_t cfg = {};
-  const int units = PAIR ? kNumSMs / 2 : kNumSMs;   // tiles (or tile pairs) in flight
-  cfg.gridDim = dim3((unsigned)((tiles < units ? tiles : units) * (PAIR ? 2 : 1)));
+  const int units = PAIR ? kNumSMs / 2 : kNumSMs;   // work items (tiles x splits, or tile pairs) in flight
+  const int work = tiles * (PAIR ? 1 : kp.splits);
+  cfg.gridDim = dim3((unsigned)((work < units ? work : units) * (PAIR ? 2 : 1)));
   cfg.blockDim = dim3(kConvThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = st;
@@ -736,6 +814,7 @@ int conv_launch(const ConvPlan& pl, const ConvEpilogue& ep, cudaStream_t st) {
   }
   kp.n_tiles = pl.cout_pad / pl.block_n;
   kp.b_batch_rows = pl.b_batch_rows;
+  kp.splits = pl.splits; kp.split_ws = pl.split_ws; kp.split_counters = pl.split_counters;
   kp.bias = ep.bias; kp.bias2 = ep.bias2; kp.temb = ep.temb; kp.temb_stride = ep.temb_stride;
   kp.out_bf16 = pl.has_out_bf16; kp.out_f32_nchw = pl.has_out_bf16 ? nullptr : ep.out_f32_nchw;
   kp.tile_stats = pl.tile_stats;
@@ -766,6 +845,11 @@ extern "C" int b2e_conv2d_nhwc_bf16(const void* x, const float* w, const float* 
   const size_t wbytes = (size_t)cout_pad * row_len * sizeof(bf16);
   bf16* wp = nullptr;
   B2E_CUDA(cudaMalloc(&wp, wbytes));
+  // split-K scratch so that small shapes exercise the split path exactly like inside the UNet
+  const size_t split_bytes = (size_t)kNumSMs * kConvBlockM * 128 * sizeof(float);
+  char* split_mem = nullptr;
+  if (cudaMalloc(&split_mem, split_bytes + 4096) != cudaSuccess) { cudaFree(wp); set_error("conv2d: cudaMalloc failed"); return B2E_CUDA_ERROR; }
+  cudaMemsetAsync(split_mem + split_bytes, 0, 4096, st);
   int rc = B2E_OK;
   do {
     if (cudaMemsetAsync(wp, 0, wbytes, st) != cudaSuccess) { set_error("conv2d: memset failed"); rc = B2E_CUDA_ERROR; break; }
@@ -780,6 +864,7 @@ extern "C" int b2e_conv2d_nhwc_bf16(const void* x, const float* w, const float* 
     if (residual) d.r0 = ConvSrc{(const bf16*)residual, (int)Cout};
     d.N = (int)N; d.H = (int)H; d.W = (int)W; d.ksize = ksize; d.stride = stride;
     d.w_packed = wp; d.Cout = (int)Cout; d.out_bf16 = (bf16*)out;
+    d.split_ws = (float*)split_mem; d.split_ws_bytes = split_bytes; d.split_counters = (int*)(split_mem + split_bytes);
     ConvPlan plan;
     rc = conv_plan_build(&plan, d);
     if (rc) break;
@@ -789,5 +874,6 @@ extern "C" int b2e_conv2d_nhwc_bf16(const void* x, const float* w, const float* 
   } while (0);
   cudaStreamSynchronize(st);
   cudaFree(wp);
+  cudaFree(split_mem);
   return rc;
 }

@@ -36,6 +36,9 @@ struct ConvDesc {
   // optional fused GroupNorm statistics of the (bf16-rounded) output: per (tile slot, channel) sum and
   // sum of squares, [conv_stats_slots()][Cout][2] floats; reduced per image by gn_finalize
   float* tile_stats = nullptr;
+  // optional split-K scratch shared by all layers of a model: fp32 partial tiles + per-tile arrival counters
+  // (counters must be zero before the first launch; the kernel re-arms them)
+  float* split_ws = nullptr; size_t split_ws_bytes = 0; int* split_counters = nullptr;
 };
 
 struct ConvEpilogue {
@@ -55,6 +58,7 @@ struct ConvPlan {
   int tap_dc[9], tap_dw[9], tap_da[9], tap_dh[9];
   int block_n;  // 16, 64 or 128
   int b_batch_rows;
+  int splits; float* split_ws; int* split_counters;
   int pair;     // 1: SM-pair kernel (tcgen05.mma.cta_group::2, 256 x 128 tile per cluster)
   int has_out_bf16;
   float* tile_stats;

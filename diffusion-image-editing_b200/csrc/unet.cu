@@ -80,7 +80,7 @@ struct b2e_unet {
   // program
   void* ws = nullptr; size_t ws_bytes = 0;
   int64_t cur_B = -1;
-  struct Op { std::function<int(cudaStream_t)> fn; int kind; double flops; double bytes; };  // kind: 0 conv, 1 groupnorm, 2 attention, 3 other
+  struct Op { std::function<int(cudaStream_t)> fn; int kind; double flops; double bytes; std::string desc; };  // kind: 0 conv, 1 groupnorm, 2 attention, 3 other
   std::vector<Op> ops;
   const float* in_x = nullptr; const int64_t* in_t = nullptr; float* out_eps = nullptr;  // per-call
   double flops = 0;
@@ -273,6 +273,11 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
   float* act = (float*)ar.alloc(sizeof(float) * B * m->temb_dim);
   float* proj = (float*)ar.alloc(sizeof(float) * B * m->sumC);
   float* gn_part = (float*)ar.alloc(sizeof(float) * B * 64 * G * 2);
+  // split-K scratch for the low-resolution convolutions (<= one 128x128 fp32 partial tile per SM) + tile counters
+  const size_t split_bytes = (size_t)kNumSMs * kConvBlockM * 128 * sizeof(float);
+  float* split_ws = (float*)ar.alloc(split_bytes);
+  int* split_cnt = (int*)ar.alloc(sizeof(int) * 1024);
+  if (!dry) cudaMemset(split_cnt, 0, sizeof(int) * 1024);
 
   auto conv = [&](const ConvL& L, Tensor x0, const Tensor* x1, int stride, ConvEpilogue ep, Tensor* out, float* out_nchw,
                   const Tensor* r0 = nullptr, const Tensor* r1 = nullptr, bool want_stats = true) {
@@ -306,6 +311,7 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
     d.N = B; d.H = x0.H; d.W = x0.W; d.ksize = L.k; d.stride = stride; d.w_packed = L.w; d.Cout = L.cout;
     d.out_bf16 = out ? out->p : nullptr;
     d.tile_stats = tstats;
+    d.split_ws = split_ws; d.split_ws_bytes = split_bytes; d.split_counters = split_cnt;
     if (L.res_c != (r0 ? r0->C : 0) + (r1 ? r1->C : 0)) { rc = B2E_INVALID_ARG; set_error("unet: residual segment mismatch"); return; }
     ConvPlan pl;
     rc = conv_plan_build(&pl, d);
@@ -313,12 +319,16 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
     ep.bias = L.b;
     ep.bias2 = L.b2;
     flops += pl.flops;
+    char desc[160];
+    snprintf(desc, sizeof(desc), "conv%dx%d s%d %dx%d cin%d+%d res%d cout%d tiles%d bn%d%s", L.k, L.k, stride, x0.H, x0.W,
+             x0.C, x1 ? x1->C : 0, L.res_c, L.cout, pl.w_blks * pl.h_blks * pl.n_blks * (pl.cout_pad / pl.block_n), pl.block_n,
+             pl.pair ? " pair" : (pl.splits > 1 ? (" splitK" + std::to_string(pl.splits)).c_str() : ""));
     if (out_nchw) {
       // the network output pointer is only known at call time
       ops.push_back({[pl, ep, m](cudaStream_t st) { ConvEpilogue e = ep; e.out_f32_nchw = m->out_eps; return conv_launch(pl, e, st); },
-                     0, pl.flops, 0.0});
+                     0, pl.flops, 0.0, desc});
     } else {
-      ops.push_back({[pl, ep](cudaStream_t st) { return conv_launch(pl, ep, st); }, 0, pl.flops, 0.0});
+      ops.push_back({[pl, ep](cudaStream_t st) { return conv_launch(pl, ep, st); }, 0, pl.flops, 0.0, desc});
     }
     if (tstats && !raw_stats) {
       float* cst = out->cstats;
@@ -572,6 +582,11 @@ int b2e_unet_forward(b2e_unet* m, const float* x, const int64_t* timesteps, floa
     if (rc) return rc;
   }
   return B2E_OK;
+}
+
+const char* b2e_unet_op_desc(const b2e_unet* m, int idx) {
+  if (!m || idx < 0 || idx >= (int)m->ops.size()) return "";
+  return m->ops[idx].desc.c_str();
 }
 
 int b2e_unet_profile(b2e_unet* m, const float* x, const int64_t* timesteps, float* eps, int64_t B, void* stream,

@@ -210,6 +210,8 @@ int b2e_unet_bind_workspace(b2e_unet* m, void* workspace, size_t workspace_bytes
 int b2e_unet_forward(b2e_unet* m, const float* x, const int64_t* timesteps, float* eps, int64_t B,
                      void* stream);
 double b2e_unet_flops(const b2e_unet* m, int64_t B);
+/* Human-readable description of op `idx` of the current plan (shape, tiling); "" if out of range. */
+const char* b2e_unet_op_desc(const b2e_unet* m, int idx);
 /* One instrumented forward: CUDA events on `stream` around every op of the plan.  Per op: elapsed ms,
  * algorithmic FLOPs (convolutions / attention) or bytes (memory-bound ops) and kind
  * (0 tcgen05 convolution, 1 GroupNorm(+SiLU), 2 attention core, 3 other).  Synchronises the stream. */
