@@ -34,18 +34,29 @@ constexpr int kABytes = kConvBlockM * kConvBlockK * 2;  // 16 KB
 // PAIR: two CTAs of a cluster (an SM pair) run ONE tcgen05.mma.cta_group::2 of shape 256 x BN x 16: each CTA
 // stages its own 128 output pixels of A and only HALF of the B tile, so a stage is 24 KB instead of 32 KB
 // for the same tensor work - the main loop needs 25 % fewer bytes in flight / from L2 per FLOP.
-template <int BN, int STAGES, bool PAIR = false>
+// HALO (3x3, stride 1): the tile is an 8x16-pixel brick and ONE TMA load brings its (8+2)x16 halo brick
+// for a given horizontal tap; the three vertical taps are then just 16-row (2 KB, swizzle-aligned) offsets of
+// the same smem tile.  A is fetched 3x per channel chunk instead of 9x - L2->SM traffic per FLOP drops ~30 %,
+// which is what bounds the 128-wide layers.  A and B live in separate rings (3 halo slots, STAGES B slots).
+constexpr int kHaloWt = 16, kHaloHt = 8;
+constexpr int kHaloRows = (kHaloHt + 2) * kHaloWt;       // 160
+constexpr int kHaloABytes = kHaloRows * 128;             // 20 KB
+constexpr int kHaloASlots = 3;
+template <int BN, int STAGES, bool PAIR = false, bool HALO = false>
 struct ConvCfg {
   static constexpr int kBRows = PAIR ? BN / 2 : BN;             // B rows staged by this CTA
   static constexpr int kBBytes = kBRows * kConvBlockK * 2;
   static constexpr int kBBytesPad = (kBBytes + 1023) / 1024 * 1024;
-  static constexpr int kStageBytes = kABytes + kBBytesPad;
+  // non-halo: STAGES x (A + B); halo: kHaloASlots x A-halo followed by STAGES x B
+  static constexpr int kStageBytes = HALO ? kBBytesPad : kABytes + kBBytesPad;
+  static constexpr int kRingBytes = HALO ? kHaloASlots * kHaloABytes + STAGES * kBBytesPad : STAGES * (kABytes + kBBytesPad);
+  static constexpr int kNumBars = HALO ? 2 * (kHaloASlots + STAGES) : 2 * STAGES;
   static constexpr int kStages = STAGES;
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;   // double-buffered accumulator
   static constexpr int kSlabs = BN / 64;                        // 64-channel output slabs (0: fp32 NCHW path)
   static constexpr int kStagingBytes = kSlabs * kConvBlockM * 128;
   static constexpr int kRedBytes = kSlabs > 0 ? 8192 : 0;       // GroupNorm-statistics scratch [row groups][BN][2]
-  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kRedBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kRingBytes + kStagingBytes + kRedBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 struct ConvKParams {
@@ -54,6 +65,7 @@ struct ConvKParams {
   int taps, c0_chunks, c1_chunks, r0_chunks, r1_chunks;
   int tap_dc[9], tap_dw[9], tap_da[9], tap_dh[9];
   int b_batch_rows;         // rows of B per image (attention GEMMs), 0 for shared weights
+  int debug;                // B2E_DEBUG micro-benchmark knobs: 1 = no TMA loads (MMA on stale smem), 2 = no MMAs
   int splits;               // split-K factor (>1: partial accumulators meet in split_ws, last CTA finishes the tile)
   float* split_ws;          // [num_tiles][splits][128][BN] fp32
   int* split_counters;      // [num_tiles], zero between launches
@@ -185,6 +197,22 @@ template <int COLS>
 __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
 }
+// Warp-uniform leader election.  The producer and MMA warps run their loops on ALL lanes with warp-uniform
+// values (descriptors, coordinates, stage counters) and only the asynchronous instructions are guarded by
+// elect.sync - the compiler then keeps the operands in uniform registers instead of broadcasting them from a
+// divergent lane for every UTCHMMA / UTMALDG (which made the single issuing thread the bottleneck).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .b32 rx;\n"
+      ".reg .pred px;\n"
+      "elect.sync rx|px, 0xffffffff;\n"
+      "selp.b32 %0, 1, 0, px;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -265,20 +293,24 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvKParams& p, int tile, 
   return t;
 }
 
-template <int BN, int STAGES, bool PAIR>
+template <int BN, int STAGES, bool PAIR, bool HALO>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                   const __grid_constant__ CUtensorMap map_r0, const __grid_constant__ CUtensorMap map_r1,
                   const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out,
                   const __grid_constant__ ConvKParams p) {
-  using Cfg = ConvCfg<BN, STAGES, PAIR>;
+  static_assert(!(HALO && PAIR), "halo and pair modes are not combined");
+  using Cfg = ConvCfg<BN, STAGES, PAIR, HALO>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* staging = smem + Cfg::kStages * Cfg::kStageBytes;
+  uint8_t* smem_b = smem + (HALO ? kHaloASlots * kHaloABytes : 0);   // halo: B ring after the A-halo slots
+  uint8_t* staging = smem + Cfg::kRingBytes;
   float* red = reinterpret_cast<float*>(staging + Cfg::kStagingBytes);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes + Cfg::kRedBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
-  uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;   // [2]
+  uint64_t* fulla_bar = empty_bar + Cfg::kStages;                    // halo only: [kHaloASlots] x 2
+  uint64_t* emptya_bar = fulla_bar + kHaloASlots;
+  uint64_t* tmem_full_bar = empty_bar + Cfg::kStages + (HALO ? 2 * kHaloASlots : 0);   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;         // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
   volatile uint32_t* split_flag = tmem_slot + 1;
@@ -303,6 +335,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     prefetch_tmap(&map_b);
     if (p.out_bf16) prefetch_tmap(&map_out);
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+    if (HALO) for (int s = 0; s < kHaloASlots; ++s) { mbar_init(fulla_bar + s, 1); mbar_init(emptya_bar + s, 1); }
     // pair: the leader's tmem_empty barrier collects the 4 epilogue warps of BOTH CTAs
     for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar + s, 1); mbar_init(tmem_empty_bar + s, PAIR ? 8 : 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -317,25 +350,67 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===== TMA producer (one thread)
-    if (lane == 0) {
+    // ===== TMA producer (whole warp walks the loop; one elected lane issues)
+    {
       int stage = 0; uint32_t phase = 0;
       // one k-block: this CTA's A brick + its share of the B tile (pair: both CTAs complete on the leader's barrier)
       auto load_kb = [&](const CUtensorMap* ma, int c0, int c1, int c2, int c3, int c4, int kcol, int brow) {
         mbar_wait(empty_bar + stage, phase ^ 1);
         uint8_t* sa = smem + stage * Cfg::kStageBytes;
         uint8_t* sb = sa + kABytes;
-        if (PAIR) {
-          if (rank == 0) mbar_expect_tx(full_bar + stage, 2 * (kABytes + Cfg::kBBytes));
-          tma_load_5d_2sm(sa, ma, full_bar + stage, c0, c1, c2, c3, c4);
-          tma_load_2d_2sm(sb, &map_b, full_bar + stage, kcol, brow + rank * Cfg::kBRows);
-        } else {
-          mbar_expect_tx(full_bar + stage, kABytes + Cfg::kBBytes);
-          tma_load_5d(sa, ma, full_bar + stage, c0, c1, c2, c3, c4);
-          tma_load_2d(sb, &map_b, full_bar + stage, kcol, brow);
+        if (p.debug & 1) {
+          if (elect_one() && rank == 0) mbar_arrive(full_bar + stage);
+        } else if (elect_one()) {
+          if (PAIR) {
+            if (rank == 0) mbar_expect_tx(full_bar + stage, 2 * (kABytes + Cfg::kBBytes));
+            tma_load_5d_2sm(sa, ma, full_bar + stage, c0, c1, c2, c3, c4);
+            tma_load_2d_2sm(sb, &map_b, full_bar + stage, kcol, brow + rank * Cfg::kBRows);
+          } else {
+            mbar_expect_tx(full_bar + stage, kABytes + Cfg::kBBytes);
+            tma_load_5d(sa, ma, full_bar + stage, c0, c1, c2, c3, c4);
+            tma_load_2d(sb, &map_b, full_bar + stage, kcol, brow);
+          }
         }
+        __syncwarp();
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       };
+      if (HALO) {
+        int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+        auto load_a = [&](const CUtensorMap* ma, uint32_t bytes, int c0, int c1, int c3, int c4) {
+          mbar_wait(emptya_bar + sa, pa ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(fulla_bar + sa, bytes);
+            tma_load_5d(smem + sa * kHaloABytes, ma, fulla_bar + sa, c0, c1, 0, c3, c4);
+          }
+          __syncwarp();
+          if (++sa == kHaloASlots) { sa = 0; pa ^= 1; }
+        };
+        auto load_b = [&](int kcol, int brow) {
+          mbar_wait(empty_bar + sb, pb ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(full_bar + sb, Cfg::kBBytes);
+            tma_load_2d(smem_b + sb * Cfg::kStageBytes, &map_b, full_bar + sb, kcol, brow);
+          }
+          __syncwarp();
+          if (++sb == Cfg::kStages) { sb = 0; pb ^= 1; }
+        };
+        for (int tile = tile_begin; tile < p.num_tiles; tile += tile_step) {
+          const TileCoord tc = tile_coord(p, tile);
+          const int brow0 = tc.n_tile * BN;
+          for (int kw = 0; kw < 3; ++kw)
+            for (int ck = 0; ck < chunks; ++ck) {
+              // (Ht+2) x Wt halo brick for horizontal tap kw: serves the three vertical taps
+              if (ck < p.c0_chunks) load_a(&map_a0, kHaloABytes, ck * kConvBlockK, tc.w0 + kw - 1, tc.h0 - 1, tc.n0);
+              else load_a(&map_a1, kHaloABytes, (ck - p.c0_chunks) * kConvBlockK, tc.w0 + kw - 1, tc.h0 - 1, tc.n0);
+              for (int kh = 0; kh < 3; ++kh) load_b(((kh * 3 + kw) * chunks + ck) * kConvBlockK, brow0);
+            }
+          for (int ck = 0; ck < r_chunks; ++ck) {   // residual segment: plain 128-pixel brick at the output position
+            if (ck < p.r0_chunks) load_a(&map_r0, kABytes, ck * kConvBlockK, tc.w0, tc.h0, tc.n0);
+            else load_a(&map_r1, kABytes, (ck - p.r0_chunks) * kConvBlockK, tc.w0, tc.h0, tc.n0);
+            load_b((main_kb + ck) * kConvBlockK, brow0);
+          }
+        }
+      } else
       for (int wi = tile_begin; wi < num_work; wi += tile_step) {
         const int tile = wi / splits, split = wi - tile * splits;
         const TileCoord tc = tile_coord(p, tile, PAIR, rank);
@@ -367,11 +442,49 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one thread)
-    if (lane == 0 && rank == 0) {   // pair: only the leader issues (for both SMs)
+    // ===== MMA issuer (whole warp walks the loop; one elected lane issues)
+    if (rank == 0) {   // pair: only the leader CTA issues (for both SMs)
       constexpr uint32_t idesc = make_idesc(PAIR ? 2 * kConvBlockM : kConvBlockM, BN);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
+      if (HALO) {
+        int sa = 0; uint32_t pa = 0;
+        for (int tile = tile_begin; tile < p.num_tiles; tile += tile_step, ++it) {
+          const int acc = it & 1;
+          mbar_wait(tmem_empty_bar + acc, ((it >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+          uint32_t first = 1;
+          const int groups = 3 * chunks + r_chunks;   // A tiles per output tile
+          for (int gidx = 0; gidx < groups; ++gidx) {
+            const int nsub = gidx < 3 * chunks ? 3 : 1;   // vertical taps served by this A tile
+            mbar_wait(fulla_bar + sa, pa);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem + sa * kHaloABytes);
+            for (int kh = 0; kh < nsub; ++kh) {
+              mbar_wait(full_bar + stage, phase);
+              tc_fence_after();
+              // vertical tap kh = rows [kh*Wt, kh*Wt + 128) of the halo tile: a 2 KB (swizzle-aligned) offset
+              const uint64_t adesc = make_smem_desc(a_addr + (uint32_t)(kh * kHaloWt * 128));
+              const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * Cfg::kStageBytes));
+              if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < kConvBlockK / 16; ++k) {
+                  umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (first && k == 0) ? 0u : 1u);
+                }
+                umma_commit(empty_bar + stage);
+                // all MMAs reading this A tile have been issued; frees it when they retire
+                if (kh == nsub - 1) umma_commit(emptya_bar + sa);
+                if (kh == nsub - 1 && gidx == groups - 1) umma_commit(tmem_full_bar + acc);
+              }
+              __syncwarp();
+              first = 0;
+              if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+            }
+            if (++sa == kHaloASlots) { sa = 0; pa ^= 1; }
+          }
+        }
+      } else
       for (int wi = tile_begin; wi < num_work; wi += tile_step, ++it) {
         const int split = wi % splits;
         const int kb0 = (int)((int64_t)split * num_kb / splits), kb1 = (int)((int64_t)(split + 1) * num_kb / splits);
@@ -385,19 +498,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint64_t adesc = make_smem_desc(sa);
           const uint64_t bdesc = make_smem_desc(sa + kABytes);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kConvBlockK / 16; ++k) {
-            // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in the (addr >> 4) field
-            const uint32_t accum = (kb > kb0 || k > 0) ? 1u : 0u;
-            if (PAIR) umma_bf16_2sm(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accum);
-            else umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accum);
+            for (int k = 0; k < kConvBlockK / 16; ++k) {
+              // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in the (addr >> 4) field
+              const uint32_t accum = (kb > kb0 || k > 0) ? 1u : 0u;
+              if (p.debug & 2) continue;
+              if (PAIR) umma_bf16_2sm(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accum);
+              else umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accum);
+            }
+            // frees this smem stage (in both CTAs of a pair) once the MMAs above retire
+            if (PAIR) umma_commit_2sm(empty_bar + stage); else umma_commit(empty_bar + stage);
+            // accumulator complete (pair: rows 0-127 in the leader's TMEM, 128-255 in the peer's)
+            if (kb == kb1 - 1) { if (PAIR) umma_commit_2sm(tmem_full_bar + acc); else umma_commit(tmem_full_bar + acc); }
           }
-          // frees this smem stage (in both CTAs of a pair) once the MMAs above retire
-          if (PAIR) umma_commit_2sm(empty_bar + stage); else umma_commit(empty_bar + stage);
+          __syncwarp();
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
-        // accumulator complete (pair: rows 0-127 in the leader's TMEM, 128-255 in the peer's)
-        if (PAIR) umma_commit_2sm(tmem_full_bar + acc); else umma_commit(tmem_full_bar + acc);
       }
     }
   } else {
@@ -683,10 +800,10 @@ ConvGeom conv_geometry(int N, int Ho, int Wo, int Cout) {
 
 // (C, W, 1, H, N) view of an NHWC tensor (stride 1) or (2C, W/2, 2, H/2, N) (stride 2), box = one tile brick
 static int encode_act_map(CUtensorMap* m, const bf16* ptr, int N, int H, int W, int C, int stride,
-                          int Wt, int Ht, int Nt, int pitch = 0) {
+                          int Wt, int Ht, int Nt, int pitch = 0, int halo = 0) {
   const uint64_t e = 2;
   uint64_t dims[5], str[4];
-  uint32_t box[5] = {(uint32_t)kConvBlockK, (uint32_t)Wt, 1, (uint32_t)Ht, (uint32_t)Nt};
+  uint32_t box[5] = {(uint32_t)kConvBlockK, (uint32_t)Wt, 1, (uint32_t)(Ht + 2 * halo), (uint32_t)Nt};
   if (stride == 1) {
     const uint64_t P = pitch ? pitch : C;   // pixel pitch in elements (channel window of a wider tensor)
     dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = N;
@@ -720,6 +837,16 @@ int conv_plan_build(ConvPlan* pl, const ConvDesc& d) {
   const ConvGeom g = conv_geometry(d.N, p.Ho, p.Wo, d.Cout);
   p.Wt = g.Wt; p.Ht = g.Ht; p.Nt = g.Nt; p.w_blks = g.w_blks; p.h_blks = g.h_blks; p.n_blks = g.n_blks;
   p.block_n = g.block_n;
+  // halo mode: big 3x3 stride-1 layers with 128-wide N tiles; tile = 8 x 16 pixels of one image
+  // (measured: not faster than the SM-pair kernel on B200 for this network - opt-in with B2E_HALO=1)
+  static const bool halo_off = !(getenv("B2E_HALO") && atoi(getenv("B2E_HALO")) > 0);
+  p.halo = (!halo_off && d.ksize == 3 && d.stride == 1 && g.block_n == 128 && !d.b_batch_rows && !d.s0.pitch &&
+            p.Wo % kHaloWt == 0 && p.Ho % kHaloHt == 0 &&
+            (int64_t)d.N * p.Ho * p.Wo / kConvBlockM * (p.cout_pad / 128) >= kNumSMs) ? 1 : 0;
+  if (p.halo) {
+    p.Wt = kHaloWt; p.Ht = kHaloHt; p.Nt = 1;
+    p.w_blks = p.Wo / p.Wt; p.h_blks = p.Ho / p.Ht; p.n_blks = d.N;
+  }
   B2E_REQUIRE(!d.tile_stats || (g.stats_ok && d.out_bf16), B2E_UNSUPPORTED_SHAPE,
               "conv: fused GroupNorm statistics are not available for this output shape");
   p.tile_stats = d.tile_stats;
@@ -738,10 +865,10 @@ int conv_plan_build(ConvPlan* pl, const ConvDesc& d) {
   }
   B2E_REQUIRE(d.stride == 1 || !d.s0.pitch, B2E_UNSUPPORTED_SHAPE, "conv: pitched input with stride 2");
   B2E_REQUIRE(!d.b_batch_rows || p.Nt == 1, B2E_UNSUPPORTED_SHAPE, "conv: batched B needs tiles within one image");
-  int rc = encode_act_map(&p.map_a0, d.s0.ptr, d.N, d.H, d.W, d.s0.C, d.stride, p.Wt, p.Ht, p.Nt, d.s0.pitch);
+  int rc = encode_act_map(&p.map_a0, d.s0.ptr, d.N, d.H, d.W, d.s0.C, d.stride, p.Wt, p.Ht, p.Nt, d.s0.pitch, p.halo);
   if (rc) return rc;
   p.map_a1 = p.map_a0; p.map_r0 = p.map_a0; p.map_r1 = p.map_a0; p.map_out = p.map_a0;
-  if (d.s1.ptr && (rc = encode_act_map(&p.map_a1, d.s1.ptr, d.N, d.H, d.W, d.s1.C, d.stride, p.Wt, p.Ht, p.Nt))) return rc;
+  if (d.s1.ptr && (rc = encode_act_map(&p.map_a1, d.s1.ptr, d.N, d.H, d.W, d.s1.C, d.stride, p.Wt, p.Ht, p.Nt, 0, p.halo))) return rc;
   if (d.r0.ptr && (rc = encode_act_map(&p.map_r0, d.r0.ptr, d.N, p.Ho, p.Wo, d.r0.C, 1, p.Wt, p.Ht, p.Nt))) return rc;
   if (d.r1.ptr && (rc = encode_act_map(&p.map_r1, d.r1.ptr, d.N, p.Ho, p.Wo, d.r1.C, 1, p.Wt, p.Ht, p.Nt))) return rc;
   p.has_out_bf16 = d.out_bf16 != nullptr;
@@ -753,7 +880,7 @@ int conv_plan_build(ConvPlan* pl, const ConvDesc& d) {
   p.b_batch_rows = d.b_batch_rows;
   // SM-pair mode: 128-wide N tiles, an even number of M tiles and enough tiles to keep every SM pair busy
   const int m_tiles = p.w_blks * p.h_blks * p.n_blks, tiles = m_tiles * (p.cout_pad / p.block_n);
-  p.pair = (p.block_n == 128 && m_tiles % 2 == 0 && tiles >= kNumSMs) ? 1 : 0;
+  p.pair = (!p.halo && p.block_n == 128 && m_tiles % 2 == 0 && tiles >= kNumSMs) ? 1 : 0;
   // split-K when the tiles alone cannot fill the chip: up to 8 splits of at least 8 k-blocks each
   const int num_kb = (int)(ktot / K);
   p.splits = 1;
@@ -774,13 +901,13 @@ int conv_plan_build(ConvPlan* pl, const ConvDesc& d) {
   return B2E_OK;
 }
 
-template <int BN, int STAGES, bool PAIR>
+template <int BN, int STAGES, bool PAIR, bool HALO = false>
 static int launch_t(const ConvPlan& pl, const ConvKParams& kp, int tiles, cudaStream_t st) {
-  using Cfg = ConvCfg<BN, STAGES, PAIR>;
+  using Cfg = ConvCfg<BN, STAGES, PAIR, HALO>;
   static_assert(Cfg::kSmemBytes <= 227 * 1024, "shared memory budget");
   static bool attr_set = false;
   if (!attr_set) {
-    B2E_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B2E_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES, PAIR, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg::kSmemBytes));
     attr_set = true;
   }
@@ -795,7 +922,7 @@ static int launch_t(const ConvPlan& pl, const ConvKParams& kp, int tiles, cudaSt
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = PAIR ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BN, STAGES, PAIR>, pl.map_a0, pl.map_a1, pl.map_r0,
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BN, STAGES, PAIR, HALO>, pl.map_a0, pl.map_a1, pl.map_r0,
                                      pl.map_r1, pl.map_b, pl.map_out, kp);
   if (e != cudaSuccess) { set_error("conv_igemm launch: %s", cudaGetErrorString(e)); return B2E_CUDA_ERROR; }
   return check_launch("conv_igemm");
@@ -814,6 +941,8 @@ int conv_launch(const ConvPlan& pl, const ConvEpilogue& ep, cudaStream_t st) {
   }
   kp.n_tiles = pl.cout_pad / pl.block_n;
   kp.b_batch_rows = pl.b_batch_rows;
+  static const int dbg = getenv("B2E_DEBUG") ? atoi(getenv("B2E_DEBUG")) : 0;
+  kp.debug = dbg;
   kp.splits = pl.splits; kp.split_ws = pl.split_ws; kp.split_counters = pl.split_counters;
   kp.bias = ep.bias; kp.bias2 = ep.bias2; kp.temb = ep.temb; kp.temb_stride = ep.temb_stride;
   kp.out_bf16 = pl.has_out_bf16; kp.out_f32_nchw = pl.has_out_bf16 ? nullptr : ep.out_f32_nchw;
@@ -823,8 +952,9 @@ int conv_launch(const ConvPlan& pl, const ConvEpilogue& ep, cudaStream_t st) {
   switch (pl.block_n) {
     case 16: return launch_t<16, 8, false>(pl, kp, kp.num_tiles, st);
     case 64: return launch_t<64, 8, false>(pl, kp, kp.num_tiles, st);
-    default: return pl.pair ? launch_t<128, 7, true>(pl, kp, kp.num_tiles, st)
-                            : launch_t<128, 5, false>(pl, kp, kp.num_tiles, st);
+    default:
+      if (pl.halo) return launch_t<128, 6, false, true>(pl, kp, kp.num_tiles, st);
+      return pl.pair ? launch_t<128, 7, true>(pl, kp, kp.num_tiles, st) : launch_t<128, 5, false>(pl, kp, kp.num_tiles, st);
   }
 }
 
