@@ -41,22 +41,21 @@ constexpr int kABytes = kConvBlockM * kConvBlockK * 2;  // 16 KB
 constexpr int kHaloWt = 16, kHaloHt = 8;
 constexpr int kHaloRows = (kHaloHt + 2) * kHaloWt;       // 160
 constexpr int kHaloABytes = kHaloRows * 128;             // 20 KB
-constexpr int kHaloASlots = 3;
 template <int BN, int STAGES, bool PAIR = false, bool HALO = false>
 struct ConvCfg {
   static constexpr int kBRows = PAIR ? BN / 2 : BN;             // B rows staged by this CTA
   static constexpr int kBBytes = kBRows * kConvBlockK * 2;
   static constexpr int kBBytesPad = (kBBytes + 1023) / 1024 * 1024;
-  // non-halo: STAGES x (A + B); halo: kHaloASlots x A-halo followed by STAGES x B
+  // non-halo: STAGES x (A + B); halo: kASlots x A-halo followed by STAGES x B
+  static constexpr int kASlots = HALO ? (PAIR ? 4 : 3) : 0;
   static constexpr int kStageBytes = HALO ? kBBytesPad : kABytes + kBBytesPad;
-  static constexpr int kRingBytes = HALO ? kHaloASlots * kHaloABytes + STAGES * kBBytesPad : STAGES * (kABytes + kBBytesPad);
-  static constexpr int kNumBars = HALO ? 2 * (kHaloASlots + STAGES) : 2 * STAGES;
+  static constexpr int kRingBytes = HALO ? kASlots * kHaloABytes + STAGES * kBBytesPad : STAGES * (kABytes + kBBytesPad);
   static constexpr int kStages = STAGES;
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;   // double-buffered accumulator
   static constexpr int kSlabs = BN / 64;                        // 64-channel output slabs (0: fp32 NCHW path)
   static constexpr int kStagingBytes = kSlabs * kConvBlockM * 128;
   static constexpr int kRedBytes = kSlabs > 0 ? 8192 : 0;       // GroupNorm-statistics scratch [row groups][BN][2]
-  static constexpr int kSmemBytes = kRingBytes + kStagingBytes + kRedBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kRingBytes + kStagingBytes + kRedBytes + 1024 /*align*/ + 512 /*barriers*/;
 };
 
 struct ConvKParams {
@@ -299,10 +298,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
                   const __grid_constant__ CUtensorMap map_r0, const __grid_constant__ CUtensorMap map_r1,
                   const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out,
                   const __grid_constant__ ConvKParams p) {
-  static_assert(!(HALO && PAIR), "halo and pair modes are not combined");
   using Cfg = ConvCfg<BN, STAGES, PAIR, HALO>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int kHaloASlots = Cfg::kASlots;
   uint8_t* smem_b = smem + (HALO ? kHaloASlots * kHaloABytes : 0);   // halo: B ring after the A-halo slots
   uint8_t* staging = smem + Cfg::kRingBytes;
   float* red = reinterpret_cast<float*>(staging + Cfg::kStagingBytes);
@@ -379,8 +378,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         auto load_a = [&](const CUtensorMap* ma, uint32_t bytes, int c0, int c1, int c3, int c4) {
           mbar_wait(emptya_bar + sa, pa ^ 1);
           if (elect_one()) {
-            mbar_expect_tx(fulla_bar + sa, bytes);
-            tma_load_5d(smem + sa * kHaloABytes, ma, fulla_bar + sa, c0, c1, 0, c3, c4);
+            if (PAIR) {   // both CTAs' bricks complete on the leader's barrier
+              if (rank == 0) mbar_expect_tx(fulla_bar + sa, 2 * bytes);
+              tma_load_5d_2sm(smem + sa * kHaloABytes, ma, fulla_bar + sa, c0, c1, 0, c3, c4);
+            } else {
+              mbar_expect_tx(fulla_bar + sa, bytes);
+              tma_load_5d(smem + sa * kHaloABytes, ma, fulla_bar + sa, c0, c1, 0, c3, c4);
+            }
           }
           __syncwarp();
           if (++sa == kHaloASlots) { sa = 0; pa ^= 1; }
@@ -388,15 +392,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         auto load_b = [&](int kcol, int brow) {
           mbar_wait(empty_bar + sb, pb ^ 1);
           if (elect_one()) {
-            mbar_expect_tx(full_bar + sb, Cfg::kBBytes);
-            tma_load_2d(smem_b + sb * Cfg::kStageBytes, &map_b, full_bar + sb, kcol, brow);
+            if (PAIR) {
+              if (rank == 0) mbar_expect_tx(full_bar + sb, 2 * Cfg::kBBytes);
+              tma_load_2d_2sm(smem_b + sb * Cfg::kStageBytes, &map_b, full_bar + sb, kcol, brow);
+            } else {
+              mbar_expect_tx(full_bar + sb, Cfg::kBBytes);
+              tma_load_2d(smem_b + sb * Cfg::kStageBytes, &map_b, full_bar + sb, kcol, brow);
+            }
           }
           __syncwarp();
           if (++sb == Cfg::kStages) { sb = 0; pb ^= 1; }
         };
         for (int tile = tile_begin; tile < p.num_tiles; tile += tile_step) {
-          const TileCoord tc = tile_coord(p, tile);
-          const int brow0 = tc.n_tile * BN;
+          const TileCoord tc = tile_coord(p, tile, PAIR, rank);
+          const int brow0 = tc.n_tile * BN + (PAIR ? rank * Cfg::kBRows : 0);
           for (int kw = 0; kw < 3; ++kw)
             for (int ck = 0; ck < chunks; ++ck) {
               // (Ht+2) x Wt halo brick for horizontal tap kw: serves the three vertical taps
@@ -470,12 +479,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
               if (elect_one()) {
 #pragma unroll
                 for (int k = 0; k < kConvBlockK / 16; ++k) {
-                  umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (first && k == 0) ? 0u : 1u);
+                  const uint32_t accum = (first && k == 0) ? 0u : 1u;
+                  if (PAIR) umma_bf16_2sm(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accum);
+                  else umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accum);
                 }
-                umma_commit(empty_bar + stage);
-                // all MMAs reading this A tile have been issued; frees it when they retire
-                if (kh == nsub - 1) umma_commit(emptya_bar + sa);
-                if (kh == nsub - 1 && gidx == groups - 1) umma_commit(tmem_full_bar + acc);
+                const bool last_sub = kh == nsub - 1;
+                if (PAIR) {
+                  umma_commit_2sm(empty_bar + stage);
+                  // all MMAs reading this A tile have been issued; frees it (in both CTAs) when they retire
+                  if (last_sub) umma_commit_2sm(emptya_bar + sa);
+                  if (last_sub && gidx == groups - 1) umma_commit_2sm(tmem_full_bar + acc);
+                } else {
+                  umma_commit(empty_bar + stage);
+                  if (last_sub) umma_commit(emptya_bar + sa);
+                  if (last_sub && gidx == groups - 1) umma_commit(tmem_full_bar + acc);
+                }
               }
               __syncwarp();
               first = 0;
@@ -838,8 +856,9 @@ int conv_plan_build(ConvPlan* pl, const ConvDesc& d) {
   p.Wt = g.Wt; p.Ht = g.Ht; p.Nt = g.Nt; p.w_blks = g.w_blks; p.h_blks = g.h_blks; p.n_blks = g.n_blks;
   p.block_n = g.block_n;
   // halo mode: big 3x3 stride-1 layers with 128-wide N tiles; tile = 8 x 16 pixels of one image
-  // (measured: not faster than the SM-pair kernel on B200 for this network - opt-in with B2E_HALO=1)
-  static const bool halo_off = !(getenv("B2E_HALO") && atoi(getenv("B2E_HALO")) > 0);
+  // (the main loop is bound by the ~42 B/clk/SM the L2 delivers: halo + SM pair needs 14.7 KB per 128x128x64
+  //  k-block instead of 24 KB; B2E_HALO=0 switches it off)
+  static const bool halo_off = getenv("B2E_HALO") && atoi(getenv("B2E_HALO")) == 0;
   p.halo = (!halo_off && d.ksize == 3 && d.stride == 1 && g.block_n == 128 && !d.b_batch_rows && !d.s0.pitch &&
             p.Wo % kHaloWt == 0 && p.Ho % kHaloHt == 0 &&
             (int64_t)d.N * p.Ho * p.Wo / kConvBlockM * (p.cout_pad / 128) >= kNumSMs) ? 1 : 0;
@@ -880,7 +899,7 @@ int conv_plan_build(ConvPlan* pl, const ConvDesc& d) {
   p.b_batch_rows = d.b_batch_rows;
   // SM-pair mode: 128-wide N tiles, an even number of M tiles and enough tiles to keep every SM pair busy
   const int m_tiles = p.w_blks * p.h_blks * p.n_blks, tiles = m_tiles * (p.cout_pad / p.block_n);
-  p.pair = (!p.halo && p.block_n == 128 && m_tiles % 2 == 0 && tiles >= kNumSMs) ? 1 : 0;
+  p.pair = (p.block_n == 128 && m_tiles % 2 == 0 && tiles >= kNumSMs) ? 1 : 0;
   // split-K when the tiles alone cannot fill the chip: up to 8 splits of at least 8 k-blocks each
   const int num_kb = (int)(ktot / K);
   p.splits = 1;
@@ -953,7 +972,8 @@ int conv_launch(const ConvPlan& pl, const ConvEpilogue& ep, cudaStream_t st) {
     case 16: return launch_t<16, 8, false>(pl, kp, kp.num_tiles, st);
     case 64: return launch_t<64, 8, false>(pl, kp, kp.num_tiles, st);
     default:
-      if (pl.halo) return launch_t<128, 6, false, true>(pl, kp, kp.num_tiles, st);
+      if (pl.halo) return pl.pair ? launch_t<128, 12, true, true>(pl, kp, kp.num_tiles, st)    // 4 x 20 KB + 12 x 8 KB
+                                  : launch_t<128, 6, false, true>(pl, kp, kp.num_tiles, st);  // 3 x 20 KB + 6 x 16 KB
       return pl.pair ? launch_t<128, 7, true>(pl, kp, kp.num_tiles, st) : launch_t<128, 5, false>(pl, kp, kp.num_tiles, st);
   }
 }
