@@ -34,24 +34,29 @@ constexpr int kABytes = kConvBlockM * kConvBlockK * 2;  // 16 KB
 // PAIR: two CTAs of a cluster (an SM pair) run ONE tcgen05.mma.cta_group::2 of shape 256 x BN x 16: each CTA
 // stages its own 128 output pixels of A and only HALF of the B tile, so a stage is 24 KB instead of 32 KB
 // for the same tensor work - the main loop needs 25 % fewer bytes in flight / from L2 per FLOP.
-// HALO (3x3, stride 1): the tile is an 8x16-pixel brick and ONE TMA load brings its (8+2)x16 halo brick
-// for a given horizontal tap; the three vertical taps are then just 16-row (2 KB, swizzle-aligned) offsets of
-// the same smem tile.  A is fetched 3x per channel chunk instead of 9x - L2->SM traffic per FLOP drops ~30 %,
-// which is what bounds the 128-wide layers.  A and B live in separate rings (3 halo slots, STAGES B slots).
+// HALO (3x3, stride 1; always an SM pair): a CTA owns an (8*MT) x 16-pixel brick of one image (MT = 1 or 2 M tiles
+// of 128 pixels).  ONE pipeline stage = one TMA load of the brick's (8*MT+2) x 16 halo for a given (horizontal tap,
+// 64-channel chunk) + the three B tiles of its vertical taps; the vertical taps are 16-row (2 KB, swizzle-aligned)
+// offsets into the same smem tile and the MT M tiles are 128-row offsets, so one mbarrier hand-shake feeds
+// 3*MT*4 tcgen05.mma instead of 4.  Why: (1) the main loop of the plain kernel is bound by the ~45 B/clk/SM the
+// L2 delivers (24 KB per 128x128x64 k-block = ~500 clk against 256 tensor clk); halo + pair needs 14.7 KB (MT=1) /
+// 10 KB (MT=2, B shared by both M tiles); (2) clock64 traces show ~170 clk per mbarrier try_wait and ~30 clk per
+// UTCHMMA issue in the single issuing warp - with one wait per k-block the issue loop itself costs ~400 clk.
 constexpr int kHaloWt = 16, kHaloHt = 8;
-constexpr int kHaloRows = (kHaloHt + 2) * kHaloWt;       // 160
-constexpr int kHaloABytes = kHaloRows * 128;             // 20 KB
-template <int BN, int STAGES, bool PAIR = false, bool HALO = false>
+template <int BN, int STAGES, bool PAIR = false, bool HALO = false, int MT = 1>
 struct ConvCfg {
+  static_assert(!HALO || (PAIR && BN == 128), "halo kernels are SM-pair kernels with 128-wide N tiles");
+  static constexpr int kMt = MT;
   static constexpr int kBRows = PAIR ? BN / 2 : BN;             // B rows staged by this CTA
   static constexpr int kBBytes = kBRows * kConvBlockK * 2;
   static constexpr int kBBytesPad = (kBBytes + 1023) / 1024 * 1024;
-  // non-halo: STAGES x (A + B); halo: kASlots x A-halo followed by STAGES x B
-  static constexpr int kASlots = HALO ? (PAIR ? 4 : 3) : 0;
-  static constexpr int kStageBytes = HALO ? kBBytesPad : kABytes + kBBytesPad;
-  static constexpr int kRingBytes = HALO ? kASlots * kHaloABytes + STAGES * kBBytesPad : STAGES * (kABytes + kBBytesPad);
+  static constexpr int kHaloABytes = (kHaloHt * MT + 2) * kHaloWt * 128;   // 20 KB (MT=1) / 36 KB (MT=2)
+  // non-halo: [A 16 KB][B]; halo: [A halo][B kh=0][B kh=1][B kh=2]
+  static constexpr int kStageBytes = HALO ? kHaloABytes + 3 * kBBytesPad : kABytes + kBBytesPad;
+  static constexpr int kRingBytes = STAGES * kStageBytes;
   static constexpr int kStages = STAGES;
-  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;   // double-buffered accumulator
+  static constexpr int kAccCols = BN * MT;                      // one accumulator buffer
+  static constexpr int kTmemCols = 2 * kAccCols < 32 ? 32 : 2 * kAccCols;   // double-buffered accumulator
   static constexpr int kSlabs = BN / 64;                        // 64-channel output slabs (0: fp32 NCHW path)
   static constexpr int kStagingBytes = kSlabs * kConvBlockM * 128;
   static constexpr int kRedBytes = kSlabs > 0 ? 8192 : 0;       // GroupNorm-statistics scratch [row groups][BN][2]
@@ -76,7 +81,11 @@ struct ConvKParams {
   int out_bf16;         // 1: stage + TMA-store the bf16 NHWC tile through map_out
   float* out_f32_nchw;
   float* tile_stats;    // fused GroupNorm statistics or null
+  long long* trace;     // B2E_TRACE: clock64 stamps of CTA 0's warp loops (halo kernels), else null
 };
+// trace regions (long long indices): MMA [0, 4*512) {iter start, A ready, B ready, issued}; producer A
+// [2048, +3*256) {start, slot free, issued}; producer B [2816, +3*512); epilogue [4352, +4*64) {start, acc full, tmem released, done}
+constexpr int kTrMma = 0, kTrPa = 2048, kTrPb = 2816, kTrEpi = 4352, kTrTotal = 4608;
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -291,25 +300,36 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvKParams& p, int tile, 
   t.n0 = (m / p.h_blks) * p.Nt;
   return t;
 }
+// halo kernels: the work item of a CTA is a brick of MT vertically adjacent 8x16 tiles of one image;
+// (w0, h0) = the brick's first pixel, m_tile = the statistics slot of its FIRST tile (tile mt: + mt * w_blks)
+template <int MT>
+__device__ __forceinline__ TileCoord halo_coord(const ConvKParams& p, int tile, int rank) {
+  TileCoord t;
+  t.n_tile = tile % p.n_tiles;
+  int m = 2 * (tile / p.n_tiles) + rank;
+  const int wb = m % p.w_blks; m /= p.w_blks;
+  const int hbricks = p.h_blks / MT;
+  const int hb = (m % hbricks) * MT;
+  t.n0 = m / hbricks;
+  t.w0 = wb * kHaloWt; t.h0 = hb * kHaloHt;
+  t.m_tile = (t.n0 * p.h_blks + hb) * p.w_blks + wb;
+  return t;
+}
 
-template <int BN, int STAGES, bool PAIR, bool HALO>
+template <int BN, int STAGES, bool PAIR, bool HALO, int MT>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                   const __grid_constant__ CUtensorMap map_r0, const __grid_constant__ CUtensorMap map_r1,
                   const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out,
                   const __grid_constant__ ConvKParams p) {
-  using Cfg = ConvCfg<BN, STAGES, PAIR, HALO>;
+  using Cfg = ConvCfg<BN, STAGES, PAIR, HALO, MT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  constexpr int kHaloASlots = Cfg::kASlots;
-  uint8_t* smem_b = smem + (HALO ? kHaloASlots * kHaloABytes : 0);   // halo: B ring after the A-halo slots
   uint8_t* staging = smem + Cfg::kRingBytes;
   float* red = reinterpret_cast<float*>(staging + Cfg::kStagingBytes);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes + Cfg::kRedBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
-  uint64_t* fulla_bar = empty_bar + Cfg::kStages;                    // halo only: [kHaloASlots] x 2
-  uint64_t* emptya_bar = fulla_bar + kHaloASlots;
-  uint64_t* tmem_full_bar = empty_bar + Cfg::kStages + (HALO ? 2 * kHaloASlots : 0);   // [2]
+  uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;         // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
   volatile uint32_t* split_flag = tmem_slot + 1;
@@ -334,7 +354,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     prefetch_tmap(&map_b);
     if (p.out_bf16) prefetch_tmap(&map_out);
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-    if (HALO) for (int s = 0; s < kHaloASlots; ++s) { mbar_init(fulla_bar + s, 1); mbar_init(emptya_bar + s, 1); }
     // pair: the leader's tmem_empty barrier collects the 4 epilogue warps of BOTH CTAs
     for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar + s, 1); mbar_init(tmem_empty_bar + s, PAIR ? 8 : 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -350,8 +369,49 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
 
   if (warp == 0) {
     // ===== TMA producer (whole warp walks the loop; one elected lane issues)
-    {
-      int stage = 0; uint32_t phase = 0;
+    int stage = 0; uint32_t phase = 0;
+    if constexpr (HALO) {
+      int tr_n = 0;
+      const bool tr = p.trace && blockIdx.x == 0 && lane == 0;
+      for (int tile = tile_begin; tile < p.num_tiles; tile += tile_step) {
+        const TileCoord tc = halo_coord<MT>(p, tile, rank);
+        const int brow0 = tc.n_tile * BN + rank * Cfg::kBRows;
+        const int groups = 3 * chunks + r_chunks;
+        int kw = 0, ck = 0;
+        for (int g = 0; g < groups; ++g) {
+          const bool main = g < 3 * chunks;
+          if (tr && tr_n < 512) p.trace[kTrPb + tr_n * 3] = clock64();
+          mbar_wait(empty_bar + stage, phase ^ 1);
+          if (tr && tr_n < 512) p.trace[kTrPb + tr_n * 3 + 1] = clock64();
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          if (elect_one()) {
+            if (main) {
+              // (8*MT+2) x 16 halo brick of horizontal tap kw + the B tiles of its three vertical taps
+              if (rank == 0) mbar_expect_tx(full_bar + stage, 2 * (Cfg::kHaloABytes + 3 * Cfg::kBBytes));
+              const bool first = ck < p.c0_chunks;
+              tma_load_5d_2sm(sa, first ? &map_a0 : &map_a1, full_bar + stage,
+                              (first ? ck : ck - p.c0_chunks) * kConvBlockK, tc.w0 + kw - 1, 0, tc.h0 - 1, tc.n0);
+#pragma unroll
+              for (int kh = 0; kh < 3; ++kh)
+                tma_load_2d_2sm(sa + Cfg::kHaloABytes + kh * Cfg::kBBytesPad, &map_b, full_bar + stage,
+                                ((kh * 3 + kw) * chunks + ck) * kConvBlockK, brow0);
+            } else {
+              // residual segment: the brick itself (MT x 128 pixels) at the output position, one B tile
+              const int rk = g - 3 * chunks;
+              if (rank == 0) mbar_expect_tx(full_bar + stage, 2 * (MT * kABytes + Cfg::kBBytes));
+              const bool first = rk < p.r0_chunks;
+              tma_load_5d_2sm(sa, first ? &map_r0 : &map_r1, full_bar + stage,
+                              (first ? rk : rk - p.r0_chunks) * kConvBlockK, tc.w0, 0, tc.h0, tc.n0);
+              tma_load_2d_2sm(sa + Cfg::kHaloABytes, &map_b, full_bar + stage, (main_kb + rk) * kConvBlockK, brow0);
+            }
+          }
+          __syncwarp();
+          if (tr && tr_n < 512) { p.trace[kTrPb + tr_n * 3 + 2] = clock64(); ++tr_n; }
+          if (++ck == chunks) { ck = 0; ++kw; }
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else {
       // one k-block: this CTA's A brick + its share of the B tile (pair: both CTAs complete on the leader's barrier)
       auto load_kb = [&](const CUtensorMap* ma, int c0, int c1, int c2, int c3, int c4, int kcol, int brow) {
         mbar_wait(empty_bar + stage, phase ^ 1);
@@ -373,53 +433,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         __syncwarp();
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       };
-      if (HALO) {
-        int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
-        auto load_a = [&](const CUtensorMap* ma, uint32_t bytes, int c0, int c1, int c3, int c4) {
-          mbar_wait(emptya_bar + sa, pa ^ 1);
-          if (elect_one()) {
-            if (PAIR) {   // both CTAs' bricks complete on the leader's barrier
-              if (rank == 0) mbar_expect_tx(fulla_bar + sa, 2 * bytes);
-              tma_load_5d_2sm(smem + sa * kHaloABytes, ma, fulla_bar + sa, c0, c1, 0, c3, c4);
-            } else {
-              mbar_expect_tx(fulla_bar + sa, bytes);
-              tma_load_5d(smem + sa * kHaloABytes, ma, fulla_bar + sa, c0, c1, 0, c3, c4);
-            }
-          }
-          __syncwarp();
-          if (++sa == kHaloASlots) { sa = 0; pa ^= 1; }
-        };
-        auto load_b = [&](int kcol, int brow) {
-          mbar_wait(empty_bar + sb, pb ^ 1);
-          if (elect_one()) {
-            if (PAIR) {
-              if (rank == 0) mbar_expect_tx(full_bar + sb, 2 * Cfg::kBBytes);
-              tma_load_2d_2sm(smem_b + sb * Cfg::kStageBytes, &map_b, full_bar + sb, kcol, brow);
-            } else {
-              mbar_expect_tx(full_bar + sb, Cfg::kBBytes);
-              tma_load_2d(smem_b + sb * Cfg::kStageBytes, &map_b, full_bar + sb, kcol, brow);
-            }
-          }
-          __syncwarp();
-          if (++sb == Cfg::kStages) { sb = 0; pb ^= 1; }
-        };
-        for (int tile = tile_begin; tile < p.num_tiles; tile += tile_step) {
-          const TileCoord tc = tile_coord(p, tile, PAIR, rank);
-          const int brow0 = tc.n_tile * BN + (PAIR ? rank * Cfg::kBRows : 0);
-          for (int kw = 0; kw < 3; ++kw)
-            for (int ck = 0; ck < chunks; ++ck) {
-              // (Ht+2) x Wt halo brick for horizontal tap kw: serves the three vertical taps
-              if (ck < p.c0_chunks) load_a(&map_a0, kHaloABytes, ck * kConvBlockK, tc.w0 + kw - 1, tc.h0 - 1, tc.n0);
-              else load_a(&map_a1, kHaloABytes, (ck - p.c0_chunks) * kConvBlockK, tc.w0 + kw - 1, tc.h0 - 1, tc.n0);
-              for (int kh = 0; kh < 3; ++kh) load_b(((kh * 3 + kw) * chunks + ck) * kConvBlockK, brow0);
-            }
-          for (int ck = 0; ck < r_chunks; ++ck) {   // residual segment: plain 128-pixel brick at the output position
-            if (ck < p.r0_chunks) load_a(&map_r0, kABytes, ck * kConvBlockK, tc.w0, tc.h0, tc.n0);
-            else load_a(&map_r1, kABytes, (ck - p.r0_chunks) * kConvBlockK, tc.w0, tc.h0, tc.n0);
-            load_b((main_kb + ck) * kConvBlockK, brow0);
-          }
-        }
-      } else
       for (int wi = tile_begin; wi < num_work; wi += tile_step) {
         const int tile = wi / splits, split = wi - tile * splits;
         const TileCoord tc = tile_coord(p, tile, PAIR, rank);
@@ -456,82 +469,77 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       constexpr uint32_t idesc = make_idesc(PAIR ? 2 * kConvBlockM : kConvBlockM, BN);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
-      if (HALO) {
-        int sa = 0; uint32_t pa = 0;
+      if constexpr (HALO) {
+        int tr_n = 0;
+        const bool tr = p.trace && blockIdx.x == 0 && lane == 0;
+        const int groups = 3 * chunks + r_chunks;   // pipeline stages per work item
         for (int tile = tile_begin; tile < p.num_tiles; tile += tile_step, ++it) {
           const int acc = it & 1;
+          if (tr && tr_n < 512) p.trace[kTrMma + tr_n * 4] = clock64();
           mbar_wait(tmem_empty_bar + acc, ((it >> 1) & 1) ^ 1);
           tc_fence_after();
-          const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-          uint32_t first = 1;
-          const int groups = 3 * chunks + r_chunks;   // A tiles per output tile
-          for (int gidx = 0; gidx < groups; ++gidx) {
-            const int nsub = gidx < 3 * chunks ? 3 : 1;   // vertical taps served by this A tile
-            mbar_wait(fulla_bar + sa, pa);
+          const uint32_t tmem_d = tmem_base + (uint32_t)(acc * Cfg::kAccCols);
+          for (int g = 0; g < groups; ++g) {
+            const int nsub = g < 3 * chunks ? 3 : 1;   // vertical taps served by this stage
+            if (tr && tr_n < 512) p.trace[kTrMma + tr_n * 4 + 1] = clock64();
+            mbar_wait(full_bar + stage, phase);
             tc_fence_after();
-            const uint32_t a_addr = smem_u32(smem + sa * kHaloABytes);
-            for (int kh = 0; kh < nsub; ++kh) {
-              mbar_wait(full_bar + stage, phase);
-              tc_fence_after();
-              // vertical tap kh = rows [kh*Wt, kh*Wt + 128) of the halo tile: a 2 KB (swizzle-aligned) offset
-              const uint64_t adesc = make_smem_desc(a_addr + (uint32_t)(kh * kHaloWt * 128));
-              const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * Cfg::kStageBytes));
-              if (elect_one()) {
+            if (tr && tr_n < 512) p.trace[kTrMma + tr_n * 4 + 2] = clock64();
+            const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
+            const uint32_t b_addr = a_addr + Cfg::kHaloABytes;
+            if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < kConvBlockK / 16; ++k) {
-                  const uint32_t accum = (first && k == 0) ? 0u : 1u;
-                  if (PAIR) umma_bf16_2sm(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accum);
-                  else umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accum);
-                }
-                const bool last_sub = kh == nsub - 1;
-                if (PAIR) {
-                  umma_commit_2sm(empty_bar + stage);
-                  // all MMAs reading this A tile have been issued; frees it (in both CTAs) when they retire
-                  if (last_sub) umma_commit_2sm(emptya_bar + sa);
-                  if (last_sub && gidx == groups - 1) umma_commit_2sm(tmem_full_bar + acc);
-                } else {
-                  umma_commit(empty_bar + stage);
-                  if (last_sub) umma_commit(emptya_bar + sa);
-                  if (last_sub && gidx == groups - 1) umma_commit(tmem_full_bar + acc);
+              for (int mt = 0; mt < MT; ++mt) {
+                for (int kh = 0; kh < nsub; ++kh) {
+                  // M tile mt / vertical tap kh = rows [(8*mt + kh) * 16, + 128) of the halo tile (2 KB-aligned)
+                  const uint64_t adesc = make_smem_desc(a_addr + (uint32_t)((mt * kHaloHt + kh) * kHaloWt * 128));
+                  const uint64_t bdesc = make_smem_desc(b_addr + (uint32_t)(kh * Cfg::kBBytesPad));
+#pragma unroll
+                  for (int k = 0; k < kConvBlockK / 16; ++k)
+                    umma_bf16_2sm(tmem_d + (uint32_t)(mt * BN), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                  (g == 0 && kh == 0 && k == 0) ? 0u : 1u);
                 }
               }
-              __syncwarp();
-              first = 0;
-              if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+              // frees this stage in both CTAs once the MMAs above retire
+              umma_commit_2sm(empty_bar + stage);
+              if (g == groups - 1) umma_commit_2sm(tmem_full_bar + acc);
             }
-            if (++sa == kHaloASlots) { sa = 0; pa ^= 1; }
+            __syncwarp();
+            if (tr && tr_n < 512) { p.trace[kTrMma + tr_n * 4 + 3] = clock64(); ++tr_n; if (tr_n < 512) p.trace[kTrMma + tr_n * 4] = 0; }
+            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
           }
         }
-      } else
-      for (int wi = tile_begin; wi < num_work; wi += tile_step, ++it) {
-        const int split = wi % splits;
-        const int kb0 = (int)((int64_t)split * num_kb / splits), kb1 = (int)((int64_t)(split + 1) * num_kb / splits);
-        const int acc = it & 1;
-        mbar_wait(tmem_empty_bar + acc, ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(full_bar + stage, phase);
+      } else {
+        for (int wi = tile_begin; wi < num_work; wi += tile_step, ++it) {
+          const int split = wi % splits;
+          const int kb0 = (int)((int64_t)split * num_kb / splits), kb1 = (int)((int64_t)(split + 1) * num_kb / splits);
+          const int acc = it & 1;
+          mbar_wait(tmem_empty_bar + acc, ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint64_t adesc = make_smem_desc(sa);
-          const uint64_t bdesc = make_smem_desc(sa + kABytes);
-          if (elect_one()) {
+          const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(full_bar + stage, phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+            const uint64_t adesc = make_smem_desc(sa);
+            const uint64_t bdesc = make_smem_desc(sa + kABytes);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < kConvBlockK / 16; ++k) {
-              // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in the (addr >> 4) field
-              const uint32_t accum = (kb > kb0 || k > 0) ? 1u : 0u;
-              if (p.debug & 2) continue;
-              if (PAIR) umma_bf16_2sm(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accum);
-              else umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accum);
+              for (int k = 0; k < kConvBlockK / 16; ++k) {
+                // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in the (addr >> 4) field
+                const uint32_t accum = (kb > kb0 || k > 0) ? 1u : 0u;
+                if (p.debug & 2) continue;
+                if (PAIR) umma_bf16_2sm(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accum);
+                else umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accum);
+              }
+              // frees this smem stage (in both CTAs of a pair) once the MMAs above retire
+              if (PAIR) umma_commit_2sm(empty_bar + stage); else umma_commit(empty_bar + stage);
+              // accumulator complete (pair: rows 0-127 in the leader's TMEM, 128-255 in the peer's)
+              if (kb == kb1 - 1) { if (PAIR) umma_commit_2sm(tmem_full_bar + acc); else umma_commit(tmem_full_bar + acc); }
             }
-            // frees this smem stage (in both CTAs of a pair) once the MMAs above retire
-            if (PAIR) umma_commit_2sm(empty_bar + stage); else umma_commit(empty_bar + stage);
-            // accumulator complete (pair: rows 0-127 in the leader's TMEM, 128-255 in the peer's)
-            if (kb == kb1 - 1) { if (PAIR) umma_commit_2sm(tmem_full_bar + acc); else umma_commit(tmem_full_bar + acc); }
+            __syncwarp();
+            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
           }
-          __syncwarp();
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -544,18 +552,27 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     int it = 0;
     for (int wi = tile_begin; wi < num_work; wi += tile_step, ++it) {
       const int tile = wi / splits, split = wi - tile * splits;
-      const TileCoord tc = tile_coord(p, tile, PAIR, rank);
+      const TileCoord tc0 = HALO ? halo_coord<MT>(p, tile, rank) : tile_coord(p, tile, PAIR, rank);
       const int acc = it & 1;
-      const int n = tc.n0 + n_l, h = tc.h0 + h_l, w = tc.w0 + w_l;
-      const bool valid = n < p.N;
+      const bool tr = p.trace && blockIdx.x == 0 && threadIdx.x == 64 && it < 64;
+      if (tr) p.trace[kTrEpi + it * 4] = clock64();
       mbar_wait(tmem_full_bar + acc, (it >> 1) & 1);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      if (tr) p.trace[kTrEpi + it * 4 + 1] = clock64();
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {   // halo kernels: the MT M tiles of the brick, one after the other
+      TileCoord tc = tc0;
+      tc.h0 += mt * kHaloHt; tc.m_tile += mt * p.w_blks;
+      const int n = tc.n0 + n_l, h = tc.h0 + h_l, w = tc.w0 + w_l;
+      const bool valid = n < p.N;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * Cfg::kAccCols + mt * BN);
       auto release_tmem = [&]() {
+        if (mt != MT - 1) return;
         // all of this warp's accumulator columns are in registers: hand the buffer back
         tc_fence_before();
         __syncwarp();
         if (lane == 0) { if (PAIR) mbar_arrive_leader(tmem_empty_bar + acc); else mbar_arrive(tmem_empty_bar + acc); }
+        if (tr) p.trace[kTrEpi + it * 4 + 2] = clock64();
       };
       const float* part_row = nullptr;
       if (splits > 1) {
@@ -711,6 +728,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           }
         }
       }
+      }   // mt
+      if (tr) p.trace[kTrEpi + it * 4 + 3] = clock64();
     }
     if (store_leader) tma_store_wait_all();
     tc_fence_before();
@@ -855,13 +874,22 @@ int conv_plan_build(ConvPlan* pl, const ConvDesc& d) {
   const ConvGeom g = conv_geometry(d.N, p.Ho, p.Wo, d.Cout);
   p.Wt = g.Wt; p.Ht = g.Ht; p.Nt = g.Nt; p.w_blks = g.w_blks; p.h_blks = g.h_blks; p.n_blks = g.n_blks;
   p.block_n = g.block_n;
-  // halo mode: big 3x3 stride-1 layers with 128-wide N tiles; tile = 8 x 16 pixels of one image
-  // (the main loop is bound by the ~42 B/clk/SM the L2 delivers: halo + SM pair needs 14.7 KB per 128x128x64
-  //  k-block instead of 24 KB; B2E_HALO=0 switches it off)
-  static const bool halo_off = getenv("B2E_HALO") && atoi(getenv("B2E_HALO")) == 0;
-  p.halo = (!halo_off && d.ksize == 3 && d.stride == 1 && g.block_n == 128 && !d.b_batch_rows && !d.s0.pitch &&
-            p.Wo % kHaloWt == 0 && p.Ho % kHaloHt == 0 &&
-            (int64_t)d.N * p.Ho * p.Wo / kConvBlockM * (p.cout_pad / 128) >= kNumSMs) ? 1 : 0;
+  // halo mode (p.halo = MT, the M tiles per CTA): big 3x3 stride-1 layers with 128-wide N tiles; a CTA owns an
+  // (8*MT) x 16-pixel brick of one image, a cluster (SM pair) two bricks.  B2E_HALO=0 switches it off, =1 / =2
+  // force MT.
+  static const int halo_env = getenv("B2E_HALO") ? atoi(getenv("B2E_HALO")) : -1;
+  p.halo = 0;
+  if (halo_env != 0 && d.ksize == 3 && d.stride == 1 && g.block_n == 128 && !d.b_batch_rows && !d.s0.pitch &&
+      p.Wo % kHaloWt == 0 && p.Ho % kHaloHt == 0) {
+    const int64_t tiles128 = (int64_t)d.N * p.Ho * p.Wo / kConvBlockM * (p.cout_pad / 128);   // 128 x 128 output tiles
+    if (tiles128 >= kNumSMs && tiles128 % 2 == 0) {
+      p.halo = 1;
+      // two M tiles per CTA share every B tile (10 KB instead of 14.7 KB from L2 per k-block, half the barrier
+      // hand-shakes) but halve the number of work items: measured worth it from ~12 waves of SM pairs
+      const bool mt2_ok = p.Ho % (2 * kHaloHt) == 0 && tiles128 % 4 == 0;
+      if (mt2_ok && (halo_env == 2 || (halo_env < 0 && tiles128 / 4 >= 12 * (kNumSMs / 2)))) p.halo = 2;
+    }
+  }
   if (p.halo) {
     p.Wt = kHaloWt; p.Ht = kHaloHt; p.Nt = 1;
     p.w_blks = p.Wo / p.Wt; p.h_blks = p.Ho / p.Ht; p.n_blks = d.N;
@@ -884,12 +912,15 @@ int conv_plan_build(ConvPlan* pl, const ConvDesc& d) {
   }
   B2E_REQUIRE(d.stride == 1 || !d.s0.pitch, B2E_UNSUPPORTED_SHAPE, "conv: pitched input with stride 2");
   B2E_REQUIRE(!d.b_batch_rows || p.Nt == 1, B2E_UNSUPPORTED_SHAPE, "conv: batched B needs tiles within one image");
-  int rc = encode_act_map(&p.map_a0, d.s0.ptr, d.N, d.H, d.W, d.s0.C, d.stride, p.Wt, p.Ht, p.Nt, d.s0.pitch, p.halo);
+  // halo kernels: A boxes are the brick's halo (8*MT + 2 rows), residual boxes the brick (8*MT rows), the output
+  // box one 8 x 16 M tile
+  const int a_ht = p.halo ? p.Ht * p.halo : p.Ht;
+  int rc = encode_act_map(&p.map_a0, d.s0.ptr, d.N, d.H, d.W, d.s0.C, d.stride, p.Wt, a_ht, p.Nt, d.s0.pitch, p.halo ? 1 : 0);
   if (rc) return rc;
   p.map_a1 = p.map_a0; p.map_r0 = p.map_a0; p.map_r1 = p.map_a0; p.map_out = p.map_a0;
-  if (d.s1.ptr && (rc = encode_act_map(&p.map_a1, d.s1.ptr, d.N, d.H, d.W, d.s1.C, d.stride, p.Wt, p.Ht, p.Nt, 0, p.halo))) return rc;
-  if (d.r0.ptr && (rc = encode_act_map(&p.map_r0, d.r0.ptr, d.N, p.Ho, p.Wo, d.r0.C, 1, p.Wt, p.Ht, p.Nt))) return rc;
-  if (d.r1.ptr && (rc = encode_act_map(&p.map_r1, d.r1.ptr, d.N, p.Ho, p.Wo, d.r1.C, 1, p.Wt, p.Ht, p.Nt))) return rc;
+  if (d.s1.ptr && (rc = encode_act_map(&p.map_a1, d.s1.ptr, d.N, d.H, d.W, d.s1.C, d.stride, p.Wt, a_ht, p.Nt, 0, p.halo ? 1 : 0))) return rc;
+  if (d.r0.ptr && (rc = encode_act_map(&p.map_r0, d.r0.ptr, d.N, p.Ho, p.Wo, d.r0.C, 1, p.Wt, a_ht, p.Nt))) return rc;
+  if (d.r1.ptr && (rc = encode_act_map(&p.map_r1, d.r1.ptr, d.N, p.Ho, p.Wo, d.r1.C, 1, p.Wt, a_ht, p.Nt))) return rc;
   p.has_out_bf16 = d.out_bf16 != nullptr;
   if (d.out_bf16 && (rc = encode_act_map(&p.map_out, d.out_bf16, d.N, p.Ho, p.Wo, d.Cout, 1, p.Wt, p.Ht, p.Nt))) return rc;
   const uint64_t ktot = (uint64_t)p.taps * (d.s0.C + (d.s1.ptr ? d.s1.C : 0)) + (d.r0.ptr ? d.r0.C : 0) +
@@ -899,7 +930,7 @@ int conv_plan_build(ConvPlan* pl, const ConvDesc& d) {
   p.b_batch_rows = d.b_batch_rows;
   // SM-pair mode: 128-wide N tiles, an even number of M tiles and enough tiles to keep every SM pair busy
   const int m_tiles = p.w_blks * p.h_blks * p.n_blks, tiles = m_tiles * (p.cout_pad / p.block_n);
-  p.pair = (p.block_n == 128 && m_tiles % 2 == 0 && tiles >= kNumSMs) ? 1 : 0;
+  p.pair = (p.halo || (p.block_n == 128 && m_tiles % 2 == 0 && tiles >= kNumSMs)) ? 1 : 0;
   // split-K when the tiles alone cannot fill the chip: up to 8 splits of at least 8 k-blocks each
   const int num_kb = (int)(ktot / K);
   p.splits = 1;
@@ -920,13 +951,14 @@ int conv_plan_build(ConvPlan* pl, const ConvDesc& d) {
   return B2E_OK;
 }
 
-template <int BN, int STAGES, bool PAIR, bool HALO = false>
+template <int BN, int STAGES, bool PAIR, bool HALO = false, int MT = 1>
 static int launch_t(const ConvPlan& pl, const ConvKParams& kp, int tiles, cudaStream_t st) {
-  using Cfg = ConvCfg<BN, STAGES, PAIR, HALO>;
+  using Cfg = ConvCfg<BN, STAGES, PAIR, HALO, MT>;
   static_assert(Cfg::kSmemBytes <= 227 * 1024, "shared memory budget");
+  static_assert(Cfg::kTmemCols <= 512, "TMEM budget");
   static bool attr_set = false;
   if (!attr_set) {
-    B2E_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES, PAIR, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B2E_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES, PAIR, HALO, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg::kSmemBytes));
     attr_set = true;
   }
@@ -941,7 +973,7 @@ static int launch_t(const ConvPlan& pl, const ConvKParams& kp, int tiles, cudaSt
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = PAIR ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BN, STAGES, PAIR, HALO>, pl.map_a0, pl.map_a1, pl.map_r0,
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BN, STAGES, PAIR, HALO, MT>, pl.map_a0, pl.map_a1, pl.map_r0,
                                      pl.map_r1, pl.map_b, pl.map_out, kp);
   if (e != cudaSuccess) { set_error("conv_igemm launch: %s", cudaGetErrorString(e)); return B2E_CUDA_ERROR; }
   return check_launch("conv_igemm");
@@ -966,14 +998,49 @@ int conv_launch(const ConvPlan& pl, const ConvEpilogue& ep, cudaStream_t st) {
   kp.bias = ep.bias; kp.bias2 = ep.bias2; kp.temb = ep.temb; kp.temb_stride = ep.temb_stride;
   kp.out_bf16 = pl.has_out_bf16; kp.out_f32_nchw = pl.has_out_bf16 ? nullptr : ep.out_f32_nchw;
   kp.tile_stats = pl.tile_stats;
-  const int grid = pl.w_blks * pl.h_blks * pl.n_blks * kp.n_tiles;
+  // B2E_TRACE=<n>: the n-th halo launch (1-based) runs with clock64 tracing of CTA 0, then dumps to stderr
+  kp.trace = nullptr;
+  static const int trace_at = getenv("B2E_TRACE") ? atoi(getenv("B2E_TRACE")) : 0;
+  static int halo_launches = 0;
+  static long long* trace_buf = nullptr;
+  const bool do_trace = trace_at > 0 && pl.halo && ++halo_launches == trace_at;
+  if (do_trace) {
+    if (!trace_buf) B2E_CUDA(cudaMalloc(&trace_buf, kTrTotal * sizeof(long long)));
+    B2E_CUDA(cudaMemsetAsync(trace_buf, 0, kTrTotal * sizeof(long long), st));
+    kp.trace = trace_buf;
+  }
+  struct TraceDump {
+    bool on; cudaStream_t st; const long long* buf; const ConvPlan& pl;
+    ~TraceDump() {
+      if (!on) return;
+      cudaStreamSynchronize(st);
+      static long long h[kTrTotal];
+      cudaMemcpy(h, buf, sizeof(h), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "TRACE conv %dx%d taps %d chunks %d+%d res %d+%d pair %d\n", pl.Ho, pl.Wo, pl.taps, pl.c0_chunks,
+              pl.c1_chunks, pl.r0_chunks, pl.r1_chunks, pl.pair);
+      const long long t0 = h[kTrMma];
+      for (int i = 0; i < 512 && h[kTrMma + i * 4 + 3]; ++i)
+        fprintf(stderr, "MMA %d start %lld a_ready %lld b_ready %lld issued %lld\n", i, h[kTrMma + i * 4] - t0,
+                h[kTrMma + i * 4 + 1] - t0, h[kTrMma + i * 4 + 2] - t0, h[kTrMma + i * 4 + 3] - t0);
+      for (int i = 0; i < 256 && h[kTrPa + i * 3 + 2]; ++i)
+        fprintf(stderr, "PA %d start %lld free %lld issued %lld\n", i, h[kTrPa + i * 3] - t0, h[kTrPa + i * 3 + 1] - t0,
+                h[kTrPa + i * 3 + 2] - t0);
+      for (int i = 0; i < 512 && h[kTrPb + i * 3 + 2]; ++i)
+        fprintf(stderr, "PB %d start %lld free %lld issued %lld\n", i, h[kTrPb + i * 3] - t0, h[kTrPb + i * 3 + 1] - t0,
+                h[kTrPb + i * 3 + 2] - t0);
+      for (int i = 0; i < 64 && h[kTrEpi + i * 4 + 3]; ++i)
+        fprintf(stderr, "EPI %d start %lld full %lld released %lld done %lld\n", i, h[kTrEpi + i * 4] - t0,
+                h[kTrEpi + i * 4 + 1] - t0, h[kTrEpi + i * 4 + 2] - t0, h[kTrEpi + i * 4 + 3] - t0);
+    }
+  } trace_dump{do_trace, st, trace_buf, pl};
+  const int grid = pl.w_blks * pl.h_blks * pl.n_blks * kp.n_tiles / (pl.halo ? pl.halo : 1);
   kp.num_tiles = pl.pair ? grid / 2 : grid;
   switch (pl.block_n) {
     case 16: return launch_t<16, 8, false>(pl, kp, kp.num_tiles, st);
     case 64: return launch_t<64, 8, false>(pl, kp, kp.num_tiles, st);
     default:
-      if (pl.halo) return pl.pair ? launch_t<128, 12, true, true>(pl, kp, kp.num_tiles, st)    // 4 x 20 KB + 12 x 8 KB
-                                  : launch_t<128, 6, false, true>(pl, kp, kp.num_tiles, st);  // 3 x 20 KB + 6 x 16 KB
+      if (pl.halo == 2) return launch_t<128, 3, true, true, 2>(pl, kp, kp.num_tiles, st);   // 3 x (36 + 24) KB
+      if (pl.halo == 1) return launch_t<128, 4, true, true, 1>(pl, kp, kp.num_tiles, st);   // 4 x (20 + 24) KB
       return pl.pair ? launch_t<128, 7, true>(pl, kp, kp.num_tiles, st) : launch_t<128, 5, false>(pl, kp, kp.num_tiles, st);
   }
 }

@@ -59,7 +59,7 @@ struct ConvPlan {
   int block_n;  // 16, 64 or 128
   int b_batch_rows;
   int splits; float* split_ws; int* split_counters;
-  int halo;     // 1: 8x16-pixel tiles, one (8+2)x16 halo load serves the three vertical taps
+  int halo;     // 0, or MT = M tiles per CTA of the halo kernel: (8*MT)x16-pixel bricks, one halo load serves 3 vertical taps
   int pair;     // 1: SM-pair kernel (tcgen05.mma.cta_group::2, 256 x 128 tile per cluster)
   int has_out_bf16;
   float* tile_stats;

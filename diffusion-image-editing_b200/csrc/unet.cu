@@ -322,7 +322,7 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
     char desc[160];
     snprintf(desc, sizeof(desc), "conv%dx%d s%d %dx%d cin%d+%d res%d cout%d tiles%d bn%d%s", L.k, L.k, stride, x0.H, x0.W,
              x0.C, x1 ? x1->C : 0, L.res_c, L.cout, pl.w_blks * pl.h_blks * pl.n_blks * (pl.cout_pad / pl.block_n), pl.block_n,
-             pl.halo ? " halo" : pl.pair ? " pair" : (pl.splits > 1 ? (" splitK" + std::to_string(pl.splits)).c_str() : ""));
+             pl.halo == 2 ? " halo2" : pl.halo ? " halo1" : pl.pair ? " pair" : (pl.splits > 1 ? (" splitK" + std::to_string(pl.splits)).c_str() : ""));
     if (out_nchw) {
       // the network output pointer is only known at call time
       ops.push_back({[pl, ep, m](cudaStream_t st) { ConvEpilogue e = ep; e.out_f32_nchw = m->out_eps; return conv_launch(pl, e, st); },
