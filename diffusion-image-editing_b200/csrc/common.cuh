@@ -44,6 +44,27 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 constexpr int kNumSMs = 148;
 
+// ---- programmatic dependent launch (PDL).  Every kernel of the guided step calls pdl_wait() before it touches
+// memory written by an earlier kernel and is launched with launch_pdl(): its CTAs may then be scheduled while the
+// previous kernel's last CTAs are still running, so launch latency and the prologue (barrier init, TMEM
+// allocation, descriptor prefetch) overlap the predecessor's tail.  Persistent / single-wave kernels call
+// pdl_trigger() right after their prologue; multi-wave kernels rely on the implicit trigger at CTA exit.
+// B2E_PDL=0 launches without the attribute (the two instructions are then no-ops).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- streaming 128-bit accesses (data touched once: keep it out of L1, evict-first in L2)
 __device__ __forceinline__ float4 ld_stream(const float4* p) { return __ldcs(p); }
 __device__ __forceinline__ void st_stream(float4* p, const float4& v) { __stcs(p, v); }

@@ -43,8 +43,14 @@ constexpr int kABytes = kConvBlockM * kConvBlockK * 2;  // 16 KB
 // 10 KB (MT=2, B shared by both M tiles); (2) clock64 traces show ~170 clk per mbarrier try_wait and ~30 clk per
 // UTCHMMA issue in the single issuing warp - with one wait per k-block the issue loop itself costs ~400 clk.
 constexpr int kHaloWt = 16, kHaloHt = 8;
-template <int BN, int STAGES, bool PAIR = false, bool HALO = false, int MT = 1>
+// KPS (plain kernels): k-blocks per pipeline stage.  The single-warp producer / MMA loops cost ~450 clk per
+// hand-shake (try_wait ~100-170, expect_tx + 2 TMA issues ~150, tcgen05.commit ~100); small grids are bound by
+// exactly that (a 128x64x64 k-block is 128 tensor clk), so they put 2 k-blocks behind one barrier.
+template <int BN, int STAGES, bool PAIR = false, bool HALO = false, int MT = 1, int KPS = 1>
 struct ConvCfg {
+  static_assert(!HALO || KPS == 1, "halo stages are already fused");
+  static constexpr int kKps = KPS;
+  static constexpr int kKbBytes = kABytes + ((PAIR ? BN / 2 : BN) * kConvBlockK * 2 + 1023) / 1024 * 1024;   // [A][B]
   static_assert(!HALO || (PAIR && BN == 128), "halo kernels are SM-pair kernels with 128-wide N tiles");
   static constexpr int kMt = MT;
   static constexpr int kBRows = PAIR ? BN / 2 : BN;             // B rows staged by this CTA
@@ -52,7 +58,7 @@ struct ConvCfg {
   static constexpr int kBBytesPad = (kBBytes + 1023) / 1024 * 1024;
   static constexpr int kHaloABytes = (kHaloHt * MT + 2) * kHaloWt * 128;   // 20 KB (MT=1) / 36 KB (MT=2)
   // non-halo: [A 16 KB][B]; halo: [A halo][B kh=0][B kh=1][B kh=2]
-  static constexpr int kStageBytes = HALO ? kHaloABytes + 3 * kBBytesPad : kABytes + kBBytesPad;
+  static constexpr int kStageBytes = HALO ? kHaloABytes + 3 * kBBytesPad : KPS * kKbBytes;
   static constexpr int kRingBytes = STAGES * kStageBytes;
   static constexpr int kStages = STAGES;
   static constexpr int kAccCols = BN * MT;                      // one accumulator buffer
@@ -316,13 +322,13 @@ __device__ __forceinline__ TileCoord halo_coord(const ConvKParams& p, int tile, 
   return t;
 }
 
-template <int BN, int STAGES, bool PAIR, bool HALO, int MT>
+template <int BN, int STAGES, bool PAIR, bool HALO, int MT, int KPS>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                   const __grid_constant__ CUtensorMap map_r0, const __grid_constant__ CUtensorMap map_r1,
                   const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out,
                   const __grid_constant__ ConvKParams p) {
-  using Cfg = ConvCfg<BN, STAGES, PAIR, HALO, MT>;
+  using Cfg = ConvCfg<BN, STAGES, PAIR, HALO, MT, KPS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* staging = smem + Cfg::kRingBytes;
@@ -334,8 +340,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
   volatile uint32_t* split_flag = tmem_slot + 1;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rank = PAIR ? (int)cluster_ctarank() : 0;      // 0 = leader CTA of the SM pair
+  // warp index / cluster rank through shfl so that the compiler can prove them warp-uniform: the role branches
+  // are then convergent and the producer / MMA loops keep coordinates, descriptors and barrier addresses in
+  // uniform registers (otherwise every UTMALDG is preceded by ELECT + up to nine R2UR.BROADCAST, ~180 clk per TMA)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[kTrTotal - 1] = clock64();   // kernel entry
+  const int rank = PAIR ? __shfl_sync(0xffffffffu, (int)cluster_ctarank(), 0) : 0;      // 0 = leader CTA of the SM pair
   const int tile_begin = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int chunks = p.c0_chunks + p.c1_chunks;
@@ -366,6 +376,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   if (PAIR) cluster_sync_all();   // peer barriers are initialised before any remote arrive / TMA completion
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above touched only parameters and shared / tensor memory: from here on the previous kernel's
+  // outputs are read (activations through TMA, time embedding in the epilogue)
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     // ===== TMA producer (whole warp walks the loop; one elected lane issues)
@@ -412,54 +426,63 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         }
       }
     } else {
-      // one k-block: this CTA's A brick + its share of the B tile (pair: both CTAs complete on the leader's barrier)
-      auto load_kb = [&](const CUtensorMap* ma, int c0, int c1, int c2, int c3, int c4, int kcol, int brow) {
-        mbar_wait(empty_bar + stage, phase ^ 1);
-        uint8_t* sa = smem + stage * Cfg::kStageBytes;
-        uint8_t* sb = sa + kABytes;
-        if (p.debug & 1) {
-          if (elect_one() && rank == 0) mbar_arrive(full_bar + stage);
-        } else if (elect_one()) {
-          if (PAIR) {
-            if (rank == 0) mbar_expect_tx(full_bar + stage, 2 * (kABytes + Cfg::kBBytes));
-            tma_load_5d_2sm(sa, ma, full_bar + stage, c0, c1, c2, c3, c4);
-            tma_load_2d_2sm(sb, &map_b, full_bar + stage, kcol, brow + rank * Cfg::kBRows);
-          } else {
-            mbar_expect_tx(full_bar + stage, kABytes + Cfg::kBBytes);
-            tma_load_5d(sa, ma, full_bar + stage, c0, c1, c2, c3, c4);
-            tma_load_2d(sb, &map_b, full_bar + stage, kcol, brow);
-          }
-        }
-        __syncwarp();
-        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
-      };
+      // a stage = KPS k-blocks, each this CTA's A brick + its share of the B tile (pair: both CTAs complete on the
+      // leader's barrier)
+      int tr_n = 0;
+      const bool tr = p.trace && blockIdx.x == 0 && lane == 0;
       for (int wi = tile_begin; wi < num_work; wi += tile_step) {
         const int tile = wi / splits, split = wi - tile * splits;
         const TileCoord tc = tile_coord(p, tile, PAIR, rank);
-        const int brow0 = tc.n_tile * BN + tc.n0 * p.b_batch_rows;   // per-image B rows for batched GEMMs (Nt == 1)
+        // per-image B rows for batched GEMMs (Nt == 1); pair: this CTA's half of the N tile
+        const int brow0 = tc.n_tile * BN + tc.n0 * p.b_batch_rows + (PAIR ? rank * Cfg::kBRows : 0);
         const int kb0 = (int)((int64_t)split * num_kb / splits), kb1 = (int)((int64_t)(split + 1) * num_kb / splits);
-        // walk (tap, chunk) incrementally: the producer is one thread and sits on the critical path
+        // walk (tap, chunk) incrementally: this warp sits on the critical path
         int tap = kb0 < main_kb ? kb0 / chunks : p.taps, ck = kb0 < main_kb ? kb0 - tap * chunks : kb0 - main_kb;
         int cw = 0, ch = 0, ca = 0, cc = 0;
         if (tap < p.taps) { cw = tc.w0 + p.tap_dw[tap]; ch = tc.h0 + p.tap_dh[tap]; ca = p.tap_da[tap]; cc = p.tap_dc[tap]; }
-        for (int kb = kb0; kb < kb1; ++kb) {
-          if (tap < p.taps) {
-            if (ck < p.c0_chunks)
-              load_kb(&map_a0, cc + ck * kConvBlockK, cw, ca, ch, tc.n0, kb * kConvBlockK, brow0);
-            else
-              load_kb(&map_a1, cc + (ck - p.c0_chunks) * kConvBlockK, cw, ca, ch, tc.n0, kb * kConvBlockK, brow0);
-            if (++ck == chunks) {
-              ck = 0;
-              if (++tap < p.taps) { cw = tc.w0 + p.tap_dw[tap]; ch = tc.h0 + p.tap_dh[tap]; ca = p.tap_da[tap]; cc = p.tap_dc[tap]; }
-            }
-          } else {
-            // residual segment: 1x1 at the output pixel
-            if (ck < p.r0_chunks)
-              load_kb(&map_r0, ck * kConvBlockK, tc.w0, 0, tc.h0, tc.n0, kb * kConvBlockK, brow0);
-            else
-              load_kb(&map_r1, (ck - p.r0_chunks) * kConvBlockK, tc.w0, 0, tc.h0, tc.n0, kb * kConvBlockK, brow0);
-            ++ck;
+        for (int kb = kb0; kb < kb1; kb += KPS) {
+          const int cnt = (kb1 - kb) < KPS ? (kb1 - kb) : KPS;   // k-blocks in this stage
+          if (tr && tr_n < 512) p.trace[kTrPb + tr_n * 3] = clock64();
+          mbar_wait(empty_bar + stage, phase ^ 1);
+          if (tr && tr_n < 512) p.trace[kTrPb + tr_n * 3 + 1] = clock64();
+          const bool leader = elect_one();
+          if (leader) {
+            if (p.debug & 1) { if (rank == 0) mbar_arrive(full_bar + stage); }
+            else if (!PAIR || rank == 0) mbar_expect_tx(full_bar + stage, (PAIR ? 2 : 1) * cnt * (kABytes + Cfg::kBBytes));
           }
+#pragma unroll
+          for (int j = 0; j < KPS; ++j) {
+            if (j < cnt) {
+              const CUtensorMap* ma; int c0, c1, c2, c3;
+              if (tap < p.taps) {
+                const bool first = ck < p.c0_chunks;
+                ma = first ? &map_a0 : &map_a1;
+                c0 = cc + (first ? ck : ck - p.c0_chunks) * kConvBlockK; c1 = cw; c2 = ca; c3 = ch;
+              } else {   // residual segment: 1x1 at the output pixel
+                const bool first = ck < p.r0_chunks;
+                ma = first ? &map_r0 : &map_r1;
+                c0 = (first ? ck : ck - p.r0_chunks) * kConvBlockK; c1 = tc.w0; c2 = 0; c3 = tc.h0;
+              }
+              if (leader && !(p.debug & 1)) {
+                uint8_t* sa = smem + stage * Cfg::kStageBytes + j * Cfg::kKbBytes;
+                if (PAIR) {
+                  tma_load_5d_2sm(sa, ma, full_bar + stage, c0, c1, c2, c3, tc.n0);
+                  tma_load_2d_2sm(sa + kABytes, &map_b, full_bar + stage, (kb + j) * kConvBlockK, brow0);
+                } else {
+                  tma_load_5d(sa, ma, full_bar + stage, c0, c1, c2, c3, tc.n0);
+                  tma_load_2d(sa + kABytes, &map_b, full_bar + stage, (kb + j) * kConvBlockK, brow0);
+                }
+              }
+              ++ck;
+              if (tap < p.taps && ck == chunks) {
+                ck = 0;
+                if (++tap < p.taps) { cw = tc.w0 + p.tap_dw[tap]; ch = tc.h0 + p.tap_dh[tap]; ca = p.tap_da[tap]; cc = p.tap_dc[tap]; }
+              }
+            }
+          }
+          __syncwarp();
+          if (tr && tr_n < 512) { p.trace[kTrPb + tr_n * 3 + 2] = clock64(); ++tr_n; }
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -510,6 +533,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           }
         }
       } else {
+        int tr_n = 0;
+        const bool tr = p.trace && blockIdx.x == 0 && lane == 0;
         for (int wi = tile_begin; wi < num_work; wi += tile_step, ++it) {
           const int split = wi % splits;
           const int kb0 = (int)((int64_t)split * num_kb / splits), kb1 = (int)((int64_t)(split + 1) * num_kb / splits);
@@ -517,27 +542,35 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           mbar_wait(tmem_empty_bar + acc, ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-          for (int kb = kb0; kb < kb1; ++kb) {
+          for (int kb = kb0; kb < kb1; kb += KPS) {
+            const int cnt = (kb1 - kb) < KPS ? (kb1 - kb) : KPS;
+            if (tr && tr_n < 512) { p.trace[kTrMma + tr_n * 4] = p.trace[kTrMma + tr_n * 4 + 1] = clock64(); }
             mbar_wait(full_bar + stage, phase);
             tc_fence_after();
-            const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-            const uint64_t adesc = make_smem_desc(sa);
-            const uint64_t bdesc = make_smem_desc(sa + kABytes);
+            if (tr && tr_n < 512) p.trace[kTrMma + tr_n * 4 + 2] = clock64();
+            const uint32_t sbase = smem_u32(smem + stage * Cfg::kStageBytes);
             if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < kConvBlockK / 16; ++k) {
-                // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in the (addr >> 4) field
-                const uint32_t accum = (kb > kb0 || k > 0) ? 1u : 0u;
-                if (p.debug & 2) continue;
-                if (PAIR) umma_bf16_2sm(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accum);
-                else umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accum);
+              for (int j = 0; j < KPS; ++j) {
+                if (j < cnt && !(p.debug & 2)) {
+                  const uint64_t adesc = make_smem_desc(sbase + j * Cfg::kKbBytes);
+                  const uint64_t bdesc = make_smem_desc(sbase + j * Cfg::kKbBytes + kABytes);
+#pragma unroll
+                  for (int k = 0; k < kConvBlockK / 16; ++k) {
+                    // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in the (addr >> 4) field
+                    const uint32_t accum = (kb > kb0 || j > 0 || k > 0) ? 1u : 0u;
+                    if (PAIR) umma_bf16_2sm(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accum);
+                    else umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accum);
+                  }
+                }
               }
               // frees this smem stage (in both CTAs of a pair) once the MMAs above retire
               if (PAIR) umma_commit_2sm(empty_bar + stage); else umma_commit(empty_bar + stage);
               // accumulator complete (pair: rows 0-127 in the leader's TMEM, 128-255 in the peer's)
-              if (kb == kb1 - 1) { if (PAIR) umma_commit_2sm(tmem_full_bar + acc); else umma_commit(tmem_full_bar + acc); }
+              if (kb + KPS >= kb1) { if (PAIR) umma_commit_2sm(tmem_full_bar + acc); else umma_commit(tmem_full_bar + acc); }
             }
             __syncwarp();
+            if (tr && tr_n < 512) { p.trace[kTrMma + tr_n * 4 + 3] = clock64(); ++tr_n; }
             if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -735,6 +768,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     tc_fence_before();
   }
   __syncthreads();
+  if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[kTrTotal - 2] = clock64();   // all roles done
   if (PAIR) cluster_sync_all();   // no CTA leaves while its peer may still signal its barriers / read its smem
   if (warp == 1) {
     tc_fence_after();
@@ -930,13 +964,12 @@ int conv_plan_build(ConvPlan* pl, const ConvDesc& d) {
   p.b_batch_rows = d.b_batch_rows;
   // SM-pair mode: 128-wide N tiles, an even number of M tiles and enough tiles to keep every SM pair busy
   const int m_tiles = p.w_blks * p.h_blks * p.n_blks, tiles = m_tiles * (p.cout_pad / p.block_n);
-  p.pair = (p.halo || (p.block_n == 128 && m_tiles % 2 == 0 && tiles >= kNumSMs)) ? 1 : 0;
+  p.pair = (p.halo || (p.block_n == 128 && m_tiles % 2 == 0 && !d.b_batch_rows)) ? 1 : 0;
   // split-K when the tiles alone cannot fill the chip: up to 8 splits of at least 8 k-blocks each
   const int num_kb = (int)(ktot / K);
   p.splits = 1;
-  // (measured on B200 at batch 8: the extra fp32 round trip through L2 costs more than the added parallelism
-  //  buys for this network, so split-K is opt-in: B2E_SPLITK=1)
-  static const bool splitk_on = getenv("B2E_SPLITK") && atoi(getenv("B2E_SPLITK")) > 0;
+  // (measured on B200 at batch 8: 28 -> 23 us on the 8x8 layers, +1 % on the whole step; B2E_SPLITK=0 disables)
+  static const bool splitk_on = !(getenv("B2E_SPLITK") && atoi(getenv("B2E_SPLITK")) == 0);
   if (splitk_on && !p.pair && d.split_ws && d.out_bf16 && tiles * 2 <= kNumSMs) {
     int sp = kNumSMs / tiles;
     if (sp > num_kb / 8) sp = num_kb / 8;
@@ -951,14 +984,14 @@ int conv_plan_build(ConvPlan* pl, const ConvDesc& d) {
   return B2E_OK;
 }
 
-template <int BN, int STAGES, bool PAIR, bool HALO = false, int MT = 1>
+template <int BN, int STAGES, bool PAIR, bool HALO = false, int MT = 1, int KPS = 1>
 static int launch_t(const ConvPlan& pl, const ConvKParams& kp, int tiles, cudaStream_t st) {
-  using Cfg = ConvCfg<BN, STAGES, PAIR, HALO, MT>;
+  using Cfg = ConvCfg<BN, STAGES, PAIR, HALO, MT, KPS>;
   static_assert(Cfg::kSmemBytes <= 227 * 1024, "shared memory budget");
   static_assert(Cfg::kTmemCols <= 512, "TMEM budget");
   static bool attr_set = false;
   if (!attr_set) {
-    B2E_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES, PAIR, HALO, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B2E_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES, PAIR, HALO, MT, KPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg::kSmemBytes));
     attr_set = true;
   }
@@ -969,11 +1002,13 @@ static int launch_t(const ConvPlan& pl, const ConvKParams& kp, int tiles, cudaSt
   cfg.blockDim = dim3(kConvThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = PAIR ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BN, STAGES, PAIR, HALO, MT>, pl.map_a0, pl.map_a1, pl.map_r0,
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BN, STAGES, PAIR, HALO, MT, KPS>, pl.map_a0, pl.map_a1, pl.map_r0,
                                      pl.map_r1, pl.map_b, pl.map_out, kp);
   if (e != cudaSuccess) { set_error("conv_igemm launch: %s", cudaGetErrorString(e)); return B2E_CUDA_ERROR; }
   return check_launch("conv_igemm");
@@ -1003,7 +1038,7 @@ int conv_launch(const ConvPlan& pl, const ConvEpilogue& ep, cudaStream_t st) {
   static const int trace_at = getenv("B2E_TRACE") ? atoi(getenv("B2E_TRACE")) : 0;
   static int halo_launches = 0;
   static long long* trace_buf = nullptr;
-  const bool do_trace = trace_at > 0 && pl.halo && ++halo_launches == trace_at;
+  const bool do_trace = trace_at > 0 && ++halo_launches == trace_at;
   if (do_trace) {
     if (!trace_buf) B2E_CUDA(cudaMalloc(&trace_buf, kTrTotal * sizeof(long long)));
     B2E_CUDA(cudaMemsetAsync(trace_buf, 0, kTrTotal * sizeof(long long), st));
@@ -1018,7 +1053,8 @@ int conv_launch(const ConvPlan& pl, const ConvEpilogue& ep, cudaStream_t st) {
       cudaMemcpy(h, buf, sizeof(h), cudaMemcpyDeviceToHost);
       fprintf(stderr, "TRACE conv %dx%d taps %d chunks %d+%d res %d+%d pair %d\n", pl.Ho, pl.Wo, pl.taps, pl.c0_chunks,
               pl.c1_chunks, pl.r0_chunks, pl.r1_chunks, pl.pair);
-      const long long t0 = h[kTrMma];
+      const long long t0 = h[kTrTotal - 1];
+      fprintf(stderr, "KERNEL entry 0 roles_done %lld\n", h[kTrTotal - 2] - t0);
       for (int i = 0; i < 512 && h[kTrMma + i * 4 + 3]; ++i)
         fprintf(stderr, "MMA %d start %lld a_ready %lld b_ready %lld issued %lld\n", i, h[kTrMma + i * 4] - t0,
                 h[kTrMma + i * 4 + 1] - t0, h[kTrMma + i * 4 + 2] - t0, h[kTrMma + i * 4 + 3] - t0);
@@ -1036,12 +1072,15 @@ int conv_launch(const ConvPlan& pl, const ConvEpilogue& ep, cudaStream_t st) {
   const int grid = pl.w_blks * pl.h_blks * pl.n_blks * kp.n_tiles / (pl.halo ? pl.halo : 1);
   kp.num_tiles = pl.pair ? grid / 2 : grid;
   switch (pl.block_n) {
-    case 16: return launch_t<16, 8, false>(pl, kp, kp.num_tiles, st);
-    case 64: return launch_t<64, 8, false>(pl, kp, kp.num_tiles, st);
+    case 16: return launch_t<16, 5, false, false, 1, 2>(pl, kp, kp.num_tiles, st);   // 5 x 2 x 18 KB
+    case 64: return launch_t<64, 4, false, false, 1, 2>(pl, kp, kp.num_tiles, st);   // 4 x 2 x 24 KB
     default:
       if (pl.halo == 2) return launch_t<128, 3, true, true, 2>(pl, kp, kp.num_tiles, st);   // 3 x (36 + 24) KB
       if (pl.halo == 1) return launch_t<128, 4, true, true, 1>(pl, kp, kp.num_tiles, st);   // 4 x (20 + 24) KB
-      return pl.pair ? launch_t<128, 7, true>(pl, kp, kp.num_tiles, st) : launch_t<128, 5, false>(pl, kp, kp.num_tiles, st);
+      if (pl.pair)   // full grids are L2-bound: deep ring of single k-blocks; small grids are hand-shake-bound
+        return kp.num_tiles >= kNumSMs / 2 ? launch_t<128, 7, true>(pl, kp, kp.num_tiles, st)                   // 7 x 24 KB
+                                           : launch_t<128, 3, true, false, 1, 2>(pl, kp, kp.num_tiles, st);   // 3 x 2 x 24 KB
+      return launch_t<128, 5, false>(pl, kp, kp.num_tiles, st);
   }
 }
 

@@ -10,12 +10,17 @@
 //                                                  src/attr_functions.py:22-37,104-163
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
 namespace b2e {
 
 std::atomic<long long> g_launches{0};
+bool pdl_enabled() {
+  static const bool on = !(getenv("B2E_PDL") && atoi(getenv("B2E_PDL")) == 0);
+  return on;
+}
 static thread_local char g_err[512] = "";
 
 void set_error(const char* fmt, ...) {
@@ -86,6 +91,7 @@ guided_step_vec4(const float4* __restrict__ x, const float4* __restrict__ e,
                  const float4* __restrict__ z, const float4* __restrict__ mask,
                  float4* __restrict__ xp, float4* __restrict__ x0o, uint32_t total4, uint32_t hw4,
                  uint32_t C, const __grid_constant__ StepK k) {
+  pdl_wait();   // eps comes from the UNet's last convolution
   const uint32_t base = blockIdx.x * (uint32_t)(kStepThreads * kStepUnroll) + threadIdx.x;
   float4 vx[kStepUnroll], ve[kStepUnroll], vz[kStepUnroll], vm[kStepUnroll];
   uint32_t ch[kStepUnroll];
@@ -506,9 +512,9 @@ int b2e_guided_step_f32(const float* x_t, const float* eps, const float* z, cons
     const int64_t total4 = total / 4;
     const int per_block = kStepThreads * kStepUnroll;
     const int64_t grid = (total4 + per_block - 1) / per_block;
-    guided_step_vec4<<<(unsigned)grid, kStepThreads, 0, st>>>(
-        (const float4*)x_t, (const float4*)eps, (const float4*)z, (const float4*)mask,
-        (float4*)x_prev, (float4*)x0_pred, (uint32_t)total4, (uint32_t)(HW / 4), (uint32_t)C, k);
+    launch_pdl(guided_step_vec4, dim3((unsigned)grid), dim3(kStepThreads), 0, st,
+               (const float4*)x_t, (const float4*)eps, (const float4*)z, (const float4*)mask,
+               (float4*)x_prev, (float4*)x0_pred, (uint32_t)total4, (uint32_t)(HW / 4), (uint32_t)C, k);
   } else {
     guided_step_scalar<<<grid_for(total, kStepThreads), kStepThreads, 0, st>>>(
         x_t, eps, z, mask, x_prev, x0_pred, total, C * HW, HW, (int)C, k);

@@ -31,6 +31,7 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 constexpr int kGNUnroll = 4;
 
 __global__ void __launch_bounds__(kGNThreads) gn_partial_kernel(GNArgs a) {
+  pdl_wait();
   __shared__ float s_sum[2048], s_sq[2048];
   const int C = a.C0 + a.C1, slots = C >> 3, ppi = kGNThreads / slots;
   const int n = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
@@ -75,6 +76,7 @@ __global__ void __launch_bounds__(kGNThreads) gn_partial_kernel(GNArgs a) {
 }
 
 __global__ void __launch_bounds__(kGNThreads) gn_apply_kernel(GNArgs a, int pix_per_block) {
+  pdl_wait();
   __shared__ float s_mean[64], s_rstd[64];
   const int C = a.C0 + a.C1, slots = C >> 3, ppi = kGNThreads / slots;
   const int n = blockIdx.y, tid = threadIdx.x;
@@ -175,14 +177,14 @@ int gn_launch(const GNArgs& a, cudaStream_t st) {
               "groupnorm: unsupported channels %d+%d / groups %d", a.C0, a.C1, a.G);
   int rc = B2E_OK;
   if (!a.cs0 && !a.ts0) {
-    gn_partial_kernel<<<dim3(a.chunks, a.N), kGNThreads, 0, st>>>(a);
+    launch_pdl(gn_partial_kernel, dim3(dim3(a.chunks, a.N)), dim3(kGNThreads), 0, st, a);
     rc = check_launch("gn_partial");
     if (rc) return rc;
   }
   const int slots = C / 8, ppi = kGNThreads / slots;
   int ppb = ppi * kGNUnroll * 2;  // two unrolled sweeps per thread
   if (ppb > a.HW) ppb = a.HW;
-  gn_apply_kernel<<<dim3((a.HW + ppb - 1) / ppb, a.N), kGNThreads, 0, st>>>(a, ppb);
+  launch_pdl(gn_apply_kernel, dim3(dim3((a.HW + ppb - 1) / ppb, a.N)), dim3(kGNThreads), 0, st, a, ppb);
   return check_launch("gn_apply");
 }
 
@@ -191,6 +193,8 @@ int gn_launch(const GNArgs& a, cudaStream_t st) {
 __global__ void __launch_bounds__(256)
 gn_finalize_kernel(const float* __restrict__ tile_stats, float* __restrict__ chan_stats, int C, int Nt, int w_blks,
                    int h_blks) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ double s_s[16][16], s_q[16][16];
   const int cl = threadIdx.x & 15, sl = threadIdx.x >> 4;
   const int c = blockIdx.x * 16 + cl, n = blockIdx.y;
@@ -218,13 +222,14 @@ gn_finalize_kernel(const float* __restrict__ tile_stats, float* __restrict__ cha
 
 int gn_finalize_launch(const float* tile_stats, float* chan_stats, int N, int C, int Nt, int w_blks, int h_blks,
                        cudaStream_t st) {
-  gn_finalize_kernel<<<dim3((C + 15) / 16, N), 256, 0, st>>>(tile_stats, chan_stats, C, Nt, w_blks, h_blks);
+  launch_pdl(gn_finalize_kernel, dim3(dim3((C + 15) / 16, N)), dim3(256), 0, st, tile_stats, chan_stats, C, Nt, w_blks, h_blks);
   return check_launch("gn_finalize");
 }
 
 // ------------------------------------------------------------------ layout helpers
 __global__ void pack_input_kernel(const float* __restrict__ x, bf16* __restrict__ out, int B, int C,
                                   int HW, int cpad) {
+  pdl_wait();
   const int64_t total = (int64_t)B * HW;
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total;
        p += (int64_t)gridDim.x * blockDim.x) {
@@ -243,12 +248,13 @@ int pack_input_launch(const float* x, bf16* out, int B, int C, int HW, int cpad,
   int64_t total = (int64_t)B * HW;
   int grid = (int)((total + 255) / 256);
   if (grid > kNumSMs * 16) grid = kNumSMs * 16;
-  pack_input_kernel<<<grid, 256, 0, st>>>(x, out, B, C, HW, cpad);
+  launch_pdl(pack_input_kernel, dim3(grid), dim3(256), 0, st, x, out, B, C, HW, cpad);
   return check_launch("pack_input");
 }
 
 __global__ void upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int N, int H,
                                   int W, int C8) {
+  pdl_wait();
   const int64_t total = (int64_t)N * (2 * H) * (2 * W) * C8;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -266,7 +272,7 @@ int upsample2x_launch(const bf16* in, bf16* out, int N, int H, int W, int C, cud
   int64_t total = (int64_t)N * 4 * H * W * (C / 8);
   int grid = (int)((total + 255) / 256);
   if (grid > kNumSMs * 32) grid = kNumSMs * 32;
-  upsample2x_kernel<<<grid, 256, 0, st>>>((const uint4*)in, (uint4*)out, N, H, W, C / 8);
+  launch_pdl(upsample2x_kernel, dim3(grid), dim3(256), 0, st, (const uint4*)in, (uint4*)out, N, H, W, C / 8);
   return check_launch("upsample2x");
 }
 
@@ -274,6 +280,8 @@ int upsample2x_launch(const bf16* in, bf16* out, int N, int H, int W, int C, cud
 // one block per sample: sinusoidal embedding -> linear_1 -> SiLU -> linear_2 -> SiLU (for the
 // per-resnet projections, which all consume silu(temb))
 __global__ void temb_mlp_kernel(TembArgs a) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float sm[];
   float* emb = sm;             // [dim0]
   float* hid = sm + a.dim0;    // [dim]
@@ -305,6 +313,8 @@ __global__ void temb_mlp_kernel(TembArgs a) {
 
 // proj[b][o] = wp[o] . act[b] + bp[o]   (warp per output)
 __global__ void temb_proj_kernel(TembArgs a) {
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.y;
   const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -317,16 +327,17 @@ __global__ void temb_proj_kernel(TembArgs a) {
 }
 
 int temb_launch(const TembArgs& a, cudaStream_t st) {
-  temb_mlp_kernel<<<a.B, 512, (a.dim0 + a.dim) * sizeof(float), st>>>(a);
+  launch_pdl(temb_mlp_kernel, dim3(a.B), dim3(512), (a.dim0 + a.dim) * sizeof(float), st, a);
   int rc = check_launch("temb_mlp");
   if (rc) return rc;
-  temb_proj_kernel<<<dim3((a.sumC + 7) / 8, a.B), 256, 0, st>>>(a);
+  launch_pdl(temb_proj_kernel, dim3(dim3((a.sumC + 7) / 8, a.B)), dim3(256), 0, st, a);
   return check_launch("temb_proj");
 }
 
 // ------------------------------------------------------------------ tensor-core attention helpers
 // one warp per row: logits (bf16) * scale -> softmax in fp32 -> probabilities (bf16), in place
 __global__ void __launch_bounds__(256) softmax_rows_kernel(bf16* __restrict__ s, int64_t rows, int T, float scale) {
+  pdl_wait();
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -346,12 +357,13 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(bf16* __restrict__ s,
 
 int softmax_rows_launch(bf16* s, int64_t rows, int T, float scale, cudaStream_t st) {
   B2E_REQUIRE(T % 32 == 0 && T <= 1024, B2E_UNSUPPORTED_SHAPE, "softmax: unsupported row length %d", T);
-  softmax_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(s, rows, T, scale);
+  launch_pdl(softmax_rows_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, st, s, rows, T, scale);
   return check_launch("softmax_rows");
 }
 
 // 32x32 smem-tiled transpose of the V columns of qkv
 __global__ void transpose_v_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ vt, int T, int C) {
+  pdl_wait();
   __shared__ bf16 tile[32][33];
   const int n = blockIdx.z, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const bf16* src = qkv + ((int64_t)n * T) * 3 * C + 2 * C;
@@ -365,7 +377,7 @@ __global__ void transpose_v_kernel(const bf16* __restrict__ qkv, bf16* __restric
 
 int transpose_v_launch(const bf16* qkv, bf16* vt, int N, int T, int C, cudaStream_t st) {
   B2E_REQUIRE(T % 32 == 0 && C % 32 == 0, B2E_UNSUPPORTED_SHAPE, "transpose_v: T and C must be multiples of 32");
-  transpose_v_kernel<<<dim3(T / 32, C / 32, N), dim3(32, 8), 0, st>>>(qkv, vt, T, C);
+  launch_pdl(transpose_v_kernel, dim3(dim3(T / 32, C / 32, N)), dim3(dim3(32, 8)), 0, st, qkv, vt, T, C);
   return check_launch("transpose_v");
 }
 
@@ -377,6 +389,7 @@ constexpr int kAttKStride = 72;  // bf16 per staged key row (64 + pad): uint4-al
 
 __global__ void __launch_bounds__(kAttThreads)
 attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, int C, int heads) {
+  pdl_wait();
   extern __shared__ __align__(16) uint8_t att_smem[];
   const int d = C / heads;
   float* Qs = reinterpret_cast<float*>(att_smem);            // [16][d]
@@ -481,7 +494,7 @@ int attention_launch(const bf16* qkv, bf16* out, int N, int T, int C, int heads,
     B2E_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  attention_kernel<<<dim3((T + kAttQ - 1) / kAttQ, heads, N), kAttThreads, smem, st>>>(qkv, out, T, C, heads);
+  launch_pdl(attention_kernel, dim3(dim3((T + kAttQ - 1) / kAttQ, heads, N)), dim3(kAttThreads), smem, st, qkv, out, T, C, heads);
   return check_launch("attention");
 }
 
