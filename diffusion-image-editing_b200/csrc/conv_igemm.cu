@@ -51,7 +51,7 @@ struct ConvCfg {
   static_assert(!HALO || KPS == 1, "halo stages are already fused");
   static constexpr int kKps = KPS;
   static constexpr int kKbBytes = kABytes + ((PAIR ? BN / 2 : BN) * kConvBlockK * 2 + 1023) / 1024 * 1024;   // [A][B]
-  static_assert(!HALO || (PAIR && BN == 128), "halo kernels are SM-pair kernels with 128-wide N tiles");
+  static_assert(!HALO || (PAIR && (BN == 128 || BN == 16)), "halo kernels are SM-pair kernels with 128- or 16-wide N tiles");
   static constexpr int kMt = MT;
   static constexpr int kBRows = PAIR ? BN / 2 : BN;             // B rows staged by this CTA
   static constexpr int kBBytes = kBRows * kConvBlockK * 2;
@@ -913,9 +913,9 @@ int conv_plan_build(ConvPlan* pl, const ConvDesc& d) {
   // force MT.
   static const int halo_env = getenv("B2E_HALO") ? atoi(getenv("B2E_HALO")) : -1;
   p.halo = 0;
-  if (halo_env != 0 && d.ksize == 3 && d.stride == 1 && g.block_n == 128 && !d.b_batch_rows && !d.s0.pitch &&
-      p.Wo % kHaloWt == 0 && p.Ho % kHaloHt == 0) {
-    const int64_t tiles128 = (int64_t)d.N * p.Ho * p.Wo / kConvBlockM * (p.cout_pad / 128);   // 128 x 128 output tiles
+  if (halo_env != 0 && d.ksize == 3 && d.stride == 1 && (g.block_n == 128 || g.block_n == 16) && !d.b_batch_rows &&
+      !d.s0.pitch && p.Wo % kHaloWt == 0 && p.Ho % kHaloHt == 0) {
+    const int64_t tiles128 = (int64_t)d.N * p.Ho * p.Wo / kConvBlockM * (p.cout_pad / g.block_n);   // 128 x BN output tiles
     if (tiles128 >= kNumSMs && tiles128 % 2 == 0) {
       p.halo = 1;
       // two M tiles per CTA share every B tile (10 KB instead of 14.7 KB from L2 per k-block, half the barrier
@@ -1072,7 +1072,10 @@ int conv_launch(const ConvPlan& pl, const ConvEpilogue& ep, cudaStream_t st) {
   const int grid = pl.w_blks * pl.h_blks * pl.n_blks * kp.n_tiles / (pl.halo ? pl.halo : 1);
   kp.num_tiles = pl.pair ? grid / 2 : grid;
   switch (pl.block_n) {
-    case 16: return launch_t<16, 5, false, false, 1, 2>(pl, kp, kp.num_tiles, st);   // 5 x 2 x 18 KB
+    case 16:   // conv_out (3-4 channels): bound by the A traffic, so the halo kernel's 3x reuse is what matters
+      if (pl.halo == 2) return launch_t<16, 5, true, true, 2>(pl, kp, kp.num_tiles, st);   // 5 x (36 + 3) KB
+      if (pl.halo == 1) return launch_t<16, 8, true, true, 1>(pl, kp, kp.num_tiles, st);   // 8 x (20 + 3) KB
+      return launch_t<16, 5, false, false, 1, 2>(pl, kp, kp.num_tiles, st);                // 5 x 2 x 18 KB
     case 64: return launch_t<64, 4, false, false, 1, 2>(pl, kp, kp.num_tiles, st);   // 4 x 2 x 24 KB
     default:
       if (pl.halo == 2) return launch_t<128, 3, true, true, 2>(pl, kp, kp.num_tiles, st);   // 3 x (36 + 24) KB

@@ -71,6 +71,7 @@ struct b2e_unet {
   std::vector<PRec> params;
   std::unordered_map<std::string, int> pindex;
   ConvL conv_in, conv_out;
+  bool in_im2col = false;
   NormL norm_out;
   float *te_w1 = nullptr, *te_b1 = nullptr, *te_w2 = nullptr, *te_b2 = nullptr, *tp_w = nullptr, *tp_b = nullptr;
   std::vector<ResnetL> resnets;
@@ -185,7 +186,24 @@ int build_model(b2e_unet* m) {
   const int nb = c.n_blocks;
   const int c0 = c.block_out_channels[0];
   m->temb_dim = 4 * c0;
-  m->conv_in = m->make_conv("conv_in", c.in_channels, c0, 3, kConvBlockK);
+  // conv_in: with <= 7 input channels the 9 taps x Cin values of a pixel fit ONE 64-channel K chunk, so the input
+  // is packed as an im2col tensor (B,S,S,64) and conv_in runs as a 1x1 convolution (1 k-block instead of 9)
+  m->in_im2col = c.in_channels == 1 || c.in_channels == 3 || c.in_channels == 4;
+  if (m->in_im2col) {
+    ConvL ci;
+    ci.cin = ci.cin_pad = kConvBlockK; ci.cout = c0; ci.k = 1; ci.cout_pad = conv_cout_pad(c0); ci.row_len = kConvBlockK;
+    ci.w = m->dmalloc<bf16>((size_t)ci.cout_pad * ci.row_len);
+    ci.b = m->dmalloc<float>(ci.cout_pad);
+    const int cin = c.in_channels;
+    m->add_param("conv_in.weight", (int64_t)c0 * cin * 9, (int64_t)cin * 9, [ci, cin](const float* src, cudaStream_t st) {
+      // column of (tap t, channel c) = t * Cin + c, the order pack_input_im2col writes
+      return conv_pack_weight(src, ci.w, ci.cout, cin, 3, cin, ci.row_len, 0, st);
+    });
+    m->add_f32("conv_in.bias", ci.b, c0, (int64_t)cin * 9);
+    m->conv_in = ci;
+  } else {
+    m->conv_in = m->make_conv("conv_in", c.in_channels, c0, 3, kConvBlockK);
+  }
   m->te_w1 = m->dmalloc<float>((size_t)m->temb_dim * c0); m->te_b1 = m->dmalloc<float>(m->temb_dim);
   m->te_w2 = m->dmalloc<float>((size_t)m->temb_dim * m->temb_dim); m->te_b2 = m->dmalloc<float>(m->temb_dim);
   m->add_f32("time_embedding.linear_1.weight", m->te_w1, (int64_t)m->temb_dim * c0, c0);
@@ -365,7 +383,8 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
   Tensor xin = talloc(B, S, S, kConvBlockK);
   if (!dry) {
     const int Cin = c.in_channels, HW = S * S;
-    ops.push_back({[m, xin, B, Cin, HW](cudaStream_t st) { return pack_input_launch(m->in_x, xin.p, B, Cin, HW, kConvBlockK, st); },
+    const bool im2col = m->in_im2col;
+    ops.push_back({[m, xin, B, Cin, S, im2col](cudaStream_t st) { return pack_input_launch(m->in_x, xin.p, B, Cin, S, S, kConvBlockK, im2col, st); },
                    3, 0.0, (double)B * HW * (4.0 * Cin + 2.0 * kConvBlockK)});
     TembArgs ta;
     ta.timesteps = nullptr; ta.B = B; ta.dim0 = c.block_out_channels[0]; ta.dim = m->temb_dim;

@@ -243,11 +243,49 @@ __global__ void pack_input_kernel(const float* __restrict__ x, bf16* __restrict_
   }
 }
 
-int pack_input_launch(const float* x, bf16* out, int B, int C, int HW, int cpad, cudaStream_t st) {
-  B2E_REQUIRE(C <= 8 && cpad % 8 == 0, B2E_UNSUPPORTED_SHAPE, "pack_input: in_channels must be <= 8");
+// im2col variant: one thread per pixel gathers its 9 x C neighbourhood (coalesced across the warp, neighbours hit
+// L1) and writes the pixel's 64 channels (128 B)
+template <int C>
+__global__ void __launch_bounds__(256) pack_input_im2col_kernel(const float* __restrict__ x, bf16* __restrict__ out, int B,
+                                                                int H, int W) {
+  pdl_wait();
+  const int HW = H * W;
+  const int64_t total = (int64_t)B * HW;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(p / HW), q = (int)(p % HW), h = q / W, w = q % W;
+    float f[64];
+#pragma unroll
+    for (int k = 0; k < 64; ++k) f[k] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int hh = h + t / 3 - 1, ww = w + t % 3 - 1;
+      const bool in = hh >= 0 && hh < H && ww >= 0 && ww < W;
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+        if (in) f[t * C + c] = __ldg(x + ((int64_t)b * C + c) * HW + hh * W + ww);
+    }
+    uint4* o = reinterpret_cast<uint4*>(out + p * 64);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = pack8(f + 8 * j);
+  }
+}
+
+int pack_input_launch(const float* x, bf16* out, int B, int C, int H, int W, int cpad, bool im2col, cudaStream_t st) {
+  const int HW = H * W;
   int64_t total = (int64_t)B * HW;
   int grid = (int)((total + 255) / 256);
   if (grid > kNumSMs * 16) grid = kNumSMs * 16;
+  if (im2col) {
+    B2E_REQUIRE(9 * C <= 64 && cpad == 64, B2E_UNSUPPORTED_SHAPE, "pack_input: im2col needs 9*C <= 64");
+    switch (C) {
+      case 1: launch_pdl(pack_input_im2col_kernel<1>, dim3(grid), dim3(256), 0, st, x, out, B, H, W); break;
+      case 3: launch_pdl(pack_input_im2col_kernel<3>, dim3(grid), dim3(256), 0, st, x, out, B, H, W); break;
+      case 4: launch_pdl(pack_input_im2col_kernel<4>, dim3(grid), dim3(256), 0, st, x, out, B, H, W); break;
+      default: B2E_REQUIRE(false, B2E_UNSUPPORTED_SHAPE, "pack_input: im2col supports 1, 3 or 4 input channels (got %d)", C);
+    }
+    return check_launch("pack_input_im2col");
+  }
+  B2E_REQUIRE(C <= 8 && cpad % 8 == 0, B2E_UNSUPPORTED_SHAPE, "pack_input: in_channels must be <= 8");
   launch_pdl(pack_input_kernel, dim3(grid), dim3(256), 0, st, x, out, B, C, HW, cpad);
   return check_launch("pack_input");
 }
@@ -277,15 +315,17 @@ int upsample2x_launch(const bf16* in, bf16* out, int N, int H, int W, int C, cud
 }
 
 // ------------------------------------------------------------------ timestep embedding
-// one block per sample: sinusoidal embedding -> linear_1 -> SiLU -> linear_2 -> SiLU (for the
-// per-resnet projections, which all consume silu(temb))
-__global__ void temb_mlp_kernel(TembArgs a) {
+// sinusoidal embedding -> linear_1 -> SiLU -> linear_2 -> SiLU (the per-resnet projections all consume
+// silu(temb)).  Grid (dim / 32, B): every block recomputes the cheap first layer of its sample and produces 32
+// outputs of the second, so the 1 MB of linear_2 weights is spread over ~128 blocks instead of B.
+constexpr int kTembSlice = 32;
+__global__ void __launch_bounds__(256) temb_mlp_kernel(TembArgs a) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ float sm[];
   float* emb = sm;             // [dim0]
   float* hid = sm + a.dim0;    // [dim]
-  const int b = blockIdx.x, tid = threadIdx.x;
+  const int b = blockIdx.y, tid = threadIdx.x;
   const int half = a.dim0 / 2;
   const float t = (float)a.timesteps[b];
   for (int i = tid; i < half; i += blockDim.x) {
@@ -296,41 +336,75 @@ __global__ void temb_mlp_kernel(TembArgs a) {
   }
   __syncthreads();
   const int warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
-  for (int o = warp; o < a.dim; o += nw) {
-    float acc = 0.f;
-    for (int i = lane; i < a.dim0; i += 32) acc += __ldg(a.w1 + (int64_t)o * a.dim0 + i) * emb[i];
-    acc = warp_sum(acc);
-    if (lane == 0) { float y = acc + a.b1[o]; hid[o] = y / (1.f + expf(-y)); }
+  // four outputs per warp iteration: their weight loads are independent, so the L2 latency is paid once per
+  // four rows instead of once per row (this loop is latency-bound)
+  for (int o0 = warp * 4; o0 < a.dim; o0 += nw * 4) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int i = lane; i < a.dim0; i += 32) {
+      const float e = emb[i];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (o0 + u < a.dim) acc[u] += __ldg(a.w1 + (int64_t)(o0 + u) * a.dim0 + i) * e;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc[u] = warp_sum(acc[u]);
+    if (lane < 4 && o0 + lane < a.dim) {
+      const float y = (lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3]) + a.b1[o0 + lane];
+      hid[o0 + lane] = y / (1.f + expf(-y));
+    }
   }
   __syncthreads();
-  for (int o = warp; o < a.dim; o += nw) {
-    float acc = 0.f;
-    for (int i = lane; i < a.dim; i += 32) acc += __ldg(a.w2 + (int64_t)o * a.dim + i) * hid[i];
-    acc = warp_sum(acc);
-    if (lane == 0) { float y = acc + a.b2[o]; a.act[(int64_t)b * a.dim + o] = y / (1.f + expf(-y)); }
+  const int o_end = min(a.dim, (int)(blockIdx.x + 1) * kTembSlice);
+  for (int o0 = blockIdx.x * kTembSlice + warp * 4; o0 < o_end; o0 += nw * 4) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int i = lane; i < a.dim; i += 32) {
+      const float hv = hid[i];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (o0 + u < o_end) acc[u] += __ldg(a.w2 + (int64_t)(o0 + u) * a.dim + i) * hv;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc[u] = warp_sum(acc[u]);
+    if (lane < 4 && o0 + lane < o_end) {
+      const float y = (lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3]) + a.b2[o0 + lane];
+      a.act[(int64_t)b * a.dim + o0 + lane] = y / (1.f + expf(-y));
+    }
   }
 }
 
-// proj[b][o] = wp[o] . act[b] + bp[o]   (warp per output)
-__global__ void temb_proj_kernel(TembArgs a) {
+// proj[b][o] = wp[o] . act[b] + bp[o]   (warp per output; the weight row is read once and reused for every sample)
+constexpr int kTembMaxPerLane = 32;   // dim <= 1024
+__global__ void __launch_bounds__(256) temb_proj_kernel(TembArgs a) {
   pdl_wait();
   pdl_trigger();
-  const int b = blockIdx.y;
   const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (o >= a.sumC) return;
-  const float* x = a.act + (int64_t)b * a.dim;
-  float acc = 0.f;
-  for (int i = lane; i < a.dim; i += 32) acc += __ldg(a.wp + (int64_t)o * a.dim + i) * x[i];
-  acc = warp_sum(acc);
-  if (lane == 0) a.proj[(int64_t)b * a.sumC + o] = acc + a.bp[o];
+  float w[kTembMaxPerLane];
+  const int per = (a.dim + 31) / 32;
+#pragma unroll
+  for (int j = 0; j < kTembMaxPerLane; ++j)
+    if (j < per) { const int i = lane + 32 * j; w[j] = i < a.dim ? __ldg(a.wp + (int64_t)o * a.dim + i) : 0.f; }
+  const float bias = a.bp[o];
+  for (int b = 0; b < a.B; ++b) {
+    const float* x = a.act + (int64_t)b * a.dim;
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < kTembMaxPerLane; ++j)
+      if (j < per) { const int i = lane + 32 * j; if (i < a.dim) acc += w[j] * x[i]; }
+    acc = warp_sum(acc);
+    if (lane == 0) a.proj[(int64_t)b * a.sumC + o] = acc + bias;
+  }
 }
 
 int temb_launch(const TembArgs& a, cudaStream_t st) {
-  launch_pdl(temb_mlp_kernel, dim3(a.B), dim3(512), (a.dim0 + a.dim) * sizeof(float), st, a);
+  B2E_REQUIRE(a.dim <= 32 * kTembMaxPerLane, B2E_UNSUPPORTED_SHAPE, "temb: embedding width %d > %d", a.dim,
+              32 * kTembMaxPerLane);
+  launch_pdl(temb_mlp_kernel, dim3((a.dim + kTembSlice - 1) / kTembSlice, a.B), dim3(256),
+             (a.dim0 + a.dim) * sizeof(float), st, a);
   int rc = check_launch("temb_mlp");
   if (rc) return rc;
-  launch_pdl(temb_proj_kernel, dim3(dim3((a.sumC + 7) / 8, a.B)), dim3(256), 0, st, a);
+  launch_pdl(temb_proj_kernel, dim3((a.sumC + 7) / 8), dim3(256), 0, st, a);
   return check_launch("temb_proj");
 }
 

@@ -28,8 +28,9 @@ int gn_launch(const GNArgs& a, cudaStream_t st);
 int gn_finalize_launch(const float* tile_stats, float* chan_stats, int N, int C, int Nt, int w_blks, int h_blks,
                        cudaStream_t st);
 
-// x fp32 NCHW (B,C,S,S) -> bf16 NHWC (B,S,S,cpad), zero padded channels
-int pack_input_launch(const float* x, bf16* out, int B, int C, int HW, int cpad, cudaStream_t st);
+// x fp32 NCHW (B,C,H,W) -> bf16 NHWC (B,H,W,cpad), zero padded channels; im2col: channel t*C + c of a pixel holds
+// x[c] at 3x3 tap t (zero outside the image), so that a 3x3 convolution becomes a 1x1 one
+int pack_input_launch(const float* x, bf16* out, int B, int C, int H, int W, int cpad, bool im2col, cudaStream_t st);
 // nearest-neighbour x2 upsample, bf16 NHWC
 int upsample2x_launch(const bf16* in, bf16* out, int N, int H, int W, int C, cudaStream_t st);
 
