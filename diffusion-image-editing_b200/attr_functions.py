@@ -213,6 +213,12 @@ class NetAttrFunc(AttrFunc):
 
     def loss(self, img, **kwargs):
         out = self.segmentation_model.net(img)[0]
+        ids = [int(c) for c in (self.idx_for_class if isinstance(self.idx_for_class, (list, tuple)) else [self.idx_for_class])]
+        if (out.is_cuda and out.dtype == torch.float32 and out.dim() == 4 and out.shape[0] == 1 and out.shape[1] <= 32
+                and len(set(ids)) == len(ids) and isinstance(self.idx_for_class, (list, tuple))):
+            # fused head: softmax + selected-class area and its analytic gradient in one kernel; the parser
+            # itself (the user's torch module) is differentiated by autograd as in the reference
+            return ops.seg_area_loss(out, ids)
         out = out.squeeze(0).softmax(dim=0)
         out = out.sum(dim=(1, 2)) / (256 * 256)
         return out[self.idx_for_class].sum()
@@ -229,7 +235,12 @@ class ClassifierAttrFunc(AttrFunc):
         self.regularize_idx_idx_score = regularize_idx_idx_score
 
     def loss(self, xt, **kwargs):
-        attr = self.predictor(xt).view(-1, 40, 2)
+        logits = self.predictor(xt)
+        if (logits.is_cuda and logits.dtype == torch.float32 and logits.numel() % 80 == 0
+                and isinstance(self.idx_for_class, int) and self.idx_of_interest in (0, 1)):
+            return ops.classifier_logit_loss(logits, self.idx_for_class, self.idx_of_interest,
+                                             self.regularize_idx_idx_score)
+        attr = logits.view(-1, 40, 2)
         value = attr[0][self.idx_for_class][self.idx_of_interest]
         r_idx, r_pred, r_score = self.regularize_idx_idx_score
         if r_idx is not None:

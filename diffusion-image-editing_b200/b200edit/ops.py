@@ -229,6 +229,83 @@ def channel_l1(img, targets):
     return out[:Cc]
 
 
+def seg_area_head(logits, classes, area_divisor=256.0 * 256.0, want_grad=True):
+    """NetAttrFunc.loss head (src/attr_functions.py:213-219) on the parser logits of ONE image, (C,H,W) or
+    (1,C,H,W): returns (loss 0-d tensor, dL/dlogits with the shape of ``logits`` or None)."""
+    lg = _f32(logits, "logits")
+    if lg.dim() == 4:
+        if lg.shape[0] != 1:
+            raise ValueError("seg_area_head: the reference head squeezes batch dimension 0 (batch 1 only)")
+        core = lg[0]
+    else:
+        core = lg
+    Cc, H, W = core.shape
+    ids = [int(c) for c in classes]
+    arr = (C.c_int32 * max(1, len(ids)))(*ids)
+    n = lib.b2e_seg_area_head_workspace_bytes()
+    ws = torch.empty(n, dtype=torch.uint8, device=lg.device)
+    loss = torch.empty(1, dtype=torch.float32, device=lg.device)
+    grad = torch.empty_like(lg) if want_grad else None
+    check(lib.b2e_seg_area_head_f32(_p(core), Cc, H * W, arr, len(ids), float(area_divisor), _p(loss), _p(grad),
+                                    _p(ws), n, _stream()), "seg_area_head")
+    return loss[0], grad
+
+
+def classifier_head(logits, idx_for_class: int, idx_of_interest: int = 0, reg=(None, None, None), want_grad=True):
+    """ClassifierAttrFunc.loss head (src/attr_functions.py:237-257) on (B,80) logits: (loss 0-d, dL/dlogits)."""
+    lg = _f32(logits, "logits")
+    r_idx, r_pred, r_score = reg
+    if r_idx is None:
+        ri, rp, rs = -1, 0, 0.0
+    else:
+        ri, rp = int(r_idx), int(r_pred)
+        rs = float(r_score[rp])
+    loss = torch.empty(1, dtype=torch.float32, device=lg.device)
+    grad = torch.empty_like(lg) if want_grad else None
+    check(lib.b2e_classifier_head_f32(_p(lg), lg.numel(), int(idx_for_class), int(idx_of_interest), ri, rp, rs,
+                                      _p(loss), _p(grad), _stream()), "classifier_head")
+    return loss[0], grad
+
+
+class _SegAreaHeadFn(torch.autograd.Function):
+    """loss = head(logits) with the analytic gradient from the same kernel launch (the network below it is the
+    user's torch module and is differentiated by autograd, exactly as in the reference)."""
+
+    @staticmethod
+    def forward(ctx, logits, classes, area_divisor):
+        loss, grad = seg_area_head(logits.detach(), classes, area_divisor, want_grad=True)
+        ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * g, None, None
+
+
+class _ClassifierHeadFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, idx_for_class, idx_of_interest, reg):
+        loss, grad = classifier_head(logits.detach(), idx_for_class, idx_of_interest, reg, want_grad=True)
+        ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * g, None, None, None
+
+
+def seg_area_loss(logits, classes, area_divisor=256.0 * 256.0):
+    """Differentiable NetAttrFunc head (fused value + analytic gradient)."""
+    return _SegAreaHeadFn.apply(logits, tuple(int(c) for c in classes), float(area_divisor))
+
+
+def classifier_logit_loss(logits, idx_for_class, idx_of_interest=0, reg=(None, None, None)):
+    """Differentiable ClassifierAttrFunc head (fused value + analytic gradient)."""
+    return _ClassifierHeadFn.apply(logits, int(idx_for_class), int(idx_of_interest), reg)
+
+
 def cfg_combine(e_first, e_second, scale: float):
     e_first, e_second = _f32(e_first, "eps_first"), _f32(e_second, "eps_second")
     out = torch.empty_like(e_first)

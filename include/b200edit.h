@@ -144,6 +144,23 @@ int b2e_l2_distance_f32(const float* x, const float* y, int64_t n, float* out, v
 int b2e_channel_l1_f32(const float* img, int64_t B, int64_t C, int64_t HW, const float* targets4,
                        float* out4, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------ loss heads of the network guidance
+ * The part of NetAttrFunc / ClassifierAttrFunc that is not a dense network: loss value AND its analytic
+ * gradient w.r.t. the network output (seed of the network's backward pass).
+ * NetAttrFunc.loss, src/attr_functions.py:213-219: logits (C,HW) of batch element 0 (C <= 32);
+ * p = softmax_c ; L = sum_{c in classes} sum_hw p[c] / area_divisor (the reference's literal 256*256);
+ * dlogits[c,hw] = p[c,hw] * (1[c in classes] - sum_{k in classes} p[k,hw]) / area_divisor  (may be NULL).
+ * classes: HOST int array of distinct ids.  loss: DEVICE fp32 [1]. */
+size_t b2e_seg_area_head_workspace_bytes(void);
+int b2e_seg_area_head_f32(const float* logits, int64_t C, int64_t HW, const int32_t* classes, int n_classes,
+                          float area_divisor, float* loss, float* dlogits, void* workspace,
+                          size_t workspace_bytes, void* stream);
+/* ClassifierAttrFunc.loss, src/attr_functions.py:237-257: logits (n = B*80) viewed (-1,40,2); only batch row 0
+ * is used: L = a[idx_for_class][idx_of_interest] (+ (a[reg_idx][reg_pred] + reg_score)^2 when reg_idx >= 0);
+ * dlogits (n) = the matching one-hot(s), zero elsewhere (may be NULL; loss may be NULL). */
+int b2e_classifier_head_f32(const float* logits, int64_t n, int idx_for_class, int idx_of_interest, int reg_idx,
+                            int reg_pred, float reg_score, float* loss, float* dlogits, void* stream);
+
 /* ------------------------------------------------------------------ edit-friendly inversion
  * sample_xts_from_x0, src/ddpm_inversion.py:31-55: xts[i] = x0*sa[i] + noise[i]*sb[i], i<T;
  * xts[T] = x0.  x0 (C,H,W); noise (T,C,H,W); sa, sb: DEVICE fp32 [T]; xts (T+1,C,H,W). */
