@@ -263,25 +263,43 @@ def main():
 
     if rank == 0:
         pk = peaks()
-        # ---- roofline of the dominant kernel: tcgen05 implicit-GEMM convolution (tensor bound)
+        # ---- roofline of the dominant kernel (tensor bound): the tcgen05 implicit-GEMM convolution.  `roofline` is
+        # the kernel variant with the largest share of the step (halo, 2 M tiles per CTA: the 256x256 layers);
+        # `roofline_unet_convs` is every conv / linear / attention GEMM launch of the forward together.
         prof = wrapper.unet.profile(x_dev, int(sch.timesteps[-1]))
         conv = [p for p in prof if p["kind"] == "conv_igemm"]
+        top = [p for p in conv if "halo2" in p["desc"] and "bn128" in p["desc"]] or conv
         tot_ms = sum(p["ms"] for p in prof)
-        conv_ms = sum(p["ms"] for p in conv)
-        conv_fl = sum(p["flops"] for p in conv)
-        achieved = conv_fl / (conv_ms * 1e-3) / 1e12
         by_kind = {}
         for p in prof:
             d = by_kind.setdefault(p["kind"], {"ms": 0.0, "launch_groups": 0})
             d["ms"] += p["ms"]
             d["launch_groups"] += 1
-        roofline = {"bound": "tensor", "kernel": "conv_igemm_kernel (tcgen05 implicit-GEMM conv, all UNet layers)",
-                    "achieved": achieved, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sust"],
-                    "frac_of_burst": achieved / pk["tf_burst"], "peak_source": pk["src"] + ", sustained bf16",
-                    "traffic": None, "launches": len(conv), "flops_per_forward": conv_fl,
-                    "share_of_unet_time": conv_ms / tot_ms,
-                    "unet_ms": tot_ms, "by_kind_ms": {k: round(v["ms"], 4) for k, v in by_kind.items()},
-                    "how": "sum of algorithmic conv FLOPs / sum of per-launch CUDA-event durations, one instrumented forward"}
+        try:
+            with open(os.path.join(REPO, "profiles", "ncu_traffic.json")) as f:
+                ncu = json.load(f)
+        except Exception:
+            ncu = {}
+
+        def tensor_roofline(launches, kernel):
+            ms = sum(p["ms"] for p in launches)
+            fl = sum(p["flops"] for p in launches)
+            ach = fl / (ms * 1e-3) / 1e12
+            return {"bound": "tensor", "kernel": kernel, "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
+                    "frac": ach / pk["tf_sust"], "frac_of_burst": ach / pk["tf_burst"],
+                    "peak_source": pk["src"] + ", sustained bf16", "launches": len(launches),
+                    "flops_per_launch": fl / len(launches), "us_per_launch": ms * 1e3 / len(launches),
+                    "share_of_unet_time": ms / tot_ms,
+                    "how": "algorithmic FLOPs (2*M*N*K of the GEMM as executed) / CUDA-event duration per launch, "
+                           "one instrumented forward (events on the launching stream)"}
+
+        roofline = tensor_roofline(top, "conv_igemm_kernel<BN=128, pair, halo, 2 M tiles/CTA> (3x3 convolutions at 256x256)")
+        roofline["traffic"] = ncu.get("conv", {}).get("dram_bytes_per_launch")
+        roofline["traffic_source"] = ncu.get("conv", {}).get("source")
+        roofline["tensor_pipe_active_pct_ncu"] = ncu.get("conv", {}).get("tensor_pipe_active_pct_time_weighted")
+        roofline_all = tensor_roofline(conv, "conv_igemm_kernel, all variants (every conv / linear / attention GEMM of the UNet)")
+        roofline_all.update({"flops_per_forward": sum(p["flops"] for p in conv), "unet_ms": tot_ms,
+                             "by_kind_ms": {k: round(v["ms"], 4) for k, v in by_kind.items()}})
         if args.profile_out:
             with open(args.profile_out, "w") as fo:
                 json.dump(prof, fo)
@@ -307,7 +325,8 @@ def main():
         step_gbs = step_bytes / (step_ms * 1e-3) / 1e9
         roofline_step = {"bound": "hbm", "kernel": "guided_step_vec4 (fused x0 + DDPM step + sigma*z + colour guidance)",
                          "achieved": step_gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": step_gbs / pk["hbm"],
-                         "peak_source": pk["src"], "traffic": None, "batch": Bs, "bytes_per_launch": step_bytes,
+                         "peak_source": pk["src"], "traffic": ncu.get("step", {}).get("dram_bytes_per_launch"),
+                         "traffic_source": ncu.get("step", {}).get("source"), "batch": Bs, "bytes_per_launch": step_bytes,
                          "ms_per_launch": step_ms,
                          "how": "16 B/elem algorithmic bytes / CUDA-event time, working set 4x%.0f MB > L2" % (xs.numel() * 4 / 1e6)}
         del xs, es
@@ -326,7 +345,8 @@ def main():
                         "ms_per_step": ms_e2e / K,
                         "how": "SegDiffEditPipeline.edit_image from pinned host x_T / z maps; final images and the "
                                "x0-prediction history copied back to pinned host memory inside the timed region"},
-                "gpu_launches": launches, "roofline": roofline, "roofline_step_kernel": roofline_step,
+                "gpu_launches": launches, "roofline": roofline, "roofline_unet_convs": roofline_all,
+                "roofline_step_kernel": roofline_step,
                 "cpu_baseline": cpu,
                 "unet_tflops_per_img": wrapper.unet.flops_per_sample / 1e12,
                 "unet_achieved_tflops": wrapper.unet.flops_per_sample * B / (tot_ms * 1e-3) / 1e12}
