@@ -34,7 +34,7 @@ class UNetConfig(C.Structure):
                 ("down_attn", C.c_int32 * 8), ("up_attn", C.c_int32 * 8),
                 ("layers_per_block", C.c_int32), ("norm_num_groups", C.c_int32),
                 ("norm_eps", C.c_float), ("attention_head_dim", C.c_int32),
-                ("flip_sin_to_cos", C.c_int32), ("freq_shift", C.c_float)]
+                ("flip_sin_to_cos", C.c_int32), ("freq_shift", C.c_float), ("downsample_padding", C.c_int32)]
 
 
 _P, _I64, _I, _F, _SZ = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_size_t

@@ -20,7 +20,17 @@ DDPM256_CONFIG = dict(
     down_block_types=("DownBlock2D",) * 4 + ("AttnDownBlock2D", "DownBlock2D"),
     up_block_types=("UpBlock2D", "AttnUpBlock2D") + ("UpBlock2D",) * 4,
     norm_num_groups=32, norm_eps=1e-6, attention_head_dim=None,
-    flip_sin_to_cos=False, freq_shift=1,
+    flip_sin_to_cos=False, freq_shift=1, downsample_padding=0,
+)
+
+# CompVis/ldm-celebahq-256 `unet` (UNet2DModel on the 64x64x3 VQ latent, ~274 M parameters)
+LDM_CELEBAHQ_CONFIG = dict(
+    sample_size=64, in_channels=3, out_channels=3,
+    block_out_channels=(224, 448, 672, 896), layers_per_block=2,
+    down_block_types=("DownBlock2D", "AttnDownBlock2D", "AttnDownBlock2D", "AttnDownBlock2D"),
+    up_block_types=("AttnUpBlock2D", "AttnUpBlock2D", "AttnUpBlock2D", "UpBlock2D"),
+    norm_num_groups=32, norm_eps=1e-6, attention_head_dim=32,
+    flip_sin_to_cos=True, freq_shift=0, downsample_padding=1,
 )
 
 
@@ -34,8 +44,8 @@ class UNet2DModel:
     def __init__(self, sample_size=256, in_channels=3, out_channels=3,
                  block_out_channels=(128, 128, 256, 256, 512, 512), layers_per_block=2,
                  down_block_types=None, up_block_types=None, norm_num_groups=32, norm_eps=1e-6,
-                 attention_head_dim=None, flip_sin_to_cos=False, freq_shift=1, max_batch=8,
-                 device="cuda"):
+                 attention_head_dim=None, flip_sin_to_cos=False, freq_shift=1, downsample_padding=0,
+                 max_batch=8, device="cuda"):
         _C.require_device()
         n = len(block_out_channels)
         down_block_types = tuple(down_block_types or ("DownBlock2D",) * n)
@@ -45,7 +55,7 @@ class UNet2DModel:
             block_out_channels=tuple(block_out_channels), layers_per_block=layers_per_block,
             down_block_types=down_block_types, up_block_types=up_block_types,
             norm_num_groups=norm_num_groups, norm_eps=norm_eps, attention_head_dim=attention_head_dim,
-            flip_sin_to_cos=flip_sin_to_cos, freq_shift=freq_shift)
+            flip_sin_to_cos=flip_sin_to_cos, freq_shift=freq_shift, downsample_padding=downsample_padding)
         self.in_channels, self.sample_size = in_channels, sample_size   # deprecated aliases
         self.device = torch.device(device)
         self.dtype = torch.float32
@@ -59,6 +69,7 @@ class UNet2DModel:
         cfg.layers_per_block, cfg.norm_num_groups, cfg.norm_eps = layers_per_block, norm_num_groups, norm_eps
         cfg.attention_head_dim = int(attention_head_dim or 0)
         cfg.flip_sin_to_cos, cfg.freq_shift = int(flip_sin_to_cos), float(freq_shift)
+        cfg.downsample_padding = int(downsample_padding)
         h = C.c_void_p()
         with torch.cuda.device(self.device):
             check(lib.b2e_unet_create(C.byref(cfg), self.max_batch, C.byref(h)), "unet_create")

@@ -778,8 +778,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
 
 // ------------------------------------------------------------------ weight packing
 __global__ void pack_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int Cin,
-                                   int kk, int tap_width, int row_len, int col_off) {
-  // out[co*row_len + col_off + t*tap_width + ci] = w[(co*Cin + ci)*kk + t]
+                                   int kk, int tap_width, int row_len, int col_off, int ci0, int cin_total) {
+  // out[co*row_len + col_off + t*tap_width + ci] = w[(co*cin_total + ci0 + ci)*kk + t]   for ci < Cin
   const int64_t total = (int64_t)Cout * kk * Cin;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -787,7 +787,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, bf16* __restrict
     const int t = (int)((i / Cin) % kk);
     const int co = (int)(i / ((int64_t)Cin * kk));
     out[(int64_t)co * row_len + col_off + (int64_t)t * tap_width + ci] =
-        __float2bfloat16_rn(w[((int64_t)co * Cin + ci) * kk + t]);
+        __float2bfloat16_rn(w[((int64_t)co * cin_total + ci0 + ci) * kk + t]);
   }
 }
 
@@ -797,12 +797,13 @@ __global__ void fill_identity_kernel(bf16* __restrict__ out, int C, int row_len,
 }
 
 int conv_pack_weight(const float* w, bf16* out, int Cout, int Cin, int ksize, int tap_width, int row_len,
-                     int col_off, cudaStream_t st) {
+                     int col_off, cudaStream_t st, int ci0, int cin_total) {
   const int kk = ksize * ksize;
   const int64_t total = (int64_t)Cout * kk * Cin;
   int grid = (int)((total + 255) / 256);
   if (grid > kNumSMs * 16) grid = kNumSMs * 16;
-  pack_weight_kernel<<<grid, 256, 0, st>>>(w, out, Cout, Cin, kk, tap_width, row_len, col_off);
+  pack_weight_kernel<<<grid, 256, 0, st>>>(w, out, Cout, Cin, kk, tap_width, row_len, col_off, ci0,
+                                           cin_total > 0 ? cin_total : Cin);
   return check_launch("pack_weight");
 }
 
@@ -940,7 +941,11 @@ int conv_plan_build(ConvPlan* pl, const ConvDesc& d) {
     const int kh = t / d.ksize, kw = t % d.ksize;
     if (d.stride == 1) {
       p.tap_dc[t] = 0; p.tap_dw[t] = kw - d.ksize / 2; p.tap_da[t] = 0; p.tap_dh[t] = kh - d.ksize / 2;
+    } else if (d.stride2_pad1) {
+      // symmetric padding 1: input index 2*o + k - 1 -> (block o - 1, parity 1), (o, 0), (o, 1)
+      p.tap_dc[t] = (kw != 1) * d.s0.C; p.tap_dw[t] = kw == 0 ? -1 : 0; p.tap_da[t] = kh != 1; p.tap_dh[t] = kh == 0 ? -1 : 0;
     } else {
+      // diffusers Downsample2D with padding 0: pad (0,1,0,1), input index 2*o + k
       p.tap_dc[t] = (kw & 1) * d.s0.C; p.tap_dw[t] = kw >> 1; p.tap_da[t] = kh & 1; p.tap_dh[t] = kh >> 1;
     }
   }

@@ -26,7 +26,8 @@ struct ConvDesc {
   ConvSrc s0, s1;            // input (virtually concatenated along channels), (N,H,W,C)
   ConvSrc r0, r1;            // residual sources at OUTPUT resolution, (N,Ho,Wo,C); stride must be 1
   int N = 0, H = 0, W = 0;
-  int ksize = 3, stride = 1; // stride 1: padding ksize/2; stride 2: ksize 3, padding (0,1,0,1)
+  int ksize = 3, stride = 1; // stride 1: padding ksize/2; stride 2: ksize 3, padding (0,1,0,1) ...
+  int stride2_pad1 = 0;      // ... or symmetric padding 1 (UNet2DModel downsample_padding = 1)
   const bf16* w_packed = nullptr;  // bf16 [cout_pad][row_len], row_len = k*k*(C0+C1) + Cr0 + Cr1
   // batched B operand (attention: Q K^T and P V): image n uses rows [n*b_batch_rows, +Cout) of a
   // [N*b_batch_rows][row_len] matrix whose rows are b_pitch elements apart (0: shared weights / dense rows)
@@ -75,8 +76,9 @@ inline int64_t conv_stats_slots(const ConvGeom& g) { return (int64_t)g.w_blks * 
 int conv_launch(const ConvPlan& plan, const ConvEpilogue& ep, cudaStream_t st);
 
 // fp32 [Cout][Cin][k][k] -> bf16 out[co*row_len + col_off + t*tap_width + ci]   (t = kh*k + kw)
+// (ci0, cin_total): pack only input channels [ci0, ci0 + Cin) of a weight with cin_total input channels
 int conv_pack_weight(const float* w, bf16* out, int Cout, int Cin, int ksize, int tap_width, int row_len,
-                     int col_off, cudaStream_t st);
+                     int col_off, cudaStream_t st, int ci0 = 0, int cin_total = 0);
 // out[c*row_len + col_off + c] = 1 for c < C (identity residual segment)
 int conv_fill_identity(bf16* out, int C, int row_len, int col_off, cudaStream_t st);
 

@@ -27,13 +27,20 @@ struct ResnetL {
   std::string name; int cin0 = 0, cin1 = 0, cout = 0; NormL n1, n2; ConvL c1, c2, sc; bool has_sc = false;
   int temb_off = 0;
 };
-struct AttnL { std::string name; int C = 0; NormL gn; ConvL qkv, proj; };
+struct AttnL { std::string name; int C = 0, P = 0; NormL gn; ConvL qkv, proj; };   // P = pad64(C): q | k | v blocks of P columns
+
+// Channel counts that are not multiples of 64 (LDM: 224, 672) live in tensors whose channel pitch is rounded up to
+// the 64-channel K chunk of the convolution kernel; the tail channels are identically zero (zero weight rows,
+// biases and time-embedding columns produce them, zero weight columns ignore them).  Only GroupNorm and the
+// attention core need the real count.
+inline int pad64(int c) { return (c + 63) / 64 * 64; }
 
 enum NodeKind { N_RESNET, N_ATTN, N_DOWN, N_UP, N_PUSH, N_POPCAT };
 struct Node { NodeKind kind; int idx; };
 
 struct Tensor {
-  bf16* p = nullptr; int N = 0, H = 0, W = 0, C = 0; size_t bytes = 0;
+  bf16* p = nullptr; int N = 0, H = 0, W = 0, C = 0; size_t bytes = 0;   // C = channel pitch (multiple of 64 for conv operands)
+  int Cr = 0;               // real channels (<= C)
   float* cstats = nullptr;  // per-(image, channel) sum / sum of squares from the producing conv's epilogue
   float* tstats = nullptr;  // small tensors: raw per-(tile slot, channel) statistics instead (no finalize kernel)
   size_t tstats_bytes = 0; int ts_nt = 0, ts_per_img = 0;
@@ -112,7 +119,7 @@ struct b2e_unet {
   // conv / linear weight that feeds the tcgen05 GEMM: packed bf16 [cout_pad][k*k][cin_pad]
   ConvL make_conv(const std::string& name, int cin, int cout, int k, int cin_pad = 0, int res_c = 0) {
     ConvL c;
-    c.cin = cin; c.cin_pad = cin_pad ? cin_pad : cin; c.cout = cout; c.k = k; c.cout_pad = conv_cout_pad(cout);
+    c.cin = cin; c.cin_pad = cin_pad ? cin_pad : pad64(cin); c.cout = cout; c.k = k; c.cout_pad = conv_cout_pad(cout);
     c.res_c = res_c; c.row_len = k * k * c.cin_pad + res_c;
     c.w = dmalloc<bf16>((size_t)c.cout_pad * c.row_len);
     c.b = dmalloc<float>(c.cout_pad);
@@ -134,18 +141,22 @@ struct b2e_unet {
     r.name = name; r.cin0 = cin0; r.cin1 = cin1; r.cout = cout;
     const int cin = cin0 + cin1;
     r.n1 = make_norm(name + ".norm1", cin);
-    r.c1 = make_conv(name + ".conv1", cin, cout, 3);
-    r.temb_off = sumC; sumC += cout;
+    r.c1 = make_conv(name + ".conv1", cin, cout, 3);   // reads the compact GroupNorm output (pitch pad64(cin))
+    r.temb_off = sumC; sumC += r.c1.cout_pad;          // padded columns stay zero
     r.n2 = make_norm(name + ".norm2", cout);
     // conv2 carries the block input as a fused 1x1 residual segment: conv_shortcut weights when the
-    // channel count changes, the identity otherwise
-    r.c2 = make_conv(name + ".conv2", cout, cout, 3, 0, cin);
+    // channel count changes, the identity otherwise.  The segment reads the un-normalised block input(s)
+    // at their own pitches: [pad64(cin0)][pad64(cin1)] columns.
+    const int p0 = pad64(cin0), p1 = cin1 ? pad64(cin1) : 0;
+    r.c2 = make_conv(name + ".conv2", cout, cout, 3, 0, p0 + p1);
     r.has_sc = cin != cout;
     if (r.has_sc) {
       r.c2.b2 = dmalloc<float>(r.c2.cout_pad);
       ConvL cc = r.c2;
-      add_param(name + ".conv_shortcut.weight", (int64_t)cout * cin, cin, [cc, cin](const float* src, cudaStream_t st) {
-        return conv_pack_weight(src, cc.w, cc.cout, cin, 1, cin, cc.row_len, 9 * cc.cin_pad, st);
+      add_param(name + ".conv_shortcut.weight", (int64_t)cout * cin, cin, [cc, cin, cin0, cin1, p0](const float* src, cudaStream_t st) {
+        int rc = conv_pack_weight(src, cc.w, cc.cout, cin0, 1, cin0, cc.row_len, 9 * cc.cin_pad, st, 0, cin);
+        if (!rc && cin1) rc = conv_pack_weight(src, cc.w, cc.cout, cin1, 1, cin1, cc.row_len, 9 * cc.cin_pad + p0, st, cin0, cin);
+        return rc;
       });
       add_f32(name + ".conv_shortcut.bias", r.c2.b2, cout, cin);
     } else if (r.c2.w) {
@@ -156,24 +167,25 @@ struct b2e_unet {
   }
   int make_attn(const std::string& name, int C) {
     AttnL a;
-    a.name = name; a.C = C;
+    a.name = name; a.C = C; a.P = pad64(C);
+    const int P = a.P;
     a.gn = make_norm(name + ".group_norm", C);
-    // q, k, v fused into one [3C][C] GEMM weight
-    a.qkv.cin = a.qkv.cin_pad = C; a.qkv.cout = 3 * C; a.qkv.cout_pad = conv_cout_pad(3 * C); a.qkv.k = 1;
-    a.qkv.w = dmalloc<bf16>((size_t)a.qkv.cout_pad * C);
+    // q, k, v fused into one [3P][P] GEMM weight (each projection padded to P rows / columns)
+    a.qkv.cin = C; a.qkv.cin_pad = P; a.qkv.cout = 3 * P; a.qkv.cout_pad = conv_cout_pad(3 * P); a.qkv.k = 1;
+    a.qkv.w = dmalloc<bf16>((size_t)a.qkv.cout_pad * P);
     a.qkv.b = dmalloc<float>(a.qkv.cout_pad);
     const char* nm[3] = {"to_q", "to_k", "to_v"};
     for (int i = 0; i < 3; ++i) {
-      bf16* wdst = a.qkv.w + (size_t)i * C * C;
-      float* bdst = a.qkv.b + (size_t)i * C;
-      add_param(name + "." + nm[i] + ".weight", (int64_t)C * C, C, [wdst, C](const float* src, cudaStream_t st) {
-        return conv_pack_weight(src, wdst, C, C, 1, C, C, 0, st);
+      bf16* wdst = a.qkv.w + (size_t)i * P * P;
+      float* bdst = a.qkv.b + (size_t)i * P;
+      add_param(name + "." + nm[i] + ".weight", (int64_t)C * C, C, [wdst, C, P](const float* src, cudaStream_t st) {
+        return conv_pack_weight(src, wdst, C, C, 1, C, P, 0, st);
       });
       add_f32(name + "." + nm[i] + ".bias", bdst, C, C);
     }
-    a.qkv.row_len = C;
-    a.proj = make_conv(name + ".to_out.0", C, C, 1, 0, C);   // + identity residual segment
-    if (a.proj.w && conv_fill_identity(a.proj.w, C, a.proj.row_len, C, 0)) build_error = B2E_CUDA_ERROR;
+    a.qkv.row_len = P;
+    a.proj = make_conv(name + ".to_out.0", C, C, 1, 0, P);   // + identity residual segment
+    if (a.proj.w && conv_fill_identity(a.proj.w, C, a.proj.row_len, a.proj.cin_pad, 0)) build_error = B2E_CUDA_ERROR;
     attns.push_back(a);
     return (int)attns.size() - 1;
   }
@@ -274,8 +286,8 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
   std::vector<b2e_unet::Op> ops;
   double flops = 0;
   int rc = B2E_OK;
-  auto talloc = [&](int N, int H, int W, int C) {
-    Tensor t; t.N = N; t.H = H; t.W = W; t.C = C; t.bytes = (size_t)N * H * W * C * sizeof(bf16);
+  auto talloc = [&](int N, int H, int W, int C, int Cr = 0) {
+    Tensor t; t.N = N; t.H = H; t.W = W; t.C = C; t.Cr = Cr ? Cr : C; t.bytes = (size_t)N * H * W * C * sizeof(bf16);
     t.p = (bf16*)ar.alloc(t.bytes);
     return t;
   };
@@ -301,11 +313,13 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
                   const Tensor* r0 = nullptr, const Tensor* r1 = nullptr, bool want_stats = true) {
     if (rc) return;
     const int Ho = x0.H / stride, Wo = x0.W / stride;
-    if (out) *out = talloc(B, Ho, Wo, L.cout);
+    // bf16 outputs are written at the padded channel count (zero weight rows / bias for the tail)
+    const int cout_x = out ? L.cout_pad : L.cout;
+    if (out) *out = talloc(B, Ho, Wo, cout_x, L.cout);
     // GroupNorm statistics of the output, emitted by the epilogue (the consumer skips its statistics pass)
-    const ConvGeom geo = conv_geometry(B, Ho, Wo, L.cout);
+    const ConvGeom geo = conv_geometry(B, Ho, Wo, cout_x);
     float* tstats = nullptr;
-    const size_t tstats_bytes = sizeof(float) * 2 * (size_t)conv_stats_slots(geo) * L.cout;
+    const size_t tstats_bytes = sizeof(float) * 2 * (size_t)conv_stats_slots(geo) * cout_x;
     // few tile slots per image (low-resolution levels): the consumer reduces them itself
     const bool raw_stats = geo.w_blks * geo.h_blks <= 16;
     if (out && want_stats && geo.stats_ok) {
@@ -313,11 +327,11 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
       if (raw_stats) {
         out->tstats = tstats; out->tstats_bytes = tstats_bytes; out->ts_nt = geo.Nt; out->ts_per_img = geo.w_blks * geo.h_blks;
       } else {
-        out->cstats = (float*)ar.alloc(sizeof(float) * 2 * B * L.cout);
+        out->cstats = (float*)ar.alloc(sizeof(float) * 2 * B * cout_x);
       }
     }
     if (dry) {
-      flops += 2.0 * B * Ho * Wo * (double)L.cout * (L.k * L.k * (x0.C + (x1 ? x1->C : 0)) + L.res_c);
+      flops += 2.0 * B * Ho * Wo * (double)cout_x * (L.k * L.k * (x0.C + (x1 ? x1->C : 0)) + L.res_c);
       if (tstats && !raw_stats) ar.release(tstats, tstats_bytes);
       return;
     }
@@ -326,7 +340,12 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
     if (x1) d.s1 = ConvSrc{x1->p, x1->C};
     if (r0) d.r0 = ConvSrc{r0->p, r0->C};
     if (r1) d.r1 = ConvSrc{r1->p, r1->C};
-    d.N = B; d.H = x0.H; d.W = x0.W; d.ksize = L.k; d.stride = stride; d.w_packed = L.w; d.Cout = L.cout;
+    d.N = B; d.H = x0.H; d.W = x0.W; d.ksize = L.k; d.stride = stride; d.w_packed = L.w; d.Cout = cout_x;
+    d.stride2_pad1 = c.downsample_padding == 1;
+    if (L.k * L.k * (x0.C + (x1 ? x1->C : 0)) + L.res_c != L.row_len) {
+      rc = B2E_INVALID_ARG; set_error("unet: weight row length %d does not match the operands (%d)", L.row_len,
+                                      L.k * L.k * (x0.C + (x1 ? x1->C : 0)) + L.res_c); return;
+    }
     d.out_bf16 = out ? out->p : nullptr;
     d.tile_stats = tstats;
     d.split_ws = split_ws; d.split_ws_bytes = split_bytes; d.split_counters = split_cnt;
@@ -350,7 +369,7 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
     }
     if (tstats && !raw_stats) {
       float* cst = out->cstats;
-      const int C = L.cout;
+      const int C = cout_x;
       const int fNt = pl.Nt, fw = pl.w_blks, fh = pl.h_blks;   // the plan's actual tiling (halo mode re-tiles)
       ops.push_back({[tstats, cst, B, C, fNt, fw, fh](cudaStream_t st) {
                        return gn_finalize_launch(tstats, cst, B, C, fNt, fw, fh, st);
@@ -360,11 +379,12 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
   };
   auto gnorm = [&](const NormL& L, Tensor x0, const Tensor* x1, int silu, Tensor* out) {
     if (rc) return;
-    const int C = x0.C + (x1 ? x1->C : 0);
-    *out = talloc(B, x0.H, x0.W, C);
+    const int C = x0.Cr + (x1 ? x1->Cr : 0);   // real channels, written compactly; pitch rounded up to 64
+    *out = talloc(B, x0.H, x0.W, pad64(C), C);
     if (dry) return;
     GNArgs a;
-    a.x0 = x0.p; a.x1 = x1 ? x1->p : nullptr; a.C0 = x0.C; a.C1 = x1 ? x1->C : 0;
+    a.x0 = x0.p; a.x1 = x1 ? x1->p : nullptr; a.C0 = x0.Cr; a.C1 = x1 ? x1->Cr : 0;
+    a.P0 = x0.C; a.P1 = x1 ? x1->C : 0; a.Pout = out->C;
     a.N = B; a.HW = x0.H * x0.W; a.G = G; a.eps = c.norm_eps; a.gamma = L.g; a.beta = L.b;
     a.partial = gn_part; a.chunks = gn_chunks(a.HW, C); a.out = out->p; a.silu = silu;
     bool fused = x0.cstats && (!x1 || x1->cstats);
@@ -432,11 +452,11 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
         gnorm(a.gn, h, nullptr, 0, &an);
         conv(a.qkv, an, nullptr, 1, ConvEpilogue{}, &qkv, nullptr, nullptr, nullptr, false);
         tfree(an);
-        o = talloc(B, h.H, h.W, a.C);
+        o = talloc(B, h.H, h.W, a.P, a.C);
         const int heads = c.attention_head_dim > 0 ? a.C / c.attention_head_dim : 1;
-        const int T = h.H * h.W, C = a.C;
+        const int T = h.H * h.W, C = a.P;   // C: padded width of q / k / v (zero tail: no effect on Q K^T, zero rows of V^T)
         const ConvGeom gq = conv_geometry(B, h.H, h.W, T);
-        if (heads == 1 && T % 128 == 0 && T <= 1024 && gq.Nt == 1 && C % 64 == 0) {
+        if (heads == 1 && T % 128 == 0 && T <= 1024 && gq.Nt == 1) {
           // tensor-core attention: S = Q K^T and O = P V are batched GEMMs on the tcgen05 kernel (the per-image
           // B operand is read straight from the qkv tensor / a transposed copy of V); softmax in fp32 between
           Tensor sc = talloc(B, h.H, h.W, T);
@@ -457,7 +477,7 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
             ConvPlan p2;
             if (!rc) rc = conv_plan_build(&p2, d2);
             if (!rc) {
-              const float scale = 1.0f / sqrtf((float)C);
+              const float scale = 1.0f / sqrtf((float)a.C);
               const int64_t rows = (int64_t)B * T;
               ops.push_back({[p1](cudaStream_t st) { return conv_launch(p1, ConvEpilogue{}, st); }, 0, p1.flops, 0.0});
               ops.push_back({[sc, rows, T, scale](cudaStream_t st) { return softmax_rows_launch(sc.p, rows, T, scale, st); },
@@ -474,8 +494,9 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
           tfree(vt);
         } else {
           if (!dry) {
-            ops.push_back({[qkv, o, B, T, C, heads](cudaStream_t st) { return attention_launch(qkv.p, o.p, B, T, C, heads, st); },
-                           2, 4.0 * B * (double)T * T * C, 0.0});
+            const int Cr = a.C;
+            ops.push_back({[qkv, o, B, T, C, Cr, heads](cudaStream_t st) { return attention_launch(qkv.p, o.p, B, T, Cr, C, heads, st); },
+                           2, 4.0 * B * (double)T * T * Cr, 0.0});
           }
           flops += 4.0 * B * (double)(h.H * h.W) * (h.H * h.W) * a.C;
         }
@@ -494,7 +515,7 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
         break;
       }
       case N_UP: {
-        Tensor up = talloc(B, h.H * 2, h.W * 2, h.C), out;
+        Tensor up = talloc(B, h.H * 2, h.W * 2, h.C, h.Cr), out;
         if (!dry) {
           Tensor hh = h;
           ops.push_back({[hh, up, B](cudaStream_t st) { return upsample2x_launch(hh.p, up.p, B, hh.H, hh.W, hh.C, st); },
@@ -538,9 +559,16 @@ int b2e_unet_create(const b2e_unet_config* cfg, int64_t max_batch, b2e_unet** ou
   B2E_REQUIRE(cfg->n_blocks >= 1 && cfg->n_blocks <= 8, B2E_UNSUPPORTED_SHAPE, "unet_create: n_blocks");
   B2E_REQUIRE(cfg->in_channels <= 8 && cfg->out_channels <= 16, B2E_UNSUPPORTED_SHAPE,
               "unet_create: in_channels <= 8 and out_channels <= 16 required");
-  for (int i = 0; i < cfg->n_blocks; ++i)
-    B2E_REQUIRE(cfg->block_out_channels[i] % 64 == 0 && cfg->block_out_channels[i] <= 512, B2E_UNSUPPORTED_SHAPE,
-                "unet_create: block_out_channels must be multiples of 64 and <= 512 (got %d)", cfg->block_out_channels[i]);
+  for (int i = 0; i < cfg->n_blocks; ++i) {
+    const int ch = cfg->block_out_channels[i];
+    B2E_REQUIRE(ch % 8 == 0 && ch >= 32 && ch <= 1024 && ch % cfg->norm_num_groups == 0, B2E_UNSUPPORTED_SHAPE,
+                "unet_create: block_out_channels must be multiples of 8 and of norm_num_groups, 32..1024 (got %d)", ch);
+    B2E_REQUIRE(cfg->attention_head_dim <= 0 || !(cfg->down_attn[i] || cfg->up_attn[i]) || ch % cfg->attention_head_dim == 0,
+                B2E_UNSUPPORTED_SHAPE, "unet_create: %d channels are not a multiple of attention_head_dim %d", ch,
+                cfg->attention_head_dim);
+  }
+  B2E_REQUIRE(cfg->downsample_padding == 0 || cfg->downsample_padding == 1, B2E_UNSUPPORTED_SHAPE,
+              "unet_create: downsample_padding must be 0 or 1");
   B2E_REQUIRE(cfg->sample_size % (1 << (cfg->n_blocks - 1)) == 0, B2E_UNSUPPORTED_SHAPE, "unet_create: sample_size");
   b2e_unet* m = new b2e_unet();
   m->cfg = *cfg;

@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(kGNThreads) gn_partial_kernel(GNArgs a) {
     for (int j = 0; j < 8; ++j) sum[j] = sq[j] = 0.f;
     const int c = s * 8;
     const bf16* src; int cs, coff;
-    if (c < a.C0) { src = a.x0; cs = a.C0; coff = c; } else { src = a.x1; cs = a.C1; coff = c - a.C0; }
+    if (c < a.C0) { src = a.x0; cs = a.P0; coff = c; } else { src = a.x1; cs = a.P1; coff = c - a.C0; }
     src += (int64_t)n * a.HW * cs + coff;
     for (int p = p0 + pl; p < p1; p += ppi * kGNUnroll) {
       uint4 v[kGNUnroll];
@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(kGNThreads) gn_partial_kernel(GNArgs a) {
 __global__ void __launch_bounds__(kGNThreads) gn_apply_kernel(GNArgs a, int pix_per_block) {
   pdl_wait();
   __shared__ float s_mean[64], s_rstd[64];
-  const int C = a.C0 + a.C1, slots = C >> 3, ppi = kGNThreads / slots;
+  const int C = a.C0 + a.C1, slots = a.Pout >> 3, ppi = kGNThreads / slots;
   const int n = blockIdx.y, tid = threadIdx.x;
   const int cpg = C / a.G;
   if (tid < a.G) {
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(kGNThreads) gn_apply_kernel(GNArgs a, int pix_
       for (int c = tid * cpg; c < (tid + 1) * cpg; ++c) {
         const bool first = c < a.C0;
         const float* t = first ? a.ts0 : a.ts1;
-        const int Cs = first ? a.C0 : a.C1, cc = first ? c : c - a.C0;
+        const int Cs = first ? a.P0 : a.P1, cc = first ? c : c - a.C0;
         for (int i = 0; i < a.ts_per_img; ++i) {
           const float2 v = __ldg(reinterpret_cast<const float2*>(t + (((base + i) * a.ts_nt + nl) * Cs + cc) * 2));
           ts += (double)v.x; tq += (double)v.y;
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(kGNThreads) gn_apply_kernel(GNArgs a, int pix_
     } else if (a.cs0) {
       // per-channel sums from the producing convolutions' epilogues (concat-aware)
       for (int c = tid * cpg; c < (tid + 1) * cpg; ++c) {
-        const float* o = c < a.C0 ? a.cs0 + ((int64_t)n * a.C0 + c) * 2 : a.cs1 + ((int64_t)n * a.C1 + (c - a.C0)) * 2;
+        const float* o = c < a.C0 ? a.cs0 + ((int64_t)n * a.P0 + c) * 2 : a.cs1 + ((int64_t)n * a.P1 + (c - a.C0)) * 2;
         ts += (double)o[0]; tq += (double)o[1];
       }
     } else {
@@ -119,6 +119,12 @@ __global__ void __launch_bounds__(kGNThreads) gn_apply_kernel(GNArgs a, int pix_
   const int s = tid % slots, pl = tid / slots;
   if (pl >= ppi) return;
   const int c = s * 8;
+  const int p0 = blockIdx.x * pix_per_block, p1 = min(a.HW, p0 + pix_per_block);
+  bf16* dst = a.out + (int64_t)n * a.HW * a.Pout + c;
+  if (c >= C) {   // zero padding of the output pitch
+    for (int p = p0 + pl; p < p1; p += ppi) *reinterpret_cast<uint4*>(dst + (int64_t)p * a.Pout) = make_uint4(0, 0, 0, 0);
+    return;
+  }
   float scale[8], shift[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -127,10 +133,8 @@ __global__ void __launch_bounds__(kGNThreads) gn_apply_kernel(GNArgs a, int pix_
     shift[j] = __ldg(a.beta + c + j) - s_mean[g] * scale[j];
   }
   const bf16* src; int cs, coff;
-  if (c < a.C0) { src = a.x0; cs = a.C0; coff = c; } else { src = a.x1; cs = a.C1; coff = c - a.C0; }
+  if (c < a.C0) { src = a.x0; cs = a.P0; coff = c; } else { src = a.x1; cs = a.P1; coff = c - a.C0; }
   src += (int64_t)n * a.HW * cs + coff;
-  bf16* dst = a.out + (int64_t)n * a.HW * C + c;
-  const int p0 = blockIdx.x * pix_per_block, p1 = min(a.HW, p0 + pix_per_block);
   for (int p = p0 + pl; p < p1; p += ppi * kGNUnroll) {
     uint4 v[kGNUnroll];
 #pragma unroll
@@ -156,7 +160,7 @@ __global__ void __launch_bounds__(kGNThreads) gn_apply_kernel(GNArgs a, int pix_
           }
           f[j] = y;
         }
-        *reinterpret_cast<uint4*>(dst + (int64_t)q * C) = pack8(f);
+        *reinterpret_cast<uint4*>(dst + (int64_t)q * a.Pout) = pack8(f);
       }
     }
   }
@@ -173,15 +177,17 @@ int gn_chunks(int HW, int C) {
 
 int gn_launch(const GNArgs& a, cudaStream_t st) {
   const int C = a.C0 + a.C1;
-  B2E_REQUIRE(C % 8 == 0 && a.C0 % 8 == 0 && C <= 1024 && a.G <= 64 && C % a.G == 0, B2E_UNSUPPORTED_SHAPE,
+  B2E_REQUIRE(C % 8 == 0 && a.C0 % 8 == 0 && a.Pout <= 2048 && a.G <= 64 && C % a.G == 0, B2E_UNSUPPORTED_SHAPE,
               "groupnorm: unsupported channels %d+%d / groups %d", a.C0, a.C1, a.G);
+  B2E_REQUIRE(a.P0 >= a.C0 && a.P1 >= a.C1 && a.Pout >= C && a.P0 % 8 == 0 && a.P1 % 8 == 0 && a.Pout % 8 == 0,
+              B2E_INVALID_ARG, "groupnorm: bad channel pitches %d/%d -> %d", a.P0, a.P1, a.Pout);
   int rc = B2E_OK;
   if (!a.cs0 && !a.ts0) {
     launch_pdl(gn_partial_kernel, dim3(dim3(a.chunks, a.N)), dim3(kGNThreads), 0, st, a);
     rc = check_launch("gn_partial");
     if (rc) return rc;
   }
-  const int slots = C / 8, ppi = kGNThreads / slots;
+  const int slots = a.Pout / 8, ppi = kGNThreads / slots;
   int ppb = ppi * kGNUnroll * 2;  // two unrolled sweeps per thread
   if (ppb > a.HW) ppb = a.HW;
   launch_pdl(gn_apply_kernel, dim3(dim3((a.HW + ppb - 1) / ppb, a.N)), dim3(kGNThreads), 0, st, a, ppb);
@@ -457,21 +463,23 @@ int transpose_v_launch(const bf16* qkv, bf16* vt, int N, int T, int C, cudaStrea
 
 // ------------------------------------------------------------------ attention core
 // Block = (image n, head h, 16 queries).  S = Q K^T * d^-1/2 in smem (fp32), softmax, O = P V.
+// qkv rows are [q | k | v] blocks of P channels each (P >= C = heads * d; the tail of a block is zero padding),
+// out rows have pitch P (the tail is zero-filled by the h == 0 blocks).
 constexpr int kAttThreads = 256;
 constexpr int kAttQ = 16;
 constexpr int kAttKStride = 72;  // bf16 per staged key row (64 + pad): uint4-aligned, conflict-free
 
 __global__ void __launch_bounds__(kAttThreads)
-attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, int C, int heads) {
+attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, int C, int P, int heads) {
   pdl_wait();
   extern __shared__ __align__(16) uint8_t att_smem[];
   const int d = C / heads;
   float* Qs = reinterpret_cast<float*>(att_smem);            // [16][d]
   float* S = Qs + kAttQ * d;                                  // [16][T]
-  bf16* Ks = reinterpret_cast<bf16*>(S + kAttQ * T);         // [256][72]
+  bf16* Ks = reinterpret_cast<bf16*>(S + kAttQ * T);         // [256][72]  (phase 3: fp32 partial sums, 32 KB)
   const int qt = blockIdx.x, h = blockIdx.y, n = blockIdx.z, tid = threadIdx.x;
   const int q0 = qt * kAttQ;
-  const int64_t row = 3 * (int64_t)C;
+  const int64_t row = 3 * (int64_t)P;
   const bf16* base = qkv + (int64_t)n * T * row;
   const float scale = rsqrtf((float)d);
   // load Q tile
@@ -479,25 +487,31 @@ attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, in
     const int q = i / d, c = i % d;
     Qs[i] = (q0 + q < T) ? __bfloat162float(base[(int64_t)(q0 + q) * row + h * d + c]) : 0.f;
   }
-  // phase 1: scores
+  if (h == 0 && P > C) {   // zero padding of the output pitch
+    for (int i = tid; i < kAttQ * (P - C); i += kAttThreads) {
+      const int q = i / (P - C), c = i % (P - C);
+      if (q0 + q < T) out[((int64_t)n * T + q0 + q) * P + C + c] = __float2bfloat16_rn(0.f);
+    }
+  }
+  // phase 1: scores, keys staged in pieces of dc = min(64, d) channels
+  const int dc = d < 64 ? d : 64, parts = dc >> 3;
   for (int kt = 0; kt < T; kt += kAttThreads) {
     float acc[kAttQ];
 #pragma unroll
     for (int q = 0; q < kAttQ; ++q) acc[q] = 0.f;
     const int key = kt + tid;
-    for (int c0 = 0; c0 < d; c0 += 64) {
+    for (int c0 = 0; c0 < d; c0 += dc) {
       __syncthreads();
-      for (int i = tid; i < kAttThreads * 8; i += kAttThreads) {
-        const int kk = i >> 3, part = i & 7;
+      for (int i = tid; i < kAttThreads * parts; i += kAttThreads) {
+        const int kk = i / parts, part = i % parts;
         uint4 v = make_uint4(0, 0, 0, 0);
         if (kt + kk < T)
-          v = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)(kt + kk) * row + C + h * d + c0 + part * 8));
+          v = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)(kt + kk) * row + P + h * d + c0 + part * 8));
         *reinterpret_cast<uint4*>(Ks + kk * kAttKStride + part * 8) = v;
       }
       __syncthreads();
       if (key < T) {
-#pragma unroll
-        for (int part = 0; part < 8; ++part) {
+        for (int part = 0; part < parts; ++part) {
           float kf[8];
           unpack8(*reinterpret_cast<const uint4*>(Ks + tid * kAttKStride + part * 8), kf);
 #pragma unroll
@@ -530,12 +544,54 @@ attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, in
     for (int j = lane; j < T; j += 32) S[q * T + j] *= inv;
   }
   __syncthreads();
-  // phase 3: O = P V ; thread owns channel pairs (2*tid, 2*tid+1) + 512*i
+  // phase 3: O = P V.  A thread owns a channel pair; with few channels per head (d/2 < 256) the keys are split
+  // over `groups` thread groups and the partial sums are combined through smem in a fixed order.
+  const int half = d >> 1;
+  int groups = half < kAttThreads ? kAttThreads / half : 1;
+  while (groups > 1 && T % (4 * groups) != 0) groups >>= 1;   // every group takes a multiple of 4 keys
+  if (groups > 1) {
+    float* red = reinterpret_cast<float*>(Ks);   // [groups][16][d] fp32, <= 32 KB (groups * d <= 512)
+    const int cp = tid % half, ks = tid / half;
+    if (ks < groups) {
+      float ax[kAttQ], ay[kAttQ];
+#pragma unroll
+      for (int q = 0; q < kAttQ; ++q) ax[q] = ay[q] = 0.f;
+      const int per = T / groups;
+      const bf16* vp = base + 2 * P + h * d + 2 * cp;
+      for (int j = ks * per; j < (ks + 1) * per; j += 4) {
+        float2 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          v[u] = __bfloat1622float2(__ldg(reinterpret_cast<const __nv_bfloat162*>(vp + (int64_t)(j + u) * row)));
+#pragma unroll
+        for (int q = 0; q < kAttQ; ++q) {
+          const float4 p = *reinterpret_cast<const float4*>(S + q * T + j);
+          ax[q] += p.x * v[0].x + p.y * v[1].x + p.z * v[2].x + p.w * v[3].x;
+          ay[q] += p.x * v[0].y + p.y * v[1].y + p.z * v[2].y + p.w * v[3].y;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < kAttQ; ++q)
+        *reinterpret_cast<float2*>(red + ((ks * kAttQ + q) * d + 2 * cp)) = make_float2(ax[q], ay[q]);
+    }
+    __syncthreads();
+    for (int i = tid; i < kAttQ * half; i += kAttThreads) {
+      const int q = i / half, c2 = i % half;
+      float sx = 0.f, sy = 0.f;
+      for (int g = 0; g < groups; ++g) {
+        const float2 v = *reinterpret_cast<const float2*>(red + ((g * kAttQ + q) * d + 2 * c2));
+        sx += v.x; sy += v.y;
+      }
+      if (q0 + q < T)
+        *reinterpret_cast<__nv_bfloat162*>(out + ((int64_t)n * T + q0 + q) * P + h * d + 2 * c2) = __floats2bfloat162_rn(sx, sy);
+    }
+    return;
+  }
   for (int c0 = 2 * tid; c0 < d; c0 += 2 * kAttThreads) {
     float ax[kAttQ], ay[kAttQ];
 #pragma unroll
     for (int q = 0; q < kAttQ; ++q) ax[q] = ay[q] = 0.f;
-    const bf16* vp = base + 2 * C + h * d + c0;
+    const bf16* vp = base + 2 * P + h * d + c0;
     for (int j = 0; j < T; j += 4) {  // T % 4 == 0 (checked on the host)
       float2 v[4];
 #pragma unroll
@@ -551,15 +607,15 @@ attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, in
 #pragma unroll
     for (int q = 0; q < kAttQ; ++q)
       if (q0 + q < T)
-        *reinterpret_cast<__nv_bfloat162*>(out + ((int64_t)n * T + q0 + q) * C + h * d + c0) =
+        *reinterpret_cast<__nv_bfloat162*>(out + ((int64_t)n * T + q0 + q) * P + h * d + c0) =
             __floats2bfloat162_rn(ax[q], ay[q]);
   }
 }
 
-int attention_launch(const bf16* qkv, bf16* out, int N, int T, int C, int heads, cudaStream_t st) {
-  B2E_REQUIRE(heads >= 1 && C % heads == 0, B2E_UNSUPPORTED_SHAPE, "attention: bad head count");
+int attention_launch(const bf16* qkv, bf16* out, int N, int T, int C, int P, int heads, cudaStream_t st) {
+  B2E_REQUIRE(heads >= 1 && C % heads == 0 && P >= C && P % 8 == 0, B2E_UNSUPPORTED_SHAPE, "attention: bad head count / pitch");
   const int d = C / heads;
-  B2E_REQUIRE(d % 64 == 0 && d <= 1024 && T % 4 == 0 && T <= 4096, B2E_UNSUPPORTED_SHAPE,
+  B2E_REQUIRE(d % 8 == 0 && (d <= 64 || d % 64 == 0) && d <= 1024 && T % 4 == 0 && T <= 4096, B2E_UNSUPPORTED_SHAPE,
               "attention: unsupported T=%d head_dim=%d", T, d);
   const size_t smem = sizeof(float) * kAttQ * (d + T) + sizeof(bf16) * kAttThreads * kAttKStride;
   B2E_REQUIRE(smem <= 200 * 1024, B2E_UNSUPPORTED_SHAPE, "attention: tile does not fit in shared memory");
@@ -568,7 +624,7 @@ int attention_launch(const bf16* qkv, bf16* out, int N, int T, int C, int heads,
     B2E_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  launch_pdl(attention_kernel, dim3(dim3((T + kAttQ - 1) / kAttQ, heads, N)), dim3(kAttThreads), smem, st, qkv, out, T, C, heads);
+  launch_pdl(attention_kernel, dim3((T + kAttQ - 1) / kAttQ, heads, N), dim3(kAttThreads), smem, st, qkv, out, T, C, P, heads);
   return check_launch("attention");
 }
 

@@ -9,17 +9,19 @@ namespace b2e {
 // writes the normalised bf16 tensor that the next convolution reads through TMA.
 struct GNArgs {
   const bf16* x0; const bf16* x1;  // x1 may be null
-  int C0, C1;
+  int C0, C1;      // REAL channels of each source (multiples of 8); groups are formed over the C0 + C1 real channels
+  int P0, P1;      // channel pitch of each source (>= C; the tail [C, P) is zero padding and is skipped)
+  int Pout;        // channel pitch of the output (>= C0 + C1): real channels are written compactly, the tail is zeroed
   int N, HW, G;
   float eps;
   const float* gamma; const float* beta;
   float* partial;  // [N][chunks][G][2]   (statistics pass; unused when cs0 is given)
-  const float* cs0; const float* cs1;  // per-channel (sum, sumsq) of x0 / x1, [N][C][2], from the conv epilogue
+  const float* cs0; const float* cs1;  // per-channel (sum, sumsq) of x0 / x1, [N][P][2], from the conv epilogue
   // small tensors: raw per-(tile slot, channel) statistics, reduced by gn_apply itself (no finalize launch)
   const float* ts0; const float* ts1;
   int ts_nt, ts_per_img;               // images per tile, tile slots per image (same geometry for both sources)
   int chunks;
-  bf16* out;       // [N][HW][C0+C1]
+  bf16* out;       // [N][HW][Pout]
   int silu;
 };
 int gn_chunks(int HW, int C);
@@ -52,7 +54,7 @@ int temb_launch(const TembArgs& a, cudaStream_t st);
 int softmax_rows_launch(bf16* s, int64_t rows, int T, float scale, cudaStream_t st);
 int transpose_v_launch(const bf16* qkv, bf16* vt, int N, int T, int C, cudaStream_t st);
 
-// single/multi-head self-attention core: qkv bf16 [N][T][3C] (q | k | v) -> out bf16 [N][T][C]
-int attention_launch(const bf16* qkv, bf16* out, int N, int T, int C, int heads, cudaStream_t st);
+// single/multi-head self-attention core: qkv bf16 [N][T][3P] (q | k | v blocks of P >= C channels) -> out bf16 [N][T][P]
+int attention_launch(const bf16* qkv, bf16* out, int N, int T, int C, int P, int heads, cudaStream_t st);
 
 }  // namespace b2e

@@ -198,7 +198,7 @@ typedef struct {
   int32_t in_channels;
   int32_t out_channels;
   int32_t n_blocks;
-  int32_t block_out_channels[8];
+  int32_t block_out_channels[8]; /* multiples of 8 and of norm_num_groups; non-multiples of 64 are zero-padded internally */
   int32_t down_attn[8]; /* 1: AttnDownBlock2D */
   int32_t up_attn[8];   /* 1: AttnUpBlock2D   */
   int32_t layers_per_block;
@@ -207,6 +207,7 @@ typedef struct {
   int32_t attention_head_dim; /* 0: single head */
   int32_t flip_sin_to_cos;
   float freq_shift;
+  int32_t downsample_padding; /* 0: pad (0,1,0,1) before the stride-2 conv (DDPM-256); 1: symmetric padding 1 (LDM) */
 } b2e_unet_config;
 
 typedef struct b2e_unet b2e_unet;

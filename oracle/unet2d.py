@@ -33,6 +33,17 @@ DDPM256_CONFIG = dict(
 )
 
 
+# CompVis/ldm-celebahq-256 `unet` (UNet2DModel on the 64x64x3 VQ latent); recalled layout, unverifiable offline
+LDM_CELEBAHQ_CONFIG = dict(
+    sample_size=64, in_channels=3, out_channels=3,
+    block_out_channels=(224, 448, 672, 896), layers_per_block=2,
+    down_block_types=("DownBlock2D", "AttnDownBlock2D", "AttnDownBlock2D", "AttnDownBlock2D"),
+    up_block_types=("AttnUpBlock2D", "AttnUpBlock2D", "AttnUpBlock2D", "UpBlock2D"),
+    norm_num_groups=32, norm_eps=1e-6, attention_head_dim=32,
+    flip_sin_to_cos=True, freq_shift=0, downsample_padding=1,
+)
+
+
 def timestep_embedding(timesteps, dim, flip_sin_to_cos=False, freq_shift=1, max_period=10000):
     half = dim // 2
     exponent = -math.log(max_period) * torch.arange(half, dtype=torch.float32,
@@ -103,12 +114,18 @@ class Attention(nn.Module):
 
 
 class Downsample2D(nn.Module):
-    def __init__(self, ch):
+    """diffusers Downsample2D(use_conv=True, padding=p): p = 0 pads (0,1,0,1) first (DDPM-256 config), p = 1 is a
+    plain padding-1 stride-2 convolution (UNet2DModel default, LDM config)."""
+
+    def __init__(self, ch, padding=0):
         super().__init__()
-        self.conv = nn.Conv2d(ch, ch, 3, stride=2, padding=0)
+        self.padding = padding
+        self.conv = nn.Conv2d(ch, ch, 3, stride=2, padding=padding)
 
     def forward(self, x):
-        return self.conv(F.pad(x, (0, 1, 0, 1)))
+        if self.padding == 0:
+            x = F.pad(x, (0, 1, 0, 1))
+        return self.conv(x)
 
 
 class Upsample2D(nn.Module):
@@ -121,13 +138,13 @@ class Upsample2D(nn.Module):
 
 
 class DownBlock(nn.Module):
-    def __init__(self, cin, cout, temb_ch, layers, groups, eps, attn, head_dim, add_down):
+    def __init__(self, cin, cout, temb_ch, layers, groups, eps, attn, head_dim, add_down, down_pad=0):
         super().__init__()
         self.resnets = nn.ModuleList(
             [ResnetBlock2D(cin if i == 0 else cout, cout, temb_ch, groups, eps) for i in range(layers)])
         self.attentions = nn.ModuleList(
             [Attention(cout, head_dim, groups, eps) for _ in range(layers)]) if attn else None
-        self.downsamplers = nn.ModuleList([Downsample2D(cout)]) if add_down else None
+        self.downsamplers = nn.ModuleList([Downsample2D(cout, down_pad)]) if add_down else None
 
     def forward(self, x, temb):
         outs = []
@@ -187,7 +204,8 @@ class UNet2DModel(nn.Module):
     def __init__(self, sample_size=256, in_channels=3, out_channels=3,
                  block_out_channels=(128, 128, 256, 256, 512, 512), layers_per_block=2,
                  down_block_types=None, up_block_types=None, norm_num_groups=32,
-                 norm_eps=1e-6, attention_head_dim=None, flip_sin_to_cos=False, freq_shift=1):
+                 norm_eps=1e-6, attention_head_dim=None, flip_sin_to_cos=False, freq_shift=1,
+                 downsample_padding=0):
         super().__init__()
         n = len(block_out_channels)
         down_block_types = tuple(down_block_types or ("DownBlock2D",) * n)
@@ -198,7 +216,7 @@ class UNet2DModel(nn.Module):
             down_block_types=down_block_types, up_block_types=up_block_types,
             norm_num_groups=norm_num_groups, norm_eps=norm_eps,
             attention_head_dim=attention_head_dim, flip_sin_to_cos=flip_sin_to_cos,
-            freq_shift=freq_shift)
+            freq_shift=freq_shift, downsample_padding=downsample_padding)
         # deprecated direct attributes the reference still reads
         self.in_channels = in_channels
         self.sample_size = sample_size
@@ -212,7 +230,7 @@ class UNet2DModel(nn.Module):
         for i, t in enumerate(down_block_types):
             in_ch, out_ch = out_ch, boc[i]
             self.down_blocks.append(DownBlock(in_ch, out_ch, temb_ch, layers_per_block, g, eps,
-                                              t.startswith("Attn"), hd, i != n - 1))
+                                              t.startswith("Attn"), hd, i != n - 1, downsample_padding))
         self.mid_block = MidBlock(boc[-1], temb_ch, g, eps, hd)
         self.up_blocks = nn.ModuleList()
         rev = boc[::-1]

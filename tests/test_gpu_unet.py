@@ -9,13 +9,21 @@ engine to be no further from the fp32 result than 1.25x that."""
 import pytest
 import torch
 
-from oracle.unet2d import DDPM256_CONFIG, UNet2DModel as OracleUNet
+from oracle.unet2d import DDPM256_CONFIG, LDM_CELEBAHQ_CONFIG, UNet2DModel as OracleUNet
 
 pytestmark = pytest.mark.gpu
 
 SMALL = dict(sample_size=32, in_channels=3, out_channels=3, block_out_channels=(64, 128, 128),
              layers_per_block=1, down_block_types=("DownBlock2D", "AttnDownBlock2D", "DownBlock2D"),
              up_block_types=("UpBlock2D", "AttnUpBlock2D", "UpBlock2D"), norm_num_groups=32, norm_eps=1e-6)
+
+
+# LDM-style layout in small: channel counts that are multiples of 32 but not of 64 (zero-padded internally),
+# multi-head attention with 32-channel heads at two resolutions, symmetric stride-2 padding, flipped embedding
+LDM_SMALL = dict(sample_size=32, in_channels=3, out_channels=3, block_out_channels=(32, 96, 160),
+                 layers_per_block=1, down_block_types=("DownBlock2D", "AttnDownBlock2D", "AttnDownBlock2D"),
+                 up_block_types=("AttnUpBlock2D", "AttnUpBlock2D", "UpBlock2D"), norm_num_groups=32, norm_eps=1e-6,
+                 attention_head_dim=32, flip_sin_to_cos=True, freq_shift=0, downsample_padding=1)
 
 
 def run_pair(cfg, B, t, seed):
@@ -52,6 +60,16 @@ def check(got, ref, ref16, tag):
 @pytest.mark.parametrize("B,t", [(1, 980), (3, 500), (2, 0)])
 def test_small_unet_matches_oracle(B, t):
     check(*run_pair(SMALL, B, t, seed=B), f"small unet B={B} t={t}")
+
+
+@pytest.mark.parametrize("B,t", [(1, 981), (3, 400)])
+def test_ldm_style_unet_matches_oracle(B, t):
+    check(*run_pair(LDM_SMALL, B, t, seed=10 + B), f"ldm-style small unet B={B} t={t}")
+
+
+def test_ldm_celebahq_unet_matches_oracle():
+    """The full LDM-CelebAHQ UNet2DModel layout (224/448/672/896 channels, 14-28 heads of 32 channels)."""
+    check(*run_pair(LDM_CELEBAHQ_CONFIG, 2, 500, seed=4), "ldm-celebahq unet")
 
 
 def test_ddpm256_unet_matches_oracle():
