@@ -492,6 +492,48 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
           }
           tfree(sc);
           tfree(vt);
+        } else if (heads > 1 && (a.C / heads) % 8 == 0 && a.C / heads <= 64 && T % 128 == 0 && T <= 1024 &&
+                   conv_geometry(B * heads, h.H, h.W, T).Nt == 1) {
+          // multi-head tensor-core attention: heads become "virtual images" v = n*heads + h of head-major copies of
+          // q, k (head_dim zero-padded to one 64-channel K chunk) and V^T; S = Q K^T and O = P V are batched GEMMs on
+          // the tcgen05 kernel, softmax in fp32 between them, heads merged back afterwards
+          const int d = a.C / heads, NV = B * heads;
+          Tensor qh = talloc(NV, h.H, h.W, 64), kh = talloc(NV, h.H, h.W, 64), vht = talloc(NV, 1, 64, T);
+          Tensor sc = talloc(NV, h.H, h.W, T), oh = talloc(NV, h.H, h.W, 64);
+          if (!dry) {
+            ConvDesc d1;
+            d1.s0.ptr = qh.p; d1.s0.C = 64;
+            d1.N = NV; d1.H = h.H; d1.W = h.W; d1.ksize = 1; d1.stride = 1;
+            d1.w_packed = kh.p; d1.b_batch_rows = T; d1.b_pitch = 64;      // K rows of virtual image v
+            d1.Cout = T; d1.out_bf16 = sc.p;
+            ConvPlan p1;
+            rc = conv_plan_build(&p1, d1);
+            ConvDesc d2;
+            d2.s0.ptr = sc.p; d2.s0.C = T;                                 // P
+            d2.N = NV; d2.H = h.H; d2.W = h.W; d2.ksize = 1; d2.stride = 1;
+            d2.w_packed = vht.p; d2.b_batch_rows = 64; d2.b_pitch = T;     // V^T rows of virtual image v
+            d2.Cout = 64; d2.out_bf16 = oh.p;
+            ConvPlan p2;
+            if (!rc) rc = conv_plan_build(&p2, d2);
+            if (!rc) {
+              const float scale = 1.0f / sqrtf((float)d);
+              const int64_t rows = (int64_t)NV * T;
+              const int P = a.P;
+              ops.push_back({[qkv, qh, kh, vht, B, T, P, heads, d](cudaStream_t st) {
+                               return split_heads_launch(qkv.p, qh.p, kh.p, vht.p, B, T, P, heads, d, st);
+                             }, 3, 0.0, 2.0 * B * T * (3.0 * P + 3.0 * heads * 64)});
+              ops.push_back({[p1](cudaStream_t st) { return conv_launch(p1, ConvEpilogue{}, st); }, 0, p1.flops, 0.0, "attention QK^T (heads batched)"});
+              ops.push_back({[sc, rows, T, scale](cudaStream_t st) { return softmax_rows_launch(sc.p, rows, T, scale, st); },
+                             3, 0.0, 4.0 * rows * T});
+              ops.push_back({[p2](cudaStream_t st) { return conv_launch(p2, ConvEpilogue{}, st); }, 0, p2.flops, 0.0, "attention PV (heads batched)"});
+              ops.push_back({[oh, o, B, T, P, heads, d](cudaStream_t st) { return merge_heads_launch(oh.p, o.p, B, T, P, heads, d, st); },
+                             3, 0.0, 2.0 * B * T * (P + heads * 64.0)});
+              flops += p1.flops + p2.flops;
+            }
+          } else {
+            flops += 4.0 * NV * (double)T * T * 64;
+          }
+          tfree(qh); tfree(kh); tfree(vht); tfree(sc); tfree(oh);
         } else {
           if (!dry) {
             const int Cr = a.C;

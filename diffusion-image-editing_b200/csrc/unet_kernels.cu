@@ -392,14 +392,21 @@ __global__ void __launch_bounds__(256) temb_proj_kernel(TembArgs a) {
   for (int j = 0; j < kTembMaxPerLane; ++j)
     if (j < per) { const int i = lane + 32 * j; w[j] = i < a.dim ? __ldg(a.wp + (int64_t)o * a.dim + i) : 0.f; }
   const float bias = a.bp[o];
-  for (int b = 0; b < a.B; ++b) {
-    const float* x = a.act + (int64_t)b * a.dim;
-    float acc = 0.f;
+  for (int b0 = 0; b0 < a.B; b0 += 4) {   // four samples per iteration: independent loads / reductions in flight
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int j = 0; j < kTembMaxPerLane; ++j)
-      if (j < per) { const int i = lane + 32 * j; if (i < a.dim) acc += w[j] * x[i]; }
-    acc = warp_sum(acc);
-    if (lane == 0) a.proj[(int64_t)b * a.sumC + o] = acc + bias;
+    for (int u = 0; u < 4; ++u) {
+      if (b0 + u < a.B) {
+        const float* x = a.act + (int64_t)(b0 + u) * a.dim;
+#pragma unroll
+        for (int j = 0; j < kTembMaxPerLane; ++j)
+          if (j < per) { const int i = lane + 32 * j; if (i < a.dim) acc[u] += w[j] * x[i]; }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc[u] = warp_sum(acc[u]);
+    if (lane < 4 && b0 + lane < a.B)
+      a.proj[(int64_t)(b0 + lane) * a.sumC + o] = (lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3]) + bias;
   }
 }
 
@@ -415,7 +422,43 @@ int temb_launch(const TembArgs& a, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------ tensor-core attention helpers
-// one warp per row: logits (bf16) * scale -> softmax in fp32 -> probabilities (bf16), in place
+// one warp per row: logits (bf16) * scale -> softmax in fp32 -> probabilities (bf16), in place.
+// 16-byte accesses: lane l owns the 8-value chunks l, l + 32, ... of the row (T % 256 == 0: no tail).
+template <int CH>   // chunks per lane = T / 256
+__global__ void __launch_bounds__(256) softmax_rows_vec_kernel(bf16* __restrict__ s, int64_t rows, float scale) {
+  pdl_wait();
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  uint4* r = reinterpret_cast<uint4*>(s + row * (CH * 256));
+  float v[CH][8];
+  uint4 raw[CH];
+#pragma unroll
+  for (int i = 0; i < CH; ++i) raw[i] = __ldcs(r + lane + 32 * i);
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    unpack8(raw[i], v[i]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { v[i][j] *= scale; m = fmaxf(m, v[i][j]); }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < CH; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { v[i][j] = __expf(v[i][j] - m); sum += v[i][j]; }
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[i][j] *= inv;
+    r[lane + 32 * i] = pack8(v[i]);
+  }
+}
+
 __global__ void __launch_bounds__(256) softmax_rows_kernel(bf16* __restrict__ s, int64_t rows, int T, float scale) {
   pdl_wait();
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -437,7 +480,14 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(bf16* __restrict__ s,
 
 int softmax_rows_launch(bf16* s, int64_t rows, int T, float scale, cudaStream_t st) {
   B2E_REQUIRE(T % 32 == 0 && T <= 1024, B2E_UNSUPPORTED_SHAPE, "softmax: unsupported row length %d", T);
-  launch_pdl(softmax_rows_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, st, s, rows, T, scale);
+  const dim3 grid((unsigned)((rows + 7) / 8));
+  switch (T) {
+    case 256: launch_pdl(softmax_rows_vec_kernel<1>, grid, dim3(256), 0, st, s, rows, scale); break;
+    case 512: launch_pdl(softmax_rows_vec_kernel<2>, grid, dim3(256), 0, st, s, rows, scale); break;
+    case 768: launch_pdl(softmax_rows_vec_kernel<3>, grid, dim3(256), 0, st, s, rows, scale); break;
+    case 1024: launch_pdl(softmax_rows_vec_kernel<4>, grid, dim3(256), 0, st, s, rows, scale); break;
+    default: launch_pdl(softmax_rows_kernel, grid, dim3(256), 0, st, s, rows, T, scale);
+  }
   return check_launch("softmax_rows");
 }
 
@@ -459,6 +509,85 @@ int transpose_v_launch(const bf16* qkv, bf16* vt, int N, int T, int C, cudaStrea
   B2E_REQUIRE(T % 32 == 0 && C % 32 == 0, B2E_UNSUPPORTED_SHAPE, "transpose_v: T and C must be multiples of 32");
   launch_pdl(transpose_v_kernel, dim3(dim3(T / 32, C / 32, N)), dim3(dim3(32, 8)), 0, st, qkv, vt, T, C);
   return check_launch("transpose_v");
+}
+
+// ------------------------------------------------------------------ multi-head layout helpers
+// qkv [N][T][3P] (q | k | v blocks of P channels, head h = channels [h*d, h*d + d) of a block, d <= 64) ->
+// head-major operands of the batched tensor-core GEMMs: qh, kh [N*heads][T][64] (channels >= d zero) and
+// vht [N*heads][64][T] (V^T, rows >= d zero).  "Virtual image" v = n * heads + h.
+__global__ void __launch_bounds__(256) split_heads_qk_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ qh,
+                                                             bf16* __restrict__ kh, int64_t NT, int T, int P, int heads, int d) {
+  pdl_wait();
+  const int64_t total = NT * heads * 8;   // (n*T + t, h, 8-channel slot)
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i & 7);
+    const int h = (int)((i >> 3) % heads);
+    const int64_t nt = (i >> 3) / heads;
+    const int64_t n = nt / T, t = nt % T;
+    uint4 q = make_uint4(0, 0, 0, 0), k = q;
+    if (j * 8 < d) {
+      const bf16* src = qkv + nt * 3 * P + h * d + j * 8;
+      q = __ldg(reinterpret_cast<const uint4*>(src));
+      k = __ldg(reinterpret_cast<const uint4*>(src + P));
+    }
+    const int64_t o = (((n * heads + h) * T + t) << 6) + j * 8;
+    *reinterpret_cast<uint4*>(qh + o) = q;
+    *reinterpret_cast<uint4*>(kh + o) = k;
+  }
+}
+
+// 32x32 smem-tiled transpose: vht[v][c][t] = V[n][t][h*d + c] (c < d), 0 otherwise
+__global__ void split_heads_vt_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ vht, int T, int P, int heads, int d) {
+  pdl_wait();
+  __shared__ bf16 tile[32][33];
+  const int v = blockIdx.z, n = v / heads, h = v % heads, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const bf16* src = qkv + ((int64_t)n * T) * 3 * P + 2 * P + h * d;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y)
+    tile[i][threadIdx.x] = (c0 + (int)threadIdx.x < d) ? src[(int64_t)(t0 + i) * 3 * P + c0 + threadIdx.x] : __float2bfloat16_rn(0.f);
+  __syncthreads();
+  bf16* dst = vht + (int64_t)v * 64 * T;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y)
+    dst[(int64_t)(c0 + i) * T + t0 + threadIdx.x] = tile[threadIdx.x][i];
+}
+
+// oh [N*heads][T][64] -> out [N][T][P]: out[n][t][h*d + c] = oh[n*heads + h][t][c]; channels [heads*d, P) zeroed
+__global__ void __launch_bounds__(256) merge_heads_kernel(const bf16* __restrict__ oh, bf16* __restrict__ out, int64_t NT,
+                                                          int T, int P, int heads, int d) {
+  pdl_wait();
+  const int slots = P >> 3;
+  const int64_t total = NT * slots;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int s = (int)(i % slots);
+    const int64_t nt = i / slots;
+    const int c0 = s * 8;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (c0 < heads * d) {
+      const int h = c0 / d, cc = c0 - h * d;
+      const int64_t n = nt / T, t = nt % T;
+      v = __ldg(reinterpret_cast<const uint4*>(oh + ((((n * heads + h) * T + t) << 6) + cc)));
+    }
+    *reinterpret_cast<uint4*>(out + nt * P + c0) = v;
+  }
+}
+
+int split_heads_launch(const bf16* qkv, bf16* qh, bf16* kh, bf16* vht, int N, int T, int P, int heads, int d, cudaStream_t st) {
+  B2E_REQUIRE(d % 8 == 0 && d <= 64 && T % 32 == 0 && heads * d <= P, B2E_UNSUPPORTED_SHAPE, "split_heads: head_dim %d, T %d", d, T);
+  const int64_t NT = (int64_t)N * T, total = NT * heads * 8;
+  int grid = (int)((total + 255) / 256);
+  if (grid > kNumSMs * 32) grid = kNumSMs * 32;
+  launch_pdl(split_heads_qk_kernel, dim3(grid), dim3(256), 0, st, qkv, qh, kh, NT, T, P, heads, d);
+  int rc = check_launch("split_heads_qk");
+  if (rc) return rc;
+  launch_pdl(split_heads_vt_kernel, dim3(T / 32, 2, N * heads), dim3(32, 8), 0, st, qkv, vht, T, P, heads, d);
+  return check_launch("split_heads_vt");
+}
+
+int merge_heads_launch(const bf16* oh, bf16* out, int N, int T, int P, int heads, int d, cudaStream_t st) {
+  const int64_t NT = (int64_t)N * T, total = NT * (P / 8);
+  int grid = (int)((total + 255) / 256);
+  if (grid > kNumSMs * 32) grid = kNumSMs * 32;
+  launch_pdl(merge_heads_kernel, dim3(grid), dim3(256), 0, st, oh, out, NT, T, P, heads, d);
+  return check_launch("merge_heads");
 }
 
 // ------------------------------------------------------------------ attention core

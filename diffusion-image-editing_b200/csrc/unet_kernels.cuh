@@ -54,6 +54,10 @@ int temb_launch(const TembArgs& a, cudaStream_t st);
 int softmax_rows_launch(bf16* s, int64_t rows, int T, float scale, cudaStream_t st);
 int transpose_v_launch(const bf16* qkv, bf16* vt, int N, int T, int C, cudaStream_t st);
 
+// multi-head tensor-core attention: head-major operands (virtual image v = n*heads + h, head_dim padded to 64)
+int split_heads_launch(const bf16* qkv, bf16* qh, bf16* kh, bf16* vht, int N, int T, int P, int heads, int d, cudaStream_t st);
+int merge_heads_launch(const bf16* oh, bf16* out, int N, int T, int P, int heads, int d, cudaStream_t st);
+
 // single/multi-head self-attention core: qkv bf16 [N][T][3P] (q | k | v blocks of P >= C channels) -> out bf16 [N][T][P]
 int attention_launch(const bf16* qkv, bf16* out, int N, int T, int C, int P, int heads, cudaStream_t st);
 

@@ -9,7 +9,7 @@ from typing import Optional
 import torch
 
 from b200edit.scheduler import DDIMScheduler
-from b200edit.unet import DDPM256_CONFIG, UNet2DModel
+from b200edit.unet import DDPM256_CONFIG, LDM_CELEBAHQ_CONFIG, UNet2DModel
 from diffusion_classes import DDPM, LDM, SD  # noqa: F401
 from utils import get_device
 
@@ -22,7 +22,10 @@ class NativePipeline(SimpleNamespace):
 
 
 def create_diffusion_model(name: str, sample_clipping: bool = True, *, max_batch: int = 8, seed: int = 0,
-                           state_dict: Optional[dict] = None, unet_config: Optional[dict] = None):
+                           state_dict: Optional[dict] = None, unet_config: Optional[dict] = None, vqvae=None):
+    """``name``: "ddpm" (google/ddpm-celebahq-256 layout) or "ldm" (CompVis/ldm-celebahq-256 layout: native UNet on
+    the 64x64x3 latent; ``vqvae`` is the caller's VQ autoencoder module with encode().latents / decode().sample,
+    as in the reference's pipeline object)."""
     device = get_device()
     if name == "ddpm":
         unet = UNet2DModel(**(unet_config or DDPM256_CONFIG), max_batch=max_batch, device=device)
@@ -33,10 +36,23 @@ def create_diffusion_model(name: str, sample_clipping: bool = True, *, max_batch
         scheduler = DDIMScheduler.from_preset("ddpm")
         scheduler.config.clip_sample = sample_clipping   # True for synthetic data, False for real images
         return DDPM(NativePipeline(unet=unet, scheduler=scheduler, device=device))
-    if name in ("ldm", "sd"):
+    if name == "ldm":
+        if vqvae is None:
+            raise NotImplementedError(
+                "create_diffusion_model('ldm'): the VQ autoencoder is not on the native engine yet; pass vqvae= "
+                "(a module with encode(x).latents / decode(z).sample, e.g. diffusers.VQModel)")
+        unet = UNet2DModel(**(unet_config or LDM_CELEBAHQ_CONFIG), max_batch=max_batch, device=device)
+        if state_dict is not None:
+            unet.load_state_dict(state_dict)
+        else:
+            unet.init_random(seed)
+        scheduler = DDIMScheduler.from_preset("ldm")
+        scheduler.config.clip_sample = sample_clipping   # src/models.py:43 ("LDM was trained with this flag=False")
+        return LDM(NativePipeline(unet=unet, scheduler=scheduler, vqvae=vqvae, device=device))
+    if name == "sd":
         raise NotImplementedError(
-            f"create_diffusion_model({name!r}): the {name.upper()} UNet / autoencoder are not on the native "
-            "engine yet (SURVEY.md section 8f); wrap your own modules with diffusion_classes.LDM / SD")
+            "create_diffusion_model('sd'): the SD UNet2DConditionModel / KL autoencoder are not on the native "
+            "engine yet (SURVEY.md section 8f); wrap your own modules with diffusion_classes.SD")
     raise ValueError(f"Unknown model name: {name}")
 
 
