@@ -263,3 +263,62 @@ def test_end_to_end_with_native_unet():
                                          guidance=loops.color_guidance([0.8, None, None], [1, 1, 1], 100.0, 0, 10))
     assert np.array_equal(out.imgs.cpu().numpy(), xf.numpy())
     assert np.array_equal(out.pred_original_samples[-1].cpu().numpy(), x0_h[-1].numpy())
+
+
+class ToyVQ(torch.nn.Module):
+    """Stand-in for the caller's VQ autoencoder (diffusers VQModel duck-type: decode(z).sample, x4 upsampling)."""
+
+    def __init__(self, seed=0):
+        super().__init__()
+        torch.manual_seed(seed)
+        self.post_quant_conv = torch.nn.Conv2d(3, 3, 1)
+        self.c1 = torch.nn.Conv2d(3, 16, 3, padding=1)
+        self.c2 = torch.nn.Conv2d(16, 3, 3, padding=1)
+
+    def decode(self, z):
+        h = torch.nn.functional.silu(self.c1(self.post_quant_conv(z)))
+        h = torch.nn.functional.interpolate(h, scale_factor=4.0, mode="nearest")
+        return SimpleNamespace(sample=self.c2(h))
+
+    def encode(self, x):
+        return SimpleNamespace(latents=torch.nn.functional.avg_pool2d(x, 4))
+
+
+def test_ldm_end_to_end_native_unet_masked_guidance_through_decoder():
+    """BASELINE config 3 in small: native LDM-layout UNet (padded channels, 32-channel heads, scaled-linear DDIM
+    scheduler, no clipping) + the caller's VQ decoder inside the guidance graph + gradient masking.  The noise
+    predictions recorded from the native UNet are replayed through the oracle loop with autograd through the same
+    decoder on the CPU: images agree to fp32 round-off of the decoder's convolutions."""
+    from attr_functions import SingleColorAttrFunc
+    from models import create_diffusion_model
+    from SegDiffEditPipeline import SegDiffEditPipeline
+    cfg = dict(sample_size=16, in_channels=3, out_channels=3, block_out_channels=(32, 96), layers_per_block=1,
+               down_block_types=("DownBlock2D", "AttnDownBlock2D"), up_block_types=("AttnUpBlock2D", "UpBlock2D"),
+               attention_head_dim=32, flip_sin_to_cos=True, freq_shift=0, downsample_padding=1)
+    vq = ToyVQ().cuda()
+    w = create_diffusion_model("ldm", sample_clipping=False, max_batch=2, seed=2, unet_config=cfg, vqvae=vq)
+    assert type(w).__name__ == "LDM" and w.scheduler.config.beta_schedule == "scaled_linear"
+    T = 6
+    w.scheduler.set_timesteps(T)
+    pipe = SegDiffEditPipeline(w, None)
+    gen = torch.Generator().manual_seed(21)
+    xt = torch.randn(1, 3, 16, 16, generator=gen)
+    mask = (torch.rand(1, 3, 16, 16, generator=gen) > 0.5).float()
+    f = SingleColorAttrFunc(target=0.8, color_idx=0, loss_scale=60.0, t1=0, t2=T, use_mask=True, mask_attr_grad=True)
+    out = pipe.edit_image(xt=xt.cuda(), attr_func=f, prog_bar=False, output_type="tensor", mask=mask.cuda())
+    assert torch.isfinite(out.imgs).all()
+    rep = iter([e.cpu() for e in out.model_outputs])
+    s = osched("ldm", T, clip=False)
+    vq_cpu = ToyVQ()
+
+    def guidance(x_post, eps, c, step_idx):
+        loss = lambda z: sm.single_color_loss(vq_cpu.decode(z).sample, 0, 0.8)   # noqa: E731
+        return sm.autograd_guidance_update(x_post, eps, c, loss, 60.0, mask=mask, mask_grad=True)[0]
+
+    xf, _, _ = loops.guided_edit_loop(s, lambda x, t: next(rep), xt, eta=0.0, zs=None, guidance=guidance)
+    with torch.no_grad():
+        img_ref = vq_cpu.decode(xf).sample
+    # edit_image returns DECODED images for latent models (src/SegDiffEditPipeline.py:142-150)
+    got = out.imgs.cpu()
+    assert got.shape == img_ref.shape
+    assert torch.allclose(got, img_ref, rtol=1e-4, atol=1e-4 * img_ref.abs().max().item())
