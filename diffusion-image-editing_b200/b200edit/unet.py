@@ -118,6 +118,8 @@ class UNet2DModel:
         for name, numel, fan in self.param_info():
             if fan == 0:
                 sd[name] = torch.ones(numel) if name.endswith(".weight") else torch.zeros(numel)
+            elif fan < 0:   # codebook: U(-1/n, 1/n) with n = -fan (diffusers VectorQuantizer init)
+                sd[name] = (torch.rand(numel, generator=g) * 2 - 1) / float(-fan)
             else:
                 bound = 1.0 / math.sqrt(fan)
                 sd[name] = (torch.rand(numel, generator=g) * 2 - 1) * bound

@@ -1,0 +1,98 @@
+"""Native decode path of ``diffusers.VQModel`` (the ``vqvae`` of CompVis/ldm-celebahq-256): the call contract the
+reference uses is ``vqvae.decode(latent).sample`` (src/diffusion_classes.py:62-70).  Nearest-code quantisation,
+post_quant_conv and the decoder run in libb200edit.so (bf16 tcgen05 implicit-GEMM convolutions, fp32 accumulation).
+
+Forward only: ``decode`` returns a tensor without an autograd graph, so it serves the post-loop decoding of the
+final sample and of the x0-prediction history; guidance THROUGH the decoder (AttrFunc.apply with no_grad=False)
+still needs the caller's differentiable module (``guidance_vqvae=``) until the decoder dgrad is native.
+``encode`` is not on the engine."""
+from __future__ import annotations
+
+import ctypes as C
+from types import SimpleNamespace
+
+import torch
+
+from . import _C
+from ._C import VQDecConfig, check, lib
+from .unet import UNet2DModel
+
+LDM_VQ_CONFIG = dict(latent_channels=3, out_channels=3, block_out_channels=(128, 256, 512), layers_per_block=2,
+                     norm_num_groups=32, norm_eps=1e-6, num_vq_embeddings=8192, sample_size=64)
+
+
+class VQModel(UNet2DModel):
+    """Shares parameter loading / random init / profiling with the UNet wrapper (same engine handle type)."""
+
+    forward_only = True   # no autograd graph through decode (see LDM.decode)
+
+    def __init__(self, latent_channels=3, out_channels=3, block_out_channels=(128, 256, 512), layers_per_block=2,
+                 norm_num_groups=32, norm_eps=1e-6, num_vq_embeddings=8192, sample_size=64, max_batch=8,
+                 device="cuda"):
+        _C.require_device()
+        n = len(block_out_channels)
+        self.config = SimpleNamespace(latent_channels=latent_channels, out_channels=out_channels,
+                                      block_out_channels=tuple(block_out_channels), layers_per_block=layers_per_block,
+                                      norm_num_groups=norm_num_groups, norm_eps=norm_eps,
+                                      num_vq_embeddings=num_vq_embeddings, sample_size=sample_size,
+                                      in_channels=latent_channels)
+        self.out_size = sample_size << (n - 1)
+        self.device = torch.device(device)
+        self.dtype = torch.float32
+        self.max_batch = int(max_batch)
+        cfg = VQDecConfig()
+        cfg.sample_size, cfg.latent_channels, cfg.out_channels, cfg.n_blocks = sample_size, latent_channels, out_channels, n
+        for i in range(n):
+            cfg.block_out_channels[i] = block_out_channels[i]
+        cfg.layers_per_block, cfg.norm_num_groups, cfg.norm_eps = layers_per_block, norm_num_groups, norm_eps
+        cfg.num_vq_embeddings = num_vq_embeddings
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib.b2e_vqdec_create(C.byref(cfg), self.max_batch, C.byref(h)), "vqdec_create")
+            self._h = h
+            nbytes = lib.b2e_unet_workspace_bytes(h)
+            self._ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)
+            base = (self._ws.data_ptr() + 255) // 256 * 256
+            check(lib.b2e_unet_bind_workspace(h, C.c_void_p(base), nbytes), "unet_bind_workspace")
+        self._t_cache = {}
+
+    def decode(self, latent: torch.Tensor, force_not_quantize: bool = False):
+        if force_not_quantize:
+            raise NotImplementedError("VQModel.decode(force_not_quantize=True) is not on the native engine")
+        if not latent.is_cuda:
+            raise _C.B2EError("VQModel.decode: latent must be a CUDA tensor (no CPU fallback)")
+        z = latent.detach().to(torch.float32).contiguous()
+        B = z.shape[0]
+        cfg = self.config
+        if tuple(z.shape[1:]) != (cfg.latent_channels, cfg.sample_size, cfg.sample_size):
+            raise ValueError(f"VQModel.decode: expected (B,{cfg.latent_channels},{cfg.sample_size},{cfg.sample_size}), "
+                             f"got {tuple(z.shape)}")
+        outs = []
+        for b0 in range(0, B, self.max_batch):      # histories can be longer than max_batch
+            zb = z[b0:b0 + self.max_batch]
+            img = torch.empty((zb.shape[0], cfg.out_channels, self.out_size, self.out_size), dtype=torch.float32,
+                              device=z.device)
+            check(lib.b2e_unet_forward(self._h, C.c_void_p(zb.data_ptr()), None, C.c_void_p(img.data_ptr()), zb.shape[0],
+                                       C.c_void_p(torch.cuda.current_stream().cuda_stream)), "vqdec_forward")
+            outs.append(img)
+        return SimpleNamespace(sample=outs[0] if len(outs) == 1 else torch.cat(outs))
+
+    def encode(self, x):
+        raise NotImplementedError("VQModel.encode is not on the native engine (SURVEY.md section 8f rank 3)")
+
+    def __call__(self, *a, **k):
+        raise TypeError("VQModel: call .decode(latent)")
+
+    def profile(self, latent):
+        z = latent.to(torch.float32).contiguous()
+        B = z.shape[0]
+        img = torch.empty((B, self.config.out_channels, self.out_size, self.out_size), dtype=torch.float32, device=z.device)
+        cap = 1024
+        n = C.c_int()
+        ms, fl, by, kd = (C.c_float * cap)(), (C.c_double * cap)(), (C.c_double * cap)(), (C.c_int * cap)()
+        check(lib.b2e_unet_profile(self._h, C.c_void_p(z.data_ptr()), None, C.c_void_p(img.data_ptr()), B,
+                                   C.c_void_p(torch.cuda.current_stream().cuda_stream), cap, C.byref(n), ms, fl, by, kd),
+              "vqdec_profile")
+        names = {0: "conv_igemm", 1: "groupnorm", 2: "attention", 3: "other"}
+        return [dict(kind=names[kd[i]], ms=ms[i], flops=fl[i], bytes=by[i],
+                     desc=lib.b2e_unet_op_desc(self._h, i).decode()) for i in range(n.value)]

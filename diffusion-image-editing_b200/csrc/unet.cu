@@ -79,6 +79,11 @@ struct b2e_unet {
   std::unordered_map<std::string, int> pindex;
   ConvL conv_in, conv_out;
   bool in_im2col = false;
+  // VQ decoder mode (b2e_vqdec_create): no time embedding, input = latent -> nearest-code quantisation + 1x1
+  // post_quant_conv (one CUDA-core kernel) -> conv_in; output at sample_size << (n_blocks - 1)
+  bool decoder = false;
+  float *codebook = nullptr, *pq_w = nullptr, *pq_b = nullptr;   // [n_codes][latent], [latent][latent], [latent]
+  int n_codes = 0;
   NormL norm_out;
   float *te_w1 = nullptr, *te_b1 = nullptr, *te_w2 = nullptr, *te_b2 = nullptr, *tp_w = nullptr, *tp_b = nullptr;
   std::vector<ResnetL> resnets;
@@ -136,13 +141,14 @@ struct b2e_unet {
     add_f32(name + ".bias", n.b, C);
     return n;
   }
-  int make_resnet(const std::string& name, int cin0, int cin1, int cout) {
+  int make_resnet(const std::string& name, int cin0, int cin1, int cout, bool with_temb = true) {
     ResnetL r;
     r.name = name; r.cin0 = cin0; r.cin1 = cin1; r.cout = cout;
     const int cin = cin0 + cin1;
     r.n1 = make_norm(name + ".norm1", cin);
     r.c1 = make_conv(name + ".conv1", cin, cout, 3);   // reads the compact GroupNorm output (pitch pad64(cin))
-    r.temb_off = sumC; sumC += r.c1.cout_pad;          // padded columns stay zero
+    if (with_temb) { r.temb_off = sumC; sumC += r.c1.cout_pad; }   // padded columns stay zero
+    else r.temb_off = -1;
     r.n2 = make_norm(name + ".norm2", cout);
     // conv2 carries the block input as a fused 1x1 residual segment: conv_shortcut weights when the
     // channel count changes, the identity otherwise.  The segment reads the un-normalised block input(s)
@@ -193,7 +199,54 @@ struct b2e_unet {
 
 namespace {
 
+// VQModel.decode graph (diffusers Decoder): conv_in -> mid (resnet, single-head attention, resnet) -> per level,
+// top-down, layers_per_block + 1 resnets (+ nearest x2 upsample + 3x3 conv) -> GroupNorm -> SiLU -> conv_out.
+// cfg.block_out_channels is bottom-up as in the diffusers config ((128, 256, 512) for ldm-celebahq-256).
+int build_model_decoder(b2e_unet* m) {
+  const b2e_unet_config& c = m->cfg;
+  const int nb = c.n_blocks, L = c.in_channels;
+  const int top = c.block_out_channels[nb - 1];
+  m->codebook = m->dmalloc<float>((size_t)m->n_codes * L);
+  m->pq_w = m->dmalloc<float>((size_t)L * L);
+  m->pq_b = m->dmalloc<float>(L);
+  m->add_f32("quantize.embedding.weight", m->codebook, (int64_t)m->n_codes * L, -m->n_codes);   // U(-1/n, 1/n)
+  m->add_f32("post_quant_conv.weight", m->pq_w, (int64_t)L * L, L);
+  m->add_f32("post_quant_conv.bias", m->pq_b, L, L);
+  m->in_im2col = true;
+  {
+    ConvL ci;
+    ci.cin = ci.cin_pad = kConvBlockK; ci.cout = top; ci.k = 1; ci.cout_pad = conv_cout_pad(top); ci.row_len = kConvBlockK;
+    ci.w = m->dmalloc<bf16>((size_t)ci.cout_pad * ci.row_len);
+    ci.b = m->dmalloc<float>(ci.cout_pad);
+    m->add_param("decoder.conv_in.weight", (int64_t)top * L * 9, (int64_t)L * 9, [ci, L](const float* src, cudaStream_t st) {
+      return conv_pack_weight(src, ci.w, ci.cout, L, 3, L, ci.row_len, 0, st);
+    });
+    m->add_f32("decoder.conv_in.bias", ci.b, top, (int64_t)L * 9);
+    m->conv_in = ci;
+  }
+  int ch = top;
+  m->nodes.push_back({N_RESNET, m->make_resnet("decoder.mid_block.resnets.0", ch, 0, ch, false)});
+  m->nodes.push_back({N_ATTN, m->make_attn("decoder.mid_block.attentions.0", ch)});
+  m->nodes.push_back({N_RESNET, m->make_resnet("decoder.mid_block.resnets.1", ch, 0, ch, false)});
+  for (int i = 0; i < nb; ++i) {
+    const int cout = c.block_out_channels[nb - 1 - i];
+    const std::string base = "decoder.up_blocks." + std::to_string(i);
+    for (int j = 0; j < c.layers_per_block + 1; ++j) {
+      m->nodes.push_back({N_RESNET, m->make_resnet(base + ".resnets." + std::to_string(j), ch, 0, cout, false)});
+      ch = cout;
+    }
+    if (i != nb - 1) {
+      m->ups.push_back(m->make_conv(base + ".upsamplers.0.conv", ch, ch, 3));
+      m->nodes.push_back({N_UP, (int)m->ups.size() - 1});
+    }
+  }
+  m->norm_out = m->make_norm("decoder.conv_norm_out", ch);
+  m->conv_out = m->make_conv("decoder.conv_out", ch, c.out_channels, 3);
+  return m->build_error;
+}
+
 int build_model(b2e_unet* m) {
+  if (m->decoder) return build_model_decoder(m);
   const b2e_unet_config& c = m->cfg;
   const int nb = c.n_blocks;
   const int c0 = c.block_out_channels[0];
@@ -300,8 +353,8 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
   const int G = c.norm_num_groups;
   const int S = c.sample_size;
   // per-forward scratch
-  float* act = (float*)ar.alloc(sizeof(float) * B * m->temb_dim);
-  float* proj = (float*)ar.alloc(sizeof(float) * B * m->sumC);
+  float* act = (float*)ar.alloc(sizeof(float) * B * (m->temb_dim > 0 ? m->temb_dim : 1));
+  float* proj = (float*)ar.alloc(sizeof(float) * B * (m->sumC > 0 ? m->sumC : 1));
   float* gn_part = (float*)ar.alloc(sizeof(float) * B * 64 * G * 2);
   // split-K scratch for the low-resolution convolutions (<= one 128x128 fp32 partial tile per SM) + tile counters
   const size_t split_bytes = (size_t)kNumSMs * kConvBlockM * 128 * sizeof(float);
@@ -401,17 +454,29 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
 
   // ---- prologue: input packing, timestep embedding
   Tensor xin = talloc(B, S, S, kConvBlockK);
+  float* zq = m->decoder ? (float*)ar.alloc(sizeof(float) * B * c.in_channels * S * S) : nullptr;
   if (!dry) {
     const int Cin = c.in_channels, HW = S * S;
     const bool im2col = m->in_im2col;
-    ops.push_back({[m, xin, B, Cin, S, im2col](cudaStream_t st) { return pack_input_launch(m->in_x, xin.p, B, Cin, S, S, kConvBlockK, im2col, st); },
-                   3, 0.0, (double)B * HW * (4.0 * Cin + 2.0 * kConvBlockK)});
+    if (m->decoder) {
+      // latent -> nearest code -> post_quant_conv (fp32 NCHW), then the usual im2col packing of conv_in
+      ops.push_back({[m, zq, B, Cin, HW](cudaStream_t st) {
+                       return vq_quantize_launch(m->in_x, m->codebook, m->n_codes, m->pq_w, m->pq_b, zq, B, Cin, HW, st);
+                     }, 3, 0.0, 8.0 * B * Cin * HW, "vq nearest code + post_quant_conv"});
+      ops.push_back({[zq, xin, B, Cin, S](cudaStream_t st) { return pack_input_launch(zq, xin.p, B, Cin, S, S, kConvBlockK, true, st); },
+                     3, 0.0, (double)B * HW * (4.0 * Cin + 2.0 * kConvBlockK)});
+    } else {
+      ops.push_back({[m, xin, B, Cin, S, im2col](cudaStream_t st) { return pack_input_launch(m->in_x, xin.p, B, Cin, S, S, kConvBlockK, im2col, st); },
+                     3, 0.0, (double)B * HW * (4.0 * Cin + 2.0 * kConvBlockK)});
+    }
+    if (!m->decoder) {
     TembArgs ta;
     ta.timesteps = nullptr; ta.B = B; ta.dim0 = c.block_out_channels[0]; ta.dim = m->temb_dim;
     ta.flip = c.flip_sin_to_cos; ta.freq_shift = c.freq_shift;
     ta.w1 = m->te_w1; ta.b1 = m->te_b1; ta.w2 = m->te_w2; ta.b2 = m->te_b2; ta.wp = m->tp_w; ta.bp = m->tp_b;
     ta.sumC = m->sumC; ta.act = act; ta.proj = proj;
     ops.push_back({[m, ta](cudaStream_t st) { TembArgs t = ta; t.timesteps = m->in_t; return temb_launch(t, st); }, 3, 0.0, 0.0});
+    }
   }
   Tensor h;
   conv(m->conv_in, xin, nullptr, 1, ConvEpilogue{}, &h, nullptr);
@@ -433,7 +498,8 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
         const Tensor* x1 = have_cat ? &cat : nullptr;
         Tensor a1, h1, a2, out;
         gnorm(r.n1, h, x1, 1, &a1);
-        ConvEpilogue e1; e1.temb = proj + r.temb_off; e1.temb_stride = m->sumC;
+        ConvEpilogue e1;
+        if (r.temb_off >= 0) { e1.temb = proj + r.temb_off; e1.temb_stride = m->sumC; }
         conv(r.c1, a1, nullptr, 1, e1, &h1, nullptr);
         tfree(a1);
         gnorm(r.n2, h1, nullptr, 1, &a2);
@@ -456,7 +522,7 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
         const int heads = c.attention_head_dim > 0 ? a.C / c.attention_head_dim : 1;
         const int T = h.H * h.W, C = a.P;   // C: padded width of q / k / v (zero tail: no effect on Q K^T, zero rows of V^T)
         const ConvGeom gq = conv_geometry(B, h.H, h.W, T);
-        if (heads == 1 && T % 128 == 0 && T <= 1024 && gq.Nt == 1) {
+        if (heads == 1 && T % 128 == 0 && (T <= 1024 || T == 2048 || T == 4096) && gq.Nt == 1) {
           // tensor-core attention: S = Q K^T and O = P V are batched GEMMs on the tcgen05 kernel (the per-image
           // B operand is read straight from the qkv tensor / a transposed copy of V); softmax in fp32 between
           Tensor sc = talloc(B, h.H, h.W, T);
@@ -623,6 +689,36 @@ int b2e_unet_create(const b2e_unet_config* cfg, int64_t max_batch, b2e_unet** ou
   return B2E_OK;
 }
 
+int b2e_vqdec_create(const b2e_vqdec_config* cfg, int64_t max_batch, b2e_unet** out) {
+  B2E_REQUIRE(cfg && out && max_batch > 0, B2E_INVALID_ARG, "vqdec_create: bad argument");
+  B2E_REQUIRE(cfg->n_blocks >= 1 && cfg->n_blocks <= 8, B2E_UNSUPPORTED_SHAPE, "vqdec_create: n_blocks");
+  B2E_REQUIRE((cfg->latent_channels == 1 || cfg->latent_channels == 3 || cfg->latent_channels == 4) && cfg->out_channels <= 16,
+              B2E_UNSUPPORTED_SHAPE, "vqdec_create: latent_channels must be 1, 3 or 4 and out_channels <= 16");
+  B2E_REQUIRE(cfg->num_vq_embeddings >= 1, B2E_INVALID_ARG, "vqdec_create: num_vq_embeddings");
+  for (int i = 0; i < cfg->n_blocks; ++i) {
+    const int ch = cfg->block_out_channels[i];
+    B2E_REQUIRE(ch % 8 == 0 && ch >= 32 && ch <= 1024 && ch % cfg->norm_num_groups == 0, B2E_UNSUPPORTED_SHAPE,
+                "vqdec_create: block_out_channels must be multiples of 8 and of norm_num_groups, 32..1024 (got %d)", ch);
+  }
+  b2e_unet* m = new b2e_unet();
+  m->decoder = true;
+  m->n_codes = cfg->num_vq_embeddings;
+  b2e_unet_config& u = m->cfg;
+  u = b2e_unet_config{};
+  u.sample_size = cfg->sample_size; u.in_channels = cfg->latent_channels; u.out_channels = cfg->out_channels;
+  u.n_blocks = cfg->n_blocks;
+  for (int i = 0; i < cfg->n_blocks; ++i) u.block_out_channels[i] = cfg->block_out_channels[i];
+  u.layers_per_block = cfg->layers_per_block; u.norm_num_groups = cfg->norm_num_groups; u.norm_eps = cfg->norm_eps;
+  u.attention_head_dim = 0;
+  m->max_batch = max_batch;
+  int rc = build_model(m);
+  if (!rc && cudaDeviceSynchronize() != cudaSuccess) { set_error("vqdec_create: device error"); rc = B2E_CUDA_ERROR; }
+  if (!rc) rc = build_program(m, (int)max_batch, nullptr, 0, &m->ws_need);
+  if (rc) { delete m; return rc; }
+  *out = m;
+  return B2E_OK;
+}
+
 void b2e_unet_destroy(b2e_unet* m) { delete m; }
 
 int b2e_unet_num_params(const b2e_unet* m) { return m ? (int)m->params.size() : 0; }
@@ -657,7 +753,7 @@ int b2e_unet_bind_workspace(b2e_unet* m, void* workspace, size_t workspace_bytes
 }
 
 int b2e_unet_forward(b2e_unet* m, const float* x, const int64_t* timesteps, float* eps, int64_t B, void* stream) {
-  B2E_REQUIRE(m && x && timesteps && eps, B2E_INVALID_ARG, "unet_forward: null pointer");
+  B2E_REQUIRE(m && x && (timesteps || m->decoder) && eps, B2E_INVALID_ARG, "unet_forward: null pointer");
   B2E_REQUIRE(m->ws, B2E_INVALID_ARG, "unet_forward: no workspace bound");
   B2E_REQUIRE(B > 0 && B <= m->max_batch, B2E_UNSUPPORTED_SHAPE, "unet_forward: batch %lld exceeds max_batch %lld",
               (long long)B, (long long)m->max_batch);
@@ -681,7 +777,7 @@ const char* b2e_unet_op_desc(const b2e_unet* m, int idx) {
 
 int b2e_unet_profile(b2e_unet* m, const float* x, const int64_t* timesteps, float* eps, int64_t B, void* stream,
                      int max_ops, int* n_ops, float* ms, double* flops, double* bytes, int* kind) {
-  B2E_REQUIRE(m && x && timesteps && eps && n_ops && ms && flops && bytes && kind, B2E_INVALID_ARG,
+  B2E_REQUIRE(m && x && (timesteps || m->decoder) && eps && n_ops && ms && flops && bytes && kind, B2E_INVALID_ARG,
               "unet_profile: null pointer");
   // one plain pass first (plan rebuild / lazy function attributes), then the instrumented pass
   int rc = b2e_unet_forward(m, x, timesteps, eps, B, stream);

@@ -479,9 +479,12 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(bf16* __restrict__ s,
 }
 
 int softmax_rows_launch(bf16* s, int64_t rows, int T, float scale, cudaStream_t st) {
-  B2E_REQUIRE(T % 32 == 0 && T <= 1024, B2E_UNSUPPORTED_SHAPE, "softmax: unsupported row length %d", T);
+  B2E_REQUIRE((T % 32 == 0 && T <= 1024) || T == 2048 || T == 4096, B2E_UNSUPPORTED_SHAPE,
+              "softmax: unsupported row length %d", T);
   const dim3 grid((unsigned)((rows + 7) / 8));
   switch (T) {
+    case 2048: launch_pdl(softmax_rows_vec_kernel<8>, grid, dim3(256), 0, st, s, rows, scale); break;
+    case 4096: launch_pdl(softmax_rows_vec_kernel<16>, grid, dim3(256), 0, st, s, rows, scale); break;
     case 256: launch_pdl(softmax_rows_vec_kernel<1>, grid, dim3(256), 0, st, s, rows, scale); break;
     case 512: launch_pdl(softmax_rows_vec_kernel<2>, grid, dim3(256), 0, st, s, rows, scale); break;
     case 768: launch_pdl(softmax_rows_vec_kernel<3>, grid, dim3(256), 0, st, s, rows, scale); break;
@@ -509,6 +512,62 @@ int transpose_v_launch(const bf16* qkv, bf16* vt, int N, int T, int C, cudaStrea
   B2E_REQUIRE(T % 32 == 0 && C % 32 == 0, B2E_UNSUPPORTED_SHAPE, "transpose_v: T and C must be multiples of 32");
   launch_pdl(transpose_v_kernel, dim3(dim3(T / 32, C / 32, N)), dim3(dim3(32, 8)), 0, st, qkv, vt, T, C);
   return check_launch("transpose_v");
+}
+
+// ------------------------------------------------------------------ VQ front of the decoder
+// VQModel.decode: nearest codebook entry per latent pixel (squared Euclidean distance accumulated channel by
+// channel with individually rounded operations, first index on ties - the oracle's order), then the 1x1
+// post_quant_conv.  z, out: fp32 NCHW (B, L, HW), L <= 4.  Codes are staged through smem in tiles.
+constexpr int kVqTile = 1024;
+__global__ void __launch_bounds__(256)
+vq_quantize_kernel(const float* __restrict__ z, const float* __restrict__ codebook, int n_codes,
+                   const float* __restrict__ pq_w, const float* __restrict__ pq_b, float* __restrict__ out, int B, int L,
+                   int HW) {
+  pdl_wait();
+  __shared__ float s_code[kVqTile * 4];
+  const int64_t total = (int64_t)B * HW;
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = p < total;
+  const int64_t b = live ? p / HW : 0, q = live ? p % HW : 0;
+  float zv[4] = {0.f, 0.f, 0.f, 0.f};
+  if (live)
+    for (int c = 0; c < L; ++c) zv[c] = z[(b * L + c) * HW + q];
+  float best = INFINITY;
+  int best_i = 0;
+  for (int k0 = 0; k0 < n_codes; k0 += kVqTile) {
+    const int nk = min(kVqTile, n_codes - k0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nk * L; i += blockDim.x) s_code[i] = codebook[(int64_t)k0 * L + i];
+    __syncthreads();
+    if (live) {
+      for (int k = 0; k < nk; ++k) {
+        float d = 0.f;
+        for (int c = 0; c < L; ++c) {
+          const float t = __fsub_rn(zv[c], s_code[k * L + c]);
+          const float t2 = __fmul_rn(t, t);
+          d = c == 0 ? t2 : __fadd_rn(d, t2);
+        }
+        if (d < best) { best = d; best_i = k0 + k; }
+      }
+    }
+  }
+  if (!live) return;
+  float e[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int c = 0; c < L; ++c) e[c] = codebook[(int64_t)best_i * L + c];
+  for (int c = 0; c < L; ++c) {
+    float acc = 0.f;
+    for (int k = 0; k < L; ++k) acc += pq_w[c * L + k] * e[k];
+    out[(b * L + c) * HW + q] = acc + pq_b[c];
+  }
+}
+
+int vq_quantize_launch(const float* z, const float* codebook, int n_codes, const float* pq_w, const float* pq_b, float* out,
+                       int B, int L, int HW, cudaStream_t st) {
+  B2E_REQUIRE(L >= 1 && L <= 4 && n_codes >= 1, B2E_UNSUPPORTED_SHAPE, "vq_quantize: latent channels %d", L);
+  const int64_t total = (int64_t)B * HW;
+  launch_pdl(vq_quantize_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, z, codebook, n_codes, pq_w, pq_b,
+             out, B, L, HW);
+  return check_launch("vq_quantize");
 }
 
 // ------------------------------------------------------------------ multi-head layout helpers

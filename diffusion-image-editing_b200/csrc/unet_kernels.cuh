@@ -54,6 +54,10 @@ int temb_launch(const TembArgs& a, cudaStream_t st);
 int softmax_rows_launch(bf16* s, int64_t rows, int T, float scale, cudaStream_t st);
 int transpose_v_launch(const bf16* qkv, bf16* vt, int N, int T, int C, cudaStream_t st);
 
+// VQModel.decode front: nearest codebook entry + 1x1 post_quant_conv; z, out fp32 NCHW (B, L <= 4, HW)
+int vq_quantize_launch(const float* z, const float* codebook, int n_codes, const float* pq_w, const float* pq_b, float* out,
+                       int B, int L, int HW, cudaStream_t st);
+
 // multi-head tensor-core attention: head-major operands (virtual image v = n*heads + h, head_dim padded to 64)
 int split_heads_launch(const bf16* qkv, bf16* qh, bf16* kh, bf16* vht, int N, int T, int P, int heads, int d, cudaStream_t st);
 int merge_heads_launch(const bf16* oh, bf16* out, int N, int T, int P, int heads, int d, cudaStream_t st);

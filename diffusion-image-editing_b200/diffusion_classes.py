@@ -1,6 +1,8 @@
 """Model wrappers that define the image <-> latent maps (drop-in for src/diffusion_classes.py)."""
 import torch
 
+from b200edit._C import B2EError
+
 from base_diffusion import Diffusion
 from diffusion_utils import prep_text
 
@@ -24,6 +26,9 @@ class LDM(Diffusion):
     def __init__(self, model):
         super().__init__(model)
         self.vqvae = model.vqvae
+        # optional differentiable twin of a native (forward-only) vqvae, used when the guidance graph runs
+        # through the decoder (AttrFunc.apply -> decode(no_grad=False), src/attr_functions.py:153)
+        self.guidance_vqvae = getattr(model, "guidance_vqvae", None)
 
     def encode(self, sample: torch.Tensor) -> torch.Tensor:
         with torch.no_grad():
@@ -34,7 +39,13 @@ class LDM(Diffusion):
         if no_grad:
             with torch.no_grad():
                 return self.vqvae.decode(latent).sample
-        return self.vqvae.decode(latent).sample
+        vq = self.vqvae
+        if getattr(vq, "forward_only", False):
+            if self.guidance_vqvae is None:
+                raise B2EError("LDM.decode(no_grad=False): the native VQ decoder is forward-only; pass a "
+                               "differentiable module as guidance_vqvae= for guidance through the decoder")
+            vq = self.guidance_vqvae
+        return vq.decode(latent).sample
 
 
 class SD(Diffusion):

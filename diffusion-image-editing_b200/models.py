@@ -22,10 +22,12 @@ class NativePipeline(SimpleNamespace):
 
 
 def create_diffusion_model(name: str, sample_clipping: bool = True, *, max_batch: int = 8, seed: int = 0,
-                           state_dict: Optional[dict] = None, unet_config: Optional[dict] = None, vqvae=None):
+                           state_dict: Optional[dict] = None, unet_config: Optional[dict] = None, vqvae=None,
+                           vq_config: Optional[dict] = None, vq_state_dict: Optional[dict] = None, guidance_module=None):
     """``name``: "ddpm" (google/ddpm-celebahq-256 layout) or "ldm" (CompVis/ldm-celebahq-256 layout: native UNet on
-    the 64x64x3 latent; ``vqvae`` is the caller's VQ autoencoder module with encode().latents / decode().sample,
-    as in the reference's pipeline object)."""
+    the 64x64x3 latent + native forward-only VQ decoder; ``vqvae=`` substitutes the caller's VQ autoencoder module
+    (encode().latents / decode().sample, as in the reference's pipeline object); ``guidance_module=`` is the
+    differentiable decoder used when guidance runs through decode)."""
     device = get_device()
     if name == "ddpm":
         unet = UNet2DModel(**(unet_config or DDPM256_CONFIG), max_batch=max_batch, device=device)
@@ -37,18 +39,28 @@ def create_diffusion_model(name: str, sample_clipping: bool = True, *, max_batch
         scheduler.config.clip_sample = sample_clipping   # True for synthetic data, False for real images
         return DDPM(NativePipeline(unet=unet, scheduler=scheduler, device=device))
     if name == "ldm":
-        if vqvae is None:
-            raise NotImplementedError(
-                "create_diffusion_model('ldm'): the VQ autoencoder is not on the native engine yet; pass vqvae= "
-                "(a module with encode(x).latents / decode(z).sample, e.g. diffusers.VQModel)")
+        from b200edit.vqmodel import LDM_VQ_CONFIG, VQModel
         unet = UNet2DModel(**(unet_config or LDM_CELEBAHQ_CONFIG), max_batch=max_batch, device=device)
         if state_dict is not None:
             unet.load_state_dict(state_dict)
         else:
             unet.init_random(seed)
+        guidance_vqvae = None
+        if vqvae is None:
+            # native forward-only decoder (post-loop decoding of the sample and of the x0 history); guidance
+            # through the decoder additionally needs a differentiable module (guidance_vqvae=)
+            vqvae = VQModel(**(vq_config or LDM_VQ_CONFIG), max_batch=max_batch, device=device)
+            if vq_state_dict is not None:
+                vqvae.load_state_dict(vq_state_dict)
+            else:
+                vqvae.init_random(seed + 1)
+        elif isinstance(vqvae, torch.nn.Module) or not getattr(vqvae, "forward_only", False):
+            guidance_vqvae = vqvae
         scheduler = DDIMScheduler.from_preset("ldm")
         scheduler.config.clip_sample = sample_clipping   # src/models.py:43 ("LDM was trained with this flag=False")
-        return LDM(NativePipeline(unet=unet, scheduler=scheduler, vqvae=vqvae, device=device))
+        return LDM(NativePipeline(unet=unet, scheduler=scheduler, vqvae=vqvae,
+                                  guidance_vqvae=guidance_vqvae if guidance_module is None else guidance_module,
+                                  device=device))
     if name == "sd":
         raise NotImplementedError(
             "create_diffusion_model('sd'): the SD UNet2DConditionModel / KL autoencoder are not on the native "

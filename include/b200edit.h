@@ -238,6 +238,27 @@ int b2e_unet_profile(b2e_unet* m, const float* x, const int64_t* timesteps, floa
                      int* kind);
 int b2e_unet_launches_per_forward(const b2e_unet* m);
 
+/* ------------------------------------------------------------------ VQ decoder (LDM.decode)
+ * src/diffusion_classes.py:62-70: vqvae.decode(latent.float()).sample for a diffusers VQModel
+ * (CompVis/ldm-celebahq-256 `vqvae` layout by default): nearest-code quantisation -> post_quant_conv ->
+ * Decoder (conv_in, mid block with single-head attention, up blocks, GroupNorm + SiLU, conv_out).
+ * The handle is a b2e_unet*: parameters (diffusers state_dict names, e.g. "decoder.up_blocks.0.resnets.1.conv1.weight",
+ * "quantize.embedding.weight", "post_quant_conv.weight"), workspace, forward (timesteps = NULL; x = latent
+ * (B, latent_channels, S, S) fp32; output (B, out_channels, S << (n_blocks-1), ...) fp32) and profile use the
+ * b2e_unet_* entry points. */
+typedef struct {
+  int32_t sample_size;       /* latent height = width */
+  int32_t latent_channels;   /* 1, 3 or 4 */
+  int32_t out_channels;
+  int32_t n_blocks;
+  int32_t block_out_channels[8]; /* bottom-up, as in the diffusers config: (128, 256, 512) */
+  int32_t layers_per_block;
+  int32_t norm_num_groups;
+  float norm_eps;
+  int32_t num_vq_embeddings;
+} b2e_vqdec_config;
+int b2e_vqdec_create(const b2e_vqdec_config* cfg, int64_t max_batch, b2e_unet** out);
+
 /* Test hook for the implicit-GEMM convolution: x (N,H,W,Cin) bf16 NHWC, w (Cout,Cin,k,k) fp32,
  * bias fp32 [Cout] or NULL, residual (N,Ho,Wo,Cout) bf16 NHWC or NULL (added through the fused
  * residual K-segment), out (N,Ho,Wo,Cout) bf16 NHWC.  ksize 1|3, stride 1|2 (stride 2 pads
