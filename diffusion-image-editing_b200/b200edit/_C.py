@@ -78,6 +78,8 @@ PROTOTYPES = {
     "b2e_morphology2d_f32": (_I, [_P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I, _I, _I, _F, _P]),
     "b2e_unet_create": (_I, [C.POINTER(UNetConfig), _I64, C.POINTER(_P)]),
     "b2e_vqdec_create": (_I, [C.POINTER(VQDecConfig), _I64, C.POINTER(_P)]),
+    "b2e_unet_enable_grad": (_I, [_P, _I]),
+    "b2e_vqdec_backward": (_I, [_P, _P, _P, _I64, _P]),
     "b2e_unet_destroy": (None, [_P]),
     "b2e_unet_num_params": (_I, [_P]),
     "b2e_unet_param_info": (_I, [_P, _I, C.POINTER(C.c_char_p), C.POINTER(_I64), C.POINTER(_I64)]),

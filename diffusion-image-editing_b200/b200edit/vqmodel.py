@@ -21,10 +21,31 @@ LDM_VQ_CONFIG = dict(latent_channels=3, out_channels=3, block_out_channels=(128,
                      norm_num_groups=32, norm_eps=1e-6, num_vq_embeddings=8192, sample_size=64)
 
 
+class _DecodeFn(torch.autograd.Function):
+    """decode as an autograd node: forward = native decoder (activations stay in the engine's workspace), backward =
+    native dgrad of the whole decoder (straight-through quantiser)."""
+
+    @staticmethod
+    def forward(ctx, latent, model):
+        ctx.model = model
+        ctx.B = latent.shape[0]
+        return model._forward(latent)
+
+    @staticmethod
+    def backward(ctx, grad_img):
+        m = ctx.model
+        g = grad_img.to(torch.float32).contiguous()
+        dz = torch.empty((ctx.B, m.config.latent_channels, m.config.sample_size, m.config.sample_size),
+                         dtype=torch.float32, device=g.device)
+        check(lib.b2e_vqdec_backward(m._h, C.c_void_p(g.data_ptr()), C.c_void_p(dz.data_ptr()), ctx.B,
+                                     C.c_void_p(torch.cuda.current_stream().cuda_stream)), "vqdec_backward")
+        return dz, None
+
+
 class VQModel(UNet2DModel):
     """Shares parameter loading / random init / profiling with the UNet wrapper (same engine handle type)."""
 
-    forward_only = True   # no autograd graph through decode (see LDM.decode)
+    forward_only = True   # until enable_grad(): no autograd graph through decode (see LDM.decode)
 
     def __init__(self, latent_channels=3, out_channels=3, block_out_channels=(128, 256, 512), layers_per_block=2,
                  norm_num_groups=32, norm_eps=1e-6, num_vq_embeddings=8192, sample_size=64, max_batch=8,
@@ -56,11 +77,36 @@ class VQModel(UNet2DModel):
             check(lib.b2e_unet_bind_workspace(h, C.c_void_p(base), nbytes), "unet_bind_workspace")
         self._t_cache = {}
 
+    def enable_grad(self, enable: bool = True):
+        """Gradient mode: decode() becomes differentiable w.r.t. the latent (native dgrad; batches <= max_batch).
+        Costs workspace: every activation of a forward pass is kept until the backward pass."""
+        with torch.cuda.device(self.device):
+            check(lib.b2e_unet_enable_grad(self._h, int(enable)), "unet_enable_grad")
+            nbytes = lib.b2e_unet_workspace_bytes(self._h)
+            self._ws = None
+            self._ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)
+            base = (self._ws.data_ptr() + 255) // 256 * 256
+            check(lib.b2e_unet_bind_workspace(self._h, C.c_void_p(base), nbytes), "unet_bind_workspace")
+        self.forward_only = not enable
+        return self
+
+    def _forward(self, z):
+        cfg = self.config
+        img = torch.empty((z.shape[0], cfg.out_channels, self.out_size, self.out_size), dtype=torch.float32, device=z.device)
+        check(lib.b2e_unet_forward(self._h, C.c_void_p(z.data_ptr()), None, C.c_void_p(img.data_ptr()), z.shape[0],
+                                   C.c_void_p(torch.cuda.current_stream().cuda_stream)), "vqdec_forward")
+        return img
+
     def decode(self, latent: torch.Tensor, force_not_quantize: bool = False):
         if force_not_quantize:
             raise NotImplementedError("VQModel.decode(force_not_quantize=True) is not on the native engine")
         if not latent.is_cuda:
             raise _C.B2EError("VQModel.decode: latent must be a CUDA tensor (no CPU fallback)")
+        if not self.forward_only and latent.requires_grad and torch.is_grad_enabled():
+            if latent.shape[0] > self.max_batch:
+                raise ValueError(f"VQModel.decode with gradient: batch {latent.shape[0]} > max_batch {self.max_batch}")
+            zz = latent if (latent.dtype == torch.float32 and latent.is_contiguous()) else latent.to(torch.float32).contiguous()
+            return SimpleNamespace(sample=_DecodeFn.apply(zz, self))
         z = latent.detach().to(torch.float32).contiguous()
         B = z.shape[0]
         cfg = self.config

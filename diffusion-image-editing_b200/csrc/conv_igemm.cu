@@ -791,6 +791,31 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, bf16* __restrict
   }
 }
 
+// dgrad weights: the gradient of y = conv_{k x k, stride 1, pad k/2}(x, W) w.r.t. x is the same convolution of dy with
+// W'[ci][co][t] = W[co][ci][kk-1-t]:  out[ci*row_len + col_off + t*tap_width + co] = w[(co*Cin + ci)*kk + (kk-1-t)]
+__global__ void pack_weight_dgrad_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int Cin, int kk,
+                                         int tap_width, int row_len, int col_off) {
+  const int64_t total = (int64_t)Cout * kk * Cin;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int co = (int)(i % Cout);
+    const int t = (int)((i / Cout) % kk);
+    const int ci = (int)(i / ((int64_t)Cout * kk));
+    out[(int64_t)ci * row_len + col_off + (int64_t)t * tap_width + co] =
+        __float2bfloat16_rn(w[((int64_t)co * Cin + ci) * kk + (kk - 1 - t)]);
+  }
+}
+
+// dgrad of conv_in run as a 1x1 convolution over im2col columns: out[(t*Cin + ci)*row_len + co] = w[(co*Cin + ci)*9 + t]
+__global__ void pack_weight_im2col_T_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int Cin, int row_len) {
+  const int64_t total = (int64_t)Cout * Cin * 9;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int co = (int)(i % Cout);
+    const int ci = (int)((i / Cout) % Cin);
+    const int t = (int)(i / ((int64_t)Cout * Cin));
+    out[(int64_t)(t * Cin + ci) * row_len + co] = __float2bfloat16_rn(w[((int64_t)co * Cin + ci) * 9 + t]);
+  }
+}
+
 __global__ void fill_identity_kernel(bf16* __restrict__ out, int C, int row_len, int col_off) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) out[(int64_t)c * row_len + col_off + c] = __float2bfloat16_rn(1.f);
@@ -805,6 +830,24 @@ int conv_pack_weight(const float* w, bf16* out, int Cout, int Cin, int ksize, in
   pack_weight_kernel<<<grid, 256, 0, st>>>(w, out, Cout, Cin, kk, tap_width, row_len, col_off, ci0,
                                            cin_total > 0 ? cin_total : Cin);
   return check_launch("pack_weight");
+}
+
+int conv_pack_weight_dgrad(const float* w, bf16* out, int Cout, int Cin, int ksize, int tap_width, int row_len, int col_off,
+                           cudaStream_t st) {
+  const int kk = ksize * ksize;
+  const int64_t total = (int64_t)Cout * kk * Cin;
+  int grid = (int)((total + 255) / 256);
+  if (grid > kNumSMs * 16) grid = kNumSMs * 16;
+  pack_weight_dgrad_kernel<<<grid, 256, 0, st>>>(w, out, Cout, Cin, kk, tap_width, row_len, col_off);
+  return check_launch("pack_weight_dgrad");
+}
+
+int conv_pack_weight_im2col_T(const float* w, bf16* out, int Cout, int Cin, int row_len, cudaStream_t st) {
+  const int64_t total = (int64_t)Cout * Cin * 9;
+  int grid = (int)((total + 255) / 256);
+  if (grid > kNumSMs * 16) grid = kNumSMs * 16;
+  pack_weight_im2col_T_kernel<<<grid, 256, 0, st>>>(w, out, Cout, Cin, row_len);
+  return check_launch("pack_weight_im2col_T");
 }
 
 int conv_fill_identity(bf16* out, int C, int row_len, int col_off, cudaStream_t st) {

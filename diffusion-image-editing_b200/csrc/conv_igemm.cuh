@@ -79,6 +79,11 @@ int conv_launch(const ConvPlan& plan, const ConvEpilogue& ep, cudaStream_t st);
 // (ci0, cin_total): pack only input channels [ci0, ci0 + Cin) of a weight with cin_total input channels
 int conv_pack_weight(const float* w, bf16* out, int Cout, int Cin, int ksize, int tap_width, int row_len,
                      int col_off, cudaStream_t st, int ci0 = 0, int cin_total = 0);
+// dgrad weights (flipped taps, transposed channels): out[ci*row_len + col_off + t*tap_width + co] = w[(co*Cin+ci)*kk + kk-1-t]
+int conv_pack_weight_dgrad(const float* w, bf16* out, int Cout, int Cin, int ksize, int tap_width, int row_len, int col_off,
+                           cudaStream_t st);
+// dgrad of the im2col conv_in: out[(t*Cin + ci)*row_len + co] = w[(co*Cin + ci)*9 + t]
+int conv_pack_weight_im2col_T(const float* w, bf16* out, int Cout, int Cin, int row_len, cudaStream_t st);
 // out[c*row_len + col_off + c] = 1 for c < C (identity residual segment)
 int conv_fill_identity(bf16* out, int C, int row_len, int col_off, cudaStream_t st);
 

@@ -21,13 +21,18 @@ using namespace b2e;
 namespace {
 
 // res_c > 0: a 1x1 residual segment of res_c channels is appended to every weight row (shortcut / identity)
-struct ConvL { bf16* w = nullptr; float* b = nullptr; float* b2 = nullptr; int cin = 0, cin_pad = 0, cout = 0, cout_pad = 0, k = 0, res_c = 0, row_len = 0; };
+struct ConvL {
+  bf16* w = nullptr; float* b = nullptr; float* b2 = nullptr;
+  int cin = 0, cin_pad = 0, cout = 0, cout_pad = 0, k = 0, res_c = 0, row_len = 0;
+  int dg = -1;   // decoder: index of the dgrad twin (flipped / transposed weights) in b2e_unet::dgrads
+};
 struct NormL { float* g = nullptr; float* b = nullptr; int C = 0; };
 struct ResnetL {
   std::string name; int cin0 = 0, cin1 = 0, cout = 0; NormL n1, n2; ConvL c1, c2, sc; bool has_sc = false;
   int temb_off = 0;
+  int sc_dg = -1;   // decoder: dgrad twin of the 1x1 shortcut convolution
 };
-struct AttnL { std::string name; int C = 0, P = 0; NormL gn; ConvL qkv, proj; };   // P = pad64(C): q | k | v blocks of P columns
+struct AttnL { std::string name; int C = 0, P = 0; NormL gn; ConvL qkv, proj; int qkv_dg = -1; };   // P = pad64(C): q | k | v blocks of P columns
 
 // Channel counts that are not multiples of 64 (LDM: 224, 672) live in tensors whose channel pitch is rounded up to
 // the 64-channel K chunk of the convolution kernel; the tail channels are identically zero (zero weight rows,
@@ -84,6 +89,13 @@ struct b2e_unet {
   bool decoder = false;
   float *codebook = nullptr, *pq_w = nullptr, *pq_b = nullptr;   // [n_codes][latent], [latent][latent], [latent]
   int n_codes = 0;
+  // decoder gradient w.r.t. the latent (b2e_vqdec_backward): dgrad twins of every convolution, and a second op
+  // list that walks the graph backwards over the activations the last forward left in the workspace
+  std::vector<ConvL> dgrads;
+  int conv_in_dg = -1, conv_out_dg = -1;
+  bool grad = false;
+  const float* in_dy = nullptr; float* out_dz = nullptr;   // per-call
+  int64_t fwd_B = -1;                                      // batch of the forward whose activations are live
   NormL norm_out;
   float *te_w1 = nullptr, *te_b1 = nullptr, *te_w2 = nullptr, *te_b2 = nullptr, *tp_w = nullptr, *tp_b = nullptr;
   std::vector<ResnetL> resnets;
@@ -94,7 +106,7 @@ struct b2e_unet {
   void* ws = nullptr; size_t ws_bytes = 0;
   int64_t cur_B = -1;
   struct Op { std::function<int(cudaStream_t)> fn; int kind; double flops; double bytes; std::string desc; };  // kind: 0 conv, 1 groupnorm, 2 attention, 3 other
-  std::vector<Op> ops;
+  std::vector<Op> ops, bops;
   const float* in_x = nullptr; const int64_t* in_t = nullptr; float* out_eps = nullptr;  // per-call
   double flops = 0;
   size_t ws_need = 0;
@@ -129,11 +141,27 @@ struct b2e_unet {
     c.w = dmalloc<bf16>((size_t)c.cout_pad * c.row_len);
     c.b = dmalloc<float>(c.cout_pad);
     ConvL cc = c;
-    add_param(name + ".weight", (int64_t)cout * cin * k * k, (int64_t)cin * k * k, [cc](const float* src, cudaStream_t st) {
-      return conv_pack_weight(src, cc.w, cc.cout, cc.cin, cc.k, cc.cin_pad, cc.row_len, 0, st);
+    ConvL dd;
+    // (a <= 16-channel output, i.e. conv_out, receives its gradient as a 64-channel padded NHWC tensor)
+    if (decoder) { c.dg = make_dgrad(cin, cout > 16 ? c.cout_pad : kConvBlockK, k); dd = dgrads[c.dg]; cc.dg = c.dg; }
+    add_param(name + ".weight", (int64_t)cout * cin * k * k, (int64_t)cin * k * k, [cc, dd](const float* src, cudaStream_t st) {
+      int rc = conv_pack_weight(src, cc.w, cc.cout, cc.cin, cc.k, cc.cin_pad, cc.row_len, 0, st);
+      if (!rc && cc.dg >= 0) rc = conv_pack_weight_dgrad(src, dd.w, cc.cout, cc.cin, cc.k, dd.cin_pad, dd.row_len, 0, st);
+      return rc;
     });
     add_f32(name + ".bias", c.b, cout, (int64_t)cin * k * k);
     return c;
+  }
+  // dgrad twin of a stride-1 convolution with `cin` input channels whose output tensor has pitch `dy_pitch`:
+  // a convolution dy (dy_pitch channels) -> dx (cin channels), zero bias; the weights are packed by the caller
+  int make_dgrad(int cin, int dy_pitch, int k, int extra_k = 0) {
+    ConvL d;
+    d.cin = dy_pitch; d.cin_pad = dy_pitch; d.cout = cin; d.cout_pad = conv_cout_pad(cin); d.k = k;
+    d.res_c = extra_k; d.row_len = k * k * dy_pitch + extra_k;
+    d.w = dmalloc<bf16>((size_t)d.cout_pad * d.row_len);
+    d.b = dmalloc<float>(d.cout_pad);
+    dgrads.push_back(d);
+    return (int)dgrads.size() - 1;
   }
   NormL make_norm(const std::string& name, int C) {
     NormL n; n.C = C; n.g = dmalloc<float>(C); n.b = dmalloc<float>(C);
@@ -159,9 +187,13 @@ struct b2e_unet {
     if (r.has_sc) {
       r.c2.b2 = dmalloc<float>(r.c2.cout_pad);
       ConvL cc = r.c2;
-      add_param(name + ".conv_shortcut.weight", (int64_t)cout * cin, cin, [cc, cin, cin0, cin1, p0](const float* src, cudaStream_t st) {
+      ConvL sd;
+      if (decoder) { r.sc_dg = make_dgrad(cin, r.c2.cout_pad, 1); sd = dgrads[r.sc_dg]; }
+      const int sc_dg = r.sc_dg;
+      add_param(name + ".conv_shortcut.weight", (int64_t)cout * cin, cin, [cc, sd, sc_dg, cin, cin0, cin1, p0](const float* src, cudaStream_t st) {
         int rc = conv_pack_weight(src, cc.w, cc.cout, cin0, 1, cin0, cc.row_len, 9 * cc.cin_pad, st, 0, cin);
         if (!rc && cin1) rc = conv_pack_weight(src, cc.w, cc.cout, cin1, 1, cin1, cc.row_len, 9 * cc.cin_pad + p0, st, cin0, cin);
+        if (!rc && sc_dg >= 0) rc = conv_pack_weight_dgrad(src, sd.w, cc.cout, cin, 1, sd.cin_pad, sd.row_len, 0, st);
         return rc;
       });
       add_f32(name + ".conv_shortcut.bias", r.c2.b2, cout, cin);
@@ -181,11 +213,16 @@ struct b2e_unet {
     a.qkv.w = dmalloc<bf16>((size_t)a.qkv.cout_pad * P);
     a.qkv.b = dmalloc<float>(a.qkv.cout_pad);
     const char* nm[3] = {"to_q", "to_k", "to_v"};
+    ConvL qd;
+    if (decoder) { a.qkv_dg = make_dgrad(C, 2 * P, 1, P); qd = dgrads[a.qkv_dg]; }   // K = (dQ ++ dK) ++ residual segment dV
+    const int qkv_dg = a.qkv_dg;
     for (int i = 0; i < 3; ++i) {
       bf16* wdst = a.qkv.w + (size_t)i * P * P;
       float* bdst = a.qkv.b + (size_t)i * P;
-      add_param(name + "." + nm[i] + ".weight", (int64_t)C * C, C, [wdst, C, P](const float* src, cudaStream_t st) {
-        return conv_pack_weight(src, wdst, C, C, 1, C, P, 0, st);
+      add_param(name + "." + nm[i] + ".weight", (int64_t)C * C, C, [wdst, qd, qkv_dg, i, C, P](const float* src, cudaStream_t st) {
+        int rc = conv_pack_weight(src, wdst, C, C, 1, C, P, 0, st);
+        if (!rc && qkv_dg >= 0) rc = conv_pack_weight_dgrad(src, qd.w, C, C, 1, P, qd.row_len, i * P, st);
+        return rc;
       });
       add_f32(name + "." + nm[i] + ".bias", bdst, C, C);
     }
@@ -218,8 +255,13 @@ int build_model_decoder(b2e_unet* m) {
     ci.cin = ci.cin_pad = kConvBlockK; ci.cout = top; ci.k = 1; ci.cout_pad = conv_cout_pad(top); ci.row_len = kConvBlockK;
     ci.w = m->dmalloc<bf16>((size_t)ci.cout_pad * ci.row_len);
     ci.b = m->dmalloc<float>(ci.cout_pad);
-    m->add_param("decoder.conv_in.weight", (int64_t)top * L * 9, (int64_t)L * 9, [ci, L](const float* src, cudaStream_t st) {
-      return conv_pack_weight(src, ci.w, ci.cout, L, 3, L, ci.row_len, 0, st);
+    // dgrad twin: gradient w.r.t. the 64 im2col columns (9 * L real) = 1x1 convolution with the transposed weights
+    m->conv_in_dg = m->make_dgrad(kConvBlockK, ci.cout_pad, 1);
+    const ConvL cd = m->dgrads[m->conv_in_dg];
+    m->add_param("decoder.conv_in.weight", (int64_t)top * L * 9, (int64_t)L * 9, [ci, cd, L](const float* src, cudaStream_t st) {
+      int rc = conv_pack_weight(src, ci.w, ci.cout, L, 3, L, ci.row_len, 0, st);
+      if (!rc) rc = conv_pack_weight_im2col_T(src, cd.w, ci.cout, L, cd.row_len, st);
+      return rc;
     });
     m->add_f32("decoder.conv_in.bias", ci.b, top, (int64_t)L * 9);
     m->conv_in = ci;
@@ -242,6 +284,7 @@ int build_model_decoder(b2e_unet* m) {
   }
   m->norm_out = m->make_norm("decoder.conv_norm_out", ch);
   m->conv_out = m->make_conv("decoder.conv_out", ch, c.out_channels, 3);
+  m->conv_out_dg = m->conv_out.dg;
   return m->build_error;
 }
 
@@ -336,7 +379,10 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
   Arena ar;
   ar.reset(ws, ws_bytes);
   const bool dry = ar.dry;
-  std::vector<b2e_unet::Op> ops;
+  std::vector<b2e_unet::Op> ops_fwd, ops_bwd;
+  std::vector<b2e_unet::Op>* cur = &ops_fwd;   // the op list being recorded
+#define ops (*cur)
+  const bool keep = m->grad;                    // gradient mode: every activation stays live for the backward pass
   double flops = 0;
   int rc = B2E_OK;
   auto talloc = [&](int N, int H, int W, int C, int Cr = 0) {
@@ -345,6 +391,7 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
     return t;
   };
   auto tfree = [&](Tensor& t) {
+    if (keep) return;
     if (t.p) ar.release(t.p, t.bytes);
     if (t.cstats) ar.release(t.cstats, sizeof(float) * 2 * t.N * t.C);
     if (t.tstats) ar.release(t.tstats, t.tstats_bytes);
@@ -430,12 +477,15 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
       ar.release(tstats, tstats_bytes);   // dead after the finalize kernel (stream order)
     }
   };
-  auto gnorm = [&](const NormL& L, Tensor x0, const Tensor* x1, int silu, Tensor* out) {
+  auto gnorm = [&](const NormL& L, Tensor x0, const Tensor* x1, int silu, Tensor* out, float** stats_out = nullptr) {
     if (rc) return;
     const int C = x0.Cr + (x1 ? x1->Cr : 0);   // real channels, written compactly; pitch rounded up to 64
     *out = talloc(B, x0.H, x0.W, pad64(C), C);
+    float* sv = (keep && stats_out) ? (float*)ar.alloc(sizeof(float) * 2 * B * G) : nullptr;
+    if (stats_out) *stats_out = sv;
     if (dry) return;
     GNArgs a;
+    a.save_stats = sv;
     a.x0 = x0.p; a.x1 = x1 ? x1->p : nullptr; a.C0 = x0.Cr; a.C1 = x1 ? x1->Cr : 0;
     a.P0 = x0.C; a.P1 = x1 ? x1->C : 0; a.Pout = out->C;
     a.N = B; a.HW = x0.H * x0.W; a.G = G; a.eps = c.norm_eps; a.gamma = L.g; a.beta = L.b;
@@ -488,8 +538,14 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
   // fake but unique per live allocation, so the same liveness logic applies)
   auto on_stack = [&](const Tensor& t) { for (auto& s : stack) if (s.p == t.p) return true; return false; };
 
+  // gradient mode: what the backward pass needs from every node
+  struct Save { Tensor x, h1, qkv, sc; float* st1 = nullptr; float* st2 = nullptr; };
+  std::vector<Save> saves(m->nodes.size());
+  int node_i = -1;
   for (const Node& nd : m->nodes) {
     if (rc) break;
+    ++node_i;
+    Save& sv = saves[node_i];
     switch (nd.kind) {
       case N_PUSH: stack.push_back(h); break;
       case N_POPCAT: cat = stack.back(); stack.pop_back(); have_cat = true; break;
@@ -497,12 +553,13 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
         const ResnetL& r = m->resnets[nd.idx];
         const Tensor* x1 = have_cat ? &cat : nullptr;
         Tensor a1, h1, a2, out;
-        gnorm(r.n1, h, x1, 1, &a1);
+        gnorm(r.n1, h, x1, 1, &a1, &sv.st1);
         ConvEpilogue e1;
         if (r.temb_off >= 0) { e1.temb = proj + r.temb_off; e1.temb_stride = m->sumC; }
         conv(r.c1, a1, nullptr, 1, e1, &h1, nullptr);
         tfree(a1);
-        gnorm(r.n2, h1, nullptr, 1, &a2);
+        gnorm(r.n2, h1, nullptr, 1, &a2, &sv.st2);
+        sv.x = h; sv.h1 = h1;
         tfree(h1);
         // out = conv2(a2) + shortcut(x) : the block input rides along as a 1x1 K segment of conv2
         conv(r.c2, a2, nullptr, 1, ConvEpilogue{}, &out, nullptr, &h, x1);
@@ -515,8 +572,9 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
       case N_ATTN: {
         const AttnL& a = m->attns[nd.idx];
         Tensor an, qkv, o, out;
-        gnorm(a.gn, h, nullptr, 0, &an);
+        gnorm(a.gn, h, nullptr, 0, &an, &sv.st1);
         conv(a.qkv, an, nullptr, 1, ConvEpilogue{}, &qkv, nullptr, nullptr, nullptr, false);
+        sv.x = h; sv.qkv = qkv;
         tfree(an);
         o = talloc(B, h.H, h.W, a.P, a.C);
         const int heads = c.attention_head_dim > 0 ? a.C / c.attention_head_dim : 1;
@@ -527,6 +585,7 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
           // B operand is read straight from the qkv tensor / a transposed copy of V); softmax in fp32 between
           Tensor sc = talloc(B, h.H, h.W, T);
           Tensor vt = talloc(B, 1, C, T);   // V^T: [N][C][T]
+          sv.sc = sc;                       // P after the in-place softmax
           if (!dry) {
             ConvDesc d1;
             d1.s0.ptr = qkv.p; d1.s0.C = C; d1.s0.pitch = 3 * C;        // Q = channel window [0,C) of qkv
@@ -623,6 +682,7 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
         break;
       }
       case N_UP: {
+        sv.x = h;
         Tensor up = talloc(B, h.H * 2, h.W * 2, h.C, h.Cr), out;
         if (!dry) {
           Tensor hh = h;
@@ -637,19 +697,142 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
       }
     }
   }
+  float* st_out = nullptr;
+  Tensor h_last = h;
   if (!rc) {
     Tensor an;
-    gnorm(m->norm_out, h, nullptr, 1, &an);
+    gnorm(m->norm_out, h, nullptr, 1, &an, &st_out);
     tfree(h);
     float dummy = 0.f;
     conv(m->conv_out, an, nullptr, 1, ConvEpilogue{}, nullptr, &dummy);
     tfree(an);
   }
+  // ---- backward program (decoder, gradient mode): d(loss)/d(latent) from d(loss)/d(image), walking the nodes in
+  // reverse over the saved activations.  Every convolution gradient is the SAME tcgen05 implicit-GEMM kernel on the
+  // dgrad twin of its weights; GroupNorm(+SiLU), softmax, upsample and the VQ front have their own backward kernels.
+  if (!rc && m->grad) {
+    if (!m->decoder) { set_error("unet: gradient mode is implemented for the VQ decoder only"); return B2E_UNSUPPORTED_SHAPE; }
+    cur = &ops_bwd;
+    const int So = S << (c.n_blocks - 1);
+    float* gpart = (float*)ar.alloc(sizeof(float) * B * 64 * G * 2);
+    auto gn_bwd = [&](const NormL& L, const Tensor& x, const float* stats, const Tensor& da, int silu, const Tensor* add,
+                      Tensor* dx) {
+      if (rc) return;
+      *dx = talloc(B, x.H, x.W, x.C, x.Cr);
+      if (dry) return;
+      GNBwdArgs a;
+      a.x = x.p; a.da = da.p; a.add = add ? add->p : nullptr; a.dx = dx->p;
+      a.C = x.Cr; a.P = x.C; a.Pda = da.C; a.N = B; a.HW = x.H * x.W; a.G = G;
+      a.gamma = L.g; a.beta = L.b; a.stats = stats; a.partial = gpart; a.chunks = gn_chunks(a.HW, a.C); a.silu = silu;
+      if (add && add->C != x.C) { rc = B2E_INVALID_ARG; set_error("unet backward: residual pitch mismatch"); return; }
+      ops.push_back({[a](cudaStream_t st) { return gn_bwd_launch(a, st); }, 1, 0.0, 10.0 * B * a.HW * a.C, "groupnorm backward"});
+    };
+    // gradient w.r.t. the image arrives as fp32 NCHW: pack to bf16 NHWC with 64 (zero-padded) channels
+    Tensor gy = talloc(B, So, So, kConvBlockK, c.out_channels);
+    if (!dry) {
+      const int Co = c.out_channels;
+      ops.push_back({[m, gy, B, Co, So](cudaStream_t st) { return pack_input_launch(m->in_dy, gy.p, B, Co, So, So, kConvBlockK, false, st); },
+                     3, 0.0, (double)B * So * So * (4.0 * Co + 2.0 * kConvBlockK), "pack d(image)"});
+    }
+    Tensor d_an, g;
+    conv(m->dgrads[m->conv_out_dg], gy, nullptr, 1, ConvEpilogue{}, &d_an, nullptr, nullptr, nullptr, false);
+    gn_bwd(m->norm_out, h_last, st_out, d_an, 1, nullptr, &g);
+    for (int ni = (int)m->nodes.size() - 1; ni >= 0 && !rc; --ni) {
+      const Node& nd = m->nodes[ni];
+      const Save& sv = saves[ni];
+      switch (nd.kind) {
+        case N_RESNET: {
+          const ResnetL& r = m->resnets[nd.idx];
+          Tensor d_a2, d_h1, d_a1, d_sc, gin;
+          conv(m->dgrads[r.c2.dg], g, nullptr, 1, ConvEpilogue{}, &d_a2, nullptr, nullptr, nullptr, false);
+          gn_bwd(r.n2, sv.h1, sv.st2, d_a2, 1, nullptr, &d_h1);
+          conv(m->dgrads[r.c1.dg], d_h1, nullptr, 1, ConvEpilogue{}, &d_a1, nullptr, nullptr, nullptr, false);
+          const Tensor* add = &g;   // identity shortcut
+          if (r.has_sc) {
+            conv(m->dgrads[r.sc_dg], g, nullptr, 1, ConvEpilogue{}, &d_sc, nullptr, nullptr, nullptr, false);
+            add = &d_sc;
+          }
+          gn_bwd(r.n1, sv.x, sv.st1, d_a1, 1, add, &gin);
+          g = gin;
+          break;
+        }
+        case N_ATTN: {
+          const AttnL& a = m->attns[nd.idx];
+          const int T = sv.x.H * sv.x.W, P = a.P, Hh = sv.x.H, Ww = sv.x.W;
+          if (!sv.sc.p && !dry) { rc = B2E_UNSUPPORTED_SHAPE; set_error("unet backward: attention needs the tensor-core path"); break; }
+          Tensor dO, dV, dP, dQ, dK, d_an2, gin;
+          conv(m->dgrads[a.proj.dg], g, nullptr, 1, ConvEpilogue{}, &dO, nullptr, nullptr, nullptr, false);
+          Tensor Pt = talloc(B, Hh, Ww, T), dSt = talloc(B, Hh, Ww, T);
+          Tensor dOt = talloc(B, 1, P, T), Kt = talloc(B, 1, P, T), Qt = talloc(B, 1, P, T);
+          dV = talloc(B, Hh, Ww, P, a.C); dP = talloc(B, Hh, Ww, T); dQ = talloc(B, Hh, Ww, P, a.C); dK = talloc(B, Hh, Ww, P, a.C);
+          if (!dry) {
+            auto gemm = [&](const Tensor& A, int K, const bf16* Bop, int brows, int bpitch, int Cout, const Tensor& out,
+                            const char* what) {
+              // out[n][t][co] = sum_k A[n][t][k] * Bop[n*brows + co][k]
+              ConvDesc d;
+              d.s0.ptr = A.p; d.s0.C = K; if (A.C != K) d.s0.pitch = A.C;
+              d.N = B; d.H = Hh; d.W = Ww; d.ksize = 1; d.stride = 1;
+              d.w_packed = Bop; d.b_batch_rows = brows; d.b_pitch = bpitch; d.Cout = Cout; d.out_bf16 = out.p;
+              ConvPlan pl;
+              if (!rc) rc = conv_plan_build(&pl, d);
+              if (!rc) { ops.push_back({[pl](cudaStream_t st) { return conv_launch(pl, ConvEpilogue{}, st); }, 0, pl.flops, 0.0, what}); flops += pl.flops; }
+            };
+            const Tensor sc = sv.sc, qkv = sv.qkv;
+            const float scale = 1.0f / sqrtf((float)a.C);
+            const int64_t rows = (int64_t)B * T;
+            // dV = P^T dO
+            ops.push_back({[sc, Pt, B, T](cudaStream_t st) { return transpose_window_launch(sc.p, Pt.p, B, T, T, T, 0, st); }, 3, 0.0, 4.0 * B * T * T, "P^T"});
+            ops.push_back({[dO, dOt, B, T, P](cudaStream_t st) { return transpose_window_launch(dO.p, dOt.p, B, T, P, P, 0, st); }, 3, 0.0, 4.0 * B * T * P, "dO^T"});
+            gemm(Pt, T, dOt.p, P, T, P, dV, "attention backward dV = P^T dO");
+            // dP = dO V^T ; dS = scale * P o (dP - rowsum(dP o P))  (in place)
+            gemm(dO, P, qkv.p + 2 * P, T, 3 * P, T, dP, "attention backward dP = dO V^T");
+            ops.push_back({[sc, dP, rows, T, scale](cudaStream_t st) { return softmax_bwd_rows_launch(sc.p, dP.p, rows, T, scale, st); },
+                           3, 0.0, 6.0 * rows * T, "softmax backward"});
+            // dQ = dS K ; dK = dS^T Q
+            ops.push_back({[qkv, Kt, B, T, P](cudaStream_t st) { return transpose_window_launch(qkv.p, Kt.p, B, T, P, 3 * P, P, st); }, 3, 0.0, 4.0 * B * T * P, "K^T"});
+            gemm(dP, T, Kt.p, P, T, P, dQ, "attention backward dQ = dS K");
+            ops.push_back({[dP, dSt, B, T](cudaStream_t st) { return transpose_window_launch(dP.p, dSt.p, B, T, T, T, 0, st); }, 3, 0.0, 4.0 * B * T * T, "dS^T"});
+            ops.push_back({[qkv, Qt, B, T, P](cudaStream_t st) { return transpose_window_launch(qkv.p, Qt.p, B, T, P, 3 * P, 0, st); }, 3, 0.0, 4.0 * B * T * P, "Q^T"});
+            gemm(dSt, T, Qt.p, P, T, P, dK, "attention backward dK = dS^T Q");
+          }
+          // d(normed input) = Wq^T dQ + Wk^T dK + Wv^T dV: one 1x1 convolution drawing K from three tensors
+          conv(m->dgrads[a.qkv_dg], dQ, &dK, 1, ConvEpilogue{}, &d_an2, nullptr, &dV, nullptr, false);
+          gn_bwd(a.gn, sv.x, sv.st1, d_an2, 0, &g, &gin);
+          g = gin;
+          break;
+        }
+        case N_UP: {
+          Tensor d_up, gin = talloc(B, sv.x.H, sv.x.W, sv.x.C, sv.x.Cr);
+          conv(m->dgrads[m->ups[nd.idx].dg], g, nullptr, 1, ConvEpilogue{}, &d_up, nullptr, nullptr, nullptr, false);
+          if (!dry) {
+            ops.push_back({[d_up, gin, B](cudaStream_t st) { return downsum2x_launch(d_up.p, gin.p, B, gin.H, gin.W, gin.C, st); },
+                           3, 0.0, 10.0 * B * gin.H * gin.W * gin.C, "upsample backward"});
+          }
+          g = gin;
+          break;
+        }
+        default: break;
+      }
+    }
+    if (!rc) {
+      Tensor dcols;
+      conv(m->dgrads[m->conv_in_dg], g, nullptr, 1, ConvEpilogue{}, &dcols, nullptr, nullptr, nullptr, false);
+      if (!dry && !rc) {
+        const int L = c.in_channels;
+        ops.push_back({[m, dcols, B, L, S](cudaStream_t st) { return vq_col2im_bwd_launch(dcols.p, m->pq_w, m->out_dz, B, L, S, S, st); },
+                       3, 0.0, (double)B * S * S * (128.0 + 4.0 * L), "col2im + post_quant_conv backward (straight-through)"});
+      }
+    }
+    cur = &ops_fwd;
+  }
+#undef ops
   if (rc) return rc;
   if (need) *need = ar.peak;
   if (!dry) {
     B2E_REQUIRE(ar.peak <= ws_bytes, B2E_WORKSPACE_TOO_SMALL, "unet: workspace too small (%zu > %zu)", ar.peak, ws_bytes);
-    m->ops = std::move(ops);
+    m->ops = std::move(ops_fwd);
+    m->bops = std::move(ops_bwd);
+    m->fwd_B = -1;
     m->flops = flops;
     m->cur_B = B;
   } else {
@@ -764,6 +947,30 @@ int b2e_unet_forward(b2e_unet* m, const float* x, const int64_t* timesteps, floa
   m->in_x = x; m->in_t = timesteps; m->out_eps = eps;
   cudaStream_t st = (cudaStream_t)stream;
   for (auto& op : m->ops) {
+    int rc = op.fn(st);
+    if (rc) return rc;
+  }
+  m->fwd_B = B;
+  return B2E_OK;
+}
+
+int b2e_unet_enable_grad(b2e_unet* m, int enable) {
+  B2E_REQUIRE(m, B2E_INVALID_ARG, "unet_enable_grad: null handle");
+  B2E_REQUIRE(!enable || m->decoder, B2E_UNSUPPORTED_SHAPE, "unet_enable_grad: gradient mode is implemented for the VQ decoder");
+  if ((enable != 0) == m->grad) return B2E_OK;
+  m->grad = enable != 0;
+  m->cur_B = -1; m->fwd_B = -1; m->ws = nullptr; m->ws_bytes = 0;   // the workspace must be re-queried and re-bound
+  return build_program(m, (int)m->max_batch, nullptr, 0, &m->ws_need);
+}
+
+int b2e_vqdec_backward(b2e_unet* m, const float* d_image, float* d_latent, int64_t B, void* stream) {
+  B2E_REQUIRE(m && d_image && d_latent, B2E_INVALID_ARG, "vqdec_backward: null pointer");
+  B2E_REQUIRE(m->decoder && m->grad, B2E_INVALID_ARG, "vqdec_backward: call b2e_unet_enable_grad on a VQ decoder first");
+  B2E_REQUIRE(m->fwd_B == B && m->cur_B == B, B2E_INVALID_ARG,
+              "vqdec_backward: no live forward pass of batch %lld (last forward: %lld)", (long long)B, (long long)m->fwd_B);
+  m->in_dy = d_image; m->out_dz = d_latent;
+  cudaStream_t st = (cudaStream_t)stream;
+  for (auto& op : m->bops) {
     int rc = op.fn(st);
     if (rc) return rc;
   }

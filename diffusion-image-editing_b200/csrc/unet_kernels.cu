@@ -114,6 +114,8 @@ __global__ void __launch_bounds__(kGNThreads) gn_apply_kernel(GNArgs a, int pix_
     if (var < 0.0) var = 0.0;
     s_mean[tid] = (float)mean;
     s_rstd[tid] = (float)(1.0 / sqrt(var + (double)a.eps));
+    if (a.save_stats && blockIdx.x == 0)
+      *reinterpret_cast<float2*>(a.save_stats + ((int64_t)n * a.G + tid) * 2) = make_float2(s_mean[tid], s_rstd[tid]);
   }
   __syncthreads();
   const int s = tid % slots, pl = tid / slots;
@@ -192,6 +194,127 @@ int gn_launch(const GNArgs& a, cudaStream_t st) {
   if (ppb > a.HW) ppb = a.HW;
   launch_pdl(gn_apply_kernel, dim3(dim3((a.HW + ppb - 1) / ppb, a.N)), dim3(kGNThreads), 0, st, a, ppb);
   return check_launch("gn_apply");
+}
+
+// ------------------------------------------------------------------ GroupNorm (+SiLU) backward
+__device__ __forceinline__ float silu_grad(float y) {
+  const float sg = 1.f / (1.f + __expf(-y));
+  return sg * (1.f + y * (1.f - sg));
+}
+
+__global__ void __launch_bounds__(kGNThreads) gn_bwd_partial_kernel(GNBwdArgs a) {
+  pdl_wait();
+  __shared__ float s_a[2048], s_b[2048];
+  const int C = a.C, slots = C >> 3, ppi = kGNThreads / slots;
+  const int n = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
+  const int s = tid % slots, pl = tid / slots;
+  const int per = (a.HW + a.chunks - 1) / a.chunks;
+  const int p0 = chunk * per, p1 = min(a.HW, p0 + per);
+  const int cpg = C / a.G;
+  if (pl < ppi) {
+    float sa[8], sb[8], mean[8], rstd[8], gam[8], bet[8];
+    const int c = s * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sa[j] = sb[j] = 0.f;
+      const float2 st = *reinterpret_cast<const float2*>(a.stats + ((int64_t)n * a.G + (c + j) / cpg) * 2);
+      mean[j] = st.x; rstd[j] = st.y; gam[j] = __ldg(a.gamma + c + j); bet[j] = __ldg(a.beta + c + j);
+    }
+    const bf16* xs = a.x + (int64_t)n * a.HW * a.P + c;
+    const bf16* ds = a.da + (int64_t)n * a.HW * a.Pda + c;
+    for (int p = p0 + pl; p < p1; p += ppi) {
+      float xf[8], df[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(xs + (int64_t)p * a.P)), xf);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(ds + (int64_t)p * a.Pda)), df);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (xf[j] - mean[j]) * rstd[j];
+        float dy = df[j];
+        if (a.silu) dy *= silu_grad(fmaf(gam[j], xh, bet[j]));
+        const float dxh = dy * gam[j];
+        sa[j] += dxh; sb[j] += dxh * xh;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s_a[pl * C + c + j] = sa[j]; s_b[pl * C + c + j] = sb[j]; }
+  }
+  __syncthreads();
+  if (tid < a.G) {
+    float ta = 0.f, tb = 0.f;
+    for (int q = 0; q < ppi; ++q)
+      for (int c = tid * cpg; c < (tid + 1) * cpg; ++c) { ta += s_a[q * C + c]; tb += s_b[q * C + c]; }
+    float* o = a.partial + (((int64_t)n * a.chunks + chunk) * a.G + tid) * 2;
+    o[0] = ta; o[1] = tb;
+  }
+}
+
+__global__ void __launch_bounds__(kGNThreads) gn_bwd_apply_kernel(GNBwdArgs a, int pix_per_block) {
+  pdl_wait();
+  __shared__ float s_ma[64], s_mb[64];
+  const int C = a.C, slots = a.P >> 3, ppi = kGNThreads / slots;
+  const int n = blockIdx.y, tid = threadIdx.x;
+  const int cpg = C / a.G;
+  if (tid < a.G) {
+    double ta = 0.0, tb = 0.0;
+    for (int ch = 0; ch < a.chunks; ++ch) {
+      const float* o = a.partial + (((int64_t)n * a.chunks + ch) * a.G + tid) * 2;
+      ta += (double)o[0]; tb += (double)o[1];
+    }
+    const double cnt = (double)a.HW * cpg;
+    s_ma[tid] = (float)(ta / cnt); s_mb[tid] = (float)(tb / cnt);
+  }
+  __syncthreads();
+  const int s = tid % slots, pl = tid / slots;
+  if (pl >= ppi) return;
+  const int c = s * 8;
+  const int p0 = blockIdx.x * pix_per_block, p1 = min(a.HW, p0 + pix_per_block);
+  bf16* dst = a.dx + (int64_t)n * a.HW * a.P + c;
+  if (c >= C) {
+    for (int p = p0 + pl; p < p1; p += ppi) *reinterpret_cast<uint4*>(dst + (int64_t)p * a.P) = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  float mean[8], rstd[8], gam[8], bet[8], ma[8], mb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = (c + j) / cpg;
+    const float2 st = *reinterpret_cast<const float2*>(a.stats + ((int64_t)n * a.G + g) * 2);
+    mean[j] = st.x; rstd[j] = st.y; gam[j] = __ldg(a.gamma + c + j); bet[j] = __ldg(a.beta + c + j);
+    ma[j] = s_ma[g]; mb[j] = s_mb[g];
+  }
+  const bf16* xs = a.x + (int64_t)n * a.HW * a.P + c;
+  const bf16* ds = a.da + (int64_t)n * a.HW * a.Pda + c;
+  const bf16* as = a.add ? a.add + (int64_t)n * a.HW * a.P + c : nullptr;
+  for (int p = p0 + pl; p < p1; p += ppi) {
+    float xf[8], df[8], af[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(xs + (int64_t)p * a.P)), xf);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(ds + (int64_t)p * a.Pda)), df);
+    if (as) unpack8(__ldg(reinterpret_cast<const uint4*>(as + (int64_t)p * a.P)), af);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = (xf[j] - mean[j]) * rstd[j];
+      float dy = df[j];
+      if (a.silu) dy *= silu_grad(fmaf(gam[j], xh, bet[j]));
+      const float dxh = dy * gam[j];
+      float dx = rstd[j] * (dxh - ma[j] - xh * mb[j]);
+      if (as) dx += af[j];
+      xf[j] = dx;
+    }
+    *reinterpret_cast<uint4*>(dst + (int64_t)p * a.P) = pack8(xf);
+  }
+}
+
+int gn_bwd_launch(const GNBwdArgs& a, cudaStream_t st) {
+  B2E_REQUIRE(a.C % 8 == 0 && a.P >= a.C && a.Pda >= a.C && a.P % 8 == 0 && a.Pda % 8 == 0 && a.P <= 2048 && a.G <= 64 &&
+                  a.C % a.G == 0 && a.x && a.da && a.dx && a.stats && a.partial,
+              B2E_UNSUPPORTED_SHAPE, "groupnorm backward: unsupported channels %d (pitch %d) / groups %d", a.C, a.P, a.G);
+  launch_pdl(gn_bwd_partial_kernel, dim3(a.chunks, a.N), dim3(kGNThreads), 0, st, a);
+  int rc = check_launch("gn_bwd_partial");
+  if (rc) return rc;
+  const int slots = a.P / 8, ppi = kGNThreads / slots;
+  int ppb = ppi * 8;
+  if (ppb > a.HW) ppb = a.HW;
+  launch_pdl(gn_bwd_apply_kernel, dim3((a.HW + ppb - 1) / ppb, a.N), dim3(kGNThreads), 0, st, a, ppb);
+  return check_launch("gn_bwd_apply");
 }
 
 // block = 16 channels x 16 slot lanes: every thread sums a strided subset of the image's tile slots
@@ -512,6 +635,127 @@ int transpose_v_launch(const bf16* qkv, bf16* vt, int N, int T, int C, cudaStrea
   B2E_REQUIRE(T % 32 == 0 && C % 32 == 0, B2E_UNSUPPORTED_SHAPE, "transpose_v: T and C must be multiples of 32");
   launch_pdl(transpose_v_kernel, dim3(dim3(T / 32, C / 32, N)), dim3(dim3(32, 8)), 0, st, qkv, vt, T, C);
   return check_launch("transpose_v");
+}
+
+// ------------------------------------------------------------------ backward helpers of the decoder
+// gradient of the nearest x2 upsample: dx[n][h][w][c] = sum of the 2x2 block of dy (bf16 NHWC, 8 channels per thread)
+__global__ void __launch_bounds__(256) downsum2x_kernel(const uint4* __restrict__ dy, uint4* __restrict__ dx, int N, int H, int W,
+                                                        int C8) {
+  pdl_wait();
+  const int64_t total = (int64_t)N * H * W * C8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8);
+    int64_t p = i / C8;
+    const int w = (int)(p % W); p /= W;
+    const int h = (int)(p % H);
+    const int64_t n = p / H;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int dh = 0; dh < 2; ++dh)
+#pragma unroll
+      for (int dw = 0; dw < 2; ++dw) {
+        float f[8];
+        unpack8(__ldg(dy + ((n * 2 * H + 2 * h + dh) * 2 * W + 2 * w + dw) * C8 + c), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+      }
+    dx[i] = pack8(acc);
+  }
+}
+
+int downsum2x_launch(const bf16* dy, bf16* dx, int N, int H, int W, int C, cudaStream_t st) {
+  B2E_REQUIRE(C % 8 == 0, B2E_UNSUPPORTED_SHAPE, "downsum2x: C %% 8");
+  const int64_t total = (int64_t)N * H * W * (C / 8);
+  int grid = (int)((total + 255) / 256);
+  if (grid > kNumSMs * 32) grid = kNumSMs * 32;
+  launch_pdl(downsum2x_kernel, dim3(grid), dim3(256), 0, st, (const uint4*)dy, (uint4*)dx, N, H, W, C / 8);
+  return check_launch("downsum2x");
+}
+
+// batched 2-D transpose of a column window: dst[n][c][r] = src[n][r][col0 + c], r < R, c < Cc (both multiples of 32)
+__global__ void transpose_window_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int R, int Cc, int src_pitch,
+                                        int col0) {
+  pdl_wait();
+  __shared__ bf16 tile[32][33];
+  const int n = blockIdx.z, r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const bf16* s = src + (int64_t)n * R * src_pitch + col0;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) tile[i][threadIdx.x] = s[(int64_t)(r0 + i) * src_pitch + c0 + threadIdx.x];
+  __syncthreads();
+  bf16* d = dst + (int64_t)n * Cc * R;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) d[(int64_t)(c0 + i) * R + r0 + threadIdx.x] = tile[threadIdx.x][i];
+}
+
+int transpose_window_launch(const bf16* src, bf16* dst, int N, int R, int Cc, int src_pitch, int col0, cudaStream_t st) {
+  B2E_REQUIRE(R % 32 == 0 && Cc % 32 == 0, B2E_UNSUPPORTED_SHAPE, "transpose: R and C must be multiples of 32");
+  launch_pdl(transpose_window_kernel, dim3(R / 32, Cc / 32, N), dim3(32, 8), 0, st, src, dst, R, Cc, src_pitch, col0);
+  return check_launch("transpose_window");
+}
+
+// softmax backward, one warp per row, in place on dP:  dS = scale * P o (dP - sum_j dP_j P_j)
+__global__ void __launch_bounds__(256) softmax_bwd_rows_kernel(const bf16* __restrict__ p, bf16* __restrict__ dp, int64_t rows,
+                                                               int T, float scale) {
+  pdl_wait();
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const uint4* pr = reinterpret_cast<const uint4*>(p + row * T);
+  uint4* dr = reinterpret_cast<uint4*>(dp + row * T);
+  const int chunks = T >> 3;
+  float dot = 0.f;
+  for (int i = lane; i < chunks; i += 32) {
+    float a[8], b[8];
+    unpack8(__ldg(pr + i), a);
+    unpack8(dr[i], b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dot += a[j] * b[j];
+  }
+  dot = warp_sum(dot);
+  for (int i = lane; i < chunks; i += 32) {
+    float a[8], b[8];
+    unpack8(__ldg(pr + i), a);
+    unpack8(dr[i], b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b[j] = scale * a[j] * (b[j] - dot);
+    dr[i] = pack8(b);
+  }
+}
+
+int softmax_bwd_rows_launch(const bf16* p, bf16* dp, int64_t rows, int T, float scale, cudaStream_t st) {
+  B2E_REQUIRE(T % 8 == 0, B2E_UNSUPPORTED_SHAPE, "softmax backward: T %% 8");
+  launch_pdl(softmax_bwd_rows_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, st, p, dp, rows, T, scale);
+  return check_launch("softmax_bwd_rows");
+}
+
+// backward of (nearest code [straight-through] -> post_quant_conv -> im2col): dcols bf16 [B][H][W][64] holds the gradient
+// w.r.t. im2col column t*L + c of every pixel; dz[b][k][h][w] = sum_c pq_w[c][k] * sum_t dcols[(h,w) - tap_t][t*L + c]
+__global__ void __launch_bounds__(256) vq_col2im_bwd_kernel(const bf16* __restrict__ dcols, const float* __restrict__ pq_w,
+                                                            float* __restrict__ dz, int B, int L, int H, int W) {
+  pdl_wait();
+  const int64_t total = (int64_t)B * H * W;
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= total) return;
+  const int HW = H * W;
+  const int b = (int)(p / HW), q = (int)(p % HW), h = q / W, w = q % W;
+  float g[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int t = 0; t < 9; ++t) {
+    // forward: cols[(hh, ww)][t*L + c] = x[c][hh + t/3 - 1][ww + t%3 - 1]  ->  (hh, ww) = (h, w) - tap
+    const int hh = h - (t / 3 - 1), ww = w - (t % 3 - 1);
+    if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+    const bf16* src = dcols + (((int64_t)b * H + hh) * W + ww) * 64 + t * L;
+    for (int c = 0; c < L; ++c) g[c] += __bfloat162float(src[c]);
+  }
+  for (int k = 0; k < L; ++k) {
+    float acc = 0.f;
+    for (int c = 0; c < L; ++c) acc += pq_w[c * L + k] * g[c];
+    dz[((int64_t)b * L + k) * HW + q] = acc;
+  }
+}
+
+int vq_col2im_bwd_launch(const bf16* dcols, const float* pq_w, float* dz, int B, int L, int H, int W, cudaStream_t st) {
+  B2E_REQUIRE(L >= 1 && L <= 4 && 9 * L <= 64, B2E_UNSUPPORTED_SHAPE, "vq_col2im_bwd: latent channels %d", L);
+  const int64_t total = (int64_t)B * H * W;
+  launch_pdl(vq_col2im_bwd_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, dcols, pq_w, dz, B, L, H, W);
+  return check_launch("vq_col2im_bwd");
 }
 
 // ------------------------------------------------------------------ VQ front of the decoder

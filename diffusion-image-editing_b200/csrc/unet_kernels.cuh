@@ -23,7 +23,27 @@ struct GNArgs {
   int chunks;
   bf16* out;       // [N][HW][Pout]
   int silu;
+  float* save_stats = nullptr;   // optional [N][G][2] (mean, rstd) for the backward pass
 };
+
+// Backward of y = GroupNorm(x) (optionally followed by SiLU), single source.  dx = d(loss)/dx (+ add):
+//   xh = (x - mean) * rstd ; y = gamma * xh + beta ; dy = da * silu'(y) (or da) ; dxh = dy * gamma
+//   dx = rstd * (dxh - mean_g(dxh) - xh * mean_g(dxh * xh))
+// Two launches: per-(image, chunk, group) partial sums of (dxh, dxh * xh), then the apply pass.
+struct GNBwdArgs {
+  const bf16* x;      // forward input, [N][HW][P] (C real channels)
+  const bf16* da;     // gradient w.r.t. the forward output, [N][HW][Pda]
+  const bf16* add;    // optional tensor added to dx (residual branch), [N][HW][P]
+  bf16* dx;           // [N][HW][P] (tail channels zeroed)
+  int C, P, Pda;
+  int N, HW, G;
+  const float* gamma; const float* beta;
+  const float* stats; // [N][G][2] (mean, rstd) saved by the forward
+  float* partial;     // [N][chunks][G][2]
+  int chunks;
+  int silu;
+};
+int gn_bwd_launch(const GNBwdArgs& a, cudaStream_t st);
 int gn_chunks(int HW, int C);
 int gn_launch(const GNArgs& a, cudaStream_t st);
 // tile statistics written by the conv epilogue -> per-(image, channel) sums
@@ -53,6 +73,12 @@ int temb_launch(const TembArgs& a, cudaStream_t st);
 // logits scaled by `scale`) and V^T extraction qkv[N][T][3C] (v = columns [2C,3C)) -> vt[N][C][T]
 int softmax_rows_launch(bf16* s, int64_t rows, int T, float scale, cudaStream_t st);
 int transpose_v_launch(const bf16* qkv, bf16* vt, int N, int T, int C, cudaStream_t st);
+
+// backward helpers of the decoder (bf16 NHWC gradients)
+int downsum2x_launch(const bf16* dy, bf16* dx, int N, int H, int W, int C, cudaStream_t st);
+int transpose_window_launch(const bf16* src, bf16* dst, int N, int R, int Cc, int src_pitch, int col0, cudaStream_t st);
+int softmax_bwd_rows_launch(const bf16* p, bf16* dp, int64_t rows, int T, float scale, cudaStream_t st);
+int vq_col2im_bwd_launch(const bf16* dcols, const float* pq_w, float* dz, int B, int L, int H, int W, cudaStream_t st);
 
 // VQModel.decode front: nearest codebook entry + 1x1 post_quant_conv; z, out fp32 NCHW (B, L <= 4, HW)
 int vq_quantize_launch(const float* z, const float* codebook, int n_codes, const float* pq_w, const float* pq_b, float* out,

@@ -258,6 +258,14 @@ typedef struct {
   int32_t num_vq_embeddings;
 } b2e_vqdec_config;
 int b2e_vqdec_create(const b2e_vqdec_config* cfg, int64_t max_batch, b2e_unet** out);
+/* Gradient through the decoder (AttrFunc.apply with decode inside the graph, src/attr_functions.py:147-158):
+ * b2e_unet_enable_grad(m, 1) switches the handle to gradient mode (every activation of a forward pass stays in the
+ * workspace: re-query b2e_unet_workspace_bytes and re-bind); after b2e_unet_forward(m, latent, NULL, image, B, s),
+ * b2e_vqdec_backward(m, d_image, d_latent, B, s) returns d(loss)/d(latent) (B, latent_channels, S, S) fp32 for
+ * d(loss)/d(image) (B, out_channels, S_out, S_out) fp32.  The quantiser is straight-through (identity gradient), every
+ * convolution gradient runs on the same tcgen05 kernel with flipped / transposed weights, bf16 gradients. */
+int b2e_unet_enable_grad(b2e_unet* m, int enable);
+int b2e_vqdec_backward(b2e_unet* m, const float* d_image, float* d_latent, int64_t B, void* stream);
 
 /* Test hook for the implicit-GEMM convolution: x (N,H,W,Cin) bf16 NHWC, w (Cout,Cin,k,k) fp32,
  * bias fp32 [Cout] or NULL, residual (N,Ho,Wo,Cout) bf16 NHWC or NULL (added through the fused
