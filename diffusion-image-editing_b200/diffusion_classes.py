@@ -39,6 +39,7 @@ class LDM(Diffusion):
         if no_grad:
             with torch.no_grad():
                 return self.vqvae.decode(latent).sample
+        # guidance graph: a native VQModel in gradient mode is itself an autograd node (native dgrad)
         vq = self.vqvae
         if getattr(vq, "forward_only", False):
             if self.guidance_vqvae is None:

@@ -23,7 +23,8 @@ class NativePipeline(SimpleNamespace):
 
 def create_diffusion_model(name: str, sample_clipping: bool = True, *, max_batch: int = 8, seed: int = 0,
                            state_dict: Optional[dict] = None, unet_config: Optional[dict] = None, vqvae=None,
-                           vq_config: Optional[dict] = None, vq_state_dict: Optional[dict] = None, guidance_module=None):
+                           vq_config: Optional[dict] = None, vq_state_dict: Optional[dict] = None, guidance_module=None,
+                           decoder_grad: bool = True):
     """``name``: "ddpm" (google/ddpm-celebahq-256 layout) or "ldm" (CompVis/ldm-celebahq-256 layout: native UNet on
     the 64x64x3 latent + native forward-only VQ decoder; ``vqvae=`` substitutes the caller's VQ autoencoder module
     (encode().latents / decode().sample, as in the reference's pipeline object); ``guidance_module=`` is the
@@ -47,13 +48,15 @@ def create_diffusion_model(name: str, sample_clipping: bool = True, *, max_batch
             unet.init_random(seed)
         guidance_vqvae = None
         if vqvae is None:
-            # native forward-only decoder (post-loop decoding of the sample and of the x0 history); guidance
-            # through the decoder additionally needs a differentiable module (guidance_vqvae=)
+            # native decoder: forward for the post-loop decoding of the sample / x0 history and, with
+            # decoder_grad=True (default), the native dgrad for guidance THROUGH the decoder
             vqvae = VQModel(**(vq_config or LDM_VQ_CONFIG), max_batch=max_batch, device=device)
             if vq_state_dict is not None:
                 vqvae.load_state_dict(vq_state_dict)
             else:
                 vqvae.init_random(seed + 1)
+            if decoder_grad:
+                vqvae.enable_grad()
         elif isinstance(vqvae, torch.nn.Module) or not getattr(vqvae, "forward_only", False):
             guidance_vqvae = vqvae
         scheduler = DDIMScheduler.from_preset("ldm")

@@ -90,7 +90,7 @@ def test_ldm_factory_native_unet_and_decoder():
     oracle = OracleVQ(**SMALL).eval()
     oracle.quantize.embedding.weight.data.uniform_(-2.0, 2.0)
     w = create_diffusion_model("ldm", sample_clipping=False, max_batch=2, seed=3, unet_config=ucfg, vq_config=SMALL,
-                               vq_state_dict=oracle.state_dict())
+                               vq_state_dict=oracle.state_dict(), decoder_grad=False)
     w.scheduler.set_timesteps(4)
     pipe = SegDiffEditPipeline(w, None)
     xt = torch.randn(2, 3, 16, 16, generator=torch.Generator().manual_seed(2)).cuda()
@@ -169,3 +169,52 @@ def test_small_vq_decoder_gradient_matches_autograd(B):
 
 def test_ldm_vq_decoder_gradient_matches_autograd():
     _check_grad(*_grad_pair(LDM_VQ_CONFIG, 1, seed=31), "ldm-celebahq vq decoder gradient")
+
+
+def test_ldm_masked_guidance_through_native_decoder():
+    """BASELINE config 3 on the engine end to end: native LDM-layout UNet, native VQ decoder forward AND gradient inside
+    the guidance graph (colour loss on the decoded image, gradient masked in latent space).  The recorded noise
+    predictions are replayed through the oracle loop with torch autograd through the fp32 oracle decoder."""
+    from attr_functions import SingleColorAttrFunc
+    from models import create_diffusion_model
+    from oracle import loops, step_math as sm
+    from oracle.ddim_scheduler import DDIMScheduler as OracleScheduler
+    from SegDiffEditPipeline import SegDiffEditPipeline
+    ucfg = dict(sample_size=16, in_channels=3, out_channels=3, block_out_channels=(32, 96), layers_per_block=1,
+                down_block_types=("DownBlock2D", "AttnDownBlock2D"), up_block_types=("AttnUpBlock2D", "UpBlock2D"),
+                attention_head_dim=32, flip_sin_to_cos=True, freq_shift=0, downsample_padding=1)
+    vcfg = dict(SMALL, block_out_channels=(64, 128), sample_size=16)
+    torch.manual_seed(11)
+    oracle = OracleVQ(**vcfg).eval()
+    oracle.quantize.embedding.weight.data.uniform_(-2.0, 2.0)
+    w = create_diffusion_model("ldm", sample_clipping=False, max_batch=1, seed=3, unet_config=ucfg, vq_config=vcfg,
+                               vq_state_dict=oracle.state_dict())
+    T = 5
+    w.scheduler.set_timesteps(T)
+    pipe = SegDiffEditPipeline(w, None)
+    gen = torch.Generator().manual_seed(5)
+    xt = torch.randn(1, 3, 16, 16, generator=gen)
+    mask = (torch.rand(1, 3, 16, 16, generator=gen) > 0.4).float()
+    scale = 200.0
+    f = SingleColorAttrFunc(target=0.8, color_idx=0, loss_scale=scale, t1=0, t2=T, use_mask=True, mask_attr_grad=True)
+    out = pipe.edit_image(xt=xt.cuda(), attr_func=f, prog_bar=False, output_type="tensor", mask=mask.cuda())
+    assert torch.isfinite(out.imgs).all()
+    # oracle: same eps (teacher-forced), guidance by autograd through the fp32 oracle decoder
+    rep = iter([e.cpu() for e in out.model_outputs])
+    s = OracleScheduler.from_preset("ldm", clip_sample=False)
+    s.set_timesteps(T)
+    updates = []
+
+    def guidance(x_post, eps, c, step_idx):
+        loss = lambda z: sm.single_color_loss(oracle.decode(z).sample, 0, 0.8)   # noqa: E731
+        new, g = sm.autograd_guidance_update(x_post, eps, c, loss, scale, mask=mask, mask_grad=True)
+        updates.append((new - x_post).abs().max().item())
+        return new
+
+    xf, _, _ = loops.guided_edit_loop(s, lambda x, t: next(rep), xt, eta=0.0, zs=None, guidance=guidance)
+    assert max(updates) > 1e-3          # the guidance actually moved the latent
+    with torch.no_grad():
+        ref = oracle.decode(xf).sample
+    rel = ((out.imgs.cpu() - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
+    print(f"config-3 small: decoded image rel-rms vs oracle {rel:.3e}, largest guidance update {max(updates):.3e}")
+    assert rel <= 3e-2
