@@ -142,3 +142,20 @@ class VQModel(UNet2DModel):
         names = {0: "conv_igemm", 1: "groupnorm", 2: "attention", 3: "other"}
         return [dict(kind=names[kd[i]], ms=ms[i], flops=fl[i], bytes=by[i],
                      desc=lib.b2e_unet_op_desc(self._h, i).decode()) for i in range(n.value)]
+
+
+# CompVis/stable-diffusion-v1-x `vae` decode path: 64x64x4 latent -> 512x512x3 image (x8), no quantiser
+SD_VAE_CONFIG = dict(latent_channels=4, out_channels=3, block_out_channels=(128, 256, 512, 512), layers_per_block=2,
+                     norm_num_groups=32, norm_eps=1e-6, sample_size=64)
+
+
+class AutoencoderKL(VQModel):
+    """Native decode path of ``diffusers.AutoencoderKL`` (``vae.decode(latent / 0.18215).sample``,
+    src/diffusion_classes.py:93-99): post_quant_conv -> decoder, same engine as the VQ decoder without the quantiser.
+    State-dict names as in diffusers (``post_quant_conv.*``, ``decoder.*``)."""
+
+    def __init__(self, latent_channels=4, out_channels=3, block_out_channels=(128, 256, 512, 512), layers_per_block=2,
+                 norm_num_groups=32, norm_eps=1e-6, sample_size=64, max_batch=8, device="cuda"):
+        super().__init__(latent_channels=latent_channels, out_channels=out_channels, block_out_channels=block_out_channels,
+                         layers_per_block=layers_per_block, norm_num_groups=norm_num_groups, norm_eps=norm_eps,
+                         num_vq_embeddings=0, sample_size=sample_size, max_batch=max_batch, device=device)

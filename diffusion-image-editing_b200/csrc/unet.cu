@@ -243,10 +243,11 @@ int build_model_decoder(b2e_unet* m) {
   const b2e_unet_config& c = m->cfg;
   const int nb = c.n_blocks, L = c.in_channels;
   const int top = c.block_out_channels[nb - 1];
-  m->codebook = m->dmalloc<float>((size_t)m->n_codes * L);
+  m->codebook = m->dmalloc<float>((size_t)(m->n_codes > 0 ? m->n_codes : 1) * L);
   m->pq_w = m->dmalloc<float>((size_t)L * L);
   m->pq_b = m->dmalloc<float>(L);
-  m->add_f32("quantize.embedding.weight", m->codebook, (int64_t)m->n_codes * L, -m->n_codes);   // U(-1/n, 1/n)
+  if (m->n_codes > 0)   // num_vq_embeddings == 0: AutoencoderKL decode path (no quantiser)
+    m->add_f32("quantize.embedding.weight", m->codebook, (int64_t)m->n_codes * L, -m->n_codes);   // U(-1/n, 1/n)
   m->add_f32("post_quant_conv.weight", m->pq_w, (int64_t)L * L, L);
   m->add_f32("post_quant_conv.bias", m->pq_b, L, L);
   m->in_im2col = true;
@@ -877,7 +878,7 @@ int b2e_vqdec_create(const b2e_vqdec_config* cfg, int64_t max_batch, b2e_unet** 
   B2E_REQUIRE(cfg->n_blocks >= 1 && cfg->n_blocks <= 8, B2E_UNSUPPORTED_SHAPE, "vqdec_create: n_blocks");
   B2E_REQUIRE((cfg->latent_channels == 1 || cfg->latent_channels == 3 || cfg->latent_channels == 4) && cfg->out_channels <= 16,
               B2E_UNSUPPORTED_SHAPE, "vqdec_create: latent_channels must be 1, 3 or 4 and out_channels <= 16");
-  B2E_REQUIRE(cfg->num_vq_embeddings >= 1, B2E_INVALID_ARG, "vqdec_create: num_vq_embeddings");
+  B2E_REQUIRE(cfg->num_vq_embeddings >= 0, B2E_INVALID_ARG, "vqdec_create: num_vq_embeddings");
   for (int i = 0; i < cfg->n_blocks; ++i) {
     const int ch = cfg->block_out_channels[i];
     B2E_REQUIRE(ch % 8 == 0 && ch >= 32 && ch <= 1024 && ch % cfg->norm_num_groups == 0, B2E_UNSUPPORTED_SHAPE,

@@ -797,7 +797,8 @@ vq_quantize_kernel(const float* __restrict__ z, const float* __restrict__ codebo
   }
   if (!live) return;
   float e[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int c = 0; c < L; ++c) e[c] = codebook[(int64_t)best_i * L + c];
+  // n_codes == 0: no quantiser (AutoencoderKL.decode: post_quant_conv only)
+  for (int c = 0; c < L; ++c) e[c] = n_codes > 0 ? codebook[(int64_t)best_i * L + c] : zv[c];
   for (int c = 0; c < L; ++c) {
     float acc = 0.f;
     for (int k = 0; k < L; ++k) acc += pq_w[c * L + k] * e[k];
@@ -807,7 +808,7 @@ vq_quantize_kernel(const float* __restrict__ z, const float* __restrict__ codebo
 
 int vq_quantize_launch(const float* z, const float* codebook, int n_codes, const float* pq_w, const float* pq_b, float* out,
                        int B, int L, int HW, cudaStream_t st) {
-  B2E_REQUIRE(L >= 1 && L <= 4 && n_codes >= 1, B2E_UNSUPPORTED_SHAPE, "vq_quantize: latent channels %d", L);
+  B2E_REQUIRE(L >= 1 && L <= 4 && n_codes >= 0, B2E_UNSUPPORTED_SHAPE, "vq_quantize: latent channels %d", L);
   const int64_t total = (int64_t)B * HW;
   launch_pdl(vq_quantize_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, z, codebook, n_codes, pq_w, pq_b,
              out, B, L, HW);

@@ -255,7 +255,7 @@ typedef struct {
   int32_t layers_per_block;
   int32_t norm_num_groups;
   float norm_eps;
-  int32_t num_vq_embeddings;
+  int32_t num_vq_embeddings; /* 0: no quantiser = AutoencoderKL.decode (post_quant_conv -> decoder), SD.decode */
 } b2e_vqdec_config;
 int b2e_vqdec_create(const b2e_vqdec_config* cfg, int64_t max_batch, b2e_unet** out);
 /* Gradient through the decoder (AttrFunc.apply with decode inside the graph, src/attr_functions.py:147-158):

@@ -118,11 +118,17 @@ class VQModel(nn.Module):
                                       block_out_channels=tuple(block_out_channels), layers_per_block=layers_per_block,
                                       norm_num_groups=norm_num_groups, norm_eps=norm_eps,
                                       num_vq_embeddings=num_vq_embeddings, sample_size=sample_size)
-        self.quantize = VectorQuantizer(num_vq_embeddings, latent_channels)
+        # num_vq_embeddings == 0: AutoencoderKL decode path (post_quant_conv -> decoder, no quantiser)
+        self.quantize = VectorQuantizer(num_vq_embeddings, latent_channels) if num_vq_embeddings > 0 else None
         self.post_quant_conv = nn.Conv2d(latent_channels, latent_channels, 1)
         self.decoder = Decoder(latent_channels, out_channels, block_out_channels, layers_per_block, norm_num_groups,
                                norm_eps)
 
     def decode(self, h, force_not_quantize=False):
-        quant = h if force_not_quantize else self.quantize(h)
+        quant = h if (force_not_quantize or self.quantize is None) else self.quantize(h)
         return SimpleNamespace(sample=self.decoder(self.post_quant_conv(quant)))
+
+
+# CompVis/stable-diffusion-v1-x vae decode path (no quantiser): 64x64x4 -> 512x512x3
+SD_VAE_CONFIG = dict(latent_channels=4, out_channels=3, block_out_channels=(128, 256, 512, 512), layers_per_block=2,
+                     norm_num_groups=32, norm_eps=1e-6, num_vq_embeddings=0, sample_size=64)

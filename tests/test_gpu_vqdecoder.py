@@ -218,3 +218,29 @@ def test_ldm_masked_guidance_through_native_decoder():
     rel = ((out.imgs.cpu() - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
     print(f"config-3 small: decoded image rel-rms vs oracle {rel:.3e}, largest guidance update {max(updates):.3e}")
     assert rel <= 3e-2
+
+
+def test_autoencoder_kl_decode_and_gradient():
+    """SD.decode path (AutoencoderKL: no quantiser, 4 latent channels, 3 upsamplings) in small: forward + gradient."""
+    from b200edit.vqmodel import AutoencoderKL
+    cfg = dict(latent_channels=4, out_channels=3, block_out_channels=(64, 64, 128), layers_per_block=1,
+               norm_num_groups=32, norm_eps=1e-6, sample_size=16)
+    torch.manual_seed(41)
+    oracle = OracleVQ(**cfg, num_vq_embeddings=0).eval()
+    native = AutoencoderKL(**cfg, max_batch=2)
+    assert "quantize.embedding.weight" not in {n for n, _, _ in native.param_info()}
+    native.load_state_dict(oracle.state_dict())
+    native.enable_grad()
+    z = torch.randn(2, 4, 16, 16, generator=torch.Generator().manual_seed(42))
+    wgt = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(43)).cuda()
+    zn = (z.cuda() / 0.18215 * 0.18215).requires_grad_(True)
+    img = native.decode(zn).sample
+    (gn,) = torch.autograd.grad((img * wgt).mean() + (img ** 2).mean(), zn)
+    oc = oracle.cuda()
+    zo = z.cuda().requires_grad_(True)
+    ref = oc.decode(zo).sample
+    (go,) = torch.autograd.grad((ref * wgt).mean() + (ref ** 2).mean(), zo)
+    rel = ((img - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
+    relg = ((gn - go).pow(2).mean().sqrt() / go.pow(2).mean().sqrt()).item()
+    print(f"autoencoder-kl small: image rel-rms {rel:.3e}, gradient rel-rms {relg:.3e}")
+    assert img.shape == (2, 3, 64, 64) and rel <= 2.5e-2 and relg <= 4e-2
