@@ -34,7 +34,8 @@ class UNetConfig(C.Structure):
                 ("down_attn", C.c_int32 * 8), ("up_attn", C.c_int32 * 8),
                 ("layers_per_block", C.c_int32), ("norm_num_groups", C.c_int32),
                 ("norm_eps", C.c_float), ("attention_head_dim", C.c_int32),
-                ("flip_sin_to_cos", C.c_int32), ("freq_shift", C.c_float), ("downsample_padding", C.c_int32)]
+                ("flip_sin_to_cos", C.c_int32), ("freq_shift", C.c_float), ("downsample_padding", C.c_int32),
+                ("cross_attention_dim", C.c_int32), ("num_attention_heads", C.c_int32)]
 
 
 class VQDecConfig(C.Structure):
@@ -87,6 +88,7 @@ PROTOTYPES = {
     "b2e_unet_workspace_bytes": (_SZ, [_P]),
     "b2e_unet_bind_workspace": (_I, [_P, _P, _SZ]),
     "b2e_unet_forward": (_I, [_P, _P, _P, _P, _I64, _P]),
+    "b2e_unet_forward_cond": (_I, [_P, _P, _P, _P, _I64, _P, _I64, _P]),
     "b2e_unet_flops": (C.c_double, [_P, _I64]),
     "b2e_unet_launches_per_forward": (_I, [_P]),
     "b2e_unet_op_desc": (C.c_char_p, [_P, _I]),

@@ -40,7 +40,17 @@ struct AttnL { std::string name; int C = 0, P = 0; NormL gn; ConvL qkv, proj; in
 // attention core need the real count.
 inline int pad64(int c) { return (c + 63) / 64 * 64; }
 
-enum NodeKind { N_RESNET, N_ATTN, N_DOWN, N_UP, N_PUSH, N_POPCAT };
+// Transformer2DModel of the SD UNet2DConditionModel: GroupNorm -> 1x1 proj_in -> BasicTransformerBlock (LayerNorm +
+// self-attention, LayerNorm + cross-attention over the text tokens, LayerNorm + GEGLU feed-forward, each with its
+// residual fused into the output projection's K segment) -> 1x1 proj_out + block input
+struct LNL { float* g = nullptr; float* b = nullptr; int C = 0; };
+struct XfL {
+  std::string name; int C = 0, heads = 0, d = 0, dpad = 0;
+  NormL gn; LNL ln1, ln2, ln3;
+  ConvL proj_in, qkv1, out1, q2, kv2, out2, ff1, ff2, proj_out;
+};
+
+enum NodeKind { N_RESNET, N_ATTN, N_DOWN, N_UP, N_PUSH, N_POPCAT, N_XFORMER };
 struct Node { NodeKind kind; int idx; };
 
 struct Tensor {
@@ -100,6 +110,8 @@ struct b2e_unet {
   float *te_w1 = nullptr, *te_b1 = nullptr, *te_w2 = nullptr, *te_b2 = nullptr, *tp_w = nullptr, *tp_b = nullptr;
   std::vector<ResnetL> resnets;
   std::vector<AttnL> attns;
+  std::vector<XfL> xfs;
+  const float* in_ctx = nullptr; int ctx_len = 0;   // per call: text conditioning (B, ctx_len, cross_attention_dim) fp32
   std::vector<ConvL> downs, ups;
   std::vector<Node> nodes;
   // program
@@ -202,6 +214,64 @@ struct b2e_unet {
     }
     resnets.push_back(r);
     return (int)resnets.size() - 1;
+  }
+  LNL make_ln(const std::string& name, int C) {
+    LNL n; n.C = C; n.g = dmalloc<float>(C); n.b = dmalloc<float>(C);
+    add_f32(name + ".weight", n.g, C);
+    add_f32(name + ".bias", n.b, C);
+    return n;
+  }
+  // token-wise linear layer = 1x1 convolution over NHWC pixels; res_c > 0 appends an identity residual segment
+  ConvL make_linear(const std::string& name, int cin, int cout, bool bias, int res_c = 0) {
+    ConvL c;
+    c.cin = cin; c.cin_pad = pad64(cin); c.cout = cout; c.k = 1; c.cout_pad = conv_cout_pad(cout);
+    c.res_c = res_c; c.row_len = c.cin_pad + res_c;
+    c.w = dmalloc<bf16>((size_t)c.cout_pad * c.row_len);
+    c.b = dmalloc<float>(c.cout_pad);
+    ConvL cc = c;
+    add_param(name + ".weight", (int64_t)cout * cin, cin, [cc](const float* src, cudaStream_t st) {
+      return conv_pack_weight(src, cc.w, cc.cout, cc.cin, 1, cc.cin_pad, cc.row_len, 0, st);
+    });
+    if (bias) add_f32(name + ".bias", c.b, cout, cin);
+    if (res_c && c.w && conv_fill_identity(c.w, cout, c.row_len, c.cin_pad, 0)) build_error = B2E_CUDA_ERROR;
+    return c;
+  }
+  // several bias-free projections of the same input fused into one GEMM: rows [i*cout, (i+1)*cout) = names[i]
+  ConvL make_fused_linear(const std::string& base, const std::vector<std::string>& names, int cin, int cout) {
+    ConvL c;
+    const int n = (int)names.size();
+    c.cin = cin; c.cin_pad = pad64(cin); c.cout = n * cout; c.k = 1; c.cout_pad = conv_cout_pad(n * cout);
+    c.row_len = c.cin_pad;
+    c.w = dmalloc<bf16>((size_t)c.cout_pad * c.row_len);
+    c.b = dmalloc<float>(c.cout_pad);
+    for (int i = 0; i < n; ++i) {
+      bf16* wdst = c.w + (size_t)i * cout * c.row_len;
+      const int rl = c.row_len, cp = c.cin_pad;
+      add_param(base + "." + names[i] + ".weight", (int64_t)cout * cin, cin, [wdst, cout, cin, rl, cp](const float* src, cudaStream_t st) {
+        return conv_pack_weight(src, wdst, cout, cin, 1, cp, rl, 0, st);
+      });
+    }
+    return c;
+  }
+  int make_xformer(const std::string& name, int C, int heads, int ctx_dim) {
+    XfL x;
+    x.name = name; x.C = C; x.heads = heads; x.d = C / heads; x.dpad = pad64(x.d);
+    x.gn = make_norm(name + ".norm", C);
+    x.proj_in = make_linear(name + ".proj_in", C, C, true);
+    const std::string tb = name + ".transformer_blocks.0";
+    x.ln1 = make_ln(tb + ".norm1", C);
+    x.ln2 = make_ln(tb + ".norm2", C);
+    x.ln3 = make_ln(tb + ".norm3", C);
+    x.qkv1 = make_fused_linear(tb + ".attn1", {"to_q", "to_k", "to_v"}, C, C);
+    x.out1 = make_linear(tb + ".attn1.to_out.0", C, C, true, C);
+    x.q2 = make_linear(tb + ".attn2.to_q", C, C, false);
+    x.kv2 = make_fused_linear(tb + ".attn2", {"to_k", "to_v"}, ctx_dim, C);
+    x.out2 = make_linear(tb + ".attn2.to_out.0", C, C, true, C);
+    x.ff1 = make_linear(tb + ".ff.net.0.proj", C, 8 * C, true);
+    x.ff2 = make_linear(tb + ".ff.net.2", 4 * C, C, true, C);
+    x.proj_out = make_linear(name + ".proj_out", C, C, true, C);
+    xfs.push_back(x);
+    return (int)xfs.size() - 1;
   }
   int make_attn(const std::string& name, int C) {
     AttnL a;
@@ -329,7 +399,12 @@ int build_model(b2e_unet* m) {
       const std::string base = "down_blocks." + std::to_string(i);
       m->nodes.push_back({N_RESNET, m->make_resnet(base + ".resnets." + std::to_string(j), ch, 0, cout)});
       ch = cout;
-      if (c.down_attn[i]) m->nodes.push_back({N_ATTN, m->make_attn(base + ".attentions." + std::to_string(j), ch)});
+      if (c.down_attn[i]) {
+        if (c.cross_attention_dim > 0)
+          m->nodes.push_back({N_XFORMER, m->make_xformer(base + ".attentions." + std::to_string(j), ch, c.num_attention_heads, c.cross_attention_dim)});
+        else
+          m->nodes.push_back({N_ATTN, m->make_attn(base + ".attentions." + std::to_string(j), ch)});
+      }
       m->nodes.push_back({N_PUSH, 0});
       stack.push_back(ch);
     }
@@ -341,7 +416,10 @@ int build_model(b2e_unet* m) {
     }
   }
   m->nodes.push_back({N_RESNET, m->make_resnet("mid_block.resnets.0", ch, 0, ch)});
-  m->nodes.push_back({N_ATTN, m->make_attn("mid_block.attentions.0", ch)});
+  if (c.cross_attention_dim > 0)
+    m->nodes.push_back({N_XFORMER, m->make_xformer("mid_block.attentions.0", ch, c.num_attention_heads, c.cross_attention_dim)});
+  else
+    m->nodes.push_back({N_ATTN, m->make_attn("mid_block.attentions.0", ch)});
   m->nodes.push_back({N_RESNET, m->make_resnet("mid_block.resnets.1", ch, 0, ch)});
   for (int i = 0; i < nb; ++i) {
     const int cout = c.block_out_channels[nb - 1 - i];
@@ -352,7 +430,12 @@ int build_model(b2e_unet* m) {
       m->nodes.push_back({N_POPCAT, 0});
       m->nodes.push_back({N_RESNET, m->make_resnet(base + ".resnets." + std::to_string(j), ch, skip, cout)});
       ch = cout;
-      if (c.up_attn[i]) m->nodes.push_back({N_ATTN, m->make_attn(base + ".attentions." + std::to_string(j), ch)});
+      if (c.up_attn[i]) {
+        if (c.cross_attention_dim > 0)
+          m->nodes.push_back({N_XFORMER, m->make_xformer(base + ".attentions." + std::to_string(j), ch, c.num_attention_heads, c.cross_attention_dim)});
+        else
+          m->nodes.push_back({N_ATTN, m->make_attn(base + ".attentions." + std::to_string(j), ch)});
+      }
     }
     if (i != nb - 1) {
       m->ups.push_back(m->make_conv(base + ".upsamplers.0.conv", ch, ch, 3));
@@ -478,7 +561,8 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
       ar.release(tstats, tstats_bytes);   // dead after the finalize kernel (stream order)
     }
   };
-  auto gnorm = [&](const NormL& L, Tensor x0, const Tensor* x1, int silu, Tensor* out, float** stats_out = nullptr) {
+  auto gnorm = [&](const NormL& L, Tensor x0, const Tensor* x1, int silu, Tensor* out, float** stats_out = nullptr,
+                   float eps_override = -1.f) {
     if (rc) return;
     const int C = x0.Cr + (x1 ? x1->Cr : 0);   // real channels, written compactly; pitch rounded up to 64
     *out = talloc(B, x0.H, x0.W, pad64(C), C);
@@ -489,7 +573,7 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
     a.save_stats = sv;
     a.x0 = x0.p; a.x1 = x1 ? x1->p : nullptr; a.C0 = x0.Cr; a.C1 = x1 ? x1->Cr : 0;
     a.P0 = x0.C; a.P1 = x1 ? x1->C : 0; a.Pout = out->C;
-    a.N = B; a.HW = x0.H * x0.W; a.G = G; a.eps = c.norm_eps; a.gamma = L.g; a.beta = L.b;
+    a.N = B; a.HW = x0.H * x0.W; a.G = G; a.eps = eps_override > 0.f ? eps_override : c.norm_eps; a.gamma = L.g; a.beta = L.b;
     a.partial = gn_part; a.chunks = gn_chunks(a.HW, C); a.out = out->p; a.silu = silu;
     bool fused = x0.cstats && (!x1 || x1->cstats);
     a.cs0 = fused ? x0.cstats : nullptr;
@@ -529,6 +613,78 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
     ops.push_back({[m, ta](cudaStream_t st) { TembArgs t = ta; t.timesteps = m->in_t; return temb_launch(t, st); }, 3, 0.0, 0.0});
     }
   }
+  // text conditioning of the conditional UNet: fp32 (B, L <= 128, D) -> bf16 (B, 1, 128, D), zero rows beyond L
+  constexpr int kCtxPad = 128;
+  Tensor ctxp;
+  if (c.cross_attention_dim > 0) {
+    ctxp = talloc(B, 1, kCtxPad, c.cross_attention_dim);
+    if (!dry) {
+      const int D = c.cross_attention_dim;
+      ops.push_back({[m, ctxp, B, D](cudaStream_t st) { return pack_context_launch(m->in_ctx, ctxp.p, B, m->ctx_len, kCtxPad, D, st); },
+                     3, 0.0, (double)B * kCtxPad * D * 6.0, "pack text context"});
+    }
+  }
+  auto lnorm = [&](const LNL& L, const Tensor& x, Tensor* out) {
+    if (rc) return;
+    *out = talloc(B, x.H, x.W, x.C);
+    if (dry) return;
+    Tensor xx = x, oo = *out;
+    const int64_t rows = (int64_t)B * x.H * x.W;
+    ops.push_back({[L, xx, oo, rows](cudaStream_t st) { return layernorm_rows_launch(xx.p, oo.p, L.g, L.b, rows, xx.C, 1e-5f, st); },
+                   1, 0.0, 4.0 * rows * x.C, "layernorm"});
+  };
+  // multi-head attention on the tensor cores: heads become "virtual images" of head-major, zero-padded copies of q, k
+  // and V^T (head_dim -> multiple of 64, tokens -> multiple of 128); S = Q K^T and O = P V are batched GEMMs on the
+  // tcgen05 kernel with a (masked) fp32 row softmax between them.  valid_k < 0: read m->ctx_len at launch time.
+  auto mh_attention = [&](const Tensor& qsrc, int qcol, const Tensor& ksrc, int kcol, int vcol, int Tq, int Tk, int valid_k,
+                          int heads, int d, int dpad, Tensor* out, int Hh, int Ww, int Cc) {
+    if (rc) return;
+    const int NV = B * heads;
+    const int Tqp = Tq < 128 ? 128 : Tq, Tkp = Tk < 128 ? 128 : Tk;
+    Tensor qh = talloc(NV, 1, Tqp, dpad), kh = talloc(NV, 1, Tkp, dpad), vht = talloc(NV, 1, dpad, Tkp);
+    Tensor sc = talloc(NV, 1, Tqp, Tkp), oh = talloc(NV, 1, Tqp, dpad);
+    *out = talloc(B, Hh, Ww, Cc);
+    if (Tqp % 128 || Tkp % 128 || (Tkp > 1024 && Tkp != 2048 && Tkp != 4096)) {
+      rc = B2E_UNSUPPORTED_SHAPE; set_error("unet: attention over %d x %d tokens is not supported", Tq, Tk); return;
+    }
+    if (!dry) {
+      ConvDesc d1;
+      d1.s0.ptr = qh.p; d1.s0.C = dpad;
+      d1.N = NV; d1.H = 1; d1.W = Tqp; d1.ksize = 1; d1.stride = 1;
+      d1.w_packed = kh.p; d1.b_batch_rows = Tkp; d1.b_pitch = dpad; d1.Cout = Tkp; d1.out_bf16 = sc.p;
+      ConvPlan p1;
+      rc = conv_plan_build(&p1, d1);
+      ConvDesc d2;
+      d2.s0.ptr = sc.p; d2.s0.C = Tkp;
+      d2.N = NV; d2.H = 1; d2.W = Tqp; d2.ksize = 1; d2.stride = 1;
+      d2.w_packed = vht.p; d2.b_batch_rows = dpad; d2.b_pitch = Tkp; d2.Cout = dpad; d2.out_bf16 = oh.p;
+      ConvPlan p2;
+      if (!rc) rc = conv_plan_build(&p2, d2);
+      if (!rc) {
+        const float scale = 1.0f / sqrtf((float)d);
+        const int64_t rows = (int64_t)NV * Tqp;
+        const Tensor q_ = qsrc, k_ = ksrc, o_ = *out;
+        const int qp = qsrc.C, kp = ksrc.C;
+        ops.push_back({[q_, qh, B, Tq, Tqp, qp, qcol, heads, d, dpad](cudaStream_t st) {
+                         return gather_heads_launch(q_.p, qh.p, B, Tq, Tqp, qp, qcol, heads, d, dpad, false, st); }, 3, 0.0, 4.0 * NV * Tqp * dpad, "gather q heads"});
+        ops.push_back({[k_, kh, B, Tk, Tkp, kp, kcol, heads, d, dpad](cudaStream_t st) {
+                         return gather_heads_launch(k_.p, kh.p, B, Tk, Tkp, kp, kcol, heads, d, dpad, false, st); }, 3, 0.0, 4.0 * NV * Tkp * dpad, "gather k heads"});
+        ops.push_back({[k_, vht, B, Tk, Tkp, kp, vcol, heads, d, dpad](cudaStream_t st) {
+                         return gather_heads_launch(k_.p, vht.p, B, Tk, Tkp, kp, vcol, heads, d, dpad, true, st); }, 3, 0.0, 4.0 * NV * Tkp * dpad, "gather V^T heads"});
+        ops.push_back({[p1](cudaStream_t st) { return conv_launch(p1, ConvEpilogue{}, st); }, 0, p1.flops, 0.0, "attention QK^T (heads batched)"});
+        ops.push_back({[m, sc, rows, Tkp, valid_k, scale](cudaStream_t st) {
+                         return softmax_rows_masked_launch(sc.p, rows, Tkp, valid_k < 0 ? m->ctx_len : valid_k, scale, st); },
+                       3, 0.0, 4.0 * rows * Tkp, "softmax"});
+        ops.push_back({[p2](cudaStream_t st) { return conv_launch(p2, ConvEpilogue{}, st); }, 0, p2.flops, 0.0, "attention PV (heads batched)"});
+        ops.push_back({[oh, o_, B, Tq, Tqp, heads, d, dpad](cudaStream_t st) {
+                         return scatter_heads_launch(oh.p, o_.p, B, Tq, Tqp, o_.C, heads, d, dpad, st); }, 3, 0.0, 4.0 * B * Tq * heads * d, "merge heads"});
+        flops += p1.flops + p2.flops;
+      }
+    } else {
+      flops += 4.0 * NV * (double)Tqp * Tkp * dpad;
+    }
+    tfree(qh); tfree(kh); tfree(vht); tfree(sc); tfree(oh);
+  };
   Tensor h;
   conv(m->conv_in, xin, nullptr, 1, ConvEpilogue{}, &h, nullptr);
   tfree(xin);
@@ -671,6 +827,49 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
         tfree(qkv);
         conv(a.proj, o, nullptr, 1, ConvEpilogue{}, &out, nullptr, &h);
         tfree(o);
+        if (!on_stack(h)) tfree(h);
+        h = out;
+        break;
+      }
+      case N_XFORMER: {
+        const XfL& x = m->xfs[nd.idx];
+        const int T = h.H * h.W, C = x.C;
+        Tensor gn, t0, l1, qkv, o1, t1, l2, q2, kv, o2, t2, l3, f1, gg, t3, out;
+        gnorm(x.gn, h, nullptr, 0, &gn, nullptr, 1e-6f);
+        conv(x.proj_in, gn, nullptr, 1, ConvEpilogue{}, &t0, nullptr, nullptr, nullptr, false);
+        tfree(gn);
+        // self-attention
+        lnorm(x.ln1, t0, &l1);
+        conv(x.qkv1, l1, nullptr, 1, ConvEpilogue{}, &qkv, nullptr, nullptr, nullptr, false);
+        tfree(l1);
+        mh_attention(qkv, 0, qkv, C, 2 * C, T, T, T, x.heads, x.d, x.dpad, &o1, h.H, h.W, C);
+        tfree(qkv);
+        conv(x.out1, o1, nullptr, 1, ConvEpilogue{}, &t1, nullptr, &t0, nullptr, false);
+        tfree(o1); tfree(t0);
+        // cross-attention over the text tokens
+        lnorm(x.ln2, t1, &l2);
+        conv(x.q2, l2, nullptr, 1, ConvEpilogue{}, &q2, nullptr, nullptr, nullptr, false);
+        tfree(l2);
+        conv(x.kv2, ctxp, nullptr, 1, ConvEpilogue{}, &kv, nullptr, nullptr, nullptr, false);
+        mh_attention(q2, 0, kv, 0, C, T, kCtxPad, -1, x.heads, x.d, x.dpad, &o2, h.H, h.W, C);
+        tfree(q2); tfree(kv);
+        conv(x.out2, o2, nullptr, 1, ConvEpilogue{}, &t2, nullptr, &t1, nullptr, false);
+        tfree(o2); tfree(t1);
+        // GEGLU feed-forward
+        lnorm(x.ln3, t2, &l3);
+        conv(x.ff1, l3, nullptr, 1, ConvEpilogue{}, &f1, nullptr, nullptr, nullptr, false);
+        tfree(l3);
+        gg = talloc(B, h.H, h.W, 4 * C);
+        if (!dry) {
+          const int64_t rows = (int64_t)B * T;
+          ops.push_back({[f1, gg, rows, C](cudaStream_t st) { return geglu_launch(f1.p, gg.p, rows, 4 * C, st); }, 3, 0.0,
+                         2.0 * rows * 12.0 * C, "geglu"});
+        }
+        tfree(f1);
+        conv(x.ff2, gg, nullptr, 1, ConvEpilogue{}, &t3, nullptr, &t2, nullptr, false);
+        tfree(gg); tfree(t2);
+        conv(x.proj_out, t3, nullptr, 1, ConvEpilogue{}, &out, nullptr, &h);
+        tfree(t3);
         if (!on_stack(h)) tfree(h);
         h = out;
         break;
@@ -861,6 +1060,16 @@ int b2e_unet_create(const b2e_unet_config* cfg, int64_t max_batch, b2e_unet** ou
   }
   B2E_REQUIRE(cfg->downsample_padding == 0 || cfg->downsample_padding == 1, B2E_UNSUPPORTED_SHAPE,
               "unet_create: downsample_padding must be 0 or 1");
+  if (cfg->cross_attention_dim > 0) {
+    B2E_REQUIRE(cfg->cross_attention_dim % 64 == 0 && cfg->num_attention_heads >= 1, B2E_UNSUPPORTED_SHAPE,
+                "unet_create: cross_attention_dim must be a multiple of 64 and num_attention_heads >= 1");
+    for (int i = 0; i < cfg->n_blocks; ++i) {
+      const int ch = cfg->block_out_channels[i];
+      B2E_REQUIRE(ch % 64 == 0 && ch % cfg->num_attention_heads == 0 && (ch / cfg->num_attention_heads) % 8 == 0,
+                  B2E_UNSUPPORTED_SHAPE, "unet_create: conditional UNet needs channels %% 64 == 0 and head_dim %% 8 == 0 (got %d / %d heads)",
+                  ch, cfg->num_attention_heads);
+    }
+  }
   B2E_REQUIRE(cfg->sample_size % (1 << (cfg->n_blocks - 1)) == 0, B2E_UNSUPPORTED_SHAPE, "unet_create: sample_size");
   b2e_unet* m = new b2e_unet();
   m->cfg = *cfg;
@@ -945,6 +1154,8 @@ int b2e_unet_forward(b2e_unet* m, const float* x, const int64_t* timesteps, floa
     int rc = build_program(m, (int)B, m->ws, m->ws_bytes, nullptr);
     if (rc) return rc;
   }
+  B2E_REQUIRE(m->cfg.cross_attention_dim <= 0 || m->in_ctx, B2E_INVALID_ARG,
+              "unet_forward: a conditional UNet needs b2e_unet_forward_cond");
   m->in_x = x; m->in_t = timesteps; m->out_eps = eps;
   cudaStream_t st = (cudaStream_t)stream;
   for (auto& op : m->ops) {
@@ -953,6 +1164,16 @@ int b2e_unet_forward(b2e_unet* m, const float* x, const int64_t* timesteps, floa
   }
   m->fwd_B = B;
   return B2E_OK;
+}
+
+int b2e_unet_forward_cond(b2e_unet* m, const float* x, const int64_t* timesteps, const float* context, int64_t ctx_len,
+                          float* eps, int64_t B, void* stream) {
+  B2E_REQUIRE(m && context, B2E_INVALID_ARG, "unet_forward_cond: null pointer");
+  B2E_REQUIRE(m->cfg.cross_attention_dim > 0, B2E_INVALID_ARG, "unet_forward_cond: the model has no cross-attention");
+  B2E_REQUIRE(ctx_len >= 1 && ctx_len <= 128, B2E_UNSUPPORTED_SHAPE, "unet_forward_cond: %lld context tokens (1..128)",
+              (long long)ctx_len);
+  m->in_ctx = context; m->ctx_len = (int)ctx_len;
+  return b2e_unet_forward(m, x, timesteps, eps, B, stream);
 }
 
 int b2e_unet_enable_grad(b2e_unet* m, int enable) {

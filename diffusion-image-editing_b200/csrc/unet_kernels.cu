@@ -502,7 +502,7 @@ __global__ void __launch_bounds__(256) temb_mlp_kernel(TembArgs a) {
 }
 
 // proj[b][o] = wp[o] . act[b] + bp[o]   (warp per output; the weight row is read once and reused for every sample)
-constexpr int kTembMaxPerLane = 32;   // dim <= 1024
+constexpr int kTembMaxPerLane = 64;   // dim <= 2048 (SD: 1280)
 __global__ void __launch_bounds__(256) temb_proj_kernel(TembArgs a) {
   pdl_wait();
   pdl_trigger();
@@ -635,6 +635,220 @@ int transpose_v_launch(const bf16* qkv, bf16* vt, int N, int T, int C, cudaStrea
   B2E_REQUIRE(T % 32 == 0 && C % 32 == 0, B2E_UNSUPPORTED_SHAPE, "transpose_v: T and C must be multiples of 32");
   launch_pdl(transpose_v_kernel, dim3(dim3(T / 32, C / 32, N)), dim3(dim3(32, 8)), 0, st, qkv, vt, T, C);
   return check_launch("transpose_v");
+}
+
+// ------------------------------------------------------------------ transformer-block kernels (SD UNet2DConditionModel)
+// LayerNorm over the channels of every token (bf16 NHWC rows of C channels, C % 8 == 0, C <= 2048): one warp per token,
+// the row lives in registers between the two passes
+__global__ void __launch_bounds__(256) layernorm_rows_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             int64_t rows, int C, float eps) {
+  pdl_wait();
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + row * C);
+  uint4* yr = reinterpret_cast<uint4*>(y + row * C);
+  const int chunks = C >> 3;
+  float v[8][8];   // up to 8 chunks per lane (C <= 2048)
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int ch = lane + 32 * i;
+    if (ch < chunks) {
+      unpack8(__ldg(xr + ch), v[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += v[i][j];
+    }
+  }
+  sum = warp_sum(sum);
+  const float mean = sum / (float)C;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int ch = lane + 32 * i;
+    if (ch < chunks) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; sq += d * d; }
+    }
+  }
+  sq = warp_sum(sq);
+  const float rstd = rsqrtf(sq / (float)C + eps);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int ch = lane + 32 * i;
+    if (ch < chunks) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * __ldg(gamma + ch * 8 + j) + __ldg(beta + ch * 8 + j);
+      yr[ch] = pack8(o);
+    }
+  }
+}
+
+int layernorm_rows_launch(const bf16* x, bf16* y, const float* gamma, const float* beta, int64_t rows, int C, float eps,
+                          cudaStream_t st) {
+  B2E_REQUIRE(C % 8 == 0 && C <= 2048, B2E_UNSUPPORTED_SHAPE, "layernorm: unsupported width %d", C);
+  launch_pdl(layernorm_rows_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, st, x, y, gamma, beta, rows, C, eps);
+  return check_launch("layernorm_rows");
+}
+
+// GEGLU: in [rows][2*inner] -> out [rows][inner] = in[:, :inner] * gelu(in[:, inner:])   (exact erf GELU)
+__global__ void __launch_bounds__(256) geglu_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int64_t rows,
+                                                    int inner8) {
+  pdl_wait();
+  const int64_t total = rows * inner8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / inner8;
+    const int c = (int)(i % inner8);
+    float a[8], g[8];
+    unpack8(__ldg(in + r * 2 * inner8 + c), a);
+    unpack8(__ldg(in + r * 2 * inner8 + inner8 + c), g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] *= 0.5f * g[j] * (1.f + erff(g[j] * 0.70710678118654752f));
+    out[i] = pack8(a);
+  }
+}
+
+int geglu_launch(const bf16* in, bf16* out, int64_t rows, int inner, cudaStream_t st) {
+  B2E_REQUIRE(inner % 8 == 0, B2E_UNSUPPORTED_SHAPE, "geglu: inner %% 8");
+  const int64_t total = rows * (inner / 8);
+  int grid = (int)((total + 255) / 256);
+  if (grid > kNumSMs * 32) grid = kNumSMs * 32;
+  launch_pdl(geglu_kernel, dim3(grid), dim3(256), 0, st, (const uint4*)in, (uint4*)out, rows, inner / 8);
+  return check_launch("geglu");
+}
+
+// text conditioning: fp32 [B][L][D] -> bf16 [B][Lpad][D], rows >= L zero
+__global__ void __launch_bounds__(256) pack_context_kernel(const float* __restrict__ ctx, bf16* __restrict__ out, int B, int L,
+                                                           int Lpad, int D) {
+  pdl_wait();
+  const int64_t total = (int64_t)B * Lpad * D;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int dcol = (int)(i % D);
+    const int l = (int)((i / D) % Lpad);
+    const int64_t b = i / ((int64_t)D * Lpad);
+    out[i] = __float2bfloat16_rn(l < L ? ctx[(b * L + l) * D + dcol] : 0.f);
+  }
+}
+
+int pack_context_launch(const float* ctx, bf16* out, int B, int L, int Lpad, int D, cudaStream_t st) {
+  const int64_t total = (int64_t)B * Lpad * D;
+  int grid = (int)((total + 255) / 256);
+  if (grid > kNumSMs * 16) grid = kNumSMs * 16;
+  launch_pdl(pack_context_kernel, dim3(grid), dim3(256), 0, st, ctx, out, B, L, Lpad, D);
+  return check_launch("pack_context");
+}
+
+// head-major gather for the batched attention GEMMs.  src rows: token (n, t), channels [col0 + h*d, + d) of a row of
+// `pitch` channels, t < Tsrc.  dst [N*heads][Tpad][dpad] with zeros for t >= Tsrc and channels >= d.
+__global__ void __launch_bounds__(256) gather_heads_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int N, int Tsrc,
+                                                           int Tpad, int pitch, int col0, int heads, int d, int dpad) {
+  pdl_wait();
+  const int d8 = dpad >> 3;
+  const int64_t total = (int64_t)N * heads * Tpad * d8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i % d8);
+    const int t = (int)((i / d8) % Tpad);
+    const int64_t v = i / ((int64_t)d8 * Tpad);
+    const int64_t n = v / heads;
+    const int h = (int)(v % heads);
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (t < Tsrc && j * 8 < d) val = __ldg(reinterpret_cast<const uint4*>(src + (n * Tsrc + t) * pitch + col0 + h * d + j * 8));
+    reinterpret_cast<uint4*>(dst)[i] = val;
+  }
+}
+
+// transposed variant: dst [N*heads][dpad][Tpad] (V^T), zeros outside
+__global__ void gather_heads_T_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int Tsrc, int Tpad, int pitch,
+                                      int col0, int heads, int d, int dpad) {
+  pdl_wait();
+  __shared__ bf16 tile[32][33];
+  const int v = blockIdx.z, n = v / heads, h = v % heads, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const bf16* s = src + ((int64_t)n * Tsrc) * pitch + col0 + h * d;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int t = t0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (t < Tsrc && c < d) ? s[(int64_t)t * pitch + c] : __float2bfloat16_rn(0.f);
+  }
+  __syncthreads();
+  bf16* dd = dst + (int64_t)v * dpad * Tpad;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) dd[(int64_t)(c0 + i) * Tpad + t0 + threadIdx.x] = tile[threadIdx.x][i];
+}
+
+// inverse of gather_heads for the attention output: out[n][t][h*d + c] = oh[n*heads + h][t][c], t < T, c < d
+__global__ void __launch_bounds__(256) scatter_heads_kernel(const bf16* __restrict__ oh, bf16* __restrict__ out, int N, int T,
+                                                            int Tpad, int pitch, int heads, int d, int dpad) {
+  pdl_wait();
+  const int c8 = (heads * d) >> 3;
+  const int64_t total = (int64_t)N * T * c8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int s = (int)(i % c8);
+    const int64_t nt = i / c8;
+    const int64_t n = nt / T;
+    const int t = (int)(nt % T);
+    const int c0 = s * 8, h = c0 / d, cc = c0 - h * d;
+    // d % 8 == 0: an 8-channel slot never straddles two heads
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(oh + (((n * heads + h) * Tpad + t) * (int64_t)dpad + cc)));
+    *reinterpret_cast<uint4*>(out + nt * pitch + c0) = v;
+  }
+}
+
+int gather_heads_launch(const bf16* src, bf16* dst, int N, int Tsrc, int Tpad, int pitch, int col0, int heads, int d, int dpad,
+                        bool transposed, cudaStream_t st) {
+  B2E_REQUIRE(d % 8 == 0 && dpad % 64 == 0 && dpad >= d && Tpad % 32 == 0 && Tpad >= Tsrc, B2E_UNSUPPORTED_SHAPE,
+              "gather_heads: head_dim %d -> %d, T %d -> %d", d, dpad, Tsrc, Tpad);
+  if (transposed) {
+    launch_pdl(gather_heads_T_kernel, dim3(Tpad / 32, dpad / 32, N * heads), dim3(32, 8), 0, st, src, dst, Tsrc, Tpad, pitch, col0,
+               heads, d, dpad);
+    return check_launch("gather_heads_T");
+  }
+  const int64_t total = (int64_t)N * heads * Tpad * (dpad / 8);
+  int grid = (int)((total + 255) / 256);
+  if (grid > kNumSMs * 32) grid = kNumSMs * 32;
+  launch_pdl(gather_heads_kernel, dim3(grid), dim3(256), 0, st, src, dst, N, Tsrc, Tpad, pitch, col0, heads, d, dpad);
+  return check_launch("gather_heads");
+}
+
+int scatter_heads_launch(const bf16* oh, bf16* out, int N, int T, int Tpad, int pitch, int heads, int d, int dpad, cudaStream_t st) {
+  B2E_REQUIRE(d % 8 == 0, B2E_UNSUPPORTED_SHAPE, "scatter_heads: head_dim %d", d);
+  const int64_t total = (int64_t)N * T * (heads * d / 8);
+  int grid = (int)((total + 255) / 256);
+  if (grid > kNumSMs * 32) grid = kNumSMs * 32;
+  launch_pdl(scatter_heads_kernel, dim3(grid), dim3(256), 0, st, oh, out, N, T, Tpad, pitch, heads, d, dpad);
+  return check_launch("scatter_heads");
+}
+
+// row softmax with masked tail: row length T (<= 1024, T % 32 == 0), only the first `valid` entries take part, the
+// rest become 0 (zero-padded keys of the batched attention GEMMs)
+__global__ void __launch_bounds__(256) softmax_rows_masked_kernel(bf16* __restrict__ s, int64_t rows, int T, int valid, float scale) {
+  pdl_wait();
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  bf16* r = s + row * T;
+  float v[32];
+  const int per = T / 32;
+  float m = -INFINITY;
+  for (int i = 0; i < per; ++i) {
+    const int j = lane + 32 * i;
+    v[i] = j < valid ? __bfloat162float(r[j]) * scale : -INFINITY;
+    m = fmaxf(m, v[i]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float sum = 0.f;
+  for (int i = 0; i < per; ++i) { v[i] = (lane + 32 * i) < valid ? __expf(v[i] - m) : 0.f; sum += v[i]; }
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+  for (int i = 0; i < per; ++i) r[lane + 32 * i] = __float2bfloat16_rn(v[i] * inv);
+}
+
+int softmax_rows_masked_launch(bf16* s, int64_t rows, int T, int valid, float scale, cudaStream_t st) {
+  if (valid == T) return softmax_rows_launch(s, rows, T, scale, st);
+  B2E_REQUIRE(T % 32 == 0 && T <= 1024 && valid >= 1 && valid < T, B2E_UNSUPPORTED_SHAPE,
+              "masked softmax: unsupported row length %d (valid %d)", T, valid);
+  launch_pdl(softmax_rows_masked_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, st, s, rows, T, valid, scale);
+  return check_launch("softmax_rows_masked");
 }
 
 // ------------------------------------------------------------------ backward helpers of the decoder

@@ -208,6 +208,10 @@ typedef struct {
   int32_t flip_sin_to_cos;
   float freq_shift;
   int32_t downsample_padding; /* 0: pad (0,1,0,1) before the stride-2 conv (DDPM-256); 1: symmetric padding 1 (LDM) */
+  /* > 0: diffusers UNet2DConditionModel (Stable Diffusion 1.x layout): blocks flagged in down_attn / up_attn and the mid
+   * block use Transformer2DModel (self-attention, cross-attention over the text tokens, GEGLU) instead of Attention */
+  int32_t cross_attention_dim;
+  int32_t num_attention_heads; /* SD 1.x: 8 (head_dim = channels / 8) */
 } b2e_unet_config;
 
 typedef struct b2e_unet b2e_unet;
@@ -229,6 +233,11 @@ int b2e_unet_forward(b2e_unet* m, const float* x, const int64_t* timesteps, floa
                      void* stream);
 double b2e_unet_flops(const b2e_unet* m, int64_t B);
 /* Human-readable description of op `idx` of the current plan (shape, tiling); "" if out of range. */
+/* get_noise_pred's CFG branch, src/diffusion_utils.py:61-70: eps = unet(x, t, encoder_hidden_states=context).sample for a
+ * conditional UNet; context: DEVICE fp32 (B, ctx_len <= 128, cross_attention_dim) (the reference's (2,77,768) text_emb
+ * for the doubled latent). */
+int b2e_unet_forward_cond(b2e_unet* m, const float* x, const int64_t* timesteps, const float* context, int64_t ctx_len,
+                          float* eps, int64_t B, void* stream);
 const char* b2e_unet_op_desc(const b2e_unet* m, int idx);
 /* One instrumented forward: CUDA events on `stream` around every op of the plan.  Per op: elapsed ms,
  * algorithmic FLOPs (convolutions / attention) or bytes (memory-bound ops) and kind
