@@ -1052,8 +1052,8 @@ int b2e_unet_create(const b2e_unet_config* cfg, int64_t max_batch, b2e_unet** ou
               "unet_create: in_channels <= 8 and out_channels <= 16 required");
   for (int i = 0; i < cfg->n_blocks; ++i) {
     const int ch = cfg->block_out_channels[i];
-    B2E_REQUIRE(ch % 8 == 0 && ch >= 32 && ch <= 1024 && ch % cfg->norm_num_groups == 0, B2E_UNSUPPORTED_SHAPE,
-                "unet_create: block_out_channels must be multiples of 8 and of norm_num_groups, 32..1024 (got %d)", ch);
+    B2E_REQUIRE(ch % 8 == 0 && ch >= 32 && ch <= 2048 && ch % cfg->norm_num_groups == 0, B2E_UNSUPPORTED_SHAPE,
+                "unet_create: block_out_channels must be multiples of 8 and of norm_num_groups, 32..2048 (got %d)", ch);
     B2E_REQUIRE(cfg->attention_head_dim <= 0 || !(cfg->down_attn[i] || cfg->up_attn[i]) || ch % cfg->attention_head_dim == 0,
                 B2E_UNSUPPORTED_SHAPE, "unet_create: %d channels are not a multiple of attention_head_dim %d", ch,
                 cfg->attention_head_dim);

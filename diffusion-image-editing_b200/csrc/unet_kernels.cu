@@ -30,10 +30,11 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 // loads in flight.
 constexpr int kGNUnroll = 4;
 
-__global__ void __launch_bounds__(kGNThreads) gn_partial_kernel(GNArgs a) {
+// (forward GroupNorm kernels: 256 threads, or 512 when the tensor has more than 2048 channels - SD concatenations)
+__global__ void __launch_bounds__(512) gn_partial_kernel(GNArgs a) {
   pdl_wait();
-  __shared__ float s_sum[2048], s_sq[2048];
-  const int C = a.C0 + a.C1, slots = C >> 3, ppi = kGNThreads / slots;
+  __shared__ float s_sum[4096], s_sq[4096];
+  const int C = a.C0 + a.C1, slots = C >> 3, ppi = (int)blockDim.x / slots;
   const int n = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
   const int s = tid % slots, pl = tid / slots;
   const int per = (a.HW + a.chunks - 1) / a.chunks;
@@ -75,10 +76,10 @@ __global__ void __launch_bounds__(kGNThreads) gn_partial_kernel(GNArgs a) {
   }
 }
 
-__global__ void __launch_bounds__(kGNThreads) gn_apply_kernel(GNArgs a, int pix_per_block) {
+__global__ void __launch_bounds__(512) gn_apply_kernel(GNArgs a, int pix_per_block) {
   pdl_wait();
   __shared__ float s_mean[64], s_rstd[64];
-  const int C = a.C0 + a.C1, slots = a.Pout >> 3, ppi = kGNThreads / slots;
+  const int C = a.C0 + a.C1, slots = a.Pout >> 3, ppi = (int)blockDim.x / slots;
   const int n = blockIdx.y, tid = threadIdx.x;
   const int cpg = C / a.G;
   if (tid < a.G) {
@@ -179,20 +180,21 @@ int gn_chunks(int HW, int C) {
 
 int gn_launch(const GNArgs& a, cudaStream_t st) {
   const int C = a.C0 + a.C1;
-  B2E_REQUIRE(C % 8 == 0 && a.C0 % 8 == 0 && a.Pout <= 2048 && a.G <= 64 && C % a.G == 0, B2E_UNSUPPORTED_SHAPE,
+  B2E_REQUIRE(C % 8 == 0 && a.C0 % 8 == 0 && a.Pout <= 4096 && a.G <= 64 && C % a.G == 0, B2E_UNSUPPORTED_SHAPE,
               "groupnorm: unsupported channels %d+%d / groups %d", a.C0, a.C1, a.G);
   B2E_REQUIRE(a.P0 >= a.C0 && a.P1 >= a.C1 && a.Pout >= C && a.P0 % 8 == 0 && a.P1 % 8 == 0 && a.Pout % 8 == 0,
               B2E_INVALID_ARG, "groupnorm: bad channel pitches %d/%d -> %d", a.P0, a.P1, a.Pout);
   int rc = B2E_OK;
   if (!a.cs0 && !a.ts0) {
-    launch_pdl(gn_partial_kernel, dim3(dim3(a.chunks, a.N)), dim3(kGNThreads), 0, st, a);
+    launch_pdl(gn_partial_kernel, dim3(dim3(a.chunks, a.N)), dim3(C > 2048 ? 512 : kGNThreads), 0, st, a);
     rc = check_launch("gn_partial");
     if (rc) return rc;
   }
-  const int slots = a.Pout / 8, ppi = kGNThreads / slots;
+  const int threads = a.Pout > 2048 ? 512 : kGNThreads;
+  const int slots = a.Pout / 8, ppi = threads / slots;
   int ppb = ppi * kGNUnroll * 2;  // two unrolled sweeps per thread
   if (ppb > a.HW) ppb = a.HW;
-  launch_pdl(gn_apply_kernel, dim3(dim3((a.HW + ppb - 1) / ppb, a.N)), dim3(kGNThreads), 0, st, a, ppb);
+  launch_pdl(gn_apply_kernel, dim3(dim3((a.HW + ppb - 1) / ppb, a.N)), dim3(threads), 0, st, a, ppb);
   return check_launch("gn_apply");
 }
 

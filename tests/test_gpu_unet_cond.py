@@ -58,6 +58,11 @@ def test_mid_cond_unet_matches_oracle():
     check(*run_pair(MID, 2, 500, seed=9), "cond unet 320/640/640, head_dim 40/80")
 
 
+def test_sd15_cond_unet_matches_oracle():
+    """The full Stable Diffusion 1.x UNet layout (320/640/1280/1280, 859.5 M parameters, 4096-token self-attention)."""
+    check(*run_pair(SD15_CONFIG, 2, 500, seed=2), "sd-1.x cond unet")
+
+
 def test_cfg_call_of_the_reference():
     """get_noise_pred's CFG branch (src/diffusion_utils.py:61-70) on the native conditional UNet."""
     from types import SimpleNamespace
