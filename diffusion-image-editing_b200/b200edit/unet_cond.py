@@ -71,9 +71,11 @@ class UNet2DConditionModel(UNet2DModel):
         if ctx.dim() != 3 or ctx.shape[2] != cfg.cross_attention_dim or ctx.shape[1] > 128:
             raise ValueError(f"encoder_hidden_states must be (B, L <= 128, {cfg.cross_attention_dim}), got {tuple(ctx.shape)}")
         if ctx.shape[0] != B:
-            if ctx.shape[0] != 1:
-                raise ValueError(f"encoder_hidden_states batch {ctx.shape[0]} != sample batch {B}")
-            ctx = ctx.expand(B, -1, -1)
+            # the reference's CFG call doubles ONE latent and passes (2, L, D) = [first, second]; for a batch of latents
+            # cat([latent] * 2) is [all firsts, all seconds], so every context row serves B / n consecutive samples
+            if B % ctx.shape[0] != 0:
+                raise ValueError(f"encoder_hidden_states batch {ctx.shape[0]} does not divide the sample batch {B}")
+            ctx = ctx.repeat_interleave(B // ctx.shape[0], dim=0)
         ctx = ctx.contiguous()
         t = self._timesteps(timestep, B)
         eps = out if out is not None else torch.empty_like(x[:, :cfg.out_channels]) if cfg.out_channels == cfg.in_channels \

@@ -24,8 +24,10 @@ class NativePipeline(SimpleNamespace):
 def create_diffusion_model(name: str, sample_clipping: bool = True, *, max_batch: int = 8, seed: int = 0,
                            state_dict: Optional[dict] = None, unet_config: Optional[dict] = None, vqvae=None,
                            vq_config: Optional[dict] = None, vq_state_dict: Optional[dict] = None, guidance_module=None,
-                           decoder_grad: bool = True):
-    """``name``: "ddpm" (google/ddpm-celebahq-256 layout) or "ldm" (CompVis/ldm-celebahq-256 layout: native UNet on
+                           decoder_grad: bool = True, tokenizer=None, text_encoder=None):
+    """``name``: "ddpm" (google/ddpm-celebahq-256 layout), "sd" (Stable Diffusion 1.x layout: native conditional UNet
+    + native KL decoder with gradient; ``vqvae=`` substitutes the vae, ``tokenizer=`` / ``text_encoder=`` are the
+    caller's CLIP modules) or "ldm" (CompVis/ldm-celebahq-256 layout: native UNet on
     the 64x64x3 latent + native forward-only VQ decoder; ``vqvae=`` substitutes the caller's VQ autoencoder module
     (encode().latents / decode().sample, as in the reference's pipeline object); ``guidance_module=`` is the
     differentiable decoder used when guidance runs through decode)."""
@@ -65,9 +67,30 @@ def create_diffusion_model(name: str, sample_clipping: bool = True, *, max_batch
                                   guidance_vqvae=guidance_vqvae if guidance_module is None else guidance_module,
                                   device=device))
     if name == "sd":
-        raise NotImplementedError(
-            "create_diffusion_model('sd'): the SD UNet2DConditionModel / KL autoencoder are not on the native "
-            "engine yet (SURVEY.md section 8f); wrap your own modules with diffusion_classes.SD")
+        from b200edit.unet_cond import SD15_CONFIG, UNet2DConditionModel
+        from b200edit.vqmodel import SD_VAE_CONFIG, AutoencoderKL
+        # CFG doubles the latent batch: the UNet engine is sized for 2 * max_batch samples
+        unet = UNet2DConditionModel(**(unet_config or SD15_CONFIG), max_batch=2 * max_batch, device=device)
+        if state_dict is not None:
+            unet.load_state_dict(state_dict)
+        else:
+            unet.init_random(seed)
+        if vqvae is None:
+            vae = AutoencoderKL(**(vq_config or SD_VAE_CONFIG), max_batch=max_batch, device=device)
+            if vq_state_dict is not None:
+                vae.load_state_dict(vq_state_dict)
+            else:
+                vae.init_random(seed + 1)
+            if decoder_grad:
+                vae.enable_grad()
+        else:
+            vae = vqvae
+        scheduler = DDIMScheduler.from_preset("sd")
+        scheduler.config.clip_sample = sample_clipping
+        # the CLIP tokenizer / text encoder are the caller's modules (no weights offline); prompts need them,
+        # precomputed text embeddings (2, 77, 768) do not
+        return SD(NativePipeline(unet=unet, scheduler=scheduler, vae=vae, tokenizer=tokenizer, text_encoder=text_encoder,
+                                 device=device))
     raise ValueError(f"Unknown model name: {name}")
 
 

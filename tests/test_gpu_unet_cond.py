@@ -90,3 +90,77 @@ def test_cfg_call_of_the_reference():
     rel16 = ((ref16 - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
     print(f"cfg 3.5: native rel-rms {rel:.3e} | torch-bf16 {rel16:.3e}")
     assert eps.shape == lat.shape and rel <= 8e-2 and rel <= 1.25 * rel16 + 1e-3, (rel, rel16)
+
+
+class FakeTokenizer:
+    """Stand-in for the caller's CLIP tokenizer (no vocabulary files offline): deterministic ids, 77 positions."""
+    model_max_length = 77
+
+    def __call__(self, prompts, padding=None, max_length=77, truncation=True, return_tensors="pt"):
+        from types import SimpleNamespace
+        ids = torch.zeros(len(prompts), max_length, dtype=torch.long)
+        for i, p in enumerate(prompts):
+            for j, ch in enumerate(p.encode()[:max_length]):
+                ids[i, j] = 1 + ch % 97
+        return SimpleNamespace(input_ids=ids)
+
+
+class FakeTextEncoder(torch.nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        torch.manual_seed(123)
+        self.emb = torch.nn.Embedding(128, dim)
+        self.pos = torch.nn.Parameter(0.1 * torch.randn(77, dim))
+
+    def forward(self, ids):
+        return (self.emb(ids) + self.pos[None],)
+
+
+def test_sd_config4_small_cfg_and_classifier_guidance_through_kl_decoder():
+    """BASELINE config 4 in small, on the engine: SD wrapper, CFG over the doubled latent on the native conditional
+    UNet, ClassifierAttrFunc whose gradient flows through the caller's predictor (torch) and the NATIVE KL decoder
+    (forward + gradient).  The recorded noise predictions are replayed through the oracle loop with autograd through
+    the fp32 oracle decoder."""
+    from attr_functions import ClassifierAttrFunc
+    from models import create_diffusion_model
+    from oracle import loops, step_math as sm
+    from oracle.ddim_scheduler import DDIMScheduler as OracleScheduler
+    from oracle.vqmodel import VQModel as OracleVQ
+    from SegDiffEditPipeline import SegDiffEditPipeline
+    vcfg = dict(latent_channels=4, out_channels=3, block_out_channels=(64, 128), layers_per_block=1, norm_num_groups=32,
+                norm_eps=1e-6, sample_size=16)
+    torch.manual_seed(77)
+    ovae = OracleVQ(**vcfg, num_vq_embeddings=0).eval()
+    predictor = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3, stride=2, padding=1), torch.nn.SiLU(),
+                                    torch.nn.AdaptiveAvgPool2d(4), torch.nn.Flatten(), torch.nn.Linear(128, 80))
+    w = create_diffusion_model("sd", sample_clipping=False, max_batch=1, seed=5, unet_config=SMALL, vq_config=vcfg,
+                               vq_state_dict=ovae.state_dict(), tokenizer=FakeTokenizer(), text_encoder=FakeTextEncoder(64).cuda())
+    assert type(w).__name__ == "SD"
+    T = 4
+    w.scheduler.set_timesteps(T)
+    pipe = SegDiffEditPipeline(w, None)
+    xt = torch.randn(1, 4, 16, 16, generator=torch.Generator().manual_seed(8))
+    import copy
+    pred_gpu = copy.deepcopy(predictor).cuda()
+    scale = 300.0
+    f = ClassifierAttrFunc(pred_gpu, idx_for_class=31, idx_of_interest=1, loss_scale=scale, t1=0, t2=T)
+    out = pipe.edit_image(xt=xt.cuda(), attr_func=f, prompt="a face", cfg_scale=3.5, prog_bar=False, output_type="tensor")
+    assert out.imgs.shape == (1, 3, 32, 32) and torch.isfinite(out.imgs).all()
+    rep = iter([e.cpu() for e in out.model_outputs])
+    s = OracleScheduler.from_preset("sd", clip_sample=False)
+    s.set_timesteps(T)
+    moved = []
+
+    def guidance(x_post, eps, c, step_idx):
+        loss = lambda z: sm.classifier_logit_loss(predictor(ovae.decode(z / 0.18215).sample), 31, 1)   # noqa: E731
+        new, _ = sm.autograd_guidance_update(x_post, eps, c, loss, scale)
+        moved.append((new - x_post).abs().max().item())
+        return new
+
+    xf, _, _ = loops.guided_edit_loop(s, lambda x, t: next(rep), xt, eta=0.0, zs=None, guidance=guidance)
+    assert max(moved) > 1e-3
+    with torch.no_grad():
+        ref = ovae.decode(xf / 0.18215).sample
+    rel = ((out.imgs.cpu() - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
+    print(f"config-4 small: decoded image rel-rms vs oracle {rel:.3e}, largest guidance update {max(moved):.3e}")
+    assert rel <= 3e-2
