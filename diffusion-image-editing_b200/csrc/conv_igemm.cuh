@@ -75,6 +75,21 @@ ConvGeom conv_geometry(int N, int Ho, int Wo, int Cout);
 inline int64_t conv_stats_slots(const ConvGeom& g) { return (int64_t)g.w_blks * g.h_blks * g.n_blks * g.Nt; }
 int conv_launch(const ConvPlan& plan, const ConvEpilogue& ep, cudaStream_t st);
 
+// 128B-swizzled bf16 TMA descriptor (rank <= 5); shared by the tensor-core kernels
+int tma_encode_bf16(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box);
+
+// Fused attention (csrc/flash_attn.cu): O = softmax(scale * Q K^T) V on head-major operands qh [NV][Tq][D],
+// kh [NV][Tk][D], vht [NV][D][Tk] -> oh [NV][Tq][D]; D in {64, 128, 192}, Tq, Tk multiples of 128; keys >= valid_k masked
+struct FlashPlan {
+  CUtensorMap map_q, map_k, map_v;
+  int NV, Tq, Tk, D;
+  bf16* out;
+  double flops;
+};
+int flash_attn_plan_build(FlashPlan* pl, const bf16* qh, const bf16* kh, const bf16* vht, bf16* oh, int NV, int Tq, int Tk, int D);
+int flash_attn_launch(const FlashPlan& pl, int valid_k, float scale, cudaStream_t st);
+
 // fp32 [Cout][Cin][k][k] -> bf16 out[co*row_len + col_off + t*tap_width + ci]   (t = kh*k + kw)
 // (ci0, cin_total): pack only input channels [ci0, ci0 + Cin) of a weight with cin_total input channels
 int conv_pack_weight(const float* w, bf16* out, int Cout, int Cin, int ksize, int tap_width, int row_len,

@@ -642,11 +642,40 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
     const int NV = B * heads;
     const int Tqp = Tq < 128 ? 128 : Tq, Tkp = Tk < 128 ? 128 : Tk;
     Tensor qh = talloc(NV, 1, Tqp, dpad), kh = talloc(NV, 1, Tkp, dpad), vht = talloc(NV, 1, dpad, Tkp);
-    Tensor sc = talloc(NV, 1, Tqp, Tkp), oh = talloc(NV, 1, Tqp, dpad);
+    Tensor oh = talloc(NV, 1, Tqp, dpad);
     *out = talloc(B, Hh, Ww, Cc);
     if (Tqp % 128 || Tkp % 128 || (Tkp > 1024 && Tkp != 2048 && Tkp != 4096)) {
       rc = B2E_UNSUPPORTED_SHAPE; set_error("unet: attention over %d x %d tokens is not supported", Tq, Tk); return;
     }
+    static const bool flash_on = !(getenv("B2E_FLASH") && atoi(getenv("B2E_FLASH")) == 0);
+    if (flash_on && dpad <= 192) {
+      // fused attention: the score matrix never leaves the SM (csrc/flash_attn.cu)
+      if (!dry) {
+        FlashPlan fp;
+        rc = flash_attn_plan_build(&fp, qh.p, kh.p, vht.p, oh.p, NV, Tqp, Tkp, dpad);
+        if (!rc) {
+          const float scale = 1.0f / sqrtf((float)d);
+          const Tensor q_ = qsrc, k_ = ksrc, o_ = *out;
+          const int qp = qsrc.C, kp = ksrc.C;
+          ops.push_back({[q_, qh, B, Tq, Tqp, qp, qcol, heads, d, dpad](cudaStream_t st) {
+                           return gather_heads_launch(q_.p, qh.p, B, Tq, Tqp, qp, qcol, heads, d, dpad, false, st); }, 3, 0.0, 4.0 * NV * Tqp * dpad, "gather q heads"});
+          ops.push_back({[k_, kh, B, Tk, Tkp, kp, kcol, heads, d, dpad](cudaStream_t st) {
+                           return gather_heads_launch(k_.p, kh.p, B, Tk, Tkp, kp, kcol, heads, d, dpad, false, st); }, 3, 0.0, 4.0 * NV * Tkp * dpad, "gather k heads"});
+          ops.push_back({[k_, vht, B, Tk, Tkp, kp, vcol, heads, d, dpad](cudaStream_t st) {
+                           return gather_heads_launch(k_.p, vht.p, B, Tk, Tkp, kp, vcol, heads, d, dpad, true, st); }, 3, 0.0, 4.0 * NV * Tkp * dpad, "gather V^T heads"});
+          ops.push_back({[m, fp, valid_k, scale](cudaStream_t st) { return flash_attn_launch(fp, valid_k < 0 ? m->ctx_len : valid_k, scale, st); },
+                         2, fp.flops, 0.0, "flash attention (tcgen05, S in TMEM)"});
+          ops.push_back({[oh, o_, B, Tq, Tqp, heads, d, dpad](cudaStream_t st) {
+                           return scatter_heads_launch(oh.p, o_.p, B, Tq, Tqp, o_.C, heads, d, dpad, st); }, 3, 0.0, 4.0 * B * Tq * heads * d, "merge heads"});
+          flops += fp.flops;
+        }
+      } else {
+        flops += 4.0 * NV * (double)Tqp * Tkp * dpad;
+      }
+      tfree(qh); tfree(kh); tfree(vht); tfree(oh);
+      return;
+    }
+    Tensor sc = talloc(NV, 1, Tqp, Tkp);   // materialised scores (B2E_FLASH=0 or head_dim > 192)
     if (!dry) {
       ConvDesc d1;
       d1.s0.ptr = qh.p; d1.s0.C = dpad;
