@@ -284,7 +284,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
             const float sc_ = __uint_as_float(sr[c >> 1][(c & 1) * 16 + e]);
-            const float v_ = exp2f(fmaf(sc_, p.scale_log2e, -mc));
+            float v_;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(v_) : "f"(fmaf(sc_, p.scale_log2e, -mc)));   // one MUFU op
             pe[e] = (full_blk || k0 + c * 16 + e < p.valid_k) ? v_ : 0.f;
           }
 #pragma unroll

@@ -803,6 +803,15 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
           }
           tfree(sc);
           tfree(vt);
+        } else if (heads > 1 && (a.C / heads) % 8 == 0 && a.C / heads <= 192 && (T == 64 || (T % 128 == 0 && T <= 1024) || T == 4096) &&
+                   !(getenv("B2E_FLASH") && atoi(getenv("B2E_FLASH")) == 0)) {
+          // multi-head attention (LDM: 14-28 heads of 32 channels): fused tcgen05 attention over head-major copies
+          const int d = a.C / heads;
+          tfree(o);
+          Tensor o2;
+          mh_attention(qkv, 0, qkv, a.P, 2 * a.P, T, T, T, heads, d, pad64(d), &o2, h.H, h.W, a.P);
+          o2.Cr = a.C;
+          o = o2;
         } else if (heads > 1 && (a.C / heads) % 8 == 0 && a.C / heads <= 64 && T % 128 == 0 && T <= 1024 &&
                    conv_geometry(B * heads, h.H, h.W, T).Nt == 1) {
           // multi-head tensor-core attention: heads become "virtual images" v = n*heads + h of head-major copies of

@@ -781,16 +781,19 @@ __global__ void gather_heads_T_kernel(const bf16* __restrict__ src, bf16* __rest
 __global__ void __launch_bounds__(256) scatter_heads_kernel(const bf16* __restrict__ oh, bf16* __restrict__ out, int N, int T,
                                                             int Tpad, int pitch, int heads, int d, int dpad) {
   pdl_wait();
-  const int c8 = (heads * d) >> 3;
+  const int c8 = pitch >> 3;   // the tail [heads*d, pitch) of every row is zero padding
   const int64_t total = (int64_t)N * T * c8;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int s = (int)(i % c8);
     const int64_t nt = i / c8;
     const int64_t n = nt / T;
     const int t = (int)(nt % T);
-    const int c0 = s * 8, h = c0 / d, cc = c0 - h * d;
-    // d % 8 == 0: an 8-channel slot never straddles two heads
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(oh + (((n * heads + h) * Tpad + t) * (int64_t)dpad + cc)));
+    const int c0 = s * 8;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (c0 < heads * d) {
+      const int h = c0 / d, cc = c0 - h * d;   // d % 8 == 0: an 8-channel slot never straddles two heads
+      v = __ldg(reinterpret_cast<const uint4*>(oh + (((n * heads + h) * Tpad + t) * (int64_t)dpad + cc)));
+    }
     *reinterpret_cast<uint4*>(out + nt * pitch + c0) = v;
   }
 }
@@ -813,7 +816,7 @@ int gather_heads_launch(const bf16* src, bf16* dst, int N, int Tsrc, int Tpad, i
 
 int scatter_heads_launch(const bf16* oh, bf16* out, int N, int T, int Tpad, int pitch, int heads, int d, int dpad, cudaStream_t st) {
   B2E_REQUIRE(d % 8 == 0, B2E_UNSUPPORTED_SHAPE, "scatter_heads: head_dim %d", d);
-  const int64_t total = (int64_t)N * T * (heads * d / 8);
+  const int64_t total = (int64_t)N * T * (pitch / 8);
   int grid = (int)((total + 255) / 256);
   if (grid > kNumSMs * 32) grid = kNumSMs * 32;
   launch_pdl(scatter_heads_kernel, dim3(grid), dim3(256), 0, st, oh, out, N, T, Tpad, pitch, heads, d, dpad);
