@@ -35,7 +35,7 @@ class UNetConfig(C.Structure):
                 ("layers_per_block", C.c_int32), ("norm_num_groups", C.c_int32),
                 ("norm_eps", C.c_float), ("attention_head_dim", C.c_int32),
                 ("flip_sin_to_cos", C.c_int32), ("freq_shift", C.c_float), ("downsample_padding", C.c_int32),
-                ("cross_attention_dim", C.c_int32), ("num_attention_heads", C.c_int32)]
+                ("cross_attention_dim", C.c_int32), ("num_attention_heads", C.c_int32), ("precision", C.c_int32)]
 
 
 class VQDecConfig(C.Structure):

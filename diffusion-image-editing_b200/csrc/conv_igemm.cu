@@ -88,6 +88,7 @@ struct ConvKParams {
   int out_bf16;         // 1: stage + TMA-store the bf16 NHWC tile through map_out
   float* out_f32_nchw;
   float* tile_stats;    // fused GroupNorm statistics or null
+  int split_pitch;      // > 0: split-bf16 output (fp32-accurate mode): planes [hi | lo | hi] of split_pitch channels each
   long long* trace;     // B2E_TRACE: clock64 stamps of CTA 0's warp loops (halo kernels), else null
 };
 // trace regions (long long indices): MMA [0, 4*512) {iter start, A ready, B ready, issued}; producer A
@@ -442,6 +443,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         __threadfence();
         part_row = p.split_ws + (int64_t)tile * splits * (kConvBlockM * BN) + r * 16;
       }
+      // split-bf16 output (fp32-accurate mode): the accumulator is walked twice - pass 0 stages bf16(v) (planes 0 and
+      // 2 of the output), pass 1 the remainder bf16(v - bf16(v)) (plane 1); TMEM is released after the last pass
+      const int npass = (Cfg::kSlabs > 0 && p.out_bf16 && p.split_pitch) ? 2 : 1;
+#pragma unroll 1
+      for (int pass = 0; pass < npass; ++pass) {
       if (Cfg::kSlabs > 0 && p.out_bf16) {
         // the previous tile's TMA store must have finished reading the staging buffer
         if (store_leader) tma_store_wait_read();
@@ -463,7 +469,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           }
         } else {
           tmem_ld16(taddr + c * 16, v);
-          if (c == BN / 16 - 1) release_tmem();
+          if (c == BN / 16 - 1 && pass == npass - 1) release_tmem();
         }
         const int col0 = tc.n_tile * BN + c * 16;
         if (Cfg::kSlabs > 0 && p.out_bf16) {
@@ -491,6 +497,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
               const float4 b = __ldg(tp + j);
               v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
             }
+          }
+          if (pass) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __fsub_rn(v[j], __bfloat162float(__float2bfloat16_rn(v[j])));
           }
           uint4 o0, o1;
           __nv_bfloat162* ob0 = reinterpret_cast<__nv_bfloat162*>(&o0);
@@ -523,8 +533,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         epi_bar_sync();
         if (store_leader) {
 #pragma unroll
-          for (int sl = 0; sl < Cfg::kSlabs; ++sl)
-            tma_store_5d(&map_out, staging + sl * (kConvBlockM * 128), tc.n_tile * BN + sl * 64, tc.w0, 0, tc.h0, tc.n0);
+          for (int sl = 0; sl < Cfg::kSlabs; ++sl) {
+            const int ch = tc.n_tile * BN + sl * 64;
+            tma_store_5d(&map_out, staging + sl * (kConvBlockM * 128), ch + pass * p.split_pitch, tc.w0, 0, tc.h0, tc.n0);
+            if (p.split_pitch && pass == 0)
+              tma_store_5d(&map_out, staging + sl * (kConvBlockM * 128), ch + 2 * p.split_pitch, tc.w0, 0, tc.h0, tc.n0);
+          }
           tma_store_commit();
         }
         if (p.tile_stats) {
@@ -567,6 +581,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           }
         }
       }
+      }   // pass
       }   // mt
       if (tr) p.trace[kTrEpi + it * 4 + 3] = clock64();
     }
@@ -584,7 +599,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
 
 // ------------------------------------------------------------------ weight packing
 __global__ void pack_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int Cin,
-                                   int kk, int tap_width, int row_len, int col_off, int ci0, int cin_total) {
+                                   int kk, int tap_width, int row_len, int col_off, int ci0, int cin_total, int lo) {
   // out[co*row_len + col_off + t*tap_width + ci] = w[(co*cin_total + ci0 + ci)*kk + t]   for ci < Cin
   const int64_t total = (int64_t)Cout * kk * Cin;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -592,8 +607,11 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, bf16* __restrict
     const int ci = (int)(i % Cin);
     const int t = (int)((i / Cin) % kk);
     const int co = (int)(i / ((int64_t)Cin * kk));
+    const float v = w[((int64_t)co * cin_total + ci0 + ci) * kk + t];
+    const bf16 hi = __float2bfloat16_rn(v);
+    // lo: the bf16-rounded remainder of the split representation v ~= hi + lo (fp32-accurate mode)
     out[(int64_t)co * row_len + col_off + (int64_t)t * tap_width + ci] =
-        __float2bfloat16_rn(w[((int64_t)co * cin_total + ci0 + ci) * kk + t]);
+        lo ? __float2bfloat16_rn(__fsub_rn(v, __bfloat162float(hi))) : hi;
   }
 }
 
@@ -628,13 +646,13 @@ __global__ void fill_identity_kernel(bf16* __restrict__ out, int C, int row_len,
 }
 
 int conv_pack_weight(const float* w, bf16* out, int Cout, int Cin, int ksize, int tap_width, int row_len,
-                     int col_off, cudaStream_t st, int ci0, int cin_total) {
+                     int col_off, cudaStream_t st, int ci0, int cin_total, int lo) {
   const int kk = ksize * ksize;
   const int64_t total = (int64_t)Cout * kk * Cin;
   int grid = (int)((total + 255) / 256);
   if (grid > kNumSMs * 16) grid = kNumSMs * 16;
   pack_weight_kernel<<<grid, 256, 0, st>>>(w, out, Cout, Cin, kk, tap_width, row_len, col_off, ci0,
-                                           cin_total > 0 ? cin_total : Cin);
+                                           cin_total > 0 ? cin_total : Cin, lo);
   return check_launch("pack_weight");
 }
 
@@ -785,6 +803,9 @@ int conv_plan_build(ConvPlan* pl, const ConvDesc& d) {
   }
   B2E_REQUIRE(!d.tile_stats || (g.stats_ok && d.out_bf16), B2E_UNSUPPORTED_SHAPE,
               "conv: fused GroupNorm statistics are not available for this output shape");
+  B2E_REQUIRE(d.out_planes == 1 || (d.out_planes == 3 && d.out_bf16 && !d.tile_stats), B2E_INVALID_ARG,
+              "conv: split-bf16 output needs 3 planes, an NHWC output and no fused statistics");
+  p.split_pitch = d.out_planes == 3 ? d.Cout : 0;
   p.tile_stats = d.tile_stats;
   p.taps = d.ksize * d.ksize;
   p.c0_chunks = d.s0.C / K;
@@ -815,7 +836,7 @@ int conv_plan_build(ConvPlan* pl, const ConvDesc& d) {
   if (d.r0.ptr && (rc = encode_act_map(&p.map_r0, d.r0.ptr, d.N, p.Ho, p.Wo, d.r0.C, 1, p.Wt, a_ht, p.Nt))) return rc;
   if (d.r1.ptr && (rc = encode_act_map(&p.map_r1, d.r1.ptr, d.N, p.Ho, p.Wo, d.r1.C, 1, p.Wt, a_ht, p.Nt))) return rc;
   p.has_out_bf16 = d.out_bf16 != nullptr;
-  if (d.out_bf16 && (rc = encode_act_map(&p.map_out, d.out_bf16, d.N, p.Ho, p.Wo, d.Cout, 1, p.Wt, p.Ht, p.Nt))) return rc;
+  if (d.out_bf16 && (rc = encode_act_map(&p.map_out, d.out_bf16, d.N, p.Ho, p.Wo, d.Cout * d.out_planes, 1, p.Wt, p.Ht, p.Nt))) return rc;
   const uint64_t ktot = (uint64_t)p.taps * (d.s0.C + (d.s1.ptr ? d.s1.C : 0)) + (d.r0.ptr ? d.r0.C : 0) +
                         (d.r1.ptr ? d.r1.C : 0);
   uint64_t bd[2] = {ktot, d.b_batch_rows ? (uint64_t)d.N * d.b_batch_rows : (uint64_t)p.cout_pad};
@@ -892,6 +913,7 @@ int conv_launch(const ConvPlan& pl, const ConvEpilogue& ep, cudaStream_t st) {
   kp.bias = ep.bias; kp.bias2 = ep.bias2; kp.temb = ep.temb; kp.temb_stride = ep.temb_stride;
   kp.out_bf16 = pl.has_out_bf16; kp.out_f32_nchw = pl.has_out_bf16 ? nullptr : ep.out_f32_nchw;
   kp.tile_stats = pl.tile_stats;
+  kp.split_pitch = pl.split_pitch;
   // B2E_TRACE=<n>: the n-th halo launch (1-based) runs with clock64 tracing of CTA 0, then dumps to stderr
   kp.trace = nullptr;
   static const int trace_at = getenv("B2E_TRACE") ? atoi(getenv("B2E_TRACE")) : 0;

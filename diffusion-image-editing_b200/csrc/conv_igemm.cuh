@@ -34,6 +34,10 @@ struct ConvDesc {
   int b_batch_rows = 0, b_pitch = 0;
   int Cout = 0;
   bf16* out_bf16 = nullptr;  // NHWC (N,Ho,Wo,Cout) through TMA store; null -> fp32 NCHW output only
+  // fp32-accurate mode: 3 -> the output is written as split bf16, channel planes [hi | lo | hi] of Cout channels each
+  // (pixel pitch 3*Cout): hi = bf16(v), lo = bf16(v - hi).  A consumer convolution reads it as ONE 3*Cout-channel
+  // source against weights packed [W_hi | W_hi | W_lo], i.e. x_hi W_hi + x_lo W_hi + x_hi W_lo (error ~2^-17 relative)
+  int out_planes = 1;
   // optional fused GroupNorm statistics of the (bf16-rounded) output: per (tile slot, channel) sum and
   // sum of squares, [conv_stats_slots()][Cout][2] floats; reduced per image by gn_finalize
   float* tile_stats = nullptr;
@@ -63,6 +67,7 @@ struct ConvPlan {
   int halo;     // 0, or MT = M tiles per CTA of the halo kernel: (8*MT)x16-pixel bricks, one halo load serves 3 vertical taps
   int pair;     // 1: SM-pair kernel (tcgen05.mma.cta_group::2, 256 x 128 tile per cluster)
   int has_out_bf16;
+  int split_pitch;   // channels per plane of a split-bf16 output (0: plain bf16)
   float* tile_stats;
   double flops;
 };
@@ -92,8 +97,9 @@ int flash_attn_launch(const FlashPlan& pl, int valid_k, float scale, cudaStream_
 
 // fp32 [Cout][Cin][k][k] -> bf16 out[co*row_len + col_off + t*tap_width + ci]   (t = kh*k + kw)
 // (ci0, cin_total): pack only input channels [ci0, ci0 + Cin) of a weight with cin_total input channels
+// lo = 1: pack the remainder bf16(w - bf16(w)) instead of bf16(w) (split-bf16 weights of the fp32-accurate mode)
 int conv_pack_weight(const float* w, bf16* out, int Cout, int Cin, int ksize, int tap_width, int row_len,
-                     int col_off, cudaStream_t st, int ci0 = 0, int cin_total = 0);
+                     int col_off, cudaStream_t st, int ci0 = 0, int cin_total = 0, int lo = 0);
 // dgrad weights (flipped taps, transposed channels): out[ci*row_len + col_off + t*tap_width + co] = w[(co*Cin+ci)*kk + kk-1-t]
 int conv_pack_weight_dgrad(const float* w, bf16* out, int Cout, int Cin, int ksize, int tap_width, int row_len, int col_off,
                            cudaStream_t st);

@@ -87,6 +87,10 @@ struct Arena {
 struct b2e_unet {
   b2e_unet_config cfg;
   int64_t max_batch = 0;
+  // fp32-accurate mode (cfg.precision == 1): PL = 3, every activation is a split-bf16 tensor with channel planes
+  // [hi | lo | hi] (value = hi + lo) and every GEMM weight segment is packed [W_hi | W_hi | W_lo], so the unchanged
+  // tcgen05 main loop computes x_hi W_hi + x_lo W_hi + x_hi W_lo with fp32 accumulation (~2^-17 relative error)
+  int PL = 1;
   int temb_dim = 0, sumC = 0, heads_dim = 0;
   std::vector<void*> owned;
   struct PRec { std::string name; int64_t numel; int64_t fan_in; std::function<int(const float*, cudaStream_t)> set; };
@@ -145,19 +149,35 @@ struct b2e_unet {
       return (int)B2E_OK;
     });
   }
+  // one K segment of a weight row: `plane_w` columns per plane starting at col_off; taps are tap_w * PL columns apart
+  static int pack_w(int PL, const float* src, bf16* w, int cout, int cin, int k, int tap_w, int row_len, int col_off,
+                    int plane_w, cudaStream_t st, int ci0 = 0, int cin_total = 0) {
+    if (PL == 1) return conv_pack_weight(src, w, cout, cin, k, tap_w, row_len, col_off, st, ci0, cin_total);
+    int rc = conv_pack_weight(src, w, cout, cin, k, tap_w * 3, row_len, col_off, st, ci0, cin_total, 0);
+    if (!rc) rc = conv_pack_weight(src, w, cout, cin, k, tap_w * 3, row_len, col_off + plane_w, st, ci0, cin_total, 0);
+    if (!rc) rc = conv_pack_weight(src, w, cout, cin, k, tap_w * 3, row_len, col_off + 2 * plane_w, st, ci0, cin_total, 1);
+    return rc;
+  }
+  // identity residual segment over the hi and lo planes (the repeated hi plane gets zero weights)
+  static int fill_id(int PL, bf16* w, int C, int row_len, int col_off, int plane_w) {
+    int rc = conv_fill_identity(w, C, row_len, col_off, 0);
+    if (!rc && PL == 3) rc = conv_fill_identity(w, C, row_len, col_off + plane_w, 0);
+    return rc;
+  }
   // conv / linear weight that feeds the tcgen05 GEMM: packed bf16 [cout_pad][k*k][cin_pad]
   ConvL make_conv(const std::string& name, int cin, int cout, int k, int cin_pad = 0, int res_c = 0) {
     ConvL c;
     c.cin = cin; c.cin_pad = cin_pad ? cin_pad : pad64(cin); c.cout = cout; c.k = k; c.cout_pad = conv_cout_pad(cout);
-    c.res_c = res_c; c.row_len = k * k * c.cin_pad + res_c;
+    c.res_c = res_c; c.row_len = PL * (k * k * c.cin_pad + res_c);
     c.w = dmalloc<bf16>((size_t)c.cout_pad * c.row_len);
     c.b = dmalloc<float>(c.cout_pad);
     ConvL cc = c;
     ConvL dd;
+    const int PL = this->PL;
     // (a <= 16-channel output, i.e. conv_out, receives its gradient as a 64-channel padded NHWC tensor)
     if (decoder) { c.dg = make_dgrad(cin, cout > 16 ? c.cout_pad : kConvBlockK, k); dd = dgrads[c.dg]; cc.dg = c.dg; }
-    add_param(name + ".weight", (int64_t)cout * cin * k * k, (int64_t)cin * k * k, [cc, dd](const float* src, cudaStream_t st) {
-      int rc = conv_pack_weight(src, cc.w, cc.cout, cc.cin, cc.k, cc.cin_pad, cc.row_len, 0, st);
+    add_param(name + ".weight", (int64_t)cout * cin * k * k, (int64_t)cin * k * k, [cc, dd, PL](const float* src, cudaStream_t st) {
+      int rc = pack_w(PL, src, cc.w, cc.cout, cc.cin, cc.k, cc.cin_pad, cc.row_len, 0, cc.cin_pad, st);
       if (!rc && cc.dg >= 0) rc = conv_pack_weight_dgrad(src, dd.w, cc.cout, cc.cin, cc.k, dd.cin_pad, dd.row_len, 0, st);
       return rc;
     });
@@ -202,15 +222,20 @@ struct b2e_unet {
       ConvL sd;
       if (decoder) { r.sc_dg = make_dgrad(cin, r.c2.cout_pad, 1); sd = dgrads[r.sc_dg]; }
       const int sc_dg = r.sc_dg;
-      add_param(name + ".conv_shortcut.weight", (int64_t)cout * cin, cin, [cc, sd, sc_dg, cin, cin0, cin1, p0](const float* src, cudaStream_t st) {
-        int rc = conv_pack_weight(src, cc.w, cc.cout, cin0, 1, cin0, cc.row_len, 9 * cc.cin_pad, st, 0, cin);
-        if (!rc && cin1) rc = conv_pack_weight(src, cc.w, cc.cout, cin1, 1, cin1, cc.row_len, 9 * cc.cin_pad + p0, st, cin0, cin);
+      const int PL = this->PL;
+      add_param(name + ".conv_shortcut.weight", (int64_t)cout * cin, cin, [cc, sd, sc_dg, cin, cin0, cin1, p0, p1, PL](const float* src, cudaStream_t st) {
+        int rc = pack_w(PL, src, cc.w, cc.cout, cin0, 1, cin0, cc.row_len, PL * 9 * cc.cin_pad, p0, st, 0, cin);
+        if (!rc && cin1) rc = pack_w(PL, src, cc.w, cc.cout, cin1, 1, cin1, cc.row_len, PL * (9 * cc.cin_pad + p0), p1, st, cin0, cin);
         if (!rc && sc_dg >= 0) rc = conv_pack_weight_dgrad(src, sd.w, cc.cout, cin, 1, sd.cin_pad, sd.row_len, 0, st);
         return rc;
       });
       add_f32(name + ".conv_shortcut.bias", r.c2.b2, cout, cin);
     } else if (r.c2.w) {
-      if (conv_fill_identity(r.c2.w, cout, r.c2.row_len, 9 * r.c2.cin_pad, 0)) build_error = B2E_CUDA_ERROR;
+      if (cin1 && PL == 3) {   // identity over two split sources: rows [0, cin0) -> source 0, rows [cin0, cout) -> source 1
+        if (fill_id(PL, r.c2.w, cin0, r.c2.row_len, PL * 9 * r.c2.cin_pad, p0) ||
+            fill_id(PL, r.c2.w + (size_t)cin0 * r.c2.row_len, cin1, r.c2.row_len, PL * (9 * r.c2.cin_pad + p0), p1))
+          build_error = B2E_CUDA_ERROR;
+      } else if (fill_id(PL, r.c2.w, cout, r.c2.row_len, PL * 9 * r.c2.cin_pad, p0)) build_error = B2E_CUDA_ERROR;
     }
     resnets.push_back(r);
     return (int)resnets.size() - 1;
@@ -280,25 +305,26 @@ struct b2e_unet {
     a.gn = make_norm(name + ".group_norm", C);
     // q, k, v fused into one [3P][P] GEMM weight (each projection padded to P rows / columns)
     a.qkv.cin = C; a.qkv.cin_pad = P; a.qkv.cout = 3 * P; a.qkv.cout_pad = conv_cout_pad(3 * P); a.qkv.k = 1;
-    a.qkv.w = dmalloc<bf16>((size_t)a.qkv.cout_pad * P);
+    a.qkv.w = dmalloc<bf16>((size_t)a.qkv.cout_pad * P * PL);
     a.qkv.b = dmalloc<float>(a.qkv.cout_pad);
+    const int PL = this->PL;
     const char* nm[3] = {"to_q", "to_k", "to_v"};
     ConvL qd;
     if (decoder) { a.qkv_dg = make_dgrad(C, 2 * P, 1, P); qd = dgrads[a.qkv_dg]; }   // K = (dQ ++ dK) ++ residual segment dV
     const int qkv_dg = a.qkv_dg;
     for (int i = 0; i < 3; ++i) {
-      bf16* wdst = a.qkv.w + (size_t)i * P * P;
+      bf16* wdst = a.qkv.w + (size_t)i * P * P * PL;
       float* bdst = a.qkv.b + (size_t)i * P;
-      add_param(name + "." + nm[i] + ".weight", (int64_t)C * C, C, [wdst, qd, qkv_dg, i, C, P](const float* src, cudaStream_t st) {
-        int rc = conv_pack_weight(src, wdst, C, C, 1, C, P, 0, st);
+      add_param(name + "." + nm[i] + ".weight", (int64_t)C * C, C, [wdst, qd, qkv_dg, i, C, P, PL](const float* src, cudaStream_t st) {
+        int rc = pack_w(PL, src, wdst, C, C, 1, C, P * PL, 0, P, st);
         if (!rc && qkv_dg >= 0) rc = conv_pack_weight_dgrad(src, qd.w, C, C, 1, P, qd.row_len, i * P, st);
         return rc;
       });
       add_f32(name + "." + nm[i] + ".bias", bdst, C, C);
     }
-    a.qkv.row_len = P;
+    a.qkv.row_len = P * PL;
     a.proj = make_conv(name + ".to_out.0", C, C, 1, 0, P);   // + identity residual segment
-    if (a.proj.w && conv_fill_identity(a.proj.w, C, a.proj.row_len, a.proj.cin_pad, 0)) build_error = B2E_CUDA_ERROR;
+    if (a.proj.w && fill_id(PL, a.proj.w, C, a.proj.row_len, PL * a.proj.cin_pad, P)) build_error = B2E_CUDA_ERROR;
     attns.push_back(a);
     return (int)attns.size() - 1;
   }
@@ -370,13 +396,17 @@ int build_model(b2e_unet* m) {
   m->in_im2col = c.in_channels == 1 || c.in_channels == 3 || c.in_channels == 4;
   if (m->in_im2col) {
     ConvL ci;
-    ci.cin = ci.cin_pad = kConvBlockK; ci.cout = c0; ci.k = 1; ci.cout_pad = conv_cout_pad(c0); ci.row_len = kConvBlockK;
+    const int PL = m->PL;
+    ci.cin = ci.cin_pad = kConvBlockK; ci.cout = c0; ci.k = 1; ci.cout_pad = conv_cout_pad(c0); ci.row_len = kConvBlockK * PL;
     ci.w = m->dmalloc<bf16>((size_t)ci.cout_pad * ci.row_len);
     ci.b = m->dmalloc<float>(ci.cout_pad);
     const int cin = c.in_channels;
-    m->add_param("conv_in.weight", (int64_t)c0 * cin * 9, (int64_t)cin * 9, [ci, cin](const float* src, cudaStream_t st) {
-      // column of (tap t, channel c) = t * Cin + c, the order pack_input_im2col writes
-      return conv_pack_weight(src, ci.w, ci.cout, cin, 3, cin, ci.row_len, 0, st);
+    m->add_param("conv_in.weight", (int64_t)c0 * cin * 9, (int64_t)cin * 9, [ci, cin, PL](const float* src, cudaStream_t st) {
+      // column of (tap t, channel c) = t * Cin + c, the order pack_input_im2col writes (per 64-column plane)
+      int rc = conv_pack_weight(src, ci.w, ci.cout, cin, 3, cin, ci.row_len, 0, st);
+      if (!rc && PL == 3) rc = conv_pack_weight(src, ci.w, ci.cout, cin, 3, cin, ci.row_len, kConvBlockK, st);
+      if (!rc && PL == 3) rc = conv_pack_weight(src, ci.w, ci.cout, cin, 3, cin, ci.row_len, 2 * kConvBlockK, st, 0, 0, 1);
+      return rc;
     });
     m->add_f32("conv_in.bias", ci.b, c0, (int64_t)cin * 9);
     m->conv_in = ci;
@@ -467,10 +497,11 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
   std::vector<b2e_unet::Op>* cur = &ops_fwd;   // the op list being recorded
 #define ops (*cur)
   const bool keep = m->grad;                    // gradient mode: every activation stays live for the backward pass
+  const int PL = m->PL;                         // channel planes per activation tensor (3: split-bf16, fp32-accurate mode)
   double flops = 0;
   int rc = B2E_OK;
   auto talloc = [&](int N, int H, int W, int C, int Cr = 0) {
-    Tensor t; t.N = N; t.H = H; t.W = W; t.C = C; t.Cr = Cr ? Cr : C; t.bytes = (size_t)N * H * W * C * sizeof(bf16);
+    Tensor t; t.N = N; t.H = H; t.W = W; t.C = C; t.Cr = Cr ? Cr : C; t.bytes = (size_t)N * H * W * C * PL * sizeof(bf16);
     t.p = (bf16*)ar.alloc(t.bytes);
     return t;
   };
@@ -506,7 +537,7 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
     const size_t tstats_bytes = sizeof(float) * 2 * (size_t)conv_stats_slots(geo) * cout_x;
     // few tile slots per image (low-resolution levels): the consumer reduces them itself
     const bool raw_stats = geo.w_blks * geo.h_blks <= 16;
-    if (out && want_stats && geo.stats_ok) {
+    if (out && want_stats && geo.stats_ok && PL == 1) {
       tstats = (float*)ar.alloc(tstats_bytes);
       if (raw_stats) {
         out->tstats = tstats; out->tstats_bytes = tstats_bytes; out->ts_nt = geo.Nt; out->ts_per_img = geo.w_blks * geo.h_blks;
@@ -515,20 +546,21 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
       }
     }
     if (dry) {
-      flops += 2.0 * B * Ho * Wo * (double)cout_x * (L.k * L.k * (x0.C + (x1 ? x1->C : 0)) + L.res_c);
+      flops += 2.0 * B * Ho * Wo * (double)cout_x * (L.k * L.k * (x0.C + (x1 ? x1->C : 0)) + L.res_c) * PL;
       if (tstats && !raw_stats) ar.release(tstats, tstats_bytes);
       return;
     }
     ConvDesc d;
-    d.s0 = ConvSrc{x0.p, x0.C};
-    if (x1) d.s1 = ConvSrc{x1->p, x1->C};
-    if (r0) d.r0 = ConvSrc{r0->p, r0->C};
-    if (r1) d.r1 = ConvSrc{r1->p, r1->C};
+    d.s0 = ConvSrc{x0.p, x0.C * PL};
+    if (x1) d.s1 = ConvSrc{x1->p, x1->C * PL};
+    if (r0) d.r0 = ConvSrc{r0->p, r0->C * PL};
+    if (r1) d.r1 = ConvSrc{r1->p, r1->C * PL};
+    d.out_planes = out ? PL : 1;
     d.N = B; d.H = x0.H; d.W = x0.W; d.ksize = L.k; d.stride = stride; d.w_packed = L.w; d.Cout = cout_x;
     d.stride2_pad1 = c.downsample_padding == 1;
-    if (L.k * L.k * (x0.C + (x1 ? x1->C : 0)) + L.res_c != L.row_len) {
+    if (PL * (L.k * L.k * (x0.C + (x1 ? x1->C : 0)) + L.res_c) != L.row_len) {
       rc = B2E_INVALID_ARG; set_error("unet: weight row length %d does not match the operands (%d)", L.row_len,
-                                      L.k * L.k * (x0.C + (x1 ? x1->C : 0)) + L.res_c); return;
+                                      PL * (L.k * L.k * (x0.C + (x1 ? x1->C : 0)) + L.res_c)); return;
     }
     d.out_bf16 = out ? out->p : nullptr;
     d.tile_stats = tstats;
@@ -574,7 +606,7 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
     a.x0 = x0.p; a.x1 = x1 ? x1->p : nullptr; a.C0 = x0.Cr; a.C1 = x1 ? x1->Cr : 0;
     a.P0 = x0.C; a.P1 = x1 ? x1->C : 0; a.Pout = out->C;
     a.N = B; a.HW = x0.H * x0.W; a.G = G; a.eps = eps_override > 0.f ? eps_override : c.norm_eps; a.gamma = L.g; a.beta = L.b;
-    a.partial = gn_part; a.chunks = gn_chunks(a.HW, C); a.out = out->p; a.silu = silu;
+    a.partial = gn_part; a.chunks = gn_chunks(a.HW, C); a.out = out->p; a.silu = silu; a.planes = PL;
     bool fused = x0.cstats && (!x1 || x1->cstats);
     a.cs0 = fused ? x0.cstats : nullptr;
     a.cs1 = fused && x1 ? x1->cstats : nullptr;
@@ -601,7 +633,7 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
       ops.push_back({[zq, xin, B, Cin, S](cudaStream_t st) { return pack_input_launch(zq, xin.p, B, Cin, S, S, kConvBlockK, true, st); },
                      3, 0.0, (double)B * HW * (4.0 * Cin + 2.0 * kConvBlockK)});
     } else {
-      ops.push_back({[m, xin, B, Cin, S, im2col](cudaStream_t st) { return pack_input_launch(m->in_x, xin.p, B, Cin, S, S, kConvBlockK, im2col, st); },
+      ops.push_back({[m, xin, B, Cin, S, im2col, PL](cudaStream_t st) { return pack_input_launch(m->in_x, xin.p, B, Cin, S, S, kConvBlockK, im2col, st, PL); },
                      3, 0.0, (double)B * HW * (4.0 * Cin + 2.0 * kConvBlockK)});
     }
     if (!m->decoder) {
@@ -766,7 +798,15 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
         const int heads = c.attention_head_dim > 0 ? a.C / c.attention_head_dim : 1;
         const int T = h.H * h.W, C = a.P;   // C: padded width of q / k / v (zero tail: no effect on Q K^T, zero rows of V^T)
         const ConvGeom gq = conv_geometry(B, h.H, h.W, T);
-        if (heads == 1 && T % 128 == 0 && (T <= 1024 || T == 2048 || T == 4096) && gq.Nt == 1) {
+        if (PL == 3) {
+          // fp32-accurate mode: fp32 attention core on the CUDA cores over the split-bf16 q | k | v planes
+          if (!dry) {
+            const int Cr = a.C;
+            ops.push_back({[qkv, o, B, T, C, Cr, heads](cudaStream_t st) { return attention_split_launch(qkv.p, o.p, B, T, Cr, C, heads, st); },
+                           2, 4.0 * B * (double)T * T * Cr, 0.0, "attention (fp32, split-bf16 operands)"});
+          }
+          flops += 4.0 * B * (double)T * T * a.C;
+        } else if (heads == 1 && T % 128 == 0 && (T <= 1024 || T == 2048 || T == 4096) && gq.Nt == 1) {
           // tensor-core attention: S = Q K^T and O = P V are batched GEMMs on the tcgen05 kernel (the per-image
           // B operand is read straight from the qkv tensor / a transposed copy of V); softmax in fp32 between
           Tensor sc = talloc(B, h.H, h.W, T);
@@ -924,8 +964,8 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
         Tensor up = talloc(B, h.H * 2, h.W * 2, h.C, h.Cr), out;
         if (!dry) {
           Tensor hh = h;
-          ops.push_back({[hh, up, B](cudaStream_t st) { return upsample2x_launch(hh.p, up.p, B, hh.H, hh.W, hh.C, st); },
-                         3, 0.0, 10.0 * B * hh.H * hh.W * hh.C});
+          ops.push_back({[hh, up, B, PL](cudaStream_t st) { return upsample2x_launch(hh.p, up.p, B, hh.H, hh.W, hh.C * PL, st); },
+                         3, 0.0, 10.0 * B * hh.H * hh.W * hh.C * PL});
         }
         if (!on_stack(h)) tfree(h);
         conv(m->ups[nd.idx], up, nullptr, 1, ConvEpilogue{}, &out, nullptr);
@@ -1109,8 +1149,14 @@ int b2e_unet_create(const b2e_unet_config* cfg, int64_t max_batch, b2e_unet** ou
     }
   }
   B2E_REQUIRE(cfg->sample_size % (1 << (cfg->n_blocks - 1)) == 0, B2E_UNSUPPORTED_SHAPE, "unet_create: sample_size");
+  B2E_REQUIRE(cfg->precision == 0 || cfg->precision == 1, B2E_INVALID_ARG, "unet_create: precision must be 0 (bf16) or 1 (fp32-accurate)");
+  if (cfg->precision == 1) {
+    B2E_REQUIRE(cfg->cross_attention_dim == 0 && (cfg->in_channels == 1 || cfg->in_channels == 3 || cfg->in_channels == 4),
+                B2E_UNSUPPORTED_SHAPE, "unet_create: the fp32-accurate mode covers UNet2DModel with 1, 3 or 4 input channels");
+  }
   b2e_unet* m = new b2e_unet();
   m->cfg = *cfg;
+  m->PL = cfg->precision == 1 ? 3 : 1;
   m->max_batch = max_batch;
   int rc = build_model(m);
   if (!rc && cudaDeviceSynchronize() != cudaSuccess) { set_error("unet_create: device error"); rc = B2E_CUDA_ERROR; }

@@ -31,6 +31,7 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 constexpr int kGNUnroll = 4;
 
 // (forward GroupNorm kernels: 256 threads, or 512 when the tensor has more than 2048 channels - SD concatenations)
+template <bool SPLIT>
 __global__ void __launch_bounds__(512) gn_partial_kernel(GNArgs a) {
   pdl_wait();
   __shared__ float s_sum[4096], s_sq[4096];
@@ -46,18 +47,28 @@ __global__ void __launch_bounds__(512) gn_partial_kernel(GNArgs a) {
     const int c = s * 8;
     const bf16* src; int cs, coff;
     if (c < a.C0) { src = a.x0; cs = a.P0; coff = c; } else { src = a.x1; cs = a.P1; coff = c - a.C0; }
+    constexpr bool split = SPLIT;         // split-bf16 tensors: value = plane 0 (hi) + plane 1 (lo), pixel pitch 3 * P
+    const int lo_off = cs;
+    cs *= a.planes;
     src += (int64_t)n * a.HW * cs + coff;
     for (int p = p0 + pl; p < p1; p += ppi * kGNUnroll) {
-      uint4 v[kGNUnroll];
+      uint4 v[kGNUnroll], w[kGNUnroll];
 #pragma unroll
       for (int u = 0; u < kGNUnroll; ++u) {
         const int q = p + u * ppi;
         v[u] = q < p1 ? __ldg(reinterpret_cast<const uint4*>(src + (int64_t)q * cs)) : make_uint4(0, 0, 0, 0);
+        w[u] = (split && q < p1) ? __ldg(reinterpret_cast<const uint4*>(src + (int64_t)q * cs + lo_off)) : make_uint4(0, 0, 0, 0);
       }
 #pragma unroll
       for (int u = 0; u < kGNUnroll; ++u) {
         float f[8];
         unpack8(v[u], f);
+        if (split) {
+          float g[8];
+          unpack8(w[u], g);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] += g[j];
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) { sum[j] += f[j]; sq[j] += f[j] * f[j]; }
       }
@@ -76,6 +87,7 @@ __global__ void __launch_bounds__(512) gn_partial_kernel(GNArgs a) {
   }
 }
 
+template <bool SPLIT>
 __global__ void __launch_bounds__(512) gn_apply_kernel(GNArgs a, int pix_per_block) {
   pdl_wait();
   __shared__ float s_mean[64], s_rstd[64];
@@ -123,9 +135,12 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(GNArgs a, int pix_per_blo
   if (pl >= ppi) return;
   const int c = s * 8;
   const int p0 = blockIdx.x * pix_per_block, p1 = min(a.HW, p0 + pix_per_block);
-  bf16* dst = a.out + (int64_t)n * a.HW * a.Pout + c;
+  constexpr bool split = SPLIT;           // split-bf16 tensors (fp32-accurate mode): planes [hi | lo | hi]
+  const int po = a.Pout * a.planes;       // output pixel pitch
+  bf16* dst = a.out + (int64_t)n * a.HW * po + c;
   if (c >= C) {   // zero padding of the output pitch
-    for (int p = p0 + pl; p < p1; p += ppi) *reinterpret_cast<uint4*>(dst + (int64_t)p * a.Pout) = make_uint4(0, 0, 0, 0);
+    for (int p = p0 + pl; p < p1; p += ppi)
+      for (int k = 0; k < a.planes; ++k) *reinterpret_cast<uint4*>(dst + (int64_t)p * po + k * a.Pout) = make_uint4(0, 0, 0, 0);
     return;
   }
   float scale[8], shift[8];
@@ -137,7 +152,45 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(GNArgs a, int pix_per_blo
   }
   const bf16* src; int cs, coff;
   if (c < a.C0) { src = a.x0; cs = a.P0; coff = c; } else { src = a.x1; cs = a.P1; coff = c - a.C0; }
+  const int lo_off = cs;
+  cs *= a.planes;
   src += (int64_t)n * a.HW * cs + coff;
+  if constexpr (split) {
+    // accurate path: x = hi + lo, exact-exp SiLU, output re-split into hi / lo (third plane repeats hi)
+    for (int p = p0 + pl; p < p1; p += ppi * kGNUnroll) {
+      uint4 v[kGNUnroll], w[kGNUnroll];
+#pragma unroll
+      for (int u = 0; u < kGNUnroll; ++u) {
+        const int q = p + u * ppi;
+        if (q < p1) {
+          v[u] = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)q * cs));
+          w[u] = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)q * cs + lo_off));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kGNUnroll; ++u) {
+        const int q = p + u * ppi;
+        if (q < p1) {
+          float f[8], g[8], l[8];
+          unpack8(v[u], f);
+          unpack8(w[u], g);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float y = fmaf(f[j] + g[j], scale[j], shift[j]);
+            if (a.silu) y = y / (1.f + expf(-y));
+            f[j] = y;
+            l[j] = __fsub_rn(y, __bfloat162float(__float2bfloat16_rn(y)));
+          }
+          const uint4 hi = pack8(f), lo = pack8(l);
+          bf16* o = dst + (int64_t)q * po;
+          *reinterpret_cast<uint4*>(o) = hi;
+          *reinterpret_cast<uint4*>(o + a.Pout) = lo;
+          *reinterpret_cast<uint4*>(o + 2 * a.Pout) = hi;
+        }
+      }
+    }
+    return;
+  }
   for (int p = p0 + pl; p < p1; p += ppi * kGNUnroll) {
     uint4 v[kGNUnroll];
 #pragma unroll
@@ -184,9 +237,12 @@ int gn_launch(const GNArgs& a, cudaStream_t st) {
               "groupnorm: unsupported channels %d+%d / groups %d", a.C0, a.C1, a.G);
   B2E_REQUIRE(a.P0 >= a.C0 && a.P1 >= a.C1 && a.Pout >= C && a.P0 % 8 == 0 && a.P1 % 8 == 0 && a.Pout % 8 == 0,
               B2E_INVALID_ARG, "groupnorm: bad channel pitches %d/%d -> %d", a.P0, a.P1, a.Pout);
+  B2E_REQUIRE(a.planes == 1 || (a.planes == 3 && !a.cs0 && !a.ts0 && !a.save_stats), B2E_INVALID_ARG,
+              "groupnorm: split-bf16 tensors take their statistics from the stand-alone pass");
   int rc = B2E_OK;
   if (!a.cs0 && !a.ts0) {
-    launch_pdl(gn_partial_kernel, dim3(dim3(a.chunks, a.N)), dim3(C > 2048 ? 512 : kGNThreads), 0, st, a);
+    if (a.planes == 3) launch_pdl(gn_partial_kernel<true>, dim3(dim3(a.chunks, a.N)), dim3(C > 2048 ? 512 : kGNThreads), 0, st, a);
+    else launch_pdl(gn_partial_kernel<false>, dim3(dim3(a.chunks, a.N)), dim3(C > 2048 ? 512 : kGNThreads), 0, st, a);
     rc = check_launch("gn_partial");
     if (rc) return rc;
   }
@@ -194,7 +250,8 @@ int gn_launch(const GNArgs& a, cudaStream_t st) {
   const int slots = a.Pout / 8, ppi = threads / slots;
   int ppb = ppi * kGNUnroll * 2;  // two unrolled sweeps per thread
   if (ppb > a.HW) ppb = a.HW;
-  launch_pdl(gn_apply_kernel, dim3(dim3((a.HW + ppb - 1) / ppb, a.N)), dim3(threads), 0, st, a, ppb);
+  if (a.planes == 3) launch_pdl(gn_apply_kernel<true>, dim3(dim3((a.HW + ppb - 1) / ppb, a.N)), dim3(threads), 0, st, a, ppb);
+  else launch_pdl(gn_apply_kernel<false>, dim3(dim3((a.HW + ppb - 1) / ppb, a.N)), dim3(threads), 0, st, a, ppb);
   return check_launch("gn_apply");
 }
 
@@ -378,7 +435,7 @@ __global__ void pack_input_kernel(const float* __restrict__ x, bf16* __restrict_
 // L1) and writes the pixel's 64 channels (128 B)
 template <int C>
 __global__ void __launch_bounds__(256) pack_input_im2col_kernel(const float* __restrict__ x, bf16* __restrict__ out, int B,
-                                                                int H, int W) {
+                                                                int H, int W, int planes) {
   pdl_wait();
   const int HW = H * W;
   const int64_t total = (int64_t)B * HW;
@@ -395,13 +452,24 @@ __global__ void __launch_bounds__(256) pack_input_im2col_kernel(const float* __r
       for (int c = 0; c < C; ++c)
         if (in) f[t * C + c] = __ldg(x + ((int64_t)b * C + c) * HW + hh * W + ww);
     }
-    uint4* o = reinterpret_cast<uint4*>(out + p * 64);
+    uint4* o = reinterpret_cast<uint4*>(out + p * 64 * planes);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = pack8(f + 8 * j);
+    for (int j = 0; j < 8; ++j) {
+      const uint4 hv = pack8(f + 8 * j);
+      o[j] = hv;
+      if (planes == 3) o[16 + j] = hv;
+    }
+    if (planes == 3) {   // split-bf16 (fp32-accurate mode): [hi | lo | hi]
+#pragma unroll
+      for (int k = 0; k < 64; ++k) f[k] = __fsub_rn(f[k], __bfloat162float(__float2bfloat16_rn(f[k])));
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[8 + j] = pack8(f + 8 * j);
+    }
   }
 }
 
-int pack_input_launch(const float* x, bf16* out, int B, int C, int H, int W, int cpad, bool im2col, cudaStream_t st) {
+int pack_input_launch(const float* x, bf16* out, int B, int C, int H, int W, int cpad, bool im2col, cudaStream_t st,
+                      int planes) {
   const int HW = H * W;
   int64_t total = (int64_t)B * HW;
   int grid = (int)((total + 255) / 256);
@@ -409,14 +477,15 @@ int pack_input_launch(const float* x, bf16* out, int B, int C, int H, int W, int
   if (im2col) {
     B2E_REQUIRE(9 * C <= 64 && cpad == 64, B2E_UNSUPPORTED_SHAPE, "pack_input: im2col needs 9*C <= 64");
     switch (C) {
-      case 1: launch_pdl(pack_input_im2col_kernel<1>, dim3(grid), dim3(256), 0, st, x, out, B, H, W); break;
-      case 3: launch_pdl(pack_input_im2col_kernel<3>, dim3(grid), dim3(256), 0, st, x, out, B, H, W); break;
-      case 4: launch_pdl(pack_input_im2col_kernel<4>, dim3(grid), dim3(256), 0, st, x, out, B, H, W); break;
+      case 1: launch_pdl(pack_input_im2col_kernel<1>, dim3(grid), dim3(256), 0, st, x, out, B, H, W, planes); break;
+      case 3: launch_pdl(pack_input_im2col_kernel<3>, dim3(grid), dim3(256), 0, st, x, out, B, H, W, planes); break;
+      case 4: launch_pdl(pack_input_im2col_kernel<4>, dim3(grid), dim3(256), 0, st, x, out, B, H, W, planes); break;
       default: B2E_REQUIRE(false, B2E_UNSUPPORTED_SHAPE, "pack_input: im2col supports 1, 3 or 4 input channels (got %d)", C);
     }
     return check_launch("pack_input_im2col");
   }
   B2E_REQUIRE(C <= 8 && cpad % 8 == 0, B2E_UNSUPPORTED_SHAPE, "pack_input: in_channels must be <= 8");
+  B2E_REQUIRE(planes == 1, B2E_UNSUPPORTED_SHAPE, "pack_input: split-bf16 output needs the im2col layout");
   launch_pdl(pack_input_kernel, dim3(grid), dim3(256), 0, st, x, out, B, C, HW, cpad);
   return check_launch("pack_input");
 }
@@ -1262,6 +1331,119 @@ attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, in
         *reinterpret_cast<__nv_bfloat162*>(out + ((int64_t)n * T + q0 + q) * P + h * d + c0) =
             __floats2bfloat162_rn(ax[q], ay[q]);
   }
+}
+
+// fp32-accurate mode: the same attention core on split-bf16 tensors, all arithmetic in fp32 on the CUDA cores
+// (1.3 % of the UNet's FLOPs).  qkv rows are [hi | lo | hi] planes of 3P channels (q | k | v blocks of P), out rows
+// [hi | lo | hi] planes of P channels.  Block = (image, head, 16 queries).
+__global__ void __launch_bounds__(kAttThreads)
+attention_split_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, int C, int P, int heads) {
+  pdl_wait();
+  extern __shared__ __align__(16) uint8_t att_smem[];
+  const int d = C / heads;
+  float* Qs = reinterpret_cast<float*>(att_smem);   // [16][d]
+  float* S = Qs + kAttQ * d;                         // [16][T]
+  const int qt = blockIdx.x, h = blockIdx.y, n = blockIdx.z, tid = threadIdx.x;
+  const int q0 = qt * kAttQ;
+  const int64_t plane = 3 * (int64_t)P, row = 3 * plane;
+  const bf16* base = qkv + (int64_t)n * T * row;
+  const float scale = 1.0f / sqrtf((float)d);
+  for (int i = tid; i < kAttQ * d; i += kAttThreads) {
+    const int q = i / d, c = i % d;
+    const bf16* qp = base + (int64_t)(q0 + q) * row + h * d + c;
+    Qs[i] = (q0 + q < T) ? __bfloat162float(qp[0]) + __bfloat162float(qp[plane]) : 0.f;
+  }
+  const int64_t orow = 3 * (int64_t)P;
+  if (h == 0 && P > C) {   // zero padding of the output pitch (all planes)
+    for (int i = tid; i < kAttQ * (P - C) * 3; i += kAttThreads) {
+      const int k = i % 3, r = i / 3, q = r / (P - C), c = r % (P - C);
+      if (q0 + q < T) out[((int64_t)n * T + q0 + q) * orow + k * P + C + c] = __float2bfloat16_rn(0.f);
+    }
+  }
+  __syncthreads();
+  // scores: a thread owns a key
+  for (int key = tid; key < T; key += kAttThreads) {
+    float acc[kAttQ];
+#pragma unroll
+    for (int q = 0; q < kAttQ; ++q) acc[q] = 0.f;
+    const bf16* kp = base + (int64_t)key * row + P + h * d;
+    for (int c0 = 0; c0 < d; c0 += 8) {
+      float kf[8], kl[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(kp + c0)), kf);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(kp + plane + c0)), kl);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) kf[j] += kl[j];
+#pragma unroll
+      for (int q = 0; q < kAttQ; ++q) {
+        const float4 a = *reinterpret_cast<const float4*>(Qs + q * d + c0);
+        const float4 b = *reinterpret_cast<const float4*>(Qs + q * d + c0 + 4);
+        acc[q] += a.x * kf[0] + a.y * kf[1] + a.z * kf[2] + a.w * kf[3] + b.x * kf[4] + b.y * kf[5] + b.z * kf[6] + b.w * kf[7];
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < kAttQ; ++q) S[q * T + key] = acc[q] * scale;
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int q = warp; q < kAttQ; q += kAttThreads / 32) {
+    float m = -INFINITY;
+    for (int j = lane; j < T; j += 32) m = fmaxf(m, S[q * T + j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float sum = 0.f;
+    for (int j = lane; j < T; j += 32) { const float e = expf(S[q * T + j] - m); S[q * T + j] = e; sum += e; }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    for (int j = lane; j < T; j += 32) S[q * T + j] *= inv;
+  }
+  __syncthreads();
+  // O = P V: a thread owns a channel pair
+  for (int c0 = 2 * tid; c0 < d; c0 += 2 * kAttThreads) {
+    float ax[kAttQ], ay[kAttQ];
+#pragma unroll
+    for (int q = 0; q < kAttQ; ++q) ax[q] = ay[q] = 0.f;
+    const bf16* vp = base + 2 * P + h * d + c0;
+    for (int j = 0; j < T; j += 4) {
+      float2 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float2 vh = __bfloat1622float2(__ldg(reinterpret_cast<const __nv_bfloat162*>(vp + (int64_t)(j + u) * row)));
+        const float2 vl = __bfloat1622float2(__ldg(reinterpret_cast<const __nv_bfloat162*>(vp + (int64_t)(j + u) * row + plane)));
+        v[u] = make_float2(vh.x + vl.x, vh.y + vl.y);
+      }
+#pragma unroll
+      for (int q = 0; q < kAttQ; ++q) {
+        const float4 p = *reinterpret_cast<const float4*>(S + q * T + j);
+        ax[q] += p.x * v[0].x + p.y * v[1].x + p.z * v[2].x + p.w * v[3].x;
+        ay[q] += p.x * v[0].y + p.y * v[1].y + p.z * v[2].y + p.w * v[3].y;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < kAttQ; ++q)
+      if (q0 + q < T) {
+        bf16* o = out + ((int64_t)n * T + q0 + q) * orow + h * d + c0;
+        const __nv_bfloat162 hi = __floats2bfloat162_rn(ax[q], ay[q]);
+        const float2 hf = __bfloat1622float2(hi);
+        *reinterpret_cast<__nv_bfloat162*>(o) = hi;
+        *reinterpret_cast<__nv_bfloat162*>(o + P) = __floats2bfloat162_rn(__fsub_rn(ax[q], hf.x), __fsub_rn(ay[q], hf.y));
+        *reinterpret_cast<__nv_bfloat162*>(o + 2 * P) = hi;
+      }
+  }
+}
+
+int attention_split_launch(const bf16* qkv, bf16* out, int N, int T, int C, int P, int heads, cudaStream_t st) {
+  B2E_REQUIRE(heads >= 1 && C % heads == 0 && P >= C && P % 8 == 0, B2E_UNSUPPORTED_SHAPE, "attention: bad head count / pitch");
+  const int d = C / heads;
+  B2E_REQUIRE(d % 8 == 0 && T % 4 == 0, B2E_UNSUPPORTED_SHAPE, "attention (fp32-accurate): unsupported T=%d head_dim=%d", T, d);
+  const size_t smem = sizeof(float) * kAttQ * (d + T);
+  B2E_REQUIRE(smem <= 200 * 1024, B2E_UNSUPPORTED_SHAPE, "attention (fp32-accurate): tile does not fit in shared memory");
+  static size_t attr = 0;
+  if (smem > attr) {
+    B2E_CUDA(cudaFuncSetAttribute(attention_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  launch_pdl(attention_split_kernel, dim3((T + kAttQ - 1) / kAttQ, heads, N), dim3(kAttThreads), smem, st, qkv, out, T, C, P, heads);
+  return check_launch("attention_split");
 }
 
 int attention_launch(const bf16* qkv, bf16* out, int N, int T, int C, int P, int heads, cudaStream_t st) {

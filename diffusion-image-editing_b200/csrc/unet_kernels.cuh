@@ -24,6 +24,9 @@ struct GNArgs {
   bf16* out;       // [N][HW][Pout]
   int silu;
   float* save_stats = nullptr;   // optional [N][G][2] (mean, rstd) for the backward pass
+  // 3: sources and output are split-bf16 tensors of the fp32-accurate mode - channel planes [hi | lo | hi] of P
+  // channels each (pixel pitch 3 * P), value = hi + lo; statistics must come from the stand-alone pass
+  int planes = 1;
 };
 
 // Backward of y = GroupNorm(x) (optionally followed by SiLU), single source.  dx = d(loss)/dx (+ add):
@@ -52,7 +55,9 @@ int gn_finalize_launch(const float* tile_stats, float* chan_stats, int N, int C,
 
 // x fp32 NCHW (B,C,H,W) -> bf16 NHWC (B,H,W,cpad), zero padded channels; im2col: channel t*C + c of a pixel holds
 // x[c] at 3x3 tap t (zero outside the image), so that a 3x3 convolution becomes a 1x1 one
-int pack_input_launch(const float* x, bf16* out, int B, int C, int H, int W, int cpad, bool im2col, cudaStream_t st);
+// planes = 3 (im2col only): split-bf16 output [hi | lo | hi] of cpad channels each (fp32-accurate mode)
+int pack_input_launch(const float* x, bf16* out, int B, int C, int H, int W, int cpad, bool im2col, cudaStream_t st,
+                      int planes = 1);
 // nearest-neighbour x2 upsample, bf16 NHWC
 int upsample2x_launch(const bf16* in, bf16* out, int N, int H, int W, int C, cudaStream_t st);
 
@@ -100,5 +105,7 @@ int merge_heads_launch(const bf16* oh, bf16* out, int N, int T, int P, int heads
 
 // single/multi-head self-attention core: qkv bf16 [N][T][3P] (q | k | v blocks of P >= C channels) -> out bf16 [N][T][P]
 int attention_launch(const bf16* qkv, bf16* out, int N, int T, int C, int P, int heads, cudaStream_t st);
+// fp32-accurate mode: qkv / out are split-bf16 tensors ([hi | lo | hi] planes of 3P / P channels), arithmetic in fp32
+int attention_split_launch(const bf16* qkv, bf16* out, int N, int T, int C, int P, int heads, cudaStream_t st);
 
 }  // namespace b2e

@@ -24,16 +24,17 @@ class NativePipeline(SimpleNamespace):
 def create_diffusion_model(name: str, sample_clipping: bool = True, *, max_batch: int = 8, seed: int = 0,
                            state_dict: Optional[dict] = None, unet_config: Optional[dict] = None, vqvae=None,
                            vq_config: Optional[dict] = None, vq_state_dict: Optional[dict] = None, guidance_module=None,
-                           decoder_grad: bool = True, tokenizer=None, text_encoder=None):
+                           decoder_grad: bool = True, tokenizer=None, text_encoder=None, precision: str = "bf16"):
     """``name``: "ddpm" (google/ddpm-celebahq-256 layout), "sd" (Stable Diffusion 1.x layout: native conditional UNet
     + native KL decoder with gradient; ``vqvae=`` substitutes the vae, ``tokenizer=`` / ``text_encoder=`` are the
     caller's CLIP modules) or "ldm" (CompVis/ldm-celebahq-256 layout: native UNet on
     the 64x64x3 latent + native forward-only VQ decoder; ``vqvae=`` substitutes the caller's VQ autoencoder module
     (encode().latents / decode().sample, as in the reference's pipeline object); ``guidance_module=`` is the
-    differentiable decoder used when guidance runs through decode)."""
+    differentiable decoder used when guidance runs through decode).  ``precision="fp32"`` selects the fp32-accurate
+    (split-bf16) noise predictor for "ddpm" / "ldm"."""
     device = get_device()
     if name == "ddpm":
-        unet = UNet2DModel(**(unet_config or DDPM256_CONFIG), max_batch=max_batch, device=device)
+        unet = UNet2DModel(**(unet_config or DDPM256_CONFIG), max_batch=max_batch, device=device, precision=precision)
         if state_dict is not None:
             unet.load_state_dict(state_dict)
         else:
@@ -43,7 +44,7 @@ def create_diffusion_model(name: str, sample_clipping: bool = True, *, max_batch
         return DDPM(NativePipeline(unet=unet, scheduler=scheduler, device=device))
     if name == "ldm":
         from b200edit.vqmodel import LDM_VQ_CONFIG, VQModel
-        unet = UNet2DModel(**(unet_config or LDM_CELEBAHQ_CONFIG), max_batch=max_batch, device=device)
+        unet = UNet2DModel(**(unet_config or LDM_CELEBAHQ_CONFIG), max_batch=max_batch, device=device, precision=precision)
         if state_dict is not None:
             unet.load_state_dict(state_dict)
         else:
@@ -67,6 +68,8 @@ def create_diffusion_model(name: str, sample_clipping: bool = True, *, max_batch
                                   guidance_vqvae=guidance_vqvae if guidance_module is None else guidance_module,
                                   device=device))
     if name == "sd":
+        if precision != "bf16":
+            raise ValueError("create_diffusion_model: the fp32-accurate mode covers the 'ddpm' and 'ldm' noise predictors")
         from b200edit.unet_cond import SD15_CONFIG, UNet2DConditionModel
         from b200edit.vqmodel import SD_VAE_CONFIG, AutoencoderKL
         # CFG doubles the latent batch: the UNet engine is sized for 2 * max_batch samples

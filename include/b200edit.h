@@ -212,6 +212,10 @@ typedef struct {
    * block use Transformer2DModel (self-attention, cross-attention over the text tokens, GEGLU) instead of Attention */
   int32_t cross_attention_dim;
   int32_t num_attention_heads; /* SD 1.x: 8 (head_dim = channels / 8) */
+  /* 0: bf16 operands (default).  1: fp32-accurate mode for the north star's 1e-4 bar (UNet2DModel only): activations and
+   * weights are kept as split bf16 (hi + lo, ~16 mantissa bits) and every GEMM computes x_hi W_hi + x_lo W_hi + x_hi W_lo
+   * on the same tcgen05 kernels with fp32 accumulation; GroupNorm / SiLU / softmax / attention run in fp32. */
+  int32_t precision;
 } b2e_unet_config;
 
 typedef struct b2e_unet b2e_unet;

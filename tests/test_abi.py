@@ -32,7 +32,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_C.StepCoeffs) == 9 * 4
     assert ctypes.sizeof(_C.GuidedStepParams) == 36 + 4 * 5 + 16 * 3 + 12
     assert ctypes.sizeof(_C.L2RegParams) == ctypes.sizeof(_C.GuidedStepParams) + 8
-    assert ctypes.sizeof(_C.UNetConfig) == 4 * 4 + 32 * 3 + 4 * 9
+    assert ctypes.sizeof(_C.UNetConfig) == 4 * 4 + 32 * 3 + 4 * 10
 
 
 def test_host_side_argument_validation():

@@ -26,11 +26,11 @@ LDM_SMALL = dict(sample_size=32, in_channels=3, out_channels=3, block_out_channe
                  attention_head_dim=32, flip_sin_to_cos=True, freq_shift=0, downsample_padding=1)
 
 
-def run_pair(cfg, B, t, seed):
+def run_pair(cfg, B, t, seed, precision="bf16"):
     from b200edit.unet import UNet2DModel
     torch.manual_seed(seed)
     oracle = OracleUNet(**cfg).eval()
-    native = UNet2DModel(**cfg, max_batch=B)
+    native = UNet2DModel(**cfg, max_batch=B, precision=precision)
     native.load_state_dict(oracle.state_dict())
     x = torch.randn(B, cfg["in_channels"], cfg["sample_size"], cfg["sample_size"],
                     generator=torch.Generator().manual_seed(seed + 1))
@@ -55,6 +55,30 @@ def check(got, ref, ref16, tag):
     assert torch.isfinite(got).all()
     assert rel <= 1.5e-2 and err <= 2.5e-2 * max(1.0, scale)
     assert rel <= 1.25 * rel16 + 1e-3
+
+
+def check_fp32(got, ref, ref16, tag):
+    """fp32-accurate mode (split-bf16 operands, three products per GEMM): the north star's fp32 bar,
+    max-abs <= 1e-4 (x max|eps| when that exceeds 1), and relative RMS <= 5e-5."""
+    scale = ref.abs().max().item()
+    err = (got - ref).abs().max().item()
+    rel = ((got - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
+    print(f"{tag}: fp32-accurate native max-abs {err:.3e} rel-rms {rel:.3e} | max|eps| {scale:.3f}")
+    assert torch.isfinite(got).all()
+    assert err <= 1e-4 * max(1.0, scale) and rel <= 5e-5
+
+
+@pytest.mark.parametrize("B,t", [(1, 980), (3, 500)])
+def test_small_unet_fp32_mode_matches_oracle(B, t):
+    check_fp32(*run_pair(SMALL, B, t, seed=B, precision="fp32"), f"small unet fp32 B={B} t={t}")
+
+
+def test_ldm_style_unet_fp32_mode_matches_oracle():
+    check_fp32(*run_pair(LDM_SMALL, 2, 400, seed=12, precision="fp32"), "ldm-style small unet fp32")
+
+
+def test_ddpm256_unet_fp32_mode_matches_oracle():
+    check_fp32(*run_pair(DDPM256_CONFIG, 2, 500, seed=0, precision="fp32"), "ddpm-256 unet fp32")
 
 
 @pytest.mark.parametrize("B,t", [(1, 980), (3, 500), (2, 0)])
