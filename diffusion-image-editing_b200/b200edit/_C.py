@@ -44,6 +44,12 @@ class VQDecConfig(C.Structure):
                 ("norm_num_groups", C.c_int32), ("norm_eps", C.c_float), ("num_vq_embeddings", C.c_int32)]
 
 
+class VQEncConfig(C.Structure):
+    _fields_ = [("sample_size", C.c_int32), ("in_channels", C.c_int32), ("latent_channels", C.c_int32),
+                ("n_blocks", C.c_int32), ("block_out_channels", C.c_int32 * 8), ("layers_per_block", C.c_int32),
+                ("norm_num_groups", C.c_int32), ("norm_eps", C.c_float), ("double_z", C.c_int32)]
+
+
 _P, _I64, _I, _F, _SZ = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_size_t
 
 # name -> (restype, argtypes); every symbol include/b200edit.h declares
@@ -79,6 +85,7 @@ PROTOTYPES = {
     "b2e_morphology2d_f32": (_I, [_P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I, _I, _I, _F, _P]),
     "b2e_unet_create": (_I, [C.POINTER(UNetConfig), _I64, C.POINTER(_P)]),
     "b2e_vqdec_create": (_I, [C.POINTER(VQDecConfig), _I64, C.POINTER(_P)]),
+    "b2e_vqenc_create": (_I, [C.POINTER(VQEncConfig), _I64, C.POINTER(_P)]),
     "b2e_unet_enable_grad": (_I, [_P, _I]),
     "b2e_vqdec_backward": (_I, [_P, _P, _P, _I64, _P]),
     "b2e_unet_destroy": (None, [_P]),

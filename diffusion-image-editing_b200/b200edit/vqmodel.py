@@ -2,10 +2,10 @@
 reference uses is ``vqvae.decode(latent).sample`` (src/diffusion_classes.py:62-70).  Nearest-code quantisation,
 post_quant_conv and the decoder run in libb200edit.so (bf16 tcgen05 implicit-GEMM convolutions, fp32 accumulation).
 
-Forward only: ``decode`` returns a tensor without an autograd graph, so it serves the post-loop decoding of the
-final sample and of the x0-prediction history; guidance THROUGH the decoder (AttrFunc.apply with no_grad=False)
-still needs the caller's differentiable module (``guidance_vqvae=``) until the decoder dgrad is native.
-``encode`` is not on the engine."""
+``decode`` is forward-only by default (post-loop decoding of the final sample and of the x0-prediction history);
+``enable_grad()`` makes it an autograd node backed by the native decoder dgrad, which is what guidance THROUGH the
+decoder (AttrFunc.apply with no_grad=False) uses.  ``with_encoder=True`` adds the native encoder + quant_conv
+(``vqvae.encode(img).latents`` / ``vae.encode(img).latent_dist.mode()``, src/diffusion_classes.py:27-30, 55-60)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -14,7 +14,7 @@ from types import SimpleNamespace
 import torch
 
 from . import _C
-from ._C import VQDecConfig, check, lib
+from ._C import VQDecConfig, VQEncConfig, check, lib
 from .unet import UNet2DModel
 
 LDM_VQ_CONFIG = dict(latent_channels=3, out_channels=3, block_out_channels=(128, 256, 512), layers_per_block=2,
@@ -42,6 +42,72 @@ class _DecodeFn(torch.autograd.Function):
         return dz, None
 
 
+class _EncoderEngine(UNet2DModel):
+    """diffusers ``Encoder`` + ``quant_conv`` on the engine (b2e_vqenc_create): image (B, C, S, S) -> (B, Q, s, s)."""
+
+    def __init__(self, image_size, in_channels, latent_channels, block_out_channels, layers_per_block, norm_num_groups,
+                 norm_eps, double_z, max_batch, device):
+        n = len(block_out_channels)
+        self.image_size, self.q = image_size, latent_channels * (2 if double_z else 1)
+        self.out_size = image_size >> (n - 1)
+        self.config = SimpleNamespace(in_channels=in_channels, sample_size=image_size, out_channels=self.q)
+        self.device = torch.device(device)
+        self.dtype = torch.float32
+        self.max_batch = int(max_batch)
+        cfg = VQEncConfig()
+        cfg.sample_size, cfg.in_channels, cfg.latent_channels, cfg.n_blocks = image_size, in_channels, latent_channels, n
+        for i in range(n):
+            cfg.block_out_channels[i] = block_out_channels[i]
+        cfg.layers_per_block, cfg.norm_num_groups, cfg.norm_eps = layers_per_block, norm_num_groups, norm_eps
+        cfg.double_z = int(double_z)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib.b2e_vqenc_create(C.byref(cfg), self.max_batch, C.byref(h)), "vqenc_create")
+            self._h = h
+            nbytes = lib.b2e_unet_workspace_bytes(h)
+            self._ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)
+            base = (self._ws.data_ptr() + 255) // 256 * 256
+            check(lib.b2e_unet_bind_workspace(h, C.c_void_p(base), nbytes), "unet_bind_workspace")
+        self._t_cache = {}
+
+    def __call__(self, image):
+        if not image.is_cuda:
+            raise _C.B2EError("encode: image must be a CUDA tensor (no CPU fallback)")
+        x = image.detach().to(torch.float32).contiguous()
+        if tuple(x.shape[1:]) != (self.config.in_channels, self.image_size, self.image_size):
+            raise ValueError(f"encode: expected (B,{self.config.in_channels},{self.image_size},{self.image_size}), "
+                             f"got {tuple(x.shape)}")
+        outs = []
+        for b0 in range(0, x.shape[0], self.max_batch):
+            xb = x[b0:b0 + self.max_batch]
+            o = torch.empty((xb.shape[0], self.q, self.out_size, self.out_size), dtype=torch.float32, device=x.device)
+            check(lib.b2e_unet_forward(self._h, C.c_void_p(xb.data_ptr()), None, C.c_void_p(o.data_ptr()), xb.shape[0],
+                                       C.c_void_p(torch.cuda.current_stream().cuda_stream)), "vqenc_forward")
+            outs.append(o)
+        return outs[0] if len(outs) == 1 else torch.cat(outs)
+
+
+class DiagonalGaussianDistribution:
+    """``vae.encode(x).latent_dist``: moments = [mean | logvar] from the native encoder; the reference only takes
+    ``mode()`` (src/diffusion_classes.py:29)."""
+
+    def __init__(self, moments: torch.Tensor):
+        self.mean, logvar = torch.chunk(moments, 2, dim=1)
+        self.logvar = torch.clamp(logvar, -30.0, 20.0)
+        self.std = torch.exp(0.5 * self.logvar)
+
+    def mode(self) -> torch.Tensor:
+        return self.mean
+
+    def sample(self, generator=None) -> torch.Tensor:
+        noise = torch.randn(self.mean.shape, generator=generator).to(self.mean.device)   # host RNG stream, as utils.py
+        return self.mean + self.std * noise
+
+
+def _is_encoder_key(k: str) -> bool:
+    return k.startswith("encoder.") or k.startswith("quant_conv.")
+
+
 class VQModel(UNet2DModel):
     """Shares parameter loading / random init / profiling with the UNet wrapper (same engine handle type)."""
 
@@ -49,9 +115,10 @@ class VQModel(UNet2DModel):
 
     def __init__(self, latent_channels=3, out_channels=3, block_out_channels=(128, 256, 512), layers_per_block=2,
                  norm_num_groups=32, norm_eps=1e-6, num_vq_embeddings=8192, sample_size=64, max_batch=8,
-                 device="cuda"):
+                 device="cuda", with_encoder=False):
         _C.require_device()
         n = len(block_out_channels)
+        self._enc = None
         self.config = SimpleNamespace(latent_channels=latent_channels, out_channels=out_channels,
                                       block_out_channels=tuple(block_out_channels), layers_per_block=layers_per_block,
                                       norm_num_groups=norm_num_groups, norm_eps=norm_eps,
@@ -76,6 +143,25 @@ class VQModel(UNet2DModel):
             base = (self._ws.data_ptr() + 255) // 256 * 256
             check(lib.b2e_unet_bind_workspace(h, C.c_void_p(base), nbytes), "unet_bind_workspace")
         self._t_cache = {}
+        if with_encoder:
+            self._enc = _EncoderEngine(self.out_size, out_channels, latent_channels, block_out_channels, layers_per_block,
+                                       norm_num_groups, norm_eps, num_vq_embeddings == 0, max_batch, device)
+
+    # ---- parameters: "encoder.*" / "quant_conv.*" belong to the encoder engine (ignored when there is none)
+    def load_state_dict(self, sd, strict=True):
+        dec = {k: v for k, v in sd.items() if not _is_encoder_key(k)}
+        enc = {k: v for k, v in sd.items() if _is_encoder_key(k)}
+        missing, unexpected = super().load_state_dict(dec, strict)
+        if self._enc is not None and enc:     # a decoder-only dictionary leaves the encoder untouched
+            m2, u2 = self._enc.load_state_dict(enc, strict)
+            missing, unexpected = missing + m2, unexpected + u2
+        return missing, unexpected
+
+    def init_random(self, seed=0):
+        super().init_random(seed)
+        if self._enc is not None:
+            self._enc.init_random(seed + 7)
+        return self
 
     def enable_grad(self, enable: bool = True):
         """Gradient mode: decode() becomes differentiable w.r.t. the latent (native dgrad; batches <= max_batch).
@@ -123,8 +209,14 @@ class VQModel(UNet2DModel):
             outs.append(img)
         return SimpleNamespace(sample=outs[0] if len(outs) == 1 else torch.cat(outs))
 
+    def _encode_raw(self, x):
+        if self._enc is None:
+            raise NotImplementedError(f"{type(self).__name__}.encode: build the model with with_encoder=True")
+        return self._enc(x)
+
     def encode(self, x):
-        raise NotImplementedError("VQModel.encode is not on the native engine (SURVEY.md section 8f rank 3)")
+        """``vqvae.encode(img).latents`` (pre-quantisation latents; the quantiser runs inside decode)."""
+        return SimpleNamespace(latents=self._encode_raw(x))
 
     def __call__(self, *a, **k):
         raise TypeError("VQModel: call .decode(latent)")
@@ -155,7 +247,12 @@ class AutoencoderKL(VQModel):
     State-dict names as in diffusers (``post_quant_conv.*``, ``decoder.*``)."""
 
     def __init__(self, latent_channels=4, out_channels=3, block_out_channels=(128, 256, 512, 512), layers_per_block=2,
-                 norm_num_groups=32, norm_eps=1e-6, sample_size=64, max_batch=8, device="cuda"):
+                 norm_num_groups=32, norm_eps=1e-6, sample_size=64, max_batch=8, device="cuda", with_encoder=False):
         super().__init__(latent_channels=latent_channels, out_channels=out_channels, block_out_channels=block_out_channels,
                          layers_per_block=layers_per_block, norm_num_groups=norm_num_groups, norm_eps=norm_eps,
-                         num_vq_embeddings=0, sample_size=sample_size, max_batch=max_batch, device=device)
+                         num_vq_embeddings=0, sample_size=sample_size, max_batch=max_batch, device=device,
+                         with_encoder=with_encoder)
+
+    def encode(self, x):
+        """``vae.encode(img).latent_dist`` (the reference takes ``.mode()``, src/diffusion_classes.py:29)."""
+        return SimpleNamespace(latent_dist=DiagonalGaussianDistribution(self._encode_raw(x)))

@@ -101,6 +101,11 @@ struct b2e_unet {
   // VQ decoder mode (b2e_vqdec_create): no time embedding, input = latent -> nearest-code quantisation + 1x1
   // post_quant_conv (one CUDA-core kernel) -> conv_in; output at sample_size << (n_blocks - 1)
   bool decoder = false;
+  // VQ / KL encoder mode (b2e_vqenc_create): image -> conv_in -> down blocks -> mid block -> GroupNorm -> SiLU -> conv_out
+  // (enc_q channels: latent, or 2 x latent moments) -> 1x1 quant_conv in fp32; output at sample_size >> (n_blocks - 1)
+  bool encoder = false;
+  int enc_q = 0;
+  float *qc_w = nullptr, *qc_b = nullptr;   // [enc_q][enc_q], [enc_q]
   float *codebook = nullptr, *pq_w = nullptr, *pq_b = nullptr;   // [n_codes][latent], [latent][latent], [latent]
   int n_codes = 0;
   // decoder gradient w.r.t. the latent (b2e_vqdec_backward): dgrad twins of every convolution, and a second op
@@ -385,8 +390,52 @@ int build_model_decoder(b2e_unet* m) {
   return m->build_error;
 }
 
+// VQModel.encode / AutoencoderKL.encode graph (diffusers Encoder): conv_in -> per level layers_per_block resnets
+// (+ pad (0,1,0,1) + 3x3 stride-2 conv) -> mid (resnet, single-head attention, resnet) -> GroupNorm -> SiLU ->
+// conv_out -> quant_conv (1x1).  LDM.encode / SD.encode, src/diffusion_classes.py:27-30, 55-60.
+int build_model_encoder(b2e_unet* m) {
+  const b2e_unet_config& c = m->cfg;
+  const int nb = c.n_blocks, cin = c.in_channels, c0 = c.block_out_channels[0], Q = m->enc_q;
+  m->in_im2col = true;
+  {
+    ConvL ci;
+    ci.cin = ci.cin_pad = kConvBlockK; ci.cout = c0; ci.k = 1; ci.cout_pad = conv_cout_pad(c0); ci.row_len = kConvBlockK;
+    ci.w = m->dmalloc<bf16>((size_t)ci.cout_pad * ci.row_len);
+    ci.b = m->dmalloc<float>(ci.cout_pad);
+    m->add_param("encoder.conv_in.weight", (int64_t)c0 * cin * 9, (int64_t)cin * 9, [ci, cin](const float* src, cudaStream_t st) {
+      return conv_pack_weight(src, ci.w, ci.cout, cin, 3, cin, ci.row_len, 0, st);
+    });
+    m->add_f32("encoder.conv_in.bias", ci.b, c0, (int64_t)cin * 9);
+    m->conv_in = ci;
+  }
+  int ch = c0;
+  for (int i = 0; i < nb; ++i) {
+    const int cout = c.block_out_channels[i];
+    const std::string base = "encoder.down_blocks." + std::to_string(i);
+    for (int j = 0; j < c.layers_per_block; ++j) {
+      m->nodes.push_back({N_RESNET, m->make_resnet(base + ".resnets." + std::to_string(j), ch, 0, cout, false)});
+      ch = cout;
+    }
+    if (i != nb - 1) {
+      m->downs.push_back(m->make_conv(base + ".downsamplers.0.conv", ch, ch, 3));
+      m->nodes.push_back({N_DOWN, (int)m->downs.size() - 1});
+    }
+  }
+  m->nodes.push_back({N_RESNET, m->make_resnet("encoder.mid_block.resnets.0", ch, 0, ch, false)});
+  m->nodes.push_back({N_ATTN, m->make_attn("encoder.mid_block.attentions.0", ch)});
+  m->nodes.push_back({N_RESNET, m->make_resnet("encoder.mid_block.resnets.1", ch, 0, ch, false)});
+  m->norm_out = m->make_norm("encoder.conv_norm_out", ch);
+  m->conv_out = m->make_conv("encoder.conv_out", ch, Q, 3);
+  m->qc_w = m->dmalloc<float>((size_t)Q * Q);
+  m->qc_b = m->dmalloc<float>(Q);
+  m->add_f32("quant_conv.weight", m->qc_w, (int64_t)Q * Q, Q);
+  m->add_f32("quant_conv.bias", m->qc_b, Q, Q);
+  return m->build_error;
+}
+
 int build_model(b2e_unet* m) {
   if (m->decoder) return build_model_decoder(m);
+  if (m->encoder) return build_model_encoder(m);
   const b2e_unet_config& c = m->cfg;
   const int nb = c.n_blocks;
   const int c0 = c.block_out_channels[0];
@@ -636,7 +685,7 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
       ops.push_back({[m, xin, B, Cin, S, im2col, PL](cudaStream_t st) { return pack_input_launch(m->in_x, xin.p, B, Cin, S, S, kConvBlockK, im2col, st, PL); },
                      3, 0.0, (double)B * HW * (4.0 * Cin + 2.0 * kConvBlockK)});
     }
-    if (!m->decoder) {
+    if (!m->decoder && !m->encoder) {
     TembArgs ta;
     ta.timesteps = nullptr; ta.B = B; ta.dim0 = c.block_out_channels[0]; ta.dim = m->temb_dim;
     ta.flip = c.flip_sin_to_cos; ta.freq_shift = c.freq_shift;
@@ -982,7 +1031,19 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
     gnorm(m->norm_out, h, nullptr, 1, &an, &st_out);
     tfree(h);
     float dummy = 0.f;
-    conv(m->conv_out, an, nullptr, 1, ConvEpilogue{}, nullptr, &dummy);
+    if (m->encoder) {
+      // conv_out -> fp32 NCHW scratch -> quant_conv (1x1, fp32) -> the caller's output
+      const int Q = m->enc_q, HWo = an.H * an.W;
+      float* hq = (float*)ar.alloc(sizeof(float) * B * Q * HWo);
+      ConvEpilogue eo;
+      eo.out_f32_nchw = hq;
+      conv(m->conv_out, an, nullptr, 1, eo, nullptr, nullptr);
+      if (!dry && !rc)
+        ops.push_back({[m, hq, B, Q, HWo](cudaStream_t st) { return pointwise_conv_f32_launch(hq, m->qc_w, m->qc_b, m->out_eps, B, Q, Q, HWo, st); },
+                       3, 0.0, 8.0 * B * Q * HWo, "quant_conv 1x1 (fp32)"});
+    } else {
+      conv(m->conv_out, an, nullptr, 1, ConvEpilogue{}, nullptr, &dummy);
+    }
     tfree(an);
   }
   // ---- backward program (decoder, gradient mode): d(loss)/d(latent) from d(loss)/d(image), walking the nodes in
@@ -1196,6 +1257,37 @@ int b2e_vqdec_create(const b2e_vqdec_config* cfg, int64_t max_batch, b2e_unet** 
   return B2E_OK;
 }
 
+int b2e_vqenc_create(const b2e_vqenc_config* cfg, int64_t max_batch, b2e_unet** out) {
+  B2E_REQUIRE(cfg && out && max_batch > 0, B2E_INVALID_ARG, "vqenc_create: bad argument");
+  B2E_REQUIRE(cfg->n_blocks >= 1 && cfg->n_blocks <= 8, B2E_UNSUPPORTED_SHAPE, "vqenc_create: n_blocks");
+  B2E_REQUIRE((cfg->in_channels == 1 || cfg->in_channels == 3 || cfg->in_channels == 4) && cfg->latent_channels >= 1 &&
+                  cfg->latent_channels * (cfg->double_z ? 2 : 1) <= 16,
+              B2E_UNSUPPORTED_SHAPE, "vqenc_create: in_channels must be 1, 3 or 4 and at most 16 output channels");
+  B2E_REQUIRE(cfg->sample_size % (1 << (cfg->n_blocks - 1)) == 0, B2E_UNSUPPORTED_SHAPE, "vqenc_create: sample_size");
+  for (int i = 0; i < cfg->n_blocks; ++i) {
+    const int ch = cfg->block_out_channels[i];
+    B2E_REQUIRE(ch % 8 == 0 && ch >= 32 && ch <= 1024 && ch % cfg->norm_num_groups == 0, B2E_UNSUPPORTED_SHAPE,
+                "vqenc_create: block_out_channels must be multiples of 8 and of norm_num_groups, 32..1024 (got %d)", ch);
+  }
+  b2e_unet* m = new b2e_unet();
+  m->encoder = true;
+  m->enc_q = cfg->latent_channels * (cfg->double_z ? 2 : 1);
+  b2e_unet_config& u = m->cfg;
+  u = b2e_unet_config{};
+  u.sample_size = cfg->sample_size; u.in_channels = cfg->in_channels; u.out_channels = m->enc_q;
+  u.n_blocks = cfg->n_blocks;
+  for (int i = 0; i < cfg->n_blocks; ++i) u.block_out_channels[i] = cfg->block_out_channels[i];
+  u.layers_per_block = cfg->layers_per_block; u.norm_num_groups = cfg->norm_num_groups; u.norm_eps = cfg->norm_eps;
+  u.attention_head_dim = 0; u.downsample_padding = 0;
+  m->max_batch = max_batch;
+  int rc = build_model(m);
+  if (!rc && cudaDeviceSynchronize() != cudaSuccess) { set_error("vqenc_create: device error"); rc = B2E_CUDA_ERROR; }
+  if (!rc) rc = build_program(m, (int)max_batch, nullptr, 0, &m->ws_need);
+  if (rc) { delete m; return rc; }
+  *out = m;
+  return B2E_OK;
+}
+
 void b2e_unet_destroy(b2e_unet* m) { delete m; }
 
 int b2e_unet_num_params(const b2e_unet* m) { return m ? (int)m->params.size() : 0; }
@@ -1230,7 +1322,7 @@ int b2e_unet_bind_workspace(b2e_unet* m, void* workspace, size_t workspace_bytes
 }
 
 int b2e_unet_forward(b2e_unet* m, const float* x, const int64_t* timesteps, float* eps, int64_t B, void* stream) {
-  B2E_REQUIRE(m && x && (timesteps || m->decoder) && eps, B2E_INVALID_ARG, "unet_forward: null pointer");
+  B2E_REQUIRE(m && x && (timesteps || m->decoder || m->encoder) && eps, B2E_INVALID_ARG, "unet_forward: null pointer");
   B2E_REQUIRE(m->ws, B2E_INVALID_ARG, "unet_forward: no workspace bound");
   B2E_REQUIRE(B > 0 && B <= m->max_batch, B2E_UNSUPPORTED_SHAPE, "unet_forward: batch %lld exceeds max_batch %lld",
               (long long)B, (long long)m->max_batch);
@@ -1290,7 +1382,7 @@ const char* b2e_unet_op_desc(const b2e_unet* m, int idx) {
 
 int b2e_unet_profile(b2e_unet* m, const float* x, const int64_t* timesteps, float* eps, int64_t B, void* stream,
                      int max_ops, int* n_ops, float* ms, double* flops, double* bytes, int* kind) {
-  B2E_REQUIRE(m && x && (timesteps || m->decoder) && eps && n_ops && ms && flops && bytes && kind, B2E_INVALID_ARG,
+  B2E_REQUIRE(m && x && (timesteps || m->decoder || m->encoder) && eps && n_ops && ms && flops && bytes && kind, B2E_INVALID_ARG,
               "unet_profile: null pointer");
   // one plain pass first (plan rebuild / lazy function attributes), then the instrumented pass
   int rc = b2e_unet_forward(m, x, timesteps, eps, B, stream);

@@ -1103,6 +1103,34 @@ int vq_quantize_launch(const float* z, const float* codebook, int n_codes, const
   return check_launch("vq_quantize");
 }
 
+// quant_conv of the VQ / KL encoders: 1x1 convolution over fp32 NCHW with few channels (Cin, Cout <= 16)
+__global__ void __launch_bounds__(256)
+pointwise_conv_f32_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                          float* __restrict__ out, int B, int Cin, int Cout, int HW) {
+  pdl_wait();
+  const int64_t total = (int64_t)B * HW;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = p / HW, q = p % HW;
+    float v[16];
+    for (int c = 0; c < Cin; ++c) v[c] = x[(n * Cin + c) * HW + q];
+    for (int o = 0; o < Cout; ++o) {
+      float acc = 0.f;
+      for (int c = 0; c < Cin; ++c) acc += __ldg(w + o * Cin + c) * v[c];
+      out[(n * Cout + o) * HW + q] = acc + __ldg(b + o);
+    }
+  }
+}
+
+int pointwise_conv_f32_launch(const float* x, const float* w, const float* b, float* out, int B, int Cin, int Cout, int HW,
+                              cudaStream_t st) {
+  B2E_REQUIRE(Cin >= 1 && Cin <= 16 && Cout >= 1 && Cout <= 16, B2E_UNSUPPORTED_SHAPE, "pointwise_conv: %d -> %d channels", Cin, Cout);
+  const int64_t total = (int64_t)B * HW;
+  int grid = (int)((total + 255) / 256);
+  if (grid > kNumSMs * 16) grid = kNumSMs * 16;
+  launch_pdl(pointwise_conv_f32_kernel, dim3(grid), dim3(256), 0, st, x, w, b, out, B, Cin, Cout, HW);
+  return check_launch("pointwise_conv_f32");
+}
+
 // ------------------------------------------------------------------ multi-head layout helpers
 // qkv [N][T][3P] (q | k | v blocks of P channels, head h = channels [h*d, h*d + d) of a block, d <= 64) ->
 // head-major operands of the batched tensor-core GEMMs: qh, kh [N*heads][T][64] (channels >= d zero) and

@@ -99,6 +99,10 @@ int vq_col2im_bwd_launch(const bf16* dcols, const float* pq_w, float* dz, int B,
 int vq_quantize_launch(const float* z, const float* codebook, int n_codes, const float* pq_w, const float* pq_b, float* out,
                        int B, int L, int HW, cudaStream_t st);
 
+// quant_conv of the VQ / KL encoders: out[n][o][p] = sum_c w[o][c] x[n][c][p] + b[o], fp32 NCHW, Cin, Cout <= 16
+int pointwise_conv_f32_launch(const float* x, const float* w, const float* b, float* out, int B, int Cin, int Cout, int HW,
+                              cudaStream_t st);
+
 // multi-head tensor-core attention: head-major operands (virtual image v = n*heads + h, head_dim padded to 64)
 int split_heads_launch(const bf16* qkv, bf16* qh, bf16* kh, bf16* vht, int N, int T, int P, int heads, int d, cudaStream_t st);
 int merge_heads_launch(const bf16* oh, bf16* out, int N, int T, int P, int heads, int d, cudaStream_t st);

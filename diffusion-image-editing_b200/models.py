@@ -24,14 +24,16 @@ class NativePipeline(SimpleNamespace):
 def create_diffusion_model(name: str, sample_clipping: bool = True, *, max_batch: int = 8, seed: int = 0,
                            state_dict: Optional[dict] = None, unet_config: Optional[dict] = None, vqvae=None,
                            vq_config: Optional[dict] = None, vq_state_dict: Optional[dict] = None, guidance_module=None,
-                           decoder_grad: bool = True, tokenizer=None, text_encoder=None, precision: str = "bf16"):
+                           decoder_grad: bool = True, tokenizer=None, text_encoder=None, precision: str = "bf16",
+                           with_encoder: bool = True):
     """``name``: "ddpm" (google/ddpm-celebahq-256 layout), "sd" (Stable Diffusion 1.x layout: native conditional UNet
     + native KL decoder with gradient; ``vqvae=`` substitutes the vae, ``tokenizer=`` / ``text_encoder=`` are the
     caller's CLIP modules) or "ldm" (CompVis/ldm-celebahq-256 layout: native UNet on
     the 64x64x3 latent + native forward-only VQ decoder; ``vqvae=`` substitutes the caller's VQ autoencoder module
     (encode().latents / decode().sample, as in the reference's pipeline object); ``guidance_module=`` is the
     differentiable decoder used when guidance runs through decode).  ``precision="fp32"`` selects the fp32-accurate
-    (split-bf16) noise predictor for "ddpm" / "ldm"."""
+    (split-bf16) noise predictor for "ddpm" / "ldm".  ``with_encoder`` (default) also builds the native VQ / KL encoder behind
+    ``LDM.encode`` / ``SD.encode``."""
     device = get_device()
     if name == "ddpm":
         unet = UNet2DModel(**(unet_config or DDPM256_CONFIG), max_batch=max_batch, device=device, precision=precision)
@@ -53,7 +55,7 @@ def create_diffusion_model(name: str, sample_clipping: bool = True, *, max_batch
         if vqvae is None:
             # native decoder: forward for the post-loop decoding of the sample / x0 history and, with
             # decoder_grad=True (default), the native dgrad for guidance THROUGH the decoder
-            vqvae = VQModel(**(vq_config or LDM_VQ_CONFIG), max_batch=max_batch, device=device)
+            vqvae = VQModel(**(vq_config or LDM_VQ_CONFIG), max_batch=max_batch, device=device, with_encoder=with_encoder)
             if vq_state_dict is not None:
                 vqvae.load_state_dict(vq_state_dict)
             else:
@@ -79,7 +81,7 @@ def create_diffusion_model(name: str, sample_clipping: bool = True, *, max_batch
         else:
             unet.init_random(seed)
         if vqvae is None:
-            vae = AutoencoderKL(**(vq_config or SD_VAE_CONFIG), max_batch=max_batch, device=device)
+            vae = AutoencoderKL(**(vq_config or SD_VAE_CONFIG), max_batch=max_batch, device=device, with_encoder=with_encoder)
             if vq_state_dict is not None:
                 vae.load_state_dict(vq_state_dict)
             else:

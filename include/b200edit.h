@@ -271,6 +271,27 @@ typedef struct {
   int32_t num_vq_embeddings; /* 0: no quantiser = AutoencoderKL.decode (post_quant_conv -> decoder), SD.decode */
 } b2e_vqdec_config;
 int b2e_vqdec_create(const b2e_vqdec_config* cfg, int64_t max_batch, b2e_unet** out);
+
+/* ------------------------------------------------------------------ VQ / KL encoder (image -> latent)
+ * LDM.encode (src/diffusion_classes.py:55-60): vqvae.encode(img).latents, and SD.encode (src/diffusion_classes.py:27-30):
+ * vae.encode(img).latent_dist.mode() - the step before the path for real-image editing (prepare_for_edit,
+ * src/SegDiffEditPipeline.py:95).  diffusers Encoder (conv_in -> DownEncoderBlock2D per level -> mid block with single-head
+ * attention -> GroupNorm -> SiLU -> conv_out) + the 1x1 quant_conv, on the same engine as the UNet.  Parameters by their
+ * diffusers names ("encoder.*", "quant_conv.*").  b2e_unet_forward(m, image, NULL, out, B, s): image (B, in_channels, S, S)
+ * fp32 -> out (B, Q, S >> (n_blocks-1), ...) fp32 with Q = latent_channels (VQ: the pre-quantisation latents) or
+ * 2 * latent_channels (double_z, KL: the moments [mean | logvar]; the distribution's mode is the first half). */
+typedef struct {
+  int32_t sample_size;       /* image height = width */
+  int32_t in_channels;       /* 1, 3 or 4 */
+  int32_t latent_channels;
+  int32_t n_blocks;
+  int32_t block_out_channels[8];
+  int32_t layers_per_block;
+  int32_t norm_num_groups;
+  float norm_eps;
+  int32_t double_z;          /* 1: AutoencoderKL (conv_out and quant_conv carry 2 * latent_channels) */
+} b2e_vqenc_config;
+int b2e_vqenc_create(const b2e_vqenc_config* cfg, int64_t max_batch, b2e_unet** out);
 /* Gradient through the decoder (AttrFunc.apply with decode inside the graph, src/attr_functions.py:147-158):
  * b2e_unet_enable_grad(m, 1) switches the handle to gradient mode (every activation of a forward pass stays in the
  * workspace: re-query b2e_unet_workspace_bytes and re-bind); after b2e_unet_forward(m, latent, NULL, image, B, s),

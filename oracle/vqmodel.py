@@ -1,4 +1,4 @@
-"""Oracle restatement of the decode path of ``diffusers.VQModel`` (CompVis/ldm-celebahq-256 ``vqvae``).
+"""Oracle restatement of the decode and encode paths of ``diffusers.VQModel`` / ``AutoencoderKL`` (CompVis/ldm-celebahq-256 ``vqvae``).
 
 TEST INFRASTRUCTURE (see oracle/__init__.py).  PARITY UNPINNED: diffusers is not vendored / installed and the
 reference holds no golden vectors for it; this file restates the published layout (recalled from diffusers 0.2x,
@@ -22,7 +22,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .unet2d import Attention, Upsample2D
+from .unet2d import Attention, Downsample2D, Upsample2D
 
 # CompVis/ldm-celebahq-256 vqvae: 64x64x3 latent -> 256x256x3 image (x4), 8192 codes of dimension 3
 LDM_VQ_CONFIG = dict(latent_channels=3, out_channels=3, block_out_channels=(128, 256, 512), layers_per_block=2,
@@ -87,6 +87,59 @@ class Decoder(nn.Module):
         return self.conv_out(F.silu(self.conv_norm_out(x)))
 
 
+class DownEncoderBlock(nn.Module):
+    def __init__(self, cin, cout, layers, groups, eps, add_down):
+        super().__init__()
+        self.resnets = nn.ModuleList([ResnetNoTemb(cin if i == 0 else cout, cout, groups, eps) for i in range(layers)])
+        self.downsamplers = nn.ModuleList([Downsample2D(cout, padding=0)]) if add_down else None
+
+    def forward(self, x):
+        for r in self.resnets:
+            x = r(x)
+        return x if self.downsamplers is None else self.downsamplers[0](x)
+
+
+class Encoder(nn.Module):
+    """diffusers ``Encoder`` (models/vae.py): conv_in 3x3 -> DownEncoderBlock2D per level (layers_per_block resnets,
+    pad (0,1,0,1) + 3x3 stride-2 convolution between levels) -> UNetMidBlock2D (resnet, single-head attention, resnet)
+    -> GroupNorm -> SiLU -> conv_out 3x3 (2 x latent channels when double_z)."""
+
+    def __init__(self, in_channels, latent_channels, block_out_channels, layers_per_block, groups, eps, double_z):
+        super().__init__()
+        chs = list(block_out_channels)
+        self.conv_in = nn.Conv2d(in_channels, chs[0], 3, padding=1)
+        blocks, prev = [], chs[0]
+        for i, ch in enumerate(chs):
+            blocks.append(DownEncoderBlock(prev, ch, layers_per_block, groups, eps, i != len(chs) - 1))
+            prev = ch
+        self.down_blocks = nn.ModuleList(blocks)
+        self.mid_block = MidBlock(chs[-1], groups, eps)
+        self.conv_norm_out = nn.GroupNorm(groups, chs[-1], eps=eps)
+        self.conv_out = nn.Conv2d(chs[-1], 2 * latent_channels if double_z else latent_channels, 3, padding=1)
+
+    def forward(self, x):
+        x = self.conv_in(x)
+        for b in self.down_blocks:
+            x = b(x)
+        return self.conv_out(F.silu(self.conv_norm_out(self.mid_block(x))))
+
+
+class DiagonalGaussianDistribution:
+    """diffusers ``DiagonalGaussianDistribution``: moments = [mean | logvar] along channels."""
+
+    def __init__(self, moments):
+        self.mean, self.logvar = torch.chunk(moments, 2, dim=1)
+        self.logvar = torch.clamp(self.logvar, -30.0, 20.0)
+        self.std = torch.exp(0.5 * self.logvar)
+
+    def mode(self):
+        return self.mean
+
+    def sample(self, generator=None):
+        noise = torch.randn(self.mean.shape, generator=generator, device=self.mean.device if generator is None else generator.device)
+        return self.mean + self.std * noise.to(self.mean.device)
+
+
 class VectorQuantizer(nn.Module):
     """Nearest codebook entry (squared Euclidean distance, first index on ties), straight-through gradient."""
 
@@ -123,6 +176,21 @@ class VQModel(nn.Module):
         self.post_quant_conv = nn.Conv2d(latent_channels, latent_channels, 1)
         self.decoder = Decoder(latent_channels, out_channels, block_out_channels, layers_per_block, norm_num_groups,
                                norm_eps)
+        # encode path (LDM.encode / SD.encode, src/diffusion_classes.py:27-30, 55-60).  Built AFTER the decoder so the
+        # decoder's random-init stream (and every decode golden) is unchanged.
+        self.double_z = num_vq_embeddings == 0
+        q = 2 * latent_channels if self.double_z else latent_channels
+        self.encoder = Encoder(out_channels, latent_channels, block_out_channels, layers_per_block, norm_num_groups,
+                               norm_eps, self.double_z)
+        self.quant_conv = nn.Conv2d(q, q, 1)
+
+    def encode(self, x):
+        """VQModel.encode(x).latents = quant_conv(encoder(x)) (quantisation happens in decode);
+        AutoencoderKL.encode(x).latent_dist = DiagonalGaussianDistribution(quant_conv(encoder(x)))."""
+        h = self.quant_conv(self.encoder(x))
+        if self.double_z:
+            return SimpleNamespace(latent_dist=DiagonalGaussianDistribution(h))
+        return SimpleNamespace(latents=h)
 
     def decode(self, h, force_not_quantize=False):
         quant = h if (force_not_quantize or self.quantize is None) else self.quantize(h)

@@ -1,0 +1,97 @@
+"""GPU numerics of the native VQ / KL encoders (``vqvae.encode(img).latents``, ``vae.encode(img).latent_dist.mode()``:
+LDM.encode / SD.encode, src/diffusion_classes.py:27-30, 55-60) against the oracle restatement of the diffusers Encoder
+run in fp32 (torch eager on the GPU as the checker) with the same weights.  Tolerance (bf16 activations, fp32
+accumulation): relative RMS <= 2.5e-2, max-abs <= 3e-2 * max|latent| and no worse than 1.25x the oracle itself run in
+bf16 by torch - the bars of the decoder tests."""
+import pytest
+import torch
+
+from oracle.vqmodel import LDM_VQ_CONFIG, SD_VAE_CONFIG, VQModel as OracleVQ
+
+pytestmark = pytest.mark.gpu
+
+SMALL_VQ = dict(latent_channels=3, out_channels=3, block_out_channels=(32, 96), layers_per_block=1, norm_num_groups=32,
+                norm_eps=1e-6, num_vq_embeddings=512, sample_size=16)
+SMALL_KL = dict(latent_channels=4, out_channels=3, block_out_channels=(64, 128, 128), layers_per_block=1, norm_num_groups=32,
+                norm_eps=1e-6, num_vq_embeddings=0, sample_size=8)
+
+
+def run_pair(cfg, B, seed):
+    from b200edit.vqmodel import AutoencoderKL, VQModel
+    torch.manual_seed(seed)
+    oracle = OracleVQ(**cfg).eval()
+    kl = cfg["num_vq_embeddings"] == 0
+    kw = {k: v for k, v in cfg.items() if not (kl and k == "num_vq_embeddings")}
+    native = (AutoencoderKL if kl else VQModel)(**kw, max_batch=B, with_encoder=True)
+    native.load_state_dict(oracle.state_dict())
+    S = cfg["sample_size"] << (len(cfg["block_out_channels"]) - 1)
+    x = torch.randn(B, cfg["out_channels"], S, S, generator=torch.Generator().manual_seed(seed + 1)).clamp(-1, 1)
+    enc = native.encode(x.cuda())
+    got = enc.latent_dist.mode() if kl else enc.latents
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        oc = oracle.cuda()
+        e = oc.encode(x.cuda())
+        ref = e.latent_dist.mode() if kl else e.latents
+        h16 = oc.encoder.bfloat16()(x.cuda().bfloat16()).float()
+        ref16 = oc.quant_conv(h16)
+        if kl:
+            ref16 = ref16[:, :cfg["latent_channels"]]
+    return got, ref, ref16
+
+
+def check(got, ref, ref16, tag):
+    scale = ref.abs().max().item()
+    err = (got - ref).abs().max().item()
+    rel = ((got - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
+    err16 = (ref16 - ref).abs().max().item()
+    rel16 = ((ref16 - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
+    print(f"{tag}: native max-abs {err:.3e} rel-rms {rel:.3e} | torch-bf16 max-abs {err16:.3e} rel-rms {rel16:.3e}"
+          f" | max|latent| {scale:.3f}")
+    assert got.shape == ref.shape and torch.isfinite(got).all()
+    assert rel <= 2.5e-2 and err <= 3e-2 * max(1.0, scale)
+    assert rel <= 1.25 * rel16 + 1e-3
+
+
+@pytest.mark.parametrize("B", [1, 3])
+def test_small_vq_encoder_matches_oracle(B):
+    check(*run_pair(SMALL_VQ, B, seed=B), f"small vq encoder B={B}")
+
+
+def test_small_kl_encoder_matches_oracle():
+    check(*run_pair(SMALL_KL, 2, seed=7), "small kl encoder")
+
+
+def test_ldm_vq_encoder_matches_oracle():
+    """Full CompVis/ldm-celebahq-256 vqvae encoder: 256x256x3 image -> 64x64x3 latent, mid-block attention over 4096 tokens."""
+    check(*run_pair(LDM_VQ_CONFIG, 2, seed=5), "ldm-celebahq vq encoder")
+
+
+def test_sd_kl_encoder_matches_oracle():
+    """Full Stable Diffusion 1.x vae encoder: 512x512x3 image -> 64x64x4 latent mean."""
+    check(*run_pair(SD_VAE_CONFIG, 1, seed=6), "sd vae encoder")
+
+
+def test_ldm_and_sd_encode_through_the_wrappers():
+    """LDM.encode / SD.encode of the drop-in wrappers use the native encoder; moments -> mode() * 0.18215 for SD;
+    encode -> decode round trip has the right shapes; the distribution object offers sample()."""
+    from models import create_diffusion_model
+    ucfg = dict(sample_size=16, in_channels=3, out_channels=3, block_out_channels=(64, 128), layers_per_block=1,
+                down_block_types=("DownBlock2D", "AttnDownBlock2D"), up_block_types=("AttnUpBlock2D", "UpBlock2D"),
+                attention_head_dim=32, flip_sin_to_cos=True, freq_shift=0, downsample_padding=1)
+    w = create_diffusion_model("ldm", sample_clipping=False, max_batch=2, seed=3, unet_config=ucfg, vq_config=SMALL_VQ,
+                               decoder_grad=False)
+    img = torch.rand(2, 3, 32, 32, generator=torch.Generator().manual_seed(1)).mul(2).sub(1).cuda()
+    z = w.encode(img)
+    assert z.shape == (2, 3, 16, 16) and torch.isfinite(z).all()
+    assert torch.equal(z, w.vqvae.encode(img).latents)
+    assert w.decode(z).shape == img.shape
+    from b200edit.vqmodel import AutoencoderKL
+    kw = {k: v for k, v in SMALL_KL.items() if k != "num_vq_embeddings"}
+    vae = AutoencoderKL(**kw, max_batch=2, with_encoder=True).init_random(4)
+    dist = vae.encode(img).latent_dist
+    assert dist.mode().shape == (2, 4, 8, 8) and dist.sample(torch.Generator().manual_seed(0)).shape == (2, 4, 8, 8)
+    with pytest.raises(NotImplementedError):
+        AutoencoderKL(**kw, max_batch=1).encode(img)
