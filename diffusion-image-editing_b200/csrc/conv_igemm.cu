@@ -88,6 +88,7 @@ struct ConvKParams {
   int out_bf16;         // 1: stage + TMA-store the bf16 NHWC tile through map_out
   float* out_f32_nchw;
   float* tile_stats;    // fused GroupNorm statistics or null
+  int relu;             // 1: ReLU before the bf16 store (classifier network)
   int split_pitch;      // > 0: split-bf16 output (fp32-accurate mode): planes [hi | lo | hi] of split_pitch channels each
   long long* trace;     // B2E_TRACE: clock64 stamps of CTA 0's warp loops (halo kernels), else null
 };
@@ -498,6 +499,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
               v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
             }
           }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
           if (pass) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = __fsub_rn(v[j], __bfloat162float(__float2bfloat16_rn(v[j])));
@@ -630,13 +635,14 @@ __global__ void pack_weight_dgrad_kernel(const float* __restrict__ w, bf16* __re
 }
 
 // dgrad of conv_in run as a 1x1 convolution over im2col columns: out[(t*Cin + ci)*row_len + co] = w[(co*Cin + ci)*9 + t]
-__global__ void pack_weight_im2col_T_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int Cin, int row_len) {
-  const int64_t total = (int64_t)Cout * Cin * 9;
+__global__ void pack_weight_im2col_T_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int Cin, int row_len,
+                                            int kk) {
+  const int64_t total = (int64_t)Cout * Cin * kk;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int co = (int)(i % Cout);
     const int ci = (int)((i / Cout) % Cin);
     const int t = (int)(i / ((int64_t)Cout * Cin));
-    out[(int64_t)(t * Cin + ci) * row_len + co] = __float2bfloat16_rn(w[((int64_t)co * Cin + ci) * 9 + t]);
+    out[(int64_t)(t * Cin + ci) * row_len + co] = __float2bfloat16_rn(w[((int64_t)co * Cin + ci) * kk + t]);
   }
 }
 
@@ -666,11 +672,11 @@ int conv_pack_weight_dgrad(const float* w, bf16* out, int Cout, int Cin, int ksi
   return check_launch("pack_weight_dgrad");
 }
 
-int conv_pack_weight_im2col_T(const float* w, bf16* out, int Cout, int Cin, int row_len, cudaStream_t st) {
-  const int64_t total = (int64_t)Cout * Cin * 9;
+int conv_pack_weight_im2col_T(const float* w, bf16* out, int Cout, int Cin, int row_len, cudaStream_t st, int kk) {
+  const int64_t total = (int64_t)Cout * Cin * kk;
   int grid = (int)((total + 255) / 256);
   if (grid > kNumSMs * 16) grid = kNumSMs * 16;
-  pack_weight_im2col_T_kernel<<<grid, 256, 0, st>>>(w, out, Cout, Cin, row_len);
+  pack_weight_im2col_T_kernel<<<grid, 256, 0, st>>>(w, out, Cout, Cin, row_len, kk);
   return check_launch("pack_weight_im2col_T");
 }
 
@@ -914,6 +920,7 @@ int conv_launch(const ConvPlan& pl, const ConvEpilogue& ep, cudaStream_t st) {
   kp.out_bf16 = pl.has_out_bf16; kp.out_f32_nchw = pl.has_out_bf16 ? nullptr : ep.out_f32_nchw;
   kp.tile_stats = pl.tile_stats;
   kp.split_pitch = pl.split_pitch;
+  kp.relu = ep.relu;
   // B2E_TRACE=<n>: the n-th halo launch (1-based) runs with clock64 tracing of CTA 0, then dumps to stderr
   kp.trace = nullptr;
   static const int trace_at = getenv("B2E_TRACE") ? atoi(getenv("B2E_TRACE")) : 0;

@@ -52,6 +52,7 @@ struct ConvEpilogue {
   const float* temb = nullptr;    // [N][temb_stride], already offset to this layer's columns
   int temb_stride = 0;
   float* out_f32_nchw = nullptr;  // NCHW [N,Cout,Ho,Wo] (network output)
+  int relu = 0;                   // bf16 NHWC output: max(v, 0) before the store
 };
 
 // Everything the kernel needs that is fixed per layer; built once at model-build time.
@@ -104,7 +105,8 @@ int conv_pack_weight(const float* w, bf16* out, int Cout, int Cin, int ksize, in
 int conv_pack_weight_dgrad(const float* w, bf16* out, int Cout, int Cin, int ksize, int tap_width, int row_len, int col_off,
                            cudaStream_t st);
 // dgrad of the im2col conv_in: out[(t*Cin + ci)*row_len + co] = w[(co*Cin + ci)*9 + t]
-int conv_pack_weight_im2col_T(const float* w, bf16* out, int Cout, int Cin, int row_len, cudaStream_t st);
+// (kk taps: 9 for the 3x3 conv_in, 49 for the 7x7 stem of the classifier network)
+int conv_pack_weight_im2col_T(const float* w, bf16* out, int Cout, int Cin, int row_len, cudaStream_t st, int kk = 9);
 // out[c*row_len + col_off + c] = 1 for c < C (identity residual segment)
 int conv_fill_identity(bf16* out, int C, int row_len, int col_off, cudaStream_t st);
 

@@ -1,0 +1,321 @@
+// Kernels around the tcgen05 convolutions of the classifier network of ClassifierAttrFunc (torchvision ResNet,
+// src/models.py:69-77, src/attr_functions.py:222-257): stem im2col (7x7 stride 2) and its col2im gradient, 3x3 stride-2
+// max pooling forward / backward, ReLU backward, stride-2 subsampling / zero insertion (stride-2 convolution gradients),
+// global average pooling + fully connected head forward / backward.  Activations are bf16 NHWC, BatchNorm (eval) is
+// folded into the convolution weights and biases by the host, ReLU is fused into the convolution epilogue.
+#include "unet_kernels.cuh"
+
+namespace b2e {
+
+namespace {
+__device__ __forceinline__ void unpack8r(const uint4& v, float* f) {
+  const __nv_bfloat162* b = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { const float2 t = __bfloat1622float2(b[j]); f[2 * j] = t.x; f[2 * j + 1] = t.y; }
+}
+__device__ __forceinline__ uint4 pack8r(const float* f) {
+  uint4 v;
+  __nv_bfloat162* b = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) b[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+  return v;
+}
+inline int grid_for(int64_t total, int per_sm = 32) {
+  int64_t g = (total + 255) / 256;
+  if (g > (int64_t)kNumSMs * per_sm) g = (int64_t)kNumSMs * per_sm;
+  return (int)(g < 1 ? 1 : g);
+}
+}  // namespace
+
+// ---- stem: x fp32 NCHW (B,C,H,W) -> bf16 (B,H/2,W/2,KP): column (kh*7 + kw)*C + c = x[c][2oh + kh - 3][2ow + kw - 3]
+__global__ void __launch_bounds__(256) im2col7s2_kernel(const float* __restrict__ x, bf16* __restrict__ out, int B, int C, int H,
+                                                        int W, int KP) {
+  pdl_wait();
+  const int Ho = H / 2, Wo = W / 2, slots = KP / 8, cols = 49 * C;
+  const int64_t total = (int64_t)B * Ho * Wo * slots;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int s = (int)(i % slots);
+    int64_t r = i / slots;
+    const int ow = (int)(r % Wo); r /= Wo;
+    const int oh = (int)(r % Ho);
+    const int b = (int)(r / Ho);
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int col = s * 8 + j;
+      float v = 0.f;
+      if (col < cols) {
+        const int t = col / C, c = col - t * C;
+        const int ih = 2 * oh + t / 7 - 3, iw = 2 * ow + t % 7 - 3;
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = __ldg(x + (((int64_t)b * C + c) * H + ih) * W + iw);
+      }
+      f[j] = v;
+    }
+    *reinterpret_cast<uint4*>(out + i * 8) = pack8r(f);
+  }
+}
+
+int im2col7s2_launch(const float* x, bf16* out, int B, int C, int H, int W, int KP, cudaStream_t st) {
+  B2E_REQUIRE(49 * C <= KP && KP % 64 == 0 && H % 2 == 0 && W % 2 == 0, B2E_UNSUPPORTED_SHAPE, "im2col7s2: bad shape");
+  const int64_t total = (int64_t)B * (H / 2) * (W / 2) * (KP / 8);
+  launch_pdl(im2col7s2_kernel, dim3(grid_for(total)), dim3(256), 0, st, x, out, B, C, H, W, KP);
+  return check_launch("im2col7s2");
+}
+
+// gradient of the stem w.r.t. the image: dx[b][c][ih][iw] = sum over taps with 2oh + kh - 3 = ih, 2ow + kw - 3 = iw of
+// dcols[b][oh][ow][(kh*7 + kw)*C + c]; dcols bf16 (B,H/2,W/2,KP), dx fp32 NCHW
+__global__ void __launch_bounds__(256) col2im7s2_kernel(const bf16* __restrict__ dcols, float* __restrict__ dx, int B, int C,
+                                                        int H, int W, int KP) {
+  pdl_wait();
+  const int Ho = H / 2, Wo = W / 2;
+  const int64_t total = (int64_t)B * H * W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int iw = (int)(i % W);
+    const int ih = (int)((i / W) % H);
+    const int b = (int)(i / ((int64_t)W * H));
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int kh = (ih + 3) & 1; kh < 7; kh += 2) {
+      const int oh = (ih + 3 - kh) >> 1;
+      if (oh < 0 || oh >= Ho) continue;
+      for (int kw = (iw + 3) & 1; kw < 7; kw += 2) {
+        const int ow = (iw + 3 - kw) >> 1;
+        if (ow < 0 || ow >= Wo) continue;
+        const bf16* p = dcols + (((int64_t)b * Ho + oh) * Wo + ow) * KP + (kh * 7 + kw) * C;
+        for (int c = 0; c < C; ++c) acc[c] += __bfloat162float(p[c]);
+      }
+    }
+    for (int c = 0; c < C; ++c) dx[(((int64_t)b * C + c) * H + ih) * W + iw] = acc[c];
+  }
+}
+
+int col2im7s2_launch(const bf16* dcols, float* dx, int B, int C, int H, int W, int KP, cudaStream_t st) {
+  B2E_REQUIRE(C >= 1 && C <= 4 && 49 * C <= KP, B2E_UNSUPPORTED_SHAPE, "col2im7s2: bad shape");
+  launch_pdl(col2im7s2_kernel, dim3(grid_for((int64_t)B * H * W)), dim3(256), 0, st, dcols, dx, B, C, H, W, KP);
+  return check_launch("col2im7s2");
+}
+
+// ---- max pooling 3x3, stride 2, padding 1 (bf16 NHWC); idx = position (kh*3 + kw) of the first maximum (scan order)
+__global__ void __launch_bounds__(256) maxpool3s2_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
+                                                         uint8_t* __restrict__ idx, int N, int H, int W, int C8) {
+  pdl_wait();
+  const int Ho = H / 2, Wo = W / 2;
+  const int64_t total = (int64_t)N * Ho * Wo * C8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int s = (int)(i % C8);
+    int64_t r = i / C8;
+    const int ow = (int)(r % Wo); r /= Wo;
+    const int oh = (int)(r % Ho);
+    const int n = (int)(r / Ho);
+    float best[8];
+    uint8_t arg[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; arg[j] = 0; }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int ih = 2 * oh + t / 3 - 1, iw = 2 * ow + t % 3 - 1;
+      if (ih < 0 || ih >= H || iw < 0 || iw >= W) continue;
+      float f[8];
+      unpack8r(__ldg(reinterpret_cast<const uint4*>(x + ((((int64_t)n * H + ih) * W + iw) * C8 + s) * 8)), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (f[j] > best[j]) { best[j] = f[j]; arg[j] = (uint8_t)t; }
+    }
+    *reinterpret_cast<uint4*>(y + i * 8) = pack8r(best);
+    uint2 a;
+    a.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | ((uint32_t)arg[3] << 24);
+    a.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | ((uint32_t)arg[7] << 24);
+    *reinterpret_cast<uint2*>(idx + i * 8) = a;
+  }
+}
+
+int maxpool3s2_launch(const bf16* x, bf16* y, uint8_t* idx, int N, int H, int W, int C, cudaStream_t st) {
+  B2E_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, B2E_UNSUPPORTED_SHAPE, "maxpool: bad shape");
+  const int64_t total = (int64_t)N * (H / 2) * (W / 2) * (C / 8);
+  launch_pdl(maxpool3s2_kernel, dim3(grid_for(total)), dim3(256), 0, st, x, y, idx, N, H, W, C / 8);
+  return check_launch("maxpool3s2");
+}
+
+// gx[p] = (x[p] > 0) * sum over the (<= 4) windows whose recorded argmax is p of gy[window]   (the x > 0 factor is the
+// backward of the ReLU that produced x)
+__global__ void __launch_bounds__(256) maxpool3s2_bwd_kernel(const bf16* __restrict__ x, const uint8_t* __restrict__ idx,
+                                                             const bf16* __restrict__ gy, bf16* __restrict__ gx, int N, int H,
+                                                             int W, int C8) {
+  pdl_wait();
+  const int Ho = H / 2, Wo = W / 2;
+  const int64_t total = (int64_t)N * H * W * C8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int s = (int)(i % C8);
+    int64_t r = i / C8;
+    const int iw = (int)(r % W); r /= W;
+    const int ih = (int)(r % H);
+    const int n = (int)(r / H);
+    float acc[8], xv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    unpack8r(__ldg(reinterpret_cast<const uint4*>(x + i * 8)), xv);
+    // windows oh with 2*oh - 1 <= ih <= 2*oh + 1
+    for (int oh = ih >> 1; oh <= ((ih + 1) >> 1); ++oh) {
+      if (oh >= Ho) continue;
+      const int kh = ih - (2 * oh - 1);
+      for (int ow = iw >> 1; ow <= ((iw + 1) >> 1); ++ow) {
+        if (ow >= Wo) continue;
+        const int t = kh * 3 + (iw - (2 * ow - 1));
+        const int64_t o = ((((int64_t)n * Ho + oh) * Wo + ow) * C8 + s) * 8;
+        const uint2 a = __ldg(reinterpret_cast<const uint2*>(idx + o));
+        float g[8];
+        unpack8r(__ldg(reinterpret_cast<const uint4*>(gy + o)), g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t aj = ((j < 4 ? a.x : a.y) >> (8 * (j & 3))) & 0xffu;
+          if ((int)aj == t) acc[j] += g[j];
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = xv[j] > 0.f ? acc[j] : 0.f;
+    *reinterpret_cast<uint4*>(gx + i * 8) = pack8r(acc);
+  }
+}
+
+int maxpool3s2_bwd_launch(const bf16* x, const uint8_t* idx, const bf16* gy, bf16* gx, int N, int H, int W, int C,
+                          cudaStream_t st) {
+  const int64_t total = (int64_t)N * H * W * (C / 8);
+  launch_pdl(maxpool3s2_bwd_kernel, dim3(grid_for(total)), dim3(256), 0, st, x, idx, gy, gx, N, H, W, C / 8);
+  return check_launch("maxpool3s2_bwd");
+}
+
+// ---- ReLU backward: out = g * (y > 0)   (out may alias g)
+__global__ void __launch_bounds__(256) relu_bwd_kernel(const uint4* __restrict__ g, const uint4* __restrict__ y,
+                                                       uint4* __restrict__ out, int64_t n8) {
+  pdl_wait();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    float gv[8], yv[8];
+    unpack8r(g[i], gv);
+    unpack8r(__ldg(y + i), yv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) gv[j] = yv[j] > 0.f ? gv[j] : 0.f;
+    out[i] = pack8r(gv);
+  }
+}
+
+int relu_bwd_launch(const bf16* g, const bf16* y, bf16* out, int64_t numel, cudaStream_t st) {
+  B2E_REQUIRE(numel % 8 == 0, B2E_UNSUPPORTED_SHAPE, "relu_bwd: numel %% 8 != 0");
+  launch_pdl(relu_bwd_kernel, dim3(grid_for(numel / 8)), dim3(256), 0, st, (const uint4*)g, (const uint4*)y, (uint4*)out, numel / 8);
+  return check_launch("relu_bwd");
+}
+
+// ---- stride-2 helpers: subsample (x[:, ::2, ::2]) and its adjoint (zero insertion)
+__global__ void __launch_bounds__(256) subsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int N, int Ho,
+                                                          int Wo, int C8) {
+  pdl_wait();
+  const int64_t total = (int64_t)N * Ho * Wo * C8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8);
+    int64_t r = i / C8;
+    const int ow = (int)(r % Wo); r /= Wo;
+    const int oh = (int)(r % Ho);
+    const int n = (int)(r / Ho);
+    out[i] = __ldg(in + (((int64_t)n * 2 * Ho + 2 * oh) * 2 * Wo + 2 * ow) * C8 + c);
+  }
+}
+
+int subsample2x_launch(const bf16* in, bf16* out, int N, int Ho, int Wo, int C, cudaStream_t st) {
+  B2E_REQUIRE(C % 8 == 0, B2E_UNSUPPORTED_SHAPE, "subsample: C %% 8 != 0");
+  launch_pdl(subsample2x_kernel, dim3(grid_for((int64_t)N * Ho * Wo * (C / 8))), dim3(256), 0, st, (const uint4*)in, (uint4*)out,
+             N, Ho, Wo, C / 8);
+  return check_launch("subsample2x");
+}
+
+__global__ void __launch_bounds__(256) zero_upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int N,
+                                                              int Hi, int Wi, int C8) {
+  pdl_wait();
+  const int64_t total = (int64_t)N * 4 * Hi * Wi * C8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8);
+    int64_t r = i / C8;
+    const int w = (int)(r % (2 * Wi)); r /= (2 * Wi);
+    const int h = (int)(r % (2 * Hi));
+    const int n = (int)(r / (2 * Hi));
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (!(h & 1) && !(w & 1)) v = __ldg(in + (((int64_t)n * Hi + (h >> 1)) * Wi + (w >> 1)) * C8 + c);
+    out[i] = v;
+  }
+}
+
+int zero_upsample2x_launch(const bf16* in, bf16* out, int N, int Hi, int Wi, int C, cudaStream_t st) {
+  B2E_REQUIRE(C % 8 == 0, B2E_UNSUPPORTED_SHAPE, "zero_upsample: C %% 8 != 0");
+  launch_pdl(zero_upsample2x_kernel, dim3(grid_for((int64_t)N * 4 * Hi * Wi * (C / 8))), dim3(256), 0, st, (const uint4*)in,
+             (uint4*)out, N, Hi, Wi, C / 8);
+  return check_launch("zero_upsample2x");
+}
+
+// ---- head: global average pooling + fully connected layer
+__global__ void __launch_bounds__(256) avgpool_kernel(const bf16* __restrict__ x, float* __restrict__ feat, int HW, int C) {
+  pdl_wait();
+  const int n = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int p = 0; p < HW; ++p) s += __bfloat162float(x[((int64_t)n * HW + p) * C + c]);
+  feat[(int64_t)n * C + c] = s / (float)HW;
+}
+
+__global__ void __launch_bounds__(256) fc_kernel(const float* __restrict__ feat, const float* __restrict__ w,
+                                                 const float* __restrict__ b, float* __restrict__ out, int N, int C, int K) {
+  pdl_wait();
+  const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (wid >= N * K) return;
+  const int n = wid / K, k = wid % K;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += __ldg(w + (int64_t)k * C + c) * feat[(int64_t)n * C + c];
+  s = warp_sum(s);
+  if (lane == 0) out[(int64_t)n * K + k] = s + b[k];
+}
+
+int avgpool_fc_launch(const bf16* x, float* feat, const float* w, const float* b, float* logits, int N, int HW, int C, int K,
+                      cudaStream_t st) {
+  launch_pdl(avgpool_kernel, dim3((C + 255) / 256, N), dim3(256), 0, st, x, feat, HW, C);
+  int rc = check_launch("avgpool");
+  if (rc) return rc;
+  launch_pdl(fc_kernel, dim3((N * K + 7) / 8), dim3(256), 0, st, (const float*)feat, w, b, logits, N, C, K);
+  return check_launch("fc");
+}
+
+// backward of the head: dfeat = W^T dlogits ; g[n][p][c] = (y[n][p][c] > 0) ? dfeat[n][c] / HW : 0   (y = the ReLU output
+// the pooling read, so g is already the gradient w.r.t. the last block's pre-activation)
+__global__ void __launch_bounds__(256) fc_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ w,
+                                                     float* __restrict__ dfeat, int C, int K, float scale) {
+  pdl_wait();
+  const int n = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int k = 0; k < K; ++k) s += dlogits[(int64_t)n * K + k] * __ldg(w + (int64_t)k * C + c);
+  dfeat[(int64_t)n * C + c] = s * scale;
+}
+
+__global__ void __launch_bounds__(256) avgpool_bwd_kernel(const float* __restrict__ dfeat, const bf16* __restrict__ y,
+                                                          bf16* __restrict__ g, int HW, int C8) {
+  pdl_wait();
+  const int n = blockIdx.y;
+  const int64_t total = (int64_t)HW * C8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int s = (int)(i % C8);
+    float yv[8], o[8];
+    unpack8r(__ldg(reinterpret_cast<const uint4*>(y + ((int64_t)n * total + i) * 8)), yv);
+    const float* d = dfeat + (int64_t)n * C8 * 8 + s * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = yv[j] > 0.f ? d[j] : 0.f;
+    *reinterpret_cast<uint4*>(g + ((int64_t)n * total + i) * 8) = pack8r(o);
+  }
+}
+
+int avgpool_fc_bwd_launch(const float* dlogits, const float* w, float* dfeat, const bf16* y, bf16* g, int N, int HW, int C, int K,
+                          cudaStream_t st) {
+  launch_pdl(fc_bwd_kernel, dim3((C + 255) / 256, N), dim3(256), 0, st, dlogits, w, dfeat, C, K, 1.0f / (float)HW);
+  int rc = check_launch("fc_bwd");
+  if (rc) return rc;
+  const int64_t total = (int64_t)HW * (C / 8);
+  launch_pdl(avgpool_bwd_kernel, dim3((unsigned)((total + 255) / 256), N), dim3(256), 0, st, (const float*)dfeat, y, g, HW, C / 8);
+  return check_launch("avgpool_bwd");
+}
+
+}  // namespace b2e

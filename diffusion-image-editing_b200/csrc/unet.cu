@@ -104,6 +104,15 @@ struct b2e_unet {
   // VQ / KL encoder mode (b2e_vqenc_create): image -> conv_in -> down blocks -> mid block -> GroupNorm -> SiLU -> conv_out
   // (enc_q channels: latent, or 2 x latent moments) -> 1x1 quant_conv in fp32; output at sample_size >> (n_blocks - 1)
   bool encoder = false;
+  // classifier mode (b2e_resnet_create): torchvision ResNet (BatchNorm folded into the convolutions by the host) ->
+  // logits; backward: d(logits) -> d(image).  The loss network of ClassifierAttrFunc, src/attr_functions.py:222-257
+  bool resnet = false;
+  b2e_resnet_config rcfg{};
+  struct RBlock { int nconv = 0; ConvL c[3]; int dg[3] = {-1, -1, -1}; int stride = 1; bool has_ds = false; int cin = 0, cout = 0; };
+  std::vector<RBlock> rblocks;
+  ConvL stem; int stem_dg = -1;
+  float *fc_w = nullptr, *fc_b = nullptr;
+  const float* in_dlogits = nullptr;
   int enc_q = 0;
   float *qc_w = nullptr, *qc_b = nullptr;   // [enc_q][enc_q], [enc_q]
   float *codebook = nullptr, *pq_w = nullptr, *pq_b = nullptr;   // [n_codes][latent], [latent][latent], [latent]
@@ -433,7 +442,299 @@ int build_model_encoder(b2e_unet* m) {
   return m->build_error;
 }
 
+// torchvision ResNet graph.  Parameter names are torchvision's convolution names with the eval-mode BatchNorm already
+// folded in by the host ("layer1.0.conv1.weight" / ".bias", "layer1.0.downsample.0.weight" / ".bias", "conv1.*", "fc.*").
+// Every block's last convolution carries the shortcut as a fused 1x1 residual K segment (identity or the downsample
+// convolution on the - for stride 2, subsampled - block input); ReLU runs in the convolution epilogue.
+int build_model_resnet(b2e_unet* m) {
+  const b2e_resnet_config& c = m->rcfg;
+  const int Cin = c.in_channels, W0 = c.width;
+  {
+    // stem 7x7 stride 2 as a 1x1 convolution over a stride-2 im2col tensor (49 * Cin columns padded to a K-chunk multiple)
+    ConvL s;
+    const int KP = pad64(49 * Cin);
+    s.cin = s.cin_pad = KP; s.cout = W0; s.k = 1; s.cout_pad = conv_cout_pad(W0); s.row_len = KP;
+    s.w = m->dmalloc<bf16>((size_t)s.cout_pad * KP);
+    s.b = m->dmalloc<float>(s.cout_pad);
+    m->stem_dg = m->make_dgrad(KP, s.cout_pad, 1);   // gradient w.r.t. the im2col columns
+    const ConvL sd = m->dgrads[m->stem_dg];
+    m->add_param("conv1.weight", (int64_t)W0 * Cin * 49, (int64_t)Cin * 49, [s, sd, Cin](const float* src, cudaStream_t st) {
+      int rc = conv_pack_weight(src, s.w, s.cout, Cin, 7, Cin, s.row_len, 0, st);
+      if (!rc) rc = conv_pack_weight_im2col_T(src, sd.w, s.cout, Cin, sd.row_len, st, 49);
+      return rc;
+    });
+    m->add_f32("conv1.bias", s.b, W0, (int64_t)Cin * 49);
+    m->stem = s;
+  }
+  const int expansion = c.bottleneck ? 4 : 1;
+  int inpl = W0;
+  for (int li = 0; li < 4; ++li) {
+    const int planes = W0 << li;
+    for (int bi = 0; bi < c.layers[li]; ++bi) {
+      b2e_unet::RBlock rb;
+      rb.stride = (bi == 0 && li > 0) ? 2 : 1;
+      rb.cin = inpl; rb.cout = planes * expansion;
+      rb.has_ds = rb.stride != 1 || inpl != rb.cout;
+      const std::string base = "layer" + std::to_string(li + 1) + "." + std::to_string(bi);
+      // convolution list: bottleneck = 1x1, 3x3 (stride), 1x1 ; basic = 3x3 (stride), 3x3
+      struct CS { int cin, cout, k; };
+      std::vector<CS> cs;
+      if (c.bottleneck) cs = {{inpl, planes, 1}, {planes, planes, 3}, {planes, rb.cout, 1}};
+      else cs = {{inpl, planes, 3}, {planes, rb.cout, 3}};
+      rb.nconv = (int)cs.size();
+      for (int j = 0; j < rb.nconv; ++j) {
+        const bool last = j == rb.nconv - 1;
+        const std::string nm = base + ".conv" + std::to_string(j + 1);
+        ConvL L;
+        L.cin = cs[j].cin; L.cin_pad = pad64(cs[j].cin); L.cout = cs[j].cout; L.cout_pad = conv_cout_pad(cs[j].cout); L.k = cs[j].k;
+        L.res_c = last ? pad64(inpl) : 0;
+        L.row_len = L.k * L.k * L.cin_pad + L.res_c;
+        L.w = m->dmalloc<bf16>((size_t)L.cout_pad * L.row_len);
+        L.b = m->dmalloc<float>(L.cout_pad);
+        // dgrad twin; the FIRST convolution's twin also carries the shortcut gradient as a residual K segment
+        // (identity, or the transposed downsample weights) so that d(block input) is ONE GEMM
+        const int extra = j == 0 ? pad64(rb.cout) : 0;
+        rb.dg[j] = m->make_dgrad(cs[j].cin, L.cout_pad, L.k, extra);
+        const ConvL D = m->dgrads[rb.dg[j]];
+        m->add_param(nm + ".weight", (int64_t)L.cout * L.cin * L.k * L.k, (int64_t)L.cin * L.k * L.k, [L, D](const float* src, cudaStream_t st) {
+          int rc = conv_pack_weight(src, L.w, L.cout, L.cin, L.k, L.cin_pad, L.row_len, 0, st);
+          if (!rc) rc = conv_pack_weight_dgrad(src, D.w, L.cout, L.cin, L.k, D.cin_pad, D.row_len, 0, st);
+          return rc;
+        });
+        m->add_f32(nm + ".bias", L.b, L.cout, (int64_t)L.cin * L.k * L.k);
+        rb.c[j] = L;
+      }
+      {
+        const ConvL L = rb.c[rb.nconv - 1];
+        const ConvL D0 = m->dgrads[rb.dg[0]];
+        const int seg = L.k * L.k * L.cin_pad;                  // forward: residual segment starts here
+        const int dseg = D0.k * D0.k * D0.cin_pad;              // backward twin of conv1: shortcut-gradient segment
+        if (rb.has_ds) {
+          rb.c[rb.nconv - 1].b2 = m->dmalloc<float>(L.cout_pad);
+          const int cin = inpl, cout = rb.cout;
+          m->add_param(base + ".downsample.0.weight", (int64_t)cout * cin, cin, [L, D0, seg, dseg, cin, cout](const float* src, cudaStream_t st) {
+            int rc = conv_pack_weight(src, L.w, cout, cin, 1, cin, L.row_len, seg, st);
+            if (!rc) rc = conv_pack_weight_dgrad(src, D0.w, cout, cin, 1, pad64(cout), D0.row_len, dseg, st);
+            return rc;
+          });
+          m->add_f32(base + ".downsample.0.bias", rb.c[rb.nconv - 1].b2, cout, cin);
+        } else if (L.w && D0.w) {
+          if (conv_fill_identity(L.w, rb.cout, L.row_len, seg, 0) || conv_fill_identity(D0.w, rb.cout, D0.row_len, dseg, 0))
+            m->build_error = B2E_CUDA_ERROR;
+        }
+      }
+      m->rblocks.push_back(rb);
+      inpl = rb.cout;
+    }
+  }
+  m->fc_w = m->dmalloc<float>((size_t)c.num_classes * inpl);
+  m->fc_b = m->dmalloc<float>(c.num_classes);
+  m->add_f32("fc.weight", m->fc_w, (int64_t)c.num_classes * inpl, inpl);
+  m->add_f32("fc.bias", m->fc_b, c.num_classes, inpl);
+  return m->build_error;
+}
+
+// Launch list of the classifier for batch B: forward (activations kept: every ReLU output is needed by the backward pass)
+// and backward (d logits -> d image).  Same arena / plan machinery as the UNet.
+int build_program_resnet(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
+  const b2e_resnet_config& c = m->rcfg;
+  Arena ar;
+  ar.reset(ws, ws_bytes);
+  const bool dry = ar.dry;
+  std::vector<b2e_unet::Op> fwd, bwd;
+  std::vector<b2e_unet::Op>* cur = &fwd;
+  double flops = 0;
+  int rc = B2E_OK;
+  auto talloc = [&](int N, int H, int W, int C) {
+    Tensor t; t.N = N; t.H = H; t.W = W; t.C = C; t.Cr = C; t.bytes = (size_t)N * H * W * C * sizeof(bf16);
+    t.p = (bf16*)ar.alloc(t.bytes);
+    return t;
+  };
+  const size_t split_bytes = (size_t)kNumSMs * kConvBlockM * 128 * sizeof(float);
+  float* split_ws = (float*)ar.alloc(split_bytes);
+  int* split_cnt = (int*)ar.alloc(sizeof(int) * 1024);
+  if (!dry) cudaMemset(split_cnt, 0, sizeof(int) * 1024);
+  // y = [relu](conv_{k, stride}(x) [+ W_r r0] + bias [+ bias2]); stride 2: symmetric padding 1 (torchvision)
+  auto conv = [&](const ConvL& L, const Tensor& x, int stride, bool relu, const Tensor* r0, Tensor* out, const char* what) {
+    if (rc) return;
+    const int Ho = x.H / stride, Wo = x.W / stride;
+    *out = talloc(B, Ho, Wo, L.cout_pad);
+    const double fl = 2.0 * B * Ho * Wo * (double)L.cout_pad * (L.k * L.k * x.C + L.res_c);
+    flops += fl;
+    if (dry) return;
+    if (L.k * L.k * x.C + L.res_c != L.row_len || L.res_c != (r0 ? r0->C : 0)) {
+      rc = B2E_INVALID_ARG; set_error("resnet: operand widths do not match the packed weights (%s)", what); return;
+    }
+    ConvDesc d;
+    d.s0 = ConvSrc{x.p, x.C};
+    if (r0) d.r0 = ConvSrc{r0->p, r0->C};
+    d.N = B; d.H = x.H; d.W = x.W; d.ksize = L.k; d.stride = stride; d.stride2_pad1 = 1;
+    d.w_packed = L.w; d.Cout = L.cout_pad; d.out_bf16 = out->p;
+    d.split_ws = split_ws; d.split_ws_bytes = split_bytes; d.split_counters = split_cnt;
+    ConvPlan pl;
+    rc = conv_plan_build(&pl, d);
+    if (rc) return;
+    ConvEpilogue ep;
+    ep.bias = L.b; ep.bias2 = L.b2; ep.relu = relu ? 1 : 0;
+    char desc[160];
+    snprintf(desc, sizeof(desc), "%s: conv%dx%d s%d %dx%d cin%d res%d cout%d bn%d%s%s", what, L.k, L.k, stride, x.H, x.W, x.C, L.res_c,
+             L.cout, pl.block_n, pl.halo ? " halo" : pl.pair ? " pair" : "", relu ? " +relu" : "");
+    cur->push_back({[pl, ep](cudaStream_t st) { return conv_launch(pl, ep, st); }, 0, pl.flops, 0.0, desc});
+  };
+  auto ew = [&](std::function<int(cudaStream_t)> fn, double bytes, const char* what) {
+    if (!dry && !rc) cur->push_back({std::move(fn), 3, 0.0, bytes, what});
+  };
+  // the stride of a block sits on the 3x3 convolution of a bottleneck (torchvision v1.5) / the first one of a basic block
+  auto cstride = [](const b2e_unet::RBlock& rb, int j) { return (rb.nconv == 3 ? j == 1 : j == 0) ? rb.stride : 1; };
+
+  // ---------------- forward
+  const int S = c.input_size, Cin = c.in_channels, KP = m->stem.cin_pad;
+  Tensor cols = talloc(B, S / 2, S / 2, KP);
+  ew([m, cols, B, Cin, S, KP](cudaStream_t st) { return im2col7s2_launch(m->in_x, cols.p, B, Cin, S, S, KP, st); },
+     (double)B * S * S * Cin * 4.0 + (double)cols.bytes, "stem im2col (7x7 stride 2)");
+  Tensor y1, y2;
+  conv(m->stem, cols, 1, true, nullptr, &y1, "stem");
+  y2 = talloc(B, y1.H / 2, y1.W / 2, y1.C);
+  uint8_t* pool_idx = (uint8_t*)ar.alloc((size_t)B * y2.H * y2.W * y2.C);
+  ew([y1, y2, pool_idx, B](cudaStream_t st) { return maxpool3s2_launch(y1.p, y2.p, pool_idx, B, y1.H, y1.W, y1.C, st); },
+     1.25 * (double)y1.bytes + (double)y2.bytes, "maxpool 3x3 stride 2");
+  struct BSave { Tensor x, xs, a[3]; };
+  std::vector<BSave> saves(m->rblocks.size());
+  Tensor h = y2;
+  for (size_t bi = 0; bi < m->rblocks.size() && !rc; ++bi) {
+    const b2e_unet::RBlock& rb = m->rblocks[bi];
+    BSave& sv = saves[bi];
+    sv.x = h;
+    // shortcut operand at the block's output resolution
+    sv.xs = h;
+    if (rb.stride == 2) {
+      sv.xs = talloc(B, h.H / 2, h.W / 2, h.C);
+      const Tensor hh = h, xs = sv.xs;
+      ew([hh, xs, B](cudaStream_t st) { return subsample2x_launch(hh.p, xs.p, B, xs.H, xs.W, xs.C, st); }, 2.0 * (double)xs.bytes,
+         "shortcut subsample");
+    }
+    Tensor t = h;
+    for (int j = 0; j < rb.nconv; ++j) {
+      const bool last = j == rb.nconv - 1;
+      // the stride sits on the 3x3 convolution (torchvision v1.5 bottleneck) / on the first convolution of a basic block
+      const int stride = cstride(rb, j);
+      conv(rb.c[j], t, stride, true, last ? &sv.xs : nullptr, &sv.a[j], last ? "block out" : "block conv");
+      t = sv.a[j];
+    }
+    h = t;
+  }
+  const int HWl = h.H * h.W, Cl = h.C, K = c.num_classes;
+  float* feat = (float*)ar.alloc(sizeof(float) * B * Cl);
+  if (!rc) {
+    const Tensor hl = h;
+    ew([m, hl, feat, B, HWl, Cl, K](cudaStream_t st) { return avgpool_fc_launch(hl.p, feat, m->fc_w, m->fc_b, m->out_eps, B, HWl, Cl, K, st); },
+       (double)hl.bytes, "global average pool + fc");
+  }
+  // ---------------- backward: d(logits) -> d(image)
+  if (!rc && m->grad) {
+    cur = &bwd;
+    float* dfeat = (float*)ar.alloc(sizeof(float) * B * Cl);
+    Tensor g = talloc(B, h.H, h.W, h.C);   // gradient w.r.t. the PRE-activation of the current block output
+    {
+      const Tensor hl = h, gg = g;
+      ew([m, hl, gg, dfeat, B, HWl, Cl, K](cudaStream_t st) {
+           return avgpool_fc_bwd_launch(m->in_dlogits, m->fc_w, dfeat, hl.p, gg.p, B, HWl, Cl, K, st); },
+         2.0 * (double)hl.bytes, "fc + average pool backward (+ relu mask)");
+    }
+    auto dconv = [&](int dg, const Tensor& dy, const Tensor* r0, Tensor* dx, const char* what) {
+      // dx = conv_{k, stride 1}(dy; flipped / transposed weights) [+ residual segment r0]
+      if (rc) return;
+      const ConvL& D = m->dgrads[dg];
+      *dx = talloc(B, dy.H, dy.W, D.cout_pad);
+      const double fl = 2.0 * B * dy.H * dy.W * (double)D.cout_pad * D.row_len;
+      flops += fl;
+      if (dry) return;
+      if (D.k * D.k * dy.C + D.res_c != D.row_len || (r0 ? r0->C : 0) != D.res_c) {
+        rc = B2E_INVALID_ARG; set_error("resnet backward: operand widths do not match (%s)", what); return;
+      }
+      ConvDesc d;
+      d.s0 = ConvSrc{dy.p, dy.C};
+      if (r0) d.r0 = ConvSrc{r0->p, r0->C};
+      d.N = B; d.H = dy.H; d.W = dy.W; d.ksize = D.k; d.stride = 1;
+      d.w_packed = D.w; d.Cout = D.cout_pad; d.out_bf16 = dx->p;
+      d.split_ws = split_ws; d.split_ws_bytes = split_bytes; d.split_counters = split_cnt;
+      ConvPlan pl;
+      rc = conv_plan_build(&pl, d);
+      if (rc) return;
+      char desc[160];
+      snprintf(desc, sizeof(desc), "%s: dgrad conv%dx%d %dx%d cin%d res%d cout%d", what, D.k, D.k, dy.H, dy.W, dy.C, D.res_c, D.cout);
+      cur->push_back({[pl](cudaStream_t st) { return conv_launch(pl, ConvEpilogue{}, st); }, 0, pl.flops, 0.0, desc});
+    };
+    auto relu_mask = [&](Tensor& gt, const Tensor& y) {   // in place: gt *= (y > 0)
+      const Tensor gg = gt, yy = y;
+      ew([gg, yy](cudaStream_t st) { return relu_bwd_launch(gg.p, yy.p, gg.p, (int64_t)(gg.bytes / sizeof(bf16)), st); }, 3.0 * (double)gt.bytes,
+         "relu backward");
+    };
+    auto zero_up = [&](const Tensor& t) {
+      Tensor u = talloc(B, t.H * 2, t.W * 2, t.C);
+      const Tensor tt = t;
+      ew([tt, u, B](cudaStream_t st) { return zero_upsample2x_launch(tt.p, u.p, B, tt.H, tt.W, tt.C, st); }, 1.25 * (double)u.bytes,
+         "zero insertion (stride-2 gradient)");
+      return u;
+    };
+    for (int bi = (int)m->rblocks.size() - 1; bi >= 0 && !rc; --bi) {
+      const b2e_unet::RBlock& rb = m->rblocks[bi];
+      const BSave& sv = saves[bi];
+      // g = d/d(pre-activation of the block output).  Walk the convolutions backwards; the first convolution's twin
+      // adds the shortcut gradient through its residual segment.
+      Tensor gs = g;                     // shortcut gradient operand at the block INPUT resolution
+      if (rb.stride == 2) gs = zero_up(g);
+      Tensor d = g;
+      for (int j = rb.nconv - 1; j >= 1; --j) {
+        const int stride = cstride(rb, j);
+        Tensor dy = d;
+        if (stride == 2) dy = zero_up(d);
+        Tensor dx;
+        dconv(rb.dg[j], dy, nullptr, &dx, "block");
+        relu_mask(dx, sv.a[j - 1]);
+        d = dx;
+      }
+      {
+        const int stride0 = cstride(rb, 0);
+        Tensor dy = d;
+        if (stride0 == 2) dy = zero_up(d);
+        Tensor dx;
+        dconv(rb.dg[0], dy, &gs, &dx, "block in");
+        // the block input is the previous block's ReLU output (or the max-pool output, whose mask is applied there)
+        if (bi > 0) relu_mask(dx, sv.x);
+        g = dx;
+      }
+    }
+    if (!rc) {
+      // max pool (+ the stem's ReLU mask) -> stem dgrad w.r.t. the im2col columns -> col2im -> fp32 NCHW image gradient
+      Tensor gy1 = talloc(B, y1.H, y1.W, y1.C), dcols;
+      const Tensor gg = g;
+      ew([y1, pool_idx, gg, gy1, B](cudaStream_t st) { return maxpool3s2_bwd_launch(y1.p, pool_idx, gg.p, gy1.p, B, y1.H, y1.W, y1.C, st); },
+         3.0 * (double)y1.bytes, "maxpool backward (+ stem relu mask)");
+      dconv(m->stem_dg, gy1, nullptr, &dcols, "stem");
+      if (!rc) {
+        const Tensor dc = dcols;
+        ew([m, dc, B, Cin, S, KP](cudaStream_t st) { return col2im7s2_launch(dc.p, m->out_dz, B, Cin, S, S, KP, st); },
+           (double)dc.bytes + 4.0 * B * Cin * S * S, "stem col2im (image gradient)");
+      }
+    }
+    cur = &fwd;
+  }
+  if (rc) return rc;
+  if (need) *need = ar.peak;
+  if (!dry) {
+    B2E_REQUIRE(ar.peak <= ws_bytes, B2E_WORKSPACE_TOO_SMALL, "resnet: workspace too small (%zu > %zu)", ar.peak, ws_bytes);
+    m->ops = std::move(fwd);
+    m->bops = std::move(bwd);
+    m->fwd_B = -1;
+    m->cur_B = B;
+  }
+  m->flops = flops;
+  return B2E_OK;
+}
+
 int build_model(b2e_unet* m) {
+  if (m->resnet) return build_model_resnet(m);
   if (m->decoder) return build_model_decoder(m);
   if (m->encoder) return build_model_encoder(m);
   const b2e_unet_config& c = m->cfg;
@@ -538,6 +839,7 @@ int build_model(b2e_unet* m) {
 // Records the launch list for batch B with all activations placed in the arena.  With a null
 // arena base this is a dry run that only measures the arena size.
 int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
+  if (m->resnet) return build_program_resnet(m, B, ws, ws_bytes, need);
   const b2e_unet_config& c = m->cfg;
   Arena ar;
   ar.reset(ws, ws_bytes);
@@ -1288,6 +1590,43 @@ int b2e_vqenc_create(const b2e_vqenc_config* cfg, int64_t max_batch, b2e_unet** 
   return B2E_OK;
 }
 
+int b2e_resnet_create(const b2e_resnet_config* cfg, int64_t max_batch, b2e_unet** out) {
+  B2E_REQUIRE(cfg && out && max_batch > 0, B2E_INVALID_ARG, "resnet_create: bad argument");
+  B2E_REQUIRE(cfg->in_channels >= 1 && cfg->in_channels <= 4, B2E_UNSUPPORTED_SHAPE, "resnet_create: 1..4 input channels");
+  B2E_REQUIRE(cfg->input_size >= 64 && cfg->input_size % 64 == 0 && (cfg->input_size & (cfg->input_size - 1)) == 0,
+              B2E_UNSUPPORTED_SHAPE, "resnet_create: input_size must be a power of two >= 64 (got %d)", cfg->input_size);
+  B2E_REQUIRE(cfg->width >= 64 && cfg->width % 64 == 0 && cfg->num_classes >= 1 && cfg->num_classes <= 4096, B2E_UNSUPPORTED_SHAPE,
+              "resnet_create: width must be a multiple of 64, 1..4096 classes");
+  for (int i = 0; i < 4; ++i) B2E_REQUIRE(cfg->layers[i] >= 1 && cfg->layers[i] <= 64, B2E_UNSUPPORTED_SHAPE, "resnet_create: layers");
+  b2e_unet* m = new b2e_unet();
+  m->resnet = true;
+  m->grad = true;   // the network exists for its input gradient (classifier guidance)
+  m->rcfg = *cfg;
+  m->cfg = b2e_unet_config{};
+  m->cfg.sample_size = cfg->input_size; m->cfg.in_channels = cfg->in_channels; m->cfg.out_channels = cfg->num_classes;
+  m->max_batch = max_batch;
+  int rc = build_model(m);
+  if (!rc && cudaDeviceSynchronize() != cudaSuccess) { set_error("resnet_create: device error"); rc = B2E_CUDA_ERROR; }
+  if (!rc) rc = build_program(m, (int)max_batch, nullptr, 0, &m->ws_need);
+  if (rc) { delete m; return rc; }
+  *out = m;
+  return B2E_OK;
+}
+
+int b2e_resnet_backward(b2e_unet* m, const float* d_logits, float* d_image, int64_t B, void* stream) {
+  B2E_REQUIRE(m && d_logits && d_image, B2E_INVALID_ARG, "resnet_backward: null pointer");
+  B2E_REQUIRE(m->resnet, B2E_INVALID_ARG, "resnet_backward: not a classifier handle");
+  B2E_REQUIRE(m->fwd_B == B && m->cur_B == B, B2E_INVALID_ARG,
+              "resnet_backward: no live forward pass of batch %lld (last forward: %lld)", (long long)B, (long long)m->fwd_B);
+  m->in_dlogits = d_logits; m->out_dz = d_image;
+  cudaStream_t st = (cudaStream_t)stream;
+  for (auto& op : m->bops) {
+    int rc = op.fn(st);
+    if (rc) return rc;
+  }
+  return B2E_OK;
+}
+
 void b2e_unet_destroy(b2e_unet* m) { delete m; }
 
 int b2e_unet_num_params(const b2e_unet* m) { return m ? (int)m->params.size() : 0; }
@@ -1322,7 +1661,7 @@ int b2e_unet_bind_workspace(b2e_unet* m, void* workspace, size_t workspace_bytes
 }
 
 int b2e_unet_forward(b2e_unet* m, const float* x, const int64_t* timesteps, float* eps, int64_t B, void* stream) {
-  B2E_REQUIRE(m && x && (timesteps || m->decoder || m->encoder) && eps, B2E_INVALID_ARG, "unet_forward: null pointer");
+  B2E_REQUIRE(m && x && (timesteps || m->decoder || m->encoder || m->resnet) && eps, B2E_INVALID_ARG, "unet_forward: null pointer");
   B2E_REQUIRE(m->ws, B2E_INVALID_ARG, "unet_forward: no workspace bound");
   B2E_REQUIRE(B > 0 && B <= m->max_batch, B2E_UNSUPPORTED_SHAPE, "unet_forward: batch %lld exceeds max_batch %lld",
               (long long)B, (long long)m->max_batch);
@@ -1354,7 +1693,8 @@ int b2e_unet_forward_cond(b2e_unet* m, const float* x, const int64_t* timesteps,
 
 int b2e_unet_enable_grad(b2e_unet* m, int enable) {
   B2E_REQUIRE(m, B2E_INVALID_ARG, "unet_enable_grad: null handle");
-  B2E_REQUIRE(!enable || m->decoder, B2E_UNSUPPORTED_SHAPE, "unet_enable_grad: gradient mode is implemented for the VQ decoder");
+  B2E_REQUIRE(!enable || m->decoder || m->resnet, B2E_UNSUPPORTED_SHAPE,
+              "unet_enable_grad: gradient mode is implemented for the VQ / KL decoder and the classifier");
   if ((enable != 0) == m->grad) return B2E_OK;
   m->grad = enable != 0;
   m->cur_B = -1; m->fwd_B = -1; m->ws = nullptr; m->ws_bytes = 0;   // the workspace must be re-queried and re-bound
@@ -1382,7 +1722,7 @@ const char* b2e_unet_op_desc(const b2e_unet* m, int idx) {
 
 int b2e_unet_profile(b2e_unet* m, const float* x, const int64_t* timesteps, float* eps, int64_t B, void* stream,
                      int max_ops, int* n_ops, float* ms, double* flops, double* bytes, int* kind) {
-  B2E_REQUIRE(m && x && (timesteps || m->decoder || m->encoder) && eps && n_ops && ms && flops && bytes && kind, B2E_INVALID_ARG,
+  B2E_REQUIRE(m && x && (timesteps || m->decoder || m->encoder || m->resnet) && eps && n_ops && ms && flops && bytes && kind, B2E_INVALID_ARG,
               "unet_profile: null pointer");
   // one plain pass first (plan rebuild / lazy function attributes), then the instrumented pass
   int rc = b2e_unet_forward(m, x, timesteps, eps, B, stream);

@@ -103,6 +103,19 @@ int vq_quantize_launch(const float* z, const float* codebook, int n_codes, const
 int pointwise_conv_f32_launch(const float* x, const float* w, const float* b, float* out, int B, int Cin, int Cout, int HW,
                               cudaStream_t st);
 
+// classifier network (torchvision ResNet) kernels, csrc/resnet_kernels.cu
+int im2col7s2_launch(const float* x, bf16* out, int B, int C, int H, int W, int KP, cudaStream_t st);
+int col2im7s2_launch(const bf16* dcols, float* dx, int B, int C, int H, int W, int KP, cudaStream_t st);
+int maxpool3s2_launch(const bf16* x, bf16* y, uint8_t* idx, int N, int H, int W, int C, cudaStream_t st);
+int maxpool3s2_bwd_launch(const bf16* x, const uint8_t* idx, const bf16* gy, bf16* gx, int N, int H, int W, int C, cudaStream_t st);
+int relu_bwd_launch(const bf16* g, const bf16* y, bf16* out, int64_t numel, cudaStream_t st);
+int subsample2x_launch(const bf16* in, bf16* out, int N, int Ho, int Wo, int C, cudaStream_t st);
+int zero_upsample2x_launch(const bf16* in, bf16* out, int N, int Hi, int Wi, int C, cudaStream_t st);
+int avgpool_fc_launch(const bf16* x, float* feat, const float* w, const float* b, float* logits, int N, int HW, int C, int K,
+                      cudaStream_t st);
+int avgpool_fc_bwd_launch(const float* dlogits, const float* w, float* dfeat, const bf16* y, bf16* g, int N, int HW, int C, int K,
+                          cudaStream_t st);
+
 // multi-head tensor-core attention: head-major operands (virtual image v = n*heads + h, head_dim padded to 64)
 int split_heads_launch(const bf16* qkv, bf16* qh, bf16* kh, bf16* vht, int N, int T, int P, int heads, int d, cudaStream_t st);
 int merge_heads_launch(const bf16* oh, bf16* out, int N, int T, int P, int heads, int d, cudaStream_t st);

@@ -99,6 +99,21 @@ def create_diffusion_model(name: str, sample_clipping: bool = True, *, max_batch
     raise ValueError(f"Unknown model name: {name}")
 
 
+def get_pretrained_anyGAN(input_size: int = 256, max_batch: int = 1, state_dict_path: str = "../attribute_predictor.pt",
+                          seed: int = 0):
+    """The attribute predictor of ClassifierAttrFunc (src/models.py:69-77: ``models.resnet50()`` with an 80-way ``fc``
+    loaded from ../attribute_predictor.pt) on the native engine: forward AND input gradient on the tcgen05 kernels, so
+    classifier guidance needs no torch network.  ``input_size`` is the resolution of the decoded images it will see (256
+    for DDPM / LDM, 512 for SD).  Offline (no checkpoint file) the weights are random-init (seeded)."""
+    import os
+    from b200edit.resnet import resnet50_predictor
+    sd = None
+    if state_dict_path and os.path.exists(state_dict_path):
+        sd = torch.load(state_dict_path, map_location="cpu")
+        sd = sd.get("state_dict", sd)
+    return resnet50_predictor(80, input_size, max_batch=max_batch, state_dict=sd, seed=seed)
+
+
 class SegmentationModel:
     """Face parser front-end.  The BiSeNet weights (79999_iter.pth) are a missing blob of the
     reference and the network is outside the hot path; pass any callable ``net`` that maps a

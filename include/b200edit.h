@@ -301,6 +301,27 @@ int b2e_vqenc_create(const b2e_vqenc_config* cfg, int64_t max_batch, b2e_unet** 
 int b2e_unet_enable_grad(b2e_unet* m, int enable);
 int b2e_vqdec_backward(b2e_unet* m, const float* d_image, float* d_latent, int64_t B, void* stream);
 
+/* ------------------------------------------------------------------ classifier network (ClassifierAttrFunc)
+ * The predictor of src/models.py:69-77 (torchvision resnet50 with an 80-way fc) inside ClassifierAttrFunc.loss,
+ * src/attr_functions.py:237-257: logits = predictor(decode(x0)) and, through autograd in the reference, d(loss)/d(image).
+ * torchvision ResNet (bottleneck or basic blocks) with eval-mode BatchNorm folded into the convolutions by the host:
+ * parameters "conv1.weight/.bias", "layerL.B.convK.weight/.bias", "layerL.B.downsample.0.weight/.bias", "fc.weight/.bias".
+ * 7x7 stem as an im2col GEMM, every convolution on the tcgen05 kernel with ReLU in the epilogue and the shortcut as a
+ * fused K segment; b2e_unet_forward(m, image, NULL, logits, B, s): image (B, C, S, S) fp32 -> logits (B, num_classes);
+ * b2e_resnet_backward: d(logits) (B, num_classes) fp32 -> d(image) (B, C, S, S) fp32 (dgrad twins of every convolution,
+ * zero insertion for the stride-2 ones, max-pool / ReLU / pooling backward kernels).  Workspace, parameters and
+ * profiling through the b2e_unet_* entry points. */
+typedef struct {
+  int32_t input_size;   /* image height = width: a power of two >= 64 */
+  int32_t in_channels;  /* 1..4 */
+  int32_t bottleneck;   /* 1: Bottleneck blocks (ResNet-50/101/152), 0: BasicBlock (ResNet-18/34) */
+  int32_t layers[4];    /* (3, 4, 6, 3) for ResNet-50 */
+  int32_t width;        /* 64 */
+  int32_t num_classes;
+} b2e_resnet_config;
+int b2e_resnet_create(const b2e_resnet_config* cfg, int64_t max_batch, b2e_unet** out);
+int b2e_resnet_backward(b2e_unet* m, const float* d_logits, float* d_image, int64_t B, void* stream);
+
 /* Test hook for the implicit-GEMM convolution: x (N,H,W,Cin) bf16 NHWC, w (Cout,Cin,k,k) fp32,
  * bias fp32 [Cout] or NULL, residual (N,Ho,Wo,Cout) bf16 NHWC or NULL (added through the fused
  * residual K-segment), out (N,Ho,Wo,Cout) bf16 NHWC.  ksize 1|3, stride 1|2 (stride 2 pads

@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """BASELINE config 4 timing (per GPU): Stable Diffusion 1.x layout, CFG (doubled latent batch) + classifier guidance whose
-gradient flows through a torchvision-style ResNet-50 (the caller's torch module) and the NATIVE KL decoder (forward +
-gradient).  One guided step = conditional UNet forward on 2B latents + CFG combine + fused DDIM step + decoder forward
-(B x 3 x 512 x 512) + classifier forward / backward + decoder gradient + update.   python tools/bench_sd.py BATCH [steps]"""
+gradient flows through the NATIVE ResNet-50 attribute predictor (or, with a third argument "torch", torchvision's module)
+and the NATIVE KL decoder (forward + gradient).  One guided step = conditional UNet forward on 2B latents + CFG combine + fused DDIM step + decoder forward
+(B x 3 x 512 x 512) + classifier forward / backward + decoder gradient + update.   python tools/bench_sd.py BATCH [steps] [native|torch]"""
 import os, sys
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(REPO, "diffusion-image-editing_b200"))
@@ -30,12 +30,13 @@ class Enc(torch.nn.Module):   # stands in for CLIP (no weights offline): (1, 77)
         return (self.e(ids),)
 
 
-try:
+PRED = sys.argv[3] if len(sys.argv) > 3 else "native"
+if PRED == "native":   # the attribute predictor on the engine (forward + input gradient on the tcgen05 kernels)
+    from models import get_pretrained_anyGAN
+    predictor = get_pretrained_anyGAN(input_size=512, max_batch=B)
+else:                  # torchvision's module differentiated by torch autograd (cuDNN), the earlier configuration
     import torchvision
     predictor = torchvision.models.resnet50(num_classes=80).cuda().eval()
-except Exception:   # torchvision missing: a small stand-in keeps the timing script usable
-    predictor = torch.nn.Sequential(torch.nn.Conv2d(3, 64, 7, stride=4), torch.nn.AdaptiveAvgPool2d(1), torch.nn.Flatten(),
-                                    torch.nn.Linear(64, 80)).cuda()
 w = create_diffusion_model("sd", sample_clipping=False, max_batch=B, seed=0, tokenizer=Tok(), text_encoder=Enc().cuda())
 w.scheduler.set_timesteps(K)
 pipe = SegDiffEditPipeline(w, None)
@@ -58,5 +59,5 @@ ms = e0.elapsed_time(e1) / K
 fl = (2 * w.unet.flops_per_sample + w.vae.flops_per_sample) * B
 print(f"config 4, B={B}/GPU: {ms:.1f} ms per guided step, {B / ms * 1e3:.1f} guided img-steps/s, ~{fl / ms / 1e9:.0f} TFLOP/s native "
       f"(UNet 2 x {w.unet.flops_per_sample / 1e12:.3f} + KL decoder fwd+bwd {w.vae.flops_per_sample / 1e12:.3f} TFLOP/img; "
-      f"classifier in torch; one final decode per {K} steps)")
+      f"classifier: {PRED}; one final decode per {K} steps)")
 print("max memory GB", torch.cuda.max_memory_allocated() / 1e9)
