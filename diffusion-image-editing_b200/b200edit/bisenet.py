@@ -1,0 +1,105 @@
+"""Native face parser: the reference's ``BiSeNet`` (src/Segmentation/model.py:234-262 on the ResNet-18 of
+src/Segmentation/resnet.py) on libb200edit.so - the network behind ``SegmentationModel`` (src/models.py:80-118), whose
+parsing map feeds the mask path (``prepare_for_edit``, src/SegDiffEditPipeline.py:79-97).  Forward only: ``net(x)[0]`` =
+logits (B, n_classes, S, S) like the reference's first output.
+
+Eval-mode BatchNorm is folded into the convolutions when the reference's ``state_dict`` is loaded; convolutions run on
+the tcgen05 implicit-GEMM kernel with ReLU in the epilogue, the channel-attention branches (global pooling -> 1x1
+convolutions -> sigmoid) as small fp32 kernels, the final align_corners bilinear upsampling as one kernel."""
+from __future__ import annotations
+
+import ctypes as C
+from types import SimpleNamespace
+
+import torch
+
+from . import _C
+from ._C import ResNetConfig, check, lib
+from .unet import UNet2DModel
+
+
+def _fold(w, sd, bn, eps=1e-5):
+    g, b = sd[bn + ".weight"].double(), sd[bn + ".bias"].double()
+    mu, var = sd[bn + ".running_mean"].double(), sd[bn + ".running_var"].double()
+    s = g / torch.sqrt(var + eps)
+    return (w.double() * s.view(-1, 1, 1, 1)).float(), (b - mu * s).float()
+
+
+class BiSeNet(UNet2DModel):
+    def __init__(self, n_classes=19, input_size=512, max_batch=1, device="cuda"):
+        _C.require_device()
+        self.config = SimpleNamespace(n_classes=n_classes, input_size=input_size, in_channels=3, sample_size=input_size,
+                                      out_channels=n_classes)
+        self.device = torch.device(device)
+        self.dtype = torch.float32
+        self.max_batch = int(max_batch)
+        cfg = ResNetConfig()
+        cfg.input_size, cfg.in_channels, cfg.bottleneck, cfg.width, cfg.num_classes, cfg.head = input_size, 3, 0, 64, n_classes, 1
+        for i in range(4):
+            cfg.layers[i] = 2
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib.b2e_resnet_create(C.byref(cfg), self.max_batch, C.byref(h)), "bisenet_create")
+            self._h = h
+            nbytes = lib.b2e_unet_workspace_bytes(h)
+            self._ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)
+            base = (self._ws.data_ptr() + 255) // 256 * 256
+            check(lib.b2e_unet_bind_workspace(h, C.c_void_p(base), nbytes), "unet_bind_workspace")
+        self._t_cache = {}
+
+    @staticmethod
+    def fold_reference_state_dict(sd, eps=1e-5):
+        """The reference's BiSeNet ``state_dict`` -> the engine's parameters (BatchNorm folded; the auxiliary heads
+        conv_out16 / conv_out32 are training-time outputs and are dropped)."""
+        out = {}
+        for k, w in sd.items():
+            if not k.endswith(".weight") or w.dim() != 4 or k.startswith(("conv_out16.", "conv_out32.")):
+                continue
+            name = k[:-len(".weight")]
+            if name.startswith("cp.resnet."):
+                if name.endswith("downsample.0"):
+                    bn = name[:-1] + "1"
+                else:
+                    head, last = name.rsplit("conv", 1)
+                    bn = f"{head}bn{last}"
+                out[name + ".weight"], out[name + ".bias"] = _fold(w, sd, bn, eps)
+            elif name.endswith(".conv") and (name + ".weight") in sd and (name[:-len(".conv")] + ".bn.weight") in sd:
+                # ConvBNReLU: <block>.conv + <block>.bn -> <block>
+                blk = name[:-len(".conv")]
+                fw, fb = _fold(w, sd, blk + ".bn", eps)
+                if blk == "cp.conv_avg":         # acts on the pooled vector: an fp32 matrix
+                    fw = fw.reshape(fw.shape[0], -1)
+                out[blk + ".weight"], out[blk + ".bias"] = fw, fb
+            elif name.endswith(".conv_atten"):
+                fw, fb = _fold(w, sd, name[:-len("conv_atten")] + "bn_atten", eps)
+                out[name + ".weight"], out[name + ".bias"] = fw.reshape(fw.shape[0], -1), fb
+            elif name in ("ffm.conv1", "ffm.conv2"):
+                out[name + ".weight"] = w.float().reshape(w.shape[0], -1)
+            elif name == "conv_out.conv_out":
+                out[name + ".weight"], out[name + ".bias"] = w.float(), torch.zeros(w.shape[0])
+        return out
+
+    def load_reference_state_dict(self, sd, eps=1e-5):
+        return self.load_state_dict(self.fold_reference_state_dict(sd, eps))
+
+    def __call__(self, image):
+        if not image.is_cuda:
+            raise _C.B2EError("BiSeNet: image must be a CUDA tensor (no CPU fallback)")
+        if image.requires_grad and torch.is_grad_enabled():
+            raise _C.B2EError("BiSeNet: the native face parser is forward-only; NetAttrFunc guidance through the parser "
+                              "needs a differentiable module")
+        cfg = self.config
+        if tuple(image.shape[1:]) != (3, cfg.input_size, cfg.input_size):
+            raise ValueError(f"BiSeNet: expected (B,3,{cfg.input_size},{cfg.input_size}), got {tuple(image.shape)}")
+        x = image.detach().to(torch.float32).contiguous()
+        outs = []
+        for b0 in range(0, x.shape[0], self.max_batch):
+            xb = x[b0:b0 + self.max_batch]
+            o = torch.empty((xb.shape[0], cfg.n_classes, cfg.input_size, cfg.input_size), dtype=torch.float32, device=x.device)
+            check(lib.b2e_unet_forward(self._h, C.c_void_p(xb.data_ptr()), None, C.c_void_p(o.data_ptr()), xb.shape[0],
+                                       C.c_void_p(torch.cuda.current_stream().cuda_stream)), "bisenet_forward")
+            outs.append(o)
+        return (outs[0] if len(outs) == 1 else torch.cat(outs), None, None)
+
+    def eval(self):
+        return self

@@ -318,4 +318,102 @@ int avgpool_fc_bwd_launch(const float* dlogits, const float* w, float* dfeat, co
   return check_launch("avgpool_bwd");
 }
 
+// ---- face parser (BiSeNet, src/Segmentation/model.py) helpers
+int avgpool_launch(const bf16* x, float* feat, int N, int HW, int C, cudaStream_t st) {
+  launch_pdl(avgpool_kernel, dim3((C + 255) / 256, N), dim3(256), 0, st, x, feat, HW, C);
+  return check_launch("avgpool");
+}
+
+// out[n][k] = act(w[k] . x[n] + b[k]); act: 0 none, 1 relu, 2 sigmoid, 3 1 + sigmoid   (1x1 convolutions on pooled vectors)
+__global__ void __launch_bounds__(256) fc_act_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                     const float* __restrict__ b, float* __restrict__ out, int N, int C, int K,
+                                                     int act) {
+  pdl_wait();
+  const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (wid >= N * K) return;
+  const int n = wid / K, k = wid % K;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += __ldg(w + (int64_t)k * C + c) * x[(int64_t)n * C + c];
+  s = warp_sum(s);
+  if (lane == 0) {
+    if (b) s += b[k];
+    if (act == 1) s = fmaxf(s, 0.f);
+    else if (act >= 2) s = 1.f / (1.f + expf(-s)) + (act == 3 ? 1.f : 0.f);
+    out[(int64_t)n * K + k] = s;
+  }
+}
+
+int fc_act_launch(const float* x, const float* w, const float* b, float* out, int N, int C, int K, int act, cudaStream_t st) {
+  launch_pdl(fc_act_kernel, dim3((N * K + 7) / 8), dim3(256), 0, st, x, w, b, out, N, C, K, act);
+  return check_launch("fc_act");
+}
+
+// out[n][p][c] = x[n][p][c] * a[n][c] (+ b[n][c]) (+ y[n][p][c])   (channel attention / broadcast add, bf16 NHWC)
+__global__ void __launch_bounds__(256) chan_affine_kernel(const bf16* __restrict__ x, const float* __restrict__ a,
+                                                          const float* __restrict__ b, const bf16* __restrict__ y,
+                                                          bf16* __restrict__ out, int HW, int C8) {
+  pdl_wait();
+  const int n = blockIdx.y;
+  const int64_t total = (int64_t)HW * C8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int s = (int)(i % C8);
+    const int64_t o = ((int64_t)n * total + i) * 8;
+    float xv[8], yv[8];
+    unpack8r(__ldg(reinterpret_cast<const uint4*>(x + o)), xv);
+    if (y) unpack8r(__ldg(reinterpret_cast<const uint4*>(y + o)), yv);
+    const float* ap = a + (int64_t)n * C8 * 8 + s * 8;
+    const float* bp = b ? b + (int64_t)n * C8 * 8 + s * 8 : nullptr;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = xv[j] * ap[j];
+      if (bp) v += bp[j];
+      if (y) v += yv[j];
+      xv[j] = v;
+    }
+    *reinterpret_cast<uint4*>(out + o) = pack8r(xv);
+  }
+}
+
+int chan_affine_launch(const bf16* x, const float* a, const float* b, const bf16* y, bf16* out, int N, int HW, int C,
+                       cudaStream_t st) {
+  B2E_REQUIRE(C % 8 == 0, B2E_UNSUPPORTED_SHAPE, "chan_affine: C %% 8 != 0");
+  const int64_t total = (int64_t)HW * (C / 8);
+  int gx = (int)((total + 255) / 256);
+  if (gx > kNumSMs * 8) gx = kNumSMs * 8;
+  launch_pdl(chan_affine_kernel, dim3(gx, N), dim3(256), 0, st, x, a, b, y, out, HW, C / 8);
+  return check_launch("chan_affine");
+}
+
+// F.interpolate(x, (Ho, Wo), mode="bilinear", align_corners=True): x bf16 NHWC (N,Hi,Wi,P), first K channels ->
+// out fp32 NCHW (N,K,Ho,Wo).  ATen's arithmetic: src = dst * (in-1)/(out-1); weights (1-l, l).
+__global__ void __launch_bounds__(256) bilinear_ac_kernel(const bf16* __restrict__ x, float* __restrict__ out, int N, int Hi,
+                                                          int Wi, int P, int K, int Ho, int Wo, float sh, float sw) {
+  pdl_wait();
+  const int64_t total = (int64_t)N * Ho * Wo;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ow = (int)(i % Wo);
+    const int oh = (int)((i / Wo) % Ho);
+    const int n = (int)(i / ((int64_t)Wo * Ho));
+    const float fh = sh * (float)oh, fw = sw * (float)ow;
+    const int h0 = (int)fh, w0 = (int)fw;
+    const int h1 = h0 + (h0 < Hi - 1 ? 1 : 0), w1 = w0 + (w0 < Wi - 1 ? 1 : 0);
+    const float lh = fh - (float)h0, lw = fw - (float)w0;
+    const bf16* p00 = x + (((int64_t)n * Hi + h0) * Wi + w0) * P;
+    const bf16* p01 = x + (((int64_t)n * Hi + h0) * Wi + w1) * P;
+    const bf16* p10 = x + (((int64_t)n * Hi + h1) * Wi + w0) * P;
+    const bf16* p11 = x + (((int64_t)n * Hi + h1) * Wi + w1) * P;
+    for (int k = 0; k < K; ++k) {
+      const float v = (1.f - lh) * ((1.f - lw) * __bfloat162float(p00[k]) + lw * __bfloat162float(p01[k])) +
+                      lh * ((1.f - lw) * __bfloat162float(p10[k]) + lw * __bfloat162float(p11[k]));
+      out[(((int64_t)n * K + k) * Ho + oh) * Wo + ow] = v;
+    }
+  }
+}
+
+int bilinear_ac_launch(const bf16* x, float* out, int N, int Hi, int Wi, int P, int K, int Ho, int Wo, cudaStream_t st) {
+  const float sh = Ho > 1 ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f, sw = Wo > 1 ? (float)(Wi - 1) / (float)(Wo - 1) : 0.f;
+  launch_pdl(bilinear_ac_kernel, dim3(grid_for((int64_t)N * Ho * Wo)), dim3(256), 0, st, x, out, N, Hi, Wi, P, K, Ho, Wo, sh, sw);
+  return check_launch("bilinear_ac");
+}
+
 }  // namespace b2e

@@ -112,6 +112,12 @@ struct b2e_unet {
   std::vector<RBlock> rblocks;
   ConvL stem; int stem_dg = -1;
   float *fc_w = nullptr, *fc_b = nullptr;
+  // face parser head (rcfg.head == 1): BiSeNet context path + feature fusion + output head (src/Segmentation/model.py)
+  struct BiSe {
+    ConvL arm32, arm16, head32, head16, ffm_blk, out_conv, out_cls;
+    float *avg_w = nullptr, *avg_b = nullptr, *a32_w = nullptr, *a32_b = nullptr, *a16_w = nullptr, *a16_b = nullptr;
+    float *f1_w = nullptr, *f2_w = nullptr;
+  } bs;
   const float* in_dlogits = nullptr;
   int enc_q = 0;
   float *qc_w = nullptr, *qc_b = nullptr;   // [enc_q][enc_q], [enc_q]
@@ -449,6 +455,7 @@ int build_model_encoder(b2e_unet* m) {
 int build_model_resnet(b2e_unet* m) {
   const b2e_resnet_config& c = m->rcfg;
   const int Cin = c.in_channels, W0 = c.width;
+  const std::string pre = c.head == 1 ? "cp.resnet." : "";   // BiSeNet keeps its backbone under cp.resnet
   {
     // stem 7x7 stride 2 as a 1x1 convolution over a stride-2 im2col tensor (49 * Cin columns padded to a K-chunk multiple)
     ConvL s;
@@ -458,12 +465,12 @@ int build_model_resnet(b2e_unet* m) {
     s.b = m->dmalloc<float>(s.cout_pad);
     m->stem_dg = m->make_dgrad(KP, s.cout_pad, 1);   // gradient w.r.t. the im2col columns
     const ConvL sd = m->dgrads[m->stem_dg];
-    m->add_param("conv1.weight", (int64_t)W0 * Cin * 49, (int64_t)Cin * 49, [s, sd, Cin](const float* src, cudaStream_t st) {
+    m->add_param(pre + "conv1.weight", (int64_t)W0 * Cin * 49, (int64_t)Cin * 49, [s, sd, Cin](const float* src, cudaStream_t st) {
       int rc = conv_pack_weight(src, s.w, s.cout, Cin, 7, Cin, s.row_len, 0, st);
       if (!rc) rc = conv_pack_weight_im2col_T(src, sd.w, s.cout, Cin, sd.row_len, st, 49);
       return rc;
     });
-    m->add_f32("conv1.bias", s.b, W0, (int64_t)Cin * 49);
+    m->add_f32(pre + "conv1.bias", s.b, W0, (int64_t)Cin * 49);
     m->stem = s;
   }
   const int expansion = c.bottleneck ? 4 : 1;
@@ -475,7 +482,7 @@ int build_model_resnet(b2e_unet* m) {
       rb.stride = (bi == 0 && li > 0) ? 2 : 1;
       rb.cin = inpl; rb.cout = planes * expansion;
       rb.has_ds = rb.stride != 1 || inpl != rb.cout;
-      const std::string base = "layer" + std::to_string(li + 1) + "." + std::to_string(bi);
+      const std::string base = pre + "layer" + std::to_string(li + 1) + "." + std::to_string(bi);
       // convolution list: bottleneck = 1x1, 3x3 (stride), 1x1 ; basic = 3x3 (stride), 3x3
       struct CS { int cin, cout, k; };
       std::vector<CS> cs;
@@ -527,6 +534,31 @@ int build_model_resnet(b2e_unet* m) {
       inpl = rb.cout;
     }
   }
+  if (c.head == 1) {
+    // BiSeNet: ConvBNReLU blocks (BatchNorm folded by the host) on the conv kernel; the 1x1 convolutions that act on
+    // globally pooled vectors (conv_avg, the attention branches) are small fp32 matrices
+    auto& bs = m->bs;
+    const int c16 = W0 * 4, c32 = W0 * 8, c8 = W0 * 2, mid = 128;
+    bs.arm32 = m->make_conv("cp.arm32.conv", c32, mid, 3);
+    bs.arm16 = m->make_conv("cp.arm16.conv", c16, mid, 3);
+    bs.head32 = m->make_conv("cp.conv_head32", mid, mid, 3);
+    bs.head16 = m->make_conv("cp.conv_head16", mid, mid, 3);
+    bs.ffm_blk = m->make_conv("ffm.convblk", c8 + mid, 256, 1);
+    bs.out_conv = m->make_conv("conv_out.conv", 256, 256, 3);
+    bs.out_cls = m->make_conv("conv_out.conv_out", 256, c.num_classes, 1);
+    auto fcp = [&](const std::string& name, int K, int C, bool bias, float** w, float** b) {
+      *w = m->dmalloc<float>((size_t)K * C);
+      m->add_f32(name + ".weight", *w, (int64_t)K * C, C);
+      if (bias) { *b = m->dmalloc<float>(K); m->add_f32(name + ".bias", *b, K, C); }
+    };
+    float* none = nullptr;
+    fcp("cp.conv_avg", mid, c32, true, &bs.avg_w, &bs.avg_b);
+    fcp("cp.arm32.conv_atten", mid, mid, true, &bs.a32_w, &bs.a32_b);
+    fcp("cp.arm16.conv_atten", mid, mid, true, &bs.a16_w, &bs.a16_b);
+    fcp("ffm.conv1", 64, 256, false, &bs.f1_w, &none);
+    fcp("ffm.conv2", 256, 64, false, &bs.f2_w, &none);
+    return m->build_error;
+  }
   m->fc_w = m->dmalloc<float>((size_t)c.num_classes * inpl);
   m->fc_b = m->dmalloc<float>(c.num_classes);
   m->add_f32("fc.weight", m->fc_w, (int64_t)c.num_classes * inpl, inpl);
@@ -555,18 +587,21 @@ int build_program_resnet(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* 
   int* split_cnt = (int*)ar.alloc(sizeof(int) * 1024);
   if (!dry) cudaMemset(split_cnt, 0, sizeof(int) * 1024);
   // y = [relu](conv_{k, stride}(x) [+ W_r r0] + bias [+ bias2]); stride 2: symmetric padding 1 (torchvision)
-  auto conv = [&](const ConvL& L, const Tensor& x, int stride, bool relu, const Tensor* r0, Tensor* out, const char* what) {
+  auto conv = [&](const ConvL& L, const Tensor& x, int stride, bool relu, const Tensor* r0, Tensor* out, const char* what,
+                  const Tensor* x1 = nullptr) {
     if (rc) return;
     const int Ho = x.H / stride, Wo = x.W / stride;
+    const int xc = x.C + (x1 ? x1->C : 0);
     *out = talloc(B, Ho, Wo, L.cout_pad);
-    const double fl = 2.0 * B * Ho * Wo * (double)L.cout_pad * (L.k * L.k * x.C + L.res_c);
+    const double fl = 2.0 * B * Ho * Wo * (double)L.cout_pad * (L.k * L.k * xc + L.res_c);
     flops += fl;
     if (dry) return;
-    if (L.k * L.k * x.C + L.res_c != L.row_len || L.res_c != (r0 ? r0->C : 0)) {
+    if (L.k * L.k * xc + L.res_c != L.row_len || L.res_c != (r0 ? r0->C : 0)) {
       rc = B2E_INVALID_ARG; set_error("resnet: operand widths do not match the packed weights (%s)", what); return;
     }
     ConvDesc d;
     d.s0 = ConvSrc{x.p, x.C};
+    if (x1) d.s1 = ConvSrc{x1->p, x1->C};
     if (r0) d.r0 = ConvSrc{r0->p, r0->C};
     d.N = B; d.H = x.H; d.W = x.W; d.ksize = L.k; d.stride = stride; d.stride2_pad1 = 1;
     d.w_packed = L.w; d.Cout = L.cout_pad; d.out_bf16 = out->p;
@@ -600,6 +635,7 @@ int build_program_resnet(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* 
      1.25 * (double)y1.bytes + (double)y2.bytes, "maxpool 3x3 stride 2");
   struct BSave { Tensor x, xs, a[3]; };
   std::vector<BSave> saves(m->rblocks.size());
+  std::vector<Tensor> layer_out;
   Tensor h = y2;
   for (size_t bi = 0; bi < m->rblocks.size() && !rc; ++bi) {
     const b2e_unet::RBlock& rb = m->rblocks[bi];
@@ -622,8 +658,83 @@ int build_program_resnet(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* 
       t = sv.a[j];
     }
     h = t;
+    layer_out.push_back(h);
   }
   const int HWl = h.H * h.W, Cl = h.C, K = c.num_classes;
+  if (!rc && c.head == 1) {
+    // ---- BiSeNet: context path (attention refinement on feat16 / feat32 + global context), feature fusion with the
+    // 1/8 backbone feature, output head, bilinear (align_corners) upsampling to the input resolution -> fp32 NCHW logits
+    const auto& bs = m->bs;
+    int nb = 0;
+    Tensor feat8, feat16, feat32;
+    for (int li = 0; li < 4; ++li) {
+      nb += c.layers[li];
+      if (li == 1) feat8 = layer_out[nb - 1];
+      if (li == 2) feat16 = layer_out[nb - 1];
+      if (li == 3) feat32 = layer_out[nb - 1];
+    }
+    auto fbuf = [&](int n) { return (float*)ar.alloc(sizeof(float) * B * n); };
+    auto pool = [&](const Tensor& t, float* dst) {
+      const Tensor tt = t;
+      ew([tt, dst, B](cudaStream_t st) { return avgpool_launch(tt.p, dst, B, tt.H * tt.W, tt.C, st); }, (double)tt.bytes, "global average pool");
+    };
+    auto fc = [&](const float* x, const float* w, const float* b, float* out, int C, int Kk, int act, const char* what) {
+      ew([x, w, b, out, B, C, Kk, act](cudaStream_t st) { return fc_act_launch(x, w, b, out, B, C, Kk, act, st); }, 4.0 * Kk * C, what);
+    };
+    auto affine = [&](const Tensor& x, const float* a, const float* b, const Tensor* y, Tensor* out, const char* what) {
+      *out = talloc(B, x.H, x.W, x.C);
+      const Tensor xx = x, oo = *out;
+      const bf16* yp = y ? y->p : nullptr;
+      ew([xx, a, b, yp, oo, B](cudaStream_t st) { return chan_affine_launch(xx.p, a, b, yp, oo.p, B, xx.H * xx.W, xx.C, st); },
+         (y ? 3.0 : 2.0) * (double)xx.bytes, what);
+    };
+    auto up2 = [&](const Tensor& x, Tensor* out) {
+      *out = talloc(B, x.H * 2, x.W * 2, x.C);
+      const Tensor xx = x, oo = *out;
+      ew([xx, oo, B](cudaStream_t st) { return upsample2x_launch(xx.p, oo.p, B, xx.H, xx.W, xx.C, st); }, 1.25 * (double)oo.bytes, "nearest upsample x2");
+    };
+    const int mid = 128;
+    float *p32 = fbuf(feat32.C), *avg = fbuf(mid), *q32 = fbuf(mid), *att32 = fbuf(mid), *q16 = fbuf(mid), *att16 = fbuf(mid);
+    float *pf = fbuf(256), *t1 = fbuf(64), *attf = fbuf(256);
+    Tensor f32, sum32, up32, h32, f16, sum16, up16, cp8, ff, fo, o1, o2;
+    pool(feat32, p32);
+    fc(p32, bs.avg_w, bs.avg_b, avg, feat32.C, mid, 1, "conv_avg (1x1 on the pooled feature)");
+    conv(bs.arm32, feat32, 1, true, nullptr, &f32, "arm32.conv");
+    pool(f32, q32);
+    fc(q32, bs.a32_w, bs.a32_b, att32, mid, mid, 2, "arm32 attention");
+    affine(f32, att32, avg, nullptr, &sum32, "arm32: feat * attention + global context");
+    up2(sum32, &up32);
+    conv(bs.head32, up32, 1, true, nullptr, &h32, "conv_head32");
+    conv(bs.arm16, feat16, 1, true, nullptr, &f16, "arm16.conv");
+    pool(f16, q16);
+    fc(q16, bs.a16_w, bs.a16_b, att16, mid, mid, 2, "arm16 attention");
+    affine(f16, att16, nullptr, &h32, &sum16, "arm16: feat * attention + feat32_up");
+    up2(sum16, &up16);
+    conv(bs.head16, up16, 1, true, nullptr, &cp8, "conv_head16");
+    conv(bs.ffm_blk, feat8, 1, true, nullptr, &ff, "ffm.convblk (concat fused)", &cp8);
+    pool(ff, pf);
+    fc(pf, bs.f1_w, nullptr, t1, 256, 64, 1, "ffm.conv1");
+    fc(t1, bs.f2_w, nullptr, attf, 64, 256, 3, "ffm.conv2 (1 + sigmoid)");
+    affine(ff, attf, nullptr, nullptr, &fo, "ffm: feat * (1 + attention)");
+    conv(bs.out_conv, fo, 1, true, nullptr, &o1, "conv_out.conv");
+    conv(bs.out_cls, o1, 1, false, nullptr, &o2, "conv_out.conv_out");
+    if (!rc) {
+      const Tensor oo = o2;
+      ew([m, oo, B, K, S](cudaStream_t st) { return bilinear_ac_launch(oo.p, m->out_eps, B, oo.H, oo.W, oo.C, K, S, S, st); },
+         (double)oo.bytes + 4.0 * B * K * S * S, "bilinear upsample (align_corners) -> logits");
+    }
+    if (rc) return rc;
+    if (need) *need = ar.peak;
+    if (!dry) {
+      B2E_REQUIRE(ar.peak <= ws_bytes, B2E_WORKSPACE_TOO_SMALL, "bisenet: workspace too small (%zu > %zu)", ar.peak, ws_bytes);
+      m->ops = std::move(fwd);
+      m->bops.clear();
+      m->fwd_B = -1;
+      m->cur_B = B;
+    }
+    m->flops = flops;
+    return B2E_OK;
+  }
   float* feat = (float*)ar.alloc(sizeof(float) * B * Cl);
   if (!rc) {
     const Tensor hl = h;
@@ -1600,7 +1711,9 @@ int b2e_resnet_create(const b2e_resnet_config* cfg, int64_t max_batch, b2e_unet*
   for (int i = 0; i < 4; ++i) B2E_REQUIRE(cfg->layers[i] >= 1 && cfg->layers[i] <= 64, B2E_UNSUPPORTED_SHAPE, "resnet_create: layers");
   b2e_unet* m = new b2e_unet();
   m->resnet = true;
-  m->grad = true;   // the network exists for its input gradient (classifier guidance)
+  B2E_REQUIRE(cfg->head == 0 || (cfg->head == 1 && !cfg->bottleneck && cfg->width == 64 && cfg->num_classes <= 64),
+              B2E_UNSUPPORTED_SHAPE, "resnet_create: the face-parser head needs a basic-block backbone of width 64 and <= 64 classes");
+  m->grad = cfg->head == 0;   // the classifier exists for its input gradient (classifier guidance)
   m->rcfg = *cfg;
   m->cfg = b2e_unet_config{};
   m->cfg.sample_size = cfg->input_size; m->cfg.in_channels = cfg->in_channels; m->cfg.out_channels = cfg->num_classes;
@@ -1615,7 +1728,7 @@ int b2e_resnet_create(const b2e_resnet_config* cfg, int64_t max_batch, b2e_unet*
 
 int b2e_resnet_backward(b2e_unet* m, const float* d_logits, float* d_image, int64_t B, void* stream) {
   B2E_REQUIRE(m && d_logits && d_image, B2E_INVALID_ARG, "resnet_backward: null pointer");
-  B2E_REQUIRE(m->resnet, B2E_INVALID_ARG, "resnet_backward: not a classifier handle");
+  B2E_REQUIRE(m->resnet && m->rcfg.head == 0, B2E_INVALID_ARG, "resnet_backward: not a classifier handle");
   B2E_REQUIRE(m->fwd_B == B && m->cur_B == B, B2E_INVALID_ARG,
               "resnet_backward: no live forward pass of batch %lld (last forward: %lld)", (long long)B, (long long)m->fwd_B);
   m->in_dlogits = d_logits; m->out_dz = d_image;

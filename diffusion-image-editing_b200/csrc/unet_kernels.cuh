@@ -116,6 +116,13 @@ int avgpool_fc_launch(const bf16* x, float* feat, const float* w, const float* b
 int avgpool_fc_bwd_launch(const float* dlogits, const float* w, float* dfeat, const bf16* y, bf16* g, int N, int HW, int C, int K,
                           cudaStream_t st);
 
+// face parser (BiSeNet) helpers
+int avgpool_launch(const bf16* x, float* feat, int N, int HW, int C, cudaStream_t st);
+int fc_act_launch(const float* x, const float* w, const float* b, float* out, int N, int C, int K, int act, cudaStream_t st);
+int chan_affine_launch(const bf16* x, const float* a, const float* b, const bf16* y, bf16* out, int N, int HW, int C,
+                       cudaStream_t st);
+int bilinear_ac_launch(const bf16* x, float* out, int N, int Hi, int Wi, int P, int K, int Ho, int Wo, cudaStream_t st);
+
 // multi-head tensor-core attention: head-major operands (virtual image v = n*heads + h, head_dim padded to 64)
 int split_heads_launch(const bf16* qkv, bf16* qh, bf16* kh, bf16* vht, int N, int T, int P, int heads, int d, cudaStream_t st);
 int merge_heads_launch(const bf16* oh, bf16* out, int N, int T, int P, int heads, int d, cudaStream_t st);

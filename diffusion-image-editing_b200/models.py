@@ -115,15 +115,22 @@ def get_pretrained_anyGAN(input_size: int = 256, max_batch: int = 1, state_dict_
 
 
 class SegmentationModel:
-    """Face parser front-end.  The BiSeNet weights (79999_iter.pth) are a missing blob of the
-    reference and the network is outside the hot path; pass any callable ``net`` that maps a
-    (1,3,512,512) image to ([1,19,H,W] logits, ...)."""
+    """Face parser front-end (src/models.py:80-118).  ``net=None`` builds the native BiSeNet (b200edit.bisenet) and loads
+    ``ckpt`` (the reference's Segmentation/res/cp/79999_iter.pth, a blob missing from the checkout) when the file
+    exists, else seeded random-init weights; any callable ``net`` mapping a (1,3,512,512) image to
+    ([1,19,H,W] logits, ...) can be substituted."""
 
-    def __init__(self, net=None, n_classes: int = 19, image_size: tuple = (512, 512)) -> None:
-        if net is None:
-            raise NotImplementedError("SegmentationModel needs a parsing network (BiSeNet weights are "
-                                      "not available offline)")
+    def __init__(self, net=None, n_classes: int = 19, image_size: tuple = (512, 512),
+                 ckpt: str = "Segmentation/res/cp/79999_iter.pth", seed: int = 0) -> None:
         self.device = get_device()
+        if net is None:
+            import os
+            from b200edit.bisenet import BiSeNet
+            net = BiSeNet(n_classes, image_size[0], max_batch=1, device=self.device)
+            if ckpt and os.path.exists(ckpt):
+                net.load_reference_state_dict(torch.load(ckpt, map_location="cpu"))
+            else:
+                net.init_random(seed)
         self.net = net
         self.image_size = image_size
         self.mean = torch.tensor((0.485, 0.456, 0.406)).view(1, 3, 1, 1)

@@ -318,6 +318,14 @@ typedef struct {
   int32_t layers[4];    /* (3, 4, 6, 3) for ResNet-50 */
   int32_t width;        /* 64 */
   int32_t num_classes;
+  /* 0: classifier (global average pool + fc -> logits (B, num_classes)).
+   * 1: face parser: BiSeNet (src/Segmentation/model.py:234-262, the network of SegmentationModel, src/models.py:80-118) on a
+   *    basic-block backbone - context path with attention refinement, feature fusion, output head, bilinear
+   *    (align_corners) upsampling: output = out[0] of the reference, logits (B, num_classes, S, S) fp32; forward only.
+   *    Parameters under the reference's names with BatchNorm folded ("cp.resnet.layer1.0.conv1.weight/.bias",
+   *    "cp.arm16.conv.*", "cp.arm16.conv_atten.*", "cp.conv_head32.*", "cp.conv_avg.*", "ffm.convblk.*", "ffm.conv1.weight",
+   *    "ffm.conv2.weight", "conv_out.conv.*", "conv_out.conv_out.*"). */
+  int32_t head;
 } b2e_resnet_config;
 int b2e_resnet_create(const b2e_resnet_config* cfg, int64_t max_batch, b2e_unet** out);
 int b2e_resnet_backward(b2e_unet* m, const float* d_logits, float* d_image, int64_t B, void* stream);

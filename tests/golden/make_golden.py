@@ -386,8 +386,26 @@ def gen_mask():
     print("mask.npz", len(out))
 
 
+def gen_bisenet():
+    """The reference's BiSeNet (src/Segmentation/model.py) on seeded weights; its ResNet-18 hub download
+    (src/Segmentation/resnet.py:83) is stubbed - the weights are overwritten by the seeded state anyway."""
+    import torch.utils.model_zoo as mz
+    mz.load_url = lambda *a, **k: {}
+    from Segmentation.model import BiSeNet
+    from oracle.bisenet import seeded_weights
+    net = seeded_weights(BiSeNet(19).eval(), 1234)
+    x = randn(77, 1, 3, 128, 128)
+    with torch.no_grad():
+        out = net(x)[0]
+    res = {"out_sub4": np_(out[:, :, ::4, ::4]), "argmax": out[0].argmax(0).numpy().astype(np.int16),
+           "n_params": np.array(sum(p.numel() for p in net.parameters()), dtype=np.int64)}
+    np.savez_compressed(os.path.join(HERE, "bisenet.npz"), **res)
+    print("bisenet.npz", len(res))
+
+
 if __name__ == "__main__":
     torch.set_grad_enabled(True)
+    gen_bisenet()
     gen_step_math()
     gen_guidance()
     gen_inversion()

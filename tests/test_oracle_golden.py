@@ -218,3 +218,17 @@ def test_resize_and_morphology(golden):
         w = g[f"morph/w{k}"]
         assert np.array_equal(omask.dilate_hard(xi, k, w), g[f"morph/dil{k}"])
         assert np.array_equal(omask.erode_hard(xi, k, w), g[f"morph/ero{k}"])
+
+
+def test_bisenet_restatement_vs_reference_module():
+    """oracle/bisenet.py reproduces the unmodified reference BiSeNet (same seeds -> same random-init weights, same
+    state_dict names): logits to fp32 round-off of the host's convolution kernels, parsing map identical."""
+    from oracle.bisenet import BiSeNet, seeded_weights
+    g = np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "bisenet.npz"))
+    net = seeded_weights(BiSeNet(19).eval(), 1234)
+    assert sum(p.numel() for p in net.parameters()) == int(g["n_params"])
+    x = torch.randn(1, 3, 128, 128, generator=torch.Generator().manual_seed(77))
+    with torch.no_grad():
+        out = net(x)[0]
+    assert np.allclose(out[:, :, ::4, ::4].numpy(), g["out_sub4"], rtol=1e-4, atol=1e-5)
+    assert (out[0].argmax(0).numpy() != g["argmax"]).mean() < 1e-3
