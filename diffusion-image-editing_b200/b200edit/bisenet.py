@@ -1,7 +1,8 @@
 """Native face parser: the reference's ``BiSeNet`` (src/Segmentation/model.py:234-262 on the ResNet-18 of
 src/Segmentation/resnet.py) on libb200edit.so - the network behind ``SegmentationModel`` (src/models.py:80-118), whose
-parsing map feeds the mask path (``prepare_for_edit``, src/SegDiffEditPipeline.py:79-97).  Forward only: ``net(x)[0]`` =
-logits (B, n_classes, S, S) like the reference's first output.
+parsing map feeds the mask path (``prepare_for_edit``, src/SegDiffEditPipeline.py:79-97), and ``NetAttrFunc.loss``
+(src/attr_functions.py:213-219), which differentiates through it.  ``net(x)[0]`` = logits (B, n_classes, S, S) like the
+reference's first output; after ``enable_grad()`` the call is an autograd node backed by the native input gradient.
 
 Eval-mode BatchNorm is folded into the convolutions when the reference's ``state_dict`` is loaded; convolutions run on
 the tcgen05 implicit-GEMM kernel with ReLU in the epilogue, the channel-attention branches (global pooling -> 1x1
@@ -16,6 +17,22 @@ import torch
 from . import _C
 from ._C import ResNetConfig, check, lib
 from .unet import UNet2DModel
+
+
+class _BiSeNetFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, image, model):
+        ctx.model, ctx.shape = model, tuple(image.shape)
+        return model._forward(image)
+
+    @staticmethod
+    def backward(ctx, d_logits):
+        m = ctx.model
+        g = d_logits.to(torch.float32).contiguous()
+        dx = torch.empty(ctx.shape, dtype=torch.float32, device=g.device)
+        check(lib.b2e_resnet_backward(m._h, C.c_void_p(g.data_ptr()), C.c_void_p(dx.data_ptr()), ctx.shape[0],
+                                      C.c_void_p(torch.cuda.current_stream().cuda_stream)), "bisenet_backward")
+        return dx, None
 
 
 def _fold(w, sd, bn, eps=1e-5):
@@ -46,6 +63,27 @@ class BiSeNet(UNet2DModel):
             base = (self._ws.data_ptr() + 255) // 256 * 256
             check(lib.b2e_unet_bind_workspace(h, C.c_void_p(base), nbytes), "unet_bind_workspace")
         self._t_cache = {}
+        self.differentiable = False
+
+    def enable_grad(self, enable: bool = True):
+        """Gradient mode: ``net(x)[0]`` becomes differentiable w.r.t. the image (native dgrad of the whole parser;
+        batches <= max_batch).  Costs workspace: the backward pass has its own buffers."""
+        with torch.cuda.device(self.device):
+            check(lib.b2e_unet_enable_grad(self._h, int(enable)), "unet_enable_grad")
+            nbytes = lib.b2e_unet_workspace_bytes(self._h)
+            self._ws = None
+            self._ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)
+            base = (self._ws.data_ptr() + 255) // 256 * 256
+            check(lib.b2e_unet_bind_workspace(self._h, C.c_void_p(base), nbytes), "unet_bind_workspace")
+        self.differentiable = bool(enable)
+        return self
+
+    def _forward(self, x):
+        cfg = self.config
+        o = torch.empty((x.shape[0], cfg.n_classes, cfg.input_size, cfg.input_size), dtype=torch.float32, device=x.device)
+        check(lib.b2e_unet_forward(self._h, C.c_void_p(x.data_ptr()), None, C.c_void_p(o.data_ptr()), x.shape[0],
+                                   C.c_void_p(torch.cuda.current_stream().cuda_stream)), "bisenet_forward")
+        return o
 
     @staticmethod
     def fold_reference_state_dict(sd, eps=1e-5):
@@ -85,12 +123,16 @@ class BiSeNet(UNet2DModel):
     def __call__(self, image):
         if not image.is_cuda:
             raise _C.B2EError("BiSeNet: image must be a CUDA tensor (no CPU fallback)")
-        if image.requires_grad and torch.is_grad_enabled():
-            raise _C.B2EError("BiSeNet: the native face parser is forward-only; NetAttrFunc guidance through the parser "
-                              "needs a differentiable module")
         cfg = self.config
         if tuple(image.shape[1:]) != (3, cfg.input_size, cfg.input_size):
             raise ValueError(f"BiSeNet: expected (B,3,{cfg.input_size},{cfg.input_size}), got {tuple(image.shape)}")
+        if image.requires_grad and torch.is_grad_enabled():
+            if not self.differentiable:
+                raise _C.B2EError("BiSeNet: call enable_grad() before differentiating through the native face parser")
+            if image.shape[0] > self.max_batch:
+                raise ValueError(f"BiSeNet with gradient: batch {image.shape[0]} > max_batch {self.max_batch}")
+            xx = image if (image.dtype == torch.float32 and image.is_contiguous()) else image.to(torch.float32).contiguous()
+            return (_BiSeNetFn.apply(xx, self), None, None)
         x = image.detach().to(torch.float32).contiguous()
         outs = []
         for b0 in range(0, x.shape[0], self.max_batch):

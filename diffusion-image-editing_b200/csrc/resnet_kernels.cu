@@ -361,11 +361,11 @@ __global__ void __launch_bounds__(256) chan_affine_kernel(const bf16* __restrict
     float xv[8], yv[8];
     unpack8r(__ldg(reinterpret_cast<const uint4*>(x + o)), xv);
     if (y) unpack8r(__ldg(reinterpret_cast<const uint4*>(y + o)), yv);
-    const float* ap = a + (int64_t)n * C8 * 8 + s * 8;
+    const float* ap = a ? a + (int64_t)n * C8 * 8 + s * 8 : nullptr;
     const float* bp = b ? b + (int64_t)n * C8 * 8 + s * 8 : nullptr;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float v = xv[j] * ap[j];
+      float v = ap ? xv[j] * ap[j] : xv[j];
       if (bp) v += bp[j];
       if (y) v += yv[j];
       xv[j] = v;
@@ -382,6 +382,148 @@ int chan_affine_launch(const bf16* x, const float* a, const float* b, const bf16
   if (gx > kNumSMs * 8) gx = kNumSMs * 8;
   launch_pdl(chan_affine_kernel, dim3(gx, N), dim3(256), 0, st, x, a, b, y, out, HW, C / 8);
   return check_launch("chan_affine");
+}
+
+// ---- backward helpers of the face parser
+// out[n][c] = scale * sum_p x[n][p][c] * (y ? y[n][p][c] : 1)   (gradient of a per-channel attention / broadcast vector)
+__global__ void __launch_bounds__(256) chan_dot_kernel(const bf16* __restrict__ x, const bf16* __restrict__ y,
+                                                       float* __restrict__ out, int HW, int C, float scale) {
+  pdl_wait();
+  __shared__ float red[256];
+  const int n = blockIdx.y, c0 = blockIdx.x * 32, lane = threadIdx.x & 31, row = threadIdx.x >> 5;   // 8 pixel rows x 32 channels
+  const int c = c0 + lane;
+  float s = 0.f;
+  if (c < C)
+    for (int p = row; p < HW; p += 8) {
+      const int64_t o = ((int64_t)n * HW + p) * C + c;
+      const float xv = __bfloat162float(x[o]);
+      s += y ? xv * __bfloat162float(y[o]) : xv;
+    }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  if (row == 0 && c < C) {
+    float t = 0.f;
+    for (int r = 0; r < 8; ++r) t += red[r * 32 + lane];
+    out[(int64_t)n * C + c] = t * scale;
+  }
+}
+
+int chan_dot_launch(const bf16* x, const bf16* y, float* out, int N, int HW, int C, float scale, cudaStream_t st) {
+  launch_pdl(chan_dot_kernel, dim3((C + 31) / 32, N), dim3(256), 0, st, x, y, out, HW, C, scale);
+  return check_launch("chan_dot");
+}
+
+// out[n][c] = scale * sum_k g[n][k] * w[k][c]   (transposed 1x1 convolution on pooled vectors)
+int fc_t_launch(const float* g, const float* w, float* out, int N, int C, int K, float scale, cudaStream_t st) {
+  launch_pdl(fc_bwd_kernel, dim3((C + 255) / 256, N), dim3(256), 0, st, g, w, out, C, K, scale);
+  return check_launch("fc_t");
+}
+
+// element-wise on [n] vectors: mode 0: out = g * (a > 0) (ReLU), 1: out = g * a * (1 - a) (sigmoid output a),
+// 2: out = g * (a - 1) * (2 - a) (a = 1 + sigmoid)
+__global__ void __launch_bounds__(256) vec_act_bwd_kernel(const float* __restrict__ g, const float* __restrict__ a,
+                                                          float* __restrict__ out, int n, int mode) {
+  pdl_wait();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float av = a[i], gv = g[i];
+  out[i] = mode == 0 ? (av > 0.f ? gv : 0.f) : mode == 1 ? gv * av * (1.f - av) : gv * (av - 1.f) * (2.f - av);
+}
+
+int vec_act_bwd_launch(const float* g, const float* a, float* out, int n, int mode, cudaStream_t st) {
+  launch_pdl(vec_act_bwd_kernel, dim3((n + 255) / 256), dim3(256), 0, st, g, a, out, n, mode);
+  return check_launch("vec_act_bwd");
+}
+
+// out[r][c] = (g[r][c] + e[r * e_pitch + e_off + c]) * (y ? y[r][c] > 0 : 1): gradient accumulation from a second
+// consumer (a channel window of a wider tensor) followed by the ReLU mask of the tensor both consumers read
+__global__ void __launch_bounds__(256) grad_merge_kernel(const bf16* __restrict__ g, const bf16* __restrict__ e, int e_pitch,
+                                                         int e_off, const bf16* __restrict__ y, bf16* __restrict__ out,
+                                                         int64_t rows, int C8) {
+  pdl_wait();
+  const int64_t total = rows * C8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int s = (int)(i % C8);
+    const int64_t r = i / C8;
+    float gv[8], ev[8], yv[8];
+    if (g) unpack8r(*reinterpret_cast<const uint4*>(g + i * 8), gv);
+    else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gv[j] = 0.f;
+    }
+    if (e) {
+      unpack8r(__ldg(reinterpret_cast<const uint4*>(e + r * e_pitch + e_off + s * 8)), ev);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gv[j] += ev[j];
+    }
+    if (y) {
+      unpack8r(__ldg(reinterpret_cast<const uint4*>(y + i * 8)), yv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gv[j] = yv[j] > 0.f ? gv[j] : 0.f;
+    }
+    *reinterpret_cast<uint4*>(out + i * 8) = pack8r(gv);
+  }
+}
+
+int grad_merge_launch(const bf16* g, const bf16* e, int e_pitch, int e_off, const bf16* y, bf16* out, int64_t rows, int C,
+                      cudaStream_t st) {
+  B2E_REQUIRE(C % 8 == 0 && e_pitch % 8 == 0 && e_off % 8 == 0, B2E_UNSUPPORTED_SHAPE, "grad_merge: alignment");
+  launch_pdl(grad_merge_kernel, dim3(grid_for(rows * (C / 8))), dim3(256), 0, st, g, e, e_pitch, e_off, y, out, rows, C / 8);
+  return check_launch("grad_merge");
+}
+
+// adjoint of the align_corners bilinear upsampling: g (N,K,Ho,Wo) fp32 NCHW -> dx bf16 NHWC (N,Hi,Wi,P), channels >= K zero
+__global__ void __launch_bounds__(128) bilinear_ac_bwd_kernel(const float* __restrict__ g, bf16* __restrict__ dx, int N, int Hi,
+                                                              int Wi, int P, int K, int Ho, int Wo, float sh, float sw) {
+  pdl_wait();
+  const int64_t total = (int64_t)N * Hi * Wi * K;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K);
+    int64_t r = i / K;
+    const int w = (int)(r % Wi); r /= Wi;
+    const int h = (int)(r % Hi);
+    const int n = (int)(r / Hi);
+    // destination rows whose source coordinate sh * oh lies in (h - 1, h + 1)
+    const int oh0 = sh > 0.f ? max(0, (int)ceilf((float)(h - 1) / sh)) : 0, oh1 = sh > 0.f ? min(Ho - 1, (int)floorf((float)(h + 1) / sh)) : Ho - 1;
+    const int ow0 = sw > 0.f ? max(0, (int)ceilf((float)(w - 1) / sw)) : 0, ow1 = sw > 0.f ? min(Wo - 1, (int)floorf((float)(w + 1) / sw)) : Wo - 1;
+    const float* gp = g + ((int64_t)n * K + k) * Ho * Wo;
+    float acc = 0.f;
+    for (int oh = oh0; oh <= oh1; ++oh) {
+      const float fh = sh * (float)oh;
+      const int h0 = (int)fh, h1 = h0 + (h0 < Hi - 1 ? 1 : 0);
+      const float lh = fh - (float)h0;
+      const float wh = (h0 == h ? 1.f - lh : 0.f) + (h1 == h ? lh : 0.f);
+      if (wh == 0.f) continue;
+      float rowacc = 0.f;
+      for (int ow = ow0; ow <= ow1; ++ow) {
+        const float fw = sw * (float)ow;
+        const int w0 = (int)fw, w1 = w0 + (w0 < Wi - 1 ? 1 : 0);
+        const float lw = fw - (float)w0;
+        const float ww = (w0 == w ? 1.f - lw : 0.f) + (w1 == w ? lw : 0.f);
+        rowacc += ww * __ldg(gp + (int64_t)oh * Wo + ow);
+      }
+      acc += wh * rowacc;
+    }
+    dx[(((int64_t)n * Hi + h) * Wi + w) * P + k] = __float2bfloat16_rn(acc);
+  }
+}
+
+__global__ void __launch_bounds__(256) zero_tail_kernel(bf16* __restrict__ x, int64_t rows, int P, int K) {
+  pdl_wait();
+  const int64_t total = rows * (P - K);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    x[(i / (P - K)) * P + K + i % (P - K)] = __float2bfloat16_rn(0.f);
+}
+
+int bilinear_ac_bwd_launch(const float* g, bf16* dx, int N, int Hi, int Wi, int P, int K, int Ho, int Wo, cudaStream_t st) {
+  const float sh = Ho > 1 ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f, sw = Wo > 1 ? (float)(Wi - 1) / (float)(Wo - 1) : 0.f;
+  if (P > K) {
+    launch_pdl(zero_tail_kernel, dim3(grid_for((int64_t)N * Hi * Wi * (P - K))), dim3(256), 0, st, dx, (int64_t)N * Hi * Wi, P, K);
+    int rc = check_launch("zero_tail");
+    if (rc) return rc;
+  }
+  launch_pdl(bilinear_ac_bwd_kernel, dim3(grid_for((int64_t)N * Hi * Wi * K, 64)), dim3(128), 0, st, g, dx, N, Hi, Wi, P, K, Ho, Wo, sh, sw);
+  return check_launch("bilinear_ac_bwd");
 }
 
 // F.interpolate(x, (Ho, Wo), mode="bilinear", align_corners=True): x bf16 NHWC (N,Hi,Wi,P), first K channels ->

@@ -195,7 +195,7 @@ struct b2e_unet {
     ConvL dd;
     const int PL = this->PL;
     // (a <= 16-channel output, i.e. conv_out, receives its gradient as a 64-channel padded NHWC tensor)
-    if (decoder) { c.dg = make_dgrad(cin, cout > 16 ? c.cout_pad : kConvBlockK, k); dd = dgrads[c.dg]; cc.dg = c.dg; }
+    if (decoder || resnet) { c.dg = make_dgrad(cin, cout > 16 ? c.cout_pad : kConvBlockK, k); dd = dgrads[c.dg]; cc.dg = c.dg; }
     add_param(name + ".weight", (int64_t)cout * cin * k * k, (int64_t)cin * k * k, [cc, dd, PL](const float* src, cudaStream_t st) {
       int rc = pack_w(PL, src, cc.w, cc.cout, cc.cin, cc.k, cc.cin_pad, cc.row_len, 0, cc.cin_pad, st);
       if (!rc && cc.dg >= 0) rc = conv_pack_weight_dgrad(src, dd.w, cc.cout, cc.cin, cc.k, dd.cin_pad, dd.row_len, 0, st);
@@ -661,6 +661,12 @@ int build_program_resnet(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* 
     layer_out.push_back(h);
   }
   const int HWl = h.H * h.W, Cl = h.C, K = c.num_classes;
+  // face-parser head: what its backward pass needs from the forward
+  struct HeadSave {
+    Tensor feat8, feat16, feat32, f32, h32, f16, cp8, ff, o1, o2;
+    float *p32 = nullptr, *avg = nullptr, *q32 = nullptr, *att32 = nullptr, *q16 = nullptr, *att16 = nullptr, *pf = nullptr, *t1 = nullptr,
+          *attf = nullptr;
+  } hs;
   if (!rc && c.head == 1) {
     // ---- BiSeNet: context path (attention refinement on feat16 / feat32 + global context), feature fusion with the
     // 1/8 backbone feature, output head, bilinear (align_corners) upsampling to the input resolution -> fp32 NCHW logits
@@ -694,49 +700,39 @@ int build_program_resnet(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* 
       ew([xx, oo, B](cudaStream_t st) { return upsample2x_launch(xx.p, oo.p, B, xx.H, xx.W, xx.C, st); }, 1.25 * (double)oo.bytes, "nearest upsample x2");
     };
     const int mid = 128;
-    float *p32 = fbuf(feat32.C), *avg = fbuf(mid), *q32 = fbuf(mid), *att32 = fbuf(mid), *q16 = fbuf(mid), *att16 = fbuf(mid);
-    float *pf = fbuf(256), *t1 = fbuf(64), *attf = fbuf(256);
-    Tensor f32, sum32, up32, h32, f16, sum16, up16, cp8, ff, fo, o1, o2;
-    pool(feat32, p32);
-    fc(p32, bs.avg_w, bs.avg_b, avg, feat32.C, mid, 1, "conv_avg (1x1 on the pooled feature)");
-    conv(bs.arm32, feat32, 1, true, nullptr, &f32, "arm32.conv");
-    pool(f32, q32);
-    fc(q32, bs.a32_w, bs.a32_b, att32, mid, mid, 2, "arm32 attention");
-    affine(f32, att32, avg, nullptr, &sum32, "arm32: feat * attention + global context");
+    hs.feat8 = feat8; hs.feat16 = feat16; hs.feat32 = feat32;
+    hs.p32 = fbuf(feat32.C); hs.avg = fbuf(mid); hs.q32 = fbuf(mid); hs.att32 = fbuf(mid); hs.q16 = fbuf(mid); hs.att16 = fbuf(mid);
+    hs.pf = fbuf(256); hs.t1 = fbuf(64); hs.attf = fbuf(256);
+    Tensor sum32, up32, sum16, up16, fo;
+    pool(feat32, hs.p32);
+    fc(hs.p32, bs.avg_w, bs.avg_b, hs.avg, feat32.C, mid, 1, "conv_avg (1x1 on the pooled feature)");
+    conv(bs.arm32, feat32, 1, true, nullptr, &hs.f32, "arm32.conv");
+    pool(hs.f32, hs.q32);
+    fc(hs.q32, bs.a32_w, bs.a32_b, hs.att32, mid, mid, 2, "arm32 attention");
+    affine(hs.f32, hs.att32, hs.avg, nullptr, &sum32, "arm32: feat * attention + global context");
     up2(sum32, &up32);
-    conv(bs.head32, up32, 1, true, nullptr, &h32, "conv_head32");
-    conv(bs.arm16, feat16, 1, true, nullptr, &f16, "arm16.conv");
-    pool(f16, q16);
-    fc(q16, bs.a16_w, bs.a16_b, att16, mid, mid, 2, "arm16 attention");
-    affine(f16, att16, nullptr, &h32, &sum16, "arm16: feat * attention + feat32_up");
+    conv(bs.head32, up32, 1, true, nullptr, &hs.h32, "conv_head32");
+    conv(bs.arm16, feat16, 1, true, nullptr, &hs.f16, "arm16.conv");
+    pool(hs.f16, hs.q16);
+    fc(hs.q16, bs.a16_w, bs.a16_b, hs.att16, mid, mid, 2, "arm16 attention");
+    affine(hs.f16, hs.att16, nullptr, &hs.h32, &sum16, "arm16: feat * attention + feat32_up");
     up2(sum16, &up16);
-    conv(bs.head16, up16, 1, true, nullptr, &cp8, "conv_head16");
-    conv(bs.ffm_blk, feat8, 1, true, nullptr, &ff, "ffm.convblk (concat fused)", &cp8);
-    pool(ff, pf);
-    fc(pf, bs.f1_w, nullptr, t1, 256, 64, 1, "ffm.conv1");
-    fc(t1, bs.f2_w, nullptr, attf, 64, 256, 3, "ffm.conv2 (1 + sigmoid)");
-    affine(ff, attf, nullptr, nullptr, &fo, "ffm: feat * (1 + attention)");
-    conv(bs.out_conv, fo, 1, true, nullptr, &o1, "conv_out.conv");
-    conv(bs.out_cls, o1, 1, false, nullptr, &o2, "conv_out.conv_out");
+    conv(bs.head16, up16, 1, true, nullptr, &hs.cp8, "conv_head16");
+    conv(bs.ffm_blk, feat8, 1, true, nullptr, &hs.ff, "ffm.convblk (concat fused)", &hs.cp8);
+    pool(hs.ff, hs.pf);
+    fc(hs.pf, bs.f1_w, nullptr, hs.t1, 256, 64, 1, "ffm.conv1");
+    fc(hs.t1, bs.f2_w, nullptr, hs.attf, 64, 256, 3, "ffm.conv2 (1 + sigmoid)");
+    affine(hs.ff, hs.attf, nullptr, nullptr, &fo, "ffm: feat * (1 + attention)");
+    conv(bs.out_conv, fo, 1, true, nullptr, &hs.o1, "conv_out.conv");
+    conv(bs.out_cls, hs.o1, 1, false, nullptr, &hs.o2, "conv_out.conv_out");
     if (!rc) {
-      const Tensor oo = o2;
+      const Tensor oo = hs.o2;
       ew([m, oo, B, K, S](cudaStream_t st) { return bilinear_ac_launch(oo.p, m->out_eps, B, oo.H, oo.W, oo.C, K, S, S, st); },
          (double)oo.bytes + 4.0 * B * K * S * S, "bilinear upsample (align_corners) -> logits");
     }
-    if (rc) return rc;
-    if (need) *need = ar.peak;
-    if (!dry) {
-      B2E_REQUIRE(ar.peak <= ws_bytes, B2E_WORKSPACE_TOO_SMALL, "bisenet: workspace too small (%zu > %zu)", ar.peak, ws_bytes);
-      m->ops = std::move(fwd);
-      m->bops.clear();
-      m->fwd_B = -1;
-      m->cur_B = B;
-    }
-    m->flops = flops;
-    return B2E_OK;
   }
   float* feat = (float*)ar.alloc(sizeof(float) * B * Cl);
-  if (!rc) {
+  if (!rc && c.head == 0) {
     const Tensor hl = h;
     ew([m, hl, feat, B, HWl, Cl, K](cudaStream_t st) { return avgpool_fc_launch(hl.p, feat, m->fc_w, m->fc_b, m->out_eps, B, HWl, Cl, K, st); },
        (double)hl.bytes, "global average pool + fc");
@@ -744,14 +740,10 @@ int build_program_resnet(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* 
   // ---------------- backward: d(logits) -> d(image)
   if (!rc && m->grad) {
     cur = &bwd;
-    float* dfeat = (float*)ar.alloc(sizeof(float) * B * Cl);
-    Tensor g = talloc(B, h.H, h.W, h.C);   // gradient w.r.t. the PRE-activation of the current block output
-    {
-      const Tensor hl = h, gg = g;
-      ew([m, hl, gg, dfeat, B, HWl, Cl, K](cudaStream_t st) {
-           return avgpool_fc_bwd_launch(m->in_dlogits, m->fc_w, dfeat, hl.p, gg.p, B, HWl, Cl, K, st); },
-         2.0 * (double)hl.bytes, "fc + average pool backward (+ relu mask)");
-    }
+    Tensor g;   // gradient w.r.t. the PRE-activation of the current block output
+    // gradients that reach a backbone feature from a second consumer (face parser: feat8 -> ffm, feat16 -> arm16):
+    // key = index of the block whose INPUT is that feature; value = (tensor, channel offset of the window)
+    std::map<int, std::pair<Tensor, int>> extra;
     auto dconv = [&](int dg, const Tensor& dy, const Tensor* r0, Tensor* dx, const char* what) {
       // dx = conv_{k, stride 1}(dy; flipped / transposed weights) [+ residual segment r0]
       if (rc) return;
@@ -788,6 +780,103 @@ int build_program_resnet(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* 
          "zero insertion (stride-2 gradient)");
       return u;
     };
+    if (c.head == 0) {
+      float* dfeat = (float*)ar.alloc(sizeof(float) * B * Cl);
+      g = talloc(B, h.H, h.W, h.C);
+      const Tensor hl = h, gg = g;
+      ew([m, hl, gg, dfeat, B, HWl, Cl, K](cudaStream_t st) {
+           return avgpool_fc_bwd_launch(m->in_dlogits, m->fc_w, dfeat, hl.p, gg.p, B, HWl, Cl, K, st); },
+         2.0 * (double)hl.bytes, "fc + average pool backward (+ relu mask)");
+    } else {
+      // ---- face parser head backward: d(logits) (B, K, S, S) -> gradients at feat8 / feat16 / feat32
+      const auto& bs = m->bs;
+      auto fbuf = [&](int n) { return (float*)ar.alloc(sizeof(float) * B * n); };
+      auto dot = [&](const Tensor& x, const Tensor* y, float* out, float scale, const char* what) {
+        const Tensor xx = x;
+        const bf16* yp = y ? y->p : nullptr;
+        ew([xx, yp, out, B, scale](cudaStream_t st) { return chan_dot_launch(xx.p, yp, out, B, xx.H * xx.W, xx.C, scale, st); },
+           (y ? 2.0 : 1.0) * (double)xx.bytes, what);
+      };
+      auto vact = [&](const float* gv, const float* a, float* out, int n, int mode) {
+        ew([gv, a, out, n, mode](cudaStream_t st) { return vec_act_bwd_launch(gv, a, out, n, mode, st); }, 12.0 * n, "attention activation backward");
+      };
+      auto fct = [&](const float* gv, const float* w, float* out, int C, int Kk, float scale) {
+        ew([gv, w, out, B, C, Kk, scale](cudaStream_t st) { return fc_t_launch(gv, w, out, B, C, Kk, scale, st); }, 4.0 * C * Kk, "transposed 1x1 on pooled vector");
+      };
+      auto affine = [&](const Tensor& x, const float* a, const float* b, Tensor* out, const char* what) {
+        *out = talloc(B, x.H, x.W, x.C);
+        const Tensor xx = x, oo = *out;
+        ew([xx, a, b, oo, B](cudaStream_t st) { return chan_affine_launch(xx.p, a, b, nullptr, oo.p, B, xx.H * xx.W, xx.C, st); },
+           2.0 * (double)xx.bytes, what);
+      };
+      auto merge = [&](const Tensor* gt, const Tensor* e, int e_off, const Tensor* y, Tensor* out, int C, int H, int W, const char* what) {
+        *out = talloc(B, H, W, C);
+        const Tensor oo = *out;
+        const bf16* gp = gt ? gt->p : nullptr; const bf16* ep = e ? e->p : nullptr; const bf16* yp = y ? y->p : nullptr;
+        const int epitch = e ? e->C : 0;
+        ew([gp, ep, epitch, e_off, yp, oo, B](cudaStream_t st) {
+             return grad_merge_launch(gp, ep, epitch, e_off, yp, oo.p, (int64_t)B * oo.H * oo.W, oo.C, st); }, 3.0 * (double)oo.bytes, what);
+      };
+      auto down2 = [&](const Tensor& dy, Tensor* dx) {
+        *dx = talloc(B, dy.H / 2, dy.W / 2, dy.C);
+        const Tensor dd = dy, xx = *dx;
+        ew([dd, xx, B](cudaStream_t st) { return downsum2x_launch(dd.p, xx.p, B, xx.H, xx.W, xx.C, st); }, 1.25 * (double)dd.bytes, "nearest upsample backward");
+      };
+      const int mid = 128;
+      const float i8 = 1.f / (float)(hs.ff.H * hs.ff.W), i16 = 1.f / (float)(hs.f16.H * hs.f16.W), i32 = 1.f / (float)(hs.f32.H * hs.f32.W);
+      Tensor g_o2 = talloc(B, hs.o2.H, hs.o2.W, hs.o2.C), g_o1, g_fo, g_ff, g_cat, g_cp8, g_up16, g_sum16, g_h32, g_f16, e16, g_up32,
+             g_sum32, g_f32, e32, g32;
+      {
+        const Tensor oo = g_o2;
+        ew([m, oo, B, K, S](cudaStream_t st) { return bilinear_ac_bwd_launch(m->in_dlogits, oo.p, B, oo.H, oo.W, oo.C, K, S, S, st); },
+           4.0 * B * K * S * S, "bilinear upsample backward");
+      }
+      dconv(bs.out_cls.dg, g_o2, nullptr, &g_o1, "conv_out.conv_out");
+      relu_mask(g_o1, hs.o1);
+      dconv(bs.out_conv.dg, g_o1, nullptr, &g_fo, "conv_out.conv");
+      // feature fusion: fo = ff * a, a = 1 + sigmoid(W2 relu(W1 mean(ff)))
+      float *ga = fbuf(256), *gz2 = fbuf(256), *gt1 = fbuf(64), *gt1m = fbuf(64), *gpf = fbuf(256);
+      dot(g_fo, &hs.ff, ga, 1.f, "ffm: d(attention)");
+      vact(ga, hs.attf, gz2, B * 256, 2);
+      fct(gz2, bs.f2_w, gt1, 64, 256, 1.f);
+      vact(gt1, hs.t1, gt1m, B * 64, 0);
+      fct(gt1m, bs.f1_w, gpf, 256, 64, i8);
+      affine(g_fo, hs.attf, gpf, &g_ff, "ffm: d(feat) = g * (1 + attention) + pooled path");
+      relu_mask(g_ff, hs.ff);
+      dconv(bs.ffm_blk.dg, g_ff, nullptr, &g_cat, "ffm.convblk");     // channels [0, c8) -> feat8, [c8, c8 + 128) -> cp8
+      const int c8 = hs.feat8.C;
+      merge(nullptr, &g_cat, c8, &hs.cp8, &g_cp8, mid, hs.cp8.H, hs.cp8.W, "d(cp8) window + relu mask");
+      dconv(bs.head16.dg, g_cp8, nullptr, &g_up16, "conv_head16");
+      down2(g_up16, &g_sum16);
+      // sum16 = f16 * att16 + h32
+      merge(&g_sum16, nullptr, 0, &hs.h32, &g_h32, mid, hs.h32.H, hs.h32.W, "d(feat32_up) + relu mask");
+      float *ga16 = fbuf(mid), *gz16 = fbuf(mid), *gq16 = fbuf(mid);
+      dot(g_sum16, &hs.f16, ga16, 1.f, "arm16: d(attention)");
+      vact(ga16, hs.att16, gz16, B * mid, 1);
+      fct(gz16, bs.a16_w, gq16, mid, mid, i16);
+      affine(g_sum16, hs.att16, gq16, &g_f16, "arm16: d(feat)");
+      relu_mask(g_f16, hs.f16);
+      dconv(bs.arm16.dg, g_f16, nullptr, &e16, "arm16.conv");
+      // feat32_up = relu(conv_head32(up(sum32)))
+      dconv(bs.head32.dg, g_h32, nullptr, &g_up32, "conv_head32");
+      down2(g_up32, &g_sum32);
+      // sum32 = f32 * att32 + avg ; avg = relu(W_avg mean(feat32) + b)
+      float *gavg = fbuf(mid), *gavgm = fbuf(mid), *gp32 = fbuf(hs.feat32.C), *ga32 = fbuf(mid), *gz32 = fbuf(mid), *gq32 = fbuf(mid);
+      dot(g_sum32, nullptr, gavg, 1.f, "d(global context)");
+      vact(gavg, hs.avg, gavgm, B * mid, 0);
+      fct(gavgm, bs.avg_w, gp32, hs.feat32.C, mid, i32);
+      dot(g_sum32, &hs.f32, ga32, 1.f, "arm32: d(attention)");
+      vact(ga32, hs.att32, gz32, B * mid, 1);
+      fct(gz32, bs.a32_w, gq32, mid, mid, i32);
+      affine(g_sum32, hs.att32, gq32, &g_f32, "arm32: d(feat)");
+      relu_mask(g_f32, hs.f32);
+      dconv(bs.arm32.dg, g_f32, nullptr, &e32, "arm32.conv");
+      affine(e32, nullptr, gp32, &g32, "d(feat32) = arm32 path + pooled path");
+      relu_mask(g32, hs.feat32);
+      g = g32;
+      extra[c.layers[0] + c.layers[1] + c.layers[2]] = {e16, 0};   // feat16 = input of layer4's first block
+      extra[c.layers[0] + c.layers[1]] = {g_cat, 0};                // feat8  = input of layer3's first block
+    }
     for (int bi = (int)m->rblocks.size() - 1; bi >= 0 && !rc; --bi) {
       const b2e_unet::RBlock& rb = m->rblocks[bi];
       const BSave& sv = saves[bi];
@@ -811,8 +900,20 @@ int build_program_resnet(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* 
         if (stride0 == 2) dy = zero_up(d);
         Tensor dx;
         dconv(rb.dg[0], dy, &gs, &dx, "block in");
-        // the block input is the previous block's ReLU output (or the max-pool output, whose mask is applied there)
-        if (bi > 0) relu_mask(dx, sv.x);
+        // the block input is the previous block's ReLU output (or the max-pool output, whose mask is applied there);
+        // a backbone feature with a second consumer collects that gradient before the mask
+        auto ex = extra.find(bi);
+        if (ex != extra.end() && !rc) {
+          const Tensor gd = dx, ee = ex->second.first, yy = sv.x;
+          const int eoff = ex->second.second;
+          Tensor merged = talloc(B, dx.H, dx.W, dx.C);
+          ew([gd, ee, eoff, yy, merged, B](cudaStream_t st) {
+               return grad_merge_launch(gd.p, ee.p, ee.C, eoff, yy.p, merged.p, (int64_t)B * merged.H * merged.W, merged.C, st); },
+             4.0 * (double)merged.bytes, "gradient merge (second consumer) + relu mask");
+          dx = merged;
+        } else if (bi > 0) {
+          relu_mask(dx, sv.x);
+        }
         g = dx;
       }
     }
@@ -1728,7 +1829,8 @@ int b2e_resnet_create(const b2e_resnet_config* cfg, int64_t max_batch, b2e_unet*
 
 int b2e_resnet_backward(b2e_unet* m, const float* d_logits, float* d_image, int64_t B, void* stream) {
   B2E_REQUIRE(m && d_logits && d_image, B2E_INVALID_ARG, "resnet_backward: null pointer");
-  B2E_REQUIRE(m->resnet && m->rcfg.head == 0, B2E_INVALID_ARG, "resnet_backward: not a classifier handle");
+  B2E_REQUIRE(m->resnet, B2E_INVALID_ARG, "resnet_backward: not a classifier / face-parser handle");
+  B2E_REQUIRE(m->grad, B2E_INVALID_ARG, "resnet_backward: call b2e_unet_enable_grad first");
   B2E_REQUIRE(m->fwd_B == B && m->cur_B == B, B2E_INVALID_ARG,
               "resnet_backward: no live forward pass of batch %lld (last forward: %lld)", (long long)B, (long long)m->fwd_B);
   m->in_dlogits = d_logits; m->out_dz = d_image;

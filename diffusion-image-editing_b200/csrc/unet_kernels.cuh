@@ -122,6 +122,12 @@ int fc_act_launch(const float* x, const float* w, const float* b, float* out, in
 int chan_affine_launch(const bf16* x, const float* a, const float* b, const bf16* y, bf16* out, int N, int HW, int C,
                        cudaStream_t st);
 int bilinear_ac_launch(const bf16* x, float* out, int N, int Hi, int Wi, int P, int K, int Ho, int Wo, cudaStream_t st);
+int bilinear_ac_bwd_launch(const float* g, bf16* dx, int N, int Hi, int Wi, int P, int K, int Ho, int Wo, cudaStream_t st);
+int chan_dot_launch(const bf16* x, const bf16* y, float* out, int N, int HW, int C, float scale, cudaStream_t st);
+int fc_t_launch(const float* g, const float* w, float* out, int N, int C, int K, float scale, cudaStream_t st);
+int vec_act_bwd_launch(const float* g, const float* a, float* out, int n, int mode, cudaStream_t st);
+int grad_merge_launch(const bf16* g, const bf16* e, int e_pitch, int e_off, const bf16* y, bf16* out, int64_t rows, int C,
+                      cudaStream_t st);
 
 // multi-head tensor-core attention: head-major operands (virtual image v = n*heads + h, head_dim padded to 64)
 int split_heads_launch(const bf16* qkv, bf16* qh, bf16* kh, bf16* vht, int N, int T, int P, int heads, int d, cudaStream_t st);

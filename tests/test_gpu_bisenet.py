@@ -64,4 +64,74 @@ def test_segmentation_model_with_native_parser_feeds_the_mask_path():
     mask = MaskCreator(dilate_mask=True, resize_size=(64, 64)).create_mask(seg, classes=[cls])
     assert mask.shape == (1, 3, 64, 64) and float(mask.max()) == 1.0
     with pytest.raises(Exception):
-        native(img.requires_grad_(True))
+        native(torch.zeros(1, 3, 512, 512, device="cuda", requires_grad=True))   # enable_grad() not called
+
+
+def grad_pair(S, seed, classes=(1, 10, 13)):
+    """Gradient of NetAttrFunc.loss (softmax area of the selected classes, src/attr_functions.py:213-219) w.r.t. the image."""
+    from b200edit.bisenet import BiSeNet
+    oracle = seeded_weights(OracleBiSeNet(19).eval(), seed)
+    native = BiSeNet(19, S, max_batch=1)
+    native.load_reference_state_dict(oracle.state_dict())
+    native.enable_grad()
+    x = torch.randn(1, 3, S, S, generator=torch.Generator().manual_seed(seed + 1))
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+    def loss_of(out):
+        p = out.squeeze(0).softmax(dim=0)
+        return (p.sum(dim=(1, 2)) / (256 * 256))[list(classes)].sum()
+
+    xn = x.cuda().requires_grad_(True)
+    gn, = torch.autograd.grad(loss_of(native(xn)[0]), xn)
+    oc = oracle.cuda()
+    xr = x.cuda().requires_grad_(True)
+    gr, = torch.autograd.grad(loss_of(oc(xr)[0]), xr)
+    o16 = oc.bfloat16()
+    x16 = x.cuda().bfloat16().requires_grad_(True)
+    g16, = torch.autograd.grad(loss_of(o16(x16)[0].float()), x16)
+    return gn, gr, g16.float()
+
+
+@pytest.mark.parametrize("S", [128, 256])
+def test_bisenet_input_gradient_matches_autograd(S):
+    """Input gradient through the native parser (dgrad twins, attention / pooling / bilinear / max-pool backward kernels)
+    against torch autograd through the fp32 oracle; yardstick = torch autograd through the same network in bf16 (ReLU /
+    max-pool masks flip under rounding, see tests/test_gpu_resnet.py): no further from fp32 than that, cosine >= 0.9."""
+    gn, gr, g16 = grad_pair(S, seed=7)
+    rel = lambda a, b: ((a - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt()).item()   # noqa: E731
+    cos = lambda a, b: torch.nn.functional.cosine_similarity(a.flatten(), b.flatten(), dim=0).item()   # noqa: E731
+    print(f"bisenet {S}x{S} input gradient: native rel-rms {rel(gn, gr):.3e} cos {cos(gn, gr):.5f} | torch-bf16 {rel(g16, gr):.3e} cos {cos(g16, gr):.5f}")
+    assert torch.isfinite(gn).all() and gr.abs().max() > 0
+    assert rel(gn, gr) <= 0.5 and cos(gn, gr) >= 0.9
+    assert rel(gn, gr) <= rel(g16, gr) + 1e-2 and cos(gn, gr) >= cos(g16, gr) - 2e-3
+
+
+def test_net_attr_func_through_the_native_parser():
+    """NetAttrFunc.apply with SegmentationModel(native parser in gradient mode): update direction on x_t vs the torch module."""
+    from attr_functions import NetAttrFunc
+    from b200edit.bisenet import BiSeNet
+    from models import SegmentationModel, create_diffusion_model
+    oracle = seeded_weights(OracleBiSeNet(19).eval(), 8)
+    native = BiSeNet(19, 256, max_batch=1)
+    native.load_reference_state_dict(oracle.state_dict())
+    native.enable_grad()
+    cfg = dict(sample_size=256, in_channels=3, out_channels=3, block_out_channels=(64, 128), layers_per_block=1,
+               down_block_types=("DownBlock2D", "DownBlock2D"), up_block_types=("UpBlock2D", "UpBlock2D"))
+    w = create_diffusion_model("ddpm", sample_clipping=False, max_batch=1, seed=1, unet_config=cfg)
+    w.scheduler.set_timesteps(10)
+    g = torch.Generator().manual_seed(9)
+    xt = torch.randn(1, 3, 256, 256, generator=g).cuda()
+    eps = torch.randn(1, 3, 256, 256, generator=g).cuda()
+    t = int(w.scheduler.timesteps[-1])     # late step (alpha_bar ~ 1) and a large scale: the area loss is normalised by 256^2
+    outs = []
+    for net in (native, oracle.cuda()):
+        f = NetAttrFunc(SegmentationModel(net=net, image_size=(256, 256)), idx_for_class=[1, 10], loss_scale=1e5)
+        f.kwargs["mask"] = None
+        x2, _ = f.apply(xt=xt.clone(), zt=None, model_output=eps, timestep=torch.tensor(t), step_idx=0, model=w, **f.kwargs)
+        outs.append((x2 - xt).detach())
+    dn, dr = outs
+    rel = ((dn - dr).pow(2).mean().sqrt() / dr.pow(2).mean().sqrt()).item()
+    cos = torch.nn.functional.cosine_similarity(dn.flatten(), dr.flatten(), dim=0).item()
+    print(f"NetAttrFunc update through the native parser: rel-rms {rel:.3e} cos {cos:.5f}")
+    assert dr.abs().max() > 0 and rel <= 0.5 and cos >= 0.9
