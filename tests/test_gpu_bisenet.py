@@ -71,6 +71,7 @@ def grad_pair(S, seed, classes=(1, 10, 13)):
     """Gradient of NetAttrFunc.loss (softmax area of the selected classes, src/attr_functions.py:213-219) w.r.t. the image."""
     from b200edit.bisenet import BiSeNet
     oracle = seeded_weights(OracleBiSeNet(19).eval(), seed)
+    oracle.conv_out.conv_out.weight.data.mul_(0.02)   # logits of O(1): an unsaturated softmax, as a trained parser has
     native = BiSeNet(19, S, max_batch=1)
     native.load_reference_state_dict(oracle.state_dict())
     native.enable_grad()
@@ -113,6 +114,7 @@ def test_net_attr_func_through_the_native_parser():
     from b200edit.bisenet import BiSeNet
     from models import SegmentationModel, create_diffusion_model
     oracle = seeded_weights(OracleBiSeNet(19).eval(), 8)
+    oracle.conv_out.conv_out.weight.data.mul_(0.02)   # logits of O(1): an unsaturated softmax, as a trained parser has
     native = BiSeNet(19, 256, max_batch=1)
     native.load_reference_state_dict(oracle.state_dict())
     native.enable_grad()
@@ -126,7 +128,7 @@ def test_net_attr_func_through_the_native_parser():
     t = int(w.scheduler.timesteps[-1])     # late step (alpha_bar ~ 1) and a large scale: the area loss is normalised by 256^2
     outs = []
     for net in (native, oracle.cuda()):
-        f = NetAttrFunc(SegmentationModel(net=net, image_size=(256, 256)), idx_for_class=[1, 10], loss_scale=1e5)
+        f = NetAttrFunc(SegmentationModel(net=net, image_size=(256, 256)), idx_for_class=[1, 10], loss_scale=1e4)
         f.kwargs["mask"] = None
         x2, _ = f.apply(xt=xt.clone(), zt=None, model_output=eps, timestep=torch.tensor(t), step_idx=0, model=w, **f.kwargs)
         outs.append((x2 - xt).detach())
