@@ -50,6 +50,11 @@ class VQEncConfig(C.Structure):
                 ("norm_num_groups", C.c_int32), ("norm_eps", C.c_float), ("double_z", C.c_int32)]
 
 
+class ClipConfig(C.Structure):
+    _fields_ = [("vocab_size", C.c_int32), ("hidden_size", C.c_int32), ("intermediate_size", C.c_int32),
+                ("num_layers", C.c_int32), ("num_heads", C.c_int32), ("max_positions", C.c_int32)]
+
+
 class ResNetConfig(C.Structure):
     _fields_ = [("input_size", C.c_int32), ("in_channels", C.c_int32), ("bottleneck", C.c_int32),
                 ("layers", C.c_int32 * 4), ("width", C.c_int32), ("num_classes", C.c_int32), ("head", C.c_int32)]
@@ -91,6 +96,8 @@ PROTOTYPES = {
     "b2e_unet_create": (_I, [C.POINTER(UNetConfig), _I64, C.POINTER(_P)]),
     "b2e_vqdec_create": (_I, [C.POINTER(VQDecConfig), _I64, C.POINTER(_P)]),
     "b2e_vqenc_create": (_I, [C.POINTER(VQEncConfig), _I64, C.POINTER(_P)]),
+    "b2e_clip_create": (_I, [C.POINTER(ClipConfig), _I64, C.POINTER(_P)]),
+    "b2e_clip_forward": (_I, [_P, _P, _I64, _P, _I64, _P]),
     "b2e_resnet_create": (_I, [C.POINTER(ResNetConfig), _I64, C.POINTER(_P)]),
     "b2e_resnet_backward": (_I, [_P, _P, _P, _I64, _P]),
     "b2e_unet_enable_grad": (_I, [_P, _I]),

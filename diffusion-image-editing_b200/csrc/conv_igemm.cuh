@@ -94,7 +94,7 @@ struct FlashPlan {
   double flops;
 };
 int flash_attn_plan_build(FlashPlan* pl, const bf16* qh, const bf16* kh, const bf16* vht, bf16* oh, int NV, int Tq, int Tk, int D);
-int flash_attn_launch(const FlashPlan& pl, int valid_k, float scale, cudaStream_t st);
+int flash_attn_launch(const FlashPlan& pl, int valid_k, float scale, cudaStream_t st, int causal = 0);
 
 // fp32 [Cout][Cin][k][k] -> bf16 out[co*row_len + col_off + t*tap_width + ci]   (t = kh*k + kw)
 // (ci0, cin_total): pack only input channels [ci0, ci0 + Cin) of a weight with cin_total input channels

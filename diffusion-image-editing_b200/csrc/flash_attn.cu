@@ -54,6 +54,7 @@ struct FaCfg {
 
 struct FaParams {
   int NV, Tq, Tk, valid_k;
+  int causal;          // 1: query i attends to keys <= i only (CLIP text encoder)
   float scale_log2e;   // softmax scale * log2(e)
   bf16* out;           // [NV][Tq][D]
 };
@@ -229,6 +230,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     int it = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
       const int v = item / q_blocks, qb = item - v * q_blocks;
+      // keys this query row may see: the valid prefix, cut at the diagonal for causal attention
+      const int lim = p.causal ? min(p.valid_k, qb * kFaBlock + r + 1) : p.valid_k;
       // ---- pass A: row maximum over the valid keys
       float m = -INFINITY;
       for (int j = 0; j < n_kb; ++j, ++g) {
@@ -243,7 +246,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(s_empty + b);   // the scores are in registers: hand the buffer back
-        if (k0 + kFaBlock <= p.valid_k) {
+        if (k0 + kFaBlock <= lim) {
 #pragma unroll
           for (int c = 0; c < 4; ++c)
 #pragma unroll
@@ -253,7 +256,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           for (int c = 0; c < 4; ++c)
 #pragma unroll
             for (int e = 0; e < 32; ++e)
-              if (k0 + c * 32 + e < p.valid_k) m = fmaxf(m, __uint_as_float(sr[c][e]));
+              if (k0 + c * 32 + e < lim) m = fmaxf(m, __uint_as_float(sr[c][e]));
         }
       }
       const float mc = m * p.scale_log2e;
@@ -274,7 +277,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         const uint32_t pb = pj & 1;
         mbar_wait(p_empty + pb, ((pj >> 1) & 1) ^ 1);   // the P V that last read this P buffer has finished
         uint8_t* ptile = p_s + pb * Cfg::kPBytes;
-        const bool full_blk = k0 + kFaBlock <= p.valid_k;
+        const bool full_blk = k0 + kFaBlock <= lim;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {   // 16 keys per step -> two 16-byte chunks of the row
           uint4 o0, o1;
@@ -286,7 +289,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             const float sc_ = __uint_as_float(sr[c >> 1][(c & 1) * 16 + e]);
             float v_;
             asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(v_) : "f"(fmaf(sc_, p.scale_log2e, -mc)));   // one MUFU op
-            pe[e] = (full_blk || k0 + c * 16 + e < p.valid_k) ? v_ : 0.f;
+            pe[e] = (full_blk || k0 + c * 16 + e < lim) ? v_ : 0.f;
           }
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -392,10 +395,10 @@ int flash_attn_plan_build(FlashPlan* pl, const bf16* qh, const bf16* kh, const b
   return B2E_OK;
 }
 
-int flash_attn_launch(const FlashPlan& pl, int valid_k, float scale, cudaStream_t st) {
+int flash_attn_launch(const FlashPlan& pl, int valid_k, float scale, cudaStream_t st, int causal) {
   B2E_REQUIRE(valid_k >= 1 && valid_k <= pl.Tk, B2E_INVALID_ARG, "flash_attn: valid_k %d of %d", valid_k, pl.Tk);
   FaParams p;
-  p.NV = pl.NV; p.Tq = pl.Tq; p.Tk = pl.Tk; p.valid_k = valid_k; p.scale_log2e = scale * 1.4426950408889634f; p.out = pl.out;
+  p.NV = pl.NV; p.Tq = pl.Tq; p.Tk = pl.Tk; p.valid_k = valid_k; p.causal = causal; p.scale_log2e = scale * 1.4426950408889634f; p.out = pl.out;
   switch (pl.D) {
     case 64: return flash_launch_t<64>(pl.map_q, pl.map_k, pl.map_v, p, st);
     case 128: return flash_launch_t<128>(pl.map_q, pl.map_k, pl.map_v, p, st);

@@ -104,6 +104,16 @@ struct b2e_unet {
   // VQ / KL encoder mode (b2e_vqenc_create): image -> conv_in -> down blocks -> mid block -> GroupNorm -> SiLU -> conv_out
   // (enc_q channels: latent, or 2 x latent moments) -> 1x1 quant_conv in fp32; output at sample_size >> (n_blocks - 1)
   bool encoder = false;
+  // CLIP text encoder mode (b2e_clip_create): transformers CLIPTextModel - token + position embedding, pre-LN
+  // transformer layers (causal 12-head self-attention on the fused kernel, quick-GELU MLP), final LayerNorm.
+  // prep_text / encode_text, src/diffusion_utils.py:34-52
+  bool clip = false;
+  b2e_clip_config ccfg{};
+  struct ClipL { LNL ln1, ln2; ConvL qkv, out, fc1, fc2; };
+  std::vector<ClipL> clayers;
+  LNL clip_final_ln;
+  float *tok_emb = nullptr, *pos_emb = nullptr;
+  const int64_t* in_ids = nullptr;
   // classifier mode (b2e_resnet_create): torchvision ResNet (BatchNorm folded into the convolutions by the host) ->
   // logits; backward: d(logits) -> d(image).  The loss network of ClassifierAttrFunc, src/attr_functions.py:222-257
   bool resnet = false;
@@ -282,7 +292,7 @@ struct b2e_unet {
     return c;
   }
   // several bias-free projections of the same input fused into one GEMM: rows [i*cout, (i+1)*cout) = names[i]
-  ConvL make_fused_linear(const std::string& base, const std::vector<std::string>& names, int cin, int cout) {
+  ConvL make_fused_linear(const std::string& base, const std::vector<std::string>& names, int cin, int cout, bool bias = false) {
     ConvL c;
     const int n = (int)names.size();
     c.cin = cin; c.cin_pad = pad64(cin); c.cout = n * cout; c.k = 1; c.cout_pad = conv_cout_pad(n * cout);
@@ -295,6 +305,7 @@ struct b2e_unet {
       add_param(base + "." + names[i] + ".weight", (int64_t)cout * cin, cin, [wdst, cout, cin, rl, cp](const float* src, cudaStream_t st) {
         return conv_pack_weight(src, wdst, cout, cin, 1, cp, rl, 0, st);
       });
+      if (bias && c.b) add_f32(base + "." + names[i] + ".bias", c.b + (size_t)i * cout, cout, cin);
     }
     return c;
   }
@@ -945,7 +956,30 @@ int build_program_resnet(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* 
   return B2E_OK;
 }
 
+int build_model_clip(b2e_unet* m) {
+  const b2e_clip_config& c = m->ccfg;
+  const int D = c.hidden_size;
+  m->tok_emb = m->dmalloc<float>((size_t)c.vocab_size * D);
+  m->pos_emb = m->dmalloc<float>((size_t)c.max_positions * D);
+  m->add_f32("text_model.embeddings.token_embedding.weight", m->tok_emb, (int64_t)c.vocab_size * D, -50);
+  m->add_f32("text_model.embeddings.position_embedding.weight", m->pos_emb, (int64_t)c.max_positions * D, -50);
+  for (int i = 0; i < c.num_layers; ++i) {
+    const std::string b = "text_model.encoder.layers." + std::to_string(i);
+    b2e_unet::ClipL L;
+    L.ln1 = m->make_ln(b + ".layer_norm1", D);
+    L.qkv = m->make_fused_linear(b + ".self_attn", {"q_proj", "k_proj", "v_proj"}, D, D, true);
+    L.out = m->make_linear(b + ".self_attn.out_proj", D, D, true, D);
+    L.ln2 = m->make_ln(b + ".layer_norm2", D);
+    L.fc1 = m->make_linear(b + ".mlp.fc1", D, c.intermediate_size, true);
+    L.fc2 = m->make_linear(b + ".mlp.fc2", c.intermediate_size, D, true, D);
+    m->clayers.push_back(L);
+  }
+  m->clip_final_ln = m->make_ln("text_model.final_layer_norm", D);
+  return m->build_error;
+}
+
 int build_model(b2e_unet* m) {
+  if (m->clip) return build_model_clip(m);
   if (m->resnet) return build_model_resnet(m);
   if (m->decoder) return build_model_decoder(m);
   if (m->encoder) return build_model_encoder(m);
@@ -1046,6 +1080,21 @@ int build_model(b2e_unet* m) {
     m->add_f32(r.name + ".time_emb_proj.bias", m->tp_b + r.temb_off, r.cout, m->temb_dim);
   }
   return m->build_error;
+}
+
+// installs a forward-only launch list (text encoder)
+int finish_forward_only(b2e_unet* m, std::vector<b2e_unet::Op>& fwd, size_t peak, size_t ws_bytes, size_t* need, bool dry,
+                        double flops, int B) {
+  if (need) *need = peak;
+  if (!dry) {
+    B2E_REQUIRE(peak <= ws_bytes, B2E_WORKSPACE_TOO_SMALL, "text encoder: workspace too small (%zu > %zu)", peak, ws_bytes);
+    m->ops = std::move(fwd);
+    m->bops.clear();
+    m->fwd_B = -1;
+    m->cur_B = B;
+  }
+  m->flops = flops;
+  return B2E_OK;
 }
 
 // Records the launch list for batch B with all activations placed in the arena.  With a null
@@ -1185,7 +1234,7 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
   // ---- prologue: input packing, timestep embedding
   Tensor xin = talloc(B, S, S, kConvBlockK);
   float* zq = m->decoder ? (float*)ar.alloc(sizeof(float) * B * c.in_channels * S * S) : nullptr;
-  if (!dry) {
+  if (!dry && !m->clip) {
     const int Cin = c.in_channels, HW = S * S;
     const bool im2col = m->in_im2col;
     if (m->decoder) {
@@ -1232,7 +1281,7 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
   // and V^T (head_dim -> multiple of 64, tokens -> multiple of 128); S = Q K^T and O = P V are batched GEMMs on the
   // tcgen05 kernel with a (masked) fp32 row softmax between them.  valid_k < 0: read m->ctx_len at launch time.
   auto mh_attention = [&](const Tensor& qsrc, int qcol, const Tensor& ksrc, int kcol, int vcol, int Tq, int Tk, int valid_k,
-                          int heads, int d, int dpad, Tensor* out, int Hh, int Ww, int Cc) {
+                          int heads, int d, int dpad, Tensor* out, int Hh, int Ww, int Cc, int causal = 0) {
     if (rc) return;
     const int NV = B * heads;
     const int Tqp = Tq < 128 ? 128 : Tq, Tkp = Tk < 128 ? 128 : Tk;
@@ -1258,7 +1307,7 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
                            return gather_heads_launch(k_.p, kh.p, B, Tk, Tkp, kp, kcol, heads, d, dpad, false, st); }, 3, 0.0, 4.0 * NV * Tkp * dpad, "gather k heads"});
           ops.push_back({[k_, vht, B, Tk, Tkp, kp, vcol, heads, d, dpad](cudaStream_t st) {
                            return gather_heads_launch(k_.p, vht.p, B, Tk, Tkp, kp, vcol, heads, d, dpad, true, st); }, 3, 0.0, 4.0 * NV * Tkp * dpad, "gather V^T heads"});
-          ops.push_back({[m, fp, valid_k, scale](cudaStream_t st) { return flash_attn_launch(fp, valid_k < 0 ? m->ctx_len : valid_k, scale, st); },
+          ops.push_back({[m, fp, valid_k, scale, causal](cudaStream_t st) { return flash_attn_launch(fp, valid_k < 0 ? m->ctx_len : valid_k, scale, st, causal); },
                          2, fp.flops, 0.0, "flash attention (tcgen05, S in TMEM)"});
           ops.push_back({[oh, o_, B, Tq, Tqp, heads, d, dpad](cudaStream_t st) {
                            return scatter_heads_launch(oh.p, o_.p, B, Tq, Tqp, o_.C, heads, d, dpad, st); }, 3, 0.0, 4.0 * B * Tq * heads * d, "merge heads"});
@@ -1270,6 +1319,7 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
       tfree(qh); tfree(kh); tfree(vht); tfree(oh);
       return;
     }
+    if (causal) { rc = B2E_UNSUPPORTED_SHAPE; set_error("unet: causal attention needs the fused attention kernel"); return; }
     Tensor sc = talloc(NV, 1, Tqp, Tkp);   // materialised scores (B2E_FLASH=0 or head_dim > 192)
     if (!dry) {
       ConvDesc d1;
@@ -1309,6 +1359,50 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
     }
     tfree(qh); tfree(kh); tfree(vht); tfree(sc); tfree(oh);
   };
+  if (m->clip) {
+    // ---- CLIP text encoder: ids (B, L <= 128) -> (B, 1, 128, D) bf16 token rows (rows >= L zero, masked as keys)
+    const b2e_clip_config& cc = m->ccfg;
+    const int D = cc.hidden_size, heads = cc.num_heads, d = D / heads;
+    tfree(xin);
+    Tensor x = talloc(B, 1, kCtxPad, D);
+    if (!dry) {
+      const Tensor xx = x;
+      ops.push_back({[m, xx, B, D](cudaStream_t st) {
+                       return clip_embed_launch(m->in_ids, m->tok_emb, m->pos_emb, xx.p, B, m->ctx_len, kCtxPad, D, m->ccfg.vocab_size, st); },
+                     3, 0.0, 6.0 * B * kCtxPad * D, "token + position embedding"});
+    }
+    for (size_t li = 0; li < m->clayers.size() && !rc; ++li) {
+      const b2e_unet::ClipL& L = m->clayers[li];
+      Tensor a, qkv, o, x1, b2, f1, x2;
+      lnorm(L.ln1, x, &a);
+      conv(L.qkv, a, nullptr, 1, ConvEpilogue{}, &qkv, nullptr, nullptr, nullptr, false);
+      tfree(a);
+      mh_attention(qkv, 0, qkv, D, 2 * D, kCtxPad, kCtxPad, -1, heads, d, pad64(d), &o, 1, kCtxPad, D, 1);
+      tfree(qkv);
+      conv(L.out, o, nullptr, 1, ConvEpilogue{}, &x1, nullptr, &x, nullptr, false);
+      tfree(o); tfree(x);
+      lnorm(L.ln2, x1, &b2);
+      conv(L.fc1, b2, nullptr, 1, ConvEpilogue{}, &f1, nullptr, nullptr, nullptr, false);
+      tfree(b2);
+      if (!dry && !rc) {
+        const Tensor ff = f1;
+        ops.push_back({[ff](cudaStream_t st) { return quick_gelu_launch(ff.p, ff.p, (int64_t)(ff.bytes / sizeof(bf16)), st); }, 3, 0.0,
+                       2.0 * (double)ff.bytes, "quick_gelu"});
+      }
+      conv(L.fc2, f1, nullptr, 1, ConvEpilogue{}, &x2, nullptr, &x1, nullptr, false);
+      tfree(f1); tfree(x1);
+      x = x2;
+    }
+    Tensor y;
+    lnorm(m->clip_final_ln, x, &y);
+    if (!dry && !rc) {
+      const Tensor yy = y;
+      ops.push_back({[m, yy, B, D](cudaStream_t st) { return unpad_rows_f32_launch(yy.p, m->out_eps, B, m->ctx_len, kCtxPad, D, st); },
+                     3, 0.0, 6.0 * B * kCtxPad * D, "final hidden states -> fp32"});
+    }
+    if (rc) return rc;
+    return finish_forward_only(m, ops_fwd, ar.peak, ws_bytes, need, dry, flops, B);
+  }
   Tensor h;
   conv(m->conv_in, xin, nullptr, 1, ConvEpilogue{}, &h, nullptr);
   tfree(xin);
@@ -1802,6 +1896,37 @@ int b2e_vqenc_create(const b2e_vqenc_config* cfg, int64_t max_batch, b2e_unet** 
   return B2E_OK;
 }
 
+int b2e_clip_create(const b2e_clip_config* cfg, int64_t max_batch, b2e_unet** out) {
+  B2E_REQUIRE(cfg && out && max_batch > 0, B2E_INVALID_ARG, "clip_create: bad argument");
+  B2E_REQUIRE(cfg->hidden_size % 64 == 0 && cfg->intermediate_size % 64 == 0 && cfg->num_heads >= 1 &&
+                  cfg->hidden_size % cfg->num_heads == 0 && (cfg->hidden_size / cfg->num_heads) % 8 == 0 &&
+                  cfg->hidden_size / cfg->num_heads <= 192 && cfg->hidden_size <= 2048,
+              B2E_UNSUPPORTED_SHAPE, "clip_create: hidden / intermediate sizes must be multiples of 64, head_dim %% 8 == 0 and <= 192");
+  B2E_REQUIRE(cfg->num_layers >= 1 && cfg->num_layers <= 64 && cfg->vocab_size >= 1 && cfg->max_positions >= 1 && cfg->max_positions <= 128,
+              B2E_UNSUPPORTED_SHAPE, "clip_create: 1..64 layers, at most 128 positions");
+  b2e_unet* m = new b2e_unet();
+  m->clip = true;
+  m->ccfg = *cfg;
+  m->cfg = b2e_unet_config{};
+  m->cfg.sample_size = 8; m->cfg.in_channels = 1; m->cfg.out_channels = 1; m->cfg.norm_num_groups = 1;
+  m->max_batch = max_batch;
+  int rc = build_model(m);
+  if (!rc && cudaDeviceSynchronize() != cudaSuccess) { set_error("clip_create: device error"); rc = B2E_CUDA_ERROR; }
+  if (!rc) rc = build_program(m, (int)max_batch, nullptr, 0, &m->ws_need);
+  if (rc) { delete m; return rc; }
+  *out = m;
+  return B2E_OK;
+}
+
+int b2e_clip_forward(b2e_unet* m, const int64_t* input_ids, int64_t seq_len, float* hidden, int64_t B, void* stream) {
+  B2E_REQUIRE(m && input_ids && hidden, B2E_INVALID_ARG, "clip_forward: null pointer");
+  B2E_REQUIRE(m->clip, B2E_INVALID_ARG, "clip_forward: not a text-encoder handle");
+  B2E_REQUIRE(seq_len >= 1 && seq_len <= m->ccfg.max_positions, B2E_UNSUPPORTED_SHAPE, "clip_forward: %lld tokens (1..%d)",
+              (long long)seq_len, m->ccfg.max_positions);
+  m->in_ids = input_ids; m->ctx_len = (int)seq_len;
+  return b2e_unet_forward(m, (const float*)input_ids, nullptr, hidden, B, stream);
+}
+
 int b2e_resnet_create(const b2e_resnet_config* cfg, int64_t max_batch, b2e_unet** out) {
   B2E_REQUIRE(cfg && out && max_batch > 0, B2E_INVALID_ARG, "resnet_create: bad argument");
   B2E_REQUIRE(cfg->in_channels >= 1 && cfg->in_channels <= 4, B2E_UNSUPPORTED_SHAPE, "resnet_create: 1..4 input channels");
@@ -1876,7 +2001,7 @@ int b2e_unet_bind_workspace(b2e_unet* m, void* workspace, size_t workspace_bytes
 }
 
 int b2e_unet_forward(b2e_unet* m, const float* x, const int64_t* timesteps, float* eps, int64_t B, void* stream) {
-  B2E_REQUIRE(m && x && (timesteps || m->decoder || m->encoder || m->resnet) && eps, B2E_INVALID_ARG, "unet_forward: null pointer");
+  B2E_REQUIRE(m && x && (timesteps || m->decoder || m->encoder || m->resnet || m->clip) && eps, B2E_INVALID_ARG, "unet_forward: null pointer");
   B2E_REQUIRE(m->ws, B2E_INVALID_ARG, "unet_forward: no workspace bound");
   B2E_REQUIRE(B > 0 && B <= m->max_batch, B2E_UNSUPPORTED_SHAPE, "unet_forward: batch %lld exceeds max_batch %lld",
               (long long)B, (long long)m->max_batch);
@@ -1937,7 +2062,7 @@ const char* b2e_unet_op_desc(const b2e_unet* m, int idx) {
 
 int b2e_unet_profile(b2e_unet* m, const float* x, const int64_t* timesteps, float* eps, int64_t B, void* stream,
                      int max_ops, int* n_ops, float* ms, double* flops, double* bytes, int* kind) {
-  B2E_REQUIRE(m && x && (timesteps || m->decoder || m->encoder || m->resnet) && eps && n_ops && ms && flops && bytes && kind, B2E_INVALID_ARG,
+  B2E_REQUIRE(m && x && (timesteps || m->decoder || m->encoder || m->resnet || m->clip) && eps && n_ops && ms && flops && bytes && kind, B2E_INVALID_ARG,
               "unet_profile: null pointer");
   // one plain pass first (plan rebuild / lazy function attributes), then the instrumented pass
   int rc = b2e_unet_forward(m, x, timesteps, eps, B, stream);

@@ -764,6 +764,78 @@ int layernorm_rows_launch(const bf16* x, bf16* y, const float* gamma, const floa
   return check_launch("layernorm_rows");
 }
 
+// ---- CLIP text encoder helpers
+// token + position embedding: ids int64 [B][L] -> x bf16 [B][Lpad][D] (rows >= L zero)
+__global__ void __launch_bounds__(256) clip_embed_kernel(const int64_t* __restrict__ ids, const float* __restrict__ tok,
+                                                         const float* __restrict__ pos, bf16* __restrict__ out, int B, int L,
+                                                         int Lpad, int D8, int vocab) {
+  pdl_wait();
+  const int64_t total = (int64_t)B * Lpad * D8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int s = (int)(i % D8);
+    const int l = (int)((i / D8) % Lpad);
+    const int b = (int)(i / ((int64_t)D8 * Lpad));
+    float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (l < L) {
+      int64_t id = ids[(int64_t)b * L + l];
+      id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+      const float4* t = reinterpret_cast<const float4*>(tok + (id * D8 + s) * 8);
+      const float4* q = reinterpret_cast<const float4*>(pos + ((int64_t)l * D8 + s) * 8);
+      const float4 t0 = __ldg(t), t1 = __ldg(t + 1), q0 = __ldg(q), q1 = __ldg(q + 1);
+      f[0] = t0.x + q0.x; f[1] = t0.y + q0.y; f[2] = t0.z + q0.z; f[3] = t0.w + q0.w;
+      f[4] = t1.x + q1.x; f[5] = t1.y + q1.y; f[6] = t1.z + q1.z; f[7] = t1.w + q1.w;
+    }
+    *reinterpret_cast<uint4*>(out + i * 8) = pack8(f);
+  }
+}
+
+int clip_embed_launch(const int64_t* ids, const float* tok, const float* pos, bf16* out, int B, int L, int Lpad, int D, int vocab,
+                      cudaStream_t st) {
+  B2E_REQUIRE(D % 8 == 0 && L <= Lpad, B2E_UNSUPPORTED_SHAPE, "clip_embed: bad shape");
+  const int64_t total = (int64_t)B * Lpad * (D / 8);
+  launch_pdl(clip_embed_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, ids, tok, pos, out, B, L, Lpad, D / 8, vocab);
+  return check_launch("clip_embed");
+}
+
+// quick_gelu: x * sigmoid(1.702 x), in place capable
+__global__ void __launch_bounds__(256) quick_gelu_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int64_t n8) {
+  pdl_wait();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    float f[8];
+    unpack8(in[i], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = f[j] / (1.f + __expf(-1.702f * f[j]));
+    out[i] = pack8(f);
+  }
+}
+
+int quick_gelu_launch(const bf16* in, bf16* out, int64_t numel, cudaStream_t st) {
+  B2E_REQUIRE(numel % 8 == 0, B2E_UNSUPPORTED_SHAPE, "quick_gelu: numel %% 8 != 0");
+  int64_t g = (numel / 8 + 255) / 256;
+  if (g > kNumSMs * 16) g = kNumSMs * 16;
+  launch_pdl(quick_gelu_kernel, dim3((unsigned)g), dim3(256), 0, st, (const uint4*)in, (uint4*)out, numel / 8);
+  return check_launch("quick_gelu");
+}
+
+// final LayerNorm output: rows [0, L) of every sequence, bf16 [B][Lpad][D] -> fp32 [B][L][D]
+__global__ void __launch_bounds__(256) unpad_rows_f32_kernel(const bf16* __restrict__ x, float* __restrict__ out, int B, int L,
+                                                             int Lpad, int D) {
+  pdl_wait();
+  const int64_t total = (int64_t)B * L * D;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int d = (int)(i % D);
+    const int l = (int)((i / D) % L);
+    const int b = (int)(i / ((int64_t)D * L));
+    out[i] = __bfloat162float(x[((int64_t)b * Lpad + l) * D + d]);
+  }
+}
+
+int unpad_rows_f32_launch(const bf16* x, float* out, int B, int L, int Lpad, int D, cudaStream_t st) {
+  const int64_t total = (int64_t)B * L * D;
+  launch_pdl(unpad_rows_f32_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, x, out, B, L, Lpad, D);
+  return check_launch("unpad_rows_f32");
+}
+
 // GEGLU: in [rows][2*inner] -> out [rows][inner] = in[:, :inner] * gelu(in[:, inner:])   (exact erf GELU)
 __global__ void __launch_bounds__(256) geglu_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int64_t rows,
                                                     int inner8) {

@@ -89,6 +89,12 @@ int gather_heads_launch(const bf16* src, bf16* dst, int N, int Tsrc, int Tpad, i
 int scatter_heads_launch(const bf16* oh, bf16* out, int N, int T, int Tpad, int pitch, int heads, int d, int dpad, cudaStream_t st);
 int softmax_rows_masked_launch(bf16* s, int64_t rows, int T, int valid, float scale, cudaStream_t st);
 
+// CLIP text encoder helpers
+int clip_embed_launch(const int64_t* ids, const float* tok, const float* pos, bf16* out, int B, int L, int Lpad, int D, int vocab,
+                      cudaStream_t st);
+int quick_gelu_launch(const bf16* in, bf16* out, int64_t numel, cudaStream_t st);
+int unpad_rows_f32_launch(const bf16* x, float* out, int B, int L, int Lpad, int D, cudaStream_t st);
+
 // backward helpers of the decoder (bf16 NHWC gradients)
 int downsum2x_launch(const bf16* dy, bf16* dx, int N, int H, int W, int C, cudaStream_t st);
 int transpose_window_launch(const bf16* src, bf16* dst, int N, int R, int Cc, int src_pitch, int col0, cudaStream_t st);

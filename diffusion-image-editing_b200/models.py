@@ -25,7 +25,8 @@ def create_diffusion_model(name: str, sample_clipping: bool = True, *, max_batch
                            state_dict: Optional[dict] = None, unet_config: Optional[dict] = None, vqvae=None,
                            vq_config: Optional[dict] = None, vq_state_dict: Optional[dict] = None, guidance_module=None,
                            decoder_grad: bool = True, tokenizer=None, text_encoder=None, precision: str = "bf16",
-                           with_encoder: bool = True):
+                           with_encoder: bool = True, text_encoder_config: Optional[dict] = None,
+                           text_encoder_state_dict: Optional[dict] = None):
     """``name``: "ddpm" (google/ddpm-celebahq-256 layout), "sd" (Stable Diffusion 1.x layout: native conditional UNet
     + native KL decoder with gradient; ``vqvae=`` substitutes the vae, ``tokenizer=`` / ``text_encoder=`` are the
     caller's CLIP modules) or "ldm" (CompVis/ldm-celebahq-256 layout: native UNet on
@@ -92,8 +93,16 @@ def create_diffusion_model(name: str, sample_clipping: bool = True, *, max_batch
             vae = vqvae
         scheduler = DDIMScheduler.from_preset("sd")
         scheduler.config.clip_sample = sample_clipping
-        # the CLIP tokenizer / text encoder are the caller's modules (no weights offline); prompts need them,
-        # precomputed text embeddings (2, 77, 768) do not
+        # text side: the CLIP text encoder runs on the engine (b200edit.clip; transformers state_dict names) unless the
+        # caller supplies a module; the tokenizer (BPE vocabulary files, unavailable offline) is always the caller's.
+        # Prompts need both, precomputed text embeddings (2, 77, 768) need neither.
+        if text_encoder is None:
+            from b200edit.clip import SD15_CLIP_CONFIG, CLIPTextModel
+            text_encoder = CLIPTextModel(**(text_encoder_config or SD15_CLIP_CONFIG), max_batch=2, device=device)
+            if text_encoder_state_dict is not None:
+                text_encoder.load_state_dict(text_encoder_state_dict)
+            else:
+                text_encoder.init_random(seed + 2)
         return SD(NativePipeline(unet=unet, scheduler=scheduler, vae=vae, tokenizer=tokenizer, text_encoder=text_encoder,
                                  device=device))
     raise ValueError(f"Unknown model name: {name}")

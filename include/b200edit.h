@@ -301,6 +301,25 @@ int b2e_vqenc_create(const b2e_vqenc_config* cfg, int64_t max_batch, b2e_unet** 
 int b2e_unet_enable_grad(b2e_unet* m, int enable);
 int b2e_vqdec_backward(b2e_unet* m, const float* d_image, float* d_latent, int64_t B, void* stream);
 
+/* ------------------------------------------------------------------ CLIP text encoder (prompt conditioning)
+ * prep_text / encode_text, src/diffusion_utils.py:34-52: model.text_encoder(input_ids)[0] for the "" and prompt sequences,
+ * i.e. transformers CLIPTextModel.last_hidden_state (token + position embedding, pre-LayerNorm transformer layers with
+ * causal multi-head self-attention and a quick-GELU MLP, final LayerNorm).  Linear layers on the tcgen05 kernel (q/k/v fused
+ * into one GEMM, residual adds as identity K segments), causal attention on the fused attention kernel.  Parameters by
+ * their transformers names ("text_model.embeddings.token_embedding.weight", "text_model.encoder.layers.0.self_attn.q_proj.weight", ...).
+ * b2e_clip_forward: input_ids DEVICE int64 (B, seq_len <= max_positions) -> hidden (B, seq_len, hidden_size) fp32.  The
+ * tokenizer (BPE vocabulary files) stays the caller's. */
+typedef struct {
+  int32_t vocab_size;         /* 49408 */
+  int32_t hidden_size;        /* 768 (SD 1.x: CLIP ViT-L/14 text tower) */
+  int32_t intermediate_size;  /* 3072 */
+  int32_t num_layers;         /* 12 */
+  int32_t num_heads;          /* 12 */
+  int32_t max_positions;      /* 77 */
+} b2e_clip_config;
+int b2e_clip_create(const b2e_clip_config* cfg, int64_t max_batch, b2e_unet** out);
+int b2e_clip_forward(b2e_unet* m, const int64_t* input_ids, int64_t seq_len, float* hidden, int64_t B, void* stream);
+
 /* ------------------------------------------------------------------ classifier network (ClassifierAttrFunc)
  * The predictor of src/models.py:69-77 (torchvision resnet50 with an 80-way fc) inside ClassifierAttrFunc.loss,
  * src/attr_functions.py:237-257: logits = predictor(decode(x0)) and, through autograd in the reference, d(loss)/d(image).
