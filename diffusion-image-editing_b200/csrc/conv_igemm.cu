@@ -733,7 +733,16 @@ int conv_cout_pad(int Cout) {
   return (Cout + 63) / 64 * 64;
 }
 
-ConvGeom conv_geometry(int N, int Ho, int Wo, int Cout) {
+// smallest number of 128 x 128 output tiles for which a 3x3 stride-1 layer runs on the halo kernels (B2E_HALO_MIN).
+// Measured at batch 8 (profiles/README.md, r79) with the threshold lowered to 32 / 64: the 32x32 layers (128 tiles) gain
+// 10-20 % over the plain SM-pair kernel, the 16x16 layers (64 tiles) are a wash against BN = 64 with twice the CTAs -
+// +1 % on the step, inside run-to-run noise, so the default stays one full wave of SMs.
+static int halo_min_tiles() {
+  static const int v = getenv("B2E_HALO_MIN") ? atoi(getenv("B2E_HALO_MIN")) : kNumSMs;
+  return v < 2 ? 2 : v;
+}
+
+ConvGeom conv_geometry(int N, int Ho, int Wo, int Cout, int ksize, int stride) {
   ConvGeom g;
   const int cout_pad = conv_cout_pad(Cout);
   g.Wt = pow2_divisor(Wo, kConvBlockM);
@@ -741,8 +750,11 @@ ConvGeom conv_geometry(int N, int Ho, int Wo, int Cout) {
   g.Nt = kConvBlockM / (g.Wt * g.Ht);
   g.w_blks = Wo / g.Wt; g.h_blks = Ho / g.Ht; g.n_blks = (N + g.Nt - 1) / g.Nt;
   g.block_n = cout_pad <= 16 ? 16 : (cout_pad % 128 == 0 ? 128 : 64);
-  // few output tiles (low-resolution levels): halve the N tile to double the number of CTAs
-  if (g.block_n == 128 && g.w_blks * g.h_blks * g.n_blks * (cout_pad / 128) < kNumSMs / 2) g.block_n = 64;
+  // few output tiles (low-resolution levels): halve the N tile to double the number of CTAs - unless the layer can run
+  // on the halo kernel, whose 3x lower L2 traffic per FLOP beats the extra CTAs
+  const bool halo_shape = ksize == 3 && stride == 1 && Wo % kHaloWt == 0 && Ho % kHaloHt == 0 && cout_pad % 128 == 0 &&
+                          (int64_t)N * Ho * Wo / kConvBlockM * (cout_pad / 128) >= halo_min_tiles();
+  if (g.block_n == 128 && !halo_shape && g.w_blks * g.h_blks * g.n_blks * (cout_pad / 128) < kNumSMs / 2) g.block_n = 64;
   // statistics are reduced over groups of block_n/8 rows, which must not straddle images
   g.stats_ok = g.block_n >= 64 && Cout % 64 == 0 && (g.Wt * g.Ht) % (g.block_n / 8) == 0;
   return g;
@@ -784,7 +796,7 @@ int conv_plan_build(ConvPlan* pl, const ConvDesc& d) {
               "conv: bf16 NHWC output needs Cout %% 64 == 0 (got %d)", d.Cout);
   ConvPlan& p = *pl;
   p.N = d.N; p.Ho = d.H / d.stride; p.Wo = d.W / d.stride; p.Cout = d.Cout; p.cout_pad = conv_cout_pad(d.Cout);
-  const ConvGeom g = conv_geometry(d.N, p.Ho, p.Wo, d.Cout);
+  const ConvGeom g = conv_geometry(d.N, p.Ho, p.Wo, d.Cout, d.ksize, d.stride);
   p.Wt = g.Wt; p.Ht = g.Ht; p.Nt = g.Nt; p.w_blks = g.w_blks; p.h_blks = g.h_blks; p.n_blks = g.n_blks;
   p.block_n = g.block_n;
   // halo mode (p.halo = MT, the M tiles per CTA): big 3x3 stride-1 layers with 128-wide N tiles; a CTA owns an
@@ -795,7 +807,7 @@ int conv_plan_build(ConvPlan* pl, const ConvDesc& d) {
   if (halo_env != 0 && d.ksize == 3 && d.stride == 1 && (g.block_n == 128 || g.block_n == 16) && !d.b_batch_rows &&
       !d.s0.pitch && p.Wo % kHaloWt == 0 && p.Ho % kHaloHt == 0) {
     const int64_t tiles128 = (int64_t)d.N * p.Ho * p.Wo / kConvBlockM * (p.cout_pad / g.block_n);   // 128 x BN output tiles
-    if (tiles128 >= kNumSMs && tiles128 % 2 == 0) {
+    if (tiles128 >= halo_min_tiles() && tiles128 % 2 == 0) {
       p.halo = 1;
       // two M tiles per CTA share every B tile (10 KB instead of 14.7 KB from L2 per k-block, half the barrier
       // hand-shakes) but halve the number of work items: measured worth it from ~12 waves of SM pairs

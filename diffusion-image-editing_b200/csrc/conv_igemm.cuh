@@ -77,7 +77,7 @@ int conv_plan_build(ConvPlan* plan, const ConvDesc& d);
 int conv_cout_pad(int Cout);
 // Tile geometry of an (N,Ho,Wo,Cout) output and whether the epilogue can emit GroupNorm statistics for it.
 struct ConvGeom { int Wt, Ht, Nt, w_blks, h_blks, n_blks, block_n, stats_ok; };
-ConvGeom conv_geometry(int N, int Ho, int Wo, int Cout);
+ConvGeom conv_geometry(int N, int Ho, int Wo, int Cout, int ksize = 1, int stride = 1);
 inline int64_t conv_stats_slots(const ConvGeom& g) { return (int64_t)g.w_blks * g.h_blks * g.n_blks * g.Nt; }
 int conv_launch(const ConvPlan& plan, const ConvEpilogue& ep, cudaStream_t st);
 

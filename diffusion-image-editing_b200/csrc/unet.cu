@@ -1144,7 +1144,7 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
     const int cout_x = out ? L.cout_pad : L.cout;
     if (out) *out = talloc(B, Ho, Wo, cout_x, L.cout);
     // GroupNorm statistics of the output, emitted by the epilogue (the consumer skips its statistics pass)
-    const ConvGeom geo = conv_geometry(B, Ho, Wo, cout_x);
+    const ConvGeom geo = conv_geometry(B, Ho, Wo, cout_x, L.k, stride);
     float* tstats = nullptr;
     const size_t tstats_bytes = sizeof(float) * 2 * (size_t)conv_stats_slots(geo) * cout_x;
     // few tile slots per image (low-resolution levels): the consumer reduces them itself
