@@ -210,6 +210,10 @@ class NetAttrFunc(AttrFunc):
         super().__init__(**kwargs)
         self.segmentation_model = segmentation_model
         self.idx_for_class = idx_for_class
+        # the native face parser differentiates through its own dgrad kernels once gradient mode is on
+        net = getattr(segmentation_model, "net", None)
+        if hasattr(net, "enable_grad") and not getattr(net, "differentiable", True):
+            net.enable_grad()
 
     def loss(self, img, **kwargs):
         out = self.segmentation_model.net(img)[0]

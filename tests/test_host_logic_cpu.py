@@ -136,3 +136,70 @@ def test_transforms_host_side():
     assert pil_to_tensor([Image.fromarray(a)] * 2).shape == (2, 3, 4, 5)
     with pytest.raises(Exception):
         pil_to_tensor(3)
+
+
+def test_batchnorm_folding_of_the_loss_networks_cpu():
+    """Host-side parameter preparation of the native classifier / face parser: eval-mode BatchNorm folded into the
+    convolution weights and biases reproduces conv -> BN exactly (fp64 folding, fp32 comparison), and every parameter the
+    reference modules own is mapped to an engine parameter name."""
+    import importlib.util
+    import os
+    import torch
+    import torchvision
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def load(name):   # import the wrapper modules without loading libb200edit.so
+        import sys
+        import types
+        pkg = types.ModuleType("b200edit_stub")
+        src = open(os.path.join(here, "diffusion-image-editing_b200", "b200edit", name + ".py")).read()
+        start = src.index("def _fold") if "def _fold" in src else None
+        return src, pkg, start
+
+    # ---- ResNet.fold_batchnorm (static, pure torch): compare conv+bn against the folded conv on a random input
+    src, _, _ = load("resnet")
+    ns = {}
+    body = src[src.index("    @staticmethod\n    def fold_batchnorm"):src.index("    def load_torchvision_state_dict")]
+    exec("import torch\nclass R:\n" + body, ns)
+    net = torchvision.models.resnet18().eval()
+    g = torch.Generator().manual_seed(0)
+    for m in net.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+            m.running_var.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+            m.weight.data.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+            m.bias.data.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+    sd = net.state_dict()
+    folded = ns["R"].fold_batchnorm(sd)
+    convs = [k[:-7] for k, v in sd.items() if k.endswith(".weight") and v.dim() == 4]
+    assert sorted(k[:-7] for k in folded if k.endswith(".weight") and folded[k].dim() == 4) == sorted(convs)
+    x = torch.randn(2, 64, 8, 8, generator=g)
+    blk = net.layer1[0]
+    with torch.no_grad():
+        want = blk.bn1(blk.conv1(x))
+        got = torch.nn.functional.conv2d(x, folded["layer1.0.conv1.weight"], folded["layer1.0.conv1.bias"], padding=1)
+        assert torch.allclose(got, want, rtol=1e-5, atol=1e-5)
+        ds = net.layer2[0].downsample
+        want = ds(x)
+        got = torch.nn.functional.conv2d(x, folded["layer2.0.downsample.0.weight"], folded["layer2.0.downsample.0.bias"], stride=2)
+        assert torch.allclose(got, want, rtol=1e-5, atol=1e-5)
+
+    # ---- BiSeNet.fold_reference_state_dict: every used parameter of the reference module gets an engine name
+    from oracle.bisenet import BiSeNet as OracleBiSeNet, seeded_weights
+    src, _, _ = load("bisenet")
+    ns2 = {}
+    fold_src = src[src.index("def _fold"):src.index("class BiSeNet")]
+    meth = src[src.index("    @staticmethod\n    def fold_reference_state_dict"):src.index("    def load_reference_state_dict")]
+    exec("import torch\n" + fold_src + "\nclass B:\n" + meth, ns2)
+    o = seeded_weights(OracleBiSeNet(19).eval(), 3)
+    f2 = ns2["B"].fold_reference_state_dict(o.state_dict())
+    for name in ("cp.resnet.conv1", "cp.resnet.layer2.0.downsample.0", "cp.arm16.conv", "cp.arm32.conv_atten", "cp.conv_head32",
+                 "cp.conv_avg", "ffm.convblk", "conv_out.conv", "conv_out.conv_out"):
+        assert name + ".weight" in f2 and name + ".bias" in f2, name
+    assert "ffm.conv1.weight" in f2 and f2["ffm.conv1.weight"].shape == (64, 256) and f2["cp.conv_avg.weight"].shape == (128, 512)
+    assert not any(k.startswith(("conv_out16", "conv_out32")) for k in f2)
+    xa = torch.randn(1, 256, 8, 8, generator=g)
+    with torch.no_grad():
+        want = o.cp.arm16.conv(xa)
+        got = torch.relu(torch.nn.functional.conv2d(xa, f2["cp.arm16.conv.weight"], f2["cp.arm16.conv.bias"], padding=1))
+        assert torch.allclose(got, want, rtol=1e-5, atol=1e-5)
