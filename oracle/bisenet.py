@@ -13,7 +13,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
-class ConvBNReLU(nn.Module):
+class ConvNormAct(nn.Module):
     def __init__(self, cin, cout, ks=3, stride=1, padding=1):
         super().__init__()
         self.conv = nn.Conv2d(cin, cout, ks, stride, padding, bias=False)
@@ -23,7 +23,7 @@ class ConvBNReLU(nn.Module):
         return F.relu(self.bn(self.conv(x)))
 
 
-class BasicBlock(nn.Module):
+class ResBlock2(nn.Module):
     def __init__(self, cin, cout, stride=1):
         super().__init__()
         self.conv1 = nn.Conv2d(cin, cout, 3, stride, 1, bias=False)
@@ -39,16 +39,16 @@ class BasicBlock(nn.Module):
         return F.relu((x if self.downsample is None else self.downsample(x)) + r)
 
 
-class Resnet18(nn.Module):
+class Backbone18(nn.Module):
     def __init__(self):
         super().__init__()
         self.conv1 = nn.Conv2d(3, 64, 7, 2, 3, bias=False)
         self.bn1 = nn.BatchNorm2d(64)
         self.maxpool = nn.MaxPool2d(3, 2, 1)
-        self.layer1 = nn.Sequential(BasicBlock(64, 64), BasicBlock(64, 64))
-        self.layer2 = nn.Sequential(BasicBlock(64, 128, 2), BasicBlock(128, 128))
-        self.layer3 = nn.Sequential(BasicBlock(128, 256, 2), BasicBlock(256, 256))
-        self.layer4 = nn.Sequential(BasicBlock(256, 512, 2), BasicBlock(512, 512))
+        self.layer1 = nn.Sequential(ResBlock2(64, 64), ResBlock2(64, 64))
+        self.layer2 = nn.Sequential(ResBlock2(64, 128, 2), ResBlock2(128, 128))
+        self.layer3 = nn.Sequential(ResBlock2(128, 256, 2), ResBlock2(256, 256))
+        self.layer4 = nn.Sequential(ResBlock2(256, 512, 2), ResBlock2(512, 512))
 
     def forward(self, x):
         x = self.layer1(self.maxpool(F.relu(self.bn1(self.conv1(x)))))
@@ -57,10 +57,10 @@ class Resnet18(nn.Module):
         return f8, f16, self.layer4(f16)
 
 
-class AttentionRefinementModule(nn.Module):
+class ChannelAttentionRefine(nn.Module):
     def __init__(self, cin, cout):
         super().__init__()
-        self.conv = ConvBNReLU(cin, cout)
+        self.conv = ConvNormAct(cin, cout)
         self.conv_atten = nn.Conv2d(cout, cout, 1, bias=False)
         self.bn_atten = nn.BatchNorm2d(cout)
 
@@ -70,15 +70,15 @@ class AttentionRefinementModule(nn.Module):
         return feat * atten
 
 
-class ContextPath(nn.Module):
+class ContextBranch(nn.Module):
     def __init__(self):
         super().__init__()
-        self.resnet = Resnet18()
-        self.arm16 = AttentionRefinementModule(256, 128)
-        self.arm32 = AttentionRefinementModule(512, 128)
-        self.conv_head32 = ConvBNReLU(128, 128)
-        self.conv_head16 = ConvBNReLU(128, 128)
-        self.conv_avg = ConvBNReLU(512, 128, ks=1, stride=1, padding=0)
+        self.resnet = Backbone18()
+        self.arm16 = ChannelAttentionRefine(256, 128)
+        self.arm32 = ChannelAttentionRefine(512, 128)
+        self.conv_head32 = ConvNormAct(128, 128)
+        self.conv_head16 = ConvNormAct(128, 128)
+        self.conv_avg = ConvNormAct(512, 128, ks=1, stride=1, padding=0)
 
     def forward(self, x):
         f8, f16, f32 = self.resnet(x)
@@ -90,10 +90,10 @@ class ContextPath(nn.Module):
         return f8, u16, u32
 
 
-class FeatureFusionModule(nn.Module):
+class FusionBlock(nn.Module):
     def __init__(self, cin, cout):
         super().__init__()
-        self.convblk = ConvBNReLU(cin, cout, ks=1, stride=1, padding=0)
+        self.convblk = ConvNormAct(cin, cout, ks=1, stride=1, padding=0)
         self.conv1 = nn.Conv2d(cout, cout // 4, 1, bias=False)
         self.conv2 = nn.Conv2d(cout // 4, cout, 1, bias=False)
 
@@ -103,10 +103,10 @@ class FeatureFusionModule(nn.Module):
         return feat * atten + feat
 
 
-class BiSeNetOutput(nn.Module):
+class ParserHead(nn.Module):
     def __init__(self, cin, mid, n_classes):
         super().__init__()
-        self.conv = ConvBNReLU(cin, mid)
+        self.conv = ConvNormAct(cin, mid)
         self.conv_out = nn.Conv2d(mid, n_classes, 1, bias=False)
 
     def forward(self, x):
@@ -116,11 +116,11 @@ class BiSeNetOutput(nn.Module):
 class BiSeNet(nn.Module):
     def __init__(self, n_classes=19):
         super().__init__()
-        self.cp = ContextPath()
-        self.ffm = FeatureFusionModule(256, 256)
-        self.conv_out = BiSeNetOutput(256, 256, n_classes)
-        self.conv_out16 = BiSeNetOutput(128, 64, n_classes)
-        self.conv_out32 = BiSeNetOutput(128, 64, n_classes)
+        self.cp = ContextBranch()
+        self.ffm = FusionBlock(256, 256)
+        self.conv_out = ParserHead(256, 256, n_classes)
+        self.conv_out16 = ParserHead(128, 64, n_classes)
+        self.conv_out32 = ParserHead(128, 64, n_classes)
 
     def forward(self, x):
         f8, cp8, cp16 = self.cp(x)

@@ -240,6 +240,14 @@ def test_batched_per_sample_equals_independent_runs():
     pil = SegDiffEditPipeline(DDPM(make_model(eps.numpy(), T=T, clip=True)), None).edit_image(
         xt=xt.cuda(), attr_func=f, prog_bar=False)
     assert len(pil.imgs) == B and len(pil.pred_original_samples) == T and len(pil.pred_original_samples[0]) == B
+    # streamed history: same values, delivered into a pinned host buffer on the copy stream
+    host = torch.empty(T, B, 3, 16, 16).pin_memory()
+    streamed = SegDiffEditPipeline(DDPM(make_model(eps.numpy(), T=T, clip=True)), None).edit_image(
+        xt=xt.cuda(), attr_func=f, prog_bar=False, output_type="tensor", x0_history_out=host)
+    torch.cuda.synchronize()
+    assert torch.equal(streamed.imgs, full.imgs)
+    for k in range(T):
+        assert torch.equal(host[k], full.pred_original_samples[k].cpu()) and streamed.pred_original_samples[k].data_ptr() == host[k].data_ptr()
 
 
 def test_end_to_end_with_native_unet():
