@@ -118,3 +118,34 @@ def test_classifier_attr_func_with_native_predictor():
           f"{rel(d16, dr):.3e} cos {cos(d16, dr):.5f}")
     assert dr.abs().max() > 0 and rel(dn, dr) <= 0.5 and cos(dn, dr) >= 0.9
     assert rel(dn, dr) <= rel(d16, dr) + 2e-2
+
+
+def test_metrics_harness_on_the_engine():
+    """src/metrics.py drop-in (evaluation harness): generation, classifier-guided editing and the attribute predictor all
+    on the engine; contract of the two metrics (keys, shapes, ranges, determinism under a fixed seed)."""
+    import metrics
+    from attr_functions import AnyGANAttrFunc
+    from b200edit.resnet import resnet50_predictor
+    from models import create_diffusion_model
+    from SegDiffEditPipeline import SegDiffEditPipeline
+    cfg = dict(sample_size=64, in_channels=3, out_channels=3, block_out_channels=(64, 128), layers_per_block=1,
+               down_block_types=("DownBlock2D", "AttnDownBlock2D"), up_block_types=("AttnUpBlock2D", "UpBlock2D"))
+    w = create_diffusion_model("ddpm", sample_clipping=True, max_batch=1, seed=1, unet_config=cfg)
+    predictor = resnet50_predictor(80, 64, max_batch=1, seed=2)
+    func = AnyGANAttrFunc(predictor=predictor, idx_for_class=31, loss_scale=500.0, t1=0, t2=8)
+    editor = SegDiffEditPipeline(w, None)
+
+    def run():
+        g = torch.Generator().manual_seed(5)
+        acc = metrics.attribute_consistency(editor, w, func, 2, g, num_inference_steps=8, predictor=predictor)
+        d0, d1 = metrics.avg_increase_decrease_per_attribute(editor, w, func, 2, g, num_inference_steps=8, predictor=predictor)
+        return acc, d0, d1
+
+    acc, d0, d1 = run()
+    assert acc.shape == (40,) and float(acc.min()) >= 0.0 and float(acc.max()) <= 1.0
+    assert len(d0) == 40 and len(d1) == 40 and "31 Smiling" in d0 and "39 Young" in d1
+    assert all(torch.isfinite(torch.tensor(list(d0.values())))) and any(abs(v) > 0 for v in d0.values())
+    acc2, d0b, _ = run()
+    assert torch.equal(acc, acc2) and d0 == d0b
+    with pytest.raises(NotImplementedError):
+        metrics.lpips(None, None)
