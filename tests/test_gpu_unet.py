@@ -77,6 +77,12 @@ def test_ldm_style_unet_fp32_mode_matches_oracle():
     check_fp32(*run_pair(LDM_SMALL, 2, 400, seed=12, precision="fp32"), "ldm-style small unet fp32")
 
 
+def test_ldm_celebahq_unet_fp32_mode_matches_oracle():
+    """Full LDM-CelebAHQ layout in the fp32-accurate mode: padded channel pitches (224 -> 256, 672 -> 704) carry three
+    planes, 14-28 heads of 32 channels go through the fp32 attention core."""
+    check_fp32(*run_pair(LDM_CELEBAHQ_CONFIG, 1, 500, seed=4, precision="fp32"), "ldm-celebahq unet fp32")
+
+
 def test_ddpm256_unet_fp32_mode_matches_oracle():
     check_fp32(*run_pair(DDPM256_CONFIG, 2, 500, seed=0, precision="fp32"), "ddpm-256 unet fp32")
 
