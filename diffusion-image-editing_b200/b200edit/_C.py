@@ -41,7 +41,8 @@ class UNetConfig(C.Structure):
 class VQDecConfig(C.Structure):
     _fields_ = [("sample_size", C.c_int32), ("latent_channels", C.c_int32), ("out_channels", C.c_int32),
                 ("n_blocks", C.c_int32), ("block_out_channels", C.c_int32 * 8), ("layers_per_block", C.c_int32),
-                ("norm_num_groups", C.c_int32), ("norm_eps", C.c_float), ("num_vq_embeddings", C.c_int32)]
+                ("norm_num_groups", C.c_int32), ("norm_eps", C.c_float), ("num_vq_embeddings", C.c_int32),
+                ("precision", C.c_int32)]
 
 
 class VQEncConfig(C.Structure):

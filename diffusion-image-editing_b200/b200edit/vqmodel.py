@@ -115,8 +115,11 @@ class VQModel(UNet2DModel):
 
     def __init__(self, latent_channels=3, out_channels=3, block_out_channels=(128, 256, 512), layers_per_block=2,
                  norm_num_groups=32, norm_eps=1e-6, num_vq_embeddings=8192, sample_size=64, max_batch=8,
-                 device="cuda", with_encoder=False):
+                 device="cuda", with_encoder=False, precision="bf16"):
         _C.require_device()
+        if precision not in ("bf16", "fp32"):
+            raise ValueError(f"{type(self).__name__}: precision must be 'bf16' or 'fp32' (got {precision!r})")
+        self.precision = precision
         n = len(block_out_channels)
         self._enc = None
         self.config = SimpleNamespace(latent_channels=latent_channels, out_channels=out_channels,
@@ -134,6 +137,7 @@ class VQModel(UNet2DModel):
             cfg.block_out_channels[i] = block_out_channels[i]
         cfg.layers_per_block, cfg.norm_num_groups, cfg.norm_eps = layers_per_block, norm_num_groups, norm_eps
         cfg.num_vq_embeddings = num_vq_embeddings
+        cfg.precision = 1 if precision == "fp32" else 0      # fp32-accurate decode: split-bf16 operands, forward only
         h = C.c_void_p()
         with torch.cuda.device(self.device):
             check(lib.b2e_vqdec_create(C.byref(cfg), self.max_batch, C.byref(h)), "vqdec_create")
@@ -247,11 +251,12 @@ class AutoencoderKL(VQModel):
     State-dict names as in diffusers (``post_quant_conv.*``, ``decoder.*``)."""
 
     def __init__(self, latent_channels=4, out_channels=3, block_out_channels=(128, 256, 512, 512), layers_per_block=2,
-                 norm_num_groups=32, norm_eps=1e-6, sample_size=64, max_batch=8, device="cuda", with_encoder=False):
+                 norm_num_groups=32, norm_eps=1e-6, sample_size=64, max_batch=8, device="cuda", with_encoder=False,
+                 precision="bf16"):
         super().__init__(latent_channels=latent_channels, out_channels=out_channels, block_out_channels=block_out_channels,
                          layers_per_block=layers_per_block, norm_num_groups=norm_num_groups, norm_eps=norm_eps,
                          num_vq_embeddings=0, sample_size=sample_size, max_batch=max_batch, device=device,
-                         with_encoder=with_encoder)
+                         with_encoder=with_encoder, precision=precision)
 
     def encode(self, x):
         """``vae.encode(img).latent_dist`` (the reference takes ``.mode()``, src/diffusion_classes.py:29)."""

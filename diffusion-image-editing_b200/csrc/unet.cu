@@ -380,14 +380,17 @@ int build_model_decoder(b2e_unet* m) {
   m->in_im2col = true;
   {
     ConvL ci;
-    ci.cin = ci.cin_pad = kConvBlockK; ci.cout = top; ci.k = 1; ci.cout_pad = conv_cout_pad(top); ci.row_len = kConvBlockK;
+    const int PL = m->PL;
+    ci.cin = ci.cin_pad = kConvBlockK; ci.cout = top; ci.k = 1; ci.cout_pad = conv_cout_pad(top); ci.row_len = kConvBlockK * PL;
     ci.w = m->dmalloc<bf16>((size_t)ci.cout_pad * ci.row_len);
     ci.b = m->dmalloc<float>(ci.cout_pad);
     // dgrad twin: gradient w.r.t. the 64 im2col columns (9 * L real) = 1x1 convolution with the transposed weights
     m->conv_in_dg = m->make_dgrad(kConvBlockK, ci.cout_pad, 1);
     const ConvL cd = m->dgrads[m->conv_in_dg];
-    m->add_param("decoder.conv_in.weight", (int64_t)top * L * 9, (int64_t)L * 9, [ci, cd, L](const float* src, cudaStream_t st) {
+    m->add_param("decoder.conv_in.weight", (int64_t)top * L * 9, (int64_t)L * 9, [ci, cd, L, PL](const float* src, cudaStream_t st) {
       int rc = conv_pack_weight(src, ci.w, ci.cout, L, 3, L, ci.row_len, 0, st);
+      if (!rc && PL == 3) rc = conv_pack_weight(src, ci.w, ci.cout, L, 3, L, ci.row_len, kConvBlockK, st);
+      if (!rc && PL == 3) rc = conv_pack_weight(src, ci.w, ci.cout, L, 3, L, ci.row_len, 2 * kConvBlockK, st, 0, 0, 1);
       if (!rc) rc = conv_pack_weight_im2col_T(src, cd.w, ci.cout, L, cd.row_len, st);
       return rc;
     });
@@ -1242,7 +1245,7 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
       ops.push_back({[m, zq, B, Cin, HW](cudaStream_t st) {
                        return vq_quantize_launch(m->in_x, m->codebook, m->n_codes, m->pq_w, m->pq_b, zq, B, Cin, HW, st);
                      }, 3, 0.0, 8.0 * B * Cin * HW, "vq nearest code + post_quant_conv"});
-      ops.push_back({[zq, xin, B, Cin, S](cudaStream_t st) { return pack_input_launch(zq, xin.p, B, Cin, S, S, kConvBlockK, true, st); },
+      ops.push_back({[zq, xin, B, Cin, S, PL](cudaStream_t st) { return pack_input_launch(zq, xin.p, B, Cin, S, S, kConvBlockK, true, st, PL); },
                      3, 0.0, (double)B * HW * (4.0 * Cin + 2.0 * kConvBlockK)});
     } else {
       ops.push_back({[m, xin, B, Cin, S, im2col, PL](cudaStream_t st) { return pack_input_launch(m->in_x, xin.p, B, Cin, S, S, kConvBlockK, im2col, st, PL); },
@@ -1458,9 +1461,15 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
         if (PL == 3) {
           // fp32-accurate mode: fp32 attention core on the CUDA cores over the split-bf16 q | k | v planes
           if (!dry) {
-            const int Cr = a.C;
-            ops.push_back({[qkv, o, B, T, C, Cr, heads](cudaStream_t st) { return attention_split_launch(qkv.p, o.p, B, T, Cr, C, heads, st); },
-                           2, 4.0 * B * (double)T * T * Cr, 0.0, "attention (fp32, split-bf16 operands)"});
+            const int Cr = a.C, dh = a.C / heads;
+            if (sizeof(float) * 16 * (size_t)(dh + T) <= 160 * 1024 && qkv.C == 3 * C) {
+              ops.push_back({[qkv, o, B, T, C, Cr, heads](cudaStream_t st) { return attention_split_launch(qkv.p, o.p, B, T, Cr, C, heads, st); },
+                             2, 4.0 * B * (double)T * T * Cr, 0.0, "attention (fp32, split-bf16 operands)"});
+            } else {   // long sequences (decoder mid block: 4096 tokens): online softmax over key tiles
+              ops.push_back({[qkv, o, B, T, C, Cr, heads, dh](cudaStream_t st) {
+                               return attention_split_tiled_launch(qkv.p, qkv.C, 0, qkv.p, qkv.C, C, 2 * C, o.p, C, Cr, B, T, T, T, heads, dh, st); },
+                             2, 4.0 * B * (double)T * T * Cr, 0.0, "attention (fp32, tiled, split-bf16 operands)"});
+            }
           }
           flops += 4.0 * B * (double)T * T * a.C;
         } else if (heads == 1 && T % 128 == 0 && (T <= 1024 || T == 2048 || T == 4096) && gq.Nt == 1) {
@@ -1846,8 +1855,10 @@ int b2e_vqdec_create(const b2e_vqdec_config* cfg, int64_t max_batch, b2e_unet** 
     B2E_REQUIRE(ch % 8 == 0 && ch >= 32 && ch <= 1024 && ch % cfg->norm_num_groups == 0, B2E_UNSUPPORTED_SHAPE,
                 "vqdec_create: block_out_channels must be multiples of 8 and of norm_num_groups, 32..1024 (got %d)", ch);
   }
+  B2E_REQUIRE(cfg->precision == 0 || cfg->precision == 1, B2E_INVALID_ARG, "vqdec_create: precision must be 0 (bf16) or 1 (fp32-accurate)");
   b2e_unet* m = new b2e_unet();
   m->decoder = true;
+  m->PL = cfg->precision == 1 ? 3 : 1;
   m->n_codes = cfg->num_vq_embeddings;
   b2e_unet_config& u = m->cfg;
   u = b2e_unet_config{};
@@ -2035,6 +2046,7 @@ int b2e_unet_enable_grad(b2e_unet* m, int enable) {
   B2E_REQUIRE(m, B2E_INVALID_ARG, "unet_enable_grad: null handle");
   B2E_REQUIRE(!enable || m->decoder || m->resnet, B2E_UNSUPPORTED_SHAPE,
               "unet_enable_grad: gradient mode is implemented for the VQ / KL decoder and the classifier");
+  B2E_REQUIRE(!enable || m->PL == 1, B2E_UNSUPPORTED_SHAPE, "unet_enable_grad: the fp32-accurate mode is forward-only");
   if ((enable != 0) == m->grad) return B2E_OK;
   m->grad = enable != 0;
   m->cur_B = -1; m->fwd_B = -1; m->ws = nullptr; m->ws_bytes = 0;   // the workspace must be re-queried and re-bound

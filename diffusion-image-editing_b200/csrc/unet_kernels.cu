@@ -1546,6 +1546,174 @@ int attention_split_launch(const bf16* qkv, bf16* out, int N, int T, int C, int 
   return check_launch("attention_split");
 }
 
+// fp32-accurate mode, any sequence length: flash-style fp32 attention on the CUDA cores (online softmax over 32-key
+// tiles, O accumulated in registers).  q / k / v are channel windows of split-bf16 tensors ([hi | lo | hi] planes):
+// q rows [n][tq] of a tensor with `q_plane` channels per plane at column q_col + h*d, k / v rows [n][tk] of a tensor with
+// `k_plane` channels per plane at columns k_col + h*d / v_col + h*d; out rows [n][tq] with o_plane channels per plane.
+// Block = (32 queries, head, image).
+constexpr int kTaQ = 32, kTaK = 32, kTaThreads = 256;
+struct TiledAttnArgs {
+  const bf16* q; const bf16* kv; bf16* out;
+  int Tq, Tk, valid_k, heads, d;
+  int q_plane, q_col, k_plane, k_col, v_col, o_plane, o_real;
+  int64_t q_img, kv_img, o_img;   // elements between consecutive images
+  float scale;
+};
+
+__global__ void __launch_bounds__(kTaThreads) attention_split_tiled_kernel(TiledAttnArgs a) {
+  pdl_wait();
+  extern __shared__ __align__(16) uint8_t ta_smem[];
+  const int d = a.d, ds = d + 1;                                  // padded row stride: conflict-free column walks
+  float* Qs = reinterpret_cast<float*>(ta_smem);                  // [32][ds]
+  float* KV = Qs + kTaQ * ds;                                     // [32][ds]  (K tile, then V tile)
+  float* S = KV + kTaK * ds;                                      // [32][33]
+  float* rowm = S + kTaQ * (kTaK + 1);                            // [32] running maximum
+  float* rowl = rowm + kTaQ;                                      // [32] running sum
+  float* rowc = rowl + kTaQ;                                      // [32] rescale factor of the current tile
+  const int tid = threadIdx.x, h = blockIdx.y, n = blockIdx.z, q0 = blockIdx.x * kTaQ;
+  const bf16* qb = a.q + (int64_t)n * a.q_img + a.q_col + h * d;
+  const bf16* kb = a.kv + (int64_t)n * a.kv_img + a.k_col + h * d;
+  const bf16* vb = a.kv + (int64_t)n * a.kv_img + a.v_col + h * d;
+  const int64_t qrow = 3 * (int64_t)a.q_plane, krow = 3 * (int64_t)a.k_plane;
+  for (int i = tid; i < kTaQ * d; i += kTaThreads) {
+    const int q = i / d, c = i - q * d;
+    float v = 0.f;
+    if (q0 + q < a.Tq) { const bf16* p = qb + (int64_t)(q0 + q) * qrow + c; v = __bfloat162float(p[0]) + __bfloat162float(p[a.q_plane]); }
+    Qs[q * ds + c] = v * a.scale;
+  }
+  if (tid < kTaQ) { rowm[tid] = -INFINITY; rowl[tid] = 0.f; }
+  // output ownership: column pair cp of query group qg
+  const int half = d >> 1;
+  const int ngroups = half >= kTaThreads ? 1 : kTaThreads / half;
+  const int cp = tid % half, qg = tid / half;
+  const int qper = (kTaQ + ngroups - 1) / ngroups;                // queries per group (<= 32)
+  const bool owner = qg < ngroups;
+  float ox[kTaQ], oy[kTaQ];
+#pragma unroll
+  for (int i = 0; i < kTaQ; ++i) ox[i] = oy[i] = 0.f;
+  __syncthreads();
+  for (int k0 = 0; k0 < a.valid_k; k0 += kTaK) {
+    // ---- K tile -> smem (fp32 = hi + lo)
+    for (int i = tid; i < kTaK * d; i += kTaThreads) {
+      const int k = i / d, c = i - k * d;
+      float v = 0.f;
+      if (k0 + k < a.valid_k) { const bf16* p = kb + (int64_t)(k0 + k) * krow + c; v = __bfloat162float(p[0]) + __bfloat162float(p[a.k_plane]); }
+      KV[k * ds + c] = v;
+    }
+    __syncthreads();
+    // ---- scores: thread = (query tid / 8, keys (tid % 8) * 4 .. + 3)
+    {
+      const int q = tid >> 3, kk = (tid & 7) * 4;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      const float* qr = Qs + q * ds;
+      const float* k0r = KV + kk * ds;
+      for (int c = 0; c < d; ++c) {
+        const float qv = qr[c];
+        s0 += qv * k0r[c]; s1 += qv * k0r[ds + c]; s2 += qv * k0r[2 * ds + c]; s3 += qv * k0r[3 * ds + c];
+      }
+      float* sr = S + q * (kTaK + 1) + kk;
+      sr[0] = k0 + kk < a.valid_k ? s0 : -INFINITY;
+      sr[1] = k0 + kk + 1 < a.valid_k ? s1 : -INFINITY;
+      sr[2] = k0 + kk + 2 < a.valid_k ? s2 : -INFINITY;
+      sr[3] = k0 + kk + 3 < a.valid_k ? s3 : -INFINITY;
+    }
+    __syncthreads();
+    // ---- online softmax per query row (one warp handles 4 rows; lane = key)
+    {
+      const int warp = tid >> 5, lane = tid & 31;
+      for (int q = warp; q < kTaQ; q += kTaThreads / 32) {
+        const float sv = S[q * (kTaK + 1) + lane];
+        float mx = sv;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        const float mold = rowm[q], mnew = fmaxf(mold, mx);
+        const float pv = sv == -INFINITY ? 0.f : expf(sv - mnew);
+        const float ps = warp_sum(pv);
+        S[q * (kTaK + 1) + lane] = pv;
+        if (lane == 0) {
+          const float corr = mold == -INFINITY ? 0.f : expf(mold - mnew);
+          rowc[q] = corr; rowm[q] = mnew; rowl[q] = rowl[q] * corr + ps;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- V tile -> smem (reuses the K buffer)
+    for (int i = tid; i < kTaK * d; i += kTaThreads) {
+      const int k = i / d, c = i - k * d;
+      float v = 0.f;
+      if (k0 + k < a.valid_k) { const bf16* p = vb + (int64_t)(k0 + k) * krow + c; v = __bfloat162float(p[0]) + __bfloat162float(p[a.k_plane]); }
+      KV[k * ds + c] = v;
+    }
+    __syncthreads();
+    // ---- O = O * corr + P V
+    if (owner) {
+      for (int c0 = 2 * cp; c0 < d; c0 += 2 * kTaThreads) {   // d <= 512: one pass
+#pragma unroll
+        for (int i = 0; i < kTaQ; ++i) {
+          const int q = qg * qper + i;
+          if (i < qper && q < kTaQ) {
+            const float corr = rowc[q];
+            float ax = ox[i] * corr, ay = oy[i] * corr;
+            const float* pr = S + q * (kTaK + 1);
+#pragma unroll 8
+            for (int k = 0; k < kTaK; ++k) {
+              const float pv = pr[k];
+              ax += pv * KV[k * ds + c0]; ay += pv * KV[k * ds + c0 + 1];
+            }
+            ox[i] = ax; oy[i] = ay;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // ---- normalise and write the split output
+  const int64_t orow = 3 * (int64_t)a.o_plane;
+  bf16* ob = a.out + (int64_t)n * a.o_img + h * d;
+  if (owner && 2 * cp < d) {
+#pragma unroll
+    for (int i = 0; i < kTaQ; ++i) {
+      const int q = qg * qper + i;
+      if (i < qper && q < kTaQ && q0 + q < a.Tq) {
+        const float inv = 1.f / rowl[q];
+        const float vx = ox[i] * inv, vy = oy[i] * inv;
+        bf16* o = ob + (int64_t)(q0 + q) * orow + 2 * cp;
+        const __nv_bfloat162 hi = __floats2bfloat162_rn(vx, vy);
+        const float2 hf = __bfloat1622float2(hi);
+        *reinterpret_cast<__nv_bfloat162*>(o) = hi;
+        *reinterpret_cast<__nv_bfloat162*>(o + a.o_plane) = __floats2bfloat162_rn(__fsub_rn(vx, hf.x), __fsub_rn(vy, hf.y));
+        *reinterpret_cast<__nv_bfloat162*>(o + 2 * a.o_plane) = hi;
+      }
+    }
+  }
+  if (h == 0 && a.o_plane > a.o_real) {   // zero padding of the output pitch (all planes)
+    const int pad = a.o_plane - a.o_real;
+    for (int i = tid; i < kTaQ * pad * 3; i += kTaThreads) {
+      const int k = i % 3, r = i / 3, q = r / pad, c = r % pad;
+      if (q0 + q < a.Tq) a.out[(int64_t)n * a.o_img + (int64_t)(q0 + q) * orow + k * a.o_plane + a.o_real + c] = __float2bfloat16_rn(0.f);
+    }
+  }
+}
+
+int attention_split_tiled_launch(const bf16* q, int q_plane, int q_col, const bf16* kv, int k_plane, int k_col, int v_col, bf16* out,
+                                 int o_plane, int o_real, int N, int Tq, int Tk_rows, int valid_k, int heads, int d, cudaStream_t st) {
+  B2E_REQUIRE(d % 2 == 0 && d >= 8 && d <= 512 && heads >= 1 && valid_k >= 1 && valid_k <= Tk_rows, B2E_UNSUPPORTED_SHAPE,
+              "attention (fp32-accurate, tiled): unsupported head_dim %d / keys %d of %d", d, valid_k, Tk_rows);
+  TiledAttnArgs a;
+  a.q = q; a.kv = kv; a.out = out; a.Tq = Tq; a.Tk = Tk_rows; a.valid_k = valid_k; a.heads = heads; a.d = d;
+  a.q_plane = q_plane; a.q_col = q_col; a.k_plane = k_plane; a.k_col = k_col; a.v_col = v_col; a.o_plane = o_plane; a.o_real = o_real;
+  a.q_img = (int64_t)Tq * 3 * q_plane; a.kv_img = (int64_t)Tk_rows * 3 * k_plane; a.o_img = (int64_t)Tq * 3 * o_plane;
+  a.scale = 1.0f / sqrtf((float)d);
+  const size_t smem = sizeof(float) * ((size_t)(kTaQ + kTaK) * (d + 1) + kTaQ * (kTaK + 1) + 3 * kTaQ);
+  static size_t attr = 0;
+  if (smem > attr) {
+    B2E_CUDA(cudaFuncSetAttribute(attention_split_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  launch_pdl(attention_split_tiled_kernel, dim3((Tq + kTaQ - 1) / kTaQ, heads, N), dim3(kTaThreads), smem, st, a);
+  return check_launch("attention_split_tiled");
+}
+
 int attention_launch(const bf16* qkv, bf16* out, int N, int T, int C, int P, int heads, cudaStream_t st) {
   B2E_REQUIRE(heads >= 1 && C % heads == 0 && P >= C && P % 8 == 0, B2E_UNSUPPORTED_SHAPE, "attention: bad head count / pitch");
   const int d = C / heads;

@@ -143,5 +143,9 @@ int merge_heads_launch(const bf16* oh, bf16* out, int N, int T, int P, int heads
 int attention_launch(const bf16* qkv, bf16* out, int N, int T, int C, int P, int heads, cudaStream_t st);
 // fp32-accurate mode: qkv / out are split-bf16 tensors ([hi | lo | hi] planes of 3P / P channels), arithmetic in fp32
 int attention_split_launch(const bf16* qkv, bf16* out, int N, int T, int C, int P, int heads, cudaStream_t st);
+// any sequence length (online softmax over key tiles); q / k / v are channel windows of split-bf16 tensors with q_plane /
+// k_plane channels per plane; keys >= valid_k are masked; out has o_plane channels per plane (o_real of them written)
+int attention_split_tiled_launch(const bf16* q, int q_plane, int q_col, const bf16* kv, int k_plane, int k_col, int v_col, bf16* out,
+                                 int o_plane, int o_real, int N, int Tq, int Tk_rows, int valid_k, int heads, int d, cudaStream_t st);
 
 }  // namespace b2e

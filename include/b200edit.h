@@ -269,6 +269,7 @@ typedef struct {
   int32_t norm_num_groups;
   float norm_eps;
   int32_t num_vq_embeddings; /* 0: no quantiser = AutoencoderKL.decode (post_quant_conv -> decoder), SD.decode */
+  int32_t precision;         /* 0: bf16; 1: fp32-accurate (split-bf16 operands, forward only), as b2e_unet_config.precision */
 } b2e_vqdec_config;
 int b2e_vqdec_create(const b2e_vqdec_config* cfg, int64_t max_batch, b2e_unet** out);
 
