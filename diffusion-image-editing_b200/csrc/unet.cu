@@ -280,15 +280,16 @@ struct b2e_unet {
   ConvL make_linear(const std::string& name, int cin, int cout, bool bias, int res_c = 0) {
     ConvL c;
     c.cin = cin; c.cin_pad = pad64(cin); c.cout = cout; c.k = 1; c.cout_pad = conv_cout_pad(cout);
-    c.res_c = res_c; c.row_len = c.cin_pad + res_c;
+    c.res_c = res_c; c.row_len = PL * (c.cin_pad + res_c);
     c.w = dmalloc<bf16>((size_t)c.cout_pad * c.row_len);
     c.b = dmalloc<float>(c.cout_pad);
     ConvL cc = c;
-    add_param(name + ".weight", (int64_t)cout * cin, cin, [cc](const float* src, cudaStream_t st) {
-      return conv_pack_weight(src, cc.w, cc.cout, cc.cin, 1, cc.cin_pad, cc.row_len, 0, st);
+    const int PL = this->PL;
+    add_param(name + ".weight", (int64_t)cout * cin, cin, [cc, PL](const float* src, cudaStream_t st) {
+      return pack_w(PL, src, cc.w, cc.cout, cc.cin, 1, cc.cin_pad, cc.row_len, 0, cc.cin_pad, st);
     });
     if (bias) add_f32(name + ".bias", c.b, cout, cin);
-    if (res_c && c.w && conv_fill_identity(c.w, cout, c.row_len, c.cin_pad, 0)) build_error = B2E_CUDA_ERROR;
+    if (res_c && c.w && fill_id(PL, c.w, cout, c.row_len, PL * c.cin_pad, res_c)) build_error = B2E_CUDA_ERROR;
     return c;
   }
   // several bias-free projections of the same input fused into one GEMM: rows [i*cout, (i+1)*cout) = names[i]
@@ -296,14 +297,15 @@ struct b2e_unet {
     ConvL c;
     const int n = (int)names.size();
     c.cin = cin; c.cin_pad = pad64(cin); c.cout = n * cout; c.k = 1; c.cout_pad = conv_cout_pad(n * cout);
-    c.row_len = c.cin_pad;
+    c.row_len = c.cin_pad * PL;
     c.w = dmalloc<bf16>((size_t)c.cout_pad * c.row_len);
     c.b = dmalloc<float>(c.cout_pad);
+    const int PL = this->PL;
     for (int i = 0; i < n; ++i) {
       bf16* wdst = c.w + (size_t)i * cout * c.row_len;
       const int rl = c.row_len, cp = c.cin_pad;
-      add_param(base + "." + names[i] + ".weight", (int64_t)cout * cin, cin, [wdst, cout, cin, rl, cp](const float* src, cudaStream_t st) {
-        return conv_pack_weight(src, wdst, cout, cin, 1, cp, rl, 0, st);
+      add_param(base + "." + names[i] + ".weight", (int64_t)cout * cin, cin, [wdst, cout, cin, rl, cp, PL](const float* src, cudaStream_t st) {
+        return pack_w(PL, src, wdst, cout, cin, 1, cp, rl, 0, cp, st);
       });
       if (bias && c.b) add_f32(base + "." + names[i] + ".bias", c.b + (size_t)i * cout, cout, cin);
     }
@@ -1267,7 +1269,7 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
     ctxp = talloc(B, 1, kCtxPad, c.cross_attention_dim);
     if (!dry) {
       const int D = c.cross_attention_dim;
-      ops.push_back({[m, ctxp, B, D](cudaStream_t st) { return pack_context_launch(m->in_ctx, ctxp.p, B, m->ctx_len, kCtxPad, D, st); },
+      ops.push_back({[m, ctxp, B, D, PL](cudaStream_t st) { return pack_context_launch(m->in_ctx, ctxp.p, B, m->ctx_len, kCtxPad, D, st, PL); },
                      3, 0.0, (double)B * kCtxPad * D * 6.0, "pack text context"});
     }
   }
@@ -1277,8 +1279,8 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
     if (dry) return;
     Tensor xx = x, oo = *out;
     const int64_t rows = (int64_t)B * x.H * x.W;
-    ops.push_back({[L, xx, oo, rows](cudaStream_t st) { return layernorm_rows_launch(xx.p, oo.p, L.g, L.b, rows, xx.C, 1e-5f, st); },
-                   1, 0.0, 4.0 * rows * x.C, "layernorm"});
+    ops.push_back({[L, xx, oo, rows, PL](cudaStream_t st) { return layernorm_rows_launch(xx.p, oo.p, L.g, L.b, rows, xx.C, 1e-5f, st, PL); },
+                   1, 0.0, 4.0 * rows * x.C * PL, "layernorm"});
   };
   // multi-head attention on the tensor cores: heads become "virtual images" of head-major, zero-padded copies of q, k
   // and V^T (head_dim -> multiple of 64, tokens -> multiple of 128); S = Q K^T and O = P V are batched GEMMs on the
@@ -1286,6 +1288,20 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
   auto mh_attention = [&](const Tensor& qsrc, int qcol, const Tensor& ksrc, int kcol, int vcol, int Tq, int Tk, int valid_k,
                           int heads, int d, int dpad, Tensor* out, int Hh, int Ww, int Cc, int causal = 0) {
     if (rc) return;
+    if (PL == 3) {
+      // fp32-accurate mode: tiled fp32 attention straight on the q / k / v channel windows of the split-bf16 tensors
+      if (causal) { rc = B2E_UNSUPPORTED_SHAPE; set_error("unet: causal attention is not available in the fp32-accurate mode"); return; }
+      *out = talloc(B, Hh, Ww, Cc);
+      flops += 4.0 * B * heads * (double)Tq * Tk * d;
+      if (!dry) {
+        const Tensor q_ = qsrc, k_ = ksrc, o_ = *out;
+        ops.push_back({[m, q_, k_, o_, B, qcol, kcol, vcol, Tq, Tk, valid_k, heads, d, Cc](cudaStream_t st) {
+                         return attention_split_tiled_launch(q_.p, q_.C, qcol, k_.p, k_.C, kcol, vcol, o_.p, o_.C, Cc, B, Tq, Tk,
+                                                             valid_k < 0 ? m->ctx_len : valid_k, heads, d, st); },
+                       2, 4.0 * B * heads * (double)Tq * Tk * d, 0.0, "attention (fp32, tiled, split-bf16 operands)"});
+      }
+      return;
+    }
     const int NV = B * heads;
     const int Tqp = Tq < 128 ? 128 : Tq, Tkp = Tk < 128 ? 128 : Tk;
     Tensor qh = talloc(NV, 1, Tqp, dpad), kh = talloc(NV, 1, Tkp, dpad), vht = talloc(NV, 1, dpad, Tkp);
@@ -1606,7 +1622,7 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
         gg = talloc(B, h.H, h.W, 4 * C);
         if (!dry) {
           const int64_t rows = (int64_t)B * T;
-          ops.push_back({[f1, gg, rows, C](cudaStream_t st) { return geglu_launch(f1.p, gg.p, rows, 4 * C, st); }, 3, 0.0,
+          ops.push_back({[f1, gg, rows, C, PL](cudaStream_t st) { return geglu_launch(f1.p, gg.p, rows, 4 * C, st, PL); }, 3, 0.0,
                          2.0 * rows * 12.0 * C, "geglu"});
         }
         tfree(f1);
@@ -1829,8 +1845,8 @@ int b2e_unet_create(const b2e_unet_config* cfg, int64_t max_batch, b2e_unet** ou
   B2E_REQUIRE(cfg->sample_size % (1 << (cfg->n_blocks - 1)) == 0, B2E_UNSUPPORTED_SHAPE, "unet_create: sample_size");
   B2E_REQUIRE(cfg->precision == 0 || cfg->precision == 1, B2E_INVALID_ARG, "unet_create: precision must be 0 (bf16) or 1 (fp32-accurate)");
   if (cfg->precision == 1) {
-    B2E_REQUIRE(cfg->cross_attention_dim == 0 && (cfg->in_channels == 1 || cfg->in_channels == 3 || cfg->in_channels == 4),
-                B2E_UNSUPPORTED_SHAPE, "unet_create: the fp32-accurate mode covers UNet2DModel with 1, 3 or 4 input channels");
+    B2E_REQUIRE(cfg->in_channels == 1 || cfg->in_channels == 3 || cfg->in_channels == 4, B2E_UNSUPPORTED_SHAPE,
+                "unet_create: the fp32-accurate mode needs 1, 3 or 4 input channels");
   }
   b2e_unet* m = new b2e_unet();
   m->cfg = *cfg;

@@ -757,8 +757,16 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const bf16* __restr
   }
 }
 
+__global__ void layernorm_rows_split_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const float* __restrict__ gamma,
+                                            const float* __restrict__ beta, int64_t rows, int C, float eps);
+
 int layernorm_rows_launch(const bf16* x, bf16* y, const float* gamma, const float* beta, int64_t rows, int C, float eps,
-                          cudaStream_t st) {
+                          cudaStream_t st, int planes) {
+  if (planes == 3) {
+    B2E_REQUIRE(C % 8 == 0 && C <= 2048, B2E_UNSUPPORTED_SHAPE, "layernorm: C = %d (multiple of 8, <= 2048)", C);
+    launch_pdl(layernorm_rows_split_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, st, x, y, gamma, beta, rows, C, eps);
+    return check_launch("layernorm_rows_split");
+  }
   B2E_REQUIRE(C % 8 == 0 && C <= 2048, B2E_UNSUPPORTED_SHAPE, "layernorm: unsupported width %d", C);
   launch_pdl(layernorm_rows_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, st, x, y, gamma, beta, rows, C, eps);
   return check_launch("layernorm_rows");
@@ -836,6 +844,85 @@ int unpad_rows_f32_launch(const bf16* x, float* out, int B, int L, int Lpad, int
   return check_launch("unpad_rows_f32");
 }
 
+// fp32-accurate mode: LayerNorm over split-bf16 rows ([hi | lo | hi] planes of C channels, value = hi + lo)
+__global__ void __launch_bounds__(256) layernorm_rows_split_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
+                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                   int64_t rows, int C, float eps) {
+  pdl_wait();
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + row * 3 * C);
+  uint4* yr = reinterpret_cast<uint4*>(y + row * 3 * C);
+  const int chunks = C >> 3;
+  float v[8][8];   // up to 8 chunks per lane (C <= 2048)
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int ch = lane + 32 * i;
+    if (ch < chunks) {
+      float l[8];
+      unpack8(__ldg(xr + ch), v[i]);
+      unpack8(__ldg(xr + chunks + ch), l);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { v[i][j] += l[j]; sum += v[i][j]; }
+    }
+  }
+  sum = warp_sum(sum);
+  const float mean = sum / (float)C;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int ch = lane + 32 * i;
+    if (ch < chunks) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; sq += d * d; }
+    }
+  }
+  sq = warp_sum(sq);
+  const float rstd = 1.0f / sqrtf(sq / (float)C + eps);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int ch = lane + 32 * i;
+    if (ch < chunks) {
+      float o[8], l[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        o[j] = (v[i][j] - mean) * rstd * __ldg(gamma + ch * 8 + j) + __ldg(beta + ch * 8 + j);
+        l[j] = __fsub_rn(o[j], __bfloat162float(__float2bfloat16_rn(o[j])));
+      }
+      const uint4 hi = pack8(o);
+      yr[ch] = hi; yr[chunks + ch] = pack8(l); yr[2 * chunks + ch] = hi;
+    }
+  }
+}
+
+// fp32-accurate GEGLU on split rows: in planes of 2*inner channels, out planes of inner channels
+__global__ void __launch_bounds__(256) geglu_split_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int64_t rows,
+                                                          int inner8) {
+  pdl_wait();
+  const int64_t total = rows * inner8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / inner8;
+    const int c = (int)(i % inner8);
+    const uint4* row = in + r * 6 * inner8;       // [hi (2*inner) | lo (2*inner) | hi]
+    float a[8], g[8], al[8], gl[8], l[8];
+    unpack8(__ldg(row + c), a);
+    unpack8(__ldg(row + inner8 + c), g);
+    unpack8(__ldg(row + 2 * inner8 + c), al);
+    unpack8(__ldg(row + 3 * inner8 + c), gl);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float av = a[j] + al[j], gv = g[j] + gl[j];
+      a[j] = av * (0.5f * gv * (1.f + erff(gv * 0.70710678118654752f)));
+      l[j] = __fsub_rn(a[j], __bfloat162float(__float2bfloat16_rn(a[j])));
+    }
+    uint4* orow = out + r * 3 * inner8;
+    const uint4 hi = pack8(a);
+    orow[c] = hi; orow[inner8 + c] = pack8(l); orow[2 * inner8 + c] = hi;
+  }
+}
+
 // GEGLU: in [rows][2*inner] -> out [rows][inner] = in[:, :inner] * gelu(in[:, inner:])   (exact erf GELU)
 __global__ void __launch_bounds__(256) geglu_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int64_t rows,
                                                     int inner8) {
@@ -853,33 +940,44 @@ __global__ void __launch_bounds__(256) geglu_kernel(const uint4* __restrict__ in
   }
 }
 
-int geglu_launch(const bf16* in, bf16* out, int64_t rows, int inner, cudaStream_t st) {
+int geglu_launch(const bf16* in, bf16* out, int64_t rows, int inner, cudaStream_t st, int planes) {
   B2E_REQUIRE(inner % 8 == 0, B2E_UNSUPPORTED_SHAPE, "geglu: inner %% 8");
   const int64_t total = rows * (inner / 8);
   int grid = (int)((total + 255) / 256);
   if (grid > kNumSMs * 32) grid = kNumSMs * 32;
+  if (planes == 3) {
+    launch_pdl(geglu_split_kernel, dim3(grid), dim3(256), 0, st, (const uint4*)in, (uint4*)out, rows, inner / 8);
+    return check_launch("geglu_split");
+  }
   launch_pdl(geglu_kernel, dim3(grid), dim3(256), 0, st, (const uint4*)in, (uint4*)out, rows, inner / 8);
   return check_launch("geglu");
 }
 
 // text conditioning: fp32 [B][L][D] -> bf16 [B][Lpad][D], rows >= L zero
 __global__ void __launch_bounds__(256) pack_context_kernel(const float* __restrict__ ctx, bf16* __restrict__ out, int B, int L,
-                                                           int Lpad, int D) {
+                                                           int Lpad, int D, int planes) {
   pdl_wait();
   const int64_t total = (int64_t)B * Lpad * D;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int dcol = (int)(i % D);
     const int l = (int)((i / D) % Lpad);
     const int64_t b = i / ((int64_t)D * Lpad);
-    out[i] = __float2bfloat16_rn(l < L ? ctx[(b * L + l) * D + dcol] : 0.f);
+    const float v = l < L ? ctx[(b * L + l) * D + dcol] : 0.f;
+    const bf16 hi = __float2bfloat16_rn(v);
+    if (planes == 3) {   // split-bf16 rows [hi | lo | hi]
+      bf16* o = out + (b * Lpad + l) * 3 * D + dcol;
+      o[0] = hi; o[D] = __float2bfloat16_rn(__fsub_rn(v, __bfloat162float(hi))); o[2 * D] = hi;
+    } else {
+      out[i] = hi;
+    }
   }
 }
 
-int pack_context_launch(const float* ctx, bf16* out, int B, int L, int Lpad, int D, cudaStream_t st) {
+int pack_context_launch(const float* ctx, bf16* out, int B, int L, int Lpad, int D, cudaStream_t st, int planes) {
   const int64_t total = (int64_t)B * Lpad * D;
   int grid = (int)((total + 255) / 256);
   if (grid > kNumSMs * 16) grid = kNumSMs * 16;
-  launch_pdl(pack_context_kernel, dim3(grid), dim3(256), 0, st, ctx, out, B, L, Lpad, D);
+  launch_pdl(pack_context_kernel, dim3(grid), dim3(256), 0, st, ctx, out, B, L, Lpad, D, planes);
   return check_launch("pack_context");
 }
 

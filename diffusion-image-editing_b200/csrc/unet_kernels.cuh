@@ -80,10 +80,11 @@ int softmax_rows_launch(bf16* s, int64_t rows, int T, float scale, cudaStream_t 
 int transpose_v_launch(const bf16* qkv, bf16* vt, int N, int T, int C, cudaStream_t st);
 
 // transformer-block kernels (SD UNet2DConditionModel)
+// (planes = 3: split-bf16 rows of the fp32-accurate mode, [hi | lo | hi] planes per row)
 int layernorm_rows_launch(const bf16* x, bf16* y, const float* gamma, const float* beta, int64_t rows, int C, float eps,
-                          cudaStream_t st);
-int geglu_launch(const bf16* in, bf16* out, int64_t rows, int inner, cudaStream_t st);
-int pack_context_launch(const float* ctx, bf16* out, int B, int L, int Lpad, int D, cudaStream_t st);
+                          cudaStream_t st, int planes = 1);
+int geglu_launch(const bf16* in, bf16* out, int64_t rows, int inner, cudaStream_t st, int planes = 1);
+int pack_context_launch(const float* ctx, bf16* out, int B, int L, int Lpad, int D, cudaStream_t st, int planes = 1);
 int gather_heads_launch(const bf16* src, bf16* dst, int N, int Tsrc, int Tpad, int pitch, int col0, int heads, int d, int dpad,
                         bool transposed, cudaStream_t st);
 int scatter_heads_launch(const bf16* oh, bf16* out, int N, int T, int Tpad, int pitch, int heads, int d, int dpad, cudaStream_t st);

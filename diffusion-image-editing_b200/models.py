@@ -33,7 +33,7 @@ def create_diffusion_model(name: str, sample_clipping: bool = True, *, max_batch
     the 64x64x3 latent + native forward-only VQ decoder; ``vqvae=`` substitutes the caller's VQ autoencoder module
     (encode().latents / decode().sample, as in the reference's pipeline object); ``guidance_module=`` is the
     differentiable decoder used when guidance runs through decode).  ``precision="fp32"`` selects the fp32-accurate
-    (split-bf16) noise predictor for "ddpm" / "ldm".  ``with_encoder`` (default) also builds the native VQ / KL encoder behind
+    (split-bf16) noise predictor (all three families) and VQ / KL decoder (forward only: guidance through the decoder needs bf16).  ``with_encoder`` (default) also builds the native VQ / KL encoder behind
     ``LDM.encode`` / ``SD.encode``."""
     device = get_device()
     if name == "ddpm":
@@ -56,7 +56,9 @@ def create_diffusion_model(name: str, sample_clipping: bool = True, *, max_batch
         if vqvae is None:
             # native decoder: forward for the post-loop decoding of the sample / x0 history and, with
             # decoder_grad=True (default), the native dgrad for guidance THROUGH the decoder
-            vqvae = VQModel(**(vq_config or LDM_VQ_CONFIG), max_batch=max_batch, device=device, with_encoder=with_encoder)
+            vqvae = VQModel(**(vq_config or LDM_VQ_CONFIG), max_batch=max_batch, device=device, with_encoder=with_encoder,
+                            precision=precision)
+            decoder_grad = decoder_grad and precision == "bf16"   # the fp32-accurate decoder is forward-only
             if vq_state_dict is not None:
                 vqvae.load_state_dict(vq_state_dict)
             else:
@@ -71,18 +73,18 @@ def create_diffusion_model(name: str, sample_clipping: bool = True, *, max_batch
                                   guidance_vqvae=guidance_vqvae if guidance_module is None else guidance_module,
                                   device=device))
     if name == "sd":
-        if precision != "bf16":
-            raise ValueError("create_diffusion_model: the fp32-accurate mode covers the 'ddpm' and 'ldm' noise predictors")
         from b200edit.unet_cond import SD15_CONFIG, UNet2DConditionModel
         from b200edit.vqmodel import SD_VAE_CONFIG, AutoencoderKL
         # CFG doubles the latent batch: the UNet engine is sized for 2 * max_batch samples
-        unet = UNet2DConditionModel(**(unet_config or SD15_CONFIG), max_batch=2 * max_batch, device=device)
+        unet = UNet2DConditionModel(**(unet_config or SD15_CONFIG), max_batch=2 * max_batch, device=device, precision=precision)
         if state_dict is not None:
             unet.load_state_dict(state_dict)
         else:
             unet.init_random(seed)
         if vqvae is None:
-            vae = AutoencoderKL(**(vq_config or SD_VAE_CONFIG), max_batch=max_batch, device=device, with_encoder=with_encoder)
+            vae = AutoencoderKL(**(vq_config or SD_VAE_CONFIG), max_batch=max_batch, device=device, with_encoder=with_encoder,
+                                precision=precision)
+            decoder_grad = decoder_grad and precision == "bf16"   # the fp32-accurate decoder is forward-only
             if vq_state_dict is not None:
                 vae.load_state_dict(vq_state_dict)
             else:

@@ -16,11 +16,11 @@ MID = dict(sample_size=32, in_channels=4, out_channels=4, block_out_channels=(32
            cross_attention_dim=128, attention_head_dim=8, norm_num_groups=32, norm_eps=1e-5)
 
 
-def run_pair(cfg, B, t, seed, L=77):
+def run_pair(cfg, B, t, seed, L=77, precision="bf16"):
     from b200edit.unet_cond import UNet2DConditionModel
     torch.manual_seed(seed)
     oracle = OracleCond(**cfg).eval()
-    native = UNet2DConditionModel(**cfg, max_batch=B)
+    native = UNet2DConditionModel(**cfg, max_batch=B, precision=precision)
     native.load_state_dict(oracle.state_dict())
     g = torch.Generator().manual_seed(seed + 1)
     x = torch.randn(B, cfg["in_channels"], cfg["sample_size"], cfg["sample_size"], generator=g)
@@ -47,6 +47,26 @@ def check(got, ref, ref16, tag):
     assert got.shape == ref.shape and torch.isfinite(got).all()
     assert rel <= 2e-2 and err <= 3e-2 * max(1.0, scale)
     assert rel <= 1.25 * rel16 + 1e-3
+
+
+def check_fp32(got, ref, ref16, tag):
+    """fp32-accurate mode: max-abs <= 1e-4 * max(1, max|eps|), relative RMS <= 5e-5 (the UNet2DModel bars)."""
+    scale = ref.abs().max().item()
+    err = (got - ref).abs().max().item()
+    rel = ((got - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
+    print(f"{tag}: fp32-accurate native max-abs {err:.3e} rel-rms {rel:.3e} | max|eps| {scale:.3f}")
+    assert got.shape == ref.shape and torch.isfinite(got).all()
+    assert err <= 1e-4 * max(1.0, scale) and rel <= 5e-5
+
+
+@pytest.mark.parametrize("B,t,L", [(1, 981, 77), (2, 401, 20)])
+def test_small_cond_unet_fp32_mode_matches_oracle(B, t, L):
+    check_fp32(*run_pair(SMALL, B, t, seed=B + L, L=L, precision="fp32"), f"small cond unet fp32 B={B} t={t} L={L}")
+
+
+def test_sd15_cond_unet_fp32_mode_matches_oracle():
+    """Full SD 1.x UNet2DConditionModel in the fp32-accurate mode (self-attention over 4096 tokens on the tiled fp32 kernel)."""
+    check_fp32(*run_pair(SD15_CONFIG, 1, 500, seed=3, precision="fp32"), "sd-1.x cond unet fp32")
 
 
 @pytest.mark.parametrize("B,t,L", [(1, 981, 77), (2, 401, 77), (2, 1, 5)])
