@@ -2076,6 +2076,24 @@ int b2e_vqdec_backward(b2e_unet* m, const float* d_image, float* d_latent, int64
               "vqdec_backward: no live forward pass of batch %lld (last forward: %lld)", (long long)B, (long long)m->fwd_B);
   m->in_dy = d_image; m->out_dz = d_latent;
   cudaStream_t st = (cudaStream_t)stream;
+  // B2E_PROFILE_BWD=1: CUDA-event time of every backward op to stderr (diagnostic; synchronises)
+  static const bool prof = getenv("B2E_PROFILE_BWD") && atoi(getenv("B2E_PROFILE_BWD")) != 0;
+  if (prof) {
+    std::vector<cudaEvent_t> ev(m->bops.size() + 1);
+    for (auto& e : ev) cudaEventCreate(&e);
+    cudaEventRecord(ev[0], st);
+    int rc = B2E_OK;
+    for (size_t i = 0; i < m->bops.size() && !rc; ++i) { rc = m->bops[i].fn(st); cudaEventRecord(ev[i + 1], st); }
+    cudaStreamSynchronize(st);
+    for (size_t i = 0; i < m->bops.size(); ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+      fprintf(stderr, "BWD %3zu %8.1f us %7.0f TF/s %7.0f GB/s  %s\n", i, ms * 1e3, m->bops[i].flops / (ms * 1e9 + 1e-9),
+              m->bops[i].bytes / (ms * 1e6 + 1e-9), m->bops[i].desc.c_str());
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    return rc;
+  }
   for (auto& op : m->bops) {
     int rc = op.fn(st);
     if (rc) return rc;
