@@ -256,10 +256,18 @@ int gn_launch(const GNArgs& a, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------ GroupNorm (+SiLU) backward
+// silu'(y) = s (1 + y (1 - s)), s = sigmoid(y) = 0.5 + 0.5 tanh(y / 2): one MUFU op
 __device__ __forceinline__ float silu_grad(float y) {
-  const float sg = 1.f / (1.f + __expf(-y));
-  return sg * (1.f + y * (1.f - sg));
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(0.5f * y));
+  const float sg = fmaf(0.5f, th, 0.5f);
+  return sg * fmaf(y, 1.f - sg, 1.f);
 }
+
+// Per-channel constants of the backward pass: y = x*sc + sh (the forward's affine), xh = x*r + mr (normalised input).
+// Both kernels keep several independent 16-byte loads in flight per thread (the loops are latency-bound otherwise:
+// measured 1.6 TB/s before unrolling against 5 TB/s for the forward apply kernel).
+constexpr int kGNBwdUnroll = 4;
 
 __global__ void __launch_bounds__(kGNThreads) gn_bwd_partial_kernel(GNBwdArgs a) {
   pdl_wait();
@@ -271,27 +279,42 @@ __global__ void __launch_bounds__(kGNThreads) gn_bwd_partial_kernel(GNBwdArgs a)
   const int p0 = chunk * per, p1 = min(a.HW, p0 + per);
   const int cpg = C / a.G;
   if (pl < ppi) {
-    float sa[8], sb[8], mean[8], rstd[8], gam[8], bet[8];
+    float sa[8], sb[8], sc[8], sh[8], r[8], mr[8], gam[8];
     const int c = s * 8;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       sa[j] = sb[j] = 0.f;
       const float2 st = *reinterpret_cast<const float2*>(a.stats + ((int64_t)n * a.G + (c + j) / cpg) * 2);
-      mean[j] = st.x; rstd[j] = st.y; gam[j] = __ldg(a.gamma + c + j); bet[j] = __ldg(a.beta + c + j);
+      gam[j] = __ldg(a.gamma + c + j);
+      r[j] = st.y; mr[j] = -st.x * st.y;
+      sc[j] = gam[j] * st.y; sh[j] = fmaf(gam[j], mr[j], __ldg(a.beta + c + j));
     }
     const bf16* xs = a.x + (int64_t)n * a.HW * a.P + c;
     const bf16* ds = a.da + (int64_t)n * a.HW * a.Pda + c;
-    for (int p = p0 + pl; p < p1; p += ppi) {
-      float xf[8], df[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(xs + (int64_t)p * a.P)), xf);
-      unpack8(__ldg(reinterpret_cast<const uint4*>(ds + (int64_t)p * a.Pda)), df);
+    for (int p = p0 + pl; p < p1; p += ppi * kGNBwdUnroll) {
+      uint4 xv[kGNBwdUnroll], dv[kGNBwdUnroll];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float xh = (xf[j] - mean[j]) * rstd[j];
-        float dy = df[j];
-        if (a.silu) dy *= silu_grad(fmaf(gam[j], xh, bet[j]));
-        const float dxh = dy * gam[j];
-        sa[j] += dxh; sb[j] += dxh * xh;
+      for (int u = 0; u < kGNBwdUnroll; ++u) {
+        const int q = p + u * ppi;
+        if (q < p1) {
+          xv[u] = __ldg(reinterpret_cast<const uint4*>(xs + (int64_t)q * a.P));
+          dv[u] = __ldg(reinterpret_cast<const uint4*>(ds + (int64_t)q * a.Pda));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kGNBwdUnroll; ++u) {
+        if (p + u * ppi < p1) {
+          float xf[8], df[8];
+          unpack8(xv[u], xf);
+          unpack8(dv[u], df);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float dy = df[j];
+            if (a.silu) dy *= silu_grad(fmaf(xf[j], sc[j], sh[j]));
+            const float dxh = dy * gam[j];
+            sa[j] += dxh; sb[j] = fmaf(dxh, fmaf(xf[j], r[j], mr[j]), sb[j]);
+          }
+        }
       }
     }
 #pragma unroll
@@ -332,33 +355,51 @@ __global__ void __launch_bounds__(kGNThreads) gn_bwd_apply_kernel(GNBwdArgs a, i
     for (int p = p0 + pl; p < p1; p += ppi) *reinterpret_cast<uint4*>(dst + (int64_t)p * a.P) = make_uint4(0, 0, 0, 0);
     return;
   }
-  float mean[8], rstd[8], gam[8], bet[8], ma[8], mb[8];
+  // dx = rstd * (dy*gam - ma - xh*mb) = dy * gr + x * k1 + k0 with gr = gam*rstd, k1 = -rstd*r*mb, k0 = -rstd*(ma + mr*mb)
+  float sc[8], sh[8], gr[8], k1[8], k0[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int g = (c + j) / cpg;
     const float2 st = *reinterpret_cast<const float2*>(a.stats + ((int64_t)n * a.G + g) * 2);
-    mean[j] = st.x; rstd[j] = st.y; gam[j] = __ldg(a.gamma + c + j); bet[j] = __ldg(a.beta + c + j);
-    ma[j] = s_ma[g]; mb[j] = s_mb[g];
+    const float gam = __ldg(a.gamma + c + j), rstd = st.y, mr = -st.x * st.y;
+    sc[j] = gam * rstd; sh[j] = fmaf(gam, mr, __ldg(a.beta + c + j));
+    gr[j] = gam * rstd;
+    k1[j] = -rstd * rstd * s_mb[g];
+    k0[j] = -rstd * fmaf(mr, s_mb[g], s_ma[g]);
   }
   const bf16* xs = a.x + (int64_t)n * a.HW * a.P + c;
   const bf16* ds = a.da + (int64_t)n * a.HW * a.Pda + c;
   const bf16* as = a.add ? a.add + (int64_t)n * a.HW * a.P + c : nullptr;
-  for (int p = p0 + pl; p < p1; p += ppi) {
-    float xf[8], df[8], af[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(xs + (int64_t)p * a.P)), xf);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(ds + (int64_t)p * a.Pda)), df);
-    if (as) unpack8(__ldg(reinterpret_cast<const uint4*>(as + (int64_t)p * a.P)), af);
+  for (int p = p0 + pl; p < p1; p += ppi * kGNBwdUnroll) {
+    uint4 xv[kGNBwdUnroll], dv[kGNBwdUnroll], av[kGNBwdUnroll];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float xh = (xf[j] - mean[j]) * rstd[j];
-      float dy = df[j];
-      if (a.silu) dy *= silu_grad(fmaf(gam[j], xh, bet[j]));
-      const float dxh = dy * gam[j];
-      float dx = rstd[j] * (dxh - ma[j] - xh * mb[j]);
-      if (as) dx += af[j];
-      xf[j] = dx;
+    for (int u = 0; u < kGNBwdUnroll; ++u) {
+      const int q = p + u * ppi;
+      if (q < p1) {
+        xv[u] = __ldg(reinterpret_cast<const uint4*>(xs + (int64_t)q * a.P));
+        dv[u] = __ldg(reinterpret_cast<const uint4*>(ds + (int64_t)q * a.Pda));
+        if (as) av[u] = __ldg(reinterpret_cast<const uint4*>(as + (int64_t)q * a.P));
+      }
     }
-    *reinterpret_cast<uint4*>(dst + (int64_t)p * a.P) = pack8(xf);
+#pragma unroll
+    for (int u = 0; u < kGNBwdUnroll; ++u) {
+      const int q = p + u * ppi;
+      if (q < p1) {
+        float xf[8], df[8], af[8];
+        unpack8(xv[u], xf);
+        unpack8(dv[u], df);
+        if (as) unpack8(av[u], af);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float dy = df[j];
+          if (a.silu) dy *= silu_grad(fmaf(xf[j], sc[j], sh[j]));
+          float dx = fmaf(dy, gr[j], fmaf(xf[j], k1[j], k0[j]));
+          if (as) dx += af[j];
+          xf[j] = dx;
+        }
+        *reinterpret_cast<uint4*>(dst + (int64_t)q * a.P) = pack8(xf);
+      }
+    }
   }
 }
 
@@ -370,7 +411,7 @@ int gn_bwd_launch(const GNBwdArgs& a, cudaStream_t st) {
   int rc = check_launch("gn_bwd_partial");
   if (rc) return rc;
   const int slots = a.P / 8, ppi = kGNThreads / slots;
-  int ppb = ppi * 8;
+  int ppb = ppi * kGNBwdUnroll * 2;   // two unrolled sweeps per thread
   if (ppb > a.HW) ppb = a.HW;
   launch_pdl(gn_bwd_apply_kernel, dim3((a.HW + ppb - 1) / ppb, a.N), dim3(kGNThreads), 0, st, a, ppb);
   return check_launch("gn_bwd_apply");
