@@ -267,7 +267,7 @@ __device__ __forceinline__ float silu_grad(float y) {
 // Per-channel constants of the backward pass: y = x*sc + sh (the forward's affine), xh = x*r + mr (normalised input).
 // Both kernels keep several independent 16-byte loads in flight per thread (the loops are latency-bound otherwise:
 // measured 1.6 TB/s before unrolling against 5 TB/s for the forward apply kernel).
-constexpr int kGNBwdUnroll = 4;
+constexpr int kGNBwdUnroll = 4;   // measured at batch 32 (decoder backward, 24 launches): unroll 2 16.9 ms, 4 13.0 ms, 8 15.4 ms
 
 __global__ void __launch_bounds__(kGNThreads) gn_bwd_partial_kernel(GNBwdArgs a) {
   pdl_wait();
