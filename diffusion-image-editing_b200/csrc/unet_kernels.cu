@@ -1262,6 +1262,7 @@ int vq_col2im_bwd_launch(const bf16* dcols, const float* pq_w, float* dz, int B,
 // channel with individually rounded operations, first index on ties - the oracle's order), then the 1x1
 // post_quant_conv.  z, out: fp32 NCHW (B, L, HW), L <= 4.  Codes are staged through smem in tiles.
 constexpr int kVqTile = 1024;
+constexpr int kVqLanes = 8;   // threads per latent pixel: each scans every 8th code (stride-L smem reads are conflict-free)
 __global__ void __launch_bounds__(256)
 vq_quantize_kernel(const float* __restrict__ z, const float* __restrict__ codebook, int n_codes,
                    const float* __restrict__ pq_w, const float* __restrict__ pq_b, float* __restrict__ out, int B, int L,
@@ -1269,32 +1270,40 @@ vq_quantize_kernel(const float* __restrict__ z, const float* __restrict__ codebo
   pdl_wait();
   __shared__ float s_code[kVqTile * 4];
   const int64_t total = (int64_t)B * HW;
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int sub = threadIdx.x & (kVqLanes - 1);
+  const int64_t p = (int64_t)blockIdx.x * (blockDim.x / kVqLanes) + (threadIdx.x / kVqLanes);
   const bool live = p < total;
   const int64_t b = live ? p / HW : 0, q = live ? p % HW : 0;
   float zv[4] = {0.f, 0.f, 0.f, 0.f};
   if (live)
     for (int c = 0; c < L; ++c) zv[c] = z[(b * L + c) * HW + q];
   float best = INFINITY;
-  int best_i = 0;
+  int best_i = 0x7fffffff;
   for (int k0 = 0; k0 < n_codes; k0 += kVqTile) {
     const int nk = min(kVqTile, n_codes - k0);
     __syncthreads();
     for (int i = threadIdx.x; i < nk * L; i += blockDim.x) s_code[i] = codebook[(int64_t)k0 * L + i];
     __syncthreads();
     if (live) {
-      for (int k = 0; k < nk; ++k) {
+      for (int k = sub; k < nk; k += kVqLanes) {
         float d = 0.f;
         for (int c = 0; c < L; ++c) {
           const float t = __fsub_rn(zv[c], s_code[k * L + c]);
           const float t2 = __fmul_rn(t, t);
           d = c == 0 ? t2 : __fadd_rn(d, t2);
         }
-        if (d < best) { best = d; best_i = k0 + k; }
+        if (d < best) { best = d; best_i = k0 + k; }   // ascending k: the lane keeps its FIRST minimum
       }
     }
   }
-  if (!live) return;
+  // combine the lanes of a pixel: smaller distance wins, ties go to the smaller index (= first index over all codes)
+#pragma unroll
+  for (int o = 1; o < kVqLanes; o <<= 1) {
+    const float od = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+    if (od < best || (od == best && oi < best_i)) { best = od; best_i = oi; }
+  }
+  if (!live || sub != 0) return;
   float e[4] = {0.f, 0.f, 0.f, 0.f};
   // n_codes == 0: no quantiser (AutoencoderKL.decode: post_quant_conv only)
   for (int c = 0; c < L; ++c) e[c] = n_codes > 0 ? codebook[(int64_t)best_i * L + c] : zv[c];
@@ -1309,7 +1318,8 @@ int vq_quantize_launch(const float* z, const float* codebook, int n_codes, const
                        int B, int L, int HW, cudaStream_t st) {
   B2E_REQUIRE(L >= 1 && L <= 4 && n_codes >= 0, B2E_UNSUPPORTED_SHAPE, "vq_quantize: latent channels %d", L);
   const int64_t total = (int64_t)B * HW;
-  launch_pdl(vq_quantize_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, z, codebook, n_codes, pq_w, pq_b,
+  const int ppb = 256 / kVqLanes;   // latent pixels per block
+  launch_pdl(vq_quantize_kernel, dim3((unsigned)((total + ppb - 1) / ppb)), dim3(256), 0, st, z, codebook, n_codes, pq_w, pq_b,
              out, B, L, HW);
   return check_launch("vq_quantize");
 }
