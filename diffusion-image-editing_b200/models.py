@@ -30,7 +30,7 @@ def create_diffusion_model(name: str, sample_clipping: bool = True, *, max_batch
     """``name``: "ddpm" (google/ddpm-celebahq-256 layout), "sd" (Stable Diffusion 1.x layout: native conditional UNet
     + native KL decoder with gradient; ``vqvae=`` substitutes the vae, ``tokenizer=`` / ``text_encoder=`` are the
     caller's CLIP modules) or "ldm" (CompVis/ldm-celebahq-256 layout: native UNet on
-    the 64x64x3 latent + native forward-only VQ decoder; ``vqvae=`` substitutes the caller's VQ autoencoder module
+    the 64x64x3 latent + native VQ decoder (forward + latent gradient) and encoder; ``vqvae=`` substitutes the caller's VQ autoencoder module
     (encode().latents / decode().sample, as in the reference's pipeline object); ``guidance_module=`` is the
     differentiable decoder used when guidance runs through decode).  ``precision="fp32"`` selects the fp32-accurate
     (split-bf16) noise predictor (all three families) and VQ / KL decoder (forward only: guidance through the decoder needs bf16).  ``with_encoder`` (default) also builds the native VQ / KL encoder behind
