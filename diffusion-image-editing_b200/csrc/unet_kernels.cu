@@ -752,6 +752,9 @@ int transpose_v_launch(const bf16* qkv, bf16* vt, int N, int T, int C, cudaStrea
 // ------------------------------------------------------------------ transformer-block kernels (SD UNet2DConditionModel)
 // LayerNorm over the channels of every token (bf16 NHWC rows of C channels, C % 8 == 0, C <= 2048): one warp per token,
 // the row lives in registers between the two passes
+// CPL = 16-byte chunks per lane: the register array is sized for the row width (a fixed 8-chunk array costs ~100 registers
+// and a third of the occupancy on 320-channel rows; the kernel is latency-bound: one row per warp)
+template <int CPL>
 __global__ void __launch_bounds__(256) layernorm_rows_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
                                                              int64_t rows, int C, float eps) {
@@ -762,10 +765,10 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const bf16* __restr
   const uint4* xr = reinterpret_cast<const uint4*>(x + row * C);
   uint4* yr = reinterpret_cast<uint4*>(y + row * C);
   const int chunks = C >> 3;
-  float v[8][8];   // up to 8 chunks per lane (C <= 2048)
+  float v[CPL][8];
   float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < CPL; ++i) {
     const int ch = lane + 32 * i;
     if (ch < chunks) {
       unpack8(__ldg(xr + ch), v[i]);
@@ -777,7 +780,7 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const bf16* __restr
   const float mean = sum / (float)C;
   float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < CPL; ++i) {
     const int ch = lane + 32 * i;
     if (ch < chunks) {
 #pragma unroll
@@ -787,7 +790,7 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const bf16* __restr
   sq = warp_sum(sq);
   const float rstd = rsqrtf(sq / (float)C + eps);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < CPL; ++i) {
     const int ch = lane + 32 * i;
     if (ch < chunks) {
       float o[8];
@@ -809,7 +812,16 @@ int layernorm_rows_launch(const bf16* x, bf16* y, const float* gamma, const floa
     return check_launch("layernorm_rows_split");
   }
   B2E_REQUIRE(C % 8 == 0 && C <= 2048, B2E_UNSUPPORTED_SHAPE, "layernorm: unsupported width %d", C);
-  launch_pdl(layernorm_rows_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, st, x, y, gamma, beta, rows, C, eps);
+  const dim3 grid((unsigned)((rows + 7) / 8));
+  const int cpl = (C / 8 + 31) / 32;
+  switch (cpl) {
+    case 1: launch_pdl(layernorm_rows_kernel<1>, grid, dim3(256), 0, st, x, y, gamma, beta, rows, C, eps); break;
+    case 2: launch_pdl(layernorm_rows_kernel<2>, grid, dim3(256), 0, st, x, y, gamma, beta, rows, C, eps); break;
+    case 3: launch_pdl(layernorm_rows_kernel<3>, grid, dim3(256), 0, st, x, y, gamma, beta, rows, C, eps); break;
+    case 4: launch_pdl(layernorm_rows_kernel<4>, grid, dim3(256), 0, st, x, y, gamma, beta, rows, C, eps); break;
+    case 5: launch_pdl(layernorm_rows_kernel<5>, grid, dim3(256), 0, st, x, y, gamma, beta, rows, C, eps); break;
+    default: launch_pdl(layernorm_rows_kernel<8>, grid, dim3(256), 0, st, x, y, gamma, beta, rows, C, eps); break;
+  }
   return check_launch("layernorm_rows");
 }
 
