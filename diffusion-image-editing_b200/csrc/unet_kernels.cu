@@ -1196,8 +1196,33 @@ __global__ void transpose_window_kernel(const bf16* __restrict__ src, bf16* __re
   for (int i = threadIdx.y; i < 32; i += blockDim.y) d[(int64_t)(c0 + i) * R + r0 + threadIdx.x] = tile[threadIdx.x][i];
 }
 
+// 64 x 64 tiles moved as 32-bit words (two adjacent columns): every warp access is 128 contiguous bytes on both sides
+// (the 32 x 32 two-byte version ran at 1.9 TB/s on the 4096 x 4096 attention matrices of the decoder backward pass)
+__global__ void __launch_bounds__(256) transpose_window64_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int R,
+                                                                 int Cc, int src_pitch, int col0) {
+  pdl_wait();
+  __shared__ uint32_t tile[64][33];
+  const int n = blockIdx.z, r0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 8 warps
+  const bf16* s = src + (int64_t)n * R * src_pitch + col0 + c0 + 2 * tx;
+#pragma unroll
+  for (int i = ty; i < 64; i += 8) tile[i][tx] = __ldg(reinterpret_cast<const uint32_t*>(s + (int64_t)(r0 + i) * src_pitch));
+  __syncthreads();
+  bf16* d = dst + (int64_t)n * Cc * R + r0 + 2 * tx;
+#pragma unroll
+  for (int c = ty; c < 64; c += 8) {
+    const uint32_t w0 = tile[2 * tx][c >> 1], w1 = tile[2 * tx + 1][c >> 1];
+    const uint32_t o = (c & 1) ? ((w0 >> 16) | (w1 & 0xffff0000u)) : ((w0 & 0xffffu) | (w1 << 16));
+    *reinterpret_cast<uint32_t*>(d + (int64_t)(c0 + c) * R) = o;
+  }
+}
+
 int transpose_window_launch(const bf16* src, bf16* dst, int N, int R, int Cc, int src_pitch, int col0, cudaStream_t st) {
   B2E_REQUIRE(R % 32 == 0 && Cc % 32 == 0, B2E_UNSUPPORTED_SHAPE, "transpose: R and C must be multiples of 32");
+  if (R % 64 == 0 && Cc % 64 == 0 && src_pitch % 2 == 0 && col0 % 2 == 0) {
+    launch_pdl(transpose_window64_kernel, dim3(R / 64, Cc / 64, N), dim3(256), 0, st, src, dst, R, Cc, src_pitch, col0);
+    return check_launch("transpose_window64");
+  }
   launch_pdl(transpose_window_kernel, dim3(R / 32, Cc / 32, N), dim3(32, 8), 0, st, src, dst, R, Cc, src_pitch, col0);
   return check_launch("transpose_window");
 }
