@@ -13,8 +13,12 @@
 // rescaled, i.e. no TMEM read-modify-write on the critical path.  S is double-buffered in TMEM so the tensor cores
 // compute block j+1's scores while the softmax warps work on block j.
 // Warp roles: warp 0 = TMA producer (Q once per item; K (+ V^T) tiles through an smem ring), warp 1 = TMEM allocator +
-// MMA issuer, warps 2-5 = softmax + epilogue (TMEM lane = query row).
+// MMA issuer, warps 2-9 = softmax + epilogue (TMEM lane = query row; two threads per row, 64 key columns / half of the D
+// output columns each, row maxima and sums exchanged through smem; B2E_FLASH_WARPS=4 selects one thread per row).
+// Measured (r93): SD UNet forward at batch 16 30.45 -> 30.05 ms, LDM UNet at batch 32 14.74 -> 14.61 ms - the softmax
+// warps were not the limiter the clock64 traces suggested; the remaining gap is in the MMA / TMEM hand-shakes.
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 #include "conv_igemm.cuh"
 #include "tcgen05_ptx.cuh"
@@ -35,8 +39,10 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-constexpr int kFaThreads = 192;
 constexpr int kFaBlock = 128;   // queries per item and keys per block
+// SW = softmax warps: 4 (one thread per query row, all 128 key columns) or 8 (two threads per row, 64 columns each: the
+// softmax phase is issue- / MUFU-latency-bound with one warp per scheduler, two warps per scheduler hide it)
+template <int SW> __device__ __forceinline__ void fa_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * SW) : "memory"); }
 
 template <int D>
 struct FaCfg {
@@ -47,7 +53,7 @@ struct FaCfg {
   static constexpr int kStages = D <= 128 ? 2 : 1;            // K/V ring (96 KB per stage at D = 192)
   static constexpr int kPBytes = 2 * kFaBlock * 128;          // P tile: 2 key chunks x [128 rows][128 B]
   static constexpr int kPBufs = 2;                            // double-buffered: softmax of block j+1 overlaps P V of block j
-  static constexpr int kSmemBytes = kQBytes + kStages * (kKBytes + kVBytes) + kPBufs * kPBytes + 1024 + 256;
+  static constexpr int kSmemBytes = kQBytes + kStages * (kKBytes + kVBytes) + kPBufs * kPBytes + 1024 + 256 + 1024;   // + row max / sum exchange [2][128] floats
   static constexpr int kTmemCols = 512;                       // S double buffer (2 x 128) + O (D <= 192)
   static constexpr uint32_t kSCol = 0, kOCol = 256;
 };
@@ -59,8 +65,8 @@ struct FaParams {
   bf16* out;           // [NV][Tq][D]
 };
 
-template <int D>
-__global__ void __launch_bounds__(kFaThreads, 1)
+template <int D, int SW>
+__global__ void __launch_bounds__(64 + 32 * SW, 1)
 flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                   const __grid_constant__ CUtensorMap map_v, const __grid_constant__ FaParams p) {
   using Cfg = FaCfg<D>;
@@ -81,6 +87,9 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   uint64_t* o_full = p_empty + 2;
   uint64_t* o_empty = o_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 1);
+  float* xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [2 halves][128 rows] max, then sum
+  constexpr int H = SW / 4;            // column halves per query row
+  constexpr int CW = kFaBlock / H;     // key columns per softmax thread and block
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int q_blocks = p.Tq / kFaBlock, n_kb = p.Tk / kFaBlock;
@@ -89,10 +98,10 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_q); prefetch_tmap(&map_k); prefetch_tmap(&map_v);
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(kv_full + s, 1); mbar_init(kv_empty + s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(s_full + s, 1); mbar_init(s_empty + s, 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(s_full + s, 1); mbar_init(s_empty + s, SW); }
     mbar_init(q_full, 1); mbar_init(q_empty, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(p_full + s, 1); mbar_init(p_empty + s, 1); }
-    mbar_init(o_full, 1); mbar_init(o_empty, 4);
+    mbar_init(o_full, 1); mbar_init(o_empty, SW);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -223,7 +232,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     }
   } else {
     // ===== softmax + epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 ; thread = one query row
-    const int q = warp & 3;
+    const int q = warp & 3;              // TMEM lane quadrant this warp may read (warp id % 4)
+    const int half = (warp - 2) >> 2;    // column half of the row this thread owns (always 0 with four softmax warps)
     const int r = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t g = 0, pj = 0;
@@ -239,25 +249,32 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         mbar_wait(s_full + b, (g >> 1) & 1);
         tc_fence_after();
         const int k0 = j * kFaBlock;
-        uint32_t sr[4][32];
+        uint32_t sr[CW / 32][32];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld32_nowait(lane_addr + Cfg::kSCol + b * kFaBlock + c * 32, sr[c]);
+        for (int c = 0; c < CW / 32; ++c) tmem_ld32_nowait(lane_addr + Cfg::kSCol + b * kFaBlock + half * CW + c * 32, sr[c]);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(s_empty + b);   // the scores are in registers: hand the buffer back
-        if (k0 + kFaBlock <= lim) {
+        const int kc0 = k0 + half * CW;            // first key of this thread's columns
+        if (kc0 + CW <= lim) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
+          for (int c = 0; c < CW / 32; ++c)
 #pragma unroll
             for (int e = 0; e < 32; ++e) m = fmaxf(m, __uint_as_float(sr[c][e]));
         } else {
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
+          for (int c = 0; c < CW / 32; ++c)
 #pragma unroll
             for (int e = 0; e < 32; ++e)
-              if (k0 + c * 32 + e < lim) m = fmaxf(m, __uint_as_float(sr[c][e]));
+              if (kc0 + c * 32 + e < lim) m = fmaxf(m, __uint_as_float(sr[c][e]));
         }
+      }
+      if (H > 1) {   // the two threads of a row exchange their maxima
+        xch[half * kFaBlock + r] = m;
+        fa_bar_sync<SW>();
+        m = fmaxf(xch[r], xch[kFaBlock + r]);
+        fa_bar_sync<SW>();   // both values read before the buffer is reused for the row sums
       }
       const float mc = m * p.scale_log2e;
       // ---- pass B: probabilities -> P tile, row sum
@@ -267,9 +284,9 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         mbar_wait(s_full + b, (g >> 1) & 1);
         tc_fence_after();
         const int k0 = j * kFaBlock;
-        uint32_t sr[4][32];
+        uint32_t sr[CW / 32][32];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld32_nowait(lane_addr + Cfg::kSCol + b * kFaBlock + c * 32, sr[c]);
+        for (int c = 0; c < CW / 32; ++c) tmem_ld32_nowait(lane_addr + Cfg::kSCol + b * kFaBlock + half * CW + c * 32, sr[c]);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
@@ -277,16 +294,17 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         const uint32_t pb = pj & 1;
         mbar_wait(p_empty + pb, ((pj >> 1) & 1) ^ 1);   // the P V that last read this P buffer has finished
         uint8_t* ptile = p_s + pb * Cfg::kPBytes;
-        const bool full_blk = k0 + kFaBlock <= lim;
+        const bool full_blk = k0 + half * CW + CW <= lim;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {   // 16 keys per step -> two 16-byte chunks of the row
+        for (int cl = 0; cl < CW / 16; ++cl) {   // 16 keys per step -> two 16-byte chunks of the row
+          const int c = half * (CW / 16) + cl;     // 16-key step index within the 128-key block
           uint4 o0, o1;
           __nv_bfloat162* ob0 = reinterpret_cast<__nv_bfloat162*>(&o0);
           __nv_bfloat162* ob1 = reinterpret_cast<__nv_bfloat162*>(&o1);
           float pe[16];
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
-            const float sc_ = __uint_as_float(sr[c >> 1][(c & 1) * 16 + e]);
+            const float sc_ = __uint_as_float(sr[cl >> 1][(cl & 1) * 16 + e]);
             float v_;
             asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(v_) : "f"(fmaf(sc_, p.scale_log2e, -mc)));   // one MUFU op
             pe[e] = (full_blk || k0 + c * 16 + e < lim) ? v_ : 0.f;
@@ -309,16 +327,22 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           *reinterpret_cast<uint4*>(row + (((j0 + 1) ^ (r & 7)) << 4)) = o1;
         }
         fence_async_smem();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
-        epi_bar_sync();
+        fa_bar_sync<SW>();
         if (warp == 2 && lane == 0) mbar_arrive(p_full + pb);
       }
-      // ---- epilogue: O / l -> bf16 -> global
+      if (H > 1) {   // the two threads of a row add their partial sums
+        xch[half * kFaBlock + r] = l;
+        fa_bar_sync<SW>();
+        l = xch[r] + xch[kFaBlock + r];
+        fa_bar_sync<SW>();
+      }
+      // ---- epilogue: O / l -> bf16 -> global (the halves split the D columns)
       mbar_wait(o_full, it & 1);
       tc_fence_after();
       const float inv = 1.f / l;
       bf16* orow = p.out + ((int64_t)v * p.Tq + qb * kFaBlock + r) * D;
 #pragma unroll 1
-      for (int c = 0; c < D / 16; ++c) {
+      for (int c = half * (D / 16 / H); c < (half + 1) * (D / 16 / H); ++c) {
         float ov[16];
         tmem_ld16(lane_addr + Cfg::kOCol + c * 16, ov);
         uint4 o0, o1;
@@ -345,26 +369,26 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   }
 }
 
-template <int D>
+template <int D, int SW>
 static int flash_launch_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const FaParams& p, cudaStream_t st) {
   using Cfg = FaCfg<D>;
   static_assert(Cfg::kSmemBytes <= 227 * 1024, "shared memory budget");
   static bool attr_set = false;
   if (!attr_set) {
-    B2E_CUDA(cudaFuncSetAttribute(flash_attn_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    B2E_CUDA(cudaFuncSetAttribute(flash_attn_kernel<D, SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
   const int items = p.NV * (p.Tq / kFaBlock);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(items < kNumSMs ? items : kNumSMs));
-  cfg.blockDim = dim3(kFaThreads);
+  cfg.blockDim = dim3(64 + 32 * SW);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, flash_attn_kernel<D>, mq, mk, mv, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, flash_attn_kernel<D, SW>, mq, mk, mv, p);
   if (e != cudaSuccess) { set_error("flash_attn launch: %s", cudaGetErrorString(e)); return B2E_CUDA_ERROR; }
   return check_launch("flash_attn");
 }
@@ -399,10 +423,19 @@ int flash_attn_launch(const FlashPlan& pl, int valid_k, float scale, cudaStream_
   B2E_REQUIRE(valid_k >= 1 && valid_k <= pl.Tk, B2E_INVALID_ARG, "flash_attn: valid_k %d of %d", valid_k, pl.Tk);
   FaParams p;
   p.NV = pl.NV; p.Tq = pl.Tq; p.Tk = pl.Tk; p.valid_k = valid_k; p.causal = causal; p.scale_log2e = scale * 1.4426950408889634f; p.out = pl.out;
+  // B2E_FLASH_WARPS=4: one softmax thread per query row (the original layout); default 8: two threads per row
+  static const int sw = getenv("B2E_FLASH_WARPS") ? atoi(getenv("B2E_FLASH_WARPS")) : 8;
+  if (sw == 8) {
+    switch (pl.D) {
+      case 64: return flash_launch_t<64, 8>(pl.map_q, pl.map_k, pl.map_v, p, st);
+      case 128: return flash_launch_t<128, 8>(pl.map_q, pl.map_k, pl.map_v, p, st);
+      default: return flash_launch_t<192, 8>(pl.map_q, pl.map_k, pl.map_v, p, st);
+    }
+  }
   switch (pl.D) {
-    case 64: return flash_launch_t<64>(pl.map_q, pl.map_k, pl.map_v, p, st);
-    case 128: return flash_launch_t<128>(pl.map_q, pl.map_k, pl.map_v, p, st);
-    default: return flash_launch_t<192>(pl.map_q, pl.map_k, pl.map_v, p, st);
+    case 64: return flash_launch_t<64, 4>(pl.map_q, pl.map_k, pl.map_v, p, st);
+    case 128: return flash_launch_t<128, 4>(pl.map_q, pl.map_k, pl.map_v, p, st);
+    default: return flash_launch_t<192, 4>(pl.map_q, pl.map_k, pl.map_v, p, st);
   }
 }
 
