@@ -128,7 +128,9 @@ class SegDiffEditPipeline:
         output_type="tensor" (extension): the final sample tensor and the x0 history as tensors.
         x0_history_out (extension, with output_type="tensor"): a pinned host tensor (steps, B, C, H, W); every step's x0
         prediction is copied into it on a side stream while the next step computes (the device->host traffic of the
-        history - 6.6 MB per step at batch 8 - leaves the critical path); the returned history are its slices."""
+        history - 6.6 MB per step at batch 8 - leaves the critical path); the returned history are its slices.  The call
+        blocks the host until the last of those copies has landed (the final decode has to be consumed anyway), so the
+        slices are safe to read as soon as it returns."""
         self.check_inputs(attr_func=attr_func, eta=eta, mask=mask, resynthesize=resynthesize, zs=zs)
         xt, zs = self.edit_noise_maps(xt, zs, mask, resynthesize)
         text_emb = self.prepare_text_emb(prompt)
@@ -148,6 +150,12 @@ class SegDiffEditPipeline:
         if x0_history_out is not None:
             if output_type != "tensor" or x0_history_out.is_cuda:
                 raise ValueError("x0_history_out needs output_type='tensor' and a host tensor")
+            n_steps = zs.shape[0] if zs is not None else len(sch.timesteps)
+            want = (xt.shape[0],) + tuple(xt.shape[1:])
+            if (x0_history_out.dtype != torch.float32 or x0_history_out.dim() != 5 or x0_history_out.shape[0] < n_steps
+                    or tuple(x0_history_out.shape[1:]) != want):
+                raise ValueError(f"x0_history_out must be a float32 host tensor of shape (>= {n_steps}, {', '.join(map(str, want))}); "
+                                 f"got {tuple(x0_history_out.shape)} {x0_history_out.dtype}")
             copy_stream = getattr(self, "_copy_stream", None)
             if copy_stream is None:
                 copy_stream = self._copy_stream = torch.cuda.Stream(device=xt.device)
@@ -186,7 +194,8 @@ class SegDiffEditPipeline:
             else:
                 x0_hist.append(x0_pred)
         if copy_stream is not None:
-            torch.cuda.current_stream().wait_stream(copy_stream)   # the history is complete when the call's work is
+            torch.cuda.current_stream().wait_stream(copy_stream)   # device order: the history precedes later work of the caller
+            copy_stream.synchronize()                              # host order: the returned slices hold their final contents
         if output_type == "tensor":
             return EditorOutput(w.decode(xt), x0_hist, eps_hist)
         img, x0_imgs = self.postprocess(xt, x0_hist)

@@ -116,7 +116,8 @@ PROTOTYPES = {
     "b2e_unet_op_desc": (C.c_char_p, [_P, _I]),
     "b2e_unet_profile": (_I, [_P, _P, _P, _P, _I64, _P, _I, C.POINTER(_I), C.POINTER(C.c_float),
                               C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_I)]),
-    "b2e_conv2d_nhwc_bf16": (_I, [_P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I, _I, _P]),
+    "b2e_act_dtype": (_I, []),
+    "b2e_conv2d_nhwc_f16": (_I, [_P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I, _I, _P]),
 }
 
 
@@ -157,3 +158,25 @@ def require_device():
             raise B2EError("no CUDA device: the b200edit operators have no CPU fallback")
         check(lib.b2e_device_check(), "b2e_device_check")
         _device_ok = True
+
+
+def fast_precision() -> str:
+    """Name of the engine's 16-bit operand type: "fp16" (default build) or "bf16" (-DB2E_ACT_BF16 build)."""
+    return "bf16" if lib.b2e_act_dtype() == 1 else "fp16"
+
+
+def resolve_precision(precision, who: str):
+    """-> (name, b2e config value).  None / "fp16" (the build's 16-bit type: fp16 operands, fp32 accumulation) or
+    "fp32" (fp32-accurate mode: split hi + lo 16-bit operands, three products per GEMM).  Asking for the 16-bit type the
+    library was NOT built for raises instead of silently computing in another precision."""
+    fast = fast_precision()
+    if precision is None:
+        precision = fast
+    if precision == "fp32":
+        return "fp32", 1
+    if precision in ("fp16", "bf16"):
+        if precision != fast:
+            raise ValueError(f"{who}: libb200edit.so is built for {fast} operands; precision={precision!r} is not available "
+                             f"(use precision=None / {fast!r} / 'fp32')")
+        return fast, 0
+    raise ValueError(f"{who}: precision must be '{fast}' or 'fp32' (got {precision!r})")

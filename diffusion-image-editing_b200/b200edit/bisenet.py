@@ -23,11 +23,16 @@ class _BiSeNetFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, image, model):
         ctx.model, ctx.shape = model, tuple(image.shape)
-        return model._forward(image)
+        out = model._forward(image)
+        ctx.gen = model._fwd_gen      # the activations of THIS forward live in the engine's single workspace
+        return out
 
     @staticmethod
     def backward(ctx, d_logits):
         m = ctx.model
+        if m._fwd_gen != ctx.gen:
+            raise _C.B2EError("BiSeNet backward: the engine ran another forward since this graph was built (its activations "
+                              "were overwritten); differentiate before the next call on the same network")
         g = d_logits.to(torch.float32).contiguous()
         dx = torch.empty(ctx.shape, dtype=torch.float32, device=g.device)
         check(lib.b2e_resnet_backward(m._h, C.c_void_p(g.data_ptr()), C.c_void_p(dx.data_ptr()), ctx.shape[0],
@@ -78,8 +83,11 @@ class BiSeNet(UNet2DModel):
         self.differentiable = bool(enable)
         return self
 
+    _fwd_gen = 0   # bumped by every forward: a backward over a stale workspace is detected (see _BiSeNetFn)
+
     def _forward(self, x):
         cfg = self.config
+        self._fwd_gen += 1
         o = torch.empty((x.shape[0], cfg.n_classes, cfg.input_size, cfg.input_size), dtype=torch.float32, device=x.device)
         check(lib.b2e_unet_forward(self._h, C.c_void_p(x.data_ptr()), None, C.c_void_p(o.data_ptr()), x.shape[0],
                                    C.c_void_p(torch.cuda.current_stream().cuda_stream)), "bisenet_forward")
@@ -136,6 +144,7 @@ class BiSeNet(UNet2DModel):
         x = image.detach().to(torch.float32).contiguous()
         outs = []
         for b0 in range(0, x.shape[0], self.max_batch):
+            self._fwd_gen += 1
             xb = x[b0:b0 + self.max_batch]
             o = torch.empty((xb.shape[0], cfg.n_classes, cfg.input_size, cfg.input_size), dtype=torch.float32, device=x.device)
             check(lib.b2e_unet_forward(self._h, C.c_void_p(xb.data_ptr()), None, C.c_void_p(o.data_ptr()), xb.shape[0],
@@ -144,4 +153,49 @@ class BiSeNet(UNet2DModel):
         return (outs[0] if len(outs) == 1 else torch.cat(outs), None, None)
 
     def eval(self):
+        return self
+
+
+class MultiResBiSeNet:
+    """ONE face parser for every square input resolution - the reference's BiSeNet is fully convolutional, and its
+    workflow shares one ``SegmentationModel`` between mask creation (512x512, src/models.py:113-118) and ``NetAttrFunc``
+    (the decoded 256x256 image goes straight into ``segmentation_model.net``, src/attr_functions.py:213-215).  The
+    engine plans its buffers per resolution, so this wrapper keeps one engine per input size (built on first use, same
+    weights) and enables the native input gradient on an engine the first time it is differentiated through."""
+
+    def __init__(self, n_classes=19, max_batch=1, device="cuda", seed=0):
+        self.n_classes, self.max_batch, self.device, self.seed = n_classes, int(max_batch), device, seed
+        self._folded = None      # engine-format state dict (BatchNorm folded); None -> seeded random init
+        self._engines = {}
+
+    def load_reference_state_dict(self, sd, eps=1e-5):
+        self._folded = BiSeNet.fold_reference_state_dict(sd, eps)
+        for e in self._engines.values():
+            e.load_state_dict(self._folded)
+        return self
+
+    def engine(self, size: int, grad: bool = False) -> BiSeNet:
+        e = self._engines.get(size)
+        if e is None:
+            if size % 32 or size < 64:
+                raise ValueError(f"BiSeNet: input resolution must be a multiple of 32 and >= 64 (got {size})")
+            e = BiSeNet(self.n_classes, size, max_batch=self.max_batch, device=self.device)
+            if self._folded is not None:
+                e.load_state_dict(self._folded)
+            else:
+                e.init_random(self.seed)
+            self._engines[size] = e
+        if grad and not e.differentiable:
+            e.enable_grad()
+        return e
+
+    def __call__(self, image):
+        if image.dim() != 4 or image.shape[1] != 3 or image.shape[-1] != image.shape[-2]:
+            raise ValueError(f"BiSeNet: expected (B,3,S,S), got {tuple(image.shape)}")
+        return self.engine(int(image.shape[-1]), grad=image.requires_grad and torch.is_grad_enabled())(image)
+
+    def eval(self):
+        return self
+
+    def to(self, *a, **k):
         return self

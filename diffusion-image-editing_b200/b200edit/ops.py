@@ -400,14 +400,21 @@ def morphology2d(x, weight, op: str, soft_max=False, beta=20.0):
     return out
 
 
-def conv2d_nhwc_bf16(x, w, bias, stride=1, residual=None):
-    """Test hook for the tcgen05 implicit-GEMM convolution (optionally + residual, bf16 NHWC)."""
+def act_dtype():
+    """torch dtype of the engine's 16-bit activations / tensor-core operands (fp16 unless built with -DB2E_ACT_BF16)."""
+    return torch.bfloat16 if lib.b2e_act_dtype() == 1 else torch.float16
+
+
+def conv2d_nhwc_f16(x, w, bias, stride=1, residual=None):
+    """Test hook for the tcgen05 implicit-GEMM convolution (optionally + residual; 16-bit NHWC, `act_dtype()`)."""
     _C.require_device()
     N, H, W, Cin = x.shape
     Cout, _, k, _ = w.shape
-    out = torch.empty((N, H // stride, W // stride, Cout), dtype=torch.bfloat16, device=x.device)
-    check(lib.b2e_conv2d_nhwc_bf16(_p(x.contiguous()), _p(w.contiguous().float()),
+    if x.dtype != act_dtype() or (residual is not None and residual.dtype != act_dtype()):
+        raise ValueError(f"conv2d_nhwc_f16: operands must be {act_dtype()}")
+    out = torch.empty((N, H // stride, W // stride, Cout), dtype=act_dtype(), device=x.device)
+    check(lib.b2e_conv2d_nhwc_f16(_p(x.contiguous()), _p(w.contiguous().float()),
                                    _p(bias.contiguous().float()) if bias is not None else None,
                                    _p(residual.contiguous()) if residual is not None else None, _p(out), N, H, W,
-                                   Cin, Cout, k, stride, _stream()), "conv2d_nhwc_bf16")
+                                   Cin, Cout, k, stride, _stream()), "conv2d_nhwc_f16")
     return out

@@ -23,11 +23,16 @@ class _ResNetFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, image, model):
         ctx.model, ctx.shape = model, tuple(image.shape)
-        return model._forward(image)
+        out = model._forward(image)
+        ctx.gen = model._fwd_gen      # the activations of THIS forward live in the engine's single workspace
+        return out
 
     @staticmethod
     def backward(ctx, d_logits):
         m = ctx.model
+        if m._fwd_gen != ctx.gen:
+            raise _C.B2EError("ResNet backward: the engine ran another forward since this graph was built (its activations "
+                              "were overwritten); differentiate before the next call on the same network")
         g = d_logits.to(torch.float32).contiguous()
         dx = torch.empty(ctx.shape, dtype=torch.float32, device=g.device)
         check(lib.b2e_resnet_backward(m._h, C.c_void_p(g.data_ptr()), C.c_void_p(dx.data_ptr()), ctx.shape[0],
@@ -90,7 +95,10 @@ class ResNet(UNet2DModel):
         return self.load_state_dict(self.fold_batchnorm(sd, eps))
 
     # ------------------------------------------------------------------ forward / backward
+    _fwd_gen = 0   # bumped by every forward: a backward over a stale workspace is detected (see _ResNetFn)
+
     def _forward(self, x):
+        self._fwd_gen += 1
         logits = torch.empty((x.shape[0], self.config.num_classes), dtype=torch.float32, device=x.device)
         check(lib.b2e_unet_forward(self._h, C.c_void_p(x.data_ptr()), None, C.c_void_p(logits.data_ptr()), x.shape[0],
                                    C.c_void_p(torch.cuda.current_stream().cuda_stream)), "resnet_forward")

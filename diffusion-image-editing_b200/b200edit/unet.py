@@ -45,14 +45,12 @@ class UNet2DModel:
                  block_out_channels=(128, 128, 256, 256, 512, 512), layers_per_block=2,
                  down_block_types=None, up_block_types=None, norm_num_groups=32, norm_eps=1e-6,
                  attention_head_dim=None, flip_sin_to_cos=False, freq_shift=1, downsample_padding=0,
-                 max_batch=8, device="cuda", precision="bf16"):
-        """precision: "bf16" (default: bf16 operands, fp32 accumulation) or "fp32" (fp32-accurate mode: split-bf16
+                 max_batch=8, device="cuda", precision=None):
+        """precision: None / "fp16" (default: fp16 operands, fp32 accumulation) or "fp32" (fp32-accurate mode: split-f16
         operands hi + lo on the same tcgen05 kernels, three products per GEMM; meets the 1e-4 bar of the fp32
-        reference at about a third of the bf16 throughput)."""
+        reference at about a third of the fp16 throughput)."""
         _C.require_device()
-        if precision not in ("bf16", "fp32"):
-            raise ValueError(f"UNet2DModel: precision must be 'bf16' or 'fp32' (got {precision!r})")
-        self.precision = precision
+        self.precision, self._precision_cfg = _C.resolve_precision(precision, "UNet2DModel")
         n = len(block_out_channels)
         down_block_types = tuple(down_block_types or ("DownBlock2D",) * n)
         up_block_types = tuple(up_block_types or ("UpBlock2D",) * n)
@@ -76,7 +74,7 @@ class UNet2DModel:
         cfg.attention_head_dim = int(attention_head_dim or 0)
         cfg.flip_sin_to_cos, cfg.freq_shift = int(flip_sin_to_cos), float(freq_shift)
         cfg.downsample_padding = int(downsample_padding)
-        cfg.precision = 1 if precision == "fp32" else 0
+        cfg.precision = self._precision_cfg
         h = C.c_void_p()
         with torch.cuda.device(self.device):
             check(lib.b2e_unet_create(C.byref(cfg), self.max_batch, C.byref(h)), "unet_create")

@@ -21,11 +21,9 @@ SD15_CONFIG = dict(sample_size=64, in_channels=4, out_channels=4, block_out_chan
 class UNet2DConditionModel(UNet2DModel):
     def __init__(self, sample_size=64, in_channels=4, out_channels=4, block_out_channels=(320, 640, 1280, 1280),
                  layers_per_block=2, cross_attention_dim=768, attention_head_dim=8, norm_num_groups=32, norm_eps=1e-5,
-                 down_block_types=None, up_block_types=None, max_batch=2, device="cuda", precision="bf16"):
+                 down_block_types=None, up_block_types=None, max_batch=2, device="cuda", precision=None):
         _C.require_device()
-        if precision not in ("bf16", "fp32"):
-            raise ValueError(f"UNet2DConditionModel: precision must be 'bf16' or 'fp32' (got {precision!r})")
-        self.precision = precision
+        self.precision, self._precision_cfg = _C.resolve_precision(precision, "UNet2DConditionModel")
         n = len(block_out_channels)
         down_block_types = tuple(down_block_types or ("CrossAttnDownBlock2D",) * (n - 1) + ("DownBlock2D",))
         up_block_types = tuple(up_block_types or ("UpBlock2D",) + ("CrossAttnUpBlock2D",) * (n - 1))
@@ -49,7 +47,7 @@ class UNet2DConditionModel(UNet2DModel):
         cfg.attention_head_dim = 0
         cfg.flip_sin_to_cos, cfg.freq_shift, cfg.downsample_padding = 1, 0.0, 1
         cfg.cross_attention_dim, cfg.num_attention_heads = cross_attention_dim, attention_head_dim   # SD 1.x: 8 heads
-        cfg.precision = 1 if precision == "fp32" else 0   # fp32-accurate mode: split-bf16 operands, fp32 attention
+        cfg.precision = self._precision_cfg   # 1: fp32-accurate mode (split-f16 operands, fp32 attention)
         h = C.c_void_p()
         with torch.cuda.device(self.device):
             check(lib.b2e_unet_create(C.byref(cfg), self.max_batch, C.byref(h)), "unet_create")

@@ -29,11 +29,16 @@ class _DecodeFn(torch.autograd.Function):
     def forward(ctx, latent, model):
         ctx.model = model
         ctx.B = latent.shape[0]
-        return model._forward(latent)
+        out = model._forward(latent)
+        ctx.gen = model._fwd_gen      # the activations of THIS forward live in the engine's single workspace
+        return out
 
     @staticmethod
     def backward(ctx, grad_img):
         m = ctx.model
+        if m._fwd_gen != ctx.gen:
+            raise _C.B2EError("VQModel.decode backward: the engine ran another forward since this graph was built (its "
+                              "activations were overwritten); differentiate before the next decode() on the same model")
         g = grad_img.to(torch.float32).contiguous()
         dz = torch.empty((ctx.B, m.config.latent_channels, m.config.sample_size, m.config.sample_size),
                          dtype=torch.float32, device=g.device)
@@ -115,11 +120,9 @@ class VQModel(UNet2DModel):
 
     def __init__(self, latent_channels=3, out_channels=3, block_out_channels=(128, 256, 512), layers_per_block=2,
                  norm_num_groups=32, norm_eps=1e-6, num_vq_embeddings=8192, sample_size=64, max_batch=8,
-                 device="cuda", with_encoder=False, precision="bf16"):
+                 device="cuda", with_encoder=False, precision=None):
         _C.require_device()
-        if precision not in ("bf16", "fp32"):
-            raise ValueError(f"{type(self).__name__}: precision must be 'bf16' or 'fp32' (got {precision!r})")
-        self.precision = precision
+        self.precision, self._precision_cfg = _C.resolve_precision(precision, type(self).__name__)
         n = len(block_out_channels)
         self._enc = None
         self.config = SimpleNamespace(latent_channels=latent_channels, out_channels=out_channels,
@@ -137,7 +140,7 @@ class VQModel(UNet2DModel):
             cfg.block_out_channels[i] = block_out_channels[i]
         cfg.layers_per_block, cfg.norm_num_groups, cfg.norm_eps = layers_per_block, norm_num_groups, norm_eps
         cfg.num_vq_embeddings = num_vq_embeddings
-        cfg.precision = 1 if precision == "fp32" else 0      # fp32-accurate decode: split-bf16 operands, forward only
+        cfg.precision = self._precision_cfg      # 1: fp32-accurate decode (split-f16 operands), forward only
         h = C.c_void_p()
         with torch.cuda.device(self.device):
             check(lib.b2e_vqdec_create(C.byref(cfg), self.max_batch, C.byref(h)), "vqdec_create")
@@ -180,8 +183,11 @@ class VQModel(UNet2DModel):
         self.forward_only = not enable
         return self
 
+    _fwd_gen = 0   # bumped by every forward: a backward over a stale workspace is detected (see _DecodeFn)
+
     def _forward(self, z):
         cfg = self.config
+        self._fwd_gen += 1
         img = torch.empty((z.shape[0], cfg.out_channels, self.out_size, self.out_size), dtype=torch.float32, device=z.device)
         check(lib.b2e_unet_forward(self._h, C.c_void_p(z.data_ptr()), None, C.c_void_p(img.data_ptr()), z.shape[0],
                                    C.c_void_p(torch.cuda.current_stream().cuda_stream)), "vqdec_forward")
@@ -192,6 +198,10 @@ class VQModel(UNet2DModel):
             raise NotImplementedError("VQModel.decode(force_not_quantize=True) is not on the native engine")
         if not latent.is_cuda:
             raise _C.B2EError("VQModel.decode: latent must be a CUDA tensor (no CPU fallback)")
+        cfg = self.config
+        if latent.dim() != 4 or tuple(latent.shape[1:]) != (cfg.latent_channels, cfg.sample_size, cfg.sample_size):
+            raise ValueError(f"VQModel.decode: expected (B,{cfg.latent_channels},{cfg.sample_size},{cfg.sample_size}), "
+                             f"got {tuple(latent.shape)}")
         if not self.forward_only and latent.requires_grad and torch.is_grad_enabled():
             if latent.shape[0] > self.max_batch:
                 raise ValueError(f"VQModel.decode with gradient: batch {latent.shape[0]} > max_batch {self.max_batch}")
@@ -199,12 +209,9 @@ class VQModel(UNet2DModel):
             return SimpleNamespace(sample=_DecodeFn.apply(zz, self))
         z = latent.detach().to(torch.float32).contiguous()
         B = z.shape[0]
-        cfg = self.config
-        if tuple(z.shape[1:]) != (cfg.latent_channels, cfg.sample_size, cfg.sample_size):
-            raise ValueError(f"VQModel.decode: expected (B,{cfg.latent_channels},{cfg.sample_size},{cfg.sample_size}), "
-                             f"got {tuple(z.shape)}")
         outs = []
         for b0 in range(0, B, self.max_batch):      # histories can be longer than max_batch
+            self._fwd_gen += 1
             zb = z[b0:b0 + self.max_batch]
             img = torch.empty((zb.shape[0], cfg.out_channels, self.out_size, self.out_size), dtype=torch.float32,
                               device=z.device)
@@ -252,7 +259,7 @@ class AutoencoderKL(VQModel):
 
     def __init__(self, latent_channels=4, out_channels=3, block_out_channels=(128, 256, 512, 512), layers_per_block=2,
                  norm_num_groups=32, norm_eps=1e-6, sample_size=64, max_batch=8, device="cuda", with_encoder=False,
-                 precision="bf16"):
+                 precision=None):
         super().__init__(latent_channels=latent_channels, out_channels=out_channels, block_out_channels=block_out_channels,
                          layers_per_block=layers_per_block, norm_num_groups=norm_num_groups, norm_eps=norm_eps,
                          num_vq_embeddings=0, sample_size=sample_size, max_batch=max_batch, device=device,

@@ -12,11 +12,11 @@
 //    After the taps, an optional 1x1 "residual segment" (K chunks read at the output pixel from up to
 //    two more tensors, weights appended to B along K) fuses the ResNet shortcut convolution or, with
 //    identity weights, the residual add - the epilogue never reads the residual.
-//  * B (weights, bf16 [Cout][tap][Cin | residual]) is a plain 2-D TMA tile.
-//  * one elected thread issues tcgen05.mma (UMMA 128 x BN x 16, bf16 in, fp32 accumulate in
+//  * B (weights, f16 [Cout][tap][Cin | residual]) is a plain 2-D TMA tile.
+//  * one elected thread issues tcgen05.mma (UMMA 128 x BN x 16, f16 in, fp32 accumulate in
 //    TMEM); tcgen05.commit releases smem stages / signals the epilogue through mbarriers.
 //  * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 =
-//    epilogue (tcgen05.ld TMEM -> registers, + bias + time-embedding, bf16 tile staged in 128B-swizzled
+//    epilogue (tcgen05.ld TMEM -> registers, + bias + time-embedding, f16 tile staged in 128B-swizzled
 //    smem and written with one TMA store per 64-channel slab; fp32 NCHW direct store for conv_out).  Persistent CTAs (one per SM), 6-8 stage smem ring that never drains
 //    between tiles, double-buffered TMEM accumulator so the epilogue overlaps the next main loop.
 #include "conv_igemm.cuh"
@@ -85,11 +85,12 @@ struct ConvKParams {
   const float* bias2;
   const float* temb;
   int temb_stride;
-  int out_bf16;         // 1: stage + TMA-store the bf16 NHWC tile through map_out
+  int out_f16;         // 1: stage + TMA-store the f16 NHWC tile through map_out
   float* out_f32_nchw;
   float* tile_stats;    // fused GroupNorm statistics or null
-  int relu;             // 1: ReLU before the bf16 store (classifier network)
-  int split_pitch;      // > 0: split-bf16 output (fp32-accurate mode): planes [hi | lo | hi] of split_pitch channels each
+  int relu;             // 1: ReLU before the f16 store (classifier network)
+  float acc_scale;      // accumulator * acc_scale before bias (weights packed with a power-of-two scale), 1: none
+  int split_pitch;      // > 0: split-f16 output (fp32-accurate mode): planes [hi | lo | hi] of split_pitch channels each
   long long* trace;     // B2E_TRACE: clock64 stamps of CTA 0's warp loops (halo kernels), else null
 };
 // trace regions (long long indices): MMA [0, 4*512) {iter start, A ready, B ready, issued}; producer A
@@ -170,7 +171,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     if (p.r0_chunks) prefetch_tmap(&map_r0);
     if (p.r1_chunks) prefetch_tmap(&map_r1);
     prefetch_tmap(&map_b);
-    if (p.out_bf16) prefetch_tmap(&map_out);
+    if (p.out_f16) prefetch_tmap(&map_out);
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
     // pair: the leader's tmem_empty barrier collects the 4 epilogue warps of BOTH CTAs
     for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar + s, 1); mbar_init(tmem_empty_bar + s, PAIR ? 8 : 4); }
@@ -327,7 +328,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
                   const uint64_t bdesc = make_smem_desc(b_addr + (uint32_t)(kh * Cfg::kBBytesPad));
 #pragma unroll
                   for (int k = 0; k < kConvBlockK / 16; ++k)
-                    umma_bf16_2sm(tmem_d + (uint32_t)(mt * BN), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                    umma_f16_2sm(tmem_d + (uint32_t)(mt * BN), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
                                   (g == 0 && kh == 0 && k == 0) ? 0u : 1u);
                 }
               }
@@ -365,10 +366,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
                   const uint64_t bdesc = make_smem_desc(sbase + j * Cfg::kKbBytes + kABytes);
 #pragma unroll
                   for (int k = 0; k < kConvBlockK / 16; ++k) {
-                    // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in the (addr >> 4) field
+                    // advance 16 f16 = 32 B along K inside the swizzle row: +2 in the (addr >> 4) field
                     const uint32_t accum = (kb > kb0 || j > 0 || k > 0) ? 1u : 0u;
-                    if (PAIR) umma_bf16_2sm(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accum);
-                    else umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accum);
+                    if (PAIR) umma_f16_2sm(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accum);
+                    else umma_f16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, accum);
                   }
                 }
               }
@@ -444,12 +445,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         __threadfence();
         part_row = p.split_ws + (int64_t)tile * splits * (kConvBlockM * BN) + r * 16;
       }
-      // split-bf16 output (fp32-accurate mode): the accumulator is walked twice - pass 0 stages bf16(v) (planes 0 and
-      // 2 of the output), pass 1 the remainder bf16(v - bf16(v)) (plane 1); TMEM is released after the last pass
-      const int npass = (Cfg::kSlabs > 0 && p.out_bf16 && p.split_pitch) ? 2 : 1;
+      // split-f16 output (fp32-accurate mode): the accumulator is walked twice - pass 0 stages f16(v) (planes 0 and
+      // 2 of the output), pass 1 the remainder f16(v - f16(v)) (plane 1); TMEM is released after the last pass
+      const int npass = (Cfg::kSlabs > 0 && p.out_f16 && p.split_pitch) ? 2 : 1;
 #pragma unroll 1
       for (int pass = 0; pass < npass; ++pass) {
-      if (Cfg::kSlabs > 0 && p.out_bf16) {
+      if (Cfg::kSlabs > 0 && p.out_f16) {
         // the previous tile's TMA store must have finished reading the staging buffer
         if (store_leader) tma_store_wait_read();
         epi_bar_sync();
@@ -473,7 +474,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           if (c == BN / 16 - 1 && pass == npass - 1) release_tmem();
         }
         const int col0 = tc.n_tile * BN + c * 16;
-        if (Cfg::kSlabs > 0 && p.out_bf16) {
+        if (p.acc_scale != 1.f) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] *= p.acc_scale;
+        }
+        if (Cfg::kSlabs > 0 && p.out_f16) {
           // Cout % 64 == 0 on this path (host-checked): whole chunks are in range
           if (p.bias) {
             const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
@@ -505,15 +510,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           }
           if (pass) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __fsub_rn(v[j], __bfloat162float(__float2bfloat16_rn(v[j])));
+            for (int j = 0; j < 16; ++j) v[j] = __fsub_rn(v[j], f16_to_float(float_to_f16(v[j])));
           }
           uint4 o0, o1;
-          __nv_bfloat162* ob0 = reinterpret_cast<__nv_bfloat162*>(&o0);
-          __nv_bfloat162* ob1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+          f16x2* ob0 = reinterpret_cast<f16x2*>(&o0);
+          f16x2* ob1 = reinterpret_cast<f16x2*>(&o1);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            ob0[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-            ob1[j] = __floats2bfloat162_rn(v[8 + 2 * j], v[8 + 2 * j + 1]);
+            ob0[j] = floats_to_f16x2(v[2 * j], v[2 * j + 1]);
+            ob1[j] = floats_to_f16x2(v[8 + 2 * j], v[8 + 2 * j + 1]);
           }
           // 128B-swizzled staging tile: row r, 16-byte chunk j stored at chunk (j ^ (r & 7))
           uint8_t* row = staging + (c >> 2) * (kConvBlockM * 128) + r * 128;
@@ -533,7 +538,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             }
         }
       }
-      if (Cfg::kSlabs > 0 && p.out_bf16) {
+      if (Cfg::kSlabs > 0 && p.out_f16) {
         fence_async_smem();   // generic-proxy smem writes -> visible to the TMA (async proxy)
         epi_bar_sync();
         if (store_leader) {
@@ -547,7 +552,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           tma_store_commit();
         }
         if (p.tile_stats) {
-          // GroupNorm statistics of the bf16 tile just staged: per-channel sum / sum of squares over the
+          // GroupNorm statistics of the f16 tile just staged: per-channel sum / sum of squares over the
           // rows of each image in the tile (thread = 8 channels x a group of rows; deterministic order)
           constexpr int NC = BN / 8, NG = kConvBlockM / NC, RP = kConvBlockM / NG;
           const int t = threadIdx.x - 64;
@@ -560,10 +565,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             const int row = g * RP + rr;
             const uint4 v = *reinterpret_cast<const uint4*>(staging + (j >> 3) * (kConvBlockM * 128) + row * 128 +
                                                             (((j & 7) ^ (row & 7)) << 4));
-            const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+            const f16x2* b2 = reinterpret_cast<const f16x2*>(&v);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float2 f = __bfloat1622float2(b2[e]);
+              const float2 f = f16x2_to_float2(b2[e]);
               sum[2 * e] += f.x; sq[2 * e] += f.x * f.x;
               sum[2 * e + 1] += f.y; sq[2 * e + 1] += f.y * f.y;
             }
@@ -603,8 +608,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
 }
 
 // ------------------------------------------------------------------ weight packing
-__global__ void pack_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int Cin,
-                                   int kk, int tap_width, int row_len, int col_off, int ci0, int cin_total, int lo) {
+__global__ void pack_weight_kernel(const float* __restrict__ w, f16* __restrict__ out, int Cout, int Cin,
+                                   int kk, int tap_width, int row_len, int col_off, int ci0, int cin_total, int lo,
+                                   float wscale) {
   // out[co*row_len + col_off + t*tap_width + ci] = w[(co*cin_total + ci0 + ci)*kk + t]   for ci < Cin
   const int64_t total = (int64_t)Cout * kk * Cin;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -612,17 +618,17 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, bf16* __restrict
     const int ci = (int)(i % Cin);
     const int t = (int)((i / Cin) % kk);
     const int co = (int)(i / ((int64_t)Cin * kk));
-    const float v = w[((int64_t)co * cin_total + ci0 + ci) * kk + t];
-    const bf16 hi = __float2bfloat16_rn(v);
-    // lo: the bf16-rounded remainder of the split representation v ~= hi + lo (fp32-accurate mode)
+    const float v = w[((int64_t)co * cin_total + ci0 + ci) * kk + t] * wscale;   // power of two: exact
+    const f16 hi = float_to_f16(v);
+    // lo: the f16-rounded remainder of the split representation v ~= hi + lo (fp32-accurate mode)
     out[(int64_t)co * row_len + col_off + (int64_t)t * tap_width + ci] =
-        lo ? __float2bfloat16_rn(__fsub_rn(v, __bfloat162float(hi))) : hi;
+        lo ? float_to_f16(__fsub_rn(v, f16_to_float(hi))) : hi;
   }
 }
 
 // dgrad weights: the gradient of y = conv_{k x k, stride 1, pad k/2}(x, W) w.r.t. x is the same convolution of dy with
 // W'[ci][co][t] = W[co][ci][kk-1-t]:  out[ci*row_len + col_off + t*tap_width + co] = w[(co*Cin + ci)*kk + (kk-1-t)]
-__global__ void pack_weight_dgrad_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int Cin, int kk,
+__global__ void pack_weight_dgrad_kernel(const float* __restrict__ w, f16* __restrict__ out, int Cout, int Cin, int kk,
                                          int tap_width, int row_len, int col_off) {
   const int64_t total = (int64_t)Cout * kk * Cin;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -630,39 +636,39 @@ __global__ void pack_weight_dgrad_kernel(const float* __restrict__ w, bf16* __re
     const int t = (int)((i / Cout) % kk);
     const int ci = (int)(i / ((int64_t)Cout * kk));
     out[(int64_t)ci * row_len + col_off + (int64_t)t * tap_width + co] =
-        __float2bfloat16_rn(w[((int64_t)co * Cin + ci) * kk + (kk - 1 - t)]);
+        float_to_f16(w[((int64_t)co * Cin + ci) * kk + (kk - 1 - t)]);
   }
 }
 
 // dgrad of conv_in run as a 1x1 convolution over im2col columns: out[(t*Cin + ci)*row_len + co] = w[(co*Cin + ci)*9 + t]
-__global__ void pack_weight_im2col_T_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int Cin, int row_len,
+__global__ void pack_weight_im2col_T_kernel(const float* __restrict__ w, f16* __restrict__ out, int Cout, int Cin, int row_len,
                                             int kk) {
   const int64_t total = (int64_t)Cout * Cin * kk;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int co = (int)(i % Cout);
     const int ci = (int)((i / Cout) % Cin);
     const int t = (int)(i / ((int64_t)Cout * Cin));
-    out[(int64_t)(t * Cin + ci) * row_len + co] = __float2bfloat16_rn(w[((int64_t)co * Cin + ci) * kk + t]);
+    out[(int64_t)(t * Cin + ci) * row_len + co] = float_to_f16(w[((int64_t)co * Cin + ci) * kk + t]);
   }
 }
 
-__global__ void fill_identity_kernel(bf16* __restrict__ out, int C, int row_len, int col_off) {
+__global__ void fill_identity_kernel(f16* __restrict__ out, int C, int row_len, int col_off, float value) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < C) out[(int64_t)c * row_len + col_off + c] = __float2bfloat16_rn(1.f);
+  if (c < C) out[(int64_t)c * row_len + col_off + c] = float_to_f16(value);
 }
 
-int conv_pack_weight(const float* w, bf16* out, int Cout, int Cin, int ksize, int tap_width, int row_len,
-                     int col_off, cudaStream_t st, int ci0, int cin_total, int lo) {
+int conv_pack_weight(const float* w, f16* out, int Cout, int Cin, int ksize, int tap_width, int row_len,
+                     int col_off, cudaStream_t st, int ci0, int cin_total, int lo, float wscale) {
   const int kk = ksize * ksize;
   const int64_t total = (int64_t)Cout * kk * Cin;
   int grid = (int)((total + 255) / 256);
   if (grid > kNumSMs * 16) grid = kNumSMs * 16;
   pack_weight_kernel<<<grid, 256, 0, st>>>(w, out, Cout, Cin, kk, tap_width, row_len, col_off, ci0,
-                                           cin_total > 0 ? cin_total : Cin, lo);
+                                           cin_total > 0 ? cin_total : Cin, lo, wscale);
   return check_launch("pack_weight");
 }
 
-int conv_pack_weight_dgrad(const float* w, bf16* out, int Cout, int Cin, int ksize, int tap_width, int row_len, int col_off,
+int conv_pack_weight_dgrad(const float* w, f16* out, int Cout, int Cin, int ksize, int tap_width, int row_len, int col_off,
                            cudaStream_t st) {
   const int kk = ksize * ksize;
   const int64_t total = (int64_t)Cout * kk * Cin;
@@ -672,7 +678,7 @@ int conv_pack_weight_dgrad(const float* w, bf16* out, int Cout, int Cin, int ksi
   return check_launch("pack_weight_dgrad");
 }
 
-int conv_pack_weight_im2col_T(const float* w, bf16* out, int Cout, int Cin, int row_len, cudaStream_t st, int kk) {
+int conv_pack_weight_im2col_T(const float* w, f16* out, int Cout, int Cin, int row_len, cudaStream_t st, int kk) {
   const int64_t total = (int64_t)Cout * Cin * kk;
   int grid = (int)((total + 255) / 256);
   if (grid > kNumSMs * 16) grid = kNumSMs * 16;
@@ -680,8 +686,8 @@ int conv_pack_weight_im2col_T(const float* w, bf16* out, int Cout, int Cin, int 
   return check_launch("pack_weight_im2col_T");
 }
 
-int conv_fill_identity(bf16* out, int C, int row_len, int col_off, cudaStream_t st) {
-  fill_identity_kernel<<<(C + 255) / 256, 256, 0, st>>>(out, C, row_len, col_off);
+int conv_fill_identity(f16* out, int C, int row_len, int col_off, cudaStream_t st, float value) {
+  fill_identity_kernel<<<(C + 255) / 256, 256, 0, st>>>(out, C, row_len, col_off, value);
   return check_launch("fill_identity");
 }
 
@@ -703,7 +709,7 @@ static int encode_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t*
   auto enc = get_encode();
   B2E_REQUIRE(enc, B2E_CUDA_ERROR, "cuTensorMapEncodeTiled entry point not available");
   uint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr),
+  CUresult r = enc(m, B2E_TMA_DTYPE, (cuuint32_t)rank, const_cast<void*>(ptr),
                    (const cuuint64_t*)dims, (const cuuint64_t*)strides_bytes, (const cuuint32_t*)box,
                    (const cuuint32_t*)estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -716,7 +722,7 @@ static int encode_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t*
   return B2E_OK;
 }
 
-int tma_encode_bf16(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+int tma_encode_f16(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                     const uint32_t* box) {
   return encode_map(m, ptr, rank, dims, strides_bytes, box);
 }
@@ -761,7 +767,7 @@ ConvGeom conv_geometry(int N, int Ho, int Wo, int Cout, int ksize, int stride) {
 }
 
 // (C, W, 1, H, N) view of an NHWC tensor (stride 1) or (2C, W/2, 2, H/2, N) (stride 2), box = one tile brick
-static int encode_act_map(CUtensorMap* m, const bf16* ptr, int N, int H, int W, int C, int stride,
+static int encode_act_map(CUtensorMap* m, const f16* ptr, int N, int H, int W, int C, int stride,
                           int Wt, int Ht, int Nt, int pitch = 0, int halo = 0) {
   const uint64_t e = 2;
   uint64_t dims[5], str[4];
@@ -789,11 +795,11 @@ int conv_plan_build(ConvPlan* pl, const ConvDesc& d) {
               B2E_UNSUPPORTED_SHAPE, "conv: unsupported ksize/stride %d/%d", d.ksize, d.stride);
   B2E_REQUIRE(d.stride == 1 || (d.H % 2 == 0 && d.W % 2 == 0), B2E_UNSUPPORTED_SHAPE, "conv: stride 2 needs even H, W");
   B2E_REQUIRE(aligned16(d.s0.ptr) && (!d.s1.ptr || aligned16(d.s1.ptr)) && (!d.r0.ptr || aligned16(d.r0.ptr)) &&
-                  (!d.r1.ptr || aligned16(d.r1.ptr)) && aligned16(d.w_packed) && (!d.out_bf16 || aligned16(d.out_bf16)),
+                  (!d.r1.ptr || aligned16(d.r1.ptr)) && aligned16(d.w_packed) && (!d.out_f16 || aligned16(d.out_f16)),
               B2E_INVALID_ARG, "conv: unaligned tensor");
   B2E_REQUIRE(!d.r1.ptr || d.r0.ptr, B2E_INVALID_ARG, "conv: r1 without r0");
-  B2E_REQUIRE(!d.out_bf16 || d.Cout % 64 == 0, B2E_UNSUPPORTED_SHAPE,
-              "conv: bf16 NHWC output needs Cout %% 64 == 0 (got %d)", d.Cout);
+  B2E_REQUIRE(!d.out_f16 || d.Cout % 64 == 0, B2E_UNSUPPORTED_SHAPE,
+              "conv: f16 NHWC output needs Cout %% 64 == 0 (got %d)", d.Cout);
   ConvPlan& p = *pl;
   p.N = d.N; p.Ho = d.H / d.stride; p.Wo = d.W / d.stride; p.Cout = d.Cout; p.cout_pad = conv_cout_pad(d.Cout);
   const ConvGeom g = conv_geometry(d.N, p.Ho, p.Wo, d.Cout, d.ksize, d.stride);
@@ -819,10 +825,10 @@ int conv_plan_build(ConvPlan* pl, const ConvDesc& d) {
     p.Wt = kHaloWt; p.Ht = kHaloHt; p.Nt = 1;
     p.w_blks = p.Wo / p.Wt; p.h_blks = p.Ho / p.Ht; p.n_blks = d.N;
   }
-  B2E_REQUIRE(!d.tile_stats || (g.stats_ok && d.out_bf16), B2E_UNSUPPORTED_SHAPE,
+  B2E_REQUIRE(!d.tile_stats || (g.stats_ok && d.out_f16), B2E_UNSUPPORTED_SHAPE,
               "conv: fused GroupNorm statistics are not available for this output shape");
-  B2E_REQUIRE(d.out_planes == 1 || (d.out_planes == 3 && d.out_bf16 && !d.tile_stats), B2E_INVALID_ARG,
-              "conv: split-bf16 output needs 3 planes, an NHWC output and no fused statistics");
+  B2E_REQUIRE(d.out_planes == 1 || (d.out_planes == 3 && d.out_f16 && !d.tile_stats), B2E_INVALID_ARG,
+              "conv: split-f16 output needs 3 planes, an NHWC output and no fused statistics");
   p.split_pitch = d.out_planes == 3 ? d.Cout : 0;
   p.tile_stats = d.tile_stats;
   p.taps = d.ksize * d.ksize;
@@ -853,8 +859,8 @@ int conv_plan_build(ConvPlan* pl, const ConvDesc& d) {
   if (d.s1.ptr && (rc = encode_act_map(&p.map_a1, d.s1.ptr, d.N, d.H, d.W, d.s1.C, d.stride, p.Wt, a_ht, p.Nt, 0, p.halo ? 1 : 0))) return rc;
   if (d.r0.ptr && (rc = encode_act_map(&p.map_r0, d.r0.ptr, d.N, p.Ho, p.Wo, d.r0.C, 1, p.Wt, a_ht, p.Nt))) return rc;
   if (d.r1.ptr && (rc = encode_act_map(&p.map_r1, d.r1.ptr, d.N, p.Ho, p.Wo, d.r1.C, 1, p.Wt, a_ht, p.Nt))) return rc;
-  p.has_out_bf16 = d.out_bf16 != nullptr;
-  if (d.out_bf16 && (rc = encode_act_map(&p.map_out, d.out_bf16, d.N, p.Ho, p.Wo, d.Cout * d.out_planes, 1, p.Wt, p.Ht, p.Nt))) return rc;
+  p.has_out_f16 = d.out_f16 != nullptr;
+  if (d.out_f16 && (rc = encode_act_map(&p.map_out, d.out_f16, d.N, p.Ho, p.Wo, d.Cout * d.out_planes, 1, p.Wt, p.Ht, p.Nt))) return rc;
   const uint64_t ktot = (uint64_t)p.taps * (d.s0.C + (d.s1.ptr ? d.s1.C : 0)) + (d.r0.ptr ? d.r0.C : 0) +
                         (d.r1.ptr ? d.r1.C : 0);
   uint64_t bd[2] = {ktot, d.b_batch_rows ? (uint64_t)d.N * d.b_batch_rows : (uint64_t)p.cout_pad};
@@ -868,7 +874,7 @@ int conv_plan_build(ConvPlan* pl, const ConvDesc& d) {
   p.splits = 1;
   // (measured on B200 at batch 8: 28 -> 23 us on the 8x8 layers, +1 % on the whole step; B2E_SPLITK=0 disables)
   static const bool splitk_on = !(getenv("B2E_SPLITK") && atoi(getenv("B2E_SPLITK")) == 0);
-  if (splitk_on && !p.pair && d.split_ws && d.out_bf16 && tiles * 2 <= kNumSMs) {
+  if (splitk_on && !p.pair && d.split_ws && d.out_f16 && tiles * 2 <= kNumSMs) {
     int sp = kNumSMs / tiles;
     if (sp > num_kb / 8) sp = num_kb / 8;
     if (sp > 8) sp = 8;
@@ -913,8 +919,8 @@ static int launch_t(const ConvPlan& pl, const ConvKParams& kp, int tiles, cudaSt
 }
 
 int conv_launch(const ConvPlan& pl, const ConvEpilogue& ep, cudaStream_t st) {
-  B2E_REQUIRE(pl.has_out_bf16 || ep.out_f32_nchw, B2E_INVALID_ARG, "conv: no output");
-  B2E_REQUIRE(!(pl.has_out_bf16 && pl.block_n == 16), B2E_UNSUPPORTED_SHAPE, "conv: bf16 output with Cout <= 16");
+  B2E_REQUIRE(pl.has_out_f16 || ep.out_f32_nchw, B2E_INVALID_ARG, "conv: no output");
+  B2E_REQUIRE(!(pl.has_out_f16 && pl.block_n == 16), B2E_UNSUPPORTED_SHAPE, "conv: f16 output with Cout <= 16");
   ConvKParams kp;
   kp.N = pl.N; kp.Ho = pl.Ho; kp.Wo = pl.Wo; kp.Cout = pl.Cout;
   kp.Wt = pl.Wt; kp.Ht = pl.Ht; kp.Nt = pl.Nt; kp.w_blks = pl.w_blks; kp.h_blks = pl.h_blks;
@@ -929,10 +935,11 @@ int conv_launch(const ConvPlan& pl, const ConvEpilogue& ep, cudaStream_t st) {
   kp.debug = dbg;
   kp.splits = pl.splits; kp.split_ws = pl.split_ws; kp.split_counters = pl.split_counters;
   kp.bias = ep.bias; kp.bias2 = ep.bias2; kp.temb = ep.temb; kp.temb_stride = ep.temb_stride;
-  kp.out_bf16 = pl.has_out_bf16; kp.out_f32_nchw = pl.has_out_bf16 ? nullptr : ep.out_f32_nchw;
+  kp.out_f16 = pl.has_out_f16; kp.out_f32_nchw = pl.has_out_f16 ? nullptr : ep.out_f32_nchw;
   kp.tile_stats = pl.tile_stats;
   kp.split_pitch = pl.split_pitch;
   kp.relu = ep.relu;
+  kp.acc_scale = ep.acc_scale;
   // B2E_TRACE=<n>: the n-th halo launch (1-based) runs with clock64 tracing of CTA 0, then dumps to stderr
   kp.trace = nullptr;
   static const int trace_at = getenv("B2E_TRACE") ? atoi(getenv("B2E_TRACE")) : 0;
@@ -991,9 +998,11 @@ int conv_launch(const ConvPlan& pl, const ConvEpilogue& ep, cudaStream_t st) {
 
 using namespace b2e;
 
-// Test hook: y = conv(x) (+ residual) as bf16 NHWC; residual (N,Ho,Wo,Cout) bf16 or NULL exercises the
+extern "C" int b2e_act_dtype(void) { return kActIsBf16; }
+
+// Test hook: y = conv(x) (+ residual) as f16 NHWC; residual (N,Ho,Wo,Cout) f16 or NULL exercises the
 // identity residual segment.
-extern "C" int b2e_conv2d_nhwc_bf16(const void* x, const float* w, const float* bias, const void* residual, void* out,
+extern "C" int b2e_conv2d_nhwc_f16(const void* x, const float* w, const float* bias, const void* residual, void* out,
                                     int64_t N, int64_t H, int64_t W, int64_t Cin, int64_t Cout, int ksize, int stride,
                                     void* stream) {
   B2E_REQUIRE(x && w && out, B2E_INVALID_ARG, "conv2d: null pointer");
@@ -1001,8 +1010,8 @@ extern "C" int b2e_conv2d_nhwc_bf16(const void* x, const float* w, const float* 
   const int cout_pad = conv_cout_pad((int)Cout);
   const int kk = ksize * ksize;
   const int row_len = (int)(kk * Cin + (residual ? Cout : 0));
-  const size_t wbytes = (size_t)cout_pad * row_len * sizeof(bf16);
-  bf16* wp = nullptr;
+  const size_t wbytes = (size_t)cout_pad * row_len * sizeof(f16);
+  f16* wp = nullptr;
   B2E_CUDA(cudaMalloc(&wp, wbytes));
   // split-K scratch so that small shapes exercise the split path exactly like inside the UNet
   const size_t split_bytes = (size_t)kNumSMs * kConvBlockM * 128 * sizeof(float);
@@ -1019,10 +1028,10 @@ extern "C" int b2e_conv2d_nhwc_bf16(const void* x, const float* w, const float* 
       if (rc) break;
     }
     ConvDesc d;
-    d.s0 = ConvSrc{(const bf16*)x, (int)Cin};
-    if (residual) d.r0 = ConvSrc{(const bf16*)residual, (int)Cout};
+    d.s0 = ConvSrc{(const f16*)x, (int)Cin};
+    if (residual) d.r0 = ConvSrc{(const f16*)residual, (int)Cout};
     d.N = (int)N; d.H = (int)H; d.W = (int)W; d.ksize = ksize; d.stride = stride;
-    d.w_packed = wp; d.Cout = (int)Cout; d.out_bf16 = (bf16*)out;
+    d.w_packed = wp; d.Cout = (int)Cout; d.out_f16 = (f16*)out;
     d.split_ws = (float*)split_mem; d.split_ws_bytes = split_bytes; d.split_counters = (int*)(split_mem + split_bytes);
     ConvPlan plan;
     rc = conv_plan_build(&plan, d);

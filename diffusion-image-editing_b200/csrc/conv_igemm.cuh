@@ -1,19 +1,15 @@
 // Implicit-GEMM convolution on tcgen05 tensor cores (sm_100a): host-side plan + launcher.
 #pragma once
-#include <cuda.h>
-#include <cuda_bf16.h>
-
+#include "act_type.cuh"
 #include "common.cuh"
 
 namespace b2e {
 
-typedef __nv_bfloat16 bf16;
-
 constexpr int kConvBlockM = 128;  // output pixels per CTA tile (UMMA_M)
-constexpr int kConvBlockK = 64;   // bf16 channels per pipeline stage (one 128B swizzle row)
+constexpr int kConvBlockK = 64;   // f16 channels per pipeline stage (one 128B swizzle row)
 
 struct ConvSrc {
-  const bf16* ptr = nullptr;  // NHWC
+  const f16* ptr = nullptr;  // NHWC
   int C = 0;                  // channels used
   int pitch = 0;              // elements between consecutive pixels (0: = C); > C selects a channel window
 };
@@ -28,17 +24,17 @@ struct ConvDesc {
   int N = 0, H = 0, W = 0;
   int ksize = 3, stride = 1; // stride 1: padding ksize/2; stride 2: ksize 3, padding (0,1,0,1) ...
   int stride2_pad1 = 0;      // ... or symmetric padding 1 (UNet2DModel downsample_padding = 1)
-  const bf16* w_packed = nullptr;  // bf16 [cout_pad][row_len], row_len = k*k*(C0+C1) + Cr0 + Cr1
+  const f16* w_packed = nullptr;  // f16 [cout_pad][row_len], row_len = k*k*(C0+C1) + Cr0 + Cr1
   // batched B operand (attention: Q K^T and P V): image n uses rows [n*b_batch_rows, +Cout) of a
   // [N*b_batch_rows][row_len] matrix whose rows are b_pitch elements apart (0: shared weights / dense rows)
   int b_batch_rows = 0, b_pitch = 0;
   int Cout = 0;
-  bf16* out_bf16 = nullptr;  // NHWC (N,Ho,Wo,Cout) through TMA store; null -> fp32 NCHW output only
-  // fp32-accurate mode: 3 -> the output is written as split bf16, channel planes [hi | lo | hi] of Cout channels each
-  // (pixel pitch 3*Cout): hi = bf16(v), lo = bf16(v - hi).  A consumer convolution reads it as ONE 3*Cout-channel
+  f16* out_f16 = nullptr;  // NHWC (N,Ho,Wo,Cout) through TMA store; null -> fp32 NCHW output only
+  // fp32-accurate mode: 3 -> the output is written as split f16, channel planes [hi | lo | hi] of Cout channels each
+  // (pixel pitch 3*Cout): hi = f16(v), lo = f16(v - hi).  A consumer convolution reads it as ONE 3*Cout-channel
   // source against weights packed [W_hi | W_hi | W_lo], i.e. x_hi W_hi + x_lo W_hi + x_hi W_lo (error ~2^-17 relative)
   int out_planes = 1;
-  // optional fused GroupNorm statistics of the (bf16-rounded) output: per (tile slot, channel) sum and
+  // optional fused GroupNorm statistics of the (f16-rounded) output: per (tile slot, channel) sum and
   // sum of squares, [conv_stats_slots()][Cout][2] floats; reduced per image by gn_finalize
   float* tile_stats = nullptr;
   // optional split-K scratch shared by all layers of a model: fp32 partial tiles + per-tile arrival counters
@@ -52,7 +48,10 @@ struct ConvEpilogue {
   const float* temb = nullptr;    // [N][temb_stride], already offset to this layer's columns
   int temb_stride = 0;
   float* out_f32_nchw = nullptr;  // NCHW [N,Cout,Ho,Wo] (network output)
-  int relu = 0;                   // bf16 NHWC output: max(v, 0) before the store
+  int relu = 0;                   // f16 NHWC output: max(v, 0) before the store
+  // the accumulator is multiplied by acc_scale before bias / time embedding: 1 / wscale of weights packed with a
+  // power-of-two scale (fp32-accurate mode: keeps the lo halves of the split weights out of the fp16 subnormals)
+  float acc_scale = 1.f;
 };
 
 // Everything the kernel needs that is fixed per layer; built once at model-build time.
@@ -67,8 +66,8 @@ struct ConvPlan {
   int splits; float* split_ws; int* split_counters;
   int halo;     // 0, or MT = M tiles per CTA of the halo kernel: (8*MT)x16-pixel bricks, one halo load serves 3 vertical taps
   int pair;     // 1: SM-pair kernel (tcgen05.mma.cta_group::2, 256 x 128 tile per cluster)
-  int has_out_bf16;
-  int split_pitch;   // channels per plane of a split-bf16 output (0: plain bf16)
+  int has_out_f16;
+  int split_pitch;   // channels per plane of a split-f16 output (0: plain f16)
   float* tile_stats;
   double flops;
 };
@@ -81,8 +80,8 @@ ConvGeom conv_geometry(int N, int Ho, int Wo, int Cout, int ksize = 1, int strid
 inline int64_t conv_stats_slots(const ConvGeom& g) { return (int64_t)g.w_blks * g.h_blks * g.n_blks * g.Nt; }
 int conv_launch(const ConvPlan& plan, const ConvEpilogue& ep, cudaStream_t st);
 
-// 128B-swizzled bf16 TMA descriptor (rank <= 5); shared by the tensor-core kernels
-int tma_encode_bf16(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+// 128B-swizzled f16 TMA descriptor (rank <= 5); shared by the tensor-core kernels
+int tma_encode_f16(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                     const uint32_t* box);
 
 // Fused attention (csrc/flash_attn.cu): O = softmax(scale * Q K^T) V on head-major operands qh [NV][Tq][D],
@@ -90,24 +89,25 @@ int tma_encode_bf16(CUtensorMap* m, const void* ptr, int rank, const uint64_t* d
 struct FlashPlan {
   CUtensorMap map_q, map_k, map_v;
   int NV, Tq, Tk, D;
-  bf16* out;
+  f16* out;
   double flops;
 };
-int flash_attn_plan_build(FlashPlan* pl, const bf16* qh, const bf16* kh, const bf16* vht, bf16* oh, int NV, int Tq, int Tk, int D);
+int flash_attn_plan_build(FlashPlan* pl, const f16* qh, const f16* kh, const f16* vht, f16* oh, int NV, int Tq, int Tk, int D);
 int flash_attn_launch(const FlashPlan& pl, int valid_k, float scale, cudaStream_t st, int causal = 0);
 
-// fp32 [Cout][Cin][k][k] -> bf16 out[co*row_len + col_off + t*tap_width + ci]   (t = kh*k + kw)
+// fp32 [Cout][Cin][k][k] -> f16 out[co*row_len + col_off + t*tap_width + ci]   (t = kh*k + kw)
 // (ci0, cin_total): pack only input channels [ci0, ci0 + Cin) of a weight with cin_total input channels
-// lo = 1: pack the remainder bf16(w - bf16(w)) instead of bf16(w) (split-bf16 weights of the fp32-accurate mode)
-int conv_pack_weight(const float* w, bf16* out, int Cout, int Cin, int ksize, int tap_width, int row_len,
-                     int col_off, cudaStream_t st, int ci0 = 0, int cin_total = 0, int lo = 0);
+// lo = 1: pack the remainder f16(w - f16(w)) instead of f16(w) (split-f16 weights of the fp32-accurate mode)
+// wscale: the weights are multiplied by this power of two first (the consumer's epilogue undoes it, ConvEpilogue::acc_scale)
+int conv_pack_weight(const float* w, f16* out, int Cout, int Cin, int ksize, int tap_width, int row_len,
+                     int col_off, cudaStream_t st, int ci0 = 0, int cin_total = 0, int lo = 0, float wscale = 1.f);
 // dgrad weights (flipped taps, transposed channels): out[ci*row_len + col_off + t*tap_width + co] = w[(co*Cin+ci)*kk + kk-1-t]
-int conv_pack_weight_dgrad(const float* w, bf16* out, int Cout, int Cin, int ksize, int tap_width, int row_len, int col_off,
+int conv_pack_weight_dgrad(const float* w, f16* out, int Cout, int Cin, int ksize, int tap_width, int row_len, int col_off,
                            cudaStream_t st);
 // dgrad of the im2col conv_in: out[(t*Cin + ci)*row_len + co] = w[(co*Cin + ci)*9 + t]
 // (kk taps: 9 for the 3x3 conv_in, 49 for the 7x7 stem of the classifier network)
-int conv_pack_weight_im2col_T(const float* w, bf16* out, int Cout, int Cin, int row_len, cudaStream_t st, int kk = 9);
-// out[c*row_len + col_off + c] = 1 for c < C (identity residual segment)
-int conv_fill_identity(bf16* out, int C, int row_len, int col_off, cudaStream_t st);
+int conv_pack_weight_im2col_T(const float* w, f16* out, int Cout, int Cin, int row_len, cudaStream_t st, int kk = 9);
+// out[c*row_len + col_off + c] = value for c < C (identity residual segment)
+int conv_fill_identity(f16* out, int C, int row_len, int col_off, cudaStream_t st, float value = 1.f);
 
 }  // namespace b2e

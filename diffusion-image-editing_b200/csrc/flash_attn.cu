@@ -6,9 +6,9 @@
 //   Tq, Tk multiples of 128; only the first `valid_k` keys take part (zero-padded text / 64-token maps).
 // One persistent CTA per SM walks (v, 128-query block) work items.  Per item, two passes over the 128-key blocks:
 //   pass A:  S = Q K^T (tcgen05.mma into TMEM)  ->  row maxima (every softmax thread owns one query row: no shuffles)
-//   pass B:  S = Q K^T again -> P = exp2((S - max) * scale * log2 e) -> bf16, 128B-swizzled smem tile (the A operand of
+//   pass B:  S = Q K^T again -> P = exp2((S - max) * scale * log2 e) -> f16, 128B-swizzled smem tile (the A operand of
 //            the second GEMM) -> O += P V (TMEM accumulator, never rescaled) ; row sums in registers
-//   end:     O / rowsum -> bf16 -> global.
+//   end:     O / rowsum -> f16 -> global.
 // Recomputing Q K^T (1.5x the tensor work of the single-pass algorithm) buys an accumulator that never has to be
 // rescaled, i.e. no TMEM read-modify-write on the critical path.  S is double-buffered in TMEM so the tensor cores
 // compute block j+1's scores while the softmax warps work on block j.
@@ -62,7 +62,7 @@ struct FaParams {
   int NV, Tq, Tk, valid_k;
   int causal;          // 1: query i attends to keys <= i only (CLIP text encoder)
   float scale_log2e;   // softmax scale * log2(e)
-  bf16* out;           // [NV][Tq][D]
+  f16* out;           // [NV][Tq][D]
 };
 
 template <int D, int SW>
@@ -165,7 +165,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           const uint64_t ad = make_smem_desc(qa + c * (kFaBlock * 128)), bd = make_smem_desc(ka + c * (kFaBlock * 128));
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base + Cfg::kSCol + b * kFaBlock, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc_s,
+            umma_f16(tmem_base + Cfg::kSCol + b * kFaBlock, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc_s,
                       (c > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(s_full + b);
@@ -211,7 +211,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             const uint64_t ad = make_smem_desc(pa + kc * (kFaBlock * 128)), bd = make_smem_desc(va + kc * (D * 128));
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_bf16(tmem_base + Cfg::kOCol, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc_o,
+              umma_f16(tmem_base + Cfg::kOCol, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc_o,
                         (j > 0 || kc > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(kv_empty + st_j);   // K and V^T of block j are free
@@ -299,8 +299,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         for (int cl = 0; cl < CW / 16; ++cl) {   // 16 keys per step -> two 16-byte chunks of the row
           const int c = half * (CW / 16) + cl;     // 16-key step index within the 128-key block
           uint4 o0, o1;
-          __nv_bfloat162* ob0 = reinterpret_cast<__nv_bfloat162*>(&o0);
-          __nv_bfloat162* ob1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+          f16x2* ob0 = reinterpret_cast<f16x2*>(&o0);
+          f16x2* ob1 = reinterpret_cast<f16x2*>(&o1);
           float pe[16];
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
@@ -311,13 +311,13 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           }
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            ob0[e] = __floats2bfloat162_rn(pe[2 * e], pe[2 * e + 1]);
-            ob1[e] = __floats2bfloat162_rn(pe[8 + 2 * e], pe[8 + 2 * e + 1]);
+            ob0[e] = floats_to_f16x2(pe[2 * e], pe[2 * e + 1]);
+            ob1[e] = floats_to_f16x2(pe[8 + 2 * e], pe[8 + 2 * e + 1]);
           }
-          // the row sum uses the ROUNDED probabilities: numerator (P V with bf16 P) and denominator stay consistent
+          // the row sum uses the ROUNDED probabilities: numerator (P V with f16 P) and denominator stay consistent
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float2 f0 = __bfloat1622float2(ob0[e]), f1 = __bfloat1622float2(ob1[e]);
+            const float2 f0 = f16x2_to_float2(ob0[e]), f1 = f16x2_to_float2(ob1[e]);
             l += f0.x + f0.y + f1.x + f1.y;
           }
           // 128B-swizzled K-major tile: key chunk (c >> 2), row r, 16-byte chunk j stored at (j ^ (r & 7))
@@ -336,22 +336,22 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         l = xch[r] + xch[kFaBlock + r];
         fa_bar_sync<SW>();
       }
-      // ---- epilogue: O / l -> bf16 -> global (the halves split the D columns)
+      // ---- epilogue: O / l -> f16 -> global (the halves split the D columns)
       mbar_wait(o_full, it & 1);
       tc_fence_after();
       const float inv = 1.f / l;
-      bf16* orow = p.out + ((int64_t)v * p.Tq + qb * kFaBlock + r) * D;
+      f16* orow = p.out + ((int64_t)v * p.Tq + qb * kFaBlock + r) * D;
 #pragma unroll 1
       for (int c = half * (D / 16 / H); c < (half + 1) * (D / 16 / H); ++c) {
         float ov[16];
         tmem_ld16(lane_addr + Cfg::kOCol + c * 16, ov);
         uint4 o0, o1;
-        __nv_bfloat162* ob0 = reinterpret_cast<__nv_bfloat162*>(&o0);
-        __nv_bfloat162* ob1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+        f16x2* ob0 = reinterpret_cast<f16x2*>(&o0);
+        f16x2* ob1 = reinterpret_cast<f16x2*>(&o1);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          ob0[e] = __floats2bfloat162_rn(ov[2 * e] * inv, ov[2 * e + 1] * inv);
-          ob1[e] = __floats2bfloat162_rn(ov[8 + 2 * e] * inv, ov[8 + 2 * e + 1] * inv);
+          ob0[e] = floats_to_f16x2(ov[2 * e] * inv, ov[2 * e + 1] * inv);
+          ob1[e] = floats_to_f16x2(ov[8 + 2 * e] * inv, ov[8 + 2 * e + 1] * inv);
         }
         *reinterpret_cast<uint4*>(orow + c * 16) = o0;
         *reinterpret_cast<uint4*>(orow + c * 16 + 8) = o1;
@@ -393,26 +393,26 @@ static int flash_launch_t(const CUtensorMap& mq, const CUtensorMap& mk, const CU
   return check_launch("flash_attn");
 }
 
-int flash_attn_plan_build(FlashPlan* pl, const bf16* qh, const bf16* kh, const bf16* vht, bf16* oh, int NV, int Tq, int Tk, int D) {
+int flash_attn_plan_build(FlashPlan* pl, const f16* qh, const f16* kh, const f16* vht, f16* oh, int NV, int Tq, int Tk, int D) {
   B2E_REQUIRE((D == 64 || D == 128 || D == 192) && Tq % kFaBlock == 0 && Tk % kFaBlock == 0 && NV >= 1, B2E_UNSUPPORTED_SHAPE,
               "flash_attn: unsupported shape NV %d Tq %d Tk %d D %d", NV, Tq, Tk, D);
   pl->NV = NV; pl->Tq = Tq; pl->Tk = Tk; pl->D = D; pl->out = oh;
   {
     uint64_t dims[2] = {(uint64_t)D, (uint64_t)NV * Tq}, str[1] = {(uint64_t)D * 2};
     uint32_t box[2] = {64, (uint32_t)kFaBlock};
-    int rc = tma_encode_bf16(&pl->map_q, qh, 2, dims, str, box);
+    int rc = tma_encode_f16(&pl->map_q, qh, 2, dims, str, box);
     if (rc) return rc;
   }
   {
     uint64_t dims[2] = {(uint64_t)D, (uint64_t)NV * Tk}, str[1] = {(uint64_t)D * 2};
     uint32_t box[2] = {64, (uint32_t)kFaBlock};
-    int rc = tma_encode_bf16(&pl->map_k, kh, 2, dims, str, box);
+    int rc = tma_encode_f16(&pl->map_k, kh, 2, dims, str, box);
     if (rc) return rc;
   }
   {
     uint64_t dims[2] = {(uint64_t)Tk, (uint64_t)NV * D}, str[1] = {(uint64_t)Tk * 2};
     uint32_t box[2] = {64, (uint32_t)D};
-    int rc = tma_encode_bf16(&pl->map_v, vht, 2, dims, str, box);
+    int rc = tma_encode_f16(&pl->map_v, vht, 2, dims, str, box);
     if (rc) return rc;
   }
   pl->flops = 4.0 * NV * (double)Tq * Tk * D;

@@ -1,7 +1,7 @@
 // Kernels around the tcgen05 convolutions of the classifier network of ClassifierAttrFunc (torchvision ResNet,
 // src/models.py:69-77, src/attr_functions.py:222-257): stem im2col (7x7 stride 2) and its col2im gradient, 3x3 stride-2
 // max pooling forward / backward, ReLU backward, stride-2 subsampling / zero insertion (stride-2 convolution gradients),
-// global average pooling + fully connected head forward / backward.  Activations are bf16 NHWC, BatchNorm (eval) is
+// global average pooling + fully connected head forward / backward.  Activations are f16 NHWC, BatchNorm (eval) is
 // folded into the convolution weights and biases by the host, ReLU is fused into the convolution epilogue.
 #include "unet_kernels.cuh"
 
@@ -9,15 +9,15 @@ namespace b2e {
 
 namespace {
 __device__ __forceinline__ void unpack8r(const uint4& v, float* f) {
-  const __nv_bfloat162* b = reinterpret_cast<const __nv_bfloat162*>(&v);
+  const f16x2* b = reinterpret_cast<const f16x2*>(&v);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) { const float2 t = __bfloat1622float2(b[j]); f[2 * j] = t.x; f[2 * j + 1] = t.y; }
+  for (int j = 0; j < 4; ++j) { const float2 t = f16x2_to_float2(b[j]); f[2 * j] = t.x; f[2 * j + 1] = t.y; }
 }
 __device__ __forceinline__ uint4 pack8r(const float* f) {
   uint4 v;
-  __nv_bfloat162* b = reinterpret_cast<__nv_bfloat162*>(&v);
+  f16x2* b = reinterpret_cast<f16x2*>(&v);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) b[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+  for (int j = 0; j < 4; ++j) b[j] = floats_to_f16x2(f[2 * j], f[2 * j + 1]);
   return v;
 }
 inline int grid_for(int64_t total, int per_sm = 32) {
@@ -27,8 +27,8 @@ inline int grid_for(int64_t total, int per_sm = 32) {
 }
 }  // namespace
 
-// ---- stem: x fp32 NCHW (B,C,H,W) -> bf16 (B,H/2,W/2,KP): column (kh*7 + kw)*C + c = x[c][2oh + kh - 3][2ow + kw - 3]
-__global__ void __launch_bounds__(256) im2col7s2_kernel(const float* __restrict__ x, bf16* __restrict__ out, int B, int C, int H,
+// ---- stem: x fp32 NCHW (B,C,H,W) -> f16 (B,H/2,W/2,KP): column (kh*7 + kw)*C + c = x[c][2oh + kh - 3][2ow + kw - 3]
+__global__ void __launch_bounds__(256) im2col7s2_kernel(const float* __restrict__ x, f16* __restrict__ out, int B, int C, int H,
                                                         int W, int KP) {
   pdl_wait();
   const int Ho = H / 2, Wo = W / 2, slots = KP / 8, cols = 49 * C;
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) im2col7s2_kernel(const float* __restrict_
   }
 }
 
-int im2col7s2_launch(const float* x, bf16* out, int B, int C, int H, int W, int KP, cudaStream_t st) {
+int im2col7s2_launch(const float* x, f16* out, int B, int C, int H, int W, int KP, cudaStream_t st) {
   B2E_REQUIRE(49 * C <= KP && KP % 64 == 0 && H % 2 == 0 && W % 2 == 0, B2E_UNSUPPORTED_SHAPE, "im2col7s2: bad shape");
   const int64_t total = (int64_t)B * (H / 2) * (W / 2) * (KP / 8);
   launch_pdl(im2col7s2_kernel, dim3(grid_for(total)), dim3(256), 0, st, x, out, B, C, H, W, KP);
@@ -63,10 +63,11 @@ int im2col7s2_launch(const float* x, bf16* out, int B, int C, int H, int W, int 
 }
 
 // gradient of the stem w.r.t. the image: dx[b][c][ih][iw] = sum over taps with 2oh + kh - 3 = ih, 2ow + kw - 3 = iw of
-// dcols[b][oh][ow][(kh*7 + kw)*C + c]; dcols bf16 (B,H/2,W/2,KP), dx fp32 NCHW
-__global__ void __launch_bounds__(256) col2im7s2_kernel(const bf16* __restrict__ dcols, float* __restrict__ dx, int B, int C,
-                                                        int H, int W, int KP) {
+// dcols[b][oh][ow][(kh*7 + kw)*C + c]; dcols f16 (B,H/2,W/2,KP), dx fp32 NCHW
+__global__ void __launch_bounds__(256) col2im7s2_kernel(const f16* __restrict__ dcols, float* __restrict__ dx, int B, int C,
+                                                        int H, int W, int KP, const float* __restrict__ gs) {
   pdl_wait();
+  const float unscale = gs ? gs[1] : 1.f;
   const int Ho = H / 2, Wo = W / 2;
   const int64_t total = (int64_t)B * H * W;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -80,22 +81,22 @@ __global__ void __launch_bounds__(256) col2im7s2_kernel(const bf16* __restrict__
       for (int kw = (iw + 3) & 1; kw < 7; kw += 2) {
         const int ow = (iw + 3 - kw) >> 1;
         if (ow < 0 || ow >= Wo) continue;
-        const bf16* p = dcols + (((int64_t)b * Ho + oh) * Wo + ow) * KP + (kh * 7 + kw) * C;
-        for (int c = 0; c < C; ++c) acc[c] += __bfloat162float(p[c]);
+        const f16* p = dcols + (((int64_t)b * Ho + oh) * Wo + ow) * KP + (kh * 7 + kw) * C;
+        for (int c = 0; c < C; ++c) acc[c] += f16_to_float(p[c]);
       }
     }
-    for (int c = 0; c < C; ++c) dx[(((int64_t)b * C + c) * H + ih) * W + iw] = acc[c];
+    for (int c = 0; c < C; ++c) dx[(((int64_t)b * C + c) * H + ih) * W + iw] = acc[c] * unscale;
   }
 }
 
-int col2im7s2_launch(const bf16* dcols, float* dx, int B, int C, int H, int W, int KP, cudaStream_t st) {
+int col2im7s2_launch(const f16* dcols, float* dx, int B, int C, int H, int W, int KP, cudaStream_t st, const float* gs) {
   B2E_REQUIRE(C >= 1 && C <= 4 && 49 * C <= KP, B2E_UNSUPPORTED_SHAPE, "col2im7s2: bad shape");
-  launch_pdl(col2im7s2_kernel, dim3(grid_for((int64_t)B * H * W)), dim3(256), 0, st, dcols, dx, B, C, H, W, KP);
+  launch_pdl(col2im7s2_kernel, dim3(grid_for((int64_t)B * H * W)), dim3(256), 0, st, dcols, dx, B, C, H, W, KP, gs);
   return check_launch("col2im7s2");
 }
 
-// ---- max pooling 3x3, stride 2, padding 1 (bf16 NHWC); idx = position (kh*3 + kw) of the first maximum (scan order)
-__global__ void __launch_bounds__(256) maxpool3s2_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
+// ---- max pooling 3x3, stride 2, padding 1 (f16 NHWC); idx = position (kh*3 + kw) of the first maximum (scan order)
+__global__ void __launch_bounds__(256) maxpool3s2_kernel(const f16* __restrict__ x, f16* __restrict__ y,
                                                          uint8_t* __restrict__ idx, int N, int H, int W, int C8) {
   pdl_wait();
   const int Ho = H / 2, Wo = W / 2;
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(256) maxpool3s2_kernel(const bf16* __restrict_
   }
 }
 
-int maxpool3s2_launch(const bf16* x, bf16* y, uint8_t* idx, int N, int H, int W, int C, cudaStream_t st) {
+int maxpool3s2_launch(const f16* x, f16* y, uint8_t* idx, int N, int H, int W, int C, cudaStream_t st) {
   B2E_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, B2E_UNSUPPORTED_SHAPE, "maxpool: bad shape");
   const int64_t total = (int64_t)N * (H / 2) * (W / 2) * (C / 8);
   launch_pdl(maxpool3s2_kernel, dim3(grid_for(total)), dim3(256), 0, st, x, y, idx, N, H, W, C / 8);
@@ -137,8 +138,8 @@ int maxpool3s2_launch(const bf16* x, bf16* y, uint8_t* idx, int N, int H, int W,
 
 // gx[p] = (x[p] > 0) * sum over the (<= 4) windows whose recorded argmax is p of gy[window]   (the x > 0 factor is the
 // backward of the ReLU that produced x)
-__global__ void __launch_bounds__(256) maxpool3s2_bwd_kernel(const bf16* __restrict__ x, const uint8_t* __restrict__ idx,
-                                                             const bf16* __restrict__ gy, bf16* __restrict__ gx, int N, int H,
+__global__ void __launch_bounds__(256) maxpool3s2_bwd_kernel(const f16* __restrict__ x, const uint8_t* __restrict__ idx,
+                                                             const f16* __restrict__ gy, f16* __restrict__ gx, int N, int H,
                                                              int W, int C8) {
   pdl_wait();
   const int Ho = H / 2, Wo = W / 2;
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(256) maxpool3s2_bwd_kernel(const bf16* __restr
   }
 }
 
-int maxpool3s2_bwd_launch(const bf16* x, const uint8_t* idx, const bf16* gy, bf16* gx, int N, int H, int W, int C,
+int maxpool3s2_bwd_launch(const f16* x, const uint8_t* idx, const f16* gy, f16* gx, int N, int H, int W, int C,
                           cudaStream_t st) {
   const int64_t total = (int64_t)N * H * W * (C / 8);
   launch_pdl(maxpool3s2_bwd_kernel, dim3(grid_for(total)), dim3(256), 0, st, x, idx, gy, gx, N, H, W, C / 8);
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(256) relu_bwd_kernel(const uint4* __restrict__
   }
 }
 
-int relu_bwd_launch(const bf16* g, const bf16* y, bf16* out, int64_t numel, cudaStream_t st) {
+int relu_bwd_launch(const f16* g, const f16* y, f16* out, int64_t numel, cudaStream_t st) {
   B2E_REQUIRE(numel % 8 == 0, B2E_UNSUPPORTED_SHAPE, "relu_bwd: numel %% 8 != 0");
   launch_pdl(relu_bwd_kernel, dim3(grid_for(numel / 8)), dim3(256), 0, st, (const uint4*)g, (const uint4*)y, (uint4*)out, numel / 8);
   return check_launch("relu_bwd");
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(256) subsample2x_kernel(const uint4* __restric
   }
 }
 
-int subsample2x_launch(const bf16* in, bf16* out, int N, int Ho, int Wo, int C, cudaStream_t st) {
+int subsample2x_launch(const f16* in, f16* out, int N, int Ho, int Wo, int C, cudaStream_t st) {
   B2E_REQUIRE(C % 8 == 0, B2E_UNSUPPORTED_SHAPE, "subsample: C %% 8 != 0");
   launch_pdl(subsample2x_kernel, dim3(grid_for((int64_t)N * Ho * Wo * (C / 8))), dim3(256), 0, st, (const uint4*)in, (uint4*)out,
              N, Ho, Wo, C / 8);
@@ -242,7 +243,7 @@ __global__ void __launch_bounds__(256) zero_upsample2x_kernel(const uint4* __res
   }
 }
 
-int zero_upsample2x_launch(const bf16* in, bf16* out, int N, int Hi, int Wi, int C, cudaStream_t st) {
+int zero_upsample2x_launch(const f16* in, f16* out, int N, int Hi, int Wi, int C, cudaStream_t st) {
   B2E_REQUIRE(C % 8 == 0, B2E_UNSUPPORTED_SHAPE, "zero_upsample: C %% 8 != 0");
   launch_pdl(zero_upsample2x_kernel, dim3(grid_for((int64_t)N * 4 * Hi * Wi * (C / 8))), dim3(256), 0, st, (const uint4*)in,
              (uint4*)out, N, Hi, Wi, C / 8);
@@ -250,12 +251,12 @@ int zero_upsample2x_launch(const bf16* in, bf16* out, int N, int Hi, int Wi, int
 }
 
 // ---- head: global average pooling + fully connected layer
-__global__ void __launch_bounds__(256) avgpool_kernel(const bf16* __restrict__ x, float* __restrict__ feat, int HW, int C) {
+__global__ void __launch_bounds__(256) avgpool_kernel(const f16* __restrict__ x, float* __restrict__ feat, int HW, int C) {
   pdl_wait();
   const int n = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float s = 0.f;
-  for (int p = 0; p < HW; ++p) s += __bfloat162float(x[((int64_t)n * HW + p) * C + c]);
+  for (int p = 0; p < HW; ++p) s += f16_to_float(x[((int64_t)n * HW + p) * C + c]);
   feat[(int64_t)n * C + c] = s / (float)HW;
 }
 
@@ -271,7 +272,7 @@ __global__ void __launch_bounds__(256) fc_kernel(const float* __restrict__ feat,
   if (lane == 0) out[(int64_t)n * K + k] = s + b[k];
 }
 
-int avgpool_fc_launch(const bf16* x, float* feat, const float* w, const float* b, float* logits, int N, int HW, int C, int K,
+int avgpool_fc_launch(const f16* x, float* feat, const float* w, const float* b, float* logits, int N, int HW, int C, int K,
                       cudaStream_t st) {
   launch_pdl(avgpool_kernel, dim3((C + 255) / 256, N), dim3(256), 0, st, x, feat, HW, C);
   int rc = check_launch("avgpool");
@@ -283,8 +284,10 @@ int avgpool_fc_launch(const bf16* x, float* feat, const float* w, const float* b
 // backward of the head: dfeat = W^T dlogits ; g[n][p][c] = (y[n][p][c] > 0) ? dfeat[n][c] / HW : 0   (y = the ReLU output
 // the pooling read, so g is already the gradient w.r.t. the last block's pre-activation)
 __global__ void __launch_bounds__(256) fc_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ w,
-                                                     float* __restrict__ dfeat, int C, int K, float scale) {
+                                                     float* __restrict__ dfeat, int C, int K, float scale,
+                                                     const float* __restrict__ gs) {
   pdl_wait();
+  if (gs) scale *= gs[0];
   const int n = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float s = 0.f;
@@ -292,8 +295,8 @@ __global__ void __launch_bounds__(256) fc_bwd_kernel(const float* __restrict__ d
   dfeat[(int64_t)n * C + c] = s * scale;
 }
 
-__global__ void __launch_bounds__(256) avgpool_bwd_kernel(const float* __restrict__ dfeat, const bf16* __restrict__ y,
-                                                          bf16* __restrict__ g, int HW, int C8) {
+__global__ void __launch_bounds__(256) avgpool_bwd_kernel(const float* __restrict__ dfeat, const f16* __restrict__ y,
+                                                          f16* __restrict__ g, int HW, int C8) {
   pdl_wait();
   const int n = blockIdx.y;
   const int64_t total = (int64_t)HW * C8;
@@ -308,9 +311,9 @@ __global__ void __launch_bounds__(256) avgpool_bwd_kernel(const float* __restric
   }
 }
 
-int avgpool_fc_bwd_launch(const float* dlogits, const float* w, float* dfeat, const bf16* y, bf16* g, int N, int HW, int C, int K,
-                          cudaStream_t st) {
-  launch_pdl(fc_bwd_kernel, dim3((C + 255) / 256, N), dim3(256), 0, st, dlogits, w, dfeat, C, K, 1.0f / (float)HW);
+int avgpool_fc_bwd_launch(const float* dlogits, const float* w, float* dfeat, const f16* y, f16* g, int N, int HW, int C, int K,
+                          cudaStream_t st, const float* gs) {
+  launch_pdl(fc_bwd_kernel, dim3((C + 255) / 256, N), dim3(256), 0, st, dlogits, w, dfeat, C, K, 1.0f / (float)HW, gs);
   int rc = check_launch("fc_bwd");
   if (rc) return rc;
   const int64_t total = (int64_t)HW * (C / 8);
@@ -319,7 +322,7 @@ int avgpool_fc_bwd_launch(const float* dlogits, const float* w, float* dfeat, co
 }
 
 // ---- face parser (BiSeNet, src/Segmentation/model.py) helpers
-int avgpool_launch(const bf16* x, float* feat, int N, int HW, int C, cudaStream_t st) {
+int avgpool_launch(const f16* x, float* feat, int N, int HW, int C, cudaStream_t st) {
   launch_pdl(avgpool_kernel, dim3((C + 255) / 256, N), dim3(256), 0, st, x, feat, HW, C);
   return check_launch("avgpool");
 }
@@ -348,10 +351,10 @@ int fc_act_launch(const float* x, const float* w, const float* b, float* out, in
   return check_launch("fc_act");
 }
 
-// out[n][p][c] = x[n][p][c] * a[n][c] (+ b[n][c]) (+ y[n][p][c])   (channel attention / broadcast add, bf16 NHWC)
-__global__ void __launch_bounds__(256) chan_affine_kernel(const bf16* __restrict__ x, const float* __restrict__ a,
-                                                          const float* __restrict__ b, const bf16* __restrict__ y,
-                                                          bf16* __restrict__ out, int HW, int C8) {
+// out[n][p][c] = x[n][p][c] * a[n][c] (+ b[n][c]) (+ y[n][p][c])   (channel attention / broadcast add, f16 NHWC)
+__global__ void __launch_bounds__(256) chan_affine_kernel(const f16* __restrict__ x, const float* __restrict__ a,
+                                                          const float* __restrict__ b, const f16* __restrict__ y,
+                                                          f16* __restrict__ out, int HW, int C8) {
   pdl_wait();
   const int n = blockIdx.y;
   const int64_t total = (int64_t)HW * C8;
@@ -374,7 +377,7 @@ __global__ void __launch_bounds__(256) chan_affine_kernel(const bf16* __restrict
   }
 }
 
-int chan_affine_launch(const bf16* x, const float* a, const float* b, const bf16* y, bf16* out, int N, int HW, int C,
+int chan_affine_launch(const f16* x, const float* a, const float* b, const f16* y, f16* out, int N, int HW, int C,
                        cudaStream_t st) {
   B2E_REQUIRE(C % 8 == 0, B2E_UNSUPPORTED_SHAPE, "chan_affine: C %% 8 != 0");
   const int64_t total = (int64_t)HW * (C / 8);
@@ -386,7 +389,7 @@ int chan_affine_launch(const bf16* x, const float* a, const float* b, const bf16
 
 // ---- backward helpers of the face parser
 // out[n][c] = scale * sum_p x[n][p][c] * (y ? y[n][p][c] : 1)   (gradient of a per-channel attention / broadcast vector)
-__global__ void __launch_bounds__(256) chan_dot_kernel(const bf16* __restrict__ x, const bf16* __restrict__ y,
+__global__ void __launch_bounds__(256) chan_dot_kernel(const f16* __restrict__ x, const f16* __restrict__ y,
                                                        float* __restrict__ out, int HW, int C, float scale) {
   pdl_wait();
   __shared__ float red[256];
@@ -396,8 +399,8 @@ __global__ void __launch_bounds__(256) chan_dot_kernel(const bf16* __restrict__ 
   if (c < C)
     for (int p = row; p < HW; p += 8) {
       const int64_t o = ((int64_t)n * HW + p) * C + c;
-      const float xv = __bfloat162float(x[o]);
-      s += y ? xv * __bfloat162float(y[o]) : xv;
+      const float xv = f16_to_float(x[o]);
+      s += y ? xv * f16_to_float(y[o]) : xv;
     }
   red[threadIdx.x] = s;
   __syncthreads();
@@ -408,14 +411,14 @@ __global__ void __launch_bounds__(256) chan_dot_kernel(const bf16* __restrict__ 
   }
 }
 
-int chan_dot_launch(const bf16* x, const bf16* y, float* out, int N, int HW, int C, float scale, cudaStream_t st) {
+int chan_dot_launch(const f16* x, const f16* y, float* out, int N, int HW, int C, float scale, cudaStream_t st) {
   launch_pdl(chan_dot_kernel, dim3((C + 31) / 32, N), dim3(256), 0, st, x, y, out, HW, C, scale);
   return check_launch("chan_dot");
 }
 
 // out[n][c] = scale * sum_k g[n][k] * w[k][c]   (transposed 1x1 convolution on pooled vectors)
 int fc_t_launch(const float* g, const float* w, float* out, int N, int C, int K, float scale, cudaStream_t st) {
-  launch_pdl(fc_bwd_kernel, dim3((C + 255) / 256, N), dim3(256), 0, st, g, w, out, C, K, scale);
+  launch_pdl(fc_bwd_kernel, dim3((C + 255) / 256, N), dim3(256), 0, st, g, w, out, C, K, scale, (const float*)nullptr);
   return check_launch("fc_t");
 }
 
@@ -437,8 +440,8 @@ int vec_act_bwd_launch(const float* g, const float* a, float* out, int n, int mo
 
 // out[r][c] = (g[r][c] + e[r * e_pitch + e_off + c]) * (y ? y[r][c] > 0 : 1): gradient accumulation from a second
 // consumer (a channel window of a wider tensor) followed by the ReLU mask of the tensor both consumers read
-__global__ void __launch_bounds__(256) grad_merge_kernel(const bf16* __restrict__ g, const bf16* __restrict__ e, int e_pitch,
-                                                         int e_off, const bf16* __restrict__ y, bf16* __restrict__ out,
+__global__ void __launch_bounds__(256) grad_merge_kernel(const f16* __restrict__ g, const f16* __restrict__ e, int e_pitch,
+                                                         int e_off, const f16* __restrict__ y, f16* __restrict__ out,
                                                          int64_t rows, int C8) {
   pdl_wait();
   const int64_t total = rows * C8;
@@ -465,17 +468,19 @@ __global__ void __launch_bounds__(256) grad_merge_kernel(const bf16* __restrict_
   }
 }
 
-int grad_merge_launch(const bf16* g, const bf16* e, int e_pitch, int e_off, const bf16* y, bf16* out, int64_t rows, int C,
+int grad_merge_launch(const f16* g, const f16* e, int e_pitch, int e_off, const f16* y, f16* out, int64_t rows, int C,
                       cudaStream_t st) {
   B2E_REQUIRE(C % 8 == 0 && e_pitch % 8 == 0 && e_off % 8 == 0, B2E_UNSUPPORTED_SHAPE, "grad_merge: alignment");
   launch_pdl(grad_merge_kernel, dim3(grid_for(rows * (C / 8))), dim3(256), 0, st, g, e, e_pitch, e_off, y, out, rows, C / 8);
   return check_launch("grad_merge");
 }
 
-// adjoint of the align_corners bilinear upsampling: g (N,K,Ho,Wo) fp32 NCHW -> dx bf16 NHWC (N,Hi,Wi,P), channels >= K zero
-__global__ void __launch_bounds__(128) bilinear_ac_bwd_kernel(const float* __restrict__ g, bf16* __restrict__ dx, int N, int Hi,
-                                                              int Wi, int P, int K, int Ho, int Wo, float sh, float sw) {
+// adjoint of the align_corners bilinear upsampling: g (N,K,Ho,Wo) fp32 NCHW -> dx f16 NHWC (N,Hi,Wi,P), channels >= K zero
+__global__ void __launch_bounds__(128) bilinear_ac_bwd_kernel(const float* __restrict__ g, f16* __restrict__ dx, int N, int Hi,
+                                                              int Wi, int P, int K, int Ho, int Wo, float sh, float sw,
+                                                              const float* __restrict__ gs) {
   pdl_wait();
+  const float sc = gs ? gs[0] : 1.f;
   const int64_t total = (int64_t)N * Hi * Wi * K;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int k = (int)(i % K);
@@ -504,31 +509,32 @@ __global__ void __launch_bounds__(128) bilinear_ac_bwd_kernel(const float* __res
       }
       acc += wh * rowacc;
     }
-    dx[(((int64_t)n * Hi + h) * Wi + w) * P + k] = __float2bfloat16_rn(acc);
+    dx[(((int64_t)n * Hi + h) * Wi + w) * P + k] = float_to_f16(acc * sc);
   }
 }
 
-__global__ void __launch_bounds__(256) zero_tail_kernel(bf16* __restrict__ x, int64_t rows, int P, int K) {
+__global__ void __launch_bounds__(256) zero_tail_kernel(f16* __restrict__ x, int64_t rows, int P, int K) {
   pdl_wait();
   const int64_t total = rows * (P - K);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
-    x[(i / (P - K)) * P + K + i % (P - K)] = __float2bfloat16_rn(0.f);
+    x[(i / (P - K)) * P + K + i % (P - K)] = float_to_f16(0.f);
 }
 
-int bilinear_ac_bwd_launch(const float* g, bf16* dx, int N, int Hi, int Wi, int P, int K, int Ho, int Wo, cudaStream_t st) {
+int bilinear_ac_bwd_launch(const float* g, f16* dx, int N, int Hi, int Wi, int P, int K, int Ho, int Wo, cudaStream_t st,
+                           const float* gs) {
   const float sh = Ho > 1 ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f, sw = Wo > 1 ? (float)(Wi - 1) / (float)(Wo - 1) : 0.f;
   if (P > K) {
     launch_pdl(zero_tail_kernel, dim3(grid_for((int64_t)N * Hi * Wi * (P - K))), dim3(256), 0, st, dx, (int64_t)N * Hi * Wi, P, K);
     int rc = check_launch("zero_tail");
     if (rc) return rc;
   }
-  launch_pdl(bilinear_ac_bwd_kernel, dim3(grid_for((int64_t)N * Hi * Wi * K, 64)), dim3(128), 0, st, g, dx, N, Hi, Wi, P, K, Ho, Wo, sh, sw);
+  launch_pdl(bilinear_ac_bwd_kernel, dim3(grid_for((int64_t)N * Hi * Wi * K, 64)), dim3(128), 0, st, g, dx, N, Hi, Wi, P, K, Ho, Wo, sh, sw, gs);
   return check_launch("bilinear_ac_bwd");
 }
 
-// F.interpolate(x, (Ho, Wo), mode="bilinear", align_corners=True): x bf16 NHWC (N,Hi,Wi,P), first K channels ->
+// F.interpolate(x, (Ho, Wo), mode="bilinear", align_corners=True): x f16 NHWC (N,Hi,Wi,P), first K channels ->
 // out fp32 NCHW (N,K,Ho,Wo).  ATen's arithmetic: src = dst * (in-1)/(out-1); weights (1-l, l).
-__global__ void __launch_bounds__(256) bilinear_ac_kernel(const bf16* __restrict__ x, float* __restrict__ out, int N, int Hi,
+__global__ void __launch_bounds__(256) bilinear_ac_kernel(const f16* __restrict__ x, float* __restrict__ out, int N, int Hi,
                                                           int Wi, int P, int K, int Ho, int Wo, float sh, float sw) {
   pdl_wait();
   const int64_t total = (int64_t)N * Ho * Wo;
@@ -540,19 +546,19 @@ __global__ void __launch_bounds__(256) bilinear_ac_kernel(const bf16* __restrict
     const int h0 = (int)fh, w0 = (int)fw;
     const int h1 = h0 + (h0 < Hi - 1 ? 1 : 0), w1 = w0 + (w0 < Wi - 1 ? 1 : 0);
     const float lh = fh - (float)h0, lw = fw - (float)w0;
-    const bf16* p00 = x + (((int64_t)n * Hi + h0) * Wi + w0) * P;
-    const bf16* p01 = x + (((int64_t)n * Hi + h0) * Wi + w1) * P;
-    const bf16* p10 = x + (((int64_t)n * Hi + h1) * Wi + w0) * P;
-    const bf16* p11 = x + (((int64_t)n * Hi + h1) * Wi + w1) * P;
+    const f16* p00 = x + (((int64_t)n * Hi + h0) * Wi + w0) * P;
+    const f16* p01 = x + (((int64_t)n * Hi + h0) * Wi + w1) * P;
+    const f16* p10 = x + (((int64_t)n * Hi + h1) * Wi + w0) * P;
+    const f16* p11 = x + (((int64_t)n * Hi + h1) * Wi + w1) * P;
     for (int k = 0; k < K; ++k) {
-      const float v = (1.f - lh) * ((1.f - lw) * __bfloat162float(p00[k]) + lw * __bfloat162float(p01[k])) +
-                      lh * ((1.f - lw) * __bfloat162float(p10[k]) + lw * __bfloat162float(p11[k]));
+      const float v = (1.f - lh) * ((1.f - lw) * f16_to_float(p00[k]) + lw * f16_to_float(p01[k])) +
+                      lh * ((1.f - lw) * f16_to_float(p10[k]) + lw * f16_to_float(p11[k]));
       out[(((int64_t)n * K + k) * Ho + oh) * Wo + ow] = v;
     }
   }
 }
 
-int bilinear_ac_launch(const bf16* x, float* out, int N, int Hi, int Wi, int P, int K, int Ho, int Wo, cudaStream_t st) {
+int bilinear_ac_launch(const f16* x, float* out, int N, int Hi, int Wi, int P, int K, int Ho, int Wo, cudaStream_t st) {
   const float sh = Ho > 1 ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f, sw = Wo > 1 ? (float)(Wi - 1) / (float)(Wo - 1) : 0.f;
   launch_pdl(bilinear_ac_kernel, dim3(grid_for((int64_t)N * Ho * Wo)), dim3(256), 0, st, x, out, N, Hi, Wi, P, K, Ho, Wo, sh, sw);
   return check_launch("bilinear_ac");

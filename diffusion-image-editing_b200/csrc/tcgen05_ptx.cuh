@@ -1,8 +1,8 @@
 // tcgen05 / TMA / mbarrier PTX wrappers shared by the tensor-core kernels (sm_100a).
 #pragma once
-#include <cuda.h>
-#include <cuda_bf16.h>
 #include <stdint.h>
+
+#include "act_type.cuh"
 
 namespace b2e {
 
@@ -91,7 +91,7 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* ma
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "l"(kEvictNormal)
       : "memory");
 }
-__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                               uint32_t accumulate) {
   const uint32_t z = 0;
   asm volatile(
@@ -157,8 +157,8 @@ template <int COLS>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]^T ; bf16 x bf16 -> fp32
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+// D[tmem] (+)= A[smem] * B[smem]^T ; f16 x f16 -> fp32
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
       "{\n"
@@ -196,9 +196,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                   // SWIZZLE_128B
   return d;
 }
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M x N
+// kind::f16 instruction descriptor: D = f32 (bits 4-5 = 1), A / B format (bits 7-9 / 10-12: 0 = f16, 1 = bf16), both K-major, M x N
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+  return (1u << 4) | ((uint32_t)kActIsBf16 << 7) | ((uint32_t)kActIsBf16 << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 

@@ -22,7 +22,7 @@ namespace {
 
 // res_c > 0: a 1x1 residual segment of res_c channels is appended to every weight row (shortcut / identity)
 struct ConvL {
-  bf16* w = nullptr; float* b = nullptr; float* b2 = nullptr;
+  f16* w = nullptr; float* b = nullptr; float* b2 = nullptr;
   int cin = 0, cin_pad = 0, cout = 0, cout_pad = 0, k = 0, res_c = 0, row_len = 0;
   int dg = -1;   // decoder: index of the dgrad twin (flipped / transposed weights) in b2e_unet::dgrads
 };
@@ -54,7 +54,7 @@ enum NodeKind { N_RESNET, N_ATTN, N_DOWN, N_UP, N_PUSH, N_POPCAT, N_XFORMER };
 struct Node { NodeKind kind; int idx; };
 
 struct Tensor {
-  bf16* p = nullptr; int N = 0, H = 0, W = 0, C = 0; size_t bytes = 0;   // C = channel pitch (multiple of 64 for conv operands)
+  f16* p = nullptr; int N = 0, H = 0, W = 0, C = 0; size_t bytes = 0;   // C = channel pitch (multiple of 64 for conv operands)
   int Cr = 0;               // real channels (<= C)
   float* cstats = nullptr;  // per-(image, channel) sum / sum of squares from the producing conv's epilogue
   float* tstats = nullptr;  // small tensors: raw per-(tile slot, channel) statistics instead (no finalize kernel)
@@ -87,7 +87,7 @@ struct Arena {
 struct b2e_unet {
   b2e_unet_config cfg;
   int64_t max_batch = 0;
-  // fp32-accurate mode (cfg.precision == 1): PL = 3, every activation is a split-bf16 tensor with channel planes
+  // fp32-accurate mode (cfg.precision == 1): PL = 3, every activation is a split-f16 tensor with channel planes
   // [hi | lo | hi] (value = hi + lo) and every GEMM weight segment is packed [W_hi | W_hi | W_lo], so the unchanged
   // tcgen05 main loop computes x_hi W_hi + x_lo W_hi + x_hi W_lo with fp32 accumulation (~2^-17 relative error)
   int PL = 1;
@@ -180,26 +180,31 @@ struct b2e_unet {
     });
   }
   // one K segment of a weight row: `plane_w` columns per plane starting at col_off; taps are tap_w * PL columns apart
-  static int pack_w(int PL, const float* src, bf16* w, int cout, int cin, int k, int tap_w, int row_len, int col_off,
+  // fp32-accurate mode: every weight is packed times 2^10 and every convolution epilogue multiplies the accumulator by
+  // 2^-10 (ConvEpilogue::acc_scale).  Exact, and it lifts the lo halves of the split weights (|w| 2^-11 ~ 1e-5 for a
+  // typical |w| ~ 0.03) out of the fp16 subnormal range, where they would keep ~8 instead of 11 bits: the split weights
+  // then carry ~22 bits like the split activations.  |w| * 2^10 <= 65504 holds for any |w| < 64.
+  static constexpr float kSplitWScale = 1024.f;
+  static int pack_w(int PL, const float* src, f16* w, int cout, int cin, int k, int tap_w, int row_len, int col_off,
                     int plane_w, cudaStream_t st, int ci0 = 0, int cin_total = 0) {
     if (PL == 1) return conv_pack_weight(src, w, cout, cin, k, tap_w, row_len, col_off, st, ci0, cin_total);
-    int rc = conv_pack_weight(src, w, cout, cin, k, tap_w * 3, row_len, col_off, st, ci0, cin_total, 0);
-    if (!rc) rc = conv_pack_weight(src, w, cout, cin, k, tap_w * 3, row_len, col_off + plane_w, st, ci0, cin_total, 0);
-    if (!rc) rc = conv_pack_weight(src, w, cout, cin, k, tap_w * 3, row_len, col_off + 2 * plane_w, st, ci0, cin_total, 1);
+    int rc = conv_pack_weight(src, w, cout, cin, k, tap_w * 3, row_len, col_off, st, ci0, cin_total, 0, kSplitWScale);
+    if (!rc) rc = conv_pack_weight(src, w, cout, cin, k, tap_w * 3, row_len, col_off + plane_w, st, ci0, cin_total, 0, kSplitWScale);
+    if (!rc) rc = conv_pack_weight(src, w, cout, cin, k, tap_w * 3, row_len, col_off + 2 * plane_w, st, ci0, cin_total, 1, kSplitWScale);
     return rc;
   }
   // identity residual segment over the hi and lo planes (the repeated hi plane gets zero weights)
-  static int fill_id(int PL, bf16* w, int C, int row_len, int col_off, int plane_w) {
-    int rc = conv_fill_identity(w, C, row_len, col_off, 0);
-    if (!rc && PL == 3) rc = conv_fill_identity(w, C, row_len, col_off + plane_w, 0);
+  static int fill_id(int PL, f16* w, int C, int row_len, int col_off, int plane_w) {
+    int rc = conv_fill_identity(w, C, row_len, col_off, 0, PL == 3 ? kSplitWScale : 1.f);
+    if (!rc && PL == 3) rc = conv_fill_identity(w, C, row_len, col_off + plane_w, 0, kSplitWScale);
     return rc;
   }
-  // conv / linear weight that feeds the tcgen05 GEMM: packed bf16 [cout_pad][k*k][cin_pad]
+  // conv / linear weight that feeds the tcgen05 GEMM: packed f16 [cout_pad][k*k][cin_pad]
   ConvL make_conv(const std::string& name, int cin, int cout, int k, int cin_pad = 0, int res_c = 0) {
     ConvL c;
     c.cin = cin; c.cin_pad = cin_pad ? cin_pad : pad64(cin); c.cout = cout; c.k = k; c.cout_pad = conv_cout_pad(cout);
     c.res_c = res_c; c.row_len = PL * (k * k * c.cin_pad + res_c);
-    c.w = dmalloc<bf16>((size_t)c.cout_pad * c.row_len);
+    c.w = dmalloc<f16>((size_t)c.cout_pad * c.row_len);
     c.b = dmalloc<float>(c.cout_pad);
     ConvL cc = c;
     ConvL dd;
@@ -220,7 +225,7 @@ struct b2e_unet {
     ConvL d;
     d.cin = dy_pitch; d.cin_pad = dy_pitch; d.cout = cin; d.cout_pad = conv_cout_pad(cin); d.k = k;
     d.res_c = extra_k; d.row_len = k * k * dy_pitch + extra_k;
-    d.w = dmalloc<bf16>((size_t)d.cout_pad * d.row_len);
+    d.w = dmalloc<f16>((size_t)d.cout_pad * d.row_len);
     d.b = dmalloc<float>(d.cout_pad);
     dgrads.push_back(d);
     return (int)dgrads.size() - 1;
@@ -281,7 +286,7 @@ struct b2e_unet {
     ConvL c;
     c.cin = cin; c.cin_pad = pad64(cin); c.cout = cout; c.k = 1; c.cout_pad = conv_cout_pad(cout);
     c.res_c = res_c; c.row_len = PL * (c.cin_pad + res_c);
-    c.w = dmalloc<bf16>((size_t)c.cout_pad * c.row_len);
+    c.w = dmalloc<f16>((size_t)c.cout_pad * c.row_len);
     c.b = dmalloc<float>(c.cout_pad);
     ConvL cc = c;
     const int PL = this->PL;
@@ -298,11 +303,11 @@ struct b2e_unet {
     const int n = (int)names.size();
     c.cin = cin; c.cin_pad = pad64(cin); c.cout = n * cout; c.k = 1; c.cout_pad = conv_cout_pad(n * cout);
     c.row_len = c.cin_pad * PL;
-    c.w = dmalloc<bf16>((size_t)c.cout_pad * c.row_len);
+    c.w = dmalloc<f16>((size_t)c.cout_pad * c.row_len);
     c.b = dmalloc<float>(c.cout_pad);
     const int PL = this->PL;
     for (int i = 0; i < n; ++i) {
-      bf16* wdst = c.w + (size_t)i * cout * c.row_len;
+      f16* wdst = c.w + (size_t)i * cout * c.row_len;
       const int rl = c.row_len, cp = c.cin_pad;
       add_param(base + "." + names[i] + ".weight", (int64_t)cout * cin, cin, [wdst, cout, cin, rl, cp, PL](const float* src, cudaStream_t st) {
         return pack_w(PL, src, wdst, cout, cin, 1, cp, rl, 0, cp, st);
@@ -338,7 +343,7 @@ struct b2e_unet {
     a.gn = make_norm(name + ".group_norm", C);
     // q, k, v fused into one [3P][P] GEMM weight (each projection padded to P rows / columns)
     a.qkv.cin = C; a.qkv.cin_pad = P; a.qkv.cout = 3 * P; a.qkv.cout_pad = conv_cout_pad(3 * P); a.qkv.k = 1;
-    a.qkv.w = dmalloc<bf16>((size_t)a.qkv.cout_pad * P * PL);
+    a.qkv.w = dmalloc<f16>((size_t)a.qkv.cout_pad * P * PL);
     a.qkv.b = dmalloc<float>(a.qkv.cout_pad);
     const int PL = this->PL;
     const char* nm[3] = {"to_q", "to_k", "to_v"};
@@ -346,7 +351,7 @@ struct b2e_unet {
     if (decoder) { a.qkv_dg = make_dgrad(C, 2 * P, 1, P); qd = dgrads[a.qkv_dg]; }   // K = (dQ ++ dK) ++ residual segment dV
     const int qkv_dg = a.qkv_dg;
     for (int i = 0; i < 3; ++i) {
-      bf16* wdst = a.qkv.w + (size_t)i * P * P * PL;
+      f16* wdst = a.qkv.w + (size_t)i * P * P * PL;
       float* bdst = a.qkv.b + (size_t)i * P;
       add_param(name + "." + nm[i] + ".weight", (int64_t)C * C, C, [wdst, qd, qkv_dg, i, C, P, PL](const float* src, cudaStream_t st) {
         int rc = pack_w(PL, src, wdst, C, C, 1, C, P * PL, 0, P, st);
@@ -384,15 +389,16 @@ int build_model_decoder(b2e_unet* m) {
     ConvL ci;
     const int PL = m->PL;
     ci.cin = ci.cin_pad = kConvBlockK; ci.cout = top; ci.k = 1; ci.cout_pad = conv_cout_pad(top); ci.row_len = kConvBlockK * PL;
-    ci.w = m->dmalloc<bf16>((size_t)ci.cout_pad * ci.row_len);
+    ci.w = m->dmalloc<f16>((size_t)ci.cout_pad * ci.row_len);
     ci.b = m->dmalloc<float>(ci.cout_pad);
     // dgrad twin: gradient w.r.t. the 64 im2col columns (9 * L real) = 1x1 convolution with the transposed weights
     m->conv_in_dg = m->make_dgrad(kConvBlockK, ci.cout_pad, 1);
     const ConvL cd = m->dgrads[m->conv_in_dg];
     m->add_param("decoder.conv_in.weight", (int64_t)top * L * 9, (int64_t)L * 9, [ci, cd, L, PL](const float* src, cudaStream_t st) {
-      int rc = conv_pack_weight(src, ci.w, ci.cout, L, 3, L, ci.row_len, 0, st);
-      if (!rc && PL == 3) rc = conv_pack_weight(src, ci.w, ci.cout, L, 3, L, ci.row_len, kConvBlockK, st);
-      if (!rc && PL == 3) rc = conv_pack_weight(src, ci.w, ci.cout, L, 3, L, ci.row_len, 2 * kConvBlockK, st, 0, 0, 1);
+      const float ws = PL == 3 ? b2e_unet::kSplitWScale : 1.f;
+      int rc = conv_pack_weight(src, ci.w, ci.cout, L, 3, L, ci.row_len, 0, st, 0, 0, 0, ws);
+      if (!rc && PL == 3) rc = conv_pack_weight(src, ci.w, ci.cout, L, 3, L, ci.row_len, kConvBlockK, st, 0, 0, 0, ws);
+      if (!rc && PL == 3) rc = conv_pack_weight(src, ci.w, ci.cout, L, 3, L, ci.row_len, 2 * kConvBlockK, st, 0, 0, 1, ws);
       if (!rc) rc = conv_pack_weight_im2col_T(src, cd.w, ci.cout, L, cd.row_len, st);
       return rc;
     });
@@ -431,7 +437,7 @@ int build_model_encoder(b2e_unet* m) {
   {
     ConvL ci;
     ci.cin = ci.cin_pad = kConvBlockK; ci.cout = c0; ci.k = 1; ci.cout_pad = conv_cout_pad(c0); ci.row_len = kConvBlockK;
-    ci.w = m->dmalloc<bf16>((size_t)ci.cout_pad * ci.row_len);
+    ci.w = m->dmalloc<f16>((size_t)ci.cout_pad * ci.row_len);
     ci.b = m->dmalloc<float>(ci.cout_pad);
     m->add_param("encoder.conv_in.weight", (int64_t)c0 * cin * 9, (int64_t)cin * 9, [ci, cin](const float* src, cudaStream_t st) {
       return conv_pack_weight(src, ci.w, ci.cout, cin, 3, cin, ci.row_len, 0, st);
@@ -477,7 +483,7 @@ int build_model_resnet(b2e_unet* m) {
     ConvL s;
     const int KP = pad64(49 * Cin);
     s.cin = s.cin_pad = KP; s.cout = W0; s.k = 1; s.cout_pad = conv_cout_pad(W0); s.row_len = KP;
-    s.w = m->dmalloc<bf16>((size_t)s.cout_pad * KP);
+    s.w = m->dmalloc<f16>((size_t)s.cout_pad * KP);
     s.b = m->dmalloc<float>(s.cout_pad);
     m->stem_dg = m->make_dgrad(KP, s.cout_pad, 1);   // gradient w.r.t. the im2col columns
     const ConvL sd = m->dgrads[m->stem_dg];
@@ -512,7 +518,7 @@ int build_model_resnet(b2e_unet* m) {
         L.cin = cs[j].cin; L.cin_pad = pad64(cs[j].cin); L.cout = cs[j].cout; L.cout_pad = conv_cout_pad(cs[j].cout); L.k = cs[j].k;
         L.res_c = last ? pad64(inpl) : 0;
         L.row_len = L.k * L.k * L.cin_pad + L.res_c;
-        L.w = m->dmalloc<bf16>((size_t)L.cout_pad * L.row_len);
+        L.w = m->dmalloc<f16>((size_t)L.cout_pad * L.row_len);
         L.b = m->dmalloc<float>(L.cout_pad);
         // dgrad twin; the FIRST convolution's twin also carries the shortcut gradient as a residual K segment
         // (identity, or the transposed downsample weights) so that d(block input) is ONE GEMM
@@ -594,8 +600,8 @@ int build_program_resnet(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* 
   double flops = 0;
   int rc = B2E_OK;
   auto talloc = [&](int N, int H, int W, int C) {
-    Tensor t; t.N = N; t.H = H; t.W = W; t.C = C; t.Cr = C; t.bytes = (size_t)N * H * W * C * sizeof(bf16);
-    t.p = (bf16*)ar.alloc(t.bytes);
+    Tensor t; t.N = N; t.H = H; t.W = W; t.C = C; t.Cr = C; t.bytes = (size_t)N * H * W * C * sizeof(f16);
+    t.p = (f16*)ar.alloc(t.bytes);
     return t;
   };
   const size_t split_bytes = (size_t)kNumSMs * kConvBlockM * 128 * sizeof(float);
@@ -620,7 +626,7 @@ int build_program_resnet(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* 
     if (x1) d.s1 = ConvSrc{x1->p, x1->C};
     if (r0) d.r0 = ConvSrc{r0->p, r0->C};
     d.N = B; d.H = x.H; d.W = x.W; d.ksize = L.k; d.stride = stride; d.stride2_pad1 = 1;
-    d.w_packed = L.w; d.Cout = L.cout_pad; d.out_bf16 = out->p;
+    d.w_packed = L.w; d.Cout = L.cout_pad; d.out_f16 = out->p;
     d.split_ws = split_ws; d.split_ws_bytes = split_bytes; d.split_counters = split_cnt;
     ConvPlan pl;
     rc = conv_plan_build(&pl, d);
@@ -706,7 +712,7 @@ int build_program_resnet(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* 
     auto affine = [&](const Tensor& x, const float* a, const float* b, const Tensor* y, Tensor* out, const char* what) {
       *out = talloc(B, x.H, x.W, x.C);
       const Tensor xx = x, oo = *out;
-      const bf16* yp = y ? y->p : nullptr;
+      const f16* yp = y ? y->p : nullptr;
       ew([xx, a, b, yp, oo, B](cudaStream_t st) { return chan_affine_launch(xx.p, a, b, yp, oo.p, B, xx.H * xx.W, xx.C, st); },
          (y ? 3.0 : 2.0) * (double)xx.bytes, what);
     };
@@ -775,7 +781,7 @@ int build_program_resnet(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* 
       d.s0 = ConvSrc{dy.p, dy.C};
       if (r0) d.r0 = ConvSrc{r0->p, r0->C};
       d.N = B; d.H = dy.H; d.W = dy.W; d.ksize = D.k; d.stride = 1;
-      d.w_packed = D.w; d.Cout = D.cout_pad; d.out_bf16 = dx->p;
+      d.w_packed = D.w; d.Cout = D.cout_pad; d.out_f16 = dx->p;
       d.split_ws = split_ws; d.split_ws_bytes = split_bytes; d.split_counters = split_cnt;
       ConvPlan pl;
       rc = conv_plan_build(&pl, d);
@@ -786,7 +792,7 @@ int build_program_resnet(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* 
     };
     auto relu_mask = [&](Tensor& gt, const Tensor& y) {   // in place: gt *= (y > 0)
       const Tensor gg = gt, yy = y;
-      ew([gg, yy](cudaStream_t st) { return relu_bwd_launch(gg.p, yy.p, gg.p, (int64_t)(gg.bytes / sizeof(bf16)), st); }, 3.0 * (double)gt.bytes,
+      ew([gg, yy](cudaStream_t st) { return relu_bwd_launch(gg.p, yy.p, gg.p, (int64_t)(gg.bytes / sizeof(f16)), st); }, 3.0 * (double)gt.bytes,
          "relu backward");
     };
     auto zero_up = [&](const Tensor& t) {
@@ -796,12 +802,23 @@ int build_program_resnet(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* 
          "zero insertion (stride-2 gradient)");
       return u;
     };
+    // gradient scale record (grad_scale_launch): keeps the f16 gradients in range; every backward op is linear in g
+    float* gsc = (float*)ar.alloc(sizeof(float) * 4);
+    if (!dry) cudaMemset(gsc, 0, sizeof(float) * 4);
+    {
+      // expected magnitude of the first f16 gradient tensor relative to max|d(logits)|: the pooling / fc adjoint of the
+      // classifier (1 / HW, weights ~ 1 / sqrt(C)), the bilinear adjoint of the parser (sums (S / Hlow)^2 logit gradients)
+      const float mult = c.head == 0 ? 1.f / ((float)HWl * sqrtf((float)Cl)) : (float)(S / (S / 8)) * (float)(S / (S / 8));
+      const int64_t n = c.head == 0 ? (int64_t)B * K : (int64_t)B * K * S * S;
+      ew([m, gsc, n, mult](cudaStream_t st) { return grad_scale_launch(m->in_dlogits, n, gsc, mult, st); }, 4.0 * (double)n,
+         "max|d(logits)| -> power-of-two gradient scale");
+    }
     if (c.head == 0) {
       float* dfeat = (float*)ar.alloc(sizeof(float) * B * Cl);
       g = talloc(B, h.H, h.W, h.C);
       const Tensor hl = h, gg = g;
-      ew([m, hl, gg, dfeat, B, HWl, Cl, K](cudaStream_t st) {
-           return avgpool_fc_bwd_launch(m->in_dlogits, m->fc_w, dfeat, hl.p, gg.p, B, HWl, Cl, K, st); },
+      ew([m, hl, gg, dfeat, gsc, B, HWl, Cl, K](cudaStream_t st) {
+           return avgpool_fc_bwd_launch(m->in_dlogits, m->fc_w, dfeat, hl.p, gg.p, B, HWl, Cl, K, st, gsc); },
          2.0 * (double)hl.bytes, "fc + average pool backward (+ relu mask)");
     } else {
       // ---- face parser head backward: d(logits) (B, K, S, S) -> gradients at feat8 / feat16 / feat32
@@ -809,7 +826,7 @@ int build_program_resnet(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* 
       auto fbuf = [&](int n) { return (float*)ar.alloc(sizeof(float) * B * n); };
       auto dot = [&](const Tensor& x, const Tensor* y, float* out, float scale, const char* what) {
         const Tensor xx = x;
-        const bf16* yp = y ? y->p : nullptr;
+        const f16* yp = y ? y->p : nullptr;
         ew([xx, yp, out, B, scale](cudaStream_t st) { return chan_dot_launch(xx.p, yp, out, B, xx.H * xx.W, xx.C, scale, st); },
            (y ? 2.0 : 1.0) * (double)xx.bytes, what);
       };
@@ -828,7 +845,7 @@ int build_program_resnet(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* 
       auto merge = [&](const Tensor* gt, const Tensor* e, int e_off, const Tensor* y, Tensor* out, int C, int H, int W, const char* what) {
         *out = talloc(B, H, W, C);
         const Tensor oo = *out;
-        const bf16* gp = gt ? gt->p : nullptr; const bf16* ep = e ? e->p : nullptr; const bf16* yp = y ? y->p : nullptr;
+        const f16* gp = gt ? gt->p : nullptr; const f16* ep = e ? e->p : nullptr; const f16* yp = y ? y->p : nullptr;
         const int epitch = e ? e->C : 0;
         ew([gp, ep, epitch, e_off, yp, oo, B](cudaStream_t st) {
              return grad_merge_launch(gp, ep, epitch, e_off, yp, oo.p, (int64_t)B * oo.H * oo.W, oo.C, st); }, 3.0 * (double)oo.bytes, what);
@@ -844,7 +861,7 @@ int build_program_resnet(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* 
              g_sum32, g_f32, e32, g32;
       {
         const Tensor oo = g_o2;
-        ew([m, oo, B, K, S](cudaStream_t st) { return bilinear_ac_bwd_launch(m->in_dlogits, oo.p, B, oo.H, oo.W, oo.C, K, S, S, st); },
+        ew([m, oo, gsc, B, K, S](cudaStream_t st) { return bilinear_ac_bwd_launch(m->in_dlogits, oo.p, B, oo.H, oo.W, oo.C, K, S, S, st, gsc); },
            4.0 * B * K * S * S, "bilinear upsample backward");
       }
       dconv(bs.out_cls.dg, g_o2, nullptr, &g_o1, "conv_out.conv_out");
@@ -942,7 +959,7 @@ int build_program_resnet(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* 
       dconv(m->stem_dg, gy1, nullptr, &dcols, "stem");
       if (!rc) {
         const Tensor dc = dcols;
-        ew([m, dc, B, Cin, S, KP](cudaStream_t st) { return col2im7s2_launch(dc.p, m->out_dz, B, Cin, S, S, KP, st); },
+        ew([m, dc, gsc, B, Cin, S, KP](cudaStream_t st) { return col2im7s2_launch(dc.p, m->out_dz, B, Cin, S, S, KP, st, gsc); },
            (double)dc.bytes + 4.0 * B * Cin * S * S, "stem col2im (image gradient)");
       }
     }
@@ -999,14 +1016,15 @@ int build_model(b2e_unet* m) {
     ConvL ci;
     const int PL = m->PL;
     ci.cin = ci.cin_pad = kConvBlockK; ci.cout = c0; ci.k = 1; ci.cout_pad = conv_cout_pad(c0); ci.row_len = kConvBlockK * PL;
-    ci.w = m->dmalloc<bf16>((size_t)ci.cout_pad * ci.row_len);
+    ci.w = m->dmalloc<f16>((size_t)ci.cout_pad * ci.row_len);
     ci.b = m->dmalloc<float>(ci.cout_pad);
     const int cin = c.in_channels;
     m->add_param("conv_in.weight", (int64_t)c0 * cin * 9, (int64_t)cin * 9, [ci, cin, PL](const float* src, cudaStream_t st) {
       // column of (tap t, channel c) = t * Cin + c, the order pack_input_im2col writes (per 64-column plane)
-      int rc = conv_pack_weight(src, ci.w, ci.cout, cin, 3, cin, ci.row_len, 0, st);
-      if (!rc && PL == 3) rc = conv_pack_weight(src, ci.w, ci.cout, cin, 3, cin, ci.row_len, kConvBlockK, st);
-      if (!rc && PL == 3) rc = conv_pack_weight(src, ci.w, ci.cout, cin, 3, cin, ci.row_len, 2 * kConvBlockK, st, 0, 0, 1);
+      const float ws = PL == 3 ? b2e_unet::kSplitWScale : 1.f;
+      int rc = conv_pack_weight(src, ci.w, ci.cout, cin, 3, cin, ci.row_len, 0, st, 0, 0, 0, ws);
+      if (!rc && PL == 3) rc = conv_pack_weight(src, ci.w, ci.cout, cin, 3, cin, ci.row_len, kConvBlockK, st, 0, 0, 0, ws);
+      if (!rc && PL == 3) rc = conv_pack_weight(src, ci.w, ci.cout, cin, 3, cin, ci.row_len, 2 * kConvBlockK, st, 0, 0, 1, ws);
       return rc;
     });
     m->add_f32("conv_in.bias", ci.b, c0, (int64_t)cin * 9);
@@ -1114,12 +1132,12 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
   std::vector<b2e_unet::Op>* cur = &ops_fwd;   // the op list being recorded
 #define ops (*cur)
   const bool keep = m->grad;                    // gradient mode: every activation stays live for the backward pass
-  const int PL = m->PL;                         // channel planes per activation tensor (3: split-bf16, fp32-accurate mode)
+  const int PL = m->PL;                         // channel planes per activation tensor (3: split-f16, fp32-accurate mode)
   double flops = 0;
   int rc = B2E_OK;
   auto talloc = [&](int N, int H, int W, int C, int Cr = 0) {
-    Tensor t; t.N = N; t.H = H; t.W = W; t.C = C; t.Cr = Cr ? Cr : C; t.bytes = (size_t)N * H * W * C * PL * sizeof(bf16);
-    t.p = (bf16*)ar.alloc(t.bytes);
+    Tensor t; t.N = N; t.H = H; t.W = W; t.C = C; t.Cr = Cr ? Cr : C; t.bytes = (size_t)N * H * W * C * PL * sizeof(f16);
+    t.p = (f16*)ar.alloc(t.bytes);
     return t;
   };
   auto tfree = [&](Tensor& t) {
@@ -1145,7 +1163,7 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
                   const Tensor* r0 = nullptr, const Tensor* r1 = nullptr, bool want_stats = true) {
     if (rc) return;
     const int Ho = x0.H / stride, Wo = x0.W / stride;
-    // bf16 outputs are written at the padded channel count (zero weight rows / bias for the tail)
+    // f16 outputs are written at the padded channel count (zero weight rows / bias for the tail)
     const int cout_x = out ? L.cout_pad : L.cout;
     if (out) *out = talloc(B, Ho, Wo, cout_x, L.cout);
     // GroupNorm statistics of the output, emitted by the epilogue (the consumer skips its statistics pass)
@@ -1179,7 +1197,7 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
       rc = B2E_INVALID_ARG; set_error("unet: weight row length %d does not match the operands (%d)", L.row_len,
                                       PL * (L.k * L.k * (x0.C + (x1 ? x1->C : 0)) + L.res_c)); return;
     }
-    d.out_bf16 = out ? out->p : nullptr;
+    d.out_f16 = out ? out->p : nullptr;
     d.tile_stats = tstats;
     d.split_ws = split_ws; d.split_ws_bytes = split_bytes; d.split_counters = split_cnt;
     if (L.res_c != (r0 ? r0->C : 0) + (r1 ? r1->C : 0)) { rc = B2E_INVALID_ARG; set_error("unet: residual segment mismatch"); return; }
@@ -1188,17 +1206,24 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
     if (rc) return;
     ep.bias = L.b;
     ep.bias2 = L.b2;
+    if (PL == 3) ep.acc_scale = 1.f / b2e_unet::kSplitWScale;
     flops += pl.flops;
     char desc[160];
     snprintf(desc, sizeof(desc), "conv%dx%d s%d %dx%d cin%d+%d res%d cout%d tiles%d bn%d%s", L.k, L.k, stride, x0.H, x0.W,
              x0.C, x1 ? x1->C : 0, L.res_c, L.cout, pl.w_blks * pl.h_blks * pl.n_blks * (pl.cout_pad / pl.block_n), pl.block_n,
              pl.halo == 2 ? " halo2" : pl.halo ? " halo1" : pl.pair ? " pair" : (pl.splits > 1 ? (" splitK" + std::to_string(pl.splits)).c_str() : ""));
+    // profile record: ALGORITHMIC FLOPs.  An identity residual segment (W_r = I: the plain residual add riding along as
+    // K chunks) is executed on the tensor cores but is not arithmetic of the algorithm - it is counted as the bytes of the
+    // residual tensor it reads instead (conv_shortcut segments, which have a bias2, are real 1x1 convolutions and count)
+    const bool id_res = L.res_c > 0 && !L.b2;
+    const double id_flops = id_res ? 2.0 * B * Ho * Wo * (double)cout_x * L.res_c * PL : 0.0;
+    const double id_bytes = id_res ? (double)B * Ho * Wo * L.res_c * PL * sizeof(f16) : 0.0;
     if (out_nchw) {
       // the network output pointer is only known at call time
       ops.push_back({[pl, ep, m](cudaStream_t st) { ConvEpilogue e = ep; e.out_f32_nchw = m->out_eps; return conv_launch(pl, e, st); },
-                     0, pl.flops, 0.0, desc});
+                     0, pl.flops - id_flops, id_bytes, desc});
     } else {
-      ops.push_back({[pl, ep](cudaStream_t st) { return conv_launch(pl, ep, st); }, 0, pl.flops, 0.0, desc});
+      ops.push_back({[pl, ep](cudaStream_t st) { return conv_launch(pl, ep, st); }, 0, pl.flops - id_flops, id_bytes, desc});
     }
     if (tstats && !raw_stats) {
       float* cst = out->cstats;
@@ -1232,7 +1257,7 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
     a.ts1 = raw && x1 ? x1->tstats : nullptr;
     a.ts_nt = x0.ts_nt; a.ts_per_img = x0.ts_per_img;
     if (raw) fused = true;
-    // algorithmic traffic: statistics pass reads x, apply pass reads x and writes y (bf16)
+    // algorithmic traffic: statistics pass reads x, apply pass reads x and writes y (f16)
     ops.push_back({[a](cudaStream_t st) { return gn_launch(a, st); }, 1, 0.0, (fused ? 4.0 : 6.0) * B * a.HW * C});
   };
 
@@ -1262,7 +1287,7 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
     ops.push_back({[m, ta](cudaStream_t st) { TembArgs t = ta; t.timesteps = m->in_t; return temb_launch(t, st); }, 3, 0.0, 0.0});
     }
   }
-  // text conditioning of the conditional UNet: fp32 (B, L <= 128, D) -> bf16 (B, 1, 128, D), zero rows beyond L
+  // text conditioning of the conditional UNet: fp32 (B, L <= 128, D) -> f16 (B, 1, 128, D), zero rows beyond L
   constexpr int kCtxPad = 128;
   Tensor ctxp;
   if (c.cross_attention_dim > 0) {
@@ -1289,7 +1314,7 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
                           int heads, int d, int dpad, Tensor* out, int Hh, int Ww, int Cc, int causal = 0) {
     if (rc) return;
     if (PL == 3) {
-      // fp32-accurate mode: tiled fp32 attention straight on the q / k / v channel windows of the split-bf16 tensors
+      // fp32-accurate mode: tiled fp32 attention straight on the q / k / v channel windows of the split-f16 tensors
       if (causal) { rc = B2E_UNSUPPORTED_SHAPE; set_error("unet: causal attention is not available in the fp32-accurate mode"); return; }
       *out = talloc(B, Hh, Ww, Cc);
       flops += 4.0 * B * heads * (double)Tq * Tk * d;
@@ -1298,7 +1323,7 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
         ops.push_back({[m, q_, k_, o_, B, qcol, kcol, vcol, Tq, Tk, valid_k, heads, d, Cc](cudaStream_t st) {
                          return attention_split_tiled_launch(q_.p, q_.C, qcol, k_.p, k_.C, kcol, vcol, o_.p, o_.C, Cc, B, Tq, Tk,
                                                              valid_k < 0 ? m->ctx_len : valid_k, heads, d, st); },
-                       2, 4.0 * B * heads * (double)Tq * Tk * d, 0.0, "attention (fp32, tiled, split-bf16 operands)"});
+                       2, 4.0 * B * heads * (double)Tq * Tk * d, 0.0, "attention (fp32, tiled, split-f16 operands)"});
       }
       return;
     }
@@ -1344,13 +1369,13 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
       ConvDesc d1;
       d1.s0.ptr = qh.p; d1.s0.C = dpad;
       d1.N = NV; d1.H = 1; d1.W = Tqp; d1.ksize = 1; d1.stride = 1;
-      d1.w_packed = kh.p; d1.b_batch_rows = Tkp; d1.b_pitch = dpad; d1.Cout = Tkp; d1.out_bf16 = sc.p;
+      d1.w_packed = kh.p; d1.b_batch_rows = Tkp; d1.b_pitch = dpad; d1.Cout = Tkp; d1.out_f16 = sc.p;
       ConvPlan p1;
       rc = conv_plan_build(&p1, d1);
       ConvDesc d2;
       d2.s0.ptr = sc.p; d2.s0.C = Tkp;
       d2.N = NV; d2.H = 1; d2.W = Tqp; d2.ksize = 1; d2.stride = 1;
-      d2.w_packed = vht.p; d2.b_batch_rows = dpad; d2.b_pitch = Tkp; d2.Cout = dpad; d2.out_bf16 = oh.p;
+      d2.w_packed = vht.p; d2.b_batch_rows = dpad; d2.b_pitch = Tkp; d2.Cout = dpad; d2.out_f16 = oh.p;
       ConvPlan p2;
       if (!rc) rc = conv_plan_build(&p2, d2);
       if (!rc) {
@@ -1379,7 +1404,7 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
     tfree(qh); tfree(kh); tfree(vht); tfree(sc); tfree(oh);
   };
   if (m->clip) {
-    // ---- CLIP text encoder: ids (B, L <= 128) -> (B, 1, 128, D) bf16 token rows (rows >= L zero, masked as keys)
+    // ---- CLIP text encoder: ids (B, L <= 128) -> (B, 1, 128, D) f16 token rows (rows >= L zero, masked as keys)
     const b2e_clip_config& cc = m->ccfg;
     const int D = cc.hidden_size, heads = cc.num_heads, d = D / heads;
     tfree(xin);
@@ -1405,7 +1430,7 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
       tfree(b2);
       if (!dry && !rc) {
         const Tensor ff = f1;
-        ops.push_back({[ff](cudaStream_t st) { return quick_gelu_launch(ff.p, ff.p, (int64_t)(ff.bytes / sizeof(bf16)), st); }, 3, 0.0,
+        ops.push_back({[ff](cudaStream_t st) { return quick_gelu_launch(ff.p, ff.p, (int64_t)(ff.bytes / sizeof(f16)), st); }, 3, 0.0,
                        2.0 * (double)ff.bytes, "quick_gelu"});
       }
       conv(L.fc2, f1, nullptr, 1, ConvEpilogue{}, &x2, nullptr, &x1, nullptr, false);
@@ -1475,16 +1500,16 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
         const int T = h.H * h.W, C = a.P;   // C: padded width of q / k / v (zero tail: no effect on Q K^T, zero rows of V^T)
         const ConvGeom gq = conv_geometry(B, h.H, h.W, T);
         if (PL == 3) {
-          // fp32-accurate mode: fp32 attention core on the CUDA cores over the split-bf16 q | k | v planes
+          // fp32-accurate mode: fp32 attention core on the CUDA cores over the split-f16 q | k | v planes
           if (!dry) {
             const int Cr = a.C, dh = a.C / heads;
             if (sizeof(float) * 16 * (size_t)(dh + T) <= 160 * 1024 && qkv.C == 3 * C) {
               ops.push_back({[qkv, o, B, T, C, Cr, heads](cudaStream_t st) { return attention_split_launch(qkv.p, o.p, B, T, Cr, C, heads, st); },
-                             2, 4.0 * B * (double)T * T * Cr, 0.0, "attention (fp32, split-bf16 operands)"});
+                             2, 4.0 * B * (double)T * T * Cr, 0.0, "attention (fp32, split-f16 operands)"});
             } else {   // long sequences (decoder mid block: 4096 tokens): online softmax over key tiles
               ops.push_back({[qkv, o, B, T, C, Cr, heads, dh](cudaStream_t st) {
                                return attention_split_tiled_launch(qkv.p, qkv.C, 0, qkv.p, qkv.C, C, 2 * C, o.p, C, Cr, B, T, T, T, heads, dh, st); },
-                             2, 4.0 * B * (double)T * T * Cr, 0.0, "attention (fp32, tiled, split-bf16 operands)"});
+                             2, 4.0 * B * (double)T * T * Cr, 0.0, "attention (fp32, tiled, split-f16 operands)"});
             }
           }
           flops += 4.0 * B * (double)T * T * a.C;
@@ -1499,14 +1524,14 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
             d1.s0.ptr = qkv.p; d1.s0.C = C; d1.s0.pitch = 3 * C;        // Q = channel window [0,C) of qkv
             d1.N = B; d1.H = h.H; d1.W = h.W; d1.ksize = 1; d1.stride = 1;
             d1.w_packed = qkv.p + C; d1.b_batch_rows = T; d1.b_pitch = 3 * C;   // K rows of image n
-            d1.Cout = T; d1.out_bf16 = sc.p;
+            d1.Cout = T; d1.out_f16 = sc.p;
             ConvPlan p1;
             rc = conv_plan_build(&p1, d1);
             ConvDesc d2;
             d2.s0.ptr = sc.p; d2.s0.C = T;                               // P
             d2.N = B; d2.H = h.H; d2.W = h.W; d2.ksize = 1; d2.stride = 1;
             d2.w_packed = vt.p; d2.b_batch_rows = C; d2.b_pitch = T;     // V^T rows of image n
-            d2.Cout = C; d2.out_bf16 = o.p;
+            d2.Cout = C; d2.out_f16 = o.p;
             ConvPlan p2;
             if (!rc) rc = conv_plan_build(&p2, d2);
             if (!rc) {
@@ -1547,14 +1572,14 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
             d1.s0.ptr = qh.p; d1.s0.C = 64;
             d1.N = NV; d1.H = h.H; d1.W = h.W; d1.ksize = 1; d1.stride = 1;
             d1.w_packed = kh.p; d1.b_batch_rows = T; d1.b_pitch = 64;      // K rows of virtual image v
-            d1.Cout = T; d1.out_bf16 = sc.p;
+            d1.Cout = T; d1.out_f16 = sc.p;
             ConvPlan p1;
             rc = conv_plan_build(&p1, d1);
             ConvDesc d2;
             d2.s0.ptr = sc.p; d2.s0.C = T;                                 // P
             d2.N = NV; d2.H = h.H; d2.W = h.W; d2.ksize = 1; d2.stride = 1;
             d2.w_packed = vht.p; d2.b_batch_rows = 64; d2.b_pitch = T;     // V^T rows of virtual image v
-            d2.Cout = 64; d2.out_bf16 = oh.p;
+            d2.Cout = 64; d2.out_f16 = oh.p;
             ConvPlan p2;
             if (!rc) rc = conv_plan_build(&p2, d2);
             if (!rc) {
@@ -1699,11 +1724,15 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
       if (add && add->C != x.C) { rc = B2E_INVALID_ARG; set_error("unet backward: residual pitch mismatch"); return; }
       ops.push_back({[a](cudaStream_t st) { return gn_bwd_launch(a, st); }, 1, 0.0, 10.0 * B * a.HW * a.C, "groupnorm backward"});
     };
-    // gradient w.r.t. the image arrives as fp32 NCHW: pack to bf16 NHWC with 64 (zero-padded) channels
+    // gradient w.r.t. the image arrives as fp32 NCHW: pack to f16 NHWC with 64 (zero-padded) channels
     Tensor gy = talloc(B, So, So, kConvBlockK, c.out_channels);
+    float* gs = (float*)ar.alloc(sizeof(float) * 4);   // gradient scale record (grad_scale_launch): keeps f16 gradients in range
     if (!dry) {
       const int Co = c.out_channels;
-      ops.push_back({[m, gy, B, Co, So](cudaStream_t st) { return pack_input_launch(m->in_dy, gy.p, B, Co, So, So, kConvBlockK, false, st); },
+      cudaMemset(gs, 0, sizeof(float) * 4);
+      ops.push_back({[m, gs, B, Co, So](cudaStream_t st) { return grad_scale_launch(m->in_dy, (int64_t)B * Co * So * So, gs, 1.f, st); },
+                     3, 0.0, 4.0 * B * Co * So * So, "max|d(image)| -> power-of-two gradient scale"});
+      ops.push_back({[m, gy, gs, B, Co, So](cudaStream_t st) { return pack_input_launch(m->in_dy, gy.p, B, Co, So, So, kConvBlockK, false, st, 1, gs); },
                      3, 0.0, (double)B * So * So * (4.0 * Co + 2.0 * kConvBlockK), "pack d(image)"});
     }
     Tensor d_an, g;
@@ -1738,13 +1767,13 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
           Tensor dOt = talloc(B, 1, P, T), Kt = talloc(B, 1, P, T), Qt = talloc(B, 1, P, T);
           dV = talloc(B, Hh, Ww, P, a.C); dP = talloc(B, Hh, Ww, T); dQ = talloc(B, Hh, Ww, P, a.C); dK = talloc(B, Hh, Ww, P, a.C);
           if (!dry) {
-            auto gemm = [&](const Tensor& A, int K, const bf16* Bop, int brows, int bpitch, int Cout, const Tensor& out,
+            auto gemm = [&](const Tensor& A, int K, const f16* Bop, int brows, int bpitch, int Cout, const Tensor& out,
                             const char* what) {
               // out[n][t][co] = sum_k A[n][t][k] * Bop[n*brows + co][k]
               ConvDesc d;
               d.s0.ptr = A.p; d.s0.C = K; if (A.C != K) d.s0.pitch = A.C;
               d.N = B; d.H = Hh; d.W = Ww; d.ksize = 1; d.stride = 1;
-              d.w_packed = Bop; d.b_batch_rows = brows; d.b_pitch = bpitch; d.Cout = Cout; d.out_bf16 = out.p;
+              d.w_packed = Bop; d.b_batch_rows = brows; d.b_pitch = bpitch; d.Cout = Cout; d.out_f16 = out.p;
               ConvPlan pl;
               if (!rc) rc = conv_plan_build(&pl, d);
               if (!rc) { ops.push_back({[pl](cudaStream_t st) { return conv_launch(pl, ConvEpilogue{}, st); }, 0, pl.flops, 0.0, what}); flops += pl.flops; }
@@ -1791,7 +1820,7 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
       conv(m->dgrads[m->conv_in_dg], g, nullptr, 1, ConvEpilogue{}, &dcols, nullptr, nullptr, nullptr, false);
       if (!dry && !rc) {
         const int L = c.in_channels;
-        ops.push_back({[m, dcols, B, L, S](cudaStream_t st) { return vq_col2im_bwd_launch(dcols.p, m->pq_w, m->out_dz, B, L, S, S, st); },
+        ops.push_back({[m, dcols, gs, B, L, S](cudaStream_t st) { return vq_col2im_bwd_launch(dcols.p, m->pq_w, m->out_dz, B, L, S, S, st, gs); },
                        3, 0.0, (double)B * S * S * (128.0 + 4.0 * L), "col2im + post_quant_conv backward (straight-through)"});
       }
     }
@@ -1843,7 +1872,7 @@ int b2e_unet_create(const b2e_unet_config* cfg, int64_t max_batch, b2e_unet** ou
     }
   }
   B2E_REQUIRE(cfg->sample_size % (1 << (cfg->n_blocks - 1)) == 0, B2E_UNSUPPORTED_SHAPE, "unet_create: sample_size");
-  B2E_REQUIRE(cfg->precision == 0 || cfg->precision == 1, B2E_INVALID_ARG, "unet_create: precision must be 0 (bf16) or 1 (fp32-accurate)");
+  B2E_REQUIRE(cfg->precision == 0 || cfg->precision == 1, B2E_INVALID_ARG, "unet_create: precision must be 0 (f16) or 1 (fp32-accurate)");
   if (cfg->precision == 1) {
     B2E_REQUIRE(cfg->in_channels == 1 || cfg->in_channels == 3 || cfg->in_channels == 4, B2E_UNSUPPORTED_SHAPE,
                 "unet_create: the fp32-accurate mode needs 1, 3 or 4 input channels");
@@ -1871,7 +1900,7 @@ int b2e_vqdec_create(const b2e_vqdec_config* cfg, int64_t max_batch, b2e_unet** 
     B2E_REQUIRE(ch % 8 == 0 && ch >= 32 && ch <= 1024 && ch % cfg->norm_num_groups == 0, B2E_UNSUPPORTED_SHAPE,
                 "vqdec_create: block_out_channels must be multiples of 8 and of norm_num_groups, 32..1024 (got %d)", ch);
   }
-  B2E_REQUIRE(cfg->precision == 0 || cfg->precision == 1, B2E_INVALID_ARG, "vqdec_create: precision must be 0 (bf16) or 1 (fp32-accurate)");
+  B2E_REQUIRE(cfg->precision == 0 || cfg->precision == 1, B2E_INVALID_ARG, "vqdec_create: precision must be 0 (f16) or 1 (fp32-accurate)");
   b2e_unet* m = new b2e_unet();
   m->decoder = true;
   m->PL = cfg->precision == 1 ? 3 : 1;

@@ -1,5 +1,5 @@
 // GroupNorm+SiLU, layout packing, upsampling, timestep embedding and attention kernels of the
-// UNet.  All activations are bf16 NHWC; statistics, softmax and accumulation are fp32/fp64.
+// UNet.  All activations are f16 NHWC; statistics, softmax and accumulation are fp32/fp64.
 #include "unet_kernels.cuh"
 
 #include <math.h>
@@ -10,18 +10,18 @@ namespace b2e {
 constexpr int kGNThreads = 256;
 
 __device__ __forceinline__ void unpack8(const uint4& v, float* f) {
-  const __nv_bfloat162* b = reinterpret_cast<const __nv_bfloat162*>(&v);
+  const f16x2* b = reinterpret_cast<const f16x2*>(&v);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    float2 t = __bfloat1622float2(b[j]);
+    float2 t = f16x2_to_float2(b[j]);
     f[2 * j] = t.x; f[2 * j + 1] = t.y;
   }
 }
 __device__ __forceinline__ uint4 pack8(const float* f) {
   uint4 v;
-  __nv_bfloat162* b = reinterpret_cast<__nv_bfloat162*>(&v);
+  f16x2* b = reinterpret_cast<f16x2*>(&v);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) b[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+  for (int j = 0; j < 4; ++j) b[j] = floats_to_f16x2(f[2 * j], f[2 * j + 1]);
   return v;
 }
 
@@ -46,9 +46,9 @@ __global__ void __launch_bounds__(512) gn_partial_kernel(GNArgs a) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) sum[j] = sq[j] = 0.f;
     const int c = s * 8;
-    const bf16* src; int cs, coff;
+    const f16* src; int cs, coff;
     if (c < a.C0) { src = a.x0; cs = a.P0; coff = c; } else { src = a.x1; cs = a.P1; coff = c - a.C0; }
-    constexpr bool split = SPLIT;         // split-bf16 tensors: value = plane 0 (hi) + plane 1 (lo), pixel pitch 3 * P
+    constexpr bool split = SPLIT;         // split-f16 tensors: value = plane 0 (hi) + plane 1 (lo), pixel pitch 3 * P
     const int lo_off = cs;
     cs *= a.planes;
     src += (int64_t)n * a.HW * cs + coff;
@@ -136,9 +136,9 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(GNArgs a, int pix_per_blo
   if (pl >= ppi) return;
   const int c = s * 8;
   const int p0 = blockIdx.x * pix_per_block, p1 = min(a.HW, p0 + pix_per_block);
-  constexpr bool split = SPLIT;           // split-bf16 tensors (fp32-accurate mode): planes [hi | lo | hi]
+  constexpr bool split = SPLIT;           // split-f16 tensors (fp32-accurate mode): planes [hi | lo | hi]
   const int po = a.Pout * a.planes;       // output pixel pitch
-  bf16* dst = a.out + (int64_t)n * a.HW * po + c;
+  f16* dst = a.out + (int64_t)n * a.HW * po + c;
   if (c >= C) {   // zero padding of the output pitch
     for (int p = p0 + pl; p < p1; p += ppi)
       for (int k = 0; k < a.planes; ++k) *reinterpret_cast<uint4*>(dst + (int64_t)p * po + k * a.Pout) = make_uint4(0, 0, 0, 0);
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(GNArgs a, int pix_per_blo
     scale[j] = s_rstd[g] * __ldg(a.gamma + c + j);
     shift[j] = __ldg(a.beta + c + j) - s_mean[g] * scale[j];
   }
-  const bf16* src; int cs, coff;
+  const f16* src; int cs, coff;
   if (c < a.C0) { src = a.x0; cs = a.P0; coff = c; } else { src = a.x1; cs = a.P1; coff = c - a.C0; }
   const int lo_off = cs;
   cs *= a.planes;
@@ -180,10 +180,10 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(GNArgs a, int pix_per_blo
             float y = fmaf(f[j] + g[j], scale[j], shift[j]);
             if (a.silu) y = y / (1.f + expf(-y));
             f[j] = y;
-            l[j] = __fsub_rn(y, __bfloat162float(__float2bfloat16_rn(y)));
+            l[j] = __fsub_rn(y, f16_to_float(float_to_f16(y)));
           }
           const uint4 hi = pack8(f), lo = pack8(l);
-          bf16* o = dst + (int64_t)q * po;
+          f16* o = dst + (int64_t)q * po;
           *reinterpret_cast<uint4*>(o) = hi;
           *reinterpret_cast<uint4*>(o + a.Pout) = lo;
           *reinterpret_cast<uint4*>(o + 2 * a.Pout) = hi;
@@ -239,7 +239,7 @@ int gn_launch(const GNArgs& a, cudaStream_t st) {
   B2E_REQUIRE(a.P0 >= a.C0 && a.P1 >= a.C1 && a.Pout >= C && a.P0 % 8 == 0 && a.P1 % 8 == 0 && a.Pout % 8 == 0,
               B2E_INVALID_ARG, "groupnorm: bad channel pitches %d/%d -> %d", a.P0, a.P1, a.Pout);
   B2E_REQUIRE(a.planes == 1 || (a.planes == 3 && !a.cs0 && !a.ts0 && !a.save_stats), B2E_INVALID_ARG,
-              "groupnorm: split-bf16 tensors take their statistics from the stand-alone pass");
+              "groupnorm: split-f16 tensors take their statistics from the stand-alone pass");
   int rc = B2E_OK;
   if (!a.cs0 && !a.ts0) {
     if (a.planes == 3) launch_pdl(gn_partial_kernel<true>, dim3(dim3(a.chunks, a.N)), dim3(C > 2048 ? 512 : kGNThreads), 0, st, a);
@@ -290,8 +290,8 @@ __global__ void __launch_bounds__(kGNThreads) gn_bwd_partial_kernel(GNBwdArgs a)
       r[j] = st.y; mr[j] = -st.x * st.y;
       sc[j] = gam[j] * st.y; sh[j] = fmaf(gam[j], mr[j], __ldg(a.beta + c + j));
     }
-    const bf16* xs = a.x + (int64_t)n * a.HW * a.P + c;
-    const bf16* ds = a.da + (int64_t)n * a.HW * a.Pda + c;
+    const f16* xs = a.x + (int64_t)n * a.HW * a.P + c;
+    const f16* ds = a.da + (int64_t)n * a.HW * a.Pda + c;
     for (int p = p0 + pl; p < p1; p += ppi * kGNBwdUnroll) {
       uint4 xv[kGNBwdUnroll], dv[kGNBwdUnroll];
 #pragma unroll
@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(kGNThreads) gn_bwd_apply_kernel(GNBwdArgs a, i
   if (pl >= ppi) return;
   const int c = s * 8;
   const int p0 = blockIdx.x * pix_per_block, p1 = min(a.HW, p0 + pix_per_block);
-  bf16* dst = a.dx + (int64_t)n * a.HW * a.P + c;
+  f16* dst = a.dx + (int64_t)n * a.HW * a.P + c;
   if (c >= C) {
     for (int p = p0 + pl; p < p1; p += ppi) *reinterpret_cast<uint4*>(dst + (int64_t)p * a.P) = make_uint4(0, 0, 0, 0);
     return;
@@ -368,9 +368,9 @@ __global__ void __launch_bounds__(kGNThreads) gn_bwd_apply_kernel(GNBwdArgs a, i
     k1[j] = -rstd * rstd * s_mb[g];
     k0[j] = -rstd * fmaf(mr, s_mb[g], s_ma[g]);
   }
-  const bf16* xs = a.x + (int64_t)n * a.HW * a.P + c;
-  const bf16* ds = a.da + (int64_t)n * a.HW * a.Pda + c;
-  const bf16* as = a.add ? a.add + (int64_t)n * a.HW * a.P + c : nullptr;
+  const f16* xs = a.x + (int64_t)n * a.HW * a.P + c;
+  const f16* ds = a.da + (int64_t)n * a.HW * a.Pda + c;
+  const f16* as = a.add ? a.add + (int64_t)n * a.HW * a.P + c : nullptr;
   for (int p = p0 + pl; p < p1; p += ppi * kGNBwdUnroll) {
     uint4 xv[kGNBwdUnroll], dv[kGNBwdUnroll], av[kGNBwdUnroll];
 #pragma unroll
@@ -416,7 +416,7 @@ int gn_bwd_launch(const GNBwdArgs& a, cudaStream_t st) {
   // Measured at batch 32 (decoder backward, r90): 12.5 ms unblocked, 17.2 / 21.1 / 22.6 ms with 96 / 64 / 32 MB groups -
   // the statistics pass of a 2-3 image group (<= 192 blocks) no longer fills the chip - so it stays off.
   static const int l2_mb = getenv("B2E_GN_L2_MB") ? atoi(getenv("B2E_GN_L2_MB")) : 0;
-  const int64_t per_img = (int64_t)a.HW * (a.P + a.Pda + (a.add ? a.P : 0)) * (int64_t)sizeof(bf16);
+  const int64_t per_img = (int64_t)a.HW * (a.P + a.Pda + (a.add ? a.P : 0)) * (int64_t)sizeof(f16);
   int group = a.N;
   if (l2_mb > 0 && per_img * a.N > (int64_t)l2_mb << 20) {
     group = (int)(((int64_t)l2_mb << 20) / per_img);
@@ -480,15 +480,53 @@ int gn_finalize_launch(const float* tile_stats, float* chan_stats, int N, int C,
 }
 
 // ------------------------------------------------------------------ layout helpers
-__global__ void pack_input_kernel(const float* __restrict__ x, bf16* __restrict__ out, int B, int C,
-                                  int HW, int cpad) {
+// ---- gradient range control for the backward passes.  fp16 gradients underflow below 6e-8 (d(loss)/d(image) of the colour
+// losses is loss_scale / (B H W) ~ 1e-6) and overflow above 65504, and every op of the backward chains is linear in the
+// incoming gradient, so the entry kernel multiplies by s = 2^e and the exit kernel by 1/s (both exact): e is chosen on the
+// device so that max|g| * mult * s lies in [2^T, 2^(T+1)).  gs = {s, 1/s, max slot (float bits; re-armed to 0 here)}.
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ gs) {
   pdl_wait();
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  // non-negative floats order like their bit patterns (NaN / inf sort above every finite value and end up as s = 1)
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<unsigned*>(gs + 2), __float_as_uint(m));
+}
+__global__ void grad_scale_finalize_kernel(float* __restrict__ gs, float mult, int target_log2) {
+  pdl_wait();
+  const float m = gs[2] * mult;
+  float sc = 1.f;
+  if (m > 0.f && m < INFINITY) {
+    int e;
+    frexpf(m, &e);                     // m = f * 2^e, f in [0.5, 1)
+    int k = target_log2 + 1 - e;       // m * 2^k in [2^T, 2^(T+1))
+    k = k > 120 ? 120 : (k < -120 ? -120 : k);
+    sc = ldexpf(1.f, k);
+  }
+  gs[0] = sc; gs[1] = 1.f / sc; gs[2] = 0.f;
+}
+int grad_scale_launch(const float* x, int64_t n, float* gs, float mult, cudaStream_t st) {
+  static const int target = getenv("B2E_GRAD_LOG2") ? atoi(getenv("B2E_GRAD_LOG2")) : 2;
+  int grid = (int)((n + 1023) / 1024);
+  if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+  launch_pdl(absmax_kernel, dim3(grid), dim3(256), 0, st, x, n, gs);
+  int rc = check_launch("absmax");
+  if (rc) return rc;
+  launch_pdl(grad_scale_finalize_kernel, dim3(1), dim3(1), 0, st, gs, mult, target);
+  return check_launch("grad_scale_finalize");
+}
+
+__global__ void pack_input_kernel(const float* __restrict__ x, f16* __restrict__ out, int B, int C,
+                                  int HW, int cpad, const float* __restrict__ gs) {
+  pdl_wait();
+  const float sc = gs ? gs[0] : 1.f;
   const int64_t total = (int64_t)B * HW;
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total;
        p += (int64_t)gridDim.x * blockDim.x) {
     const int64_t b = p / HW, q = p % HW;
     float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int c = 0; c < C && c < 8; ++c) f[c] = x[(b * C + c) * HW + q];
+    for (int c = 0; c < C && c < 8; ++c) f[c] = x[(b * C + c) * HW + q] * sc;
     uint4* o = reinterpret_cast<uint4*>(out + p * cpad);
     o[0] = pack8(f);
     const uint4 z = make_uint4(0, 0, 0, 0);
@@ -499,7 +537,7 @@ __global__ void pack_input_kernel(const float* __restrict__ x, bf16* __restrict_
 // im2col variant: one thread per pixel gathers its 9 x C neighbourhood (coalesced across the warp, neighbours hit
 // L1) and writes the pixel's 64 channels (128 B)
 template <int C>
-__global__ void __launch_bounds__(256) pack_input_im2col_kernel(const float* __restrict__ x, bf16* __restrict__ out, int B,
+__global__ void __launch_bounds__(256) pack_input_im2col_kernel(const float* __restrict__ x, f16* __restrict__ out, int B,
                                                                 int H, int W, int planes) {
   pdl_wait();
   const int HW = H * W;
@@ -524,23 +562,23 @@ __global__ void __launch_bounds__(256) pack_input_im2col_kernel(const float* __r
       o[j] = hv;
       if (planes == 3) o[16 + j] = hv;
     }
-    if (planes == 3) {   // split-bf16 (fp32-accurate mode): [hi | lo | hi]
+    if (planes == 3) {   // split-f16 (fp32-accurate mode): [hi | lo | hi]
 #pragma unroll
-      for (int k = 0; k < 64; ++k) f[k] = __fsub_rn(f[k], __bfloat162float(__float2bfloat16_rn(f[k])));
+      for (int k = 0; k < 64; ++k) f[k] = __fsub_rn(f[k], f16_to_float(float_to_f16(f[k])));
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[8 + j] = pack8(f + 8 * j);
     }
   }
 }
 
-int pack_input_launch(const float* x, bf16* out, int B, int C, int H, int W, int cpad, bool im2col, cudaStream_t st,
-                      int planes) {
+int pack_input_launch(const float* x, f16* out, int B, int C, int H, int W, int cpad, bool im2col, cudaStream_t st,
+                      int planes, const float* gs) {
   const int HW = H * W;
   int64_t total = (int64_t)B * HW;
   int grid = (int)((total + 255) / 256);
   if (grid > kNumSMs * 16) grid = kNumSMs * 16;
   if (im2col) {
-    B2E_REQUIRE(9 * C <= 64 && cpad == 64, B2E_UNSUPPORTED_SHAPE, "pack_input: im2col needs 9*C <= 64");
+    B2E_REQUIRE(9 * C <= 64 && cpad == 64 && !gs, B2E_UNSUPPORTED_SHAPE, "pack_input: im2col needs 9*C <= 64 (and takes no gradient scale)");
     switch (C) {
       case 1: launch_pdl(pack_input_im2col_kernel<1>, dim3(grid), dim3(256), 0, st, x, out, B, H, W, planes); break;
       case 3: launch_pdl(pack_input_im2col_kernel<3>, dim3(grid), dim3(256), 0, st, x, out, B, H, W, planes); break;
@@ -550,8 +588,8 @@ int pack_input_launch(const float* x, bf16* out, int B, int C, int H, int W, int
     return check_launch("pack_input_im2col");
   }
   B2E_REQUIRE(C <= 8 && cpad % 8 == 0, B2E_UNSUPPORTED_SHAPE, "pack_input: in_channels must be <= 8");
-  B2E_REQUIRE(planes == 1, B2E_UNSUPPORTED_SHAPE, "pack_input: split-bf16 output needs the im2col layout");
-  launch_pdl(pack_input_kernel, dim3(grid), dim3(256), 0, st, x, out, B, C, HW, cpad);
+  B2E_REQUIRE(planes == 1, B2E_UNSUPPORTED_SHAPE, "pack_input: split-f16 output needs the im2col layout");
+  launch_pdl(pack_input_kernel, dim3(grid), dim3(256), 0, st, x, out, B, C, HW, cpad, gs);
   return check_launch("pack_input");
 }
 
@@ -570,7 +608,7 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ in, uint4* __restric
   }
 }
 
-int upsample2x_launch(const bf16* in, bf16* out, int N, int H, int W, int C, cudaStream_t st) {
+int upsample2x_launch(const f16* in, f16* out, int N, int H, int W, int C, cudaStream_t st) {
   B2E_REQUIRE(C % 8 == 0, B2E_UNSUPPORTED_SHAPE, "upsample: C %% 8 != 0");
   int64_t total = (int64_t)N * 4 * H * W * (C / 8);
   int grid = (int)((total + 255) / 256);
@@ -681,10 +719,10 @@ int temb_launch(const TembArgs& a, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------ tensor-core attention helpers
-// one warp per row: logits (bf16) * scale -> softmax in fp32 -> probabilities (bf16), in place.
+// one warp per row: logits (f16) * scale -> softmax in fp32 -> probabilities (f16), in place.
 // 16-byte accesses: lane l owns the 8-value chunks l, l + 32, ... of the row (T % 256 == 0: no tail).
 template <int CH>   // chunks per lane = T / 256
-__global__ void __launch_bounds__(256) softmax_rows_vec_kernel(bf16* __restrict__ s, int64_t rows, float scale) {
+__global__ void __launch_bounds__(256) softmax_rows_vec_kernel(f16* __restrict__ s, int64_t rows, float scale) {
   pdl_wait();
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -718,26 +756,26 @@ __global__ void __launch_bounds__(256) softmax_rows_vec_kernel(bf16* __restrict_
   }
 }
 
-__global__ void __launch_bounds__(256) softmax_rows_kernel(bf16* __restrict__ s, int64_t rows, int T, float scale) {
+__global__ void __launch_bounds__(256) softmax_rows_kernel(f16* __restrict__ s, int64_t rows, int T, float scale) {
   pdl_wait();
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
-  bf16* r = s + row * T;
+  f16* r = s + row * T;
   float v[32];   // T <= 1024 -> at most 32 values per lane
   const int per = T / 32;
   float m = -INFINITY;
-  for (int i = 0; i < per; ++i) { v[i] = __bfloat162float(r[lane + 32 * i]) * scale; m = fmaxf(m, v[i]); }
+  for (int i = 0; i < per; ++i) { v[i] = f16_to_float(r[lane + 32 * i]) * scale; m = fmaxf(m, v[i]); }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   float sum = 0.f;
   for (int i = 0; i < per; ++i) { v[i] = __expf(v[i] - m); sum += v[i]; }
   sum = warp_sum(sum);
   const float inv = 1.f / sum;
-  for (int i = 0; i < per; ++i) r[lane + 32 * i] = __float2bfloat16_rn(v[i] * inv);
+  for (int i = 0; i < per; ++i) r[lane + 32 * i] = float_to_f16(v[i] * inv);
 }
 
-int softmax_rows_launch(bf16* s, int64_t rows, int T, float scale, cudaStream_t st) {
+int softmax_rows_launch(f16* s, int64_t rows, int T, float scale, cudaStream_t st) {
   B2E_REQUIRE((T % 32 == 0 && T <= 1024) || T == 2048 || T == 4096, B2E_UNSUPPORTED_SHAPE,
               "softmax: unsupported row length %d", T);
   const dim3 grid((unsigned)((rows + 7) / 8));
@@ -754,32 +792,32 @@ int softmax_rows_launch(bf16* s, int64_t rows, int T, float scale, cudaStream_t 
 }
 
 // 32x32 smem-tiled transpose of the V columns of qkv
-__global__ void transpose_v_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ vt, int T, int C) {
+__global__ void transpose_v_kernel(const f16* __restrict__ qkv, f16* __restrict__ vt, int T, int C) {
   pdl_wait();
-  __shared__ bf16 tile[32][33];
+  __shared__ f16 tile[32][33];
   const int n = blockIdx.z, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  const bf16* src = qkv + ((int64_t)n * T) * 3 * C + 2 * C;
+  const f16* src = qkv + ((int64_t)n * T) * 3 * C + 2 * C;
   for (int i = threadIdx.y; i < 32; i += blockDim.y)
     tile[i][threadIdx.x] = src[(int64_t)(t0 + i) * 3 * C + c0 + threadIdx.x];
   __syncthreads();
-  bf16* dst = vt + (int64_t)n * C * T;
+  f16* dst = vt + (int64_t)n * C * T;
   for (int i = threadIdx.y; i < 32; i += blockDim.y)
     dst[(int64_t)(c0 + i) * T + t0 + threadIdx.x] = tile[threadIdx.x][i];
 }
 
-int transpose_v_launch(const bf16* qkv, bf16* vt, int N, int T, int C, cudaStream_t st) {
+int transpose_v_launch(const f16* qkv, f16* vt, int N, int T, int C, cudaStream_t st) {
   B2E_REQUIRE(T % 32 == 0 && C % 32 == 0, B2E_UNSUPPORTED_SHAPE, "transpose_v: T and C must be multiples of 32");
   launch_pdl(transpose_v_kernel, dim3(dim3(T / 32, C / 32, N)), dim3(dim3(32, 8)), 0, st, qkv, vt, T, C);
   return check_launch("transpose_v");
 }
 
 // ------------------------------------------------------------------ transformer-block kernels (SD UNet2DConditionModel)
-// LayerNorm over the channels of every token (bf16 NHWC rows of C channels, C % 8 == 0, C <= 2048): one warp per token,
+// LayerNorm over the channels of every token (f16 NHWC rows of C channels, C % 8 == 0, C <= 2048): one warp per token,
 // the row lives in registers between the two passes
 // CPL = 16-byte chunks per lane: the register array is sized for the row width (a fixed 8-chunk array costs ~100 registers
 // and a third of the occupancy on 320-channel rows; the kernel is latency-bound: one row per warp)
 template <int CPL>
-__global__ void __launch_bounds__(256) layernorm_rows_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
+__global__ void __launch_bounds__(256) layernorm_rows_kernel(const f16* __restrict__ x, f16* __restrict__ y,
                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
                                                              int64_t rows, int C, float eps) {
   pdl_wait();
@@ -825,10 +863,10 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const bf16* __restr
   }
 }
 
-__global__ void layernorm_rows_split_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const float* __restrict__ gamma,
+__global__ void layernorm_rows_split_kernel(const f16* __restrict__ x, f16* __restrict__ y, const float* __restrict__ gamma,
                                             const float* __restrict__ beta, int64_t rows, int C, float eps);
 
-int layernorm_rows_launch(const bf16* x, bf16* y, const float* gamma, const float* beta, int64_t rows, int C, float eps,
+int layernorm_rows_launch(const f16* x, f16* y, const float* gamma, const float* beta, int64_t rows, int C, float eps,
                           cudaStream_t st, int planes) {
   if (planes == 3) {
     B2E_REQUIRE(C % 8 == 0 && C <= 2048, B2E_UNSUPPORTED_SHAPE, "layernorm: C = %d (multiple of 8, <= 2048)", C);
@@ -850,9 +888,9 @@ int layernorm_rows_launch(const bf16* x, bf16* y, const float* gamma, const floa
 }
 
 // ---- CLIP text encoder helpers
-// token + position embedding: ids int64 [B][L] -> x bf16 [B][Lpad][D] (rows >= L zero)
+// token + position embedding: ids int64 [B][L] -> x f16 [B][Lpad][D] (rows >= L zero)
 __global__ void __launch_bounds__(256) clip_embed_kernel(const int64_t* __restrict__ ids, const float* __restrict__ tok,
-                                                         const float* __restrict__ pos, bf16* __restrict__ out, int B, int L,
+                                                         const float* __restrict__ pos, f16* __restrict__ out, int B, int L,
                                                          int Lpad, int D8, int vocab) {
   pdl_wait();
   const int64_t total = (int64_t)B * Lpad * D8;
@@ -874,7 +912,7 @@ __global__ void __launch_bounds__(256) clip_embed_kernel(const int64_t* __restri
   }
 }
 
-int clip_embed_launch(const int64_t* ids, const float* tok, const float* pos, bf16* out, int B, int L, int Lpad, int D, int vocab,
+int clip_embed_launch(const int64_t* ids, const float* tok, const float* pos, f16* out, int B, int L, int Lpad, int D, int vocab,
                       cudaStream_t st) {
   B2E_REQUIRE(D % 8 == 0 && L <= Lpad, B2E_UNSUPPORTED_SHAPE, "clip_embed: bad shape");
   const int64_t total = (int64_t)B * Lpad * (D / 8);
@@ -894,7 +932,7 @@ __global__ void __launch_bounds__(256) quick_gelu_kernel(const uint4* __restrict
   }
 }
 
-int quick_gelu_launch(const bf16* in, bf16* out, int64_t numel, cudaStream_t st) {
+int quick_gelu_launch(const f16* in, f16* out, int64_t numel, cudaStream_t st) {
   B2E_REQUIRE(numel % 8 == 0, B2E_UNSUPPORTED_SHAPE, "quick_gelu: numel %% 8 != 0");
   int64_t g = (numel / 8 + 255) / 256;
   if (g > kNumSMs * 16) g = kNumSMs * 16;
@@ -902,8 +940,8 @@ int quick_gelu_launch(const bf16* in, bf16* out, int64_t numel, cudaStream_t st)
   return check_launch("quick_gelu");
 }
 
-// final LayerNorm output: rows [0, L) of every sequence, bf16 [B][Lpad][D] -> fp32 [B][L][D]
-__global__ void __launch_bounds__(256) unpad_rows_f32_kernel(const bf16* __restrict__ x, float* __restrict__ out, int B, int L,
+// final LayerNorm output: rows [0, L) of every sequence, f16 [B][Lpad][D] -> fp32 [B][L][D]
+__global__ void __launch_bounds__(256) unpad_rows_f32_kernel(const f16* __restrict__ x, float* __restrict__ out, int B, int L,
                                                              int Lpad, int D) {
   pdl_wait();
   const int64_t total = (int64_t)B * L * D;
@@ -911,18 +949,18 @@ __global__ void __launch_bounds__(256) unpad_rows_f32_kernel(const bf16* __restr
     const int d = (int)(i % D);
     const int l = (int)((i / D) % L);
     const int b = (int)(i / ((int64_t)D * L));
-    out[i] = __bfloat162float(x[((int64_t)b * Lpad + l) * D + d]);
+    out[i] = f16_to_float(x[((int64_t)b * Lpad + l) * D + d]);
   }
 }
 
-int unpad_rows_f32_launch(const bf16* x, float* out, int B, int L, int Lpad, int D, cudaStream_t st) {
+int unpad_rows_f32_launch(const f16* x, float* out, int B, int L, int Lpad, int D, cudaStream_t st) {
   const int64_t total = (int64_t)B * L * D;
   launch_pdl(unpad_rows_f32_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, x, out, B, L, Lpad, D);
   return check_launch("unpad_rows_f32");
 }
 
-// fp32-accurate mode: LayerNorm over split-bf16 rows ([hi | lo | hi] planes of C channels, value = hi + lo)
-__global__ void __launch_bounds__(256) layernorm_rows_split_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
+// fp32-accurate mode: LayerNorm over split-f16 rows ([hi | lo | hi] planes of C channels, value = hi + lo)
+__global__ void __launch_bounds__(256) layernorm_rows_split_kernel(const f16* __restrict__ x, f16* __restrict__ y,
                                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                    int64_t rows, int C, float eps) {
   pdl_wait();
@@ -966,7 +1004,7 @@ __global__ void __launch_bounds__(256) layernorm_rows_split_kernel(const bf16* _
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         o[j] = (v[i][j] - mean) * rstd * __ldg(gamma + ch * 8 + j) + __ldg(beta + ch * 8 + j);
-        l[j] = __fsub_rn(o[j], __bfloat162float(__float2bfloat16_rn(o[j])));
+        l[j] = __fsub_rn(o[j], f16_to_float(float_to_f16(o[j])));
       }
       const uint4 hi = pack8(o);
       yr[ch] = hi; yr[chunks + ch] = pack8(l); yr[2 * chunks + ch] = hi;
@@ -992,7 +1030,7 @@ __global__ void __launch_bounds__(256) geglu_split_kernel(const uint4* __restric
     for (int j = 0; j < 8; ++j) {
       const float av = a[j] + al[j], gv = g[j] + gl[j];
       a[j] = av * (0.5f * gv * (1.f + erff(gv * 0.70710678118654752f)));
-      l[j] = __fsub_rn(a[j], __bfloat162float(__float2bfloat16_rn(a[j])));
+      l[j] = __fsub_rn(a[j], f16_to_float(float_to_f16(a[j])));
     }
     uint4* orow = out + r * 3 * inner8;
     const uint4 hi = pack8(a);
@@ -1017,7 +1055,7 @@ __global__ void __launch_bounds__(256) geglu_kernel(const uint4* __restrict__ in
   }
 }
 
-int geglu_launch(const bf16* in, bf16* out, int64_t rows, int inner, cudaStream_t st, int planes) {
+int geglu_launch(const f16* in, f16* out, int64_t rows, int inner, cudaStream_t st, int planes) {
   B2E_REQUIRE(inner % 8 == 0, B2E_UNSUPPORTED_SHAPE, "geglu: inner %% 8");
   const int64_t total = rows * (inner / 8);
   int grid = (int)((total + 255) / 256);
@@ -1030,8 +1068,8 @@ int geglu_launch(const bf16* in, bf16* out, int64_t rows, int inner, cudaStream_
   return check_launch("geglu");
 }
 
-// text conditioning: fp32 [B][L][D] -> bf16 [B][Lpad][D], rows >= L zero
-__global__ void __launch_bounds__(256) pack_context_kernel(const float* __restrict__ ctx, bf16* __restrict__ out, int B, int L,
+// text conditioning: fp32 [B][L][D] -> f16 [B][Lpad][D], rows >= L zero
+__global__ void __launch_bounds__(256) pack_context_kernel(const float* __restrict__ ctx, f16* __restrict__ out, int B, int L,
                                                            int Lpad, int D, int planes) {
   pdl_wait();
   const int64_t total = (int64_t)B * Lpad * D;
@@ -1040,17 +1078,17 @@ __global__ void __launch_bounds__(256) pack_context_kernel(const float* __restri
     const int l = (int)((i / D) % Lpad);
     const int64_t b = i / ((int64_t)D * Lpad);
     const float v = l < L ? ctx[(b * L + l) * D + dcol] : 0.f;
-    const bf16 hi = __float2bfloat16_rn(v);
-    if (planes == 3) {   // split-bf16 rows [hi | lo | hi]
-      bf16* o = out + (b * Lpad + l) * 3 * D + dcol;
-      o[0] = hi; o[D] = __float2bfloat16_rn(__fsub_rn(v, __bfloat162float(hi))); o[2 * D] = hi;
+    const f16 hi = float_to_f16(v);
+    if (planes == 3) {   // split-f16 rows [hi | lo | hi]
+      f16* o = out + (b * Lpad + l) * 3 * D + dcol;
+      o[0] = hi; o[D] = float_to_f16(__fsub_rn(v, f16_to_float(hi))); o[2 * D] = hi;
     } else {
       out[i] = hi;
     }
   }
 }
 
-int pack_context_launch(const float* ctx, bf16* out, int B, int L, int Lpad, int D, cudaStream_t st, int planes) {
+int pack_context_launch(const float* ctx, f16* out, int B, int L, int Lpad, int D, cudaStream_t st, int planes) {
   const int64_t total = (int64_t)B * Lpad * D;
   int grid = (int)((total + 255) / 256);
   if (grid > kNumSMs * 16) grid = kNumSMs * 16;
@@ -1060,7 +1098,7 @@ int pack_context_launch(const float* ctx, bf16* out, int B, int L, int Lpad, int
 
 // head-major gather for the batched attention GEMMs.  src rows: token (n, t), channels [col0 + h*d, + d) of a row of
 // `pitch` channels, t < Tsrc.  dst [N*heads][Tpad][dpad] with zeros for t >= Tsrc and channels >= d.
-__global__ void __launch_bounds__(256) gather_heads_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int N, int Tsrc,
+__global__ void __launch_bounds__(256) gather_heads_kernel(const f16* __restrict__ src, f16* __restrict__ dst, int N, int Tsrc,
                                                            int Tpad, int pitch, int col0, int heads, int d, int dpad) {
   pdl_wait();
   const int d8 = dpad >> 3;
@@ -1078,23 +1116,23 @@ __global__ void __launch_bounds__(256) gather_heads_kernel(const bf16* __restric
 }
 
 // transposed variant: dst [N*heads][dpad][Tpad] (V^T), zeros outside
-__global__ void gather_heads_T_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int Tsrc, int Tpad, int pitch,
+__global__ void gather_heads_T_kernel(const f16* __restrict__ src, f16* __restrict__ dst, int Tsrc, int Tpad, int pitch,
                                       int col0, int heads, int d, int dpad) {
   pdl_wait();
-  __shared__ bf16 tile[32][33];
+  __shared__ f16 tile[32][33];
   const int v = blockIdx.z, n = v / heads, h = v % heads, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  const bf16* s = src + ((int64_t)n * Tsrc) * pitch + col0 + h * d;
+  const f16* s = src + ((int64_t)n * Tsrc) * pitch + col0 + h * d;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int t = t0 + i, c = c0 + threadIdx.x;
-    tile[i][threadIdx.x] = (t < Tsrc && c < d) ? s[(int64_t)t * pitch + c] : __float2bfloat16_rn(0.f);
+    tile[i][threadIdx.x] = (t < Tsrc && c < d) ? s[(int64_t)t * pitch + c] : float_to_f16(0.f);
   }
   __syncthreads();
-  bf16* dd = dst + (int64_t)v * dpad * Tpad;
+  f16* dd = dst + (int64_t)v * dpad * Tpad;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) dd[(int64_t)(c0 + i) * Tpad + t0 + threadIdx.x] = tile[threadIdx.x][i];
 }
 
 // inverse of gather_heads for the attention output: out[n][t][h*d + c] = oh[n*heads + h][t][c], t < T, c < d
-__global__ void __launch_bounds__(256) scatter_heads_kernel(const bf16* __restrict__ oh, bf16* __restrict__ out, int N, int T,
+__global__ void __launch_bounds__(256) scatter_heads_kernel(const f16* __restrict__ oh, f16* __restrict__ out, int N, int T,
                                                             int Tpad, int pitch, int heads, int d, int dpad) {
   pdl_wait();
   const int c8 = pitch >> 3;   // the tail [heads*d, pitch) of every row is zero padding
@@ -1114,7 +1152,7 @@ __global__ void __launch_bounds__(256) scatter_heads_kernel(const bf16* __restri
   }
 }
 
-int gather_heads_launch(const bf16* src, bf16* dst, int N, int Tsrc, int Tpad, int pitch, int col0, int heads, int d, int dpad,
+int gather_heads_launch(const f16* src, f16* dst, int N, int Tsrc, int Tpad, int pitch, int col0, int heads, int d, int dpad,
                         bool transposed, cudaStream_t st) {
   B2E_REQUIRE(d % 8 == 0 && dpad % 64 == 0 && dpad >= d && Tpad % 32 == 0 && Tpad >= Tsrc, B2E_UNSUPPORTED_SHAPE,
               "gather_heads: head_dim %d -> %d, T %d -> %d", d, dpad, Tsrc, Tpad);
@@ -1130,7 +1168,7 @@ int gather_heads_launch(const bf16* src, bf16* dst, int N, int Tsrc, int Tpad, i
   return check_launch("gather_heads");
 }
 
-int scatter_heads_launch(const bf16* oh, bf16* out, int N, int T, int Tpad, int pitch, int heads, int d, int dpad, cudaStream_t st) {
+int scatter_heads_launch(const f16* oh, f16* out, int N, int T, int Tpad, int pitch, int heads, int d, int dpad, cudaStream_t st) {
   B2E_REQUIRE(d % 8 == 0, B2E_UNSUPPORTED_SHAPE, "scatter_heads: head_dim %d", d);
   const int64_t total = (int64_t)N * T * (pitch / 8);
   int grid = (int)((total + 255) / 256);
@@ -1141,18 +1179,18 @@ int scatter_heads_launch(const bf16* oh, bf16* out, int N, int T, int Tpad, int 
 
 // row softmax with masked tail: row length T (<= 1024, T % 32 == 0), only the first `valid` entries take part, the
 // rest become 0 (zero-padded keys of the batched attention GEMMs)
-__global__ void __launch_bounds__(256) softmax_rows_masked_kernel(bf16* __restrict__ s, int64_t rows, int T, int valid, float scale) {
+__global__ void __launch_bounds__(256) softmax_rows_masked_kernel(f16* __restrict__ s, int64_t rows, int T, int valid, float scale) {
   pdl_wait();
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
-  bf16* r = s + row * T;
+  f16* r = s + row * T;
   float v[32];
   const int per = T / 32;
   float m = -INFINITY;
   for (int i = 0; i < per; ++i) {
     const int j = lane + 32 * i;
-    v[i] = j < valid ? __bfloat162float(r[j]) * scale : -INFINITY;
+    v[i] = j < valid ? f16_to_float(r[j]) * scale : -INFINITY;
     m = fmaxf(m, v[i]);
   }
 #pragma unroll
@@ -1161,10 +1199,10 @@ __global__ void __launch_bounds__(256) softmax_rows_masked_kernel(bf16* __restri
   for (int i = 0; i < per; ++i) { v[i] = (lane + 32 * i) < valid ? __expf(v[i] - m) : 0.f; sum += v[i]; }
   sum = warp_sum(sum);
   const float inv = 1.f / sum;
-  for (int i = 0; i < per; ++i) r[lane + 32 * i] = __float2bfloat16_rn(v[i] * inv);
+  for (int i = 0; i < per; ++i) r[lane + 32 * i] = float_to_f16(v[i] * inv);
 }
 
-int softmax_rows_masked_launch(bf16* s, int64_t rows, int T, int valid, float scale, cudaStream_t st) {
+int softmax_rows_masked_launch(f16* s, int64_t rows, int T, int valid, float scale, cudaStream_t st) {
   if (valid == T) return softmax_rows_launch(s, rows, T, scale, st);
   B2E_REQUIRE(T % 32 == 0 && T <= 1024 && valid >= 1 && valid < T, B2E_UNSUPPORTED_SHAPE,
               "masked softmax: unsupported row length %d (valid %d)", T, valid);
@@ -1173,7 +1211,7 @@ int softmax_rows_masked_launch(bf16* s, int64_t rows, int T, int valid, float sc
 }
 
 // ------------------------------------------------------------------ backward helpers of the decoder
-// gradient of the nearest x2 upsample: dx[n][h][w][c] = sum of the 2x2 block of dy (bf16 NHWC, 8 channels per thread)
+// gradient of the nearest x2 upsample: dx[n][h][w][c] = sum of the 2x2 block of dy (f16 NHWC, 8 channels per thread)
 __global__ void __launch_bounds__(256) downsum2x_kernel(const uint4* __restrict__ dy, uint4* __restrict__ dx, int N, int H, int W,
                                                         int C8) {
   pdl_wait();
@@ -1198,7 +1236,7 @@ __global__ void __launch_bounds__(256) downsum2x_kernel(const uint4* __restrict_
   }
 }
 
-int downsum2x_launch(const bf16* dy, bf16* dx, int N, int H, int W, int C, cudaStream_t st) {
+int downsum2x_launch(const f16* dy, f16* dx, int N, int H, int W, int C, cudaStream_t st) {
   B2E_REQUIRE(C % 8 == 0, B2E_UNSUPPORTED_SHAPE, "downsum2x: C %% 8");
   const int64_t total = (int64_t)N * H * W * (C / 8);
   int grid = (int)((total + 255) / 256);
@@ -1208,31 +1246,31 @@ int downsum2x_launch(const bf16* dy, bf16* dx, int N, int H, int W, int C, cudaS
 }
 
 // batched 2-D transpose of a column window: dst[n][c][r] = src[n][r][col0 + c], r < R, c < Cc (both multiples of 32)
-__global__ void transpose_window_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int R, int Cc, int src_pitch,
+__global__ void transpose_window_kernel(const f16* __restrict__ src, f16* __restrict__ dst, int R, int Cc, int src_pitch,
                                         int col0) {
   pdl_wait();
-  __shared__ bf16 tile[32][33];
+  __shared__ f16 tile[32][33];
   const int n = blockIdx.z, r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  const bf16* s = src + (int64_t)n * R * src_pitch + col0;
+  const f16* s = src + (int64_t)n * R * src_pitch + col0;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) tile[i][threadIdx.x] = s[(int64_t)(r0 + i) * src_pitch + c0 + threadIdx.x];
   __syncthreads();
-  bf16* d = dst + (int64_t)n * Cc * R;
+  f16* d = dst + (int64_t)n * Cc * R;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) d[(int64_t)(c0 + i) * R + r0 + threadIdx.x] = tile[threadIdx.x][i];
 }
 
 // 64 x 64 tiles moved as 32-bit words (two adjacent columns): every warp access is 128 contiguous bytes on both sides
 // (the 32 x 32 two-byte version ran at 1.9 TB/s on the 4096 x 4096 attention matrices of the decoder backward pass)
-__global__ void __launch_bounds__(256) transpose_window64_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int R,
+__global__ void __launch_bounds__(256) transpose_window64_kernel(const f16* __restrict__ src, f16* __restrict__ dst, int R,
                                                                  int Cc, int src_pitch, int col0) {
   pdl_wait();
   __shared__ uint32_t tile[64][33];
   const int n = blockIdx.z, r0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 8 warps
-  const bf16* s = src + (int64_t)n * R * src_pitch + col0 + c0 + 2 * tx;
+  const f16* s = src + (int64_t)n * R * src_pitch + col0 + c0 + 2 * tx;
 #pragma unroll
   for (int i = ty; i < 64; i += 8) tile[i][tx] = __ldg(reinterpret_cast<const uint32_t*>(s + (int64_t)(r0 + i) * src_pitch));
   __syncthreads();
-  bf16* d = dst + (int64_t)n * Cc * R + r0 + 2 * tx;
+  f16* d = dst + (int64_t)n * Cc * R + r0 + 2 * tx;
 #pragma unroll
   for (int c = ty; c < 64; c += 8) {
     const uint32_t w0 = tile[2 * tx][c >> 1], w1 = tile[2 * tx + 1][c >> 1];
@@ -1241,7 +1279,7 @@ __global__ void __launch_bounds__(256) transpose_window64_kernel(const bf16* __r
   }
 }
 
-int transpose_window_launch(const bf16* src, bf16* dst, int N, int R, int Cc, int src_pitch, int col0, cudaStream_t st) {
+int transpose_window_launch(const f16* src, f16* dst, int N, int R, int Cc, int src_pitch, int col0, cudaStream_t st) {
   B2E_REQUIRE(R % 32 == 0 && Cc % 32 == 0, B2E_UNSUPPORTED_SHAPE, "transpose: R and C must be multiples of 32");
   if (R % 64 == 0 && Cc % 64 == 0 && src_pitch % 2 == 0 && col0 % 2 == 0) {
     launch_pdl(transpose_window64_kernel, dim3(R / 64, Cc / 64, N), dim3(256), 0, st, src, dst, R, Cc, src_pitch, col0);
@@ -1252,7 +1290,7 @@ int transpose_window_launch(const bf16* src, bf16* dst, int N, int R, int Cc, in
 }
 
 // softmax backward, one warp per row, in place on dP:  dS = scale * P o (dP - sum_j dP_j P_j)
-__global__ void __launch_bounds__(256) softmax_bwd_rows_kernel(const bf16* __restrict__ p, bf16* __restrict__ dp, int64_t rows,
+__global__ void __launch_bounds__(256) softmax_bwd_rows_kernel(const f16* __restrict__ p, f16* __restrict__ dp, int64_t rows,
                                                                int T, float scale) {
   pdl_wait();
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -1280,17 +1318,19 @@ __global__ void __launch_bounds__(256) softmax_bwd_rows_kernel(const bf16* __res
   }
 }
 
-int softmax_bwd_rows_launch(const bf16* p, bf16* dp, int64_t rows, int T, float scale, cudaStream_t st) {
+int softmax_bwd_rows_launch(const f16* p, f16* dp, int64_t rows, int T, float scale, cudaStream_t st) {
   B2E_REQUIRE(T % 8 == 0, B2E_UNSUPPORTED_SHAPE, "softmax backward: T %% 8");
   launch_pdl(softmax_bwd_rows_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, st, p, dp, rows, T, scale);
   return check_launch("softmax_bwd_rows");
 }
 
-// backward of (nearest code [straight-through] -> post_quant_conv -> im2col): dcols bf16 [B][H][W][64] holds the gradient
+// backward of (nearest code [straight-through] -> post_quant_conv -> im2col): dcols f16 [B][H][W][64] holds the gradient
 // w.r.t. im2col column t*L + c of every pixel; dz[b][k][h][w] = sum_c pq_w[c][k] * sum_t dcols[(h,w) - tap_t][t*L + c]
-__global__ void __launch_bounds__(256) vq_col2im_bwd_kernel(const bf16* __restrict__ dcols, const float* __restrict__ pq_w,
-                                                            float* __restrict__ dz, int B, int L, int H, int W) {
+__global__ void __launch_bounds__(256) vq_col2im_bwd_kernel(const f16* __restrict__ dcols, const float* __restrict__ pq_w,
+                                                            float* __restrict__ dz, int B, int L, int H, int W,
+                                                            const float* __restrict__ gs) {
   pdl_wait();
+  const float unscale = gs ? gs[1] : 1.f;
   const int64_t total = (int64_t)B * H * W;
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= total) return;
@@ -1301,20 +1341,21 @@ __global__ void __launch_bounds__(256) vq_col2im_bwd_kernel(const bf16* __restri
     // forward: cols[(hh, ww)][t*L + c] = x[c][hh + t/3 - 1][ww + t%3 - 1]  ->  (hh, ww) = (h, w) - tap
     const int hh = h - (t / 3 - 1), ww = w - (t % 3 - 1);
     if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
-    const bf16* src = dcols + (((int64_t)b * H + hh) * W + ww) * 64 + t * L;
-    for (int c = 0; c < L; ++c) g[c] += __bfloat162float(src[c]);
+    const f16* src = dcols + (((int64_t)b * H + hh) * W + ww) * 64 + t * L;
+    for (int c = 0; c < L; ++c) g[c] += f16_to_float(src[c]);
   }
   for (int k = 0; k < L; ++k) {
     float acc = 0.f;
     for (int c = 0; c < L; ++c) acc += pq_w[c * L + k] * g[c];
-    dz[((int64_t)b * L + k) * HW + q] = acc;
+    dz[((int64_t)b * L + k) * HW + q] = acc * unscale;
   }
 }
 
-int vq_col2im_bwd_launch(const bf16* dcols, const float* pq_w, float* dz, int B, int L, int H, int W, cudaStream_t st) {
+int vq_col2im_bwd_launch(const f16* dcols, const float* pq_w, float* dz, int B, int L, int H, int W, cudaStream_t st,
+                         const float* gs) {
   B2E_REQUIRE(L >= 1 && L <= 4 && 9 * L <= 64, B2E_UNSUPPORTED_SHAPE, "vq_col2im_bwd: latent channels %d", L);
   const int64_t total = (int64_t)B * H * W;
-  launch_pdl(vq_col2im_bwd_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, dcols, pq_w, dz, B, L, H, W);
+  launch_pdl(vq_col2im_bwd_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, dcols, pq_w, dz, B, L, H, W, gs);
   return check_launch("vq_col2im_bwd");
 }
 
@@ -1417,8 +1458,8 @@ int pointwise_conv_f32_launch(const float* x, const float* w, const float* b, fl
 // qkv [N][T][3P] (q | k | v blocks of P channels, head h = channels [h*d, h*d + d) of a block, d <= 64) ->
 // head-major operands of the batched tensor-core GEMMs: qh, kh [N*heads][T][64] (channels >= d zero) and
 // vht [N*heads][64][T] (V^T, rows >= d zero).  "Virtual image" v = n * heads + h.
-__global__ void __launch_bounds__(256) split_heads_qk_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ qh,
-                                                             bf16* __restrict__ kh, int64_t NT, int T, int P, int heads, int d) {
+__global__ void __launch_bounds__(256) split_heads_qk_kernel(const f16* __restrict__ qkv, f16* __restrict__ qh,
+                                                             f16* __restrict__ kh, int64_t NT, int T, int P, int heads, int d) {
   pdl_wait();
   const int64_t total = NT * heads * 8;   // (n*T + t, h, 8-channel slot)
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -1428,7 +1469,7 @@ __global__ void __launch_bounds__(256) split_heads_qk_kernel(const bf16* __restr
     const int64_t n = nt / T, t = nt % T;
     uint4 q = make_uint4(0, 0, 0, 0), k = q;
     if (j * 8 < d) {
-      const bf16* src = qkv + nt * 3 * P + h * d + j * 8;
+      const f16* src = qkv + nt * 3 * P + h * d + j * 8;
       q = __ldg(reinterpret_cast<const uint4*>(src));
       k = __ldg(reinterpret_cast<const uint4*>(src + P));
     }
@@ -1439,21 +1480,21 @@ __global__ void __launch_bounds__(256) split_heads_qk_kernel(const bf16* __restr
 }
 
 // 32x32 smem-tiled transpose: vht[v][c][t] = V[n][t][h*d + c] (c < d), 0 otherwise
-__global__ void split_heads_vt_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ vht, int T, int P, int heads, int d) {
+__global__ void split_heads_vt_kernel(const f16* __restrict__ qkv, f16* __restrict__ vht, int T, int P, int heads, int d) {
   pdl_wait();
-  __shared__ bf16 tile[32][33];
+  __shared__ f16 tile[32][33];
   const int v = blockIdx.z, n = v / heads, h = v % heads, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  const bf16* src = qkv + ((int64_t)n * T) * 3 * P + 2 * P + h * d;
+  const f16* src = qkv + ((int64_t)n * T) * 3 * P + 2 * P + h * d;
   for (int i = threadIdx.y; i < 32; i += blockDim.y)
-    tile[i][threadIdx.x] = (c0 + (int)threadIdx.x < d) ? src[(int64_t)(t0 + i) * 3 * P + c0 + threadIdx.x] : __float2bfloat16_rn(0.f);
+    tile[i][threadIdx.x] = (c0 + (int)threadIdx.x < d) ? src[(int64_t)(t0 + i) * 3 * P + c0 + threadIdx.x] : float_to_f16(0.f);
   __syncthreads();
-  bf16* dst = vht + (int64_t)v * 64 * T;
+  f16* dst = vht + (int64_t)v * 64 * T;
   for (int i = threadIdx.y; i < 32; i += blockDim.y)
     dst[(int64_t)(c0 + i) * T + t0 + threadIdx.x] = tile[threadIdx.x][i];
 }
 
 // oh [N*heads][T][64] -> out [N][T][P]: out[n][t][h*d + c] = oh[n*heads + h][t][c]; channels [heads*d, P) zeroed
-__global__ void __launch_bounds__(256) merge_heads_kernel(const bf16* __restrict__ oh, bf16* __restrict__ out, int64_t NT,
+__global__ void __launch_bounds__(256) merge_heads_kernel(const f16* __restrict__ oh, f16* __restrict__ out, int64_t NT,
                                                           int T, int P, int heads, int d) {
   pdl_wait();
   const int slots = P >> 3;
@@ -1472,7 +1513,7 @@ __global__ void __launch_bounds__(256) merge_heads_kernel(const bf16* __restrict
   }
 }
 
-int split_heads_launch(const bf16* qkv, bf16* qh, bf16* kh, bf16* vht, int N, int T, int P, int heads, int d, cudaStream_t st) {
+int split_heads_launch(const f16* qkv, f16* qh, f16* kh, f16* vht, int N, int T, int P, int heads, int d, cudaStream_t st) {
   B2E_REQUIRE(d % 8 == 0 && d <= 64 && T % 32 == 0 && heads * d <= P, B2E_UNSUPPORTED_SHAPE, "split_heads: head_dim %d, T %d", d, T);
   const int64_t NT = (int64_t)N * T, total = NT * heads * 8;
   int grid = (int)((total + 255) / 256);
@@ -1484,7 +1525,7 @@ int split_heads_launch(const bf16* qkv, bf16* qh, bf16* kh, bf16* vht, int N, in
   return check_launch("split_heads_vt");
 }
 
-int merge_heads_launch(const bf16* oh, bf16* out, int N, int T, int P, int heads, int d, cudaStream_t st) {
+int merge_heads_launch(const f16* oh, f16* out, int N, int T, int P, int heads, int d, cudaStream_t st) {
   const int64_t NT = (int64_t)N * T, total = NT * (P / 8);
   int grid = (int)((total + 255) / 256);
   if (grid > kNumSMs * 32) grid = kNumSMs * 32;
@@ -1498,30 +1539,30 @@ int merge_heads_launch(const bf16* oh, bf16* out, int N, int T, int P, int heads
 // out rows have pitch P (the tail is zero-filled by the h == 0 blocks).
 constexpr int kAttThreads = 256;
 constexpr int kAttQ = 16;
-constexpr int kAttKStride = 72;  // bf16 per staged key row (64 + pad): uint4-aligned, conflict-free
+constexpr int kAttKStride = 72;  // f16 per staged key row (64 + pad): uint4-aligned, conflict-free
 
 __global__ void __launch_bounds__(kAttThreads)
-attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, int C, int P, int heads) {
+attention_kernel(const f16* __restrict__ qkv, f16* __restrict__ out, int T, int C, int P, int heads) {
   pdl_wait();
   extern __shared__ __align__(16) uint8_t att_smem[];
   const int d = C / heads;
   float* Qs = reinterpret_cast<float*>(att_smem);            // [16][d]
   float* S = Qs + kAttQ * d;                                  // [16][T]
-  bf16* Ks = reinterpret_cast<bf16*>(S + kAttQ * T);         // [256][72]  (phase 3: fp32 partial sums, 32 KB)
+  f16* Ks = reinterpret_cast<f16*>(S + kAttQ * T);         // [256][72]  (phase 3: fp32 partial sums, 32 KB)
   const int qt = blockIdx.x, h = blockIdx.y, n = blockIdx.z, tid = threadIdx.x;
   const int q0 = qt * kAttQ;
   const int64_t row = 3 * (int64_t)P;
-  const bf16* base = qkv + (int64_t)n * T * row;
+  const f16* base = qkv + (int64_t)n * T * row;
   const float scale = rsqrtf((float)d);
   // load Q tile
   for (int i = tid; i < kAttQ * d; i += kAttThreads) {
     const int q = i / d, c = i % d;
-    Qs[i] = (q0 + q < T) ? __bfloat162float(base[(int64_t)(q0 + q) * row + h * d + c]) : 0.f;
+    Qs[i] = (q0 + q < T) ? f16_to_float(base[(int64_t)(q0 + q) * row + h * d + c]) : 0.f;
   }
   if (h == 0 && P > C) {   // zero padding of the output pitch
     for (int i = tid; i < kAttQ * (P - C); i += kAttThreads) {
       const int q = i / (P - C), c = i % (P - C);
-      if (q0 + q < T) out[((int64_t)n * T + q0 + q) * P + C + c] = __float2bfloat16_rn(0.f);
+      if (q0 + q < T) out[((int64_t)n * T + q0 + q) * P + C + c] = float_to_f16(0.f);
     }
   }
   // phase 1: scores, keys staged in pieces of dc = min(64, d) channels
@@ -1588,12 +1629,12 @@ attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, in
 #pragma unroll
       for (int q = 0; q < kAttQ; ++q) ax[q] = ay[q] = 0.f;
       const int per = T / groups;
-      const bf16* vp = base + 2 * P + h * d + 2 * cp;
+      const f16* vp = base + 2 * P + h * d + 2 * cp;
       for (int j = ks * per; j < (ks + 1) * per; j += 4) {
         float2 v[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u)
-          v[u] = __bfloat1622float2(__ldg(reinterpret_cast<const __nv_bfloat162*>(vp + (int64_t)(j + u) * row)));
+          v[u] = f16x2_to_float2(__ldg(reinterpret_cast<const f16x2*>(vp + (int64_t)(j + u) * row)));
 #pragma unroll
         for (int q = 0; q < kAttQ; ++q) {
           const float4 p = *reinterpret_cast<const float4*>(S + q * T + j);
@@ -1614,7 +1655,7 @@ attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, in
         sx += v.x; sy += v.y;
       }
       if (q0 + q < T)
-        *reinterpret_cast<__nv_bfloat162*>(out + ((int64_t)n * T + q0 + q) * P + h * d + 2 * c2) = __floats2bfloat162_rn(sx, sy);
+        *reinterpret_cast<f16x2*>(out + ((int64_t)n * T + q0 + q) * P + h * d + 2 * c2) = floats_to_f16x2(sx, sy);
     }
     return;
   }
@@ -1622,12 +1663,12 @@ attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, in
     float ax[kAttQ], ay[kAttQ];
 #pragma unroll
     for (int q = 0; q < kAttQ; ++q) ax[q] = ay[q] = 0.f;
-    const bf16* vp = base + 2 * P + h * d + c0;
+    const f16* vp = base + 2 * P + h * d + c0;
     for (int j = 0; j < T; j += 4) {  // T % 4 == 0 (checked on the host)
       float2 v[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u)
-        v[u] = __bfloat1622float2(__ldg(reinterpret_cast<const __nv_bfloat162*>(vp + (int64_t)(j + u) * row)));
+        v[u] = f16x2_to_float2(__ldg(reinterpret_cast<const f16x2*>(vp + (int64_t)(j + u) * row)));
 #pragma unroll
       for (int q = 0; q < kAttQ; ++q) {
         const float4 p = *reinterpret_cast<const float4*>(S + q * T + j);
@@ -1638,16 +1679,16 @@ attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, in
 #pragma unroll
     for (int q = 0; q < kAttQ; ++q)
       if (q0 + q < T)
-        *reinterpret_cast<__nv_bfloat162*>(out + ((int64_t)n * T + q0 + q) * P + h * d + c0) =
-            __floats2bfloat162_rn(ax[q], ay[q]);
+        *reinterpret_cast<f16x2*>(out + ((int64_t)n * T + q0 + q) * P + h * d + c0) =
+            floats_to_f16x2(ax[q], ay[q]);
   }
 }
 
-// fp32-accurate mode: the same attention core on split-bf16 tensors, all arithmetic in fp32 on the CUDA cores
+// fp32-accurate mode: the same attention core on split-f16 tensors, all arithmetic in fp32 on the CUDA cores
 // (1.3 % of the UNet's FLOPs).  qkv rows are [hi | lo | hi] planes of 3P channels (q | k | v blocks of P), out rows
 // [hi | lo | hi] planes of P channels.  Block = (image, head, 16 queries).
 __global__ void __launch_bounds__(kAttThreads)
-attention_split_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int T, int C, int P, int heads) {
+attention_split_kernel(const f16* __restrict__ qkv, f16* __restrict__ out, int T, int C, int P, int heads) {
   pdl_wait();
   extern __shared__ __align__(16) uint8_t att_smem[];
   const int d = C / heads;
@@ -1656,18 +1697,18 @@ attention_split_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int
   const int qt = blockIdx.x, h = blockIdx.y, n = blockIdx.z, tid = threadIdx.x;
   const int q0 = qt * kAttQ;
   const int64_t plane = 3 * (int64_t)P, row = 3 * plane;
-  const bf16* base = qkv + (int64_t)n * T * row;
+  const f16* base = qkv + (int64_t)n * T * row;
   const float scale = 1.0f / sqrtf((float)d);
   for (int i = tid; i < kAttQ * d; i += kAttThreads) {
     const int q = i / d, c = i % d;
-    const bf16* qp = base + (int64_t)(q0 + q) * row + h * d + c;
-    Qs[i] = (q0 + q < T) ? __bfloat162float(qp[0]) + __bfloat162float(qp[plane]) : 0.f;
+    const f16* qp = base + (int64_t)(q0 + q) * row + h * d + c;
+    Qs[i] = (q0 + q < T) ? f16_to_float(qp[0]) + f16_to_float(qp[plane]) : 0.f;
   }
   const int64_t orow = 3 * (int64_t)P;
   if (h == 0 && P > C) {   // zero padding of the output pitch (all planes)
     for (int i = tid; i < kAttQ * (P - C) * 3; i += kAttThreads) {
       const int k = i % 3, r = i / 3, q = r / (P - C), c = r % (P - C);
-      if (q0 + q < T) out[((int64_t)n * T + q0 + q) * orow + k * P + C + c] = __float2bfloat16_rn(0.f);
+      if (q0 + q < T) out[((int64_t)n * T + q0 + q) * orow + k * P + C + c] = float_to_f16(0.f);
     }
   }
   __syncthreads();
@@ -1676,7 +1717,7 @@ attention_split_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int
     float acc[kAttQ];
 #pragma unroll
     for (int q = 0; q < kAttQ; ++q) acc[q] = 0.f;
-    const bf16* kp = base + (int64_t)key * row + P + h * d;
+    const f16* kp = base + (int64_t)key * row + P + h * d;
     for (int c0 = 0; c0 < d; c0 += 8) {
       float kf[8], kl[8];
       unpack8(__ldg(reinterpret_cast<const uint4*>(kp + c0)), kf);
@@ -1712,13 +1753,13 @@ attention_split_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int
     float ax[kAttQ], ay[kAttQ];
 #pragma unroll
     for (int q = 0; q < kAttQ; ++q) ax[q] = ay[q] = 0.f;
-    const bf16* vp = base + 2 * P + h * d + c0;
+    const f16* vp = base + 2 * P + h * d + c0;
     for (int j = 0; j < T; j += 4) {
       float2 v[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const float2 vh = __bfloat1622float2(__ldg(reinterpret_cast<const __nv_bfloat162*>(vp + (int64_t)(j + u) * row)));
-        const float2 vl = __bfloat1622float2(__ldg(reinterpret_cast<const __nv_bfloat162*>(vp + (int64_t)(j + u) * row + plane)));
+        const float2 vh = f16x2_to_float2(__ldg(reinterpret_cast<const f16x2*>(vp + (int64_t)(j + u) * row)));
+        const float2 vl = f16x2_to_float2(__ldg(reinterpret_cast<const f16x2*>(vp + (int64_t)(j + u) * row + plane)));
         v[u] = make_float2(vh.x + vl.x, vh.y + vl.y);
       }
 #pragma unroll
@@ -1731,17 +1772,17 @@ attention_split_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int
 #pragma unroll
     for (int q = 0; q < kAttQ; ++q)
       if (q0 + q < T) {
-        bf16* o = out + ((int64_t)n * T + q0 + q) * orow + h * d + c0;
-        const __nv_bfloat162 hi = __floats2bfloat162_rn(ax[q], ay[q]);
-        const float2 hf = __bfloat1622float2(hi);
-        *reinterpret_cast<__nv_bfloat162*>(o) = hi;
-        *reinterpret_cast<__nv_bfloat162*>(o + P) = __floats2bfloat162_rn(__fsub_rn(ax[q], hf.x), __fsub_rn(ay[q], hf.y));
-        *reinterpret_cast<__nv_bfloat162*>(o + 2 * P) = hi;
+        f16* o = out + ((int64_t)n * T + q0 + q) * orow + h * d + c0;
+        const f16x2 hi = floats_to_f16x2(ax[q], ay[q]);
+        const float2 hf = f16x2_to_float2(hi);
+        *reinterpret_cast<f16x2*>(o) = hi;
+        *reinterpret_cast<f16x2*>(o + P) = floats_to_f16x2(__fsub_rn(ax[q], hf.x), __fsub_rn(ay[q], hf.y));
+        *reinterpret_cast<f16x2*>(o + 2 * P) = hi;
       }
   }
 }
 
-int attention_split_launch(const bf16* qkv, bf16* out, int N, int T, int C, int P, int heads, cudaStream_t st) {
+int attention_split_launch(const f16* qkv, f16* out, int N, int T, int C, int P, int heads, cudaStream_t st) {
   B2E_REQUIRE(heads >= 1 && C % heads == 0 && P >= C && P % 8 == 0, B2E_UNSUPPORTED_SHAPE, "attention: bad head count / pitch");
   const int d = C / heads;
   B2E_REQUIRE(d % 8 == 0 && T % 4 == 0, B2E_UNSUPPORTED_SHAPE, "attention (fp32-accurate): unsupported T=%d head_dim=%d", T, d);
@@ -1757,13 +1798,13 @@ int attention_split_launch(const bf16* qkv, bf16* out, int N, int T, int C, int 
 }
 
 // fp32-accurate mode, any sequence length: flash-style fp32 attention on the CUDA cores (online softmax over 32-key
-// tiles, O accumulated in registers).  q / k / v are channel windows of split-bf16 tensors ([hi | lo | hi] planes):
+// tiles, O accumulated in registers).  q / k / v are channel windows of split-f16 tensors ([hi | lo | hi] planes):
 // q rows [n][tq] of a tensor with `q_plane` channels per plane at column q_col + h*d, k / v rows [n][tk] of a tensor with
 // `k_plane` channels per plane at columns k_col + h*d / v_col + h*d; out rows [n][tq] with o_plane channels per plane.
 // Block = (32 queries, head, image).
 constexpr int kTaQ = 32, kTaK = 32, kTaThreads = 256;
 struct TiledAttnArgs {
-  const bf16* q; const bf16* kv; bf16* out;
+  const f16* q; const f16* kv; f16* out;
   int Tq, Tk, valid_k, heads, d;
   int q_plane, q_col, k_plane, k_col, v_col, o_plane, o_real;
   int64_t q_img, kv_img, o_img;   // elements between consecutive images
@@ -1781,14 +1822,14 @@ __global__ void __launch_bounds__(kTaThreads) attention_split_tiled_kernel(Tiled
   float* rowl = rowm + kTaQ;                                      // [32] running sum
   float* rowc = rowl + kTaQ;                                      // [32] rescale factor of the current tile
   const int tid = threadIdx.x, h = blockIdx.y, n = blockIdx.z, q0 = blockIdx.x * kTaQ;
-  const bf16* qb = a.q + (int64_t)n * a.q_img + a.q_col + h * d;
-  const bf16* kb = a.kv + (int64_t)n * a.kv_img + a.k_col + h * d;
-  const bf16* vb = a.kv + (int64_t)n * a.kv_img + a.v_col + h * d;
+  const f16* qb = a.q + (int64_t)n * a.q_img + a.q_col + h * d;
+  const f16* kb = a.kv + (int64_t)n * a.kv_img + a.k_col + h * d;
+  const f16* vb = a.kv + (int64_t)n * a.kv_img + a.v_col + h * d;
   const int64_t qrow = 3 * (int64_t)a.q_plane, krow = 3 * (int64_t)a.k_plane;
   for (int i = tid; i < kTaQ * d; i += kTaThreads) {
     const int q = i / d, c = i - q * d;
     float v = 0.f;
-    if (q0 + q < a.Tq) { const bf16* p = qb + (int64_t)(q0 + q) * qrow + c; v = __bfloat162float(p[0]) + __bfloat162float(p[a.q_plane]); }
+    if (q0 + q < a.Tq) { const f16* p = qb + (int64_t)(q0 + q) * qrow + c; v = f16_to_float(p[0]) + f16_to_float(p[a.q_plane]); }
     Qs[q * ds + c] = v * a.scale;
   }
   if (tid < kTaQ) { rowm[tid] = -INFINITY; rowl[tid] = 0.f; }
@@ -1807,7 +1848,7 @@ __global__ void __launch_bounds__(kTaThreads) attention_split_tiled_kernel(Tiled
     for (int i = tid; i < kTaK * d; i += kTaThreads) {
       const int k = i / d, c = i - k * d;
       float v = 0.f;
-      if (k0 + k < a.valid_k) { const bf16* p = kb + (int64_t)(k0 + k) * krow + c; v = __bfloat162float(p[0]) + __bfloat162float(p[a.k_plane]); }
+      if (k0 + k < a.valid_k) { const f16* p = kb + (int64_t)(k0 + k) * krow + c; v = f16_to_float(p[0]) + f16_to_float(p[a.k_plane]); }
       KV[k * ds + c] = v;
     }
     __syncthreads();
@@ -1851,7 +1892,7 @@ __global__ void __launch_bounds__(kTaThreads) attention_split_tiled_kernel(Tiled
     for (int i = tid; i < kTaK * d; i += kTaThreads) {
       const int k = i / d, c = i - k * d;
       float v = 0.f;
-      if (k0 + k < a.valid_k) { const bf16* p = vb + (int64_t)(k0 + k) * krow + c; v = __bfloat162float(p[0]) + __bfloat162float(p[a.k_plane]); }
+      if (k0 + k < a.valid_k) { const f16* p = vb + (int64_t)(k0 + k) * krow + c; v = f16_to_float(p[0]) + f16_to_float(p[a.k_plane]); }
       KV[k * ds + c] = v;
     }
     __syncthreads();
@@ -1879,7 +1920,7 @@ __global__ void __launch_bounds__(kTaThreads) attention_split_tiled_kernel(Tiled
   }
   // ---- normalise and write the split output
   const int64_t orow = 3 * (int64_t)a.o_plane;
-  bf16* ob = a.out + (int64_t)n * a.o_img + h * d;
+  f16* ob = a.out + (int64_t)n * a.o_img + h * d;
   if (owner && 2 * cp < d) {
 #pragma unroll
     for (int i = 0; i < kTaQ; ++i) {
@@ -1887,12 +1928,12 @@ __global__ void __launch_bounds__(kTaThreads) attention_split_tiled_kernel(Tiled
       if (i < qper && q < kTaQ && q0 + q < a.Tq) {
         const float inv = 1.f / rowl[q];
         const float vx = ox[i] * inv, vy = oy[i] * inv;
-        bf16* o = ob + (int64_t)(q0 + q) * orow + 2 * cp;
-        const __nv_bfloat162 hi = __floats2bfloat162_rn(vx, vy);
-        const float2 hf = __bfloat1622float2(hi);
-        *reinterpret_cast<__nv_bfloat162*>(o) = hi;
-        *reinterpret_cast<__nv_bfloat162*>(o + a.o_plane) = __floats2bfloat162_rn(__fsub_rn(vx, hf.x), __fsub_rn(vy, hf.y));
-        *reinterpret_cast<__nv_bfloat162*>(o + 2 * a.o_plane) = hi;
+        f16* o = ob + (int64_t)(q0 + q) * orow + 2 * cp;
+        const f16x2 hi = floats_to_f16x2(vx, vy);
+        const float2 hf = f16x2_to_float2(hi);
+        *reinterpret_cast<f16x2*>(o) = hi;
+        *reinterpret_cast<f16x2*>(o + a.o_plane) = floats_to_f16x2(__fsub_rn(vx, hf.x), __fsub_rn(vy, hf.y));
+        *reinterpret_cast<f16x2*>(o + 2 * a.o_plane) = hi;
       }
     }
   }
@@ -1900,12 +1941,12 @@ __global__ void __launch_bounds__(kTaThreads) attention_split_tiled_kernel(Tiled
     const int pad = a.o_plane - a.o_real;
     for (int i = tid; i < kTaQ * pad * 3; i += kTaThreads) {
       const int k = i % 3, r = i / 3, q = r / pad, c = r % pad;
-      if (q0 + q < a.Tq) a.out[(int64_t)n * a.o_img + (int64_t)(q0 + q) * orow + k * a.o_plane + a.o_real + c] = __float2bfloat16_rn(0.f);
+      if (q0 + q < a.Tq) a.out[(int64_t)n * a.o_img + (int64_t)(q0 + q) * orow + k * a.o_plane + a.o_real + c] = float_to_f16(0.f);
     }
   }
 }
 
-int attention_split_tiled_launch(const bf16* q, int q_plane, int q_col, const bf16* kv, int k_plane, int k_col, int v_col, bf16* out,
+int attention_split_tiled_launch(const f16* q, int q_plane, int q_col, const f16* kv, int k_plane, int k_col, int v_col, f16* out,
                                  int o_plane, int o_real, int N, int Tq, int Tk_rows, int valid_k, int heads, int d, cudaStream_t st) {
   B2E_REQUIRE(d % 2 == 0 && d >= 8 && d <= 512 && heads >= 1 && valid_k >= 1 && valid_k <= Tk_rows, B2E_UNSUPPORTED_SHAPE,
               "attention (fp32-accurate, tiled): unsupported head_dim %d / keys %d of %d", d, valid_k, Tk_rows);
@@ -1924,12 +1965,12 @@ int attention_split_tiled_launch(const bf16* q, int q_plane, int q_col, const bf
   return check_launch("attention_split_tiled");
 }
 
-int attention_launch(const bf16* qkv, bf16* out, int N, int T, int C, int P, int heads, cudaStream_t st) {
+int attention_launch(const f16* qkv, f16* out, int N, int T, int C, int P, int heads, cudaStream_t st) {
   B2E_REQUIRE(heads >= 1 && C % heads == 0 && P >= C && P % 8 == 0, B2E_UNSUPPORTED_SHAPE, "attention: bad head count / pitch");
   const int d = C / heads;
   B2E_REQUIRE(d % 8 == 0 && (d <= 64 || d % 64 == 0) && d <= 1024 && T % 4 == 0 && T <= 4096, B2E_UNSUPPORTED_SHAPE,
               "attention: unsupported T=%d head_dim=%d", T, d);
-  const size_t smem = sizeof(float) * kAttQ * (d + T) + sizeof(bf16) * kAttThreads * kAttKStride;
+  const size_t smem = sizeof(float) * kAttQ * (d + T) + sizeof(f16) * kAttThreads * kAttKStride;
   B2E_REQUIRE(smem <= 200 * 1024, B2E_UNSUPPORTED_SHAPE, "attention: tile does not fit in shared memory");
   static size_t attr = 0;
   if (smem > attr) {

@@ -24,7 +24,7 @@ class NativePipeline(SimpleNamespace):
 def create_diffusion_model(name: str, sample_clipping: bool = True, *, max_batch: int = 8, seed: int = 0,
                            state_dict: Optional[dict] = None, unet_config: Optional[dict] = None, vqvae=None,
                            vq_config: Optional[dict] = None, vq_state_dict: Optional[dict] = None, guidance_module=None,
-                           decoder_grad: bool = True, tokenizer=None, text_encoder=None, precision: str = "bf16",
+                           decoder_grad: bool = True, tokenizer=None, text_encoder=None, precision: Optional[str] = None,
                            with_encoder: bool = True, text_encoder_config: Optional[dict] = None,
                            text_encoder_state_dict: Optional[dict] = None):
     """``name``: "ddpm" (google/ddpm-celebahq-256 layout), "sd" (Stable Diffusion 1.x layout: native conditional UNet
@@ -33,7 +33,7 @@ def create_diffusion_model(name: str, sample_clipping: bool = True, *, max_batch
     the 64x64x3 latent + native VQ decoder (forward + latent gradient) and encoder; ``vqvae=`` substitutes the caller's VQ autoencoder module
     (encode().latents / decode().sample, as in the reference's pipeline object); ``guidance_module=`` is the
     differentiable decoder used when guidance runs through decode).  ``precision="fp32"`` selects the fp32-accurate
-    (split-bf16) noise predictor (all three families) and VQ / KL decoder (forward only: guidance through the decoder needs bf16).  ``with_encoder`` (default) also builds the native VQ / KL encoder behind
+    (split-f16) noise predictor (all three families) and VQ / KL decoder (forward only: guidance through the decoder uses the fp16 engine).  ``with_encoder`` (default) also builds the native VQ / KL encoder behind
     ``LDM.encode`` / ``SD.encode``."""
     device = get_device()
     if name == "ddpm":
@@ -58,7 +58,7 @@ def create_diffusion_model(name: str, sample_clipping: bool = True, *, max_batch
             # decoder_grad=True (default), the native dgrad for guidance THROUGH the decoder
             vqvae = VQModel(**(vq_config or LDM_VQ_CONFIG), max_batch=max_batch, device=device, with_encoder=with_encoder,
                             precision=precision)
-            decoder_grad = decoder_grad and precision == "bf16"   # the fp32-accurate decoder is forward-only
+            decoder_grad = decoder_grad and precision != "fp32"   # the fp32-accurate decoder is forward-only
             if vq_state_dict is not None:
                 vqvae.load_state_dict(vq_state_dict)
             else:
@@ -84,7 +84,7 @@ def create_diffusion_model(name: str, sample_clipping: bool = True, *, max_batch
         if vqvae is None:
             vae = AutoencoderKL(**(vq_config or SD_VAE_CONFIG), max_batch=max_batch, device=device, with_encoder=with_encoder,
                                 precision=precision)
-            decoder_grad = decoder_grad and precision == "bf16"   # the fp32-accurate decoder is forward-only
+            decoder_grad = decoder_grad and precision != "fp32"   # the fp32-accurate decoder is forward-only
             if vq_state_dict is not None:
                 vae.load_state_dict(vq_state_dict)
             else:
@@ -126,22 +126,25 @@ def get_pretrained_anyGAN(input_size: int = 256, max_batch: int = 1, state_dict_
 
 
 class SegmentationModel:
-    """Face parser front-end (src/models.py:80-118).  ``net=None`` builds the native BiSeNet (b200edit.bisenet) and loads
-    ``ckpt`` (the reference's Segmentation/res/cp/79999_iter.pth, a blob missing from the checkout) when the file
-    exists, else seeded random-init weights; any callable ``net`` mapping a (1,3,512,512) image to
-    ([1,19,H,W] logits, ...) can be substituted."""
+    """Face parser front-end (src/models.py:80-118), same leading positional arguments as the reference:
+    ``SegmentationModel(ckpt, n_classes, image_size)``.  The network is the native BiSeNet (b200edit.bisenet) for ANY
+    square input resolution - mask creation feeds it 512x512, ``NetAttrFunc`` the decoded 256x256 image, both through
+    this one object as in the reference - loaded from ``ckpt`` (the reference's Segmentation/res/cp/79999_iter.pth, a blob
+    missing from the checkout) when the file exists, else seeded random-init weights.  ``net=`` (keyword-only)
+    substitutes any callable mapping a (1,3,S,S) image to ([1,19,S,S] logits, ...)."""
 
-    def __init__(self, net=None, n_classes: int = 19, image_size: tuple = (512, 512),
-                 ckpt: str = "Segmentation/res/cp/79999_iter.pth", seed: int = 0) -> None:
+    def __init__(self, ckpt: str = "Segmentation/res/cp/79999_iter.pth", n_classes: int = 19, image_size: tuple = (512, 512),
+                 *, net=None, seed: int = 0) -> None:
         self.device = get_device()
+        if not (ckpt is None or isinstance(ckpt, (str, bytes)) or hasattr(ckpt, "__fspath__")):
+            raise TypeError("SegmentationModel: the first argument is the checkpoint path (as in the reference); pass a "
+                            "network with net=...")
         if net is None:
             import os
-            from b200edit.bisenet import BiSeNet
-            net = BiSeNet(n_classes, image_size[0], max_batch=1, device=self.device)
+            from b200edit.bisenet import MultiResBiSeNet
+            net = MultiResBiSeNet(n_classes, max_batch=1, device=self.device, seed=seed)
             if ckpt and os.path.exists(ckpt):
                 net.load_reference_state_dict(torch.load(ckpt, map_location="cpu"))
-            else:
-                net.init_random(seed)
         self.net = net
         self.image_size = image_size
         self.mean = torch.tensor((0.485, 0.456, 0.406)).view(1, 3, 1, 1)

@@ -350,11 +350,15 @@ typedef struct {
 int b2e_resnet_create(const b2e_resnet_config* cfg, int64_t max_batch, b2e_unet** out);
 int b2e_resnet_backward(b2e_unet* m, const float* d_logits, float* d_image, int64_t B, void* stream);
 
-/* Test hook for the implicit-GEMM convolution: x (N,H,W,Cin) bf16 NHWC, w (Cout,Cin,k,k) fp32,
- * bias fp32 [Cout] or NULL, residual (N,Ho,Wo,Cout) bf16 NHWC or NULL (added through the fused
- * residual K-segment), out (N,Ho,Wo,Cout) bf16 NHWC.  ksize 1|3, stride 1|2 (stride 2 pads
+/* The 16-bit storage / tensor-core operand type the library was built for: 0 = IEEE fp16 (default), 1 = bf16
+ * (-DB2E_ACT_BF16 builds).  Accumulation is fp32 either way. */
+int b2e_act_dtype(void);
+
+/* Test hook for the implicit-GEMM convolution: x (N,H,W,Cin) 16-bit NHWC (b2e_act_dtype), w (Cout,Cin,k,k) fp32,
+ * bias fp32 [Cout] or NULL, residual (N,Ho,Wo,Cout) 16-bit NHWC or NULL (added through the fused
+ * residual K-segment), out (N,Ho,Wo,Cout) 16-bit NHWC.  ksize 1|3, stride 1|2 (stride 2 pads
  * (0,1,0,1) like diffusers' Downsample2D).  Allocates temporaries itself and synchronises. */
-int b2e_conv2d_nhwc_bf16(const void* x, const float* w, const float* bias, const void* residual,
+int b2e_conv2d_nhwc_f16(const void* x, const float* w, const float* bias, const void* residual,
                          void* out, int64_t N, int64_t H, int64_t W, int64_t Cin, int64_t Cout,
                          int ksize, int stride, void* stream);
 

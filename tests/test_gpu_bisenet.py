@@ -137,3 +137,35 @@ def test_net_attr_func_through_the_native_parser():
     cos = torch.nn.functional.cosine_similarity(dn.flatten(), dr.flatten(), dim=0).item()
     print(f"NetAttrFunc update through the native parser: rel-rms {rel:.3e} cos {cos:.5f}")
     assert dr.abs().max() > 0 and rel <= 0.5 and cos >= 0.9
+
+
+def test_one_default_segmentation_model_serves_mask_creation_and_net_attr_func():
+    """The reference workflow (src/models.py:80-118, src/attr_functions.py:202-219): ONE SegmentationModel() - the
+    reference's positional signature (ckpt, n_classes, image_size) - produces the 512x512 parsing map for the mask AND is
+    the loss network of NetAttrFunc, which feeds it the decoded 256x256 image (the reference's BiSeNet is fully
+    convolutional).  The native parser keeps one engine per resolution behind the same object."""
+    from attr_functions import NetAttrFunc
+    from mask_creator import MaskCreator
+    from models import SegmentationModel, create_diffusion_model
+    seg_model = SegmentationModel("no/such/checkpoint.pth", 19, (512, 512))      # positional, as the reference is called
+    with pytest.raises(TypeError):
+        SegmentationModel(torch.nn.Identity())                                     # a network is NOT the first argument
+    img = torch.rand(1, 3, 256, 256, generator=torch.Generator().manual_seed(6)).mul(2).sub(1).cuda()
+    seg = seg_model(img)
+    assert seg.shape == (512, 512) and seg.dtype == torch.int64
+    mask = MaskCreator(dilate_mask=True, resize_size=(256, 256)).create_mask(seg, classes=[int(torch.bincount(seg.flatten()).argmax())])
+    assert mask.shape == (1, 3, 256, 256)
+    cfg = dict(sample_size=256, in_channels=3, out_channels=3, block_out_channels=(64, 128), layers_per_block=1,
+               down_block_types=("DownBlock2D", "DownBlock2D"), up_block_types=("UpBlock2D", "UpBlock2D"))
+    w = create_diffusion_model("ddpm", sample_clipping=False, max_batch=1, seed=1, unet_config=cfg)
+    w.scheduler.set_timesteps(10)
+    g = torch.Generator().manual_seed(9)
+    xt = torch.randn(1, 3, 256, 256, generator=g).cuda()
+    eps = torch.randn(1, 3, 256, 256, generator=g).cuda()
+    f = NetAttrFunc(seg_model, idx_for_class=[1, 10], loss_scale=1e4)
+    f.kwargs["mask"] = None
+    x2, _ = f.apply(xt=xt.clone(), zt=None, model_output=eps, timestep=torch.tensor(int(w.scheduler.timesteps[-1])), step_idx=0,
+                    model=w, **f.kwargs)
+    assert torch.isfinite(x2).all() and (x2 - xt).abs().max() > 0
+    # same parser, same weights at both resolutions: the 512-engine still answers after the 256-engine was used
+    assert torch.equal(seg_model(img), seg)

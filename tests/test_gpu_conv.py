@@ -1,7 +1,7 @@
 """GPU numerics of the tcgen05 implicit-GEMM convolution against a plain PyTorch fp32 reference
-(cuDNN is used here only as the checker).  Inputs and weights are pre-rounded to bf16 so the only
-differences are fp32 accumulation order and the final bf16 rounding of the output:
-tolerance = 2^-7 relative to the output scale."""
+(cuDNN is used here only as the checker).  Inputs and weights are pre-rounded to the engine's 16-bit type (fp16; bf16
+in -DB2E_ACT_BF16 builds) so the only differences are fp32 accumulation order and the final 16-bit rounding of the
+output: tolerance = 2^-10 (fp16) / 2^-7 (bf16) relative to the output scale."""
 import pytest
 import torch
 import torch.nn.functional as F
@@ -28,13 +28,15 @@ CASES = [
 @pytest.mark.parametrize("case", CASES, ids=[str(c) for c in CASES])
 def test_conv_vs_torch(case):
     from b200edit import ops
+    dt = ops.act_dtype()
+    rel = 2 ** -10 if dt == torch.float16 else 2 ** -7
     N, H, W, Cin, Cout, k, stride = case
     g = torch.Generator(device="cpu").manual_seed(sum(case))
-    x = torch.randn(N, Cin, H, W, generator=g).bfloat16()
-    w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).bfloat16()
+    x = torch.randn(N, Cin, H, W, generator=g).to(dt)
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).to(dt)
     b = torch.randn(Cout, generator=g)
     xd = x.cuda().permute(0, 2, 3, 1).contiguous()
-    out = ops.conv2d_nhwc_bf16(xd, w.float().cuda(), b.cuda(), stride=stride)
+    out = ops.conv2d_nhwc_f16(xd, w.float().cuda(), b.cuda(), stride=stride)
     torch.cuda.synchronize()
     xf = x.float().cuda()
     if stride == 2:
@@ -45,13 +47,13 @@ def test_conv_vs_torch(case):
     assert got.shape == ref.shape
     err = (got - ref).abs().max().item()
     scale = ref.abs().max().item()
-    assert err <= 2 ** -7 * scale + 1e-3, f"max abs err {err} (scale {scale})"
+    assert err <= rel * scale + 1e-3 * rel * 128, f"max abs err {err} (scale {scale})"
     # fused residual segment (identity weights appended to K): out = conv(x) + r
-    r = torch.randn(ref.shape, generator=g).bfloat16()
-    out_r = ops.conv2d_nhwc_bf16(xd, w.float().cuda(), b.cuda(), stride=stride,
+    r = torch.randn(ref.shape, generator=g).to(dt)
+    out_r = ops.conv2d_nhwc_f16(xd, w.float().cuda(), b.cuda(), stride=stride,
                                  residual=r.cuda().permute(0, 2, 3, 1).contiguous()) if stride == 1 else None
     if out_r is not None:
         ref_r = ref + r.float().cuda()
         err = (out_r.float().permute(0, 3, 1, 2) - ref_r).abs().max().item()
         scale = ref_r.abs().max().item()
-        assert err <= 2 ** -7 * scale + 1e-3, f"residual: max abs err {err} (scale {scale})"
+        assert err <= rel * scale + 1e-3 * rel * 128, f"residual: max abs err {err} (scale {scale})"

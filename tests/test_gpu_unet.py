@@ -26,7 +26,7 @@ LDM_SMALL = dict(sample_size=32, in_channels=3, out_channels=3, block_out_channe
                  attention_head_dim=32, flip_sin_to_cos=True, freq_shift=0, downsample_padding=1)
 
 
-def run_pair(cfg, B, t, seed, precision="bf16"):
+def run_pair(cfg, B, t, seed, precision=None):
     from b200edit.unet import UNet2DModel
     torch.manual_seed(seed)
     oracle = OracleUNet(**cfg).eval()

@@ -16,7 +16,7 @@ MID = dict(sample_size=32, in_channels=4, out_channels=4, block_out_channels=(32
            cross_attention_dim=128, attention_head_dim=8, norm_num_groups=32, norm_eps=1e-5)
 
 
-def run_pair(cfg, B, t, seed, L=77, precision="bf16"):
+def run_pair(cfg, B, t, seed, L=77, precision=None):
     from b200edit.unet_cond import UNet2DConditionModel
     torch.manual_seed(seed)
     oracle = OracleCond(**cfg).eval()

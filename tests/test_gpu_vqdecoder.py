@@ -14,7 +14,7 @@ SMALL = dict(latent_channels=3, out_channels=3, block_out_channels=(32, 96), lay
              norm_eps=1e-6, num_vq_embeddings=512, sample_size=16)
 
 
-def run_pair(cfg, B, seed, codebook_scale=None, precision="bf16"):
+def run_pair(cfg, B, seed, codebook_scale=None, precision=None):
     from b200edit.vqmodel import VQModel
     torch.manual_seed(seed)
     oracle = OracleVQ(**cfg).eval()

@@ -11,5 +11,5 @@ x = torch.randn(N, H, H, cin, device="cuda").bfloat16()
 w = torch.randn(cout, cin, k, k, device="cuda") / (cin * k * k) ** 0.5
 b = torch.randn(cout, device="cuda")
 for _ in range(4):
-    out = ops.conv2d_nhwc_bf16(x, w, b)
+    out = ops.conv2d_nhwc_f16(x, w, b)
 torch.cuda.synchronize()
