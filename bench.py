@@ -344,6 +344,8 @@ def config2(c, precision, B, K, W, headline=False):
     wrapper = create_diffusion_model("ddpm", sample_clipping=False, max_batch=B, seed=0, precision=precision)
     sch = wrapper.scheduler
     sch.set_timesteps(max(T_INFER, D))
+    if os.environ.get("B2E_BENCH_GRAPH_HEADLINE") == "1":      # experiment knob (profiles/README.md): no gain at batch 8
+        wrapper.unet.enable_cuda_graph()
     pipe = SegDiffEditPipeline(wrapper, None)
     f = SingleColorAttrFunc(target=TARGET, color_idx=CHANNEL, loss_scale=LOSS_SCALE, t1=0, t2=10 ** 9, per_sample=True)
     gen = torch.Generator().manual_seed(1000 + rank)        # per-rank shard of the global batch
@@ -509,6 +511,8 @@ def config1(c, precision, B, K, W, headline=False):
     D = c.args.denoise_steps
     w = create_diffusion_model("ddpm", sample_clipping=True, max_batch=B, seed=0, precision=precision)
     w.scheduler.set_timesteps(max(T_INFER, D))
+    if os.environ.get("B2E_BENCH_GRAPH", "1") != "0":
+        w.unet.enable_cuda_graph()     # batch 1 is launch-bound: replay the forward as one CUDA graph
     pipe = SegDiffEditPipeline(w, None)
     f = SingleColorAttrFunc(target=0.8, color_idx=0, loss_scale=100.0, t1=0, t2=10 ** 9, per_sample=True)
     x_host = torch.randn(B, 3, 256, 256, generator=torch.Generator().manual_seed(1234)).pin_memory()
@@ -534,6 +538,7 @@ def config1(c, precision, B, K, W, headline=False):
                       (out_host.numel() + x0_host.numel()) * 4, cfg, w.unet.flops_per_sample, "as the headline")
     res["metric"] = "guided img-steps/s (DDPM-256, colour-guided DDIM-50, batch 1)"
     res["precision"] = precision
+    res["cuda_graph"] = bool(w.unet._graph_on)
     del pipe, w
     return res
 

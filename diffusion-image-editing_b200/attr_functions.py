@@ -6,10 +6,12 @@ predicted clean image:  x <- x + (-d(loss_scale*loss)/dx) * alphas_cumprod[t]**2
 * Built-in colour strategies with an identity decoder (pixel-space DDPM) use the ANALYTIC gradient
   inside one fused CUDA kernel - no autograd graph, no reduction (the loss value is never needed
   for the update); masked-gradient and masked + L2-regularised variants included.
-* Any other strategy (user subclasses, network losses, latent decoders) evaluates ``loss`` with
-  torch autograd on the device - exactly the reference's procedure - and the resulting gradient is
-  applied by a CUDA kernel.  That is the extension contract of the reference: subclass, implement
-  ``loss``, register.
+* The same colour strategies on a latent model (LDM / SD) whose decoder runs on the engine: the loss gradient w.r.t. the
+  DECODED image is closed-form too, so the nudge is x0' kernel -> native decoder forward -> analytic d(loss)/d(image) kernel ->
+  native decoder backward -> update kernel, again without autograd (``_apply_native_decoder``).
+* Any other strategy (user subclasses, network losses) evaluates ``loss`` with torch autograd on the device - exactly the
+  reference's procedure - and the resulting gradient is applied by a CUDA kernel.  That is the extension contract of the
+  reference: subclass, implement ``loss``, register.
 """
 from abc import ABC, abstractmethod
 
@@ -104,6 +106,10 @@ class AttrFunc(ABC):
 
     def get_attr_grad(self, xt, pred_original_sample, loss_scale, **kwargs):
         attr_loss = self.calculate_loss(pred_original_sample, **kwargs) * loss_scale
+        if self.per_sample and self.colour_spec() is not None:
+            # the colour losses average over the batch as well; per_sample (extension) makes every image its own problem:
+            # the sum of the per-image means = batch size x the batch mean
+            attr_loss = attr_loss * pred_original_sample.shape[0]
         attr_grad = -torch.autograd.grad(attr_loss, xt)[0]
         return self.edit_attr_grad(attr_grad, **kwargs)
 
@@ -145,6 +151,47 @@ class AttrFunc(ABC):
             fk.update(l2reg=True, x_ref=kwargs["x_0"], lambda_=kwargs["lambda_"])
         return fk
 
+    def _apply_native_decoder(self, xt, model_output, coeffs, model, **kwargs):
+        """Built-in colour strategies on a latent model whose decoder runs on the engine in gradient mode: the whole nudge is
+        native CUDA with the ANALYTIC loss gradient - x0' prediction kernel -> decoder forward -> closed-form d(loss)/d(image)
+        kernel -> decoder backward (dgrad twins) -> fused update kernel.  No autograd graph, no torch arithmetic.
+        Returns None when the strategy / model does not qualify (the caller falls back to autograd, as the reference)."""
+        spec = self.colour_spec()
+        nd = getattr(model, "native_decoder", None)
+        nd = nd() if callable(nd) else None
+        if spec is None or nd is None or self.nudge_zt or not self.nudge_xt:
+            return None
+        dec, chain = nd
+        targets, weights = spec
+        mask = kwargs.get("mask")
+        mask_pred = bool(kwargs.get("mask_pred_original_sample", False))
+        if kwargs.get("mask_attr_grad", False) and mask is None:
+            raise ValueError("No mask specified")
+        out_size = getattr(dec, "out_size", None)
+        if mask_pred:
+            if kwargs.get("use_lpips", False) or not kwargs.get("use_l2", False):
+                return None            # the generic path raises the reference's errors
+            x_0, lam = kwargs.get("x_0"), kwargs.get("lambda_")
+            if mask is None or x_0 is None or lam is None or mask.shape[-1] != out_size or x_0.shape[-1] != out_size:
+                return None            # shapes that do not broadcast against the decoded image: let torch report it
+        if xt.shape[0] > dec.max_batch:
+            return None
+        # x0' = (x - sqrt(1-a) eps) / sqrt(a), then the wrapper's decode scaling (SD: 1 / 0.18215 * latent) as its own
+        # rounding step - the reference's op order, so the decoder sees bit-identical input on both paths
+        lat = ops.pred_x0(xt, model_output, coeffs.sqrt_a_t, coeffs.sqrt_b_t)
+        if chain != 1.0:
+            lat = ops.axpby(lat, lat, chain, 0.0)
+        img = dec.decode_keep(lat)
+        n_mean = img.shape[-1] * img.shape[-2] * (1 if self.per_sample else img.shape[0])
+        d_img = ops.color_loss_grad(img, targets, weights, self.loss_scale, n_mean,
+                                    mask=mask if mask_pred else None, x_ref=kwargs.get("x_0") if mask_pred else None,
+                                    lambda_=kwargs.get("lambda_") if mask_pred else None)
+        d_lat = dec.latent_grad(d_img)
+        gmask = mask if kwargs.get("mask_attr_grad", False) else None
+        if gmask is not None and gmask.shape[-1] != xt.shape[-1]:
+            return None                # a mask that does not match the latent: the generic path reports it
+        return ops.apply_latent_guidance(xt, d_lat, chain, coeffs.sqrt_a_t, coeffs.a_t_sq, mask=gmask)
+
     def in_window(self, step_idx: int) -> bool:
         return self.t1 <= step_idx < self.t2
 
@@ -156,6 +203,9 @@ class AttrFunc(ABC):
         coeffs = model.scheduler.coeffs(int(timestep), 0.0, "ddim")
         fk = self.fused_kwargs(xt, model, **kwargs)
         if fk is None:
+            out = self._apply_native_decoder(xt, model_output, coeffs, model, **kwargs)
+            if out is not None:
+                return out, zt
             return self._apply_autograd(xt, zt, model_output, coeffs, model, **kwargs)
         if fk.pop("l2reg", False):
             out, _ = ops.guided_step_l2reg(xt, model_output, coeffs, x_ref=fk["x_ref"], mask=fk["mask"],

@@ -28,6 +28,11 @@ class L2RegParams(C.Structure):
     _fields_ = [("base", GuidedStepParams), ("lambda_", C.c_float), ("loss_scale", C.c_float)]
 
 
+class ColorGradParams(C.Structure):
+    _fields_ = [("has_target", C.c_int32 * 4), ("target", C.c_float * 4), ("k", C.c_float * 4), ("lam_scale", C.c_float),
+                ("use_mask_pred", C.c_int32), ("mask_batched", C.c_int32)]
+
+
 class UNetConfig(C.Structure):
     _fields_ = [("sample_size", C.c_int32), ("in_channels", C.c_int32), ("out_channels", C.c_int32),
                 ("n_blocks", C.c_int32), ("block_out_channels", C.c_int32 * 8),
@@ -75,6 +80,9 @@ PROTOTYPES = {
     "b2e_guided_step_l2reg_f32": (_I, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64,
                                        C.POINTER(L2RegParams), _P, _SZ, _P]),
     "b2e_apply_guidance_grad_f32": (_I, [_P, _P, _P, _I64, _I64, _I, _F, _P]),
+    "b2e_color_loss_grad_workspace_bytes": (_SZ, []),
+    "b2e_color_loss_grad_f32": (_I, [_P, _P, _P, _P, _I64, _I64, _I64, C.POINTER(ColorGradParams), _P, _SZ, _P]),
+    "b2e_apply_latent_guidance_f32": (_I, [_P, _P, _P, _I64, _I64, _I, _F, _F, _F, _P]),
     "b2e_pred_x0_f32": (_I, [_P, _P, _P, _I64, _F, _F, _P]),
     "b2e_renoise_f32": (_I, [_P, _P, _P, _I64, _F, _F, _F, _F, _P]),
     "b2e_cfg_combine_f32": (_I, [_P, _P, _P, _I64, _F, _P]),

@@ -176,6 +176,55 @@ def apply_guidance_grad(x, neg_grad, a_t_sq: float, mask=None):
     return x
 
 
+def color_loss_grad(img, targets, weights, loss_scale, n_mean, mask=None, x_ref=None, lambda_=None):
+    """d(loss_scale * colour loss)/d(decoded image) in closed form (guidance through a latent decoder; the result feeds the
+    decoder's native backward pass).  targets / weights as in guided_step; n_mean = elements the loss mean runs over.
+    mask + x_ref + lambda_: the masked-prediction + L2-regularised variant (mask_pred_original_sample, use_l2)."""
+    img = _f32(img, "decoded image")
+    B, Cc, H, W = img.shape
+    p = _C.ColorGradParams()
+    for c in range(4):
+        t = targets[c] if c < len(targets) else None
+        w = 1.0 if weights is None else (weights[c] if c < len(weights) and weights[c] is not None else 0.0)
+        p.has_target[c] = int(t is not None and c < Cc)
+        p.target[c] = float(t) if t is not None else 0.0
+        p.k[c] = float(torch.tensor(float(loss_scale), dtype=torch.float32) * torch.tensor(float(w), dtype=torch.float32)
+                       / torch.tensor(float(n_mean), dtype=torch.float32)) if t is not None else 0.0
+    ws = None
+    ws_bytes = 0
+    if x_ref is not None:
+        if mask is None or lambda_ is None:
+            raise ValueError("color_loss_grad: the L2-regularised variant needs mask, x_0 and lambda_")
+        mask = _f32(mask, "mask").expand(-1, Cc, H, W).contiguous() if mask.shape[1:] != img.shape[1:] else _f32(mask, "mask")
+        x_ref = _f32(x_ref, "x_0")
+        if x_ref.shape != img.shape:
+            x_ref = x_ref.expand_as(img).contiguous()
+        p.use_mask_pred = 1
+        p.mask_batched = int(mask.shape[0] == B and B > 1)
+        p.lam_scale = float(loss_scale) * float(lambda_)
+        ws_bytes = lib.b2e_color_loss_grad_workspace_bytes()
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=img.device)
+    out = torch.empty_like(img)
+    check(lib.b2e_color_loss_grad_f32(_p(img), _p(mask) if x_ref is not None else None, _p(x_ref), _p(out), B, Cc, H * W,
+                                      C.byref(p), _p(ws), ws_bytes, _stream()), "color_loss_grad")
+    return out
+
+
+def apply_latent_guidance(x, d_latent, chain: float, sqrt_a_t: float, a_t_sq: float, mask=None):
+    """x + (mask *) (-(d_latent * chain) / sqrt_a_t) * a_t_sq  (new tensor): the nudge of AttrFunc.apply once the decoder's
+    backward pass has produced d_latent = dL/d(decoder input)."""
+    x, d_latent = _f32(x, "x").clone(), _f32(d_latent, "d_latent")
+    B = x.shape[0]
+    chw = x.numel() // B
+    mb = 0
+    if mask is not None:
+        mask = _f32(mask, "mask").expand(-1, *x.shape[1:]).contiguous() if mask.dim() == 4 else _f32(mask, "mask")
+        mb = int(mask.numel() == x.numel() and B > 1)
+    check(lib.b2e_apply_latent_guidance_f32(_p(x), _p(d_latent), _p(mask), B, chw, mb, float(chain), float(sqrt_a_t),
+                                            float(a_t_sq), _stream()), "apply_latent_guidance")
+    return x
+
+
 # ----------------------------------------------------------------------------- single ops
 def pred_x0(x_t, eps, sqrt_a_t: float, sqrt_b_t: float):
     x_t, eps = _f32(x_t, "sample"), _f32(eps, "model_output")

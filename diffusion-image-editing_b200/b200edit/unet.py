@@ -187,7 +187,48 @@ class UNet2DModel:
         t = self._timesteps(timestep, B)
         eps = out if out is not None else torch.empty(
             (B, cfg.out_channels, cfg.sample_size, cfg.sample_size), dtype=torch.float32, device=x.device)
+        if self._graph_on and B == self.max_batch and not torch.cuda.is_current_stream_capturing():
+            return UNetOutput(sample=self._replay(x, t, eps))
+        if self._graph_on and self._graphs:
+            self._graphs.clear()      # an eager forward at another batch re-plans the workspace: captured launches are stale
         check(lib.b2e_unet_forward(self._h, C.c_void_p(x.data_ptr()), C.c_void_p(t.data_ptr()),
                                    C.c_void_p(eps.data_ptr()), B,
                                    C.c_void_p(torch.cuda.current_stream().cuda_stream)), "unet_forward")
         return UNetOutput(sample=eps)
+
+    # ------------------------------------------------------------------ CUDA-graph replay (launch-bound regime)
+    _graph_on = False
+
+    def enable_cuda_graph(self, enable: bool = True):
+        """Replay the forward's ~225 launches as ONE captured CUDA graph for calls at batch == max_batch (the launch-bound
+        regime: at batch 1 the forward is 225 kernels of ~10 us).  The plan has fixed buffers, no allocation and no host
+        synchronisation, so it captures as is (programmatic-dependent-launch edges included); inputs / timesteps / output go
+        through static buffers.  Captured on first use; any eager call at another batch size re-plans the workspace and
+        drops the capture."""
+        self._graph_on = bool(enable)
+        self._graphs = {}
+        return self
+
+    def _replay(self, x, t, eps):
+        B = x.shape[0]
+        g = self._graphs.get(B)
+        if g is None:
+            sx, st, se = torch.empty_like(x), torch.empty_like(t), torch.empty_like(eps)
+            sx.copy_(x); st.copy_(t)
+            stream = C.c_void_p
+            # warm-up outside capture (plan rebuild for this batch, lazy function attributes), then capture
+            check(lib.b2e_unet_forward(self._h, C.c_void_p(sx.data_ptr()), C.c_void_p(st.data_ptr()), C.c_void_p(se.data_ptr()), B,
+                                       stream(torch.cuda.current_stream().cuda_stream)), "unet_forward")
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                check(lib.b2e_unet_forward(self._h, C.c_void_p(sx.data_ptr()), C.c_void_p(st.data_ptr()),
+                                           C.c_void_p(se.data_ptr()), B, stream(torch.cuda.current_stream().cuda_stream)),
+                      "unet_forward (capture)")
+            g = self._graphs[B] = (graph, sx, st, se)
+        graph, sx, st, se = g
+        sx.copy_(x)
+        st.copy_(t)
+        graph.replay()
+        eps.copy_(se)
+        return eps

@@ -193,6 +193,33 @@ class VQModel(UNet2DModel):
                                    C.c_void_p(torch.cuda.current_stream().cuda_stream)), "vqdec_forward")
         return img
 
+    # ---- decode + latent gradient WITHOUT an autograd graph (analytic guidance: the caller supplies d(loss)/d(image))
+    def decode_keep(self, latent: torch.Tensor) -> torch.Tensor:
+        """decode(latent).sample with the activations kept in the engine's workspace for ``latent_grad``."""
+        if self.forward_only:
+            raise _C.B2EError(f"{type(self).__name__}.decode_keep: call enable_grad() first")
+        cfg = self.config
+        if latent.dim() != 4 or tuple(latent.shape[1:]) != (cfg.latent_channels, cfg.sample_size, cfg.sample_size):
+            raise ValueError(f"VQModel.decode: expected (B,{cfg.latent_channels},{cfg.sample_size},{cfg.sample_size}), "
+                             f"got {tuple(latent.shape)}")
+        if latent.shape[0] > self.max_batch:
+            raise ValueError(f"VQModel.decode with gradient: batch {latent.shape[0]} > max_batch {self.max_batch}")
+        z = latent.detach().to(torch.float32).contiguous()
+        img = self._forward(z)
+        self._keep_gen, self._keep_B = self._fwd_gen, z.shape[0]
+        return img
+
+    def latent_grad(self, d_image: torch.Tensor) -> torch.Tensor:
+        """d(loss)/d(latent) for the last ``decode_keep`` given d(loss)/d(image) (native dgrad of the whole decoder)."""
+        if getattr(self, "_keep_gen", None) != self._fwd_gen:
+            raise _C.B2EError("VQModel.latent_grad: the engine ran another forward since decode_keep (activations overwritten)")
+        g = d_image.detach().to(torch.float32).contiguous()
+        cfg = self.config
+        dz = torch.empty((self._keep_B, cfg.latent_channels, cfg.sample_size, cfg.sample_size), dtype=torch.float32, device=g.device)
+        check(lib.b2e_vqdec_backward(self._h, C.c_void_p(g.data_ptr()), C.c_void_p(dz.data_ptr()), self._keep_B,
+                                     C.c_void_p(torch.cuda.current_stream().cuda_stream)), "vqdec_backward")
+        return dz
+
     def decode(self, latent: torch.Tensor, force_not_quantize: bool = False):
         if force_not_quantize:
             raise NotImplementedError("VQModel.decode(force_not_quantize=True) is not on the native engine")

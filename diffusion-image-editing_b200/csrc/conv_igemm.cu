@@ -20,6 +20,7 @@
 //    smem and written with one TMA store per 64-channel slab; fp32 NCHW direct store for conv_out).  Persistent CTAs (one per SM), 6-8 stage smem ring that never drains
 //    between tiles, double-buffered TMEM accumulator so the epilogue overlaps the next main loop.
 #include "conv_igemm.cuh"
+#include "gn_math.cuh"
 #include "tcgen05_ptx.cuh"
 
 #include <cudaTypedefs.h>
@@ -27,7 +28,9 @@
 
 namespace b2e {
 
-constexpr int kConvThreads = 192;
+constexpr int kConvThreads = 192;       // TMA producer warp + MMA warp + 4 epilogue warps
+constexpr int kXfWarps = 8;             // + 8 transform warps in the fused-GroupNorm variants (XF)
+constexpr int kConvThreadsXf = kConvThreads + 32 * kXfWarps;
 constexpr int kABytes = kConvBlockM * kConvBlockK * 2;  // 16 KB
 
 // One persistent CTA per SM; STAGES x (A 16 KB + B) fills the ~190 KB of shared memory it can use, so
@@ -68,6 +71,7 @@ struct ConvCfg {
   static constexpr int kStagingBytes = kSlabs * kConvBlockM * 128;
   static constexpr int kRedBytes = kSlabs > 0 ? 8192 : 0;       // GroupNorm-statistics scratch [row groups][BN][2]
   static constexpr int kSmemBytes = kRingBytes + kStagingBytes + kRedBytes + 1024 /*align*/ + 512 /*barriers*/;
+  static_assert((3 * STAGES + 4) * 8 + 8 <= 512, "barrier block");
 };
 
 struct ConvKParams {
@@ -90,6 +94,10 @@ struct ConvKParams {
   float* tile_stats;    // fused GroupNorm statistics or null
   int relu;             // 1: ReLU before the f16 store (classifier network)
   float acc_scale;      // accumulator * acc_scale before bias (weights packed with a power-of-two scale), 1: none
+  // XF kernels: fused GroupNorm(+SiLU) of the A operand.  The TMA lands the RAW activation tile; the transform warps
+  // rewrite it in shared memory as f16(silu(x * scale[n][c] + shift[n][c])) (zero where the convolution pads) before the
+  // MMA warp sees it.  gn_coef = (scale, shift) per (image, K position of the concatenated sources), from gn_coeffs_kernel
+  const float2* gn_coef; int coef_stride; int gn_silu; int Hin, Win;
   int split_pitch;      // > 0: split-f16 output (fp32-accurate mode): planes [hi | lo | hi] of split_pitch channels each
   long long* trace;     // B2E_TRACE: clock64 stamps of CTA 0's warp loops (halo kernels), else null
 };
@@ -131,8 +139,8 @@ __device__ __forceinline__ TileCoord halo_coord(const ConvKParams& p, int tile, 
   return t;
 }
 
-template <int BN, int STAGES, bool PAIR, bool HALO, int MT, int KPS>
-__global__ void __launch_bounds__(kConvThreads, 1)
+template <int BN, int STAGES, bool PAIR, bool HALO, int MT, int KPS, bool XF>
+__global__ void __launch_bounds__(XF ? kConvThreadsXf : kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                   const __grid_constant__ CUtensorMap map_r0, const __grid_constant__ CUtensorMap map_r1,
                   const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_out,
@@ -146,7 +154,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;         // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  // XF: the A tile of a stage completes on THIS CTA's araw_bar (raw activations landed); the transform warps then
+  // rewrite it and arrive on the (leader's) full_bar, which also collects the B tile's TMA bytes as before
+  uint64_t* araw_bar = tmem_empty_bar + 2;              // [STAGES]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(araw_bar + Cfg::kStages);
   volatile uint32_t* split_flag = tmem_slot + 1;
 
   // warp index / cluster rank through shfl so that the compiler can prove them warp-uniform: the role branches
@@ -172,7 +183,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     if (p.r1_chunks) prefetch_tmap(&map_r1);
     prefetch_tmap(&map_b);
     if (p.out_f16) prefetch_tmap(&map_out);
-    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(full_bar + s, XF ? 1 + kXfWarps * (PAIR ? 2 : 1) : 1);
+      mbar_init(empty_bar + s, 1);
+      mbar_init(araw_bar + s, 1);
+    }
     // pair: the leader's tmem_empty barrier collects the 4 epilogue warps of BOTH CTAs
     for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar + s, 1); mbar_init(tmem_empty_bar + s, PAIR ? 8 : 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -210,10 +225,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           if (elect_one()) {
             if (main) {
               // (8*MT+2) x 16 halo brick of horizontal tap kw + the B tiles of its three vertical taps
-              if (rank == 0) mbar_expect_tx(full_bar + stage, 2 * (Cfg::kHaloABytes + 3 * Cfg::kBBytes));
               const bool first = ck < p.c0_chunks;
+              if constexpr (XF) {
+                // raw activations: completion on this CTA's own barrier, the transform warps take it from there
+                mbar_expect_tx(araw_bar + stage, Cfg::kHaloABytes);
+                tma_load_5d(sa, first ? &map_a0 : &map_a1, araw_bar + stage,
+                            (first ? ck : ck - p.c0_chunks) * kConvBlockK, tc.w0 + kw - 1, 0, tc.h0 - 1, tc.n0);
+                if (rank == 0) mbar_expect_tx(full_bar + stage, 2 * 3 * Cfg::kBBytes);
+              } else {
+              if (rank == 0) mbar_expect_tx(full_bar + stage, 2 * (Cfg::kHaloABytes + 3 * Cfg::kBBytes));
               tma_load_5d_2sm(sa, first ? &map_a0 : &map_a1, full_bar + stage,
                               (first ? ck : ck - p.c0_chunks) * kConvBlockK, tc.w0 + kw - 1, 0, tc.h0 - 1, tc.n0);
+              }
 #pragma unroll
               for (int kh = 0; kh < 3; ++kh)
                 tma_load_2d_2sm(sa + Cfg::kHaloABytes + kh * Cfg::kBBytesPad, &map_b, full_bar + stage,
@@ -221,10 +244,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             } else {
               // residual segment: the brick itself (MT x 128 pixels) at the output position, one B tile
               const int rk = g - 3 * chunks;
-              if (rank == 0) mbar_expect_tx(full_bar + stage, 2 * (MT * kABytes + Cfg::kBBytes));
               const bool first = rk < p.r0_chunks;
+              if constexpr (XF) {
+                mbar_expect_tx(araw_bar + stage, MT * kABytes);
+                tma_load_5d(sa, first ? &map_r0 : &map_r1, araw_bar + stage,
+                            (first ? rk : rk - p.r0_chunks) * kConvBlockK, tc.w0, 0, tc.h0, tc.n0);
+                if (rank == 0) mbar_expect_tx(full_bar + stage, 2 * Cfg::kBBytes);
+              } else {
+              if (rank == 0) mbar_expect_tx(full_bar + stage, 2 * (MT * kABytes + Cfg::kBBytes));
               tma_load_5d_2sm(sa, first ? &map_r0 : &map_r1, full_bar + stage,
                               (first ? rk : rk - p.r0_chunks) * kConvBlockK, tc.w0, 0, tc.h0, tc.n0);
+              }
               tma_load_2d_2sm(sa + Cfg::kHaloABytes, &map_b, full_bar + stage, (main_kb + rk) * kConvBlockK, brow0);
             }
           }
@@ -256,8 +286,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           if (tr && tr_n < 512) p.trace[kTrPb + tr_n * 3 + 1] = clock64();
           const bool leader = elect_one();
           if (leader) {
+            if constexpr (XF) {
+              mbar_expect_tx(araw_bar + stage, cnt * kABytes);
+              if (!PAIR || rank == 0) mbar_expect_tx(full_bar + stage, (PAIR ? 2 : 1) * cnt * Cfg::kBBytes);
+            } else {
             if (p.debug & 1) { if (rank == 0) mbar_arrive(full_bar + stage); }
             else if (!PAIR || rank == 0) mbar_expect_tx(full_bar + stage, (PAIR ? 2 : 1) * cnt * (kABytes + Cfg::kBBytes));
+            }
           }
 #pragma unroll
           for (int j = 0; j < KPS; ++j) {
@@ -275,10 +310,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
               if (leader && !(p.debug & 1)) {
                 uint8_t* sa = smem + stage * Cfg::kStageBytes + j * Cfg::kKbBytes;
                 if (PAIR) {
-                  tma_load_5d_2sm(sa, ma, full_bar + stage, c0, c1, c2, c3, tc.n0);
+                  if constexpr (XF) tma_load_5d(sa, ma, araw_bar + stage, c0, c1, c2, c3, tc.n0);
+                  else tma_load_5d_2sm(sa, ma, full_bar + stage, c0, c1, c2, c3, tc.n0);
                   tma_load_2d_2sm(sa + kABytes, &map_b, full_bar + stage, (kb + j) * kConvBlockK, brow0);
                 } else {
-                  tma_load_5d(sa, ma, full_bar + stage, c0, c1, c2, c3, tc.n0);
+                  tma_load_5d(sa, ma, (XF ? araw_bar : full_bar) + stage, c0, c1, c2, c3, tc.n0);
                   tma_load_2d(sa + kABytes, &map_b, full_bar + stage, (kb + j) * kConvBlockK, brow0);
                 }
               }
@@ -314,7 +350,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           for (int g = 0; g < groups; ++g) {
             const int nsub = g < 3 * chunks ? 3 : 1;   // vertical taps served by this stage
             if (tr && tr_n < 512) p.trace[kTrMma + tr_n * 4 + 1] = clock64();
-            mbar_wait(full_bar + stage, phase);
+            if constexpr (XF) mbar_wait_cluster(full_bar + stage, phase); else mbar_wait(full_bar + stage, phase);
             tc_fence_after();
             if (tr && tr_n < 512) p.trace[kTrMma + tr_n * 4 + 2] = clock64();
             const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
@@ -354,7 +390,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           for (int kb = kb0; kb < kb1; kb += KPS) {
             const int cnt = (kb1 - kb) < KPS ? (kb1 - kb) : KPS;
             if (tr && tr_n < 512) { p.trace[kTrMma + tr_n * 4] = p.trace[kTrMma + tr_n * 4 + 1] = clock64(); }
-            mbar_wait(full_bar + stage, phase);
+            if constexpr (XF) mbar_wait_cluster(full_bar + stage, phase); else mbar_wait(full_bar + stage, phase);
             tc_fence_after();
             if (tr && tr_n < 512) p.trace[kTrMma + tr_n * 4 + 2] = clock64();
             const uint32_t sbase = smem_u32(smem + stage * Cfg::kStageBytes);
@@ -385,7 +421,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         }
       }
     }
-  } else {
+  } else if (!XF || warp < 6) {
     // ===== epilogue: 4 warps, warp w owns TMEM lanes 32*(w%4) .. +31
     const int q = warp & 3;
     const int r = q * 32 + lane;  // row of the tile = output pixel
@@ -597,6 +633,105 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     }
     if (store_leader) tma_store_wait_all();
     tc_fence_before();
+  } else {
+    // ===== transform warps (XF): fused GroupNorm(+SiLU) of the A operand.  Per stage: wait for this CTA's raw tile
+    // (araw_bar), rewrite it in place - thread = one 16-byte chunk column (8 channels) x every 32nd row, so its swizzled
+    // chunk position and its 8 (scale, shift) pairs are fixed per k-block - zero the positions the convolution pads
+    // (TMA filled them with raw zeros, which GroupNorm would turn into silu(shift)), make the writes visible to the
+    // async proxy and arrive on the (leader's) full_bar.  Residual-segment stages pass through untouched.
+    const int lt = (int)threadIdx.x - kConvThreads;
+    const int cj = lt & 7, rr = lt >> 3;                     // chunk column, first row (rows rr + 32 i)
+    const uint32_t swz = (uint32_t)((cj ^ (rr & 7)) << 4);   // (rr + 32 i) & 7 == rr & 7
+    const bool silu = p.gn_silu != 0 && !(p.debug & 4);   // B2E_DEBUG micro-benchmark knobs: 4 = no SiLU, 8 = no rewrite at all
+    const bool xf_skip = (p.debug & 8) != 0;
+    int stage = 0; uint32_t phase = 0;
+    auto xf_arrive = [&]() {
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) { if (PAIR) mbar_arrive_leader_release(full_bar + stage); else mbar_arrive(full_bar + stage); }
+      if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+    };
+    auto load_coef = [&](int n, int kpos, float* sc, float* sh) {
+      const float4* cp = reinterpret_cast<const float4*>(p.gn_coef + (int64_t)n * p.coef_stride + kpos + cj * 8);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float4 v = __ldg(cp + e);
+        sc[2 * e] = v.x; sh[2 * e] = v.y; sc[2 * e + 1] = v.z; sh[2 * e + 1] = v.w;
+      }
+    };
+    if constexpr (HALO) {
+      constexpr int kRows = (kHaloHt * MT + 2) * kHaloWt, kNI = kRows / 32;
+      static_assert(kRows % 32 == 0, "halo rows");
+      const int groups = 3 * chunks + r_chunks;
+      for (int tile = tile_begin; tile < p.num_tiles; tile += tile_step) {
+        const TileCoord tc = halo_coord<MT>(p, tile, rank);
+        int kw = 0, ck = 0;
+        for (int g = 0; g < groups; ++g) {
+          const bool main = g < 3 * chunks;
+          float sc[8], sh[8];
+          if (main) load_coef(tc.n0, ck * kConvBlockK, sc, sh);     // before the wait: overlaps the TMA flight
+          mbar_wait(araw_bar + stage, phase);
+          if (main) {
+            uint8_t* sa = smem + stage * Cfg::kStageBytes;
+            const int wbase = tc.w0 + kw - 1, hbase = tc.h0 - 1;
+            if (!xf_skip) {
+#pragma unroll
+              for (int i = 0; i < kNI; ++i) {
+                const int r = rr + 32 * i;
+                const int h = hbase + (r >> 4), w = wbase + (r & 15);
+                uint4* ptr = reinterpret_cast<uint4*>(sa + r * 128 + swz);
+                const bool in = (unsigned)h < (unsigned)p.Hin && (unsigned)w < (unsigned)p.Win;
+                *ptr = in ? gn_apply8(*ptr, sc, sh, silu) : make_uint4(0, 0, 0, 0);
+              }
+            }
+            if (++ck == chunks) { ck = 0; ++kw; }
+          }
+          xf_arrive();
+        }
+      }
+    } else {
+      // rows of the 128-pixel tile: r -> (image, row, column) within the Nt x Ht x Wt brick, fixed per thread
+      int wl[4], hl[4], nl[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = rr + 32 * i;
+        wl[i] = r % p.Wt; hl[i] = (r / p.Wt) % p.Ht; nl[i] = r / (p.Wt * p.Ht);
+      }
+      for (int wi = tile_begin; wi < num_work; wi += tile_step) {
+        const int tile = wi / splits, split = wi - tile * splits;
+        const TileCoord tc = tile_coord(p, tile, PAIR, rank);
+        const int kb0 = (int)((int64_t)split * num_kb / splits), kb1 = (int)((int64_t)(split + 1) * num_kb / splits);
+        for (int kb = kb0; kb < kb1; kb += KPS) {
+          const int cnt = (kb1 - kb) < KPS ? (kb1 - kb) : KPS;
+          mbar_wait(araw_bar + stage, phase);
+#pragma unroll
+          for (int j = 0; j < KPS; ++j) {
+            const int k = kb + j;
+            if (j < cnt && k < main_kb) {
+              const int tap = k / chunks, ck = k - tap * chunks;
+              const int dh = p.tap_dh[tap], dw = p.tap_dw[tap];
+              uint8_t* sa = smem + stage * Cfg::kStageBytes + j * Cfg::kKbBytes;
+              float sc[8], sh[8];
+              int n_have = -1;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int r = rr + 32 * i;
+                const int n = tc.n0 + nl[i], h = tc.h0 + hl[i] + dh, w = tc.w0 + wl[i] + dw;
+                uint4* ptr = reinterpret_cast<uint4*>(sa + r * 128 + swz);
+                const bool in = n < p.N && (unsigned)h < (unsigned)p.Hin && (unsigned)w < (unsigned)p.Win;
+                if (in) {
+                  if (n != n_have) { load_coef(n, ck * kConvBlockK, sc, sh); n_have = n; }
+                  *ptr = gn_apply8(*ptr, sc, sh, silu);
+                } else {
+                  *ptr = make_uint4(0, 0, 0, 0);
+                }
+              }
+            }
+          }
+          xf_arrive();
+        }
+      }
+    }
   }
   __syncthreads();
   if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[kTrTotal - 2] = clock64();   // all roles done
@@ -831,6 +966,10 @@ int conv_plan_build(ConvPlan* pl, const ConvDesc& d) {
               "conv: split-f16 output needs 3 planes, an NHWC output and no fused statistics");
   p.split_pitch = d.out_planes == 3 ? d.Cout : 0;
   p.tile_stats = d.tile_stats;
+  B2E_REQUIRE(!d.gn_coef || (d.stride == 1 && !d.b_batch_rows && !d.s0.pitch && d.out_planes == 1), B2E_UNSUPPORTED_SHAPE,
+              "conv: the fused GroupNorm transform needs a stride-1 convolution with shared weights over plain f16 sources");
+  p.gn_coef = d.gn_coef; p.gn_silu = d.gn_silu;
+  p.coef_stride = d.s0.C + (d.s1.ptr ? d.s1.C : 0);
   p.taps = d.ksize * d.ksize;
   p.c0_chunks = d.s0.C / K;
   p.c1_chunks = d.s1.ptr ? d.s1.C / K : 0;
@@ -888,14 +1027,14 @@ int conv_plan_build(ConvPlan* pl, const ConvDesc& d) {
   return B2E_OK;
 }
 
-template <int BN, int STAGES, bool PAIR, bool HALO = false, int MT = 1, int KPS = 1>
-static int launch_t(const ConvPlan& pl, const ConvKParams& kp, int tiles, cudaStream_t st) {
+template <int BN, int STAGES, bool PAIR, bool HALO, int MT, int KPS, bool XF>
+static int launch_x(const ConvPlan& pl, const ConvKParams& kp, int tiles, cudaStream_t st) {
   using Cfg = ConvCfg<BN, STAGES, PAIR, HALO, MT, KPS>;
   static_assert(Cfg::kSmemBytes <= 227 * 1024, "shared memory budget");
   static_assert(Cfg::kTmemCols <= 512, "TMEM budget");
   static bool attr_set = false;
   if (!attr_set) {
-    B2E_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES, PAIR, HALO, MT, KPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B2E_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES, PAIR, HALO, MT, KPS, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg::kSmemBytes));
     attr_set = true;
   }
@@ -903,7 +1042,7 @@ static int launch_t(const ConvPlan& pl, const ConvKParams& kp, int tiles, cudaSt
   const int units = PAIR ? kNumSMs / 2 : kNumSMs;   // work items (tiles x splits, or tile pairs) in flight
   const int work = tiles * (PAIR ? 1 : kp.splits);
   cfg.gridDim = dim3((unsigned)((work < units ? work : units) * (PAIR ? 2 : 1)));
-  cfg.blockDim = dim3(kConvThreads);
+  cfg.blockDim = dim3(XF ? kConvThreadsXf : kConvThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
@@ -912,10 +1051,17 @@ static int launch_t(const ConvPlan& pl, const ConvKParams& kp, int tiles, cudaSt
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BN, STAGES, PAIR, HALO, MT, KPS>, pl.map_a0, pl.map_a1, pl.map_r0,
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BN, STAGES, PAIR, HALO, MT, KPS, XF>, pl.map_a0, pl.map_a1, pl.map_r0,
                                      pl.map_r1, pl.map_b, pl.map_out, kp);
   if (e != cudaSuccess) { set_error("conv_igemm launch: %s", cudaGetErrorString(e)); return B2E_CUDA_ERROR; }
   return check_launch("conv_igemm");
+}
+
+// XF (fused GroupNorm of the A operand) is a second instantiation of every variant, selected per plan
+template <int BN, int STAGES, bool PAIR, bool HALO = false, int MT = 1, int KPS = 1>
+static int launch_t(const ConvPlan& pl, const ConvKParams& kp, int tiles, cudaStream_t st) {
+  return kp.gn_coef ? launch_x<BN, STAGES, PAIR, HALO, MT, KPS, true>(pl, kp, tiles, st)
+                    : launch_x<BN, STAGES, PAIR, HALO, MT, KPS, false>(pl, kp, tiles, st);
 }
 
 int conv_launch(const ConvPlan& pl, const ConvEpilogue& ep, cudaStream_t st) {
@@ -940,6 +1086,8 @@ int conv_launch(const ConvPlan& pl, const ConvEpilogue& ep, cudaStream_t st) {
   kp.split_pitch = pl.split_pitch;
   kp.relu = ep.relu;
   kp.acc_scale = ep.acc_scale;
+  kp.gn_coef = reinterpret_cast<const float2*>(pl.gn_coef); kp.coef_stride = pl.coef_stride; kp.gn_silu = pl.gn_silu;
+  kp.Hin = pl.Ho; kp.Win = pl.Wo;     // XF plans are stride-1 convolutions: input and output maps coincide
   // B2E_TRACE=<n>: the n-th halo launch (1-based) runs with clock64 tracing of CTA 0, then dumps to stderr
   kp.trace = nullptr;
   static const int trace_at = getenv("B2E_TRACE") ? atoi(getenv("B2E_TRACE")) : 0;

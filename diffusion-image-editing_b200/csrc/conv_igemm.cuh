@@ -37,6 +37,10 @@ struct ConvDesc {
   // optional fused GroupNorm statistics of the (f16-rounded) output: per (tile slot, channel) sum and
   // sum of squares, [conv_stats_slots()][Cout][2] floats; reduced per image by gn_finalize
   float* tile_stats = nullptr;
+  // optional fused GroupNorm(+SiLU) of the input: the kernel normalises the A operand on the fly in shared memory,
+  // y = f16(silu(x * scale + shift)) with (scale, shift) float2 [N][s0.C + s1.C] from gn_coeffs_launch - the
+  // normalised activation tensor is never written to memory.  Stride 1 only.
+  const float* gn_coef = nullptr; int gn_silu = 0;
   // optional split-K scratch shared by all layers of a model: fp32 partial tiles + per-tile arrival counters
   // (counters must be zero before the first launch; the kernel re-arms them)
   float* split_ws = nullptr; size_t split_ws_bytes = 0; int* split_counters = nullptr;
@@ -69,6 +73,7 @@ struct ConvPlan {
   int has_out_f16;
   int split_pitch;   // channels per plane of a split-f16 output (0: plain f16)
   float* tile_stats;
+  const float* gn_coef; int coef_stride; int gn_silu;   // fused GroupNorm transform of the A operand (null: none)
   double flops;
 };
 

@@ -182,27 +182,45 @@ l2reg_pass1(const float4* __restrict__ x, const float4* __restrict__ e, const fl
   double acc = 0.0;
   StepK s = k.s;
   s.guide = 0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    float4 vx = ld_stream(x + i), ve = ld_stream(e + i);
-    float4 vz = make_float4(0, 0, 0, 0);
-    if (s.has_noise) vz = s.noise_batched ? ld_stream(z + i) : ld_reuse(z + (i % chw4));
-    float4 vm = k.s.mask_batched ? ld_stream(mask + i) : ld_reuse(mask + (i % chw4));
-    float4 vr = ld_stream(xref + i);
-    float4 o, o0;
-    step_elem(vx.x, ve.x, vz.x, 1.f, 0, 0.f, 0.f, s, o.x, o0.x);
-    step_elem(vx.y, ve.y, vz.y, 1.f, 0, 0.f, 0.f, s, o.y, o0.y);
-    step_elem(vx.z, ve.z, vz.z, 1.f, 0, 0.f, 0.f, s, o.z, o0.z);
-    step_elem(vx.w, ve.w, vz.w, 1.f, 0, 0.f, 0.f, s, o.w, o0.w);
-    xp[i] = o;  // re-read by pass 2: keep default caching
-    if (x0o) st_stream(x0o + i, o0);
-    const float xo[4] = {o.x, o.y, o.z, o.w}, ee[4] = {ve.x, ve.y, ve.z, ve.w};
-    const float mm[4] = {vm.x, vm.y, vm.z, vm.w}, rr[4] = {vr.x, vr.y, vr.z, vr.w};
+  // two float4 per thread per iteration, every load issued before the first use (the plain grid-stride loop kept one
+  // iteration's 3-5 loads in flight: 0.64 of the HBM peak)
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total4; i0 += 2 * stride) {
+    float4 vx[2], ve[2], vz[2], vm[2], vr[2];
+    bool ok[2];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float x0g = __fdiv_rn(__fsub_rn(xo[j], __fmul_rn(s.sb, ee[j])), s.sa);
-      float r = __fsub_rn(__fsub_rn(1.f, __fmul_rn(mm[j], x0g)), rr[j]);
-      acc += (double)__fmul_rn(r, r);
+    for (int u = 0; u < 2; ++u) {
+      const int64_t i = i0 + u * stride;
+      ok[u] = i < total4;
+      vz[u] = make_float4(0, 0, 0, 0);
+      if (ok[u]) {
+        vx[u] = ld_stream(x + i); ve[u] = ld_stream(e + i);
+        if (s.has_noise) vz[u] = s.noise_batched ? ld_stream(z + i) : ld_reuse(z + (i % chw4));
+        vm[u] = k.s.mask_batched ? ld_stream(mask + i) : ld_reuse(mask + (i % chw4));
+        vr[u] = ld_stream(xref + i);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (!ok[u]) continue;
+      const int64_t i = i0 + u * stride;
+      float4 o, o0;
+      step_elem(vx[u].x, ve[u].x, vz[u].x, 1.f, 0, 0.f, 0.f, s, o.x, o0.x);
+      step_elem(vx[u].y, ve[u].y, vz[u].y, 1.f, 0, 0.f, 0.f, s, o.y, o0.y);
+      step_elem(vx[u].z, ve[u].z, vz[u].z, 1.f, 0, 0.f, 0.f, s, o.z, o0.z);
+      step_elem(vx[u].w, ve[u].w, vz[u].w, 1.f, 0, 0.f, 0.f, s, o.w, o0.w);
+      xp[i] = o;  // re-read by pass 2: keep default caching
+      if (x0o) st_stream(x0o + i, o0);
+      const float xo[4] = {o.x, o.y, o.z, o.w}, ee[4] = {ve[u].x, ve[u].y, ve[u].z, ve[u].w};
+      const float mm[4] = {vm[u].x, vm[u].y, vm[u].z, vm[u].w}, rr[4] = {vr[u].x, vr[u].y, vr[u].z, vr[u].w};
+      float part = 0.f;     // four squares in fp32, ONE fp64 add per float4 (fp64 adds per element capped the kernel)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float x0g = __fdiv_rn(__fsub_rn(xo[j], __fmul_rn(s.sb, ee[j])), s.sa);
+        float r = __fsub_rn(__fsub_rn(1.f, __fmul_rn(mm[j], x0g)), rr[j]);
+        part = __fadd_rn(part, __fmul_rn(r, r));
+      }
+      acc += (double)part;
     }
   }
   block_sum_to_double(acc, red);
@@ -221,27 +239,41 @@ l2reg_pass2(float4* __restrict__ xp, const float4* __restrict__ e, const float4*
   const float R = sqrtf((float)red[0]);
   const float t_reg = __fdiv_rn(k.lam_scale, __fmul_rn(2.f, R));  // grad / (2*sqrt(s))
   const StepK& s = k.s;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    float4 vo = xp[i], ve = ld_stream(e + i);
-    float4 vm = s.mask_batched ? ld_stream(mask + i) : ld_reuse(mask + (i % chw4));
-    float4 vr = ld_stream(xref + i);
-    const int c = (int)((i / hw4) % C);
-    float xo[4] = {vo.x, vo.y, vo.z, vo.w};
-    const float ee[4] = {ve.x, ve.y, ve.z, ve.w}, mm[4] = {vm.x, vm.y, vm.z, vm.w},
-                rr[4] = {vr.x, vr.y, vr.z, vr.w};
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total4; i0 += 2 * stride) {
+    float4 vo[2], ve[2], vm[2], vr[2];
+    bool ok[2];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float x0g = __fdiv_rn(__fsub_rn(xo[j], __fmul_rn(s.sb, ee[j])), s.sa);
-      float img = __fmul_rn(mm[j], x0g);
-      float r = __fsub_rn(__fsub_rn(1.f, img), rr[j]);
-      float dimg = -__fmul_rn(t_reg, __fmul_rn(2.f, r));  // d/dimg of lambda*||r|| (r = 1-img-xref)
-      if (s.has_target[c]) dimg = __fadd_rn(dimg, __fmul_rn(k.k[c], sign_torch(__fsub_rn(img, s.target[c]))));
-      float g = -__fdiv_rn(__fmul_rn(dimg, mm[j]), s.sa);
-      if (s.mask_grad) g = __fmul_rn(mm[j], g);
-      xo[j] = __fadd_rn(xo[j], __fmul_rn(g, s.a2));
+    for (int u = 0; u < 2; ++u) {
+      const int64_t i = i0 + u * stride;
+      ok[u] = i < total4;
+      if (ok[u]) {
+        vo[u] = xp[i]; ve[u] = ld_stream(e + i);
+        vm[u] = s.mask_batched ? ld_stream(mask + i) : ld_reuse(mask + (i % chw4));
+        vr[u] = ld_stream(xref + i);
+      }
     }
-    st_stream(xp + i, make_float4(xo[0], xo[1], xo[2], xo[3]));
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (!ok[u]) continue;
+      const int64_t i = i0 + u * stride;
+      const int c = (int)((i / hw4) % C);
+      float xo[4] = {vo[u].x, vo[u].y, vo[u].z, vo[u].w};
+      const float ee[4] = {ve[u].x, ve[u].y, ve[u].z, ve[u].w}, mm[4] = {vm[u].x, vm[u].y, vm[u].z, vm[u].w},
+                  rr[4] = {vr[u].x, vr[u].y, vr[u].z, vr[u].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float x0g = __fdiv_rn(__fsub_rn(xo[j], __fmul_rn(s.sb, ee[j])), s.sa);
+        float img = __fmul_rn(mm[j], x0g);
+        float r = __fsub_rn(__fsub_rn(1.f, img), rr[j]);
+        float dimg = -__fmul_rn(t_reg, __fmul_rn(2.f, r));  // d/dimg of lambda*||r|| (r = 1-img-xref)
+        if (s.has_target[c]) dimg = __fadd_rn(dimg, __fmul_rn(k.k[c], sign_torch(__fsub_rn(img, s.target[c]))));
+        float g = -__fdiv_rn(__fmul_rn(dimg, mm[j]), s.sa);
+        if (s.mask_grad) g = __fmul_rn(mm[j], g);
+        xo[j] = __fadd_rn(xo[j], __fmul_rn(g, s.a2));
+      }
+      st_stream(xp + i, make_float4(xo[0], xo[1], xo[2], xo[3]));
+    }
   }
 }
 
@@ -311,16 +343,29 @@ extract_noise_kernel(const float* __restrict__ x, const float* __restrict__ e, f
   };
   if (vec) {
     const int64_t n4 = n >> 2;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
-         i += (int64_t)gridDim.x * blockDim.x) {
-      float4 vx = ld_stream(reinterpret_cast<const float4*>(x) + i);
-      float4 ve = ld_stream(reinterpret_cast<const float4*>(e) + i);
-      float4 vm = ld_stream(reinterpret_cast<const float4*>(xm) + i);
-      float4 zo, xo;
-      f(vx.x, ve.x, vm.x, zo.x, xo.x); f(vx.y, ve.y, vm.y, zo.y, xo.y);
-      f(vx.z, ve.z, vm.z, zo.z, xo.z); f(vx.w, ve.w, vm.w, zo.w, xo.w);
-      st_stream(reinterpret_cast<float4*>(z) + i, zo);
-      st_stream(reinterpret_cast<float4*>(xm) + i, xo);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += 2 * stride) {
+      float4 vx[2], ve[2], vm[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int64_t i = i0 + u * stride;
+        if (i < n4) {
+          vx[u] = ld_stream(reinterpret_cast<const float4*>(x) + i);
+          ve[u] = ld_stream(reinterpret_cast<const float4*>(e) + i);
+          vm[u] = ld_stream(reinterpret_cast<const float4*>(xm) + i);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int64_t i = i0 + u * stride;
+        if (i < n4) {
+          float4 zo, xo;
+          f(vx[u].x, ve[u].x, vm[u].x, zo.x, xo.x); f(vx[u].y, ve[u].y, vm[u].y, zo.y, xo.y);
+          f(vx[u].z, ve[u].z, vm[u].z, zo.z, xo.z); f(vx[u].w, ve[u].w, vm[u].w, zo.w, xo.w);
+          st_stream(reinterpret_cast<float4*>(z) + i, zo);
+          st_stream(reinterpret_cast<float4*>(xm) + i, xo);
+        }
+      }
     }
     if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
       const int64_t i = (n4 << 2) + threadIdx.x;
@@ -353,14 +398,37 @@ sample_xts_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
 }
 
 // out = mask*zv + (1-mask)*zo, mask broadcast over T            (src/utils.py:23-28)
+// vec: chw % 4 == 0 and 16-byte aligned pointers - two float4 per thread per iteration, loads first
 __global__ void __launch_bounds__(kStepThreads)
 apply_mask_kernel(const float* __restrict__ mask, const float* __restrict__ zo,
-                  const float* __restrict__ zv, float* __restrict__ out, int64_t n, int64_t chw) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const float m = __ldg(mask + (i % chw));
-    out[i] = __fadd_rn(__fmul_rn(m, zv[i]), __fmul_rn(__fsub_rn(1.f, m), zo[i]));
+                  const float* __restrict__ zv, float* __restrict__ out, int64_t n, int64_t chw, int vec) {
+  auto f = [](float m, float v, float o) { return __fadd_rn(__fmul_rn(m, v), __fmul_rn(__fsub_rn(1.f, m), o)); };
+  if (vec) {
+    const int64_t n4 = n >> 2, chw4 = chw >> 2, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += 2 * stride) {
+      float4 vm[2], vv[2], vo[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int64_t i = i0 + u * stride;
+        if (i < n4) {
+          vm[u] = ld_reuse(reinterpret_cast<const float4*>(mask) + (i % chw4));
+          vv[u] = ld_stream(reinterpret_cast<const float4*>(zv) + i);
+          vo[u] = ld_stream(reinterpret_cast<const float4*>(zo) + i);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int64_t i = i0 + u * stride;
+        if (i < n4)
+          st_stream(reinterpret_cast<float4*>(out) + i, make_float4(f(vm[u].x, vv[u].x, vo[u].x), f(vm[u].y, vv[u].y, vo[u].y),
+                                                                    f(vm[u].z, vv[u].z, vo[u].z), f(vm[u].w, vv[u].w, vo[u].w)));
+      }
+    }
+    return;
   }
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = f(__ldg(mask + (i % chw)), zv[i], zo[i]);
 }
 
 // x += (mask*)g * a2
@@ -376,20 +444,160 @@ apply_grad_kernel(float* __restrict__ x, const float* __restrict__ g, const floa
 }
 
 // (B,C,HW) fp32 -> (B,HW,C) u8 ; trunc(clamp(x/2+0.5,0,1)*255)  (src/transforms.py:8-35)
+__device__ __forceinline__ uint32_t u8_of(float v) {
+  v = clamp_torch(__fadd_rn(__fmul_rn(v, 0.5f), 0.5f), 0.f, 1.f);
+  return (uint32_t)(uint8_t)__fmul_rn(v, 255.f);
+}
+// vec (C == 3, hw % 4 == 0, aligned): a thread converts four consecutive pixels - three float4 loads (one per channel
+// plane), three 32-bit stores (12 interleaved bytes); two such groups per iteration with the loads first
 __global__ void __launch_bounds__(kStepThreads)
-to_uint8_kernel(const float* __restrict__ x, uint8_t* __restrict__ out, int64_t B, int C, int64_t hw) {
+to_uint8_kernel(const float* __restrict__ x, uint8_t* __restrict__ out, int64_t B, int C, int64_t hw, int vec) {
+  if (vec) {
+    const int64_t hw4 = hw >> 2, total4 = B * hw4, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t g0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g0 < total4; g0 += 2 * stride) {
+      float4 v[2][3];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int64_t g = g0 + u * stride;
+        if (g < total4) {
+          const int64_t b = g / hw4, q4 = g - b * hw4;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) v[u][c] = ld_stream(reinterpret_cast<const float4*>(x + (b * 3 + c) * hw) + q4);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int64_t g = g0 + u * stride;
+        if (g < total4) {
+          const float r[4] = {v[u][0].x, v[u][0].y, v[u][0].z, v[u][0].w}, gg[4] = {v[u][1].x, v[u][1].y, v[u][1].z, v[u][1].w},
+                      bb[4] = {v[u][2].x, v[u][2].y, v[u][2].z, v[u][2].w};
+          uint32_t by[12];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { by[3 * j] = u8_of(r[j]); by[3 * j + 1] = u8_of(gg[j]); by[3 * j + 2] = u8_of(bb[j]); }
+          uint32_t* o = reinterpret_cast<uint32_t*>(out + g * 12);
+#pragma unroll
+          for (int w = 0; w < 3; ++w)
+            __stcs(o + w, by[4 * w] | (by[4 * w + 1] << 8) | (by[4 * w + 2] << 16) | (by[4 * w + 3] << 24));
+        }
+      }
+    }
+    return;
+  }
   const int64_t total = B * hw;
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total;
        p += (int64_t)gridDim.x * blockDim.x) {
     const int64_t b = p / hw, q = p % hw;
-    for (int c = 0; c < C; ++c) {
-      float v = x[(b * C + c) * hw + q];
-      v = clamp_torch(__fadd_rn(__fmul_rn(v, 0.5f), 0.5f), 0.f, 1.f);
-      out[p * C + c] = (uint8_t)__fmul_rn(v, 255.f);
+    for (int c = 0; c < C; ++c) out[p * C + c] = (uint8_t)u8_of(x[(b * C + c) * hw + q]);
+  }
+}
+
+
+// ---- analytic colour-loss gradient w.r.t. a decoded image (guidance through a latent decoder) + the latent update
+struct ColorGradK { int has_target[4]; float target[4], k[4]; float lam_scale; int use_mask_pred, mask_batched; };
+
+// pass 1 (mask_pred variant only): sum of r^2, r = 1 - mask*img - x_ref
+__global__ void __launch_bounds__(kStepThreads)
+color_grad_norm_kernel(const float4* __restrict__ img, const float4* __restrict__ mask, const float4* __restrict__ xref,
+                       double* __restrict__ partial, int64_t total4, int64_t chw4, int mask_batched) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total4; i0 += 2 * stride) {
+    float4 vi[2], vm[2], vr[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < total4) {
+        vi[u] = __ldg(img + i);      // re-read by pass 2: default caching
+        vm[u] = mask_batched ? ld_stream(mask + i) : ld_reuse(mask + (i % chw4));
+        vr[u] = __ldg(xref + i);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (i0 + u * stride >= total4) continue;
+      const float ii[4] = {vi[u].x, vi[u].y, vi[u].z, vi[u].w}, mm[4] = {vm[u].x, vm[u].y, vm[u].z, vm[u].w},
+                  rr[4] = {vr[u].x, vr[u].y, vr[u].z, vr[u].w};
+      float part = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float r = __fsub_rn(__fsub_rn(1.f, __fmul_rn(mm[j], ii[j])), rr[j]);
+        part = __fadd_rn(part, __fmul_rn(r, r));
+      }
+      acc += (double)part;
+    }
+  }
+  block_sum_to_double(acc, red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+
+// pass 2 (or the only pass): the gradient itself
+__global__ void __launch_bounds__(kStepThreads)
+color_grad_kernel(const float4* __restrict__ img, const float4* __restrict__ mask, const float4* __restrict__ xref,
+                  float4* __restrict__ dimg, const double* __restrict__ partial, int n_partial, int64_t total4, int64_t chw4,
+                  int64_t hw4, int C, ColorGradK k) {
+  __shared__ double red[32];
+  float t_reg = 0.f;
+  if (k.use_mask_pred) {
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n_partial; i += blockDim.x) acc += partial[i];
+    block_sum_to_double(acc, red);
+    const float R = sqrtf((float)red[0]);
+    t_reg = __fdiv_rn(k.lam_scale, __fmul_rn(2.f, R));     // d(lambda ||r||)/dr = lam r / R, written as the autograd chain does
+  }
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total4; i0 += 2 * stride) {
+    float4 vi[2], vm[2], vr[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < total4) {
+        vi[u] = ld_stream(img + i);
+        if (k.use_mask_pred) {
+          vm[u] = k.mask_batched ? ld_stream(mask + i) : ld_reuse(mask + (i % chw4));
+          vr[u] = ld_stream(xref + i);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i >= total4) continue;
+      const int c = (int)((i / hw4) % C);
+      const int ht = c == 0 ? k.has_target[0] : c == 1 ? k.has_target[1] : c == 2 ? k.has_target[2] : k.has_target[3];
+      const float tau = c == 0 ? k.target[0] : c == 1 ? k.target[1] : c == 2 ? k.target[2] : k.target[3];
+      const float kc = c == 0 ? k.k[0] : c == 1 ? k.k[1] : c == 2 ? k.k[2] : k.k[3];
+      const float ii[4] = {vi[u].x, vi[u].y, vi[u].z, vi[u].w};
+      float o[4];
+      if (k.use_mask_pred) {
+        const float mm[4] = {vm[u].x, vm[u].y, vm[u].z, vm[u].w}, rr[4] = {vr[u].x, vr[u].y, vr[u].z, vr[u].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float im = __fmul_rn(mm[j], ii[j]);
+          const float r = __fsub_rn(__fsub_rn(1.f, im), rr[j]);
+          float d = -__fmul_rn(t_reg, __fmul_rn(2.f, r));
+          if (ht) d = __fadd_rn(d, __fmul_rn(kc, sign_torch(__fsub_rn(im, tau))));
+          o[j] = __fmul_rn(d, mm[j]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = ht ? __fmul_rn(kc, sign_torch(__fsub_rn(ii[j], tau))) : 0.f;
+      }
+      st_stream(dimg + i, make_float4(o[0], o[1], o[2], o[3]));
     }
   }
 }
 
+// x += (mask*) (-(d * chain) / sa) * a2
+__global__ void __launch_bounds__(kStepThreads)
+latent_guidance_kernel(float* __restrict__ x, const float* __restrict__ d, const float* __restrict__ mask, int64_t n,
+                       int64_t chw, int mask_batched, float chain, float sa, float a2) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float g = -__fdiv_rn(__fmul_rn(d[i], chain), sa);
+    if (mask) g = __fmul_rn(mask[mask_batched ? i : i % chw], g);
+    x[i] = __fadd_rn(x[i], __fmul_rn(g, a2));
+  }
+}
 
 // out = a*x + b*y
 __global__ void __launch_bounds__(kStepThreads)
@@ -569,6 +777,41 @@ int b2e_apply_guidance_grad_f32(float* x, const float* neg_grad, const float* ma
   return check_launch("apply_guidance_grad");
 }
 
+size_t b2e_color_loss_grad_workspace_bytes(void) { return sizeof(double) * kNumSMs * 8; }
+
+int b2e_color_loss_grad_f32(const float* img, const float* mask, const float* x_ref, float* d_img, int64_t B, int64_t C,
+                            int64_t HW, const b2e_color_grad_params* p, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+  B2E_REQUIRE(img && d_img && p && B > 0 && C > 0 && C <= 4 && HW > 0, B2E_INVALID_ARG, "color_loss_grad: bad argument");
+  B2E_REQUIRE(HW % 4 == 0 && aligned16(img) && aligned16(d_img) && (!mask || aligned16(mask)) && (!x_ref || aligned16(x_ref)),
+              B2E_UNSUPPORTED_SHAPE, "color_loss_grad: needs HW %% 4 == 0 and 16-byte aligned tensors");
+  B2E_REQUIRE(!p->use_mask_pred || (mask && x_ref && workspace && workspace_bytes >= b2e_color_loss_grad_workspace_bytes()),
+              B2E_INVALID_ARG, "color_loss_grad: the masked + L2-regularised variant needs mask, x_ref and a workspace");
+  ColorGradK k;
+  for (int i = 0; i < 4; ++i) { k.has_target[i] = p->has_target[i]; k.target[i] = p->target[i]; k.k[i] = p->k[i]; }
+  k.lam_scale = p->lam_scale; k.use_mask_pred = p->use_mask_pred; k.mask_batched = p->mask_batched;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t total4 = B * C * HW / 4, chw4 = C * HW / 4;
+  const int grid = grid_for(total4 / 2 + 1, kStepThreads, kNumSMs * 8);
+  if (p->use_mask_pred) {
+    color_grad_norm_kernel<<<grid, kStepThreads, 0, st>>>((const float4*)img, (const float4*)mask, (const float4*)x_ref,
+                                                          (double*)workspace, total4, chw4, p->mask_batched);
+    int rc = check_launch("color_grad_norm");
+    if (rc) return rc;
+  }
+  color_grad_kernel<<<grid, kStepThreads, 0, st>>>((const float4*)img, (const float4*)mask, (const float4*)x_ref, (float4*)d_img,
+                                                   (const double*)workspace, grid, total4, chw4, HW / 4, (int)C, k);
+  return check_launch("color_grad");
+}
+
+int b2e_apply_latent_guidance_f32(float* x, const float* d_latent, const float* mask, int64_t B, int64_t CHW,
+                                  int mask_batched, float chain, float sqrt_a_t, float a_t_sq, void* stream) {
+  B2E_REQUIRE(x && d_latent && B > 0 && CHW > 0, B2E_INVALID_ARG, "apply_latent_guidance: bad argument");
+  latent_guidance_kernel<<<grid_for(B * CHW, kStepThreads), kStepThreads, 0, (cudaStream_t)stream>>>(
+      x, d_latent, mask, B * CHW, CHW, mask_batched, chain, sqrt_a_t, a_t_sq);
+  return check_launch("apply_latent_guidance");
+}
+
 int b2e_pred_x0_f32(const float* x_t, const float* eps, float* x0, int64_t n, float sqrt_a_t,
                     float sqrt_b_t, void* stream) {
   return launch_map2<OP_PRED_X0>(x_t, eps, x0, n, MapK{sqrt_a_t, sqrt_b_t, 0.f, 0.f}, stream, "pred_x0");
@@ -587,15 +830,17 @@ int b2e_cfg_combine_f32(const float* e_first, const float* e_second, float* out,
 int b2e_apply_mask_f32(const float* mask, const float* zo, const float* zv, float* out, int64_t T,
                        int64_t CHW, void* stream) {
   B2E_REQUIRE(mask && zo && zv && out && T > 0 && CHW > 0, B2E_INVALID_ARG, "apply_mask: bad argument");
-  apply_mask_kernel<<<grid_for(T * CHW, kStepThreads), kStepThreads, 0, (cudaStream_t)stream>>>(
-      mask, zo, zv, out, T * CHW, CHW);
+  const int vec = CHW % 4 == 0 && aligned16(mask) && aligned16(zo) && aligned16(zv) && aligned16(out);
+  apply_mask_kernel<<<grid_for(vec ? T * CHW / 8 : T * CHW, kStepThreads), kStepThreads, 0, (cudaStream_t)stream>>>(
+      mask, zo, zv, out, T * CHW, CHW, vec);
   return check_launch("apply_mask");
 }
 
 int b2e_to_uint8_f32(const float* x, uint8_t* out, int64_t B, int64_t C, int64_t HW, void* stream) {
   B2E_REQUIRE(x && out && B > 0 && C > 0 && HW > 0, B2E_INVALID_ARG, "to_uint8: bad argument");
-  to_uint8_kernel<<<grid_for(B * HW, kStepThreads), kStepThreads, 0, (cudaStream_t)stream>>>(
-      x, out, B, (int)C, HW);
+  const int vec = C == 3 && HW % 4 == 0 && aligned16(x) && (reinterpret_cast<uintptr_t>(out) & 3) == 0;
+  to_uint8_kernel<<<grid_for(vec ? B * HW / 8 : B * HW, kStepThreads), kStepThreads, 0, (cudaStream_t)stream>>>(
+      x, out, B, (int)C, HW, vec);
   return check_launch("to_uint8");
 }
 

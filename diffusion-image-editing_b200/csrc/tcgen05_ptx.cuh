@@ -33,6 +33,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// acquire at cluster scope: pairs with mbar_arrive_leader_release of the peer CTA's transform warps
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0,
                                             int c1, int c2, int c3, int c4) {
   asm volatile(
@@ -113,6 +127,11 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
 }
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+// same, with release semantics at cluster scope: generic-proxy shared-memory writes of this CTA (made visible to the
+// async proxy by fence.proxy.async) are ordered before the leader's MMA warp observes the phase completion
+__device__ __forceinline__ void mbar_arrive_leader_release(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
 }
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem) {

@@ -7,6 +7,7 @@
 // forward pass is just the recorded list of launches on the caller's stream - no allocation,
 // no host synchronisation, graph-capturable.
 #include <math.h>
+#include <string.h>
 
 #include <functional>
 #include <map>
@@ -59,6 +60,9 @@ struct Tensor {
   float* cstats = nullptr;  // per-(image, channel) sum / sum of squares from the producing conv's epilogue
   float* tstats = nullptr;  // small tensors: raw per-(tile slot, channel) statistics instead (no finalize kernel)
   size_t tstats_bytes = 0; int ts_nt = 0, ts_per_img = 0;
+  // fused GroupNorm: this "tensor" is the normalised VIEW of raw source(s) - p (C0 channels) ++ p1 (C1 channels) - that the
+  // consumer convolution materialises on the fly in shared memory from gn_coef (float2 [N][C0 + C1]); it owns no memory
+  bool alias = false; f16* p1 = nullptr; int C0 = 0, C1 = 0; float* gn_coef = nullptr; int gn_silu = 0;
 };
 
 struct Arena {
@@ -1141,6 +1145,11 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
     return t;
   };
   auto tfree = [&](Tensor& t) {
+    if (t.alias) {   // a fused-GroupNorm view owns only its coefficient table
+      if (t.gn_coef && !keep) ar.release(t.gn_coef, sizeof(float) * 2 * (size_t)t.N * t.C);
+      t.gn_coef = nullptr; t.p = nullptr;
+      return;
+    }
     if (keep) return;
     if (t.p) ar.release(t.p, t.bytes);
     if (t.cstats) ar.release(t.cstats, sizeof(float) * 2 * t.N * t.C);
@@ -1188,6 +1197,12 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
     ConvDesc d;
     d.s0 = ConvSrc{x0.p, x0.C * PL};
     if (x1) d.s1 = ConvSrc{x1->p, x1->C * PL};
+    if (x0.alias) {
+      if (x1 || stride != 1) { rc = B2E_INVALID_ARG; set_error("unet: fused GroupNorm view used as a second source / strided input"); return; }
+      d.s0 = ConvSrc{x0.p, x0.C0};
+      if (x0.p1) d.s1 = ConvSrc{x0.p1, x0.C1};
+      d.gn_coef = x0.gn_coef; d.gn_silu = x0.gn_silu;
+    }
     if (r0) d.r0 = ConvSrc{r0->p, r0->C * PL};
     if (r1) d.r1 = ConvSrc{r1->p, r1->C * PL};
     d.out_planes = out ? PL : 1;
@@ -1212,6 +1227,7 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
     snprintf(desc, sizeof(desc), "conv%dx%d s%d %dx%d cin%d+%d res%d cout%d tiles%d bn%d%s", L.k, L.k, stride, x0.H, x0.W,
              x0.C, x1 ? x1->C : 0, L.res_c, L.cout, pl.w_blks * pl.h_blks * pl.n_blks * (pl.cout_pad / pl.block_n), pl.block_n,
              pl.halo == 2 ? " halo2" : pl.halo ? " halo1" : pl.pair ? " pair" : (pl.splits > 1 ? (" splitK" + std::to_string(pl.splits)).c_str() : ""));
+    if (x0.alias) snprintf(desc + strlen(desc), sizeof(desc) - strlen(desc), " +gn%s", x0.gn_silu ? "+silu" : "");
     // profile record: ALGORITHMIC FLOPs.  An identity residual segment (W_r = I: the plain residual add riding along as
     // K chunks) is executed on the tensor cores but is not arithmetic of the algorithm - it is counted as the bytes of the
     // residual tensor it reads instead (conv_shortcut segments, which have a bias2, are real 1x1 convolutions and count)
@@ -1235,20 +1251,40 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
       ar.release(tstats, tstats_bytes);   // dead after the finalize kernel (stream order)
     }
   };
+  // GroupNorm(+SiLU): statistics come from the producing convolution's epilogue, the apply pass is a stand-alone
+  // memory-bound kernel (4 B/elem).  B2E_GN_FUSE=1 (experimental, OFF by default) instead fuses the apply into the consumer
+  // convolution (16-bit mode, sources a multiple of 64 channels wide): only the per-(image, channel) coefficients are
+  // computed here and *out is a view of the raw source(s); the convolution's transform warps normalise its A operand in
+  // shared memory (conv_igemm XF kernels), so the normalised tensor never exists.  Bit-identical results, but measured
+  // SLOWER on B200 (profiles/r2_gn_fusion.md): the extra barrier hop per pipeline stage (TMA -> transform warps -> MMA)
+  // stalls the 3-4 stage smem ring (+44 % on the 256x256 layers with the transform itself switched off), more than the
+  // 1.8 ms of GroupNorm launches it removes.
+  static const bool gn_fuse_on = getenv("B2E_GN_FUSE") && atoi(getenv("B2E_GN_FUSE")) != 0;
   auto gnorm = [&](const NormL& L, Tensor x0, const Tensor* x1, int silu, Tensor* out, float** stats_out = nullptr,
                    float eps_override = -1.f) {
     if (rc) return;
     const int C = x0.Cr + (x1 ? x1->Cr : 0);   // real channels, written compactly; pitch rounded up to 64
-    *out = talloc(B, x0.H, x0.W, pad64(C), C);
+    const bool fuse = gn_fuse_on && PL == 1 && x0.Cr == x0.C && x0.C % kConvBlockK == 0 &&
+                      (!x1 || (x1->Cr == x1->C && x1->C % kConvBlockK == 0));
+    float* coef = nullptr;
+    if (fuse) {
+      Tensor t; t.N = B; t.H = x0.H; t.W = x0.W; t.C = C; t.Cr = C; t.bytes = 0;
+      t.alias = true; t.p = x0.p; t.C0 = x0.C; t.p1 = x1 ? x1->p : nullptr; t.C1 = x1 ? x1->C : 0; t.gn_silu = silu;
+      coef = (float*)ar.alloc(sizeof(float) * 2 * (size_t)B * C);
+      t.gn_coef = coef;
+      *out = t;
+    } else {
+      *out = talloc(B, x0.H, x0.W, pad64(C), C);
+    }
     float* sv = (keep && stats_out) ? (float*)ar.alloc(sizeof(float) * 2 * B * G) : nullptr;
     if (stats_out) *stats_out = sv;
     if (dry) return;
     GNArgs a;
     a.save_stats = sv;
     a.x0 = x0.p; a.x1 = x1 ? x1->p : nullptr; a.C0 = x0.Cr; a.C1 = x1 ? x1->Cr : 0;
-    a.P0 = x0.C; a.P1 = x1 ? x1->C : 0; a.Pout = out->C;
+    a.P0 = x0.C; a.P1 = x1 ? x1->C : 0; a.Pout = fuse ? C : out->C;
     a.N = B; a.HW = x0.H * x0.W; a.G = G; a.eps = eps_override > 0.f ? eps_override : c.norm_eps; a.gamma = L.g; a.beta = L.b;
-    a.partial = gn_part; a.chunks = gn_chunks(a.HW, C); a.out = out->p; a.silu = silu; a.planes = PL;
+    a.partial = gn_part; a.chunks = gn_chunks(a.HW, C); a.out = fuse ? nullptr : out->p; a.silu = silu; a.planes = PL;
     bool fused = x0.cstats && (!x1 || x1->cstats);
     a.cs0 = fused ? x0.cstats : nullptr;
     a.cs1 = fused && x1 ? x1->cstats : nullptr;
@@ -1257,6 +1293,12 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
     a.ts1 = raw && x1 ? x1->tstats : nullptr;
     a.ts_nt = x0.ts_nt; a.ts_per_img = x0.ts_per_img;
     if (raw) fused = true;
+    if (fuse) {
+      // algorithmic traffic: the statistics pass reads x only when no producing convolution supplied them
+      ops.push_back({[a, coef](cudaStream_t st) { return gn_coeffs_launch(a, coef, st); }, 1, 0.0, (fused ? 0.0 : 2.0) * B * a.HW * C,
+                     "groupnorm coefficients (apply fused into the consumer conv)"});
+      return;
+    }
     // algorithmic traffic: statistics pass reads x, apply pass reads x and writes y (f16)
     ops.push_back({[a](cudaStream_t st) { return gn_launch(a, st); }, 1, 0.0, (fused ? 4.0 : 6.0) * B * a.HW * C});
   };
@@ -1479,9 +1521,11 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
         tfree(a1);
         gnorm(r.n2, h1, nullptr, 1, &a2, &sv.st2);
         sv.x = h; sv.h1 = h1;
-        tfree(h1);
+        const bool a2_view = a2.alias;          // a fused-GroupNorm view of h1: h1 must outlive conv2
+        if (!a2_view) tfree(h1);
         // out = conv2(a2) + shortcut(x) : the block input rides along as a 1x1 K segment of conv2
         conv(r.c2, a2, nullptr, 1, ConvEpilogue{}, &out, nullptr, &h, x1);
+        if (a2_view) tfree(h1);
         tfree(a2);
         if (!on_stack(h)) tfree(h);
         if (have_cat) { tfree(cat); have_cat = false; }
@@ -1687,7 +1731,8 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
   if (!rc) {
     Tensor an;
     gnorm(m->norm_out, h, nullptr, 1, &an, &st_out);
-    tfree(h);
+    const bool an_view = an.alias;              // a fused-GroupNorm view of h: h must outlive conv_out
+    if (!an_view) tfree(h);
     float dummy = 0.f;
     if (m->encoder) {
       // conv_out -> fp32 NCHW scratch -> quant_conv (1x1, fp32) -> the caller's output
@@ -1702,6 +1747,7 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
     } else {
       conv(m->conv_out, an, nullptr, 1, ConvEpilogue{}, nullptr, &dummy);
     }
+    if (an_view) tfree(h);
     tfree(an);
   }
   // ---- backward program (decoder, gradient mode): d(loss)/d(latent) from d(loss)/d(image), walking the nodes in

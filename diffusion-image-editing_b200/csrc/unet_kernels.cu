@@ -1,6 +1,7 @@
 // GroupNorm+SiLU, layout packing, upsampling, timestep embedding and attention kernels of the
 // UNet.  All activations are f16 NHWC; statistics, softmax and accumulation are fp32/fp64.
 #include "unet_kernels.cuh"
+#include "gn_math.cuh"
 
 #include <math.h>
 #include <stdlib.h>
@@ -8,22 +9,6 @@
 namespace b2e {
 
 constexpr int kGNThreads = 256;
-
-__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
-  const f16x2* b = reinterpret_cast<const f16x2*>(&v);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    float2 t = f16x2_to_float2(b[j]);
-    f[2 * j] = t.x; f[2 * j + 1] = t.y;
-  }
-}
-__device__ __forceinline__ uint4 pack8(const float* f) {
-  uint4 v;
-  f16x2* b = reinterpret_cast<f16x2*>(&v);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) b[j] = floats_to_f16x2(f[2 * j], f[2 * j + 1]);
-  return v;
-}
 
 // ------------------------------------------------------------------ GroupNorm
 // Thread layout: a "slot" is 8 consecutive channels (one 16-byte access); 256 / slots pixels are
@@ -92,30 +77,40 @@ template <bool SPLIT>
 __global__ void __launch_bounds__(512) gn_apply_kernel(GNArgs a, int pix_per_block) {
   pdl_wait();
   __shared__ float s_mean[64], s_rstd[64];
+  extern __shared__ double s_ch[];          // [C][2]: per-channel (sum, sum of squares) of image n (fused-statistics paths)
   const int C = a.C0 + a.C1, slots = a.Pout >> 3, ppi = (int)blockDim.x / slots;
   const int n = blockIdx.y, tid = threadIdx.x;
   const int cpg = C / a.G;
-  if (tid < a.G) {
-    double ts = 0.0, tq = 0.0;
-    if (a.ts0) {
-      // raw tile statistics of a small tensor: slots of image n are (n/Nt * per_img + i) * Nt + n % Nt
-      const int64_t base = (int64_t)(n / a.ts_nt) * a.ts_per_img;
-      const int nl = n % a.ts_nt;
-      for (int c = tid * cpg; c < (tid + 1) * cpg; ++c) {
-        const bool first = c < a.C0;
+  if (a.ts0 || a.cs0) {
+    // statistics from the producing convolutions' epilogues (concat-aware): ALL threads gather the per-channel sums of
+    // image n with independent loads in flight (one thread per group walking its channels serially exposed ~16-64
+    // dependent L2 round trips: 10 of the 13 us of a low-resolution launch), then the group threads combine them
+    for (int c = tid; c < C; c += blockDim.x) {
+      const bool first = c < a.C0;
+      const int Cs = first ? a.P0 : a.P1, cc = first ? c : c - a.C0;
+      double ts = 0.0, tq = 0.0;
+      if (a.ts0) {
+        // raw tile statistics of a small tensor: slots of image n are (n/Nt * per_img + i) * Nt + n % Nt
         const float* t = first ? a.ts0 : a.ts1;
-        const int Cs = first ? a.P0 : a.P1, cc = first ? c : c - a.C0;
+        const int64_t base = (int64_t)(n / a.ts_nt) * a.ts_per_img;
+        const int nl = n % a.ts_nt;
+#pragma unroll 4
         for (int i = 0; i < a.ts_per_img; ++i) {
           const float2 v = __ldg(reinterpret_cast<const float2*>(t + (((base + i) * a.ts_nt + nl) * Cs + cc) * 2));
           ts += (double)v.x; tq += (double)v.y;
         }
+      } else {
+        const float2 v = __ldg(reinterpret_cast<const float2*>((first ? a.cs0 : a.cs1) + ((int64_t)n * Cs + cc) * 2));
+        ts = (double)v.x; tq = (double)v.y;
       }
-    } else if (a.cs0) {
-      // per-channel sums from the producing convolutions' epilogues (concat-aware)
-      for (int c = tid * cpg; c < (tid + 1) * cpg; ++c) {
-        const float* o = c < a.C0 ? a.cs0 + ((int64_t)n * a.P0 + c) * 2 : a.cs1 + ((int64_t)n * a.P1 + (c - a.C0)) * 2;
-        ts += (double)o[0]; tq += (double)o[1];
-      }
+      s_ch[2 * c] = ts; s_ch[2 * c + 1] = tq;
+    }
+    __syncthreads();
+  }
+  if (tid < a.G) {
+    double ts = 0.0, tq = 0.0;
+    if (a.ts0 || a.cs0) {
+      for (int c = tid * cpg; c < (tid + 1) * cpg; ++c) { ts += s_ch[2 * c]; tq += s_ch[2 * c + 1]; }
     } else {
       for (int ch = 0; ch < a.chunks; ++ch) {
         const float* o = a.partial + (((int64_t)n * a.chunks + ch) * a.G + tid) * 2;
@@ -202,25 +197,97 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(GNArgs a, int pix_per_blo
 #pragma unroll
     for (int u = 0; u < kGNUnroll; ++u) {
       const int q = p + u * ppi;
-      if (q < p1) {
-        float f[8];
-        unpack8(v[u], f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float y = fmaf(f[j], scale[j], shift[j]);
-          if (a.silu) {
-            // y*sigmoid(y) = 0.5y + 0.5y*tanh(0.5y): one MUFU op per element
-            const float hy = 0.5f * y;
-            float th;
-            asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(hy));
-            y = fmaf(hy, th, hy);
-          }
-          f[j] = y;
-        }
-        *reinterpret_cast<uint4*>(dst + (int64_t)q * a.Pout) = pack8(f);
-      }
+      if (q < p1) *reinterpret_cast<uint4*>(dst + (int64_t)q * a.Pout) = gn_apply8(v[u], scale, shift, a.silu != 0);
     }
   }
+}
+
+// Coefficients of the FUSED GroupNorm (conv_igemm XF kernels): per image n and per K position p of the consumer
+// convolution's A operand (source 0 at [0, P0), source 1 at [P0, P0 + P1), pitches included) the pair
+// (scale, shift) = (rstd_g gamma_c, beta_c - mean_g scale) - the arithmetic of gn_apply_kernel - and (0, 0) on the zero
+// tails of pitched sources.  One block per image; statistics from the producing convolutions' epilogues (per-channel
+// sums cs*, or raw tile slots ts* of small tensors) or from the stand-alone gn_partial pass.
+__global__ void __launch_bounds__(256) gn_coeffs_kernel(GNArgs a, float2* __restrict__ coef) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ double s_ch[];          // [C][2] per-channel (sum, sum of squares) of image n
+  __shared__ float s_mean[64], s_rstd[64];
+  const int C = a.C0 + a.C1, n = blockIdx.x, tid = threadIdx.x;
+  const int cpg = C / a.G;
+  if (a.ts0 || a.cs0) {
+    for (int c = tid; c < C; c += blockDim.x) {
+      const bool first = c < a.C0;
+      const int Cs = first ? a.P0 : a.P1, cc = first ? c : c - a.C0;
+      double ts = 0.0, tq = 0.0;
+      if (a.ts0) {
+        const float* t = first ? a.ts0 : a.ts1;
+        const int64_t base = (int64_t)(n / a.ts_nt) * a.ts_per_img;
+        const int nl = n % a.ts_nt;
+        for (int i = 0; i < a.ts_per_img; ++i) {
+          const float2 v = __ldg(reinterpret_cast<const float2*>(t + (((base + i) * a.ts_nt + nl) * Cs + cc) * 2));
+          ts += (double)v.x; tq += (double)v.y;
+        }
+      } else {
+        const float* o = (first ? a.cs0 : a.cs1) + ((int64_t)n * Cs + cc) * 2;
+        ts = (double)o[0]; tq = (double)o[1];
+      }
+      s_ch[2 * c] = ts; s_ch[2 * c + 1] = tq;
+    }
+    __syncthreads();
+  }
+  if (tid < a.G) {
+    double ts = 0.0, tq = 0.0;
+    if (a.ts0 || a.cs0) {
+      for (int c = tid * cpg; c < (tid + 1) * cpg; ++c) { ts += s_ch[2 * c]; tq += s_ch[2 * c + 1]; }
+    } else {
+      for (int ch = 0; ch < a.chunks; ++ch) {
+        const float* o = a.partial + (((int64_t)n * a.chunks + ch) * a.G + tid) * 2;
+        ts += (double)o[0]; tq += (double)o[1];
+      }
+    }
+    const double cnt = (double)a.HW * cpg;
+    const double mean = ts / cnt;
+    double var = tq / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[tid] = (float)mean;
+    s_rstd[tid] = (float)(1.0 / sqrt(var + (double)a.eps));
+    if (a.save_stats) *reinterpret_cast<float2*>(a.save_stats + ((int64_t)n * a.G + tid) * 2) = make_float2(s_mean[tid], s_rstd[tid]);
+  }
+  __syncthreads();
+  const int K = a.P0 + a.P1;
+  for (int p = tid; p < K; p += blockDim.x) {
+    const bool first = p < a.P0;
+    const int q = first ? p : p - a.P0;
+    float2 o = make_float2(0.f, 0.f);
+    if (q < (first ? a.C0 : a.C1)) {
+      const int c = first ? q : a.C0 + q;
+      const int g = c / cpg;
+      o.x = s_rstd[g] * __ldg(a.gamma + c);
+      o.y = __ldg(a.beta + c) - s_mean[g] * o.x;
+    }
+    coef[(int64_t)n * K + p] = o;
+  }
+}
+
+int gn_coeffs_launch(const GNArgs& a, float* coef, cudaStream_t st) {
+  const int C = a.C0 + a.C1;
+  B2E_REQUIRE(C % 8 == 0 && a.C0 % 8 == 0 && a.G <= 64 && C % a.G == 0 && a.planes == 1, B2E_UNSUPPORTED_SHAPE,
+              "groupnorm coefficients: unsupported channels %d+%d / groups %d", a.C0, a.C1, a.G);
+  int rc = B2E_OK;
+  if (!a.cs0 && !a.ts0) {   // no statistics from a producing convolution: stand-alone pass over the raw tensor(s)
+    launch_pdl(gn_partial_kernel<false>, dim3(dim3(a.chunks, a.N)), dim3(C > 2048 ? 512 : kGNThreads), 0, st, a);
+    rc = check_launch("gn_partial");
+    if (rc) return rc;
+  }
+  const size_t smem = sizeof(double) * 2 * (size_t)C;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2E_CUDA(cudaFuncSetAttribute(gn_coeffs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr_set = true;
+  }
+  B2E_REQUIRE(smem <= 96 * 1024, B2E_UNSUPPORTED_SHAPE, "groupnorm coefficients: %d channels", C);
+  launch_pdl(gn_coeffs_kernel, dim3(a.N), dim3(256), smem, st, a, reinterpret_cast<float2*>(coef));
+  return check_launch("gn_coeffs");
 }
 
 int gn_chunks(int HW, int C) {
@@ -251,8 +318,14 @@ int gn_launch(const GNArgs& a, cudaStream_t st) {
   const int slots = a.Pout / 8, ppi = threads / slots;
   int ppb = ppi * kGNUnroll * 2;  // two unrolled sweeps per thread
   if (ppb > a.HW) ppb = a.HW;
-  if (a.planes == 3) launch_pdl(gn_apply_kernel<true>, dim3(dim3((a.HW + ppb - 1) / ppb, a.N)), dim3(threads), 0, st, a, ppb);
-  else launch_pdl(gn_apply_kernel<false>, dim3(dim3((a.HW + ppb - 1) / ppb, a.N)), dim3(threads), 0, st, a, ppb);
+  const size_t smem = (a.cs0 || a.ts0) ? sizeof(double) * 2 * (size_t)C : 0;   // per-channel sums of the fused-statistics paths
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2E_CUDA(cudaFuncSetAttribute(gn_apply_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    attr_set = true;
+  }
+  if (a.planes == 3) launch_pdl(gn_apply_kernel<true>, dim3(dim3((a.HW + ppb - 1) / ppb, a.N)), dim3(threads), smem, st, a, ppb);
+  else launch_pdl(gn_apply_kernel<false>, dim3(dim3((a.HW + ppb - 1) / ppb, a.N)), dim3(threads), smem, st, a, ppb);
   return check_launch("gn_apply");
 }
 

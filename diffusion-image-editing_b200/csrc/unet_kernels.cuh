@@ -49,6 +49,9 @@ struct GNBwdArgs {
 int gn_bwd_launch(const GNBwdArgs& a, cudaStream_t st);
 int gn_chunks(int HW, int C);
 int gn_launch(const GNArgs& a, cudaStream_t st);
+// fused GroupNorm: only the (scale, shift) coefficients, float2 [N][P0 + P1]; the consumer convolution applies them to its
+// A operand in shared memory (ConvDesc::gn_coef) and the normalised tensor never exists in memory
+int gn_coeffs_launch(const GNArgs& a, float* coef, cudaStream_t st);
 // tile statistics written by the conv epilogue -> per-(image, channel) sums
 int gn_finalize_launch(const float* tile_stats, float* chan_stats, int N, int C, int Nt, int w_blks, int h_blks,
                        cudaStream_t st);

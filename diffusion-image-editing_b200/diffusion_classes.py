@@ -30,6 +30,14 @@ class LDM(Diffusion):
         # through the decoder (AttrFunc.apply -> decode(no_grad=False), src/attr_functions.py:153)
         self.guidance_vqvae = getattr(model, "guidance_vqvae", None)
 
+    def native_decoder(self):
+        """(decoder engine, chain factor d(decoder input)/d(x0 prediction)) when the guidance graph can run on the native
+        decoder without autograd (analytic colour guidance, AttrFunc.apply); None otherwise."""
+        vq = self.vqvae
+        if hasattr(vq, "decode_keep") and not getattr(vq, "forward_only", True):
+            return vq, 1.0
+        return None
+
     def encode(self, sample: torch.Tensor) -> torch.Tensor:
         with torch.no_grad():
             return self.vqvae.encode(sample.to(dtype=torch.float32)).latents
@@ -59,6 +67,13 @@ class SD(Diffusion):
         self.vae = model.vae
         self.tokenizer = model.tokenizer
         self.text_encoder = model.text_encoder
+
+    def native_decoder(self):
+        """See LDM.native_decoder; SD.decode feeds the decoder latent / 0.18215."""
+        vae = self.vae
+        if hasattr(vae, "decode_keep") and not getattr(vae, "forward_only", True):
+            return vae, 1.0 / self.SCALE
+        return None
 
     def encode(self, sample: torch.Tensor) -> torch.Tensor:
         with torch.no_grad():

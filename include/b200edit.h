@@ -115,6 +115,33 @@ int b2e_guided_step_l2reg_f32(const float* x_t, const float* eps, const float* z
 int b2e_apply_guidance_grad_f32(float* x, const float* neg_grad, const float* mask, int64_t B,
                                 int64_t CHW, int mask_batched, float a_t_sq, void* stream);
 
+/* Analytic guidance THROUGH a latent decoder (LDM / SD; AttrFunc.apply with decode inside the graph,
+ * src/attr_functions.py:120-163 + :22-37, :78-102): the built-in colour losses need no autograd - their gradient
+ * w.r.t. the DECODED image is closed-form and enters b2e_vqdec_backward directly.
+ *   d_img[b,c,p] = k[c] * sign(img - target[c])                      (0 where the channel has no target)
+ * and, with use_mask_pred (mask_pred_original_sample + use_l2: loss(mask*img) + lambda*||1 - mask*img - x_0||_2):
+ *   r = 1 - mask*img - x_ref ;  R = sqrt(sum_all r^2)  (one global reduction, fixed order, fp64 partials)
+ *   d_img = mask * (k[c] * sign(mask*img - target[c]) - lam_scale * r / R)
+ * k[c] = loss_scale * weight_c / N (N = B*H*W of the decoded image, or H*W per sample), lam_scale = loss_scale*lambda.
+ * img, d_img (B,C,HW) fp32; mask (1|B,C,HW) or NULL; x_ref (B,C,HW) or NULL. */
+typedef struct {
+  int32_t has_target[4];
+  float target[4];
+  float k[4];
+  float lam_scale;
+  int32_t use_mask_pred;
+  int32_t mask_batched;
+} b2e_color_grad_params;
+size_t b2e_color_loss_grad_workspace_bytes(void);
+int b2e_color_loss_grad_f32(const float* img, const float* mask, const float* x_ref, float* d_img, int64_t B, int64_t C,
+                            int64_t HW, const b2e_color_grad_params* p, void* workspace, size_t workspace_bytes,
+                            void* stream);
+/* ... and the update on the latent after the decoder's backward pass returned d_latent = dL/d(decoder input):
+ *   g = -(d_latent * chain) / sqrt_a_t ;  x <- x + (mask? mask*g : g) * a_t_sq
+ * chain = d(decoder input)/d(x0 prediction): 1 for LDM, 1/0.18215 for SD (src/diffusion_classes.py:33). */
+int b2e_apply_latent_guidance_f32(float* x, const float* d_latent, const float* mask, int64_t B, int64_t CHW,
+                                  int mask_batched, float chain, float sqrt_a_t, float a_t_sq, void* stream);
+
 /* ------------------------------------------------------------------ single ops
  * compute_predicted_original_sample, src/diffusion_utils.py:27-31 */
 int b2e_pred_x0_f32(const float* x_t, const float* eps, float* x0, int64_t n, float sqrt_a_t,
