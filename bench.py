@@ -288,7 +288,9 @@ def main():
         if args.config != 4:
             todo.append(("config4", lambda: config4(c, precision, None, 2, 1)))
         for name, fn in todo:
-            if time.time() - T_START > 240:
+            # every rank must take the same branch (the extras synchronise across ranks): agree on the time guard and on
+            # failures collectively
+            if max_over_ranks(1.0 if time.time() - T_START > 240 else 0.0) > 0:
                 extra[name] = {"skipped": "time guard (240 s)"}
                 continue
             try:
@@ -297,6 +299,8 @@ def main():
                 extra[name] = r
             except Exception as ex:   # an extra must never take the headline line down
                 extra[name] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+                if world > 1:         # a rank that failed inside a collective region cannot rejoin safely: stop the extras
+                    break
             torch.cuda.empty_cache()
         if world == 1:
             try:

@@ -24,8 +24,10 @@ def short(name):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("csv")
-    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--steps", type=int, default=2, help="guided denoising steps in the summarised region")
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--before", type=int, default=None,
+                    help="guided denoising steps before the timed region (round-2 bench.py: (warmup + 1) passes x --denoise-steps)")
     a = ap.parse_args()
     rows = []
     with open(a.csv, newline="") as f:
@@ -41,7 +43,7 @@ def main():
     # cut into steps at guided_step launches
     ends = [i for i, r in enumerate(rows) if "guided_step" in r[1]]
     K, W = a.steps, a.warmup
-    n_before = W + min(W, K) + K + K            # warm-up + priming steps before the timed region
+    n_before = a.before if a.before is not None else W + min(W, K) + K + K   # warm-up + priming steps before the timed region
     if len(ends) < n_before + K:
         print(f"only {len(ends)} guided_step launches in the list (need {n_before + K}); summarising everything", file=sys.stderr)
         lo, hi = 0, len(rows)
@@ -54,7 +56,7 @@ def main():
     for _, name, ns in region:
         by[short(name)][0] += 1
         by[short(name)][1] += ns
-    print(f"# ncu launch list: timed region of `bench.py --steps {K} --warmup {W}` (launch IDs {region[0][0]}..{region[-1][0]})\n")
+    print(f"# ncu launch list: {K} guided denoising steps of the timed region of bench.py (launch IDs {region[0][0]}..{region[-1][0]})\n")
     print(f"{len(region)} launches, {tot / 1e6:.3f} ms serialised device time ({tot / 1e6 / max(K, 1):.3f} ms/step), "
           f"{len(region) / max(K, 1):.0f} launches/step\n")
     print("| kernel | launches | total ms | share | avg us |")

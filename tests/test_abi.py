@@ -33,6 +33,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_C.GuidedStepParams) == 36 + 4 * 5 + 16 * 3 + 12
     assert ctypes.sizeof(_C.L2RegParams) == ctypes.sizeof(_C.GuidedStepParams) + 8
     assert ctypes.sizeof(_C.UNetConfig) == 4 * 4 + 32 * 3 + 4 * 10
+    assert ctypes.sizeof(_C.ColorGradParams) == 16 * 3 + 4 * 3
 
 
 def test_host_side_argument_validation():
@@ -76,3 +77,29 @@ def test_c_coefficients_within_one_ulp_of_torch():
                         if x == x and x != 0:
                             worst = max(worst, abs(x - y) / float(np.spacing(np.float32(abs(x)))))
     assert worst <= 1.0
+
+
+def test_precision_names_follow_the_build():
+    """The library is built for ONE 16-bit operand type (fp16 unless -DB2E_ACT_BF16); asking for the other raises instead of
+    silently computing in a different precision."""
+    from b200edit import _C
+    fast = _C.fast_precision()
+    assert fast == ("bf16" if _C.lib.b2e_act_dtype() == 1 else "fp16")
+    assert _C.resolve_precision(None, "x") == (fast, 0)
+    assert _C.resolve_precision(fast, "x") == (fast, 0)
+    assert _C.resolve_precision("fp32", "x") == ("fp32", 1)
+    other = "bf16" if fast == "fp16" else "fp16"
+    with pytest.raises(ValueError):
+        _C.resolve_precision(other, "x")
+    with pytest.raises(ValueError):
+        _C.resolve_precision("fp8", "x")
+
+
+def test_new_guidance_entry_points_validate_arguments():
+    from b200edit import _C
+    lib = _C.lib
+    p = _C.ColorGradParams()
+    assert lib.b2e_color_loss_grad_f32(None, None, None, None, 1, 3, 16, ctypes.byref(p), None, 0, None) == -1
+    assert b"color_loss_grad" in lib.b2e_last_error()
+    assert lib.b2e_apply_latent_guidance_f32(None, None, None, 1, 48, 0, 1.0, 1.0, 1.0, None) == -1
+    assert lib.b2e_color_loss_grad_workspace_bytes() >= 8 * 148

@@ -35,7 +35,7 @@ def check(got, ref, ref16, tag):
     mis16 = (ref16.argmax(1) != ref.argmax(1)).float().mean().item()
     print(f"{tag}: logits rel-rms native {rel:.3e} torch-bf16 {rel16:.3e} | parsing-map mismatch native {mis:.3e} torch-bf16 {mis16:.3e}")
     assert got.shape == ref.shape and torch.isfinite(got).all()
-    assert rel <= 2.5e-2 and rel <= 1.25 * rel16 + 1e-3
+    assert rel <= 3e-3 and rel <= 1.25 * rel16 + 1e-3      # measured 8e-4 .. 9e-4 (bf16 build of round 1: 8e-3)
     assert mis <= 1.25 * mis16 + 2e-3
 
 
@@ -104,7 +104,7 @@ def test_bisenet_input_gradient_matches_autograd(S):
     cos = lambda a, b: torch.nn.functional.cosine_similarity(a.flatten(), b.flatten(), dim=0).item()   # noqa: E731
     print(f"bisenet {S}x{S} input gradient: native rel-rms {rel(gn, gr):.3e} cos {cos(gn, gr):.5f} | torch-bf16 {rel(g16, gr):.3e} cos {cos(g16, gr):.5f}")
     assert torch.isfinite(gn).all() and gr.abs().max() > 0
-    assert rel(gn, gr) <= 0.5 and cos(gn, gr) >= 0.9
+    assert rel(gn, gr) <= 0.12 and cos(gn, gr) >= 0.99      # measured 7.7e-2 .. 8.8e-2 / 0.996 .. 0.997 (round 1, bf16: 0.23 / 0.975)
     assert rel(gn, gr) <= rel(g16, gr) + 1e-2 and cos(gn, gr) >= cos(g16, gr) - 2e-3
 
 
@@ -136,7 +136,7 @@ def test_net_attr_func_through_the_native_parser():
     rel = ((dn - dr).pow(2).mean().sqrt() / dr.pow(2).mean().sqrt()).item()
     cos = torch.nn.functional.cosine_similarity(dn.flatten(), dr.flatten(), dim=0).item()
     print(f"NetAttrFunc update through the native parser: rel-rms {rel:.3e} cos {cos:.5f}")
-    assert dr.abs().max() > 0 and rel <= 0.5 and cos >= 0.9
+    assert dr.abs().max() > 0 and rel <= 0.12 and cos >= 0.99      # measured 6.7e-2 / 0.998
 
 
 def test_one_default_segmentation_model_serves_mask_creation_and_net_attr_func():

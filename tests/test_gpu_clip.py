@@ -23,7 +23,7 @@ def run_pair(cfg, B, L, seed):
         torch.backends.cuda.matmul.allow_tf32 = False
         rc = ref.cuda()
         want = rc(ids.cuda())[0]
-        want16 = rc.bfloat16()(ids.cuda())[0].float()
+        want16 = rc.half()(ids.cuda())[0].float()
     return got, want, want16
 
 
@@ -33,7 +33,7 @@ def check(got, ref, ref16, tag):
     err = (got - ref).abs().max().item()
     print(f"{tag}: last_hidden_state rel-rms native {rel:.3e} max-abs {err:.3e} | transformers-bf16 {rel16:.3e}")
     assert got.shape == ref.shape and torch.isfinite(got).all()
-    assert rel <= 2.5e-2 and rel <= 1.25 * rel16 + 1e-3
+    assert rel <= 4e-3 and rel <= 1.5 * rel16 + 2e-4      # measured 0.8e-3 .. 1.3e-3 (bf16 build of round 1: 1.0e-2)
 
 
 SMALL = dict(vocab_size=1000, hidden_size=128, intermediate_size=512, num_hidden_layers=2, num_attention_heads=2,

@@ -69,8 +69,11 @@ def check(ln, lr, l16, gn, gr, g16, tag):
     print(f"{tag}: logits rel-rms native {rel(ln, lr):.3e} torch-bf16 {rel(l16, lr):.3e} | input-gradient rel-rms native "
           f"{rel(gn, gr):.3e} cos {cos(gn, gr):.5f} torch-bf16 {rel(g16, gr):.3e} cos {cos(g16, gr):.5f}")
     assert ln.shape == lr.shape and gn.shape == gr.shape and torch.isfinite(ln).all() and torch.isfinite(gn).all()
-    assert rel(ln, lr) <= 2.5e-2 and rel(ln, lr) <= 1.25 * rel(l16, lr) + 1e-3
-    assert rel(gn, gr) <= 0.5 and cos(gn, gr) >= 0.9
+    assert rel(ln, lr) <= 2e-3 and rel(ln, lr) <= 1.25 * rel(l16, lr) + 1e-3      # logits: measured 3.5e-4 .. 5e-4
+    # input gradient with fp16 operands: measured 3.7e-2 / 0.9993 (ResNet-18, 64x64), 0.14 / 0.990 (ResNet-50, 256x256),
+    # 0.147 / 0.989 (512x512) - 3x closer to fp32 than the bf16 build of round 1 (0.41 / 0.917) and than torch-bf16
+    # autograd; what remains are ReLU / max-pool masks flipped by the 4e-4 forward rounding (see the module docstring)
+    assert rel(gn, gr) <= 0.2 and cos(gn, gr) >= 0.98
     assert rel(gn, gr) <= rel(g16, gr) + 5e-3 and cos(gn, gr) >= cos(g16, gr) - 1e-3
     assert gn.shape[0] == 1 or gn[1:].abs().max().item() == 0.0      # the reference's loss only sees batch element 0
 
@@ -116,7 +119,7 @@ def test_classifier_attr_func_with_native_predictor():
     dn, dr, d16 = outs
     print(f"ClassifierAttrFunc update: native rel-rms {rel(dn, dr):.3e} cos {cos(dn, dr):.5f} | torch-bf16 predictor "
           f"{rel(d16, dr):.3e} cos {cos(d16, dr):.5f}")
-    assert dr.abs().max() > 0 and rel(dn, dr) <= 0.5 and cos(dn, dr) >= 0.9
+    assert dr.abs().max() > 0 and rel(dn, dr) <= 0.2 and cos(dn, dr) >= 0.98      # measured 0.146 / 0.989
     assert rel(dn, dr) <= rel(d16, dr) + 2e-2
 
 

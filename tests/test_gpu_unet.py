@@ -1,11 +1,11 @@
-"""GPU numerics of the native UNet (bf16 tensor-core path, fp32 accumulation) against the oracle
+"""GPU numerics of the native UNet (fp16 tensor-core operands, fp32 accumulation) against the oracle
 UNet2DModel run in fp32 with the same weights.
 
-Tolerance (stated, bf16): relative RMS error of the predicted noise <= 1.5e-2 and max-abs error
-<= 2.5e-2 * max|eps| (|eps| is O(1) for a random-init network; every bf16 rounding is 2^-9 relative
-and ~100 layers accumulate).  As a yardstick the same test evaluates the ORACLE itself in bf16
-with torch (what the reference's diffusers+PyTorch path gives in bf16) and requires the native
-engine to be no further from the fp32 result than 1.25x that."""
+Tolerance (stated): the north star's bar for the 16-bit mode, LITERALLY - max-abs error of the predicted noise
+<= 1e-2 (|eps| <= 1.9 on these inputs; measured 1.4e-3 .. 3.2e-3) - and relative RMS <= 3e-3 (measured 0.9e-3 ..
+1.6e-3; the bf16 build of round 1 sat at 8e-3 / 1.45e-2).  As a yardstick the same test evaluates the ORACLE itself in
+fp16 with torch (what the reference's diffusers + PyTorch path gives in half precision) and requires the native engine
+to be no further from the fp32 result than 1.5x that."""
 import pytest
 import torch
 
@@ -40,7 +40,7 @@ def run_pair(cfg, B, t, seed, precision=None):
         torch.backends.cuda.matmul.allow_tf32 = False
         torch.backends.cudnn.allow_tf32 = False
         ref = oracle.cuda()(x.cuda(), torch.tensor(t))["sample"]   # torch fp32 eager as the checker
-        ref16 = oracle.bfloat16()(x.cuda().bfloat16(), torch.tensor(t))["sample"].float()
+        ref16 = oracle.half()(x.cuda().half(), torch.tensor(t))["sample"].float()
     return got, ref, ref16
 
 
@@ -50,15 +50,15 @@ def check(got, ref, ref16, tag):
     rel = ((got - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
     err16 = (ref16 - ref).abs().max().item()
     rel16 = ((ref16 - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
-    print(f"{tag}: native max-abs {err:.3e} rel-rms {rel:.3e} | torch-bf16 max-abs {err16:.3e} rel-rms {rel16:.3e}"
+    print(f"{tag}: native max-abs {err:.3e} rel-rms {rel:.3e} | torch-fp16 max-abs {err16:.3e} rel-rms {rel16:.3e}"
           f" | max|eps| {scale:.3f}")
     assert torch.isfinite(got).all()
-    assert rel <= 1.5e-2 and err <= 2.5e-2 * max(1.0, scale)
-    assert rel <= 1.25 * rel16 + 1e-3
+    assert err <= 1e-2 and rel <= 3e-3          # the literal 1e-2 max-abs bar of the 16-bit mode
+    assert rel <= 1.5 * rel16 + 2e-4
 
 
 def check_fp32(got, ref, ref16, tag):
-    """fp32-accurate mode (split-bf16 operands, three products per GEMM): the north star's fp32 bar,
+    """fp32-accurate mode (split-fp16 operands, three products per GEMM): the north star's fp32 bar,
     max-abs <= 1e-4 (x max|eps| when that exceeds 1), and relative RMS <= 5e-5."""
     scale = ref.abs().max().item()
     err = (got - ref).abs().max().item()

@@ -32,7 +32,7 @@ def run_pair(cfg, B, t, seed, L=77, precision=None):
         torch.backends.cudnn.allow_tf32 = False
         oc = oracle.cuda()
         ref = oc(x.cuda(), torch.tensor(t), encoder_hidden_states=ctx.cuda())["sample"]
-        ref16 = oc.bfloat16()(x.cuda().bfloat16(), torch.tensor(t), encoder_hidden_states=ctx.cuda().bfloat16())["sample"].float()
+        ref16 = oc.half()(x.cuda().half(), torch.tensor(t), encoder_hidden_states=ctx.cuda().half())["sample"].float()
     return got, ref, ref16
 
 
@@ -42,11 +42,11 @@ def check(got, ref, ref16, tag):
     rel = ((got - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
     err16 = (ref16 - ref).abs().max().item()
     rel16 = ((ref16 - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
-    print(f"{tag}: native max-abs {err:.3e} rel-rms {rel:.3e} | torch-bf16 max-abs {err16:.3e} rel-rms {rel16:.3e}"
+    print(f"{tag}: native max-abs {err:.3e} rel-rms {rel:.3e} | torch-fp16 max-abs {err16:.3e} rel-rms {rel16:.3e}"
           f" | max|eps| {scale:.3f}")
     assert got.shape == ref.shape and torch.isfinite(got).all()
-    assert rel <= 2e-2 and err <= 3e-2 * max(1.0, scale)
-    assert rel <= 1.25 * rel16 + 1e-3
+    assert err <= 1e-2 and rel <= 3e-3          # the literal 1e-2 max-abs bar of the 16-bit mode (measured <= 1.9e-3)
+    assert rel <= 1.5 * rel16 + 2e-4
 
 
 def check_fp32(got, ref, ref16, tag):
@@ -102,14 +102,14 @@ def test_cfg_call_of_the_reference():
         both = oc(torch.cat([lat] * 2), torch.tensor(500), encoder_hidden_states=text)["sample"]
         u, cnd = both.chunk(2)
         ref = u + 3.5 * (cnd - u)
-        b16 = oc.bfloat16()(torch.cat([lat] * 2).bfloat16(), torch.tensor(500), encoder_hidden_states=text.bfloat16())["sample"].float()
+        b16 = oc.half()(torch.cat([lat] * 2).half(), torch.tensor(500), encoder_hidden_states=text.half())["sample"].float()
         u16, c16 = b16.chunk(2)
         ref16 = u16 + 3.5 * (c16 - u16)
-    # the combination u + s (c - u) amplifies the per-branch bf16 error by up to (1 + 2 s): yardstick = torch in bf16
+    # the combination u + s (c - u) amplifies the per-branch rounding error by up to (1 + 2 s): yardstick = torch in fp16
     rel = ((eps - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
     rel16 = ((ref16 - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
-    print(f"cfg 3.5: native rel-rms {rel:.3e} | torch-bf16 {rel16:.3e}")
-    assert eps.shape == lat.shape and rel <= 8e-2 and rel <= 1.25 * rel16 + 1e-3, (rel, rel16)
+    print(f"cfg 3.5: native rel-rms {rel:.3e} | torch-fp16 {rel16:.3e}")
+    assert eps.shape == lat.shape and rel <= 1e-2 and rel <= 1.5 * rel16 + 5e-4, (rel, rel16)
 
 
 class FakeTokenizer:

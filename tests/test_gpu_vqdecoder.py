@@ -33,7 +33,7 @@ def run_pair(cfg, B, seed, codebook_scale=None, precision=None):
         oc = oracle.cuda()
         ref = oc.decode(z.cuda()).sample
         zq = oc.post_quant_conv(oc.quantize(z.cuda()))
-        ref16 = oc.decoder.bfloat16()(zq.bfloat16()).float()
+        ref16 = oc.decoder.half()(zq.half()).float()
     return got, ref, ref16
 
 
@@ -43,11 +43,11 @@ def check(got, ref, ref16, tag):
     rel = ((got - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
     err16 = (ref16 - ref).abs().max().item()
     rel16 = ((ref16 - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
-    print(f"{tag}: native max-abs {err:.3e} rel-rms {rel:.3e} | torch-bf16 max-abs {err16:.3e} rel-rms {rel16:.3e}"
+    print(f"{tag}: native max-abs {err:.3e} rel-rms {rel:.3e} | torch-fp16 max-abs {err16:.3e} rel-rms {rel16:.3e}"
           f" | max|img| {scale:.3f}")
     assert got.shape == ref.shape and torch.isfinite(got).all()
-    assert rel <= 2.5e-2 and err <= 3e-2 * max(1.0, scale)
-    assert rel <= 1.25 * rel16 + 1e-3
+    assert err <= 1e-2 and rel <= 5e-3          # literal 1e-2 max-abs on the decoded image (measured 3e-3 .. 5.4e-3, |img| <= 2.2)
+    assert rel <= 1.5 * rel16 + 2e-4
 
 
 def check_fp32(got, ref, ref16, tag):
@@ -159,13 +159,13 @@ def _grad_pair(cfg, B, seed):
     oc = oracle.cuda()
     zo = z.cuda().requires_grad_(True)
     (go,) = torch.autograd.grad(loss_fn(oc.decode(zo).sample, wgt.cuda()), zo)
-    # yardstick: the oracle decoder itself in bf16 (what diffusers + PyTorch autograd gives in bf16)
+    # yardstick: the oracle decoder itself in fp16 (what diffusers + PyTorch autograd gives in half precision, unscaled)
     zb = z.cuda().requires_grad_(True)
     ob = OracleVQ(**cfg).eval()
     ob.load_state_dict(oracle.state_dict())
     ob = ob.cuda()
     zq = ob.post_quant_conv(zb + (ob.quantize(zb) - zb).detach())
-    img16 = ob.decoder.bfloat16()(zq.bfloat16()).float()
+    img16 = ob.decoder.half()(zq.half()).float()
     (gb,) = torch.autograd.grad(loss_fn(img16, wgt.cuda()), zb)
     return gn, go, gb
 
@@ -174,11 +174,12 @@ def _check_grad(gn, go, gb, tag):
     rel = ((gn - go).pow(2).mean().sqrt() / go.pow(2).mean().sqrt()).item()
     rel16 = ((gb - go).pow(2).mean().sqrt() / go.pow(2).mean().sqrt()).item()
     cos = torch.nn.functional.cosine_similarity(gn.flatten(), go.flatten(), dim=0).item()
-    print(f"{tag}: native grad rel-rms {rel:.3e} cos {cos:.5f} | torch-bf16 rel-rms {rel16:.3e}")
+    print(f"{tag}: native grad rel-rms {rel:.3e} cos {cos:.5f} | torch-fp16 rel-rms {rel16:.3e}")
     assert gn.shape == go.shape and torch.isfinite(gn).all()
-    # bf16 gradients through ~40 layers: within 4e-2 relative RMS of the fp32 gradient and no worse than 1.5x torch-bf16
-    assert rel <= 4e-2 and cos >= 0.999
-    assert rel <= 1.5 * rel16 + 2e-3
+    # fp16 gradients (power-of-two scaled on the device) through ~40 layers: within 1e-2 relative RMS of the fp32 gradient,
+    # cosine >= 0.9999 (measured 2.0e-3 .. 3.1e-3 / 1.00000; the bf16 build of round 1: 2.5e-2 / 0.99968)
+    assert rel <= 1e-2 and cos >= 0.9999
+    assert rel <= 1.5 * rel16 + 1e-3
 
 
 @pytest.mark.parametrize("B", [1, 2])

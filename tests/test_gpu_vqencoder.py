@@ -35,7 +35,7 @@ def run_pair(cfg, B, seed):
         oc = oracle.cuda()
         e = oc.encode(x.cuda())
         ref = e.latent_dist.mode() if kl else e.latents
-        h16 = oc.encoder.bfloat16()(x.cuda().bfloat16()).float()
+        h16 = oc.encoder.half()(x.cuda().half()).float()
         ref16 = oc.quant_conv(h16)
         if kl:
             ref16 = ref16[:, :cfg["latent_channels"]]
@@ -51,8 +51,8 @@ def check(got, ref, ref16, tag):
     print(f"{tag}: native max-abs {err:.3e} rel-rms {rel:.3e} | torch-bf16 max-abs {err16:.3e} rel-rms {rel16:.3e}"
           f" | max|latent| {scale:.3f}")
     assert got.shape == ref.shape and torch.isfinite(got).all()
-    assert rel <= 2.5e-2 and err <= 3e-2 * max(1.0, scale)
-    assert rel <= 1.25 * rel16 + 1e-3
+    assert err <= 1e-2 and rel <= 4e-3          # literal 1e-2 max-abs on the latent (measured <= 1.7e-3 / 1.4e-3)
+    assert rel <= 1.5 * rel16 + 2e-4
 
 
 @pytest.mark.parametrize("B", [1, 3])
