@@ -491,8 +491,83 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         if (store_leader) tma_store_wait_read();
         epi_bar_sync();
       }
+      // Fast path (f16 NHWC output straight from TMEM, BN >= 32): 32 accumulator columns per iteration - both tcgen05.ld
+      // and every bias / shortcut-bias / time-embedding load of the iteration are issued BEFORE the single wait, so their
+      // latencies overlap (the 16-column loop below paid a TMEM round trip plus an L1 round trip eight times per tile:
+      // ~4 500 clk per 128 x 128 tile, which made the K-short layers epilogue-bound - ncu tensor pipe 74 % at Cin 128).
+      // Same arithmetic, same order of the adds.
+      bool fast_done = false;
+      if constexpr (Cfg::kSlabs > 0) {
+        if (p.out_f16 && !part_row) {
+          fast_done = true;
 #pragma unroll 1
-      for (int c = 0; c < BN / 16; ++c) {
+          for (int c2 = 0; c2 < BN / 32; ++c2) {
+            uint32_t raw[32];
+            tmem_ld16_issue(taddr + c2 * 32, raw);
+            tmem_ld16_issue(taddr + c2 * 32 + 16, raw + 16);
+            const int col0 = tc.n_tile * BN + c2 * 32;
+            float4 b1[8], b2[8], tb[8];
+            const bool hb1 = p.bias != nullptr, hb2 = p.bias2 != nullptr, htb = p.temb != nullptr && valid;
+            if (hb1) {
+              const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) b1[j] = __ldg(bp + j);
+            }
+            if (hb2) {
+              const float4* bp = reinterpret_cast<const float4*>(p.bias2 + col0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) b2[j] = __ldg(bp + j);
+            }
+            if (htb) {
+              const float4* tp = reinterpret_cast<const float4*>(p.temb + (int64_t)n * p.temb_stride + col0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) tb[j] = __ldg(tp + j);
+            }
+            tmem_ld_wait();
+            if (c2 == BN / 32 - 1 && pass == npass - 1) release_tmem();
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+            if (p.acc_scale != 1.f) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] *= p.acc_scale;
+            }
+            if (hb1) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { v[4 * j] += b1[j].x; v[4 * j + 1] += b1[j].y; v[4 * j + 2] += b1[j].z; v[4 * j + 3] += b1[j].w; }
+            }
+            if (hb2) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { v[4 * j] += b2[j].x; v[4 * j + 1] += b2[j].y; v[4 * j + 2] += b2[j].z; v[4 * j + 3] += b2[j].w; }
+            }
+            if (htb) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { v[4 * j] += tb[j].x; v[4 * j + 1] += tb[j].y; v[4 * j + 2] += tb[j].z; v[4 * j + 3] += tb[j].w; }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (pass) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = __fsub_rn(v[j], f16_to_float(float_to_f16(v[j])));
+            }
+            // 128B-swizzled staging tile: row r, 16-byte chunk j stored at chunk (j ^ (r & 7)); 32 columns = 4 chunks
+            uint8_t* row = staging + (c2 >> 1) * (kConvBlockM * 128) + r * 128;
+            const int j0 = (c2 & 1) * 4;
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              uint4 o;
+              f16x2* ob = reinterpret_cast<f16x2*>(&o);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) ob[j] = floats_to_f16x2(v[8 * k4 + 2 * j], v[8 * k4 + 2 * j + 1]);
+              *reinterpret_cast<uint4*>(row + (((j0 + k4) ^ (r & 7)) << 4)) = o;
+            }
+          }
+        }
+      }
+#pragma unroll 1
+      for (int c = 0; c < (fast_done ? 0 : BN / 16); ++c) {
         float v[16];
         if (part_row) {
 #pragma unroll

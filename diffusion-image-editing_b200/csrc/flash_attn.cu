@@ -37,7 +37,7 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
         "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
 }
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// (tmem_ld_wait: tcgen05_ptx.cuh)
 
 constexpr int kFaBlock = 128;   // queries per item and keys per block
 // SW = softmax warps: 4 (one thread per query row, all 128 key columns) or 8 (two threads per row, 64 columns each: the

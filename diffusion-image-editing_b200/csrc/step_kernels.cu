@@ -195,8 +195,8 @@ l2reg_pass1(const float4* __restrict__ x, const float4* __restrict__ e, const fl
       vz[u] = make_float4(0, 0, 0, 0);
       if (ok[u]) {
         vx[u] = ld_stream(x + i); ve[u] = ld_stream(e + i);
-        if (s.has_noise) vz[u] = s.noise_batched ? ld_stream(z + i) : ld_reuse(z + ((uint32_t)i % (uint32_t)chw4));
-        vm[u] = k.s.mask_batched ? ld_stream(mask + i) : ld_reuse(mask + ((uint32_t)i % (uint32_t)chw4));
+        if (s.has_noise) vz[u] = s.noise_batched ? ld_stream(z + i) : ld_reuse(z + (i % chw4));
+        vm[u] = k.s.mask_batched ? ld_stream(mask + i) : ld_reuse(mask + (i % chw4));
         vr[u] = ld_stream(xref + i);
       }
     }
@@ -249,7 +249,7 @@ l2reg_pass2(float4* __restrict__ xp, const float4* __restrict__ e, const float4*
       ok[u] = i < total4;
       if (ok[u]) {
         vo[u] = xp[i]; ve[u] = ld_stream(e + i);
-        vm[u] = s.mask_batched ? ld_stream(mask + i) : ld_reuse(mask + ((uint32_t)i % (uint32_t)chw4));
+        vm[u] = s.mask_batched ? ld_stream(mask + i) : ld_reuse(mask + (i % chw4));
         vr[u] = ld_stream(xref + i);
       }
     }
@@ -257,8 +257,7 @@ l2reg_pass2(float4* __restrict__ xp, const float4* __restrict__ e, const float4*
     for (int u = 0; u < 2; ++u) {
       if (!ok[u]) continue;
       const int64_t i = i0 + u * stride;
-      const int c = (int)(((uint32_t)i / (uint32_t)hw4) % (uint32_t)C);   // 32-bit: total4 < 2^31 (host-checked); the 64-bit
-                                                                          // divide per float4 capped this pass at 3.2 TB/s
+      const int c = (int)((i / hw4) % C);
       float xo[4] = {vo[u].x, vo[u].y, vo[u].z, vo[u].w};
       const float ee[4] = {ve[u].x, ve[u].y, ve[u].z, ve[u].w}, mm[4] = {vm[u].x, vm[u].y, vm[u].z, vm[u].w},
                   rr[4] = {vr[u].x, vr[u].y, vr[u].z, vr[u].w};
@@ -510,7 +509,7 @@ color_grad_norm_kernel(const float4* __restrict__ img, const float4* __restrict_
       const int64_t i = i0 + u * stride;
       if (i < total4) {
         vi[u] = __ldg(img + i);      // re-read by pass 2: default caching
-        vm[u] = mask_batched ? ld_stream(mask + i) : ld_reuse(mask + ((uint32_t)i % (uint32_t)chw4));
+        vm[u] = mask_batched ? ld_stream(mask + i) : ld_reuse(mask + (i % chw4));
         vr[u] = __ldg(xref + i);
       }
     }
@@ -555,7 +554,7 @@ color_grad_kernel(const float4* __restrict__ img, const float4* __restrict__ mas
       if (i < total4) {
         vi[u] = ld_stream(img + i);
         if (k.use_mask_pred) {
-          vm[u] = k.mask_batched ? ld_stream(mask + i) : ld_reuse(mask + ((uint32_t)i % (uint32_t)chw4));
+          vm[u] = k.mask_batched ? ld_stream(mask + i) : ld_reuse(mask + (i % chw4));
           vr[u] = ld_stream(xref + i);
         }
       }
@@ -564,7 +563,7 @@ color_grad_kernel(const float4* __restrict__ img, const float4* __restrict__ mas
     for (int u = 0; u < 2; ++u) {
       const int64_t i = i0 + u * stride;
       if (i >= total4) continue;
-      const int c = (int)(((uint32_t)i / (uint32_t)hw4) % (uint32_t)C);   // 32-bit index math (total4 < 2^31, host-checked)
+      const int c = (int)((i / hw4) % C);
       const int ht = c == 0 ? k.has_target[0] : c == 1 ? k.has_target[1] : c == 2 ? k.has_target[2] : k.has_target[3];
       const float tau = c == 0 ? k.target[0] : c == 1 ? k.target[1] : c == 2 ? k.target[2] : k.target[3];
       const float kc = c == 0 ? k.k[0] : c == 1 ? k.k[1] : c == 2 ? k.k[2] : k.k[3];
