@@ -596,7 +596,8 @@ def config4(c, precision, B, K, W, headline=False):
     from SegDiffEditPipeline import SegDiffEditPipeline
     B = B or 8
     D = 3 if not headline else min(c.args.denoise_steps, 6)
-    predictor = get_pretrained_anyGAN(input_size=512, max_batch=B)
+    pprec = os.environ.get("B2E_BENCH_PREDICTOR_PRECISION", "fp32")    # get_pretrained_anyGAN's default: fp32-accurate forward
+    predictor = get_pretrained_anyGAN(input_size=512, max_batch=B, precision=pprec)
     w = create_diffusion_model("sd", sample_clipping=False, max_batch=B, seed=0, precision=precision, with_encoder=False)
     w.scheduler.set_timesteps(D)
     pipe = SegDiffEditPipeline(w, None)
@@ -623,7 +624,8 @@ def config4(c, precision, B, K, W, headline=False):
     cfg = {"workload": f"BASELINE configs[3]: Stable Diffusion 1.x layout (64x64x4 latent, random-init), CFG 7.5 (doubled latent batch, "
                        f"precomputed (2,77,768) text embedding) + classifier guidance through the native KL decoder and ResNet-50 "
                        f"predictor (forward + gradient), batch {B} per GPU, {D} DDIM steps per pass + one final decode",
-           "batch_per_gpu": B, "global_batch": B * c.world, "guidance": "ClassifierAttrFunc(idx_for_class=31, idx_of_interest=0)"}
+           "batch_per_gpu": B, "global_batch": B * c.world, "guidance": "ClassifierAttrFunc(idx_for_class=31, idx_of_interest=0)",
+           "predictor_precision": pprec}
     res = pass_result(c, "BASELINE configs[3]", B, D, K, ms_dev, ms_e2e, launches, x_host.numel() * 4, out_host.numel() * 4, cfg, fl,
                       "edit_image from a pinned host latent batch; decoded 512x512 images copied to pinned host memory")
     res["metric"] = "guided img-steps/s (SD-1.x 64x64x4 latent, CFG + classifier guidance)"

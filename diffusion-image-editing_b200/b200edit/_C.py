@@ -63,7 +63,8 @@ class ClipConfig(C.Structure):
 
 class ResNetConfig(C.Structure):
     _fields_ = [("input_size", C.c_int32), ("in_channels", C.c_int32), ("bottleneck", C.c_int32),
-                ("layers", C.c_int32 * 4), ("width", C.c_int32), ("num_classes", C.c_int32), ("head", C.c_int32)]
+                ("layers", C.c_int32 * 4), ("width", C.c_int32), ("num_classes", C.c_int32), ("head", C.c_int32),
+                ("precision", C.c_int32)]
 
 
 _P, _I64, _I, _F, _SZ = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_size_t

@@ -48,8 +48,12 @@ def _fold(w, sd, bn, eps=1e-5):
 
 
 class BiSeNet(UNet2DModel):
-    def __init__(self, n_classes=19, input_size=512, max_batch=1, device="cuda"):
+    def __init__(self, n_classes=19, input_size=512, max_batch=1, device="cuda", precision=None):
+        """precision: None / "fp16" - f16 operands throughout; "fp32" - fp32-accurate FORWARD (split f16 operands), so
+        the ReLU / max-pool masks the backward pass routes gradients with are those of the fp32 network (see
+        b200edit.resnet.ResNet)."""
         _C.require_device()
+        self.precision, precision_cfg = _C.resolve_precision(precision, "BiSeNet")
         self.config = SimpleNamespace(n_classes=n_classes, input_size=input_size, in_channels=3, sample_size=input_size,
                                       out_channels=n_classes)
         self.device = torch.device(device)
@@ -59,6 +63,7 @@ class BiSeNet(UNet2DModel):
         cfg.input_size, cfg.in_channels, cfg.bottleneck, cfg.width, cfg.num_classes, cfg.head = input_size, 3, 0, 64, n_classes, 1
         for i in range(4):
             cfg.layers[i] = 2
+        cfg.precision = precision_cfg
         h = C.c_void_p()
         with torch.cuda.device(self.device):
             check(lib.b2e_resnet_create(C.byref(cfg), self.max_batch, C.byref(h)), "bisenet_create")
@@ -161,10 +166,17 @@ class MultiResBiSeNet:
     workflow shares one ``SegmentationModel`` between mask creation (512x512, src/models.py:113-118) and ``NetAttrFunc``
     (the decoded 256x256 image goes straight into ``segmentation_model.net``, src/attr_functions.py:213-215).  The
     engine plans its buffers per resolution, so this wrapper keeps one engine per input size (built on first use, same
-    weights) and enables the native input gradient on an engine the first time it is differentiated through."""
+    weights); differentiated calls get their own engine with the native input gradient enabled.
 
-    def __init__(self, n_classes=19, max_batch=1, device="cuda", seed=0):
+    ``precision``: None - forward-only engines (mask creation: an argmax) run f16 operands, the differentiated engines
+    the fp32-accurate forward ("fp32"), so the guidance gradient has the fp32 network's ReLU / max-pool masks;
+    "fp16" / "fp32" force one mode for both."""
+
+    def __init__(self, n_classes=19, max_batch=1, device="cuda", seed=0, precision=None):
         self.n_classes, self.max_batch, self.device, self.seed = n_classes, int(max_batch), device, seed
+        if precision not in (None, "fp16", "fp32"):
+            raise ValueError(f"MultiResBiSeNet: precision must be None, 'fp16' or 'fp32' (got {precision!r})")
+        self.precision = precision
         self._folded = None      # engine-format state dict (BatchNorm folded); None -> seeded random init
         self._engines = {}
 
@@ -175,18 +187,20 @@ class MultiResBiSeNet:
         return self
 
     def engine(self, size: int, grad: bool = False) -> BiSeNet:
-        e = self._engines.get(size)
+        grad = bool(grad)
+        e = self._engines.get((size, grad))
         if e is None:
             if size % 32 or size < 64:
                 raise ValueError(f"BiSeNet: input resolution must be a multiple of 32 and >= 64 (got {size})")
-            e = BiSeNet(self.n_classes, size, max_batch=self.max_batch, device=self.device)
+            precision = self.precision or ("fp32" if grad else "fp16")
+            e = BiSeNet(self.n_classes, size, max_batch=self.max_batch, device=self.device, precision=precision)
             if self._folded is not None:
                 e.load_state_dict(self._folded)
             else:
                 e.init_random(self.seed)
-            self._engines[size] = e
-        if grad and not e.differentiable:
-            e.enable_grad()
+            if grad:
+                e.enable_grad()
+            self._engines[(size, grad)] = e
         return e
 
     def __call__(self, image):

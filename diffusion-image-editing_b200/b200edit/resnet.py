@@ -45,8 +45,12 @@ class ResNet(UNet2DModel):
     random init / profiling with the UNet wrapper (same engine handle type)."""
 
     def __init__(self, block="bottleneck", layers=RESNET50_LAYERS, num_classes=80, input_size=256, in_channels=3, width=64,
-                 max_batch=8, device="cuda"):
+                 max_batch=8, device="cuda", precision=None):
+        """precision: None / "fp16" - f16 operands throughout; "fp32" - fp32-accurate FORWARD (split f16 operands, three
+        tensor-core products per GEMM) so that the ReLU / max-pool masks of the input gradient agree with an fp32 evaluation
+        of the network; the backward pass stays on f16 operands."""
         _C.require_device()
+        self.precision, precision_cfg = _C.resolve_precision(precision, "ResNet")
         if block not in ("bottleneck", "basic"):
             raise ValueError("ResNet: block must be 'bottleneck' or 'basic'")
         self.config = SimpleNamespace(block=block, layers=tuple(layers), num_classes=num_classes, input_size=input_size,
@@ -59,6 +63,7 @@ class ResNet(UNet2DModel):
         for i in range(4):
             cfg.layers[i] = layers[i]
         cfg.width, cfg.num_classes = width, num_classes
+        cfg.precision = precision_cfg
         h = C.c_void_p()
         with torch.cuda.device(self.device):
             check(lib.b2e_resnet_create(C.byref(cfg), self.max_batch, C.byref(h)), "resnet_create")
@@ -134,9 +139,9 @@ class ResNet(UNet2DModel):
                      desc=lib.b2e_unet_op_desc(self._h, i).decode()) for i in range(n.value)]
 
 
-def resnet50_predictor(num_classes=80, input_size=256, max_batch=8, state_dict=None, seed=0):
+def resnet50_predictor(num_classes=80, input_size=256, max_batch=8, state_dict=None, seed=0, precision=None):
     """The attribute predictor of src/models.py:69-77 (``models.resnet50()`` with ``fc = Linear(2048, 40 * 2)``)."""
-    net = ResNet("bottleneck", RESNET50_LAYERS, num_classes, input_size, max_batch=max_batch)
+    net = ResNet("bottleneck", RESNET50_LAYERS, num_classes, input_size, max_batch=max_batch, precision=precision)
     if state_dict is not None:
         net.load_torchvision_state_dict(state_dict)
     else:

@@ -28,8 +28,9 @@ inline int grid_for(int64_t total, int per_sm = 32) {
 }  // namespace
 
 // ---- stem: x fp32 NCHW (B,C,H,W) -> f16 (B,H/2,W/2,KP): column (kh*7 + kw)*C + c = x[c][2oh + kh - 3][2ow + kw - 3]
+// planes = 3 (fp32-accurate forward): the pixel holds three KP-column planes [hi | lo | hi], hi = f16(v), lo = f16(v - hi)
 __global__ void __launch_bounds__(256) im2col7s2_kernel(const float* __restrict__ x, f16* __restrict__ out, int B, int C, int H,
-                                                        int W, int KP) {
+                                                        int W, int KP, int planes) {
   pdl_wait();
   const int Ho = H / 2, Wo = W / 2, slots = KP / 8, cols = 49 * C;
   const int64_t total = (int64_t)B * Ho * Wo * slots;
@@ -51,14 +52,26 @@ __global__ void __launch_bounds__(256) im2col7s2_kernel(const float* __restrict_
       }
       f[j] = v;
     }
-    *reinterpret_cast<uint4*>(out + i * 8) = pack8r(f);
+    if (planes == 1) {
+      *reinterpret_cast<uint4*>(out + i * 8) = pack8r(f);
+    } else {
+      f16* o = out + (i / slots) * (int64_t)(3 * KP) + s * 8;
+      const uint4 hi = pack8r(f);
+      float hf[8];
+      unpack8r(hi, hf);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = __fsub_rn(f[j], hf[j]);
+      *reinterpret_cast<uint4*>(o) = hi;
+      *reinterpret_cast<uint4*>(o + KP) = pack8r(f);
+      *reinterpret_cast<uint4*>(o + 2 * KP) = hi;
+    }
   }
 }
 
-int im2col7s2_launch(const float* x, f16* out, int B, int C, int H, int W, int KP, cudaStream_t st) {
+int im2col7s2_launch(const float* x, f16* out, int B, int C, int H, int W, int KP, cudaStream_t st, int planes) {
   B2E_REQUIRE(49 * C <= KP && KP % 64 == 0 && H % 2 == 0 && W % 2 == 0, B2E_UNSUPPORTED_SHAPE, "im2col7s2: bad shape");
   const int64_t total = (int64_t)B * (H / 2) * (W / 2) * (KP / 8);
-  launch_pdl(im2col7s2_kernel, dim3(grid_for(total)), dim3(256), 0, st, x, out, B, C, H, W, KP);
+  launch_pdl(im2col7s2_kernel, dim3(grid_for(total)), dim3(256), 0, st, x, out, B, C, H, W, KP, planes);
   return check_launch("im2col7s2");
 }
 
@@ -96,8 +109,9 @@ int col2im7s2_launch(const f16* dcols, float* dx, int B, int C, int H, int W, in
 }
 
 // ---- max pooling 3x3, stride 2, padding 1 (f16 NHWC); idx = position (kh*3 + kw) of the first maximum (scan order)
+// planes = 3: x and y are split tensors [hi | lo | hi] (pixel pitch 3 C); candidates are compared on hi + lo
 __global__ void __launch_bounds__(256) maxpool3s2_kernel(const f16* __restrict__ x, f16* __restrict__ y,
-                                                         uint8_t* __restrict__ idx, int N, int H, int W, int C8) {
+                                                         uint8_t* __restrict__ idx, int N, int H, int W, int C8, int planes) {
   pdl_wait();
   const int Ho = H / 2, Wo = W / 2;
   const int64_t total = (int64_t)N * Ho * Wo * C8;
@@ -116,12 +130,31 @@ __global__ void __launch_bounds__(256) maxpool3s2_kernel(const f16* __restrict__
       const int ih = 2 * oh + t / 3 - 1, iw = 2 * ow + t % 3 - 1;
       if (ih < 0 || ih >= H || iw < 0 || iw >= W) continue;
       float f[8];
-      unpack8r(__ldg(reinterpret_cast<const uint4*>(x + ((((int64_t)n * H + ih) * W + iw) * C8 + s) * 8)), f);
+      const f16* xp = x + ((((int64_t)n * H + ih) * W + iw) * (planes * C8) + s) * 8;
+      unpack8r(__ldg(reinterpret_cast<const uint4*>(xp)), f);
+      if (planes == 3) {
+        float l[8];
+        unpack8r(__ldg(reinterpret_cast<const uint4*>(xp + C8 * 8)), l);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] += l[j];
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         if (f[j] > best[j]) { best[j] = f[j]; arg[j] = (uint8_t)t; }
     }
-    *reinterpret_cast<uint4*>(y + i * 8) = pack8r(best);
+    if (planes == 1) {
+      *reinterpret_cast<uint4*>(y + i * 8) = pack8r(best);
+    } else {
+      f16* o = y + ((i / C8) * (int64_t)(3 * C8) + s) * 8;
+      const uint4 hi = pack8r(best);
+      float hf[8];
+      unpack8r(hi, hf);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) hf[j] = __fsub_rn(best[j], hf[j]);
+      *reinterpret_cast<uint4*>(o) = hi;
+      *reinterpret_cast<uint4*>(o + C8 * 8) = pack8r(hf);
+      *reinterpret_cast<uint4*>(o + 2 * C8 * 8) = hi;
+    }
     uint2 a;
     a.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | ((uint32_t)arg[3] << 24);
     a.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | ((uint32_t)arg[7] << 24);
@@ -129,10 +162,10 @@ __global__ void __launch_bounds__(256) maxpool3s2_kernel(const f16* __restrict__
   }
 }
 
-int maxpool3s2_launch(const f16* x, f16* y, uint8_t* idx, int N, int H, int W, int C, cudaStream_t st) {
+int maxpool3s2_launch(const f16* x, f16* y, uint8_t* idx, int N, int H, int W, int C, cudaStream_t st, int planes) {
   B2E_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, B2E_UNSUPPORTED_SHAPE, "maxpool: bad shape");
   const int64_t total = (int64_t)N * (H / 2) * (W / 2) * (C / 8);
-  launch_pdl(maxpool3s2_kernel, dim3(grid_for(total)), dim3(256), 0, st, x, y, idx, N, H, W, C / 8);
+  launch_pdl(maxpool3s2_kernel, dim3(grid_for(total)), dim3(256), 0, st, x, y, idx, N, H, W, C / 8, planes);
   return check_launch("maxpool3s2");
 }
 
@@ -140,7 +173,7 @@ int maxpool3s2_launch(const f16* x, f16* y, uint8_t* idx, int N, int H, int W, i
 // backward of the ReLU that produced x)
 __global__ void __launch_bounds__(256) maxpool3s2_bwd_kernel(const f16* __restrict__ x, const uint8_t* __restrict__ idx,
                                                              const f16* __restrict__ gy, f16* __restrict__ gx, int N, int H,
-                                                             int W, int C8) {
+                                                             int W, int C8, int xplanes) {
   pdl_wait();
   const int Ho = H / 2, Wo = W / 2;
   const int64_t total = (int64_t)N * H * W * C8;
@@ -153,7 +186,16 @@ __global__ void __launch_bounds__(256) maxpool3s2_bwd_kernel(const f16* __restri
     float acc[8], xv[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    unpack8r(__ldg(reinterpret_cast<const uint4*>(x + i * 8)), xv);
+    {
+      const f16* xp = x + ((i / C8) * (int64_t)(xplanes * C8) + s) * 8;     // forward activation: split tensor when xplanes = 3
+      unpack8r(__ldg(reinterpret_cast<const uint4*>(xp)), xv);
+      if (xplanes == 3) {
+        float l[8];
+        unpack8r(__ldg(reinterpret_cast<const uint4*>(xp + C8 * 8)), l);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xv[j] += l[j];
+      }
+    }
     // windows oh with 2*oh - 1 <= ih <= 2*oh + 1
     for (int oh = ih >> 1; oh <= ((ih + 1) >> 1); ++oh) {
       if (oh >= Ho) continue;
@@ -179,9 +221,9 @@ __global__ void __launch_bounds__(256) maxpool3s2_bwd_kernel(const f16* __restri
 }
 
 int maxpool3s2_bwd_launch(const f16* x, const uint8_t* idx, const f16* gy, f16* gx, int N, int H, int W, int C,
-                          cudaStream_t st) {
+                          cudaStream_t st, int xplanes) {
   const int64_t total = (int64_t)N * H * W * (C / 8);
-  launch_pdl(maxpool3s2_bwd_kernel, dim3(grid_for(total)), dim3(256), 0, st, x, idx, gy, gx, N, H, W, C / 8);
+  launch_pdl(maxpool3s2_bwd_kernel, dim3(grid_for(total)), dim3(256), 0, st, x, idx, gy, gx, N, H, W, C / 8, xplanes);
   return check_launch("maxpool3s2_bwd");
 }
 
@@ -199,8 +241,31 @@ __global__ void __launch_bounds__(256) relu_bwd_kernel(const uint4* __restrict__
   }
 }
 
-int relu_bwd_launch(const f16* g, const f16* y, f16* out, int64_t numel, cudaStream_t st) {
+// the same with y a split tensor [hi | lo | hi] of the fp32-accurate forward (pixel pitch 3 C): mask = (hi + lo > 0)
+__global__ void __launch_bounds__(256) relu_bwd_split_kernel(const uint4* __restrict__ g, const uint4* __restrict__ y,
+                                                             uint4* __restrict__ out, int64_t n8, int C8) {
+  pdl_wait();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / C8;
+    const int s = (int)(i - row * C8);
+    float gv[8], yv[8], lv[8];
+    unpack8r(g[i], gv);
+    unpack8r(__ldg(y + row * 3 * C8 + s), yv);
+    unpack8r(__ldg(y + row * 3 * C8 + C8 + s), lv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) gv[j] = (yv[j] + lv[j]) > 0.f ? gv[j] : 0.f;
+    out[i] = pack8r(gv);
+  }
+}
+
+int relu_bwd_launch(const f16* g, const f16* y, f16* out, int64_t numel, cudaStream_t st, int yplanes, int C) {
   B2E_REQUIRE(numel % 8 == 0, B2E_UNSUPPORTED_SHAPE, "relu_bwd: numel %% 8 != 0");
+  if (yplanes == 3) {
+    B2E_REQUIRE(C > 0 && C % 8 == 0, B2E_UNSUPPORTED_SHAPE, "relu_bwd: split activation needs the channel count");
+    launch_pdl(relu_bwd_split_kernel, dim3(grid_for(numel / 8)), dim3(256), 0, st, (const uint4*)g, (const uint4*)y, (uint4*)out,
+               numel / 8, C / 8);
+    return check_launch("relu_bwd_split");
+  }
   launch_pdl(relu_bwd_kernel, dim3(grid_for(numel / 8)), dim3(256), 0, st, (const uint4*)g, (const uint4*)y, (uint4*)out, numel / 8);
   return check_launch("relu_bwd");
 }
@@ -251,12 +316,21 @@ int zero_upsample2x_launch(const f16* in, f16* out, int N, int Hi, int Wi, int C
 }
 
 // ---- head: global average pooling + fully connected layer
-__global__ void __launch_bounds__(256) avgpool_kernel(const f16* __restrict__ x, float* __restrict__ feat, int HW, int C) {
+__global__ void __launch_bounds__(256) avgpool_kernel(const f16* __restrict__ x, float* __restrict__ feat, int HW, int C,
+                                                      int planes) {
   pdl_wait();
   const int n = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float s = 0.f;
-  for (int p = 0; p < HW; ++p) s += f16_to_float(x[((int64_t)n * HW + p) * C + c]);
+  const int P = planes * C;
+  if (planes == 3) {
+    for (int p = 0; p < HW; ++p) {
+      const f16* q = x + ((int64_t)n * HW + p) * P + c;
+      s += f16_to_float(q[0]) + f16_to_float(q[C]);
+    }
+  } else {
+    for (int p = 0; p < HW; ++p) s += f16_to_float(x[((int64_t)n * HW + p) * C + c]);
+  }
   feat[(int64_t)n * C + c] = s / (float)HW;
 }
 
@@ -273,8 +347,8 @@ __global__ void __launch_bounds__(256) fc_kernel(const float* __restrict__ feat,
 }
 
 int avgpool_fc_launch(const f16* x, float* feat, const float* w, const float* b, float* logits, int N, int HW, int C, int K,
-                      cudaStream_t st) {
-  launch_pdl(avgpool_kernel, dim3((C + 255) / 256, N), dim3(256), 0, st, x, feat, HW, C);
+                      cudaStream_t st, int planes) {
+  launch_pdl(avgpool_kernel, dim3((C + 255) / 256, N), dim3(256), 0, st, x, feat, HW, C, planes);
   int rc = check_launch("avgpool");
   if (rc) return rc;
   launch_pdl(fc_kernel, dim3((N * K + 7) / 8), dim3(256), 0, st, (const float*)feat, w, b, logits, N, C, K);
@@ -296,14 +370,21 @@ __global__ void __launch_bounds__(256) fc_bwd_kernel(const float* __restrict__ d
 }
 
 __global__ void __launch_bounds__(256) avgpool_bwd_kernel(const float* __restrict__ dfeat, const f16* __restrict__ y,
-                                                          f16* __restrict__ g, int HW, int C8) {
+                                                          f16* __restrict__ g, int HW, int C8, int yplanes) {
   pdl_wait();
   const int n = blockIdx.y;
   const int64_t total = (int64_t)HW * C8;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int s = (int)(i % C8);
     float yv[8], o[8];
-    unpack8r(__ldg(reinterpret_cast<const uint4*>(y + ((int64_t)n * total + i) * 8)), yv);
+    const f16* yp = y + (((int64_t)n * HW + i / C8) * (yplanes * C8) + s) * 8;
+    unpack8r(__ldg(reinterpret_cast<const uint4*>(yp)), yv);
+    if (yplanes == 3) {
+      float l[8];
+      unpack8r(__ldg(reinterpret_cast<const uint4*>(yp + C8 * 8)), l);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) yv[j] += l[j];
+    }
     const float* d = dfeat + (int64_t)n * C8 * 8 + s * 8;
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = yv[j] > 0.f ? d[j] : 0.f;
@@ -312,18 +393,18 @@ __global__ void __launch_bounds__(256) avgpool_bwd_kernel(const float* __restric
 }
 
 int avgpool_fc_bwd_launch(const float* dlogits, const float* w, float* dfeat, const f16* y, f16* g, int N, int HW, int C, int K,
-                          cudaStream_t st, const float* gs) {
+                          cudaStream_t st, const float* gs, int yplanes) {
   launch_pdl(fc_bwd_kernel, dim3((C + 255) / 256, N), dim3(256), 0, st, dlogits, w, dfeat, C, K, 1.0f / (float)HW, gs);
   int rc = check_launch("fc_bwd");
   if (rc) return rc;
   const int64_t total = (int64_t)HW * (C / 8);
-  launch_pdl(avgpool_bwd_kernel, dim3((unsigned)((total + 255) / 256), N), dim3(256), 0, st, (const float*)dfeat, y, g, HW, C / 8);
+  launch_pdl(avgpool_bwd_kernel, dim3((unsigned)((total + 255) / 256), N), dim3(256), 0, st, (const float*)dfeat, y, g, HW, C / 8, yplanes);
   return check_launch("avgpool_bwd");
 }
 
 // ---- face parser (BiSeNet, src/Segmentation/model.py) helpers
-int avgpool_launch(const f16* x, float* feat, int N, int HW, int C, cudaStream_t st) {
-  launch_pdl(avgpool_kernel, dim3((C + 255) / 256, N), dim3(256), 0, st, x, feat, HW, C);
+int avgpool_launch(const f16* x, float* feat, int N, int HW, int C, cudaStream_t st, int planes) {
+  launch_pdl(avgpool_kernel, dim3((C + 255) / 256, N), dim3(256), 0, st, x, feat, HW, C, planes);
   return check_launch("avgpool");
 }
 
@@ -354,16 +435,28 @@ int fc_act_launch(const float* x, const float* w, const float* b, float* out, in
 // out[n][p][c] = x[n][p][c] * a[n][c] (+ b[n][c]) (+ y[n][p][c])   (channel attention / broadcast add, f16 NHWC)
 __global__ void __launch_bounds__(256) chan_affine_kernel(const f16* __restrict__ x, const float* __restrict__ a,
                                                           const float* __restrict__ b, const f16* __restrict__ y,
-                                                          f16* __restrict__ out, int HW, int C8) {
+                                                          f16* __restrict__ out, int HW, int C8, int planes) {
   pdl_wait();
   const int n = blockIdx.y;
   const int64_t total = (int64_t)HW * C8;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int s = (int)(i % C8);
-    const int64_t o = ((int64_t)n * total + i) * 8;
+    // planes = 3: x, y and out are split tensors [hi | lo | hi] (pixel pitch 3 C): value = hi + lo
+    const int64_t o = planes == 1 ? ((int64_t)n * total + i) * 8 : ((((int64_t)n * HW + i / C8) * 3) * C8 + s) * 8;
     float xv[8], yv[8];
     unpack8r(__ldg(reinterpret_cast<const uint4*>(x + o)), xv);
     if (y) unpack8r(__ldg(reinterpret_cast<const uint4*>(y + o)), yv);
+    if (planes == 3) {
+      float l[8];
+      unpack8r(__ldg(reinterpret_cast<const uint4*>(x + o + C8 * 8)), l);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) xv[j] += l[j];
+      if (y) {
+        unpack8r(__ldg(reinterpret_cast<const uint4*>(y + o + C8 * 8)), l);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) yv[j] += l[j];
+      }
+    }
     const float* ap = a ? a + (int64_t)n * C8 * 8 + s * 8 : nullptr;
     const float* bp = b ? b + (int64_t)n * C8 * 8 + s * 8 : nullptr;
 #pragma unroll
@@ -373,24 +466,33 @@ __global__ void __launch_bounds__(256) chan_affine_kernel(const f16* __restrict_
       if (y) v += yv[j];
       xv[j] = v;
     }
-    *reinterpret_cast<uint4*>(out + o) = pack8r(xv);
+    const uint4 hi = pack8r(xv);
+    *reinterpret_cast<uint4*>(out + o) = hi;
+    if (planes == 3) {
+      float hf[8];
+      unpack8r(hi, hf);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) hf[j] = __fsub_rn(xv[j], hf[j]);
+      *reinterpret_cast<uint4*>(out + o + C8 * 8) = pack8r(hf);
+      *reinterpret_cast<uint4*>(out + o + 2 * C8 * 8) = hi;
+    }
   }
 }
 
 int chan_affine_launch(const f16* x, const float* a, const float* b, const f16* y, f16* out, int N, int HW, int C,
-                       cudaStream_t st) {
+                       cudaStream_t st, int planes) {
   B2E_REQUIRE(C % 8 == 0, B2E_UNSUPPORTED_SHAPE, "chan_affine: C %% 8 != 0");
   const int64_t total = (int64_t)HW * (C / 8);
   int gx = (int)((total + 255) / 256);
   if (gx > kNumSMs * 8) gx = kNumSMs * 8;
-  launch_pdl(chan_affine_kernel, dim3(gx, N), dim3(256), 0, st, x, a, b, y, out, HW, C / 8);
+  launch_pdl(chan_affine_kernel, dim3(gx, N), dim3(256), 0, st, x, a, b, y, out, HW, C / 8, planes);
   return check_launch("chan_affine");
 }
 
 // ---- backward helpers of the face parser
 // out[n][c] = scale * sum_p x[n][p][c] * (y ? y[n][p][c] : 1)   (gradient of a per-channel attention / broadcast vector)
 __global__ void __launch_bounds__(256) chan_dot_kernel(const f16* __restrict__ x, const f16* __restrict__ y,
-                                                       float* __restrict__ out, int HW, int C, float scale) {
+                                                       float* __restrict__ out, int HW, int C, float scale, int yplanes) {
   pdl_wait();
   __shared__ float red[256];
   const int n = blockIdx.y, c0 = blockIdx.x * 32, lane = threadIdx.x & 31, row = threadIdx.x >> 5;   // 8 pixel rows x 32 channels
@@ -400,7 +502,12 @@ __global__ void __launch_bounds__(256) chan_dot_kernel(const f16* __restrict__ x
     for (int p = row; p < HW; p += 8) {
       const int64_t o = ((int64_t)n * HW + p) * C + c;
       const float xv = f16_to_float(x[o]);
-      s += y ? xv * f16_to_float(y[o]) : xv;
+      if (y) {
+        const f16* yp = y + ((int64_t)n * HW + p) * (yplanes * C) + c;     // yplanes = 3: split forward activation, hi + lo
+        s += xv * (yplanes == 3 ? f16_to_float(yp[0]) + f16_to_float(yp[C]) : f16_to_float(yp[0]));
+      } else {
+        s += xv;
+      }
     }
   red[threadIdx.x] = s;
   __syncthreads();
@@ -411,8 +518,8 @@ __global__ void __launch_bounds__(256) chan_dot_kernel(const f16* __restrict__ x
   }
 }
 
-int chan_dot_launch(const f16* x, const f16* y, float* out, int N, int HW, int C, float scale, cudaStream_t st) {
-  launch_pdl(chan_dot_kernel, dim3((C + 31) / 32, N), dim3(256), 0, st, x, y, out, HW, C, scale);
+int chan_dot_launch(const f16* x, const f16* y, float* out, int N, int HW, int C, float scale, cudaStream_t st, int yplanes) {
+  launch_pdl(chan_dot_kernel, dim3((C + 31) / 32, N), dim3(256), 0, st, x, y, out, HW, C, scale, yplanes);
   return check_launch("chan_dot");
 }
 
@@ -442,7 +549,7 @@ int vec_act_bwd_launch(const float* g, const float* a, float* out, int n, int mo
 // consumer (a channel window of a wider tensor) followed by the ReLU mask of the tensor both consumers read
 __global__ void __launch_bounds__(256) grad_merge_kernel(const f16* __restrict__ g, const f16* __restrict__ e, int e_pitch,
                                                          int e_off, const f16* __restrict__ y, f16* __restrict__ out,
-                                                         int64_t rows, int C8) {
+                                                         int64_t rows, int C8, int yplanes) {
   pdl_wait();
   const int64_t total = rows * C8;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -460,7 +567,14 @@ __global__ void __launch_bounds__(256) grad_merge_kernel(const f16* __restrict__
       for (int j = 0; j < 8; ++j) gv[j] += ev[j];
     }
     if (y) {
-      unpack8r(__ldg(reinterpret_cast<const uint4*>(y + i * 8)), yv);
+      const f16* yp = y + (r * (yplanes * C8) + s) * 8;      // yplanes = 3: split forward activation, mask on hi + lo
+      unpack8r(__ldg(reinterpret_cast<const uint4*>(yp)), yv);
+      if (yplanes == 3) {
+        float l[8];
+        unpack8r(__ldg(reinterpret_cast<const uint4*>(yp + C8 * 8)), l);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) yv[j] += l[j];
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) gv[j] = yv[j] > 0.f ? gv[j] : 0.f;
     }
@@ -469,9 +583,9 @@ __global__ void __launch_bounds__(256) grad_merge_kernel(const f16* __restrict__
 }
 
 int grad_merge_launch(const f16* g, const f16* e, int e_pitch, int e_off, const f16* y, f16* out, int64_t rows, int C,
-                      cudaStream_t st) {
+                      cudaStream_t st, int yplanes) {
   B2E_REQUIRE(C % 8 == 0 && e_pitch % 8 == 0 && e_off % 8 == 0, B2E_UNSUPPORTED_SHAPE, "grad_merge: alignment");
-  launch_pdl(grad_merge_kernel, dim3(grid_for(rows * (C / 8))), dim3(256), 0, st, g, e, e_pitch, e_off, y, out, rows, C / 8);
+  launch_pdl(grad_merge_kernel, dim3(grid_for(rows * (C / 8))), dim3(256), 0, st, g, e, e_pitch, e_off, y, out, rows, C / 8, yplanes);
   return check_launch("grad_merge");
 }
 
@@ -535,7 +649,7 @@ int bilinear_ac_bwd_launch(const float* g, f16* dx, int N, int Hi, int Wi, int P
 // F.interpolate(x, (Ho, Wo), mode="bilinear", align_corners=True): x f16 NHWC (N,Hi,Wi,P), first K channels ->
 // out fp32 NCHW (N,K,Ho,Wo).  ATen's arithmetic: src = dst * (in-1)/(out-1); weights (1-l, l).
 __global__ void __launch_bounds__(256) bilinear_ac_kernel(const f16* __restrict__ x, float* __restrict__ out, int N, int Hi,
-                                                          int Wi, int P, int K, int Ho, int Wo, float sh, float sw) {
+                                                          int Wi, int P, int K, int Ho, int Wo, float sh, float sw, int planes) {
   pdl_wait();
   const int64_t total = (int64_t)N * Ho * Wo;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -546,21 +660,23 @@ __global__ void __launch_bounds__(256) bilinear_ac_kernel(const f16* __restrict_
     const int h0 = (int)fh, w0 = (int)fw;
     const int h1 = h0 + (h0 < Hi - 1 ? 1 : 0), w1 = w0 + (w0 < Wi - 1 ? 1 : 0);
     const float lh = fh - (float)h0, lw = fw - (float)w0;
-    const f16* p00 = x + (((int64_t)n * Hi + h0) * Wi + w0) * P;
-    const f16* p01 = x + (((int64_t)n * Hi + h0) * Wi + w1) * P;
-    const f16* p10 = x + (((int64_t)n * Hi + h1) * Wi + w0) * P;
-    const f16* p11 = x + (((int64_t)n * Hi + h1) * Wi + w1) * P;
+    const int PP = P * planes;     // planes = 3: split tensor [hi | lo | hi] per pixel, value = hi + lo
+    const f16* p00 = x + (((int64_t)n * Hi + h0) * Wi + w0) * PP;
+    const f16* p01 = x + (((int64_t)n * Hi + h0) * Wi + w1) * PP;
+    const f16* p10 = x + (((int64_t)n * Hi + h1) * Wi + w0) * PP;
+    const f16* p11 = x + (((int64_t)n * Hi + h1) * Wi + w1) * PP;
+    auto val = [&](const f16* q, int k) { return planes == 3 ? f16_to_float(q[k]) + f16_to_float(q[P + k]) : f16_to_float(q[k]); };
     for (int k = 0; k < K; ++k) {
-      const float v = (1.f - lh) * ((1.f - lw) * f16_to_float(p00[k]) + lw * f16_to_float(p01[k])) +
-                      lh * ((1.f - lw) * f16_to_float(p10[k]) + lw * f16_to_float(p11[k]));
+      const float v = (1.f - lh) * ((1.f - lw) * val(p00, k) + lw * val(p01, k)) +
+                      lh * ((1.f - lw) * val(p10, k) + lw * val(p11, k));
       out[(((int64_t)n * K + k) * Ho + oh) * Wo + ow] = v;
     }
   }
 }
 
-int bilinear_ac_launch(const f16* x, float* out, int N, int Hi, int Wi, int P, int K, int Ho, int Wo, cudaStream_t st) {
+int bilinear_ac_launch(const f16* x, float* out, int N, int Hi, int Wi, int P, int K, int Ho, int Wo, cudaStream_t st, int planes) {
   const float sh = Ho > 1 ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f, sw = Wo > 1 ? (float)(Wi - 1) / (float)(Wo - 1) : 0.f;
-  launch_pdl(bilinear_ac_kernel, dim3(grid_for((int64_t)N * Ho * Wo)), dim3(256), 0, st, x, out, N, Hi, Wi, P, K, Ho, Wo, sh, sw);
+  launch_pdl(bilinear_ac_kernel, dim3(grid_for((int64_t)N * Ho * Wo)), dim3(256), 0, st, x, out, N, Hi, Wi, P, K, Ho, Wo, sh, sw, planes);
   return check_launch("bilinear_ac");
 }
 

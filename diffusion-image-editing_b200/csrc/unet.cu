@@ -204,7 +204,9 @@ struct b2e_unet {
     return rc;
   }
   // conv / linear weight that feeds the tcgen05 GEMM: packed f16 [cout_pad][k*k][cin_pad]
-  ConvL make_conv(const std::string& name, int cin, int cout, int k, int cin_pad = 0, int res_c = 0) {
+  // src0 > 0: the convolution reads TWO concatenated sources of src0 and cin - src0 channels (multiples of 64); in the
+  // split mode every source carries its own [hi | lo | hi] planes, so the weight columns are packed per source
+  ConvL make_conv(const std::string& name, int cin, int cout, int k, int cin_pad = 0, int res_c = 0, int src0 = 0) {
     ConvL c;
     c.cin = cin; c.cin_pad = cin_pad ? cin_pad : pad64(cin); c.cout = cout; c.k = k; c.cout_pad = conv_cout_pad(cout);
     c.res_c = res_c; c.row_len = PL * (k * k * c.cin_pad + res_c);
@@ -215,8 +217,14 @@ struct b2e_unet {
     const int PL = this->PL;
     // (a <= 16-channel output, i.e. conv_out, receives its gradient as a 64-channel padded NHWC tensor)
     if (decoder || resnet) { c.dg = make_dgrad(cin, cout > 16 ? c.cout_pad : kConvBlockK, k); dd = dgrads[c.dg]; cc.dg = c.dg; }
-    add_param(name + ".weight", (int64_t)cout * cin * k * k, (int64_t)cin * k * k, [cc, dd, PL](const float* src, cudaStream_t st) {
-      int rc = pack_w(PL, src, cc.w, cc.cout, cc.cin, cc.k, cc.cin_pad, cc.row_len, 0, cc.cin_pad, st);
+    add_param(name + ".weight", (int64_t)cout * cin * k * k, (int64_t)cin * k * k, [cc, dd, PL, src0](const float* src, cudaStream_t st) {
+      int rc;
+      if (PL == 3 && src0 > 0 && cc.k == 1) {
+        rc = pack_w(PL, src, cc.w, cc.cout, src0, 1, src0, cc.row_len, 0, src0, st, 0, cc.cin);
+        if (!rc) rc = pack_w(PL, src, cc.w, cc.cout, cc.cin - src0, 1, cc.cin - src0, cc.row_len, 3 * src0, cc.cin - src0, st, src0, cc.cin);
+      } else {
+        rc = pack_w(PL, src, cc.w, cc.cout, cc.cin, cc.k, cc.cin_pad, cc.row_len, 0, cc.cin_pad, st);
+      }
       if (!rc && cc.dg >= 0) rc = conv_pack_weight_dgrad(src, dd.w, cc.cout, cc.cin, cc.k, dd.cin_pad, dd.row_len, 0, st);
       return rc;
     });
@@ -484,15 +492,23 @@ int build_model_resnet(b2e_unet* m) {
   const std::string pre = c.head == 1 ? "cp.resnet." : "";   // BiSeNet keeps its backbone under cp.resnet
   {
     // stem 7x7 stride 2 as a 1x1 convolution over a stride-2 im2col tensor (49 * Cin columns padded to a K-chunk multiple)
+    // fp32-accurate forward (rcfg.precision == 1, PL = 3): forward activations are split tensors [hi | lo | hi] and the
+    // forward weights are packed [W_hi | W_hi | W_lo] (x 2^10, undone in the epilogue) exactly as in the UNet's split mode,
+    // so ReLU / max-pool masks agree with the fp32 reference; the backward pass (dgrad twins, gradients) stays on plain
+    // f16 operands and reads its masks from the split activations.
+    const int PL = m->PL;
     ConvL s;
     const int KP = pad64(49 * Cin);
-    s.cin = s.cin_pad = KP; s.cout = W0; s.k = 1; s.cout_pad = conv_cout_pad(W0); s.row_len = KP;
-    s.w = m->dmalloc<f16>((size_t)s.cout_pad * KP);
+    s.cin = s.cin_pad = KP; s.cout = W0; s.k = 1; s.cout_pad = conv_cout_pad(W0); s.row_len = KP * PL;
+    s.w = m->dmalloc<f16>((size_t)s.cout_pad * KP * PL);
     s.b = m->dmalloc<float>(s.cout_pad);
     m->stem_dg = m->make_dgrad(KP, s.cout_pad, 1);   // gradient w.r.t. the im2col columns
     const ConvL sd = m->dgrads[m->stem_dg];
-    m->add_param(pre + "conv1.weight", (int64_t)W0 * Cin * 49, (int64_t)Cin * 49, [s, sd, Cin](const float* src, cudaStream_t st) {
-      int rc = conv_pack_weight(src, s.w, s.cout, Cin, 7, Cin, s.row_len, 0, st);
+    m->add_param(pre + "conv1.weight", (int64_t)W0 * Cin * 49, (int64_t)Cin * 49, [s, sd, Cin, PL, KP](const float* src, cudaStream_t st) {
+      const float ws = PL == 3 ? b2e_unet::kSplitWScale : 1.f;
+      int rc = conv_pack_weight(src, s.w, s.cout, Cin, 7, Cin, s.row_len, 0, st, 0, 0, 0, ws);
+      if (!rc && PL == 3) rc = conv_pack_weight(src, s.w, s.cout, Cin, 7, Cin, s.row_len, KP, st, 0, 0, 0, ws);
+      if (!rc && PL == 3) rc = conv_pack_weight(src, s.w, s.cout, Cin, 7, Cin, s.row_len, 2 * KP, st, 0, 0, 1, ws);
       if (!rc) rc = conv_pack_weight_im2col_T(src, sd.w, s.cout, Cin, sd.row_len, st, 49);
       return rc;
     });
@@ -521,7 +537,7 @@ int build_model_resnet(b2e_unet* m) {
         ConvL L;
         L.cin = cs[j].cin; L.cin_pad = pad64(cs[j].cin); L.cout = cs[j].cout; L.cout_pad = conv_cout_pad(cs[j].cout); L.k = cs[j].k;
         L.res_c = last ? pad64(inpl) : 0;
-        L.row_len = L.k * L.k * L.cin_pad + L.res_c;
+        L.row_len = m->PL * (L.k * L.k * L.cin_pad + L.res_c);
         L.w = m->dmalloc<f16>((size_t)L.cout_pad * L.row_len);
         L.b = m->dmalloc<float>(L.cout_pad);
         // dgrad twin; the FIRST convolution's twin also carries the shortcut gradient as a residual K segment
@@ -529,8 +545,9 @@ int build_model_resnet(b2e_unet* m) {
         const int extra = j == 0 ? pad64(rb.cout) : 0;
         rb.dg[j] = m->make_dgrad(cs[j].cin, L.cout_pad, L.k, extra);
         const ConvL D = m->dgrads[rb.dg[j]];
-        m->add_param(nm + ".weight", (int64_t)L.cout * L.cin * L.k * L.k, (int64_t)L.cin * L.k * L.k, [L, D](const float* src, cudaStream_t st) {
-          int rc = conv_pack_weight(src, L.w, L.cout, L.cin, L.k, L.cin_pad, L.row_len, 0, st);
+        const int PLc = m->PL;
+        m->add_param(nm + ".weight", (int64_t)L.cout * L.cin * L.k * L.k, (int64_t)L.cin * L.k * L.k, [L, D, PLc](const float* src, cudaStream_t st) {
+          int rc = b2e_unet::pack_w(PLc, src, L.w, L.cout, L.cin, L.k, L.cin_pad, L.row_len, 0, L.cin_pad, st);
           if (!rc) rc = conv_pack_weight_dgrad(src, D.w, L.cout, L.cin, L.k, D.cin_pad, D.row_len, 0, st);
           return rc;
         });
@@ -540,19 +557,20 @@ int build_model_resnet(b2e_unet* m) {
       {
         const ConvL L = rb.c[rb.nconv - 1];
         const ConvL D0 = m->dgrads[rb.dg[0]];
-        const int seg = L.k * L.k * L.cin_pad;                  // forward: residual segment starts here
+        const int PLc = m->PL;
+        const int seg = PLc * L.k * L.k * L.cin_pad;            // forward: residual segment starts here (all planes of the taps first)
         const int dseg = D0.k * D0.k * D0.cin_pad;              // backward twin of conv1: shortcut-gradient segment
         if (rb.has_ds) {
           rb.c[rb.nconv - 1].b2 = m->dmalloc<float>(L.cout_pad);
           const int cin = inpl, cout = rb.cout;
-          m->add_param(base + ".downsample.0.weight", (int64_t)cout * cin, cin, [L, D0, seg, dseg, cin, cout](const float* src, cudaStream_t st) {
-            int rc = conv_pack_weight(src, L.w, cout, cin, 1, cin, L.row_len, seg, st);
+          m->add_param(base + ".downsample.0.weight", (int64_t)cout * cin, cin, [L, D0, seg, dseg, cin, cout, PLc](const float* src, cudaStream_t st) {
+            int rc = b2e_unet::pack_w(PLc, src, L.w, cout, cin, 1, cin, L.row_len, seg, pad64(cin), st);
             if (!rc) rc = conv_pack_weight_dgrad(src, D0.w, cout, cin, 1, pad64(cout), D0.row_len, dseg, st);
             return rc;
           });
           m->add_f32(base + ".downsample.0.bias", rb.c[rb.nconv - 1].b2, cout, cin);
         } else if (L.w && D0.w) {
-          if (conv_fill_identity(L.w, rb.cout, L.row_len, seg, 0) || conv_fill_identity(D0.w, rb.cout, D0.row_len, dseg, 0))
+          if (b2e_unet::fill_id(PLc, L.w, rb.cout, L.row_len, seg, pad64(inpl)) || conv_fill_identity(D0.w, rb.cout, D0.row_len, dseg, 0))
             m->build_error = B2E_CUDA_ERROR;
         }
       }
@@ -569,7 +587,7 @@ int build_model_resnet(b2e_unet* m) {
     bs.arm16 = m->make_conv("cp.arm16.conv", c16, mid, 3);
     bs.head32 = m->make_conv("cp.conv_head32", mid, mid, 3);
     bs.head16 = m->make_conv("cp.conv_head16", mid, mid, 3);
-    bs.ffm_blk = m->make_conv("ffm.convblk", c8 + mid, 256, 1);
+    bs.ffm_blk = m->make_conv("ffm.convblk", c8 + mid, 256, 1, 0, 0, c8);   // reads feat8 (c8) ++ context path (mid)
     bs.out_conv = m->make_conv("conv_out.conv", 256, 256, 3);
     bs.out_cls = m->make_conv("conv_out.conv_out", 256, c.num_classes, 1);
     auto fcp = [&](const std::string& name, int K, int C, bool bias, float** w, float** b) {
@@ -603,8 +621,9 @@ int build_program_resnet(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* 
   std::vector<b2e_unet::Op>* cur = &fwd;
   double flops = 0;
   int rc = B2E_OK;
-  auto talloc = [&](int N, int H, int W, int C) {
-    Tensor t; t.N = N; t.H = H; t.W = W; t.C = C; t.Cr = C; t.bytes = (size_t)N * H * W * C * sizeof(f16);
+  const int PL = m->PL;     // planes of the FORWARD activations (3: split tensors of the fp32-accurate forward); gradients: 1
+  auto talloc = [&](int N, int H, int W, int C, int planes = 1) {
+    Tensor t; t.N = N; t.H = H; t.W = W; t.C = C; t.Cr = C; t.bytes = (size_t)N * H * W * C * planes * sizeof(f16);
     t.p = (f16*)ar.alloc(t.bytes);
     return t;
   };
@@ -618,17 +637,18 @@ int build_program_resnet(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* 
     if (rc) return;
     const int Ho = x.H / stride, Wo = x.W / stride;
     const int xc = x.C + (x1 ? x1->C : 0);
-    *out = talloc(B, Ho, Wo, L.cout_pad);
-    const double fl = 2.0 * B * Ho * Wo * (double)L.cout_pad * (L.k * L.k * xc + L.res_c);
+    *out = talloc(B, Ho, Wo, L.cout_pad, PL);
+    const double fl = 2.0 * B * Ho * Wo * (double)L.cout_pad * (L.k * L.k * xc + L.res_c) * PL;
     flops += fl;
     if (dry) return;
-    if (L.k * L.k * xc + L.res_c != L.row_len || L.res_c != (r0 ? r0->C : 0)) {
+    if (PL * (L.k * L.k * xc + L.res_c) != L.row_len || L.res_c != (r0 ? r0->C : 0)) {
       rc = B2E_INVALID_ARG; set_error("resnet: operand widths do not match the packed weights (%s)", what); return;
     }
     ConvDesc d;
-    d.s0 = ConvSrc{x.p, x.C};
-    if (x1) d.s1 = ConvSrc{x1->p, x1->C};
-    if (r0) d.r0 = ConvSrc{r0->p, r0->C};
+    d.s0 = ConvSrc{x.p, x.C * PL};
+    if (x1) d.s1 = ConvSrc{x1->p, x1->C * PL};
+    if (r0) d.r0 = ConvSrc{r0->p, r0->C * PL};
+    d.out_planes = PL;
     d.N = B; d.H = x.H; d.W = x.W; d.ksize = L.k; d.stride = stride; d.stride2_pad1 = 1;
     d.w_packed = L.w; d.Cout = L.cout_pad; d.out_f16 = out->p;
     d.split_ws = split_ws; d.split_ws_bytes = split_bytes; d.split_counters = split_cnt;
@@ -637,6 +657,7 @@ int build_program_resnet(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* 
     if (rc) return;
     ConvEpilogue ep;
     ep.bias = L.b; ep.bias2 = L.b2; ep.relu = relu ? 1 : 0;
+    if (PL == 3) ep.acc_scale = 1.f / b2e_unet::kSplitWScale;
     char desc[160];
     snprintf(desc, sizeof(desc), "%s: conv%dx%d s%d %dx%d cin%d res%d cout%d bn%d%s%s", what, L.k, L.k, stride, x.H, x.W, x.C, L.res_c,
              L.cout, pl.block_n, pl.halo ? " halo" : pl.pair ? " pair" : "", relu ? " +relu" : "");
@@ -650,14 +671,14 @@ int build_program_resnet(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* 
 
   // ---------------- forward
   const int S = c.input_size, Cin = c.in_channels, KP = m->stem.cin_pad;
-  Tensor cols = talloc(B, S / 2, S / 2, KP);
-  ew([m, cols, B, Cin, S, KP](cudaStream_t st) { return im2col7s2_launch(m->in_x, cols.p, B, Cin, S, S, KP, st); },
+  Tensor cols = talloc(B, S / 2, S / 2, KP, PL);
+  ew([m, cols, B, Cin, S, KP, PL](cudaStream_t st) { return im2col7s2_launch(m->in_x, cols.p, B, Cin, S, S, KP, st, PL); },
      (double)B * S * S * Cin * 4.0 + (double)cols.bytes, "stem im2col (7x7 stride 2)");
   Tensor y1, y2;
   conv(m->stem, cols, 1, true, nullptr, &y1, "stem");
-  y2 = talloc(B, y1.H / 2, y1.W / 2, y1.C);
+  y2 = talloc(B, y1.H / 2, y1.W / 2, y1.C, PL);
   uint8_t* pool_idx = (uint8_t*)ar.alloc((size_t)B * y2.H * y2.W * y2.C);
-  ew([y1, y2, pool_idx, B](cudaStream_t st) { return maxpool3s2_launch(y1.p, y2.p, pool_idx, B, y1.H, y1.W, y1.C, st); },
+  ew([y1, y2, pool_idx, B, PL](cudaStream_t st) { return maxpool3s2_launch(y1.p, y2.p, pool_idx, B, y1.H, y1.W, y1.C, st, PL); },
      1.25 * (double)y1.bytes + (double)y2.bytes, "maxpool 3x3 stride 2");
   struct BSave { Tensor x, xs, a[3]; };
   std::vector<BSave> saves(m->rblocks.size());
@@ -670,9 +691,9 @@ int build_program_resnet(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* 
     // shortcut operand at the block's output resolution
     sv.xs = h;
     if (rb.stride == 2) {
-      sv.xs = talloc(B, h.H / 2, h.W / 2, h.C);
+      sv.xs = talloc(B, h.H / 2, h.W / 2, h.C, PL);
       const Tensor hh = h, xs = sv.xs;
-      ew([hh, xs, B](cudaStream_t st) { return subsample2x_launch(hh.p, xs.p, B, xs.H, xs.W, xs.C, st); }, 2.0 * (double)xs.bytes,
+      ew([hh, xs, B, PL](cudaStream_t st) { return subsample2x_launch(hh.p, xs.p, B, xs.H, xs.W, xs.C * PL, st); }, 2.0 * (double)xs.bytes,
          "shortcut subsample");
     }
     Tensor t = h;
@@ -708,22 +729,22 @@ int build_program_resnet(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* 
     auto fbuf = [&](int n) { return (float*)ar.alloc(sizeof(float) * B * n); };
     auto pool = [&](const Tensor& t, float* dst) {
       const Tensor tt = t;
-      ew([tt, dst, B](cudaStream_t st) { return avgpool_launch(tt.p, dst, B, tt.H * tt.W, tt.C, st); }, (double)tt.bytes, "global average pool");
+      ew([tt, dst, B, PL](cudaStream_t st) { return avgpool_launch(tt.p, dst, B, tt.H * tt.W, tt.C, st, PL); }, (double)tt.bytes, "global average pool");
     };
     auto fc = [&](const float* x, const float* w, const float* b, float* out, int C, int Kk, int act, const char* what) {
       ew([x, w, b, out, B, C, Kk, act](cudaStream_t st) { return fc_act_launch(x, w, b, out, B, C, Kk, act, st); }, 4.0 * Kk * C, what);
     };
     auto affine = [&](const Tensor& x, const float* a, const float* b, const Tensor* y, Tensor* out, const char* what) {
-      *out = talloc(B, x.H, x.W, x.C);
+      *out = talloc(B, x.H, x.W, x.C, PL);
       const Tensor xx = x, oo = *out;
       const f16* yp = y ? y->p : nullptr;
-      ew([xx, a, b, yp, oo, B](cudaStream_t st) { return chan_affine_launch(xx.p, a, b, yp, oo.p, B, xx.H * xx.W, xx.C, st); },
+      ew([xx, a, b, yp, oo, B, PL](cudaStream_t st) { return chan_affine_launch(xx.p, a, b, yp, oo.p, B, xx.H * xx.W, xx.C, st, PL); },
          (y ? 3.0 : 2.0) * (double)xx.bytes, what);
     };
     auto up2 = [&](const Tensor& x, Tensor* out) {
-      *out = talloc(B, x.H * 2, x.W * 2, x.C);
+      *out = talloc(B, x.H * 2, x.W * 2, x.C, PL);
       const Tensor xx = x, oo = *out;
-      ew([xx, oo, B](cudaStream_t st) { return upsample2x_launch(xx.p, oo.p, B, xx.H, xx.W, xx.C, st); }, 1.25 * (double)oo.bytes, "nearest upsample x2");
+      ew([xx, oo, B, PL](cudaStream_t st) { return upsample2x_launch(xx.p, oo.p, B, xx.H, xx.W, xx.C * PL, st); }, 1.25 * (double)oo.bytes, "nearest upsample x2");
     };
     const int mid = 128;
     hs.feat8 = feat8; hs.feat16 = feat16; hs.feat32 = feat32;
@@ -753,14 +774,14 @@ int build_program_resnet(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* 
     conv(bs.out_cls, hs.o1, 1, false, nullptr, &hs.o2, "conv_out.conv_out");
     if (!rc) {
       const Tensor oo = hs.o2;
-      ew([m, oo, B, K, S](cudaStream_t st) { return bilinear_ac_launch(oo.p, m->out_eps, B, oo.H, oo.W, oo.C, K, S, S, st); },
+      ew([m, oo, B, K, S, PL](cudaStream_t st) { return bilinear_ac_launch(oo.p, m->out_eps, B, oo.H, oo.W, oo.C, K, S, S, st, PL); },
          (double)oo.bytes + 4.0 * B * K * S * S, "bilinear upsample (align_corners) -> logits");
     }
   }
   float* feat = (float*)ar.alloc(sizeof(float) * B * Cl);
   if (!rc && c.head == 0) {
     const Tensor hl = h;
-    ew([m, hl, feat, B, HWl, Cl, K](cudaStream_t st) { return avgpool_fc_launch(hl.p, feat, m->fc_w, m->fc_b, m->out_eps, B, HWl, Cl, K, st); },
+    ew([m, hl, feat, B, HWl, Cl, K, PL](cudaStream_t st) { return avgpool_fc_launch(hl.p, feat, m->fc_w, m->fc_b, m->out_eps, B, HWl, Cl, K, st, PL); },
        (double)hl.bytes, "global average pool + fc");
   }
   // ---------------- backward: d(logits) -> d(image)
@@ -794,10 +815,10 @@ int build_program_resnet(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* 
       snprintf(desc, sizeof(desc), "%s: dgrad conv%dx%d %dx%d cin%d res%d cout%d", what, D.k, D.k, dy.H, dy.W, dy.C, D.res_c, D.cout);
       cur->push_back({[pl](cudaStream_t st) { return conv_launch(pl, ConvEpilogue{}, st); }, 0, pl.flops, 0.0, desc});
     };
-    auto relu_mask = [&](Tensor& gt, const Tensor& y) {   // in place: gt *= (y > 0)
+    auto relu_mask = [&](Tensor& gt, const Tensor& y) {   // in place: gt *= (y > 0); y = forward activation (PL planes)
       const Tensor gg = gt, yy = y;
-      ew([gg, yy](cudaStream_t st) { return relu_bwd_launch(gg.p, yy.p, gg.p, (int64_t)(gg.bytes / sizeof(f16)), st); }, 3.0 * (double)gt.bytes,
-         "relu backward");
+      ew([gg, yy, PL](cudaStream_t st) { return relu_bwd_launch(gg.p, yy.p, gg.p, (int64_t)(gg.bytes / sizeof(f16)), st, PL, gg.C); },
+         3.0 * (double)gt.bytes, "relu backward");
     };
     auto zero_up = [&](const Tensor& t) {
       Tensor u = talloc(B, t.H * 2, t.W * 2, t.C);
@@ -821,8 +842,8 @@ int build_program_resnet(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* 
       float* dfeat = (float*)ar.alloc(sizeof(float) * B * Cl);
       g = talloc(B, h.H, h.W, h.C);
       const Tensor hl = h, gg = g;
-      ew([m, hl, gg, dfeat, gsc, B, HWl, Cl, K](cudaStream_t st) {
-           return avgpool_fc_bwd_launch(m->in_dlogits, m->fc_w, dfeat, hl.p, gg.p, B, HWl, Cl, K, st, gsc); },
+      ew([m, hl, gg, dfeat, gsc, B, HWl, Cl, K, PL](cudaStream_t st) {
+           return avgpool_fc_bwd_launch(m->in_dlogits, m->fc_w, dfeat, hl.p, gg.p, B, HWl, Cl, K, st, gsc, PL); },
          2.0 * (double)hl.bytes, "fc + average pool backward (+ relu mask)");
     } else {
       // ---- face parser head backward: d(logits) (B, K, S, S) -> gradients at feat8 / feat16 / feat32
@@ -831,7 +852,7 @@ int build_program_resnet(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* 
       auto dot = [&](const Tensor& x, const Tensor* y, float* out, float scale, const char* what) {
         const Tensor xx = x;
         const f16* yp = y ? y->p : nullptr;
-        ew([xx, yp, out, B, scale](cudaStream_t st) { return chan_dot_launch(xx.p, yp, out, B, xx.H * xx.W, xx.C, scale, st); },
+        ew([xx, yp, out, B, scale, PL](cudaStream_t st) { return chan_dot_launch(xx.p, yp, out, B, xx.H * xx.W, xx.C, scale, st, PL); },
            (y ? 2.0 : 1.0) * (double)xx.bytes, what);
       };
       auto vact = [&](const float* gv, const float* a, float* out, int n, int mode) {
@@ -851,8 +872,8 @@ int build_program_resnet(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* 
         const Tensor oo = *out;
         const f16* gp = gt ? gt->p : nullptr; const f16* ep = e ? e->p : nullptr; const f16* yp = y ? y->p : nullptr;
         const int epitch = e ? e->C : 0;
-        ew([gp, ep, epitch, e_off, yp, oo, B](cudaStream_t st) {
-             return grad_merge_launch(gp, ep, epitch, e_off, yp, oo.p, (int64_t)B * oo.H * oo.W, oo.C, st); }, 3.0 * (double)oo.bytes, what);
+        ew([gp, ep, epitch, e_off, yp, oo, B, PL](cudaStream_t st) {
+             return grad_merge_launch(gp, ep, epitch, e_off, yp, oo.p, (int64_t)B * oo.H * oo.W, oo.C, st, PL); }, 3.0 * (double)oo.bytes, what);
       };
       auto down2 = [&](const Tensor& dy, Tensor* dx) {
         *dx = talloc(B, dy.H / 2, dy.W / 2, dy.C);
@@ -944,8 +965,8 @@ int build_program_resnet(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* 
           const Tensor gd = dx, ee = ex->second.first, yy = sv.x;
           const int eoff = ex->second.second;
           Tensor merged = talloc(B, dx.H, dx.W, dx.C);
-          ew([gd, ee, eoff, yy, merged, B](cudaStream_t st) {
-               return grad_merge_launch(gd.p, ee.p, ee.C, eoff, yy.p, merged.p, (int64_t)B * merged.H * merged.W, merged.C, st); },
+          ew([gd, ee, eoff, yy, merged, B, PL](cudaStream_t st) {
+               return grad_merge_launch(gd.p, ee.p, ee.C, eoff, yy.p, merged.p, (int64_t)B * merged.H * merged.W, merged.C, st, PL); },
              4.0 * (double)merged.bytes, "gradient merge (second consumer) + relu mask");
           dx = merged;
         } else if (bi > 0) {
@@ -958,7 +979,7 @@ int build_program_resnet(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* 
       // max pool (+ the stem's ReLU mask) -> stem dgrad w.r.t. the im2col columns -> col2im -> fp32 NCHW image gradient
       Tensor gy1 = talloc(B, y1.H, y1.W, y1.C), dcols;
       const Tensor gg = g;
-      ew([y1, pool_idx, gg, gy1, B](cudaStream_t st) { return maxpool3s2_bwd_launch(y1.p, pool_idx, gg.p, gy1.p, B, y1.H, y1.W, y1.C, st); },
+      ew([y1, pool_idx, gg, gy1, B, PL](cudaStream_t st) { return maxpool3s2_bwd_launch(y1.p, pool_idx, gg.p, gy1.p, B, y1.H, y1.W, y1.C, st, PL); },
          3.0 * (double)y1.bytes, "maxpool backward (+ stem relu mask)");
       dconv(m->stem_dg, gy1, nullptr, &dcols, "stem");
       if (!rc) {
@@ -2042,6 +2063,8 @@ int b2e_resnet_create(const b2e_resnet_config* cfg, int64_t max_batch, b2e_unet*
   B2E_REQUIRE(cfg->head == 0 || (cfg->head == 1 && !cfg->bottleneck && cfg->width == 64 && cfg->num_classes <= 64),
               B2E_UNSUPPORTED_SHAPE, "resnet_create: the face-parser head needs a basic-block backbone of width 64 and <= 64 classes");
   m->grad = cfg->head == 0;   // the classifier exists for its input gradient (classifier guidance)
+  B2E_REQUIRE(cfg->precision == 0 || cfg->precision == 1, B2E_INVALID_ARG, "resnet_create: precision must be 0 or 1");
+  m->PL = cfg->precision == 1 ? 3 : 1;
   m->rcfg = *cfg;
   m->cfg = b2e_unet_config{};
   m->cfg.sample_size = cfg->input_size; m->cfg.in_channels = cfg->in_channels; m->cfg.out_channels = cfg->num_classes;
@@ -2137,7 +2160,7 @@ int b2e_unet_enable_grad(b2e_unet* m, int enable) {
   B2E_REQUIRE(m, B2E_INVALID_ARG, "unet_enable_grad: null handle");
   B2E_REQUIRE(!enable || m->decoder || m->resnet, B2E_UNSUPPORTED_SHAPE,
               "unet_enable_grad: gradient mode is implemented for the VQ / KL decoder and the classifier");
-  B2E_REQUIRE(!enable || m->PL == 1, B2E_UNSUPPORTED_SHAPE, "unet_enable_grad: the fp32-accurate mode is forward-only");
+  B2E_REQUIRE(!enable || m->PL == 1 || m->resnet, B2E_UNSUPPORTED_SHAPE, "unet_enable_grad: the fp32-accurate mode is forward-only");
   if ((enable != 0) == m->grad) return B2E_OK;
   m->grad = enable != 0;
   m->cur_B = -1; m->fwd_B = -1; m->ws = nullptr; m->ws_bytes = 0;   // the workspace must be re-queried and re-bound

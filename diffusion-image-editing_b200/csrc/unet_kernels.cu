@@ -79,7 +79,11 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(GNArgs a, int pix_per_blo
   __shared__ float s_mean[64], s_rstd[64];
   extern __shared__ double s_ch[];          // [C][2]: per-channel (sum, sum of squares) of image n (fused-statistics paths)
   const int C = a.C0 + a.C1, slots = a.Pout >> 3, ppi = (int)blockDim.x / slots;
-  const int n = blockIdx.y, tid = threadIdx.x;
+  // REVERSE block order (B2E_GN_REVERSE, default on): the producing convolution wrote the tensor front to back, so its
+  // tail is what the 126 MB L2 still holds - start there; the normalised tensor is then written back to front and its
+  // FRONT is what L2 holds when the consumer convolution starts at tile 0
+  const int n = a.reverse ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y, tid = threadIdx.x;
+  const int bx = a.reverse ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
   const int cpg = C / a.G;
   if (a.ts0 || a.cs0) {
     // statistics from the producing convolutions' epilogues (concat-aware): ALL threads gather the per-channel sums of
@@ -123,14 +127,14 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(GNArgs a, int pix_per_blo
     if (var < 0.0) var = 0.0;
     s_mean[tid] = (float)mean;
     s_rstd[tid] = (float)(1.0 / sqrt(var + (double)a.eps));
-    if (a.save_stats && blockIdx.x == 0)
+    if (a.save_stats && bx == 0)
       *reinterpret_cast<float2*>(a.save_stats + ((int64_t)n * a.G + tid) * 2) = make_float2(s_mean[tid], s_rstd[tid]);
   }
   __syncthreads();
   const int s = tid % slots, pl = tid / slots;
   if (pl >= ppi) return;
   const int c = s * 8;
-  const int p0 = blockIdx.x * pix_per_block, p1 = min(a.HW, p0 + pix_per_block);
+  const int p0 = bx * pix_per_block, p1 = min(a.HW, p0 + pix_per_block);
   constexpr bool split = SPLIT;           // split-f16 tensors (fp32-accurate mode): planes [hi | lo | hi]
   const int po = a.Pout * a.planes;       // output pixel pitch
   f16* dst = a.out + (int64_t)n * a.HW * po + c;
@@ -299,7 +303,10 @@ int gn_chunks(int HW, int C) {
   return ch;
 }
 
-int gn_launch(const GNArgs& a, cudaStream_t st) {
+int gn_launch(const GNArgs& a_in, cudaStream_t st) {
+  static const int rev = getenv("B2E_GN_REVERSE") ? atoi(getenv("B2E_GN_REVERSE")) : 1;
+  GNArgs a = a_in;
+  a.reverse = rev;
   const int C = a.C0 + a.C1;
   B2E_REQUIRE(C % 8 == 0 && a.C0 % 8 == 0 && a.Pout <= 4096 && a.G <= 64 && C % a.G == 0, B2E_UNSUPPORTED_SHAPE,
               "groupnorm: unsupported channels %d+%d / groups %d", a.C0, a.C1, a.G);

@@ -27,6 +27,7 @@ struct GNArgs {
   // 3: sources and output are split-f16 tensors of the fp32-accurate mode - channel planes [hi | lo | hi] of P
   // channels each (pixel pitch 3 * P), value = hi + lo; statistics must come from the stand-alone pass
   int planes = 1;
+  int reverse = 0;   // apply pass walks the tensor back to front (L2 reuse of the producer's tail; set by gn_launch)
 };
 
 // Backward of y = GroupNorm(x) (optionally followed by SiLU), single source.  dx = d(loss)/dx (+ add):
@@ -119,31 +120,33 @@ int pointwise_conv_f32_launch(const float* x, const float* w, const float* b, fl
                               cudaStream_t st);
 
 // classifier network (torchvision ResNet) kernels, csrc/resnet_kernels.cu
-int im2col7s2_launch(const float* x, f16* out, int B, int C, int H, int W, int KP, cudaStream_t st);
+// planes = 3 / xplanes / yplanes = 3: split tensors [hi | lo | hi] of the fp32-accurate forward (pixel pitch 3 C)
+int im2col7s2_launch(const float* x, f16* out, int B, int C, int H, int W, int KP, cudaStream_t st, int planes = 1);
 int col2im7s2_launch(const f16* dcols, float* dx, int B, int C, int H, int W, int KP, cudaStream_t st, const float* gs = nullptr);
-int maxpool3s2_launch(const f16* x, f16* y, uint8_t* idx, int N, int H, int W, int C, cudaStream_t st);
-int maxpool3s2_bwd_launch(const f16* x, const uint8_t* idx, const f16* gy, f16* gx, int N, int H, int W, int C, cudaStream_t st);
-int relu_bwd_launch(const f16* g, const f16* y, f16* out, int64_t numel, cudaStream_t st);
+int maxpool3s2_launch(const f16* x, f16* y, uint8_t* idx, int N, int H, int W, int C, cudaStream_t st, int planes = 1);
+int maxpool3s2_bwd_launch(const f16* x, const uint8_t* idx, const f16* gy, f16* gx, int N, int H, int W, int C, cudaStream_t st,
+                          int xplanes = 1);
+int relu_bwd_launch(const f16* g, const f16* y, f16* out, int64_t numel, cudaStream_t st, int yplanes = 1, int C = 0);
 int subsample2x_launch(const f16* in, f16* out, int N, int Ho, int Wo, int C, cudaStream_t st);
 int zero_upsample2x_launch(const f16* in, f16* out, int N, int Hi, int Wi, int C, cudaStream_t st);
 int avgpool_fc_launch(const f16* x, float* feat, const float* w, const float* b, float* logits, int N, int HW, int C, int K,
-                      cudaStream_t st);
+                      cudaStream_t st, int planes = 1);
 int avgpool_fc_bwd_launch(const float* dlogits, const float* w, float* dfeat, const f16* y, f16* g, int N, int HW, int C, int K,
-                          cudaStream_t st, const float* gs = nullptr);
+                          cudaStream_t st, const float* gs = nullptr, int yplanes = 1);
 
 // face parser (BiSeNet) helpers
-int avgpool_launch(const f16* x, float* feat, int N, int HW, int C, cudaStream_t st);
+int avgpool_launch(const f16* x, float* feat, int N, int HW, int C, cudaStream_t st, int planes = 1);
 int fc_act_launch(const float* x, const float* w, const float* b, float* out, int N, int C, int K, int act, cudaStream_t st);
 int chan_affine_launch(const f16* x, const float* a, const float* b, const f16* y, f16* out, int N, int HW, int C,
-                       cudaStream_t st);
-int bilinear_ac_launch(const f16* x, float* out, int N, int Hi, int Wi, int P, int K, int Ho, int Wo, cudaStream_t st);
+                       cudaStream_t st, int planes = 1);
+int bilinear_ac_launch(const f16* x, float* out, int N, int Hi, int Wi, int P, int K, int Ho, int Wo, cudaStream_t st, int planes = 1);
 int bilinear_ac_bwd_launch(const float* g, f16* dx, int N, int Hi, int Wi, int P, int K, int Ho, int Wo, cudaStream_t st,
                            const float* gs = nullptr);
-int chan_dot_launch(const f16* x, const f16* y, float* out, int N, int HW, int C, float scale, cudaStream_t st);
+int chan_dot_launch(const f16* x, const f16* y, float* out, int N, int HW, int C, float scale, cudaStream_t st, int yplanes = 1);
 int fc_t_launch(const float* g, const float* w, float* out, int N, int C, int K, float scale, cudaStream_t st);
 int vec_act_bwd_launch(const float* g, const float* a, float* out, int n, int mode, cudaStream_t st);
 int grad_merge_launch(const f16* g, const f16* e, int e_pitch, int e_off, const f16* y, f16* out, int64_t rows, int C,
-                      cudaStream_t st);
+                      cudaStream_t st, int yplanes = 1);
 
 // multi-head tensor-core attention: head-major operands (virtual image v = n*heads + h, head_dim padded to 64)
 int split_heads_launch(const f16* qkv, f16* qh, f16* kh, f16* vht, int N, int T, int P, int heads, int d, cudaStream_t st);

@@ -111,18 +111,21 @@ def create_diffusion_model(name: str, sample_clipping: bool = True, *, max_batch
 
 
 def get_pretrained_anyGAN(input_size: int = 256, max_batch: int = 1, state_dict_path: str = "../attribute_predictor.pt",
-                          seed: int = 0):
+                          seed: int = 0, precision: Optional[str] = "fp32"):
     """The attribute predictor of ClassifierAttrFunc (src/models.py:69-77: ``models.resnet50()`` with an 80-way ``fc``
     loaded from ../attribute_predictor.pt) on the native engine: forward AND input gradient on the tcgen05 kernels, so
     classifier guidance needs no torch network.  ``input_size`` is the resolution of the decoded images it will see (256
-    for DDPM / LDM, 512 for SD).  Offline (no checkpoint file) the weights are random-init (seeded)."""
+    for DDPM / LDM, 512 for SD).  Offline (no checkpoint file) the weights are random-init (seeded).  ``precision``:
+    "fp32" (default) runs the fp32-accurate forward, so the guidance gradient is routed through the fp32 network's
+    ReLU / max-pool masks (input gradient within 1e-2 relative RMS of fp32 autograd); "fp16" is the f16-operand forward
+    (3x fewer forward flops, gradient 0.15 relative RMS from fp32)."""
     import os
     from b200edit.resnet import resnet50_predictor
     sd = None
     if state_dict_path and os.path.exists(state_dict_path):
         sd = torch.load(state_dict_path, map_location="cpu")
         sd = sd.get("state_dict", sd)
-    return resnet50_predictor(80, input_size, max_batch=max_batch, state_dict=sd, seed=seed)
+    return resnet50_predictor(80, input_size, max_batch=max_batch, state_dict=sd, seed=seed, precision=precision)
 
 
 class SegmentationModel:
@@ -134,7 +137,7 @@ class SegmentationModel:
     substitutes any callable mapping a (1,3,S,S) image to ([1,19,S,S] logits, ...)."""
 
     def __init__(self, ckpt: str = "Segmentation/res/cp/79999_iter.pth", n_classes: int = 19, image_size: tuple = (512, 512),
-                 *, net=None, seed: int = 0) -> None:
+                 *, net=None, seed: int = 0, precision: Optional[str] = None) -> None:
         self.device = get_device()
         if not (ckpt is None or isinstance(ckpt, (str, bytes)) or hasattr(ckpt, "__fspath__")):
             raise TypeError("SegmentationModel: the first argument is the checkpoint path (as in the reference); pass a "
@@ -142,7 +145,7 @@ class SegmentationModel:
         if net is None:
             import os
             from b200edit.bisenet import MultiResBiSeNet
-            net = MultiResBiSeNet(n_classes, max_batch=1, device=self.device, seed=seed)
+            net = MultiResBiSeNet(n_classes, max_batch=1, device=self.device, seed=seed, precision=precision)
             if ckpt and os.path.exists(ckpt):
                 net.load_reference_state_dict(torch.load(ckpt, map_location="cpu"))
         self.net = net

@@ -373,6 +373,11 @@ typedef struct {
    *    "cp.arm16.conv.*", "cp.arm16.conv_atten.*", "cp.conv_head32.*", "cp.conv_avg.*", "ffm.convblk.*", "ffm.conv1.weight",
    *    "ffm.conv2.weight", "conv_out.conv.*", "conv_out.conv_out.*"). */
   int32_t head;
+  /* 0: f16 operands throughout.  1 (head 0): fp32-accurate FORWARD - split f16 operands hi + lo, three tensor-core products
+   * per GEMM, as b2e_unet_config.precision - so the ReLU / max-pool masks the backward pass reads agree with an fp32
+   * evaluation of the network (a 16-bit forward flips the masks of near-zero activations, which dominates the error of
+   * the INPUT GRADIENT); the backward pass itself stays on f16 operands. */
+  int32_t precision;
 } b2e_resnet_config;
 int b2e_resnet_create(const b2e_resnet_config* cfg, int64_t max_batch, b2e_unet** out);
 int b2e_resnet_backward(b2e_unet* m, const float* d_logits, float* d_image, int64_t B, void* stream);

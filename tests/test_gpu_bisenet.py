@@ -67,12 +67,12 @@ def test_segmentation_model_with_native_parser_feeds_the_mask_path():
         native(torch.zeros(1, 3, 512, 512, device="cuda", requires_grad=True))   # enable_grad() not called
 
 
-def grad_pair(S, seed, classes=(1, 10, 13)):
+def grad_pair(S, seed, classes=(1, 10, 13), precision=None):
     """Gradient of NetAttrFunc.loss (softmax area of the selected classes, src/attr_functions.py:213-219) w.r.t. the image."""
     from b200edit.bisenet import BiSeNet
     oracle = seeded_weights(OracleBiSeNet(19).eval(), seed)
     oracle.conv_out.conv_out.weight.data.mul_(0.02)   # logits of O(1): an unsaturated softmax, as a trained parser has
-    native = BiSeNet(19, S, max_batch=1)
+    native = BiSeNet(19, S, max_batch=1, precision=precision)
     native.load_reference_state_dict(oracle.state_dict())
     native.enable_grad()
     x = torch.randn(1, 3, S, S, generator=torch.Generator().manual_seed(seed + 1))
@@ -108,14 +108,37 @@ def test_bisenet_input_gradient_matches_autograd(S):
     assert rel(gn, gr) <= rel(g16, gr) + 1e-2 and cos(gn, gr) >= cos(g16, gr) - 2e-3
 
 
-def test_net_attr_func_through_the_native_parser():
-    """NetAttrFunc.apply with SegmentationModel(native parser in gradient mode): update direction on x_t vs the torch module."""
+@pytest.mark.parametrize("S", [128, 256])
+def test_bisenet_fp32_accurate_forward_gives_fp32_grade_input_gradient(S):
+    """precision="fp32" (what MultiResBiSeNet / SegmentationModel run a differentiated parser in): the forward is
+    fp32-accurate, so the backward pass routes gradients through the fp32 network's ReLU / max-pool masks.  Bar: the
+    fp32 grade the review asked for - relative RMS <= 2e-2 and cosine >= 0.999 against fp32 autograd."""
+    from b200edit.bisenet import BiSeNet
+    gn, gr, _ = grad_pair(S, seed=7, precision="fp32")
+    rel = ((gn - gr).pow(2).mean().sqrt() / gr.pow(2).mean().sqrt()).item()
+    cos = torch.nn.functional.cosine_similarity(gn.flatten(), gr.flatten(), dim=0).item()
+    oracle = seeded_weights(OracleBiSeNet(19).eval(), 3)
+    native = BiSeNet(19, S, max_batch=2, precision="fp32")
+    native.load_reference_state_dict(oracle.state_dict())
+    x = torch.randn(2, 3, S, S, generator=torch.Generator().manual_seed(4)).cuda()
+    with torch.no_grad():
+        lrel = ((native(x)[0] - oracle.cuda()(x)[0]).pow(2).mean().sqrt() / oracle(x)[0].pow(2).mean().sqrt()).item()
+    print(f"bisenet {S}x{S} [fp32-accurate forward]: logits rel-rms {lrel:.3e} | input gradient rel-rms {rel:.3e} cos {cos:.5f}")
+    assert torch.isfinite(gn).all() and gr.abs().max() > 0
+    assert lrel <= 1e-4
+    assert rel <= 2e-2 and cos >= 0.999
+
+
+@pytest.mark.parametrize("precision,rel_bar,cos_bar", [("fp16", 0.12, 0.99), ("fp32", 2e-2, 0.999)])
+def test_net_attr_func_through_the_native_parser(precision, rel_bar, cos_bar):
+    """NetAttrFunc.apply with SegmentationModel(native parser in gradient mode): update direction on x_t vs the torch module.
+    "fp32" is the mode SegmentationModel() runs a differentiated parser in (MultiResBiSeNet)."""
     from attr_functions import NetAttrFunc
     from b200edit.bisenet import BiSeNet
     from models import SegmentationModel, create_diffusion_model
     oracle = seeded_weights(OracleBiSeNet(19).eval(), 8)
     oracle.conv_out.conv_out.weight.data.mul_(0.02)   # logits of O(1): an unsaturated softmax, as a trained parser has
-    native = BiSeNet(19, 256, max_batch=1)
+    native = BiSeNet(19, 256, max_batch=1, precision=precision)
     native.load_reference_state_dict(oracle.state_dict())
     native.enable_grad()
     cfg = dict(sample_size=256, in_channels=3, out_channels=3, block_out_channels=(64, 128), layers_per_block=1,
@@ -135,8 +158,8 @@ def test_net_attr_func_through_the_native_parser():
     dn, dr = outs
     rel = ((dn - dr).pow(2).mean().sqrt() / dr.pow(2).mean().sqrt()).item()
     cos = torch.nn.functional.cosine_similarity(dn.flatten(), dr.flatten(), dim=0).item()
-    print(f"NetAttrFunc update through the native parser: rel-rms {rel:.3e} cos {cos:.5f}")
-    assert dr.abs().max() > 0 and rel <= 0.12 and cos >= 0.99      # measured 6.7e-2 / 0.998
+    print(f"NetAttrFunc update through the native parser [{precision}]: rel-rms {rel:.3e} cos {cos:.5f}")
+    assert dr.abs().max() > 0 and rel <= rel_bar and cos >= cos_bar      # measured 6.7e-2 / 0.998 (fp16)
 
 
 def test_one_default_segmentation_model_serves_mask_creation_and_net_attr_func():
