@@ -1,8 +1,11 @@
 """GPU numerics of the native face parser (BiSeNet behind SegmentationModel, src/models.py:80-118) against the oracle
 restatement (pinned bit-exactly to the unmodified reference module, tests/test_oracle_golden.py) run in fp32 with the
-same seeded weights and non-trivial eval-mode BatchNorm statistics.  Tolerance (bf16 operands, fp32 accumulation):
-logits relative RMS <= 2.5e-2 and no worse than 1.25x the oracle itself run in bf16 by torch; the parsing map (argmax)
-may differ from the fp32 one only where the top two logits are within bf16 noise: mismatch rate <= 1.25x torch-bf16's."""
+same seeded weights and non-trivial eval-mode BatchNorm statistics.  Tolerance (IEEE f16 operands, fp32 accumulation):
+logits relative RMS <= 3e-3 (measured 8e-4 .. 9e-4) and no worse than 1.25x the oracle itself run in bf16 by torch; the
+parsing map (argmax) may differ from the fp32 one only where the top two logits are within rounding noise: mismatch
+rate <= 1.25x torch-bf16's (measured 3e-4 .. 5e-4 vs 6e-3).  The differentiated parser runs the fp32-accurate forward
+(precision="fp32"): logits <= 1e-4, input gradient relative RMS <= 2e-2 / cosine >= 0.999 vs fp32 autograd (measured
+1.2e-3 .. 1.4e-3 / 1.00000); with f16 operands the gradient bar is 0.12 / 0.99 (ReLU / max-pool masks flip)."""
 import pytest
 import torch
 

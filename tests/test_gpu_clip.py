@@ -1,7 +1,7 @@
 """GPU numerics of the native CLIP text encoder (``text_encoder(ids)[0]`` of prep_text, src/diffusion_utils.py:34-52)
 against transformers' CLIPTextModel - the reference's own dependency - in fp32 (torch eager on the GPU as the checker)
-with the same random-init weights.  Tolerance (bf16 operands / residual stream, fp32 accumulation): relative RMS of the
-last hidden state <= 2.5e-2 and no worse than 1.25x transformers itself run in bf16."""
+with the same random-init weights.  Tolerance (IEEE f16 operands / residual stream, fp32 accumulation): relative RMS of
+the last hidden state <= 4e-3 (measured 0.8e-3 .. 1.3e-3) and no worse than 1.5x transformers itself run in 16 bit."""
 import pytest
 import torch
 

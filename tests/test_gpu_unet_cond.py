@@ -1,7 +1,8 @@
 """GPU numerics of the native UNet2DConditionModel (SD 1.x layout: Transformer2DModel blocks with self-attention,
 cross-attention over the text tokens and GEGLU) against the oracle restatement in fp32 with the same weights.
-Tolerance as for the other networks: relative RMS <= 2e-2, max-abs <= 3e-2 * max|eps| and no worse than 1.25x the oracle
-itself run in bf16 by torch."""
+Tolerance as for the other networks: the north star's literal bars - max-abs <= 1e-2 on eps with IEEE f16 operands
+(measured <= 1.9e-3, relative RMS <= 3e-3, no worse than 1.5x the oracle itself run in fp16 by torch), <= 1e-4 in the
+fp32-accurate mode (measured 4e-5)."""
 import pytest
 import torch
 
@@ -183,4 +184,4 @@ def test_sd_config4_small_cfg_and_classifier_guidance_through_kl_decoder():
         ref = ovae.decode(xf / 0.18215).sample
     rel = ((out.imgs.cpu() - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
     print(f"config-4 small: decoded image rel-rms vs oracle {rel:.3e}, largest guidance update {max(moved):.3e}")
-    assert rel <= 3e-2
+    assert rel <= 5e-3      # measured 8.7e-4

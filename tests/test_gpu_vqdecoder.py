@@ -1,8 +1,8 @@
 """GPU numerics of the native VQ decoder (VQModel.decode: nearest-code quantisation, post_quant_conv, decoder) against
-the oracle restatement run in fp32 with the same weights.  Tolerance (bf16 activations, fp32 accumulation; a
-random-init decoder amplifies rounding more than the UNet - the torch-bf16 run of the oracle itself is at 2.4e-2
-relative RMS on the full layout): relative RMS <= 2.5e-2, max-abs <= 3e-2 * max|img|, and no worse than 1.25x the
-oracle itself run in bf16 by torch.  The quantisation indices are integer work: bit-exact."""
+the oracle restatement run in fp32 with the same weights.  Tolerance (IEEE f16 operands, fp32 accumulation): the
+literal 1e-2 max-abs of the north star on the decoded image and relative RMS <= 5e-3 (measured 3e-3 .. 5.4e-3 /
+1.6e-3 .. 2.2e-3), no worse than 1.5x the oracle itself run in fp16 by torch; fp32-accurate mode: 1e-4.  The
+quantisation indices are integer work: bit-exact."""
 import pytest
 import torch
 
@@ -117,7 +117,7 @@ def test_ldm_factory_native_unet_and_decoder():
     idle = SingleColorAttrFunc(target=0.8, color_idx=0, loss_scale=10.0, t1=100, t2=101)   # never inside its window
     out = pipe.edit_image(xt=xt, attr_func=idle, prog_bar=False, output_type="tensor")
     assert out.imgs.shape == (2, 3, 32, 32) and torch.isfinite(out.imgs).all()
-    # decode of the same latents by the oracle (fp32): bf16 tolerance
+    # decode of the same latents by the oracle (fp32): f16-operand tolerance
     lat = xt
     from oracle import loops
     from oracle.ddim_scheduler import DDIMScheduler as OracleScheduler
@@ -128,7 +128,7 @@ def test_ldm_factory_native_unet_and_decoder():
     with torch.no_grad():
         ref = oracle.decode(xf).sample
     rel = ((out.imgs.cpu() - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
-    assert rel <= 2.5e-2, rel
+    assert rel <= 5e-3, rel      # f16 operands: measured ~1.5e-3
     f = SingleColorAttrFunc(target=0.8, color_idx=0, loss_scale=10.0, t1=0, t2=4)
     with pytest.raises(B2EError):
         pipe.edit_image(xt=xt[:1], attr_func=f, prog_bar=False, output_type="tensor")
@@ -249,7 +249,7 @@ def test_ldm_masked_guidance_through_native_decoder():
         ref = oracle.decode(xf).sample
     rel = ((out.imgs.cpu() - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
     print(f"config-3 small: decoded image rel-rms vs oracle {rel:.3e}, largest guidance update {max(updates):.3e}")
-    assert rel <= 3e-2
+    assert rel <= 5e-3      # measured 1.3e-3
 
 
 @pytest.mark.parametrize("family", ["ldm", "sd"])
@@ -352,4 +352,4 @@ def test_autoencoder_kl_decode_and_gradient():
     rel = ((img - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item()
     relg = ((gn - go).pow(2).mean().sqrt() / go.pow(2).mean().sqrt()).item()
     print(f"autoencoder-kl small: image rel-rms {rel:.3e}, gradient rel-rms {relg:.3e}")
-    assert img.shape == (2, 3, 64, 64) and rel <= 2.5e-2 and relg <= 4e-2
+    assert img.shape == (2, 3, 64, 64) and rel <= 5e-3 and relg <= 1e-2      # measured 1.9e-3 / 3.1e-3
