@@ -25,6 +25,7 @@
 
 #include <cudaTypedefs.h>
 #include <stdlib.h>
+#include <vector>
 
 namespace b2e {
 
@@ -71,7 +72,7 @@ struct ConvCfg {
   static constexpr int kStagingBytes = kSlabs * kConvBlockM * 128;
   static constexpr int kRedBytes = kSlabs > 0 ? 8192 : 0;       // GroupNorm-statistics scratch [row groups][BN][2]
   static constexpr int kSmemBytes = kRingBytes + kStagingBytes + kRedBytes + 1024 /*align*/ + 512 /*barriers*/;
-  static_assert((3 * STAGES + 4) * 8 + 8 <= 512, "barrier block");
+  static_assert((3 * STAGES + 6) * 8 + 8 <= 512, "barrier block");
 };
 
 struct ConvKParams {
@@ -82,6 +83,7 @@ struct ConvKParams {
   int b_batch_rows;         // rows of B per image (attention GEMMs), 0 for shared weights
   int debug;                // B2E_DEBUG micro-benchmark knobs: 1 = no TMA loads (MMA on stale smem), 2 = no MMAs
   int splits;               // split-K factor (>1: partial accumulators meet in split_ws, last CTA finishes the tile)
+  int split_cluster;        // 1: the splits of a tile form a thread-block cluster; partials meet in the leader's smem (DSMEM)
   float* split_ws;          // [num_tiles][splits][128][BN] fp32
   int* split_counters;      // [num_tiles], zero between launches
   int n_tiles, num_tiles;   // PAIR kernels: num_tiles counts tile PAIRS (two adjacent M tiles, same N tile)
@@ -103,7 +105,14 @@ struct ConvKParams {
 };
 // trace regions (long long indices): MMA [0, 4*512) {iter start, A ready, B ready, issued}; producer A
 // [2048, +3*256) {start, slot free, issued}; producer B [2816, +3*512); epilogue [4352, +4*64) {start, acc full, tmem released, done}
+constexpr int kConvMaxSplits = 8;   // split-K factor bound (the finishing CTA keeps one load per split in flight)
+// cluster split-K (64-wide N tiles): the leader's 192 KB ring holds the 6 other splits' 32 KB partial tiles
+constexpr int kConvMaxClusterSplits = 7;
+int conv_cluster_split_capacity(int splits);   // co-resident clusters of `splits` CTAs of the 64-wide kernel (0: cannot launch)
 constexpr int kTrMma = 0, kTrPa = 2048, kTrPb = 2816, kTrEpi = 4352, kTrTotal = 4608;
+// per-CTA wall clock (%globaltimer, ns): [kTrCta + 4 b + {0 entry, 1 after the prologue / grid dependency, 2 exit, 3 last split}]
+constexpr int kTrCta = kTrTotal, kTrCtaMax = 160, kTrAll = kTrTotal + 8 * kTrCtaMax;
+__device__ __forceinline__ long long global_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
 // ------------------------------------------------------------------ the kernel
 // Persistent: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The accumulator is
@@ -157,7 +166,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   // XF: the A tile of a stage completes on THIS CTA's araw_bar (raw activations landed); the transform warps then
   // rewrite it and arrive on the (leader's) full_bar, which also collects the B tile's TMA bytes as before
   uint64_t* araw_bar = tmem_empty_bar + 2;              // [STAGES]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(araw_bar + Cfg::kStages);
+  // cluster split-K: part_bar (leader) collects the other splits' partial tiles, go_bar (others) = "the leader's ring is free"
+  uint64_t* part_bar = araw_bar + Cfg::kStages;
+  uint64_t* go_bar = part_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(go_bar + 1);
   volatile uint32_t* split_flag = tmem_slot + 1;
 
   // warp index / cluster rank through shfl so that the compiler can prove them warp-uniform: the role branches
@@ -165,6 +177,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   // uniform registers (otherwise every UTMALDG is preceded by ELECT + up to nine R2UR.BROADCAST, ~180 clk per TMA)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[kTrTotal - 1] = clock64();   // kernel entry
+  if (p.trace && blockIdx.x < kTrCtaMax && threadIdx.x == 0) p.trace[kTrCta + 8 * blockIdx.x] = global_ns();
   const int rank = PAIR ? __shfl_sync(0xffffffffu, (int)cluster_ctarank(), 0) : 0;      // 0 = leader CTA of the SM pair
   const int tile_begin = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -175,6 +188,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   // work item = (tile, K split); consecutive CTAs take the splits of one tile
   const int splits = PAIR ? 1 : p.splits;
   const int num_work = p.num_tiles * splits;
+  // cluster split-K (host: grid == num_work, cluster = the `splits` consecutive CTAs of one tile, split == cluster rank)
+  const bool cl_split = !PAIR && !HALO && p.split_cluster != 0;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_a0);
@@ -190,6 +205,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     }
     // pair: the leader's tmem_empty barrier collects the 4 epilogue warps of BOTH CTAs
     for (int s = 0; s < 2; ++s) { mbar_init(tmem_full_bar + s, 1); mbar_init(tmem_empty_bar + s, PAIR ? 8 : 4); }
+    mbar_init(part_bar, 1);
+    mbar_init(go_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -197,13 +214,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   }
   tc_fence_before();
   __syncthreads();
-  if (PAIR) cluster_sync_all();   // peer barriers are initialised before any remote arrive / TMA completion
+  if (PAIR || cl_split) cluster_sync_all();   // peer barriers are initialised before any remote arrive / TMA completion
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // everything above touched only parameters and shared / tensor memory: from here on the previous kernel's
   // outputs are read (activations through TMA, time embedding in the epilogue)
   pdl_wait();
   pdl_trigger();
+  if (p.trace && blockIdx.x < kTrCtaMax && threadIdx.x == 0) p.trace[kTrCta + 8 * blockIdx.x + 1] = global_ns();
 
   if (warp == 0) {
     // ===== TMA producer (whole warp walks the loop; one elected lane issues)
@@ -453,7 +471,44 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         if (tr) p.trace[kTrEpi + it * 4 + 2] = clock64();
       };
       const float* part_row = nullptr;
-      if (splits > 1) {
+      const float* part_smem = nullptr;
+      if (splits > 1 && cl_split) {
+        // cluster split-K: the splits of this tile are the CTAs of one cluster.  Every other split parks its raw fp32
+        // accumulator in its OWN (drained) smem ring as [16-col chunk][float4 j][row][4] and, once the leader's ring is
+        // free too, bulk-copies it into the leader's ring (DSMEM, completes on the leader's part_bar); the leader sums
+        // own accumulator + partials in split order and runs the normal epilogue.  No global workspace, fence or atomics.
+        constexpr uint32_t kPartBytes = kConvBlockM * BN * sizeof(float);
+        if (split != 0) {
+          float* mine = reinterpret_cast<float*>(smem);
+#pragma unroll 1
+          for (int c = 0; c < BN / 16; ++c) {
+            float v[16];
+            tmem_ld16(taddr + c * 16, v);
+            if (c == BN / 16 - 1) release_tmem();
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<float4*>(mine + ((c * 4 + j) * kConvBlockM + r) * 4) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          fence_async_smem();
+          epi_bar_sync();
+          if (store_leader) {
+            mbar_wait_cluster(go_bar, 0);
+            bulk_copy_to_cluster(mapa_shared(smem_u32(smem) + (uint32_t)(split - 1) * kPartBytes, 0), smem_u32(smem), kPartBytes,
+                                 mapa_shared(smem_u32(part_bar), 0));
+          }
+          continue;
+        }
+        if (warp == 2) {
+          // this CTA's MMAs have retired (tmem_full): its ring is free.  One lane per other split signals it (in parallel:
+          // a serial loop of release-arrives costs ~0.17 us per split)
+          if (lane == 0) mbar_expect_tx(part_bar, (uint32_t)(splits - 1) * kPartBytes);
+          __syncwarp();
+          if (lane >= 1 && lane < splits) mbar_arrive_remote_release(mapa_shared(smem_u32(go_bar), (uint32_t)lane));
+        }
+        mbar_wait_cluster(part_bar, 0);
+        part_smem = reinterpret_cast<const float*>(smem);
+        if (p.trace && blockIdx.x < kTrCtaMax && store_leader) p.trace[kTrCta + 8 * blockIdx.x + 3] = global_ns();
+      } else if (splits > 1) {
         // split-K: park the raw fp32 partial tile; the CTA that arrives last sums all partials (fixed order) and
         // runs the normal epilogue - no extra kernel, deterministic result
         // layout [tile][split][16-col chunk][row][16]: a warp's 32 rows write / read 2 KB contiguous
@@ -479,6 +534,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         epi_bar_sync();
         if (!*split_flag) continue;
         __threadfence();
+        if (p.trace && blockIdx.x < kTrCtaMax && store_leader) p.trace[kTrCta + 8 * blockIdx.x + 3] = global_ns();
         part_row = p.split_ws + (int64_t)tile * splits * (kConvBlockM * BN) + r * 16;
       }
       // split-f16 output (fp32-accurate mode): the accumulator is walked twice - pass 0 stages f16(v) (planes 0 and
@@ -528,6 +584,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+            if (part_smem) {
+              // cluster split-K leader: own accumulator (split 0) + the other splits' partial tiles, in split order
+              for (int sp = 1; sp < splits; ++sp) {
+                const float* pp = part_smem + (int64_t)(sp - 1) * (kConvBlockM * BN) + (c2 * 8 * kConvBlockM + r) * 4;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 b = *reinterpret_cast<const float4*>(pp + j * kConvBlockM * 4);
+                  v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+                }
+              }
+            }
             if (p.acc_scale != 1.f) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] *= p.acc_scale;
@@ -570,14 +637,34 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       for (int c = 0; c < (fast_done ? 0 : BN / 16); ++c) {
         float v[16];
         if (part_row) {
+          // sum of the partial tiles in split order (deterministic).  The loads of ALL splits of an 8-column half are
+          // issued before the first add - unconditionally, from a clamped split index, so that no branch keeps the
+          // compiler from hoisting them: one L2 round trip per half.  (A per-split loop, and also predicated loads,
+          // compile to one dependent round trip per split: 64 per tile, 12 of the 18 us of a low-resolution launch.)
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = 0.f;
-          for (int sp = 0; sp < splits; ++sp) {
-            const float4* pp = reinterpret_cast<const float4*>(part_row + (int64_t)sp * (kConvBlockM * BN) + c * (kConvBlockM * 16));
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 b = __ldcg(pp + j);
-              v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+          for (int hh = 0; hh < 2; ++hh) {
+            float4 b[kConvMaxSplits][2];
+#pragma unroll
+            for (int sp = 0; sp < kConvMaxSplits; ++sp) {
+              const int spc = sp < splits ? sp : 0;
+              const float4* pp = reinterpret_cast<const float4*>(part_row + (int64_t)spc * (kConvBlockM * BN) + c * (kConvBlockM * 16)) + 2 * hh;
+              if (p.debug & 16) { b[sp][0] = b[sp][1] = make_float4(0.f, 0.f, 0.f, 0.f); }
+              else if (p.debug & 32) { b[sp][0] = *pp; b[sp][1] = *(pp + 1); }
+              else { b[sp][0] = __ldcg(pp); b[sp][1] = __ldcg(pp + 1); }
+            }
+#pragma unroll
+            for (int sp = 0; sp < kConvMaxSplits; ++sp) {
+              const bool on = sp < splits;
+              v[8 * hh] = on ? v[8 * hh] + b[sp][0].x : v[8 * hh];
+              v[8 * hh + 1] = on ? v[8 * hh + 1] + b[sp][0].y : v[8 * hh + 1];
+              v[8 * hh + 2] = on ? v[8 * hh + 2] + b[sp][0].z : v[8 * hh + 2];
+              v[8 * hh + 3] = on ? v[8 * hh + 3] + b[sp][0].w : v[8 * hh + 3];
+              v[8 * hh + 4] = on ? v[8 * hh + 4] + b[sp][1].x : v[8 * hh + 4];
+              v[8 * hh + 5] = on ? v[8 * hh + 5] + b[sp][1].y : v[8 * hh + 5];
+              v[8 * hh + 6] = on ? v[8 * hh + 6] + b[sp][1].z : v[8 * hh + 6];
+              v[8 * hh + 7] = on ? v[8 * hh + 7] + b[sp][1].w : v[8 * hh + 7];
             }
           }
         } else {
@@ -649,6 +736,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             }
         }
       }
+      if (p.trace && blockIdx.x < kTrCtaMax && store_leader && (part_row || part_smem)) p.trace[kTrCta + 8 * blockIdx.x + 4] = global_ns();
       if (Cfg::kSlabs > 0 && p.out_f16) {
         fence_async_smem();   // generic-proxy smem writes -> visible to the TMA (async proxy)
         epi_bar_sync();
@@ -661,6 +749,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
               tma_store_5d(&map_out, staging + sl * (kConvBlockM * 128), ch + 2 * p.split_pitch, tc.w0, 0, tc.h0, tc.n0);
           }
           tma_store_commit();
+          if (p.trace && blockIdx.x < kTrCtaMax && (part_row || part_smem)) p.trace[kTrCta + 8 * blockIdx.x + 5] = global_ns();
         }
         if (p.tile_stats) {
           // GroupNorm statistics of the f16 tile just staged: per-channel sum / sum of squares over the
@@ -707,6 +796,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       if (tr) p.trace[kTrEpi + it * 4 + 3] = clock64();
     }
     if (store_leader) tma_store_wait_all();
+    if (p.trace && blockIdx.x < kTrCtaMax && store_leader) p.trace[kTrCta + 8 * blockIdx.x + 6] = global_ns();
     tc_fence_before();
   } else {
     // ===== transform warps (XF): fused GroupNorm(+SiLU) of the A operand.  Per stage: wait for this CTA's raw tile
@@ -810,11 +900,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   }
   __syncthreads();
   if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[kTrTotal - 2] = clock64();   // all roles done
-  if (PAIR) cluster_sync_all();   // no CTA leaves while its peer may still signal its barriers / read its smem
+  if (PAIR || cl_split) cluster_sync_all();   // no CTA leaves while its peer may still signal its barriers / read its smem
   if (warp == 1) {
     tc_fence_after();
     if (PAIR) tmem_dealloc_2sm<Cfg::kTmemCols>(tmem_base); else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
+  if (p.trace && blockIdx.x < kTrCtaMax && threadIdx.x == 0) p.trace[kTrCta + 8 * blockIdx.x + 2] = global_ns();
 }
 
 // ------------------------------------------------------------------ weight packing
@@ -970,7 +1061,8 @@ ConvGeom conv_geometry(int N, int Ho, int Wo, int Cout, int ksize, int stride) {
   // on the halo kernel, whose 3x lower L2 traffic per FLOP beats the extra CTAs
   const bool halo_shape = ksize == 3 && stride == 1 && Wo % kHaloWt == 0 && Ho % kHaloHt == 0 && cout_pad % 128 == 0 &&
                           (int64_t)N * Ho * Wo / kConvBlockM * (cout_pad / 128) >= halo_min_tiles();
-  if (g.block_n == 128 && !halo_shape && g.w_blks * g.h_blks * g.n_blks * (cout_pad / 128) < kNumSMs / 2) g.block_n = 64;
+  static const int bn64_below = getenv("B2E_BN64_BELOW") ? atoi(getenv("B2E_BN64_BELOW")) : kNumSMs / 2;   // experiments
+  if (g.block_n == 128 && !halo_shape && g.w_blks * g.h_blks * g.n_blks * (cout_pad / 128) < bn64_below) g.block_n = 64;
   // statistics are reduced over groups of block_n/8 rows, which must not straddle images
   g.stats_ok = g.block_n >= 64 && Cout % 64 == 0 && (g.Wt * g.Ht) % (g.block_n / 8) == 0;
   return g;
@@ -1083,15 +1175,31 @@ int conv_plan_build(ConvPlan* pl, const ConvDesc& d) {
   // SM-pair mode: 128-wide N tiles, an even number of M tiles and enough tiles to keep every SM pair busy
   const int m_tiles = p.w_blks * p.h_blks * p.n_blks, tiles = m_tiles * (p.cout_pad / p.block_n);
   p.pair = (p.halo || (p.block_n == 128 && m_tiles % 2 == 0 && !d.b_batch_rows)) ? 1 : 0;
-  // split-K when the tiles alone cannot fill the chip: up to 8 splits of at least 8 k-blocks each
+  // split-K when the tiles alone cannot fill the chip.  64-wide N tiles: the splits of a tile form a thread-block
+  // cluster (up to 7 CTAs, at least 8 k-blocks each, all clusters co-resident) and exchange their partial accumulators
+  // through distributed shared memory; other shapes: up to 8 splits of at least 8 k-blocks each through a global
+  // fp32 workspace, finished by the CTA that arrives last.
   const int num_kb = (int)(ktot / K);
   p.splits = 1;
+  p.split_cluster = 0;
+  static const bool cluster_on = !(getenv("B2E_SPLIT_CLUSTER") && atoi(getenv("B2E_SPLIT_CLUSTER")) == 0);
   // (measured on B200 at batch 8: 28 -> 23 us on the 8x8 layers, +1 % on the whole step; B2E_SPLITK=0 disables)
   static const bool splitk_on = !(getenv("B2E_SPLITK") && atoi(getenv("B2E_SPLITK")) == 0);
-  if (splitk_on && !p.pair && d.split_ws && d.out_f16 && tiles * 2 <= kNumSMs) {
+  if (splitk_on && cluster_on && !p.pair && p.block_n == 64 && d.out_f16 && tiles * 2 <= kNumSMs) {
     int sp = kNumSMs / tiles;
     if (sp > num_kb / 8) sp = num_kb / 8;
-    if (sp > 8) sp = 8;
+    if (sp > kConvMaxClusterSplits) sp = kConvMaxClusterSplits;
+    static const int sp_max = getenv("B2E_SPLITK_MAX") ? atoi(getenv("B2E_SPLITK_MAX")) : kConvMaxClusterSplits;   // experiments
+    if (sp > sp_max) sp = sp_max;
+    while (sp >= 2 && conv_cluster_split_capacity(sp) < tiles) --sp;   // every cluster resident at once
+    if (sp >= 2) { p.splits = sp; p.split_cluster = 1; }
+  }
+  if (p.splits == 1 && splitk_on && !p.pair && d.split_ws && d.out_f16 && tiles * 2 <= kNumSMs) {
+    int sp = kNumSMs / tiles;
+    if (sp > num_kb / 8) sp = num_kb / 8;
+    static const int sp_max = getenv("B2E_SPLITK_MAX") ? atoi(getenv("B2E_SPLITK_MAX")) : kConvMaxSplits;   // experiments
+    if (sp > kConvMaxSplits) sp = kConvMaxSplits;
+    if (sp > sp_max) sp = sp_max;
     if (sp >= 2 && (size_t)tiles * sp * kConvBlockM * p.block_n * sizeof(float) <= d.split_ws_bytes) p.splits = sp;
   }
   p.split_ws = d.split_ws; p.split_counters = d.split_counters;
@@ -1117,12 +1225,18 @@ static int launch_x(const ConvPlan& pl, const ConvKParams& kp, int tiles, cudaSt
   const int units = PAIR ? kNumSMs / 2 : kNumSMs;   // work items (tiles x splits, or tile pairs) in flight
   const int work = tiles * (PAIR ? 1 : kp.splits);
   cfg.gridDim = dim3((unsigned)((work < units ? work : units) * (PAIR ? 2 : 1)));
+  if (!PAIR && kp.split_cluster) {
+    // one work item per CTA, cluster = the splits of one tile (the plan guarantees work <= SMs and smem for the partials)
+    B2E_REQUIRE(!HALO && work <= units && (size_t)(kp.splits - 1) * kConvBlockM * BN * sizeof(float) <= (size_t)Cfg::kRingBytes,
+                B2E_INVALID_ARG, "conv: cluster split-K plan does not fit the kernel variant");
+    cfg.gridDim = dim3((unsigned)work);
+  }
   cfg.blockDim = dim3(XF ? kConvThreadsXf : kConvThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = PAIR ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[0].val.clusterDim.x = PAIR ? 2 : (kp.split_cluster ? kp.splits : 1); attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
@@ -1137,6 +1251,30 @@ template <int BN, int STAGES, bool PAIR, bool HALO = false, int MT = 1, int KPS 
 static int launch_t(const ConvPlan& pl, const ConvKParams& kp, int tiles, cudaStream_t st) {
   return kp.gn_coef ? launch_x<BN, STAGES, PAIR, HALO, MT, KPS, true>(pl, kp, tiles, st)
                     : launch_x<BN, STAGES, PAIR, HALO, MT, KPS, false>(pl, kp, tiles, st);
+}
+
+int conv_cluster_split_capacity(int splits) {
+  static int cache[kConvMaxClusterSplits + 1] = {};
+  if (splits < 2 || splits > kConvMaxClusterSplits) return 0;
+  if (cache[splits]) return cache[splits] < 0 ? 0 : cache[splits];
+  using Cfg = ConvCfg<64, 4, false, false, 1, 2>;
+  auto kern = conv_igemm_kernel<64, 4, false, false, 1, 2, false>;
+  int n = 0;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) == cudaSuccess) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(splits * (kNumSMs / splits)));
+    cfg.blockDim = dim3(kConvThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = splits; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { n = 0; cudaGetLastError(); }
+  } else {
+    cudaGetLastError();
+  }
+  cache[splits] = n > 0 ? n : -1;
+  return n > 0 ? n : 0;
 }
 
 int conv_launch(const ConvPlan& pl, const ConvEpilogue& ep, cudaStream_t st) {
@@ -1155,6 +1293,7 @@ int conv_launch(const ConvPlan& pl, const ConvEpilogue& ep, cudaStream_t st) {
   static const int dbg = getenv("B2E_DEBUG") ? atoi(getenv("B2E_DEBUG")) : 0;
   kp.debug = dbg;
   kp.splits = pl.splits; kp.split_ws = pl.split_ws; kp.split_counters = pl.split_counters;
+  kp.split_cluster = pl.split_cluster;
   kp.bias = ep.bias; kp.bias2 = ep.bias2; kp.temb = ep.temb; kp.temb_stride = ep.temb_stride;
   kp.out_f16 = pl.has_out_f16; kp.out_f32_nchw = pl.has_out_f16 ? nullptr : ep.out_f32_nchw;
   kp.tile_stats = pl.tile_stats;
@@ -1170,8 +1309,8 @@ int conv_launch(const ConvPlan& pl, const ConvEpilogue& ep, cudaStream_t st) {
   static long long* trace_buf = nullptr;
   const bool do_trace = trace_at > 0 && ++halo_launches == trace_at;
   if (do_trace) {
-    if (!trace_buf) B2E_CUDA(cudaMalloc(&trace_buf, kTrTotal * sizeof(long long)));
-    B2E_CUDA(cudaMemsetAsync(trace_buf, 0, kTrTotal * sizeof(long long), st));
+    if (!trace_buf) B2E_CUDA(cudaMalloc(&trace_buf, kTrAll * sizeof(long long)));
+    B2E_CUDA(cudaMemsetAsync(trace_buf, 0, kTrAll * sizeof(long long), st));
     kp.trace = trace_buf;
   }
   struct TraceDump {
@@ -1179,12 +1318,20 @@ int conv_launch(const ConvPlan& pl, const ConvEpilogue& ep, cudaStream_t st) {
     ~TraceDump() {
       if (!on) return;
       cudaStreamSynchronize(st);
-      static long long h[kTrTotal];
+      static long long h[kTrAll];
       cudaMemcpy(h, buf, sizeof(h), cudaMemcpyDeviceToHost);
       fprintf(stderr, "TRACE conv %dx%d taps %d chunks %d+%d res %d+%d pair %d\n", pl.Ho, pl.Wo, pl.taps, pl.c0_chunks,
               pl.c1_chunks, pl.r0_chunks, pl.r1_chunks, pl.pair);
       const long long t0 = h[kTrTotal - 1];
       fprintf(stderr, "KERNEL entry 0 roles_done %lld\n", h[kTrTotal - 2] - t0);
+      long long g0 = 0;
+      for (int b = 0; b < kTrCtaMax; ++b) if (h[kTrCta + 8 * b] && (!g0 || h[kTrCta + 8 * b] < g0)) g0 = h[kTrCta + 8 * b];
+      for (int b = 0; b < kTrCtaMax && h[kTrCta + 8 * b]; ++b)
+        fprintf(stderr, "CTA %d entry %lld ns, dependency resolved %lld, exit %lld, last-split reduce began %lld, chunks done %lld, store issued %lld, "
+                "epilogue loop left %lld\n", b, h[kTrCta + 8 * b] - g0,
+                h[kTrCta + 8 * b + 1] - g0, h[kTrCta + 8 * b + 2] - g0, h[kTrCta + 8 * b + 3] ? h[kTrCta + 8 * b + 3] - g0 : -1,
+                h[kTrCta + 8 * b + 4] ? h[kTrCta + 8 * b + 4] - g0 : -1, h[kTrCta + 8 * b + 5] ? h[kTrCta + 8 * b + 5] - g0 : -1,
+                h[kTrCta + 8 * b + 6] ? h[kTrCta + 8 * b + 6] - g0 : -1);
       for (int i = 0; i < 512 && h[kTrMma + i * 4 + 3]; ++i)
         fprintf(stderr, "MMA %d start %lld a_ready %lld b_ready %lld issued %lld\n", i, h[kTrMma + i * 4] - t0,
                 h[kTrMma + i * 4 + 1] - t0, h[kTrMma + i * 4 + 2] - t0, h[kTrMma + i * 4 + 3] - t0);
@@ -1266,5 +1413,61 @@ extern "C" int b2e_conv2d_nhwc_f16(const void* x, const float* w, const float* b
   cudaStreamSynchronize(st);
   cudaFree(wp);
   cudaFree(split_mem);
+  return rc;
+}
+
+// Measurement hook: one convolution plan per weight copy (`copies` packed weight sets, so that consecutive launches
+// miss the L2 like the layers of a network do), `iters` launches back to back on `stream`, CUDA-event time per launch.
+// Inputs / weights are whatever the allocations hold (zero-filled): the kernel's timing does not depend on the values.
+extern "C" int b2e_conv2d_bench_f16(int64_t N, int64_t H, int64_t W, int64_t Cin, int64_t Cout, int ksize, int stride,
+                                     int iters, int copies, float* us_per_launch, void* stream) {
+  B2E_REQUIRE(us_per_launch && iters > 0 && copies > 0 && copies <= 256, B2E_INVALID_ARG, "conv2d_bench: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int cout_pad = conv_cout_pad((int)Cout);
+  const int row_len = (int)(ksize * ksize * Cin);
+  const size_t wbytes = ((size_t)cout_pad * row_len * sizeof(f16) + 1023) / 1024 * 1024;
+  const size_t xbytes = (size_t)N * H * W * Cin * sizeof(f16);
+  const size_t obytes = (size_t)N * (H / stride) * (W / stride) * cout_pad * sizeof(f16);
+  const size_t split_bytes = (size_t)kNumSMs * kConvBlockM * 128 * sizeof(float);
+  char *wp = nullptr, *xp = nullptr, *op = nullptr, *split_mem = nullptr;
+  float* bias = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  int rc = B2E_OK;
+  do {
+    if (cudaMalloc(&wp, wbytes * copies) != cudaSuccess || cudaMalloc(&xp, xbytes) != cudaSuccess ||
+        cudaMalloc(&op, obytes) != cudaSuccess || cudaMalloc(&split_mem, split_bytes + 4096) != cudaSuccess ||
+        cudaMalloc(&bias, sizeof(float) * cout_pad) != cudaSuccess) {
+      set_error("conv2d_bench: cudaMalloc failed"); rc = B2E_CUDA_ERROR; break;
+    }
+    cudaMemsetAsync(wp, 0, wbytes * copies, st);
+    cudaMemsetAsync(xp, 0, xbytes, st);
+    cudaMemsetAsync(bias, 0, sizeof(float) * cout_pad, st);
+    cudaMemsetAsync(split_mem + split_bytes, 0, 4096, st);
+    std::vector<ConvPlan> plans(copies);
+    for (int i = 0; i < copies && !rc; ++i) {
+      ConvDesc d;
+      d.s0 = ConvSrc{(const f16*)xp, (int)Cin};
+      d.N = (int)N; d.H = (int)H; d.W = (int)W; d.ksize = ksize; d.stride = stride;
+      d.w_packed = (const f16*)(wp + wbytes * i); d.Cout = cout_pad; d.out_f16 = (f16*)op;
+      d.split_ws = (float*)split_mem; d.split_ws_bytes = split_bytes; d.split_counters = (int*)(split_mem + split_bytes);
+      rc = conv_plan_build(&plans[i], d);
+    }
+    if (rc) break;
+    ConvEpilogue ep;
+    ep.bias = bias;
+    for (int i = 0; i < copies && !rc; ++i) rc = conv_launch(plans[i], ep, st);   // warm-up
+    if (rc) break;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+    for (int i = 0; i < iters && !rc; ++i) rc = conv_launch(plans[i % copies], ep, st);
+    cudaEventRecord(e1, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("conv2d_bench: %s", cudaGetErrorString(cudaGetLastError())); rc = B2E_CUDA_ERROR; break; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    *us_per_launch = ms * 1000.f / iters;
+  } while (0);
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  cudaFree(wp); cudaFree(xp); cudaFree(op); cudaFree(split_mem); cudaFree(bias);
   return rc;
 }

@@ -68,6 +68,7 @@ struct ConvPlan {
   int block_n;  // 16, 64 or 128
   int b_batch_rows;
   int splits; float* split_ws; int* split_counters;
+  int split_cluster;   // 1: the splits of a tile run as one thread-block cluster and meet in the leader's smem (DSMEM)
   int halo;     // 0, or MT = M tiles per CTA of the halo kernel: (8*MT)x16-pixel bricks, one halo load serves 3 vertical taps
   int pair;     // 1: SM-pair kernel (tcgen05.mma.cta_group::2, 256 x 128 tile per cluster)
   int has_out_f16;

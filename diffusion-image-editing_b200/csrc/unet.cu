@@ -1247,7 +1247,7 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
     char desc[160];
     snprintf(desc, sizeof(desc), "conv%dx%d s%d %dx%d cin%d+%d res%d cout%d tiles%d bn%d%s", L.k, L.k, stride, x0.H, x0.W,
              x0.C, x1 ? x1->C : 0, L.res_c, L.cout, pl.w_blks * pl.h_blks * pl.n_blks * (pl.cout_pad / pl.block_n), pl.block_n,
-             pl.halo == 2 ? " halo2" : pl.halo ? " halo1" : pl.pair ? " pair" : (pl.splits > 1 ? (" splitK" + std::to_string(pl.splits)).c_str() : ""));
+             pl.halo == 2 ? " halo2" : pl.halo ? " halo1" : pl.pair ? " pair" : (pl.splits > 1 ? ((pl.split_cluster ? " clusterK" : " splitK") + std::to_string(pl.splits)).c_str() : ""));
     if (x0.alias) snprintf(desc + strlen(desc), sizeof(desc) - strlen(desc), " +gn%s", x0.gn_silu ? "+silu" : "");
     // profile record: ALGORITHMIC FLOPs.  An identity residual segment (W_r = I: the plain residual add riding along as
     // K chunks) is executed on the tensor cores but is not arithmetic of the algorithm - it is counted as the bytes of the

@@ -74,8 +74,7 @@ __global__ void __launch_bounds__(512) gn_partial_kernel(GNArgs a) {
 }
 
 template <bool SPLIT>
-__global__ void __launch_bounds__(512) gn_apply_kernel(GNArgs a, int pix_per_block) {
-  pdl_wait();
+__global__ void __launch_bounds__(512, SPLIT ? 1 : 2) gn_apply_kernel(GNArgs a, int pix_per_block) {
   __shared__ float s_mean[64], s_rstd[64];
   extern __shared__ double s_ch[];          // [C][2]: per-channel (sum, sum of squares) of image n (fused-statistics paths)
   const int C = a.C0 + a.C1, slots = a.Pout >> 3, ppi = (int)blockDim.x / slots;
@@ -85,6 +84,36 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(GNArgs a, int pix_per_blo
   const int n = a.reverse ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y, tid = threadIdx.x;
   const int bx = a.reverse ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
   const int cpg = C / a.G;
+  // role of this thread in the apply pass: 8 channels [c, c + 8) of every ppi-th pixel of the block's pixel range
+  const int s = tid % slots, pl = tid / slots, c = s * 8;
+  const int p0 = bx * pix_per_block, p1 = min(a.HW, p0 + pix_per_block);
+  const bool streams = pl < ppi && c < C;
+  const f16* src = nullptr; int cs = 0, lo_off = 0;
+  if (streams) {
+    int coff;
+    if (c < a.C0) { src = a.x0; cs = a.P0; coff = c; } else { src = a.x1; cs = a.P1; coff = c - a.C0; }
+    lo_off = cs;
+    cs *= a.planes;
+    src += (int64_t)n * a.HW * cs + coff;
+  }
+  // the affine parameters are weights (not written by the preceding kernel): fetch them before the grid dependency
+  float scale[8], shift[8];
+  if (streams) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { scale[j] = __ldg(a.gamma + c + j); shift[j] = __ldg(a.beta + c + j); }
+  }
+  pdl_wait();
+  // first sweep of the streaming pass: in flight while the statistics prologue below runs (plain tensors)
+  uint4 v[kGNUnroll];
+  if constexpr (!SPLIT) {
+    if (streams) {
+#pragma unroll
+      for (int u = 0; u < kGNUnroll; ++u) {
+        const int q = p0 + pl + u * ppi;
+        if (q < p1) v[u] = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)q * cs));
+      }
+    }
+  }
   if (a.ts0 || a.cs0) {
     // statistics from the producing convolutions' epilogues (concat-aware): ALL threads gather the per-channel sums of
     // image n with independent loads in flight (one thread per group walking its channels serially exposed ~16-64
@@ -131,10 +160,7 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(GNArgs a, int pix_per_blo
       *reinterpret_cast<float2*>(a.save_stats + ((int64_t)n * a.G + tid) * 2) = make_float2(s_mean[tid], s_rstd[tid]);
   }
   __syncthreads();
-  const int s = tid % slots, pl = tid / slots;
   if (pl >= ppi) return;
-  const int c = s * 8;
-  const int p0 = bx * pix_per_block, p1 = min(a.HW, p0 + pix_per_block);
   constexpr bool split = SPLIT;           // split-f16 tensors (fp32-accurate mode): planes [hi | lo | hi]
   const int po = a.Pout * a.planes;       // output pixel pitch
   f16* dst = a.out + (int64_t)n * a.HW * po + c;
@@ -143,18 +169,12 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(GNArgs a, int pix_per_blo
       for (int k = 0; k < a.planes; ++k) *reinterpret_cast<uint4*>(dst + (int64_t)p * po + k * a.Pout) = make_uint4(0, 0, 0, 0);
     return;
   }
-  float scale[8], shift[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int g = (c + j) / cpg;
-    scale[j] = s_rstd[g] * __ldg(a.gamma + c + j);
-    shift[j] = __ldg(a.beta + c + j) - s_mean[g] * scale[j];
+    scale[j] = s_rstd[g] * scale[j];
+    shift[j] = shift[j] - s_mean[g] * scale[j];
   }
-  const f16* src; int cs, coff;
-  if (c < a.C0) { src = a.x0; cs = a.P0; coff = c; } else { src = a.x1; cs = a.P1; coff = c - a.C0; }
-  const int lo_off = cs;
-  cs *= a.planes;
-  src += (int64_t)n * a.HW * cs + coff;
   if constexpr (split) {
     // accurate path: x = hi + lo, exact-exp SiLU, output re-split into hi / lo (third plane repeats hi)
     for (int p = p0 + pl; p < p1; p += ppi * kGNUnroll) {
@@ -191,18 +211,22 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(GNArgs a, int pix_per_blo
     }
     return;
   }
+  // double-buffered sweeps: the loads of sweep i + 1 are issued before sweep i is transformed and stored
   for (int p = p0 + pl; p < p1; p += ppi * kGNUnroll) {
-    uint4 v[kGNUnroll];
+    uint4 w[kGNUnroll];
+    const int pn = p + ppi * kGNUnroll;
 #pragma unroll
     for (int u = 0; u < kGNUnroll; ++u) {
-      const int q = p + u * ppi;
-      if (q < p1) v[u] = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)q * cs));
+      const int q = pn + u * ppi;
+      if (q < p1) w[u] = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)q * cs));
     }
 #pragma unroll
     for (int u = 0; u < kGNUnroll; ++u) {
       const int q = p + u * ppi;
       if (q < p1) *reinterpret_cast<uint4*>(dst + (int64_t)q * a.Pout) = gn_apply8(v[u], scale, shift, a.silu != 0);
     }
+#pragma unroll
+    for (int u = 0; u < kGNUnroll; ++u) v[u] = w[u];
   }
 }
 

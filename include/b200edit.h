@@ -394,6 +394,12 @@ int b2e_conv2d_nhwc_f16(const void* x, const float* w, const float* bias, const 
                          void* out, int64_t N, int64_t H, int64_t W, int64_t Cin, int64_t Cout,
                          int ksize, int stride, void* stream);
 
+/* Measurement hook for the same kernel: `iters` back-to-back launches of one convolution (zero-filled operands of the
+ * given shape, `copies` distinct packed weight sets used round-robin so that launches miss the L2 like the layers of a
+ * network), CUDA-event time per launch in microseconds.  Allocates temporaries itself and synchronises. */
+int b2e_conv2d_bench_f16(int64_t N, int64_t H, int64_t W, int64_t Cin, int64_t Cout, int ksize, int stride,
+                          int iters, int copies, float* us_per_launch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,6 +16,11 @@ tot = {}
 for p in prof:
     tot[p["kind"]] = tot.get(p["kind"], 0) + p["ms"]
 print("GN_FUSE", os.environ.get("B2E_GN_FUSE", "1"), "total ms", sum(tot.values()), tot)
+if os.environ.get("B2E_PROFILE_ALL"):      # every op, not only the GEMM launches
+    for i, p in enumerate(prof):
+        gbs = p.get("bytes", 0) / p["ms"] / 1e6 if p["ms"] > 0 else 0
+        print(f"{i:3d} {p['ms'] * 1e3:7.1f}us {p['kind']:10s} {p['flops'] / p['ms'] / 1e9:7.0f}TF {gbs:7.0f}GB/s {p['desc']}")
+    sys.exit(0)
 for i, p in enumerate(prof):
     if p["kind"] == "conv_igemm":
         print(f"{i:3d} {p['ms'] * 1e3:7.1f}us {p['flops'] / p['ms'] / 1e9:7.0f}TF {p['desc']}")

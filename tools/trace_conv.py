@@ -7,7 +7,7 @@ import torch
 from b200edit import ops
 N, H, cin, cout = (int(v) for v in sys.argv[1:5])
 k = int(sys.argv[5]) if len(sys.argv) > 5 else 3
-x = torch.randn(N, H, H, cin, device="cuda").bfloat16()
+x = torch.randn(N, H, H, cin, device="cuda").to(ops.act_dtype())
 w = torch.randn(cout, cin, k, k, device="cuda") / (cin * k * k) ** 0.5
 b = torch.randn(cout, device="cuda")
 for _ in range(4):
