@@ -29,7 +29,11 @@
 
 namespace b2e {
 
-constexpr int kConvThreads = 192;       // TMA producer warp + MMA warp + 4 epilogue warps
+// TMA producer warp (non-halo kernels: the A operand) + MMA warp + 4 epilogue warps + B-operand TMA producer warp
+// (non-halo kernels; the single producer warp needed ~620 clk of address arithmetic and issue per 2-k-block stage and
+// was the critical path of the 64-wide low-resolution layers)
+constexpr int kConvThreads = 224;
+constexpr int kConvBWarp = 6;
 constexpr int kXfWarps = 8;             // + 8 transform warps in the fused-GroupNorm variants (XF)
 constexpr int kConvThreadsXf = kConvThreads + 32 * kXfWarps;
 constexpr int kABytes = kConvBlockM * kConvBlockK * 2;  // 16 KB
@@ -199,7 +203,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     prefetch_tmap(&map_b);
     if (p.out_f16) prefetch_tmap(&map_out);
     for (int s = 0; s < Cfg::kStages; ++s) {
-      mbar_init(full_bar + s, XF ? 1 + kXfWarps * (PAIR ? 2 : 1) : 1);
+      // non-halo: one arrival per producer warp (A, B); XF: the A tile arrives through the transform warps instead
+      mbar_init(full_bar + s, XF ? 1 + kXfWarps * (PAIR ? 2 : 1) : (HALO ? 1 : 2));
       mbar_init(empty_bar + s, 1);
       mbar_init(araw_bar + s, 1);
     }
@@ -290,8 +295,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       for (int wi = tile_begin; wi < num_work; wi += tile_step) {
         const int tile = wi / splits, split = wi - tile * splits;
         const TileCoord tc = tile_coord(p, tile, PAIR, rank);
-        // per-image B rows for batched GEMMs (Nt == 1); pair: this CTA's half of the N tile
-        const int brow0 = tc.n_tile * BN + tc.n0 * p.b_batch_rows + (PAIR ? rank * Cfg::kBRows : 0);
         const int kb0 = (int)((int64_t)split * num_kb / splits), kb1 = (int)((int64_t)(split + 1) * num_kb / splits);
         // walk (tap, chunk) incrementally: this warp sits on the critical path
         int tap = kb0 < main_kb ? kb0 / chunks : p.taps, ck = kb0 < main_kb ? kb0 - tap * chunks : kb0 - main_kb;
@@ -306,10 +309,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           if (leader) {
             if constexpr (XF) {
               mbar_expect_tx(araw_bar + stage, cnt * kABytes);
-              if (!PAIR || rank == 0) mbar_expect_tx(full_bar + stage, (PAIR ? 2 : 1) * cnt * Cfg::kBBytes);
             } else {
             if (p.debug & 1) { if (rank == 0) mbar_arrive(full_bar + stage); }
-            else if (!PAIR || rank == 0) mbar_expect_tx(full_bar + stage, (PAIR ? 2 : 1) * cnt * (kABytes + Cfg::kBBytes));
+            else if (!PAIR || rank == 0) mbar_expect_tx(full_bar + stage, (PAIR ? 2 : 1) * cnt * kABytes);
             }
           }
 #pragma unroll
@@ -330,10 +332,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
                 if (PAIR) {
                   if constexpr (XF) tma_load_5d(sa, ma, araw_bar + stage, c0, c1, c2, c3, tc.n0);
                   else tma_load_5d_2sm(sa, ma, full_bar + stage, c0, c1, c2, c3, tc.n0);
-                  tma_load_2d_2sm(sa + kABytes, &map_b, full_bar + stage, (kb + j) * kConvBlockK, brow0);
                 } else {
                   tma_load_5d(sa, ma, (XF ? araw_bar : full_bar) + stage, c0, c1, c2, c3, tc.n0);
-                  tma_load_2d(sa + kABytes, &map_b, full_bar + stage, (kb + j) * kConvBlockK, brow0);
                 }
               }
               ++ck;
@@ -439,7 +439,39 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         }
       }
     }
-  } else if (!XF || warp < 6) {
+  } else if (warp == kConvBWarp) {
+    // ===== B-operand TMA producer (non-halo kernels): same stage walk as warp 0, one 2D load of the weight tile per k-block
+    if constexpr (!HALO) {
+      int stage = 0; uint32_t phase = 0;
+      for (int wi = tile_begin; wi < num_work; wi += tile_step) {
+        const int tile = wi / splits, split = wi - tile * splits;
+        const TileCoord tc = tile_coord(p, tile, PAIR, rank);
+        // per-image B rows for batched GEMMs (Nt == 1); pair: this CTA's half of the N tile
+        const int brow0 = tc.n_tile * BN + tc.n0 * p.b_batch_rows + (PAIR ? rank * Cfg::kBRows : 0);
+        const int kb0 = (int)((int64_t)split * num_kb / splits), kb1 = (int)((int64_t)(split + 1) * num_kb / splits);
+        for (int kb = kb0; kb < kb1; kb += KPS) {
+          const int cnt = (kb1 - kb) < KPS ? (kb1 - kb) : KPS;
+          mbar_wait(empty_bar + stage, phase ^ 1);
+          if (elect_one()) {
+            if (p.debug & 1) { if (!XF && rank == 0) mbar_arrive(full_bar + stage); }
+            else {
+              if (!PAIR || rank == 0) mbar_expect_tx(full_bar + stage, (PAIR ? 2 : 1) * cnt * Cfg::kBBytes);
+#pragma unroll
+              for (int j = 0; j < KPS; ++j) {
+                if (j < cnt) {
+                  uint8_t* sb = smem + stage * Cfg::kStageBytes + j * Cfg::kKbBytes + kABytes;
+                  if (PAIR) tma_load_2d_2sm(sb, &map_b, full_bar + stage, (kb + j) * kConvBlockK, brow0);
+                  else tma_load_2d(sb, &map_b, full_bar + stage, (kb + j) * kConvBlockK, brow0);
+                }
+              }
+            }
+          }
+          __syncwarp();
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp < kConvBWarp) {
     // ===== epilogue: 4 warps, warp w owns TMEM lanes 32*(w%4) .. +31
     const int q = warp & 3;
     const int r = q * 32 + lane;  // row of the tile = output pixel

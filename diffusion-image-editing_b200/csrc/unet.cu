@@ -1280,12 +1280,15 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
   // SLOWER on B200 (profiles/r2_gn_fusion.md): the extra barrier hop per pipeline stage (TMA -> transform warps -> MMA)
   // stalls the 3-4 stage smem ring (+44 % on the 256x256 layers with the transform itself switched off), more than the
   // 1.8 ms of GroupNorm launches it removes.
-  static const bool gn_fuse_on = getenv("B2E_GN_FUSE") && atoi(getenv("B2E_GN_FUSE")) != 0;
+  static const int gn_fuse_mode = getenv("B2E_GN_FUSE") ? atoi(getenv("B2E_GN_FUSE")) : 0;
+  static const bool gn_fuse_on = gn_fuse_mode != 0;
+  // B2E_GN_FUSE=<r> with r >= 8: fuse only on feature maps of at most r x r (the latency-bound low-resolution levels)
+  const int gn_fuse_max_res = gn_fuse_mode >= 8 ? gn_fuse_mode : (1 << 30);
   auto gnorm = [&](const NormL& L, Tensor x0, const Tensor* x1, int silu, Tensor* out, float** stats_out = nullptr,
                    float eps_override = -1.f) {
     if (rc) return;
     const int C = x0.Cr + (x1 ? x1->Cr : 0);   // real channels, written compactly; pitch rounded up to 64
-    const bool fuse = gn_fuse_on && PL == 1 && x0.Cr == x0.C && x0.C % kConvBlockK == 0 &&
+    const bool fuse = gn_fuse_on && x0.H <= gn_fuse_max_res && PL == 1 && x0.Cr == x0.C && x0.C % kConvBlockK == 0 &&
                       (!x1 || (x1->Cr == x1->C && x1->C % kConvBlockK == 0));
     float* coef = nullptr;
     if (fuse) {

@@ -545,14 +545,16 @@ int gn_bwd_launch(const GNBwdArgs& a, cudaStream_t st) {
   return B2E_OK;
 }
 
-// block = 16 channels x 16 slot lanes: every thread sums a strided subset of the image's tile slots
-// (independent loads in flight), then the 16 slot lanes are combined in a fixed order through smem.
-__global__ void __launch_bounds__(256)
+// block = 16 channels x L slot lanes (L = 16, or 64 for images of >= 256 tile slots: a 256x256 layer has 512, and 16
+// lanes walked them in four dependent rounds of loads - 11 us at batch 1): every thread sums a strided subset of the
+// image's tile slots (independent loads in flight), then the lanes are combined in a fixed order through smem.
+template <int L>
+__global__ void __launch_bounds__(16 * L)
 gn_finalize_kernel(const float* __restrict__ tile_stats, float* __restrict__ chan_stats, int C, int Nt, int w_blks,
                    int h_blks) {
   pdl_wait();
   pdl_trigger();
-  __shared__ double s_s[16][16], s_q[16][16];
+  __shared__ double s_s[L][16], s_q[L][16];
   const int cl = threadIdx.x & 15, sl = threadIdx.x >> 4;
   const int c = blockIdx.x * 16 + cl, n = blockIdx.y;
   const int n_blk = n / Nt, nl = n % Nt;
@@ -561,7 +563,7 @@ gn_finalize_kernel(const float* __restrict__ tile_stats, float* __restrict__ cha
   if (c < C) {
     const int64_t base = (int64_t)n_blk * per_img;
 #pragma unroll 8
-    for (int i = sl; i < per_img; i += 16) {
+    for (int i = sl; i < per_img; i += L) {
       const int64_t slot = (base + i) * Nt + nl;
       const float2 v = __ldg(reinterpret_cast<const float2*>(tile_stats + (slot * C + c) * 2));
       s += (double)v.x; q += (double)v.y;
@@ -572,14 +574,17 @@ gn_finalize_kernel(const float* __restrict__ tile_stats, float* __restrict__ cha
   if (sl == 0 && c < C) {
     double ts = 0.0, tq = 0.0;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { ts += s_s[i][cl]; tq += s_q[i][cl]; }
+    for (int i = 0; i < L; ++i) { ts += s_s[i][cl]; tq += s_q[i][cl]; }
     *reinterpret_cast<float2*>(chan_stats + ((int64_t)n * C + c) * 2) = make_float2((float)ts, (float)tq);
   }
 }
 
 int gn_finalize_launch(const float* tile_stats, float* chan_stats, int N, int C, int Nt, int w_blks, int h_blks,
                        cudaStream_t st) {
-  launch_pdl(gn_finalize_kernel, dim3(dim3((C + 15) / 16, N)), dim3(256), 0, st, tile_stats, chan_stats, C, Nt, w_blks, h_blks);
+  if (w_blks * h_blks >= 256)
+    launch_pdl(gn_finalize_kernel<64>, dim3(dim3((C + 15) / 16, N)), dim3(1024), 0, st, tile_stats, chan_stats, C, Nt, w_blks, h_blks);
+  else
+    launch_pdl(gn_finalize_kernel<16>, dim3(dim3((C + 15) / 16, N)), dim3(256), 0, st, tile_stats, chan_stats, C, Nt, w_blks, h_blks);
   return check_launch("gn_finalize");
 }
 
