@@ -785,17 +785,20 @@ __global__ void __launch_bounds__(256) temb_mlp_kernel(TembArgs a) {
 }
 
 // proj[b][o] = wp[o] . act[b] + bp[o]   (warp per output; the weight row is read once and reused for every sample)
+// PER = weight elements per lane held in registers: 16 covers dim <= 512 (DDPM / LDM: ~50 registers, five blocks per
+// SM; the 64-wide instantiation needs 150 registers = one block per SM, six waves over the ~900 blocks)
 constexpr int kTembMaxPerLane = 64;   // dim <= 2048 (SD: 1280)
+template <int PER>
 __global__ void __launch_bounds__(256) temb_proj_kernel(TembArgs a) {
   pdl_wait();
   pdl_trigger();
   const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (o >= a.sumC) return;
-  float w[kTembMaxPerLane];
+  float w[PER];
   const int per = (a.dim + 31) / 32;
 #pragma unroll
-  for (int j = 0; j < kTembMaxPerLane; ++j)
+  for (int j = 0; j < PER; ++j)
     if (j < per) { const int i = lane + 32 * j; w[j] = i < a.dim ? __ldg(a.wp + (int64_t)o * a.dim + i) : 0.f; }
   const float bias = a.bp[o];
   for (int b0 = 0; b0 < a.B; b0 += 4) {   // four samples per iteration: independent loads / reductions in flight
@@ -805,7 +808,7 @@ __global__ void __launch_bounds__(256) temb_proj_kernel(TembArgs a) {
       if (b0 + u < a.B) {
         const float* x = a.act + (int64_t)(b0 + u) * a.dim;
 #pragma unroll
-        for (int j = 0; j < kTembMaxPerLane; ++j)
+        for (int j = 0; j < PER; ++j)
           if (j < per) { const int i = lane + 32 * j; if (i < a.dim) acc[u] += w[j] * x[i]; }
       }
     }
@@ -823,7 +826,8 @@ int temb_launch(const TembArgs& a, cudaStream_t st) {
              (a.dim0 + a.dim) * sizeof(float), st, a);
   int rc = check_launch("temb_mlp");
   if (rc) return rc;
-  launch_pdl(temb_proj_kernel, dim3((a.sumC + 7) / 8), dim3(256), 0, st, a);
+  if (a.dim <= 32 * 16) launch_pdl(temb_proj_kernel<16>, dim3((a.sumC + 7) / 8), dim3(256), 0, st, a);
+  else launch_pdl(temb_proj_kernel<kTembMaxPerLane>, dim3((a.sumC + 7) / 8), dim3(256), 0, st, a);
   return check_launch("temb_proj");
 }
 
@@ -1650,26 +1654,28 @@ constexpr int kAttThreads = 256;
 constexpr int kAttQ = 16;
 constexpr int kAttKStride = 72;  // f16 per staged key row (64 + pad): uint4-aligned, conflict-free
 
+// Q = queries per block: 16, or 4 when 16-query blocks would leave most SMs idle (8x8 mid-block attention: T = 64)
+template <int Q>
 __global__ void __launch_bounds__(kAttThreads)
 attention_kernel(const f16* __restrict__ qkv, f16* __restrict__ out, int T, int C, int P, int heads) {
   pdl_wait();
   extern __shared__ __align__(16) uint8_t att_smem[];
   const int d = C / heads;
   float* Qs = reinterpret_cast<float*>(att_smem);            // [16][d]
-  float* S = Qs + kAttQ * d;                                  // [16][T]
-  f16* Ks = reinterpret_cast<f16*>(S + kAttQ * T);         // [256][72]  (phase 3: fp32 partial sums, 32 KB)
+  float* S = Qs + Q * d;                                  // [16][T]
+  f16* Ks = reinterpret_cast<f16*>(S + Q * T);         // [256][72]  (phase 3: fp32 partial sums, 32 KB)
   const int qt = blockIdx.x, h = blockIdx.y, n = blockIdx.z, tid = threadIdx.x;
-  const int q0 = qt * kAttQ;
+  const int q0 = qt * Q;
   const int64_t row = 3 * (int64_t)P;
   const f16* base = qkv + (int64_t)n * T * row;
   const float scale = rsqrtf((float)d);
   // load Q tile
-  for (int i = tid; i < kAttQ * d; i += kAttThreads) {
+  for (int i = tid; i < Q * d; i += kAttThreads) {
     const int q = i / d, c = i % d;
     Qs[i] = (q0 + q < T) ? f16_to_float(base[(int64_t)(q0 + q) * row + h * d + c]) : 0.f;
   }
   if (h == 0 && P > C) {   // zero padding of the output pitch
-    for (int i = tid; i < kAttQ * (P - C); i += kAttThreads) {
+    for (int i = tid; i < Q * (P - C); i += kAttThreads) {
       const int q = i / (P - C), c = i % (P - C);
       if (q0 + q < T) out[((int64_t)n * T + q0 + q) * P + C + c] = float_to_f16(0.f);
     }
@@ -1677,9 +1683,9 @@ attention_kernel(const f16* __restrict__ qkv, f16* __restrict__ out, int T, int 
   // phase 1: scores, keys staged in pieces of dc = min(64, d) channels
   const int dc = d < 64 ? d : 64, parts = dc >> 3;
   for (int kt = 0; kt < T; kt += kAttThreads) {
-    float acc[kAttQ];
+    float acc[Q];
 #pragma unroll
-    for (int q = 0; q < kAttQ; ++q) acc[q] = 0.f;
+    for (int q = 0; q < Q; ++q) acc[q] = 0.f;
     const int key = kt + tid;
     for (int c0 = 0; c0 < d; c0 += dc) {
       __syncthreads();
@@ -1696,7 +1702,7 @@ attention_kernel(const f16* __restrict__ qkv, f16* __restrict__ out, int T, int 
           float kf[8];
           unpack8(*reinterpret_cast<const uint4*>(Ks + tid * kAttKStride + part * 8), kf);
 #pragma unroll
-          for (int q = 0; q < kAttQ; ++q) {
+          for (int q = 0; q < Q; ++q) {
             const float4 a = *reinterpret_cast<const float4*>(Qs + q * d + c0 + part * 8);
             const float4 b = *reinterpret_cast<const float4*>(Qs + q * d + c0 + part * 8 + 4);
             acc[q] += a.x * kf[0] + a.y * kf[1] + a.z * kf[2] + a.w * kf[3] + b.x * kf[4] + b.y * kf[5] +
@@ -1707,13 +1713,13 @@ attention_kernel(const f16* __restrict__ qkv, f16* __restrict__ out, int T, int 
     }
     if (key < T) {
 #pragma unroll
-      for (int q = 0; q < kAttQ; ++q) S[q * T + key] = acc[q] * scale;
+      for (int q = 0; q < Q; ++q) S[q * T + key] = acc[q] * scale;
     }
   }
   __syncthreads();
   // phase 2: softmax rows (warp per row)
   const int warp = tid >> 5, lane = tid & 31;
-  for (int q = warp; q < kAttQ; q += kAttThreads / 32) {
+  for (int q = warp; q < Q; q += kAttThreads / 32) {
     float m = -INFINITY;
     for (int j = lane; j < T; j += 32) m = fmaxf(m, S[q * T + j]);
 #pragma unroll
@@ -1734,9 +1740,9 @@ attention_kernel(const f16* __restrict__ qkv, f16* __restrict__ out, int T, int 
     float* red = reinterpret_cast<float*>(Ks);   // [groups][16][d] fp32, <= 32 KB (groups * d <= 512)
     const int cp = tid % half, ks = tid / half;
     if (ks < groups) {
-      float ax[kAttQ], ay[kAttQ];
+      float ax[Q], ay[Q];
 #pragma unroll
-      for (int q = 0; q < kAttQ; ++q) ax[q] = ay[q] = 0.f;
+      for (int q = 0; q < Q; ++q) ax[q] = ay[q] = 0.f;
       const int per = T / groups;
       const f16* vp = base + 2 * P + h * d + 2 * cp;
       for (int j = ks * per; j < (ks + 1) * per; j += 4) {
@@ -1745,22 +1751,22 @@ attention_kernel(const f16* __restrict__ qkv, f16* __restrict__ out, int T, int 
         for (int u = 0; u < 4; ++u)
           v[u] = f16x2_to_float2(__ldg(reinterpret_cast<const f16x2*>(vp + (int64_t)(j + u) * row)));
 #pragma unroll
-        for (int q = 0; q < kAttQ; ++q) {
+        for (int q = 0; q < Q; ++q) {
           const float4 p = *reinterpret_cast<const float4*>(S + q * T + j);
           ax[q] += p.x * v[0].x + p.y * v[1].x + p.z * v[2].x + p.w * v[3].x;
           ay[q] += p.x * v[0].y + p.y * v[1].y + p.z * v[2].y + p.w * v[3].y;
         }
       }
 #pragma unroll
-      for (int q = 0; q < kAttQ; ++q)
-        *reinterpret_cast<float2*>(red + ((ks * kAttQ + q) * d + 2 * cp)) = make_float2(ax[q], ay[q]);
+      for (int q = 0; q < Q; ++q)
+        *reinterpret_cast<float2*>(red + ((ks * Q + q) * d + 2 * cp)) = make_float2(ax[q], ay[q]);
     }
     __syncthreads();
-    for (int i = tid; i < kAttQ * half; i += kAttThreads) {
+    for (int i = tid; i < Q * half; i += kAttThreads) {
       const int q = i / half, c2 = i % half;
       float sx = 0.f, sy = 0.f;
       for (int g = 0; g < groups; ++g) {
-        const float2 v = *reinterpret_cast<const float2*>(red + ((g * kAttQ + q) * d + 2 * c2));
+        const float2 v = *reinterpret_cast<const float2*>(red + ((g * Q + q) * d + 2 * c2));
         sx += v.x; sy += v.y;
       }
       if (q0 + q < T)
@@ -1769,9 +1775,9 @@ attention_kernel(const f16* __restrict__ qkv, f16* __restrict__ out, int T, int 
     return;
   }
   for (int c0 = 2 * tid; c0 < d; c0 += 2 * kAttThreads) {
-    float ax[kAttQ], ay[kAttQ];
+    float ax[Q], ay[Q];
 #pragma unroll
-    for (int q = 0; q < kAttQ; ++q) ax[q] = ay[q] = 0.f;
+    for (int q = 0; q < Q; ++q) ax[q] = ay[q] = 0.f;
     const f16* vp = base + 2 * P + h * d + c0;
     for (int j = 0; j < T; j += 4) {  // T % 4 == 0 (checked on the host)
       float2 v[4];
@@ -1779,14 +1785,14 @@ attention_kernel(const f16* __restrict__ qkv, f16* __restrict__ out, int T, int 
       for (int u = 0; u < 4; ++u)
         v[u] = f16x2_to_float2(__ldg(reinterpret_cast<const f16x2*>(vp + (int64_t)(j + u) * row)));
 #pragma unroll
-      for (int q = 0; q < kAttQ; ++q) {
+      for (int q = 0; q < Q; ++q) {
         const float4 p = *reinterpret_cast<const float4*>(S + q * T + j);
         ax[q] += p.x * v[0].x + p.y * v[1].x + p.z * v[2].x + p.w * v[3].x;
         ay[q] += p.x * v[0].y + p.y * v[1].y + p.z * v[2].y + p.w * v[3].y;
       }
     }
 #pragma unroll
-    for (int q = 0; q < kAttQ; ++q)
+    for (int q = 0; q < Q; ++q)
       if (q0 + q < T)
         *reinterpret_cast<f16x2*>(out + ((int64_t)n * T + q0 + q) * P + h * d + c0) =
             floats_to_f16x2(ax[q], ay[q]);
@@ -2079,14 +2085,19 @@ int attention_launch(const f16* qkv, f16* out, int N, int T, int C, int P, int h
   const int d = C / heads;
   B2E_REQUIRE(d % 8 == 0 && (d <= 64 || d % 64 == 0) && d <= 1024 && T % 4 == 0 && T <= 4096, B2E_UNSUPPORTED_SHAPE,
               "attention: unsupported T=%d head_dim=%d", T, d);
-  const size_t smem = sizeof(float) * kAttQ * (d + T) + sizeof(f16) * kAttThreads * kAttKStride;
+  // 4-query blocks when 16-query blocks cannot fill the chip (each block re-stages the keys, so only then)
+  const bool small = (int64_t)((T + kAttQ - 1) / kAttQ) * heads * N < kNumSMs;
+  const int Q = small ? 4 : kAttQ;
+  const size_t smem = sizeof(float) * Q * (d + T) + sizeof(f16) * kAttThreads * kAttKStride;
   B2E_REQUIRE(smem <= 200 * 1024, B2E_UNSUPPORTED_SHAPE, "attention: tile does not fit in shared memory");
-  static size_t attr = 0;
-  if (smem > attr) {
-    B2E_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
+  static size_t attr[2] = {0, 0};
+  if (smem > attr[small]) {
+    if (small) B2E_CUDA(cudaFuncSetAttribute(attention_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else B2E_CUDA(cudaFuncSetAttribute(attention_kernel<kAttQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr[small] = smem;
   }
-  launch_pdl(attention_kernel, dim3((T + kAttQ - 1) / kAttQ, heads, N), dim3(kAttThreads), smem, st, qkv, out, T, C, P, heads);
+  if (small) launch_pdl(attention_kernel<4>, dim3((T + 3) / 4, heads, N), dim3(kAttThreads), smem, st, qkv, out, T, C, P, heads);
+  else launch_pdl(attention_kernel<kAttQ>, dim3((T + kAttQ - 1) / kAttQ, heads, N), dim3(kAttThreads), smem, st, qkv, out, T, C, P, heads);
   return check_launch("attention");
 }
 

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Key metrics of an `ncu --set full` report as a markdown table:  summarize_ncu.py <file.ncu-rep>"""
+"""Key metrics of an `ncu --set full` report as a markdown table:  summarize_ncu.py <file.ncu-rep | raw.csv>"""
 import csv, subprocess, sys
 
 WANT = [("gpu__time_duration.sum", "time"), ("launch__grid_size", "grid"), ("launch__registers_per_thread", "regs"),
@@ -10,7 +10,10 @@ WANT = [("gpu__time_duration.sum", "time"), ("launch__grid_size", "grid"), ("lau
         ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM %"),
         ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps active %"),
         ("sm__cycles_active.avg", "SM active cycles")]
-out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+if sys.argv[1].endswith(".csv"):      # already exported on the GPU box (`ncu -i x.ncu-rep --page raw --csv`)
+    out = open(sys.argv[1]).read()
+else:
+    out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr, units = rows[0], rows[1]
 idx = {h: i for i, h in enumerate(hdr)}
