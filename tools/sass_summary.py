@@ -5,7 +5,8 @@ in every sm_100a cubin function of libb200edit.so (cuobjdump -sass).  Regenerate
     python tools/sass_summary.py [out.txt]
 
 UTCHMMA(.2CTA) = tcgen05.mma (kind::f16, one / two CTAs), UTMALDG / UTMASTG = TMA tensor load / store, LDTM = tcgen05.ld
-(TMEM -> registers), UTCBAR = tcgen05.commit -> mbarrier, SYNCS = mbarrier ops, HMMA = legacy warp-level mma.sync (must be 0)."""
+(TMEM -> registers), UTCBAR = tcgen05.commit -> mbarrier, SYNCS = mbarrier ops, UBLKCP = cp.async.bulk (here: the shared::cta ->
+shared::cluster copy of the cluster split-K partial tiles), UCGABAR = barrier.cluster, HMMA = legacy warp-level mma.sync (must be 0)."""
 import collections
 import os
 import re
@@ -14,7 +15,7 @@ import sys
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(REPO, "diffusion-image-editing_b200", "b200edit", "libb200edit.so")
-KEYS = ["UTCHMMA", "UTMALDG", "UTMASTG", "LDTM", "UTCBAR", "SYNCS", "HMMA", "MUFU", "LDG", "STG"]
+KEYS = ["UTCHMMA", "UTMALDG", "UTMASTG", "LDTM", "UTCBAR", "SYNCS", "HMMA", "MUFU", "LDG", "STG", "UBLKCP", "UCGABAR_ARV"]
 
 
 def main():
@@ -45,16 +46,16 @@ def main():
         rows.append((cur, counts))
     total = collections.Counter()
     lines = [f"# SASS summary of {os.path.relpath(LIB, REPO)} ({arch}); regenerate with tools/sass_summary.py", "#",
-             "# " + " ".join(f"{k:>8s}" for k in ["UTCHMMA", "(.2CTA)", "UTMALDG", "(.2CTA)", "UTMASTG", "LDTM", "UTCBAR", "SYNCS", "HMMA", "MUFU"]) + "  kernel"]
+             "# " + " ".join(f"{k:>8s}" for k in ["UTCHMMA", "(.2CTA)", "UTMALDG", "(.2CTA)", "UTMASTG", "LDTM", "UTCBAR", "SYNCS", "UBLKCP", "UCGABAR", "HMMA", "MUFU"]) + "  kernel"]
     for name, c in sorted(rows, key=lambda r: -r[1]["UTCHMMA"]):
         total.update(c)
         if not (c["UTCHMMA"] or c["UTMALDG"] or c["UTMASTG"] or c["LDTM"]):
             continue
         d = demangle(name)
         d = re.sub(r"\(.*", "", d)
-        lines.append("  " + " ".join(f"{c[k]:8d}" for k in ["UTCHMMA", "UTCHMMA.2CTA", "UTMALDG", "UTMALDG.2CTA", "UTMASTG", "LDTM", "UTCBAR", "SYNCS", "HMMA", "MUFU"]) + "  " + d)
+        lines.append("  " + " ".join(f"{c[k]:8d}" for k in ["UTCHMMA", "UTCHMMA.2CTA", "UTMALDG", "UTMALDG.2CTA", "UTMASTG", "LDTM", "UTCBAR", "SYNCS", "UBLKCP", "UCGABAR_ARV", "HMMA", "MUFU"]) + "  " + d)
     lines.append("#")
-    lines.append(f"# all {len(rows)} functions: " + ", ".join(f"{k} {total[k]}" for k in ["UTCHMMA", "UTCHMMA.2CTA", "UTMALDG", "UTMASTG", "LDTM", "UTCBAR", "HMMA"]))
+    lines.append(f"# all {len(rows)} functions: " + ", ".join(f"{k} {total[k]}" for k in ["UTCHMMA", "UTCHMMA.2CTA", "UTMALDG", "UTMASTG", "LDTM", "UTCBAR", "UBLKCP", "HMMA"]))
     lines.append("# HMMA (warp-level mma.sync) must be 0: every dense contraction goes through tcgen05.mma with the accumulator in TMEM")
     with open(out_path, "w") as f:
         f.write("\n".join(lines) + "\n")
