@@ -22,6 +22,13 @@ CASES = [
     (1, 256, 256, 128, 128, 3, 2),
     (2, 16, 16, 64, 64, 3, 1),         # BLOCK_N = 64
     (1, 4, 4, 64, 64, 3, 1),           # tiny map: 8 images per tile
+    # cluster split-K (64-wide tiles, the K-splits of a tile = one thread-block cluster meeting in the leader's smem):
+    (8, 16, 16, 512, 256, 3, 1),       # 64 tiles  -> 2 splits
+    (3, 16, 16, 512, 512, 3, 1),       # 48 tiles  -> 3 splits
+    (8, 8, 8, 512, 512, 3, 1),         # 32 tiles  -> 4 splits (the batch-8 layers of the 8x8 level)
+    (14, 8, 8, 512, 256, 3, 1),        # 28 tiles  -> 5 splits
+    (3, 16, 16, 512, 256, 3, 1),       # 24 tiles  -> 6 splits
+    (1, 16, 16, 1024, 512, 3, 1),      # 16 tiles  -> 7 splits, 144 k-blocks (uneven split boundaries)
 ]
 
 
@@ -57,3 +64,16 @@ def test_conv_vs_torch(case):
         err = (out_r.float().permute(0, 3, 1, 2) - ref_r).abs().max().item()
         scale = ref_r.abs().max().item()
         assert err <= rel * scale + 1e-3 * rel * 128, f"residual: max abs err {err} (scale {scale})"
+
+
+def test_split_k_is_deterministic():
+    """The cluster split-K sums the partial tiles in split order: two runs of the same launch are bit-identical."""
+    from b200edit import ops
+    dt = ops.act_dtype()
+    g = torch.Generator(device="cpu").manual_seed(7)
+    x = torch.randn(1, 8, 8, 512, generator=g).to(dt).cuda()
+    w = (torch.randn(512, 512, 3, 3, generator=g) / 68.0).cuda()
+    b = torch.randn(512, generator=g).cuda()
+    outs = [ops.conv2d_nhwc_f16(x, w, b) for _ in range(4)]
+    torch.cuda.synchronize()
+    assert all(torch.equal(outs[0], o) for o in outs[1:])
