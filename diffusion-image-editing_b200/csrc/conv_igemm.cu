@@ -1219,7 +1219,10 @@ int conv_plan_build(ConvPlan* pl, const ConvDesc& d) {
   static const bool splitk_on = !(getenv("B2E_SPLITK") && atoi(getenv("B2E_SPLITK")) == 0);
   if (splitk_on && cluster_on && !p.pair && p.block_n == 64 && d.out_f16 && tiles * 2 <= kNumSMs) {
     int sp = kNumSMs / tiles;
-    if (sp > num_kb / 8) sp = num_kb / 8;
+    // more splits shorten the MMA phase but every extra partial tile costs 0.55 us of DSMEM ingress at the leader:
+    // measured optimum (tools/conv_bench.py, B2E_SPLITK_MAX sweep) 3 splits at 36 k-blocks, 4 at 72, 5-7 at 144
+    const int sp_k = num_kb >= 128 ? kConvMaxClusterSplits : num_kb >= 64 ? 4 : num_kb >= 24 ? 3 : num_kb / 8;
+    if (sp > sp_k) sp = sp_k;
     if (sp > kConvMaxClusterSplits) sp = kConvMaxClusterSplits;
     static const int sp_max = getenv("B2E_SPLITK_MAX") ? atoi(getenv("B2E_SPLITK_MAX")) : kConvMaxClusterSplits;   // experiments
     if (sp > sp_max) sp = sp_max;

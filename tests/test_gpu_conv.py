@@ -26,8 +26,9 @@ CASES = [
     (8, 16, 16, 512, 256, 3, 1),       # 64 tiles  -> 2 splits
     (3, 16, 16, 512, 512, 3, 1),       # 48 tiles  -> 3 splits
     (8, 8, 8, 512, 512, 3, 1),         # 32 tiles  -> 4 splits (the batch-8 layers of the 8x8 level)
-    (14, 8, 8, 512, 256, 3, 1),        # 28 tiles  -> 5 splits
-    (3, 16, 16, 512, 256, 3, 1),       # 24 tiles  -> 6 splits
+    (14, 8, 8, 1024, 256, 3, 1),       # 28 tiles, 144 k-blocks -> 5 splits
+    (3, 16, 16, 1024, 256, 3, 1),      # 24 tiles, 144 k-blocks -> 6 splits
+    (2, 8, 8, 256, 256, 3, 1),         # 4 tiles, 36 k-blocks -> 3 splits
     (1, 16, 16, 1024, 512, 3, 1),      # 16 tiles  -> 7 splits, 144 k-blocks (uneven split boundaries)
 ]
 
