@@ -432,7 +432,9 @@ def rooflines(c, wrapper, sch, x_dev, precision):
                 "flops_per_launch": fl / max(1, len(launches)), "us_per_launch": ms * 1e3 / max(1, len(launches)),
                 "share_of_unet_time": ms / tot_ms,
                 "how": "ALGORITHMIC FLOPs (2*M*N*K of the convolution / linear / attention GEMM; identity-residual K segments "
-                       "excluded, counted as bytes) / CUDA-event duration per launch, one instrumented forward (events on the "
+                       "excluded, counted as bytes; the two large upsampler convolutions are counted as the four 2x2-tap "
+                       "sub-pixel phase convolutions actually executed - 2.25x fewer FLOPs than nearest-upsample + 3x3, "
+                       "-4 % on the forward) / CUDA-event duration per launch, one instrumented forward (events on the "
                        "launching stream)"}
 
     roof = tensor_roofline(conv, "conv_igemm_kernel, all variants (every conv / linear / attention GEMM launch of the UNet forward)")

@@ -990,6 +990,37 @@ __global__ void fill_identity_kernel(f16* __restrict__ out, int C, int row_len, 
   if (c < C) out[(int64_t)c * row_len + col_off + c] = float_to_f16(value);
 }
 
+__global__ void pack_weight_up2_kernel(const float* __restrict__ w, f16* __restrict__ out, int Cout, int Cin, int tap_width,
+                                       int row_len, int col_off, int phase, int lo, float wscale) {
+  const int a = phase >> 1, b = phase & 1;
+  const int64_t total = (int64_t)Cout * 4 * Cin;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % Cin);
+    const int t = (int)((i / Cin) % 4);
+    const int co = (int)(i / ((int64_t)Cin * 4));
+    const int th = t >> 1, tw = t & 1;
+    // 3x3 rows / columns folded into this 2x2 tap
+    const int kh0 = a == 0 ? (th == 0 ? 0 : 1) : (th == 0 ? 0 : 2), kh1 = a == 0 ? (th == 0 ? 0 : 2) : (th == 0 ? 1 : 2);
+    const int kw0 = b == 0 ? (tw == 0 ? 0 : 1) : (tw == 0 ? 0 : 2), kw1 = b == 0 ? (tw == 0 ? 0 : 2) : (tw == 0 ? 1 : 2);
+    const float* wp = w + ((int64_t)co * Cin + ci) * 9;
+    float v = 0.f;
+    for (int kh = kh0; kh <= kh1; ++kh)
+      for (int kw = kw0; kw <= kw1; ++kw) v = __fadd_rn(v, wp[kh * 3 + kw]);
+    v *= wscale;   // power of two: exact
+    const f16 hi = float_to_f16(v);
+    out[(int64_t)co * row_len + col_off + (int64_t)t * tap_width + ci] = lo ? float_to_f16(__fsub_rn(v, f16_to_float(hi))) : hi;
+  }
+}
+
+int conv_pack_weight_up2(const float* w, f16* out, int Cout, int Cin, int tap_width, int row_len, int col_off, int phase,
+                         cudaStream_t st, int lo, float wscale) {
+  const int64_t total = (int64_t)Cout * 4 * Cin;
+  int grid = (int)((total + 255) / 256);
+  if (grid > kNumSMs * 16) grid = kNumSMs * 16;
+  pack_weight_up2_kernel<<<grid, 256, 0, st>>>(w, out, Cout, Cin, tap_width, row_len, col_off, phase, lo, wscale);
+  return check_launch("pack_weight_up2");
+}
+
 int conv_pack_weight(const float* w, f16* out, int Cout, int Cin, int ksize, int tap_width, int row_len,
                      int col_off, cudaStream_t st, int ci0, int cin_total, int lo, float wscale) {
   const int kk = ksize * ksize;
@@ -1101,11 +1132,19 @@ ConvGeom conv_geometry(int N, int Ho, int Wo, int Cout, int ksize, int stride) {
 }
 
 // (C, W, 1, H, N) view of an NHWC tensor (stride 1) or (2C, W/2, 2, H/2, N) (stride 2), box = one tile brick
+// up2_phase >= 0: (N,H,W,C) is the sub-grid of pixels (2i + a, 2j + b) of a (N,2H,2W,C) tensor at `ptr`
 static int encode_act_map(CUtensorMap* m, const f16* ptr, int N, int H, int W, int C, int stride,
-                          int Wt, int Ht, int Nt, int pitch = 0, int halo = 0) {
+                          int Wt, int Ht, int Nt, int pitch = 0, int halo = 0, int up2_phase = -1) {
   const uint64_t e = 2;
   uint64_t dims[5], str[4];
   uint32_t box[5] = {(uint32_t)kConvBlockK, (uint32_t)Wt, 1, (uint32_t)(Ht + 2 * halo), (uint32_t)Nt};
+  if (up2_phase >= 0) {
+    const int a = up2_phase >> 1, b = up2_phase & 1;
+    dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = N;
+    str[0] = 2 * (uint64_t)C * e; str[1] = 2 * (uint64_t)(2 * W) * C * e; str[2] = str[1];
+    str[3] = (uint64_t)(2 * H) * (2 * W) * C * e;
+    return encode_map(m, ptr + ((int64_t)a * 2 * W + b) * C, 5, dims, str, box);
+  }
   if (stride == 1) {
     const uint64_t P = pitch ? pitch : C;   // pixel pitch in elements (channel window of a wider tensor)
     dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = N;
@@ -1124,8 +1163,10 @@ int conv_plan_build(ConvPlan* pl, const ConvDesc& d) {
   B2E_REQUIRE(d.s0.ptr && d.s0.C > 0 && d.s0.C % K == 0 && d.s1.C % K == 0 && d.r0.C % K == 0 && d.r1.C % K == 0,
               B2E_UNSUPPORTED_SHAPE, "conv: channel counts must be multiples of %d (got %d+%d, residual %d+%d)", K,
               d.s0.C, d.s1.C, d.r0.C, d.r1.C);
-  B2E_REQUIRE((d.ksize == 1 || d.ksize == 3) &&
-                  (d.stride == 1 || (d.stride == 2 && d.ksize == 3 && !d.s1.ptr && !d.r0.ptr)),
+  B2E_REQUIRE(((d.ksize == 1 || d.ksize == 3) && d.up2_phase < 0 &&
+               (d.stride == 1 || (d.stride == 2 && d.ksize == 3 && !d.s1.ptr && !d.r0.ptr))) ||
+                  (d.up2_phase >= 0 && d.up2_phase < 4 && d.ksize == 2 && d.stride == 1 && !d.s1.ptr && !d.r0.ptr && !d.s0.pitch &&
+                   !d.b_batch_rows && !d.gn_coef && d.out_f16),
               B2E_UNSUPPORTED_SHAPE, "conv: unsupported ksize/stride %d/%d", d.ksize, d.stride);
   B2E_REQUIRE(d.stride == 1 || (d.H % 2 == 0 && d.W % 2 == 0), B2E_UNSUPPORTED_SHAPE, "conv: stride 2 needs even H, W");
   B2E_REQUIRE(aligned16(d.s0.ptr) && (!d.s1.ptr || aligned16(d.s1.ptr)) && (!d.r0.ptr || aligned16(d.r0.ptr)) &&
@@ -1176,7 +1217,10 @@ int conv_plan_build(ConvPlan* pl, const ConvDesc& d) {
   p.r1_chunks = d.r1.ptr ? d.r1.C / K : 0;
   for (int t = 0; t < p.taps; ++t) {
     const int kh = t / d.ksize, kw = t % d.ksize;
-    if (d.stride == 1) {
+    if (d.up2_phase >= 0) {
+      // phase (a, b): input rows {i + a - 1, i + a}, columns {j + b - 1, j + b} of the low-resolution tensor
+      p.tap_dc[t] = 0; p.tap_dw[t] = (d.up2_phase & 1) - 1 + kw; p.tap_da[t] = 0; p.tap_dh[t] = (d.up2_phase >> 1) - 1 + kh;
+    } else if (d.stride == 1) {
       p.tap_dc[t] = 0; p.tap_dw[t] = kw - d.ksize / 2; p.tap_da[t] = 0; p.tap_dh[t] = kh - d.ksize / 2;
     } else if (d.stride2_pad1) {
       // symmetric padding 1: input index 2*o + k - 1 -> (block o - 1, parity 1), (o, 0), (o, 1)
@@ -1198,7 +1242,8 @@ int conv_plan_build(ConvPlan* pl, const ConvDesc& d) {
   if (d.r0.ptr && (rc = encode_act_map(&p.map_r0, d.r0.ptr, d.N, p.Ho, p.Wo, d.r0.C, 1, p.Wt, a_ht, p.Nt))) return rc;
   if (d.r1.ptr && (rc = encode_act_map(&p.map_r1, d.r1.ptr, d.N, p.Ho, p.Wo, d.r1.C, 1, p.Wt, a_ht, p.Nt))) return rc;
   p.has_out_f16 = d.out_f16 != nullptr;
-  if (d.out_f16 && (rc = encode_act_map(&p.map_out, d.out_f16, d.N, p.Ho, p.Wo, d.Cout * d.out_planes, 1, p.Wt, p.Ht, p.Nt))) return rc;
+  if (d.out_f16 && (rc = encode_act_map(&p.map_out, d.out_f16, d.N, p.Ho, p.Wo, d.Cout * d.out_planes, 1, p.Wt, p.Ht, p.Nt, 0, 0,
+                                        d.up2_phase))) return rc;
   const uint64_t ktot = (uint64_t)p.taps * (d.s0.C + (d.s1.ptr ? d.s1.C : 0)) + (d.r0.ptr ? d.r0.C : 0) +
                         (d.r1.ptr ? d.r1.C : 0);
   uint64_t bd[2] = {ktot, d.b_batch_rows ? (uint64_t)d.N * d.b_batch_rows : (uint64_t)p.cout_pad};

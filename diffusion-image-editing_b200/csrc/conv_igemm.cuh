@@ -34,6 +34,12 @@ struct ConvDesc {
   // (pixel pitch 3*Cout): hi = f16(v), lo = f16(v - hi).  A consumer convolution reads it as ONE 3*Cout-channel
   // source against weights packed [W_hi | W_hi | W_lo], i.e. x_hi W_hi + x_lo W_hi + x_hi W_lo (error ~2^-17 relative)
   int out_planes = 1;
+  // >= 0: one PHASE of "nearest-upsample x2 then 3x3 convolution" computed on the LOW-resolution input (N,H,W,C): output
+  // pixels (2i + a, 2j + b), a = phase >> 1, b = phase & 1, only see two input rows {i + a - 1, i + a} and two columns
+  // {j + b - 1, j + b}, so the 3x3 taps collapse into 2x2 taps with pre-summed weights (conv_pack_weight_up2): 2.25x fewer
+  // FLOPs than convolving the upsampled tensor, which is never materialised.  ksize must be 2, stride 1; out_f16 is the
+  // full (N,2H,2W,Cout) tensor, written through a strided tensor map.
+  int up2_phase = -1;
   // optional fused GroupNorm statistics of the (f16-rounded) output: per (tile slot, channel) sum and
   // sum of squares, [conv_stats_slots()][Cout][2] floats; reduced per image by gn_finalize
   float* tile_stats = nullptr;
@@ -105,6 +111,10 @@ int flash_attn_launch(const FlashPlan& pl, int valid_k, float scale, cudaStream_
 // (ci0, cin_total): pack only input channels [ci0, ci0 + Cin) of a weight with cin_total input channels
 // lo = 1: pack the remainder f16(w - f16(w)) instead of f16(w) (split-f16 weights of the fp32-accurate mode)
 // wscale: the weights are multiplied by this power of two first (the consumer's epilogue undoes it, ConvEpilogue::acc_scale)
+// 2x2 taps of phase (a, b) of the upsample-then-3x3 convolution: tap (th, tw) = sum of the 3x3 taps it stands for
+// (rows {0} | {1,2} for a = 0, {0,1} | {2} for a = 1; columns likewise with b), summed in fp32, then rounded / split
+int conv_pack_weight_up2(const float* w, f16* out, int Cout, int Cin, int tap_width, int row_len, int col_off, int phase,
+                         cudaStream_t st, int lo = 0, float wscale = 1.f);
 int conv_pack_weight(const float* w, f16* out, int Cout, int Cin, int ksize, int tap_width, int row_len,
                      int col_off, cudaStream_t st, int ci0 = 0, int cin_total = 0, int lo = 0, float wscale = 1.f);
 // dgrad weights (flipped taps, transposed channels): out[ci*row_len + col_off + t*tap_width + co] = w[(co*Cin+ci)*kk + kk-1-t]

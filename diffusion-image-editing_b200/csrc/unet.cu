@@ -26,6 +26,8 @@ struct ConvL {
   f16* w = nullptr; float* b = nullptr; float* b2 = nullptr;
   int cin = 0, cin_pad = 0, cout = 0, cout_pad = 0, k = 0, res_c = 0, row_len = 0;
   int dg = -1;   // decoder: index of the dgrad twin (flipped / transposed weights) in b2e_unet::dgrads
+  // upsampler convolutions: the four sub-pixel phases' 2x2-tap weights, [4][cout_pad][row_len_up2] (conv_pack_weight_up2)
+  f16* w_up2 = nullptr; int row_len_up2 = 0;
 };
 struct NormL { float* g = nullptr; float* b = nullptr; int C = 0; };
 struct ResnetL {
@@ -206,12 +208,16 @@ struct b2e_unet {
   // conv / linear weight that feeds the tcgen05 GEMM: packed f16 [cout_pad][k*k][cin_pad]
   // src0 > 0: the convolution reads TWO concatenated sources of src0 and cin - src0 channels (multiples of 64); in the
   // split mode every source carries its own [hi | lo | hi] planes, so the weight columns are packed per source
-  ConvL make_conv(const std::string& name, int cin, int cout, int k, int cin_pad = 0, int res_c = 0, int src0 = 0) {
+  ConvL make_conv(const std::string& name, int cin, int cout, int k, int cin_pad = 0, int res_c = 0, int src0 = 0, bool up2 = false) {
     ConvL c;
     c.cin = cin; c.cin_pad = cin_pad ? cin_pad : pad64(cin); c.cout = cout; c.k = k; c.cout_pad = conv_cout_pad(cout);
     c.res_c = res_c; c.row_len = PL * (k * k * c.cin_pad + res_c);
     c.w = dmalloc<f16>((size_t)c.cout_pad * c.row_len);
     c.b = dmalloc<float>(c.cout_pad);
+    if (up2 && k == 3 && res_c == 0) {
+      c.row_len_up2 = PL * 4 * c.cin_pad;
+      c.w_up2 = dmalloc<f16>((size_t)4 * c.cout_pad * c.row_len_up2);
+    }
     ConvL cc = c;
     ConvL dd;
     const int PL = this->PL;
@@ -226,6 +232,16 @@ struct b2e_unet {
         rc = pack_w(PL, src, cc.w, cc.cout, cc.cin, cc.k, cc.cin_pad, cc.row_len, 0, cc.cin_pad, st);
       }
       if (!rc && cc.dg >= 0) rc = conv_pack_weight_dgrad(src, dd.w, cc.cout, cc.cin, cc.k, dd.cin_pad, dd.row_len, 0, st);
+      for (int ph = 0; ph < 4 && !rc && cc.w_up2; ++ph) {
+        f16* wp = cc.w_up2 + (size_t)ph * cc.cout_pad * cc.row_len_up2;
+        if (PL == 1) {
+          rc = conv_pack_weight_up2(src, wp, cc.cout, cc.cin, cc.cin_pad, cc.row_len_up2, 0, ph, st);
+        } else {   // split mode: [W_hi | W_hi | W_lo] per tap, x 2^10 (as pack_w)
+          rc = conv_pack_weight_up2(src, wp, cc.cout, cc.cin, 3 * cc.cin_pad, cc.row_len_up2, 0, ph, st, 0, kSplitWScale);
+          if (!rc) rc = conv_pack_weight_up2(src, wp, cc.cout, cc.cin, 3 * cc.cin_pad, cc.row_len_up2, cc.cin_pad, ph, st, 0, kSplitWScale);
+          if (!rc) rc = conv_pack_weight_up2(src, wp, cc.cout, cc.cin, 3 * cc.cin_pad, cc.row_len_up2, 2 * cc.cin_pad, ph, st, 1, kSplitWScale);
+        }
+      }
       return rc;
     });
     add_f32(name + ".bias", c.b, cout, (int64_t)cin * k * k);
@@ -429,7 +445,7 @@ int build_model_decoder(b2e_unet* m) {
       ch = cout;
     }
     if (i != nb - 1) {
-      m->ups.push_back(m->make_conv(base + ".upsamplers.0.conv", ch, ch, 3));
+      m->ups.push_back(m->make_conv(base + ".upsamplers.0.conv", ch, ch, 3, 0, 0, 0, true));
       m->nodes.push_back({N_UP, (int)m->ups.size() - 1});
     }
   }
@@ -1112,7 +1128,7 @@ int build_model(b2e_unet* m) {
       }
     }
     if (i != nb - 1) {
-      m->ups.push_back(m->make_conv(base + ".upsamplers.0.conv", ch, ch, 3));
+      m->ups.push_back(m->make_conv(base + ".upsamplers.0.conv", ch, ch, 3, 0, 0, 0, true));
       m->nodes.push_back({N_UP, (int)m->ups.size() - 1});
     }
   }
@@ -1270,6 +1286,67 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
                        return gn_finalize_launch(tstats, cst, B, C, fNt, fw, fh, st);
                      }, 3, 0.0, (double)tstats_bytes});
       ar.release(tstats, tstats_bytes);   // dead after the finalize kernel (stream order)
+    }
+  };
+  // Upsampler: nearest x2 followed by a 3x3 convolution, computed as FOUR 2x2 convolutions over the low-resolution tensor
+  // (one per output-pixel parity, weights pre-summed at set_param time): 2.25x fewer FLOPs, and the upsampled tensor is
+  // never written or read.  Each phase writes its sub-grid of the output through a strided TMA map and its own block of
+  // GroupNorm tile statistics; ONE gn_finalize reduces the four blocks.  Forward-only programs, outputs of >= 128x128.
+  // Measured at batch 8 (DDPM-256, tools/profile_ops.py): 128 -> 256 at 128 channels 4 x 31.8 us against 115 us + 52 us of
+  // upsample2x; 64 -> 128 at 256 channels 4 x 27.4 against 98 + 29; 32 -> 64 at 256 channels 4 x 15 against 36 + 15 (worse:
+  // excluded).  The phase launches are K-short (8-16 k-blocks per tile) and therefore epilogue-bound at 520-650 TFLOP/s:
+  // the gain is the upsample pass they remove, not their 2.25x fewer FLOPs.  B2E_UP2=0 restores upsample2x + conv3x3.
+  static const bool up2_on = !(getenv("B2E_UP2") && atoi(getenv("B2E_UP2")) == 0);
+  auto conv_up2 = [&](const ConvL& L, const Tensor& x, Tensor* out) {
+    if (rc) return;
+    const int cout_x = L.cout_pad;
+    *out = talloc(B, 2 * x.H, 2 * x.W, cout_x, L.cout);
+    const ConvGeom geo = conv_geometry(B, x.H, x.W, cout_x, 2, 1);     // tiling of ONE phase (the low-resolution grid)
+    const size_t slots = (size_t)conv_stats_slots(geo);
+    const size_t tstats_bytes = sizeof(float) * 2 * 4 * slots * cout_x;
+    float* tstats = nullptr;
+    if (geo.stats_ok && PL == 1) {
+      tstats = (float*)ar.alloc(tstats_bytes);
+      out->cstats = (float*)ar.alloc(sizeof(float) * 2 * B * cout_x);
+    }
+    const double fl = 4 * 2.0 * B * x.H * x.W * (double)cout_x * (4.0 * x.C) * PL;
+    if (dry) {
+      flops += fl;
+      if (tstats) ar.release(tstats, tstats_bytes);
+      return;
+    }
+    if (PL * 4 * x.C != L.row_len_up2) { rc = B2E_INVALID_ARG; set_error("unet: upsampler operand width does not match the packed phase weights"); return; }
+    int fNt = geo.Nt, fw = geo.w_blks, fh = geo.h_blks;
+    for (int ph = 0; ph < 4 && !rc; ++ph) {
+      ConvDesc d;
+      d.s0 = ConvSrc{x.p, x.C * PL};
+      d.out_planes = PL;
+      d.N = B; d.H = x.H; d.W = x.W; d.ksize = 2; d.stride = 1; d.up2_phase = ph;
+      d.w_packed = L.w_up2 + (size_t)ph * L.cout_pad * L.row_len_up2; d.Cout = cout_x; d.out_f16 = out->p;
+      d.tile_stats = tstats ? tstats + (size_t)ph * slots * cout_x * 2 : nullptr;
+      d.split_ws = split_ws; d.split_ws_bytes = split_bytes; d.split_counters = split_cnt;
+      ConvPlan pl;
+      rc = conv_plan_build(&pl, d);
+      if (rc) return;
+      ConvEpilogue ep;
+      ep.bias = L.b;
+      if (PL == 3) ep.acc_scale = 1.f / b2e_unet::kSplitWScale;
+      flops += pl.flops;
+      fNt = pl.Nt; fw = pl.w_blks; fh = pl.h_blks;
+      char desc[160];
+      snprintf(desc, sizeof(desc), "upsample x2 + conv3x3 as 2x2 phase %d: %dx%d -> %dx%d cin%d cout%d tiles%d bn%d%s", ph, x.H, x.W,
+               2 * x.H, 2 * x.W, x.C, L.cout, pl.w_blks * pl.h_blks * pl.n_blks * (pl.cout_pad / pl.block_n), pl.block_n,
+               pl.pair ? " pair" : "");
+      ops.push_back({[pl, ep](cudaStream_t st) { return conv_launch(pl, ep, st); }, 0, pl.flops, 0.0, desc});
+    }
+    if (tstats) {
+      float* cst = out->cstats;
+      const int C = cout_x;
+      const int64_t pstride = (int64_t)slots * cout_x * 2;
+      ops.push_back({[tstats, cst, B, C, fNt, fw, fh, pstride](cudaStream_t st) {
+                       return gn_finalize_launch(tstats, cst, B, C, fNt, fw, fh, st, 4, pstride);
+                     }, 3, 0.0, (double)tstats_bytes});
+      ar.release(tstats, tstats_bytes);
     }
   };
   // GroupNorm(+SiLU): statistics come from the producing convolution's epilogue, the apply pass is a stand-alone
@@ -1736,6 +1813,13 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
       }
       case N_UP: {
         sv.x = h;
+        if (up2_on && !keep && !h.alias && m->ups[nd.idx].w_up2 && h.H >= 64 && h.C == m->ups[nd.idx].cin_pad) {
+          Tensor out;
+          conv_up2(m->ups[nd.idx], h, &out);
+          if (!on_stack(h)) tfree(h);
+          h = out;
+          break;
+        }
         Tensor up = talloc(B, h.H * 2, h.W * 2, h.C, h.Cr), out;
         if (!dry) {
           Tensor hh = h;

@@ -551,7 +551,7 @@ int gn_bwd_launch(const GNBwdArgs& a, cudaStream_t st) {
 template <int L>
 __global__ void __launch_bounds__(16 * L)
 gn_finalize_kernel(const float* __restrict__ tile_stats, float* __restrict__ chan_stats, int C, int Nt, int w_blks,
-                   int h_blks) {
+                   int h_blks, int phases, int64_t phase_stride) {
   pdl_wait();
   pdl_trigger();
   __shared__ double s_s[L][16], s_q[L][16];
@@ -563,9 +563,12 @@ gn_finalize_kernel(const float* __restrict__ tile_stats, float* __restrict__ cha
   if (c < C) {
     const int64_t base = (int64_t)n_blk * per_img;
 #pragma unroll 8
-    for (int i = sl; i < per_img; i += L) {
-      const int64_t slot = (base + i) * Nt + nl;
-      const float2 v = __ldg(reinterpret_cast<const float2*>(tile_stats + (slot * C + c) * 2));
+    // phases > 1: the tensor was written by `phases` launches (sub-pixel phases of an upsampling convolution), each with
+    // its own block of slots `phase_stride` floats apart
+    for (int i = sl; i < per_img * phases; i += L) {
+      const int ph = i / per_img, ii = i - ph * per_img;
+      const int64_t slot = (base + ii) * Nt + nl;
+      const float2 v = __ldg(reinterpret_cast<const float2*>(tile_stats + ph * phase_stride + (slot * C + c) * 2));
       s += (double)v.x; q += (double)v.y;
     }
   }
@@ -580,11 +583,13 @@ gn_finalize_kernel(const float* __restrict__ tile_stats, float* __restrict__ cha
 }
 
 int gn_finalize_launch(const float* tile_stats, float* chan_stats, int N, int C, int Nt, int w_blks, int h_blks,
-                       cudaStream_t st) {
-  if (w_blks * h_blks >= 256)
-    launch_pdl(gn_finalize_kernel<64>, dim3(dim3((C + 15) / 16, N)), dim3(1024), 0, st, tile_stats, chan_stats, C, Nt, w_blks, h_blks);
+                       cudaStream_t st, int phases, int64_t phase_stride) {
+  if (w_blks * h_blks * phases >= 256)
+    launch_pdl(gn_finalize_kernel<64>, dim3(dim3((C + 15) / 16, N)), dim3(1024), 0, st, tile_stats, chan_stats, C, Nt, w_blks, h_blks,
+               phases, phase_stride);
   else
-    launch_pdl(gn_finalize_kernel<16>, dim3(dim3((C + 15) / 16, N)), dim3(256), 0, st, tile_stats, chan_stats, C, Nt, w_blks, h_blks);
+    launch_pdl(gn_finalize_kernel<16>, dim3(dim3((C + 15) / 16, N)), dim3(256), 0, st, tile_stats, chan_stats, C, Nt, w_blks, h_blks,
+               phases, phase_stride);
   return check_launch("gn_finalize");
 }
 

@@ -55,7 +55,7 @@ int gn_launch(const GNArgs& a, cudaStream_t st);
 int gn_coeffs_launch(const GNArgs& a, float* coef, cudaStream_t st);
 // tile statistics written by the conv epilogue -> per-(image, channel) sums
 int gn_finalize_launch(const float* tile_stats, float* chan_stats, int N, int C, int Nt, int w_blks, int h_blks,
-                       cudaStream_t st);
+                       cudaStream_t st, int phases = 1, int64_t phase_stride = 0);
 
 // x fp32 NCHW (B,C,H,W) -> f16 NHWC (B,H,W,cpad), zero padded channels; im2col: channel t*C + c of a pixel holds
 // x[c] at 3x3 tap t (zero outside the image), so that a 3x3 convolution becomes a 1x1 one
