@@ -454,6 +454,20 @@ def act_dtype():
     return torch.bfloat16 if lib.b2e_act_dtype() == 1 else torch.float16
 
 
+def upsample_conv3x3_nhwc_f16(x, w, bias):
+    """Test hook: conv3x3(nearest-upsample x2 (x)) + bias as four 2x2 sub-pixel phase convolutions (16-bit NHWC)."""
+    _C.require_device()
+    N, H, W, Cin = x.shape
+    Cout = w.shape[0]
+    if x.dtype != act_dtype() or tuple(w.shape[1:]) != (Cin, 3, 3):
+        raise ValueError(f"upsample_conv3x3_nhwc_f16: x must be {act_dtype()} (N,H,W,Cin), w (Cout,Cin,3,3)")
+    out = torch.empty((N, 2 * H, 2 * W, Cout), dtype=act_dtype(), device=x.device)
+    check(lib.b2e_upsample_conv3x3_nhwc_f16(_p(x.contiguous()), _p(w.contiguous().float()),
+                                            _p(bias.contiguous().float()) if bias is not None else None, _p(out), N, H, W,
+                                            Cin, Cout, _stream()), "upsample_conv3x3_nhwc_f16")
+    return out
+
+
 def conv2d_nhwc_f16(x, w, bias, stride=1, residual=None):
     """Test hook for the tcgen05 implicit-GEMM convolution (optionally + residual; 16-bit NHWC, `act_dtype()`)."""
     _C.require_device()

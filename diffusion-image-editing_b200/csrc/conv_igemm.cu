@@ -1551,3 +1551,42 @@ extern "C" int b2e_conv2d_bench_f16(int64_t N, int64_t H, int64_t W, int64_t Cin
   cudaFree(wp); cudaFree(xp); cudaFree(op); cudaFree(split_mem); cudaFree(bias);
   return rc;
 }
+
+// Test hook: y = conv3x3(nearest_upsample_x2(x)) + bias computed as the four 2x2 sub-pixel phase convolutions over the
+// low-resolution input (ConvDesc::up2_phase), f16 NHWC (N,H,W,Cin) -> (N,2H,2W,Cout).  Allocates temporaries and synchronises.
+extern "C" int b2e_upsample_conv3x3_nhwc_f16(const void* x, const float* w, const float* bias, void* out, int64_t N, int64_t H,
+                                             int64_t W, int64_t Cin, int64_t Cout, void* stream) {
+  B2E_REQUIRE(x && w && out, B2E_INVALID_ARG, "upsample_conv3x3: null pointer");
+  B2E_REQUIRE(Cin % kConvBlockK == 0 && Cout % 64 == 0, B2E_UNSUPPORTED_SHAPE, "upsample_conv3x3: Cin, Cout must be multiples of 64");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int cout_pad = conv_cout_pad((int)Cout);
+  const int row_len = (int)(4 * Cin);
+  const size_t wbytes = (size_t)cout_pad * row_len * sizeof(f16);
+  const size_t split_bytes = (size_t)kNumSMs * kConvBlockM * 128 * sizeof(float);
+  char *wp = nullptr, *split_mem = nullptr;
+  B2E_CUDA(cudaMalloc(&wp, 4 * wbytes));
+  if (cudaMalloc(&split_mem, split_bytes + 4096) != cudaSuccess) { cudaFree(wp); set_error("upsample_conv3x3: cudaMalloc failed"); return B2E_CUDA_ERROR; }
+  cudaMemsetAsync(wp, 0, 4 * wbytes, st);
+  cudaMemsetAsync(split_mem + split_bytes, 0, 4096, st);
+  int rc = B2E_OK;
+  for (int ph = 0; ph < 4 && !rc; ++ph) {
+    f16* wph = (f16*)(wp + ph * wbytes);
+    rc = conv_pack_weight_up2(w, wph, (int)Cout, (int)Cin, (int)Cin, row_len, 0, ph, st);
+    if (rc) break;
+    ConvDesc d;
+    d.s0 = ConvSrc{(const f16*)x, (int)Cin};
+    d.N = (int)N; d.H = (int)H; d.W = (int)W; d.ksize = 2; d.stride = 1; d.up2_phase = ph;
+    d.w_packed = wph; d.Cout = (int)Cout; d.out_f16 = (f16*)out;
+    d.split_ws = (float*)split_mem; d.split_ws_bytes = split_bytes; d.split_counters = (int*)(split_mem + split_bytes);
+    ConvPlan plan;
+    rc = conv_plan_build(&plan, d);
+    if (rc) break;
+    ConvEpilogue ep;
+    ep.bias = bias;
+    rc = conv_launch(plan, ep, st);
+  }
+  cudaStreamSynchronize(st);
+  cudaFree(wp);
+  cudaFree(split_mem);
+  return rc;
+}

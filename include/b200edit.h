@@ -394,6 +394,13 @@ int b2e_conv2d_nhwc_f16(const void* x, const float* w, const float* bias, const 
                          void* out, int64_t N, int64_t H, int64_t W, int64_t Cin, int64_t Cout,
                          int ksize, int stride, void* stream);
 
+/* Test hook for the upsampler: out (N,2H,2W,Cout) = conv3x3(nearest_upsample_x2(x)) + bias, x (N,H,W,Cin) 16-bit NHWC,
+ * w (Cout,Cin,3,3) fp32 - computed the way the engine does it (diffusers Upsample2D, src-side call: the UNets' and
+ * decoders' `upsamplers.0`): four 2x2 sub-pixel phase convolutions over the LOW-resolution input with pre-summed weights,
+ * each writing its sub-grid of the output through a strided TMA map.  Cin, Cout multiples of 64.  Allocates + synchronises. */
+int b2e_upsample_conv3x3_nhwc_f16(const void* x, const float* w, const float* bias, void* out, int64_t N, int64_t H,
+                                   int64_t W, int64_t Cin, int64_t Cout, void* stream);
+
 /* Measurement hook for the same kernel: `iters` back-to-back launches of one convolution (zero-filled operands of the
  * given shape, `copies` distinct packed weight sets used round-robin so that launches miss the L2 like the layers of a
  * network), CUDA-event time per launch in microseconds.  Allocates temporaries itself and synchronises. */

@@ -78,3 +78,37 @@ def test_split_k_is_deterministic():
     outs = [ops.conv2d_nhwc_f16(x, w, b) for _ in range(4)]
     torch.cuda.synchronize()
     assert all(torch.equal(outs[0], o) for o in outs[1:])
+
+
+UP2_CASES = [
+    # N, H, W, Cin, Cout  (low-resolution input)
+    (1, 8, 8, 64, 64),        # tiny: tiles span the whole image, every border tap is out of bounds somewhere
+    (2, 16, 16, 128, 128),
+    (3, 8, 16, 64, 128),      # non-square, odd batch
+    (1, 64, 64, 128, 128),    # the 64 -> 128 level in small
+    (2, 128, 128, 128, 128),  # DDPM-256's last upsampler (128 -> 256)
+    (1, 32, 32, 256, 192),    # Cout not a multiple of 128 (64-wide N tiles)
+]
+
+
+@pytest.mark.parametrize("case", UP2_CASES, ids=[str(c) for c in UP2_CASES])
+def test_upsample_conv_as_subpixel_phases_vs_torch(case):
+    """Upsample2D (nearest x2 + conv3x3) computed as four 2x2 phase convolutions on the low-resolution input against
+    torch's interpolate + conv2d in fp32 on the same 16-bit-rounded operands.  Tolerance as above; the pre-summed phase
+    weights are rounded once to 16 bit, so the weight-rounding part of the error is 2^-11 of |w_a + w_b| per tap."""
+    from b200edit import ops
+    dt = ops.act_dtype()
+    rel = 2 ** -10 if dt == torch.float16 else 2 ** -7
+    N, H, W, Cin, Cout = case
+    g = torch.Generator(device="cpu").manual_seed(sum(case))
+    x = torch.randn(N, Cin, H, W, generator=g).to(dt)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5)
+    b = torch.randn(Cout, generator=g)
+    out = ops.upsample_conv3x3_nhwc_f16(x.cuda().permute(0, 2, 3, 1).contiguous(), w.cuda(), b.cuda())
+    torch.cuda.synchronize()
+    ref = F.conv2d(F.interpolate(x.float().cuda(), scale_factor=2.0, mode="nearest"), w.cuda(), b.cuda(), padding=1)
+    got = out.float().permute(0, 3, 1, 2)
+    assert got.shape == ref.shape
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 2 * rel * scale, f"max abs err {err} (scale {scale})"
