@@ -33,9 +33,9 @@ class LDM(Diffusion):
     def native_decoder(self):
         """(decoder engine, chain factor d(decoder input)/d(x0 prediction)) when the guidance graph can run on the native
         decoder without autograd (analytic colour guidance, AttrFunc.apply); None otherwise."""
-        vq = self.vqvae
-        if hasattr(vq, "decode_keep") and not getattr(vq, "forward_only", True):
-            return vq, 1.0
+        for vq in (self.vqvae, self.guidance_vqvae):     # the twin: the gradient engine of an fp32-accurate pipeline
+            if vq is not None and hasattr(vq, "decode_keep") and not getattr(vq, "forward_only", True):
+                return vq, 1.0
         return None
 
     def encode(self, sample: torch.Tensor) -> torch.Tensor:
@@ -65,14 +65,17 @@ class SD(Diffusion):
     def __init__(self, model):
         super().__init__(model)
         self.vae = model.vae
+        # optional gradient twin of a forward-only native vae (fp32-accurate pipelines: the split-operand decoder has no
+        # backward pass; guidance runs through an f16-operand engine with the same weights, gradient within 3e-3 of fp32)
+        self.guidance_vae = getattr(model, "guidance_vae", None)
         self.tokenizer = model.tokenizer
         self.text_encoder = model.text_encoder
 
     def native_decoder(self):
         """See LDM.native_decoder; SD.decode feeds the decoder latent / 0.18215."""
-        vae = self.vae
-        if hasattr(vae, "decode_keep") and not getattr(vae, "forward_only", True):
-            return vae, 1.0 / self.SCALE
+        for vae in (self.vae, self.guidance_vae):
+            if vae is not None and hasattr(vae, "decode_keep") and not getattr(vae, "forward_only", True):
+                return vae, 1.0 / self.SCALE
         return None
 
     def encode(self, sample: torch.Tensor) -> torch.Tensor:
@@ -85,7 +88,10 @@ class SD(Diffusion):
         if no_grad:
             with torch.no_grad():
                 return self.vae.decode(latent).sample
-        return self.vae.decode(latent).sample
+        vae = self.vae
+        if getattr(vae, "forward_only", False) and self.guidance_vae is not None:
+            vae = self.guidance_vae
+        return vae.decode(latent).sample
 
     def additional_prep(self, model, prompt):
         return prep_text(model, prompt)

@@ -58,12 +58,20 @@ def create_diffusion_model(name: str, sample_clipping: bool = True, *, max_batch
             # decoder_grad=True (default), the native dgrad for guidance THROUGH the decoder
             vqvae = VQModel(**(vq_config or LDM_VQ_CONFIG), max_batch=max_batch, device=device, with_encoder=with_encoder,
                             precision=precision)
-            decoder_grad = decoder_grad and precision != "fp32"   # the fp32-accurate decoder is forward-only
             if vq_state_dict is not None:
                 vqvae.load_state_dict(vq_state_dict)
             else:
                 vqvae.init_random(seed + 1)
-            if decoder_grad:
+            # decoder weights for a gradient twin (random init: the decoder part of what init_random just loaded)
+            vq_sd = vq_state_dict if vq_state_dict is not None else vqvae.random_state_dict(seed + 1)
+            if decoder_grad and precision == "fp32":
+                # the fp32-accurate (split-operand) decoder is forward-only: guidance THROUGH the decoder runs on a second,
+                # f16-operand engine with the same weights (decoder gradient within 3e-3 relative RMS of fp32 autograd)
+                guidance_vqvae = VQModel(**(vq_config or LDM_VQ_CONFIG), max_batch=max_batch, device=device, with_encoder=False,
+                                         precision="fp16")
+                guidance_vqvae.load_state_dict(vq_sd, strict=False)     # the encoder's entries are simply not used
+                guidance_vqvae.enable_grad()
+            elif decoder_grad:
                 vqvae.enable_grad()
         elif isinstance(vqvae, torch.nn.Module) or not getattr(vqvae, "forward_only", False):
             guidance_vqvae = vqvae
@@ -84,15 +92,21 @@ def create_diffusion_model(name: str, sample_clipping: bool = True, *, max_batch
         if vqvae is None:
             vae = AutoencoderKL(**(vq_config or SD_VAE_CONFIG), max_batch=max_batch, device=device, with_encoder=with_encoder,
                                 precision=precision)
-            decoder_grad = decoder_grad and precision != "fp32"   # the fp32-accurate decoder is forward-only
             if vq_state_dict is not None:
                 vae.load_state_dict(vq_state_dict)
             else:
                 vae.init_random(seed + 1)
-            if decoder_grad:
+            vq_sd = vq_state_dict if vq_state_dict is not None else vae.random_state_dict(seed + 1)
+            guidance_vae = None
+            if decoder_grad and precision == "fp32":      # see the "ldm" branch: f16-operand gradient twin
+                guidance_vae = AutoencoderKL(**(vq_config or SD_VAE_CONFIG), max_batch=max_batch, device=device, with_encoder=False,
+                                             precision="fp16")
+                guidance_vae.load_state_dict(vq_sd, strict=False)
+                guidance_vae.enable_grad()
+            elif decoder_grad:
                 vae.enable_grad()
         else:
-            vae = vqvae
+            vae, guidance_vae = vqvae, None
         scheduler = DDIMScheduler.from_preset("sd")
         scheduler.config.clip_sample = sample_clipping
         # text side: the CLIP text encoder runs on the engine (b200edit.clip; transformers state_dict names) unless the
@@ -105,7 +119,8 @@ def create_diffusion_model(name: str, sample_clipping: bool = True, *, max_batch
                 text_encoder.load_state_dict(text_encoder_state_dict)
             else:
                 text_encoder.init_random(seed + 2)
-        return SD(NativePipeline(unet=unet, scheduler=scheduler, vae=vae, tokenizer=tokenizer, text_encoder=text_encoder,
+        return SD(NativePipeline(unet=unet, scheduler=scheduler, vae=vae, guidance_vae=guidance_vae, tokenizer=tokenizer,
+                                 text_encoder=text_encoder,
                                  device=device))
     raise ValueError(f"Unknown model name: {name}")
 

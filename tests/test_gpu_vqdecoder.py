@@ -353,3 +353,48 @@ def test_autoencoder_kl_decode_and_gradient():
     relg = ((gn - go).pow(2).mean().sqrt() / go.pow(2).mean().sqrt()).item()
     print(f"autoencoder-kl small: image rel-rms {rel:.3e}, gradient rel-rms {relg:.3e}")
     assert img.shape == (2, 3, 64, 64) and rel <= 5e-3 and relg <= 1e-2      # measured 1.9e-3 / 3.1e-3
+
+
+def test_fp32_accurate_pipeline_guides_through_the_decoder_twin():
+    """precision="fp32" pipelines: the split-operand decoder is forward-only, so guidance THROUGH the decoder runs on an
+    f16-operand gradient twin with the same weights (models.create_diffusion_model).  The guided trajectory must (a) run
+    without autograd, (b) move the latent, (c) stay close to the f16 pipeline's trajectory given the same noise predictions
+    are NOT shared (different UNet precision): compare the decoded images loosely, and the twin's decode with the main's."""
+    from attr_functions import SingleColorAttrFunc
+    from models import create_diffusion_model
+    from SegDiffEditPipeline import SegDiffEditPipeline
+    ucfg = dict(sample_size=16, in_channels=3, out_channels=3, block_out_channels=(32, 96), layers_per_block=1,
+                down_block_types=("DownBlock2D", "AttnDownBlock2D"), up_block_types=("AttnUpBlock2D", "UpBlock2D"),
+                attention_head_dim=32, flip_sin_to_cos=True, freq_shift=0, downsample_padding=1)
+    vcfg = dict(SMALL, block_out_channels=(64, 128), sample_size=16)
+    outs = {}
+    for prec in ("fp32", "fp16"):
+        w = create_diffusion_model("ldm", sample_clipping=False, max_batch=1, seed=3, unet_config=ucfg, vq_config=vcfg,
+                                   precision=prec)
+        if prec == "fp32":
+            assert w.vqvae.forward_only and w.guidance_vqvae is not None and not w.guidance_vqvae.forward_only
+            assert w.native_decoder()[0] is w.guidance_vqvae
+            z = torch.randn(1, 3, 16, 16, generator=torch.Generator().manual_seed(1)).cuda()
+            a, b = w.vqvae.decode(z).sample, w.guidance_vqvae.decode(z).sample      # same weights in both engines
+            assert ((a - b).pow(2).mean().sqrt() / a.pow(2).mean().sqrt()).item() <= 5e-3
+        w.scheduler.set_timesteps(4)
+        pipe = SegDiffEditPipeline(w, None)
+        xt = torch.randn(1, 3, 16, 16, generator=torch.Generator().manual_seed(5)).cuda()
+        f = SingleColorAttrFunc(target=0.8, color_idx=0, loss_scale=200.0, t1=0, t2=4)
+        real_grad = torch.autograd.grad
+
+        def no_autograd(*a, **k):
+            raise AssertionError("torch.autograd.grad called on the native analytic guidance path")
+
+        torch.autograd.grad = no_autograd
+        try:
+            guided = pipe.edit_image(xt=xt.clone(), attr_func=f, prog_bar=False, output_type="tensor").imgs
+        finally:
+            torch.autograd.grad = real_grad
+        idle = SingleColorAttrFunc(target=0.8, color_idx=0, loss_scale=200.0, t1=10 ** 6, t2=10 ** 6 + 1)   # window never open
+        plain = pipe.edit_image(xt=xt.clone(), attr_func=idle, prog_bar=False, output_type="tensor").imgs
+        assert torch.isfinite(guided).all() and (guided - plain).abs().max() > 1e-3      # the guidance acted
+        outs[prec] = guided
+    rel = ((outs["fp32"] - outs["fp16"]).pow(2).mean().sqrt() / outs["fp16"].pow(2).mean().sqrt()).item()
+    print(f"guided LDM images, fp32-accurate pipeline (decoder-gradient twin) vs f16 pipeline: rel-rms {rel:.3e}")
+    assert rel <= 2e-2
