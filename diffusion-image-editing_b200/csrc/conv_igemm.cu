@@ -88,6 +88,9 @@ struct ConvKParams {
   int debug;                // B2E_DEBUG micro-benchmark knobs: 1 = no TMA loads (MMA on stale smem), 2 = no MMAs
   int splits;               // split-K factor (>1: partial accumulators meet in split_ws, last CTA finishes the tile)
   int split_cluster;        // 1: the splits of a tile form a thread-block cluster; partials meet in the leader's smem (DSMEM)
+  // halo kernels: taps served per halo load (vertical) / loads per channel chunk (horizontal) and the offset of the
+  // halo's first pixel from the brick's: 3, 3, (-1, -1) for a 3x3 convolution; 2, 2, (a - 1, b - 1) for sub-pixel phase (a, b)
+  int halo_vt, halo_ht, halo_dh0, halo_dw0;
   float* split_ws;          // [num_tiles][splits][128][BN] fp32
   int* split_counters;      // [num_tiles], zero between launches
   int n_tiles, num_tiles;   // PAIR kernels: num_tiles counts tile PAIRS (two adjacent M tiles, same N tile)
@@ -237,10 +240,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       for (int tile = tile_begin; tile < p.num_tiles; tile += tile_step) {
         const TileCoord tc = halo_coord<MT>(p, tile, rank);
         const int brow0 = tc.n_tile * BN + rank * Cfg::kBRows;
-        const int groups = 3 * chunks + r_chunks;
+        const int groups = p.halo_ht * chunks + r_chunks;
+        const uint32_t a_bytes = (uint32_t)((kHaloHt * MT + p.halo_vt - 1) * kHaloWt * 128);   // the TMA box of the halo
         int kw = 0, ck = 0;
         for (int g = 0; g < groups; ++g) {
-          const bool main = g < 3 * chunks;
+          const bool main = g < p.halo_ht * chunks;
           if (tr && tr_n < 512) p.trace[kTrPb + tr_n * 3] = clock64();
           mbar_wait(empty_bar + stage, phase ^ 1);
           if (tr && tr_n < 512) p.trace[kTrPb + tr_n * 3 + 1] = clock64();
@@ -251,22 +255,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
               const bool first = ck < p.c0_chunks;
               if constexpr (XF) {
                 // raw activations: completion on this CTA's own barrier, the transform warps take it from there
-                mbar_expect_tx(araw_bar + stage, Cfg::kHaloABytes);
+                mbar_expect_tx(araw_bar + stage, a_bytes);
                 tma_load_5d(sa, first ? &map_a0 : &map_a1, araw_bar + stage,
-                            (first ? ck : ck - p.c0_chunks) * kConvBlockK, tc.w0 + kw - 1, 0, tc.h0 - 1, tc.n0);
-                if (rank == 0) mbar_expect_tx(full_bar + stage, 2 * 3 * Cfg::kBBytes);
+                            (first ? ck : ck - p.c0_chunks) * kConvBlockK, tc.w0 + kw + p.halo_dw0, 0, tc.h0 + p.halo_dh0, tc.n0);
+                if (rank == 0) mbar_expect_tx(full_bar + stage, 2 * p.halo_vt * Cfg::kBBytes);
               } else {
-              if (rank == 0) mbar_expect_tx(full_bar + stage, 2 * (Cfg::kHaloABytes + 3 * Cfg::kBBytes));
+              if (rank == 0) mbar_expect_tx(full_bar + stage, 2 * (a_bytes + p.halo_vt * Cfg::kBBytes));
               tma_load_5d_2sm(sa, first ? &map_a0 : &map_a1, full_bar + stage,
-                              (first ? ck : ck - p.c0_chunks) * kConvBlockK, tc.w0 + kw - 1, 0, tc.h0 - 1, tc.n0);
+                              (first ? ck : ck - p.c0_chunks) * kConvBlockK, tc.w0 + kw + p.halo_dw0, 0, tc.h0 + p.halo_dh0, tc.n0);
               }
 #pragma unroll
               for (int kh = 0; kh < 3; ++kh)
-                tma_load_2d_2sm(sa + Cfg::kHaloABytes + kh * Cfg::kBBytesPad, &map_b, full_bar + stage,
-                                ((kh * 3 + kw) * chunks + ck) * kConvBlockK, brow0);
+                if (kh < p.halo_vt)
+                  tma_load_2d_2sm(sa + Cfg::kHaloABytes + kh * Cfg::kBBytesPad, &map_b, full_bar + stage,
+                                  ((kh * p.halo_ht + kw) * chunks + ck) * kConvBlockK, brow0);
             } else {
               // residual segment: the brick itself (MT x 128 pixels) at the output position, one B tile
-              const int rk = g - 3 * chunks;
+              const int rk = g - p.halo_ht * chunks;
               const bool first = rk < p.r0_chunks;
               if constexpr (XF) {
                 mbar_expect_tx(araw_bar + stage, MT * kABytes);
@@ -358,7 +363,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       if constexpr (HALO) {
         int tr_n = 0;
         const bool tr = p.trace && blockIdx.x == 0 && lane == 0;
-        const int groups = 3 * chunks + r_chunks;   // pipeline stages per work item
+        const int groups = p.halo_ht * chunks + r_chunks;   // pipeline stages per work item
         for (int tile = tile_begin; tile < p.num_tiles; tile += tile_step, ++it) {
           const int acc = it & 1;
           if (tr && tr_n < 512) p.trace[kTrMma + tr_n * 4] = clock64();
@@ -366,7 +371,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + (uint32_t)(acc * Cfg::kAccCols);
           for (int g = 0; g < groups; ++g) {
-            const int nsub = g < 3 * chunks ? 3 : 1;   // vertical taps served by this stage
+            const int nsub = g < p.halo_ht * chunks ? p.halo_vt : 1;   // vertical taps served by this stage
             if (tr && tr_n < 512) p.trace[kTrMma + tr_n * 4 + 1] = clock64();
             if constexpr (XF) mbar_wait_cluster(full_bar + stage, phase); else mbar_wait(full_bar + stage, phase);
             tc_fence_after();
@@ -859,18 +864,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     if constexpr (HALO) {
       constexpr int kRows = (kHaloHt * MT + 2) * kHaloWt, kNI = kRows / 32;
       static_assert(kRows % 32 == 0, "halo rows");
-      const int groups = 3 * chunks + r_chunks;
+      const int groups = p.halo_ht * chunks + r_chunks;
       for (int tile = tile_begin; tile < p.num_tiles; tile += tile_step) {
         const TileCoord tc = halo_coord<MT>(p, tile, rank);
         int kw = 0, ck = 0;
         for (int g = 0; g < groups; ++g) {
-          const bool main = g < 3 * chunks;
+          const bool main = g < p.halo_ht * chunks;
           float sc[8], sh[8];
           if (main) load_coef(tc.n0, ck * kConvBlockK, sc, sh);     // before the wait: overlaps the TMA flight
           mbar_wait(araw_bar + stage, phase);
           if (main) {
             uint8_t* sa = smem + stage * Cfg::kStageBytes;
-            const int wbase = tc.w0 + kw - 1, hbase = tc.h0 - 1;
+            const int wbase = tc.w0 + kw + p.halo_dw0, hbase = tc.h0 + p.halo_dh0;
             if (!xf_skip) {
 #pragma unroll
               for (int i = 0; i < kNI; ++i) {
@@ -1122,7 +1127,7 @@ ConvGeom conv_geometry(int N, int Ho, int Wo, int Cout, int ksize, int stride) {
   g.block_n = cout_pad <= 16 ? 16 : (cout_pad % 128 == 0 ? 128 : 64);
   // few output tiles (low-resolution levels): halve the N tile to double the number of CTAs - unless the layer can run
   // on the halo kernel, whose 3x lower L2 traffic per FLOP beats the extra CTAs
-  const bool halo_shape = ksize == 3 && stride == 1 && Wo % kHaloWt == 0 && Ho % kHaloHt == 0 && cout_pad % 128 == 0 &&
+  const bool halo_shape = (ksize == 3 || ksize == 2) && stride == 1 && Wo % kHaloWt == 0 && Ho % kHaloHt == 0 && cout_pad % 128 == 0 &&
                           (int64_t)N * Ho * Wo / kConvBlockM * (cout_pad / 128) >= halo_min_tiles();
   static const int bn64_below = getenv("B2E_BN64_BELOW") ? atoi(getenv("B2E_BN64_BELOW")) : kNumSMs / 2;   // experiments
   if (g.block_n == 128 && !halo_shape && g.w_blks * g.h_blks * g.n_blks * (cout_pad / 128) < bn64_below) g.block_n = 64;
@@ -1134,10 +1139,11 @@ ConvGeom conv_geometry(int N, int Ho, int Wo, int Cout, int ksize, int stride) {
 // (C, W, 1, H, N) view of an NHWC tensor (stride 1) or (2C, W/2, 2, H/2, N) (stride 2), box = one tile brick
 // up2_phase >= 0: (N,H,W,C) is the sub-grid of pixels (2i + a, 2j + b) of a (N,2H,2W,C) tensor at `ptr`
 static int encode_act_map(CUtensorMap* m, const f16* ptr, int N, int H, int W, int C, int stride,
-                          int Wt, int Ht, int Nt, int pitch = 0, int halo = 0, int up2_phase = -1) {
+                          int Wt, int Ht, int Nt, int pitch = 0, int halo_rows = 0, int up2_phase = -1) {
   const uint64_t e = 2;
   uint64_t dims[5], str[4];
-  uint32_t box[5] = {(uint32_t)kConvBlockK, (uint32_t)Wt, 1, (uint32_t)(Ht + 2 * halo), (uint32_t)Nt};
+  // halo_rows: extra rows of a halo brick (vertical taps - 1)
+  uint32_t box[5] = {(uint32_t)kConvBlockK, (uint32_t)Wt, 1, (uint32_t)(Ht + halo_rows), (uint32_t)Nt};
   if (up2_phase >= 0) {
     const int a = up2_phase >> 1, b = up2_phase & 1;
     dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = N;
@@ -1185,7 +1191,8 @@ int conv_plan_build(ConvPlan* pl, const ConvDesc& d) {
   // force MT.
   static const int halo_env = getenv("B2E_HALO") ? atoi(getenv("B2E_HALO")) : -1;
   p.halo = 0;
-  if (halo_env != 0 && d.ksize == 3 && d.stride == 1 && (g.block_n == 128 || g.block_n == 16) && !d.b_batch_rows &&
+  p.up2_phase = d.up2_phase;
+  if (halo_env != 0 && (d.ksize == 3 || d.up2_phase >= 0) && d.stride == 1 && (g.block_n == 128 || g.block_n == 16) && !d.b_batch_rows &&
       !d.s0.pitch && p.Wo % kHaloWt == 0 && p.Ho % kHaloHt == 0) {
     const int64_t tiles128 = (int64_t)d.N * p.Ho * p.Wo / kConvBlockM * (p.cout_pad / g.block_n);   // 128 x BN output tiles
     if (tiles128 >= halo_min_tiles() && tiles128 % 2 == 0) {
@@ -1235,10 +1242,11 @@ int conv_plan_build(ConvPlan* pl, const ConvDesc& d) {
   // halo kernels: A boxes are the brick's halo (8*MT + 2 rows), residual boxes the brick (8*MT rows), the output
   // box one 8 x 16 M tile
   const int a_ht = p.halo ? p.Ht * p.halo : p.Ht;
-  int rc = encode_act_map(&p.map_a0, d.s0.ptr, d.N, d.H, d.W, d.s0.C, d.stride, p.Wt, a_ht, p.Nt, d.s0.pitch, p.halo ? 1 : 0);
+  const int halo_rows = p.halo ? d.ksize - 1 : 0;     // 3x3: 2; sub-pixel phase (2x2): 1
+  int rc = encode_act_map(&p.map_a0, d.s0.ptr, d.N, d.H, d.W, d.s0.C, d.stride, p.Wt, a_ht, p.Nt, d.s0.pitch, halo_rows);
   if (rc) return rc;
   p.map_a1 = p.map_a0; p.map_r0 = p.map_a0; p.map_r1 = p.map_a0; p.map_out = p.map_a0;
-  if (d.s1.ptr && (rc = encode_act_map(&p.map_a1, d.s1.ptr, d.N, d.H, d.W, d.s1.C, d.stride, p.Wt, a_ht, p.Nt, 0, p.halo ? 1 : 0))) return rc;
+  if (d.s1.ptr && (rc = encode_act_map(&p.map_a1, d.s1.ptr, d.N, d.H, d.W, d.s1.C, d.stride, p.Wt, a_ht, p.Nt, 0, halo_rows))) return rc;
   if (d.r0.ptr && (rc = encode_act_map(&p.map_r0, d.r0.ptr, d.N, p.Ho, p.Wo, d.r0.C, 1, p.Wt, a_ht, p.Nt))) return rc;
   if (d.r1.ptr && (rc = encode_act_map(&p.map_r1, d.r1.ptr, d.N, p.Ho, p.Wo, d.r1.C, 1, p.Wt, a_ht, p.Nt))) return rc;
   p.has_out_f16 = d.out_f16 != nullptr;
@@ -1374,6 +1382,8 @@ int conv_launch(const ConvPlan& pl, const ConvEpilogue& ep, cudaStream_t st) {
   kp.debug = dbg;
   kp.splits = pl.splits; kp.split_ws = pl.split_ws; kp.split_counters = pl.split_counters;
   kp.split_cluster = pl.split_cluster;
+  if (pl.up2_phase >= 0) { kp.halo_vt = 2; kp.halo_ht = 2; kp.halo_dh0 = (pl.up2_phase >> 1) - 1; kp.halo_dw0 = (pl.up2_phase & 1) - 1; }
+  else { kp.halo_vt = 3; kp.halo_ht = 3; kp.halo_dh0 = -1; kp.halo_dw0 = -1; }
   kp.bias = ep.bias; kp.bias2 = ep.bias2; kp.temb = ep.temb; kp.temb_stride = ep.temb_stride;
   kp.out_f16 = pl.has_out_f16; kp.out_f32_nchw = pl.has_out_f16 ? nullptr : ep.out_f32_nchw;
   kp.tile_stats = pl.tile_stats;

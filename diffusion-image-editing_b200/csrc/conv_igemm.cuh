@@ -76,6 +76,7 @@ struct ConvPlan {
   int splits; float* split_ws; int* split_counters;
   int split_cluster;   // 1: the splits of a tile run as one thread-block cluster and meet in the leader's smem (DSMEM)
   int halo;     // 0, or MT = M tiles per CTA of the halo kernel: (8*MT)x16-pixel bricks, one halo load serves 3 vertical taps
+  int up2_phase;   // ConvDesc::up2_phase (halo kernels: 2 x 2 taps, halo offset (a - 1, b - 1))
   int pair;     // 1: SM-pair kernel (tcgen05.mma.cta_group::2, 256 x 128 tile per cluster)
   int has_out_f16;
   int split_pitch;   // channels per plane of a split-f16 output (0: plain f16)

@@ -1292,9 +1292,9 @@ int build_program(b2e_unet* m, int B, void* ws, size_t ws_bytes, size_t* need) {
   // (one per output-pixel parity, weights pre-summed at set_param time): 2.25x fewer FLOPs, and the upsampled tensor is
   // never written or read.  Each phase writes its sub-grid of the output through a strided TMA map and its own block of
   // GroupNorm tile statistics; ONE gn_finalize reduces the four blocks.  Forward-only programs, outputs of >= 128x128.
-  // Measured at batch 8 (DDPM-256, tools/profile_ops.py): 128 -> 256 at 128 channels 4 x 31.8 us against 115 us + 52 us of
-  // upsample2x; 64 -> 128 at 256 channels 4 x 27.4 against 98 + 29; 32 -> 64 at 256 channels 4 x 15 against 36 + 15 (worse:
-  // excluded).  The phase launches are K-short (8-16 k-blocks per tile) and therefore epilogue-bound at 520-650 TFLOP/s:
+  // Measured at batch 8 (DDPM-256, tools/profile_ops.py): 128 -> 256 at 128 channels 4 x 29.2 us against 115 us + 52 us of
+  // upsample2x; 64 -> 128 at 256 channels 4 x 24.6 against 98 + 29; 32 -> 64 at 256 channels 4 x 15 against 36 + 15 (worse:
+  // excluded).  The phase launches are K-short (8-16 k-blocks per tile) and therefore epilogue-bound at 580-700 TFLOP/s:
   // the gain is the upsample pass they remove, not their 2.25x fewer FLOPs.  B2E_UP2=0 restores upsample2x + conv3x3.
   static const bool up2_on = !(getenv("B2E_UP2") && atoi(getenv("B2E_UP2")) == 0);
   auto conv_up2 = [&](const ConvL& L, const Tensor& x, Tensor* out) {
