@@ -119,6 +119,7 @@ class UNet2DModel:
     def init_random(self, seed=0):
         """PyTorch-default-style init (U(-1/sqrt(fan_in), 1/sqrt(fan_in)); norm scale 1, shift 0)."""
         self.load_state_dict(self.random_state_dict(seed))
+        return self
 
     def random_state_dict(self, seed=0):
         """The state dict ``init_random(seed)`` loads (so that a second engine can be given the same weights)."""
@@ -133,7 +134,6 @@ class UNet2DModel:
                 bound = 1.0 / math.sqrt(fan)
                 sd[name] = (torch.rand(numel, generator=g) * 2 - 1) * bound
         return sd
-        return self
 
     def to(self, *a, **k):
         return self
