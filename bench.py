@@ -287,6 +287,8 @@ def main():
             todo.append(("config3", lambda: config3(c, precision, None, 2, 1)))
         if args.config != 4:
             todo.append(("config4", lambda: config4(c, precision, None, 2, 1)))
+        if args.config == 2:
+            todo.append(("batch_sweep", lambda: batch_sweep(c, precision)))
         for name, fn in todo:
             # every rank must take the same branch (the extras synchronise across ranks): agree on the time guard and on
             # failures collectively
@@ -547,6 +549,32 @@ def config1(c, precision, B, K, W, headline=False):
     res["cuda_graph"] = bool(w.unet._graph_on)
     del pipe, w
     return res
+
+
+# ----- BASELINE configs[4]: colour-guided DDIM throughput over the batch size (per GPU of this run)
+def batch_sweep(c, precision, batches=(2, 4, 16, 32, 64, 128, 256), D=4, K=2):
+    """img-steps/s of the colour-guided DDIM step (configs[0]'s workload) at each batch size, HBM-resident inputs, a D-step
+    schedule (the per-step work does not depend on the schedule length), K passes after one warm-up pass."""
+    from attr_functions import SingleColorAttrFunc
+    from models import create_diffusion_model
+    from SegDiffEditPipeline import SegDiffEditPipeline
+    f = SingleColorAttrFunc(target=0.8, color_idx=0, loss_scale=100.0, t1=0, t2=10 ** 9, per_sample=True)
+    points = []
+    for B in batches:
+        w = create_diffusion_model("ddpm", sample_clipping=True, max_batch=B, seed=0, precision=precision)
+        w.scheduler.set_timesteps(D)
+        pipe = SegDiffEditPipeline(w, None)
+        x = torch.randn(B, 3, 256, 256, generator=torch.Generator().manual_seed(77 + c.rank)).to(c.dev)
+        run = lambda: pipe.edit_image(xt=x, eta=0.0, attr_func=f, prog_bar=False, output_type="tensor")   # noqa: E731
+        run()
+        ms, _ = c.timed(run, K)
+        points.append({"batch_per_gpu": B, "value": c.world * B * D * K / (ms * 1e-3), "ms_per_denoising_step": ms / (K * D),
+                       "achieved_tflops_per_gpu": B * w.unet.flops_per_sample / (ms / (K * D) * 1e-3) / 1e12})
+        del pipe, w, x
+        torch.cuda.empty_cache()
+    return {"workload": "BASELINE configs[4]: colour-guided DDIM on DDPM-256 over the batch size (batch 1: extra.batch1, batch 8: "
+                        "the headline)", "unit": UNIT, "denoising_steps_per_pass": D, "passes": K, "precision": precision,
+            "n_gpus": c.world, "points": points}
 
 
 # ----- BASELINE configs[2]: LDM, segmentation-mask colour guidance THROUGH the VQ decoder
