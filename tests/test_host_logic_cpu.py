@@ -203,3 +203,28 @@ def test_batchnorm_folding_of_the_loss_networks_cpu():
         want = o.cp.arm16.conv(xa)
         got = torch.relu(torch.nn.functional.conv2d(xa, f2["cp.arm16.conv.weight"], f2["cp.arm16.conv.bias"], padding=1))
         assert torch.allclose(got, want, rtol=1e-5, atol=1e-5)
+
+
+def test_precision_selection_of_the_engines_cpu():
+    """Precision names are validated on the host before any device work: the 16-bit type the library was not built for and
+    unknown names raise instead of silently computing in another precision (b200edit/_C.py::resolve_precision); the face
+    parser wrapper validates its own argument and defaults to f16 operands for mask creation / fp32-accurate forward for
+    differentiated calls (b200edit/bisenet.py::MultiResBiSeNet)."""
+    import pytest
+    from b200edit import _C
+    from b200edit.bisenet import MultiResBiSeNet
+    fast = _C.fast_precision()
+    assert fast in ("fp16", "bf16")
+    assert _C.resolve_precision(None, "t") == (fast, 0) and _C.resolve_precision(fast, "t") == (fast, 0)
+    assert _C.resolve_precision("fp32", "t") == ("fp32", 1)
+    other = "bf16" if fast == "fp16" else "fp16"
+    with pytest.raises(ValueError, match="built for"):
+        _C.resolve_precision(other, "t")
+    with pytest.raises(ValueError, match="precision must be"):
+        _C.resolve_precision("fp8", "t")
+    with pytest.raises(ValueError, match="precision"):
+        MultiResBiSeNet(precision="fp64")
+    net = MultiResBiSeNet(19, max_batch=1, device="cpu", precision=None)     # engines are built lazily: no device work here
+    assert net.precision is None and net._engines == {}
+    with pytest.raises(ValueError, match="multiple of 32"):
+        net.engine(100)
