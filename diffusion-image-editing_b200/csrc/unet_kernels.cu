@@ -230,6 +230,105 @@ __global__ void __launch_bounds__(512, SPLIT ? 1 : 2) gn_apply_kernel(GNArgs a, 
   }
 }
 
+// Bulk-copy variant of the apply pass (plain f16 tensors, channel pitch == channels, statistics from the producing
+// convolution): thread 0 issues the block's whole input - one contiguous chunk per source - as cp.async.bulk copies into
+// shared memory BEFORE the statistics prologue, so up to 32 KB per block are in flight while the prologue runs, without
+// holding them in registers; the transform then reads shared memory.  Same arithmetic, same results as gn_apply_kernel.
+constexpr int kGNBulkBytes = 32 * 1024;
+__global__ void __launch_bounds__(kGNThreads) gn_apply_bulk_kernel(GNArgs a, int pix_per_block) {
+  __shared__ float s_mean[64], s_rstd[64];
+  __shared__ __align__(8) uint64_t s_bar;
+  extern __shared__ __align__(128) uint8_t s_dyn[];
+  const int C = a.C0 + a.C1, slots = C >> 3, ppi = (int)blockDim.x / slots;
+  const int n = a.reverse ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y, tid = threadIdx.x;
+  const int bx = a.reverse ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
+  const int cpg = C / a.G;
+  const int p0 = bx * pix_per_block, p1 = min(a.HW, p0 + pix_per_block), np = p1 - p0;
+  // [x0 chunk: np x C0][x1 chunk: np x C1] f16, then the per-channel sums (doubles)
+  f16* t0 = reinterpret_cast<f16*>(s_dyn);
+  f16* t1 = t0 + (size_t)pix_per_block * a.C0;
+  double* s_ch = reinterpret_cast<double*>(s_dyn + (size_t)pix_per_block * C * sizeof(f16));
+  const int s = tid % slots, pl = tid / slots, c = s * 8;
+  float scale[8], shift[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { scale[j] = __ldg(a.gamma + c + j); shift[j] = __ldg(a.beta + c + j); }
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  pdl_wait();
+  if (tid == 0) {
+    const uint32_t b0 = (uint32_t)np * a.C0 * sizeof(f16), b1 = (uint32_t)np * a.C1 * sizeof(f16);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(b0 + b1) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(t0)), "l"(a.x0 + ((int64_t)n * a.HW + p0) * a.C0), "r"(b0), "r"(bar) : "memory");
+    if (b1)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"((uint32_t)__cvta_generic_to_shared(t1)), "l"(a.x1 + ((int64_t)n * a.HW + p0) * a.C1), "r"(b1), "r"(bar) : "memory");
+  }
+  // statistics prologue (as gn_apply_kernel)
+  for (int ch = tid; ch < C; ch += blockDim.x) {
+    const bool first = ch < a.C0;
+    const int Cs = first ? a.C0 : a.C1, cc = first ? ch : ch - a.C0;
+    double ts = 0.0, tq = 0.0;
+    if (a.ts0) {
+      const float* t = first ? a.ts0 : a.ts1;
+      const int64_t base = (int64_t)(n / a.ts_nt) * a.ts_per_img;
+      const int nl = n % a.ts_nt;
+#pragma unroll 4
+      for (int i = 0; i < a.ts_per_img; ++i) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(t + (((base + i) * a.ts_nt + nl) * Cs + cc) * 2));
+        ts += (double)v.x; tq += (double)v.y;
+      }
+    } else {
+      const float2 v = __ldg(reinterpret_cast<const float2*>((first ? a.cs0 : a.cs1) + ((int64_t)n * Cs + cc) * 2));
+      ts = (double)v.x; tq = (double)v.y;
+    }
+    s_ch[2 * ch] = ts; s_ch[2 * ch + 1] = tq;
+  }
+  __syncthreads();
+  if (tid < a.G) {
+    double ts = 0.0, tq = 0.0;
+    for (int ch = tid * cpg; ch < (tid + 1) * cpg; ++ch) { ts += s_ch[2 * ch]; tq += s_ch[2 * ch + 1]; }
+    const double cnt = (double)a.HW * cpg;
+    const double mean = ts / cnt;
+    double var = tq / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[tid] = (float)mean;
+    s_rstd[tid] = (float)(1.0 / sqrt(var + (double)a.eps));
+    if (a.save_stats && bx == 0)
+      *reinterpret_cast<float2*>(a.save_stats + ((int64_t)n * a.G + tid) * 2) = make_float2(s_mean[tid], s_rstd[tid]);
+  }
+  __syncthreads();
+  if (pl >= ppi) return;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = (c + j) / cpg;
+    scale[j] = s_rstd[g] * scale[j];
+    shift[j] = shift[j] - s_mean[g] * scale[j];
+  }
+  // wait for the chunk(s)
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "GNB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], 0;\n"
+      "@P1 bra GNB_DONE;\n"
+      "bra GNB_WAIT;\n"
+      "GNB_DONE:\n"
+      "}\n" ::"r"(bar) : "memory");
+  const bool first = c < a.C0;
+  const f16* src = first ? t0 + c : t1 + (c - a.C0);
+  const int cs = first ? a.C0 : a.C1;
+  f16* dst = a.out + ((int64_t)n * a.HW + p0) * a.Pout + c;
+#pragma unroll 4
+  for (int q = pl; q < np; q += ppi) {
+    const uint4 v = *reinterpret_cast<const uint4*>(src + (size_t)q * cs);
+    *reinterpret_cast<uint4*>(dst + (int64_t)q * a.Pout) = gn_apply8(v, scale, shift, a.silu != 0);
+  }
+}
+
 // Coefficients of the FUSED GroupNorm (conv_igemm XF kernels): per image n and per K position p of the consumer
 // convolution's A operand (source 0 at [0, P0), source 1 at [P0, P0 + P1), pitches included) the pair
 // (scale, shift) = (rstd_g gamma_c, beta_c - mean_g scale) - the arithmetic of gn_apply_kernel - and (0, 0) on the zero
@@ -354,6 +453,23 @@ int gn_launch(const GNArgs& a_in, cudaStream_t st) {
   if (!attr_set) {
     B2E_CUDA(cudaFuncSetAttribute(gn_apply_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     attr_set = true;
+  }
+  // bulk-copy variant: plain tensors with compact channels and fused statistics, chunks of <= 32 KB per block
+  static const int bulk_on = getenv("B2E_GN_BULK") ? atoi(getenv("B2E_GN_BULK")) : 1;
+  if (bulk_on && a.planes == 1 && (a.cs0 || a.ts0) && a.P0 == a.C0 && (a.C1 == 0 || a.P1 == a.C1) && a.Pout == C && C <= 2048 &&
+      threads == kGNThreads && (int64_t)a.HW * C * 2 >= 4 * kGNBulkBytes) {
+    int bp = kGNBulkBytes / (C * 2);           // pixels per block: a multiple of the pixel lanes
+    bp -= bp % ppi;
+    if (bp >= ppi) {
+      const size_t bsmem = (size_t)bp * C * sizeof(f16) + sizeof(double) * 2 * (size_t)C;
+      static bool battr = false;
+      if (!battr) {
+        B2E_CUDA(cudaFuncSetAttribute(gn_apply_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        battr = true;
+      }
+      launch_pdl(gn_apply_bulk_kernel, dim3(dim3((a.HW + bp - 1) / bp, a.N)), dim3(threads), bsmem, st, a, bp);
+      return check_launch("gn_apply_bulk");
+    }
   }
   if (a.planes == 3) launch_pdl(gn_apply_kernel<true>, dim3(dim3((a.HW + ppb - 1) / ppb, a.N)), dim3(threads), smem, st, a, ppb);
   else launch_pdl(gn_apply_kernel<false>, dim3(dim3((a.HW + ppb - 1) / ppb, a.N)), dim3(threads), smem, st, a, ppb);
