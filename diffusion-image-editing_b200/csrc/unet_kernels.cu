@@ -232,9 +232,8 @@ __global__ void __launch_bounds__(512, SPLIT ? 1 : 2) gn_apply_kernel(GNArgs a, 
 
 // Bulk-copy variant of the apply pass (plain f16 tensors, channel pitch == channels, statistics from the producing
 // convolution): thread 0 issues the block's whole input - one contiguous chunk per source - as cp.async.bulk copies into
-// shared memory BEFORE the statistics prologue, so up to 32 KB per block are in flight while the prologue runs, without
+// shared memory BEFORE the statistics prologue, so up to 64 KB per block are in flight while the prologue runs, without
 // holding them in registers; the transform then reads shared memory.  Same arithmetic, same results as gn_apply_kernel.
-constexpr int kGNBulkBytes = 32 * 1024;
 __global__ void __launch_bounds__(kGNThreads) gn_apply_bulk_kernel(GNArgs a, int pix_per_block) {
   __shared__ float s_mean[64], s_rstd[64];
   __shared__ __align__(8) uint64_t s_bar;
@@ -454,17 +453,26 @@ int gn_launch(const GNArgs& a_in, cudaStream_t st) {
     B2E_CUDA(cudaFuncSetAttribute(gn_apply_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     attr_set = true;
   }
-  // bulk-copy variant: plain tensors with compact channels and fused statistics, chunks of <= 32 KB per block
+  // bulk-copy variant: plain tensors with compact channels and fused statistics.  Chunk per block (measured on B200 at batch 8,
+  // all GroupNorm launches of a DDPM-256 forward, tools/profile_ops.py: stand-alone kernel 1.573 ms; 8 / 16 / 32 / 48 / 64 / 96 /
+  // 128 KB chunks 2.89 / 1.94 / 1.515 / 1.459 / 1.449 / 1.51 / 1.70 ms): 64 KB where that still gives two waves of blocks
+  // (the 256x256 concatenated layers: 104 -> 86 us = 0.93 of the HBM copy peak), 32 KB for mid-size tensors of <= 256
+  // channels, the register-staged kernel below for everything smaller.  B2E_GN_BULK=0 disables, B2E_GN_BULK_KB forces a size.
   static const int bulk_on = getenv("B2E_GN_BULK") ? atoi(getenv("B2E_GN_BULK")) : 1;
-  if (bulk_on && a.planes == 1 && (a.cs0 || a.ts0) && a.P0 == a.C0 && (a.C1 == 0 || a.P1 == a.C1) && a.Pout == C && C <= 2048 &&
-      threads == kGNThreads && (int64_t)a.HW * C * 2 >= 4 * kGNBulkBytes) {
-    int bp = kGNBulkBytes / (C * 2);           // pixels per block: a multiple of the pixel lanes
+  static const int bulk_kb = getenv("B2E_GN_BULK_KB") ? atoi(getenv("B2E_GN_BULK_KB")) : 0;
+  const int64_t tensor_bytes = (int64_t)a.N * a.HW * C * 2;
+  int bulk_bytes = bulk_kb > 0 ? bulk_kb * 1024
+                               : tensor_bytes >= (int64_t)2 * kNumSMs * 65536 ? 65536
+                               : (tensor_bytes >= (int64_t)8 << 20 && C <= 256) ? 32768 : 0;
+  if (bulk_on && bulk_bytes && a.planes == 1 && (a.cs0 || a.ts0) && a.P0 == a.C0 && (a.C1 == 0 || a.P1 == a.C1) && a.Pout == C &&
+      C <= 2048 && threads == kGNThreads && (int64_t)a.HW * C * 2 >= 2 * (int64_t)bulk_bytes) {
+    int bp = bulk_bytes / (C * 2);             // pixels per block: a multiple of the pixel lanes
     bp -= bp % ppi;
     if (bp >= ppi) {
       const size_t bsmem = (size_t)bp * C * sizeof(f16) + sizeof(double) * 2 * (size_t)C;
       static bool battr = false;
       if (!battr) {
-        B2E_CUDA(cudaFuncSetAttribute(gn_apply_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        B2E_CUDA(cudaFuncSetAttribute(gn_apply_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         battr = true;
       }
       launch_pdl(gn_apply_bulk_kernel, dim3(dim3((a.HW + bp - 1) / bp, a.N)), dim3(threads), bsmem, st, a, bp);
