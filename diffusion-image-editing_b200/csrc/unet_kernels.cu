@@ -632,6 +632,90 @@ __global__ void __launch_bounds__(kGNThreads) gn_bwd_apply_kernel(GNBwdArgs a, i
   }
 }
 
+// Bulk-copy variant of the backward apply pass (compact channels: C == P == Pda): the block's x / da / add chunks are issued
+// as cp.async.bulk copies into shared memory before the per-group prologue (see gn_apply_bulk_kernel).  Same arithmetic.
+__global__ void __launch_bounds__(kGNThreads) gn_bwd_apply_bulk_kernel(GNBwdArgs a, int pix_per_block) {
+  __shared__ float s_ma[64], s_mb[64];
+  __shared__ __align__(8) uint64_t s_bar;
+  extern __shared__ __align__(128) uint8_t s_dyn[];
+  const int C = a.C, slots = C >> 3, ppi = kGNThreads / slots;
+  const int n = blockIdx.y, tid = threadIdx.x;
+  const int cpg = C / a.G;
+  const int p0 = blockIdx.x * pix_per_block, p1 = min(a.HW, p0 + pix_per_block), np = p1 - p0;
+  f16* tx = reinterpret_cast<f16*>(s_dyn);
+  f16* td = tx + (size_t)pix_per_block * C;
+  f16* ta = td + (size_t)pix_per_block * C;
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  pdl_wait();
+  if (tid == 0) {
+    const uint32_t bytes = (uint32_t)np * C * sizeof(f16);
+    const int64_t off = ((int64_t)n * a.HW + p0) * C;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * (a.add ? 3u : 2u)) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(tx)), "l"(a.x + off), "r"(bytes), "r"(bar) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(td)), "l"(a.da + off), "r"(bytes), "r"(bar) : "memory");
+    if (a.add)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"((uint32_t)__cvta_generic_to_shared(ta)), "l"(a.add + off), "r"(bytes), "r"(bar) : "memory");
+  }
+  if (tid < a.G) {
+    double ta2 = 0.0, tb2 = 0.0;
+    for (int ch = 0; ch < a.chunks; ++ch) {
+      const float* o = a.partial + (((int64_t)n * a.chunks + ch) * a.G + tid) * 2;
+      ta2 += (double)o[0]; tb2 += (double)o[1];
+    }
+    const double cnt = (double)a.HW * cpg;
+    s_ma[tid] = (float)(ta2 / cnt); s_mb[tid] = (float)(tb2 / cnt);
+  }
+  __syncthreads();
+  const int s = tid % slots, pl = tid / slots;
+  if (pl >= ppi) return;
+  const int c = s * 8;
+  float sc[8], sh[8], gr[8], k1[8], k0[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = (c + j) / cpg;
+    const float2 st = *reinterpret_cast<const float2*>(a.stats + ((int64_t)n * a.G + g) * 2);
+    const float gam = __ldg(a.gamma + c + j), rstd = st.y, mr = -st.x * st.y;
+    sc[j] = gam * rstd; sh[j] = fmaf(gam, mr, __ldg(a.beta + c + j));
+    gr[j] = gam * rstd;
+    k1[j] = -rstd * rstd * s_mb[g];
+    k0[j] = -rstd * fmaf(mr, s_mb[g], s_ma[g]);
+  }
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "GNBB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], 0;\n"
+      "@P1 bra GNBB_DONE;\n"
+      "bra GNBB_WAIT;\n"
+      "GNBB_DONE:\n"
+      "}\n" ::"r"(bar) : "memory");
+  f16* dst = a.dx + ((int64_t)n * a.HW + p0) * C + c;
+  const bool has_add = a.add != nullptr;
+#pragma unroll 2
+  for (int q = pl; q < np; q += ppi) {
+    float xf[8], df[8], af[8];
+    unpack8(*reinterpret_cast<const uint4*>(tx + (size_t)q * C + c), xf);
+    unpack8(*reinterpret_cast<const uint4*>(td + (size_t)q * C + c), df);
+    if (has_add) unpack8(*reinterpret_cast<const uint4*>(ta + (size_t)q * C + c), af);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float dy = df[j];
+      if (a.silu) dy *= silu_grad(fmaf(xf[j], sc[j], sh[j]));
+      float dx = fmaf(dy, gr[j], fmaf(xf[j], k1[j], k0[j]));
+      if (has_add) dx += af[j];
+      xf[j] = dx;
+    }
+    *reinterpret_cast<uint4*>(dst + (int64_t)q * C) = pack8(xf);
+  }
+}
+
 int gn_bwd_launch(const GNBwdArgs& a, cudaStream_t st) {
   B2E_REQUIRE(a.C % 8 == 0 && a.P >= a.C && a.Pda >= a.C && a.P % 8 == 0 && a.Pda % 8 == 0 && a.P <= 2048 && a.G <= 64 &&
                   a.C % a.G == 0 && a.x && a.da && a.dx && a.stats && a.partial,
@@ -662,6 +746,24 @@ int gn_bwd_launch(const GNBwdArgs& a, cudaStream_t st) {
     launch_pdl(gn_bwd_partial_kernel, dim3(g.chunks, g.N), dim3(kGNThreads), 0, st, g);
     int rc = check_launch("gn_bwd_partial");
     if (rc) return rc;
+    // bulk-copy variant (compact channels): 64 KB of inputs per block where the grid keeps two waves, else 32 KB
+    static const int bulk_on = getenv("B2E_GN_BULK") ? atoi(getenv("B2E_GN_BULK")) : 1;
+    const int streams = g.add ? 3 : 2;
+    const int64_t in_bytes = (int64_t)g.N * g.HW * g.C * 2 * streams;
+    const int bulk_bytes = in_bytes >= (int64_t)2 * kNumSMs * 65536 ? 65536 : in_bytes >= (int64_t)8 << 20 ? 32768 : 0;
+    int bp = bulk_bytes ? bulk_bytes / (g.C * 2 * streams) : 0;
+    if (bp) bp -= bp % ppi;
+    if (bulk_on && bp >= ppi && g.C == g.P && g.C == g.Pda && g.C <= 1024) {
+      static bool battr = false;
+      if (!battr) {
+        B2E_CUDA(cudaFuncSetAttribute(gn_bwd_apply_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        battr = true;
+      }
+      launch_pdl(gn_bwd_apply_bulk_kernel, dim3((g.HW + bp - 1) / bp, g.N), dim3(kGNThreads), (size_t)bp * g.C * 2 * streams, st, g, bp);
+      rc = check_launch("gn_bwd_apply_bulk");
+      if (rc) return rc;
+      continue;
+    }
     launch_pdl(gn_bwd_apply_kernel, dim3((g.HW + ppb - 1) / ppb, g.N), dim3(kGNThreads), 0, st, g, ppb);
     rc = check_launch("gn_bwd_apply");
     if (rc) return rc;
