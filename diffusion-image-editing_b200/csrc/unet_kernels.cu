@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(512, SPLIT ? 1 : 2) gn_apply_kernel(GNArgs a, 
   }
 }
 
-// Bulk-copy variant of the apply pass (plain f16 tensors, channel pitch == channels, statistics from the producing
+// Bulk-copy variant of the apply pass (plain f16 tensors - channel pitches allowed -, statistics from the producing
 // convolution): thread 0 issues the block's whole input - one contiguous chunk per source - as cp.async.bulk copies into
 // shared memory BEFORE the statistics prologue, so up to 64 KB per block are in flight while the prologue runs, without
 // holding them in registers; the transform then reads shared memory.  Same arithmetic, same results as gn_apply_kernel.
@@ -238,19 +238,22 @@ __global__ void __launch_bounds__(kGNThreads) gn_apply_bulk_kernel(GNArgs a, int
   __shared__ float s_mean[64], s_rstd[64];
   __shared__ __align__(8) uint64_t s_bar;
   extern __shared__ __align__(128) uint8_t s_dyn[];
-  const int C = a.C0 + a.C1, slots = C >> 3, ppi = (int)blockDim.x / slots;
+  const int C = a.C0 + a.C1, slots = a.Pout >> 3, ppi = (int)blockDim.x / slots;
   const int n = a.reverse ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y, tid = threadIdx.x;
   const int bx = a.reverse ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
   const int cpg = C / a.G;
   const int p0 = bx * pix_per_block, p1 = min(a.HW, p0 + pix_per_block), np = p1 - p0;
-  // [x0 chunk: np x C0][x1 chunk: np x C1] f16, then the per-channel sums (doubles)
+  // [x0 chunk: np x P0][x1 chunk: np x P1] f16 (channel pitches as in memory), then the per-channel sums (doubles)
   f16* t0 = reinterpret_cast<f16*>(s_dyn);
-  f16* t1 = t0 + (size_t)pix_per_block * a.C0;
-  double* s_ch = reinterpret_cast<double*>(s_dyn + (size_t)pix_per_block * C * sizeof(f16));
+  f16* t1 = t0 + (size_t)pix_per_block * a.P0;
+  double* s_ch = reinterpret_cast<double*>(s_dyn + (size_t)pix_per_block * (a.P0 + a.P1) * sizeof(f16));
   const int s = tid % slots, pl = tid / slots, c = s * 8;
+  const bool live = c < C;     // slots beyond the real channels write the zero padding of the output pitch
   float scale[8], shift[8];
+  if (live) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { scale[j] = __ldg(a.gamma + c + j); shift[j] = __ldg(a.beta + c + j); }
+    for (int j = 0; j < 8; ++j) { scale[j] = __ldg(a.gamma + c + j); shift[j] = __ldg(a.beta + c + j); }
+  }
   const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
@@ -258,18 +261,18 @@ __global__ void __launch_bounds__(kGNThreads) gn_apply_bulk_kernel(GNArgs a, int
   }
   pdl_wait();
   if (tid == 0) {
-    const uint32_t b0 = (uint32_t)np * a.C0 * sizeof(f16), b1 = (uint32_t)np * a.C1 * sizeof(f16);
+    const uint32_t b0 = (uint32_t)np * a.P0 * sizeof(f16), b1 = a.C1 ? (uint32_t)np * a.P1 * sizeof(f16) : 0u;
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(b0 + b1) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"((uint32_t)__cvta_generic_to_shared(t0)), "l"(a.x0 + ((int64_t)n * a.HW + p0) * a.C0), "r"(b0), "r"(bar) : "memory");
+                 ::"r"((uint32_t)__cvta_generic_to_shared(t0)), "l"(a.x0 + ((int64_t)n * a.HW + p0) * a.P0), "r"(b0), "r"(bar) : "memory");
     if (b1)
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                   ::"r"((uint32_t)__cvta_generic_to_shared(t1)), "l"(a.x1 + ((int64_t)n * a.HW + p0) * a.C1), "r"(b1), "r"(bar) : "memory");
+                   ::"r"((uint32_t)__cvta_generic_to_shared(t1)), "l"(a.x1 + ((int64_t)n * a.HW + p0) * a.P1), "r"(b1), "r"(bar) : "memory");
   }
   // statistics prologue (as gn_apply_kernel)
   for (int ch = tid; ch < C; ch += blockDim.x) {
     const bool first = ch < a.C0;
-    const int Cs = first ? a.C0 : a.C1, cc = first ? ch : ch - a.C0;
+    const int Cs = first ? a.P0 : a.P1, cc = first ? ch : ch - a.C0;
     double ts = 0.0, tq = 0.0;
     if (a.ts0) {
       const float* t = first ? a.ts0 : a.ts1;
@@ -301,6 +304,11 @@ __global__ void __launch_bounds__(kGNThreads) gn_apply_bulk_kernel(GNArgs a, int
   }
   __syncthreads();
   if (pl >= ppi) return;
+  f16* dst = a.out + ((int64_t)n * a.HW + p0) * a.Pout + c;
+  if (!live) {
+    for (int q = pl; q < np; q += ppi) *reinterpret_cast<uint4*>(dst + (int64_t)q * a.Pout) = make_uint4(0, 0, 0, 0);
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int g = (c + j) / cpg;
@@ -319,8 +327,7 @@ __global__ void __launch_bounds__(kGNThreads) gn_apply_bulk_kernel(GNArgs a, int
       "}\n" ::"r"(bar) : "memory");
   const bool first = c < a.C0;
   const f16* src = first ? t0 + c : t1 + (c - a.C0);
-  const int cs = first ? a.C0 : a.C1;
-  f16* dst = a.out + ((int64_t)n * a.HW + p0) * a.Pout + c;
+  const int cs = first ? a.P0 : a.P1;
 #pragma unroll 4
   for (int q = pl; q < np; q += ppi) {
     const uint4 v = *reinterpret_cast<const uint4*>(src + (size_t)q * cs);
@@ -464,12 +471,13 @@ int gn_launch(const GNArgs& a_in, cudaStream_t st) {
   int bulk_bytes = bulk_kb > 0 ? bulk_kb * 1024
                                : tensor_bytes >= (int64_t)2 * kNumSMs * 65536 ? 65536
                                : (tensor_bytes >= (int64_t)8 << 20 && C <= 256) ? 32768 : 0;
-  if (bulk_on && bulk_bytes && a.planes == 1 && (a.cs0 || a.ts0) && a.P0 == a.C0 && (a.C1 == 0 || a.P1 == a.C1) && a.Pout == C &&
-      C <= 2048 && threads == kGNThreads && (int64_t)a.HW * C * 2 >= 2 * (int64_t)bulk_bytes) {
-    int bp = bulk_bytes / (C * 2);             // pixels per block: a multiple of the pixel lanes
+  const int Pin = a.P0 + (a.C1 ? a.P1 : 0);     // input f16 per pixel as stored (channel pitches: LDM's 224 -> 256, ...)
+  if (bulk_on && bulk_bytes && a.planes == 1 && (a.cs0 || a.ts0) && Pin <= 2048 && threads == kGNThreads &&
+      (int64_t)a.HW * Pin * 2 >= 2 * (int64_t)bulk_bytes) {
+    int bp = bulk_bytes / (Pin * 2);           // pixels per block: a multiple of the pixel lanes
     bp -= bp % ppi;
     if (bp >= ppi) {
-      const size_t bsmem = (size_t)bp * C * sizeof(f16) + sizeof(double) * 2 * (size_t)C;
+      const size_t bsmem = (size_t)bp * Pin * sizeof(f16) + sizeof(double) * 2 * (size_t)C;
       static bool battr = false;
       if (!battr) {
         B2E_CUDA(cudaFuncSetAttribute(gn_apply_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
