@@ -11,6 +11,8 @@ the hot path of JohanLundberg12/diffusion-image-editing:
   src/attr_functions.py, src/utils.py).
 * ``oracle.mask``            - src/mask_creator.py + src/Morphology.py in numpy.
 * ``oracle.loops``           - the loop compositions (edit_image / invert / sample).
+* ``oracle.upsample_phases`` - the sub-pixel phase decomposition of ``Upsample2D`` (nearest x2 + conv3x3) the engine
+  computes, restated and pinned against the plain composition (tests/test_upsample_phases_cpu.py).
 * ``oracle/shims``           - stub packages named ``diffusers`` and ``lpips`` so
   that the UNMODIFIED reference ``src/*.py`` can be imported in the dev container
   (``tests/golden/make_golden.py``); they re-export the restatements above.
